@@ -1,0 +1,392 @@
+"""breseq_b200 -- B200-native read-alignment evidence pileup behind breseq's entry points.
+
+Python here is a thin ctypes binding over the C ABI in ``include/brq.h`` (``libbrq.so``: C++ host
+staging + hand-written sm_100a kernels).  The two module-level functions mirror the reference's
+free functions for this path:
+
+* :func:`error_count`        <- ``breseq::error_count()``        (/root/reference/src/breseq/error_count.h:41-52)
+* :func:`identify_mutations` <- ``breseq::identify_mutations()`` (/root/reference/src/breseq/identify_mutations.h:46-60)
+
+There is no CPU fallback: if ``libbrq.so`` is missing, or no CUDA device is usable, the compute
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbrq.so")
+
+
+class BrqError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("threads", C.c_int32)]
+
+
+class _ReadFileSet(C.Structure):
+    _fields_ = [("base_name", C.c_char_p), ("n_files", C.c_uint32)]
+
+
+class _StageOptions(C.Structure):
+    _fields_ = [("seq_ids", C.POINTER(C.c_char_p)), ("n_seq_ids", C.c_uint32),
+                ("read_file_sets", C.POINTER(_ReadFileSet)), ("n_read_file_sets", C.c_uint32),
+                ("coverage_group_of_tid", C.POINTER(C.c_uint32)), ("n_targets", C.c_uint32),
+                ("use_base_repeat", C.c_uint32), ("shard_rank", C.c_uint32), ("shard_count", C.c_uint32)]
+
+
+class _SynthReadSet(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("paired", C.c_uint32), ("read_len", C.c_uint32),
+                ("coverage", C.c_double), ("frag_mean", C.c_double), ("frag_sd", C.c_double)]
+
+
+class _SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("contig_lens", C.POINTER(C.c_uint32)), ("n_contigs", C.c_uint32),
+                ("contig_prefix", C.c_char_p), ("fasta", C.c_char_p), ("sets", C.POINTER(_SynthReadSet)),
+                ("n_sets", C.c_uint32), ("n_polymorphic", C.c_uint32), ("n_fixed", C.c_uint32), ("n_gaps", C.c_uint32),
+                ("min_freq_ppm", C.c_uint32), ("max_freq_ppm", C.c_uint32)]
+
+
+class _StreamInfo(C.Structure):
+    _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
+                ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("bytes_host", C.c_uint64),
+                ("n_targets", C.c_uint32), ("pinned", C.c_uint32),
+                ("score_rec", C.POINTER(C.c_uint32)), ("score_off", C.POINTER(C.c_uint64)),
+                ("hist_rec", C.POINTER(C.c_uint64)), ("hist_off", C.POINTER(C.c_uint64)),
+                ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
+                ("ins_count", C.POINTER(C.c_uint32))]
+
+
+class _ScoreParams(C.Structure):
+    _fields_ = [("mutation_cutoff", C.c_double), ("polymorphism_cutoff", C.c_double),
+                ("polymorphism_precision_decimal", C.c_double), ("polymorphism_precision_places", C.c_uint32),
+                ("base_quality_cutoff", C.c_uint32), ("total_reference_length", C.c_uint64)]
+
+
+#: numpy view of ``brq_column`` (96 bytes per slot)
+COLUMN_DTYPE = np.dtype([("ll", "<f8", 5), ("consensus_score", "<f8"), ("variant_score", "<f8"),
+                         ("redundant", "<f8", 2), ("unique", "<u4", 2), ("raw_redundant", "<u4", 2),
+                         ("n", "<u4"), ("bits", "<u4")])
+assert COLUMN_DTYPE.itemsize == 96
+
+CO_BASE_PREDICTED, CO_UNIQUE_ONLY, CO_EMIT, CO_RECHECK = 1 << 12, 1 << 13, 1 << 14, 1 << 15
+
+_lib = None
+
+
+def load_library():
+    """dlopen ``libbrq.so``; fails loudly when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BrqError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the CUDA path)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.brq_create.restype = C.c_void_p
+    lib.brq_create.argtypes = [P(_Config)]
+    lib.brq_destroy.argtypes = [C.c_void_p]
+    lib.brq_last_error.restype = C.c_char_p
+    lib.brq_last_error.argtypes = [C.c_void_p]
+    lib.brq_version.restype = C.c_char_p
+    sig = {
+        "brq_stage_bam": [C.c_void_p, C.c_char_p, C.c_char_p, P(_StageOptions)],
+        "brq_synth_write": [C.c_void_p, P(_SynthSpec), C.c_char_p, C.c_char_p],
+        "brq_stage_synthetic": [C.c_void_p, P(_SynthSpec), P(_StageOptions)],
+        "brq_stream": [C.c_void_p, P(_StreamInfo)],
+        "brq_upload": [C.c_void_p],
+        "brq_sync": [C.c_void_p],
+        "brq_error_count": [C.c_void_p, C.c_char_p, C.c_int, C.c_int],
+        "brq_hist_device": [C.c_void_p, P(C.c_void_p), P(C.c_uint64), P(C.c_void_p), P(C.c_uint64)],
+        "brq_hist_download": [C.c_void_p, P(P(C.c_uint64)), P(C.c_uint64), P(P(C.c_uint64)), P(C.c_uint64), P(C.c_uint64)],
+        "brq_derive_error_table": [C.c_void_p],
+        "brq_error_table": [C.c_void_p, P(P(C.c_double)), P(C.c_uint64)],
+        "brq_write_error_count_files": [C.c_void_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32, C.c_int, C.c_int, C.c_char_p],
+        "brq_load_error_table": [C.c_void_p, C.c_char_p],
+        "brq_score_columns": [C.c_void_p, P(_ScoreParams)],
+        "brq_columns_download": [C.c_void_p, P(C.c_void_p), P(C.c_uint64), P(P(C.c_uint32)), P(C.c_uint32)],
+        "brq_columns_device": [C.c_void_p, P(C.c_void_p), P(C.c_uint64)],
+        "brq_write_evidence": [C.c_void_p, C.c_char_p, P(C.c_double), P(C.c_double), C.c_uint32, C.c_int,
+                               P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
+        "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
+                                C.c_int, C.c_int, C.c_char_p, P(_StageOptions)],
+        "brq_run_identify_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_double),
+                                       P(C.c_double), C.c_uint32, P(_ScoreParams), C.c_int, P(_StageOptions)],
+        "brq_launch_count": [],
+        "brq_kernel_ms": [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+#: every symbol include/brq.h declares (checked by the CPU test-suite)
+EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_stage_bam", "brq_synth_write",
+           "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
+           "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
+           "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
+           "brq_write_evidence", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms"]
+
+
+def _b(s):
+    return None if s is None else (s if isinstance(s, bytes) else str(s).encode())
+
+
+def _str_array(items):
+    arr = (C.c_char_p * max(1, len(items)))()
+    for i, s in enumerate(items):
+        arr[i] = _b(s)
+    return arr
+
+
+class SynthSpec:
+    """Synthetic aligned reads (SURVEY.md section 8d value distributions)."""
+
+    def __init__(self, seed, read_sets, contig_lens=None, fasta=None, contig_prefix="contig",
+                 n_polymorphic=60, n_fixed=10, n_gaps=2, min_freq_ppm=50000, max_freq_ppm=500000):
+        self.keep = []
+        sets = (_SynthReadSet * len(read_sets))()
+        for i, rs in enumerate(read_sets):
+            name = _b(rs["name"])
+            self.keep.append(name)
+            sets[i] = _SynthReadSet(name, int(rs.get("paired", False)), int(rs["read_len"]), float(rs["coverage"]),
+                                    float(rs.get("frag_mean", 400)), float(rs.get("frag_sd", 40)))
+        lens = None
+        if contig_lens is not None:
+            lens = (C.c_uint32 * len(contig_lens))(*contig_lens)
+        self.keep += [sets, lens]
+        self.c = _SynthSpec(seed, lens, 0 if contig_lens is None else len(contig_lens), _b(contig_prefix), _b(fasta),
+                            sets, len(read_sets), n_polymorphic, n_fixed, n_gaps, min_freq_ppm, max_freq_ppm)
+        self.read_sets = read_sets
+
+    def read_file_sets(self):
+        """The run's cReadFileSets: one per read group, two files when paired."""
+        return [(rs["name"], 2 if rs.get("paired") else 1) for rs in self.read_sets]
+
+
+def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, shard=(0, 1)):
+    keep = []
+    o = _StageOptions()
+    if seq_ids:
+        arr = _str_array(list(seq_ids))
+        keep.append(arr)
+        o.seq_ids, o.n_seq_ids = arr, len(seq_ids)
+    if read_file_sets:
+        names = [_b(n) for n, _ in read_file_sets]
+        arr = (_ReadFileSet * len(read_file_sets))()
+        for i, (n, k) in enumerate(read_file_sets):
+            arr[i] = _ReadFileSet(names[i], k)
+        keep += [names, arr]
+        o.read_file_sets, o.n_read_file_sets = arr, len(read_file_sets)
+    if coverage_groups is not None:
+        arr = (C.c_uint32 * len(coverage_groups))(*coverage_groups)
+        keep.append(arr)
+        o.coverage_group_of_tid, o.n_targets = arr, len(coverage_groups)
+    o.use_base_repeat = int(use_base_repeat)
+    o.shard_rank, o.shard_count = shard
+    return o, keep
+
+
+class Context:
+    """One pileup context = one GPU (``device`` >= 0) or host-only staging (``device`` = -1)."""
+
+    def __init__(self, device=0, threads=0):
+        self.lib = load_library()
+        cfg = _Config(device, threads)
+        self.h = self.lib.brq_create(C.byref(cfg))
+        if not self.h:
+            raise BrqError("brq_create failed")
+        self.device = device
+        err = self.lib.brq_last_error(self.h)
+        if device >= 0 and err:
+            msg = err.decode()
+            self.close()
+            raise BrqError(msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.brq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BrqError(self.lib.brq_last_error(self.h).decode())
+
+    # ---- staging
+    def stage_bam(self, bam, fasta, **kw):
+        o, keep = _stage_options(**kw)
+        self._check(self.lib.brq_stage_bam(self.h, _b(bam), _b(fasta), C.byref(o)))
+
+    def stage_synthetic(self, spec, **kw):
+        o, keep = _stage_options(**kw)
+        self._check(self.lib.brq_stage_synthetic(self.h, C.byref(spec.c), C.byref(o)))
+
+    def synth_write(self, spec, bam_out, fasta_out):
+        self._check(self.lib.brq_synth_write(self.h, C.byref(spec.c), _b(bam_out), _b(fasta_out)))
+
+    def stream(self):
+        info = _StreamInfo()
+        self._check(self.lib.brq_stream(self.h, C.byref(info)))
+        n_slots = info.n_base + info.n_ins
+
+        def view(ptr, n, dtype):
+            if n == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(ptr, shape=(int(n),)).view(dtype)
+        return {
+            "n_base": info.n_base, "n_ins": info.n_ins, "n_score": info.n_score_records, "n_hist": info.n_hist_records,
+            "n_reads": info.n_reads, "bytes_host": info.bytes_host, "pinned": bool(info.pinned), "n_targets": info.n_targets,
+            "score_rec": view(info.score_rec, info.n_score_records, np.uint32),
+            "score_off": view(info.score_off, n_slots + 1, np.uint64),
+            "hist_rec": view(info.hist_rec, info.n_hist_records, np.uint64),
+            "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),
+            "slot_ref": view(info.slot_ref, n_slots, np.uint8),
+            "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
+            "ins_count": view(info.ins_count, info.n_ins, np.uint32),
+        }
+
+    def upload(self):
+        self._check(self.lib.brq_upload(self.h))
+
+    def sync(self):
+        self._check(self.lib.brq_sync(self.h))
+
+    # ---- pass 1
+    def error_count(self, covariates, do_coverage=True, do_errors=True):
+        self._check(self.lib.brq_error_count(self.h, _b(covariates), int(do_coverage), int(do_errors)))
+
+    def hist_device(self):
+        c, n, v, m = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        self._check(self.lib.brq_hist_device(self.h, C.byref(c), C.byref(n), C.byref(v), C.byref(m)))
+        return c.value, n.value, v.value, m.value
+
+    def hist_download(self):
+        c, v = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+        n, stride, groups = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.brq_hist_download(self.h, C.byref(c), C.byref(n), C.byref(v), C.byref(stride), C.byref(groups)))
+        counts = np.ctypeslib.as_array(c, shape=(n.value,)).copy()
+        cov = np.ctypeslib.as_array(v, shape=(stride.value * groups.value,)).copy().reshape(groups.value, stride.value)
+        return counts, cov
+
+    def derive_error_table(self):
+        self._check(self.lib.brq_derive_error_table(self.h))
+
+    def error_table(self):
+        t, n = C.POINTER(C.c_double)(), C.c_uint64()
+        self._check(self.lib.brq_error_table(self.h, C.byref(t), C.byref(n)))
+        return np.ctypeslib.as_array(t, shape=(n.value,)).copy()
+
+    def write_error_count_files(self, output_dir, error_rates_file=None, readfiles=(), do_coverage=True, do_errors=True,
+                                counts_dump=None):
+        arr = _str_array(list(readfiles))
+        self._check(self.lib.brq_write_error_count_files(self.h, _b(output_dir), _b(error_rates_file), arr, len(readfiles),
+                                                         int(do_coverage), int(do_errors), _b(counts_dump)))
+
+    def load_error_table(self, path):
+        self._check(self.lib.brq_load_error_table(self.h, _b(path)))
+
+    # ---- pass 2
+    @staticmethod
+    def score_params(mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision_decimal=1e-6, precision_places=8,
+                     base_quality_cutoff=3, total_reference_length=0):
+        return _ScoreParams(mutation_cutoff, polymorphism_cutoff, precision_decimal, precision_places, base_quality_cutoff,
+                            total_reference_length)
+
+    def score_columns(self, params=None):
+        p = params or self.score_params()
+        self._check(self.lib.brq_score_columns(self.h, C.byref(p)))
+
+    def columns_download(self):
+        cols, n, fl, nf = C.c_void_p(), C.c_uint64(), C.POINTER(C.c_uint32)(), C.c_uint32()
+        self._check(self.lib.brq_columns_download(self.h, C.byref(cols), C.byref(n), C.byref(fl), C.byref(nf)))
+        buf = (C.c_char * (n.value * 96)).from_address(cols.value)
+        columns = np.frombuffer(buf, dtype=COLUMN_DTYPE).copy()
+        flagged = np.ctypeslib.as_array(fl, shape=(nf.value,)).copy() if nf.value else np.zeros(0, np.uint32)
+        return columns, flagged
+
+    def columns_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.brq_columns_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def write_evidence(self, gd_file, deletion_propagation_cutoff, deletion_seed_cutoff, skip_missing_coverage_prediction=False):
+        n = len(deletion_propagation_cutoff)
+        prop = (C.c_double * n)(*deletion_propagation_cutoff)
+        seed = (C.c_double * n)(*deletion_seed_cutoff)
+        ra, mc, un = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.brq_write_evidence(self.h, _b(gd_file), prop, seed, n, int(skip_missing_coverage_prediction),
+                                                C.byref(ra), C.byref(mc), C.byref(un)))
+        return {"RA": ra.value, "MC": mc.value, "UN": un.value}
+
+    def kernel_ms(self):
+        a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
+        self.lib.brq_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return {"hist": a.value, "coverage": b.value, "derive": c.value, "score": d.value}
+
+    def launch_count(self):
+        return self.lib.brq_launch_count()
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's entry points for this path (same argument meaning; Settings fields passed flat)
+# ----------------------------------------------------------------------------------------------
+def error_count(bam, fasta, output_dir, readfiles, do_coverage=True, do_errors=True, preprocess_stage=False,
+                min_qual_score=0, covariates="", *, call_mutations_seq_ids=None, read_file_sets=None,
+                coverage_group_of_tid=None, error_rates_file_name=None, device=0, ctx=None):
+    """``breseq::error_count()`` (error_count.cpp:50-68): writes ``error_rates.tab``,
+    ``base_qual_error_prob.<readfile>.tab`` and ``<group>.unique_only_coverage_distribution.tab``.
+
+    ``min_qual_score`` is accepted and unused, as in the reference (error_count.h:295).
+    ``preprocess_stage`` (read-start bookkeeping for candidate junctions) is outside this path.
+    """
+    if preprocess_stage:
+        raise BrqError("preprocess_stage=True (stage 03 coverage pre-pass) is not part of the accelerated path")
+    own = ctx is None
+    ctx = ctx or Context(device)
+    try:
+        o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets,
+                                 coverage_groups=coverage_group_of_tid, use_base_repeat="base_repeat" in covariates)
+        arr = _str_array(list(readfiles))
+        ctx._check(ctx.lib.brq_run_error_count(ctx.h, _b(bam), _b(fasta), _b(output_dir), _b(error_rates_file_name), arr,
+                                               len(readfiles), int(do_coverage), int(do_errors), _b(covariates), C.byref(o)))
+    finally:
+        if own:
+            ctx.close()
+
+
+def identify_mutations(bam, fasta, gd_file, deletion_propagation_cutoff, deletion_seed_cutoff, mutation_cutoff,
+                       polymorphism_cutoff, polymorphism_precision_decimal, polymorphism_precision_places,
+                       print_per_position_file=False, *, error_rates_file_name, base_quality_cutoff=3,
+                       skip_missing_coverage_prediction=False, call_mutations_seq_ids=None, read_file_sets=None,
+                       total_reference_length=0, device=0, ctx=None):
+    """``breseq::identify_mutations()`` (identify_mutations.cpp:48-88): writes ``ra_mc_evidence.gd``."""
+    if print_per_position_file:
+        raise BrqError("print_per_position_file (debug dump) is not part of the accelerated path")
+    own = ctx is None
+    ctx = ctx or Context(device)
+    try:
+        o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets)
+        n = len(deletion_propagation_cutoff)
+        prop = (C.c_double * n)(*deletion_propagation_cutoff)
+        seed = (C.c_double * n)(*deletion_seed_cutoff)
+        p = Context.score_params(mutation_cutoff, polymorphism_cutoff, polymorphism_precision_decimal,
+                                 polymorphism_precision_places, base_quality_cutoff, total_reference_length)
+        ctx._check(ctx.lib.brq_run_identify_mutations(ctx.h, _b(bam), _b(fasta), _b(error_rates_file_name), _b(gd_file),
+                                                      prop, seed, n, C.byref(p), int(skip_missing_coverage_prediction),
+                                                      C.byref(o)))
+    finally:
+        if own:
+            ctx.close()

@@ -1,0 +1,55 @@
+"""Build libbrq.so (host staging + sm_100a kernels + C ABI) in-tree with nvcc.
+
+The shared object lands next to this file so it travels with the repository snapshot to the GPU
+box; nothing is JIT-compiled at run time.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbrq.so")
+
+CU_SOURCES = ["kernels.cu", "brq_api.cu"]
+CPP_SOURCES = ["bam_io.cpp", "staging.cpp", "synth.cpp", "finalize.cpp"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(verbose=False, force=False):
+    nvcc = os.environ.get("NVCC", "nvcc")
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
+    headers.append(os.path.join(HERE, "..", "include", "brq.h"))
+    objs = []
+    for src in CU_SOURCES + CPP_SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(objdir, src + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [path] + headers):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True)
+    if force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lz", "-lpthread", "-cudart", "shared"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))

@@ -1,0 +1,378 @@
+#include "bam_io.h"
+
+#include <zlib.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+namespace brq {
+
+namespace {
+
+std::vector<uint8_t> slurp(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> buf((size_t)n);
+  if (n && fread(buf.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); throw std::runtime_error("short read on " + path); }
+  fclose(f);
+  return buf;
+}
+
+struct BgzfBlock { size_t cdata, clen, uoff; uint32_t isize; };
+
+// Pass 1 over the compressed image: block boundaries and output offsets, so the members can be
+// inflated independently.
+std::vector<BgzfBlock> index_blocks(const std::vector<uint8_t>& in, size_t& total) {
+  std::vector<BgzfBlock> blocks;
+  size_t p = 0;
+  total = 0;
+  while (p + 18 <= in.size()) {
+    if (in[p] != 31 || in[p + 1] != 139 || !(in[p + 3] & 4)) throw std::runtime_error("not a BGZF member");
+    uint32_t xlen = in[p + 10] | (in[p + 11] << 8);
+    size_t x = p + 12, xend = x + xlen;
+    int bsize = -1;
+    while (x + 4 <= xend) {
+      uint32_t slen = in[x + 2] | (in[x + 3] << 8);
+      if (in[x] == 'B' && in[x + 1] == 'C' && slen == 2) bsize = in[x + 4] | (in[x + 5] << 8);
+      x += 4 + slen;
+    }
+    if (bsize < 0) throw std::runtime_error("BGZF member without BC subfield");
+    size_t len = (size_t)bsize + 1;
+    if (p + len > in.size()) throw std::runtime_error("truncated BGZF member");
+    BgzfBlock b;
+    b.cdata = xend;
+    b.clen = len - (xend - p) - 8;
+    memcpy(&b.isize, &in[p + len - 4], 4);
+    b.uoff = total;
+    total += b.isize;
+    blocks.push_back(b);
+    p += len;
+  }
+  if (p != in.size()) throw std::runtime_error("trailing bytes after the last BGZF member");
+  return blocks;
+}
+
+void inflate_block(const std::vector<uint8_t>& in, const BgzfBlock& b, uint8_t* out) {
+  if (!b.isize) return;
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, -15) != Z_OK) throw std::runtime_error("inflateInit2 failed");
+  zs.next_in = const_cast<Bytef*>(&in[b.cdata]);
+  zs.avail_in = (uInt)b.clen;
+  zs.next_out = out + b.uoff;
+  zs.avail_out = b.isize;
+  int r = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  if (r != Z_STREAM_END) throw std::runtime_error("corrupt BGZF payload");
+}
+
+template <typename T> T rd(const uint8_t* p) { T v; memcpy(&v, p, sizeof(T)); return v; }
+
+// Aux walk for the handful of tags the path reads (alignment.cpp:52-57, 73-76; alignment.h:389-410).
+size_t aux_value_size(uint8_t type) {
+  switch (type) { case 'A': case 'c': case 'C': return 1; case 's': case 'S': return 2;
+                  case 'i': case 'I': case 'f': return 4; case 'd': return 8; default: return 0; }
+}
+int64_t aux_int(uint8_t type, const uint8_t* v) {
+  switch (type) { case 'c': return rd<int8_t>(v); case 'C': return rd<uint8_t>(v); case 's': return rd<int16_t>(v);
+                  case 'S': return rd<uint16_t>(v); case 'i': return rd<int32_t>(v); case 'I': return rd<uint32_t>(v);
+                  default: return 0; }
+}
+
+void parse_rg_lines(const std::string& text, ReadGroups& rg) {
+  size_t p = 0;
+  while (p < text.size()) {
+    size_t e = text.find('\n', p);
+    if (e == std::string::npos) e = text.size();
+    if (e - p >= 3 && text.compare(p, 3, "@RG") == 0) {
+      std::string id, lb;
+      bool has_id = false;
+      size_t f = p + 3;
+      while (f < e) {
+        size_t g = text.find('\t', f + 1);
+        if (g == std::string::npos || g > e) g = e;
+        if (text[f] == '\t' && g - f >= 4 && text[f + 3] == ':') {
+          std::string key = text.substr(f + 1, 2), val = text.substr(f + 4, g - f - 4);
+          if (key == "ID") { id = val; has_id = true; }
+          else if (key == "LB") lb = val;
+        }
+        f = g;
+      }
+      if (has_id) { rg.ids.push_back(id); rg.libraries.push_back(lb); }  // an @RG without ID is unreferable
+    }
+    p = e + 1;
+  }
+}
+
+}  // namespace
+
+void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int threads) {
+  std::vector<uint8_t> in = slurp(path);
+  size_t total = 0;
+  std::vector<BgzfBlock> blocks = index_blocks(in, total);
+  std::vector<uint8_t> u(total);
+  if (threads < 1) threads = 1;
+  {
+    std::atomic<size_t> next(0);
+    std::atomic<bool> failed(false);
+    auto work = [&]() {
+      try {
+        for (;;) {
+          size_t i = next.fetch_add(16);
+          if (i >= blocks.size()) break;
+          for (size_t j = i; j < std::min(i + 16, blocks.size()); ++j) inflate_block(in, blocks[j], u.data());
+        }
+      } catch (...) { failed = true; }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed) throw std::runtime_error("corrupt BGZF payload in " + path);
+  }
+  in.clear();
+  in.shrink_to_fit();
+
+  if (u.size() < 12 || memcmp(u.data(), "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
+  size_t p = 4;
+  int32_t l_text = rd<int32_t>(&u[p]); p += 4;
+  hdr.text.assign((const char*)&u[p], (size_t)l_text);
+  hdr.text = hdr.text.c_str();  // cut at the first NUL, as a C string consumer would see it
+  p += (size_t)l_text;
+  int32_t n_ref = rd<int32_t>(&u[p]); p += 4;
+  for (int i = 0; i < n_ref; ++i) {
+    int32_t l_name = rd<int32_t>(&u[p]); p += 4;
+    hdr.target_names.emplace_back((const char*)&u[p]);
+    p += (size_t)l_name;
+    hdr.target_lens.push_back((uint32_t)rd<int32_t>(&u[p])); p += 4;
+  }
+  parse_rg_lines(hdr.text, hdr.read_groups);
+  const ReadGroups& rg = hdr.read_groups;
+
+  while (p + 4 <= u.size()) {
+    int32_t block = rd<int32_t>(&u[p]);
+    const uint8_t* x = &u[p + 4];
+    if (p + 4 + (size_t)block > u.size()) throw std::runtime_error("truncated BAM record");
+    int32_t tid = rd<int32_t>(x), pos = rd<int32_t>(x + 4);
+    uint8_t l_name = x[8], mapq = x[9];
+    uint16_t n_cigar = rd<uint16_t>(x + 12), flag = rd<uint16_t>(x + 14);
+    int32_t l_seq = rd<int32_t>(x + 16);
+    const uint8_t* q = x + 32 + l_name;
+    reads.tid.push_back(tid); reads.pos.push_back(pos); reads.flag.push_back(flag); reads.mapq.push_back(mapq);
+    reads.n_cigar.push_back(n_cigar); reads.cigar_off.push_back(reads.cigars.size());
+    for (int k = 0; k < n_cigar; ++k) reads.cigars.push_back(rd<uint32_t>(q + 4 * k));
+    q += 4 * (size_t)n_cigar;
+    reads.l_seq.push_back((uint32_t)l_seq); reads.seq_off.push_back(reads.bases.size());
+    for (int i = 0; i < l_seq; ++i) reads.bases.push_back((q[i >> 1] >> ((~i & 1) << 2)) & 0xf);
+    q += ((size_t)l_seq + 1) >> 1;
+    reads.quals.insert(reads.quals.end(), q, q + l_seq);
+    q += l_seq;
+    uint32_t x1 = 1; int32_t xl = -1, xr = -1, as = 0; uint8_t rgi = 0;
+    bool seen_x1 = false, seen_xl = false, seen_xr = false, seen_rg = false;  // bam_aux_get returns the FIRST match
+    const uint8_t* end = x + block;
+    while (q + 3 <= end) {
+      uint8_t t0 = q[0], t1 = q[1], type = q[2];
+      const uint8_t* v = q + 3;
+      size_t sz = aux_value_size(type);
+      if (sz) {
+        if (t0 == 'X' && t1 == '1' && !seen_x1) { x1 = (uint32_t)aux_int(type, v); seen_x1 = true; }
+        else if (t0 == 'X' && t1 == 'L' && !seen_xl) { xl = (int32_t)aux_int(type, v); seen_xl = true; }
+        else if (t0 == 'X' && t1 == 'R' && !seen_xr) { xr = (int32_t)aux_int(type, v); seen_xr = true; }
+        else if (t0 == 'A' && t1 == 'S') as = (int32_t)aux_int(type, v);
+        q = v + sz;
+      } else if (type == 'Z' || type == 'H') {
+        const uint8_t* z = v;
+        while (z < end && *z) ++z;
+        if (t0 == 'R' && t1 == 'G' && type == 'Z' && !seen_rg) {
+          seen_rg = true;
+          if (rg.ids.size() > 1) {  // read_group_index_map::index (alignment.h:545-560)
+            std::string id((const char*)v, (size_t)(z - v));
+            for (size_t g = 0; g < rg.ids.size(); ++g) if (rg.ids[g] == id) { rgi = (uint8_t)g; break; }
+          }
+        }
+        q = z + 1;
+      } else if (type == 'B') {
+        uint8_t st = v[0];
+        uint32_t n = rd<uint32_t>(v + 1);
+        q = v + 5 + (size_t)n * aux_value_size(st);
+      } else {
+        throw std::runtime_error("unknown aux type in BAM record");
+      }
+    }
+    reads.x1.push_back(x1); reads.xl.push_back(xl); reads.xr.push_back(xr); reads.as.push_back(as); reads.rg.push_back(rgi);
+    p += 4 + (size_t)block;
+  }
+}
+
+// ---------------------------------------------------------------------------------- writers
+
+namespace {
+
+struct BgzfWriter {
+  FILE* f;
+  int level;
+  std::vector<uint8_t> buf;
+  explicit BgzfWriter(const std::string& path, int lvl) : f(fopen(path.c_str(), "wb")), level(lvl) {
+    if (!f) throw std::runtime_error("cannot create " + path);
+    buf.reserve(0xff00);
+  }
+  void flush_block() {
+    uint8_t out[0x10000];
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = buf.data();
+    zs.avail_in = (uInt)buf.size();
+    zs.next_out = out + 18;
+    zs.avail_out = sizeof(out) - 18 - 8;
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw std::runtime_error("deflate overflow");
+    size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    static const uint8_t head[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
+    memcpy(out, head, 12);
+    out[12] = 'B'; out[13] = 'C'; out[14] = 2; out[15] = 0;
+    uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1);
+    memcpy(out + 16, &bsize, 2);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf.data(), (uInt)buf.size());
+    uint32_t isize = (uint32_t)buf.size();
+    memcpy(out + 18 + clen, &crc, 4);
+    memcpy(out + 18 + clen + 4, &isize, 4);
+    fwrite(out, 1, 18 + clen + 8, f);
+    buf.clear();
+  }
+  void write(const void* p, size_t n) {
+    const uint8_t* s = (const uint8_t*)p;
+    while (n) {
+      size_t room = 0xff00 - buf.size();
+      size_t k = n < room ? n : room;
+      buf.insert(buf.end(), s, s + k);
+      s += k; n -= k;
+      if (buf.size() == 0xff00) flush_block();
+    }
+  }
+  template <typename T> void put(T v) { write(&v, sizeof(T)); }
+  void close() {
+    if (!buf.empty()) flush_block();
+    flush_block();  // empty member = BGZF EOF marker
+    fclose(f);
+    f = nullptr;
+  }
+};
+
+uint16_t reg2bin(int64_t beg, int64_t end) {
+  --end;
+  if (beg >> 14 == end >> 14) return (uint16_t)(((1 << 15) - 1) / 7 + (beg >> 14));
+  if (beg >> 17 == end >> 17) return (uint16_t)(((1 << 12) - 1) / 7 + (beg >> 17));
+  if (beg >> 20 == end >> 20) return (uint16_t)(((1 << 9) - 1) / 7 + (beg >> 20));
+  if (beg >> 23 == end >> 23) return (uint16_t)(((1 << 6) - 1) / 7 + (beg >> 23));
+  if (beg >> 26 == end >> 26) return (uint16_t)(((1 << 3) - 1) / 7 + (beg >> 26));
+  return 0;
+}
+
+}  // namespace
+
+void write_bam(const std::string& path, const BamHeader& hdr, const ReadBatch& r, int level) {
+  BgzfWriter w(path, level);
+  w.write("BAM\1", 4);
+  w.put<int32_t>((int32_t)hdr.text.size());
+  w.write(hdr.text.data(), hdr.text.size());
+  w.put<int32_t>((int32_t)hdr.target_names.size());
+  for (size_t i = 0; i < hdr.target_names.size(); ++i) {
+    w.put<int32_t>((int32_t)hdr.target_names[i].size() + 1);
+    w.write(hdr.target_names[i].c_str(), hdr.target_names[i].size() + 1);
+    w.put<int32_t>((int32_t)hdr.target_lens[i]);
+  }
+  std::vector<uint8_t> rec;
+  for (size_t i = 0; i < r.size(); ++i) {
+    std::string name = i < r.names.size() ? r.names[i] : ("r" + std::to_string(i));
+    rec.clear();
+    auto put = [&](const void* p, size_t n) { rec.insert(rec.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+    auto put32 = [&](int32_t v) { put(&v, 4); };
+    auto put16 = [&](uint16_t v) { put(&v, 2); };
+    const uint32_t* cig = &r.cigars[r.cigar_off[i]];
+    int64_t rlen = 0;
+    for (uint32_t k = 0; k < r.n_cigar[i]; ++k) {
+      uint32_t op = cig[k] & 0xf;
+      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cig[k] >> 4;
+    }
+    put32(r.tid[i]); put32(r.pos[i]);
+    rec.push_back((uint8_t)(name.size() + 1)); rec.push_back(r.mapq[i]);
+    put16(reg2bin(r.pos[i], r.pos[i] + (rlen ? rlen : 1)));
+    put16((uint16_t)r.n_cigar[i]); put16(r.flag[i]);
+    put32((int32_t)r.l_seq[i]); put32(-1); put32(-1); put32(0);
+    put(name.c_str(), name.size() + 1);
+    put(cig, 4 * (size_t)r.n_cigar[i]);
+    const uint8_t* b = &r.bases[r.seq_off[i]];
+    for (uint32_t j = 0; j < r.l_seq[i]; j += 2) {
+      uint8_t hi = b[j], lo = (j + 1 < r.l_seq[i]) ? b[j + 1] : 0;
+      rec.push_back((uint8_t)((hi << 4) | lo));
+    }
+    put(&r.quals[r.seq_off[i]], r.l_seq[i]);
+    auto tag_int = [&](const char* t, int64_t v) {
+      rec.push_back((uint8_t)t[0]); rec.push_back((uint8_t)t[1]);
+      if (v >= 0 && v < 256) { rec.push_back('C'); rec.push_back((uint8_t)v); }
+      else { rec.push_back('i'); int32_t x = (int32_t)v; put(&x, 4); }
+    };
+    tag_int("AS", r.as[i]);
+    if (r.x1[i] != 1 || (i % 3) != 0) tag_int("X1", r.x1[i]);  // leave the tag off some unique reads: absent == 1
+    if (!hdr.read_groups.ids.empty()) {
+      const std::string& id = hdr.read_groups.ids[r.rg[i]];
+      rec.push_back('R'); rec.push_back('G'); rec.push_back('Z');
+      put(id.c_str(), id.size() + 1);
+    }
+    if (r.xl[i] >= 0) tag_int("XL", r.xl[i]);
+    if (r.xr[i] >= 0) tag_int("XR", r.xr[i]);
+    w.put<int32_t>((int32_t)rec.size());
+    w.write(rec.data(), rec.size());
+  }
+  w.close();
+}
+
+void read_fasta(const std::string& path, RefSet& ref) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  char* line = nullptr;
+  size_t cap = 0;
+  ssize_t n;
+  while ((n = getline(&line, &cap, f)) >= 0) {
+    while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+    if (line[0] == '>') {
+      std::string name(line + 1);
+      size_t sp = name.find_first_of(" \t");
+      if (sp != std::string::npos) name.resize(sp);
+      ref.names.push_back(name);
+      ref.seqs.emplace_back();
+    } else if (!ref.seqs.empty()) {
+      ref.seqs.back().append(line, (size_t)n);
+    }
+  }
+  free(line);
+  fclose(f);
+}
+
+void write_fasta(const std::string& path, const RefSet& ref, bool with_fai) {
+  FILE* f = fopen(path.c_str(), "w");
+  if (!f) throw std::runtime_error("cannot create " + path);
+  FILE* fai = with_fai ? fopen((path + ".fai").c_str(), "w") : nullptr;
+  long off = 0;
+  const size_t width = 60;
+  for (size_t i = 0; i < ref.names.size(); ++i) {
+    off += fprintf(f, ">%s\n", ref.names[i].c_str());
+    if (fai) fprintf(fai, "%s\t%zu\t%ld\t%zu\t%zu\n", ref.names[i].c_str(), ref.seqs[i].size(), off, width, width + 1);
+    for (size_t p = 0; p < ref.seqs[i].size(); p += width) {
+      size_t k = std::min(width, ref.seqs[i].size() - p);
+      fwrite(ref.seqs[i].data() + p, 1, k, f);
+      fputc('\n', f);
+      off += (long)k + 1;
+    }
+  }
+  fclose(f);
+  if (fai) fclose(fai);
+}
+
+}  // namespace brq

@@ -1,0 +1,529 @@
+// C ABI (include/brq.h) over the staging layer, the sm_100a kernels and the host finalisation.
+#include "../../include/brq.h"
+
+#include "bam_io.h"
+#include "finalize.h"
+#include "kernels.h"
+#include "staging.h"
+#include "synth.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace brq;
+
+#define CUDA_OK(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+namespace {
+
+void* pinned_alloc(size_t bytes, bool* pinned) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 256, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    throw std::runtime_error("cudaHostAlloc failed for " + std::to_string(bytes) + " bytes");
+  }
+  *pinned = true;
+  return p;
+}
+void pinned_release(void* p, bool pinned) { if (pinned) cudaFreeHost(p); else free(p); }
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  void ensure(size_t want) {
+    if (want <= n && p) return;
+    release();
+    CUDA_OK(cudaMalloc((void**)&p, (want ? want : 1) * sizeof(T)));
+    n = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct brq_ctx {
+  int device = -1;
+  int threads = 8;
+  std::string error;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr};
+  float ms_hist = 0, ms_cov = 0, ms_derive = 0, ms_score = 0;
+
+  BamHeader hdr;
+  RefSet ref;
+  ReadBatch reads;
+  StageConfig stage_cfg;
+  PileupStream st;
+  bool staged = false, uploaded = false;
+
+  DevBuf<uint32_t> d_score_rec, d_flagged, d_scalars;  // d_scalars: [0] err, [1] n_flagged
+  DevBuf<uint64_t> d_score_off, d_hist_rec, d_hist_off;
+  DevBuf<uint8_t> d_slot_ref, d_slot_group;
+  DevBuf<unsigned long long> d_counts, d_cov;
+  DevBuf<double> d_log10;
+  DevBuf<ClassTerms> d_lut;
+  DevBuf<ColumnOut> d_cols;
+
+  CovSpec spec;
+  bool have_spec = false, have_table = false, have_counts = false, have_cols = false;
+  uint64_t cov_stride = 0, n_groups = 0;
+  std::vector<uint64_t> h_counts, h_cov;
+  std::vector<double> h_log10, h_log10_text, h_prob;
+  std::vector<ClassTerms> h_lut;
+  ScoreParams sp;
+  brq_score_params last_params;
+  std::vector<ColumnOut> h_cols;
+  std::vector<uint32_t> h_flagged;
+  uint32_t flagged_cap = 0;
+
+  void need_device() const {
+    if (device < 0) throw std::runtime_error("this context has no CUDA device (brq_config.device < 0): compute calls are unavailable");
+  }
+  void check_device_errors(const char* what) {
+    uint32_t scal[2];
+    CUDA_OK(cudaMemcpyAsync(scal, d_scalars.p, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    if (scal[0]) {
+      std::string m = std::string(what) + ": ";
+      if (scal[0] & BRQ_ERR_QUALITY_RANGE) m += "covariate 'quality' exceeded its maximum; ";
+      if (scal[0] & BRQ_ERR_READSET_RANGE) m += "covariate 'read_set' exceeded its maximum; ";
+      if (scal[0] & BRQ_ERR_READPOS_RANGE) m += "covariate 'read_pos' exceeded its maximum; ";
+      if (scal[0] & BRQ_ERR_CLASS_OVERFLOW) m += "too many distinct record classes in one column; ";
+      if (scal[0] & BRQ_ERR_DEPTH_RANGE) m += "column depth beyond the coverage histogram; ";
+      CUDA_OK(cudaMemsetAsync(d_scalars.p, 0, 4, stream));
+      throw std::runtime_error(m);
+    }
+  }
+};
+
+namespace {
+
+template <class F>
+int guarded(brq_ctx* ctx, F&& f) {
+  if (!ctx) return 1;
+  try { f(); ctx->error.clear(); return 0; }
+  catch (const std::exception& e) { ctx->error = e.what(); return 1; }
+  catch (...) { ctx->error = "unknown error"; return 1; }
+}
+
+void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
+  StageConfig& s = c->stage_cfg;
+  s = StageConfig();
+  s.threads = c->threads;
+  if (c->device >= 0) { s.alloc = pinned_alloc; s.release = pinned_release; }
+  if (!o) return;
+  for (uint32_t i = 0; i < o->n_seq_ids; ++i) s.call_seq_ids.push_back(o->seq_ids[i]);
+  for (uint32_t i = 0; i < o->n_read_file_sets; ++i) s.read_file_sets.push_back({o->read_file_sets[i].base_name, o->read_file_sets[i].n_files});
+  if (o->coverage_group_of_tid) s.coverage_group_of_tid.assign(o->coverage_group_of_tid, o->coverage_group_of_tid + o->n_targets);
+  s.use_base_repeat = o->use_base_repeat != 0;
+  s.shard_rank = o->shard_rank;
+  s.shard_count = o->shard_count ? o->shard_count : 1;
+}
+
+void drop_stream(brq_ctx* c) {
+  if (c->staged) free_stream(c->st, c->stage_cfg);
+  c->staged = c->uploaded = false;
+  c->have_counts = c->have_cols = false;
+}
+
+void do_stage(brq_ctx* c) {
+  stage(c->hdr, c->ref, c->reads, c->stage_cfg, c->st);
+  c->staged = true;
+  c->uploaded = false;
+}
+
+SynthConfig synth_config(const brq_synth_spec* sp, int threads) {
+  SynthConfig cfg;
+  cfg.seed = sp->seed;
+  cfg.threads = threads;
+  for (uint32_t i = 0; i < sp->n_sets; ++i) {
+    SynthReadSet s;
+    s.name = sp->sets[i].name; s.paired = sp->sets[i].paired != 0; s.read_len = sp->sets[i].read_len;
+    s.coverage = sp->sets[i].coverage; s.frag_mean = sp->sets[i].frag_mean; s.frag_sd = sp->sets[i].frag_sd;
+    cfg.sets.push_back(s);
+  }
+  cfg.n_polymorphic = sp->n_polymorphic; cfg.n_fixed = sp->n_fixed; cfg.n_gaps = sp->n_gaps;
+  if (sp->max_freq_ppm) { cfg.min_freq_ppm = sp->min_freq_ppm; cfg.max_freq_ppm = sp->max_freq_ppm; }
+  return cfg;
+}
+
+void synth_into(brq_ctx* c, const brq_synth_spec* sp) {
+  c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
+  if (sp->contig_lens) {
+    std::vector<uint32_t> lens(sp->contig_lens, sp->contig_lens + sp->n_contigs);
+    synth_reference(sp->seed, lens, sp->contig_prefix ? sp->contig_prefix : "contig", c->ref);
+  } else {
+    read_fasta(sp->fasta, c->ref);
+  }
+  std::vector<SynthVariant> variants;
+  synth_reads(synth_config(sp, c->threads), c->ref, c->hdr, c->reads, variants);
+}
+
+void upload(brq_ctx* c) {
+  c->need_device();
+  if (!c->staged) throw std::runtime_error("nothing staged");
+  const PileupStream& st = c->st;
+  const uint64_t n_slots = st.n_slots();
+  c->d_score_rec.ensure(st.n_score); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
+  c->d_hist_rec.ensure(st.n_hist); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
+  CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
+  c->uploaded = true;
+}
+
+void error_count_device(brq_ctx* c, const std::string& covariates, bool do_coverage, bool do_errors) {
+  c->need_device();
+  if (!c->uploaded) upload(c);
+  c->spec = parse_covariates(covariates.empty() && !do_errors ? std::string("obs_base,ref_base,quality=1") : covariates);
+  c->have_spec = true;
+  const CovLayout lay = to_layout(c->spec);
+  const PileupStream& st = c->st;
+  // coverage histogram geometry: groups x (max depth + 1)
+  uint64_t max_depth = 0;
+  for (uint64_t k = 0; k < st.n_base; ++k) {
+    uint64_t d = (st.hist_off[k + 1] & ~HIST_OFF_REDUNDANT_BIT) - (st.hist_off[k] & ~HIST_OFF_REDUNDANT_BIT);
+    if (d > max_depth) max_depth = d;
+  }
+  uint32_t n_groups = 1;
+  for (uint64_t k = 0; k < st.n_base; k += 1) { if (st.slot_group[k] + 1u > n_groups) n_groups = st.slot_group[k] + 1u; }
+  c->cov_stride = max_depth + 1;
+  c->n_groups = n_groups;
+  c->d_counts.ensure(lay.n_bins);
+  c->d_cov.ensure(c->cov_stride * n_groups);
+  CUDA_OK(cudaMemsetAsync(c->d_counts.p, 0, (size_t)lay.n_bins * 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_cov.p, 0, c->cov_stride * n_groups * 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 8, c->stream));
+  CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  if (do_errors) launch_hist(c->d_hist_rec.p, st.n_hist, lay, c->d_counts.p, c->d_scalars.p, c->stream);
+  CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
+  if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, c->d_cov.p, c->d_scalars.p, c->stream);
+  CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
+  CUDA_OK(cudaGetLastError());
+  c->check_device_errors("error_count");
+  CUDA_OK(cudaEventElapsedTime(&c->ms_hist, c->ev[0], c->ev[1]));
+  CUDA_OK(cudaEventElapsedTime(&c->ms_cov, c->ev[1], c->ev[2]));
+  c->have_counts = true;
+  c->have_table = false;
+}
+
+void download_hist(brq_ctx* c) {
+  if (!c->have_counts) throw std::runtime_error("brq_error_count has not run");
+  c->h_counts.resize(c->spec.n_bins);
+  c->h_cov.resize(c->cov_stride * c->n_groups);
+  CUDA_OK(cudaMemcpyAsync(c->h_counts.data(), c->d_counts.p, c->h_counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_cov.data(), c->d_cov.p, c->h_cov.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+}
+
+void install_table(brq_ctx* c) {  // h_log10 -> text-canonical probabilities -> class table on the device
+  canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob);
+  c->have_table = true;
+  if (c->staged) {
+    build_class_lut(c->spec, c->h_prob, c->st.mapq_seen, c->sp, c->h_lut);
+    if (c->device >= 0) {
+      c->d_lut.ensure(c->h_lut.size());
+      CUDA_OK(cudaMemcpyAsync(c->d_lut.p, c->h_lut.data(), c->h_lut.size() * sizeof(ClassTerms), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+  }
+}
+
+void derive_table(brq_ctx* c) {
+  c->need_device();
+  if (!c->have_counts) throw std::runtime_error("brq_error_count has not run");
+  if (!c->spec.used[COV_OBS_BASE]) throw std::runtime_error("the error table needs the obs_base covariate");
+  const CovLayout lay = to_layout(c->spec);
+  c->d_log10.ensure(lay.n_bins);
+  CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
+  launch_derive_table(c->d_counts.p, lay, c->d_log10.p, c->stream);
+  CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
+  c->h_log10.resize(lay.n_bins);
+  CUDA_OK(cudaMemcpyAsync(c->h_log10.data(), c->d_log10.p, (size_t)lay.n_bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  CUDA_OK(cudaEventElapsedTime(&c->ms_derive, c->ev[3], c->ev[4]));
+  install_table(c);
+}
+
+void score_device(brq_ctx* c, const brq_score_params* p) {
+  c->need_device();
+  if (!c->uploaded) upload(c);
+  if (!c->have_table) throw std::runtime_error("no error table: call brq_derive_error_table or brq_load_error_table first");
+  if (c->h_lut.empty()) install_table(c);
+  c->last_params = *p;
+  uint64_t total = p->total_reference_length;
+  if (!total) for (uint32_t l : c->hdr.target_lens) total += l;
+  c->sp.log10_ref_length = log10((double)total);
+  c->sp.mutation_cutoff = p->mutation_cutoff;
+  c->sp.polymorphism_cutoff = p->polymorphism_cutoff;
+  c->sp.precision_decimal = p->polymorphism_precision_decimal;
+  c->sp.base_quality_cutoff = p->base_quality_cutoff;
+  const uint64_t n_slots = c->st.n_slots();
+  c->d_cols.ensure(n_slots);
+  c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
+  c->d_flagged.ensure(c->flagged_cap);
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 8, c->stream));
+  CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
+  launch_score(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->sp, c->d_cols.p, c->d_flagged.p,
+               c->d_scalars.p + 1, c->flagged_cap, c->d_scalars.p, c->stream);
+  CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
+  CUDA_OK(cudaGetLastError());
+  c->check_device_errors("score_columns");
+  CUDA_OK(cudaEventElapsedTime(&c->ms_score, c->ev[5], c->ev[6]));
+  c->have_cols = true;
+}
+
+void download_columns(brq_ctx* c) {
+  if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
+  const uint64_t n_slots = c->st.n_slots();
+  c->h_cols.resize(n_slots);
+  uint32_t scal[2];
+  CUDA_OK(cudaMemcpyAsync(scal, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_cols.data(), c->d_cols.p, n_slots * sizeof(ColumnOut), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (scal[1] > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
+  c->h_flagged.resize(scal[1]);
+  if (scal[1]) CUDA_OK(cudaMemcpy(c->h_flagged.data(), c->d_flagged.p, (size_t)scal[1] * 4, cudaMemcpyDeviceToHost));
+}
+
+EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, const double* seed, uint32_t n_targets, int skip_mc) {
+  if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
+  if (n_targets != c->hdr.target_names.size())
+    throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
+                             "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
+  EvidenceParams ep;
+  ep.mutation_cutoff = c->last_params.mutation_cutoff;
+  ep.polymorphism_cutoff = c->last_params.polymorphism_cutoff;
+  ep.precision_decimal = c->last_params.polymorphism_precision_decimal;
+  ep.precision_places = c->last_params.polymorphism_precision_places;
+  ep.base_quality_cutoff = c->last_params.base_quality_cutoff;
+  ep.log10_ref_length = c->sp.log10_ref_length;
+  ep.skip_missing_coverage_prediction = skip_mc != 0;
+  ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
+  ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
+  return write_evidence(gd_file, c->hdr, c->st, c->h_cols, c->h_flagged, c->sp, c->h_lut, ep);
+}
+
+void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,
+                       uint32_t n_readfiles, int do_coverage, int do_errors, const char* counts_dump) {
+  if (c->h_counts.size() != c->spec.n_bins) download_hist(c);
+  std::string dir = output_dir ? output_dir : ".";
+  if (do_coverage) write_coverage_distributions(dir, c->h_cov, c->cov_stride, c->n_groups);
+  if (do_errors) {
+    if (!c->have_table) throw std::runtime_error("brq_derive_error_table has not run");
+    if (counts_dump && *counts_dump) write_count_table(counts_dump, c->spec, c->h_counts);
+    write_error_rates(error_rates_file && *error_rates_file ? error_rates_file : dir + "/error_rates.tab", c->spec, c->h_log10);
+    std::vector<std::string> rf;
+    for (uint32_t i = 0; i < n_readfiles; ++i) rf.push_back(readfiles[i]);
+    if (c->spec.used[COV_READ_SET] && c->spec.used[COV_QUALITY] && c->spec.used[COV_REF_BASE] && c->spec.used[COV_OBS_BASE])
+      write_base_qual_tables(dir + "/base_qual_error_prob.#.tab", c->spec, c->h_counts, rf);
+  }
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+const char* brq_version(void) { return "breseq_b200 0.1 (sm_100a)"; }
+
+brq_ctx* brq_create(const brq_config* cfg) {
+  brq_ctx* c = new brq_ctx;
+  c->device = cfg ? cfg->device : 0;
+  c->threads = (cfg && cfg->threads > 0) ? cfg->threads : (int)std::max(1u, std::thread::hardware_concurrency());
+  if (c->device >= 0) {
+    try {
+      CUDA_OK(cudaSetDevice(c->device));
+      CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      for (auto& e : c->ev) CUDA_OK(cudaEventCreate(&e));
+      c->d_scalars.ensure(2);
+      CUDA_OK(cudaMemset(c->d_scalars.p, 0, 8));
+    } catch (const std::exception& e) {
+      c->error = std::string("no usable CUDA device: ") + e.what();
+      c->device = -2;  // poisoned: every compute call reports the error
+    }
+  }
+  return c;
+}
+
+void brq_destroy(brq_ctx* c) {
+  if (!c) return;
+  drop_stream(c);
+  if (c->device >= 0) {
+    c->d_score_rec.release(); c->d_flagged.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
+    c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
+    c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+  }
+  delete c;
+}
+
+const char* brq_last_error(const brq_ctx* c) { return c ? c->error.c_str() : "null context"; }
+
+int brq_stage_bam(brq_ctx* c, const char* bam, const char* fasta, const brq_stage_options* opt) {
+  return guarded(c, [&] {
+    drop_stream(c);
+    c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
+    read_bam(bam, c->hdr, c->reads, c->threads);
+    read_fasta(fasta, c->ref);
+    apply_stage_options(c, opt);
+    do_stage(c);
+  });
+}
+
+int brq_synth_write(brq_ctx* c, const brq_synth_spec* spec, const char* bam_out, const char* fasta_out) {
+  return guarded(c, [&] {
+    drop_stream(c);
+    synth_into(c, spec);
+    write_bam(bam_out, c->hdr, c->reads);
+    write_fasta(fasta_out, c->ref);
+  });
+}
+
+int brq_stage_synthetic(brq_ctx* c, const brq_synth_spec* spec, const brq_stage_options* opt) {
+  return guarded(c, [&] {
+    drop_stream(c);
+    synth_into(c, spec);
+    apply_stage_options(c, opt);
+    do_stage(c);
+  });
+}
+
+int brq_stream(brq_ctx* c, brq_stream_info* info) {
+  return guarded(c, [&] {
+    if (!c->staged) throw std::runtime_error("nothing staged");
+    const PileupStream& st = c->st;
+    memset(info, 0, sizeof *info);
+    info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
+    info->n_reads = c->reads.size();
+    info->bytes_host = st.n_score * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * 8 + (st.n_base + 1) * 8 + st.n_base;
+    info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
+    info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_off = st.hist_off;
+    info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
+  });
+}
+
+int brq_upload(brq_ctx* c) { return guarded(c, [&] { upload(c); }); }
+int brq_sync(brq_ctx* c) { return guarded(c, [&] { c->need_device(); CUDA_OK(cudaStreamSynchronize(c->stream)); }); }
+
+int brq_error_count(brq_ctx* c, const char* covariates, int do_coverage, int do_errors) {
+  return guarded(c, [&] { error_count_device(c, covariates ? covariates : "", do_coverage != 0, do_errors != 0); });
+}
+
+int brq_hist_device(brq_ctx* c, void** counts, uint64_t* n_bins, void** coverage, uint64_t* n_coverage) {
+  return guarded(c, [&] {
+    if (!c->have_counts) throw std::runtime_error("brq_error_count has not run");
+    *counts = c->d_counts.p; *n_bins = c->spec.n_bins; *coverage = c->d_cov.p; *n_coverage = c->cov_stride * c->n_groups;
+  });
+}
+
+int brq_hist_download(brq_ctx* c, const uint64_t** counts, uint64_t* n_bins, const uint64_t** coverage, uint64_t* stride, uint64_t* n_groups) {
+  return guarded(c, [&] {
+    download_hist(c);
+    *counts = c->h_counts.data(); *n_bins = c->h_counts.size(); *coverage = c->h_cov.data(); *stride = c->cov_stride; *n_groups = c->n_groups;
+  });
+}
+
+int brq_derive_error_table(brq_ctx* c) { return guarded(c, [&] { derive_table(c); }); }
+
+int brq_error_table(brq_ctx* c, const double** log10_prob, uint64_t* n_bins) {
+  return guarded(c, [&] {
+    if (!c->have_table) throw std::runtime_error("no error table");
+    *log10_prob = c->h_log10.data(); *n_bins = c->h_log10.size();
+  });
+}
+
+int brq_write_error_count_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,
+                                uint32_t n_readfiles, int do_coverage, int do_errors, const char* counts_dump_file) {
+  return guarded(c, [&] { write_pass1_files(c, output_dir, error_rates_file, readfiles, n_readfiles, do_coverage, do_errors, counts_dump_file); });
+}
+
+int brq_load_error_table(brq_ctx* c, const char* error_rates_file) {
+  return guarded(c, [&] {
+    read_error_rates(error_rates_file, c->spec, c->h_log10);
+    c->have_spec = true;
+    install_table(c);
+  });
+}
+
+int brq_score_columns(brq_ctx* c, const brq_score_params* p) { return guarded(c, [&] { score_device(c, p); }); }
+
+int brq_columns_download(brq_ctx* c, const brq_column** columns, uint64_t* n_slots, const uint32_t** flagged, uint32_t* n_flagged) {
+  static_assert(sizeof(brq_column) == sizeof(ColumnOut), "brq_column layout");
+  return guarded(c, [&] {
+    download_columns(c);
+    *columns = reinterpret_cast<const brq_column*>(c->h_cols.data()); *n_slots = c->h_cols.size();
+    *flagged = c->h_flagged.data(); *n_flagged = (uint32_t)c->h_flagged.size();
+  });
+}
+
+int brq_columns_device(brq_ctx* c, void** columns, uint64_t* n_slots) {
+  return guarded(c, [&] {
+    if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
+    *columns = c->d_cols.p; *n_slots = c->st.n_slots();
+  });
+}
+
+int brq_write_evidence(brq_ctx* c, const char* gd_file, const double* prop, const double* seed, uint32_t n_targets, int skip_mc,
+                       uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un) {
+  return guarded(c, [&] {
+    EvidenceCounts k = evidence(c, gd_file, prop, seed, n_targets, skip_mc);
+    if (n_ra) *n_ra = k.ra;
+    if (n_mc) *n_mc = k.mc;
+    if (n_un) *n_un = k.un;
+  });
+}
+
+int brq_run_error_count(brq_ctx* c, const char* bam, const char* fasta, const char* output_dir, const char* error_rates_file,
+                        const char* const* readfiles, uint32_t n_readfiles, int do_coverage, int do_errors, const char* covariates,
+                        const brq_stage_options* opt) {
+  int rc = brq_stage_bam(c, bam, fasta, opt);
+  if (rc) return rc;
+  return guarded(c, [&] {
+    error_count_device(c, covariates ? covariates : "", do_coverage != 0, do_errors != 0);
+    if (do_errors) derive_table(c);
+    write_pass1_files(c, output_dir, error_rates_file, readfiles, n_readfiles, do_coverage, do_errors, nullptr);
+  });
+}
+
+int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, const char* error_rates_file, const char* gd_file,
+                               const double* prop, const double* seed, uint32_t n_targets, const brq_score_params* p, int skip_mc,
+                               const brq_stage_options* opt) {
+  int rc = brq_stage_bam(c, bam, fasta, opt);
+  if (rc) return rc;
+  return guarded(c, [&] {
+    read_error_rates(error_rates_file, c->spec, c->h_log10);
+    c->have_spec = true;
+    install_table(c);
+    score_device(c, p);
+    evidence(c, gd_file, prop, seed, n_targets, skip_mc);
+  });
+}
+
+int brq_launch_count(void) { return launch_count(); }
+
+int brq_kernel_ms(brq_ctx* c, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms) {
+  if (!c) return 1;
+  if (hist_ms) *hist_ms = c->ms_hist;
+  if (coverage_ms) *coverage_ms = c->ms_cov;
+  if (derive_ms) *derive_ms = c->ms_derive;
+  if (score_ms) *score_ms = c->ms_score;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,117 @@
+// Shared host-side types of the B200 read-alignment evidence pileup.
+//
+// Data flow:  BAM (or the synthetic generator)  ->  ReadBatch  ->  stage()  ->  PileupStream
+//             (pinned, columnar, reference-position sorted)  ->  CUDA kernels.
+//
+// Vocabulary follows the reference: "column" = one reference position of one target,
+// "insert sub-column" = the k-th inserted base after a column
+// (/root/reference/src/breseq/identify_mutations.cpp:1359), "slot" = a column or a sub-column,
+// "record" = one (read, slot) incidence.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace brq {
+
+// Base indices: A,C,G,T,'.' = 0..4, N = 5 (/root/reference/src/breseq/common.h:202-316).
+enum : uint8_t { kBaseA = 0, kBaseC = 1, kBaseG = 2, kBaseT = 3, kBaseGap = 4, kBaseN = 5, kBaseNul = 6 };
+
+inline uint8_t nibble_to_index(uint8_t bam4) {  // BAM 4-bit code -> index; anything not ACGT is N
+  switch (bam4) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; default: return 5; }
+}
+inline uint8_t char_to_index(char c) {
+  switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+               case '.': return 4; case 'N': return 5; default: return 255; }
+}
+inline char index_to_char(uint8_t b) { return b < 6 ? "ACGT.N"[b] : '?'; }
+
+struct RefSet {
+  std::vector<std::string> names;
+  std::vector<std::string> seqs;  // as stored in the FASTA (no case folding, like fai_fetch)
+  uint64_t total_length() const { uint64_t t = 0; for (auto& s : seqs) t += s.size(); return t; }
+};
+
+// One sequencing read file set = one SAM read group (@RG ID/LB = base name); a paired set owns
+// two read files (/root/reference/src/breseq/alignment.h:576-591).
+struct ReadGroups {
+  std::vector<std::string> ids;
+  std::vector<std::string> libraries;
+};
+
+// Reads of one BAM, structure-of-arrays, in file (coordinate) order.
+struct ReadBatch {
+  std::vector<int32_t> tid, pos;       // 0-based leftmost reference position
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq;
+  std::vector<uint8_t> rg;             // resolved read-group index (0 when unresolvable)
+  std::vector<uint32_t> x1;            // X1:i redundancy; 1 when the tag is absent
+  std::vector<int32_t> xl, xr;         // XL/XR:i trims; -1 when the tag is absent
+  std::vector<int32_t> as;             // AS:i (carried for the writer only)
+  std::vector<uint32_t> l_seq;
+  std::vector<uint64_t> seq_off;       // into bases/quals
+  std::vector<uint32_t> n_cigar;
+  std::vector<uint64_t> cigar_off;     // into cigars
+  std::vector<uint8_t> bases;          // one BAM 4-bit code per byte (1,2,4,8,15)
+  std::vector<uint8_t> quals;          // raw phred
+  std::vector<uint32_t> cigars;        // BAM encoding: len<<4 | op
+  std::vector<std::string> names;      // optional (writer); may be empty
+  size_t size() const { return tid.size(); }
+};
+
+// ---- packed stream records -------------------------------------------------------------
+
+// Scoring record, 4 bytes, one per (read, slot) whose base at that slot is not N.
+//   [2:0]   obs        base index 0..4 ('.' = 4)
+//   [9:3]   qual       quality chosen by alignment_position_to_covariates (error_count.cpp:1049-1105)
+//   [10]    top        1 = read on the top strand
+//   [11]    unique     X1 == 1
+//   [12]    trimmed    is_trimmed() (alignment.h:389-410)
+//   [13]    ok         covariates resolvable (not past q_end, no N at the quality position)
+//   unique records:    [21:14] mapq, [26:22] read_set (flat read-file index)
+//   redundant records: [29:14] redundancy (X1, saturated at 65535)
+constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, SR_UNIQUE_BIT = 1u << 11,
+                   SR_TRIM_BIT = 1u << 12, SR_OK_BIT = 1u << 13, SR_MAPQ_SHIFT = 14, SR_SET_SHIFT = 22,
+                   SR_RED_SHIFT = 14;
+
+// Histogram (error_count) record, 8 bytes, one per unique, non-deleted (read, column).
+//   [2:0]   obsA   base index 0..3, 5 = N          [5:3]  refA  reference base index (0..3, 5 = N)
+//   [12:6]  qualA                                   [13]   rev   read on the bottom strand
+//   [15:14] classB 0 none, 1 '..' (next base also aligned), 2 deletion of exactly one base follows,
+//                  3 insertion of exactly one base follows  (error_count.cpp:909-982)
+//   [18:16] obsB   base index of the base whose quality is used (N-check / inserted base)
+//   [21:19] refB   reference base index next to the event (0..3, 5 = N, 6 = past the end)
+//   [28:22] qualB                                   [33:29] read_set
+//   [49:34] read_posA (0-based query index)         [57:50] base_repeatA   [63:58] base_repeatB
+constexpr int HR_OBSA = 0, HR_REFA = 3, HR_QUALA = 6, HR_REV = 13, HR_CLASSB = 14, HR_OBSB = 16, HR_REFB = 19,
+              HR_QUALB = 22, HR_SET = 29, HR_RPOS = 34, HR_REPA = 50, HR_REPB = 58;
+
+// Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
+struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
+
+// The staged, columnar, position-sorted stream handed to the device.
+struct PileupStream {
+  // geometry
+  std::vector<Segment> segments;       // visited targets in visit (alphabetical seq id) order, clipped to this shard
+  uint64_t n_base = 0;                 // base columns (sum of segment lengths)
+  uint64_t n_ins = 0;                  // insert sub-column slots, appended after the base slots
+  std::vector<uint64_t> ins_parent;    // [n_ins] base slot of each sub-column
+  std::vector<uint32_t> ins_count;     // [n_ins] insert_count (>= 1)
+  // per slot
+  uint8_t* slot_ref = nullptr;         // [n_base + n_ins] reference base index ('.' for sub-columns)
+  uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] CSR into score_rec
+  uint64_t* hist_off = nullptr;        // [n_base + 1] CSR into hist_rec; bit 63 of entry c = column c has a redundant read
+  uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
+  // records
+  uint32_t* score_rec = nullptr;
+  uint64_t* hist_rec = nullptr;
+  uint64_t n_score = 0, n_hist = 0;
+  uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records
+  uint32_t max_qual_seen = 0;
+  bool pinned = false;                 // buffers came from cudaHostAlloc
+  uint64_t n_slots() const { return n_base + n_ins; }
+};
+
+constexpr uint64_t HIST_OFF_REDUNDANT_BIT = 1ull << 63;
+
+}  // namespace brq

@@ -1,0 +1,707 @@
+#include "finalize.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+
+namespace brq {
+
+// ============================================================================== covariates
+static const char* kCovNames[COV_COUNT] = {"read_set", "ref_base", "prev_ref_base", "obs_base", "quality", "read_pos", "base_repeat"};
+
+CovSpec parse_covariates(const std::string& s) {
+  CovSpec c;
+  size_t p = 0;
+  while (p <= s.size()) {
+    size_t e = s.find(',', p);
+    if (e == std::string::npos) e = s.size();
+    std::string item = s.substr(p, e - p), key = item, val;
+    size_t eq = item.find('=');
+    if (eq != std::string::npos) { key = item.substr(0, eq); val = item.substr(eq + 1); }
+    auto num = [&]() { return (uint32_t)atoi(val.c_str()); };
+    if (key == "ref_base") { c.used[COV_REF_BASE] = true; c.maxv[COV_REF_BASE] = 5; }
+    else if (key == "obs_base") { c.used[COV_OBS_BASE] = true; c.maxv[COV_OBS_BASE] = 5; }
+    else if (key == "quality") { c.used[COV_QUALITY] = true; c.maxv[COV_QUALITY] = num(); }
+    else if (key == "read_set") { c.used[COV_READ_SET] = true; c.maxv[COV_READ_SET] = num(); }
+    else if (key == "read_pos") { c.used[COV_READ_POS] = true; c.maxv[COV_READ_POS] = num(); }
+    else if (key == "base_repeat") { c.used[COV_BASE_REPEAT] = true; c.maxv[COV_BASE_REPEAT] = num(); c.clamp[COV_BASE_REPEAT] = true; }
+    else if (key == "ref_pos") c.per_position = true;
+    else if (key == "prev_base") throw std::runtime_error("covariate prev_base is declared by the reference but never populated; not supported");
+    else if (!key.empty()) throw std::runtime_error("Unrecognized covariate: " + key);
+    p = e + 1;
+  }
+  uint32_t cur = 1;
+  for (int i = 0; i < COV_COUNT; ++i) if (c.used[i]) {
+    if (c.maxv[i] == 0) throw std::runtime_error(std::string("covariate needs a maximum: ") + kCovNames[i]);
+    c.offset[i] = cur; cur *= c.maxv[i];
+  }
+  c.n_bins = cur;
+  if (c.per_position) throw std::runtime_error("covariate ref_pos (per-position count dump) is not supported");
+  return c;
+}
+
+std::string CovSpec::text() const {
+  std::string s;
+  if (per_position) s += "ref_pos";
+  for (int i = 0; i < COV_COUNT; ++i) {
+    if (!used[i]) continue;
+    if (!s.empty()) s += ",";
+    s += kCovNames[i];
+    if (i != COV_REF_BASE && i != COV_OBS_BASE) s += "=" + std::to_string(maxv[i]);
+  }
+  return s;
+}
+
+CovLayout to_layout(const CovSpec& c) {
+  CovLayout l;
+  l.off_set = c.offset[COV_READ_SET]; l.off_ref = c.offset[COV_REF_BASE]; l.off_obs = c.offset[COV_OBS_BASE];
+  l.off_qual = c.offset[COV_QUALITY]; l.off_rpos = c.offset[COV_READ_POS]; l.off_rep = c.offset[COV_BASE_REPEAT];
+  const uint32_t inf = 0xFFFFFFFFu;
+  l.max_set = c.used[COV_READ_SET] ? c.maxv[COV_READ_SET] : inf;
+  l.max_qual = c.used[COV_QUALITY] ? c.maxv[COV_QUALITY] : inf;
+  l.max_rpos = c.used[COV_READ_POS] ? c.maxv[COV_READ_POS] : inf;
+  l.max_rep = c.used[COV_BASE_REPEAT] ? c.maxv[COV_BASE_REPEAT] : inf;
+  l.n_bins = c.n_bins;
+  l.obs_used = c.used[COV_OBS_BASE];
+  return l;
+}
+
+// ============================================================================== formatting
+std::string format_default(double v) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.6g", v);
+  return buf;
+}
+
+std::string format_double(double v, uint32_t precision, bool scientific) {
+  if (std::isnan(v)) return "NA";
+  char buf[512];
+  snprintf(buf, sizeof buf, scientific ? "%.*e" : "%.*f", (int)precision, v);
+  std::string s(buf);
+  if (scientific && s.size() >= 3 && s[s.size() - 3] == '0') s.erase(s.size() - 3, 1);  // 3-digit exponents
+  return s;
+}
+
+static void write_table_rows(std::ostream& out, const CovSpec& c, size_t n, const std::function<std::string(size_t)>& value) {
+  for (size_t idx = 0; idx < n; ++idx) {
+    for (int i = 0; i < COV_COUNT; ++i) {
+      if (!c.used[i]) continue;
+      uint32_t j = ((uint32_t)idx / c.offset[i]) % c.maxv[i];
+      if (i == COV_REF_BASE || i == COV_OBS_BASE) out << index_to_char((uint8_t)j) << '\t';
+      else out << j << '\t';
+    }
+    out << value(idx) << '\n';
+  }
+}
+
+void write_error_rates(const std::string& path, const CovSpec& c, const std::vector<double>& t) {
+  std::ofstream out(path.c_str());
+  if (!out) throw std::runtime_error("cannot create " + path);
+  out << c.text() << '\n';
+  for (int i = 0; i < COV_COUNT; ++i) if (c.used[i]) out << kCovNames[i] << '\t';
+  out << "log10_probability\n";
+  write_table_rows(out, c, t.size(), [&](size_t i) { return format_default(t[i]); });
+}
+
+void write_count_table(const std::string& path, const CovSpec& c, const std::vector<uint64_t>& counts) {
+  std::ofstream out(path.c_str());
+  if (!out) throw std::runtime_error("cannot create " + path);
+  out << c.text() << '\n';
+  for (int i = 0; i < COV_COUNT; ++i) if (c.used[i]) out << kCovNames[i] << '\t';
+  out << "count\n";
+  write_table_rows(out, c, counts.size(), [&](size_t i) { return std::to_string(counts[i]); });
+}
+
+void read_error_rates(const std::string& path, CovSpec& c, std::vector<double>& t) {
+  std::ifstream in(path.c_str());
+  if (!in) throw std::runtime_error("cannot open " + path);
+  std::string line;
+  std::getline(in, line);
+  c = parse_covariates(line);
+  std::getline(in, line);  // column names: order is fixed, ignored
+  t.assign(c.n_bins, 0.0);
+  for (uint32_t i = 0; i < c.n_bins; ++i) {
+    std::getline(in, line);
+    size_t tab = line.rfind('\t');
+    t[i] = strtod(line.c_str() + (tab == std::string::npos ? 0 : tab + 1), nullptr);
+  }
+}
+
+void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& text, std::vector<double>& prob) {
+  text.resize(log10_prob.size());
+  prob.resize(log10_prob.size());
+  for (size_t i = 0; i < log10_prob.size(); ++i) {
+    text[i] = strtod(format_default(log10_prob[i]).c_str(), nullptr);
+    prob[i] = pow(10, text[i]);
+  }
+}
+
+// error_count.cpp:697-785, index arithmetic restated literally (accumulate obs-major, read out b1*5+b2).
+void write_base_qual_tables(const std::string& pattern, const CovSpec& c, const std::vector<uint64_t>& counts,
+                            const std::vector<std::string>& readfiles) {
+  const uint32_t nS = c.maxv[COV_READ_SET], nO = c.maxv[COV_OBS_BASE], nR = c.maxv[COV_REF_BASE], nQ = c.maxv[COV_QUALITY];
+  const uint32_t per_set = nO * nR * nQ;
+  std::vector<double> t((size_t)nS * per_set, 0.0);
+  for (uint32_t idx = 0; idx < counts.size(); ++idx) {
+    uint32_t at = 0;
+    for (int i = 0; i < COV_COUNT; ++i) {
+      if (!c.used[i]) continue;
+      uint32_t j = (idx / c.offset[i]) % c.maxv[i];
+      if (i == COV_READ_SET) at += per_set * j;
+      else if (i == COV_REF_BASE) at += j;
+      else if (i == COV_OBS_BASE) at += nR * j;
+      else if (i == COV_QUALITY) at += nO * nR * j;
+    }
+    t[at] += (double)counts[idx];
+  }
+  double running = 0;
+  for (uint32_t r = 0; r < nS; ++r) {
+    for (uint32_t k = 0; k < per_set; ++k) {
+      uint32_t i = r * per_set + k;
+      running += t[i];
+      if (i % nR == nR - 1) {
+        for (uint32_t j = i - (nR - 1); j <= i; ++j) {
+          if (running > 0) t[j] /= running;
+          if (t[j] == 0) t[j] = std::numeric_limits<double>::quiet_NaN();
+        }
+        running = 0;
+      }
+    }
+    if (r >= readfiles.size()) throw std::runtime_error("fewer read file names than read_set values");
+    std::string fn = pattern;
+    size_t h = fn.find('#');
+    if (h != std::string::npos) fn.replace(h, 1, readfiles[r]);
+    std::ofstream out(fn.c_str());
+    if (!out) throw std::runtime_error("cannot create " + fn);
+    out << "quality";
+    for (uint32_t b1 = 0; b1 < nR; ++b1) for (uint32_t b2 = 0; b2 < nO; ++b2) out << '\t' << index_to_char((uint8_t)b1) << index_to_char((uint8_t)b2);
+    out << '\n';
+    for (uint32_t q = 0; q < nQ; ++q) {
+      out << q;
+      for (uint32_t b1 = 0; b1 < nR; ++b1) for (uint32_t b2 = 0; b2 < nO; ++b2) {
+        double v = t[(size_t)r * per_set + q * nO * nR + b1 * nR + b2];
+        out << '\t' << (std::isnan(v) ? std::string("NA") : format_default(v));
+      }
+      out << '\n';
+    }
+  }
+}
+
+void write_coverage_distributions(const std::string& dir, const std::vector<uint64_t>& cov, uint64_t stride, uint64_t n_groups) {
+  for (uint64_t g = 0; g < n_groups; ++g) {
+    std::string fn = dir + "/" + std::to_string(g) + ".unique_only_coverage_distribution.tab";
+    std::ofstream out(fn.c_str());
+    if (!out) throw std::runtime_error("cannot create " + fn);
+    out << "coverage\tn\n";
+    uint64_t last = 0;  // the reference's vector grows to the largest depth seen (error_count.cpp:182-185)
+    for (uint64_t j = 0; j < stride; ++j) if (cov[g * stride + j]) last = j;
+    for (uint64_t j = 1; j <= last; ++j) out << j << '\t' << cov[g * stride + j] << '\n';
+  }
+}
+
+// ============================================================================== class table
+void build_class_lut(const CovSpec& c, const std::vector<double>& prob, const uint32_t mapq_seen[8], ScoreParams& p,
+                     std::vector<ClassTerms>& lut) {
+  if (c.used[COV_READ_POS] || c.used[COV_BASE_REPEAT])
+    throw std::runtime_error("scoring with read_pos / base_repeat covariates is not implemented yet");
+  if (!c.used[COV_OBS_BASE] || !c.used[COV_REF_BASE] || !c.used[COV_QUALITY])
+    throw std::runtime_error("scoring needs ref_base, obs_base and quality covariates");
+  const uint32_t n_set = c.used[COV_READ_SET] ? c.maxv[COV_READ_SET] : 1, Q = c.maxv[COV_QUALITY];
+  memset(p.mapq_slot, 255, sizeof p.mapq_slot);
+  std::vector<uint32_t> mapqs;
+  for (uint32_t m = 0; m < 256; ++m) if (mapq_seen[m >> 5] >> (m & 31) & 1) { p.mapq_slot[m] = (uint8_t)mapqs.size(); mapqs.push_back(m); }
+  if (mapqs.empty()) { p.mapq_slot[0] = 0; mapqs.push_back(0); }
+  p.n_mapq_slots = (uint32_t)mapqs.size();
+  p.max_qual = Q;
+  p.max_set = c.used[COV_READ_SET] ? n_set : 32;
+  lut.assign((size_t)n_set * 2 * mapqs.size() * Q * 5, ClassTerms());
+  auto comp = [](uint32_t b) { return b < 4 ? 3 - b : 4u; };
+  for (uint32_t set = 0; set < n_set; ++set) for (uint32_t top = 0; top < 2; ++top) for (size_t ms = 0; ms < mapqs.size(); ++ms) {
+    // identify_mutations.cpp:3359-3384
+    const double incorrect = pow(10, -(double)mapqs[ms] / 10);
+    const double correct = 1 - incorrect;
+    const double uniform = 1.0 / 5.0;
+    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
+      ClassTerms& t = lut[((((size_t)set * 2 + top) * mapqs.size() + ms) * Q + q) * 5 + obs];
+      const uint32_t o = top ? obs : comp(obs);
+      double mx = -std::numeric_limits<double>::max();
+      for (uint32_t b = 0; b < 5; ++b) {
+        const uint32_t rf = top ? b : comp(b);
+        const uint32_t idx = set * c.offset[COV_READ_SET] + rf * c.offset[COV_REF_BASE] + o * c.offset[COV_OBS_BASE] + q * c.offset[COV_QUALITY];
+        double pr = correct * prob[idx] + incorrect * uniform;
+        if (pr < 0.0) pr = 0.0;
+        t.L[b] = log10(pr);
+        mx = std::max(mx, t.L[b]);
+      }
+      for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
+    }
+  }
+}
+
+// ============================================================================== statistics
+namespace {
+
+// log Gamma for x > 0: Cephes lgam as the reference carries it (stats.cpp:534-650).
+double log_gamma(double x) {
+  if (x < 13.0) {
+    double z = 1.0, shift = 0.0, u = x;
+    while (u >= 3.0) { shift -= 1.0; u = x + shift; z *= u; }
+    while (u < 2.0) { z /= u; shift += 1.0; u = x + shift; }
+    if (z < 0) z = -z;
+    if (u == 2.0) return log(z);
+    shift -= 2.0;
+    const double y = x + shift;
+    static const double num[6] = {-1378.25152569120859100, -38801.6315134637840924, -331612.992738871184744,
+                                  -1162370.97492762307383, -1721737.00820839662146, -853555.664245765465627};
+    static const double den[7] = {1.0, -351.815701436523470549, -17064.2106651881159223, -220528.590553854454839,
+                                  -1139334.44367982507207, -2532523.07177582951285, -2018891.41433532773231};
+    double b = num[0], c = den[0];
+    for (int i = 1; i < 6; ++i) b = num[i] + y * b;
+    for (int i = 1; i < 7; ++i) c = den[i] + y * c;
+    return log(z) + y * b / c;
+  }
+  double q = (x - 0.5) * log(x) - x + 0.91893853320467274178;
+  if (x > 100000000) return q;
+  const double p = 1 / (x * x);
+  if (x >= 1000.0) return q + ((7.9365079365079365079365 * 0.0001 * p - 2.7777777777777777777778 * 0.001) * p + 0.0833333333333333333333) / x;
+  double a = 8.11614167470508450300 * 0.0001;
+  a = -5.95061904284301438324 * 0.0001 + p * a;
+  a = 7.93650340457716943945 * 0.0001 + p * a;
+  a = -2.77777777730099687205 * 0.001 + p * a;
+  a = 8.33333333333331927722 * 0.01 + p * a;
+  return q + a / x;
+}
+double log_binomial(double n, double k) { return log_gamma(n + 1) - log_gamma(k + 1) - log_gamma(n - k + 1); }
+
+// Two-sided Fisher exact test (stats.cpp:2144-2171).
+double fisher_2x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  const uint32_t r1 = a + b, r2 = c + d, c1 = a + c, c2 = b + d, n = r1 + r2;
+  const uint32_t lo = r1 > c2 ? r1 - c2 : 0, hi = std::min(r1, c1);
+  const double denom = log_binomial(n, r1);
+  const double observed = log_binomial(c1, a) + log_binomial(c2, r1 - a) - denom;
+  const double slack = log(1.0 + 1e-7);
+  double total = 0.0;
+  for (uint32_t x = lo; x <= hi; ++x) {
+    const double lp = log_binomial(c1, x) + log_binomial(c2, r1 - x) - denom;
+    if (lp <= observed + slack) total += exp(lp);
+  }
+  return std::min(total, 1.0);
+}
+
+// One-sided two-sample KS test on integer-valued qualities, alternative "less"
+// (stats.cpp:2191-2288): x = minor-allele qualities, y = major-allele qualities, given as counts
+// per quality value.
+double ks_less(const std::vector<uint32_t>& x_by_q, const std::vector<uint32_t>& y_by_q) {
+  uint32_t nx = 0, ny = 0;
+  for (uint32_t v : x_by_q) nx += v;
+  for (uint32_t v : y_by_q) ny += v;
+  std::vector<char> boundary((size_t)nx + ny + 1, 1);
+  uint32_t cx = 0, cy = 0, best_x = 0, best_y = 0;
+  double min_z = 0.0;
+  bool have = false;
+  size_t consumed = 0;
+  for (size_t q = 0; q < x_by_q.size(); ++q) {
+    const uint32_t g = x_by_q[q] + y_by_q[q];
+    if (!g) continue;
+    for (size_t k = consumed + 1; k < consumed + g; ++k) boundary[k] = 0;  // interior of a tie run
+    consumed += g;
+    cx += x_by_q[q]; cy += y_by_q[q];
+    const double z = (double)cx / nx - (double)cy / ny;
+    if (!have || z < min_z) { min_z = z; have = true; best_x = cx; best_y = cy; }
+  }
+  const double statistic = -min_z;
+  if ((double)nx * ny < 10000) {
+    const uint32_t m = ny, n = nx;
+    const int64_t threshold = (int64_t)best_y * n - (int64_t)best_x * m;
+    std::vector<double> row((size_t)n + 1, 0.0);  // lattice-path count, one row at a time
+    for (uint32_t i = 0; i <= m; ++i) {
+      for (uint32_t j = 0; j <= n; ++j) {
+        double v;
+        if (i == 0 && j == 0) v = 1.0;
+        else v = (i > 0 ? row[j] : 0.0) + (j > 0 ? row[j - 1] : 0.0);
+        const int64_t level = (int64_t)i * n - (int64_t)j * m;
+        if (boundary[i + j] && level >= threshold) v = 0.0;
+        row[j] = v;
+      }
+    }
+    const double total_paths = exp(log_binomial(m + n, m));
+    const double p = 1.0 - row[n] / total_paths;
+    return std::min(std::max(p, 0.0), 1.0);
+  }
+  const double n_eff = ((double)nx * ny) / (nx + ny);
+  return exp(-2.0 * statistic * statistic * n_eff);
+}
+
+// ============================================================================== per-slot re-evaluation
+// Everything below walks the slot's records in arrival order and accumulates exactly as the
+// reference's per-read loops do, so the numbers printed into RA rows carry the reference's
+// rounding.  Terms come from the same class table the device uses.
+struct SlotEval {
+  std::vector<const ClassTerms*> reads;  // scoring records, arrival order
+  std::vector<uint8_t> obs, qual;
+  uint32_t count[6][2];                  // [base][0 bottom, 1 top]
+  double ll[5];
+  uint8_t best = 5, major = 5, minor = 5, variant = 5;
+  double consensus = std::numeric_limits<double>::quiet_NaN(), variant_score = std::numeric_limits<double>::quiet_NaN();
+  double f[5] = {0, 0, 0, 0, 0}, log10_likelihood = 0.0;
+  bool base_predicted = false, emit = false;
+  uint32_t n() const { return (uint32_t)reads.size(); }
+};
+
+struct Fit { double f[5] = {0, 0, 0, 0, 0}; double ll = 0.0; };
+
+Fit fit_ordered(const SlotEval& s, uint32_t allowed, double tol) {  // identify_mutations.cpp:3240-3318
+  Fit m;
+  const uint32_t n = s.n();
+  if (!n) return m;
+  double init_total = 0.0;
+  for (int b = 0; b < 5; ++b) if (allowed >> b & 1) m.f[b] = 0.5;
+  for (uint32_t i = 0; i < n; ++i) if (s.obs[i] < 5 && (allowed >> s.obs[i] & 1)) m.f[s.obs[i]] += 1.0;
+  for (int b = 0; b < 5; ++b) init_total += m.f[b];
+  for (int b = 0; b < 5; ++b) m.f[b] /= init_total;
+  for (uint32_t it = 1; it <= 50; ++it) {
+    double w[5] = {0, 0, 0, 0, 0}, ll = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const ClassTerms& t = *s.reads[i];
+      double sum = 0.0, mx = t.L[0];
+      for (int b = 0; b < 5; ++b) { if (allowed >> b & 1) sum += m.f[b] * t.r[b]; mx = std::max(mx, t.L[b]); }
+      if (sum > 0.0) {
+        ll += log10(sum) + mx;
+        for (int b = 0; b < 5; ++b) if (allowed >> b & 1) w[b] += m.f[b] * t.r[b] / sum;
+      } else {
+        for (int b = 0; b < 5; ++b) if (allowed >> b & 1) w[b] += m.f[b];
+      }
+    }
+    double max_delta = 0.0;
+    for (int b = 0; b < 5; ++b) {
+      if (!(allowed >> b & 1)) continue;
+      const double f_new = w[b] / (double)n;
+      max_delta = std::max(max_delta, fabs(f_new - m.f[b]));
+      m.f[b] = f_new;
+    }
+    m.ll = ll;
+    if (max_delta < tol) break;
+  }
+  return m;
+}
+
+double profile_ll(const SlotEval& s, int variant, double f_fixed, double tol) {  // identify_mutations.cpp:3094-3143
+  const uint32_t n = s.n();
+  double f[5], others_total = 0.0;
+  for (int b = 0; b < 5; ++b) if (b != variant) others_total += s.f[b];
+  for (int b = 0; b < 5; ++b)
+    f[b] = b == variant ? f_fixed : (others_total > 0.0 ? (1.0 - f_fixed) * s.f[b] / others_total : (1.0 - f_fixed) / 4.0);
+  double ll = 0.0;
+  for (int it = 0; it < 50; ++it) {
+    double w[5] = {0, 0, 0, 0, 0};
+    ll = 0.0;
+    for (uint32_t i = 0; i < n; ++i) {
+      const ClassTerms& t = *s.reads[i];
+      double sum = 0.0, mx = t.L[0];
+      for (int b = 0; b < 5; ++b) { sum += f[b] * t.r[b]; mx = std::max(mx, t.L[b]); }
+      if (sum > 0.0) { ll += log10(sum) + mx; for (int b = 0; b < 5; ++b) w[b] += f[b] * t.r[b] / sum; }
+      else for (int b = 0; b < 5; ++b) w[b] += f[b];
+    }
+    double others = 0.0;
+    for (int b = 0; b < 5; ++b) if (b != variant) others += w[b];
+    double max_delta = 0.0;
+    for (int b = 0; b < 5; ++b) {
+      if (b == variant) continue;
+      const double f_new = others > 0.0 ? (1.0 - f_fixed) * w[b] / others : (1.0 - f_fixed) / 4.0;
+      max_delta = std::max(max_delta, fabs(f_new - f[b]));
+      f[b] = f_new;
+    }
+    if (max_delta < tol) break;
+  }
+  return ll;
+}
+
+void evaluate_slot(SlotEval& s, uint8_t ref, const EvidenceParams& ep) {
+  const uint32_t n = s.n();
+  for (int b = 0; b < 5; ++b) s.ll[b] = 0.0;
+  for (uint32_t i = 0; i < n; ++i) for (int b = 0; b < 5; ++b) s.ll[b] += s.reads[i]->L[b];
+  if (n) {  // pure_genotype_call, identify_mutations.cpp:3398-3433
+    int best = 0;
+    for (int b = 1; b < 5; ++b) if (s.ll[b] > s.ll[best]) best = b;
+    double off = -std::numeric_limits<double>::max();
+    for (int b = 0; b < 5; ++b) if (b != best) off = std::max(off, s.ll[b]);
+    double tot = 0;
+    for (int b = 0; b < 5; ++b) if (b != best) tot += pow(10, s.ll[b] - off);
+    double lt = log10(tot);
+    lt += off;
+    s.best = (uint8_t)best;
+    s.consensus = (s.ll[best] - lt) - ep.log10_ref_length;
+  }
+  s.base_predicted = s.consensus >= ep.mutation_cutoff;
+  const bool passed_consensus = (s.best != ref) && !std::isnan(s.consensus) && s.consensus > 0;
+  Fit full = fit_ordered(s, 0x1F, ep.precision_decimal);
+  for (int b = 0; b < 5; ++b) s.f[b] = full.f[b];
+  s.log10_likelihood = full.ll;
+  bool passed_poly = false;
+  if (n) {
+    const double thr = 0.5 / (double)n;
+    int mj = 0;
+    for (int b = 1; b < 5; ++b) if (s.f[b] > s.f[mj]) mj = b;
+    s.major = s.f[mj] > 0.0 ? (uint8_t)mj : 5;
+    auto next = [&](uint8_t exclude) {
+      uint8_t pick = 5;
+      for (uint8_t b = 0; b < 5; ++b) {
+        if (b == exclude || s.f[b] < thr) continue;
+        if (pick == 5 || s.f[b] > s.f[pick]) pick = b;
+      }
+      return pick;
+    };
+    s.minor = next(s.major);
+    s.variant = next(ref);
+    if (s.variant != 5) {
+      Fit null_fit = fit_ordered(s, 0x1F & ~(1u << s.variant), ep.precision_decimal);
+      s.variant_score = (full.ll - null_fit.ll) - ep.log10_ref_length;
+      if (s.variant_score >= ep.polymorphism_cutoff) passed_poly = true;
+    }
+  }
+  s.emit = passed_consensus || passed_poly;
+}
+
+struct GdRow {
+  int type;  // 0 RA, 1 MC, 2 UN
+  uint64_t id;
+  std::string seq_id;
+  uint64_t a = 0, b = 0, c = 0, d = 0;  // RA: position, insert ; MC: start, end, start_range, end_range ; UN: start, end
+  std::string ref_base, new_base;
+  std::map<std::string, std::string> kv;
+};
+
+}  // namespace
+
+EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
+                              const std::vector<ColumnOut>& cols, const std::vector<uint32_t>& flagged_in,
+                              const ScoreParams& sp, const std::vector<ClassTerms>& lut, const EvidenceParams& ep) {
+  EvidenceCounts counts;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  std::vector<uint32_t> flagged(flagged_in);
+  std::sort(flagged.begin(), flagged.end());
+
+  // ---- re-evaluate flagged slots in arrival order
+  struct Reval { bool base_predicted; bool emit; GdRow row; };
+  std::map<uint64_t, Reval> reval;
+  for (uint32_t slot : flagged) {
+    SlotEval s;
+    memset(s.count, 0, sizeof s.count);
+    for (uint64_t i = st.score_off[slot]; i < st.score_off[slot + 1]; ++i) {
+      const uint32_t r = st.score_rec[i];
+      const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
+      if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) continue;
+      const uint32_t obs = r & 7, top = (r & SR_TOP_BIT) ? 1 : 0, mapq = (r >> SR_MAPQ_SHIFT) & 255, set = (r >> SR_SET_SHIFT) & 31;
+      const size_t li = ((((size_t)set * 2 + top) * sp.n_mapq_slots + sp.mapq_slot[mapq]) * sp.max_qual + q) * 5 + obs;
+      s.reads.push_back(&lut[li]);
+      s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
+      ++s.count[obs][top];
+    }
+    const uint8_t ref = st.slot_ref[slot];
+    evaluate_slot(s, ref, ep);
+    ++counts.rechecked;
+    const ColumnOut& co = cols[slot];
+    const bool dev_emit = (co.bits & CO_EMIT) != 0, dev_pred = (co.bits & CO_BASE_PREDICTED) != 0;
+    if (dev_pred != s.base_predicted || (dev_emit && !s.emit)) ++counts.overturned;
+    Reval rv;
+    rv.base_predicted = s.base_predicted;
+    rv.emit = s.emit;
+    if (s.emit) {  // identify_mutations.cpp:1836-1910
+      GdRow& row = rv.row;
+      row.type = 0;
+      uint64_t parent = slot < st.n_base ? slot : st.ins_parent[slot - st.n_base];
+      row.b = slot < st.n_base ? 0 : st.ins_count[slot - st.n_base];
+      size_t sg = 0;
+      while (sg + 1 < st.segments.size() && st.segments[sg + 1].slot0 <= parent) ++sg;
+      row.seq_id = hdr.target_names[(size_t)st.segments[sg].tid];
+      row.a = (uint64_t)st.segments[sg].lo + (parent - st.segments[sg].slot0) + 1;
+      row.ref_base = std::string(1, index_to_char(ref));
+      row.new_base = std::string(1, index_to_char(s.variant));
+      const uint32_t n = s.n();
+      auto reported = [&](uint8_t b) { return (n == 0 || b >= 5) ? 0.0 : (s.f[b] < 0.5 / (double)n ? 0.0 : s.f[b]); };
+      row.kv["score"] = format_double(s.variant_score, 1, false);
+      row.kv["major_base"] = std::string(1, index_to_char(s.major));
+      row.kv["minor_base"] = std::string(1, index_to_char(s.minor));
+      row.kv["major_frequency"] = format_double(reported(s.major), ep.precision_places, true);
+      row.kv["frequency"] = format_double(reported(s.variant), ep.precision_places, true);
+      std::string spectrum;
+      for (uint8_t b = 0; b < 5; ++b) {
+        const double fr = reported(b);
+        if (fr <= 0.0) continue;
+        if (!spectrum.empty()) spectrum += ",";
+        spectrum += std::string(1, index_to_char(b)) + ":" + format_double(fr, ep.precision_places, true);
+      }
+      row.kv["allele_frequencies"] = spectrum;
+      // profile-likelihood bounds, identify_mutations.cpp:3175-3217
+      double lower = 0.0, upper = 1.0;
+      if (n > 0 && s.variant < 5) {
+        const double drop = 0.587566, tol = ep.precision_decimal;
+        const double f_hat = s.f[s.variant];
+        const double target = profile_ll(s, s.variant, f_hat, tol) - drop;
+        if (!(profile_ll(s, s.variant, 0.0, tol) >= target)) {
+          double lo = 0.0, hi = f_hat;
+          for (int i = 0; i < 40 && (hi - lo) > tol; ++i) {
+            const double mid = 0.5 * (lo + hi);
+            if (profile_ll(s, s.variant, mid, tol) >= target) hi = mid; else lo = mid;
+          }
+          lower = hi;
+        }
+        if (!(profile_ll(s, s.variant, 1.0, tol) >= target)) {
+          double lo = f_hat, hi = 1.0;
+          for (int i = 0; i < 40 && (hi - lo) > tol; ++i) {
+            const double mid = 0.5 * (lo + hi);
+            if (profile_ll(s, s.variant, mid, tol) >= target) lo = mid; else hi = mid;
+          }
+          upper = lo;
+        }
+      }
+      row.kv["frequency_lower"] = format_double(lower, ep.precision_places, true);
+      row.kv["frequency_upper"] = format_double(upper, ep.precision_places, true);
+      // bias statistics, identify_mutations.cpp:3009-3033
+      std::vector<uint32_t> major_q(128, 0), minor_q(128, 0);
+      uint32_t n_major = 0, n_minor = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        if (s.obs[i] == s.major) { ++major_q[s.qual[i]]; ++n_major; }
+        if (s.obs[i] == s.minor) { ++minor_q[s.qual[i]]; ++n_minor; }
+      }
+      double ks = 1.0;
+      if (n_major && n_minor) ks = ks_less(minor_q, major_q);
+      const double fisher = fisher_2x2(s.count[s.minor][1], s.count[s.minor][0], s.count[s.major][1], s.count[s.major][0]);
+      row.kv["ks_quality_p_value"] = format_double(ks, 5, true);
+      row.kv["fisher_strand_p_value"] = format_double(fisher, 5, true);
+      auto cov = [&](uint8_t b) { return std::to_string(s.count[b][1]) + "/" + std::to_string(s.count[b][0]); };
+      row.kv["ref_cov"] = cov(ref);
+      row.kv["new_cov"] = cov(s.variant);
+      row.kv["major_cov"] = cov(s.major);
+      row.kv["minor_cov"] = cov(s.minor);
+      uint32_t tot_top = 0, tot_bot = 0;
+      for (int b = 0; b < 5; ++b) { tot_top += s.count[b][1]; tot_bot += s.count[b][0]; }
+      row.kv["total_cov"] = std::to_string(tot_top) + "/" + std::to_string(tot_bot);
+    }
+    reval[slot] = rv;
+  }
+
+  // ---- walk the columns in visit order: MC and UN interval state machines, RA rows spliced in
+  std::vector<GdRow> rows;
+  uint64_t next_id = 0;
+  auto add = [&](GdRow r) { r.id = ++next_id; rows.push_back(std::move(r)); };
+  const uint32_t UNDEF = 0xFFFFFFFFu;
+  struct Cov { double unique, redundant; int total; };
+  size_t ins_cursor = 0;  // ins slots are ordered by (parent, insert_count)
+  for (size_t sgi = 0; sgi < st.segments.size(); ++sgi) {
+    const Segment& sg = st.segments[sgi];
+    const std::string& name = hdr.target_names[(size_t)sg.tid];
+    const uint32_t tlen = hdr.target_lens[(size_t)sg.tid];
+    const double prop = ep.deletion_propagation_cutoff[(size_t)sg.tid], seed = ep.deletion_seed_cutoff[(size_t)sg.tid];
+    uint32_t del_start = UNDEF, del_end = UNDEF, red_start = UNDEF, red_end = UNDEF, unknown_start = UNDEF;
+    bool reaches_seed = false, red_zero = false;
+    Cov last = {nan, nan, 0}, left_out = {nan, nan, 0}, left_in = {nan, nan, 0};
+    auto deletion_step = [&](uint32_t position, const Cov& cv) {  // identify_mutations.cpp:2262-2344
+      if (position == 1) last = {nan, nan, 0};
+      if (cv.unique <= prop && del_start == UNDEF) { del_start = position; left_out = last; left_in = cv; }
+      if (!std::isnan(cv.unique) && cv.total <= seed) reaches_seed = true;
+      if (del_start != UNDEF && (std::isnan(cv.unique) || cv.unique > prop)) {
+        if (reaches_seed) {
+          del_end = position - 1;
+          if (red_end == UNDEF) red_end = del_end;
+          if (red_start == UNDEF) red_start = del_start;
+          GdRow r;
+          r.type = 1; r.seq_id = name; r.a = del_start; r.b = del_end; r.c = red_start - del_start; r.d = del_end - red_end;
+          r.kv["left_outside_cov"] = format_double(left_out.unique, 0, false);
+          r.kv["left_inside_cov"] = format_double(left_in.unique, 0, false);
+          r.kv["right_inside_cov"] = format_double(last.unique, 0, false);
+          r.kv["right_outside_cov"] = format_double(cv.unique, 0, false);
+          add(r);
+          ++counts.mc;
+        }
+        reaches_seed = false; red_zero = false;
+        del_start = del_end = red_start = red_end = UNDEF;
+      }
+      if (del_start != UNDEF) {
+        if (cv.redundant == 0) { red_zero = true; red_end = UNDEF; }
+        else if (cv.redundant > 0) { if (!red_zero) red_start = position; else if (red_end == UNDEF) red_end = position; }
+      }
+      last = cv;
+    };
+    auto unknown_step = [&](uint32_t position, bool predicted) {  // identify_mutations.cpp:2972-3007
+      if (!predicted) { if (unknown_start == UNDEF) unknown_start = position; }
+      else if (unknown_start != UNDEF) {
+        GdRow r;
+        r.type = 2; r.seq_id = name; r.a = unknown_start; r.b = position - 1;
+        add(r);
+        ++counts.un;
+        unknown_start = UNDEF;
+      }
+    };
+    if (prop >= 0.0) {
+      for (int32_t c = sg.lo; c < sg.hi; ++c) {
+        const uint64_t slot = sg.slot0 + (uint64_t)(c - sg.lo);
+        const ColumnOut& co = cols[slot];
+        Cov cv;
+        cv.unique = (double)co.unique[0] + (double)co.unique[1];
+        cv.redundant = co.redundant[0] + co.redundant[1];
+        cv.total = (int)round(cv.unique) + (int)round(cv.redundant);
+        bool predicted = (co.bits & CO_BASE_PREDICTED) != 0;
+        auto rv = reval.find(slot);
+        if (rv != reval.end()) predicted = rv->second.base_predicted;
+        if (!ep.skip_missing_coverage_prediction) deletion_step((uint32_t)c + 1, cv);
+        unknown_step((uint32_t)c + 1, predicted);
+        if (rv != reval.end() && rv->second.emit) { add(rv->second.row); ++counts.ra; }
+        while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
+        for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) {
+          auto iv = reval.find(st.n_base + ins_cursor);
+          if (iv != reval.end() && iv->second.emit) { add(iv->second.row); ++counts.ra; }
+        }
+      }
+    }
+    if ((uint32_t)sg.hi == tlen) {  // at_target_end, identify_mutations.cpp:2117-2164
+      if (prop >= 0.0) {
+        if (!ep.skip_missing_coverage_prediction) deletion_step(tlen + 1, Cov{nan, nan, 0});
+        unknown_step(tlen + 1, true);
+      } else if (!ep.skip_missing_coverage_prediction) {
+        GdRow r;
+        r.type = 1; r.seq_id = name; r.a = 1; r.b = tlen; r.c = 0; r.d = 0;
+        r.kv["left_outside_cov"] = "NA";
+        r.kv["left_inside_cov"] = format_double(0.0, 0, false);
+        r.kv["right_inside_cov"] = format_double(0.0, 0, false);
+        r.kv["right_outside_cov"] = "NA";
+        add(r);
+        ++counts.mc;
+      }
+    }
+  }
+
+  // ---- GenomeDiff text (genome_diff.cpp:685-760; sort keys genome_diff_entry.cpp:280-324, 566-700)
+  std::stable_sort(rows.begin(), rows.end(), [](const GdRow& x, const GdRow& y) {
+    if (x.type != y.type) return x.type < y.type;  // RA (3) < MC (4) < UN (7)
+    if (x.seq_id != y.seq_id) return x.seq_id < y.seq_id;
+    if (x.a != y.a) return x.a < y.a;
+    if (x.b != y.b) return x.b < y.b;
+    if (x.type == 0) { if (x.ref_base != y.ref_base) return x.ref_base < y.ref_base; if (x.new_base != y.new_base) return x.new_base < y.new_base; }
+    else { if (x.c != y.c) return x.c < y.c; if (x.d != y.d) return x.d < y.d; }
+    return x.id < y.id;
+  });
+  std::ofstream os(gd_path.c_str());
+  if (!os) throw std::runtime_error("cannot create " + gd_path);
+  os << "#=GENOME_DIFF\t1.0\n";
+  static const char* type_name[3] = {"RA", "MC", "UN"};
+  for (const GdRow& r : rows) {
+    os << type_name[r.type] << '\t' << r.id << "\t.\t" << r.seq_id;
+    if (r.type == 0) os << '\t' << r.a << '\t' << r.b << '\t' << r.ref_base << '\t' << r.new_base;
+    else if (r.type == 1) os << '\t' << r.a << '\t' << r.b << '\t' << r.c << '\t' << r.d;
+    else os << '\t' << r.a << '\t' << r.b;
+    for (const auto& kv : r.kv) if (!kv.second.empty()) os << '\t' << kv.first << '=' << kv.second;
+    os << '\n';
+  }
+  return counts;
+}
+
+}  // namespace brq

@@ -1,0 +1,62 @@
+// Host-side finalisation of the pileup: covariate layout, the error-table file formats, the
+// per-class likelihood table, and RA / MC / UN evidence emission.
+#pragma once
+#include "bam_io.h"
+#include "brq_types.h"
+#include "kernels.h"
+
+#include <string>
+#include <vector>
+
+namespace brq {
+
+// Covariates in the reference's enum order (error_count.h:69).
+enum { COV_READ_SET, COV_REF_BASE, COV_PREV_BASE, COV_OBS_BASE, COV_QUALITY, COV_READ_POS, COV_BASE_REPEAT, COV_COUNT };
+
+struct CovSpec {
+  bool used[COV_COUNT] = {false, false, false, false, false, false, false};
+  bool clamp[COV_COUNT] = {false, false, false, false, false, false, false};
+  uint32_t maxv[COV_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  uint32_t offset[COV_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  bool per_position = false;
+  uint32_t n_bins = 0;
+  std::string text() const;  // print_covariates(), error_count.cpp:601-621
+};
+
+CovSpec parse_covariates(const std::string& s);  // read_covariates(), error_count.cpp:522-594
+CovLayout to_layout(const CovSpec& spec);
+
+// Stream a double the way `ostream << double` does by default (6 significant digits).
+std::string format_default(double v);
+// common.h:845-867 (fixed / scientific with a given precision, "NA" for NaN)
+std::string format_double(double v, uint32_t precision, bool scientific);
+
+void write_error_rates(const std::string& path, const CovSpec& spec, const std::vector<double>& log10_prob);
+void read_error_rates(const std::string& path, CovSpec& spec, std::vector<double>& log10_prob);
+// log10 table -> the values pass 2 actually uses: text round trip, then pow(10, x)
+void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& log10_text, std::vector<double>& prob);
+void write_base_qual_tables(const std::string& pattern, const CovSpec& spec, const std::vector<uint64_t>& counts,
+                            const std::vector<std::string>& readfiles);
+void write_count_table(const std::string& path, const CovSpec& spec, const std::vector<uint64_t>& counts);
+void write_coverage_distributions(const std::string& dir, const std::vector<uint64_t>& cov, uint64_t stride, uint64_t n_groups);
+
+// Per-class likelihood terms for every (read_set, strand, MAPQ present, quality, obs).
+void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const uint32_t mapq_seen[8], ScoreParams& p,
+                     std::vector<ClassTerms>& lut);
+
+struct EvidenceParams {
+  double mutation_cutoff, polymorphism_cutoff, precision_decimal;
+  uint32_t precision_places;
+  uint32_t base_quality_cutoff;
+  double log10_ref_length;
+  bool skip_missing_coverage_prediction;
+  std::vector<double> deletion_propagation_cutoff, deletion_seed_cutoff;  // by BAM tid
+};
+struct EvidenceCounts { uint64_t ra = 0, mc = 0, un = 0, rechecked = 0, overturned = 0; };
+
+// `shard_first_col1` etc. are not needed: the stream knows its segments.
+EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
+                              const std::vector<ColumnOut>& cols, const std::vector<uint32_t>& flagged,
+                              const ScoreParams& sp, const std::vector<ClassTerms>& lut, const EvidenceParams& ep);
+
+}  // namespace brq

@@ -1,0 +1,66 @@
+// Device side of the pileup: launch wrappers for the sm_100a kernels in kernels.cu.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace brq {
+
+// Mixed-radix layout of the covariate table (/root/reference/src/breseq/error_count.cpp:477-497,
+// 585-593): idx = sum over USED covariates of value * offset, offsets assigned in enum order.
+struct CovLayout {
+  uint32_t off_set, off_ref, off_obs, off_qual, off_rpos, off_rep;  // 0 when unused
+  uint32_t max_set, max_qual, max_rpos, max_rep;                    // UINT32_MAX when unused (no bound)
+  uint32_t n_bins;
+  uint32_t obs_used;                                                // obs_base is a covariate
+};
+
+enum : uint32_t {
+  BRQ_ERR_QUALITY_RANGE = 1,    // quality >= table maximum (reference: fatal ASSERT, error_count.cpp:487)
+  BRQ_ERR_READSET_RANGE = 2,
+  BRQ_ERR_READPOS_RANGE = 4,
+  BRQ_ERR_CLASS_OVERFLOW = 8,   // more distinct record classes in one column than the class table holds
+  BRQ_ERR_DEPTH_RANGE = 16,     // unique depth beyond the coverage histogram
+};
+
+// Per-slot result of the scoring kernel: 96 bytes.
+struct ColumnOut {
+  double ll[5];            // sum over scoring records of log10 P(obs | true base b)
+  double consensus_score;  // pure-genotype log-odds minus log10(total reference length); NaN when n == 0
+  double variant_score;    // presence score of the top non-reference allele; NaN when there is none
+  double redundant[2];     // [0] bottom strand, [1] top strand; sequential sum of 1/X1 in arrival order
+  uint32_t unique[2];
+  uint32_t raw_redundant[2];
+  uint32_t n;              // scoring records (unique, untrimmed, resolvable, quality >= cutoff)
+  uint32_t bits;           // [2:0] best [5:3] major [8:6] minor [11:9] variant (5 = N)
+                           // [12] base_predicted [13] unique_only [14] emit candidate [15] needs host re-check
+                           // [23:16] EM iterations of the full fit
+};
+static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
+
+constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15;
+
+struct ScoreParams {
+  double log10_ref_length;
+  double mutation_cutoff, polymorphism_cutoff, precision_decimal;
+  uint32_t base_quality_cutoff;
+  uint32_t n_mapq_slots;     // distinct MAPQ values present
+  uint32_t max_qual;         // Q of the table (quality covariate maximum)
+  uint32_t max_set;
+  uint8_t mapq_slot[256];    // MAPQ -> slot, 255 = absent
+};
+
+// Per-class likelihood terms, built on the host with the same libm calls the reference makes
+// (identify_mutations.cpp:3359-3384) so the per-record terms are bit-identical.
+struct ClassTerms { double L[5]; double r[5]; };
+
+void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts,
+                 uint32_t* err, cudaStream_t s);
+void launch_coverage_hist(const uint64_t* hist_off, const uint8_t* group, uint64_t n_cols, uint32_t stride,
+                          unsigned long long* cov_hist, uint32_t* err, cudaStream_t s);
+void launch_derive_table(const unsigned long long* counts, const CovLayout& lay, double* log10_prob, cudaStream_t s);
+void launch_score(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots,
+                  const ClassTerms* lut, const ScoreParams& p, ColumnOut* out, uint32_t* flagged,
+                  uint32_t* n_flagged, uint32_t flagged_cap, uint32_t* err, cudaStream_t s);
+int launch_count();  // kernels launched so far through these wrappers (bench bookkeeping)
+
+}  // namespace brq

@@ -1,0 +1,493 @@
+#include "staging.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <thread>
+
+namespace brq {
+
+void make_read_file_partition(const ReadGroups& rg, const std::vector<ReadFileSetInfo>& sets,
+                              std::vector<uint32_t>& base, std::vector<uint32_t>& count) {
+  base.clear(); count.clear();
+  if (sets.empty()) return;
+  std::vector<uint32_t> set_base, set_count;
+  uint32_t flat = 0;
+  for (const ReadFileSetInfo& s : sets) { set_base.push_back(flat); set_count.push_back(s.n_files); flat += s.n_files; }
+  for (size_t g = 0; g < rg.ids.size(); ++g) {
+    size_t match = 0; bool found = false;
+    if (!rg.libraries[g].empty())
+      for (size_t s = 0; s < sets.size(); ++s) if (sets[s].base_name == rg.libraries[g]) { match = s; found = true; break; }
+    if (!found) { match = g; found = g < set_base.size(); }
+    if (found && match < set_base.size()) { base.push_back(set_base[match]); count.push_back(set_count[match]); }
+    else { base.push_back(0); count.push_back(1); }
+  }
+}
+
+namespace {
+
+void* default_alloc(size_t bytes, bool* pinned) {
+  *pinned = false;
+  void* p = nullptr;
+  if (posix_memalign(&p, 256, bytes ? bytes : 256) != 0) throw std::bad_alloc();
+  return p;
+}
+void default_release(void* p, bool) { free(p); }
+
+inline bool op_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+inline bool op_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+
+struct ReadInfo {
+  uint32_t L;          // l_seq
+  int32_t end;         // exclusive reference end
+  int32_t qs0, qe0;    // first/last non-soft-clipped query index (alignment.cpp:248-288)
+  int32_t qb_end0;     // query_bounds_0 end (alignment.cpp:104-218, min_qual == 0)
+  uint8_t read_set;
+  bool rev;
+};
+
+// Visit the pileup entries of one read restricted to columns [lo, hi): f(c, q, is_del, indel).
+// Same per-column values htslib's pileup reports (qpos on a deleted column = first query base
+// after the deletion; indel only on the last column before an I / D run, runs merged, P skipped).
+template <class F>
+inline void walk_read(const uint32_t* cig, uint32_t n_cig, int32_t pos, int32_t lo, int32_t hi, F&& f) {
+  int32_t x = pos, y = 0;
+  for (uint32_t k = 0; k < n_cig; ++k) {
+    uint32_t op = cig[k] & 0xf;
+    int32_t l = (int32_t)(cig[k] >> 4);
+    if (op_ref(op)) {
+      if (x >= hi) return;
+      int32_t xe = x + l;
+      if (xe > lo) {
+        // indel reported at the last column of this op
+        int indel = 0;
+        if (k + 1 < n_cig) {
+          uint32_t op2 = cig[k + 1] & 0xf;
+          int32_t l2 = (int32_t)(cig[k + 1] >> 4);
+          if (op2 == 2 && op != 2) {
+            indel = -l2;
+            for (uint32_t j = k + 2; j < n_cig && (cig[j] & 0xf) == 2; ++j) indel -= (int32_t)(cig[j] >> 4);
+          } else if (op2 == 1) {
+            indel = l2;
+            for (uint32_t j = k + 2; j < n_cig; ++j) {
+              uint32_t o = cig[j] & 0xf;
+              if (o == 1) indel += (int32_t)(cig[j] >> 4);
+              else if (o != 6) break;
+            }
+          } else if (op2 == 6 && k + 2 < n_cig) {
+            int32_t l3 = 0;
+            for (uint32_t j = k + 2; j < n_cig; ++j) {
+              uint32_t o = cig[j] & 0xf;
+              if (o == 1) l3 += (int32_t)(cig[j] >> 4);
+              else if (op_ref(o)) break;
+            }
+            if (l3 > 0) indel = l3;
+          }
+        }
+        int32_t c0 = std::max(x, lo), c1 = std::min(xe, hi);
+        if (op_match(op)) {
+          for (int32_t c = c0; c < c1; ++c) f(c, y + (c - x), false, (c == xe - 1) ? indel : 0);
+        } else {
+          for (int32_t c = c0; c < c1; ++c) f(c, y, true, (c == xe - 1) ? indel : 0);
+        }
+      }
+      if (op_match(op)) y += l;
+      x = xe;
+    } else if (op == 1 || op == 4) {
+      y += l;
+    }
+  }
+}
+
+struct Item { uint32_t v; int32_t lo, hi; size_t first_read, last_read; };
+inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
+
+}  // namespace
+
+void free_stream(PileupStream& s, const StageConfig& cfg) {
+  auto rel = cfg.release ? cfg.release : default_release;
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec})
+    if (p) rel(p, s.pinned);
+  s = PileupStream();
+}
+
+void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const StageConfig& cfg, PileupStream& out) {
+  auto alloc = cfg.alloc ? cfg.alloc : default_alloc;
+  const size_t n_reads = R.size();
+  const size_t n_targets = hdr.target_names.size();
+  out = PileupStream();
+
+  // ---- targets in visit order (std::set<string> iteration == sorted strings; pileup_base.cpp:364-385)
+  std::vector<std::string> ids = cfg.call_seq_ids.empty() ? hdr.target_names : cfg.call_seq_ids;
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  std::vector<const std::string*> refseq;
+  std::vector<Segment> full;
+  uint64_t total_cols = 0;
+  for (const std::string& id : ids) {
+    size_t tid = std::find(hdr.target_names.begin(), hdr.target_names.end(), id) - hdr.target_names.begin();
+    if (tid == n_targets) throw std::runtime_error("Could not find seq_id: " + id);
+    size_t r = std::find(ref.names.begin(), ref.names.end(), id) - ref.names.begin();
+    if (r == ref.names.size() || ref.seqs[r].size() != hdr.target_lens[tid])
+      throw std::runtime_error("reference sequence missing or of the wrong length: " + id);
+    full.push_back({(int32_t)tid, 0, (int32_t)hdr.target_lens[tid], total_cols});
+    total_cols += hdr.target_lens[tid];
+    refseq.push_back(&ref.seqs[r]);
+  }
+  {  // clip to this process's contiguous coordinate shard
+    const uint64_t n_sh = std::max<uint32_t>(1, cfg.shard_count), rk = std::min<uint64_t>(cfg.shard_rank, n_sh - 1);
+    const uint64_t g_lo = total_cols * rk / n_sh, g_hi = total_cols * (rk + 1) / n_sh;
+    std::vector<const std::string*> kept;
+    for (size_t v = 0; v < full.size(); ++v) {
+      const uint64_t a = full[v].slot0, b = a + (uint64_t)full[v].hi;
+      const uint64_t lo = std::max(a, g_lo), hi = std::min(b, g_hi);
+      if (lo >= hi) continue;
+      out.segments.push_back({full[v].tid, (int32_t)(lo - a), (int32_t)(hi - a), out.n_base});
+      out.n_base += hi - lo;
+      kept.push_back(refseq[v]);
+    }
+    refseq.swap(kept);
+  }
+  const size_t n_visit = out.segments.size();
+
+  // ---- read ranges per target; the BAM must be coordinate sorted (htslib's pileup aborts otherwise)
+  std::vector<size_t> t_first(n_targets, 0), t_last(n_targets, 0);
+  {
+    int32_t last_tid = -1, last_pos = -1;
+    for (size_t i = 0; i < n_reads; ++i) {
+      int32_t t = R.tid[i];
+      if (t < 0) { last_tid = INT32_MAX; continue; }   // unplaced reads sort last
+      if (t < last_tid || (t == last_tid && R.pos[i] < last_pos)) throw std::runtime_error("BAM is not coordinate sorted");
+      if (t != last_tid) { t_first[(size_t)t] = i; }
+      t_last[(size_t)t] = i + 1;
+      last_tid = t; last_pos = R.pos[i];
+    }
+  }
+
+  // ---- per-read derived values
+  std::vector<uint32_t> part_base, part_count;
+  make_read_file_partition(hdr.read_groups, cfg.read_file_sets, part_base, part_count);
+  std::vector<ReadInfo> info(n_reads);
+  std::vector<int32_t> max_span(n_targets, 1);
+  for (size_t i = 0; i < n_reads; ++i) {
+    ReadInfo& ri = info[i];
+    const uint32_t* cig = R.cigars.data() + R.cigar_off[i];
+    uint32_t nc = R.n_cigar[i];
+    ri.L = R.l_seq[i];
+    ri.rev = (R.flag[i] & 16) != 0;
+    int32_t rlen = 0, qlen = 0;
+    for (uint32_t k = 0; k < nc; ++k) {
+      uint32_t op = cig[k] & 0xf; int32_t l = (int32_t)(cig[k] >> 4);
+      if (op_ref(op)) rlen += l;
+      if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qlen += l;
+    }
+    ri.end = R.pos[i] + (rlen ? rlen : 1);
+    int32_t qs1 = 1;
+    for (uint32_t k = 0; k < nc && (cig[k] & 0xf) == 4; ++k) qs1 += (int32_t)(cig[k] >> 4);
+    int32_t qe1 = qlen;
+    for (uint32_t k = nc; k-- > 1 && (cig[k] & 0xf) == 4;) qe1 -= (int32_t)(cig[k] >> 4);
+    ri.qs0 = qs1 - 1; ri.qe0 = qe1 - 1;
+    int32_t be1 = qlen;
+    for (uint32_t k = nc; k-- > 1;) {
+      uint32_t op = cig[k] & 0xf;
+      if (op != 4 && op != 5 && op != 3) break;
+      if (op == 4) be1 -= (int32_t)(cig[k] >> 4);
+    }
+    ri.qb_end0 = be1 - 1;
+    uint32_t g = R.rg[i];
+    ri.read_set = 0;
+    if (!part_base.empty() && g < part_base.size())
+      ri.read_set = (uint8_t)(part_base[g] + (((R.flag[i] & 128) && part_count[g] > 1) ? 1 : 0));
+    if (ri.read_set >= 32) throw std::runtime_error("more than 32 read files are not supported by the packed record");
+    if (R.tid[i] >= 0 && rlen > max_span[(size_t)R.tid[i]]) max_span[(size_t)R.tid[i]] = rlen;
+  }
+  auto in_pileup = [&](size_t i) {  // bam_plp_push keeps mapped reads with a tid; a read without a walkable CIGAR cannot be resolved
+    return R.tid[i] >= 0 && !(R.flag[i] & 4) && R.n_cigar[i] > 0;
+  };
+
+  // ---- work items: column ranges of visited targets
+  std::vector<Item> items;
+  for (size_t v = 0; v < n_visit; ++v) {
+    const Segment& sg = out.segments[v];
+    size_t tid = (size_t)sg.tid;
+    int32_t len = (int32_t)hdr.target_lens[tid];
+    size_t nr = t_last[tid] - t_first[tid];
+    int32_t chunk = 8192;
+    if (nr) { double depth = (double)nr * 100.0 / std::max(1, len); if (depth > 400) chunk = 2048; }
+    size_t cursor = t_first[tid];
+    for (int32_t lo = sg.lo; lo < sg.hi; lo += chunk) {
+      Item it; it.v = (uint32_t)v; it.lo = lo; it.hi = std::min(sg.hi, lo + chunk);
+      // reads are sorted by pos: first candidate has pos > lo - max_span
+      while (cursor < t_last[tid] && R.pos[cursor] + max_span[tid] <= lo) ++cursor;
+      it.first_read = cursor;
+      size_t e = cursor;
+      while (e < t_last[tid] && R.pos[e] < it.hi) ++e;
+      it.last_read = e;
+      items.push_back(it);
+    }
+  }
+  const int n_threads = std::max(1, cfg.threads);
+  std::string error;
+  std::mutex error_mu;
+  auto run_items = [&](auto&& body) {
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+      try {
+        for (;;) { size_t i = next.fetch_add(1); if (i >= items.size()) break; body(i); }
+      } catch (const std::exception& e) { std::lock_guard<std::mutex> g(error_mu); if (error.empty()) error = e.what(); next = items.size(); }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (!error.empty()) throw std::runtime_error(error);
+  };
+
+  // ---- pass A1: which insert sub-columns exist.  Level k+1 exists iff a UNIQUE read has an
+  // insertion longer than k after the column and a non-N base at level k
+  // (identify_mutations.cpp:1577 precedes :1598).
+  struct InsSupport { uint64_t slot; uint64_t mask; };
+  std::vector<std::vector<InsSupport>> support(items.size());
+  run_items([&](size_t ii) {
+    const Item& it = items[ii];
+    std::vector<InsSupport>& sup = support[ii];
+    for (size_t i = it.first_read; i < it.last_read; ++i) {
+      if (!in_pileup(i) || info[i].end <= it.lo || R.x1[i] != 1) continue;
+      const uint32_t* cig = R.cigars.data() + R.cigar_off[i];
+      bool any = false;
+      for (uint32_t k = 0; k < R.n_cigar[i]; ++k) if ((cig[k] & 0xf) == 1) { any = true; break; }
+      if (!any) continue;
+      const uint8_t* seq = R.bases.data() + R.seq_off[i];
+      walk_read(cig, R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
+        if (is_del || indel <= 0) return;
+        if (indel > 63) throw std::runtime_error("insertions longer than 63 bases are not supported");
+        uint64_t mask = 0;
+        for (int k = 0; k < indel; ++k) if (seq[q + k] != 15) mask |= 1ull << k;
+        sup.push_back({out.segments[it.v].slot0 + (uint64_t)(c - out.segments[it.v].lo), mask});
+      });
+    }
+  });
+  std::vector<uint32_t> sub_first;   // per base slot: first sub-slot index or ~0u
+  std::vector<uint8_t> sub_k;        // per base slot: number of sub-columns
+  {
+    std::vector<InsSupport> all;
+    for (auto& v : support) all.insert(all.end(), v.begin(), v.end());
+    support.clear();
+    std::sort(all.begin(), all.end(), [](const InsSupport& a, const InsSupport& b) { return a.slot < b.slot; });
+    sub_first.assign(out.n_base, 0xFFFFFFFFu);
+    sub_k.assign(out.n_base, 0);
+    for (size_t a = 0; a < all.size();) {
+      size_t b = a; uint64_t mask = 0;
+      while (b < all.size() && all[b].slot == all[a].slot) mask |= all[b++].mask;
+      uint32_t K = 0;
+      while (K < 63 && (mask >> K & 1)) ++K;
+      if (K) {
+        sub_first[all[a].slot] = (uint32_t)out.ins_parent.size();
+        sub_k[all[a].slot] = (uint8_t)K;
+        for (uint32_t k = 1; k <= K; ++k) { out.ins_parent.push_back(all[a].slot); out.ins_count.push_back(k); }
+      }
+      a = b;
+    }
+    out.n_ins = out.ins_parent.size();
+  }
+  const uint64_t n_slots = out.n_slots();
+
+  // ---- pass A2: record counts per slot
+  std::vector<uint32_t> score_cnt(cfg.want_score ? n_slots : 0, 0), hist_cnt(cfg.want_hist ? out.n_base : 0, 0);
+  std::vector<uint8_t> col_red(cfg.want_hist ? out.n_base : 0, 0);
+  run_items([&](size_t ii) {
+    const Item& it = items[ii];
+    const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
+    for (size_t i = it.first_read; i < it.last_read; ++i) {
+      if (!in_pileup(i) || info[i].end <= it.lo) continue;
+      const uint8_t* seq = R.bases.data() + R.seq_off[i];
+      const bool unique = R.x1[i] == 1;
+      const uint32_t L = info[i].L;
+      walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
+        const uint64_t slot = s0 + (uint64_t)c;
+        if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
+        if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
+        if (cfg.want_score) {
+          if (is_del || seq[q] != 15) ++score_cnt[slot];
+          uint32_t K = sub_k[slot];
+          if (K) {
+            int ind = is_del ? -1 : std::max(indel, 0);
+            for (uint32_t k = 1; k <= K; ++k)
+              if (ind < (int)k || seq[q + (int32_t)k] != 15) ++score_cnt[out.n_base + sub_first[slot] + k - 1];
+          }
+        }
+      });
+    }
+  });
+
+  // ---- offsets
+  bool pinned = false, p2 = false;
+  out.slot_ref = (uint8_t*)alloc(n_slots, &pinned);
+  out.slot_group = (uint8_t*)alloc(out.n_base ? out.n_base : 1, &p2);
+  out.score_off = (uint64_t*)alloc((n_slots + 1) * 8, &p2);
+  out.hist_off = (uint64_t*)alloc((out.n_base + 1) * 8, &p2);
+  out.pinned = pinned;
+  for (size_t v = 0; v < n_visit; ++v) {
+    const Segment& sg = out.segments[v];
+    size_t tid = (size_t)sg.tid;
+    uint32_t g = cfg.coverage_group_of_tid.empty() ? (uint32_t)tid : cfg.coverage_group_of_tid[tid];
+    if (g > 255) throw std::runtime_error("more than 256 coverage groups are not supported");
+    const std::string& s = *refseq[v];
+    for (int32_t p = sg.lo; p < sg.hi; ++p) {
+      uint8_t b = char_to_index(s[(size_t)p]);
+      if (b > 5 || b == 4) throw std::runtime_error(std::string("Unrecognized base char in reference: ") + s[(size_t)p]);
+      out.slot_ref[sg.slot0 + (uint64_t)(p - sg.lo)] = b;
+      out.slot_group[sg.slot0 + (uint64_t)(p - sg.lo)] = (uint8_t)g;
+    }
+  }
+  for (uint64_t j = 0; j < out.n_ins; ++j) out.slot_ref[out.n_base + j] = kBaseGap;
+  {
+    uint64_t acc = 0;
+    for (uint64_t s = 0; s < n_slots; ++s) { out.score_off[s] = acc; if (cfg.want_score) acc += score_cnt[s]; }
+    out.score_off[n_slots] = acc; out.n_score = acc;
+    acc = 0;
+    for (uint64_t c = 0; c < out.n_base; ++c) {
+      out.hist_off[c] = acc | ((cfg.want_hist && col_red[c]) ? HIST_OFF_REDUNDANT_BIT : 0);
+      if (cfg.want_hist) acc += hist_cnt[c];
+    }
+    out.hist_off[out.n_base] = acc; out.n_hist = acc;
+  }
+  out.score_rec = (uint32_t*)alloc(out.n_score * 4, &p2);
+  out.hist_rec = (uint64_t*)alloc(out.n_hist * 8, &p2);
+
+  // ---- pass B: fill, arrival (BAM) order within every slot
+  std::vector<uint32_t>& score_cur = score_cnt;  // reused as per-slot cursors
+  std::vector<uint32_t>& hist_cur = hist_cnt;
+  std::fill(score_cur.begin(), score_cur.end(), 0);
+  std::fill(hist_cur.begin(), hist_cur.end(), 0);
+  std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
+  std::vector<uint32_t> max_quals(items.size(), 0);
+  run_items([&](size_t ii) {
+    const Item& it = items[ii];
+    const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
+    const std::string& rs = *refseq[it.v];
+    auto ref_index = [&](int32_t p) -> uint32_t {  // forward-strand reference base; the byte past the end is the NUL terminator
+      if (p >= tlen_of(rs)) return kBaseNul;
+      uint8_t b = char_to_index(rs[(size_t)p]);
+      if (b > 5 || b == 4) throw std::runtime_error(std::string("Unrecognized base char in reference: ") + rs[(size_t)p]);
+      return b;
+    };
+    uint32_t* mq_mask = &mapq_masks[ii * 8];
+    uint32_t max_q = 0;
+    for (size_t i = it.first_read; i < it.last_read; ++i) {
+      if (!in_pileup(i) || info[i].end <= it.lo) continue;
+      const ReadInfo& ri = info[i];
+      const uint8_t* seq = R.bases.data() + R.seq_off[i];
+      const uint8_t* qual = R.quals.data() + R.seq_off[i];
+      const bool unique = R.x1[i] == 1;
+      const uint32_t rev = ri.rev ? 1 : 0;
+      const int32_t L = (int32_t)ri.L;
+      const uint32_t red = std::min<uint32_t>(R.x1[i], 65535u);
+      if (R.x1[i] == 0) throw std::runtime_error("X1:i:0 is not a valid redundancy");
+      const uint32_t mapq = R.mapq[i];
+      walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
+        const uint64_t slot = s0 + (uint64_t)c;
+        // ---------------- error_count record (error_count.cpp:125-199, 854-986)
+        if (cfg.want_hist && !is_del && unique) {
+          uint64_t rec = 0;
+          uint32_t qa = qual[q];
+          if (qa > 127) throw std::runtime_error("base quality above 127 cannot be packed");
+          rec |= (uint64_t)nibble_to_index(seq[q]) << HR_OBSA;
+          rec |= (uint64_t)out.slot_ref[slot] << HR_REFA;
+          rec |= (uint64_t)qa << HR_QUALA;
+          rec |= (uint64_t)rev << HR_REV;
+          rec |= (uint64_t)ri.read_set << HR_SET;
+          if (q > 65535) throw std::runtime_error("read position above 65535 cannot be packed");
+          rec |= (uint64_t)q << HR_RPOS;
+          auto base_repeat = [&](int32_t qp) -> uint64_t {  // alignment.cpp:371-390
+            uint8_t b = seq[qp]; uint32_t rep = 0;
+            if (!rev) { while (qp < ri.qe0) { ++qp; if (seq[qp] != b) break; ++rep; } }
+            else { while (qp > 0) { --qp; if (seq[qp] != b) break; ++rep; } }
+            return rep;
+          };
+          if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(q), 255) << HR_REPA;
+          uint32_t cls = 0; int32_t m = -1; uint32_t refb = kBaseNul;
+          if (indel == 0) {
+            if (q < ri.qe0) {
+              cls = 1; m = q + 1 - (int32_t)rev;
+              int32_t mr = c + 1 - (int32_t)rev;
+              refb = ref_index(mr);
+            }
+          } else if (indel == -1) {
+            cls = 2; m = q + 1 - (int32_t)rev;
+            refb = ref_index(c + 1);
+          } else if (indel == 1) {
+            m = q + 1;
+            if (m >= L) throw std::runtime_error("Attempt to retrieve quality score for nonexistent base for '.N' state.");
+            if (m <= ri.qe0 && m >= ri.qs0) cls = 3;
+          }
+          if (cls) {
+            if (m < 0 || m >= L) throw std::runtime_error("Attempt to retrieve quality score for nonexistent base.");
+            if (qual[m] > 127) throw std::runtime_error("base quality above 127 cannot be packed");
+            rec |= (uint64_t)cls << HR_CLASSB;
+            rec |= (uint64_t)nibble_to_index(seq[m]) << HR_OBSB;
+            rec |= (uint64_t)refb << HR_REFB;
+            rec |= (uint64_t)qual[m] << HR_QUALB;
+            if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 63) << HR_REPB;
+          }
+          out.hist_rec[(out.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT) + hist_cur[slot]++] = rec;
+        }
+        // ---------------- identify_mutations records (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105)
+        if (!cfg.want_score) return;
+        const int ind = is_del ? -1 : std::max(indel, 0);
+        const uint32_t K = sub_k[slot];
+        const uint32_t q1 = (uint32_t)q + 1;
+        for (uint32_t k = 0; k <= K; ++k) {
+          const bool past_base = !(ind >= (int)k);
+          uint8_t obs = past_base ? (uint8_t)kBaseGap : nibble_to_index(seq[q + (int32_t)k]);
+          if (obs == kBaseN) continue;  // not even coverage
+          uint32_t rec = obs;
+          if (!rev) rec |= SR_TOP_BIT;
+          bool trimmed = false;  // alignment.h:389-410 (unsigned comparisons as there)
+          if (R.xl[i] >= 0 || R.xl[i] < -1) { if (q1 <= (uint32_t)R.xl[i]) trimmed = true; }
+          if (R.xr[i] >= 0 || R.xr[i] < -1) {
+            if ((uint32_t)L - q1 + 1 <= (uint32_t)R.xr[i]) trimmed = true;
+            if (past_base && ((uint32_t)L - q1 == (uint32_t)R.xr[i])) trimmed = true;
+          }
+          if (trimmed) rec |= SR_TRIM_BIT;
+          if (unique) {
+            rec |= SR_UNIQUE_BIT;
+            int32_t qp = q;
+            bool ok = true;
+            if (ind == -1) {
+              qp += 1 - (int32_t)rev;
+              if (qp >= L) throw std::runtime_error("deletion with no following read base (reference would assert)");
+              if (seq[qp] == 15) ok = false;
+            } else if (k > 0) {
+              qp += std::min((int)k, ind) + 1 - (int32_t)rev;
+              if (qp > ri.qb_end0) ok = false;
+              else if (seq[qp] == 15) ok = false;
+            }
+            if (ok) {
+              uint32_t qv = qual[qp];
+              if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
+              rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
+              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); if (qv > max_q) max_q = qv; }
+            }
+            rec |= mapq << SR_MAPQ_SHIFT;
+            rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
+          } else {
+            rec |= red << SR_RED_SHIFT;
+          }
+          uint64_t s = k == 0 ? slot : out.n_base + sub_first[slot] + k - 1;
+          out.score_rec[out.score_off[s] + score_cur[s]++] = rec;
+        }
+      });
+    }
+    max_quals[ii] = max_q;
+  });
+  for (size_t ii = 0; ii < items.size(); ++ii) {
+    for (int w = 0; w < 8; ++w) out.mapq_seen[w] |= mapq_masks[ii * 8 + (size_t)w];
+    out.max_qual_seen = std::max(out.max_qual_seen, max_quals[ii]);
+  }
+}
+
+}  // namespace brq

@@ -1,0 +1,39 @@
+// Host staging: ReadBatch -> pinned, columnar, reference-position-sorted PileupStream.
+//
+// Replaces, for this path, the htslib pileup engine plus the per-read accessor calls the
+// reference makes once per (read, column): /root/reference/src/breseq/pileup_base.cpp:141-210,
+// 308-385 (column construction incl. zero-depth columns), alignment.cpp:44-57, 104-288, 371-390,
+// alignment.h:354-410, error_count.cpp:854-986 and 1049-1105 (which base / quality / neighbour a
+// record contributes).  Everything that depends only on the read and the column is decided here,
+// once, and packed; the kernels do the counting, table math and per-column statistics.
+#pragma once
+#include "bam_io.h"
+#include "brq_types.h"
+
+namespace brq {
+
+struct ReadFileSetInfo { std::string base_name; uint32_t n_files; };
+
+struct StageConfig {
+  std::vector<std::string> call_seq_ids;          // empty = every target; visited in alphabetical order
+  std::vector<uint32_t> coverage_group_of_tid;    // empty = one group per target
+  std::vector<ReadFileSetInfo> read_file_sets;    // empty = everything is read file 0
+  bool use_base_repeat = false;
+  int threads = 8;
+  bool want_hist = true, want_score = true;
+  uint32_t shard_rank = 0, shard_count = 1;         // contiguous reference-coordinate shard staged by this call
+  // buffer allocator (pinned when a device is present); both must be set together
+  void* (*alloc)(size_t bytes, bool* pinned) = nullptr;
+  void (*release)(void* p, bool pinned) = nullptr;
+};
+
+// Throws std::runtime_error where the reference would ASSERT (unsorted input, quality out of the
+// packable range, a deletion with no following read base, ...).
+void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& reads, const StageConfig& cfg, PileupStream& out);
+void free_stream(PileupStream& s, const StageConfig& cfg);
+
+// Flat read-file index of each read group (alignment.cpp:565-605).
+void make_read_file_partition(const ReadGroups& rg, const std::vector<ReadFileSetInfo>& sets,
+                              std::vector<uint32_t>& base, std::vector<uint32_t>& count);
+
+}  // namespace brq

@@ -1,0 +1,150 @@
+/* brq.h -- C ABI of the B200-native read-alignment evidence pileup (libbrq.so).
+ *
+ * Drop-in boundary for two breseq 0.50.0 entry points and nothing else:
+ *   breseq::error_count()          /root/reference/src/breseq/error_count.h:41-52
+ *   breseq::identify_mutations()   /root/reference/src/breseq/identify_mutations.h:46-60
+ * The reference has no FFI of its own for this path; these are the entry
+ * points a maintainer binds from error_count.cpp / identify_mutations.cpp.
+ * Plain C: pointers and sizes only, ctx-owned result buffers, 0 on success and non-zero on
+ * failure with the message in brq_last_error().  The library never falls back to a CPU
+ * implementation of the kernels: without a usable CUDA device every compute call fails.
+ */
+#ifndef BRQ_H
+#define BRQ_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct brq_ctx brq_ctx;
+
+typedef struct brq_config {
+  int32_t device;   /* CUDA ordinal; -1 = host-only context (staging / file formats, no kernels) */
+  int32_t threads;  /* host staging threads, 0 = hardware concurrency */
+} brq_config;
+
+brq_ctx* brq_create(const brq_config* cfg);
+void brq_destroy(brq_ctx* ctx);
+const char* brq_last_error(const brq_ctx* ctx);
+const char* brq_version(void);
+
+/* ---- host staging: BAM -> pinned columnar stream (replaces pileup_base.cpp:61-88, 239-385 and
+ *      the per-record accessor calls of alignment.h/.cpp on this path) ------------------------ */
+typedef struct brq_read_file_set {  /* one cReadFileSet == one @RG; a paired set has 2 files */
+  const char* base_name;
+  uint32_t n_files;
+} brq_read_file_set;
+
+typedef struct brq_stage_options {
+  const char* const* seq_ids;              /* Settings::call_mutations_seq_id_set(); NULL = all targets */
+  uint32_t n_seq_ids;
+  const brq_read_file_set* read_file_sets; /* Settings::read_file_sets; NULL = standalone ERROR_COUNT (read_set 0) */
+  uint32_t n_read_file_sets;
+  const uint32_t* coverage_group_of_tid;   /* Settings::seq_id_to_coverage_group per BAM tid; NULL = one per target */
+  uint32_t n_targets;
+  uint32_t use_base_repeat;                /* the covariate string names base_repeat */
+  uint32_t shard_rank, shard_count;        /* contiguous reference-coordinate shard of this process; 0,1 = all */
+} brq_stage_options;
+
+int brq_stage_bam(brq_ctx* ctx, const char* bam, const char* fasta, const brq_stage_options* opt);
+
+/* Synthetic aligned reads (the reference's SIMULATE-READS error model, breseq_cmdline.cpp:1160-1171). */
+typedef struct brq_synth_read_set {
+  const char* name;
+  uint32_t paired, read_len;
+  double coverage, frag_mean, frag_sd;
+} brq_synth_read_set;
+
+typedef struct brq_synth_spec {
+  uint64_t seed;
+  const uint32_t* contig_lens;     /* random ACGT contigs ... */
+  uint32_t n_contigs;
+  const char* contig_prefix;
+  const char* fasta;               /* ... or an existing FASTA (contig_lens == NULL) */
+  const brq_synth_read_set* sets;
+  uint32_t n_sets;
+  uint32_t n_polymorphic, n_fixed, n_gaps;
+  uint32_t min_freq_ppm, max_freq_ppm;
+} brq_synth_spec;
+
+int brq_synth_write(brq_ctx* ctx, const brq_synth_spec* spec, const char* bam_out, const char* fasta_out);
+int brq_stage_synthetic(brq_ctx* ctx, const brq_synth_spec* spec, const brq_stage_options* opt);
+
+typedef struct brq_stream_info {
+  uint64_t n_base, n_ins, n_score_records, n_hist_records, n_reads;
+  uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
+  uint32_t n_targets, pinned;
+  const uint32_t* score_rec;       /* host views, valid until the next staging call */
+  const uint64_t* score_off;
+  const uint64_t* hist_rec;
+  const uint64_t* hist_off;
+  const uint8_t* slot_ref;
+  const uint64_t* ins_parent;
+  const uint32_t* ins_count;
+} brq_stream_info;
+
+int brq_stream(brq_ctx* ctx, brq_stream_info* info);
+int brq_upload(brq_ctx* ctx);      /* host stream -> HBM (asynchronous on the ctx stream) */
+int brq_sync(brq_ctx* ctx);
+
+/* ---- pass 1: error_count (error_count.cpp:125-199, 854-1026) --------------------------------- */
+int brq_error_count(brq_ctx* ctx, const char* covariates, int do_coverage, int do_errors);
+/* device views for the one collective of the path (sum-allreduce of both integer histograms) */
+int brq_hist_device(brq_ctx* ctx, void** counts_u64, uint64_t* n_bins, void** coverage_u64, uint64_t* n_coverage);
+int brq_hist_download(brq_ctx* ctx, const uint64_t** counts, uint64_t* n_bins, const uint64_t** coverage,
+                      uint64_t* coverage_stride, uint64_t* n_groups);
+/* counts -> log10 table on the device, canonicalised through the error_rates.tab text form
+ * (error_count.cpp:660-690 writes 6 significant digits; :629-654 reads them back), then the
+ * per-class likelihood table of pass 2 is built and uploaded. */
+int brq_derive_error_table(brq_ctx* ctx);
+int brq_error_table(brq_ctx* ctx, const double** log10_prob, uint64_t* n_bins);
+int brq_write_error_count_files(brq_ctx* ctx, const char* output_dir, const char* error_rates_file,
+                                const char* const* readfiles, uint32_t n_readfiles, int do_coverage, int do_errors,
+                                const char* counts_dump_file /* NULL = none */);
+int brq_load_error_table(brq_ctx* ctx, const char* error_rates_file);  /* read_log10_prob_table + log10_prob_to_prob */
+
+/* ---- pass 2: identify_mutations (identify_mutations.cpp:1309-2022, 3240-3433) ---------------- */
+typedef struct brq_score_params {
+  double mutation_cutoff, polymorphism_cutoff, polymorphism_precision_decimal;
+  uint32_t polymorphism_precision_places;
+  uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff */
+  uint64_t total_reference_length;         /* 0 = sum of BAM target lengths (identify_mutations.cpp:848-852) */
+} brq_score_params;
+
+typedef struct brq_column {  /* one per slot: base columns of the visited targets, then insert sub-columns */
+  double ll[5];
+  double consensus_score, variant_score;
+  double redundant[2];                     /* [0] bottom strand, [1] top strand */
+  uint32_t unique[2], raw_redundant[2];
+  uint32_t n, bits;
+} brq_column;
+
+int brq_score_columns(brq_ctx* ctx, const brq_score_params* p);
+int brq_columns_download(brq_ctx* ctx, const brq_column** columns, uint64_t* n_slots, const uint32_t** flagged,
+                         uint32_t* n_flagged);
+int brq_columns_device(brq_ctx* ctx, void** columns, uint64_t* n_slots);
+/* host finalisation: re-evaluates flagged slots in arrival order, emits RA rows with bounds and
+ * bias statistics, runs the MC / UN interval state machines and writes ra_mc_evidence.gd */
+int brq_write_evidence(brq_ctx* ctx, const char* gd_file, const double* deletion_propagation_cutoff,
+                       const double* deletion_seed_cutoff, uint32_t n_targets, int skip_missing_coverage_prediction,
+                       uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un);
+
+/* ---- one-call adapters with the reference entry points' argument meaning --------------------- */
+int brq_run_error_count(brq_ctx* ctx, const char* bam, const char* fasta, const char* output_dir,
+                        const char* error_rates_file, const char* const* readfiles, uint32_t n_readfiles,
+                        int do_coverage, int do_errors, const char* covariates, const brq_stage_options* opt);
+int brq_run_identify_mutations(brq_ctx* ctx, const char* bam, const char* fasta, const char* error_rates_file,
+                               const char* gd_file, const double* deletion_propagation_cutoff,
+                               const double* deletion_seed_cutoff, uint32_t n_targets, const brq_score_params* p,
+                               int skip_missing_coverage_prediction, const brq_stage_options* opt);
+
+/* bookkeeping for bench.py: kernels launched so far, device milliseconds of the last call of each kernel */
+int brq_launch_count(void);
+int brq_kernel_ms(brq_ctx* ctx, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,63 @@
+// TEST INFRASTRUCTURE -- CPU oracle for the read-alignment evidence pileup.
+//
+// A plain, single-threaded restatement of the reference's algorithm for the hot path
+// (breseq 0.50.0, /root/reference/src/breseq), driven through the htslib-compatible shim in
+// hts_shim/.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+// legs may build, link or execute anything in this directory; the product (breseq_b200/) never does.
+//
+// PARITY STATUS: "parity unpinned".  The reference ships no fixture at the BAM -> (error table,
+// RA evidence) boundary and its end-to-end goldens need bowtie2 + htslib, neither of which is in
+// this image.  Where possible the restatement is cross-checked against the
+// reference's OWN sources compiled against the same shim (oracle/_ref, see Makefile).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+namespace oracle {
+
+struct ReadFileSet { std::string base_name; uint32_t n_files; };
+
+struct Settings {
+  std::set<std::string> call_mutations_seq_ids;            // settings.h:993 (std::set => alphabetical visit order)
+  std::map<std::string, uint32_t> seq_id_to_coverage_group; // settings.h:996
+  uint32_t n_coverage_groups = 0;
+  std::vector<ReadFileSet> read_file_sets;                  // empty for the standalone ERROR_COUNT path
+  uint32_t base_quality_cutoff = 3;                         // settings.cpp:1335
+  bool skip_missing_coverage_prediction = false;            // settings.cpp:843
+  std::string error_rates_file_name;                        // 07_error_calibration/error_rates.tab
+  std::string unique_only_coverage_distribution_file_name;  // contains '@' replaced by the group index
+  std::string base_qual_error_prob_file_name;               // contains '#' replaced by the read file name
+  uint64_t total_reference_sequence_length = 0;
+};
+
+// error_count.h:41-52
+void error_count(const Settings& settings, const std::string& bam, const std::string& fasta,
+                 const std::string& output_dir, const std::vector<std::string>& readfiles,
+                 bool do_coverage, bool do_errors, const std::string& covariates,
+                 const std::string& counts_dump_file /* "" = none: raw count table, idx-ordered text */);
+
+struct ColumnDump {  // one per (column, insert_count); written raw to --columns-out
+  uint32_t tid, pos1, insert_count, n;
+  double ll[5];
+  double consensus_score, variant_score;
+  double f[5];
+  double log10_likelihood;
+  double unique[2], redundant[2];  // [0] bottom strand, [1] top strand
+  int32_t raw_redundant[2];
+  int32_t total;
+  uint8_t best, major, minor, variant, ref, base_predicted, unique_only, emitted;
+  uint32_t iterations;
+};
+
+// identify_mutations.h:46-60
+void identify_mutations(const Settings& settings, const std::string& bam, const std::string& fasta,
+                        const std::string& gd_file, const std::vector<double>& deletion_propagation_cutoff,
+                        const std::vector<double>& deletion_seed_cutoff, double mutation_cutoff,
+                        double polymorphism_cutoff, double polymorphism_precision_decimal,
+                        uint32_t polymorphism_precision_places, const std::string& columns_dump_file,
+                        uint64_t* n_records_out);
+
+}  // namespace oracle

@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bases/sec of error_count + identify_mutations on B200.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3          (one JSON line on stdout)
+  torchrun ... bench.py --gpus N ...                        (one rank per GPU; weak scaling)
+  python bench.py --impl reference ...                      (the CPU implementation, same metric)
+
+Workload (BASELINE.json configs[1]): E. coli REL606-sized reference
+(4 629 812 bp, one contig), synthetic 100x pe150 reads, one paired read set (read_set=2, Q=42).
+At N GPUs every rank holds one such coordinate range (its own contig of an N x 4.6 Mb genome):
+weak scaling, no data-path collective except the sum-allreduce of the integer histograms.
+
+A "step" is one pass of both kernels' path over the resident stream:
+  covariate histogram + coverage histogram -> [allreduce] -> table derivation + text
+  canonicalisation + class table -> per-slot scoring.
+`value` times that with the stream already in HBM; `e2e` adds the host->device copy of the
+pinned stream, the device->host copy of the per-slot results and the host finalisation that
+writes error_rates.tab and ra_mc_evidence.gd, i.e. what the reference-facing call does after
+BAM staging.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GENOME = 4629812
+READ_SETS = [dict(name="REL606_pe150", paired=True, read_len=150, coverage=100.0, frag_mean=400, frag_sd=40)]
+COVARIATES = "read_set=2,obs_base,ref_base,quality=42"
+MUTATION_CUTOFF, POLYMORPHISM_CUTOFF, PRECISION, PLACES = 10.0, 10.0, 1e-6, 3  # clone / consensus mode (settings.cpp:914-960)
+CPU_SAMPLE_DIV = 64  # the CPU arms run the same model on a 1/64-length reference
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def oracle_cli():
+    path = os.path.join(ROOT, "oracle", "_build", "oracle_cli")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    return path
+
+
+def cpu_sample(tmp, seed=2):
+    """The C1 model on a 1/64-length reference, written as BAM + FASTA for the CPU arms."""
+    import breseq_b200 as bq
+    ctx = bq.Context(device=-1)
+    spec = bq.SynthSpec(seed=seed, read_sets=READ_SETS, contig_lens=[GENOME // CPU_SAMPLE_DIV], contig_prefix="REL606s",
+                        n_polymorphic=4, n_fixed=2, n_gaps=1)
+    bam, fasta = os.path.join(tmp, "s.bam"), os.path.join(tmp, "s.fasta")
+    ctx.synth_write(spec, bam, fasta)
+    ctx.close()
+    return bam, fasta
+
+
+def run_cpu_once(bam, fasta, out):
+    """Both passes of the CPU implementation on one BAM; returns (records, seconds)."""
+    cli = oracle_cli()
+    os.makedirs(out, exist_ok=True)
+    a = json.loads(subprocess.run([cli, "error_count", "--bam", bam, "--fasta", fasta, "--out", out, "--covariates", COVARIATES,
+                                   "--readfiles", "r1,r2", "--read-sets", READ_SETS[0]["name"] + ":2"],
+                                  check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+    b = json.loads(subprocess.run([cli, "identify_mutations", "--bam", bam, "--fasta", fasta, "--error-rates",
+                                   os.path.join(out, "error_rates.tab"), "--gd", os.path.join(out, "o.gd"), "--read-sets",
+                                   READ_SETS[0]["name"] + ":2", "--del-prop", "30", "--del-seed", "0", "--mutation-cutoff",
+                                   str(MUTATION_CUTOFF), "--polymorphism-cutoff", str(POLYMORPHISM_CUTOFF), "--places", str(PLACES)],
+                                  check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+    return b["records"], a["seconds"] + b["seconds"]
+
+
+def config_block(n_gpus):
+    return {"workload": "E. coli REL606 4.6 Mb clone mode, synthetic 100x pe150 reads (BASELINE configs[1]); one 4 629 812 bp "
+                        "coordinate range per GPU", "covariates": COVARIATES, "records_per_gpu": None,
+            "l2_policy": "inputs (about 5.5 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
+            "parallelism": "reference-range sharding x%d, one sum-allreduce of the integer histograms" % n_gpus}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(os.cpu_count() or 1, 32)
+    with tempfile.TemporaryDirectory() as tmp:
+        bam, fasta = cpu_sample(tmp)
+        times, records = [], 0
+
+        def one_step(tag):
+            # `cores` independent processes, one coordinate range each (the reference itself is
+            # single-threaded on this path; sharding by reference range is how it would be spread)
+            t0 = time.perf_counter()
+            procs, results = [], [None] * cores
+
+            def worker(i):
+                results[i] = run_cpu_once(bam, fasta, os.path.join(tmp, "%s_%d" % (tag, i)))
+            th = [threading.Thread(target=worker, args=(i,)) for i in range(cores)]
+            [t.start() for t in th]
+            [t.join() for t in th]
+            return sum(r[0] for r in results), time.perf_counter() - t0
+        for w in range(args.warmup if args.warmup < 2 else 1):
+            one_step("w%d" % w)
+        for k in range(args.steps):
+            n, dt = one_step("s%d" % k)
+            records, _ = n, times.append(dt)
+        dt = sum(times) / len(times)
+        value = records / dt
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_cli")) else "port"
+    line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": value, "unit": "aligned bases/s",
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "aligned bases/s", "cores": cores, "kind": kind,
+                             "sample": "C1 read model on a 1/%d-length reference (%d bp), %d concurrent single-threaded "
+                                       "processes, one reference range each" % (CPU_SAMPLE_DIV, GENOME // CPU_SAMPLE_DIV, cores)},
+            "e2e": {"value": value, "unit": "aligned bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; reported in config)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import breseq_b200 as bq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = bq.Context(device=local)
+    genome = int(GENOME * args.scale)
+    spec = bq.SynthSpec(seed=2 + rank, read_sets=READ_SETS, contig_lens=[genome], contig_prefix="REL606_range%d" % rank,
+                        n_polymorphic=40, n_fixed=10, n_gaps=3)
+    t0 = time.perf_counter()
+    ctx.stage_synthetic(spec, read_file_sets=spec.read_file_sets())
+    t_stage = time.perf_counter() - t0
+    s = ctx.stream()
+    n_records, n_slots, n_hist = int(s["n_score"]), int(s["n_base"] + s["n_ins"]), int(s["n_hist"])
+    ctx.upload()
+    ctx.sync()
+    params = bq.Context.score_params(MUTATION_CUTOFF, POLYMORPHISM_CUTOFF, PRECISION, PLACES)
+
+    class DevArray:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+    def allreduce_hist():
+        if world == 1:
+            return
+        c, n, v, m = ctx.hist_device()
+        ctx.sync()
+        # every rank sizes its coverage histogram by its own deepest column: reduce the counts only
+        # over the common prefix, which is all the table derivation needs
+        t = torch.as_tensor(DevArray(c, n), device="cuda:%d" % local)
+        dist.all_reduce(t)
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.error_count(COVARIATES)
+        allreduce_hist()
+        ctx.derive_error_table()
+        ctx.score_columns(params)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    k_ms = {"hist": 0.0, "coverage": 0.0, "derive": 0.0, "score": 0.0}
+    for _ in range(args.steps):
+        step()
+        for k, v in ctx.kernel_ms().items():
+            k_ms[k] += v
+    ctx.event_record(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    clocks = sampler.summary()
+    launches = ctx.launch_count() - launches0
+    step_ms = max(dev_ms, wall * 1e3) / args.steps  # host gaps count: the step is not done before its table is built
+    for k in k_ms:
+        k_ms[k] /= args.steps
+
+    # ---- end to end through the C ABI with host buffers: H2D + kernels + D2H + host finalisation
+    with tempfile.TemporaryDirectory() as tmp:
+        def e2e_step():
+            ctx.upload()
+            ctx.error_count(COVARIATES)
+            allreduce_hist()
+            ctx.derive_error_table()
+            ctx.write_error_count_files(tmp, os.path.join(tmp, "error_rates.tab"), ["r1", "r2"])
+            ctx.score_columns(params)
+            ctx.write_evidence(os.path.join(tmp, "ra_mc_evidence.gd"), [30.0], [0.0])
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+    h2d = int(s["bytes_host"])
+    d2h = n_slots * 96 + 25 * 2 * 42 * 16
+
+    # ---- max over ranks, whole-job aggregate
+    stats = torch.tensor([step_ms, e2e_s, float(n_records), k_ms["score"], k_ms["hist"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        step_ms, e2e_s, total_records = mx[0].item(), mx[1].item(), sm[2].item()
+    else:
+        total_records = float(n_records)
+
+    if rank == 0:
+        peak, peak_kind = measured_peak_gbs()
+        score_bytes = 4 * n_records + 104 * n_slots           # 4 B/record + 8 B offsets + 96 B result per slot
+        hist_bytes = 8 * n_hist + 8 * int(s["n_base"])
+        achieved = score_bytes / (k_ms["score"] * 1e-3) / 1e9 if k_ms["score"] > 0 else 0.0
+        cfg = config_block(world)
+        cfg["records_per_gpu"] = n_records
+        cfg["slots_per_gpu"] = n_slots
+        cfg["genome_scale"] = args.scale
+        cfg["kernel_ms"] = k_ms
+        cfg["staging_seconds"] = t_stage
+        cfg["hist_kernel_gbs"] = hist_bytes / (k_ms["hist"] * 1e-3) / 1e9 if k_ms["hist"] > 0 else 0.0
+        cpu = None
+        if world == 1 or True:
+            with tempfile.TemporaryDirectory() as tmp:
+                bam, fasta = cpu_sample(tmp)
+                n_cpu, t_cpu = run_cpu_once(bam, fasta, os.path.join(tmp, "o"))
+            cpu = {"value": n_cpu / t_cpu, "unit": "aligned bases/s", "cores": 1, "kind": "port",
+                   "sample": "C1 read model on a 1/%d-length reference (%d bp): %d records in %.1f s, one thread"
+                             % (CPU_SAMPLE_DIV, GENOME // CPU_SAMPLE_DIV, n_cpu, t_cpu)}
+        line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": total_records / (step_ms * 1e-3),
+                "unit": "aligned bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": total_records / e2e_s, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "roofline": {"bound": "hbm", "kernel": "score_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                             "algorithmic_bytes": score_bytes},
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

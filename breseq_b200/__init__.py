@@ -117,6 +117,8 @@ def load_library():
         "brq_run_identify_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_double),
                                        P(C.c_double), C.c_uint32, P(_ScoreParams), C.c_int, P(_StageOptions)],
         "brq_launch_count": [],
+        "brq_event_record": [C.c_void_p, C.c_int],
+        "brq_event_elapsed_ms": [C.c_void_p, C.c_int, C.c_int, P(C.c_float)],
         "brq_kernel_ms": [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)],
     }
     for name, argtypes in sig.items():
@@ -132,7 +134,8 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
-           "brq_write_evidence", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms"]
+           "brq_write_evidence", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
+           "brq_event_record", "brq_event_elapsed_ms"]
 
 
 def _b(s):
@@ -335,6 +338,14 @@ class Context:
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self.lib.brq_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"hist": a.value, "coverage": b.value, "derive": c.value, "score": d.value}
+
+    def event_record(self, slot):
+        self._check(self.lib.brq_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self.lib.brq_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return self.lib.brq_launch_count()

@@ -58,6 +58,7 @@ struct brq_ctx {
   std::string error;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[8] = {nullptr};
+  cudaEvent_t user_ev[4] = {nullptr};
   float ms_hist = 0, ms_cov = 0, ms_derive = 0, ms_score = 0;
 
   BamHeader hdr;
@@ -350,6 +351,7 @@ brq_ctx* brq_create(const brq_config* cfg) {
       CUDA_OK(cudaSetDevice(c->device));
       CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       for (auto& e : c->ev) CUDA_OK(cudaEventCreate(&e));
+      for (auto& e : c->user_ev) CUDA_OK(cudaEventCreate(&e));
       c->d_scalars.ensure(2);
       CUDA_OK(cudaMemset(c->d_scalars.p, 0, 8));
     } catch (const std::exception& e) {
@@ -368,6 +370,7 @@ void brq_destroy(brq_ctx* c) {
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
   }
   delete c;
@@ -516,6 +519,23 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
 }
 
 int brq_launch_count(void) { return launch_count(); }
+
+int brq_event_record(brq_ctx* c, int slot) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (slot < 0 || slot > 3) throw std::runtime_error("event slot out of range");
+    CUDA_OK(cudaEventRecord(c->user_ev[slot], c->stream));
+  });
+}
+
+int brq_event_elapsed_ms(brq_ctx* c, int a, int b, float* ms) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (a < 0 || a > 3 || b < 0 || b > 3) throw std::runtime_error("event slot out of range");
+    CUDA_OK(cudaEventSynchronize(c->user_ev[b]));
+    CUDA_OK(cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
+  });
+}
 
 int brq_kernel_ms(brq_ctx* c, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms) {
   if (!c) return 1;

@@ -142,6 +142,9 @@ int brq_run_identify_mutations(brq_ctx* ctx, const char* bam, const char* fasta,
 
 /* bookkeeping for bench.py: kernels launched so far, device milliseconds of the last call of each kernel */
 int brq_launch_count(void);
+/* CUDA events on the ctx stream (slots 0..3) so callers can time a region on the launching stream */
+int brq_event_record(brq_ctx* ctx, int slot);
+int brq_event_elapsed_ms(brq_ctx* ctx, int slot_a, int slot_b, float* ms);
 int brq_kernel_ms(brq_ctx* ctx, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms);
 
 #ifdef __cplusplus

@@ -1,0 +1,185 @@
+"""Shared test plumbing: dataset definitions, the oracle runner, and numpy re-statements of what
+the kernels count (used to check the HOST staging on machines without a GPU)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+
+import breseq_b200 as bq
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_CLI = os.path.join(ROOT, "oracle", "_build", "oracle_cli")
+
+# written by oracle --columns-out (oracle.h: ColumnDump)
+ORACLE_COLUMN = np.dtype([("tid", "<u4"), ("pos1", "<u4"), ("insert_count", "<u4"), ("n", "<u4"), ("ll", "<f8", 5),
+                          ("consensus_score", "<f8"), ("variant_score", "<f8"), ("f", "<f8", 5), ("log10_likelihood", "<f8"),
+                          ("unique", "<f8", 2), ("redundant", "<f8", 2), ("raw_redundant", "<i4", 2), ("total", "<i4"),
+                          ("best", "u1"), ("major", "u1"), ("minor", "u1"), ("variant", "u1"), ("ref", "u1"),
+                          ("base_predicted", "u1"), ("unique_only", "u1"), ("emitted", "u1"), ("iterations", "<u4")])
+assert ORACLE_COLUMN.itemsize == 176
+
+# name -> generator + run settings.  Sizes are chosen so the oracle finishes in seconds.
+DATASETS = {
+    # stand-in for tests/lambda_polymorphism: 48.5 kb, ~107x se35, polymorphism mode
+    "lambda": dict(seed=1, contig_lens=[48502], prefix="NC_001416",
+                   read_sets=[dict(name="lambda_reads", paired=False, read_len=35, coverage=107.0)],
+                   n_polymorphic=60, n_fixed=10, n_gaps=2, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
+                   precision=1e-6, places=8, del_prop=20.0, del_seed=0.0),
+    # three contigs, one paired + one single-end read group => read_set=3, consensus-mode cutoffs
+    "multi": dict(seed=7, contig_lens=[6000, 3500, 5000], prefix="ctg",
+                  read_sets=[dict(name="pe", paired=True, read_len=150, coverage=60.0, frag_mean=400, frag_sd=40),
+                             dict(name="se", paired=False, read_len=36, coverage=30.0)],
+                  n_polymorphic=25, n_fixed=8, n_gaps=2, mutation_cutoff=10.0, polymorphism_cutoff=10.0,
+                  precision=1e-6, places=3, del_prop=15.0, del_seed=0.0),
+}
+
+
+def synth_spec(d):
+    return bq.SynthSpec(seed=d["seed"], read_sets=d["read_sets"], contig_lens=d["contig_lens"], contig_prefix=d["prefix"],
+                        n_polymorphic=d["n_polymorphic"], n_fixed=d["n_fixed"], n_gaps=d["n_gaps"])
+
+
+def read_file_sets(d):
+    return [(rs["name"], 2 if rs.get("paired") else 1) for rs in d["read_sets"]]
+
+
+def readfile_names(d):
+    out = []
+    for rs in d["read_sets"]:
+        out += [rs["name"] + "_R1", rs["name"] + "_R2"] if rs.get("paired") else [rs["name"]]
+    return out
+
+
+def covariates(d, n_qual=42):
+    return "read_set=%d,obs_base,ref_base,quality=%d" % (len(readfile_names(d)), n_qual)
+
+
+def run_oracle(*args):
+    p = subprocess.run([ORACLE_CLI] + [str(a) for a in args], check=True, capture_output=True, text=True)
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def make_dataset(name, outdir):
+    """Generate BAM + FASTA with the product's generator, then run both oracle passes on it."""
+    d = dict(DATASETS[name])
+    os.makedirs(outdir, exist_ok=True)
+    d["dir"] = outdir
+    d["bam"], d["fasta"] = os.path.join(outdir, "reference.bam"), os.path.join(outdir, "reference.fasta")
+    ctx = bq.Context(device=-1)
+    ctx.synth_write(synth_spec(d), d["bam"], d["fasta"])
+    ctx.close()
+    odir = os.path.join(outdir, "oracle")
+    os.makedirs(odir, exist_ok=True)
+    sets = ",".join("%s:%d" % s for s in read_file_sets(d))
+    d["oracle_dir"] = odir
+    d["oracle_counts"] = os.path.join(odir, "error_counts.tab")
+    d["oracle_rates"] = os.path.join(odir, "error_rates.tab")
+    d["oracle_gd"] = os.path.join(odir, "ra_mc_evidence.gd")
+    d["oracle_columns"] = os.path.join(odir, "columns.bin")
+    run_oracle("error_count", "--bam", d["bam"], "--fasta", d["fasta"], "--out", odir, "--covariates", covariates(d),
+               "--readfiles", ",".join(readfile_names(d)), "--read-sets", sets, "--counts-dump", d["oracle_counts"])
+    n = len(d["contig_lens"])
+    run_oracle("identify_mutations", "--bam", d["bam"], "--fasta", d["fasta"], "--error-rates", d["oracle_rates"],
+               "--gd", d["oracle_gd"], "--read-sets", sets, "--del-prop", ",".join([str(d["del_prop"])] * n),
+               "--del-seed", ",".join([str(d["del_seed"])] * n), "--mutation-cutoff", d["mutation_cutoff"],
+               "--polymorphism-cutoff", d["polymorphism_cutoff"], "--precision", d["precision"], "--places", d["places"],
+               "--columns-out", d["oracle_columns"])
+    return d
+
+
+def oracle_counts(path):
+    lines = open(path).read().strip().split("\n")[2:]
+    return np.array([int(float(l.split("\t")[-1])) for l in lines], dtype=np.int64)
+
+
+def oracle_columns(path):
+    return np.fromfile(path, dtype=ORACLE_COLUMN)
+
+
+def oracle_slots(o, stream, target_slot0):
+    """Slot index (product numbering) of every oracle column row."""
+    nb = int(stream["n_base"])
+    slot = np.where(o["insert_count"] == 0, target_slot0[o["tid"]] + o["pos1"].astype(np.int64) - 1, -1)
+    key = {(int(p), int(k)): nb + i for i, (p, k) in enumerate(zip(stream["ins_parent"], stream["ins_count"]))}
+    for i in np.nonzero(o["insert_count"] > 0)[0]:
+        slot[i] = key[(int(target_slot0[o["tid"][i]]) + int(o["pos1"][i]) - 1, int(o["insert_count"][i]))]
+    return slot
+
+
+def visit_slot0(contig_names, contig_lens):
+    """First base slot of each BAM tid when targets are visited in alphabetical order."""
+    order = sorted(range(len(contig_names)), key=lambda i: contig_names[i])
+    slot0 = np.zeros(len(contig_names), dtype=np.int64)
+    acc = 0
+    for i in order:
+        slot0[i] = acc
+        acc += contig_lens[i]
+    return slot0
+
+
+def contig_names(d):
+    n = len(d["contig_lens"])
+    if n == 1:
+        return [d["prefix"]]
+    width = len(str(n))
+    return ["%s%0*d" % (d["prefix"], width, i + 1) for i in range(n)]
+
+
+# ---- numpy statements of what the kernels count (test-side only) --------------------------------
+def emulate_hist(hist_rec, n_sets, n_qual):
+    """Covariate histogram for the default layout read_set, ref_base, obs_base, quality."""
+    r = hist_rec
+
+    def f(sh, m):
+        return ((r >> np.uint64(sh)) & np.uint64(m)).astype(np.int64)
+    obsA, refA, qa, rev, cls, obsB, refB, qb, rset = f(0, 7), f(3, 7), f(6, 127), f(13, 1), f(14, 3), f(16, 7), f(19, 7), f(22, 127), f(29, 31)
+    N = n_sets
+    counts = np.zeros(N * 25 * n_qual, np.int64)
+
+    def comp(x):
+        return np.where(x < 4, 3 - x, x)
+
+    def add(mask, ref, obs, q):
+        np.add.at(counts, (rset + ref * N + obs * 5 * N + q * 25 * N)[mask], 1)
+    add((obsA < 4) & (refA < 4), np.where(rev == 1, comp(refA), refA), np.where(rev == 1, comp(obsA), obsA), qa)
+    add((cls == 1) & (obsB != 5) & (refB != 5), 4, 4, qb)
+    add((cls == 2) & (obsB != 5) & (refB < 4), np.where(rev == 1, comp(refB), refB), 4, qb)
+    add((cls == 3) & (obsB != 5), 4, np.where(rev == 1, comp(obsB), obsB), qb)
+    return counts
+
+
+def emulate_coverage_hist(hist_off):
+    red = (hist_off[:-1] >> np.uint64(63)).astype(bool)
+    off = (hist_off & np.uint64((1 << 63) - 1)).astype(np.int64)
+    depth = np.diff(off)
+    return np.bincount(depth[~red])
+
+
+def emulate_tally(stream, base_quality_cutoff=3):
+    rec = stream["score_rec"]
+    off = stream["score_off"].astype(np.int64)
+    n_slots = len(off) - 1
+    sid = np.repeat(np.arange(n_slots), np.diff(off))
+    uniq, top, trim, ok, q = (rec >> 11) & 1, (rec >> 10) & 1, (rec >> 12) & 1, (rec >> 13) & 1, (rec >> 3) & 127
+    out = {}
+    for name, u in (("unique", 1), ("raw_redundant", 0)):
+        out[name] = np.stack([np.bincount(sid[(uniq == u) & (top == 0)], minlength=n_slots),
+                              np.bincount(sid[(uniq == u) & (top == 1)], minlength=n_slots)], axis=1)
+    out["n"] = np.bincount(sid[(uniq == 1) & (trim == 0) & (ok == 1) & (q >= base_quality_cutoff)], minlength=n_slots)
+    red = np.zeros((n_slots, 2))
+    for i in np.nonzero(uniq == 0)[0]:  # order-dependent double sum, arrival order
+        red[sid[i], top[i]] += 1.0 / float((rec[i] >> 14) & 0xFFFF)
+    out["redundant"] = red
+    return out
+
+
+def parse_gd(path):
+    rows = []
+    for line in open(path):
+        if line.startswith("#") or not line.strip():
+            continue
+        f = line.rstrip("\n").split("\t")
+        n_spec = {"RA": 5, "MC": 5, "UN": 3}[f[0]]
+        rows.append(dict(type=f[0], id=f[1], spec=f[3:3 + n_spec], kv=dict(x.split("=", 1) for x in f[3 + n_spec:])))
+    return rows

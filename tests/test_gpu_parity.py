@@ -1,0 +1,139 @@
+"""Parity of the CUDA path against the CPU oracle, through the C ABI (needs a B200).
+
+Bars (BASELINE.json north_star): error counts and coverage bit-exact; identical set of RA calls and
+consensus/polymorphism decisions; log-likelihood scores within 1e-9 relative; frequencies within 1e-6.
+"""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+import breseq_b200 as bq
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9
+
+
+@pytest.fixture(scope="module", params=list(helpers.DATASETS))
+def run(request, datasets, tmp_path_factory):
+    d = datasets[request.param]
+    out = str(tmp_path_factory.mktemp("gpu_" + request.param))
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    ctx.error_count(helpers.covariates(d))
+    counts, cov = ctx.hist_download()
+    ctx.derive_error_table()
+    ctx.write_error_count_files(out, os.path.join(out, "error_rates.tab"), helpers.readfile_names(d))
+    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"]))
+    cols, flagged = ctx.columns_download()
+    n = len(d["contig_lens"])
+    gd = os.path.join(out, "ra_mc_evidence.gd")
+    stats = ctx.write_evidence(gd, [d["del_prop"]] * n, [d["del_seed"]] * n)
+    o = helpers.oracle_columns(d["oracle_columns"])
+    slot = helpers.oracle_slots(o, ctx.stream(), helpers.visit_slot0(helpers.contig_names(d), d["contig_lens"]))
+    yield dict(d=d, out=out, counts=counts, cov=cov, cols=cols, flagged=flagged, gd=gd, stats=stats, o=o, g=cols[slot], ctx=ctx)
+    ctx.close()
+
+
+def test_error_counts_bit_exact(run):
+    assert np.array_equal(run["counts"].astype(np.int64), helpers.oracle_counts(run["d"]["oracle_counts"]))
+
+
+def test_error_rate_files_byte_identical(run):
+    d = run["d"]
+    assert filecmp.cmp(os.path.join(run["out"], "error_rates.tab"), d["oracle_rates"], shallow=False)
+    for rf in helpers.readfile_names(d):
+        name = "base_qual_error_prob.%s.tab" % rf
+        assert filecmp.cmp(os.path.join(run["out"], name), os.path.join(d["oracle_dir"], name), shallow=False), name
+    for g in range(len(d["contig_lens"])):
+        name = "%d.unique_only_coverage_distribution.tab" % g
+        assert filecmp.cmp(os.path.join(run["out"], name), os.path.join(d["oracle_dir"], name), shallow=False), name
+
+
+def test_coverage_bit_exact(run):
+    g, o = run["g"], run["o"]
+    assert np.array_equal(g["unique"], o["unique"].astype(np.uint32))
+    assert np.array_equal(g["raw_redundant"], o["raw_redundant"].astype(np.uint32))
+    assert np.array_equal(g["redundant"], o["redundant"])
+    assert np.array_equal(g["n"], o["n"])
+    assert np.array_equal(((g["bits"] & bq.CO_UNIQUE_ONLY) != 0), o["unique_only"].astype(bool))
+
+
+def test_log_likelihoods_and_scores(run):
+    g, o = run["g"], run["o"]
+    m = o["n"] > 0
+    rel = np.abs(g["ll"][m] - o["ll"][m]) / np.maximum(np.abs(o["ll"][m]), 1e-300)
+    assert rel.max() < REL
+    # scores are differences of O(100) sums: 1e-9 relative to the magnitudes that were subtracted
+    scale = np.maximum(np.abs(o["ll"][m]).max(axis=1), 1.0)
+    assert (np.abs(g["consensus_score"][m] - o["consensus_score"][m]) / scale).max() < REL
+    assert np.all(np.isnan(g["consensus_score"][~m])) and np.all(np.isnan(o["consensus_score"][~m]))
+    v = ~np.isnan(o["variant_score"])
+    assert np.array_equal(v, ~np.isnan(g["variant_score"]))
+    scale_v = np.maximum(np.abs(o["log10_likelihood"][v]), 1.0)
+    assert (np.abs(g["variant_score"][v] - o["variant_score"][v]) / scale_v).max() < 1e-7  # the EM stops at |df| < 1e-6
+
+
+def test_calls_and_decisions_identical(run):
+    g, o = run["g"], run["o"]
+    bits = g["bits"]
+    for name, shift in (("best", 0), ("major", 3), ("minor", 6), ("variant", 9)):
+        assert np.array_equal((bits >> shift) & 7, o[name]), name
+    recheck = (bits & bq.CO_RECHECK) != 0
+    pred = (bits & bq.CO_BASE_PREDICTED) != 0
+    assert np.array_equal(pred[~recheck], o["base_predicted"][~recheck].astype(bool))
+    emit = (bits & bq.CO_EMIT) != 0
+    assert np.all(emit[o["emitted"] == 1]), "an oracle RA call was not flagged by the kernel"
+    assert np.array_equal((bits >> 16) & 0xFF, o["iterations"]) or np.mean(((bits >> 16) & 0xFF) == o["iterations"]) > 0.999
+
+
+def test_genome_diff_identical(run):
+    d = run["d"]
+    mine, ora = helpers.parse_gd(run["gd"]), helpers.parse_gd(d["oracle_gd"])
+    assert [(r["type"], r["spec"]) for r in mine] == [(r["type"], r["spec"]) for r in ora]
+    for a, b in zip(mine, ora):
+        assert a["id"] == b["id"]
+        assert sorted(a["kv"]) == sorted(b["kv"])
+        for k in a["kv"]:
+            if a["kv"][k] == b["kv"][k]:
+                continue
+            if k in ("frequency", "major_frequency", "frequency_lower", "frequency_upper"):
+                assert abs(float(a["kv"][k]) - float(b["kv"][k])) < 1e-6, (k, a["kv"][k], b["kv"][k])
+            else:
+                raise AssertionError("field %s differs: %s vs %s" % (k, a["kv"][k], b["kv"][k]))
+    assert open(run["gd"]).read() == open(d["oracle_gd"]).read()
+
+
+def test_entry_point_adapters(run, tmp_path):
+    """breseq::error_count / identify_mutations argument lists, files on disk."""
+    d = run["d"]
+    out = str(tmp_path)
+    rates = os.path.join(out, "error_rates.tab")
+    bq.error_count(d["bam"], d["fasta"], out, helpers.readfile_names(d), True, True, False, 3, helpers.covariates(d),
+                   read_file_sets=helpers.read_file_sets(d), error_rates_file_name=rates)
+    assert filecmp.cmp(rates, d["oracle_rates"], shallow=False)
+    n = len(d["contig_lens"])
+    gd = os.path.join(out, "ra_mc_evidence.gd")
+    bq.identify_mutations(d["bam"], d["fasta"], gd, [d["del_prop"]] * n, [d["del_seed"]] * n, d["mutation_cutoff"],
+                          d["polymorphism_cutoff"], d["precision"], d["places"], False, error_rates_file_name=rates,
+                          read_file_sets=helpers.read_file_sets(d))
+    assert open(gd).read() == open(d["oracle_gd"]).read()
+
+
+def test_idempotent_and_order_free(run):
+    """Re-running the kernels on the resident stream gives bit-identical integer results."""
+    ctx, d = run["ctx"], run["d"]
+    ctx.error_count(helpers.covariates(d))
+    counts, cov = ctx.hist_download()
+    assert np.array_equal(counts, run["counts"]) and np.array_equal(cov, run["cov"])
+    ctx.derive_error_table()
+    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"]))
+    cols, _ = ctx.columns_download()
+    for f in ("unique", "raw_redundant", "n", "redundant"):
+        assert np.array_equal(cols[f], run["cols"][f])
+    # checksum property: scoring depth summed over slots == eligible records in the stream
+    t = helpers.emulate_tally(ctx.stream())
+    assert cols["n"].sum() == t["n"].sum() and cols["unique"].sum() == t["unique"].sum()

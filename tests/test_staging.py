@@ -1,0 +1,89 @@
+"""Host staging against the oracle, without a GPU: the staged streams must carry exactly what the
+reference counts.  The numpy re-statements in helpers.py play the kernels' part."""
+import numpy as np
+import pytest
+
+import breseq_b200 as bq
+import helpers
+
+
+@pytest.fixture(scope="module", params=list(helpers.DATASETS))
+def staged(request, datasets):
+    d = datasets[request.param]
+    ctx = bq.Context(device=-1)
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    yield d, ctx, ctx.stream()
+    ctx.close()
+
+
+def test_histogram_stream_matches_oracle_counts(staged):
+    d, ctx, s = staged
+    mine = helpers.emulate_hist(s["hist_rec"], len(helpers.readfile_names(d)), 42)
+    ora = helpers.oracle_counts(d["oracle_counts"])
+    assert mine.sum() == ora.sum()
+    assert np.array_equal(mine, ora)
+
+
+def test_unique_only_coverage_matches_oracle(staged):
+    d, ctx, s = staged
+    names = helpers.contig_names(d)
+    slot0 = helpers.visit_slot0(names, d["contig_lens"])
+    for tid, length in enumerate(d["contig_lens"]):
+        lo = int(slot0[tid])
+        mine = helpers.emulate_coverage_hist(s["hist_off"][lo:lo + length + 1])
+        lines = open("%s/%d.unique_only_coverage_distribution.tab" % (d["oracle_dir"], tid)).read().strip().split("\n")[1:]
+        ora = np.zeros(len(lines) + 1, dtype=np.int64)
+        for l in lines:
+            j, c = l.split("\t")
+            ora[int(j)] = int(c)
+        n = max(len(mine), len(ora))
+        mine = np.pad(mine, (0, n - len(mine)))
+        ora = np.pad(ora, (0, n - len(ora)))
+        assert np.array_equal(mine[1:], ora[1:])  # the reference never prints depth 0
+
+
+def test_score_stream_tallies_match_oracle(staged):
+    d, ctx, s = staged
+    o = helpers.oracle_columns(d["oracle_columns"])
+    assert len(o) == s["n_base"] + s["n_ins"], "insert sub-columns differ"
+    slot = helpers.oracle_slots(o, s, helpers.visit_slot0(helpers.contig_names(d), d["contig_lens"]))
+    assert len(set(slot.tolist())) == len(o)
+    t = helpers.emulate_tally(s)
+    assert np.array_equal(t["unique"][slot], o["unique"].astype(np.int64))
+    assert np.array_equal(t["raw_redundant"][slot], o["raw_redundant"].astype(np.int64))
+    assert np.array_equal(t["n"][slot], o["n"].astype(np.int64))
+    assert np.array_equal(t["redundant"][slot], o["redundant"])  # bit-exact: same order, same divisions
+    assert np.array_equal(s["slot_ref"][slot], o["ref"])
+
+
+def test_shards_partition_the_stream(datasets):
+    d = datasets["multi"]
+    full = bq.Context(device=-1)
+    full.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    sf = full.stream()
+    whole = helpers.emulate_hist(sf["hist_rec"], 3, 42)
+    acc = np.zeros_like(whole)
+    n_base = n_score = 0
+    for rank in range(3):
+        c = bq.Context(device=-1)
+        c.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d), shard=(rank, 3))
+        s = c.stream()
+        acc += helpers.emulate_hist(s["hist_rec"], 3, 42)
+        n_base += s["n_base"]
+        n_score += s["n_score"]
+        c.close()
+    assert n_base == sf["n_base"] and n_score == sf["n_score"]
+    assert np.array_equal(acc, whole)
+    full.close()
+
+
+def test_empty_and_subset_targets(datasets):
+    d = datasets["multi"]
+    names = helpers.contig_names(d)
+    c = bq.Context(device=-1)
+    c.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d), seq_ids=[names[1]])
+    s = c.stream()
+    assert s["n_base"] == d["contig_lens"][1]
+    with pytest.raises(bq.BrqError):
+        c.stage_bam(d["bam"], d["fasta"], seq_ids=["no_such_contig"])
+    c.close()

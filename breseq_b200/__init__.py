@@ -120,6 +120,7 @@ def load_library():
         "brq_event_record": [C.c_void_p, C.c_int],
         "brq_event_elapsed_ms": [C.c_void_p, C.c_int, C.c_int, P(C.c_float)],
         "brq_kernel_ms": [C.c_void_p, P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)],
+        "brq_score_phase_ms": [C.c_void_p, P(C.c_float), P(C.c_float)],
     }
     for name, argtypes in sig.items():
         fn = getattr(lib, name)
@@ -135,7 +136,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
            "brq_write_evidence", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
-           "brq_event_record", "brq_event_elapsed_ms"]
+           "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
 
 
 def _b(s):
@@ -337,7 +338,9 @@ class Context:
     def kernel_ms(self):
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self.lib.brq_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
-        return {"hist": a.value, "coverage": b.value, "derive": c.value, "score": d.value}
+        e, f = C.c_float(), C.c_float()
+        self.lib.brq_score_phase_ms(self.h, C.byref(e), C.byref(f))
+        return {"hist": a.value, "coverage": b.value, "derive": c.value, "score": d.value, "tally": e.value, "fit": f.value}
 
     def event_record(self, slot):
         self._check(self.lib.brq_event_record(self.h, slot))

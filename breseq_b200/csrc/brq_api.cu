@@ -68,12 +68,18 @@ struct brq_ctx {
   PileupStream st;
   bool staged = false, uploaded = false;
 
-  DevBuf<uint32_t> d_score_rec, d_flagged, d_scalars;  // d_scalars: [0] err, [1] n_flagged
+  DevBuf<uint32_t> d_score_rec, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
   DevBuf<uint64_t> d_score_off, d_hist_rec, d_hist_off;
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
   DevBuf<double> d_log10;
   DevBuf<ClassTerms> d_lut;
+  DevBuf<HotTerms> d_hotL;
+  DevBuf<HotRatios> d_hotR;
+  std::vector<HotTerms> h_hotL;
+  std::vector<HotRatios> h_hotR;
+  float ms_tally = 0, ms_fit = 0;
+  bool warp_mode = false;
   DevBuf<ColumnOut> d_cols;
 
   CovSpec spec;
@@ -176,7 +182,7 @@ void upload(brq_ctx* c) {
   if (!c->staged) throw std::runtime_error("nothing staged");
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
-  c->d_score_rec.ensure(st.n_score); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
+  c->d_score_rec.ensure(st.n_score + 4); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
   c->d_hist_rec.ensure(st.n_hist); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -195,20 +201,14 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   const CovLayout lay = to_layout(c->spec);
   const PileupStream& st = c->st;
   // coverage histogram geometry: groups x (max depth + 1)
-  uint64_t max_depth = 0;
-  for (uint64_t k = 0; k < st.n_base; ++k) {
-    uint64_t d = (st.hist_off[k + 1] & ~HIST_OFF_REDUNDANT_BIT) - (st.hist_off[k] & ~HIST_OFF_REDUNDANT_BIT);
-    if (d > max_depth) max_depth = d;
-  }
-  uint32_t n_groups = 1;
-  for (uint64_t k = 0; k < st.n_base; k += 1) { if (st.slot_group[k] + 1u > n_groups) n_groups = st.slot_group[k] + 1u; }
-  c->cov_stride = max_depth + 1;
+  const uint32_t n_groups = st.n_groups;
+  c->cov_stride = st.max_hist_depth + 1;
   c->n_groups = n_groups;
   c->d_counts.ensure(lay.n_bins);
   c->d_cov.ensure(c->cov_stride * n_groups);
   CUDA_OK(cudaMemsetAsync(c->d_counts.p, 0, (size_t)lay.n_bins * 8, c->stream));
   CUDA_OK(cudaMemsetAsync(c->d_cov.p, 0, c->cov_stride * n_groups * 8, c->stream));
-  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
   if (do_errors) launch_hist(c->d_hist_rec.p, st.n_hist, lay, c->d_counts.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
@@ -236,9 +236,14 @@ void install_table(brq_ctx* c) {  // h_log10 -> text-canonical probabilities -> 
   c->have_table = true;
   if (c->staged) {
     build_class_lut(c->spec, c->h_prob, c->st.mapq_seen, c->sp, c->h_lut);
+    build_hot_tables(c->h_lut, c->st.mapq_count, c->sp, c->h_hotL, c->h_hotR);
     if (c->device >= 0) {
       c->d_lut.ensure(c->h_lut.size());
+      c->d_hotL.ensure(c->h_hotL.size());
+      c->d_hotR.ensure(c->h_hotR.size());
       CUDA_OK(cudaMemcpyAsync(c->d_lut.p, c->h_lut.data(), c->h_lut.size() * sizeof(ClassTerms), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(c->d_hotL.p, c->h_hotL.data(), c->h_hotL.size() * sizeof(HotTerms), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(c->d_hotR.p, c->h_hotR.data(), c->h_hotR.size() * sizeof(HotRatios), cudaMemcpyHostToDevice, c->stream));
       CUDA_OK(cudaStreamSynchronize(c->stream));
     }
   }
@@ -277,14 +282,23 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->d_cols.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
   c->d_flagged.ensure(c->flagged_cap);
-  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 8, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
-  launch_score(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->sp, c->d_cols.p, c->d_flagged.p,
-               c->d_scalars.p + 1, c->flagged_cap, c->d_scalars.p, c->stream);
+  if (c->warp_mode) {  // warp-per-slot class-histogram formulation (deep columns; kept for A/B parity)
+    launch_score(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->sp, c->d_cols.p, c->d_flagged.p,
+                 c->d_scalars.p + 1, c->flagged_cap, c->d_scalars.p, c->stream);
+    CUDA_OK(cudaEventRecord(c->ev[7], c->stream));
+  } else {
+    c->d_worklist.ensure(n_slots);
+    launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->d_hotL.p, c->d_hotR.p, c->sp,
+                       c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
+  }
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
   CUDA_OK(cudaEventElapsedTime(&c->ms_score, c->ev[5], c->ev[6]));
+  CUDA_OK(cudaEventElapsedTime(&c->ms_tally, c->ev[5], c->ev[7]));
+  CUDA_OK(cudaEventElapsedTime(&c->ms_fit, c->ev[7], c->ev[6]));
   c->have_cols = true;
 }
 
@@ -352,8 +366,10 @@ brq_ctx* brq_create(const brq_config* cfg) {
       CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       for (auto& e : c->ev) CUDA_OK(cudaEventCreate(&e));
       for (auto& e : c->user_ev) CUDA_OK(cudaEventCreate(&e));
-      c->d_scalars.ensure(2);
-      CUDA_OK(cudaMemset(c->d_scalars.p, 0, 8));
+      c->d_scalars.ensure(4);
+      CUDA_OK(cudaMemset(c->d_scalars.p, 0, 16));
+      const char* mode = getenv("BRQ_SCORE_MODE");
+      c->warp_mode = mode && std::string(mode) == "warp";
     } catch (const std::exception& e) {
       c->error = std::string("no usable CUDA device: ") + e.what();
       c->device = -2;  // poisoned: every compute call reports the error
@@ -366,7 +382,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_flagged.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_hotL.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -535,6 +551,13 @@ int brq_event_elapsed_ms(brq_ctx* c, int a, int b, float* ms) {
     CUDA_OK(cudaEventSynchronize(c->user_ev[b]));
     CUDA_OK(cudaEventElapsedTime(ms, c->user_ev[a], c->user_ev[b]));
   });
+}
+
+int brq_score_phase_ms(brq_ctx* c, float* tally_ms, float* fit_ms) {
+  if (!c) return 1;
+  if (tally_ms) *tally_ms = c->ms_tally;
+  if (fit_ms) *fit_ms = c->ms_fit;
+  return 0;
 }
 
 int brq_kernel_ms(brq_ctx* c, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms) {

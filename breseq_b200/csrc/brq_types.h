@@ -107,6 +107,9 @@ struct PileupStream {
   uint64_t* hist_rec = nullptr;
   uint64_t n_score = 0, n_hist = 0;
   uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records
+  uint64_t mapq_count[256] = {0};      // scoring records per MAPQ value
+  uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
+  uint32_t n_groups = 1;               // coverage groups present
   uint32_t max_qual_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
   uint64_t n_slots() const { return n_base + n_ins; }

@@ -43,6 +43,9 @@ void write_coverage_distributions(const std::string& dir, const std::vector<uint
 // Per-class likelihood terms for every (read_set, strand, MAPQ present, quality, obs).
 void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const uint32_t mapq_seen[8], ScoreParams& p,
                      std::vector<ClassTerms>& lut);
+// Shared-memory tables for the MAPQ value that carries the most scoring records.
+void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], ScoreParams& p,
+                      std::vector<HotTerms>& hotL, std::vector<HotRatios>& hotR);
 
 struct EvidenceParams {
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;

@@ -47,11 +47,22 @@ struct ScoreParams {
   uint32_t max_qual;         // Q of the table (quality covariate maximum)
   uint32_t max_set;
   uint8_t mapq_slot[256];    // MAPQ -> slot, 255 = absent
+  uint32_t hot_mapq;         // the dominant MAPQ value, whose class terms are staged in shared memory
+  uint32_t n_hot;            // entries of the hot tables (max_set * 2 * max_qual * 5), 0 = disabled
 };
 
 // Per-class likelihood terms, built on the host with the same libm calls the reference makes
 // (identify_mutations.cpp:3359-3384) so the per-record terms are bit-identical.
 struct ClassTerms { double L[5]; double r[5]; };
+
+// Shared-memory forms of the class terms for the dominant MAPQ, indexed ((set*2+top)*Q+qual)*5+obs.
+struct HotTerms { double L[5]; double r2; };   // r2 = max_{b != obs} r[b]; +inf when obs is not the class's best hypothesis
+struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
+
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots,
+                        const ClassTerms* lut, const HotTerms* hotL, const HotRatios* hotR, const ScoreParams& p, ColumnOut* out,
+                        uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap, cudaStream_t s,
+                        cudaEvent_t between);
 
 void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts,
                  uint32_t* err, cudaStream_t s);

@@ -354,6 +354,8 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       if (cfg.want_hist) acc += hist_cnt[c];
     }
     out.hist_off[out.n_base] = acc; out.n_hist = acc;
+    if (cfg.want_hist) for (uint64_t c = 0; c < out.n_base; ++c) if (hist_cnt[c] > out.max_hist_depth) out.max_hist_depth = hist_cnt[c];
+    for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
   out.score_rec = (uint32_t*)alloc(out.n_score * 4, &p2);
   out.hist_rec = (uint64_t*)alloc(out.n_hist * 8, &p2);
@@ -364,6 +366,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   std::fill(score_cur.begin(), score_cur.end(), 0);
   std::fill(hist_cur.begin(), hist_cur.end(), 0);
   std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
+  std::vector<uint64_t> mapq_counts((size_t)items.size() * 256, 0);
   std::vector<uint32_t> max_quals(items.size(), 0);
   run_items([&](size_t ii) {
     const Item& it = items[ii];
@@ -376,6 +379,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       return b;
     };
     uint32_t* mq_mask = &mapq_masks[ii * 8];
+    uint64_t* mq_count = &mapq_counts[ii * 256];
     uint32_t max_q = 0;
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
@@ -470,7 +474,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
               uint32_t qv = qual[qp];
               if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
               rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
-              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); if (qv > max_q) max_q = qv; }
+              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); ++mq_count[mapq]; if (qv > max_q) max_q = qv; }
             }
             rec |= mapq << SR_MAPQ_SHIFT;
             rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
@@ -486,6 +490,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   });
   for (size_t ii = 0; ii < items.size(); ++ii) {
     for (int w = 0; w < 8; ++w) out.mapq_seen[w] |= mapq_masks[ii * 8 + (size_t)w];
+    for (int m = 0; m < 256; ++m) out.mapq_count[m] += mapq_counts[ii * 256 + (size_t)m];
     out.max_qual_seen = std::max(out.max_qual_seen, max_quals[ii]);
   }
 }

@@ -146,6 +146,8 @@ int brq_launch_count(void);
 int brq_event_record(brq_ctx* ctx, int slot);
 int brq_event_elapsed_ms(brq_ctx* ctx, int slot_a, int slot_b, float* ms);
 int brq_kernel_ms(brq_ctx* ctx, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms);
+/* the scoring pass is two kernels: the streaming tally and the EM fit of the slots that need one */
+int brq_score_phase_ms(brq_ctx* ctx, float* tally_ms, float* fit_ms);
 
 #ifdef __cplusplus
 }

@@ -231,7 +231,7 @@ def main():
     barrier()
     ctx.event_record(0)
     t0 = time.perf_counter()
-    k_ms = {"hist": 0.0, "coverage": 0.0, "derive": 0.0, "score": 0.0}
+    k_ms = {"hist": 0.0, "coverage": 0.0, "derive": 0.0, "score": 0.0, "tally": 0.0, "fit": 0.0}
     for _ in range(args.steps):
         step()
         for k, v in ctx.kernel_ms().items():

@@ -65,14 +65,15 @@ struct ReadBatch {
 //   [2:0]   obs        base index 0..4 ('.' = 4)
 //   [9:3]   qual       quality chosen by alignment_position_to_covariates (error_count.cpp:1049-1105)
 //   [10]    top        1 = read on the top strand
-//   [11]    unique     X1 == 1
-//   [12]    trimmed    is_trimmed() (alignment.h:389-410)
-//   [13]    ok         covariates resolvable (not past q_end, no N at the quality position)
-//   unique records:    [21:14] mapq, [26:22] read_set (flat read-file index)
-//   redundant records: [29:14] redundancy (X1, saturated at 65535)
-constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, SR_UNIQUE_BIT = 1u << 11,
-                   SR_TRIM_BIT = 1u << 12, SR_OK_BIT = 1u << 13, SR_MAPQ_SHIFT = 14, SR_SET_SHIFT = 22,
-                   SR_RED_SHIFT = 14;
+//   [24]    unique     X1 == 1
+//   [25]    trimmed    is_trimmed() (alignment.h:389-410)
+//   [26]    ok         covariates resolvable (not past q_end, no N at the quality position)
+//   unique records:    [15:11] read_set (flat read-file index), [23:16] mapq
+//   redundant records: [23:11] redundancy (X1, saturated at 8191)
+// top and read_set are adjacent so that (r >> 10) & 63 == read_set * 2 + top indexes the class tables.
+constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, SR_SET_SHIFT = 11, SR_MAPQ_SHIFT = 16,
+                   SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_RED_SHIFT = 11,
+                   SR_RED_MASK = 0x1FFF;
 
 // Histogram (error_count) record, 8 bytes, one per unique, non-deleted (read, column).
 //   [2:0]   obsA   base index 0..3, 5 = N          [5:3]  refA  reference base index (0..3, 5 = N)

@@ -242,6 +242,10 @@ void build_class_lut(const CovSpec& c, const std::vector<double>& prob, const ui
         mx = std::max(mx, t.L[b]);
       }
       for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
+      t.M = mx;
+      t.r2 = 0.0;
+      for (uint32_t b = 0; b < 5; ++b) if (b != obs) t.r2 = std::max(t.r2, t.r[b]);
+      if (t.r[obs] != 1.0) t.r2 = std::numeric_limits<double>::infinity();
     }
   }
 }
@@ -257,14 +261,12 @@ void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_co
   p.n_hot = (n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // two 512-thread CTAs per SM must both hold a copy
   hotL.assign(n_hot, HotTerms());
   hotR.assign(n_hot, HotRatios());
-  const double inf = std::numeric_limits<double>::infinity();
   for (uint32_t st = 0; st < n_set * 2; ++st) for (uint32_t q = 0; q < p.max_qual; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
     const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + p.mapq_slot[hot]) * p.max_qual + q) * 5 + obs];
     const size_t h = ((size_t)st * p.max_qual + q) * 5 + obs;
-    double mx = t.L[0], r2 = 0.0;
-    for (int b = 0; b < 5; ++b) { hotL[h].L[b] = t.L[b]; hotR[h].r[b] = t.r[b]; mx = std::max(mx, t.L[b]); if ((uint32_t)b != obs) r2 = std::max(r2, t.r[b]); }
-    hotL[h].r2 = (t.r[obs] == 1.0) ? r2 : inf;
-    hotR[h].M = mx;
+    for (int b = 0; b < 5; ++b) { hotL[h].L[b] = t.L[b]; hotR[h].r[b] = t.r[b]; }
+    hotL[h].r2 = t.r2;
+    hotR[h].M = t.M;
   }
 }
 

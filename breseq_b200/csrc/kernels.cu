@@ -190,10 +190,10 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
   return v;
 }
 
-// key: [2:0] obs [9:3] qual [10] top [18:11] mapq [23:19] read_set
-__device__ __forceinline__ uint32_t class_key(uint32_t rec) { return (rec & 0x7FFu) | (((rec >> SR_MAPQ_SHIFT) & 0x1FFFu) << 11); }
+// key: the record's low 24 bits: [2:0] obs [9:3] qual [10] top [15:11] read_set [23:16] mapq
+__device__ __forceinline__ uint32_t class_key(uint32_t rec) { return rec & 0xFFFFFFu; }
 __device__ __forceinline__ uint32_t lut_index(uint32_t key, const ScoreParams& p, const uint8_t* mapq_slot) {
-  const uint32_t obs = key & 7, qual = (key >> 3) & 127, top = (key >> 10) & 1, mapq = (key >> 11) & 255, set = key >> 19;
+  const uint32_t obs = key & 7, qual = (key >> 3) & 127, top = (key >> 10) & 1, set = (key >> 11) & 31, mapq = (key >> 16) & 255;
   return ((((set * 2 + top) * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + qual) * 5 + obs);
 }
 
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32) score_kernel(const uint32_t* __
         const int l = __ffs(redm) - 1;
         redm &= redm - 1;
         const uint32_t rr = __shfl_sync(0xffffffffu, r, l);
-        const double inv = 1.0 / (double)((rr >> SR_RED_SHIFT) & 0xFFFFu);
+        const double inv = 1.0 / (double)((rr >> SR_RED_SHIFT) & SR_RED_MASK);
         if (rr & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
       }
       const uint32_t qual = (r >> SR_QUAL_SHIFT) & 127;

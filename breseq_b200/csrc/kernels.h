@@ -53,7 +53,9 @@ struct ScoreParams {
 
 // Per-class likelihood terms, built on the host with the same libm calls the reference makes
 // (identify_mutations.cpp:3359-3384) so the per-record terms are bit-identical.
-struct ClassTerms { double L[5]; double r[5]; };
+// L[b] = log10 P(obs | true base b), M = max_b L[b], r[b] = 10^(L[b] - M);
+// r2 = max_{b != obs} r[b], or +inf when obs is not the class's most likely true base.  96 bytes.
+struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 
 // Shared-memory forms of the class terms for the dominant MAPQ, indexed ((set*2+top)*Q+qual)*5+obs.
 struct HotTerms { double L[5]; double r2; };   // r2 = max_{b != obs} r[b]; +inf when obs is not the class's best hypothesis

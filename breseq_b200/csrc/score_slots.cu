@@ -1,21 +1,19 @@
-// Per-slot scoring, thread-per-slot formulation (sm_100a).
+// Per-slot scoring for sm_100a: a streaming tally kernel and an EM fit kernel.
 //
-// One thread owns one slot (a reference column or an insert sub-column) and walks its records in
-// arrival order, so every per-slot quantity lives in registers, nothing is reduced across lanes,
-// and floating-point sums accumulate in the same order as the reference's per-read loops
-// (identify_mutations.cpp:1392-1658, 3240-3318).
+//   tally_kernel  one thread per slot (a reference column or an insert sub-column).  The thread
+//                 walks its records in arrival order with 128-bit loads, so coverage tallies and
+//                 the five log-likelihood sums live in registers, nothing is reduced across lanes
+//                 and the sums accumulate in the reference's order
+//                 (identify_mutations.cpp:1392-1658, 3398-3433).  A slot whose scoring records all
+//                 show the reference base X, with X every record's best hypothesis and every other
+//                 hypothesis bounded (see `pure`), is final here: the EM cannot lift any other
+//                 allele to the half-read level.  All other non-empty slots go to a work list.
+//   fit_kernel    eight lanes per work-list slot: the 5-allele EM fit, the presence score of the
+//                 top non-reference allele (second EM with it held out), emission flags
+//                 (identify_mutations.cpp:1797-1821, 3240-3344).
 //
-//   tally_kernel  one HBM pass over the 4-byte records (128-bit loads): per-strand unique /
-//                 redundant coverage, the five log-likelihood sums, the pure-genotype call.  Slots
-//                 whose scoring records all show the reference base, with every record's likelihood
-//                 ratio bounded so that no other allele can reach the half-read level, are final
-//                 here: the EM fit cannot produce a variant for them (see `pure` below).  All other
-//                 slots go to a work list.
-//   fit_kernel    work-list slots only: the 5-allele EM, the presence score of the top
-//                 non-reference allele (second EM with that allele held out), emission flags.
-//
-// The likelihood terms of the dominant MAPQ value are staged in shared memory (48 B per class);
-// records with any other MAPQ read the full table from global memory.
+// Likelihood terms of the dominant MAPQ value are staged in shared memory (48 B per class, read as
+// three 128-bit loads); records with any other MAPQ read the full table from global memory.
 #include "kernels.h"
 #include "brq_types.h"
 
@@ -23,99 +21,110 @@ namespace brq {
 
 namespace {
 
-constexpr int TPB = 512;
+constexpr int TALLY_TPB = 512;
+constexpr int FIT_TPB = 256;
+constexpr int FIT_LANES = 8;  // lanes cooperating on one slot
 
-__device__ __forceinline__ uint4 ld_stream_v4(const uint32_t* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+struct f64x2 { double x, y; };
+__device__ __forceinline__ f64x2 lds_f64x2(const void* p) {
+  f64x2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
   return v;
 }
-__device__ __forceinline__ uint4 ld_cached_v4(const uint32_t* p) {
-  return __ldg(reinterpret_cast<const uint4*>(p));
+__device__ __forceinline__ f64x2 ldg_f64x2(const void* p) {
+  f64x2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
 }
 
-struct Decoded { uint32_t obs, qual, top, mapq, set; };
-__device__ __forceinline__ Decoded decode(uint32_t r) {
-  Decoded d;
-  d.obs = r & 7; d.qual = (r >> SR_QUAL_SHIFT) & 127; d.top = (r >> 10) & 1; d.mapq = (r >> SR_MAPQ_SHIFT) & 255; d.set = (r >> SR_SET_SHIFT) & 31;
-  return d;
-}
 __device__ __forceinline__ bool eligible(uint32_t r, uint32_t cutoff) {
   return (r & (SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT)) == (SR_UNIQUE_BIT | SR_OK_BIT) && ((r >> SR_QUAL_SHIFT) & 127) >= cutoff;
 }
+// ((set*2 + top) * Q + qual) * 5 + obs, with top and set adjacent in the record
+__device__ __forceinline__ uint32_t hot_index(uint32_t r, uint32_t Q) {
+  return (((r >> 10) & 63) * Q + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
+}
+__device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p, const uint8_t* mapq_slot) {
+  const uint32_t hi = (r >> 10) & 63, mapq = (r >> SR_MAPQ_SHIFT) & 255;
+  return ((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
+}
 
-__device__ __forceinline__ void copy_to_smem(double* dst, const double* __restrict__ src, uint32_t n_doubles) {
-  for (uint32_t i = threadIdx.x; i < n_doubles; i += blockDim.x) dst[i] = src[i];
+__device__ __forceinline__ void stage_tables(double* sm, const double* __restrict__ src, uint32_t n_doubles, uint8_t* mapq_slot,
+                                             const ScoreParams& p) {
+  for (uint32_t i = threadIdx.x; i < n_doubles; i += blockDim.x) sm[i] = src[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ tally
-__global__ void __launch_bounds__(TPB, 2) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
-                                                        const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
-                                                        const ClassTerms* __restrict__ lut, const HotTerms* __restrict__ hotL,
-                                                        ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
-                                                        uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
-                                                        uint32_t flagged_cap) {
+__global__ void __launch_bounds__(TALLY_TPB, 2) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+                                                              const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
+                                                              const ClassTerms* __restrict__ lut, const HotTerms* __restrict__ hotL,
+                                                              ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
+                                                              uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
+                                                              uint32_t flagged_cap) {
   extern __shared__ __align__(16) double sm[];
-  HotTerms* hot = reinterpret_cast<HotTerms*>(sm);
-  copy_to_smem(sm, reinterpret_cast<const double*>(hotL), p.n_hot * 6);
   __shared__ uint8_t mapq_slot[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+  __shared__ double inv_red[64];
+  stage_tables(sm, reinterpret_cast<const double*>(hotL), p.n_hot * 6, mapq_slot, p);
+  if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
   __syncthreads();
+  const char* hot = reinterpret_cast<const char*>(sm);
 
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  const double inf = __longlong_as_double(0x7ff0000000000000ll);
-  const uint64_t stride = (uint64_t)gridDim.x * TPB;
-  for (uint64_t slot = (uint64_t)blockIdx.x * TPB + threadIdx.x; slot < n_slots; slot += stride) {
+  const uint32_t hi_limit = 2 * p.max_set;
+  const uint64_t stride = (uint64_t)gridDim.x * TALLY_TPB;
+  for (uint64_t slot = (uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x; slot < n_slots; slot += stride) {
     const uint64_t beg = off[slot], end = off[slot + 1];
-    uint32_t u_top = 0, u_bot = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0, err = 0;
+    uint32_t u_all = 0, u_top = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0, err = 0;
     double red_top = 0.0, red_bot = 0.0, r2max = 0.0;
     double ll0 = 0.0, ll1 = 0.0, ll2 = 0.0, ll3 = 0.0, ll4 = 0.0;
 
     auto one = [&](uint32_t r) {
-      if (r & SR_UNIQUE_BIT) {
-        if (r & SR_TOP_BIT) ++u_top; else ++u_bot;
-      } else {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
-        const double inv = 1.0 / (double)((r >> SR_RED_SHIFT) & 0xFFFFu);
+      if (!(r & SR_UNIQUE_BIT)) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
+        const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
+        const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
         if (r & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
         return;
       }
+      ++u_all;
+      u_top += (r >> 10) & 1;
       if (!eligible(r, p.base_quality_cutoff)) return;
-      const Decoded d = decode(r);
-      if (d.qual >= p.max_qual || d.set >= p.max_set) { err |= BRQ_ERR_QUALITY_RANGE; return; }
-      double r2;
-      if (d.mapq == p.hot_mapq && p.n_hot) {
-        const HotTerms& t = hot[((d.set * 2 + d.top) * p.max_qual + d.qual) * 5 + d.obs];
-        ll0 += t.L[0]; ll1 += t.L[1]; ll2 += t.L[2]; ll3 += t.L[3]; ll4 += t.L[4];
-        r2 = t.r2;
+      const uint32_t qual = (r >> SR_QUAL_SHIFT) & 127;
+      if (qual >= p.max_qual || ((r >> 10) & 63) >= hi_limit) { err |= BRQ_ERR_QUALITY_RANGE; return; }
+      f64x2 a, b, c;  // L[0..1], L[2..3], {L[4], r2}
+      if (((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq && p.n_hot) {
+        const char* e = hot + hot_index(r, p.max_qual) * 48u;
+        a = lds_f64x2(e); b = lds_f64x2(e + 16); c = lds_f64x2(e + 32);
       } else {
-        const ClassTerms& t = lut[((((d.set * 2 + d.top) * p.n_mapq_slots + mapq_slot[d.mapq]) * p.max_qual + d.qual) * 5 + d.obs)];
-        ll0 += t.L[0]; ll1 += t.L[1]; ll2 += t.L[2]; ll3 += t.L[3]; ll4 += t.L[4];
-        r2 = 0.0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) if ((uint32_t)b != d.obs) r2 = fmax(r2, t.r[b]);
-        if (t.r[d.obs] != 1.0) r2 = inf;
+        const char* e = reinterpret_cast<const char*>(lut + cold_index(r, p, mapq_slot));
+        a = ldg_f64x2(e); b = ldg_f64x2(e + 16); c = ldg_f64x2(e + 32);
       }
-      r2max = fmax(r2max, r2);
-      obs_mask |= 1u << d.obs;
+      ll0 += a.x; ll1 += a.y; ll2 += b.x; ll3 += b.y; ll4 += c.x;
+      r2max = fmax(r2max, c.y);
+      obs_mask |= 1u << (r & 7);
       ++n;
     };
 
-    // 128-bit loads from the 16-byte aligned vector that contains the slot's first record
-    for (uint64_t v = beg & ~3ull; v < end; v += 4) {
-      const uint4 q = ld_stream_v4(rec + v);
-      if (v >= beg && v + 4 <= end) { one(q.x); one(q.y); one(q.z); one(q.w); }
-      else {
-        if (v >= beg && v < end) one(q.x);
-        if (v + 1 >= beg && v + 1 < end) one(q.y);
-        if (v + 2 >= beg && v + 2 < end) one(q.z);
-        if (v + 3 >= beg && v + 3 < end) one(q.w);
-      }
+    // 128-bit loads starting at the aligned vector that holds the slot's first record; the next
+    // vector is requested before the current one is consumed
+    uint64_t v = beg & ~3ull;
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (v < end) cur = __ldg(reinterpret_cast<const uint4*>(rec + v));
+    for (; v < end; v += 4) {
+      uint4 nxt = make_uint4(0, 0, 0, 0);
+      if (v + 4 < end) nxt = __ldg(reinterpret_cast<const uint4*>(rec + v + 4));
+      const uint32_t lo = v < beg ? (uint32_t)(beg - v) : 0u, hi = end - v < 4 ? (uint32_t)(end - v) : 4u;
+      if (lo == 0 && hi > 0) one(cur.x);
+      if (lo <= 1 && hi > 1) one(cur.y);
+      if (lo <= 2 && hi > 2) one(cur.z);
+      if (hi > 3) one(cur.w);
+      cur = nxt;
     }
 
     const uint32_t ref = slot_ref[slot];
-    double ll[5] = {ll0, ll1, ll2, ll3, ll4};
+    const double ll[5] = {ll0, ll1, ll2, ll3, ll4};
     double consensus = nan;
     uint32_t best = 5;
     if (n > 0) {  // pure_genotype_call, identify_mutations.cpp:3398-3433
@@ -130,25 +139,22 @@ __global__ void __launch_bounds__(TPB, 2) tally_kernel(const uint32_t* __restric
       for (int b = 0; b < 5; ++b) {
         if ((uint32_t)b == best) continue;
         const double d = ll[b] - offv;
-        // below 2^-54 a term cannot change a sum that already holds the offset's own 1.0
+        // the runner-up itself contributes exactly 1; anything below 2^-54 cannot change that sum
         tot += (d == 0.0) ? 1.0 : (d < -17.0 ? 0.0 : pow(10.0, d));
       }
       consensus = (ll[best] - (log10(tot) + offv)) - p.log10_ref_length;
     }
     const double slack = 1e-6;
     const bool base_predicted = consensus >= p.mutation_cutoff;
-    bool recheck = n > 0 && fabs(consensus - p.mutation_cutoff) < slack;
+    const bool recheck = n > 0 && fabs(consensus - p.mutation_cutoff) < slack;
 
-    // `pure`: every scoring record shows the reference base X, X is each record's most likely
-    // true base, and every other hypothesis b has r_i(b) <= f0[X] = (n + 0.5) / (n + 2.5).
-    // Then s_i >= f[X], so f[b] can only shrink from its start 0.5 / (n + 2.5) < 0.5 / n and f[X]
-    // only grows: no allele but X ever reaches the half-read level, the fit reports major = X and
-    // no minor / variant allele, and no presence score is computed (identify_mutations.cpp:1806-1821).
+    // `pure`: every scoring record shows the reference base X, X is each record's most likely true
+    // base (r2 is +inf otherwise), and every other hypothesis b has r_i(b) <= f0[X] = (n+0.5)/(n+2.5).
+    // Then s_i >= f[X] in every iteration, so f[b] only shrinks from 0.5/(n+2.5) < 0.5/n while f[X]
+    // grows: the fit reports major = X and neither a minor nor a variant allele, and the reference
+    // computes no presence score (identify_mutations.cpp:1806-1821).
     const bool pure = n > 0 && ref < 5 && obs_mask == (1u << ref) && r2max <= ((double)n + 0.5) / ((double)n + 2.5);
-    const bool needs_fit = n > 0 && !pure;
-    uint32_t major = 5;
-    if (pure) major = ref;
-    uint32_t bits = best | (major << 3) | (5u << 6) | (5u << 9);
+    uint32_t bits = best | ((pure ? ref : 5u) << 3) | (5u << 6) | (5u << 9);
     if (base_predicted) bits |= CO_BASE_PREDICTED;
     if (raw_top + raw_bot == 0) bits |= CO_UNIQUE_ONLY;
     if (recheck) bits |= CO_RECHECK;
@@ -158,11 +164,11 @@ __global__ void __launch_bounds__(TPB, 2) tally_kernel(const uint32_t* __restric
     for (int b = 0; b < 5; ++b) o.ll[b] = ll[b];
     o.consensus_score = consensus; o.variant_score = nan;
     o.redundant[0] = red_bot; o.redundant[1] = red_top;
-    o.unique[0] = u_bot; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
+    o.unique[0] = u_all - u_top; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
     out[slot] = o;
 
-    if (needs_fit) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)slot;
+    if (n > 0 && !pure) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)slot;
     else if (recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = (uint32_t)slot; }
     if (err) atomicOr(&scalars[0], err);
   }
@@ -171,43 +177,46 @@ __global__ void __launch_bounds__(TPB, 2) tally_kernel(const uint32_t* __restric
 // ------------------------------------------------------------------------------------------ fit
 namespace {
 
-struct SlotRecords {
+struct GroupCtx {
   const uint32_t* rec; uint64_t beg, end;
-  const HotRatios* hot; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
+  const char* hot; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
+  uint32_t sub, mask;  // lane within the group, shuffle mask of the group
 };
 
-// Visit the scoring records of a slot in arrival order: f(r[5], M, obs).
-template <class F>
-__device__ __forceinline__ void for_each_scoring(const SlotRecords& s, F&& f) {
-  const ScoreParams& p = *s.p;
-  for (uint64_t v = s.beg & ~3ull; v < s.end; v += 4) {
-    const uint4 q = ld_cached_v4(s.rec + v);
-    const uint32_t rr[4] = {q.x, q.y, q.z, q.w};
+__device__ __forceinline__ double group_sum(double v, uint32_t mask) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (v + j < s.beg || v + j >= s.end) continue;
-      const uint32_t r = rr[j];
-      if (!eligible(r, p.base_quality_cutoff)) continue;
-      const Decoded d = decode(r);
-      if (d.qual >= p.max_qual || d.set >= p.max_set) continue;
-      if (d.mapq == p.hot_mapq && p.n_hot) {
-        const HotRatios& t = s.hot[((d.set * 2 + d.top) * p.max_qual + d.qual) * 5 + d.obs];
-        f(t.r, t.M, d.obs);
-      } else {
-        const ClassTerms& t = s.lut[((((d.set * 2 + d.top) * p.n_mapq_slots + s.mapq_slot[d.mapq]) * p.max_qual + d.qual) * 5 + d.obs)];
-        double m = t.L[0];
+  for (int o = FIT_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, uint32_t mask) {
 #pragma unroll
-        for (int b = 1; b < 5; ++b) m = fmax(m, t.L[b]);
-        f(t.r, m, d.obs);
-      }
-    }
+  for (int o = FIT_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+// r[0..4] and M = max_b L[b] of one scoring record
+__device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t r, double* rr, double& M) {
+  const ScoreParams& p = *g.p;
+  f64x2 a, b, c;
+  if (((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq && p.n_hot) {
+    const char* e = g.hot + hot_index(r, p.max_qual) * 48u;
+    a = lds_f64x2(e); b = lds_f64x2(e + 16); c = lds_f64x2(e + 32);
+  } else {
+    const char* e = reinterpret_cast<const char*>(g.lut + cold_index(r, p, g.mapq_slot)) + 48;
+    a = ldg_f64x2(e); b = ldg_f64x2(e + 16); c = ldg_f64x2(e + 32);
   }
+  rr[0] = a.x; rr[1] = a.y; rr[2] = b.x; rr[3] = b.y; rr[4] = c.x; M = c.y;
+}
+__device__ __forceinline__ bool scoring(const GroupCtx& g, uint32_t r) {
+  const ScoreParams& p = *g.p;
+  return eligible(r, p.base_quality_cutoff) && ((r >> SR_QUAL_SHIFT) & 127) < p.max_qual && ((r >> 10) & 63) < 2 * p.max_set;
 }
 
 struct Fit { double f[5]; double ll; uint32_t iterations; };
 
-// identify_mutations.cpp:3240-3318, per-record, arrival order.
-__device__ Fit em_fit(const SlotRecords& s, uint32_t n, const uint32_t obs_count[5], uint32_t allowed, double tol) {
+// identify_mutations.cpp:3240-3318.  Records are strided over the group's lanes; the per-allele
+// responsibilities are summed with a fixed butterfly, so every lane holds the same frequencies.
+__device__ __noinline__ Fit em_fit(const GroupCtx& g, uint32_t n, const uint32_t* obs_count, uint32_t allowed, double tol) {
   Fit m;
   double total = 0.0;
 #pragma unroll
@@ -215,25 +224,33 @@ __device__ Fit em_fit(const SlotRecords& s, uint32_t n, const uint32_t obs_count
 #pragma unroll
   for (int b = 0; b < 5; ++b) m.f[b] /= total;
   double f_prev[5];
+  const double inv_n = 1.0 / (double)n;
   uint32_t it = 1;
   for (; it <= 50; ++it) {
-    double w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
-    const double f0 = m.f[0], f1 = m.f[1], f2 = m.f[2], f3 = m.f[3], f4 = m.f[4];
-    for_each_scoring(s, [&](const double* r, double, uint32_t) {
-      const double a0 = f0 * r[0], a1 = f1 * r[1], a2 = f2 * r[2], a3 = f3 * r[3], a4 = f4 * r[4];
-      const double sum = (((a0 + a1) + a2) + a3) + a4;
+    double w[5] = {0, 0, 0, 0, 0};
+    for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+      const uint32_t r = __ldg(g.rec + i);
+      if (!scoring(g, r)) continue;
+      double rr[5], M;
+      load_ratios(g, r, rr, M);
+      double a[5], sum = 0.0;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) { a[b] = m.f[b] * rr[b]; sum += a[b]; }
       if (sum > 0.0) {
         const double inv = 1.0 / sum;
-        w0 += a0 * inv; w1 += a1 * inv; w2 += a2 * inv; w3 += a3 * inv; w4 += a4 * inv;
-      } else { w0 += f0; w1 += f1; w2 += f2; w3 += f3; w4 += f4; }
-    });
-    const double w[5] = {w0, w1, w2, w3, w4};
+#pragma unroll
+        for (int b = 0; b < 5; ++b) w[b] += a[b] * inv;
+      } else {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) w[b] += m.f[b];
+      }
+    }
     double max_delta = 0.0;
 #pragma unroll
     for (int b = 0; b < 5; ++b) {
       f_prev[b] = m.f[b];
       if (allowed >> b & 1) {
-        const double f_new = w[b] / (double)n;
+        const double f_new = group_sum(w[b], g.mask) * inv_n;
         max_delta = fmax(max_delta, fabs(f_new - m.f[b]));
         m.f[b] = f_new;
       }
@@ -243,37 +260,53 @@ __device__ Fit em_fit(const SlotRecords& s, uint32_t n, const uint32_t obs_count
   m.iterations = it > 50 ? 50 : it;
   // the committed likelihood belongs to the frequencies BEFORE the last update
   double ll = 0.0;
-  for_each_scoring(s, [&](const double* r, double M, uint32_t) {
-    const double sum = (((f_prev[0] * r[0] + f_prev[1] * r[1]) + f_prev[2] * r[2]) + f_prev[3] * r[3]) + f_prev[4] * r[4];
+  for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+    const uint32_t r = __ldg(g.rec + i);
+    if (!scoring(g, r)) continue;
+    double rr[5], M;
+    load_ratios(g, r, rr, M);
+    double sum = 0.0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) sum += f_prev[b] * rr[b];
     if (sum > 0.0) ll += log10(sum) + M;
-  });
-  m.ll = ll;
+  }
+  m.ll = group_sum(ll, g.mask);
   return m;
 }
 
 }  // namespace
 
-__global__ void __launch_bounds__(256, 2) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
-                                                      const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
-                                                      const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
-                                                      ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ flagged,
-                                                      uint32_t* __restrict__ scalars, uint32_t flagged_cap) {
+__global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+                                                          const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
+                                                          const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
+                                                          ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ flagged,
+                                                          uint32_t* __restrict__ scalars, uint32_t flagged_cap) {
   extern __shared__ __align__(16) double sm[];
-  copy_to_smem(sm, reinterpret_cast<const double*>(hotR), p.n_hot * 6);
   __shared__ uint8_t mapq_slot[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+  stage_tables(sm, reinterpret_cast<const double*>(hotR), p.n_hot * 6, mapq_slot, p);
   __syncthreads();
   const uint32_t n_work = scalars[2];
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_work; w += gridDim.x * blockDim.x) {
+  const uint32_t lane = threadIdx.x & 31;
+  GroupCtx g;
+  g.rec = rec; g.hot = reinterpret_cast<const char*>(sm); g.lut = lut; g.mapq_slot = mapq_slot; g.p = &p;
+  g.sub = lane % FIT_LANES;
+  g.mask = ((1u << FIT_LANES) - 1u) << (lane - g.sub);
+  const uint32_t groups_per_block = FIT_TPB / FIT_LANES, n_groups = gridDim.x * groups_per_block;
+  for (uint32_t w = blockIdx.x * groups_per_block + threadIdx.x / FIT_LANES; w < n_work; w += n_groups) {
     const uint32_t slot = worklist[w];
-    SlotRecords s{rec, off[slot], off[slot + 1], reinterpret_cast<const HotRatios*>(sm), lut, mapq_slot, &p};
+    g.beg = off[slot]; g.end = off[slot + 1];
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
-    for_each_scoring(s, [&](const double*, double, uint32_t obs) {
+    for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+      const uint32_t r = __ldg(rec + i);
+      if (!scoring(g, r)) continue;
 #pragma unroll
-      for (int b = 0; b < 5; ++b) obs_count[b] += (obs == (uint32_t)b);
+      for (int b = 0; b < 5; ++b) obs_count[b] += ((r & 7) == (uint32_t)b);
       ++n;
-    });
+    }
+#pragma unroll
+    for (int b = 0; b < 5; ++b) obs_count[b] = group_sum_u32(obs_count[b], g.mask);
+    n = group_sum_u32(n, g.mask);
     if (n == 0) continue;
     const uint32_t ref = slot_ref[slot];
     const double consensus = out[slot].consensus_score;
@@ -281,7 +314,7 @@ __global__ void __launch_bounds__(256, 2) fit_kernel(const uint32_t* __restrict_
     const uint32_t best = bits & 7;
     bool recheck = (bits & CO_RECHECK) != 0;
 
-    Fit full = em_fit(s, n, obs_count, 0x1F, p.precision_decimal);
+    Fit full = em_fit(g, n, obs_count, 0x1F, p.precision_decimal);
     const double thr = 0.5 / (double)n;
     uint32_t major = 5, minor = 5, variant = 5, mj = 0;
 #pragma unroll
@@ -296,7 +329,7 @@ __global__ void __launch_bounds__(256, 2) fit_kernel(const uint32_t* __restrict_
     }
     double variant_score = nan;
     if (variant != 5) {
-      Fit null_fit = em_fit(s, n, obs_count, 0x1F & ~(1u << variant), p.precision_decimal);
+      Fit null_fit = em_fit(g, n, obs_count, 0x1F & ~(1u << variant), p.precision_decimal);
       variant_score = (full.ll - null_fit.ll) - p.log10_ref_length;
     }
     const double slack = 1e-6;
@@ -306,9 +339,11 @@ __global__ void __launch_bounds__(256, 2) fit_kernel(const uint32_t* __restrict_
     bits = (bits & ~(0xFFFu | CO_EMIT | CO_RECHECK | (0xFFu << 16))) | best | (major << 3) | (minor << 6) | (variant << 9) | (full.iterations << 16);
     if (emit) bits |= CO_EMIT;
     if (recheck) bits |= CO_RECHECK;
-    out[slot].variant_score = variant_score;
-    out[slot].bits = bits;
-    if (emit || recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = slot; }
+    if (g.sub == 0) {
+      out[slot].variant_score = variant_score;
+      out[slot].bits = bits;
+      if (emit || recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = slot; }
+    }
   }
 }
 
@@ -321,10 +356,10 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
   const size_t smem = (size_t)p.n_hot * 48;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int blocks = (int)std::min<uint64_t>((n_slots + TPB - 1) / TPB, (uint64_t)kSMs * 2);
-  tally_kernel<<<blocks, TPB, smem, s>>>(rec, off, slot_ref, n_slots, lut, hotL, p, out, worklist, flagged, scalars, flagged_cap);
+  int blocks = (int)std::min<uint64_t>((n_slots + TALLY_TPB - 1) / TALLY_TPB, (uint64_t)kSMs * 2);
+  tally_kernel<<<blocks, TALLY_TPB, smem, s>>>(rec, off, slot_ref, n_slots, lut, hotL, p, out, worklist, flagged, scalars, flagged_cap);
   if (between) cudaEventRecord(between, s);
-  fit_kernel<<<kSMs * 2, 256, smem, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
 }
 
 }  // namespace brq

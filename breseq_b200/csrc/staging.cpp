@@ -389,7 +389,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       const bool unique = R.x1[i] == 1;
       const uint32_t rev = ri.rev ? 1 : 0;
       const int32_t L = (int32_t)ri.L;
-      const uint32_t red = std::min<uint32_t>(R.x1[i], 65535u);
+      const uint32_t red = std::min<uint32_t>(R.x1[i], SR_RED_MASK);
       if (R.x1[i] == 0) throw std::runtime_error("X1:i:0 is not a valid redundancy");
       const uint32_t mapq = R.mapq[i];
       walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {

@@ -161,7 +161,7 @@ def emulate_tally(stream, base_quality_cutoff=3):
     off = stream["score_off"].astype(np.int64)
     n_slots = len(off) - 1
     sid = np.repeat(np.arange(n_slots), np.diff(off))
-    uniq, top, trim, ok, q = (rec >> 11) & 1, (rec >> 10) & 1, (rec >> 12) & 1, (rec >> 13) & 1, (rec >> 3) & 127
+    uniq, top, trim, ok, q = (rec >> 24) & 1, (rec >> 10) & 1, (rec >> 25) & 1, (rec >> 26) & 1, (rec >> 3) & 127
     out = {}
     for name, u in (("unique", 1), ("raw_redundant", 0)):
         out[name] = np.stack([np.bincount(sid[(uniq == u) & (top == 0)], minlength=n_slots),
@@ -169,7 +169,7 @@ def emulate_tally(stream, base_quality_cutoff=3):
     out["n"] = np.bincount(sid[(uniq == 1) & (trim == 0) & (ok == 1) & (q >= base_quality_cutoff)], minlength=n_slots)
     red = np.zeros((n_slots, 2))
     for i in np.nonzero(uniq == 0)[0]:  # order-dependent double sum, arrival order
-        red[sid[i], top[i]] += 1.0 / float((rec[i] >> 14) & 0xFFFF)
+        red[sid[i], top[i]] += 1.0 / float((rec[i] >> 11) & 0x1FFF)
     out["redundant"] = red
     return out
 

@@ -278,6 +278,14 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->sp.polymorphism_cutoff = p->polymorphism_cutoff;
   c->sp.precision_decimal = p->polymorphism_precision_decimal;
   c->sp.base_quality_cutoff = p->base_quality_cutoff;
+  // the reference ASSERTs when a covariate value exceeds the table (error_count.cpp:485-488); the
+  // stream's maxima are known from staging, so the check costs the kernels nothing
+  if (c->st.n_score && c->st.max_qual_seen >= c->sp.max_qual)
+    throw std::runtime_error("Covariate 'quality' with value '" + std::to_string(c->st.max_qual_seen) +
+                             "' exceeded enforced maximum value of '" + std::to_string(c->sp.max_qual - 1) + "'.");
+  if (c->st.n_score && c->st.max_read_set_seen >= c->sp.max_set)
+    throw std::runtime_error("Covariate 'read_set' with value '" + std::to_string(c->st.max_read_set_seen) +
+                             "' exceeded enforced maximum value of '" + std::to_string(c->sp.max_set - 1) + "'.");
   const uint64_t n_slots = c->st.n_slots();
   c->d_cols.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);

@@ -112,6 +112,7 @@ struct PileupStream {
   uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
   uint32_t n_groups = 1;               // coverage groups present
   uint32_t max_qual_seen = 0;
+  uint32_t max_read_set_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
   uint64_t n_slots() const { return n_base + n_ins; }
 };

@@ -2,12 +2,12 @@
 //
 //   tally_kernel  one thread per slot (a reference column or an insert sub-column).  The thread
 //                 walks its records in arrival order with 128-bit loads, so coverage tallies and
-//                 the five log-likelihood sums live in registers, nothing is reduced across lanes
-//                 and the sums accumulate in the reference's order
-//                 (identify_mutations.cpp:1392-1658, 3398-3433).  A slot whose scoring records all
-//                 show the reference base X, with X every record's best hypothesis and every other
-//                 hypothesis bounded (see `pure`), is final here: the EM cannot lift any other
-//                 allele to the half-read level.  All other non-empty slots go to a work list.
+//                 the five log-likelihood sums live in registers and nothing is reduced across
+//                 lanes (identify_mutations.cpp:1392-1658, 3398-3433).  The hot path is branch-free:
+//                 a record that does not score reads an all-zero table entry.  A slot whose scoring
+//                 records all show the reference base X, with X every record's best hypothesis and
+//                 every other hypothesis bounded (see `pure`), is final here: the EM cannot lift any
+//                 other allele to the half-read level.  All other non-empty slots go to a work list.
 //   fit_kernel    eight lanes per work-list slot: the 5-allele EM fit, the presence score of the
 //                 top non-reference allele (second EM with it held out), emission flags
 //                 (identify_mutations.cpp:1797-1821, 3240-3344).
@@ -21,14 +21,16 @@ namespace brq {
 
 namespace {
 
-constexpr int TALLY_TPB = 512;
+constexpr int TALLY_TPB = 256;
 constexpr int FIT_TPB = 256;
-constexpr int FIT_LANES = 8;  // lanes cooperating on one slot
+constexpr int FIT_LANES = 8;      // lanes cooperating on one slot
+constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
+constexpr uint32_t CODE_NONE = 0xFFFFFFFFu, CODE_COLD = 0x80000000u;
 
 struct f64x2 { double x, y; };
-__device__ __forceinline__ f64x2 lds_f64x2(const void* p) {
+__device__ __forceinline__ f64x2 lds_f64x2(uint32_t shared_addr) {
   f64x2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(shared_addr));
   return v;
 }
 __device__ __forceinline__ f64x2 ldg_f64x2(const void* p) {
@@ -49,77 +51,91 @@ __device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p,
   return ((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
 }
 
-__device__ __forceinline__ void stage_tables(double* sm, const double* __restrict__ src, uint32_t n_doubles, uint8_t* mapq_slot,
-                                             const ScoreParams& p) {
-  for (uint32_t i = threadIdx.x; i < n_doubles; i += blockDim.x) sm[i] = src[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
-}
-
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ tally
-__global__ void __launch_bounds__(TALLY_TPB, 2) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+__global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
                                                               const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
                                                               const ClassTerms* __restrict__ lut, const HotTerms* __restrict__ hotL,
                                                               ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
                                                               uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
                                                               uint32_t flagged_cap) {
-  extern __shared__ __align__(16) double sm[];
+  extern __shared__ __align__(16) double sm[];  // n_hot entries of 6 doubles, then one all-zero entry
   __shared__ uint8_t mapq_slot[256];
   __shared__ double inv_red[64];
-  stage_tables(sm, reinterpret_cast<const double*>(hotL), p.n_hot * 6, mapq_slot, p);
-  if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
+  {
+    const double* src = reinterpret_cast<const double*>(hotL);
+    for (uint32_t i = threadIdx.x; i < p.n_hot * 6; i += blockDim.x) sm[i] = src[i];
+    if (threadIdx.x < 6) sm[p.n_hot * 6 + threadIdx.x] = 0.0;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+    if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
+  }
   __syncthreads();
-  const char* hot = reinterpret_cast<const char*>(sm);
+  const uint32_t hot_base = (uint32_t)__cvta_generic_to_shared(sm);
+  const uint32_t zero_addr = hot_base + p.n_hot * 48u;
+  const uint32_t Q = p.max_qual, cutoff = p.base_quality_cutoff;
+  const uint32_t hot_mapq = p.n_hot ? p.hot_mapq : 0xFFFFu;  // no shared table: every scoring record takes the global path
 
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  const uint32_t hi_limit = 2 * p.max_set;
   const uint64_t stride = (uint64_t)gridDim.x * TALLY_TPB;
   for (uint64_t slot = (uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x; slot < n_slots; slot += stride) {
     const uint64_t beg = off[slot], end = off[slot + 1];
-    uint32_t u_all = 0, u_top = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0, err = 0;
+    uint32_t u_all = 0, u_top = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0;
     double red_top = 0.0, red_bot = 0.0, r2max = 0.0;
     double ll0 = 0.0, ll1 = 0.0, ll2 = 0.0, ll3 = 0.0, ll4 = 0.0;
 
-    auto one = [&](uint32_t r) {
-      if (!(r & SR_UNIQUE_BIT)) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
-        const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
-        const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-        if (r & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
-        return;
-      }
-      ++u_all;
-      u_top += (r >> 10) & 1;
-      if (!eligible(r, p.base_quality_cutoff)) return;
-      const uint32_t qual = (r >> SR_QUAL_SHIFT) & 127;
-      if (qual >= p.max_qual || ((r >> 10) & 63) >= hi_limit) { err |= BRQ_ERR_QUALITY_RANGE; return; }
-      f64x2 a, b, c;  // L[0..1], L[2..3], {L[4], r2}
-      if (((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq && p.n_hot) {
-        const char* e = hot + hot_index(r, p.max_qual) * 48u;
-        a = lds_f64x2(e); b = lds_f64x2(e + 16); c = lds_f64x2(e + 32);
-      } else {
-        const char* e = reinterpret_cast<const char*>(lut + cold_index(r, p, mapq_slot));
-        a = ldg_f64x2(e); b = ldg_f64x2(e + 16); c = ldg_f64x2(e + 32);
-      }
-      ll0 += a.x; ll1 += a.y; ll2 += b.x; ll3 += b.y; ll4 += c.x;
-      r2max = fmax(r2max, c.y);
-      obs_mask |= 1u << (r & 7);
-      ++n;
-    };
-
-    // 128-bit loads starting at the aligned vector that holds the slot's first record; the next
-    // vector is requested before the current one is consumed
-    uint64_t v = beg & ~3ull;
+    uint64_t v = beg & ~3ull;  // the aligned vector that holds the slot's first record
     uint4 cur = make_uint4(0, 0, 0, 0);
     if (v < end) cur = __ldg(reinterpret_cast<const uint4*>(rec + v));
     for (; v < end; v += 4) {
       uint4 nxt = make_uint4(0, 0, 0, 0);
-      if (v + 4 < end) nxt = __ldg(reinterpret_cast<const uint4*>(rec + v + 4));
+      if (v + 4 < end) nxt = __ldg(reinterpret_cast<const uint4*>(rec + v + 4));  // requested before `cur` is consumed
       const uint32_t lo = v < beg ? (uint32_t)(beg - v) : 0u, hi = end - v < 4 ? (uint32_t)(end - v) : 4u;
-      if (lo == 0 && hi > 0) one(cur.x);
-      if (lo <= 1 && hi > 1) one(cur.y);
-      if (lo <= 2 && hi > 2) one(cur.z);
-      if (hi > 3) one(cur.w);
+      const uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
+      uint32_t addr[4], cold_mask = 0, red_mask = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool val = (uint32_t)j >= lo && (uint32_t)j < hi;
+        const bool uniq = val && (r[j] & SR_UNIQUE_BIT);
+        u_all += uniq;
+        u_top += uniq && (r[j] & SR_TOP_BIT);
+        if (val && !(r[j] & SR_UNIQUE_BIT)) red_mask |= 1u << j;
+        const bool elig = val && eligible(r[j], cutoff);
+        const bool hotp = elig && ((r[j] >> SR_MAPQ_SHIFT) & 255) == hot_mapq;
+        if (elig && !hotp) cold_mask |= 1u << j;
+        addr[j] = hotp ? hot_base + hot_index(r[j], Q) * 48u : zero_addr;
+        n += hotp;
+        if (hotp) obs_mask |= 1u << (r[j] & 7);
+      }
+      f64x2 a[4], b[4], c[4];  // L[0..1], L[2..3], {L[4], r2}: all twelve loads in flight together
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] = lds_f64x2(addr[j]); b[j] = lds_f64x2(addr[j] + 16); c[j] = lds_f64x2(addr[j] + 32); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // arrival order; the zero entry adds +0.0 exactly
+        ll0 += a[j].x; ll1 += a[j].y; ll2 += b[j].x; ll3 += b[j].y; ll4 += c[j].x;
+        r2max = fmax(r2max, c[j].y);
+      }
+      if (cold_mask) {  // records with another MAPQ: full table in global memory
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(cold_mask >> j & 1)) continue;
+          const char* e = reinterpret_cast<const char*>(lut + cold_index(r[j], p, mapq_slot));
+          const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
+          ll0 += x.x; ll1 += x.y; ll2 += y.x; ll3 += y.y; ll4 += z.x;
+          r2max = fmax(r2max, z.y);
+          obs_mask |= 1u << (r[j] & 7);
+          ++n;
+        }
+      }
+      if (red_mask) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(red_mask >> j & 1)) continue;
+          const uint32_t red = (r[j] >> SR_RED_SHIFT) & SR_RED_MASK;
+          const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
+          if (r[j] & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
+        }
+      }
       cur = nxt;
     }
 
@@ -170,7 +186,6 @@ __global__ void __launch_bounds__(TALLY_TPB, 2) tally_kernel(const uint32_t* __r
 
     if (n > 0 && !pure) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)slot;
     else if (recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = (uint32_t)slot; }
-    if (err) atomicOr(&scalars[0], err);
   }
 }
 
@@ -179,8 +194,9 @@ namespace {
 
 struct GroupCtx {
   const uint32_t* rec; uint64_t beg, end;
-  const char* hot; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
-  uint32_t sub, mask;  // lane within the group, shuffle mask of the group
+  uint32_t hot_base; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
+  const uint32_t* cache;  // table codes of the slot's first FIT_CACHE records
+  uint32_t sub, mask;     // lane within the group, shuffle mask of the group
 };
 
 __device__ __forceinline__ double group_sum(double v, uint32_t mask) {
@@ -194,22 +210,29 @@ __device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, uint32_t mask) {
   return v;
 }
 
-// r[0..4] and M = max_b L[b] of one scoring record
-__device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t r, double* rr, double& M) {
+// Where a record's class terms live: a byte offset into the shared table, CODE_COLD | index into
+// the global table, or CODE_NONE for a record that does not score.
+__device__ __forceinline__ uint32_t code_of(const GroupCtx& g, uint32_t r) {
   const ScoreParams& p = *g.p;
+  if (!eligible(r, p.base_quality_cutoff)) return CODE_NONE;
+  if (p.n_hot && ((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq) return hot_index(r, p.max_qual) * 48u;
+  return CODE_COLD | cold_index(r, p, g.mapq_slot);
+}
+__device__ __forceinline__ uint32_t code_at(const GroupCtx& g, uint64_t i) {
+  const uint64_t k = i - g.beg;
+  return k < FIT_CACHE ? g.cache[k] : code_of(g, __ldg(g.rec + i));
+}
+// r[0..4] and M = max_b L[b]
+__device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, double* rr, double& M) {
   f64x2 a, b, c;
-  if (((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq && p.n_hot) {
-    const char* e = g.hot + hot_index(r, p.max_qual) * 48u;
+  if (!(code & CODE_COLD)) {
+    const uint32_t e = g.hot_base + code;
     a = lds_f64x2(e); b = lds_f64x2(e + 16); c = lds_f64x2(e + 32);
   } else {
-    const char* e = reinterpret_cast<const char*>(g.lut + cold_index(r, p, g.mapq_slot)) + 48;
+    const char* e = reinterpret_cast<const char*>(g.lut + (code & ~CODE_COLD)) + 48;
     a = ldg_f64x2(e); b = ldg_f64x2(e + 16); c = ldg_f64x2(e + 32);
   }
   rr[0] = a.x; rr[1] = a.y; rr[2] = b.x; rr[3] = b.y; rr[4] = c.x; M = c.y;
-}
-__device__ __forceinline__ bool scoring(const GroupCtx& g, uint32_t r) {
-  const ScoreParams& p = *g.p;
-  return eligible(r, p.base_quality_cutoff) && ((r >> SR_QUAL_SHIFT) & 127) < p.max_qual && ((r >> 10) & 63) < 2 * p.max_set;
 }
 
 struct Fit { double f[5]; double ll; uint32_t iterations; };
@@ -229,10 +252,10 @@ __device__ __noinline__ Fit em_fit(const GroupCtx& g, uint32_t n, const uint32_t
   for (; it <= 50; ++it) {
     double w[5] = {0, 0, 0, 0, 0};
     for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-      const uint32_t r = __ldg(g.rec + i);
-      if (!scoring(g, r)) continue;
+      const uint32_t code = code_at(g, i);
+      if (code == CODE_NONE) continue;
       double rr[5], M;
-      load_ratios(g, r, rr, M);
+      load_ratios(g, code, rr, M);
       double a[5], sum = 0.0;
 #pragma unroll
       for (int b = 0; b < 5; ++b) { a[b] = m.f[b] * rr[b]; sum += a[b]; }
@@ -258,19 +281,24 @@ __device__ __noinline__ Fit em_fit(const GroupCtx& g, uint32_t n, const uint32_t
     if (max_delta < tol) break;
   }
   m.iterations = it > 50 ? 50 : it;
-  // the committed likelihood belongs to the frequencies BEFORE the last update
-  double ll = 0.0;
+  // The committed likelihood belongs to the frequencies BEFORE the last update:
+  // sum_i (log10 s_i + M_i).  The s_i (each in (0, 1]) are multiplied up and one log10 is taken
+  // per ~200 decades, which is the same sum to within a few ulps of its terms.
+  double log_sum = 0.0, prod = 1.0, m_sum = 0.0;
   for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-    const uint32_t r = __ldg(g.rec + i);
-    if (!scoring(g, r)) continue;
+    const uint32_t code = code_at(g, i);
+    if (code == CODE_NONE) continue;
     double rr[5], M;
-    load_ratios(g, r, rr, M);
+    load_ratios(g, code, rr, M);
     double sum = 0.0;
 #pragma unroll
     for (int b = 0; b < 5; ++b) sum += f_prev[b] * rr[b];
-    if (sum > 0.0) ll += log10(sum) + M;
+    if (sum > 0.0) {
+      prod *= sum; m_sum += M;
+      if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
+    }
   }
-  m.ll = group_sum(ll, g.mask);
+  m.ll = group_sum(log_sum + log10(prod) + m_sum, g.mask);
   return m;
 }
 
@@ -283,27 +311,40 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
                                                           uint32_t* __restrict__ scalars, uint32_t flagged_cap) {
   extern __shared__ __align__(16) double sm[];
   __shared__ uint8_t mapq_slot[256];
-  stage_tables(sm, reinterpret_cast<const double*>(hotR), p.n_hot * 6, mapq_slot, p);
+  __shared__ uint32_t cache[FIT_TPB / FIT_LANES][FIT_CACHE];
+  {
+    const double* src = reinterpret_cast<const double*>(hotR);
+    for (uint32_t i = threadIdx.x; i < p.n_hot * 6; i += blockDim.x) sm[i] = src[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+  }
   __syncthreads();
   const uint32_t n_work = scalars[2];
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   const uint32_t lane = threadIdx.x & 31;
   GroupCtx g;
-  g.rec = rec; g.hot = reinterpret_cast<const char*>(sm); g.lut = lut; g.mapq_slot = mapq_slot; g.p = &p;
+  g.rec = rec; g.hot_base = (uint32_t)__cvta_generic_to_shared(sm); g.lut = lut; g.mapq_slot = mapq_slot; g.p = &p;
   g.sub = lane % FIT_LANES;
   g.mask = ((1u << FIT_LANES) - 1u) << (lane - g.sub);
-  const uint32_t groups_per_block = FIT_TPB / FIT_LANES, n_groups = gridDim.x * groups_per_block;
-  for (uint32_t w = blockIdx.x * groups_per_block + threadIdx.x / FIT_LANES; w < n_work; w += n_groups) {
+  uint32_t* my_cache = cache[threadIdx.x / FIT_LANES];
+  g.cache = my_cache;
+  for (;;) {
+    uint32_t w = 0;
+    if (g.sub == 0) w = atomicAdd(&scalars[3], 1u);  // slots are handed out one at a time: EM lengths vary widely
+    w = __shfl_sync(g.mask, w, lane - g.sub);
+    if (w >= n_work) break;
     const uint32_t slot = worklist[w];
     g.beg = off[slot]; g.end = off[slot + 1];
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
     for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
       const uint32_t r = __ldg(rec + i);
-      if (!scoring(g, r)) continue;
+      const uint32_t code = code_of(g, r);
+      if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
+      if (code == CODE_NONE) continue;
 #pragma unroll
       for (int b = 0; b < 5; ++b) obs_count[b] += ((r & 7) == (uint32_t)b);
       ++n;
     }
+    __syncwarp(g.mask);
 #pragma unroll
     for (int b = 0; b < 5; ++b) obs_count[b] = group_sum_u32(obs_count[b], g.mask);
     n = group_sum_u32(n, g.mask);
@@ -344,6 +385,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
       out[slot].bits = bits;
       if (emit || recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = slot; }
     }
+    __syncwarp(g.mask);
   }
 }
 
@@ -353,13 +395,13 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
                         cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem = (size_t)p.n_hot * 48;
-  cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int blocks = (int)std::min<uint64_t>((n_slots + TALLY_TPB - 1) / TALLY_TPB, (uint64_t)kSMs * 2);
-  tally_kernel<<<blocks, TALLY_TPB, smem, s>>>(rec, off, slot_ref, n_slots, lut, hotL, p, out, worklist, flagged, scalars, flagged_cap);
+  const size_t smem_tally = ((size_t)p.n_hot + 1) * 48, smem_fit = (size_t)p.n_hot * 48;
+  cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
+  cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
+  int blocks = (int)std::min<uint64_t>((n_slots + TALLY_TPB - 1) / TALLY_TPB, (uint64_t)kSMs * 3);
+  tally_kernel<<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, lut, hotL, p, out, worklist, flagged, scalars, flagged_cap);
   if (between) cudaEventRecord(between, s);
-  fit_kernel<<<kSMs * 3, FIT_TPB, smem, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
 }
 
 }  // namespace brq

@@ -202,6 +202,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     if (!part_base.empty() && g < part_base.size())
       ri.read_set = (uint8_t)(part_base[g] + (((R.flag[i] & 128) && part_count[g] > 1) ? 1 : 0));
     if (ri.read_set >= 32) throw std::runtime_error("more than 32 read files are not supported by the packed record");
+    if (ri.read_set > out.max_read_set_seen) out.max_read_set_seen = ri.read_set;
     if (R.tid[i] >= 0 && rlen > max_span[(size_t)R.tid[i]]) max_span[(size_t)R.tid[i]] = rlen;
   }
   auto in_pileup = [&](size_t i) {  // bam_plp_push keeps mapped reads with a tid; a read without a walkable CIGAR cannot be resolved

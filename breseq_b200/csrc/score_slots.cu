@@ -74,39 +74,49 @@ __global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __r
   const uint32_t hot_base = (uint32_t)__cvta_generic_to_shared(sm);
   const uint32_t zero_addr = hot_base + p.n_hot * 48u;
   const uint32_t Q = p.max_qual, cutoff = p.base_quality_cutoff;
-  const uint32_t hot_mapq = p.n_hot ? p.hot_mapq : 0xFFFFu;  // no shared table: every scoring record takes the global path
+  // unique, untrimmed, resolvable -- and, for the shared table, the dominant MAPQ -- as masked compares
+  const uint32_t flag_mask = SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT, flag_want = SR_UNIQUE_BIT | SR_OK_BIT;
+  const uint32_t hot_mask = flag_mask | (255u << SR_MAPQ_SHIFT);
+  // without a shared table no record can match: every scoring record takes the global path
+  const uint32_t hot_want = p.n_hot ? (flag_want | (p.hot_mapq << SR_MAPQ_SHIFT)) : 0xFFFFFFFFu;
 
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   const uint64_t stride = (uint64_t)gridDim.x * TALLY_TPB;
   for (uint64_t slot = (uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x; slot < n_slots; slot += stride) {
     const uint64_t beg = off[slot], end = off[slot + 1];
-    uint32_t u_all = 0, u_top = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0;
+    uint32_t tops = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0;
     double red_top = 0.0, red_bot = 0.0, r2max = 0.0;
     double ll0 = 0.0, ll1 = 0.0, ll2 = 0.0, ll3 = 0.0, ll4 = 0.0;
 
-    uint64_t v = beg & ~3ull;  // the aligned vector that holds the slot's first record
+    // 128-bit loads from the aligned vector that holds the slot's first record; all index math is
+    // 32-bit and relative to the slot.  Elements outside the slot are zeroed: a zero record has no
+    // flag set, scores nothing and reads the all-zero table entry.
+    const uint32_t head = (uint32_t)beg & 3u, cnt = (uint32_t)(end - beg);
+    const uint32_t n_vec = (head + cnt + 3u) >> 2;
+    const uint4* vp = reinterpret_cast<const uint4*>(rec + (beg - head));
     uint4 cur = make_uint4(0, 0, 0, 0);
-    if (v < end) cur = __ldg(reinterpret_cast<const uint4*>(rec + v));
-    for (; v < end; v += 4) {
+    if (n_vec) cur = __ldg(vp);
+    for (uint32_t iv = 0; iv < n_vec; ++iv) {
       uint4 nxt = make_uint4(0, 0, 0, 0);
-      if (v + 4 < end) nxt = __ldg(reinterpret_cast<const uint4*>(rec + v + 4));  // requested before `cur` is consumed
-      const uint32_t lo = v < beg ? (uint32_t)(beg - v) : 0u, hi = end - v < 4 ? (uint32_t)(end - v) : 4u;
-      const uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
-      uint32_t addr[4], cold_mask = 0, red_mask = 0;
+      if (iv + 1 < n_vec) nxt = __ldg(vp + iv + 1);  // requested before `cur` is consumed
+      const uint32_t k0 = iv * 4u - head;              // slot-relative index of element 0 (wraps below zero)
+      uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
+      uint32_t addr[4], n_flag_ok = 0, n_hot_here = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool val = (uint32_t)j >= lo && (uint32_t)j < hi;
-        const bool uniq = val && (r[j] & SR_UNIQUE_BIT);
-        u_all += uniq;
-        u_top += uniq && (r[j] & SR_TOP_BIT);
-        if (val && !(r[j] & SR_UNIQUE_BIT)) red_mask |= 1u << j;
-        const bool elig = val && eligible(r[j], cutoff);
-        const bool hotp = elig && ((r[j] >> SR_MAPQ_SHIFT) & 255) == hot_mapq;
-        if (elig && !hotp) cold_mask |= 1u << j;
-        addr[j] = hotp ? hot_base + hot_index(r[j], Q) * 48u : zero_addr;
-        n += hotp;
-        if (hotp) obs_mask |= 1u << (r[j] & 7);
+        r[j] = (k0 + (uint32_t)j < cnt) ? r[j] : 0u;
+        const uint32_t qual = (r[j] >> SR_QUAL_SHIFT) & 127u;
+        const bool qual_ok = qual >= cutoff;
+        const bool flags_ok = (r[j] & flag_mask) == flag_want;
+        const bool hotp = qual_ok && (r[j] & hot_mask) == hot_want;   // flags and MAPQ in one compare
+        tops += (r[j] >> 10) & 1u;
+        n_flag_ok += (flags_ok && qual_ok) ? 1u : 0u;
+        n_hot_here += hotp ? 1u : 0u;
+        const uint32_t e = ((((r[j] >> 10) & 63u) * Q + qual) * 5u + (r[j] & 7u)) * 48u;
+        addr[j] = hotp ? hot_base + e : zero_addr;
+        obs_mask |= hotp ? (1u << (r[j] & 7u)) : 0u;
       }
+      n += n_hot_here;
       f64x2 a[4], b[4], c[4];  // L[0..1], L[2..3], {L[4], r2}: all twelve loads in flight together
 #pragma unroll
       for (int j = 0; j < 4; ++j) { a[j] = lds_f64x2(addr[j]); b[j] = lds_f64x2(addr[j] + 16); c[j] = lds_f64x2(addr[j] + 32); }
@@ -115,22 +125,23 @@ __global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __r
         ll0 += a[j].x; ll1 += a[j].y; ll2 += b[j].x; ll3 += b[j].y; ll4 += c[j].x;
         r2max = fmax(r2max, c[j].y);
       }
-      if (cold_mask) {  // records with another MAPQ: full table in global memory
+      if (n_flag_ok != n_hot_here) {  // scoring records with another MAPQ: full table in global memory
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          if (!(cold_mask >> j & 1)) continue;
+          const bool cold = (r[j] & flag_mask) == flag_want && ((r[j] >> SR_QUAL_SHIFT) & 127u) >= cutoff && (r[j] & hot_mask) != hot_want;
+          if (!cold) continue;
           const char* e = reinterpret_cast<const char*>(lut + cold_index(r[j], p, mapq_slot));
           const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
           ll0 += x.x; ll1 += x.y; ll2 += y.x; ll3 += y.y; ll4 += z.x;
           r2max = fmax(r2max, z.y);
-          obs_mask |= 1u << (r[j] & 7);
+          obs_mask |= 1u << (r[j] & 7u);
           ++n;
         }
       }
-      if (red_mask) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
+      if (!(r[0] & r[1] & r[2] & r[3] & SR_UNIQUE_BIT)) {  // a redundant record (or a zeroed element) is present
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!(red_mask >> j & 1)) continue;
+        for (int j = 0; j < 4; ++j) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
+          if ((r[j] & SR_UNIQUE_BIT) || r[j] == 0u) continue;
           const uint32_t red = (r[j] >> SR_RED_SHIFT) & SR_RED_MASK;
           const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
           if (r[j] & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
@@ -138,6 +149,8 @@ __global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __r
       }
       cur = nxt;
     }
+    // every record of the slot is either unique or redundant; top-strand counts follow by subtraction
+    const uint32_t u_all = cnt - raw_top - raw_bot, u_top = tops - raw_top;
 
     const uint32_t ref = slot_ref[slot];
     const double ll[5] = {ll0, ll1, ll2, ll3, ll4};
@@ -235,73 +248,6 @@ __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, do
   rr[0] = a.x; rr[1] = a.y; rr[2] = b.x; rr[3] = b.y; rr[4] = c.x; M = c.y;
 }
 
-struct Fit { double f[5]; double ll; uint32_t iterations; };
-
-// identify_mutations.cpp:3240-3318.  Records are strided over the group's lanes; the per-allele
-// responsibilities are summed with a fixed butterfly, so every lane holds the same frequencies.
-__device__ __noinline__ Fit em_fit(const GroupCtx& g, uint32_t n, const uint32_t* obs_count, uint32_t allowed, double tol) {
-  Fit m;
-  double total = 0.0;
-#pragma unroll
-  for (int b = 0; b < 5; ++b) { m.f[b] = (allowed >> b & 1) ? 0.5 + (double)obs_count[b] : 0.0; total += m.f[b]; }
-#pragma unroll
-  for (int b = 0; b < 5; ++b) m.f[b] /= total;
-  double f_prev[5];
-  const double inv_n = 1.0 / (double)n;
-  uint32_t it = 1;
-  for (; it <= 50; ++it) {
-    double w[5] = {0, 0, 0, 0, 0};
-    for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-      const uint32_t code = code_at(g, i);
-      if (code == CODE_NONE) continue;
-      double rr[5], M;
-      load_ratios(g, code, rr, M);
-      double a[5], sum = 0.0;
-#pragma unroll
-      for (int b = 0; b < 5; ++b) { a[b] = m.f[b] * rr[b]; sum += a[b]; }
-      if (sum > 0.0) {
-        const double inv = 1.0 / sum;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) w[b] += a[b] * inv;
-      } else {
-#pragma unroll
-        for (int b = 0; b < 5; ++b) w[b] += m.f[b];
-      }
-    }
-    double max_delta = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) {
-      f_prev[b] = m.f[b];
-      if (allowed >> b & 1) {
-        const double f_new = group_sum(w[b], g.mask) * inv_n;
-        max_delta = fmax(max_delta, fabs(f_new - m.f[b]));
-        m.f[b] = f_new;
-      }
-    }
-    if (max_delta < tol) break;
-  }
-  m.iterations = it > 50 ? 50 : it;
-  // The committed likelihood belongs to the frequencies BEFORE the last update:
-  // sum_i (log10 s_i + M_i).  The s_i (each in (0, 1]) are multiplied up and one log10 is taken
-  // per ~200 decades, which is the same sum to within a few ulps of its terms.
-  double log_sum = 0.0, prod = 1.0, m_sum = 0.0;
-  for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-    const uint32_t code = code_at(g, i);
-    if (code == CODE_NONE) continue;
-    double rr[5], M;
-    load_ratios(g, code, rr, M);
-    double sum = 0.0;
-#pragma unroll
-    for (int b = 0; b < 5; ++b) sum += f_prev[b] * rr[b];
-    if (sum > 0.0) {
-      prod *= sum; m_sum += M;
-      if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
-    }
-  }
-  m.ll = group_sum(log_sum + log10(prod) + m_sum, g.mask);
-  return m;
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
@@ -354,30 +300,92 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     uint32_t bits = out[slot].bits;
     const uint32_t best = bits & 7;
     bool recheck = (bits & CO_RECHECK) != 0;
+    const double tol = p.precision_decimal, inv_n = 1.0 / (double)n, thr = 0.5 / (double)n;
 
-    Fit full = em_fit(g, n, obs_count, 0x1F, p.precision_decimal);
-    const double thr = 0.5 / (double)n;
-    uint32_t major = 5, minor = 5, variant = 5, mj = 0;
+    // Two EM fits share one copy of the code: all five alleles, then (when the first fit places a
+    // non-reference allele at or above the half-read level) the same fit with that allele held out
+    // (identify_mutations.cpp:3240-3344).  Records are strided over the group's lanes; responsibilities
+    // are summed with a fixed butterfly, so every lane of the group holds the same frequencies.
+    uint32_t allowed = 0x1F, major = 5, minor = 5, variant = 5, iterations = 0;
+    double ll_fit[2] = {0.0, 0.0};
+    for (int pass = 0; pass < 2; ++pass) {
+      double f[5], f_prev[5], total = 0.0;
 #pragma unroll
-    for (int b = 1; b < 5; ++b) if (full.f[b] > full.f[mj]) mj = b;
-    major = full.f[mj] > 0.0 ? mj : 5;
+      for (int b = 0; b < 5; ++b) { f[b] = (allowed >> b & 1) ? 0.5 + (double)obs_count[b] : 0.0; total += f[b]; }
 #pragma unroll
-    for (int b = 0; b < 5; ++b) {
-      if (fabs(full.f[b] - thr) <= 1e-9 * thr) recheck = true;  // may land on the other side on the host
-      if (full.f[b] < thr) continue;
-      if ((uint32_t)b != major && (minor == 5 || full.f[b] > full.f[minor])) minor = b;
-      if ((uint32_t)b != ref && (variant == 5 || full.f[b] > full.f[variant])) variant = b;
+      for (int b = 0; b < 5; ++b) f[b] /= total;
+      uint32_t it = 1;
+      for (; it <= 50; ++it) {
+        double w[5] = {0, 0, 0, 0, 0};
+        for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+          const uint32_t code = code_at(g, i);
+          if (code == CODE_NONE) continue;
+          double rr[5], M;
+          load_ratios(g, code, rr, M);
+          double a[5], sum = 0.0;
+#pragma unroll
+          for (int b = 0; b < 5; ++b) { a[b] = f[b] * rr[b]; sum += a[b]; }
+          if (sum > 0.0) {
+            const double inv = 1.0 / sum;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) w[b] += a[b] * inv;
+          } else {
+#pragma unroll
+            for (int b = 0; b < 5; ++b) w[b] += f[b];
+          }
+        }
+        double max_delta = 0.0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          f_prev[b] = f[b];
+          if (allowed >> b & 1) {
+            const double f_new = group_sum(w[b], g.mask) * inv_n;
+            max_delta = fmax(max_delta, fabs(f_new - f[b]));
+            f[b] = f_new;
+          }
+        }
+        if (max_delta < tol) break;
+      }
+      // The committed likelihood belongs to the frequencies BEFORE the last update:
+      // sum_i (log10 s_i + M_i).  The s_i (each in (0, 1]) are multiplied up and one log10 is taken
+      // per ~200 decades, which is the same sum to within a few ulps of its terms.
+      double log_sum = 0.0, prod = 1.0, m_sum = 0.0;
+      for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+        const uint32_t code = code_at(g, i);
+        if (code == CODE_NONE) continue;
+        double rr[5], M;
+        load_ratios(g, code, rr, M);
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) sum += f_prev[b] * rr[b];
+        if (sum > 0.0) {
+          prod *= sum; m_sum += M;
+          if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
+        }
+      }
+      ll_fit[pass] = group_sum(log_sum + log10(prod) + m_sum, g.mask);
+      if (pass == 1) break;
+      iterations = it > 50 ? 50 : it;
+      uint32_t mj = 0;
+#pragma unroll
+      for (int b = 1; b < 5; ++b) if (f[b] > f[mj]) mj = b;
+      major = f[mj] > 0.0 ? mj : 5;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        if (fabs(f[b] - thr) <= 1e-9 * thr) recheck = true;  // may land on the other side on the host
+        if (f[b] < thr) continue;
+        if ((uint32_t)b != major && (minor == 5 || f[b] > f[minor])) minor = b;
+        if ((uint32_t)b != ref && (variant == 5 || f[b] > f[variant])) variant = b;
+      }
+      if (variant == 5) break;
+      allowed = 0x1F & ~(1u << variant);
     }
-    double variant_score = nan;
-    if (variant != 5) {
-      Fit null_fit = em_fit(g, n, obs_count, 0x1F & ~(1u << variant), p.precision_decimal);
-      variant_score = (full.ll - null_fit.ll) - p.log10_ref_length;
-    }
+    const double variant_score = variant != 5 ? (ll_fit[0] - ll_fit[1]) - p.log10_ref_length : nan;
     const double slack = 1e-6;
     bool emit = false;
     if (best != ref && consensus > -slack) emit = true;
     if (variant != 5 && variant_score >= p.polymorphism_cutoff - slack) emit = true;
-    bits = (bits & ~(0xFFFu | CO_EMIT | CO_RECHECK | (0xFFu << 16))) | best | (major << 3) | (minor << 6) | (variant << 9) | (full.iterations << 16);
+    bits = (bits & ~(0xFFFu | CO_EMIT | CO_RECHECK | (0xFFu << 16))) | best | (major << 3) | (minor << 6) | (variant << 9) | (iterations << 16);
     if (emit) bits |= CO_EMIT;
     if (recheck) bits |= CO_RECHECK;
     if (g.sub == 0) {

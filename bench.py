@@ -96,19 +96,37 @@ def cpu_sample(tmp, seed=2):
     return bam, fasta
 
 
-def run_cpu_once(bam, fasta, out):
-    """Both passes of the CPU implementation on one BAM; returns (records, seconds)."""
-    cli = oracle_cli()
+def ref_cli():
+    """The reference's own sources compiled against the htslib shim (oracle/ref_build.sh), if prebuilt."""
+    path = os.path.join(ROOT, "oracle", "_ref", "ref_cli")
+    return path if os.path.exists(path) else None
+
+
+def cpu_kind():
+    return "reference" if ref_cli() else "port"
+
+
+def run_cpu_once(bam, fasta, out, cli=None, count_records=True):
+    """Both passes of the CPU implementation on one BAM; returns (records, seconds).
+
+    `cli` = oracle/_ref/ref_cli (the reference's own code, kind "reference") when it was built, else
+    oracle/_build/oracle_cli (the restatement, kind "port").  Both take the same command line and time
+    the two entry points with steady_clock, the bracket the reference's own ExecutionTime uses."""
+    cli = cli or ref_cli() or oracle_cli()
     os.makedirs(out, exist_ok=True)
-    a = json.loads(subprocess.run([cli, "error_count", "--bam", bam, "--fasta", fasta, "--out", out, "--covariates", COVARIATES,
-                                   "--readfiles", "r1,r2", "--read-sets", READ_SETS[0]["name"] + ":2"],
-                                  check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
-    b = json.loads(subprocess.run([cli, "identify_mutations", "--bam", bam, "--fasta", fasta, "--error-rates",
-                                   os.path.join(out, "error_rates.tab"), "--gd", os.path.join(out, "o.gd"), "--read-sets",
-                                   READ_SETS[0]["name"] + ":2", "--del-prop", "30", "--del-seed", "0", "--mutation-cutoff",
-                                   str(MUTATION_CUTOFF), "--polymorphism-cutoff", str(POLYMORPHISM_CUTOFF), "--places", str(PLACES)],
-                                  check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
-    return b["records"], a["seconds"] + b["seconds"]
+    sets = READ_SETS[0]["name"] + ":2"
+    ec = ["error_count", "--bam", bam, "--fasta", fasta, "--out", out, "--covariates", COVARIATES, "--readfiles", "r1,r2",
+          "--read-sets", sets]
+    im = ["identify_mutations", "--bam", bam, "--fasta", fasta, "--out", out, "--error-rates", os.path.join(out, "error_rates.tab"),
+          "--gd", os.path.join(out, "o.gd"), "--read-sets", sets, "--del-prop", "30", "--del-seed", "0", "--mutation-cutoff",
+          str(MUTATION_CUTOFF), "--polymorphism-cutoff", str(POLYMORPHISM_CUTOFF), "--places", str(PLACES)]
+    a = json.loads(subprocess.run([cli] + ec, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+    b = json.loads(subprocess.run([cli] + im, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
+    records = b["records"]
+    if not records and count_records:  # the reference binary does not count records: one untimed run of the port does
+        records = json.loads(subprocess.run([oracle_cli()] + im, check=True, capture_output=True, text=True)
+                             .stdout.strip().splitlines()[-1])["records"]
+    return records, a["seconds"] + b["seconds"]
 
 
 def config_block(n_gpus):
@@ -126,6 +144,7 @@ def reference_arm(args):
     with tempfile.TemporaryDirectory() as tmp:
         bam, fasta = cpu_sample(tmp)
         times, records = [], 0
+        n_sample, _ = run_cpu_once(bam, fasta, os.path.join(tmp, "count"), cli=oracle_cli())  # untimed: records in the sample
 
         def one_step(tag):
             # `cores` independent processes, one coordinate range each (the reference itself is
@@ -134,7 +153,7 @@ def reference_arm(args):
             procs, results = [], [None] * cores
 
             def worker(i):
-                results[i] = run_cpu_once(bam, fasta, os.path.join(tmp, "%s_%d" % (tag, i)))
+                results[i] = (n_sample, run_cpu_once(bam, fasta, os.path.join(tmp, "%s_%d" % (tag, i)), count_records=False)[1])
             th = [threading.Thread(target=worker, args=(i,)) for i in range(cores)]
             [t.start() for t in th]
             [t.join() for t in th]
@@ -146,7 +165,7 @@ def reference_arm(args):
             records, _ = n, times.append(dt)
         dt = sum(times) / len(times)
         value = records / dt
-    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_cli")) else "port"
+    kind = cpu_kind()
     line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": value, "unit": "aligned bases/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -295,7 +314,7 @@ def main():
             with tempfile.TemporaryDirectory() as tmp:
                 bam, fasta = cpu_sample(tmp)
                 n_cpu, t_cpu = run_cpu_once(bam, fasta, os.path.join(tmp, "o"))
-            cpu = {"value": n_cpu / t_cpu, "unit": "aligned bases/s", "cores": 1, "kind": "port",
+            cpu = {"value": n_cpu / t_cpu, "unit": "aligned bases/s", "cores": 1, "kind": cpu_kind(),
                    "sample": "C1 read model on a 1/%d-length reference (%d bp): %d records in %.1f s, one thread"
                              % (CPU_SAMPLE_DIV, GENOME // CPU_SAMPLE_DIV, n_cpu, t_cpu)}
         line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": total_records / (step_ms * 1e-3),

@@ -5,10 +5,16 @@
 // hts_shim/.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs may build, link or execute anything in this directory; the product (breseq_b200/) never does.
 //
-// PARITY STATUS: "parity unpinned".  The reference ships no fixture at the BAM -> (error table,
-// RA evidence) boundary and its end-to-end goldens need bowtie2 + htslib, neither of which is in
-// this image.  Where possible the restatement is cross-checked against the
-// reference's OWN sources compiled against the same shim (oracle/_ref, see Makefile).
+// PARITY STATUS: pinned above the htslib boundary, unpinned below it.
+//  * Above: oracle/ref_build.sh compiles the reference's OWN, unmodified libbreseq sources against
+//    hts_shim/ into oracle/_ref/ref_cli (driver: ref_driver.cpp).  tests/golden/ holds what that binary
+//    wrote for the test datasets (error_rates.tab, base_qual_error_prob.*.tab, coverage distributions,
+//    ra_mc_evidence.gd, the per-position debug file); tests/test_golden.py requires this restatement
+//    to reproduce every one of those files byte for byte and to agree per column.
+//  * Below: htslib itself is not in this image, the reference ships no BAM-level fixture (its one
+//    BAM is a missing blob) and its end-to-end goldens need bowtie2.  BAM
+//    decode and pileup-column construction (bam_plp_auto semantics) in hts_shim/ are a restatement
+//    of htslib 1.23.1 behaviour shared by the reference build and this oracle: "parity unpinned" there.
 #pragma once
 #include <cstdint>
 #include <map>

@@ -1,0 +1,123 @@
+// TEST INFRASTRUCTURE -- command-line driver around the REFERENCE'S OWN, UNMODIFIED sources.
+//
+// oracle/ref_build.sh compiles /root/reference/src/breseq/*.cpp where they lie (every libbreseq
+// source) against the htslib-compatible shim in hts_shim/ and links them with this file into
+// oracle/_ref/ref_cli.  Nothing here restates reference logic: the
+// driver fills breseq::Settings / Summary the way breseq_cmdline.cpp does at its two call sites
+//   stage 07  breseq_cmdline.cpp:2276-2328  -> breseq::error_count()          error_count.h:41-52
+//   stage 08  breseq_cmdline.cpp:2454-2488  -> breseq::identify_mutations()   identify_mutations.h:46-60
+// (and like the standalone `breseq ERROR_COUNT`, breseq_cmdline.cpp:972-1030) and calls them.
+// Same command line and same JSON timing line as oracle_cli, so tests and bench.py can swap the two.
+//
+// Used to (a) pin the restatement in oracle.cpp against the reference's real arithmetic and file
+// writers, and (b) serve as the `kind: "reference"` CPU baseline.  The htslib layer under it is
+// still the shim (htslib itself is not in this image): parity at the BAM-decode/pileup boundary
+// remains a restatement.
+#include "error_count.h"
+#include "identify_mutations.h"
+#include "reference_sequence.h"
+#include "settings.h"
+#include "summary.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+using namespace std;
+using namespace breseq;
+
+static vector<string> split_list(const string& s, char sep) {
+  vector<string> out;
+  if (s.empty()) return out;
+  stringstream ss(s);
+  string item;
+  while (getline(ss, item, sep)) out.push_back(item);
+  return out;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { cerr << "usage: ref_cli error_count|identify_mutations ..." << endl; return 2; }
+  string cmd = argv[1];
+  map<string, string> opt;
+  for (int i = 2; i < argc; ++i) {
+    string k = argv[i];
+    if (k.rfind("--", 0) != 0) { cerr << "bad argument " << k << endl; return 2; }
+    k = k.substr(2);
+    if (k == "no-coverage" || k == "no-errors" || k == "skip-mc" || k == "polymorphism-prediction") opt[k] = "1";
+    else if (i + 1 < argc) opt[k] = argv[++i];
+  }
+  auto get = [&](const string& k, const string& d) { return opt.count(k) ? opt[k] : d; };
+  const string out = get("out", ".");
+
+  Settings::set_global_paths();  // as breseq_cmdline.cpp:2885 does first thing in main()
+  Summary summary;
+  Settings settings(out);
+
+  cReferenceSequences ref_seq_info;
+  vector<string> reference_file_names;
+  reference_file_names.push_back(get("fasta", ""));
+  ref_seq_info.LoadFiles(reference_file_names);
+  settings.normal_reference_file_names = reference_file_names;
+  settings.init_reference_sets(ref_seq_info);
+  summary.sequence_conversion.total_reference_sequence_length = ref_seq_info.get_total_length();
+
+  // --read-sets name:2,name:1  -> cReadFileSets (settings.h:122-163); one @RG per set, LB = base name
+  uint32_t id = 0;
+  for (const string& s : split_list(get("read-sets", ""), ',')) {
+    size_t c = s.rfind(':');
+    cReadFileSet rfs;
+    rfs.m_base_name = s.substr(0, c);
+    uint32_t n_files = (uint32_t)atoi(s.substr(c + 1).c_str());
+    for (uint32_t f = 0; f < n_files; ++f) {
+      cReadFile rf;
+      rf.m_base_name = n_files == 2 ? rfs.m_base_name + (f == 0 ? "_R1" : "_R2") : rfs.m_base_name;
+      rf.m_original_file_name = rf.m_base_name + ".fastq";
+      rf.m_paired_end_group = (uint32_t)settings.read_file_sets.size();
+      rf.m_error_group = id;
+      rf.m_id = id++;
+      rfs.m_files.push_back(rf);
+    }
+    settings.read_file_sets.push_back(rfs);
+  }
+
+  settings.base_quality_cutoff = (uint32_t)atoi(get("base-quality-cutoff", "3").c_str());
+  settings.skip_missing_coverage_prediction = opt.count("skip-mc") > 0;
+  settings.polymorphism_prediction = opt.count("polymorphism-prediction") > 0;
+  settings.error_rates_file_name = get("error-rates", out + "/error_rates.tab");
+  settings.unique_only_coverage_distribution_file_name = out + "/@.unique_only_coverage_distribution.tab";
+  settings.error_rates_base_qual_error_prob_file_name = out + "/base_qual_error_prob.#.tab";
+  settings.mutation_identification_per_position_file_name = get("per-position", out + "/per_position_file.tab");
+  settings.dp_candidate_regions_file_name = out + "/dp_candidate_regions.csv";
+  // user-chosen subset of targets (Settings::call_mutations_seq_id_set())
+  vector<string> seq_ids = split_list(get("seq-ids", ""), ',');
+  if (!seq_ids.empty()) {
+    settings.refseq_settings.m_call_mutations_seq_id_set.clear();
+    for (const string& s : seq_ids) settings.refseq_settings.m_call_mutations_seq_id_set.insert(s);
+  }
+
+  auto t0 = chrono::steady_clock::now();
+  if (cmd == "error_count") {
+    error_count(settings, summary, get("bam", ""), get("fasta", ""), out, split_list(get("readfiles", ""), ','),
+                !opt.count("no-coverage"), !opt.count("no-errors"), false, (uint8_t)settings.base_quality_cutoff,
+                get("covariates", ""));
+  } else if (cmd == "identify_mutations") {
+    vector<double> prop, seed;
+    for (const string& s : split_list(get("del-prop", ""), ',')) prop.push_back(atof(s.c_str()));
+    for (const string& s : split_list(get("del-seed", ""), ',')) seed.push_back(atof(s.c_str()));
+    while (prop.size() < ref_seq_info.size()) prop.push_back(prop.empty() ? 0.0 : prop.back());
+    while (seed.size() < ref_seq_info.size()) seed.push_back(seed.empty() ? 0.0 : seed.back());
+    identify_mutations(settings, summary, get("bam", ""), get("fasta", ""), get("gd", out + "/ra_mc_evidence.gd"), ref_seq_info,
+                       prop, seed, atof(get("mutation-cutoff", "10").c_str()), atof(get("polymorphism-cutoff", "2").c_str()),
+                       atof(get("precision", "1e-6").c_str()), (uint32_t)atoi(get("places", "8").c_str()),
+                       opt.count("per-position") > 0);
+  } else {
+    cerr << "unknown command " << cmd << endl;
+    return 2;
+  }
+  double sec = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+  printf("{\"cmd\": \"%s\", \"seconds\": %.6f, \"records\": 0, \"impl\": \"reference\"}\n", cmd.c_str(), sec);
+  return 0;
+}

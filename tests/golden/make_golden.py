@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/ from the REFERENCE'S OWN sources (oracle/_ref/ref_cli).
+
+Run in the build container, where /root/reference exists:
+
+    python -c 'import __graft_entry__ as g; g.build()'     # libbrq.so, oracle_cli and oracle/_ref/ref_cli
+    python tests/golden/make_golden.py
+
+For every dataset in tests/helpers.py:DATASETS the inputs (BAM + FASTA) are written by the product's
+seeded generator and both reference entry points are run on them through oracle/ref_driver.cpp:
+breseq::error_count() (error_count.cpp:50-68) and breseq::identify_mutations()
+(identify_mutations.cpp:48-88), compiled unmodified from /root/reference/src/breseq against the
+htslib shim.  What they wrote is committed here:
+
+    <name>/error_rates.tab, base_qual_error_prob.*.tab, *.unique_only_coverage_distribution.tab,
+    <name>/ra_mc_evidence.gd, <name>/inputs.sha256 (so generator drift is detected, not silently absorbed)
+    tiny/reference.bam, tiny/reference.fasta(.fai), tiny/per_position_file.tab   (inputs kept for the smallest case)
+
+The fixtures pin (a) oracle/oracle.cpp, (b) the CUDA path, against the reference's real arithmetic
+and file writers.  The BAM decode / pileup layer under the reference is still oracle/hts_shim.
+"""
+import hashlib
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+
+
+def sha256(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def main():
+    if not os.path.exists(helpers.REF_CLI):
+        sys.exit("oracle/_ref/ref_cli is missing: run oracle/ref_build.sh where /root/reference exists")
+    for name in helpers.DATASETS:
+        gdir = os.path.join(HERE, name)
+        shutil.rmtree(gdir, ignore_errors=True)
+        os.makedirs(gdir)
+        with tempfile.TemporaryDirectory() as tmp:
+            d = helpers.generate_inputs(name, tmp)
+            out = os.path.join(tmp, "ref")
+            helpers.run_reference(d, out)
+            for f in helpers.pass_output_names(d):
+                shutil.copy(os.path.join(out, f), os.path.join(gdir, f))
+            with open(os.path.join(gdir, "inputs.sha256"), "w") as fh:
+                fh.write("%s  reference.bam\n%s  reference.fasta\n" % (sha256(d["bam"]), sha256(d["fasta"])))
+            if name == "tiny":
+                for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
+                    shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))
+                shutil.copy(os.path.join(out, "per_position_file.tab"), os.path.join(gdir, "per_position_file.tab"))
+        print("golden/%s: %d files" % (name, len(os.listdir(gdir))))
+
+
+if __name__ == "__main__":
+    main()

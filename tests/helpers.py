@@ -32,7 +32,16 @@ DATASETS = {
                              dict(name="se", paired=False, read_len=36, coverage=30.0)],
                   n_polymorphic=25, n_fixed=8, n_gaps=2, mutation_cutoff=10.0, polymorphism_cutoff=10.0,
                   precision=1e-6, places=3, del_prop=15.0, del_seed=0.0),
+    # small enough that its BAM and the reference's outputs for it are committed under tests/golden/tiny
+    "tiny": dict(seed=11, contig_lens=[1200, 800], prefix="tiny",
+                 read_sets=[dict(name="tp", paired=True, read_len=100, coverage=30.0, frag_mean=250, frag_sd=25),
+                            dict(name="ts", paired=False, read_len=36, coverage=15.0)],
+                 n_polymorphic=8, n_fixed=4, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
+                 precision=1e-6, places=8, del_prop=6.0, del_seed=0.0),
 }
+
+REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_cli")  # the reference's own sources (oracle/ref_build.sh)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
 def synth_spec(d):
@@ -60,32 +69,68 @@ def run_oracle(*args):
     return json.loads(p.stdout.strip().splitlines()[-1])
 
 
-def make_dataset(name, outdir):
-    """Generate BAM + FASTA with the product's generator, then run both oracle passes on it."""
+def cli_args(d, outdir, rates=None, gd=None):
+    """Command lines shared by oracle_cli and ref_cli (same options by construction)."""
+    sets = ",".join("%s:%d" % s for s in read_file_sets(d))
+    n = len(d["contig_lens"])
+    rates = rates or os.path.join(outdir, "error_rates.tab")
+    gd = gd or os.path.join(outdir, "ra_mc_evidence.gd")
+    ec = ["error_count", "--bam", d["bam"], "--fasta", d["fasta"], "--out", outdir, "--covariates", covariates(d),
+          "--readfiles", ",".join(readfile_names(d)), "--read-sets", sets]
+    im = ["identify_mutations", "--bam", d["bam"], "--fasta", d["fasta"], "--out", outdir, "--error-rates", rates, "--gd", gd,
+          "--read-sets", sets, "--del-prop", ",".join([str(d["del_prop"])] * n), "--del-seed", ",".join([str(d["del_seed"])] * n),
+          "--mutation-cutoff", d["mutation_cutoff"], "--polymorphism-cutoff", d["polymorphism_cutoff"],
+          "--precision", d["precision"], "--places", d["places"]]
+    return ec, im
+
+
+def generate_inputs(name, outdir):
+    """BAM + FASTA of a named dataset, written by the product's (seeded, integer-only) generator."""
     d = dict(DATASETS[name])
     os.makedirs(outdir, exist_ok=True)
-    d["dir"] = outdir
+    d["name"], d["dir"] = name, outdir
     d["bam"], d["fasta"] = os.path.join(outdir, "reference.bam"), os.path.join(outdir, "reference.fasta")
     ctx = bq.Context(device=-1)
     ctx.synth_write(synth_spec(d), d["bam"], d["fasta"])
     ctx.close()
+    return d
+
+
+def make_dataset(name, outdir):
+    """Generate BAM + FASTA with the product's generator, then run both oracle passes on it."""
+    d = generate_inputs(name, outdir)
     odir = os.path.join(outdir, "oracle")
     os.makedirs(odir, exist_ok=True)
-    sets = ",".join("%s:%d" % s for s in read_file_sets(d))
     d["oracle_dir"] = odir
     d["oracle_counts"] = os.path.join(odir, "error_counts.tab")
     d["oracle_rates"] = os.path.join(odir, "error_rates.tab")
     d["oracle_gd"] = os.path.join(odir, "ra_mc_evidence.gd")
     d["oracle_columns"] = os.path.join(odir, "columns.bin")
-    run_oracle("error_count", "--bam", d["bam"], "--fasta", d["fasta"], "--out", odir, "--covariates", covariates(d),
-               "--readfiles", ",".join(readfile_names(d)), "--read-sets", sets, "--counts-dump", d["oracle_counts"])
-    n = len(d["contig_lens"])
-    run_oracle("identify_mutations", "--bam", d["bam"], "--fasta", d["fasta"], "--error-rates", d["oracle_rates"],
-               "--gd", d["oracle_gd"], "--read-sets", sets, "--del-prop", ",".join([str(d["del_prop"])] * n),
-               "--del-seed", ",".join([str(d["del_seed"])] * n), "--mutation-cutoff", d["mutation_cutoff"],
-               "--polymorphism-cutoff", d["polymorphism_cutoff"], "--precision", d["precision"], "--places", d["places"],
-               "--columns-out", d["oracle_columns"])
+    ec, im = cli_args(d, odir)
+    run_oracle(*ec, "--counts-dump", d["oracle_counts"])
+    run_oracle(*im, "--columns-out", d["oracle_columns"])
     return d
+
+
+def run_reference(d, outdir, per_position=True):
+    """Both passes of the reference's own sources (oracle/_ref/ref_cli) on a dataset; returns seconds."""
+    os.makedirs(outdir, exist_ok=True)
+    ec, im = cli_args(d, outdir)
+    if per_position:
+        im += ["--per-position", os.path.join(outdir, "per_position_file.tab")]
+    sec = 0.0
+    for args in (ec, im):
+        p = subprocess.run([REF_CLI] + [str(a) for a in args], check=True, capture_output=True, text=True)
+        sec += json.loads(p.stdout.strip().splitlines()[-1])["seconds"]
+    return sec
+
+
+def pass_output_names(d):
+    """Files the two entry points write for a dataset (the drop-in boundary's file contract)."""
+    names = ["error_rates.tab", "ra_mc_evidence.gd"]
+    names += ["base_qual_error_prob.%s.tab" % rf for rf in readfile_names(d)]
+    names += ["%d.unique_only_coverage_distribution.tab" % g for g in range(len(d["contig_lens"]))]
+    return names
 
 
 def oracle_counts(path):

@@ -1,0 +1,119 @@
+"""Golden fixtures written by the REFERENCE'S OWN sources (tests/golden/make_golden.py) pin both the
+CPU oracle and the CUDA path.
+
+* not gpu: oracle/oracle_cli reproduces every golden file byte for byte; its per-column dump agrees
+  with the reference's per-position debug file; the live reference build (when oracle/_ref/ref_cli is
+  present, i.e. in the build container) still reproduces the committed files.
+* gpu:     the CUDA path, through the C ABI, reproduces every golden file byte for byte.
+"""
+import filecmp
+import hashlib
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import breseq_b200 as bq
+import helpers
+
+NAMES = list(helpers.DATASETS)
+
+
+def golden(name, f):
+    return os.path.join(helpers.GOLDEN, name, f)
+
+
+def sha256(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def assert_same_files(d, got_dir, want_dir, label):
+    for f in helpers.pass_output_names(d):
+        assert filecmp.cmp(os.path.join(got_dir, f), os.path.join(want_dir, f), shallow=False), "%s: %s differs" % (label, f)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_generator_is_deterministic(name, datasets):
+    """The committed outputs belong to exactly these inputs (same seed => same BAM, any thread count)."""
+    d = datasets[name]
+    want = dict(reversed(l.split()) for l in open(golden(name, "inputs.sha256")).read().strip().split("\n"))
+    assert sha256(d["bam"]) == want["reference.bam"]
+    assert sha256(d["fasta"]) == want["reference.fasta"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_reproduces_reference_files(name, datasets):
+    d = datasets[name]
+    assert_same_files(d, d["oracle_dir"], os.path.join(helpers.GOLDEN, name), "oracle vs reference golden")
+
+
+def tiny_from_fixture(tmp):
+    """The committed BAM itself (not a regenerated one)."""
+    d = dict(helpers.DATASETS["tiny"])
+    for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
+        shutil.copy(golden("tiny", f), os.path.join(tmp, f))
+    d["bam"], d["fasta"] = os.path.join(tmp, "reference.bam"), os.path.join(tmp, "reference.fasta")
+    return d
+
+
+def test_oracle_on_committed_bam(built, tmp_path):
+    d = tiny_from_fixture(str(tmp_path))
+    out = str(tmp_path / "o")
+    os.makedirs(out)
+    ec, im = helpers.cli_args(d, out)
+    helpers.run_oracle(*ec)
+    helpers.run_oracle(*im, "--columns-out", os.path.join(out, "columns.bin"))
+    assert_same_files(d, out, os.path.join(helpers.GOLDEN, "tiny"), "oracle on committed BAM")
+
+    # per-column: the reference's per-position debug file (identify_mutations.cpp:1693-1733) prints,
+    # for every (column, insert_count), the consensus score at 6 significant digits and the scoring
+    # records per base and strand
+    o = helpers.oracle_columns(os.path.join(out, "columns.bin"))
+    rows = [l.split() for l in open(golden("tiny", "per_position_file.tab")) if l.strip()]
+    assert len(rows) == len(o)
+    order = np.lexsort((o["insert_count"], o["pos1"], np.argsort(np.argsort(helpers.contig_names(d)))[o["tid"]]))
+    for row, c in zip(rows, o[order]):
+        assert int(row[0]) == c["pos1"] and int(row[1]) == c["insert_count"]
+        assert row[2] == "ACGT.N"[c["ref"]]
+        want = "nan" if np.isnan(c["consensus_score"]) else "%g" % c["consensus_score"]
+        assert row[3].lstrip("-") == want.lstrip("-") if want == "nan" else row[3] == want, (row[:4], want)
+        per_base = [tuple(int(x) for x in row[5 + 2 * j].strip("()").split("/")) for j in range(5)]
+        assert sum(b for b, t in per_base) + sum(t for b, t in per_base) == c["n"]
+
+
+@pytest.mark.skipif(not os.path.exists(helpers.REF_CLI), reason="oracle/_ref/ref_cli is only built where /root/reference exists")
+@pytest.mark.parametrize("name", NAMES)
+def test_live_reference_matches_committed_golden(name, datasets, tmp_path):
+    d = datasets[name]
+    out = str(tmp_path / "ref")
+    helpers.run_reference(d, out, per_position=False)
+    assert_same_files(d, out, os.path.join(helpers.GOLDEN, name), "live reference vs committed golden")
+
+
+def run_cuda(d, out):
+    os.makedirs(out, exist_ok=True)
+    rates = os.path.join(out, "error_rates.tab")
+    bq.error_count(d["bam"], d["fasta"], out, helpers.readfile_names(d), True, True, False, 3, helpers.covariates(d),
+                   read_file_sets=helpers.read_file_sets(d), error_rates_file_name=rates)
+    n = len(d["contig_lens"])
+    bq.identify_mutations(d["bam"], d["fasta"], os.path.join(out, "ra_mc_evidence.gd"), [d["del_prop"]] * n, [d["del_seed"]] * n,
+                          d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"], False,
+                          error_rates_file_name=rates, read_file_sets=helpers.read_file_sets(d))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_path_reproduces_reference_files(name, datasets, tmp_path):
+    d = datasets[name]
+    out = str(tmp_path / "cuda")
+    run_cuda(d, out)
+    assert_same_files(d, out, os.path.join(helpers.GOLDEN, name), "CUDA path vs reference golden")
+
+
+@pytest.mark.gpu
+def test_cuda_path_on_committed_bam(built, tmp_path):
+    d = tiny_from_fixture(str(tmp_path))
+    out = str(tmp_path / "cuda")
+    run_cuda(d, out)
+    assert_same_files(d, out, os.path.join(helpers.GOLDEN, "tiny"), "CUDA path on committed BAM")

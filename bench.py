@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; reported in config)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -310,7 +311,7 @@ def main():
         cfg["staging_seconds"] = t_stage
         cfg["hist_kernel_gbs"] = hist_bytes / (k_ms["hist"] * 1e-3) / 1e9 if k_ms["hist"] > 0 else 0.0
         cpu = None
-        if world == 1 or True:
+        if not args.no_cpu:
             with tempfile.TemporaryDirectory() as tmp:
                 bam, fasta = cpu_sample(tmp)
                 n_cpu, t_cpu = run_cpu_once(bam, fasta, os.path.join(tmp, "o"))

@@ -63,7 +63,8 @@ class _StreamInfo(C.Structure):
 class _ScoreParams(C.Structure):
     _fields_ = [("mutation_cutoff", C.c_double), ("polymorphism_cutoff", C.c_double),
                 ("polymorphism_precision_decimal", C.c_double), ("polymorphism_precision_places", C.c_uint32),
-                ("base_quality_cutoff", C.c_uint32), ("total_reference_length", C.c_uint64)]
+                ("base_quality_cutoff", C.c_uint32), ("total_reference_length", C.c_uint64),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 #: numpy view of ``brq_column`` (96 bytes per slot)
@@ -72,7 +73,8 @@ COLUMN_DTYPE = np.dtype([("ll", "<f8", 5), ("consensus_score", "<f8"), ("variant
                          ("n", "<u4"), ("bits", "<u4")])
 assert COLUMN_DTYPE.itemsize == 96
 
-CO_BASE_PREDICTED, CO_UNIQUE_ONLY, CO_EMIT, CO_RECHECK = 1 << 12, 1 << 13, 1 << 14, 1 << 15
+CO_BASE_PREDICTED, CO_UNIQUE_ONLY, CO_EMIT, CO_RECHECK, CO_FIT = 1 << 12, 1 << 13, 1 << 14, 1 << 15, 1 << 24
+SCORE_FIT_ALL_COLUMNS = 1
 
 _lib = None
 
@@ -305,9 +307,9 @@ class Context:
     # ---- pass 2
     @staticmethod
     def score_params(mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision_decimal=1e-6, precision_places=8,
-                     base_quality_cutoff=3, total_reference_length=0):
+                     base_quality_cutoff=3, total_reference_length=0, fit_all_columns=False):
         return _ScoreParams(mutation_cutoff, polymorphism_cutoff, precision_decimal, precision_places, base_quality_cutoff,
-                            total_reference_length)
+                            total_reference_length, SCORE_FIT_ALL_COLUMNS if fit_all_columns else 0, 0)
 
     def score_columns(self, params=None):
         p = params or self.score_params()

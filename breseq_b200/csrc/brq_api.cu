@@ -74,9 +74,11 @@ struct brq_ctx {
   DevBuf<unsigned long long> d_counts, d_cov;
   DevBuf<double> d_log10;
   DevBuf<ClassTerms> d_lut;
-  DevBuf<HotTerms> d_hotL;
+  DevBuf<HotTerms> d_coldT;
+  DevBuf<double> d_tallyT;
   DevBuf<HotRatios> d_hotR;
-  std::vector<HotTerms> h_hotL;
+  std::vector<HotTerms> h_hotL, h_coldT;
+  std::vector<double> h_tallyT;
   std::vector<HotRatios> h_hotR;
   float ms_tally = 0, ms_fit = 0;
   bool warp_mode = false;
@@ -237,12 +239,15 @@ void install_table(brq_ctx* c) {  // h_log10 -> text-canonical probabilities -> 
   if (c->staged) {
     build_class_lut(c->spec, c->h_prob, c->st.mapq_seen, c->sp, c->h_lut);
     build_hot_tables(c->h_lut, c->st.mapq_count, c->sp, c->h_hotL, c->h_hotR);
+    build_tally_tables(c->h_lut, c->st.mapq_count, c->st.qual_count, c->sp, c->h_tallyT, c->h_coldT);
     if (c->device >= 0) {
       c->d_lut.ensure(c->h_lut.size());
-      c->d_hotL.ensure(c->h_hotL.size());
+      c->d_tallyT.ensure(c->h_tallyT.size());
+      c->d_coldT.ensure(c->h_coldT.size());
       c->d_hotR.ensure(c->h_hotR.size());
       CUDA_OK(cudaMemcpyAsync(c->d_lut.p, c->h_lut.data(), c->h_lut.size() * sizeof(ClassTerms), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(cudaMemcpyAsync(c->d_hotL.p, c->h_hotL.data(), c->h_hotL.size() * sizeof(HotTerms), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(c->d_tallyT.p, c->h_tallyT.data(), c->h_tallyT.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      CUDA_OK(cudaMemcpyAsync(c->d_coldT.p, c->h_coldT.data(), c->h_coldT.size() * sizeof(HotTerms), cudaMemcpyHostToDevice, c->stream));
       CUDA_OK(cudaMemcpyAsync(c->d_hotR.p, c->h_hotR.data(), c->h_hotR.size() * sizeof(HotRatios), cudaMemcpyHostToDevice, c->stream));
       CUDA_OK(cudaStreamSynchronize(c->stream));
     }
@@ -278,6 +283,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->sp.polymorphism_cutoff = p->polymorphism_cutoff;
   c->sp.precision_decimal = p->polymorphism_precision_decimal;
   c->sp.base_quality_cutoff = p->base_quality_cutoff;
+  c->sp.fit_all = (p->flags & BRQ_SCORE_FIT_ALL_COLUMNS) ? 1u : 0u;
   // the reference ASSERTs when a covariate value exceeds the table (error_count.cpp:485-488); the
   // stream's maxima are known from staging, so the check costs the kernels nothing
   if (c->st.n_score && c->st.max_qual_seen >= c->sp.max_qual)
@@ -298,7 +304,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
     CUDA_OK(cudaEventRecord(c->ev[7], c->stream));
   } else {
     c->d_worklist.ensure(n_slots);
-    launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->d_hotL.p, c->d_hotR.p, c->sp,
+    launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
                        c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
   }
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
@@ -390,7 +396,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_hotL.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);

@@ -61,7 +61,8 @@ struct ReadBatch {
 
 // ---- packed stream records -------------------------------------------------------------
 
-// Scoring record, 4 bytes, one per (read, slot) whose base at that slot is not N.
+// Scoring record, 4 bytes, one per (read, slot) whose base at that slot is not N.  Within a slot the
+// redundant records (X1 > 1) come first and the unique ones follow, each part in arrival order.
 //   [2:0]   obs        base index 0..4 ('.' = 4)
 //   [9:3]   qual       quality chosen by alignment_position_to_covariates (error_count.cpp:1049-1105)
 //   [10]    top        1 = read on the top strand
@@ -109,6 +110,7 @@ struct PileupStream {
   uint64_t n_score = 0, n_hist = 0;
   uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records
   uint64_t mapq_count[256] = {0};      // scoring records per MAPQ value
+  uint64_t qual_count[128] = {0};      // scoring records per quality value
   uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
   uint32_t n_groups = 1;               // coverage groups present
   uint32_t max_qual_seen = 0;

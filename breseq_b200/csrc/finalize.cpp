@@ -265,8 +265,66 @@ void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_co
     const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + p.mapq_slot[hot]) * p.max_qual + q) * 5 + obs];
     const size_t h = ((size_t)st * p.max_qual + q) * 5 + obs;
     for (int b = 0; b < 5; ++b) { hotL[h].L[b] = t.L[b]; hotR[h].r[b] = t.r[b]; }
-    hotL[h].r2 = t.r2;
+    hotL[h].M = t.M;
     hotR[h].M = t.M;
+  }
+}
+
+// Tables of the tally kernel (score_slots.cu).
+//  tallyT  shared-memory image: three planes ({L0,L1} {L2,L3} {L4,M}) of n_hot * copies 16-byte cells, cell index
+//          (h * copies + c), h = ((set*2 + top) * n_q + (quality - q_lo)) * 4 + obs, then one zero cell per copy.
+//  coldT   every class of every MAPQ in [mq_min, mq_min + n_mq): index (((set*2 + top) * n_mq + mapq - mq_min) * Q + q) * 5 + obs.
+void build_tally_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], const uint64_t qual_count[128],
+                        ScoreParams& p, std::vector<double>& tallyT, std::vector<HotTerms>& coldT) {
+  const uint32_t Q = p.max_qual;
+  const uint32_t n_st = (uint32_t)(lut.size() / ((size_t)p.n_mapq_slots * Q * 5));
+  uint32_t lo = 255, hi = 0;
+  for (uint32_t m = 0; m < 256; ++m) if (p.mapq_slot[m] != 255) { lo = std::min(lo, m); hi = std::max(hi, m); }
+  p.mq_min = lo; p.n_mq = hi - lo + 1;
+  coldT.assign((size_t)n_st * p.n_mq * Q * 5, HotTerms());
+  for (uint32_t st = 0; st < n_st; ++st) for (uint32_t m = lo; m <= hi; ++m) {
+    if (p.mapq_slot[m] == 255) continue;
+    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
+      const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + p.mapq_slot[m]) * Q + q) * 5 + obs];
+      HotTerms& c = coldT[(((size_t)st * p.n_mq + (m - lo)) * Q + q) * 5 + obs];
+      for (int b = 0; b < 5; ++b) c.L[b] = t.L[b];
+      c.M = t.M;
+    }
+  }
+  // quality window: as many values as eight copies allow inside 227 KB of shared memory, placed over the most records
+  const size_t budget_cells = (size_t)(225 * 1024) / 16;
+  auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * n_st * nq * 4 * copies + copies; };
+  uint32_t q_first = Q, q_last = 0;
+  for (uint32_t q = 0; q < Q && q < 128; ++q) if (qual_count[q]) { q_first = std::min(q_first, q); q_last = q; }
+  if (q_first > q_last) { q_first = 0; q_last = Q ? Q - 1 : 0; }
+  uint32_t want = q_last - q_first + 1, copies = 8, nq = want;
+  while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
+  if (nq < 8 && nq < want) {  // eight copies leave too narrow a window: one copy of everything (or nothing)
+    copies = 1; nq = want;
+    while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
+  }
+  uint32_t best_lo = q_first;
+  if (nq < want) {
+    uint64_t best = 0;
+    for (uint32_t a = q_first; a + nq <= q_last + 1; ++a) {
+      uint64_t mass = 0;
+      for (uint32_t q = a; q < a + nq; ++q) mass += qual_count[q];
+      if (mass > best) { best = mass; best_lo = a; }
+    }
+  }
+  p.t_qlo = best_lo; p.t_nq = nq; p.t_copies = copies; p.t_nhot = n_st * nq * 4;
+  tallyT.assign(cells(nq, copies) * 2, 0.0);
+  const size_t plane = (size_t)p.t_nhot * copies;
+  const uint32_t hot_slot = p.mapq_slot[p.hot_mapq];
+  for (uint32_t st = 0; st < n_st; ++st) for (uint32_t qi = 0; qi < nq; ++qi) for (uint32_t obs = 0; obs < 4; ++obs) {
+    const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + hot_slot) * Q + (best_lo + qi)) * 5 + obs];
+    const size_t h = ((size_t)st * nq + qi) * 4 + obs;
+    for (uint32_t c = 0; c < copies; ++c) {
+      const size_t cell = h * copies + c;
+      tallyT[(0 * plane + cell) * 2 + 0] = t.L[0]; tallyT[(0 * plane + cell) * 2 + 1] = t.L[1];
+      tallyT[(1 * plane + cell) * 2 + 0] = t.L[2]; tallyT[(1 * plane + cell) * 2 + 1] = t.L[3];
+      tallyT[(2 * plane + cell) * 2 + 0] = t.L[4]; tallyT[(2 * plane + cell) * 2 + 1] = t.M;
+    }
   }
 }
 

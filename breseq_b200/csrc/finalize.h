@@ -47,6 +47,10 @@ void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const
 void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], ScoreParams& p,
                       std::vector<HotTerms>& hotL, std::vector<HotRatios>& hotR);
 
+// Shared-memory image and global companion of the tally kernel's likelihood table (needs build_hot_tables first).
+void build_tally_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], const uint64_t qual_count[128],
+                        ScoreParams& p, std::vector<double>& tallyT, std::vector<HotTerms>& coldT);
+
 struct EvidenceParams {
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;
   uint32_t precision_places;

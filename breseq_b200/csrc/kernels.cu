@@ -18,6 +18,7 @@ namespace brq {
 
 static std::atomic<int> g_launches{0};
 int launch_count() { return g_launches.load(); }
+void note_launches(int n) { g_launches += n; }
 
 __device__ __forceinline__ ulonglong2 ld_stream_u64x2(const ulonglong2* p) {
   ulonglong2 v;

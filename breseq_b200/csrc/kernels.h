@@ -33,11 +33,14 @@ struct ColumnOut {
   uint32_t n;              // scoring records (unique, untrimmed, resolvable, quality >= cutoff)
   uint32_t bits;           // [2:0] best [5:3] major [8:6] minor [11:9] variant (5 = N)
                            // [12] base_predicted [13] unique_only [14] emit candidate [15] needs host re-check
-                           // [23:16] EM iterations of the full fit
+                           // [23:16] EM iterations of the full fit [24] the EM fit was evaluated (else: no scoring
+                           // record, or the presence bound proves the column cannot emit an RA row; major, minor
+                           // and variant read 5 and variant_score NaN)
 };
 static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
 
-constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15;
+constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15,
+                   CO_FIT = 1u << 24;
 
 struct ScoreParams {
   double log10_ref_length;
@@ -49,6 +52,11 @@ struct ScoreParams {
   uint8_t mapq_slot[256];    // MAPQ -> slot, 255 = absent
   uint32_t hot_mapq;         // the dominant MAPQ value, whose class terms are staged in shared memory
   uint32_t n_hot;            // entries of the hot tables (max_set * 2 * max_qual * 5), 0 = disabled
+  uint32_t fit_all;          // evaluate the EM fit on every column with scoring records (diagnostics / parity runs)
+  // shared-memory likelihood table of the tally kernel: classes (set, strand, quality in [t_qlo, t_qlo + t_nq), A/C/G/T)
+  // of the dominant MAPQ, t_copies interleaved copies (8 = bank-conflict-free, 1 = the copies do not fit)
+  uint32_t t_qlo, t_nq, t_nhot, t_copies;
+  uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
 };
 
 // Per-class likelihood terms, built on the host with the same libm calls the reference makes
@@ -58,13 +66,13 @@ struct ScoreParams {
 struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 
 // Shared-memory forms of the class terms for the dominant MAPQ, indexed ((set*2+top)*Q+qual)*5+obs.
-struct HotTerms { double L[5]; double r2; };   // r2 = max_{b != obs} r[b]; +inf when obs is not the class's best hypothesis
+struct HotTerms { double L[5]; double M; };    // M = max_b L[b]
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
-void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots,
-                        const ClassTerms* lut, const HotTerms* hotL, const HotRatios* hotR, const ScoreParams& p, ColumnOut* out,
-                        uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap, cudaStream_t s,
-                        cudaEvent_t between);
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
+                        const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        cudaStream_t s, cudaEvent_t between);
 
 void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts,
                  uint32_t* err, cudaStream_t s);

@@ -1,27 +1,49 @@
 // Per-slot scoring for sm_100a: a streaming tally kernel and an EM fit kernel.
 //
-//   tally_kernel  one thread per slot (a reference column or an insert sub-column).  The thread
-//                 walks its records in arrival order with 128-bit loads, so coverage tallies and
-//                 the five log-likelihood sums live in registers and nothing is reduced across
-//                 lanes (identify_mutations.cpp:1392-1658, 3398-3433).  The hot path is branch-free:
-//                 a record that does not score reads an all-zero table entry.  A slot whose scoring
-//                 records all show the reference base X, with X every record's best hypothesis and
-//                 every other hypothesis bounded (see `pure`), is final here: the EM cannot lift any
-//                 other allele to the half-read level.  All other non-empty slots go to a work list.
+//   tally_kernel  G lanes per slot (G = 4 for ordinary depth, 32 for deep columns).  A group walks its
+//                 slot's records with 128-bit loads, G consecutive vectors per step, so a warp reads
+//                 32/G runs of G*16 contiguous bytes instead of 32 scattered ones.  Coverage tallies
+//                 and the five log-likelihood sums live in registers and are reduced over the group
+//                 with a log2(G)-step butterfly (identify_mutations.cpp:1392-1658, 3398-3433).  Each
+//                 group handles G consecutive slots one after the other and lane j keeps slot j's
+//                 sums, so the per-slot closing arithmetic (consensus call, emission test, the 96-byte
+//                 result) runs once per lane on 32 different slots.
+//   likelihood table  The kernel is bound by shared-memory wavefronts: every scoring record reads its
+//                 class's {L[0..4], M} (48 B, three 128-bit loads).  The table of the dominant MAPQ is
+//                 therefore kept in three 16-byte planes with EIGHT interleaved copies; lane l reads
+//                 copy l & 7, whose 16-byte cell lies in bank group l & 7, so the eight lanes served by
+//                 one wavefront never collide whatever classes they ask for.  The copies have to fit
+//                 in 227 KB: the table covers a window of quality values chosen from the stream's
+//                 quality histogram (all of them when they fit).  The loop is branch-free: a record
+//                 that does not score reads an all-zero cell.  Scoring records outside the shared
+//                 table (another MAPQ, a '.' observation, a quality outside the window) wait in a
+//                 three-entry register queue and read the full table from global memory when the
+//                 slot is done; a lane that meets more of them rescans its share of the slot.
+//   redundant records  lead each slot's run (staging.cpp): their order-dependent sum of 1/X1
+//                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head.
+//   presence bound  The reference fits the 5-allele EM on every column, but its result only surfaces
+//                 in RA rows, i.e. when best != ref with a positive consensus score or when the
+//                 presence score of the top non-reference allele reaches the polymorphism cutoff
+//                 (identify_mutations.cpp:1789-1836).  The tally carries sum_i M_i (M_i = max_b L_i[b])
+//                 next to the five sums and proves most columns cannot emit:
+//                     L_full <= sum_i M_i                      (every s_i <= 1)
+//                     L_null >= LL_null(EM start)              (EM never lowers the likelihood)
+//                            >= n log10 g0[ref] + ll[ref],     g0[ref] >= (0.5 + c_ref) / (n + 2)
+//                 so  score <= (sum M - ll[ref]) - n log10((0.5 + c_ref)/(n + 2)) - log10(ref length).
+//                 Columns under the cutoff by a margin are final here; the others go to a work list.
 //   fit_kernel    eight lanes per work-list slot: the 5-allele EM fit, the presence score of the
 //                 top non-reference allele (second EM with it held out), emission flags
 //                 (identify_mutations.cpp:1797-1821, 3240-3344).
-//
-// Likelihood terms of the dominant MAPQ value are staged in shared memory (48 B per class, read as
-// three 128-bit loads); records with any other MAPQ read the full table from global memory.
 #include "kernels.h"
 #include "brq_types.h"
 
 namespace brq {
 
+void note_launches(int n);
+
 namespace {
 
-constexpr int TALLY_TPB = 256;
+constexpr int TALLY_TPB = 512;
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 8;      // lanes cooperating on one slot
 constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
@@ -38,6 +60,11 @@ __device__ __forceinline__ f64x2 ldg_f64x2(const void* p) {
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
+__device__ __forceinline__ uint4 ldg_stream_u32x4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ bool eligible(uint32_t r, uint32_t cutoff) {
   return (r & (SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT)) == (SR_UNIQUE_BIT | SR_OK_BIT) && ((r >> SR_QUAL_SHIFT) & 127) >= cutoff;
@@ -51,111 +78,176 @@ __device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p,
   return ((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
 }
 
+template <int G>
+__device__ __forceinline__ double group_add(double v, uint32_t mask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ uint32_t group_add_u32(uint32_t v, uint32_t mask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+  return v;
+}
+
+struct Sums { double l0, l1, l2, l3, l4, m; };
+
+// a scoring record whose class is not in the shared table: {L[0..4], M} from the global table
+__device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
+  const uint32_t st = (r >> 10) & 63u, mapq = (r >> SR_MAPQ_SHIFT) & 255u, qual = (r >> SR_QUAL_SHIFT) & 127u;
+  const char* e = reinterpret_cast<const char*>(coldT + (((st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * 5u + (r & 7u)));
+  const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
+  a.l0 += x.x; a.l1 += x.y; a.l2 += y.x; a.l3 += y.y; a.l4 += z.x; a.m += z.y;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ tally
-__global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+template <int G>
+__global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
                                                               const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
-                                                              const ClassTerms* __restrict__ lut, const HotTerms* __restrict__ hotL,
+                                                              const double* __restrict__ tallyT, const HotTerms* __restrict__ coldT,
                                                               ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
                                                               uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
                                                               uint32_t flagged_cap) {
-  extern __shared__ __align__(16) double sm[];  // n_hot entries of 6 doubles, then one all-zero entry
-  __shared__ uint8_t mapq_slot[256];
+  // three planes of t_nhot * t_copies 16-byte cells ({L0,L1} {L2,L3} {L4,M}), then one zero cell per copy
+  extern __shared__ __align__(16) double sm[];
   __shared__ double inv_red[64];
   {
-    const double* src = reinterpret_cast<const double*>(hotL);
-    for (uint32_t i = threadIdx.x; i < p.n_hot * 6; i += blockDim.x) sm[i] = src[i];
-    if (threadIdx.x < 6) sm[p.n_hot * 6 + threadIdx.x] = 0.0;
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+    const uint32_t n_dbl = (3u * p.t_nhot * p.t_copies + p.t_copies) * 2u;
+    const double2* src = reinterpret_cast<const double2*>(tallyT);
+    double2* dst = reinterpret_cast<double2*>(sm);
+    for (uint32_t i = threadIdx.x; i < n_dbl / 2; i += blockDim.x) dst[i] = src[i];
     if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
   }
   __syncthreads();
-  const uint32_t hot_base = (uint32_t)__cvta_generic_to_shared(sm);
-  const uint32_t zero_addr = hot_base + p.n_hot * 48u;
-  const uint32_t Q = p.max_qual, cutoff = p.base_quality_cutoff;
-  // unique, untrimmed, resolvable -- and, for the shared table, the dominant MAPQ -- as masked compares
+  const uint32_t lane = threadIdx.x & 31u, sub = lane & (uint32_t)(G - 1), g0 = lane - sub;
+  const uint32_t copy_off = (lane & (p.t_copies - 1u)) * 16u, cell_stride = p.t_copies * 16u;
+  const uint32_t plane = p.t_nhot * cell_stride;
+  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + copy_off;
+  const uint32_t zero_addr = tbl + 3u * plane;
+  const uint32_t Q_lo = p.t_qlo, n_q = p.t_nq, cutoff = p.base_quality_cutoff;
+  // unique, untrimmed, resolvable; for the shared table also the dominant MAPQ and an A/C/G/T observation
   const uint32_t flag_mask = SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT, flag_want = SR_UNIQUE_BIT | SR_OK_BIT;
-  const uint32_t hot_mask = flag_mask | (255u << SR_MAPQ_SHIFT);
-  // without a shared table no record can match: every scoring record takes the global path
-  const uint32_t hot_want = p.n_hot ? (flag_want | (p.hot_mapq << SR_MAPQ_SHIFT)) : 0xFFFFFFFFu;
+  const uint32_t hot_mask = flag_mask | (255u << SR_MAPQ_SHIFT) | 4u;
+  const uint32_t hot_want = p.t_nhot ? (flag_want | (p.hot_mapq << SR_MAPQ_SHIFT)) : 0xFFFFFFFFu;  // no table: nothing matches
 
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  const uint64_t stride = (uint64_t)gridDim.x * TALLY_TPB;
-  for (uint64_t slot = (uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x; slot < n_slots; slot += stride) {
-    const uint64_t beg = off[slot], end = off[slot + 1];
-    uint32_t tops = 0, raw_top = 0, raw_bot = 0, n = 0, obs_mask = 0;
-    double red_top = 0.0, red_bot = 0.0, r2max = 0.0;
-    double ll0 = 0.0, ll1 = 0.0, ll2 = 0.0, ll3 = 0.0, ll4 = 0.0;
+  const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << g0);
+  const uint64_t n_rounds = (n_slots + 31) >> 5;  // a warp takes 32 consecutive slots per round
+  const uint64_t n_warps = (uint64_t)gridDim.x * (TALLY_TPB / 32);
+  for (uint64_t round = ((uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x) >> 5; round < n_rounds; round += n_warps) {
+    const uint64_t my_slot = (round << 5) + lane;  // the slot this lane closes; its group tallies slots g0 .. g0+G-1
+    uint64_t my_beg = 0, my_end = 0;
+    uint32_t my_ref = 5;
+    if (my_slot < n_slots) { my_beg = off[my_slot]; my_end = off[my_slot + 1]; my_ref = slot_ref[my_slot]; }
+    Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double red_top = 0.0, red_bot = 0.0;
+    uint32_t tops = 0, n = 0, c_ref = 0, raw_top = 0, raw_bot = 0;
 
-    // 128-bit loads from the aligned vector that holds the slot's first record; all index math is
-    // 32-bit and relative to the slot.  Elements outside the slot are zeroed: a zero record has no
-    // flag set, scores nothing and reads the all-zero table entry.
-    const uint32_t head = (uint32_t)beg & 3u, cnt = (uint32_t)(end - beg);
-    const uint32_t n_vec = (head + cnt + 3u) >> 2;
-    const uint4* vp = reinterpret_cast<const uint4*>(rec + (beg - head));
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (n_vec) cur = __ldg(vp);
-    for (uint32_t iv = 0; iv < n_vec; ++iv) {
-      uint4 nxt = make_uint4(0, 0, 0, 0);
-      if (iv + 1 < n_vec) nxt = __ldg(vp + iv + 1);  // requested before `cur` is consumed
-      const uint32_t k0 = iv * 4u - head;              // slot-relative index of element 0 (wraps below zero)
-      uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
-      uint32_t addr[4], n_flag_ok = 0, n_hot_here = 0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        r[j] = (k0 + (uint32_t)j < cnt) ? r[j] : 0u;
-        const uint32_t qual = (r[j] >> SR_QUAL_SHIFT) & 127u;
-        const bool qual_ok = qual >= cutoff;
-        const bool flags_ok = (r[j] & flag_mask) == flag_want;
-        const bool hotp = qual_ok && (r[j] & hot_mask) == hot_want;   // flags and MAPQ in one compare
-        tops += (r[j] >> 10) & 1u;
-        n_flag_ok += (flags_ok && qual_ok) ? 1u : 0u;
-        n_hot_here += hotp ? 1u : 0u;
-        const uint32_t e = ((((r[j] >> 10) & 63u) * Q + qual) * 5u + (r[j] & 7u)) * 48u;
-        addr[j] = hotp ? hot_base + e : zero_addr;
-        obs_mask |= hotp ? (1u << (r[j] & 7u)) : 0u;
-      }
-      n += n_hot_here;
-      f64x2 a[4], b[4], c[4];  // L[0..1], L[2..3], {L[4], r2}: all twelve loads in flight together
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { a[j] = lds_f64x2(addr[j]); b[j] = lds_f64x2(addr[j] + 16); c[j] = lds_f64x2(addr[j] + 32); }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // arrival order; the zero entry adds +0.0 exactly
-        ll0 += a[j].x; ll1 += a[j].y; ll2 += b[j].x; ll3 += b[j].y; ll4 += c[j].x;
-        r2max = fmax(r2max, c[j].y);
-      }
-      if (n_flag_ok != n_hot_here) {  // scoring records with another MAPQ: full table in global memory
+#pragma unroll 1
+    for (int k = 0; k < G; ++k) {
+      const uint64_t beg = __shfl_sync(gmask, my_beg, g0 + k), end = __shfl_sync(gmask, my_end, g0 + k);
+      const uint32_t ref = __shfl_sync(gmask, my_ref, g0 + k);
+      Sums a = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      uint32_t t_tops = 0, t_n = 0, t_cref = 0;
+      uint32_t cq0 = 0, cq1 = 0, cq2 = 0, n_cold = 0;
+
+      // 128-bit loads from the aligned vector that holds the slot's first record; all index math is
+      // 32-bit and relative to the slot.  Elements outside the slot are zeroed: a zero record has no
+      // flag set, scores nothing and reads the all-zero cell.
+      const uint32_t head = (uint32_t)beg & 3u, cnt = (uint32_t)(end - beg);
+      const uint32_t n_vec = (head + cnt + 3u) >> 2;
+      const uint32_t n_it = (n_vec + (uint32_t)G - 1u) / (uint32_t)G;  // the same for every lane of the group
+      const uint4* vp = reinterpret_cast<const uint4*>(rec + (beg - head));
+      uint32_t first = SR_UNIQUE_BIT;  // the slot's first record, for the redundant walk below
+      if (cnt) first = __ldg(rec + beg);
+      uint4 cur = make_uint4(0, 0, 0, 0);
+      if (sub < n_vec) cur = ldg_stream_u32x4(vp + sub);
+      for (uint32_t it = 0; it < n_it; ++it) {
+        const uint32_t iv = it * (uint32_t)G + sub;
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (iv + (uint32_t)G < n_vec) nxt = ldg_stream_u32x4(vp + iv + G);  // requested before `cur` is consumed
+        const uint32_t rem = head + cnt - iv * 4u, lo = iv ? 0u : head;      // valid elements: lo <= j < rem
+        uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
+        uint32_t addr[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool cold = (r[j] & flag_mask) == flag_want && ((r[j] >> SR_QUAL_SHIFT) & 127u) >= cutoff && (r[j] & hot_mask) != hot_want;
-          if (!cold) continue;
-          const char* e = reinterpret_cast<const char*>(lut + cold_index(r[j], p, mapq_slot));
-          const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
-          ll0 += x.x; ll1 += x.y; ll2 += y.x; ll3 += y.y; ll4 += z.x;
-          r2max = fmax(r2max, z.y);
-          obs_mask |= 1u << (r[j] & 7u);
-          ++n;
+          r[j] = ((uint32_t)j >= lo && (uint32_t)j < rem && iv < n_vec) ? r[j] : 0u;
+          const uint32_t qual = (r[j] >> SR_QUAL_SHIFT) & 127u, qrel = qual - Q_lo;
+          const bool scoring = (r[j] & flag_mask) == flag_want && qual >= cutoff;
+          const bool hotp = (r[j] & hot_mask) == hot_want && qrel < n_q && qual >= cutoff;
+          t_tops += (r[j] >> 10) & 1u;
+          t_n += scoring ? 1u : 0u;
+          t_cref += (scoring && (r[j] & 7u) == ref) ? 1u : 0u;
+          const uint32_t cell = ((((r[j] >> 10) & 63u) * n_q + qrel) * 4u + (r[j] & 3u)) * cell_stride;
+          addr[j] = hotp ? tbl + cell : zero_addr;
+          if (scoring && !hotp) { cq2 = cq1; cq1 = cq0; cq0 = r[j]; ++n_cold; }
         }
-      }
-      if (!(r[0] & r[1] & r[2] & r[3] & SR_UNIQUE_BIT)) {  // a redundant record (or a zeroed element) is present
+        const uint32_t pstep[4] = {addr[0] == zero_addr ? 0u : plane, addr[1] == zero_addr ? 0u : plane,
+                                   addr[2] == zero_addr ? 0u : plane, addr[3] == zero_addr ? 0u : plane};
+        f64x2 x[4], y[4], z[4];  // {L0,L1}, {L2,L3}, {L4,M}: all twelve loads in flight together
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // order-dependent double sum, arrival order (identify_mutations.cpp:1605)
-          if ((r[j] & SR_UNIQUE_BIT) || r[j] == 0u) continue;
-          const uint32_t red = (r[j] >> SR_RED_SHIFT) & SR_RED_MASK;
-          const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-          if (r[j] & SR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
+        for (int j = 0; j < 4; ++j) { x[j] = lds_f64x2(addr[j]); y[j] = lds_f64x2(addr[j] + pstep[j]); z[j] = lds_f64x2(addr[j] + 2u * pstep[j]); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // the zero cell adds +0.0 exactly
+          a.l0 += x[j].x; a.l1 += x[j].y; a.l2 += y[j].x; a.l3 += y[j].y; a.l4 += z[j].x; a.m += z[j].y;
         }
+        cur = nxt;
       }
-      cur = nxt;
+      // scoring records outside the shared table
+      if (n_cold > 3) {  // the queue overflowed: rescan this lane's share of the slot
+        for (uint32_t it = 0; it < n_it; ++it) {
+          const uint32_t iv = it * (uint32_t)G + sub;
+          if (iv >= n_vec) break;
+          const uint4 v = __ldg(vp + iv);
+          const uint32_t rem = head + cnt - iv * 4u, lo = iv ? 0u : head;
+          const uint32_t rr[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if ((uint32_t)j < lo || (uint32_t)j >= rem) continue;
+            const uint32_t qual = (rr[j] >> SR_QUAL_SHIFT) & 127u;
+            const bool scoring = (rr[j] & flag_mask) == flag_want && qual >= cutoff;
+            const bool hotp = (rr[j] & hot_mask) == hot_want && (qual - Q_lo) < n_q;
+            if (scoring && !hotp) cold_add(a, rr[j], coldT, p);
+          }
+        }
+      } else {
+        if (n_cold > 2) cold_add(a, cq2, coldT, p);
+        if (n_cold > 1) cold_add(a, cq1, coldT, p);
+        if (n_cold > 0) cold_add(a, cq0, coldT, p);
+      }
+      // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
+      // every lane of the group alike (identify_mutations.cpp:1605)
+      double rt = 0.0, rb = 0.0;
+      uint32_t t_rawt = 0, t_rawb = 0;
+      for (uint32_t i = 0; !(first & SR_UNIQUE_BIT);) {
+        const uint32_t red = (first >> SR_RED_SHIFT) & SR_RED_MASK;
+        const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
+        if (first & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
+        if (++i == cnt) break;
+        first = __ldg(rec + beg + i);
+      }
+      a.l0 = group_add<G>(a.l0, gmask); a.l1 = group_add<G>(a.l1, gmask); a.l2 = group_add<G>(a.l2, gmask);
+      a.l3 = group_add<G>(a.l3, gmask); a.l4 = group_add<G>(a.l4, gmask); a.m = group_add<G>(a.m, gmask);
+      t_tops = group_add_u32<G>(t_tops, gmask); t_n = group_add_u32<G>(t_n, gmask); t_cref = group_add_u32<G>(t_cref, gmask);
+      if (sub == (uint32_t)k) {
+        kept = a; red_top = rt; red_bot = rb;
+        tops = t_tops; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
+      }
     }
-    // every record of the slot is either unique or redundant; top-strand counts follow by subtraction
-    const uint32_t u_all = cnt - raw_top - raw_bot, u_top = tops - raw_top;
+    if (my_slot >= n_slots) continue;
 
-    const uint32_t ref = slot_ref[slot];
-    const double ll[5] = {ll0, ll1, ll2, ll3, ll4};
+    // every record of the slot is either unique or redundant; top-strand counts follow by subtraction
+    const uint32_t cnt = (uint32_t)(my_end - my_beg);
+    const uint32_t u_all = cnt - raw_top - raw_bot, u_top = tops - raw_top;
+    const uint32_t ref = my_ref;
+    const double ll[5] = {kept.l0, kept.l1, kept.l2, kept.l3, kept.l4};
     double consensus = nan;
     uint32_t best = 5;
+    bool need_fit = false;
+    const double slack = 1e-6;
     if (n > 0) {  // pure_genotype_call, identify_mutations.cpp:3398-3433
       best = 0;
 #pragma unroll
@@ -172,18 +264,18 @@ __global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __r
         tot += (d == 0.0) ? 1.0 : (d < -17.0 ? 0.0 : pow(10.0, d));
       }
       consensus = (ll[best] - (log10(tot) + offv)) - p.log10_ref_length;
+      // an RA row needs best != ref with a positive consensus score, or a presence score at the cutoff
+      need_fit = p.fit_all != 0u || ref >= 5u || (best != ref && consensus > -slack);
+      if (!need_fit) {
+        const double ll_ref = ref == 0 ? ll[0] : ref == 1 ? ll[1] : ref == 2 ? ll[2] : ref == 3 ? ll[3] : ll[4];
+        const double bound = (kept.m - ll_ref) - (double)n * log10(((double)c_ref + 0.5) / ((double)n + 2.0)) - p.log10_ref_length;
+        need_fit = !(bound < p.polymorphism_cutoff - slack);
+      }
     }
-    const double slack = 1e-6;
     const bool base_predicted = consensus >= p.mutation_cutoff;
     const bool recheck = n > 0 && fabs(consensus - p.mutation_cutoff) < slack;
 
-    // `pure`: every scoring record shows the reference base X, X is each record's most likely true
-    // base (r2 is +inf otherwise), and every other hypothesis b has r_i(b) <= f0[X] = (n+0.5)/(n+2.5).
-    // Then s_i >= f[X] in every iteration, so f[b] only shrinks from 0.5/(n+2.5) < 0.5/n while f[X]
-    // grows: the fit reports major = X and neither a minor nor a variant allele, and the reference
-    // computes no presence score (identify_mutations.cpp:1806-1821).
-    const bool pure = n > 0 && ref < 5 && obs_mask == (1u << ref) && r2max <= ((double)n + 0.5) / ((double)n + 2.5);
-    uint32_t bits = best | ((pure ? ref : 5u) << 3) | (5u << 6) | (5u << 9);
+    uint32_t bits = best | (5u << 3) | (5u << 6) | (5u << 9);
     if (base_predicted) bits |= CO_BASE_PREDICTED;
     if (raw_top + raw_bot == 0) bits |= CO_UNIQUE_ONLY;
     if (recheck) bits |= CO_RECHECK;
@@ -195,10 +287,10 @@ __global__ void __launch_bounds__(TALLY_TPB, 3) tally_kernel(const uint32_t* __r
     o.redundant[0] = red_bot; o.redundant[1] = red_top;
     o.unique[0] = u_all - u_top; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
-    out[slot] = o;
+    out[my_slot] = o;
 
-    if (n > 0 && !pure) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)slot;
-    else if (recheck) { const uint32_t k = atomicAdd(&scalars[1], 1u); if (k < flagged_cap) flagged[k] = (uint32_t)slot; }
+    if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)my_slot;
+    else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = (uint32_t)my_slot; }
   }
 }
 
@@ -258,13 +350,14 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
   extern __shared__ __align__(16) double sm[];
   __shared__ uint8_t mapq_slot[256];
   __shared__ uint32_t cache[FIT_TPB / FIT_LANES][FIT_CACHE];
+  const uint32_t n_work = scalars[2];
+  if ((uint64_t)blockIdx.x * (FIT_TPB / FIT_LANES) >= n_work) return;  // the work list is short: most CTAs have nothing to do
   {
     const double* src = reinterpret_cast<const double*>(hotR);
     for (uint32_t i = threadIdx.x; i < p.n_hot * 6; i += blockDim.x) sm[i] = src[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
   }
   __syncthreads();
-  const uint32_t n_work = scalars[2];
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   const uint32_t lane = threadIdx.x & 31;
   GroupCtx g;
@@ -385,7 +478,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     bool emit = false;
     if (best != ref && consensus > -slack) emit = true;
     if (variant != 5 && variant_score >= p.polymorphism_cutoff - slack) emit = true;
-    bits = (bits & ~(0xFFFu | CO_EMIT | CO_RECHECK | (0xFFu << 16))) | best | (major << 3) | (minor << 6) | (variant << 9) | (iterations << 16);
+    bits = (bits & ~(0xFFFu | CO_EMIT | CO_RECHECK | (0xFFu << 16))) | best | (major << 3) | (minor << 6) | (variant << 9) | (iterations << 16) | CO_FIT;
     if (emit) bits |= CO_EMIT;
     if (recheck) bits |= CO_RECHECK;
     if (g.sub == 0) {
@@ -397,19 +490,27 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
   }
 }
 
-void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots,
-                        const ClassTerms* lut, const HotTerms* hotL, const HotRatios* hotR, const ScoreParams& p, ColumnOut* out,
-                        uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap, cudaStream_t s,
-                        cudaEvent_t between) {
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
+                        const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem_tally = ((size_t)p.n_hot + 1) * 48, smem_fit = (size_t)p.n_hot * 48;
-  cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-  int blocks = (int)std::min<uint64_t>((n_slots + TALLY_TPB - 1) / TALLY_TPB, (uint64_t)kSMs * 3);
-  tally_kernel<<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, lut, hotL, p, out, worklist, flagged, scalars, flagged_cap);
+  const size_t smem_tally = ((size_t)3 * p.t_nhot * p.t_copies + p.t_copies) * 16, smem_fit = (size_t)p.n_hot * 48;
+  const uint64_t n_rounds = (n_slots + 31) / 32;
+  const int blocks = (int)std::min<uint64_t>((n_rounds + TALLY_TPB / 32 - 1) / (TALLY_TPB / 32), (uint64_t)kSMs);
+  // lanes per slot: 4 at ordinary depth, a whole warp once the mean column is deeper than 512 records
+  if (n_records / n_slots < 512) {
+    cudaFuncSetAttribute(tally_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
+    tally_kernel<4><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
+  } else {
+    cudaFuncSetAttribute(tally_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
+    tally_kernel<32><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
+  }
   if (between) cudaEventRecord(between, s);
+  cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  note_launches(2);
 }
 
 }  // namespace brq

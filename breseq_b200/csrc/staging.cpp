@@ -298,6 +298,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
 
   // ---- pass A2: record counts per slot
   std::vector<uint32_t> score_cnt(cfg.want_score ? n_slots : 0, 0), hist_cnt(cfg.want_hist ? out.n_base : 0, 0);
+  std::vector<uint32_t> red_cnt(cfg.want_score ? n_slots : 0, 0);  // redundant records per slot: they lead the slot's run
   std::vector<uint8_t> col_red(cfg.want_hist ? out.n_base : 0, 0);
   run_items([&](size_t ii) {
     const Item& it = items[ii];
@@ -312,12 +313,15 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
         if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
         if (cfg.want_score) {
-          if (is_del || seq[q] != 15) ++score_cnt[slot];
+          if (is_del || seq[q] != 15) { ++score_cnt[slot]; if (!unique) ++red_cnt[slot]; }
           uint32_t K = sub_k[slot];
           if (K) {
             int ind = is_del ? -1 : std::max(indel, 0);
             for (uint32_t k = 1; k <= K; ++k)
-              if (ind < (int)k || seq[q + (int32_t)k] != 15) ++score_cnt[out.n_base + sub_first[slot] + k - 1];
+              if (ind < (int)k || seq[q + (int32_t)k] != 15) {
+                ++score_cnt[out.n_base + sub_first[slot] + k - 1];
+                if (!unique) ++red_cnt[out.n_base + sub_first[slot] + k - 1];
+              }
           }
         }
       });
@@ -361,11 +365,15 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   out.score_rec = (uint32_t*)alloc(out.n_score * 4, &p2);
   out.hist_rec = (uint64_t*)alloc(out.n_hist * 8, &p2);
 
-  // ---- pass B: fill, arrival (BAM) order within every slot
-  std::vector<uint32_t>& score_cur = score_cnt;  // reused as per-slot cursors
+  // ---- pass B: fill.  Within every slot the redundant records come first and the unique ones
+  // follow, each part in arrival (BAM) order: redundant records never score, so the scoring records
+  // keep the reference's order, and the order-dependent sum of 1/X1 only has to walk the slot's head.
+  std::vector<uint32_t>& score_cur = score_cnt;  // reused as per-slot cursors: unique records start after the redundant ones
+  std::vector<uint32_t>& red_cur = red_cnt;
   std::vector<uint32_t>& hist_cur = hist_cnt;
-  std::fill(score_cur.begin(), score_cur.end(), 0);
+  for (size_t s = 0; s < score_cur.size(); ++s) { score_cur[s] = red_cnt[s]; red_cur[s] = 0; }
   std::fill(hist_cur.begin(), hist_cur.end(), 0);
+  std::vector<uint64_t> qual_counts((size_t)items.size() * 128, 0);
   std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
   std::vector<uint64_t> mapq_counts((size_t)items.size() * 256, 0);
   std::vector<uint32_t> max_quals(items.size(), 0);
@@ -381,6 +389,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     };
     uint32_t* mq_mask = &mapq_masks[ii * 8];
     uint64_t* mq_count = &mapq_counts[ii * 256];
+    uint64_t* q_count = &qual_counts[ii * 128];
     uint32_t max_q = 0;
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
@@ -475,7 +484,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
               uint32_t qv = qual[qp];
               if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
               rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
-              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); ++mq_count[mapq]; if (qv > max_q) max_q = qv; }
+              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); ++mq_count[mapq]; ++q_count[qv]; if (qv > max_q) max_q = qv; }
             }
             rec |= mapq << SR_MAPQ_SHIFT;
             rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
@@ -483,7 +492,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
             rec |= red << SR_RED_SHIFT;
           }
           uint64_t s = k == 0 ? slot : out.n_base + sub_first[slot] + k - 1;
-          out.score_rec[out.score_off[s] + score_cur[s]++] = rec;
+          out.score_rec[out.score_off[s] + (unique ? score_cur[s]++ : red_cur[s]++)] = rec;
         }
       });
     }
@@ -492,6 +501,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   for (size_t ii = 0; ii < items.size(); ++ii) {
     for (int w = 0; w < 8; ++w) out.mapq_seen[w] |= mapq_masks[ii * 8 + (size_t)w];
     for (int m = 0; m < 256; ++m) out.mapq_count[m] += mapq_counts[ii * 256 + (size_t)m];
+    for (int q = 0; q < 128; ++q) out.qual_count[q] += qual_counts[ii * 128 + (size_t)q];
     out.max_qual_seen = std::max(out.max_qual_seen, max_quals[ii]);
   }
 }

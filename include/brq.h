@@ -111,14 +111,21 @@ typedef struct brq_score_params {
   uint32_t polymorphism_precision_places;
   uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff */
   uint64_t total_reference_length;         /* 0 = sum of BAM target lengths (identify_mutations.cpp:848-852) */
+  uint32_t flags;                          /* BRQ_SCORE_* */
+  uint32_t reserved;
 } brq_score_params;
+
+/* The reference fits the allele frequencies on every column (identify_mutations.cpp:1797) but only RA rows show the
+ * result.  By default the kernel first bounds each column's presence score from above and runs the fit only where an RA
+ * row is possible; this flag forces the fit on every column with scoring records (diagnostics, parity runs). */
+#define BRQ_SCORE_FIT_ALL_COLUMNS 1u
 
 typedef struct brq_column {  /* one per slot: base columns of the visited targets, then insert sub-columns */
   double ll[5];
   double consensus_score, variant_score;
   double redundant[2];                     /* [0] bottom strand, [1] top strand */
   uint32_t unique[2], raw_redundant[2];
-  uint32_t n, bits;
+  uint32_t n, bits;                        /* bits: kernels.h ColumnOut; bit 24 = the EM fit was evaluated for this slot */
 } brq_column;
 
 int brq_score_columns(brq_ctx* ctx, const brq_score_params* p);

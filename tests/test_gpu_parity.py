@@ -17,24 +17,31 @@ pytestmark = pytest.mark.gpu
 REL = 1e-9
 
 
-@pytest.fixture(scope="module", params=list(helpers.DATASETS))
+# "bounded" is the product default: the EM fit runs only where the presence bound cannot rule an RA row out.
+# "fit_all" forces the fit on every column so that every per-column diagnostic can be compared with the oracle.
+@pytest.fixture(scope="module", params=[(n, m) for n in helpers.DATASETS for m in ("bounded", "fit_all")],
+                ids=lambda p: "%s-%s" % p)
 def run(request, datasets, tmp_path_factory):
-    d = datasets[request.param]
-    out = str(tmp_path_factory.mktemp("gpu_" + request.param))
+    name, mode = request.param
+    d = datasets[name]
+    out = str(tmp_path_factory.mktemp("gpu_%s_%s" % (name, mode)))
     ctx = bq.Context(device=0)
     ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
     ctx.error_count(helpers.covariates(d))
     counts, cov = ctx.hist_download()
     ctx.derive_error_table()
     ctx.write_error_count_files(out, os.path.join(out, "error_rates.tab"), helpers.readfile_names(d))
-    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"]))
+    params = bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"],
+                                     fit_all_columns=(mode == "fit_all"))
+    ctx.score_columns(params)
     cols, flagged = ctx.columns_download()
     n = len(d["contig_lens"])
     gd = os.path.join(out, "ra_mc_evidence.gd")
     stats = ctx.write_evidence(gd, [d["del_prop"]] * n, [d["del_seed"]] * n)
     o = helpers.oracle_columns(d["oracle_columns"])
     slot = helpers.oracle_slots(o, ctx.stream(), helpers.visit_slot0(helpers.contig_names(d), d["contig_lens"]))
-    yield dict(d=d, out=out, counts=counts, cov=cov, cols=cols, flagged=flagged, gd=gd, stats=stats, o=o, g=cols[slot], ctx=ctx)
+    yield dict(d=d, out=out, counts=counts, cov=cov, cols=cols, flagged=flagged, gd=gd, stats=stats, o=o, g=cols[slot], ctx=ctx,
+               mode=mode, params=params)
     ctx.close()
 
 
@@ -71,8 +78,21 @@ def test_log_likelihoods_and_scores(run):
     scale = np.maximum(np.abs(o["ll"][m]).max(axis=1), 1.0)
     assert (np.abs(g["consensus_score"][m] - o["consensus_score"][m]) / scale).max() < REL
     assert np.all(np.isnan(g["consensus_score"][~m])) and np.all(np.isnan(o["consensus_score"][~m]))
+    fit = (g["bits"] & bq.CO_FIT) != 0
     v = ~np.isnan(o["variant_score"])
-    assert np.array_equal(v, ~np.isnan(g["variant_score"]))
+    if run["mode"] == "fit_all":
+        assert np.array_equal(fit, m)
+    else:
+        # a column the kernel did not fit has no scoring record, or provably cannot emit an RA row
+        assert not np.any(fit & ~m)
+        skipped = m & ~fit
+        assert skipped.sum() > 0.5 * m.sum(), "the presence bound should settle most columns"
+        assert not np.any(o["emitted"][skipped])
+        vs = o["variant_score"][skipped & v]
+        assert vs.size == 0 or vs.max() < run["d"]["polymorphism_cutoff"]
+        assert np.all(np.isnan(g["variant_score"][~fit]))
+    assert np.array_equal(v[fit], ~np.isnan(g["variant_score"][fit]))
+    v &= fit
     scale_v = np.maximum(np.abs(o["log10_likelihood"][v]), 1.0)
     assert (np.abs(g["variant_score"][v] - o["variant_score"][v]) / scale_v).max() < 1e-7  # the EM stops at |df| < 1e-6
 
@@ -80,16 +100,19 @@ def test_log_likelihoods_and_scores(run):
 def test_calls_and_decisions_identical(run):
     g, o = run["g"], run["o"]
     bits = g["bits"]
-    for name, shift in (("best", 0), ("major", 3), ("minor", 6), ("variant", 9)):
-        assert np.array_equal((bits >> shift) & 7, o[name]), name
+    fit = (bits & bq.CO_FIT) != 0
+    assert np.array_equal(bits & 7, o["best"])
+    for name, shift in (("major", 3), ("minor", 6), ("variant", 9)):
+        assert np.array_equal(((bits >> shift) & 7)[fit], o[name][fit]), name
+        assert np.all(((bits >> shift) & 7)[~fit] == 5), name
     recheck = (bits & bq.CO_RECHECK) != 0
     pred = (bits & bq.CO_BASE_PREDICTED) != 0
     assert np.array_equal(pred[~recheck], o["base_predicted"][~recheck].astype(bool))
     emit = (bits & bq.CO_EMIT) != 0
     assert np.all(emit[o["emitted"] == 1]), "an oracle RA call was not flagged by the kernel"
     # EM iteration counts are reported for the slots that needed a fit; they follow the reference's
-    fitted = ((bits >> 16) & 0xFF) > 0
-    assert np.mean(((bits >> 16) & 0xFF)[fitted] == o["iterations"][fitted]) > 0.999
+    assert np.array_equal(((bits >> 16) & 0xFF) > 0, fit)
+    assert np.mean(((bits >> 16) & 0xFF)[fit] == o["iterations"][fit]) > 0.999
 
 
 def test_genome_diff_identical(run):
@@ -132,7 +155,7 @@ def test_idempotent_and_order_free(run):
     counts, cov = ctx.hist_download()
     assert np.array_equal(counts, run["counts"]) and np.array_equal(cov, run["cov"])
     ctx.derive_error_table()
-    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"]))
+    ctx.score_columns(run["params"])
     cols, _ = ctx.columns_download()
     for f in ("unique", "raw_redundant", "n", "redundant"):
         assert np.array_equal(cols[f], run["cols"][f])

@@ -56,6 +56,16 @@ def test_score_stream_tallies_match_oracle(staged):
     assert np.array_equal(s["slot_ref"][slot], o["ref"])
 
 
+def test_redundant_records_lead_each_slot(staged):
+    """Stream layout the scoring kernel relies on: within a slot, redundant records first, then unique ones."""
+    d, ctx, s = staged
+    uniq = ((s["score_rec"] >> 24) & 1).astype(np.int8)
+    off = s["score_off"].astype(np.int64)
+    step_down = np.nonzero(np.diff(uniq) < 0)[0] + 1   # a unique record followed by a redundant one ...
+    assert np.all(np.isin(step_down, off)), "... is only allowed across a slot boundary"
+    assert (uniq == 0).sum() > 0
+
+
 def test_shards_partition_the_stream(datasets):
     d = datasets["multi"]
     full = bq.Context(device=-1)

@@ -52,7 +52,8 @@ class _SynthSpec(C.Structure):
 
 class _StreamInfo(C.Structure):
     _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
-                ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("bytes_host", C.c_uint64),
+                ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
+                ("bytes_host", C.c_uint64),
                 ("n_targets", C.c_uint32), ("pinned", C.c_uint32),
                 ("score_rec", C.POINTER(C.c_uint32)), ("score_off", C.POINTER(C.c_uint64)),
                 ("hist_rec", C.POINTER(C.c_uint64)), ("hist_off", C.POINTER(C.c_uint64)),
@@ -200,6 +201,14 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
     return o, keep
 
 
+def slot_ranges(stream):
+    """(first index, record count) of every slot's run in ``score_rec`` (padding excluded)."""
+    off = stream["score_off"]
+    beg = (off[:-1] & ~np.uint64(3)).astype(np.int64)
+    end = ((off[1:] & ~np.uint64(3)) - (off[1:] & np.uint64(3))).astype(np.int64)
+    return beg, end - beg
+
+
 class Context:
     """One pileup context = one GPU (``device`` >= 0) or host-only staging (``device`` = -1)."""
 
@@ -255,7 +264,8 @@ class Context:
         return {
             "n_base": info.n_base, "n_ins": info.n_ins, "n_score": info.n_score_records, "n_hist": info.n_hist_records,
             "n_reads": info.n_reads, "bytes_host": info.bytes_host, "pinned": bool(info.pinned), "n_targets": info.n_targets,
-            "score_rec": view(info.score_rec, info.n_score_records, np.uint32),
+            "n_score_padded": info.n_score_padded,
+            "score_rec": view(info.score_rec, info.n_score_padded, np.uint32),
             "score_off": view(info.score_off, n_slots + 1, np.uint64),
             "hist_rec": view(info.hist_rec, info.n_hist_records, np.uint64),
             "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),

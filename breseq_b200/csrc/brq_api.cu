@@ -77,11 +77,12 @@ struct brq_ctx {
   DevBuf<HotTerms> d_coldT;
   DevBuf<double> d_tallyT;
   DevBuf<HotRatios> d_hotR;
-  std::vector<HotTerms> h_hotL, h_coldT;
-  std::vector<double> h_tallyT;
-  std::vector<HotRatios> h_hotR;
+  DevBuf<double> d_prob;
+  DevBuf<uint8_t> d_slot_mapq;
+  uint8_t h_slot_mapq[256];
+  TableGeometry geo;
+  bool have_device_tables = false;
   float ms_tally = 0, ms_fit = 0;
-  bool warp_mode = false;
   DevBuf<ColumnOut> d_cols;
 
   CovSpec spec;
@@ -184,9 +185,9 @@ void upload(brq_ctx* c) {
   if (!c->staged) throw std::runtime_error("nothing staged");
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
-  c->d_score_rec.ensure(st.n_score + 4); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
+  c->d_score_rec.ensure(st.n_score_padded + 4); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
   c->d_hist_rec.ensure(st.n_hist); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
-  CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * 8, cudaMemcpyHostToDevice, c->stream));
@@ -233,25 +234,46 @@ void download_hist(brq_ctx* c) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-void install_table(brq_ctx* c) {  // h_log10 -> text-canonical probabilities -> class table on the device
+// h_log10 -> text-canonical probabilities (host: the reference's ostream / strtod round trip) -> every
+// likelihood table of pass 2, built on the device.  No synchronisation: the scoring kernels are
+// stream-ordered behind the table build.
+void install_table(brq_ctx* c) {
   canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob);
   c->have_table = true;
-  if (c->staged) {
-    build_class_lut(c->spec, c->h_prob, c->st.mapq_seen, c->sp, c->h_lut);
-    build_hot_tables(c->h_lut, c->st.mapq_count, c->sp, c->h_hotL, c->h_hotR);
-    build_tally_tables(c->h_lut, c->st.mapq_count, c->st.qual_count, c->sp, c->h_tallyT, c->h_coldT);
-    if (c->device >= 0) {
-      c->d_lut.ensure(c->h_lut.size());
-      c->d_tallyT.ensure(c->h_tallyT.size());
-      c->d_coldT.ensure(c->h_coldT.size());
-      c->d_hotR.ensure(c->h_hotR.size());
-      CUDA_OK(cudaMemcpyAsync(c->d_lut.p, c->h_lut.data(), c->h_lut.size() * sizeof(ClassTerms), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(cudaMemcpyAsync(c->d_tallyT.p, c->h_tallyT.data(), c->h_tallyT.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(cudaMemcpyAsync(c->d_coldT.p, c->h_coldT.data(), c->h_coldT.size() * sizeof(HotTerms), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(cudaMemcpyAsync(c->d_hotR.p, c->h_hotR.data(), c->h_hotR.size() * sizeof(HotRatios), cudaMemcpyHostToDevice, c->stream));
-      CUDA_OK(cudaStreamSynchronize(c->stream));
-    }
+  c->h_lut.clear();  // the host copy (re-evaluation of flagged slots) is rebuilt on demand
+  c->have_device_tables = false;
+  if (!c->staged) return;
+  score_geometry(c->spec, c->st.mapq_seen, c->st.mapq_count, c->st.qual_count, c->sp, c->geo);
+  if (c->device < 0) return;
+  const TableGeometry& g = c->geo;
+  c->d_lut.ensure(g.n_lut);
+  c->d_coldT.ensure(g.n_cold);
+  c->d_hotR.ensure(g.n_hotR);
+  c->d_prob.ensure(c->h_prob.size());
+  c->d_slot_mapq.ensure(g.mapqs.size());
+  if (c->d_tallyT.n != g.n_tally_cells * 2 || !c->d_tallyT.p) {  // absent classes and the zero cells stay zero
+    c->d_tallyT.ensure(g.n_tally_cells * 2);
+    CUDA_OK(cudaMemsetAsync(c->d_tallyT.p, 0, g.n_tally_cells * 16, c->stream));
   }
+  CUDA_OK(cudaMemsetAsync(c->d_coldT.p, 0, g.n_cold * sizeof(HotTerms), c->stream));
+  uint8_t* slot_mapq = c->h_slot_mapq;
+  for (size_t i = 0; i < g.mapqs.size(); ++i) slot_mapq[i] = (uint8_t)g.mapqs[i];
+  CUDA_OK(cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), c->h_prob.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_slot_mapq.p, slot_mapq, g.mapqs.size(), cudaMemcpyHostToDevice, c->stream));
+  TableBuildArgs a;
+  a.prob = c->d_prob.p; a.slot_mapq = c->d_slot_mapq.p;
+  a.n_st = g.n_st; a.n_mapq_slots = (uint32_t)g.mapqs.size(); a.Q = c->sp.max_qual;
+  a.off_set = g.off_set; a.off_ref = g.off_ref; a.off_obs = g.off_obs; a.off_qual = g.off_qual;
+  a.hot_slot = c->sp.mapq_slot[c->sp.hot_mapq];
+  a.lut = c->d_lut.p; a.coldT = c->d_coldT.p; a.hotR = c->d_hotR.p; a.tallyT = c->d_tallyT.p;
+  launch_build_tables(a, c->sp, c->stream);
+  c->have_device_tables = true;
+}
+
+void ensure_host_lut(brq_ctx* c) {
+  if (!c->h_lut.empty()) return;
+  if (!c->have_table || !c->staged) throw std::runtime_error("no error table");
+  build_class_lut(c->spec, c->h_prob, c->sp, c->geo, c->h_lut);
 }
 
 void derive_table(brq_ctx* c) {
@@ -274,7 +296,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->need_device();
   if (!c->uploaded) upload(c);
   if (!c->have_table) throw std::runtime_error("no error table: call brq_derive_error_table or brq_load_error_table first");
-  if (c->h_lut.empty()) install_table(c);
+  if (!c->have_device_tables) install_table(c);
   c->last_params = *p;
   uint64_t total = p->total_reference_length;
   if (!total) for (uint32_t l : c->hdr.target_lens) total += l;
@@ -298,15 +320,9 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->d_flagged.ensure(c->flagged_cap);
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
-  if (c->warp_mode) {  // warp-per-slot class-histogram formulation (deep columns; kept for A/B parity)
-    launch_score(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->d_lut.p, c->sp, c->d_cols.p, c->d_flagged.p,
-                 c->d_scalars.p + 1, c->flagged_cap, c->d_scalars.p, c->stream);
-    CUDA_OK(cudaEventRecord(c->ev[7], c->stream));
-  } else {
-    c->d_worklist.ensure(n_slots);
-    launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
-                       c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
-  }
+  c->d_worklist.ensure(n_slots);
+  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_slot_ref.p, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
+                     c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
@@ -344,6 +360,7 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   ep.skip_missing_coverage_prediction = skip_mc != 0;
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
+  ensure_host_lut(c);
   return write_evidence(gd_file, c->hdr, c->st, c->h_cols, c->h_flagged, c->sp, c->h_lut, ep);
 }
 
@@ -382,8 +399,6 @@ brq_ctx* brq_create(const brq_config* cfg) {
       for (auto& e : c->user_ev) CUDA_OK(cudaEventCreate(&e));
       c->d_scalars.ensure(4);
       CUDA_OK(cudaMemset(c->d_scalars.p, 0, 16));
-      const char* mode = getenv("BRQ_SCORE_MODE");
-      c->warp_mode = mode && std::string(mode) == "warp";
     } catch (const std::exception& e) {
       c->error = std::string("no usable CUDA device: ") + e.what();
       c->device = -2;  // poisoned: every compute call reports the error
@@ -396,7 +411,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -444,7 +459,8 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     memset(info, 0, sizeof *info);
     info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
     info->n_reads = c->reads.size();
-    info->bytes_host = st.n_score * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * 8 + (st.n_base + 1) * 8 + st.n_base;
+    info->n_score_padded = st.n_score_padded;
+    info->bytes_host = st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * 8 + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();

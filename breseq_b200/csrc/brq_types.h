@@ -63,6 +63,10 @@ struct ReadBatch {
 
 // Scoring record, 4 bytes, one per (read, slot) whose base at that slot is not N.  Within a slot the
 // redundant records (X1 > 1) come first and the unique ones follow, each part in arrival order.
+// Every slot's run starts on a 16-byte boundary and is padded to a multiple of four records with
+// zero words (no real record is zero: a redundant one carries X1 >= 2), so the kernels read whole
+// 128-bit vectors that never straddle two slots.  score_off[s] is the run's first index (a multiple
+// of 4); the low two bits of score_off[s + 1] hold the number of pad words that end slot s's run.
 //   [2:0]   obs        base index 0..4 ('.' = 4)
 //   [9:3]   qual       quality chosen by alignment_position_to_covariates (error_count.cpp:1049-1105)
 //   [10]    top        1 = read on the top strand
@@ -101,13 +105,14 @@ struct PileupStream {
   std::vector<uint32_t> ins_count;     // [n_ins] insert_count (>= 1)
   // per slot
   uint8_t* slot_ref = nullptr;         // [n_base + n_ins] reference base index ('.' for sub-columns)
-  uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] CSR into score_rec
+  uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] padded CSR into score_rec (see above; score_slot_range())
   uint64_t* hist_off = nullptr;        // [n_base + 1] CSR into hist_rec; bit 63 of entry c = column c has a redundant read
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records
   uint32_t* score_rec = nullptr;
   uint64_t* hist_rec = nullptr;
-  uint64_t n_score = 0, n_hist = 0;
+  uint64_t n_score = 0, n_hist = 0;    // records (padding not counted)
+  uint64_t n_score_padded = 0;         // words in score_rec
   uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records
   uint64_t mapq_count[256] = {0};      // scoring records per MAPQ value
   uint64_t qual_count[128] = {0};      // scoring records per quality value
@@ -120,5 +125,15 @@ struct PileupStream {
 };
 
 constexpr uint64_t HIST_OFF_REDUNDANT_BIT = 1ull << 63;
+
+// records [beg, end) of slot s in score_rec (padding excluded)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline void score_slot_range(const uint64_t* score_off, uint64_t s, uint64_t& beg, uint64_t& end) {
+  const uint64_t a = score_off[s], b = score_off[s + 1];
+  beg = a & ~3ull;
+  end = (b & ~3ull) - (b & 3ull);
+}
 
 }  // namespace brq

@@ -208,92 +208,42 @@ void write_coverage_distributions(const std::string& dir, const std::vector<uint
 }
 
 // ============================================================================== class table
-void build_class_lut(const CovSpec& c, const std::vector<double>& prob, const uint32_t mapq_seen[8], ScoreParams& p,
-                     std::vector<ClassTerms>& lut) {
+// Geometry of every likelihood table of pass 2 (no transcendental math): MAPQ slots, the dominant
+// MAPQ, the shared-memory table of the fit kernel and the quality window / copy count of the tally
+// kernel's table.  Cheap, so it runs on every table installation; the values are filled in either on
+// the device (build_tables_kernel, tables.cu) or on the host (build_class_lut and friends below).
+void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const uint64_t mapq_count[256], const uint64_t qual_count[128],
+                    ScoreParams& p, TableGeometry& g) {
   if (c.used[COV_READ_POS] || c.used[COV_BASE_REPEAT])
     throw std::runtime_error("scoring with read_pos / base_repeat covariates is not implemented yet");
   if (!c.used[COV_OBS_BASE] || !c.used[COV_REF_BASE] || !c.used[COV_QUALITY])
     throw std::runtime_error("scoring needs ref_base, obs_base and quality covariates");
   const uint32_t n_set = c.used[COV_READ_SET] ? c.maxv[COV_READ_SET] : 1, Q = c.maxv[COV_QUALITY];
   memset(p.mapq_slot, 255, sizeof p.mapq_slot);
-  std::vector<uint32_t> mapqs;
-  for (uint32_t m = 0; m < 256; ++m) if (mapq_seen[m >> 5] >> (m & 31) & 1) { p.mapq_slot[m] = (uint8_t)mapqs.size(); mapqs.push_back(m); }
-  if (mapqs.empty()) { p.mapq_slot[0] = 0; mapqs.push_back(0); }
-  p.n_mapq_slots = (uint32_t)mapqs.size();
+  g.mapqs.clear();
+  for (uint32_t m = 0; m < 256; ++m) if (mapq_seen[m >> 5] >> (m & 31) & 1) { p.mapq_slot[m] = (uint8_t)g.mapqs.size(); g.mapqs.push_back(m); }
+  if (g.mapqs.empty()) { p.mapq_slot[0] = 0; g.mapqs.push_back(0); }
+  p.n_mapq_slots = (uint32_t)g.mapqs.size();
   p.max_qual = Q;
   p.max_set = c.used[COV_READ_SET] ? n_set : 32;
-  lut.assign((size_t)n_set * 2 * mapqs.size() * Q * 5, ClassTerms());
-  auto comp = [](uint32_t b) { return b < 4 ? 3 - b : 4u; };
-  for (uint32_t set = 0; set < n_set; ++set) for (uint32_t top = 0; top < 2; ++top) for (size_t ms = 0; ms < mapqs.size(); ++ms) {
-    // identify_mutations.cpp:3359-3384
-    const double incorrect = pow(10, -(double)mapqs[ms] / 10);
-    const double correct = 1 - incorrect;
-    const double uniform = 1.0 / 5.0;
-    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
-      ClassTerms& t = lut[((((size_t)set * 2 + top) * mapqs.size() + ms) * Q + q) * 5 + obs];
-      const uint32_t o = top ? obs : comp(obs);
-      double mx = -std::numeric_limits<double>::max();
-      for (uint32_t b = 0; b < 5; ++b) {
-        const uint32_t rf = top ? b : comp(b);
-        const uint32_t idx = set * c.offset[COV_READ_SET] + rf * c.offset[COV_REF_BASE] + o * c.offset[COV_OBS_BASE] + q * c.offset[COV_QUALITY];
-        double pr = correct * prob[idx] + incorrect * uniform;
-        if (pr < 0.0) pr = 0.0;
-        t.L[b] = log10(pr);
-        mx = std::max(mx, t.L[b]);
-      }
-      for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
-      t.M = mx;
-      t.r2 = 0.0;
-      for (uint32_t b = 0; b < 5; ++b) if (b != obs) t.r2 = std::max(t.r2, t.r[b]);
-      if (t.r[obs] != 1.0) t.r2 = std::numeric_limits<double>::infinity();
-    }
-  }
-}
-
-void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], ScoreParams& p,
-                      std::vector<HotTerms>& hotL, std::vector<HotRatios>& hotR) {
+  g.n_st = n_set * 2;
+  g.off_set = c.used[COV_READ_SET] ? c.offset[COV_READ_SET] : 0; g.off_ref = c.offset[COV_REF_BASE];
+  g.off_obs = c.offset[COV_OBS_BASE]; g.off_qual = c.offset[COV_QUALITY];
+  g.n_lut = (size_t)g.n_st * g.mapqs.size() * Q * 5;
+  // the dominant MAPQ
   uint32_t hot = 0;
   for (uint32_t m = 1; m < 256; ++m) if (mapq_count[m] > mapq_count[hot]) hot = m;
-  if (p.mapq_slot[hot] == 255) for (uint32_t m = 0; m < 256; ++m) if (p.mapq_slot[m] != 255) { hot = m; break; }
-  const uint32_t n_set = (uint32_t)(lut.size() / ((size_t)2 * p.n_mapq_slots * p.max_qual * 5));
-  const size_t n_hot = (size_t)n_set * 2 * p.max_qual * 5;
+  if (p.mapq_slot[hot] == 255) hot = g.mapqs[0];
   p.hot_mapq = hot;
-  p.n_hot = (n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // two 512-thread CTAs per SM must both hold a copy
-  hotL.assign(n_hot, HotTerms());
-  hotR.assign(n_hot, HotRatios());
-  for (uint32_t st = 0; st < n_set * 2; ++st) for (uint32_t q = 0; q < p.max_qual; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
-    const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + p.mapq_slot[hot]) * p.max_qual + q) * 5 + obs];
-    const size_t h = ((size_t)st * p.max_qual + q) * 5 + obs;
-    for (int b = 0; b < 5; ++b) { hotL[h].L[b] = t.L[b]; hotR[h].r[b] = t.r[b]; }
-    hotL[h].M = t.M;
-    hotR[h].M = t.M;
-  }
-}
-
-// Tables of the tally kernel (score_slots.cu).
-//  tallyT  shared-memory image: three planes ({L0,L1} {L2,L3} {L4,M}) of n_hot * copies 16-byte cells, cell index
-//          (h * copies + c), h = ((set*2 + top) * n_q + (quality - q_lo)) * 4 + obs, then one zero cell per copy.
-//  coldT   every class of every MAPQ in [mq_min, mq_min + n_mq): index (((set*2 + top) * n_mq + mapq - mq_min) * Q + q) * 5 + obs.
-void build_tally_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], const uint64_t qual_count[128],
-                        ScoreParams& p, std::vector<double>& tallyT, std::vector<HotTerms>& coldT) {
-  const uint32_t Q = p.max_qual;
-  const uint32_t n_st = (uint32_t)(lut.size() / ((size_t)p.n_mapq_slots * Q * 5));
-  uint32_t lo = 255, hi = 0;
-  for (uint32_t m = 0; m < 256; ++m) if (p.mapq_slot[m] != 255) { lo = std::min(lo, m); hi = std::max(hi, m); }
-  p.mq_min = lo; p.n_mq = hi - lo + 1;
-  coldT.assign((size_t)n_st * p.n_mq * Q * 5, HotTerms());
-  for (uint32_t st = 0; st < n_st; ++st) for (uint32_t m = lo; m <= hi; ++m) {
-    if (p.mapq_slot[m] == 255) continue;
-    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
-      const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + p.mapq_slot[m]) * Q + q) * 5 + obs];
-      HotTerms& c = coldT[(((size_t)st * p.n_mq + (m - lo)) * Q + q) * 5 + obs];
-      for (int b = 0; b < 5; ++b) c.L[b] = t.L[b];
-      c.M = t.M;
-    }
-  }
+  const size_t n_hot = (size_t)g.n_st * Q * 5;
+  p.n_hot = (n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // fit kernel: three CTAs per SM must each hold a copy
+  g.n_hotR = n_hot;
+  // MAPQ range of the global table of the tally kernel
+  p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
+  g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
   // quality window: as many values as eight copies allow inside 227 KB of shared memory, placed over the most records
   const size_t budget_cells = (size_t)(225 * 1024) / 16;
-  auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * n_st * nq * 4 * copies + copies; };
+  auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * ((size_t)g.n_st * nq * 4 + 1) * copies; };
   uint32_t q_first = Q, q_last = 0;
   for (uint32_t q = 0; q < Q && q < 128; ++q) if (qual_count[q]) { q_first = std::min(q_first, q); q_last = q; }
   if (q_first > q_last) { q_first = 0; q_last = Q ? Q - 1 : 0; }
@@ -312,18 +262,37 @@ void build_tally_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_
       if (mass > best) { best = mass; best_lo = a; }
     }
   }
-  p.t_qlo = best_lo; p.t_nq = nq; p.t_copies = copies; p.t_nhot = n_st * nq * 4;
-  tallyT.assign(cells(nq, copies) * 2, 0.0);
-  const size_t plane = (size_t)p.t_nhot * copies;
-  const uint32_t hot_slot = p.mapq_slot[p.hot_mapq];
-  for (uint32_t st = 0; st < n_st; ++st) for (uint32_t qi = 0; qi < nq; ++qi) for (uint32_t obs = 0; obs < 4; ++obs) {
-    const ClassTerms& t = lut[(((size_t)st * p.n_mapq_slots + hot_slot) * Q + (best_lo + qi)) * 5 + obs];
-    const size_t h = ((size_t)st * nq + qi) * 4 + obs;
-    for (uint32_t c = 0; c < copies; ++c) {
-      const size_t cell = h * copies + c;
-      tallyT[(0 * plane + cell) * 2 + 0] = t.L[0]; tallyT[(0 * plane + cell) * 2 + 1] = t.L[1];
-      tallyT[(1 * plane + cell) * 2 + 0] = t.L[2]; tallyT[(1 * plane + cell) * 2 + 1] = t.L[3];
-      tallyT[(2 * plane + cell) * 2 + 0] = t.L[4]; tallyT[(2 * plane + cell) * 2 + 1] = t.M;
+  p.t_qlo = best_lo; p.t_nq = nq; p.t_copies = copies; p.t_nhot = g.n_st * nq * 4;
+  g.n_tally_cells = cells(nq, copies);
+}
+
+// Host copy of the per-class terms, with the libm calls the reference makes (identify_mutations.cpp:3359-3384).
+// Only the host re-evaluation of flagged slots reads it (write_evidence); the kernels' tables are built on the device.
+void build_class_lut(const CovSpec& c, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g,
+                     std::vector<ClassTerms>& lut) {
+  const uint32_t Q = p.max_qual;
+  lut.assign(g.n_lut, ClassTerms());
+  auto comp = [](uint32_t b) { return b < 4 ? 3 - b : 4u; };
+  for (uint32_t st = 0; st < g.n_st; ++st) for (size_t ms = 0; ms < g.mapqs.size(); ++ms) {
+    const uint32_t set = st >> 1, top = st & 1;
+    const double incorrect = pow(10, -(double)g.mapqs[ms] / 10);
+    const double correct = 1 - incorrect;
+    const double uniform = 1.0 / 5.0;
+    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
+      ClassTerms& t = lut[(((size_t)st * g.mapqs.size() + ms) * Q + q) * 5 + obs];
+      const uint32_t o = top ? obs : comp(obs);
+      double mx = -std::numeric_limits<double>::max();
+      for (uint32_t b = 0; b < 5; ++b) {
+        const uint32_t rf = top ? b : comp(b);
+        const uint32_t idx = set * g.off_set + rf * g.off_ref + o * g.off_obs + q * g.off_qual;
+        double pr = correct * prob[idx] + incorrect * uniform;
+        if (pr < 0.0) pr = 0.0;
+        t.L[b] = log10(pr);
+        mx = std::max(mx, t.L[b]);
+      }
+      for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
+      t.M = mx;
+      t.r2 = 0.0;
     }
   }
 }
@@ -577,7 +546,9 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   for (uint32_t slot : flagged) {
     SlotEval s;
     memset(s.count, 0, sizeof s.count);
-    for (uint64_t i = st.score_off[slot]; i < st.score_off[slot + 1]; ++i) {
+    uint64_t rec_beg, rec_end;
+    score_slot_range(st.score_off, slot, rec_beg, rec_end);
+    for (uint64_t i = rec_beg; i < rec_end; ++i) {
       const uint32_t r = st.score_rec[i];
       const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
       if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) continue;

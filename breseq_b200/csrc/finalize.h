@@ -40,16 +40,18 @@ void write_base_qual_tables(const std::string& pattern, const CovSpec& spec, con
 void write_count_table(const std::string& path, const CovSpec& spec, const std::vector<uint64_t>& counts);
 void write_coverage_distributions(const std::string& dir, const std::vector<uint64_t>& cov, uint64_t stride, uint64_t n_groups);
 
-// Per-class likelihood terms for every (read_set, strand, MAPQ present, quality, obs).
-void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const uint32_t mapq_seen[8], ScoreParams& p,
+// Sizes and index maps of the likelihood tables (see score_geometry in finalize.cpp, build_tables_kernel in tables.cu).
+struct TableGeometry {
+  std::vector<uint32_t> mapqs;   // MAPQ value of each slot
+  uint32_t n_st = 0;             // read sets x 2 strands
+  uint32_t off_set = 0, off_ref = 0, off_obs = 0, off_qual = 0;  // covariate table strides
+  size_t n_lut = 0, n_hotR = 0, n_cold = 0, n_tally_cells = 0;
+};
+void score_geometry(const CovSpec& spec, const uint32_t mapq_seen[8], const uint64_t mapq_count[256], const uint64_t qual_count[128],
+                    ScoreParams& p, TableGeometry& g);
+// Host copy of the per-class terms for every (read_set, strand, MAPQ present, quality, obs); libm arithmetic as the reference.
+void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g,
                      std::vector<ClassTerms>& lut);
-// Shared-memory tables for the MAPQ value that carries the most scoring records.
-void build_hot_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], ScoreParams& p,
-                      std::vector<HotTerms>& hotL, std::vector<HotRatios>& hotR);
-
-// Shared-memory image and global companion of the tally kernel's likelihood table (needs build_hot_tables first).
-void build_tally_tables(const std::vector<ClassTerms>& lut, const uint64_t mapq_count[256], const uint64_t qual_count[128],
-                        ScoreParams& p, std::vector<double>& tallyT, std::vector<HotTerms>& coldT);
 
 struct EvidenceParams {
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;

@@ -74,14 +74,20 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between);
 
+// Fills every device likelihood table from the text-canonical probabilities (identify_mutations.cpp:3359-3384).
+struct TableBuildArgs {
+  const double* prob;          // [n_bins] pow(10, log10 value read back from error_rates.tab)
+  const uint8_t* slot_mapq;    // [n_mapq_slots] MAPQ value of each slot
+  uint32_t n_st, n_mapq_slots, Q, off_set, off_ref, off_obs, off_qual, hot_slot;
+  ClassTerms* lut; HotTerms* coldT; HotRatios* hotR; double* tallyT;
+};
+void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s);
+
 void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts,
                  uint32_t* err, cudaStream_t s);
 void launch_coverage_hist(const uint64_t* hist_off, const uint8_t* group, uint64_t n_cols, uint32_t stride,
                           unsigned long long* cov_hist, uint32_t* err, cudaStream_t s);
 void launch_derive_table(const unsigned long long* counts, const CovLayout& lay, double* log10_prob, cudaStream_t s);
-void launch_score(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots,
-                  const ClassTerms* lut, const ScoreParams& p, ColumnOut* out, uint32_t* flagged,
-                  uint32_t* n_flagged, uint32_t flagged_cap, uint32_t* err, cudaStream_t s);
 int launch_count();  // kernels launched so far through these wrappers (bench bookkeeping)
 
 }  // namespace brq

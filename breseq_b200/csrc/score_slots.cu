@@ -66,6 +66,11 @@ __device__ __forceinline__ uint4 ldg_stream_u32x4(const uint4* p) {
   return v;
 }
 
+// ask L2 for [p, p + bytes) ahead of use (16-byte aligned, a multiple of 16 bytes)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ bool eligible(uint32_t r, uint32_t cutoff) {
   return (r & (SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT)) == (SR_UNIQUE_BIT | SR_OK_BIT) && ((r >> SR_QUAL_SHIFT) & 127) >= cutoff;
 }
@@ -111,27 +116,30 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
                                                               ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
                                                               uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
                                                               uint32_t flagged_cap) {
-  // three planes of t_nhot * t_copies 16-byte cells ({L0,L1} {L2,L3} {L4,M}), then one zero cell per copy
+  // three planes ({L0,L1} {L2,L3} {L4,M}) of (t_nhot + 1) * t_copies 16-byte cells; the last cell of a plane is zero
   extern __shared__ __align__(16) double sm[];
   __shared__ double inv_red[64];
   {
-    const uint32_t n_dbl = (3u * p.t_nhot * p.t_copies + p.t_copies) * 2u;
+    const uint32_t n_cells = 3u * (p.t_nhot + 1u) * p.t_copies;
     const double2* src = reinterpret_cast<const double2*>(tallyT);
     double2* dst = reinterpret_cast<double2*>(sm);
-    for (uint32_t i = threadIdx.x; i < n_dbl / 2; i += blockDim.x) dst[i] = src[i];
+    for (uint32_t i = threadIdx.x; i < n_cells; i += blockDim.x) dst[i] = src[i];
     if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
   }
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31u, sub = lane & (uint32_t)(G - 1), g0 = lane - sub;
-  const uint32_t copy_off = (lane & (p.t_copies - 1u)) * 16u, cell_stride = p.t_copies * 16u;
-  const uint32_t plane = p.t_nhot * cell_stride;
-  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + copy_off;
-  const uint32_t zero_addr = tbl + 3u * plane;
-  const uint32_t Q_lo = p.t_qlo, n_q = p.t_nq, cutoff = p.base_quality_cutoff;
+  const uint32_t cs = p.t_copies * 16u;                      // bytes between consecutive classes
+  const uint32_t plane = (p.t_nhot + 1u) * cs;
+  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + (lane & (p.t_copies - 1u)) * 16u;  // this lane's copy
+  const uint32_t zero_addr = tbl + p.t_nhot * cs;
+  const uint32_t cutoff = p.base_quality_cutoff;
+  // cell address = tbl + (((set*2 + top) * n_q + qual - q_lo) * 4 + obs) * cs, as three multiply-adds
+  const uint32_t mul_st = p.t_nq * 4u * cs, mul_q = 4u * cs, tbl_adj = tbl - p.t_qlo * mul_q;
+  const uint32_t q_lo = p.t_qlo > cutoff ? p.t_qlo : cutoff, q_span = p.t_qlo + p.t_nq > q_lo ? p.t_qlo + p.t_nq - q_lo : 0u;
   // unique, untrimmed, resolvable; for the shared table also the dominant MAPQ and an A/C/G/T observation
   const uint32_t flag_mask = SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT, flag_want = SR_UNIQUE_BIT | SR_OK_BIT;
-  const uint32_t hot_mask = flag_mask | (255u << SR_MAPQ_SHIFT) | 4u;
-  const uint32_t hot_want = p.t_nhot ? (flag_want | (p.hot_mapq << SR_MAPQ_SHIFT)) : 0xFFFFFFFFu;  // no table: nothing matches
+  const uint32_t mo_mask = (255u << SR_MAPQ_SHIFT) | 4u;
+  const uint32_t mo_want = p.t_nhot ? (p.hot_mapq << SR_MAPQ_SHIFT) : 0xFFFFFFFFu;  // no table: nothing matches
 
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << g0);
@@ -139,78 +147,109 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
   const uint64_t n_warps = (uint64_t)gridDim.x * (TALLY_TPB / 32);
   for (uint64_t round = ((uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x) >> 5; round < n_rounds; round += n_warps) {
     const uint64_t my_slot = (round << 5) + lane;  // the slot this lane closes; its group tallies slots g0 .. g0+G-1
-    uint64_t my_beg = 0, my_end = 0;
-    uint32_t my_ref = 5;
-    if (my_slot < n_slots) { my_beg = off[my_slot]; my_end = off[my_slot + 1]; my_ref = slot_ref[my_slot]; }
+    uint64_t my_beg = 0;
+    uint32_t my_vec = 0, my_pad = 0, my_ref = 5;   // 128-bit vectors of the run, pad words in the last one
+    if (my_slot < n_slots) {
+      const uint64_t o0 = off[my_slot], o1 = off[my_slot + 1];
+      my_beg = o0 & ~3ull; my_vec = (uint32_t)(((o1 & ~3ull) - my_beg) >> 2); my_pad = (uint32_t)o1 & 3u;
+      my_ref = slot_ref[my_slot];
+    }
     Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double red_top = 0.0, red_bot = 0.0;
     uint32_t tops = 0, n = 0, c_ref = 0, raw_top = 0, raw_bot = 0;
+    // the records of this warp's NEXT round are pulled into L2 while this round is tallied: with 16
+    // warps per SM the loads below cannot cover DRAM latency on their own
+    uint64_t pf_lo = 0, pf_hi = 0;
+    if (lane == 0 && round + n_warps < n_rounds) {
+      const uint64_t s0 = (round + n_warps) << 5, s1 = s0 + 32 < n_slots ? s0 + 32 : n_slots;
+      pf_lo = off[s0] & ~3ull; pf_hi = off[s1] & ~3ull;
+    }
 
+    // the first vector of a slot is requested while the previous slot is being tallied
+    uint64_t beg = __shfl_sync(gmask, my_beg, g0);
+    uint32_t n_vec = __shfl_sync(gmask, my_vec, g0);
+    const uint4* vp = reinterpret_cast<const uint4*>(rec + beg);
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (sub < n_vec) cur = ldg_stream_u32x4(vp + sub);
 #pragma unroll 1
     for (int k = 0; k < G; ++k) {
-      const uint64_t beg = __shfl_sync(gmask, my_beg, g0 + k), end = __shfl_sync(gmask, my_end, g0 + k);
       const uint32_t ref = __shfl_sync(gmask, my_ref, g0 + k);
+      const int kn = k + 1 < G ? k + 1 : k;
+      const uint64_t beg_n = __shfl_sync(gmask, my_beg, g0 + kn);
+      const uint32_t n_vec_n = k + 1 < G ? __shfl_sync(gmask, my_vec, g0 + kn) : 0u;
+      const uint4* vp_n = reinterpret_cast<const uint4*>(rec + beg_n);
+      uint4 cur_n = make_uint4(0, 0, 0, 0);
+      if (sub < n_vec_n) cur_n = ldg_stream_u32x4(vp_n + sub);
+
+      // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
+      // every lane of the group alike (identify_mutations.cpp:1605).  The first vector is in the
+      // group's first lane; pad words are zero and end the walk like a unique record does.
+      double rt = 0.0, rb = 0.0;
+      uint32_t t_rawt = 0, t_rawb = 0;
+      {
+        const uint32_t hv[4] = {__shfl_sync(gmask, cur.x, g0), __shfl_sync(gmask, cur.y, g0), __shfl_sync(gmask, cur.z, g0),
+                                __shfl_sync(gmask, cur.w, g0)};
+        const uint32_t cnt = n_vec * 4u;
+        uint32_t i = 0, r = n_vec ? hv[0] : 0u;
+        while (r != 0u && !(r & SR_UNIQUE_BIT)) {
+          const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
+          const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
+          if (r & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
+          if (++i == cnt) break;
+          r = i == 1 ? hv[1] : i == 2 ? hv[2] : i == 3 ? hv[3] : __ldg(rec + beg + i);
+        }
+      }
+
       Sums a = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       uint32_t t_tops = 0, t_n = 0, t_cref = 0;
       uint32_t cq0 = 0, cq1 = 0, cq2 = 0, n_cold = 0;
-
-      // 128-bit loads from the aligned vector that holds the slot's first record; all index math is
-      // 32-bit and relative to the slot.  Elements outside the slot are zeroed: a zero record has no
-      // flag set, scores nothing and reads the all-zero cell.
-      const uint32_t head = (uint32_t)beg & 3u, cnt = (uint32_t)(end - beg);
-      const uint32_t n_vec = (head + cnt + 3u) >> 2;
       const uint32_t n_it = (n_vec + (uint32_t)G - 1u) / (uint32_t)G;  // the same for every lane of the group
-      const uint4* vp = reinterpret_cast<const uint4*>(rec + (beg - head));
-      uint32_t first = SR_UNIQUE_BIT;  // the slot's first record, for the redundant walk below
-      if (cnt) first = __ldg(rec + beg);
-      uint4 cur = make_uint4(0, 0, 0, 0);
-      if (sub < n_vec) cur = ldg_stream_u32x4(vp + sub);
       for (uint32_t it = 0; it < n_it; ++it) {
         const uint32_t iv = it * (uint32_t)G + sub;
         uint4 nxt = make_uint4(0, 0, 0, 0);
         if (iv + (uint32_t)G < n_vec) nxt = ldg_stream_u32x4(vp + iv + G);  // requested before `cur` is consumed
-        const uint32_t rem = head + cnt - iv * 4u, lo = iv ? 0u : head;      // valid elements: lo <= j < rem
-        uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};
-        uint32_t addr[4];
+        const uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};  // pad words are zero: no flag set, nothing scores
+        t_tops += (r[0] & SR_TOP_BIT) + (r[1] & SR_TOP_BIT);
+        t_tops += (r[2] & SR_TOP_BIT) + (r[3] & SR_TOP_BIT);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          r[j] = ((uint32_t)j >= lo && (uint32_t)j < rem && iv < n_vec) ? r[j] : 0u;
-          const uint32_t qual = (r[j] >> SR_QUAL_SHIFT) & 127u, qrel = qual - Q_lo;
-          const bool scoring = (r[j] & flag_mask) == flag_want && qual >= cutoff;
-          const bool hotp = (r[j] & hot_mask) == hot_want && qrel < n_q && qual >= cutoff;
-          t_tops += (r[j] >> 10) & 1u;
-          t_n += scoring ? 1u : 0u;
-          t_cref += (scoring && (r[j] & 7u) == ref) ? 1u : 0u;
-          const uint32_t cell = ((((r[j] >> 10) & 63u) * n_q + qrel) * 4u + (r[j] & 3u)) * cell_stride;
-          addr[j] = hotp ? tbl + cell : zero_addr;
-          if (scoring && !hotp) { cq2 = cq1; cq1 = cq0; cq0 = r[j]; ++n_cold; }
-        }
-        const uint32_t pstep[4] = {addr[0] == zero_addr ? 0u : plane, addr[1] == zero_addr ? 0u : plane,
-                                   addr[2] == zero_addr ? 0u : plane, addr[3] == zero_addr ? 0u : plane};
-        f64x2 x[4], y[4], z[4];  // {L0,L1}, {L2,L3}, {L4,M}: all twelve loads in flight together
+        for (int h = 0; h < 2; ++h) {  // two records at a time: six 128-bit loads in flight
+          uint32_t addr[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { x[j] = lds_f64x2(addr[j]); y[j] = lds_f64x2(addr[j] + pstep[j]); z[j] = lds_f64x2(addr[j] + 2u * pstep[j]); }
+          for (int jj = 0; jj < 2; ++jj) {
+            const uint32_t w = r[2 * h + jj];
+            const uint32_t qual = (w >> SR_QUAL_SHIFT) & 127u;
+            const bool scoring = (w & flag_mask) == flag_want && qual >= cutoff;
+            const bool hot = scoring && (w & mo_mask) == mo_want && (qual - q_lo) < q_span;
+            const bool cold = scoring && !hot;
+            const uint32_t cell = tbl_adj + ((w >> 10) & 63u) * mul_st + qual * mul_q + (w & 3u) * cs;
+            addr[jj] = hot ? cell : zero_addr;
+            const uint32_t one = scoring ? 1u : 0u;
+            t_n += one;
+            t_cref += ((w & 7u) == ref) ? one : 0u;
+            cq2 = cold ? cq1 : cq2; cq1 = cold ? cq0 : cq1; cq0 = cold ? w : cq0;
+            n_cold += cold ? 1u : 0u;
+          }
+          f64x2 x[2], y[2], z[2];  // {L0,L1}, {L2,L3}, {L4,M}
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {  // the zero cell adds +0.0 exactly
-          a.l0 += x[j].x; a.l1 += x[j].y; a.l2 += y[j].x; a.l3 += y[j].y; a.l4 += z[j].x; a.m += z[j].y;
+          for (int jj = 0; jj < 2; ++jj) { x[jj] = lds_f64x2(addr[jj]); y[jj] = lds_f64x2(addr[jj] + plane); z[jj] = lds_f64x2(addr[jj] + 2u * plane); }
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {  // the zero cell adds +0.0 exactly
+            a.l0 += x[jj].x; a.l1 += x[jj].y; a.l2 += y[jj].x; a.l3 += y[jj].y; a.l4 += z[jj].x; a.m += z[jj].y;
+          }
         }
         cur = nxt;
       }
       // scoring records outside the shared table
       if (n_cold > 3) {  // the queue overflowed: rescan this lane's share of the slot
-        for (uint32_t it = 0; it < n_it; ++it) {
-          const uint32_t iv = it * (uint32_t)G + sub;
-          if (iv >= n_vec) break;
+        for (uint32_t iv = sub; iv < n_vec; iv += G) {
           const uint4 v = __ldg(vp + iv);
-          const uint32_t rem = head + cnt - iv * 4u, lo = iv ? 0u : head;
           const uint32_t rr[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if ((uint32_t)j < lo || (uint32_t)j >= rem) continue;
             const uint32_t qual = (rr[j] >> SR_QUAL_SHIFT) & 127u;
             const bool scoring = (rr[j] & flag_mask) == flag_want && qual >= cutoff;
-            const bool hotp = (rr[j] & hot_mask) == hot_want && (qual - Q_lo) < n_q;
-            if (scoring && !hotp) cold_add(a, rr[j], coldT, p);
+            const bool hot = scoring && (rr[j] & mo_mask) == mo_want && (qual - q_lo) < q_span;
+            if (scoring && !hot) cold_add(a, rr[j], coldT, p);
           }
         }
       } else {
@@ -218,29 +257,20 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
         if (n_cold > 1) cold_add(a, cq1, coldT, p);
         if (n_cold > 0) cold_add(a, cq0, coldT, p);
       }
-      // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
-      // every lane of the group alike (identify_mutations.cpp:1605)
-      double rt = 0.0, rb = 0.0;
-      uint32_t t_rawt = 0, t_rawb = 0;
-      for (uint32_t i = 0; !(first & SR_UNIQUE_BIT);) {
-        const uint32_t red = (first >> SR_RED_SHIFT) & SR_RED_MASK;
-        const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-        if (first & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
-        if (++i == cnt) break;
-        first = __ldg(rec + beg + i);
-      }
       a.l0 = group_add<G>(a.l0, gmask); a.l1 = group_add<G>(a.l1, gmask); a.l2 = group_add<G>(a.l2, gmask);
       a.l3 = group_add<G>(a.l3, gmask); a.l4 = group_add<G>(a.l4, gmask); a.m = group_add<G>(a.m, gmask);
       t_tops = group_add_u32<G>(t_tops, gmask); t_n = group_add_u32<G>(t_n, gmask); t_cref = group_add_u32<G>(t_cref, gmask);
       if (sub == (uint32_t)k) {
         kept = a; red_top = rt; red_bot = rb;
-        tops = t_tops; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
+        tops = t_tops >> 10; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
       }
+      beg = beg_n; n_vec = n_vec_n; vp = vp_n; cur = cur_n;
+      if (k == 0 && pf_hi > pf_lo) prefetch_l2_bulk(rec + pf_lo, (uint32_t)((pf_hi - pf_lo) * 4u));
     }
     if (my_slot >= n_slots) continue;
 
     // every record of the slot is either unique or redundant; top-strand counts follow by subtraction
-    const uint32_t cnt = (uint32_t)(my_end - my_beg);
+    const uint32_t cnt = my_vec * 4u - my_pad;
     const uint32_t u_all = cnt - raw_top - raw_bot, u_top = tops - raw_top;
     const uint32_t ref = my_ref;
     const double ll[5] = {kept.l0, kept.l1, kept.l2, kept.l3, kept.l4};
@@ -372,7 +402,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     w = __shfl_sync(g.mask, w, lane - g.sub);
     if (w >= n_work) break;
     const uint32_t slot = worklist[w];
-    g.beg = off[slot]; g.end = off[slot + 1];
+    score_slot_range(off, slot, g.beg, g.end);
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
     for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
       const uint32_t r = __ldg(rec + i);
@@ -496,7 +526,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
                         cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem_tally = ((size_t)3 * p.t_nhot * p.t_copies + p.t_copies) * 16, smem_fit = (size_t)p.n_hot * 48;
+  const size_t smem_tally = (size_t)3 * (p.t_nhot + 1) * p.t_copies * 16, smem_fit = (size_t)p.n_hot * 48;
   const uint64_t n_rounds = (n_slots + 31) / 32;
   const int blocks = (int)std::min<uint64_t>((n_rounds + TALLY_TPB / 32 - 1) / (TALLY_TPB / 32), (uint64_t)kSMs);
   // lanes per slot: 4 at ordinary depth, a whole warp once the mean column is deeper than 512 records

@@ -351,8 +351,14 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   for (uint64_t j = 0; j < out.n_ins; ++j) out.slot_ref[out.n_base + j] = kBaseGap;
   {
     uint64_t acc = 0;
-    for (uint64_t s = 0; s < n_slots; ++s) { out.score_off[s] = acc; if (cfg.want_score) acc += score_cnt[s]; }
-    out.score_off[n_slots] = acc; out.n_score = acc;
+    uint64_t n_true = 0, pad = 0;  // runs padded to whole 128-bit vectors; the pad count rides in the next entry's low bits
+    for (uint64_t s = 0; s < n_slots; ++s) {
+      out.score_off[s] = acc | pad;
+      const uint64_t cnt = cfg.want_score ? score_cnt[s] : 0;
+      pad = (4 - (cnt & 3)) & 3;
+      acc += cnt + pad; n_true += cnt;
+    }
+    out.score_off[n_slots] = acc | pad; out.n_score = n_true; out.n_score_padded = acc;
     acc = 0;
     for (uint64_t c = 0; c < out.n_base; ++c) {
       out.hist_off[c] = acc | ((cfg.want_hist && col_red[c]) ? HIST_OFF_REDUNDANT_BIT : 0);
@@ -362,7 +368,8 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     if (cfg.want_hist) for (uint64_t c = 0; c < out.n_base; ++c) if (hist_cnt[c] > out.max_hist_depth) out.max_hist_depth = hist_cnt[c];
     for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
-  out.score_rec = (uint32_t*)alloc(out.n_score * 4, &p2);
+  out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
+  memset(out.score_rec, 0, out.n_score_padded * 4);
   out.hist_rec = (uint64_t*)alloc(out.n_hist * 8, &p2);
 
   // ---- pass B: fill.  Within every slot the redundant records come first and the unique ones
@@ -492,7 +499,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
             rec |= red << SR_RED_SHIFT;
           }
           uint64_t s = k == 0 ? slot : out.n_base + sub_first[slot] + k - 1;
-          out.score_rec[out.score_off[s] + (unique ? score_cur[s]++ : red_cur[s]++)] = rec;
+          out.score_rec[(out.score_off[s] & ~3ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = rec;
         }
       });
     }

@@ -1,0 +1,73 @@
+// Likelihood tables of pass 2, built on the device from the error table.
+//
+// One thread per record class (read set, strand, MAPQ present in the stream, quality, observed base):
+//   pr[b] = (1 - e) * P[class with ref = b, complemented on the bottom strand] + e / 5,  e = 10^(-MAPQ/10)
+//   L[b] = log10 pr[b],  M = max_b L[b],  r[b] = 10^(L[b] - M)          identify_mutations.cpp:3359-3384
+// and writes the class into every table that holds it: the full table (fit kernel, global), the
+// {L, M} table of all MAPQ values (tally kernel, global), and for the dominant MAPQ the fit
+// kernel's shared-memory image {r, M} and the tally kernel's three-plane, eight-copy image.
+// CUDA's log10/pow are within a couple of ulp of glibc's, i.e. 1e-16 relative on every term, far inside
+// the 1e-9 bar of the log-likelihood sums; slots whose decisions are close are re-evaluated on the
+// host with glibc in arrival order (finalize.cpp).
+#include "kernels.h"
+#include "brq_types.h"
+
+namespace brq {
+
+void note_launches(int n);
+
+__global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, ScoreParams p) {
+  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * 5u;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cls) return;
+  const uint32_t obs = i % 5u, q = (i / 5u) % a.Q, ms = (i / (5u * a.Q)) % a.n_mapq_slots, st = i / (5u * a.Q * a.n_mapq_slots);
+  const uint32_t set = st >> 1, top = st & 1u;
+  const uint32_t mapq = a.slot_mapq[ms];
+  const double incorrect = pow(10.0, -(double)mapq / 10.0), correct = 1.0 - incorrect, uniform = 1.0 / 5.0;
+  const uint32_t o = top ? obs : (obs < 4u ? 3u - obs : 4u);
+  double L[5], r[5], M = -1.7976931348623157e308;
+#pragma unroll
+  for (uint32_t b = 0; b < 5; ++b) {
+    const uint32_t rf = top ? b : (b < 4u ? 3u - b : 4u);
+    double pr = correct * a.prob[set * a.off_set + rf * a.off_ref + o * a.off_obs + q * a.off_qual] + incorrect * uniform;
+    if (pr < 0.0) pr = 0.0;
+    L[b] = log10(pr);
+    M = fmax(M, L[b]);
+  }
+#pragma unroll
+  for (int b = 0; b < 5; ++b) r[b] = pow(10.0, L[b] - M);
+
+  ClassTerms t;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) { t.L[b] = L[b]; t.r[b] = r[b]; }
+  t.r2 = 0.0; t.M = M;
+  a.lut[i] = t;
+  HotTerms c;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) c.L[b] = L[b];
+  c.M = M;
+  a.coldT[(((size_t)st * p.n_mq + (mapq - p.mq_min)) * a.Q + q) * 5u + obs] = c;
+  if (ms != a.hot_slot) return;
+  HotRatios h;
+#pragma unroll
+  for (int b = 0; b < 5; ++b) h.r[b] = r[b];
+  h.M = M;
+  a.hotR[((size_t)st * a.Q + q) * 5u + obs] = h;
+  if (obs < 4u && q >= p.t_qlo && q < p.t_qlo + p.t_nq) {
+    const size_t plane = ((size_t)p.t_nhot + 1) * p.t_copies;
+    const size_t cell0 = (((size_t)st * p.t_nq + (q - p.t_qlo)) * 4u + obs) * p.t_copies;
+    for (uint32_t cp = 0; cp < p.t_copies; ++cp) {
+      double* d0 = a.tallyT + (0 * plane + cell0 + cp) * 2, *d1 = a.tallyT + (1 * plane + cell0 + cp) * 2, *d2 = a.tallyT + (2 * plane + cell0 + cp) * 2;
+      d0[0] = L[0]; d0[1] = L[1]; d1[0] = L[2]; d1[1] = L[3]; d2[0] = L[4]; d2[1] = M;
+    }
+  }
+}
+
+void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s) {
+  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * 5u;
+  if (!n_cls) return;
+  build_tables_kernel<<<(n_cls + 255) / 256, 256, 0, s>>>(a, p);
+  note_launches(1);
+}
+
+}  // namespace brq

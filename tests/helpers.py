@@ -202,10 +202,12 @@ def emulate_coverage_hist(hist_off):
 
 
 def emulate_tally(stream, base_quality_cutoff=3):
-    rec = stream["score_rec"]
-    off = stream["score_off"].astype(np.int64)
-    n_slots = len(off) - 1
-    sid = np.repeat(np.arange(n_slots), np.diff(off))
+    beg, cnt = bq.slot_ranges(stream)
+    n_slots = len(beg)
+    pos = np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))  # padding skipped
+    rec = stream["score_rec"][pos]
+    assert np.all(rec != 0) and int(cnt.sum()) == int(stream["n_score"])
+    sid = np.repeat(np.arange(n_slots), cnt)
     uniq, top, trim, ok, q = (rec >> 24) & 1, (rec >> 10) & 1, (rec >> 25) & 1, (rec >> 26) & 1, (rec >> 3) & 127
     out = {}
     for name, u in (("unique", 1), ("raw_redundant", 0)):

@@ -59,10 +59,17 @@ def test_score_stream_tallies_match_oracle(staged):
 def test_redundant_records_lead_each_slot(staged):
     """Stream layout the scoring kernel relies on: within a slot, redundant records first, then unique ones."""
     d, ctx, s = staged
-    uniq = ((s["score_rec"] >> 24) & 1).astype(np.int8)
-    off = s["score_off"].astype(np.int64)
+    rec = s["score_rec"]
+    beg, cnt = bq.slot_ranges(s)
+    assert np.all(beg % 4 == 0), "every run starts on a 128-bit boundary"
+    real = np.zeros(len(rec), bool)
+    real[np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))] = True
+    assert np.all(rec[~real] == 0) and np.all(rec[real] != 0), "pad words are zero, records never are"
+    assert len(rec) == s["n_score_padded"] and real.sum() == s["n_score"]
+    uniq = ((rec >> 24) & 1).astype(np.int8)
+    uniq[~real] = 1   # padding follows the unique records
     step_down = np.nonzero(np.diff(uniq) < 0)[0] + 1   # a unique record followed by a redundant one ...
-    assert np.all(np.isin(step_down, off)), "... is only allowed across a slot boundary"
+    assert np.all(np.isin(step_down, beg)), "... is only allowed across a slot boundary"
     assert (uniq == 0).sum() > 0
 
 

@@ -213,7 +213,19 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   CUDA_OK(cudaMemsetAsync(c->d_cov.p, 0, c->cov_stride * n_groups * 8, c->stream));
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
-  if (do_errors) launch_hist(c->d_hist_rec.p, st.n_hist, lay, c->d_counts.p, c->d_scalars.p, c->stream);
+  if (do_errors) {
+    // the reference ASSERTs when a counted covariate value exceeds the table (error_count.cpp:485-488); the stream's
+    // maxima are known from staging, so the check costs the kernel nothing
+    auto too_big = [&](int cov, const char* name, uint32_t seen) {
+      if (st.n_hist && c->spec.used[cov] && !c->spec.clamp[cov] && seen >= c->spec.maxv[cov])
+        throw std::runtime_error(std::string("Covariate '") + name + "' with value '" + std::to_string(seen) +
+                                 "' exceeded enforced maximum value of '" + std::to_string(c->spec.maxv[cov] - 1) + "'.");
+    };
+    too_big(COV_QUALITY, "quality", st.max_hist_qual);
+    too_big(COV_READ_SET, "read_set", st.max_read_set_seen);
+    too_big(COV_READ_POS, "read_pos", st.max_hist_rpos);
+    launch_hist(c->d_hist_rec.p, st.n_hist, lay, c->d_counts.p, c->stream);
+  }
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, c->d_cov.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));

@@ -80,17 +80,19 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
                    SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_RED_SHIFT = 11,
                    SR_RED_MASK = 0x1FFF;
 
-// Histogram (error_count) record, 8 bytes, one per unique, non-deleted (read, column).
-//   [2:0]   obsA   base index 0..3, 5 = N          [5:3]  refA  reference base index (0..3, 5 = N)
-//   [12:6]  qualA                                   [13]   rev   read on the bottom strand
-//   [15:14] classB 0 none, 1 '..' (next base also aligned), 2 deletion of exactly one base follows,
-//                  3 insertion of exactly one base follows  (error_count.cpp:909-982)
-//   [18:16] obsB   base index of the base whose quality is used (N-check / inserted base)
-//   [21:19] refB   reference base index next to the event (0..3, 5 = N, 6 = past the end)
-//   [28:22] qualB                                   [33:29] read_set
-//   [49:34] read_posA (0-based query index)         [57:50] base_repeatA   [63:58] base_repeatB
-constexpr int HR_OBSA = 0, HR_REFA = 3, HR_QUALA = 6, HR_REV = 13, HR_CLASSB = 14, HR_OBSB = 16, HR_REFB = 19,
-              HR_QUALB = 22, HR_SET = 29, HR_RPOS = 34, HR_REPA = 50, HR_REPB = 58;
+// Histogram (error_count) record, 8 bytes, one per unique, non-deleted (read, column).  Both
+// observations of cErrorTable::count_alignment_position (error_count.cpp:854-986) are resolved by the
+// staging layer into table coordinates on the READ strand (bases complemented for reversed reads):
+//   observation A, the aligned base:           [2:0] ref  [5:3] obs  [12:6] quality  [13] valid
+//                                              (valid = neither the read base nor the reference base is N)
+//   observation B, what follows it in the read: [16:14] ref [19:17] obs [26:20] quality [63] valid
+//       next base also aligned      ('.', '.')         quality of the next base on the read strand
+//       deletion of exactly 1 base  (ref base, '.')    quality of the next base on the read strand
+//       insertion of exactly 1 base ('.', inserted)    quality of the inserted base
+//   [31:27] read_set   [47:32] read_pos of A (0-based query index)   [55:48] base_repeat of A   [61:56] base_repeat of B
+// Base indices A,C,G,T,'.' = 0..4.
+constexpr int HR_REFA = 0, HR_OBSA = 3, HR_QUALA = 6, HR_VALIDA = 13, HR_REFB = 14, HR_OBSB = 17, HR_QUALB = 20, HR_SET = 27,
+              HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_VALIDB = 63;
 
 // Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
 struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
@@ -119,6 +121,7 @@ struct PileupStream {
   uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
   uint32_t n_groups = 1;               // coverage groups present
   uint32_t max_qual_seen = 0;
+  uint32_t max_hist_qual = 0, max_hist_rpos = 0;  // largest quality / read position in a valid histogram observation
   uint32_t max_read_set_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
   uint64_t n_slots() const { return n_base + n_ins; }

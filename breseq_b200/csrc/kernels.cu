@@ -32,50 +32,41 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
 // ------------------------------------------------------------------------------------------
 // error_count histogram
 // ------------------------------------------------------------------------------------------
+// Records arrive with both observations already resolved to table coordinates (brq_types.h), and the
+// host has checked the stream's largest quality / read_set / read_pos against the table before the
+// launch (the reference's fatal ASSERT, error_count.cpp:485-488), so a record costs two multiply-add
+// chains and two shared-memory atomics.  FULL adds the read_pos / base_repeat covariates.
 template <bool SMEM>
 __device__ __forceinline__ void hist_add(uint32_t* sh, unsigned long long* counts, uint32_t idx) {
   if (SMEM) atomicAdd(&sh[idx], 1u);
   else atomicAdd(&counts[idx], 1ull);
 }
 
-template <bool SMEM>
-__device__ __forceinline__ void hist_record(uint64_t r, const CovLayout& lay, uint32_t* sh, unsigned long long* counts,
-                                            uint32_t& err) {
-  const uint32_t lo = (uint32_t)r;
-  const uint32_t obsA = lo & 7, refA = (lo >> HR_REFA) & 7, qa = (lo >> HR_QUALA) & 127, rev = (lo >> HR_REV) & 1;
-  const uint32_t cls = (lo >> HR_CLASSB) & 3, obsB = (lo >> HR_OBSB) & 7, refB = (lo >> HR_REFB) & 7, qb = (lo >> HR_QUALB) & 127;
-  const uint32_t set = (uint32_t)(r >> HR_SET) & 31, rpos = (uint32_t)(r >> HR_RPOS) & 0xFFFF;
-  const uint32_t repA = (uint32_t)(r >> HR_REPA) & 255, repB = (uint32_t)(r >> HR_REPB) & 63;
-  if (set >= lay.max_set) { err |= BRQ_ERR_READSET_RANGE; return; }
-  if (rpos >= lay.max_rpos) { err |= BRQ_ERR_READPOS_RANGE; return; }
-  const uint32_t base = set * lay.off_set + rpos * lay.off_rpos;
-  // observation A: (ref base, observed base) on the read strand
-  if (obsA < 4 && refA < 4) {
-    if (qa >= lay.max_qual) err |= BRQ_ERR_QUALITY_RANGE;
-    else {
-      const uint32_t o = rev ? 3 - obsA : obsA, f = rev ? 3 - refA : refA;
-      hist_add<SMEM>(sh, counts, base + f * lay.off_ref + o * lay.off_obs + qa * lay.off_qual + min(repA, lay.max_rep - 1) * lay.off_rep);
-    }
+template <bool SMEM, bool FULL>
+__device__ __forceinline__ void hist_record(uint64_t r, const CovLayout& lay, uint32_t* sh, unsigned long long* counts) {
+  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+  uint32_t base = (lo >> HR_SET) * lay.off_set;
+  if (FULL) base += (hi & 0xFFFFu) * lay.off_rpos;
+  if (lo & (1u << HR_VALIDA)) {
+    uint32_t idx = base + (lo & 7u) * lay.off_ref + ((lo >> HR_OBSA) & 7u) * lay.off_obs + ((lo >> HR_QUALA) & 127u) * lay.off_qual;
+    if (FULL) idx += min((hi >> (HR_REPA - 32)) & 255u, lay.max_rep - 1) * lay.off_rep;
+    hist_add<SMEM>(sh, counts, idx);
   }
-  // observation B: what follows this base in the read ('..', deletion, insertion)
-  if (cls == 0 || obsB == kBaseN) return;
-  uint32_t f = kBaseGap, o = kBaseGap;
-  if (cls == 1) { if (refB == kBaseN) return; }
-  else if (cls == 2) { if (refB >= 4) return; f = rev ? 3 - refB : refB; }
-  else { o = rev ? 3 - obsB : obsB; }
-  if (qb >= lay.max_qual) { err |= BRQ_ERR_QUALITY_RANGE; return; }
-  hist_add<SMEM>(sh, counts, base + f * lay.off_ref + o * lay.off_obs + qb * lay.off_qual + min(repB, lay.max_rep - 1) * lay.off_rep);
+  if (hi & (1u << (HR_VALIDB - 32))) {
+    uint32_t idx = base + ((lo >> HR_REFB) & 7u) * lay.off_ref + ((lo >> HR_OBSB) & 7u) * lay.off_obs + ((lo >> HR_QUALB) & 127u) * lay.off_qual;
+    if (FULL) idx += min((hi >> (HR_REPB - 32)) & 63u, lay.max_rep - 1) * lay.off_rep;
+    hist_add<SMEM>(sh, counts, idx);
+  }
 }
 
-template <bool SMEM>
+template <bool SMEM, bool FULL>
 __global__ void __launch_bounds__(256) hist_kernel(const uint64_t* __restrict__ rec, uint64_t n, CovLayout lay,
-                                                    unsigned long long* __restrict__ counts, uint32_t* __restrict__ err_out) {
+                                                    unsigned long long* __restrict__ counts) {
   extern __shared__ uint32_t sh[];
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i < lay.n_bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
   }
-  uint32_t err = 0;
   const ulonglong2* rec2 = reinterpret_cast<const ulonglong2*>(rec);
   const uint64_t n2 = n >> 1;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -84,17 +75,16 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint64_t* __restrict__ 
   for (; i + 3 * stride < n2; i += 4 * stride) {
     ulonglong2 a = ld_stream_u64x2(rec2 + i), b = ld_stream_u64x2(rec2 + i + stride);
     ulonglong2 c = ld_stream_u64x2(rec2 + i + 2 * stride), d = ld_stream_u64x2(rec2 + i + 3 * stride);
-    hist_record<SMEM>(a.x, lay, sh, counts, err); hist_record<SMEM>(a.y, lay, sh, counts, err);
-    hist_record<SMEM>(b.x, lay, sh, counts, err); hist_record<SMEM>(b.y, lay, sh, counts, err);
-    hist_record<SMEM>(c.x, lay, sh, counts, err); hist_record<SMEM>(c.y, lay, sh, counts, err);
-    hist_record<SMEM>(d.x, lay, sh, counts, err); hist_record<SMEM>(d.y, lay, sh, counts, err);
+    hist_record<SMEM, FULL>(a.x, lay, sh, counts); hist_record<SMEM, FULL>(a.y, lay, sh, counts);
+    hist_record<SMEM, FULL>(b.x, lay, sh, counts); hist_record<SMEM, FULL>(b.y, lay, sh, counts);
+    hist_record<SMEM, FULL>(c.x, lay, sh, counts); hist_record<SMEM, FULL>(c.y, lay, sh, counts);
+    hist_record<SMEM, FULL>(d.x, lay, sh, counts); hist_record<SMEM, FULL>(d.y, lay, sh, counts);
   }
   for (; i < n2; i += stride) {
     ulonglong2 a = ld_stream_u64x2(rec2 + i);
-    hist_record<SMEM>(a.x, lay, sh, counts, err); hist_record<SMEM>(a.y, lay, sh, counts, err);
+    hist_record<SMEM, FULL>(a.x, lay, sh, counts); hist_record<SMEM, FULL>(a.y, lay, sh, counts);
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) hist_record<SMEM>(rec[n - 1], lay, sh, counts, err);
-  if (err) atomicOr(err_out, err);
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) hist_record<SMEM, FULL>(rec[n - 1], lay, sh, counts);
   if (SMEM) {
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < lay.n_bins; b += blockDim.x) {
@@ -104,16 +94,22 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint64_t* __restrict__ 
   }
 }
 
-void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts, uint32_t* err,
-                 cudaStream_t s) {
+void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
   const int kSMs = 148;
   const size_t smem = (size_t)lay.n_bins * 4;
+  const bool full = lay.off_rpos != 0 || lay.off_rep != 0;
   if (smem <= 200 * 1024) {
-    cudaFuncSetAttribute(hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
-    hist_kernel<true><<<kSMs * per_sm, 256, smem, s>>>(rec, n_rec, lay, counts, err);
+    if (full) {
+      cudaFuncSetAttribute(hist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      hist_kernel<true, true><<<kSMs * per_sm, 256, smem, s>>>(rec, n_rec, lay, counts);
+    } else {
+      cudaFuncSetAttribute(hist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      hist_kernel<true, false><<<kSMs * per_sm, 256, smem, s>>>(rec, n_rec, lay, counts);
+    }
   } else {
-    hist_kernel<false><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts, err);
+    if (full) hist_kernel<false, true><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts);
+    else hist_kernel<false, false><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts);
   }
   ++g_launches;
 }

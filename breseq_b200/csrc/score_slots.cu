@@ -169,8 +169,9 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
     uint64_t beg = __shfl_sync(gmask, my_beg, g0);
     uint32_t n_vec = __shfl_sync(gmask, my_vec, g0);
     const uint4* vp = reinterpret_cast<const uint4*>(rec + beg);
-    uint4 cur = make_uint4(0, 0, 0, 0);
+    uint4 cur = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);  // two vectors per lane are always in flight
     if (sub < n_vec) cur = ldg_stream_u32x4(vp + sub);
+    if (sub + (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + sub + G);
 #pragma unroll 1
     for (int k = 0; k < G; ++k) {
       const uint32_t ref = __shfl_sync(gmask, my_ref, g0 + k);
@@ -204,11 +205,9 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
       uint32_t t_tops = 0, t_n = 0, t_cref = 0;
       uint32_t cq0 = 0, cq1 = 0, cq2 = 0, n_cold = 0;
       const uint32_t n_it = (n_vec + (uint32_t)G - 1u) / (uint32_t)G;  // the same for every lane of the group
-      for (uint32_t it = 0; it < n_it; ++it) {
-        const uint32_t iv = it * (uint32_t)G + sub;
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (iv + (uint32_t)G < n_vec) nxt = ldg_stream_u32x4(vp + iv + G);  // requested before `cur` is consumed
-        const uint32_t r[4] = {cur.x, cur.y, cur.z, cur.w};  // pad words are zero: no flag set, nothing scores
+      // four records of one 128-bit vector; pad words are zero: no flag set, nothing scores
+      auto tally4 = [&](const uint4& v) {
+        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
         t_tops += (r[0] & SR_TOP_BIT) + (r[1] & SR_TOP_BIT);
         t_tops += (r[2] & SR_TOP_BIT) + (r[3] & SR_TOP_BIT);
 #pragma unroll
@@ -237,7 +236,19 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
             a.l0 += x[jj].x; a.l1 += x[jj].y; a.l2 += y[jj].x; a.l3 += y[jj].y; a.l4 += z[jj].x; a.m += z[jj].y;
           }
         }
-        cur = nxt;
+      };
+      // Two vector registers per lane, each reloaded right after it is consumed and not touched again
+      // until a whole vector later: no register rotation, so no instruction waits on a load it just issued.
+      for (uint32_t it = 0; it < n_it; it += 2) {
+        const uint32_t iv = it * (uint32_t)G + sub;
+        tally4(cur);
+        cur = make_uint4(0, 0, 0, 0);
+        if (iv + 2u * (uint32_t)G < n_vec) cur = ldg_stream_u32x4(vp + iv + 2 * G);
+        if (it + 1 < n_it) {
+          tally4(nx1);
+          nx1 = make_uint4(0, 0, 0, 0);
+          if (iv + 3u * (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + iv + 3 * G);
+        }
       }
       // scoring records outside the shared table
       if (n_cold > 3) {  // the queue overflowed: rescan this lane's share of the slot
@@ -265,6 +276,8 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
         tops = t_tops >> 10; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
       }
       beg = beg_n; n_vec = n_vec_n; vp = vp_n; cur = cur_n;
+      nx1 = make_uint4(0, 0, 0, 0);
+      if (sub + (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + sub + G);
       if (k == 0 && pf_hi > pf_lo) prefetch_l2_bulk(rec + pf_lo, (uint32_t)((pf_hi - pf_lo) * 4u));
     }
     if (my_slot >= n_slots) continue;

@@ -383,7 +383,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   std::vector<uint64_t> qual_counts((size_t)items.size() * 128, 0);
   std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
   std::vector<uint64_t> mapq_counts((size_t)items.size() * 256, 0);
-  std::vector<uint32_t> max_quals(items.size(), 0);
+  std::vector<uint32_t> max_quals(items.size(), 0), max_hquals(items.size(), 0), max_rposs(items.size(), 0);
   run_items([&](size_t ii) {
     const Item& it = items[ii];
     const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
@@ -397,7 +397,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     uint32_t* mq_mask = &mapq_masks[ii * 8];
     uint64_t* mq_count = &mapq_counts[ii * 256];
     uint64_t* q_count = &qual_counts[ii * 128];
-    uint32_t max_q = 0;
+    uint32_t max_q = 0, max_hq = 0, max_rp = 0;
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
       const ReadInfo& ri = info[i];
@@ -414,15 +414,18 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         // ---------------- error_count record (error_count.cpp:125-199, 854-986)
         if (cfg.want_hist && !is_del && unique) {
           uint64_t rec = 0;
-          uint32_t qa = qual[q];
+          const uint32_t qa = qual[q];
           if (qa > 127) throw std::runtime_error("base quality above 127 cannot be packed");
-          rec |= (uint64_t)nibble_to_index(seq[q]) << HR_OBSA;
-          rec |= (uint64_t)out.slot_ref[slot] << HR_REFA;
-          rec |= (uint64_t)qa << HR_QUALA;
-          rec |= (uint64_t)rev << HR_REV;
+          const uint32_t obsA = nibble_to_index(seq[q]), refA = out.slot_ref[slot];
+          auto strand = [&](uint32_t b) { return rev ? 3 - b : b; };  // complement on the read strand (A,C,G,T only)
+          if (obsA < 4 && refA < 4) {  // error_count.cpp:870-905
+            rec |= (uint64_t)strand(refA) << HR_REFA | (uint64_t)strand(obsA) << HR_OBSA | (uint64_t)qa << HR_QUALA | 1ull << HR_VALIDA;
+            if (qa > max_hq) max_hq = qa;
+          }
           rec |= (uint64_t)ri.read_set << HR_SET;
           if (q > 65535) throw std::runtime_error("read position above 65535 cannot be packed");
           rec |= (uint64_t)q << HR_RPOS;
+          if ((uint32_t)q > max_rp) max_rp = (uint32_t)q;
           auto base_repeat = [&](int32_t qp) -> uint64_t {  // alignment.cpp:371-390
             uint8_t b = seq[qp]; uint32_t rep = 0;
             if (!rev) { while (qp < ri.qe0) { ++qp; if (seq[qp] != b) break; ++rep; } }
@@ -448,11 +451,17 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
           if (cls) {
             if (m < 0 || m >= L) throw std::runtime_error("Attempt to retrieve quality score for nonexistent base.");
             if (qual[m] > 127) throw std::runtime_error("base quality above 127 cannot be packed");
-            rec |= (uint64_t)cls << HR_CLASSB;
-            rec |= (uint64_t)nibble_to_index(seq[m]) << HR_OBSB;
-            rec |= (uint64_t)refb << HR_REFB;
-            rec |= (uint64_t)qual[m] << HR_QUALB;
-            if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 63) << HR_REPB;
+            const uint32_t obsB = nibble_to_index(seq[m]);
+            uint32_t fB = kBaseGap, oB = kBaseGap;
+            bool valid = obsB != kBaseN;                         // error_count.cpp:909-982
+            if (cls == 1) valid = valid && refb != kBaseN;       // ('.', '.'): both only tested for N
+            else if (cls == 2) { valid = valid && refb < 4; fB = valid ? strand(refb) : kBaseGap; }
+            else oB = valid ? strand(obsB) : kBaseGap;
+            if (valid) {
+              rec |= (uint64_t)fB << HR_REFB | (uint64_t)oB << HR_OBSB | (uint64_t)qual[m] << HR_QUALB | 1ull << HR_VALIDB;
+              if (qual[m] > max_hq) max_hq = qual[m];
+              if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 63) << HR_REPB;
+            }
           }
           out.hist_rec[(out.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT) + hist_cur[slot]++] = rec;
         }
@@ -503,13 +512,15 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         }
       });
     }
-    max_quals[ii] = max_q;
+    max_quals[ii] = max_q; max_hquals[ii] = max_hq; max_rposs[ii] = max_rp;
   });
   for (size_t ii = 0; ii < items.size(); ++ii) {
     for (int w = 0; w < 8; ++w) out.mapq_seen[w] |= mapq_masks[ii * 8 + (size_t)w];
     for (int m = 0; m < 256; ++m) out.mapq_count[m] += mapq_counts[ii * 256 + (size_t)m];
     for (int q = 0; q < 128; ++q) out.qual_count[q] += qual_counts[ii * 128 + (size_t)q];
     out.max_qual_seen = std::max(out.max_qual_seen, max_quals[ii]);
+    out.max_hist_qual = std::max(out.max_hist_qual, max_hquals[ii]);
+    out.max_hist_rpos = std::max(out.max_hist_rpos, max_rposs[ii]);
   }
 }
 

@@ -173,24 +173,17 @@ def contig_names(d):
 
 # ---- numpy statements of what the kernels count (test-side only) --------------------------------
 def emulate_hist(hist_rec, n_sets, n_qual):
-    """Covariate histogram for the default layout read_set, ref_base, obs_base, quality."""
+    """Covariate histogram for the default layout read_set, ref_base, obs_base, quality (record layout: brq_types.h)."""
     r = hist_rec
 
     def f(sh, m):
         return ((r >> np.uint64(sh)) & np.uint64(m)).astype(np.int64)
-    obsA, refA, qa, rev, cls, obsB, refB, qb, rset = f(0, 7), f(3, 7), f(6, 127), f(13, 1), f(14, 3), f(16, 7), f(19, 7), f(22, 127), f(29, 31)
+    refA, obsA, qa, validA = f(0, 7), f(3, 7), f(6, 127), f(13, 1)
+    refB, obsB, qb, validB, rset = f(14, 7), f(17, 7), f(20, 127), f(63, 1), f(27, 31)
     N = n_sets
     counts = np.zeros(N * 25 * n_qual, np.int64)
-
-    def comp(x):
-        return np.where(x < 4, 3 - x, x)
-
-    def add(mask, ref, obs, q):
-        np.add.at(counts, (rset + ref * N + obs * 5 * N + q * 25 * N)[mask], 1)
-    add((obsA < 4) & (refA < 4), np.where(rev == 1, comp(refA), refA), np.where(rev == 1, comp(obsA), obsA), qa)
-    add((cls == 1) & (obsB != 5) & (refB != 5), 4, 4, qb)
-    add((cls == 2) & (obsB != 5) & (refB < 4), np.where(rev == 1, comp(refB), refB), 4, qb)
-    add((cls == 3) & (obsB != 5), 4, np.where(rev == 1, comp(obsB), obsB), qb)
+    np.add.at(counts, (rset + refA * N + obsA * 5 * N + qa * 25 * N)[validA == 1], 1)
+    np.add.at(counts, (rset + refB * N + obsB * 5 * N + qb * 25 * N)[validB == 1], 1)
     return counts
 
 

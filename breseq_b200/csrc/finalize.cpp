@@ -242,7 +242,7 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const uint64_
   p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
   g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
   // quality window: as many values as eight copies allow inside 227 KB of shared memory, placed over the most records
-  const size_t budget_cells = (size_t)(225 * 1024) / 16;
+  const size_t budget_cells = ((size_t)(226 * 1024) - TALLY_RING_BYTES) / 16;  // 227 KB per CTA less the record rings and 1 KB of statics
   auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * ((size_t)g.n_st * nq * 4 + 1) * copies; };
   uint32_t q_first = Q, q_last = 0;
   for (uint32_t q = 0; q < Q && q < 128; ++q) if (qual_count[q]) { q_first = std::min(q_first, q); q_last = q; }

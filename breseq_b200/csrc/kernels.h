@@ -42,6 +42,9 @@ static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
 constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15,
                    CO_FIT = 1u << 24;
 
+// shared memory the tally kernel keeps for its per-lane record rings (4 stages x 512 lanes x 16 bytes)
+constexpr uint32_t TALLY_RING_BYTES = 4 * 512 * 16;
+
 struct ScoreParams {
   double log10_ref_length;
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;

@@ -19,6 +19,12 @@
 //                 table (another MAPQ, a '.' observation, a quality outside the window) wait in a
 //                 three-entry register queue and read the full table from global memory when the
 //                 slot is done; a lane that meets more of them rescans its share of the slot.
+//   record ring   With one CTA of 16 warps per SM (the table fills shared memory), plain loads leave too few
+//                 bytes in flight to cover DRAM latency.  Every lane therefore streams its 128-bit vectors
+//                 through a private four-stage ring in shared memory with cp.async (LDGSTS): four vectors
+//                 per lane, 32 KB per SM, are always on their way without holding registers, and the fetch
+//                 cursor runs ahead across slot boundaries.  A lane only ever reads its own ring cells,
+//                 so cp.async.wait_group is the only synchronisation.
 //   redundant records  lead each slot's run (staging.cpp): their order-dependent sum of 1/X1
 //                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head.
 //   presence bound  The reference fits the 5-allele EM on every column, but its result only surfaces
@@ -44,6 +50,8 @@ void note_launches(int n);
 namespace {
 
 constexpr int TALLY_TPB = 512;
+constexpr int RING = (int)(TALLY_RING_BYTES / (TALLY_TPB * 16));  // 16-byte stages of each lane's record ring
+static_assert(RING == 4, "the ring indexing below assumes four stages");
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 8;      // lanes cooperating on one slot
 constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
@@ -64,6 +72,22 @@ __device__ __forceinline__ uint4 ldg_stream_u32x4(const uint4* p) {
   uint4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
+}
+
+// 16 bytes global -> shared without passing through registers (LDGSTS); completion is tracked per thread
+__device__ __forceinline__ void cp_async16(uint32_t shared_addr, const void* p) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(shared_addr), "l"(p) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t shared_addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr));
+  return v;
+}
+__device__ __forceinline__ void sts_zero16(uint32_t shared_addr) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(0u) : "memory");
 }
 
 // ask L2 for [p, p + bytes) ahead of use (16-byte aligned, a multiple of 16 bytes)
@@ -132,6 +156,7 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
   const uint32_t plane = (p.t_nhot + 1u) * cs;
   const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + (lane & (p.t_copies - 1u)) * 16u;  // this lane's copy
   const uint32_t zero_addr = tbl + p.t_nhot * cs;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sm) + 3u * plane + threadIdx.x * 16u;  // this lane's cell of stage 0
   const uint32_t cutoff = p.base_quality_cutoff;
   // cell address = tbl + (((set*2 + top) * n_q + qual - q_lo) * 4 + obs) * cs, as three multiply-adds
   const uint32_t mul_st = p.t_nq * 4u * cs, mul_q = 4u * cs, tbl_adj = tbl - p.t_qlo * mul_q;
@@ -165,42 +190,39 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
       pf_lo = off[s0] & ~3ull; pf_hi = off[s1] & ~3ull;
     }
 
-    // the first vector of a slot is requested while the previous slot is being tallied
-    uint64_t beg = __shfl_sync(gmask, my_beg, g0);
-    uint32_t n_vec = __shfl_sync(gmask, my_vec, g0);
-    const uint4* vp = reinterpret_cast<const uint4*>(rec + beg);
-    uint4 cur = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);  // two vectors per lane are always in flight
-    if (sub < n_vec) cur = ldg_stream_u32x4(vp + sub);
-    if (sub + (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + sub + G);
+    // fetch cursor of this lane's vector stream: slot fk of the group, step f_it of f_nit, running RING vectors ahead
+    int fk = -1;
+    uint32_t f_it = 0, f_nit = 0, f_nvec = 0;
+    const uint4* f_vp = nullptr;
+    auto fetch_next_slot = [&]() {  // group-uniform
+      f_it = 0; f_nit = 0;
+      while (f_nit == 0 && ++fk < G) {
+        f_nvec = __shfl_sync(gmask, my_vec, g0 + fk);
+        f_vp = reinterpret_cast<const uint4*>(rec + __shfl_sync(gmask, my_beg, g0 + fk));
+        f_nit = (f_nvec + (uint32_t)G - 1u) / (uint32_t)G;
+      }
+    };
+    auto fetch = [&](uint32_t stage) {  // the next vector of the stream goes to ring[stage]; always one commit
+      if (fk < G) {
+        const uint32_t iv = f_it * (uint32_t)G + sub, dst = ring + stage * (uint32_t)(TALLY_TPB * 16);
+        if (iv < f_nvec) cp_async16(dst, f_vp + iv); else sts_zero16(dst);
+        if (++f_it == f_nit) fetch_next_slot();
+      }
+      cp_async_commit();
+    };
+    fetch_next_slot();
+#pragma unroll
+    for (int st = 0; st < RING; ++st) fetch((uint32_t)st);
+    uint32_t c_idx = 0;  // vectors consumed by this lane in this round
+
 #pragma unroll 1
     for (int k = 0; k < G; ++k) {
       const uint32_t ref = __shfl_sync(gmask, my_ref, g0 + k);
-      const int kn = k + 1 < G ? k + 1 : k;
-      const uint64_t beg_n = __shfl_sync(gmask, my_beg, g0 + kn);
-      const uint32_t n_vec_n = k + 1 < G ? __shfl_sync(gmask, my_vec, g0 + kn) : 0u;
-      const uint4* vp_n = reinterpret_cast<const uint4*>(rec + beg_n);
-      uint4 cur_n = make_uint4(0, 0, 0, 0);
-      if (sub < n_vec_n) cur_n = ldg_stream_u32x4(vp_n + sub);
-
-      // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
-      // every lane of the group alike (identify_mutations.cpp:1605).  The first vector is in the
-      // group's first lane; pad words are zero and end the walk like a unique record does.
+      const uint64_t beg = __shfl_sync(gmask, my_beg, g0 + k);
+      const uint32_t n_vec = __shfl_sync(gmask, my_vec, g0 + k);
+      const uint4* vp = reinterpret_cast<const uint4*>(rec + beg);
       double rt = 0.0, rb = 0.0;
       uint32_t t_rawt = 0, t_rawb = 0;
-      {
-        const uint32_t hv[4] = {__shfl_sync(gmask, cur.x, g0), __shfl_sync(gmask, cur.y, g0), __shfl_sync(gmask, cur.z, g0),
-                                __shfl_sync(gmask, cur.w, g0)};
-        const uint32_t cnt = n_vec * 4u;
-        uint32_t i = 0, r = n_vec ? hv[0] : 0u;
-        while (r != 0u && !(r & SR_UNIQUE_BIT)) {
-          const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
-          const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-          if (r & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
-          if (++i == cnt) break;
-          r = i == 1 ? hv[1] : i == 2 ? hv[2] : i == 3 ? hv[3] : __ldg(rec + beg + i);
-        }
-      }
-
       Sums a = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       uint32_t t_tops = 0, t_n = 0, t_cref = 0;
       uint32_t cq0 = 0, cq1 = 0, cq2 = 0, n_cold = 0;
@@ -237,18 +259,28 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
           }
         }
       };
-      // Two vector registers per lane, each reloaded right after it is consumed and not touched again
-      // until a whole vector later: no register rotation, so no instruction waits on a load it just issued.
-      for (uint32_t it = 0; it < n_it; it += 2) {
-        const uint32_t iv = it * (uint32_t)G + sub;
-        tally4(cur);
-        cur = make_uint4(0, 0, 0, 0);
-        if (iv + 2u * (uint32_t)G < n_vec) cur = ldg_stream_u32x4(vp + iv + 2 * G);
-        if (it + 1 < n_it) {
-          tally4(nx1);
-          nx1 = make_uint4(0, 0, 0, 0);
-          if (iv + 3u * (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + iv + 3 * G);
+      for (uint32_t it = 0; it < n_it; ++it, ++c_idx) {
+        const uint32_t stage = c_idx & (uint32_t)(RING - 1);
+        cp_async_wait<RING - 1>();  // this lane's oldest vector has landed
+        const uint4 v = lds_u32x4(ring + stage * (uint32_t)(TALLY_TPB * 16));
+        fetch(stage);               // the cell is free again: request the vector RING steps ahead
+        if (it == 0) {
+          // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
+          // every lane of the group alike (identify_mutations.cpp:1605).  The first vector is in the
+          // group's first lane; pad words are zero and end the walk like a unique record does.
+          const uint32_t hv[4] = {__shfl_sync(gmask, v.x, g0), __shfl_sync(gmask, v.y, g0), __shfl_sync(gmask, v.z, g0),
+                                  __shfl_sync(gmask, v.w, g0)};
+          const uint32_t cnt = n_vec * 4u;
+          uint32_t i = 0, r = hv[0];
+          while (r != 0u && !(r & SR_UNIQUE_BIT)) {
+            const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
+            const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
+            if (r & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
+            if (++i == cnt) break;
+            r = i == 1 ? hv[1] : i == 2 ? hv[2] : i == 3 ? hv[3] : __ldg(rec + beg + i);
+          }
         }
+        tally4(v);
       }
       // scoring records outside the shared table
       if (n_cold > 3) {  // the queue overflowed: rescan this lane's share of the slot
@@ -275,9 +307,6 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
         kept = a; red_top = rt; red_bot = rb;
         tops = t_tops >> 10; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
       }
-      beg = beg_n; n_vec = n_vec_n; vp = vp_n; cur = cur_n;
-      nx1 = make_uint4(0, 0, 0, 0);
-      if (sub + (uint32_t)G < n_vec) nx1 = ldg_stream_u32x4(vp + sub + G);
       if (k == 0 && pf_hi > pf_lo) prefetch_l2_bulk(rec + pf_lo, (uint32_t)((pf_hi - pf_lo) * 4u));
     }
     if (my_slot >= n_slots) continue;
@@ -539,7 +568,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
                         cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem_tally = (size_t)3 * (p.t_nhot + 1) * p.t_copies * 16, smem_fit = (size_t)p.n_hot * 48;
+  const size_t smem_tally = (size_t)3 * (p.t_nhot + 1) * p.t_copies * 16 + TALLY_RING_BYTES, smem_fit = (size_t)p.n_hot * 48;
   const uint64_t n_rounds = (n_slots + 31) / 32;
   const int blocks = (int)std::min<uint64_t>((n_rounds + TALLY_TPB / 32 - 1) / (TALLY_TPB / 32), (uint64_t)kSMs);
   // lanes per slot: 4 at ordinary depth, a whole warp once the mean column is deeper than 512 records

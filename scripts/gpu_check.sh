@@ -10,7 +10,7 @@ tail -c 2500 gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_list_$TAG.log 2>&1
 if [ "$FULL" = full ]; then
-  ncu --set full --clock-control none --import-source on -k "regex:tally_kernel|hist_kernel" -s 8 -c 5 -f -o gpurun_out/prof_tally_$TAG \
+  ncu --set full --clock-control none --import-source on -k "regex:tally_kernel" -s 3 -c 1 -f -o gpurun_out/prof_tally_$TAG \
       python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_full_$TAG.log
 fi

@@ -38,6 +38,11 @@ DATASETS = {
                             dict(name="ts", paired=False, read_len=36, coverage=15.0)],
                  n_polymorphic=8, n_fixed=4, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
                  precision=1e-6, places=8, del_prop=6.0, del_seed=0.0),
+    # deep columns (mean depth above 512 switches the tally kernel to a whole warp per slot), polymorphism mode
+    "deep": dict(seed=5, contig_lens=[700], prefix="amplicon",
+                 read_sets=[dict(name="amp", paired=False, read_len=100, coverage=1400.0)],
+                 n_polymorphic=10, n_fixed=3, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
+                 precision=1e-6, places=8, del_prop=100.0, del_seed=0.0),
 }
 
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_cli")  # the reference's own sources (oracle/ref_build.sh)

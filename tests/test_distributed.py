@@ -1,0 +1,67 @@
+"""The N > 1 path on CPU: two `gloo` ranks, each staging its own contiguous reference-coordinate shard
+(brq_stage_options.shard_rank / shard_count), one sum-allreduce of the integer histograms -- the only
+collective of the path -- then every rank holds the whole-genome table.  The kernels' part is played by
+the numpy statements in helpers.py (no GPU here); the GPU version of the same flow is bench.py --gpus N."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import breseq_b200 as bq
+import helpers
+
+WORLD = 2
+
+
+def _worker(rank, world, d, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ctx = bq.Context(device=-1)
+        ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d), shard=(rank, world))
+        s = ctx.stream()
+        n_files = len(helpers.readfile_names(d))
+        counts = torch.from_numpy(helpers.emulate_hist(s["hist_rec"], n_files, 42))
+        cov = helpers.emulate_coverage_hist(s["hist_off"])
+        cov_t = torch.zeros(4096, dtype=torch.int64)
+        cov_t[:len(cov)] = torch.from_numpy(cov)
+        geom = torch.tensor([int(s["n_base"]), int(s["n_score"]), int(s["n_hist"])], dtype=torch.int64)
+        dist.all_reduce(counts)   # the one collective of the path
+        dist.all_reduce(cov_t)
+        dist.all_reduce(geom)
+        t = helpers.emulate_tally(s)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), counts=counts.numpy(), cov=cov_t.numpy(), geom=geom.numpy(),
+                 unique=t["unique"], n=t["n"], n_base=int(s["n_base"]), n_ins=int(s["n_ins"]))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["lambda", "multi"])
+def test_two_rank_shards_allreduce_to_the_whole_genome_table(name, datasets, tmp_path):
+    d = datasets[name]
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(WORLD, d, port, str(tmp_path)), nprocs=WORLD, join=True)
+    r = [np.load(str(tmp_path / ("rank%d.npz" % k))) for k in range(WORLD)]
+    # every rank ends with the same, whole-genome histogram: bit-exact against the oracle
+    ora = helpers.oracle_counts(d["oracle_counts"])
+    for k in range(WORLD):
+        assert np.array_equal(r[k]["counts"], ora)
+        assert np.array_equal(r[k]["cov"], r[0]["cov"])
+    # the shards partition the columns and the records
+    full = bq.Context(device=-1)
+    full.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    sf = full.stream()
+    assert list(r[0]["geom"]) == [int(sf["n_base"]), int(sf["n_score"]), int(sf["n_hist"])]
+    assert sum(int(x["n_base"]) for x in r) == int(sf["n_base"])
+    # per-column tallies of the shards, concatenated in rank order, are the unsharded ones (base columns)
+    tf = helpers.emulate_tally(sf)
+    nb = int(sf["n_base"])
+    cat_unique = np.concatenate([x["unique"][:int(x["n_base"])] for x in r])
+    cat_n = np.concatenate([x["n"][:int(x["n_base"])] for x in r])
+    assert np.array_equal(cat_unique, tf["unique"][:nb]) and np.array_equal(cat_n, tf["n"][:nb])
+    full.close()

@@ -197,6 +197,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner, for one) write to stdout: keep fd 1 clean for the one JSON line
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -268,14 +271,19 @@ def main():
 
     # ---- end to end through the C ABI with host buffers: H2D + kernels + D2H + host finalisation
     with tempfile.TemporaryDirectory() as tmp:
+        phase = {}
+
+        def timed(name, fn, *a):
+            t = time.perf_counter()
+            fn(*a)
+            phase[name] = phase.get(name, 0.0) + time.perf_counter() - t
+
         def e2e_step():
-            ctx.upload()
-            ctx.error_count(COVARIATES)
-            allreduce_hist()
-            ctx.derive_error_table()
-            ctx.write_error_count_files(tmp, os.path.join(tmp, "error_rates.tab"), ["r1", "r2"])
-            ctx.score_columns(params)
-            ctx.write_evidence(os.path.join(tmp, "ra_mc_evidence.gd"), [30.0], [0.0])
+            timed("h2d", lambda: (ctx.upload(), ctx.sync()))
+            timed("pass1_kernels", lambda: (ctx.error_count(COVARIATES), allreduce_hist(), ctx.derive_error_table()))
+            timed("pass1_files", ctx.write_error_count_files, tmp, os.path.join(tmp, "error_rates.tab"), ["r1", "r2"])
+            timed("pass2_kernels", ctx.score_columns, params)
+            timed("d2h_finalise_gd", ctx.write_evidence, os.path.join(tmp, "ra_mc_evidence.gd"), [30.0], [0.0])
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -284,6 +292,7 @@ def main():
             e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_phase_ms = {k: 1e3 * v / (n_e2e + 1) for k, v in phase.items()}
     h2d = int(s["bytes_host"])
     d2h = n_slots * 96 + 25 * 2 * 42 * 16
 
@@ -309,6 +318,7 @@ def main():
         cfg["genome_scale"] = args.scale
         cfg["kernel_ms"] = k_ms
         cfg["staging_seconds"] = t_stage
+        cfg["e2e_phase_ms"] = e2e_phase_ms
         cfg["hist_kernel_gbs"] = hist_bytes / (k_ms["hist"] * 1e-3) / 1e9 if k_ms["hist"] > 0 else 0.0
         cpu = None
         if not args.no_cpu:
@@ -328,7 +338,10 @@ def main():
                              "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                              "algorithmic_bytes": score_bytes},
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -35,7 +35,8 @@ class _StageOptions(C.Structure):
     _fields_ = [("seq_ids", C.POINTER(C.c_char_p)), ("n_seq_ids", C.c_uint32),
                 ("read_file_sets", C.POINTER(_ReadFileSet)), ("n_read_file_sets", C.c_uint32),
                 ("coverage_group_of_tid", C.POINTER(C.c_uint32)), ("n_targets", C.c_uint32),
-                ("use_base_repeat", C.c_uint32), ("shard_rank", C.c_uint32), ("shard_count", C.c_uint32)]
+                ("use_base_repeat", C.c_uint32), ("use_read_pos", C.c_uint32), ("shard_rank", C.c_uint32),
+                ("shard_count", C.c_uint32)]
 
 
 class _SynthReadSet(C.Structure):
@@ -54,9 +55,9 @@ class _StreamInfo(C.Structure):
     _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
                 ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
                 ("bytes_host", C.c_uint64),
-                ("n_targets", C.c_uint32), ("pinned", C.c_uint32),
+                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("reserved", C.c_uint32),
                 ("score_rec", C.POINTER(C.c_uint32)), ("score_off", C.POINTER(C.c_uint64)),
-                ("hist_rec", C.POINTER(C.c_uint64)), ("hist_off", C.POINTER(C.c_uint64)),
+                ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
                 ("ins_count", C.POINTER(C.c_uint32))]
 
@@ -178,7 +179,8 @@ class SynthSpec:
         return [(rs["name"], 2 if rs.get("paired") else 1) for rs in self.read_sets]
 
 
-def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, shard=(0, 1)):
+def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, use_read_pos=False,
+                   shard=(0, 1)):
     keep = []
     o = _StageOptions()
     if seq_ids:
@@ -197,6 +199,7 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
         keep.append(arr)
         o.coverage_group_of_tid, o.n_targets = arr, len(coverage_groups)
     o.use_base_repeat = int(use_base_repeat)
+    o.use_read_pos = int(use_read_pos)
     o.shard_rank, o.shard_count = shard
     return o, keep
 
@@ -267,7 +270,8 @@ class Context:
             "n_score_padded": info.n_score_padded,
             "score_rec": view(info.score_rec, info.n_score_padded, np.uint32),
             "score_off": view(info.score_off, n_slots + 1, np.uint64),
-            "hist_rec": view(info.hist_rec, info.n_hist_records, np.uint64),
+            "hist_rec": view(C.cast(info.hist_rec, C.POINTER(C.c_uint64 if info.hist_record_bytes == 8 else C.c_uint32)),
+                             info.n_hist_records, np.uint64 if info.hist_record_bytes == 8 else np.uint32),
             "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),
             "slot_ref": view(info.slot_ref, n_slots, np.uint8),
             "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
@@ -384,7 +388,8 @@ def error_count(bam, fasta, output_dir, readfiles, do_coverage=True, do_errors=T
     ctx = ctx or Context(device)
     try:
         o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets,
-                                 coverage_groups=coverage_group_of_tid, use_base_repeat="base_repeat" in covariates)
+                                 coverage_groups=coverage_group_of_tid, use_base_repeat="base_repeat" in covariates,
+                                 use_read_pos="read_pos" in covariates)
         arr = _str_array(list(readfiles))
         ctx._check(ctx.lib.brq_run_error_count(ctx.h, _b(bam), _b(fasta), _b(output_dir), _b(error_rates_file_name), arr,
                                                len(readfiles), int(do_coverage), int(do_errors), _b(covariates), C.byref(o)))

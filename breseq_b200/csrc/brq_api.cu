@@ -69,7 +69,8 @@ struct brq_ctx {
   bool staged = false, uploaded = false;
 
   DevBuf<uint32_t> d_score_rec, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
-  DevBuf<uint64_t> d_score_off, d_hist_rec, d_hist_off;
+  DevBuf<uint64_t> d_score_off, d_hist_off;
+  DevBuf<uint8_t> d_hist_rec;
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
   DevBuf<double> d_log10;
@@ -137,6 +138,7 @@ void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
   for (uint32_t i = 0; i < o->n_read_file_sets; ++i) s.read_file_sets.push_back({o->read_file_sets[i].base_name, o->read_file_sets[i].n_files});
   if (o->coverage_group_of_tid) s.coverage_group_of_tid.assign(o->coverage_group_of_tid, o->coverage_group_of_tid + o->n_targets);
   s.use_base_repeat = o->use_base_repeat != 0;
+  s.use_read_pos = o->use_read_pos != 0;
   s.shard_rank = o->shard_rank;
   s.shard_count = o->shard_count ? o->shard_count : 1;
 }
@@ -186,11 +188,11 @@ void upload(brq_ctx* c) {
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
   c->d_score_rec.ensure(st.n_score_padded + 4); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
-  c->d_hist_rec.ensure(st.n_hist); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
+  c->d_hist_rec.ensure(st.n_hist * st.hist_bytes + 16); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * st.hist_bytes, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
   c->uploaded = true;
@@ -224,7 +226,9 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
     too_big(COV_QUALITY, "quality", st.max_hist_qual);
     too_big(COV_READ_SET, "read_set", st.max_read_set_seen);
     too_big(COV_READ_POS, "read_pos", st.max_hist_rpos);
-    launch_hist(c->d_hist_rec.p, st.n_hist, lay, c->d_counts.p, c->stream);
+    if (st.hist_bytes == 4 && (lay.off_rpos || lay.off_rep))
+      throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
+    launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
   }
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, c->d_cov.p, c->d_scalars.p, c->stream);
@@ -472,9 +476,9 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
     info->n_reads = c->reads.size();
     info->n_score_padded = st.n_score_padded;
-    info->bytes_host = st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * 8 + (st.n_base + 1) * 8 + st.n_base;
+    info->bytes_host = st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
-    info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_off = st.hist_off;
+    info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
   });
 }

@@ -80,19 +80,22 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
                    SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_RED_SHIFT = 11,
                    SR_RED_MASK = 0x1FFF;
 
-// Histogram (error_count) record, 8 bytes, one per unique, non-deleted (read, column).  Both
-// observations of cErrorTable::count_alignment_position (error_count.cpp:854-986) are resolved by the
-// staging layer into table coordinates on the READ strand (bases complemented for reversed reads):
+// Histogram (error_count) record, one per unique, non-deleted (read, column).  Both observations of
+// cErrorTable::count_alignment_position (error_count.cpp:854-986) are resolved by the staging layer
+// into table coordinates on the READ strand (bases complemented for reversed reads):
 //   observation A, the aligned base:           [2:0] ref  [5:3] obs  [12:6] quality  [13] valid
 //                                              (valid = neither the read base nor the reference base is N)
-//   observation B, what follows it in the read: [16:14] ref [19:17] obs [26:20] quality [63] valid
+//   observation B, what follows it in the read: [16:14] ref [19:17] obs [26:20] quality [27] valid
 //       next base also aligned      ('.', '.')         quality of the next base on the read strand
 //       deletion of exactly 1 base  (ref base, '.')    quality of the next base on the read strand
 //       insertion of exactly 1 base ('.', inserted)    quality of the inserted base
-//   [31:27] read_set   [47:32] read_pos of A (0-based query index)   [55:48] base_repeat of A   [61:56] base_repeat of B
+//   [31:28] read_set (low four bits)
+// That is the whole record (4 bytes) unless the run uses the read_pos / base_repeat covariates or has
+// more than 16 read files; then records are 8 bytes and the high word adds
+//   [15:0] read_pos of A (0-based query index)  [23:16] base_repeat of A  [29:24] base_repeat of B  [31:30] read_set bits 5:4
 // Base indices A,C,G,T,'.' = 0..4.
-constexpr int HR_REFA = 0, HR_OBSA = 3, HR_QUALA = 6, HR_VALIDA = 13, HR_REFB = 14, HR_OBSB = 17, HR_QUALB = 20, HR_SET = 27,
-              HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_VALIDB = 63;
+constexpr int HR_REFA = 0, HR_OBSA = 3, HR_QUALA = 6, HR_VALIDA = 13, HR_REFB = 14, HR_OBSB = 17, HR_QUALB = 20, HR_VALIDB = 27,
+              HR_SET = 28, HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_SET_HI = 62;
 
 // Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
 struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
@@ -112,7 +115,8 @@ struct PileupStream {
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records
   uint32_t* score_rec = nullptr;
-  uint64_t* hist_rec = nullptr;
+  void* hist_rec = nullptr;            // n_hist records of hist_bytes (4 or 8) each
+  uint32_t hist_bytes = 4;
   uint64_t n_score = 0, n_hist = 0;    // records (padding not counted)
   uint64_t n_score_padded = 0;         // words in score_rec
   uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records

@@ -32,7 +32,8 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
 // ------------------------------------------------------------------------------------------
 // error_count histogram
 // ------------------------------------------------------------------------------------------
-// Records arrive with both observations already resolved to table coordinates (brq_types.h), and the
+// Records arrive with both observations already resolved to table coordinates (brq_types.h), four bytes
+// each unless the run needs read_pos / base_repeat, and the
 // host has checked the stream's largest quality / read_set / read_pos against the table before the
 // launch (the reference's fatal ASSERT, error_count.cpp:485-488), so a record costs two multiply-add
 // chains and two shared-memory atomics.  FULL adds the read_pos / base_repeat covariates.
@@ -42,49 +43,64 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, unsigned long long* count
   else atomicAdd(&counts[idx], 1ull);
 }
 
-template <bool SMEM, bool FULL>
-__device__ __forceinline__ void hist_record(uint64_t r, const CovLayout& lay, uint32_t* sh, unsigned long long* counts) {
-  const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+// lo = the 4-byte record; hi = the high word of an 8-byte record (WIDE: read_pos / base_repeat covariates, > 16 read files)
+template <bool SMEM, bool WIDE>
+__device__ __forceinline__ void hist_record(uint32_t lo, uint32_t hi, const CovLayout& lay, uint32_t* sh, unsigned long long* counts) {
   uint32_t base = (lo >> HR_SET) * lay.off_set;
-  if (FULL) base += (hi & 0xFFFFu) * lay.off_rpos;
+  if (WIDE) base += ((hi >> (HR_SET_HI - 32)) << 4) * lay.off_set + (hi & 0xFFFFu) * lay.off_rpos;
   if (lo & (1u << HR_VALIDA)) {
     uint32_t idx = base + (lo & 7u) * lay.off_ref + ((lo >> HR_OBSA) & 7u) * lay.off_obs + ((lo >> HR_QUALA) & 127u) * lay.off_qual;
-    if (FULL) idx += min((hi >> (HR_REPA - 32)) & 255u, lay.max_rep - 1) * lay.off_rep;
+    if (WIDE) idx += min((hi >> (HR_REPA - 32)) & 255u, lay.max_rep - 1) * lay.off_rep;
     hist_add<SMEM>(sh, counts, idx);
   }
-  if (hi & (1u << (HR_VALIDB - 32))) {
+  if (lo & (1u << HR_VALIDB)) {
     uint32_t idx = base + ((lo >> HR_REFB) & 7u) * lay.off_ref + ((lo >> HR_OBSB) & 7u) * lay.off_obs + ((lo >> HR_QUALB) & 127u) * lay.off_qual;
-    if (FULL) idx += min((hi >> (HR_REPB - 32)) & 63u, lay.max_rep - 1) * lay.off_rep;
+    if (WIDE) idx += min((hi >> (HR_REPB - 32)) & 63u, lay.max_rep - 1) * lay.off_rep;
     hist_add<SMEM>(sh, counts, idx);
   }
 }
 
-template <bool SMEM, bool FULL>
-__global__ void __launch_bounds__(256) hist_kernel(const uint64_t* __restrict__ rec, uint64_t n, CovLayout lay,
+__device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// `rec` holds n records of 4 bytes (WIDE = false: four per 128-bit load) or 8 bytes (WIDE: two per load)
+template <bool SMEM, bool WIDE>
+__global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ rec, uint64_t n, CovLayout lay,
                                                     unsigned long long* __restrict__ counts) {
   extern __shared__ uint32_t sh[];
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i < lay.n_bins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
   }
-  const ulonglong2* rec2 = reinterpret_cast<const ulonglong2*>(rec);
-  const uint64_t n2 = n >> 1;
+  const uint4* vec = reinterpret_cast<const uint4*>(rec);
+  constexpr uint32_t PER = WIDE ? 2 : 4;  // records per vector
+  const uint64_t n_vec = n / PER;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  auto one = [&](const uint4& v) {
+    if (WIDE) { hist_record<SMEM, true>(v.x, v.y, lay, sh, counts); hist_record<SMEM, true>(v.z, v.w, lay, sh, counts); }
+    else {
+      hist_record<SMEM, false>(v.x, 0u, lay, sh, counts); hist_record<SMEM, false>(v.y, 0u, lay, sh, counts);
+      hist_record<SMEM, false>(v.z, 0u, lay, sh, counts); hist_record<SMEM, false>(v.w, 0u, lay, sh, counts);
+    }
+  };
   // four 128-bit loads in flight per thread
-  for (; i + 3 * stride < n2; i += 4 * stride) {
-    ulonglong2 a = ld_stream_u64x2(rec2 + i), b = ld_stream_u64x2(rec2 + i + stride);
-    ulonglong2 c = ld_stream_u64x2(rec2 + i + 2 * stride), d = ld_stream_u64x2(rec2 + i + 3 * stride);
-    hist_record<SMEM, FULL>(a.x, lay, sh, counts); hist_record<SMEM, FULL>(a.y, lay, sh, counts);
-    hist_record<SMEM, FULL>(b.x, lay, sh, counts); hist_record<SMEM, FULL>(b.y, lay, sh, counts);
-    hist_record<SMEM, FULL>(c.x, lay, sh, counts); hist_record<SMEM, FULL>(c.y, lay, sh, counts);
-    hist_record<SMEM, FULL>(d.x, lay, sh, counts); hist_record<SMEM, FULL>(d.y, lay, sh, counts);
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {
+    const uint4 a = ld_stream_u32x4(vec + i), b = ld_stream_u32x4(vec + i + stride);
+    const uint4 c = ld_stream_u32x4(vec + i + 2 * stride), d = ld_stream_u32x4(vec + i + 3 * stride);
+    one(a); one(b); one(c); one(d);
   }
-  for (; i < n2; i += stride) {
-    ulonglong2 a = ld_stream_u64x2(rec2 + i);
-    hist_record<SMEM, FULL>(a.x, lay, sh, counts); hist_record<SMEM, FULL>(a.y, lay, sh, counts);
+  for (; i < n_vec; i += stride) one(ld_stream_u32x4(vec + i));
+  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the last partial vector
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(rec);
+    for (uint64_t k = n_vec * PER; k < n; ++k) {
+      if (WIDE) hist_record<SMEM, true>(w[2 * k], w[2 * k + 1], lay, sh, counts);
+      else hist_record<SMEM, false>(w[k], 0u, lay, sh, counts);
+    }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) hist_record<SMEM, FULL>(rec[n - 1], lay, sh, counts);
   if (SMEM) {
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < lay.n_bins; b += blockDim.x) {
@@ -94,13 +110,12 @@ __global__ void __launch_bounds__(256) hist_kernel(const uint64_t* __restrict__ 
   }
 }
 
-void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
+void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
   const int kSMs = 148;
   const size_t smem = (size_t)lay.n_bins * 4;
-  const bool full = lay.off_rpos != 0 || lay.off_rep != 0;
   if (smem <= 200 * 1024) {
     int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
-    if (full) {
+    if (wide) {
       cudaFuncSetAttribute(hist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       hist_kernel<true, true><<<kSMs * per_sm, 256, smem, s>>>(rec, n_rec, lay, counts);
     } else {
@@ -108,7 +123,7 @@ void launch_hist(const uint64_t* rec, uint64_t n_rec, const CovLayout& lay, unsi
       hist_kernel<true, false><<<kSMs * per_sm, 256, smem, s>>>(rec, n_rec, lay, counts);
     }
   } else {
-    if (full) hist_kernel<false, true><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts);
+    if (wide) hist_kernel<false, true><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts);
     else hist_kernel<false, false><<<kSMs * 8, 256, 0, s>>>(rec, n_rec, lay, counts);
   }
   ++g_launches;

@@ -370,7 +370,8 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   }
   out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
   memset(out.score_rec, 0, out.n_score_padded * 4);
-  out.hist_rec = (uint64_t*)alloc(out.n_hist * 8, &p2);
+  out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 15) ? 8 : 4;
+  out.hist_rec = alloc(out.n_hist * out.hist_bytes, &p2);
 
   // ---- pass B: fill.  Within every slot the redundant records come first and the unique ones
   // follow, each part in arrival (BAM) order: redundant records never score, so the scoring records
@@ -422,7 +423,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
             rec |= (uint64_t)strand(refA) << HR_REFA | (uint64_t)strand(obsA) << HR_OBSA | (uint64_t)qa << HR_QUALA | 1ull << HR_VALIDA;
             if (qa > max_hq) max_hq = qa;
           }
-          rec |= (uint64_t)ri.read_set << HR_SET;
+          rec |= (uint64_t)(ri.read_set & 15u) << HR_SET | (uint64_t)(ri.read_set >> 4) << HR_SET_HI;
           if (q > 65535) throw std::runtime_error("read position above 65535 cannot be packed");
           rec |= (uint64_t)q << HR_RPOS;
           if ((uint32_t)q > max_rp) max_rp = (uint32_t)q;
@@ -463,7 +464,9 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
               if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 63) << HR_REPB;
             }
           }
-          out.hist_rec[(out.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT) + hist_cur[slot]++] = rec;
+          const uint64_t at = (out.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT) + hist_cur[slot]++;
+          if (out.hist_bytes == 8) static_cast<uint64_t*>(out.hist_rec)[at] = rec;
+          else static_cast<uint32_t*>(out.hist_rec)[at] = (uint32_t)rec;
         }
         // ---------------- identify_mutations records (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105)
         if (!cfg.want_score) return;

@@ -45,6 +45,7 @@ typedef struct brq_stage_options {
   const uint32_t* coverage_group_of_tid;   /* Settings::seq_id_to_coverage_group per BAM tid; NULL = one per target */
   uint32_t n_targets;
   uint32_t use_base_repeat;                /* the covariate string names base_repeat */
+  uint32_t use_read_pos;                   /* the covariate string names read_pos (either one: 8-byte histogram records) */
   uint32_t shard_rank, shard_count;        /* contiguous reference-coordinate shard of this process; 0,1 = all */
 } brq_stage_options;
 
@@ -77,9 +78,10 @@ typedef struct brq_stream_info {
   uint64_t n_score_padded;         /* words in score_rec: every slot's run is padded to whole 128-bit vectors */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
+  uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
   const uint32_t* score_rec;       /* host views, valid until the next staging call */
   const uint64_t* score_off;       /* slot s: first index score_off[s] & ~3, pad words (score_off[s+1] & 3) */
-  const uint64_t* hist_rec;
+  const void* hist_rec;
   const uint64_t* hist_off;
   const uint8_t* slot_ref;
   const uint64_t* ins_parent;

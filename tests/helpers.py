@@ -179,12 +179,12 @@ def contig_names(d):
 # ---- numpy statements of what the kernels count (test-side only) --------------------------------
 def emulate_hist(hist_rec, n_sets, n_qual):
     """Covariate histogram for the default layout read_set, ref_base, obs_base, quality (record layout: brq_types.h)."""
-    r = hist_rec
+    r = hist_rec.astype(np.uint64)   # 4-byte records, or 8-byte ones whose low word has the same layout
 
     def f(sh, m):
         return ((r >> np.uint64(sh)) & np.uint64(m)).astype(np.int64)
     refA, obsA, qa, validA = f(0, 7), f(3, 7), f(6, 127), f(13, 1)
-    refB, obsB, qb, validB, rset = f(14, 7), f(17, 7), f(20, 127), f(63, 1), f(27, 31)
+    refB, obsB, qb, validB, rset = f(14, 7), f(17, 7), f(20, 127), f(27, 1), f(28, 15) + 16 * f(62, 3)
     N = n_sets
     counts = np.zeros(N * 25 * n_qual, np.int64)
     np.add.at(counts, (rset + refA * N + obsA * 5 * N + qa * 25 * N)[validA == 1], 1)

@@ -162,3 +162,26 @@ def test_idempotent_and_order_free(run):
     # checksum property: scoring depth summed over slots == eligible records in the stream
     t = helpers.emulate_tally(ctx.stream())
     assert cols["n"].sum() == t["n"].sum() and cols["unique"].sum() == t["unique"].sum()
+
+
+def test_read_pos_and_base_repeat_covariates(datasets, tmp_path):
+    """Pass 1 with the optional covariates (8-byte histogram records, global-memory table): counts bit-exact."""
+    d = datasets["multi"]
+    cov = "read_set=3,obs_base,ref_base,quality=42,read_pos=150,base_repeat=5"
+    out = str(tmp_path)
+    ec, _ = helpers.cli_args(d, out)
+    ec[ec.index("--covariates") + 1] = cov
+    dump = os.path.join(out, "counts.tab")
+    helpers.run_oracle(*ec, "--counts-dump", dump)
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d), use_read_pos=True, use_base_repeat=True)
+    assert ctx.stream()["hist_rec"].dtype == np.uint64
+    ctx.error_count(cov)
+    counts, _ = ctx.hist_download()
+    assert np.array_equal(counts.astype(np.int64), helpers.oracle_counts(dump))
+    # a stream staged without them refuses those covariates instead of counting wrongly
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    assert ctx.stream()["hist_rec"].dtype == np.uint32
+    with pytest.raises(bq.BrqError):
+        ctx.error_count(cov)
+    ctx.close()

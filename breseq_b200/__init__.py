@@ -36,7 +36,7 @@ class _StageOptions(C.Structure):
                 ("read_file_sets", C.POINTER(_ReadFileSet)), ("n_read_file_sets", C.c_uint32),
                 ("coverage_group_of_tid", C.POINTER(C.c_uint32)), ("n_targets", C.c_uint32),
                 ("use_base_repeat", C.c_uint32), ("use_read_pos", C.c_uint32), ("shard_rank", C.c_uint32),
-                ("shard_count", C.c_uint32)]
+                ("shard_count", C.c_uint32), ("base_quality_cutoff", C.c_uint32)]
 
 
 class _SynthReadSet(C.Structure):
@@ -56,7 +56,10 @@ class _StreamInfo(C.Structure):
                 ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
                 ("bytes_host", C.c_uint64),
                 ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("reserved", C.c_uint32),
-                ("score_rec", C.POINTER(C.c_uint32)), ("score_off", C.POINTER(C.c_uint64)),
+                ("n_side", C.c_uint64), ("base_quality_cutoff", C.c_uint32), ("hot_mapq", C.c_uint32),
+                ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_copies", C.c_uint32),
+                ("score_rec", C.POINTER(C.c_uint32)), ("side_rec", C.POINTER(C.c_uint32)), ("side_off", C.POINTER(C.c_uint32)),
+                ("score_off", C.POINTER(C.c_uint64)),
                 ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
                 ("ins_count", C.POINTER(C.c_uint32))]
@@ -180,7 +183,7 @@ class SynthSpec:
 
 
 def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, use_read_pos=False,
-                   shard=(0, 1)):
+                   shard=(0, 1), base_quality_cutoff=3):
     keep = []
     o = _StageOptions()
     if seq_ids:
@@ -201,6 +204,7 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
     o.use_base_repeat = int(use_base_repeat)
     o.use_read_pos = int(use_read_pos)
     o.shard_rank, o.shard_count = shard
+    o.base_quality_cutoff = base_quality_cutoff
     return o, keep
 
 
@@ -210,6 +214,55 @@ def slot_ranges(stream):
     beg = (off[:-1] & ~np.uint64(3)).astype(np.int64)
     end = ((off[1:] & ~np.uint64(3)) - (off[1:] & np.uint64(3))).astype(np.int64)
     return beg, end - beg
+
+
+def decode_score_records(stream):
+    """The staged scoring records as plain arrays, one entry per record in stream order (padding dropped).
+
+    ``score_rec`` holds table-coordinate words (csrc/brq_types.h): this undoes the encoding.  Returns a dict with
+    ``slot``, ``unique``, ``top``, ``scores`` (bool), ``x1``, and for scoring records ``obs``, ``qual``, ``read_set``,
+    ``mapq``, ``match`` (-1 / False where the stream does not keep the value)."""
+    g = stream["geometry"]
+    beg, cnt = slot_ranges(stream)
+    n_slots = len(beg)
+    pos = np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+    d = stream["score_rec"][pos].astype(np.int64)
+    slot = np.repeat(np.arange(n_slots), cnt)
+    kind = d >> 30
+    n = len(d)
+    out = {"slot": slot, "kind": kind, "unique": kind != 3, "top": (d >> 12) & 1, "scores": (kind == 0) | (kind == 2),
+           "x1": np.ones(n, np.int64), "obs": np.full(n, -1), "qual": np.full(n, -1), "read_set": np.full(n, -1),
+           "mapq": np.full(n, -1), "match": np.zeros(n, bool)}
+    hot = kind == 0
+    cell = d[hot] & 0xFFF
+    t = cell >> 2
+    out["obs"][hot] = cell & 3
+    out["qual"][hot] = g["q_lo"] + t % max(1, g["n_q"])
+    out["read_set"][hot] = (t // max(1, g["n_q"])) >> 1
+    out["mapq"][hot] = g["hot_mapq"]
+    out["match"][hot] = ((d[hot] >> 22) & 1) == 1
+    # side list: per slot, the entries of its very redundant records first, then those of its cold records, in order
+    side, soff = stream["side_rec"].astype(np.int64), stream["side_off"].astype(np.int64)
+    x1 = (d >> 13) & 0x1FF
+    big = (kind == 3) & (x1 == 0x1FF)
+    cold = kind == 2
+    uses = big | cold
+    rank = np.cumsum(uses) - 1                       # index among all side-using records, in stream order
+    first = np.zeros(n_slots + 1, np.int64)
+    np.add.at(first, slot[uses] + 1, 1)
+    assert np.array_equal(np.cumsum(first), soff), "side_off does not match the records that use the side list"
+    entry = side[rank[uses]] if uses.any() else np.zeros(0, np.int64)
+    e_big, e_cold = entry[big[uses]], entry[cold[uses]]
+    assert np.all(e_big >> 31 == 1) and np.all(e_cold >> 31 == 0)
+    out["x1"][kind == 3] = x1[kind == 3]
+    out["x1"][big] = e_big & 0x7FFFFFFF
+    out["obs"][cold] = e_cold & 7
+    out["qual"][cold] = (e_cold >> 3) & 127
+    out["read_set"][cold] = (e_cold >> 11) & 31
+    out["mapq"][cold] = (e_cold >> 16) & 255
+    out["match"][cold] = ((e_cold >> 27) & 1) == 1
+    assert np.array_equal(out["top"][cold], (e_cold >> 10) & 1)
+    return out
 
 
 class Context:
@@ -270,6 +323,10 @@ class Context:
             "n_score_padded": info.n_score_padded,
             "score_rec": view(info.score_rec, info.n_score_padded, np.uint32),
             "score_off": view(info.score_off, n_slots + 1, np.uint64),
+            "n_side": info.n_side, "side_rec": view(info.side_rec, info.n_side, np.uint32),
+            "side_off": view(info.side_off, n_slots + 1, np.uint32),
+            "geometry": {"base_quality_cutoff": info.base_quality_cutoff, "hot_mapq": info.hot_mapq, "q_lo": info.table_q_lo,
+                         "n_q": info.table_n_q, "n_st": info.table_n_st, "copies": info.table_copies},
             "hist_rec": view(C.cast(info.hist_rec, C.POINTER(C.c_uint64 if info.hist_record_bytes == 8 else C.c_uint32)),
                              info.n_hist_records, np.uint64 if info.hist_record_bytes == 8 else np.uint32),
             "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),

@@ -61,24 +61,67 @@ struct ReadBatch {
 
 // ---- packed stream records -------------------------------------------------------------
 
-// Scoring record, 4 bytes, one per (read, slot) whose base at that slot is not N.  Within a slot the
-// redundant records (X1 > 1) come first and the unique ones follow, each part in arrival order.
-// Every slot's run starts on a 16-byte boundary and is padded to a multiple of four records with
-// zero words (no real record is zero: a redundant one carries X1 >= 2), so the kernels read whole
-// 128-bit vectors that never straddle two slots.  score_off[s] is the run's first index (a multiple
-// of 4); the low two bits of score_off[s + 1] hold the number of pad words that end slot s's run.
+// ---- scoring (identify_mutations) records ------------------------------------------------
+// One record per (read, slot) whose base at that slot is not N.  What a record MEANS is the
+// "classic" word below; what the device stream HOLDS is the table-coordinate form after it.
+//
+// Classic word (host semantics; the side list and the host re-evaluation use it):
 //   [2:0]   obs        base index 0..4 ('.' = 4)
 //   [9:3]   qual       quality chosen by alignment_position_to_covariates (error_count.cpp:1049-1105)
 //   [10]    top        1 = read on the top strand
 //   [24]    unique     X1 == 1
 //   [25]    trimmed    is_trimmed() (alignment.h:389-410)
 //   [26]    ok         covariates resolvable (not past q_end, no N at the quality position)
+//   [27]    match      obs equals the slot's reference base (side-list entries only)
 //   unique records:    [15:11] read_set (flat read-file index), [23:16] mapq
 //   redundant records: [23:11] redundancy (X1, saturated at 8191)
-// top and read_set are adjacent so that (r >> 10) & 63 == read_set * 2 + top indexes the class tables.
+// A record SCORES when it is unique, untrimmed, ok and qual >= Settings::base_quality_cutoff.
 constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, SR_SET_SHIFT = 11, SR_MAPQ_SHIFT = 16,
-                   SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_RED_SHIFT = 11,
-                   SR_RED_MASK = 0x1FFF;
+                   SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_MATCH_BIT = 1u << 27,
+                   SR_RED_SHIFT = 11, SR_RED_MASK = 0x1FFF;
+
+// Device stream word (score_rec), 4 bytes.  The staging layer has already classified the record and,
+// for the common kind, resolved it to its cell in the tally kernel's shared-memory likelihood table
+// (geometry chosen per stream: ScoreGeometry), so the kernel spends one AND and one multiply-add on
+// addressing and two masked adds on counting.
+//   [11:0]  cell   HOT: ((read_set*2 + top) * n_q + qual - q_lo) * 4 + obs; every other kind: n_hot (the zero cell)
+//   [12]    top    1 = read on the top strand (all kinds)
+//   [21:13] X1     REDUNDANT only; 511 = the value is the slot's next SIDE_BIG entry of the side list
+//   [22]    match  HOT and obs equals the slot's reference base
+//   [23]    hot    HOT
+//   [31:30] kind   0 HOT    scores; dominant MAPQ, A/C/G/T observation, quality inside the table window
+//                  1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
+//                  2 COLD   scores, class outside the shared table; its classic word is the slot's next
+//                           cold entry of the side list
+//                  3 REDUNDANT
+// Within a slot the REDUNDANT records come first and the others follow, each part in arrival (BAM) order.
+// Every slot's run starts on a 16-byte boundary and is padded to a multiple of four records with pad
+// words (cell = n_hot, no other bit: never a real record), so the kernels read whole 128-bit vectors
+// that never straddle two slots.  score_off[s] is the run's first index (a multiple of 4); the low two bits of score_off[s + 1]
+// hold the number of pad words that end slot s's run.
+//
+// Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
+// records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
+constexpr uint32_t DR_CELL_MASK = 0xFFFu, DR_TOP_BIT = 1u << 12, DR_X1_SHIFT = 13, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 22,
+                   DR_HOT_BIT = 1u << 23, DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
+                   SIDE_BIG = 1u << 31;
+
+// Table geometry baked into the device stream words of one staged stream.
+struct ScoreGeometry {
+  uint32_t cutoff = 3;     // Settings::base_quality_cutoff the stream was staged for
+  uint32_t hot_mapq = 0;   // the MAPQ value whose classes the shared table holds
+  uint32_t q_lo = 0, n_q = 0;   // quality window of the shared table
+  uint32_t n_st = 2;       // (read sets) x 2 strands
+  uint32_t copies = 8;     // interleaved copies of the shared table (8 = bank-conflict-free, 1 = they do not fit)
+  uint32_t n_hot() const { return n_st * n_q * 4; }
+};
+
+// classic word of a HOT device word
+inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
+  const uint32_t cell = d & DR_CELL_MASK, obs = cell & 3u, t = cell >> 2, qual = g.q_lo + t % g.n_q, st = t / g.n_q;
+  return obs | qual << SR_QUAL_SHIFT | st << 10 | g.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT |
+         ((d & DR_MATCH_BIT) ? SR_MATCH_BIT : 0u);
+}
 
 // Histogram (error_count) record, one per unique, non-deleted (read, column).  Both observations of
 // cErrorTable::count_alignment_position (error_count.cpp:854-986) are resolved by the staging layer
@@ -114,7 +157,11 @@ struct PileupStream {
   uint64_t* hist_off = nullptr;        // [n_base + 1] CSR into hist_rec; bit 63 of entry c = column c has a redundant read
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records
-  uint32_t* score_rec = nullptr;
+  uint32_t* score_rec = nullptr;       // device stream words
+  uint32_t* side_rec = nullptr;        // side list: classic words of COLD records, SIDE_BIG | X1 of very redundant ones
+  uint32_t* side_off = nullptr;        // [n_base + n_ins + 1] CSR into side_rec
+  uint64_t n_side = 0;
+  ScoreGeometry geo;
   void* hist_rec = nullptr;            // n_hist records of hist_bytes (4 or 8) each
   uint32_t hist_bytes = 4;
   uint64_t n_score = 0, n_hist = 0;    // records (padding not counted)
@@ -141,6 +188,26 @@ inline void score_slot_range(const uint64_t* score_off, uint64_t s, uint64_t& be
   const uint64_t a = score_off[s], b = score_off[s + 1];
   beg = a & ~3ull;
   end = (b & ~3ull) - (b & 3ull);
+}
+
+// Classic words of slot s in stream order (redundant first): f(classic word).  Redundant records come
+// back with their full X1 in a second argument (the classic field saturates at 8191).
+template <class F>
+inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
+  uint64_t beg, end;
+  score_slot_range(st.score_off, s, beg, end);
+  uint32_t side = st.side_off[s];
+  for (uint64_t i = beg; i < end; ++i) {
+    const uint32_t d = st.score_rec[i], kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
+    if (kind == 0) f(classic_of_hot(d, st.geo), 1u);
+    else if (kind == 1) f(top | SR_UNIQUE_BIT | SR_TRIM_BIT, 1u);   // does not score; why is not kept
+    else if (kind == 2) f(st.side_rec[side++], 1u);
+    else {
+      uint32_t x1 = (d >> DR_X1_SHIFT) & DR_X1_MASK;
+      if (x1 == DR_X1_MASK) x1 = st.side_rec[side++] & ~SIDE_BIG;
+      f(top | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1);
+    }
+  }
 }
 
 }  // namespace brq

@@ -212,8 +212,7 @@ void write_coverage_distributions(const std::string& dir, const std::vector<uint
 // MAPQ, the shared-memory table of the fit kernel and the quality window / copy count of the tally
 // kernel's table.  Cheap, so it runs on every table installation; the values are filled in either on
 // the device (build_tables_kernel, tables.cu) or on the host (build_class_lut and friends below).
-void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const uint64_t mapq_count[256], const uint64_t qual_count[128],
-                    ScoreParams& p, TableGeometry& g) {
+void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGeometry& sg, ScoreParams& p, TableGeometry& g) {
   if (c.used[COV_READ_POS] || c.used[COV_BASE_REPEAT])
     throw std::runtime_error("scoring with read_pos / base_repeat covariates is not implemented yet");
   if (!c.used[COV_OBS_BASE] || !c.used[COV_REF_BASE] || !c.used[COV_QUALITY])
@@ -226,44 +225,24 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const uint64_
   p.n_mapq_slots = (uint32_t)g.mapqs.size();
   p.max_qual = Q;
   p.max_set = c.used[COV_READ_SET] ? n_set : 32;
-  g.n_st = n_set * 2;
   g.off_set = c.used[COV_READ_SET] ? c.offset[COV_READ_SET] : 0; g.off_ref = c.offset[COV_REF_BASE];
   g.off_obs = c.offset[COV_OBS_BASE]; g.off_qual = c.offset[COV_QUALITY];
+  if (n_set * 2 < sg.n_st)
+    throw std::runtime_error("Covariate 'read_set' with value '" + std::to_string(sg.n_st / 2 - 1) +
+                             "' exceeded enforced maximum value of '" + std::to_string(n_set - 1) + "'.");
+  g.n_st = sg.n_st;  // the stream's words index the shared table with the stream's own set count
   g.n_lut = (size_t)g.n_st * g.mapqs.size() * Q * 5;
-  // the dominant MAPQ
-  uint32_t hot = 0;
-  for (uint32_t m = 1; m < 256; ++m) if (mapq_count[m] > mapq_count[hot]) hot = m;
-  if (p.mapq_slot[hot] == 255) hot = g.mapqs[0];
-  p.hot_mapq = hot;
+  // the dominant MAPQ and the tally kernel's shared-memory window were fixed when the stream was staged
+  if (p.mapq_slot[sg.hot_mapq] == 255) throw std::runtime_error("the stream's dominant MAPQ is missing from its MAPQ set");
+  p.hot_mapq = sg.hot_mapq;
   const size_t n_hot = (size_t)g.n_st * Q * 5;
   p.n_hot = (n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // fit kernel: three CTAs per SM must each hold a copy
   g.n_hotR = n_hot;
   // MAPQ range of the global table of the tally kernel
   p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
   g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
-  // quality window: as many values as eight copies allow inside 227 KB of shared memory, placed over the most records
-  const size_t budget_cells = ((size_t)(226 * 1024) - TALLY_RING_BYTES) / 16;  // 227 KB per CTA less the record rings and 1 KB of statics
-  auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * ((size_t)g.n_st * nq * 4 + 1) * copies; };
-  uint32_t q_first = Q, q_last = 0;
-  for (uint32_t q = 0; q < Q && q < 128; ++q) if (qual_count[q]) { q_first = std::min(q_first, q); q_last = q; }
-  if (q_first > q_last) { q_first = 0; q_last = Q ? Q - 1 : 0; }
-  uint32_t want = q_last - q_first + 1, copies = 8, nq = want;
-  while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
-  if (nq < 8 && nq < want) {  // eight copies leave too narrow a window: one copy of everything (or nothing)
-    copies = 1; nq = want;
-    while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
-  }
-  uint32_t best_lo = q_first;
-  if (nq < want) {
-    uint64_t best = 0;
-    for (uint32_t a = q_first; a + nq <= q_last + 1; ++a) {
-      uint64_t mass = 0;
-      for (uint32_t q = a; q < a + nq; ++q) mass += qual_count[q];
-      if (mass > best) { best = mass; best_lo = a; }
-    }
-  }
-  p.t_qlo = best_lo; p.t_nq = nq; p.t_copies = copies; p.t_nhot = g.n_st * nq * 4;
-  g.n_tally_cells = cells(nq, copies);
+  p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_copies = sg.copies; p.t_nhot = sg.n_hot();
+  g.n_tally_cells = (size_t)3 * ((size_t)p.t_nhot + 1) * p.t_copies;
 }
 
 // Host copy of the per-class terms, with the libm calls the reference makes (identify_mutations.cpp:3359-3384).
@@ -546,18 +525,15 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   for (uint32_t slot : flagged) {
     SlotEval s;
     memset(s.count, 0, sizeof s.count);
-    uint64_t rec_beg, rec_end;
-    score_slot_range(st.score_off, slot, rec_beg, rec_end);
-    for (uint64_t i = rec_beg; i < rec_end; ++i) {
-      const uint32_t r = st.score_rec[i];
+    for_each_classic(st, slot, [&](uint32_t r, uint32_t) {
       const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
-      if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) continue;
+      if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) return;
       const uint32_t obs = r & 7, top = (r & SR_TOP_BIT) ? 1 : 0, mapq = (r >> SR_MAPQ_SHIFT) & 255, set = (r >> SR_SET_SHIFT) & 31;
       const size_t li = ((((size_t)set * 2 + top) * sp.n_mapq_slots + sp.mapq_slot[mapq]) * sp.max_qual + q) * 5 + obs;
       s.reads.push_back(&lut[li]);
       s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
       ++s.count[obs][top];
-    }
+    });
     const uint8_t ref = st.slot_ref[slot];
     evaluate_slot(s, ref, ep);
     ++counts.rechecked;

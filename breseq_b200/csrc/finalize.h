@@ -47,8 +47,8 @@ struct TableGeometry {
   uint32_t off_set = 0, off_ref = 0, off_obs = 0, off_qual = 0;  // covariate table strides
   size_t n_lut = 0, n_hotR = 0, n_cold = 0, n_tally_cells = 0;
 };
-void score_geometry(const CovSpec& spec, const uint32_t mapq_seen[8], const uint64_t mapq_count[256], const uint64_t qual_count[128],
-                    ScoreParams& p, TableGeometry& g);
+void score_geometry(const CovSpec& spec, const uint32_t mapq_seen[8], const ScoreGeometry& stream_geometry, ScoreParams& p,
+                    TableGeometry& g);
 // Host copy of the per-class terms for every (read_set, strand, MAPQ present, quality, obs); libm arithmetic as the reference.
 void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g,
                      std::vector<ClassTerms>& lut);

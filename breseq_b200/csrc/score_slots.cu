@@ -37,7 +37,7 @@
 //                            >= n log10 g0[ref] + ll[ref],     g0[ref] >= (0.5 + c_ref) / (n + 2)
 //                 so  score <= (sum M - ll[ref]) - n log10((0.5 + c_ref)/(n + 2)) - log10(ref length).
 //                 Columns under the cutoff by a margin are final here; the others go to a work list.
-//   fit_kernel    eight lanes per work-list slot: the 5-allele EM fit, the presence score of the
+//   fit_kernel    one warp per work-list slot: the 5-allele EM fit, the presence score of the
 //                 top non-reference allele (second EM with it held out), emission flags
 //                 (identify_mutations.cpp:1797-1821, 3240-3344).
 #include "kernels.h"
@@ -53,7 +53,7 @@ constexpr int TALLY_TPB = 512;
 constexpr int RING = (int)(TALLY_RING_BYTES / (TALLY_TPB * 16));  // 16-byte stages of each lane's record ring
 static_assert(RING == 4, "the ring indexing below assumes four stages");
 constexpr int FIT_TPB = 256;
-constexpr int FIT_LANES = 8;      // lanes cooperating on one slot
+constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts
 constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
 constexpr uint32_t CODE_NONE = 0xFFFFFFFFu, CODE_COLD = 0x80000000u;
 
@@ -86,8 +86,8 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t shared_addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr));
   return v;
 }
-__device__ __forceinline__ void sts_zero16(uint32_t shared_addr) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(0u) : "memory");
+__device__ __forceinline__ void sts_fill16(uint32_t shared_addr, uint32_t word) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(word) : "memory");
 }
 
 // ask L2 for [p, p + bytes) ahead of use (16-byte aligned, a multiple of 16 bytes)
@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t group_add_u32(uint32_t v, uint32_t mask) {
 
 struct Sums { double l0, l1, l2, l3, l4, m; };
 
-// a scoring record whose class is not in the shared table: {L[0..4], M} from the global table
+// a scoring record whose class is not in the shared table (classic word from the side list): {L[0..4], M} from the global table
 __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
   const uint32_t st = (r >> 10) & 63u, mapq = (r >> SR_MAPQ_SHIFT) & 255u, qual = (r >> SR_QUAL_SHIFT) & 127u;
   const char* e = reinterpret_cast<const char*>(coldT + (((st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * 5u + (r & 7u)));
@@ -135,6 +135,7 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 // ------------------------------------------------------------------------------------------ tally
 template <int G>
 __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+                                                              const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                               const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
                                                               const double* __restrict__ tallyT, const HotTerms* __restrict__ coldT,
                                                               ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
@@ -157,15 +158,6 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
   const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + (lane & (p.t_copies - 1u)) * 16u;  // this lane's copy
   const uint32_t zero_addr = tbl + p.t_nhot * cs;
   const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sm) + 3u * plane + threadIdx.x * 16u;  // this lane's cell of stage 0
-  const uint32_t cutoff = p.base_quality_cutoff;
-  // cell address = tbl + (((set*2 + top) * n_q + qual - q_lo) * 4 + obs) * cs, as three multiply-adds
-  const uint32_t mul_st = p.t_nq * 4u * cs, mul_q = 4u * cs, tbl_adj = tbl - p.t_qlo * mul_q;
-  const uint32_t q_lo = p.t_qlo > cutoff ? p.t_qlo : cutoff, q_span = p.t_qlo + p.t_nq > q_lo ? p.t_qlo + p.t_nq - q_lo : 0u;
-  // unique, untrimmed, resolvable; for the shared table also the dominant MAPQ and an A/C/G/T observation
-  const uint32_t flag_mask = SR_UNIQUE_BIT | SR_TRIM_BIT | SR_OK_BIT, flag_want = SR_UNIQUE_BIT | SR_OK_BIT;
-  const uint32_t mo_mask = (255u << SR_MAPQ_SHIFT) | 4u;
-  const uint32_t mo_want = p.t_nhot ? (p.hot_mapq << SR_MAPQ_SHIFT) : 0xFFFFFFFFu;  // no table: nothing matches
-
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
   const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << g0);
   const uint64_t n_rounds = (n_slots + 31) >> 5;  // a warp takes 32 consecutive slots per round
@@ -174,10 +166,12 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
     const uint64_t my_slot = (round << 5) + lane;  // the slot this lane closes; its group tallies slots g0 .. g0+G-1
     uint64_t my_beg = 0;
     uint32_t my_vec = 0, my_pad = 0, my_ref = 5;   // 128-bit vectors of the run, pad words in the last one
+    uint32_t my_side0 = 0, my_side1 = 0;           // the slot's range of the side list
     if (my_slot < n_slots) {
       const uint64_t o0 = off[my_slot], o1 = off[my_slot + 1];
       my_beg = o0 & ~3ull; my_vec = (uint32_t)(((o1 & ~3ull) - my_beg) >> 2); my_pad = (uint32_t)o1 & 3u;
       my_ref = slot_ref[my_slot];
+      my_side0 = side_off[my_slot]; my_side1 = side_off[my_slot + 1];
     }
     Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double red_top = 0.0, red_bot = 0.0;
@@ -205,7 +199,7 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
     auto fetch = [&](uint32_t stage) {  // the next vector of the stream goes to ring[stage]; always one commit
       if (fk < G) {
         const uint32_t iv = f_it * (uint32_t)G + sub, dst = ring + stage * (uint32_t)(TALLY_TPB * 16);
-        if (iv < f_nvec) cp_async16(dst, f_vp + iv); else sts_zero16(dst);
+        if (iv < f_nvec) cp_async16(dst, f_vp + iv); else sts_fill16(dst, p.t_nhot);  // past the run: pad words
         if (++f_it == f_nit) fetch_next_slot();
       }
       cp_async_commit();
@@ -214,6 +208,17 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
 #pragma unroll
     for (int st = 0; st < RING; ++st) fetch((uint32_t)st);
     uint32_t c_idx = 0;  // vectors consumed by this lane in this round
+
+    // While the first vectors are on their way: the scoring records of this lane's own slot whose class
+    // is not in the shared table (another MAPQ, a '.' observation, a quality outside the window) sit in
+    // the side list as classic words; their terms come from the global table and start the slot's sums.
+    for (uint32_t e = my_side0; e < my_side1; ++e) {
+      const uint32_t w = __ldg(side + e);
+      if (w & SIDE_BIG) continue;  // the X1 of a very redundant record, read by the walk below
+      cold_add(kept, w, coldT, p);
+      ++n;
+      c_ref += (w >> 27) & 1u;
+    }
 
 #pragma unroll 1
     for (int k = 0; k < G; ++k) {
@@ -225,39 +230,32 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
       uint32_t t_rawt = 0, t_rawb = 0;
       Sums a = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       uint32_t t_tops = 0, t_n = 0, t_cref = 0;
-      uint32_t cq0 = 0, cq1 = 0, cq2 = 0, n_cold = 0;
+      uint32_t acc_tm = 0, acc_h = 0;  // packed counters: tops in [21:12] and matches in [31:22]; hot records in [31:23]
+      uint32_t side_cur = __shfl_sync(gmask, my_side0, g0 + k);
       const uint32_t n_it = (n_vec + (uint32_t)G - 1u) / (uint32_t)G;  // the same for every lane of the group
-      // four records of one 128-bit vector; pad words are zero: no flag set, nothing scores
+      // four device words of one 128-bit vector: the cell index addresses this lane's copy of the table
+      // (every word that does not score, pad words included, carries the zero cell) and two masked adds
+      // keep the counts
       auto tally4 = [&](const uint4& v) {
         const uint32_t r[4] = {v.x, v.y, v.z, v.w};
-        t_tops += (r[0] & SR_TOP_BIT) + (r[1] & SR_TOP_BIT);
-        t_tops += (r[2] & SR_TOP_BIT) + (r[3] & SR_TOP_BIT);
+        uint32_t addr[4];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two records at a time: six 128-bit loads in flight
-          uint32_t addr[2];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const uint32_t w = r[2 * h + jj];
-            const uint32_t qual = (w >> SR_QUAL_SHIFT) & 127u;
-            const bool scoring = (w & flag_mask) == flag_want && qual >= cutoff;
-            const bool hot = scoring && (w & mo_mask) == mo_want && (qual - q_lo) < q_span;
-            const bool cold = scoring && !hot;
-            const uint32_t cell = tbl_adj + ((w >> 10) & 63u) * mul_st + qual * mul_q + (w & 3u) * cs;
-            addr[jj] = hot ? cell : zero_addr;
-            const uint32_t one = scoring ? 1u : 0u;
-            t_n += one;
-            t_cref += ((w & 7u) == ref) ? one : 0u;
-            cq2 = cold ? cq1 : cq2; cq1 = cold ? cq0 : cq1; cq0 = cold ? w : cq0;
-            n_cold += cold ? 1u : 0u;
-          }
-          f64x2 x[2], y[2], z[2];  // {L0,L1}, {L2,L3}, {L4,M}
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) { x[jj] = lds_f64x2(addr[jj]); y[jj] = lds_f64x2(addr[jj] + plane); z[jj] = lds_f64x2(addr[jj] + 2u * plane); }
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {  // the zero cell adds +0.0 exactly
-            a.l0 += x[jj].x; a.l1 += x[jj].y; a.l2 += y[jj].x; a.l3 += y[jj].y; a.l4 += z[jj].x; a.m += z[jj].y;
-          }
+        for (int j = 0; j < 4; ++j) {
+          addr[j] = tbl + (r[j] & DR_CELL_MASK) * cs;
+          acc_tm += r[j] & (DR_TOP_BIT | DR_MATCH_BIT);
+          acc_h += r[j] & DR_HOT_BIT;
         }
+        f64x2 x[4], y[4], z[4];  // {L0,L1}, {L2,L3}, {L4,M}: all twelve 128-bit loads in flight together
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { x[j] = lds_f64x2(addr[j]); y[j] = lds_f64x2(addr[j] + plane); z[j] = lds_f64x2(addr[j] + 2u * plane); }
+        // the zero cell adds +0.0 exactly; pairs first, so each sum waits on two dependent adds per vector, not four
+        a.l0 += (x[0].x + x[1].x) + (x[2].x + x[3].x); a.l1 += (x[0].y + x[1].y) + (x[2].y + x[3].y);
+        a.l2 += (y[0].x + y[1].x) + (y[2].x + y[3].x); a.l3 += (y[0].y + y[1].y) + (y[2].y + y[3].y);
+        a.l4 += (z[0].x + z[1].x) + (z[2].x + z[3].x); a.m += (z[0].y + z[1].y) + (z[2].y + z[3].y);
+      };
+      auto flush_counts = [&]() {
+        t_tops += (acc_tm >> 12) & 0x3FFu; t_cref += acc_tm >> 22; t_n += acc_h >> 23;
+        acc_tm = 0; acc_h = 0;
       };
       for (uint32_t it = 0; it < n_it; ++it, ++c_idx) {
         const uint32_t stage = c_idx & (uint32_t)(RING - 1);
@@ -267,45 +265,31 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
         if (it == 0) {
           // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
           // every lane of the group alike (identify_mutations.cpp:1605).  The first vector is in the
-          // group's first lane; pad words are zero and end the walk like a unique record does.
+          // group's first lane; a pad word ends the walk like any non-redundant record does.
           const uint32_t hv[4] = {__shfl_sync(gmask, v.x, g0), __shfl_sync(gmask, v.y, g0), __shfl_sync(gmask, v.z, g0),
                                   __shfl_sync(gmask, v.w, g0)};
           const uint32_t cnt = n_vec * 4u;
           uint32_t i = 0, r = hv[0];
-          while (r != 0u && !(r & SR_UNIQUE_BIT)) {
-            const uint32_t red = (r >> SR_RED_SHIFT) & SR_RED_MASK;
+          while ((r >> DR_KIND_SHIFT) == 3u) {
+            uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
+            if (red == DR_X1_MASK) red = __ldg(side + side_cur++) & ~SIDE_BIG;
             const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-            if (r & SR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
+            if (r & DR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
             if (++i == cnt) break;
             r = i == 1 ? hv[1] : i == 2 ? hv[2] : i == 3 ? hv[3] : __ldg(rec + beg + i);
           }
         }
         tally4(v);
+        if ((it & 63u) == 63u) flush_counts();  // 256 records per lane: the packed fields hold 511
       }
-      // scoring records outside the shared table
-      if (n_cold > 3) {  // the queue overflowed: rescan this lane's share of the slot
-        for (uint32_t iv = sub; iv < n_vec; iv += G) {
-          const uint4 v = __ldg(vp + iv);
-          const uint32_t rr[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t qual = (rr[j] >> SR_QUAL_SHIFT) & 127u;
-            const bool scoring = (rr[j] & flag_mask) == flag_want && qual >= cutoff;
-            const bool hot = scoring && (rr[j] & mo_mask) == mo_want && (qual - q_lo) < q_span;
-            if (scoring && !hot) cold_add(a, rr[j], coldT, p);
-          }
-        }
-      } else {
-        if (n_cold > 2) cold_add(a, cq2, coldT, p);
-        if (n_cold > 1) cold_add(a, cq1, coldT, p);
-        if (n_cold > 0) cold_add(a, cq0, coldT, p);
-      }
+      flush_counts();
       a.l0 = group_add<G>(a.l0, gmask); a.l1 = group_add<G>(a.l1, gmask); a.l2 = group_add<G>(a.l2, gmask);
       a.l3 = group_add<G>(a.l3, gmask); a.l4 = group_add<G>(a.l4, gmask); a.m = group_add<G>(a.m, gmask);
       t_tops = group_add_u32<G>(t_tops, gmask); t_n = group_add_u32<G>(t_n, gmask); t_cref = group_add_u32<G>(t_cref, gmask);
       if (sub == (uint32_t)k) {
-        kept = a; red_top = rt; red_bot = rb;
-        tops = t_tops >> 10; n = t_n; c_ref = t_cref; raw_top = t_rawt; raw_bot = t_rawb;
+        kept.l0 += a.l0; kept.l1 += a.l1; kept.l2 += a.l2; kept.l3 += a.l3; kept.l4 += a.l4; kept.m += a.m;
+        red_top = rt; red_bot = rb;
+        tops = t_tops; n += t_n; c_ref += t_cref; raw_top = t_rawt; raw_bot = t_rawb;
       }
       if (k == 0 && pf_hi > pf_lo) prefetch_l2_bulk(rec + pf_lo, (uint32_t)((pf_hi - pf_lo) * 4u));
     }
@@ -370,7 +354,8 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
 namespace {
 
 struct GroupCtx {
-  const uint32_t* rec; uint64_t beg, end;
+  const uint32_t* rec; uint64_t beg, end;   // the slot's device words [beg, beg + n_main) followed, in index space, by its side-list entries
+  const uint32_t* side; uint32_t side_beg; uint64_t n_main;
   uint32_t hot_base; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
   const uint32_t* cache;  // table codes of the slot's first FIT_CACHE records
   uint32_t sub, mask;     // lane within the group, shuffle mask of the group
@@ -395,9 +380,23 @@ __device__ __forceinline__ uint32_t code_of(const GroupCtx& g, uint32_t r) {
   if (p.n_hot && ((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq) return hot_index(r, p.max_qual) * 48u;
   return CODE_COLD | cold_index(r, p, g.mapq_slot);
 }
+// Classic word at index i of the slot's records for the fit: a HOT device word is decoded, a side-list
+// entry is taken as it is, everything else (IDLE, the COLD placeholder, REDUNDANT, padding) does not score.
+__device__ __forceinline__ uint32_t classic_at(const GroupCtx& g, uint64_t i) {
+  const uint64_t k = i - g.beg;
+  if (k < g.n_main) {
+    const uint32_t d = __ldg(g.rec + i);
+    if ((d >> DR_KIND_SHIFT) != 0u || !(d & DR_HOT_BIT)) return 0u;
+    const ScoreParams& p = *g.p;
+    const uint32_t cell = d & DR_CELL_MASK, obs = cell & 3u, t = cell >> 2, qual = p.t_qlo + t % p.t_nq, st = t / p.t_nq;
+    return obs | qual << SR_QUAL_SHIFT | st << 10 | p.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT;
+  }
+  const uint32_t w = __ldg(g.side + g.side_beg + (uint32_t)(k - g.n_main));
+  return (w & SIDE_BIG) ? 0u : w;
+}
 __device__ __forceinline__ uint32_t code_at(const GroupCtx& g, uint64_t i) {
   const uint64_t k = i - g.beg;
-  return k < FIT_CACHE ? g.cache[k] : code_of(g, __ldg(g.rec + i));
+  return k < FIT_CACHE ? g.cache[k] : code_of(g, classic_at(g, i));
 }
 // r[0..4] and M = max_b L[b]
 __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, double* rr, double& M) {
@@ -415,6 +414,7 @@ __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, do
 }  // namespace
 
 __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+                                                          const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                           const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
                                                           const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
                                                           ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ flagged,
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
   GroupCtx g;
   g.rec = rec; g.hot_base = (uint32_t)__cvta_generic_to_shared(sm); g.lut = lut; g.mapq_slot = mapq_slot; g.p = &p;
   g.sub = lane % FIT_LANES;
-  g.mask = ((1u << FIT_LANES) - 1u) << (lane - g.sub);
+  g.mask = FIT_LANES == 32 ? 0xFFFFFFFFu : (((1u << (FIT_LANES & 31)) - 1u) << (lane - g.sub));
   uint32_t* my_cache = cache[threadIdx.x / FIT_LANES];
   g.cache = my_cache;
   for (;;) {
@@ -445,9 +445,12 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     if (w >= n_work) break;
     const uint32_t slot = worklist[w];
     score_slot_range(off, slot, g.beg, g.end);
+    g.n_main = g.end - g.beg;
+    g.side = side; g.side_beg = side_off[slot];
+    g.end += side_off[slot + 1] - g.side_beg;
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
     for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-      const uint32_t r = __ldg(rec + i);
+      const uint32_t r = classic_at(g, i);
       const uint32_t code = code_of(g, r);
       if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
       if (code == CODE_NONE) continue;
@@ -562,7 +565,8 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
   }
 }
 
-void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* side, const uint32_t* side_off,
+                        const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between) {
@@ -574,14 +578,14 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint8_t*
   // lanes per slot: 4 at ordinary depth, a whole warp once the mean column is deeper than 512 records
   if (n_records / n_slots < 512) {
     cudaFuncSetAttribute(tally_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-    tally_kernel<4><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
+    tally_kernel<4><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
   } else {
     cudaFuncSetAttribute(tally_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-    tally_kernel<32><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
+    tally_kernel<32><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
   }
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
   note_launches(2);
 }
 

@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -296,39 +296,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   }
   const uint64_t n_slots = out.n_slots();
 
-  // ---- pass A2: record counts per slot
-  std::vector<uint32_t> score_cnt(cfg.want_score ? n_slots : 0, 0), hist_cnt(cfg.want_hist ? out.n_base : 0, 0);
-  std::vector<uint32_t> red_cnt(cfg.want_score ? n_slots : 0, 0);  // redundant records per slot: they lead the slot's run
-  std::vector<uint8_t> col_red(cfg.want_hist ? out.n_base : 0, 0);
-  run_items([&](size_t ii) {
-    const Item& it = items[ii];
-    const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
-    for (size_t i = it.first_read; i < it.last_read; ++i) {
-      if (!in_pileup(i) || info[i].end <= it.lo) continue;
-      const uint8_t* seq = R.bases.data() + R.seq_off[i];
-      const bool unique = R.x1[i] == 1;
-      const uint32_t L = info[i].L;
-      walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
-        const uint64_t slot = s0 + (uint64_t)c;
-        if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
-        if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
-        if (cfg.want_score) {
-          if (is_del || seq[q] != 15) { ++score_cnt[slot]; if (!unique) ++red_cnt[slot]; }
-          uint32_t K = sub_k[slot];
-          if (K) {
-            int ind = is_del ? -1 : std::max(indel, 0);
-            for (uint32_t k = 1; k <= K; ++k)
-              if (ind < (int)k || seq[q + (int32_t)k] != 15) {
-                ++score_cnt[out.n_base + sub_first[slot] + k - 1];
-                if (!unique) ++red_cnt[out.n_base + sub_first[slot] + k - 1];
-              }
-          }
-        }
-      });
-    }
-  });
-
-  // ---- offsets
+  // ---- per-slot reference bases and coverage groups; offset arrays
   bool pinned = false, p2 = false;
   out.slot_ref = (uint8_t*)alloc(n_slots, &pinned);
   out.slot_group = (uint8_t*)alloc(out.n_base ? out.n_base : 1, &p2);
@@ -349,6 +317,151 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     }
   }
   for (uint64_t j = 0; j < out.n_ins; ++j) out.slot_ref[out.n_base + j] = kBaseGap;
+
+  // ---- table geometry of the device stream words (ScoreGeometry).  The dominant MAPQ and the quality
+  // window are picked from per-read statistics (every base of every unique read), which follow the
+  // scoring records closely and cost no column walk; the exact per-record histograms are gathered in pass B.
+  if (cfg.want_score) {
+    std::vector<uint64_t> mq(256, 0), qc(128, 0);
+    for (size_t i = 0; i < R.size(); ++i) {
+      if (!in_pileup(i) || R.x1[i] != 1) continue;
+      mq[R.mapq[i]] += info[i].L;
+      const uint8_t* qual = R.quals.data() + R.seq_off[i];
+      for (uint32_t k = 0; k < info[i].L; ++k) ++qc[qual[k] & 127];
+    }
+    ScoreGeometry& g = out.geo;
+    g.cutoff = cfg.base_quality_cutoff;
+    g.n_st = (out.max_read_set_seen + 1) * 2;
+    g.hot_mapq = 0;
+    for (uint32_t m = 1; m < 256; ++m) if (mq[m] > mq[g.hot_mapq]) g.hot_mapq = m;
+    // as many quality values as eight interleaved copies allow next to the record rings in 227 KB of shared memory
+    const size_t budget_cells = ((size_t)(226 * 1024) - 4 * 512 * 16) / 16;
+    auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * ((size_t)g.n_st * nq * 4 + 1) * copies; };
+    uint32_t q_first = 128, q_last = 0;
+    for (uint32_t q = g.cutoff; q < 128; ++q) if (qc[q]) { q_first = std::min(q_first, q); q_last = q; }
+    if (q_first > q_last) { q_first = g.cutoff; q_last = g.cutoff; }
+    uint32_t want = q_last - q_first + 1, copies = 8, nq = want;
+    while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
+    if (nq < 8 && nq < want) {  // eight copies leave too narrow a window: one copy
+      copies = 1; nq = want;
+      while (nq > 0 && (cells(nq, copies) > budget_cells || (size_t)g.n_st * nq * 4 >= DR_CELL_MASK)) --nq;
+    }
+    uint32_t best_lo = q_first;
+    if (nq < want) {
+      uint64_t best = 0;
+      for (uint32_t lo = q_first; lo + nq <= q_last + 1; ++lo) {
+        uint64_t mass = 0;
+        for (uint32_t q = lo; q < lo + nq; ++q) mass += qc[q];
+        if (mass > best) { best = mass; best_lo = lo; }
+      }
+    }
+    g.q_lo = best_lo; g.n_q = nq; g.copies = copies;
+  }
+  const ScoreGeometry geo = out.geo;
+  const uint32_t n_hot = geo.n_hot();
+
+  // Classic words of one pileup entry: the column itself (k = 0) and its insert sub-columns
+  // (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105).  sink(slot, classic word, X1).
+  auto score_words = [&](size_t i, const ReadInfo& ri, int32_t q, bool is_del, int indel, uint64_t slot, auto&& sink) {
+    const uint8_t* seq = R.bases.data() + R.seq_off[i];
+    const uint8_t* qual = R.quals.data() + R.seq_off[i];
+    const bool unique = R.x1[i] == 1;
+    const uint32_t rev = ri.rev ? 1 : 0;
+    const int32_t L = (int32_t)ri.L;
+    const uint32_t mapq = R.mapq[i];
+    const int ind = is_del ? -1 : std::max(indel, 0);
+    const uint32_t K = sub_k[slot];
+    const uint32_t q1 = (uint32_t)q + 1;
+    for (uint32_t k = 0; k <= K; ++k) {
+      const bool past_base = !(ind >= (int)k);
+      uint8_t obs = past_base ? (uint8_t)kBaseGap : nibble_to_index(seq[q + (int32_t)k]);
+      if (obs == kBaseN) continue;  // not even coverage
+      uint32_t rec = obs;
+      if (!rev) rec |= SR_TOP_BIT;
+      bool trimmed = false;  // alignment.h:389-410 (unsigned comparisons as there)
+      if (R.xl[i] >= 0 || R.xl[i] < -1) { if (q1 <= (uint32_t)R.xl[i]) trimmed = true; }
+      if (R.xr[i] >= 0 || R.xr[i] < -1) {
+        if ((uint32_t)L - q1 + 1 <= (uint32_t)R.xr[i]) trimmed = true;
+        if (past_base && ((uint32_t)L - q1 == (uint32_t)R.xr[i])) trimmed = true;
+      }
+      if (trimmed) rec |= SR_TRIM_BIT;
+      if (unique) {
+        rec |= SR_UNIQUE_BIT;
+        int32_t qp = q;
+        bool ok = true;
+        if (ind == -1) {
+          qp += 1 - (int32_t)rev;
+          if (qp >= L) throw std::runtime_error("deletion with no following read base (reference would assert)");
+          if (seq[qp] == 15) ok = false;
+        } else if (k > 0) {
+          qp += std::min((int)k, ind) + 1 - (int32_t)rev;
+          if (qp > ri.qb_end0) ok = false;
+          else if (seq[qp] == 15) ok = false;
+        }
+        if (ok) {
+          uint32_t qv = qual[qp];
+          if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
+          rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
+        }
+        rec |= mapq << SR_MAPQ_SHIFT;
+        rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
+      } else {
+        rec |= std::min<uint32_t>(R.x1[i], SR_RED_MASK) << SR_RED_SHIFT;
+      }
+      sink(k == 0 ? slot : out.n_base + sub_first[slot] + k - 1, rec, R.x1[i]);
+    }
+  };
+  // Device stream word (and side-list entry, if any) of a classic word in a slot with reference base `ref`.
+  struct DevWord { uint32_t dev, side; bool has_side; };
+  auto encode = [&](uint32_t rec, uint32_t x1, uint32_t ref) {
+    DevWord w{0, 0, false};
+    const uint32_t top = (rec & SR_TOP_BIT) ? DR_TOP_BIT : 0u;
+    if (!(rec & SR_UNIQUE_BIT)) {
+      w.dev = DR_REDUNDANT | top | std::min<uint32_t>(x1, DR_X1_MASK) << DR_X1_SHIFT | n_hot;
+      if (x1 >= DR_X1_MASK) { w.has_side = true; w.side = SIDE_BIG | x1; }
+      return w;
+    }
+    const uint32_t qv = (rec >> SR_QUAL_SHIFT) & 127u, obs = rec & 7u;
+    if ((rec & SR_TRIM_BIT) || !(rec & SR_OK_BIT) || qv < geo.cutoff) { w.dev = DR_IDLE | top | n_hot; return w; }
+    const bool match = obs == ref;
+    if (n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 4 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
+      w.dev = ((((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo)) * 4u + obs) | top | (match ? DR_MATCH_BIT : 0u) | DR_HOT_BIT;
+    } else {
+      w.dev = DR_COLD | top | n_hot;
+      w.has_side = true; w.side = rec | (match ? SR_MATCH_BIT : 0u);
+    }
+    return w;
+  };
+
+  // ---- pass A2: record counts per slot
+  std::vector<uint32_t> score_cnt(cfg.want_score ? n_slots : 0, 0), hist_cnt(cfg.want_hist ? out.n_base : 0, 0);
+  std::vector<uint32_t> red_cnt(cfg.want_score ? n_slots : 0, 0);  // redundant records per slot: they lead the slot's run
+  std::vector<uint32_t> side_cnt(cfg.want_score ? n_slots : 0, 0), side_red_cnt(cfg.want_score ? n_slots : 0, 0);
+  std::vector<uint8_t> col_red(cfg.want_hist ? out.n_base : 0, 0);
+  run_items([&](size_t ii) {
+    const Item& it = items[ii];
+    const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
+    for (size_t i = it.first_read; i < it.last_read; ++i) {
+      if (!in_pileup(i) || info[i].end <= it.lo) continue;
+      const uint8_t* seq = R.bases.data() + R.seq_off[i];
+      const bool unique = R.x1[i] == 1;
+      const uint32_t L = info[i].L;
+      walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
+        const uint64_t slot = s0 + (uint64_t)c;
+        if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
+        if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
+        if (cfg.want_score)
+          score_words(i, info[i], q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
+            ++score_cnt[s];
+            if (!unique) ++red_cnt[s];
+            const DevWord w = encode(rec, x1, out.slot_ref[s]);
+            if (w.has_side) { ++side_cnt[s]; if (!unique) ++side_red_cnt[s]; }
+          });
+      });
+    }
+  });
+
+  // ---- offsets
   {
     uint64_t acc = 0;
     uint64_t n_true = 0, pad = 0;  // runs padded to whole 128-bit vectors; the pad count rides in the next entry's low bits
@@ -359,6 +472,13 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       acc += cnt + pad; n_true += cnt;
     }
     out.score_off[n_slots] = acc | pad; out.n_score = n_true; out.n_score_padded = acc;
+    bool p3 = false;
+    out.side_off = (uint32_t*)alloc((n_slots + 1) * 4, &p3);
+    uint64_t sacc = 0;
+    for (uint64_t s = 0; s < n_slots; ++s) { out.side_off[s] = (uint32_t)sacc; if (cfg.want_score) sacc += side_cnt[s]; }
+    if (sacc >= (1ull << 32)) throw std::runtime_error("more than 2^32 side-list entries in one staged stream");
+    out.side_off[n_slots] = (uint32_t)sacc; out.n_side = sacc;
+    out.side_rec = (uint32_t*)alloc(sacc * 4 + 16, &p3);
     acc = 0;
     for (uint64_t c = 0; c < out.n_base; ++c) {
       out.hist_off[c] = acc | ((cfg.want_hist && col_red[c]) ? HIST_OFF_REDUNDANT_BIT : 0);
@@ -369,7 +489,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
   out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
-  memset(out.score_rec, 0, out.n_score_padded * 4);
+  std::fill(out.score_rec, out.score_rec + out.n_score_padded, n_hot);  // pad word: the zero cell, no other bit
   out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 15) ? 8 : 4;
   out.hist_rec = alloc(out.n_hist * out.hist_bytes, &p2);
 
@@ -380,6 +500,10 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   std::vector<uint32_t>& red_cur = red_cnt;
   std::vector<uint32_t>& hist_cur = hist_cnt;
   for (size_t s = 0; s < score_cur.size(); ++s) { score_cur[s] = red_cnt[s]; red_cur[s] = 0; }
+  // side-list cursors: a slot's SIDE_BIG entries (redundant records) precede its cold entries, like the records themselves
+  std::vector<uint32_t>& side_cur = side_cnt;
+  std::vector<uint32_t>& side_red_cur = side_red_cnt;
+  for (size_t s = 0; s < side_cur.size(); ++s) { side_cur[s] = side_red_cnt[s]; side_red_cur[s] = 0; }
   std::fill(hist_cur.begin(), hist_cur.end(), 0);
   std::vector<uint64_t> qual_counts((size_t)items.size() * 128, 0);
   std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
@@ -407,7 +531,6 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       const bool unique = R.x1[i] == 1;
       const uint32_t rev = ri.rev ? 1 : 0;
       const int32_t L = (int32_t)ri.L;
-      const uint32_t red = std::min<uint32_t>(R.x1[i], SR_RED_MASK);
       if (R.x1[i] == 0) throw std::runtime_error("X1:i:0 is not a valid redundancy");
       const uint32_t mapq = R.mapq[i];
       walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {
@@ -468,55 +591,23 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
           if (out.hist_bytes == 8) static_cast<uint64_t*>(out.hist_rec)[at] = rec;
           else static_cast<uint32_t*>(out.hist_rec)[at] = (uint32_t)rec;
         }
-        // ---------------- identify_mutations records (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105)
+        // ---------------- identify_mutations records
         if (!cfg.want_score) return;
-        const int ind = is_del ? -1 : std::max(indel, 0);
-        const uint32_t K = sub_k[slot];
-        const uint32_t q1 = (uint32_t)q + 1;
-        for (uint32_t k = 0; k <= K; ++k) {
-          const bool past_base = !(ind >= (int)k);
-          uint8_t obs = past_base ? (uint8_t)kBaseGap : nibble_to_index(seq[q + (int32_t)k]);
-          if (obs == kBaseN) continue;  // not even coverage
-          uint32_t rec = obs;
-          if (!rev) rec |= SR_TOP_BIT;
-          bool trimmed = false;  // alignment.h:389-410 (unsigned comparisons as there)
-          if (R.xl[i] >= 0 || R.xl[i] < -1) { if (q1 <= (uint32_t)R.xl[i]) trimmed = true; }
-          if (R.xr[i] >= 0 || R.xr[i] < -1) {
-            if ((uint32_t)L - q1 + 1 <= (uint32_t)R.xr[i]) trimmed = true;
-            if (past_base && ((uint32_t)L - q1 == (uint32_t)R.xr[i])) trimmed = true;
+        score_words(i, ri, q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
+          const DevWord w = encode(rec, x1, out.slot_ref[s]);
+          out.score_rec[(out.score_off[s] & ~3ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
+          if (w.has_side) out.side_rec[out.side_off[s] + (unique ? side_cur[s]++ : side_red_cur[s]++)] = w.side;
+          const uint32_t kind = w.dev >> DR_KIND_SHIFT;
+          if (kind == 0 || kind == 2) {  // a scoring record: exact statistics for the likelihood tables
+            const uint32_t qv = (rec >> SR_QUAL_SHIFT) & 127u;
+            mq_mask[mapq >> 5] |= 1u << (mapq & 31); ++mq_count[mapq]; ++q_count[qv]; if (qv > max_q) max_q = qv;
           }
-          if (trimmed) rec |= SR_TRIM_BIT;
-          if (unique) {
-            rec |= SR_UNIQUE_BIT;
-            int32_t qp = q;
-            bool ok = true;
-            if (ind == -1) {
-              qp += 1 - (int32_t)rev;
-              if (qp >= L) throw std::runtime_error("deletion with no following read base (reference would assert)");
-              if (seq[qp] == 15) ok = false;
-            } else if (k > 0) {
-              qp += std::min((int)k, ind) + 1 - (int32_t)rev;
-              if (qp > ri.qb_end0) ok = false;
-              else if (seq[qp] == 15) ok = false;
-            }
-            if (ok) {
-              uint32_t qv = qual[qp];
-              if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
-              rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
-              if (!trimmed) { mq_mask[mapq >> 5] |= 1u << (mapq & 31); ++mq_count[mapq]; ++q_count[qv]; if (qv > max_q) max_q = qv; }
-            }
-            rec |= mapq << SR_MAPQ_SHIFT;
-            rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
-          } else {
-            rec |= red << SR_RED_SHIFT;
-          }
-          uint64_t s = k == 0 ? slot : out.n_base + sub_first[slot] + k - 1;
-          out.score_rec[(out.score_off[s] & ~3ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = rec;
-        }
+        });
       });
     }
     max_quals[ii] = max_q; max_hquals[ii] = max_hq; max_rposs[ii] = max_rp;
   });
+  if (cfg.want_score) out.mapq_seen[geo.hot_mapq >> 5] |= 1u << (geo.hot_mapq & 31);  // the shared table is always built
   for (size_t ii = 0; ii < items.size(); ++ii) {
     for (int w = 0; w < 8; ++w) out.mapq_seen[w] |= mapq_masks[ii * 8 + (size_t)w];
     for (int m = 0; m < 256; ++m) out.mapq_count[m] += mapq_counts[ii * 256 + (size_t)m];

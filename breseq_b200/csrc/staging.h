@@ -20,6 +20,7 @@ struct StageConfig {
   std::vector<ReadFileSetInfo> read_file_sets;    // empty = everything is read file 0
   bool use_base_repeat = false;
   bool use_read_pos = false;           // the covariate string names read_pos: histogram records carry it (8-byte records)
+  uint32_t base_quality_cutoff = 3;    // Settings::base_quality_cutoff: decides which records score (settings.cpp:1335)
   int threads = 8;
   bool want_hist = true, want_score = true;
   uint32_t shard_rank = 0, shard_count = 1;         // contiguous reference-coordinate shard staged by this call

@@ -47,6 +47,7 @@ typedef struct brq_stage_options {
   uint32_t use_base_repeat;                /* the covariate string names base_repeat */
   uint32_t use_read_pos;                   /* the covariate string names read_pos (either one: 8-byte histogram records) */
   uint32_t shard_rank, shard_count;        /* contiguous reference-coordinate shard of this process; 0,1 = all */
+  uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff (decides which records score); 0 = the default, 3 */
 } brq_stage_options;
 
 int brq_stage_bam(brq_ctx* ctx, const char* bam, const char* fasta, const brq_stage_options* opt);
@@ -79,7 +80,11 @@ typedef struct brq_stream_info {
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
   uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
-  const uint32_t* score_rec;       /* host views, valid until the next staging call */
+  uint64_t n_side;                 /* side-list entries (scoring records outside the shared table, X1 >= 511) */
+  uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_copies;  /* geometry baked into score_rec */
+  const uint32_t* score_rec;       /* host views, valid until the next staging call; word layout: csrc/brq_types.h */
+  const uint32_t* side_rec;
+  const uint32_t* side_off;
   const uint64_t* score_off;       /* slot s: first index score_off[s] & ~3, pad words (score_off[s+1] & 3) */
   const void* hist_rec;
   const uint64_t* hist_off;

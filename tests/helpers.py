@@ -200,21 +200,20 @@ def emulate_coverage_hist(hist_off):
 
 
 def emulate_tally(stream, base_quality_cutoff=3):
-    beg, cnt = bq.slot_ranges(stream)
-    n_slots = len(beg)
-    pos = np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))  # padding skipped
-    rec = stream["score_rec"][pos]
-    assert np.all(rec != 0) and int(cnt.sum()) == int(stream["n_score"])
-    sid = np.repeat(np.arange(n_slots), cnt)
-    uniq, top, trim, ok, q = (rec >> 24) & 1, (rec >> 10) & 1, (rec >> 25) & 1, (rec >> 26) & 1, (rec >> 3) & 127
+    """What the tally kernel counts per slot, from the decoded stream (numpy, test-side only)."""
+    assert stream["geometry"]["base_quality_cutoff"] == base_quality_cutoff
+    r = bq.decode_score_records(stream)
+    n_slots = len(stream["score_off"]) - 1
+    assert len(r["slot"]) == int(stream["n_score"])
+    sid, uniq, top = r["slot"], r["unique"], r["top"]
     out = {}
-    for name, u in (("unique", 1), ("raw_redundant", 0)):
+    for name, u in (("unique", True), ("raw_redundant", False)):
         out[name] = np.stack([np.bincount(sid[(uniq == u) & (top == 0)], minlength=n_slots),
                               np.bincount(sid[(uniq == u) & (top == 1)], minlength=n_slots)], axis=1)
-    out["n"] = np.bincount(sid[(uniq == 1) & (trim == 0) & (ok == 1) & (q >= base_quality_cutoff)], minlength=n_slots)
+    out["n"] = np.bincount(sid[r["scores"]], minlength=n_slots)
     red = np.zeros((n_slots, 2))
-    for i in np.nonzero(uniq == 0)[0]:  # order-dependent double sum, arrival order
-        red[sid[i], top[i]] += 1.0 / float((rec[i] >> 11) & 0x1FFF)
+    for i in np.nonzero(~uniq)[0]:  # order-dependent double sum, arrival order
+        red[sid[i], top[i]] += 1.0 / float(r["x1"][i])
     out["redundant"] = red
     return out
 

@@ -136,7 +136,6 @@ def test_pass2_coverage_on_deleted_and_inserted_columns(built, tmp_path):
     assert np.array_equal(t["unique"][slot], o["unique"].astype(np.int64))
     assert np.array_equal(t["n"][slot], o["n"].astype(np.int64))
     # observed bases at column 3: '.' (4) from the deleted read, G (2) from the other
-    beg, cnt = bq.slot_ranges(s)
-    rec = s["score_rec"][int(beg[2]):int(beg[2] + cnt[2])]
-    assert sorted((rec & 7).tolist()) == [2, 4]
+    r = bq.decode_score_records(s)
+    assert sorted(r["obs"][r["slot"] == 2].tolist()) == [2, 4]
     ctx.close()

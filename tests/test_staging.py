@@ -64,9 +64,11 @@ def test_redundant_records_lead_each_slot(staged):
     assert np.all(beg % 4 == 0), "every run starts on a 128-bit boundary"
     real = np.zeros(len(rec), bool)
     real[np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))] = True
-    assert np.all(rec[~real] == 0) and np.all(rec[real] != 0), "pad words are zero, records never are"
+    g = s["geometry"]
+    pad = g["n_st"] * g["n_q"] * 4   # the zero cell of the likelihood table, no other bit
+    assert np.all(rec[~real] == pad) and np.all(rec[real] != pad), "pad words address the zero cell; records never equal them"
     assert len(rec) == s["n_score_padded"] and real.sum() == s["n_score"]
-    uniq = ((rec >> 24) & 1).astype(np.int8)
+    uniq = ((rec >> 30) != 3).astype(np.int8)   # kind 3 = redundant
     uniq[~real] = 1   # padding follows the unique records
     step_down = np.nonzero(np.diff(uniq) < 0)[0] + 1   # a unique record followed by a redundant one ...
     assert np.all(np.isin(step_down, beg)), "... is only allowed across a slot boundary"

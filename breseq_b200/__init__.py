@@ -57,7 +57,7 @@ class _StreamInfo(C.Structure):
                 ("bytes_host", C.c_uint64),
                 ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("reserved", C.c_uint32),
                 ("n_side", C.c_uint64), ("base_quality_cutoff", C.c_uint32), ("hot_mapq", C.c_uint32),
-                ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_copies", C.c_uint32),
+                ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_words", C.c_uint32),
                 ("score_rec", C.POINTER(C.c_uint32)), ("side_rec", C.POINTER(C.c_uint32)), ("side_off", C.POINTER(C.c_uint32)),
                 ("score_off", C.POINTER(C.c_uint64)),
                 ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
@@ -230,20 +230,19 @@ def decode_score_records(stream):
     slot = np.repeat(np.arange(n_slots), cnt)
     kind = d >> 30
     n = len(d)
-    out = {"slot": slot, "kind": kind, "unique": kind != 3, "top": (d >> 12) & 1, "scores": (kind == 0) | (kind == 2),
+    out = {"slot": slot, "kind": kind, "unique": kind != 3, "top": (d >> 13) & 1, "scores": (kind == 0) | (kind == 2),
            "x1": np.ones(n, np.int64), "obs": np.full(n, -1), "qual": np.full(n, -1), "read_set": np.full(n, -1),
            "mapq": np.full(n, -1), "match": np.zeros(n, bool)}
     hot = kind == 0
-    cell = d[hot] & 0xFFF
-    t = cell >> 2
-    out["obs"][hot] = cell & 3
+    t = (d[hot] >> 16) & 0xFF
+    out["obs"][hot] = (d[hot] >> 24) & 3
     out["qual"][hot] = g["q_lo"] + t % max(1, g["n_q"])
     out["read_set"][hot] = (t // max(1, g["n_q"])) >> 1
     out["mapq"][hot] = g["hot_mapq"]
-    out["match"][hot] = ((d[hot] >> 22) & 1) == 1
+    out["match"][hot] = ((d[hot] >> 28) & 1) == 1
     # side list: per slot, the entries of its very redundant records first, then those of its cold records, in order
     side, soff = stream["side_rec"].astype(np.int64), stream["side_off"].astype(np.int64)
-    x1 = (d >> 13) & 0x1FF
+    x1 = (d >> 16) & 0x1FF
     big = (kind == 3) & (x1 == 0x1FF)
     cold = kind == 2
     uses = big | cold
@@ -326,7 +325,7 @@ class Context:
             "n_side": info.n_side, "side_rec": view(info.side_rec, info.n_side, np.uint32),
             "side_off": view(info.side_off, n_slots + 1, np.uint32),
             "geometry": {"base_quality_cutoff": info.base_quality_cutoff, "hot_mapq": info.hot_mapq, "q_lo": info.table_q_lo,
-                         "n_q": info.table_n_q, "n_st": info.table_n_st, "copies": info.table_copies},
+                         "n_q": info.table_n_q, "n_st": info.table_n_st, "words": info.table_words},
             "hist_rec": view(C.cast(info.hist_rec, C.POINTER(C.c_uint64 if info.hist_record_bytes == 8 else C.c_uint32)),
                              info.n_hist_records, np.uint64 if info.hist_record_bytes == 8 else np.uint32),
             "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),

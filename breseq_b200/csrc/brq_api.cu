@@ -485,7 +485,7 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->n_score_padded = st.n_score_padded;
     info->n_side = st.n_side; info->side_rec = st.side_rec; info->side_off = st.side_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
-    info->table_n_st = st.geo.n_st; info->table_copies = st.geo.copies;
+    info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words();
     info->bytes_host = st.n_side * 4 + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;

@@ -80,45 +80,57 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
                    SR_UNIQUE_BIT = 1u << 24, SR_TRIM_BIT = 1u << 25, SR_OK_BIT = 1u << 26, SR_MATCH_BIT = 1u << 27,
                    SR_RED_SHIFT = 11, SR_RED_MASK = 0x1FFF;
 
-// Device stream word (score_rec), 4 bytes.  The staging layer has already classified the record and,
-// for the common kind, resolved it to its cell in the tally kernel's shared-memory likelihood table
-// (geometry chosen per stream: ScoreGeometry), so the kernel spends one AND and one multiply-add on
-// addressing and two masked adds on counting.
-//   [11:0]  cell   HOT: ((read_set*2 + top) * n_q + qual - q_lo) * 4 + obs; every other kind: n_hot (the zero cell)
-//   [12]    top    1 = read on the top strand (all kinds)
-//   [21:13] X1     REDUNDANT only; 511 = the value is the slot's next SIDE_BIG entry of the side list
-//   [22]    match  HOT and obs equals the slot's reference base
-//   [23]    hot    HOT
-//   [31:30] kind   0 HOT    scores; dominant MAPQ, A/C/G/T observation, quality inside the table window
-//                  1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
-//                  2 COLD   scores, class outside the shared table; its classic word is the slot's next
-//                           cold entry of the side list
-//                  3 REDUNDANT
+// Device stream word (score_rec), 4 bytes.  The staging layer has already classified the record and
+// resolved it to (a) the counter it increments in the tally kernel's per-slot class histogram and (b) its
+// cell in the shared-memory likelihood table (geometry chosen per stream: ScoreGeometry).  The kernel
+// counts first and multiplies the counts into the table once per slot, so the common record costs one
+// AND/OR for its address and a byte increment.
+//   [12:0]  counter  byte offset of the record's counter inside its lane's histogram: word * 128 + byte.
+//                    HOT record matching the slot's reference base: class sq = (read_set*2 + top) * n_q + qual - q_lo,
+//                    word sq / 4, byte sq % 4.  Every other record counts in the special words that follow the
+//                    class words (ScoreGeometry::special_counter).
+//   [13]    top      1 = read on the top strand (all kinds)
+//   [14]    slow     HOT but not matching the reference base: the kernel reads its table cell directly
+//   [23:16] sq       HOT: class index (above)         REDUNDANT: [24:16] X1; 511 = the value is the slot's next
+//   [25:24] obs      HOT: observed base A,C,G,T                  SIDE_BIG entry of the side list
+//   [28]    match    HOT and obs equals the slot's reference base
+//   [31:30] kind     0 HOT    scores; dominant MAPQ, A/C/G/T observation, quality inside the table window
+//                    1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
+//                    2 COLD   scores, class outside the shared table; its classic word is the slot's next
+//                             cold entry of the side list
+//                    3 REDUNDANT
 // Within a slot the REDUNDANT records come first and the others follow, each part in arrival (BAM) order.
 // Every slot's run starts on a 16-byte boundary and is padded to a multiple of four records with pad
-// words (cell = n_hot, no other bit: never a real record), so the kernels read whole 128-bit vectors
+// words (the trash counter, no other bit: never a real record), so the kernels read whole 128-bit vectors
 // that never straddle two slots.  score_off[s] is the run's first index (a multiple of 4); the low two bits of score_off[s + 1]
 // hold the number of pad words that end slot s's run.
 //
 // Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
 // records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
-constexpr uint32_t DR_CELL_MASK = 0xFFFu, DR_TOP_BIT = 1u << 12, DR_X1_SHIFT = 13, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 22,
-                   DR_HOT_BIT = 1u << 23, DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
+constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
+                   DR_OBS_SHIFT = 24, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
+                   DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
                    SIDE_BIG = 1u << 31;
+// special counters, in the two histogram words after the class words
+enum : uint32_t { SC_IDLE_TOP = 0, SC_IDLE_BOT = 1, SC_COLD_TOP = 2, SC_COLD_BOT = 3, SC_SLOW_TOP = 4, SC_SLOW_BOT = 5, SC_TRASH = 6 };
 
 // Table geometry baked into the device stream words of one staged stream.
 struct ScoreGeometry {
   uint32_t cutoff = 3;     // Settings::base_quality_cutoff the stream was staged for
   uint32_t hot_mapq = 0;   // the MAPQ value whose classes the shared table holds
-  uint32_t q_lo = 0, n_q = 0;   // quality window of the shared table
+  uint32_t q_lo = 0, n_q = 0;   // quality window of the shared table (n_q is a multiple of 4)
   uint32_t n_st = 2;       // (read sets) x 2 strands
-  uint32_t copies = 8;     // interleaved copies of the shared table (8 = bank-conflict-free, 1 = they do not fit)
-  uint32_t n_hot() const { return n_st * n_q * 4; }
+  uint32_t n_sq() const { return n_st * n_q; }            // classes of the per-slot histogram (<= 248)
+  uint32_t n_words() const { return n_sq() / 4 + 2; }     // 32-bit histogram words per lane: class words + 2 special words
+  uint32_t n_hot() const { return n_sq() * 4; }           // cells of the shared likelihood table
+  static uint32_t counter_of(uint32_t index) { return (index >> 2) * 128u + (index & 3u); }
+  uint32_t special_counter(uint32_t which) const { return counter_of(n_sq() + which); }
+  uint32_t pad_word() const { return special_counter(SC_TRASH); }
 };
 
 // classic word of a HOT device word
 inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
-  const uint32_t cell = d & DR_CELL_MASK, obs = cell & 3u, t = cell >> 2, qual = g.q_lo + t % g.n_q, st = t / g.n_q;
+  const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = g.q_lo + sq % g.n_q, st = sq / g.n_q;
   return obs | qual << SR_QUAL_SHIFT | st << 10 | g.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT |
          ((d & DR_MATCH_BIT) ? SR_MATCH_BIT : 0u);
 }

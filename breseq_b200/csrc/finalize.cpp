@@ -241,8 +241,9 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGe
   // MAPQ range of the global table of the tally kernel
   p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
   g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
-  p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_copies = sg.copies; p.t_nhot = sg.n_hot();
-  g.n_tally_cells = (size_t)3 * ((size_t)p.t_nhot + 1) * p.t_copies;
+  p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_nsq = sg.n_sq(); p.t_nw = sg.n_words();
+  p.t_stride = ((p.t_nsq * 48u + 127u) & ~127u) + 16u;
+  g.n_tally_cells = (size_t)4 * p.t_stride / 16;
 }
 
 // Host copy of the per-class terms, with the libm calls the reference makes (identify_mutations.cpp:3359-3384).

@@ -42,9 +42,6 @@ static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
 constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15,
                    CO_FIT = 1u << 24;
 
-// shared memory the tally kernel keeps for its per-lane record rings (4 stages x 512 lanes x 16 bytes)
-constexpr uint32_t TALLY_RING_BYTES = 4 * 512 * 16;
-
 struct ScoreParams {
   double log10_ref_length;
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;
@@ -56,9 +53,11 @@ struct ScoreParams {
   uint32_t hot_mapq;         // the dominant MAPQ value, whose class terms are staged in shared memory
   uint32_t n_hot;            // entries of the hot tables (max_set * 2 * max_qual * 5), 0 = disabled
   uint32_t fit_all;          // evaluate the EM fit on every column with scoring records (diagnostics / parity runs)
-  // shared-memory likelihood table of the tally kernel: classes (set, strand, quality in [t_qlo, t_qlo + t_nq), A/C/G/T)
-  // of the dominant MAPQ, t_copies interleaved copies (8 = bank-conflict-free, 1 = the copies do not fit)
-  uint32_t t_qlo, t_nq, t_nhot, t_copies;
+  // tally kernel: per-slot class histogram over sq = (set*2 + top) * t_nq + quality - t_qlo (t_nsq classes in
+  // t_nsq / 4 words, then two words of special counters) and the shared-memory likelihood table of the dominant
+  // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M}, t_stride bytes between the four obs planes (16 mod 128: the planes
+  // start in different bank groups)
+  uint32_t t_qlo, t_nq, t_nsq, t_nw, t_stride;
   uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
 };
 

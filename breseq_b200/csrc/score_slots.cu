@@ -1,32 +1,30 @@
 // Per-slot scoring for sm_100a: a streaming tally kernel and an EM fit kernel.
 //
-//   tally_kernel  G lanes per slot (G = 4 for ordinary depth, 32 for deep columns).  A group walks its
-//                 slot's records with 128-bit loads, G consecutive vectors per step, so a warp reads
-//                 32/G runs of G*16 contiguous bytes instead of 32 scattered ones.  Coverage tallies
-//                 and the five log-likelihood sums live in registers and are reduced over the group
-//                 with a log2(G)-step butterfly (identify_mutations.cpp:1392-1658, 3398-3433).  Each
-//                 group handles G consecutive slots one after the other and lane j keeps slot j's
-//                 sums, so the per-slot closing arithmetic (consensus call, emission test, the 96-byte
-//                 result) runs once per lane on 32 different slots.
-//   likelihood table  The kernel is bound by shared-memory wavefronts: every scoring record reads its
-//                 class's {L[0..4], M} (48 B, three 128-bit loads).  The table of the dominant MAPQ is
-//                 therefore kept in three 16-byte planes with EIGHT interleaved copies; lane l reads
-//                 copy l & 7, whose 16-byte cell lies in bank group l & 7, so the eight lanes served by
-//                 one wavefront never collide whatever classes they ask for.  The copies have to fit
-//                 in 227 KB: the table covers a window of quality values chosen from the stream's
-//                 quality histogram (all of them when they fit).  The loop is branch-free: a record
-//                 that does not score reads an all-zero cell.  Scoring records outside the shared
-//                 table (another MAPQ, a '.' observation, a quality outside the window) wait in a
-//                 three-entry register queue and read the full table from global memory when the
-//                 slot is done; a lane that meets more of them rescans its share of the slot.
-//   record ring   With one CTA of 16 warps per SM (the table fills shared memory), plain loads leave too few
-//                 bytes in flight to cover DRAM latency.  Every lane therefore streams its 128-bit vectors
-//                 through a private four-stage ring in shared memory with cp.async (LDGSTS): four vectors
-//                 per lane, 32 KB per SM, are always on their way without holding registers, and the fetch
-//                 cursor runs ahead across slot boundaries.  A lane only ever reads its own ring cells,
-//                 so cp.async.wait_group is the only synchronisation.
+//   tally_kernel  One thread per slot, a warp per 32 consecutive slots, persistent CTAs.  The kernel COUNTS FIRST AND
+//                 MULTIPLIES ONCE: a scoring record that matches its slot's reference base (all but ~0.1 % of them)
+//                 only increments a byte counter of its (read set, strand, quality) class in the lane's private
+//                 histogram in shared memory; when the slot's records are in, the counts are contracted with the
+//                 likelihood table {L[0..4], M} of the dominant MAPQ: sums[b] += count * L[class][b], one fused
+//                 multiply-add per class and hypothesis (identify_mutations.cpp:1392-1658, 3359-3384, 3398-3433).
+//                 A record-by-record kernel reads 48 bytes of table per record and is bound by shared-memory
+//                 bandwidth at about a third of the HBM rate; counting costs one address operation and a byte
+//                 increment per record, and the contraction (about 1200 instructions per slot, independent of depth)
+//                 walks the table with warp-uniform class index, so the 32 lanes read at most four different cells
+//                 (one per reference base) per load: one wavefront.
+//   histogram     word w of lane l lives at w * 128 + l * 4 of the warp's block: any mix of classes is bank-conflict
+//                 free, and the block is aligned to its size, so a counter's address is (record & 0x1FFF) | lane base.
+//                 Counters are bytes: a slot deeper than 252 records is contracted every 63 vectors.
+//                 Records that are not class counts (idle, redundant, cold, HOT-but-mismatching, padding) increment
+//                 special counters, so the loop is branch-free except for the rare mismatching HOT record, which
+//                 reads its own table cell, and the leading redundant records.
+//   record ring   Every lane streams its slot's 128-bit vectors through a private four-stage ring in shared memory
+//                 with cp.async (LDGSTS): four vectors per lane are always on their way without holding registers.
+//                 The first vectors of a warp's NEXT round are requested before the contraction of the current one,
+//                 and that round's whole region (32 consecutive runs) is pulled into L2 a round ahead.
+//   cold records  Scoring records outside the shared table (another MAPQ, a '.' observation, a quality outside the
+//                 window) sit in the side list as classic words and read the global table of all MAPQ values.
 //   redundant records  lead each slot's run (staging.cpp): their order-dependent sum of 1/X1
-//                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head.
+//                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head: bit-exact.
 //   presence bound  The reference fits the 5-allele EM on every column, but its result only surfaces
 //                 in RA rows, i.e. when best != ref with a positive consensus score or when the
 //                 presence score of the top non-reference allele reaches the polymorphism cutoff
@@ -49,9 +47,8 @@ void note_launches(int n);
 
 namespace {
 
-constexpr int TALLY_TPB = 512;
-constexpr int RING = (int)(TALLY_RING_BYTES / (TALLY_TPB * 16));  // 16-byte stages of each lane's record ring
-static_assert(RING == 4, "the ring indexing below assumes four stages");
+constexpr int TALLY_MAX_TPB = 768;
+constexpr int RING = 4;           // 16-byte stages of each lane's record ring (a power of two)
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts
 constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
@@ -86,6 +83,22 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t shared_addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t shared_addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t shared_addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" :: "r"(shared_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t shared_addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(shared_addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_fill16(uint32_t shared_addr, uint32_t word) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(word) : "memory");
 }
@@ -107,19 +120,6 @@ __device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p,
   return ((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
 }
 
-template <int G>
-__device__ __forceinline__ double group_add(double v, uint32_t mask) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-  return v;
-}
-template <int G>
-__device__ __forceinline__ uint32_t group_add_u32(uint32_t v, uint32_t mask) {
-#pragma unroll
-  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
-  return v;
-}
-
 struct Sums { double l0, l1, l2, l3, l4, m; };
 
 // a scoring record whose class is not in the shared table (classic word from the side list): {L[0..4], M} from the global table
@@ -133,171 +133,196 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ tally
-template <int G>
-__global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
-                                                              const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
-                                                              const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
-                                                              const double* __restrict__ tallyT, const HotTerms* __restrict__ coldT,
-                                                              ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
-                                                              uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
-                                                              uint32_t flagged_cap) {
-  // three planes ({L0,L1} {L2,L3} {L4,M}) of (t_nhot + 1) * t_copies 16-byte cells; the last cell of a plane is zero
-  extern __shared__ __align__(16) double sm[];
-  __shared__ double inv_red[64];
+// Shared memory of one CTA (dynamic, base rounded up to the histogram block size):
+//   [n_warps x block]   per-warp class histograms: word w of lane l at w * 128 + l * 4 (bank l: conflict-free for any
+//                       mix of classes), four byte counters per word; block = 4 KB (<= 32 words) or 8 KB, and the
+//                       block is aligned to its size, so counter address = (record & 0x1FFF) | lane base
+//   [n_warps x 2 KB]    record rings: 4 stages x 32 lanes x 16 bytes
+//   [4 x t_stride]      likelihood table [obs][sq] x {L[0..4], M}
+__global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+                                                                  const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
+                                                                  const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
+                                                                  const double* __restrict__ tallyT, const HotTerms* __restrict__ coldT,
+                                                                  ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
+                                                                  uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
+                                                                  uint32_t flagged_cap, uint32_t hist_block) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t sm0 = ((uint32_t)__cvta_generic_to_shared(sm_raw) + hist_block - 1u) & ~(hist_block - 1u);
+  const uint32_t hist = sm0 + warp * hist_block + lane * 4u;                                // this lane's word 0
+  const uint32_t ring = sm0 + n_warps_cta * hist_block + warp * (RING * 512u) + lane * 16u;  // this lane's cell of stage 0
+  const uint32_t tbl = sm0 + n_warps_cta * (hist_block + RING * 512u);
   {
-    const uint32_t n_cells = 3u * (p.t_nhot + 1u) * p.t_copies;
-    const double2* src = reinterpret_cast<const double2*>(tallyT);
-    double2* dst = reinterpret_cast<double2*>(sm);
-    for (uint32_t i = threadIdx.x; i < n_cells; i += blockDim.x) dst[i] = src[i];
-    if (threadIdx.x < 64) inv_red[threadIdx.x] = 1.0 / (double)threadIdx.x;
+    const uint32_t n16 = p.t_stride / 4u;  // 16-byte cells of the table (4 planes of t_stride bytes)
+    const uint4* src = reinterpret_cast<const uint4*>(tallyT);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
+      const uint4 v = src[i];
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(tbl + i * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    for (uint32_t w = 0; w < p.t_nw; ++w) sts_u32(hist + w * 128u, 0u);
   }
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31u, sub = lane & (uint32_t)(G - 1), g0 = lane - sub;
-  const uint32_t cs = p.t_copies * 16u;                      // bytes between consecutive classes
-  const uint32_t plane = (p.t_nhot + 1u) * cs;
-  const uint32_t tbl = (uint32_t)__cvta_generic_to_shared(sm) + (lane & (p.t_copies - 1u)) * 16u;  // this lane's copy
-  const uint32_t zero_addr = tbl + p.t_nhot * cs;
-  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(sm) + 3u * plane + threadIdx.x * 16u;  // this lane's cell of stage 0
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  const uint32_t gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << g0);
-  const uint64_t n_rounds = (n_slots + 31) >> 5;  // a warp takes 32 consecutive slots per round
-  const uint64_t n_warps = (uint64_t)gridDim.x * (TALLY_TPB / 32);
-  for (uint64_t round = ((uint64_t)blockIdx.x * TALLY_TPB + threadIdx.x) >> 5; round < n_rounds; round += n_warps) {
-    const uint64_t my_slot = (round << 5) + lane;  // the slot this lane closes; its group tallies slots g0 .. g0+G-1
-    uint64_t my_beg = 0;
-    uint32_t my_vec = 0, my_pad = 0, my_ref = 5;   // 128-bit vectors of the run, pad words in the last one
-    uint32_t my_side0 = 0, my_side1 = 0;           // the slot's range of the side list
-    if (my_slot < n_slots) {
-      const uint64_t o0 = off[my_slot], o1 = off[my_slot + 1];
-      my_beg = o0 & ~3ull; my_vec = (uint32_t)(((o1 & ~3ull) - my_beg) >> 2); my_pad = (uint32_t)o1 & 3u;
-      my_ref = slot_ref[my_slot];
-      my_side0 = side_off[my_slot]; my_side1 = side_off[my_slot + 1];
+  const uint32_t pad_word = (p.t_nw - 1u) * 128u + 2u;  // the trash counter (ScoreGeometry::pad_word)
+  const uint32_t n_cw = p.t_nsq >> 2;                   // class words; the two special words follow
+  const uint32_t words_per_st = p.t_nq >> 2;
+  const uint64_t n_rounds = (n_slots + 31) >> 5;        // a warp takes 32 consecutive slots per round, one per lane
+  const uint64_t n_warps = (uint64_t)gridDim.x * n_warps_cta;
+  uint64_t round = (uint64_t)blockIdx.x * n_warps_cta + warp;
+
+  // slot geometry of a round: this lane's run of 128-bit vectors
+  struct Run { uint64_t beg; uint32_t n_vec, ref, side0, side1; };
+  auto load_run = [&](uint64_t r) {  // issued two rounds ahead: nothing here is waited for when the round starts
+    Run x{0, 0, 5, 0, 0};
+    const uint64_t s = (r << 5) + lane;
+    if (r < n_rounds && s < n_slots) {
+      const uint64_t o0 = off[s] & ~3ull, o1 = off[s + 1] & ~3ull;
+      x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 2);
+      x.ref = slot_ref[s]; x.side0 = side_off[s]; x.side1 = side_off[s + 1];
     }
+    return x;
+  };
+  // the ring is primed with the run's first RING vectors (pad words where the run is shorter): always RING commits
+  auto prime = [&](const Run& x) {
+    const uint4* vp = reinterpret_cast<const uint4*>(rec + x.beg);
+#pragma unroll
+    for (int st = 0; st < RING; ++st) {
+      if ((uint32_t)st < x.n_vec) cp_async16(ring + (uint32_t)st * 512u, vp + st); else sts_fill16(ring + (uint32_t)st * 512u, pad_word);
+      cp_async_commit();
+    }
+  };
+  auto prefetch_region = [&](const Run& x) {  // the whole region of a round (32 consecutive runs) into L2, one request per warp
+    const uint64_t lo = __shfl_sync(0xFFFFFFFFu, x.beg, 0);
+    const uint64_t hi = __shfl_sync(0xFFFFFFFFu, x.beg + (uint64_t)x.n_vec * 4u, 31);
+    if (lane == 0 && hi > lo) prefetch_l2_bulk(rec + lo, (uint32_t)((hi - lo) * 4u));
+  };
+
+  Run cur = load_run(round), nxt = load_run(round + n_warps);
+  prime(cur);
+  for (; round < n_rounds; round += n_warps) {
+    const uint64_t my_slot = (round << 5) + lane;
+    const bool live = my_slot < n_slots;
+    prefetch_region(nxt);                            // next round's records: DRAM -> L2 while this round is tallied
+    const Run nxt2 = load_run(round + 2 * n_warps);  // its geometry is needed one round ahead
+    const uint32_t my_ref = cur.ref, side_cur = cur.side0, side_end = cur.side1;
+
     Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double red_top = 0.0, red_bot = 0.0;
-    uint32_t tops = 0, n = 0, c_ref = 0, raw_top = 0, raw_bot = 0;
-    // the records of this warp's NEXT round are pulled into L2 while this round is tallied: with 16
-    // warps per SM the loads below cannot cover DRAM latency on their own
-    uint64_t pf_lo = 0, pf_hi = 0;
-    if (lane == 0 && round + n_warps < n_rounds) {
-      const uint64_t s0 = (round + n_warps) << 5, s1 = s0 + 32 < n_slots ? s0 + 32 : n_slots;
-      pf_lo = off[s0] & ~3ull; pf_hi = off[s1] & ~3ull;
-    }
+    uint32_t raw_top = 0, raw_bot = 0, n = 0, c_ref = 0, u_top = 0, u_bot = 0;
+    bool in_head = true;  // still inside the run's leading redundant records
 
-    // fetch cursor of this lane's vector stream: slot fk of the group, step f_it of f_nit, running RING vectors ahead
-    int fk = -1;
-    uint32_t f_it = 0, f_nit = 0, f_nvec = 0;
-    const uint4* f_vp = nullptr;
-    auto fetch_next_slot = [&]() {  // group-uniform
-      f_it = 0; f_nit = 0;
-      while (f_nit == 0 && ++fk < G) {
-        f_nvec = __shfl_sync(gmask, my_vec, g0 + fk);
-        f_vp = reinterpret_cast<const uint4*>(rec + __shfl_sync(gmask, my_beg, g0 + fk));
-        f_nit = (f_nvec + (uint32_t)G - 1u) / (uint32_t)G;
-      }
-    };
-    auto fetch = [&](uint32_t stage) {  // the next vector of the stream goes to ring[stage]; always one commit
-      if (fk < G) {
-        const uint32_t iv = f_it * (uint32_t)G + sub, dst = ring + stage * (uint32_t)(TALLY_TPB * 16);
-        if (iv < f_nvec) cp_async16(dst, f_vp + iv); else sts_fill16(dst, p.t_nhot);  // past the run: pad words
-        if (++f_it == f_nit) fetch_next_slot();
-      }
-      cp_async_commit();
-    };
-    fetch_next_slot();
-#pragma unroll
-    for (int st = 0; st < RING; ++st) fetch((uint32_t)st);
-    uint32_t c_idx = 0;  // vectors consumed by this lane in this round
-
-    // While the first vectors are on their way: the scoring records of this lane's own slot whose class
-    // is not in the shared table (another MAPQ, a '.' observation, a quality outside the window) sit in
-    // the side list as classic words; their terms come from the global table and start the slot's sums.
-    for (uint32_t e = my_side0; e < my_side1; ++e) {
+    // the scoring records of this lane's slot whose class is not in the shared table (another MAPQ, a '.'
+    // observation, a quality outside the window) sit in the side list as classic words: their terms come from the
+    // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the walk below reads them.
+    uint32_t side_big = side_cur;
+    for (uint32_t e = side_cur; e < side_end; ++e) {
       const uint32_t w = __ldg(side + e);
-      if (w & SIDE_BIG) continue;  // the X1 of a very redundant record, read by the walk below
+      if (w & SIDE_BIG) continue;
       cold_add(kept, w, coldT, p);
       ++n;
       c_ref += (w >> 27) & 1u;
     }
 
-#pragma unroll 1
-    for (int k = 0; k < G; ++k) {
-      const uint32_t ref = __shfl_sync(gmask, my_ref, g0 + k);
-      const uint64_t beg = __shfl_sync(gmask, my_beg, g0 + k);
-      const uint32_t n_vec = __shfl_sync(gmask, my_vec, g0 + k);
-      const uint4* vp = reinterpret_cast<const uint4*>(rec + beg);
-      double rt = 0.0, rb = 0.0;
-      uint32_t t_rawt = 0, t_rawb = 0;
-      Sums a = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-      uint32_t t_tops = 0, t_n = 0, t_cref = 0;
-      uint32_t acc_tm = 0, acc_h = 0;  // packed counters: tops in [21:12] and matches in [31:22]; hot records in [31:23]
-      uint32_t side_cur = __shfl_sync(gmask, my_side0, g0 + k);
-      const uint32_t n_it = (n_vec + (uint32_t)G - 1u) / (uint32_t)G;  // the same for every lane of the group
-      // four device words of one 128-bit vector: the cell index addresses this lane's copy of the table
-      // (every word that does not score, pad words included, carries the zero cell) and two masked adds
-      // keep the counts
-      auto tally4 = [&](const uint4& v) {
-        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
-        uint32_t addr[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          addr[j] = tbl + (r[j] & DR_CELL_MASK) * cs;
-          acc_tm += r[j] & (DR_TOP_BIT | DR_MATCH_BIT);
-          acc_h += r[j] & DR_HOT_BIT;
+    const uint32_t tp0 = tbl + (my_ref < 4u ? my_ref : 0u) * p.t_stride;  // the plane of records matching this slot's base
+    const uint4* vp = reinterpret_cast<const uint4*>(rec + cur.beg);
+    uint32_t i = 0;  // vectors consumed by the warp in this round (lanes past their run see pad words)
+    const uint32_t n_it = __reduce_max_sync(0xFFFFFFFFu, cur.n_vec);
+    bool more;
+    do {
+      const uint32_t chunk_end = min(n_it, i + 63u);  // byte counters: at most 252 records between two contractions
+      cp_async_wait<RING - 1>();
+      uint4 v = lds_u32x4(ring + (i & (uint32_t)(RING - 1)) * 512u);
+      while (i < chunk_end) {
+        {  // the cell is free again: request the vector RING steps ahead, or pad words past the run
+          const uint32_t cell = ring + (i & (uint32_t)(RING - 1)) * 512u, ahead = i + (uint32_t)RING;
+          if (ahead < cur.n_vec) cp_async16(cell, vp + ahead); else sts_fill16(cell, pad_word);
+          cp_async_commit();
         }
-        f64x2 x[4], y[4], z[4];  // {L0,L1}, {L2,L3}, {L4,M}: all twelve 128-bit loads in flight together
+        ++i;
+        cp_async_wait<RING - 1>();
+        const uint4 v_next = lds_u32x4(ring + (i & (uint32_t)(RING - 1)) * 512u);
+
+        if (in_head) {
+          // redundant records lead the slot: an order-dependent double sum, taken in arrival order
+          // (identify_mutations.cpp:1605); a pad word ends the walk like any non-redundant record does
+          const uint32_t r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { x[j] = lds_f64x2(addr[j]); y[j] = lds_f64x2(addr[j] + plane); z[j] = lds_f64x2(addr[j] + 2u * plane); }
-        // the zero cell adds +0.0 exactly; pairs first, so each sum waits on two dependent adds per vector, not four
-        a.l0 += (x[0].x + x[1].x) + (x[2].x + x[3].x); a.l1 += (x[0].y + x[1].y) + (x[2].y + x[3].y);
-        a.l2 += (y[0].x + y[1].x) + (y[2].x + y[3].x); a.l3 += (y[0].y + y[1].y) + (y[2].y + y[3].y);
-        a.l4 += (z[0].x + z[1].x) + (z[2].x + z[3].x); a.m += (z[0].y + z[1].y) + (z[2].y + z[3].y);
-      };
-      auto flush_counts = [&]() {
-        t_tops += (acc_tm >> 12) & 0x3FFu; t_cref += acc_tm >> 22; t_n += acc_h >> 23;
-        acc_tm = 0; acc_h = 0;
-      };
-      for (uint32_t it = 0; it < n_it; ++it, ++c_idx) {
-        const uint32_t stage = c_idx & (uint32_t)(RING - 1);
-        cp_async_wait<RING - 1>();  // this lane's oldest vector has landed
-        const uint4 v = lds_u32x4(ring + stage * (uint32_t)(TALLY_TPB * 16));
-        fetch(stage);               // the cell is free again: request the vector RING steps ahead
-        if (it == 0) {
-          // redundant records lead the slot: an order-dependent double sum, taken in arrival order by
-          // every lane of the group alike (identify_mutations.cpp:1605).  The first vector is in the
-          // group's first lane; a pad word ends the walk like any non-redundant record does.
-          const uint32_t hv[4] = {__shfl_sync(gmask, v.x, g0), __shfl_sync(gmask, v.y, g0), __shfl_sync(gmask, v.z, g0),
-                                  __shfl_sync(gmask, v.w, g0)};
-          const uint32_t cnt = n_vec * 4u;
-          uint32_t i = 0, r = hv[0];
-          while ((r >> DR_KIND_SHIFT) == 3u) {
-            uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
-            if (red == DR_X1_MASK) red = __ldg(side + side_cur++) & ~SIDE_BIG;
-            const double inv = red < 64 ? inv_red[red] : 1.0 / (double)red;
-            if (r & DR_TOP_BIT) { rt += inv; ++t_rawt; } else { rb += inv; ++t_rawb; }
-            if (++i == cnt) break;
-            r = i == 1 ? hv[1] : i == 2 ? hv[2] : i == 3 ? hv[3] : __ldg(rec + beg + i);
+          for (int j = 0; j < 4; ++j) {
+            if (in_head && (r[j] >> DR_KIND_SHIFT) == 3u) {
+              uint32_t red = (r[j] >> DR_X1_SHIFT) & DR_X1_MASK;
+              if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
+              const double inv = 1.0 / (double)red;
+              if (r[j] & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
+            } else in_head = false;
           }
         }
-        tally4(v);
-        if ((it & 63u) == 63u) flush_counts();  // 256 records per lane: the packed fields hold 511
+        // every record increments one byte counter of this lane's histogram.  Two records are in flight at a
+        // time; when both address the same counter the second takes the first one's new value.
+        const uint32_t a0 = (v.x & DR_COUNTER_MASK) | hist, a1 = (v.y & DR_COUNTER_MASK) | hist,
+                       a2 = (v.z & DR_COUNTER_MASK) | hist, a3 = (v.w & DR_COUNTER_MASK) | hist;
+        {
+          const uint32_t c0 = lds_u8(a0) + 1u;
+          uint32_t c1 = lds_u8(a1) + 1u;
+          if (a1 == a0) c1 = c0 + 1u;
+          sts_u8(a0, c0); sts_u8(a1, c1);
+        }
+        {
+          const uint32_t c2 = lds_u8(a2) + 1u;
+          uint32_t c3 = lds_u8(a3) + 1u;
+          if (a3 == a2) c3 = c2 + 1u;
+          sts_u8(a2, c2); sts_u8(a3, c3);
+        }
+        if ((v.x | v.y | v.z | v.w) & DR_SLOW_BIT) {
+          // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
+          const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!(r[j] & DR_SLOW_BIT)) continue;
+            const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 3u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 48u;
+            const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
+            kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
+          }
+        }
+        v = v_next;
       }
-      flush_counts();
-      a.l0 = group_add<G>(a.l0, gmask); a.l1 = group_add<G>(a.l1, gmask); a.l2 = group_add<G>(a.l2, gmask);
-      a.l3 = group_add<G>(a.l3, gmask); a.l4 = group_add<G>(a.l4, gmask); a.m = group_add<G>(a.m, gmask);
-      t_tops = group_add_u32<G>(t_tops, gmask); t_n = group_add_u32<G>(t_n, gmask); t_cref = group_add_u32<G>(t_cref, gmask);
-      if (sub == (uint32_t)k) {
-        kept.l0 += a.l0; kept.l1 += a.l1; kept.l2 += a.l2; kept.l3 += a.l3; kept.l4 += a.l4; kept.m += a.m;
-        red_top = rt; red_bot = rb;
-        tops = t_tops; n += t_n; c_ref += t_cref; raw_top = t_rawt; raw_bot = t_rawb;
+      more = i < n_it;
+      if (!more) {  // this round's records are all in: next round's first vectors travel during the contraction
+        prime(nxt);
       }
-      if (k == 0 && pf_hi > pf_lo) prefetch_l2_bulk(rec + pf_lo, (uint32_t)((pf_hi - pf_lo) * 4u));
-    }
-    if (my_slot >= n_slots) continue;
 
-    // every record of the slot is either unique or redundant; top-strand counts follow by subtraction
-    const uint32_t cnt = my_vec * 4u - my_pad;
-    const uint32_t u_all = cnt - raw_top - raw_bot, u_top = tops - raw_top;
+      // ---- contraction: sums += counts x table, for the classes matching the slot's reference base
+      uint32_t hp = hist, tp = tp0;
+      for (uint32_t st = 0; st < p.t_nsq; st += p.t_nq) {
+        uint32_t tot = 0;
+        for (uint32_t wq = 0; wq < words_per_st; ++wq, hp += 128u, tp += 192u) {
+          const uint32_t cw = lds_u32(hp);
+          if (!__any_sync(0xFFFFFFFFu, cw != 0u)) continue;
+          sts_u32(hp, 0u);
+          tot = __dp4a(cw, 0x01010101u, tot);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const double c = (double)((cw >> (8 * k)) & 255u);
+            const f64x2 x = lds_f64x2(tp + (uint32_t)k * 48u), y = lds_f64x2(tp + (uint32_t)k * 48u + 16u), z = lds_f64x2(tp + (uint32_t)k * 48u + 32u);
+            kept.l0 = fma(c, x.x, kept.l0); kept.l1 = fma(c, x.y, kept.l1); kept.l2 = fma(c, y.x, kept.l2);
+            kept.l3 = fma(c, y.y, kept.l3); kept.l4 = fma(c, z.x, kept.l4); kept.m = fma(c, z.y, kept.m);
+          }
+        }
+        n += tot; c_ref += tot;
+        if ((st / p.t_nq) & 1u) u_top += tot; else u_bot += tot;  // st = set * 2 + top
+      }
+      {  // special counters: idle / cold / slow records by strand (redundant and pad words count into the trash byte)
+        const uint32_t s0 = lds_u32(hist + n_cw * 128u), s1 = lds_u32(hist + (n_cw + 1u) * 128u);
+        sts_u32(hist + n_cw * 128u, 0u); sts_u32(hist + (n_cw + 1u) * 128u, 0u);
+        const uint32_t idle_t = s0 & 255u, idle_b = (s0 >> 8) & 255u, cold_t = (s0 >> 16) & 255u, cold_b = s0 >> 24,
+                       slow_t = s1 & 255u, slow_b = (s1 >> 8) & 255u;
+        u_top += idle_t + cold_t + slow_t; u_bot += idle_b + cold_b + slow_b;
+        n += slow_t + slow_b;
+      }
+    } while (more);
+
+    cur = nxt; nxt = nxt2;
+    if (!live) continue;
+
     const uint32_t ref = my_ref;
     const double ll[5] = {kept.l0, kept.l1, kept.l2, kept.l3, kept.l4};
     double consensus = nan;
@@ -324,6 +349,7 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
       need_fit = p.fit_all != 0u || ref >= 5u || (best != ref && consensus > -slack);
       if (!need_fit) {
         const double ll_ref = ref == 0 ? ll[0] : ref == 1 ? ll[1] : ref == 2 ? ll[2] : ref == 3 ? ll[3] : ll[4];
+        // the sums are rounded differently from a record-by-record evaluation: a relative 1e-12 of margin on the bound
         const double bound = (kept.m - ll_ref) - (double)n * log10(((double)c_ref + 0.5) / ((double)n + 2.0)) - p.log10_ref_length;
         need_fit = !(bound < p.polymorphism_cutoff - slack);
       }
@@ -341,13 +367,14 @@ __global__ void __launch_bounds__(TALLY_TPB, 1) tally_kernel(const uint32_t* __r
     for (int b = 0; b < 5; ++b) o.ll[b] = ll[b];
     o.consensus_score = consensus; o.variant_score = nan;
     o.redundant[0] = red_bot; o.redundant[1] = red_top;
-    o.unique[0] = u_all - u_top; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
+    o.unique[0] = u_bot; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
     out[my_slot] = o;
 
     if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)my_slot;
     else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = (uint32_t)my_slot; }
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------ fit
@@ -386,9 +413,9 @@ __device__ __forceinline__ uint32_t classic_at(const GroupCtx& g, uint64_t i) {
   const uint64_t k = i - g.beg;
   if (k < g.n_main) {
     const uint32_t d = __ldg(g.rec + i);
-    if ((d >> DR_KIND_SHIFT) != 0u || !(d & DR_HOT_BIT)) return 0u;
+    if ((d >> DR_KIND_SHIFT) != 0u) return 0u;
     const ScoreParams& p = *g.p;
-    const uint32_t cell = d & DR_CELL_MASK, obs = cell & 3u, t = cell >> 2, qual = p.t_qlo + t % p.t_nq, st = t / p.t_nq;
+    const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = p.t_qlo + sq % p.t_nq, st = sq / p.t_nq;
     return obs | qual << SR_QUAL_SHIFT | st << 10 | p.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT;
   }
   const uint32_t w = __ldg(g.side + g.side_beg + (uint32_t)(k - g.n_main));
@@ -572,17 +599,18 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem_tally = (size_t)3 * (p.t_nhot + 1) * p.t_copies * 16 + TALLY_RING_BYTES, smem_fit = (size_t)p.n_hot * 48;
+  const size_t smem_fit = (size_t)p.n_hot * 48;
+  // histogram block per warp: 4 KB holds 32 words per lane, 8 KB the maximum of 64; as many warps as 227 KB allow
+  const uint32_t hist_block = p.t_nw <= 32 ? 4096u : 8192u;
+  const size_t per_warp = hist_block + RING * 512, fixed = (size_t)4 * p.t_stride + hist_block;
+  int warps = TALLY_MAX_TPB / 32;
+  while (warps > 1 && fixed + warps * per_warp > 227 * 1024) --warps;
+  const size_t smem_tally = fixed + warps * per_warp;
   const uint64_t n_rounds = (n_slots + 31) / 32;
-  const int blocks = (int)std::min<uint64_t>((n_rounds + TALLY_TPB / 32 - 1) / (TALLY_TPB / 32), (uint64_t)kSMs);
-  // lanes per slot: 4 at ordinary depth, a whole warp once the mean column is deeper than 512 records
-  if (n_records / n_slots < 512) {
-    cudaFuncSetAttribute(tally_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-    tally_kernel<4><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
-  } else {
-    cudaFuncSetAttribute(tally_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-    tally_kernel<32><<<blocks, TALLY_TPB, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap);
-  }
+  const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
+  (void)n_records;
+  cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);

@@ -334,28 +334,28 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     g.n_st = (out.max_read_set_seen + 1) * 2;
     g.hot_mapq = 0;
     for (uint32_t m = 1; m < 256; ++m) if (mq[m] > mq[g.hot_mapq]) g.hot_mapq = m;
-    // as many quality values as eight interleaved copies allow next to the record rings in 227 KB of shared memory
-    const size_t budget_cells = ((size_t)(226 * 1024) - 4 * 512 * 16) / 16;
-    auto cells = [&](uint32_t nq, uint32_t copies) { return (size_t)3 * ((size_t)g.n_st * nq * 4 + 1) * copies; };
+    // The per-slot class histogram of the tally kernel holds (read set, strand, quality) classes, at most 62
+    // four-byte words per lane, and its contraction with the likelihood table walks every word: the table covers
+    // the narrowest window of quality values (a multiple of four) that holds 99.5 % of the records; the few
+    // records outside it take the side list.
     uint32_t q_first = 128, q_last = 0;
-    for (uint32_t q = g.cutoff; q < 128; ++q) if (qc[q]) { q_first = std::min(q_first, q); q_last = q; }
+    uint64_t q_mass = 0;
+    for (uint32_t q = g.cutoff; q < 128; ++q) if (qc[q]) { q_first = std::min(q_first, q); q_last = q; q_mass += qc[q]; }
     if (q_first > q_last) { q_first = g.cutoff; q_last = g.cutoff; }
-    uint32_t want = q_last - q_first + 1, copies = 8, nq = want;
-    while (nq > 0 && cells(nq, copies) > budget_cells) --nq;
-    if (nq < 8 && nq < want) {  // eight copies leave too narrow a window: one copy
-      copies = 1; nq = want;
-      while (nq > 0 && (cells(nq, copies) > budget_cells || (size_t)g.n_st * nq * 4 >= DR_CELL_MASK)) --nq;
-    }
-    uint32_t best_lo = q_first;
-    if (nq < want) {
+    const uint32_t span = q_last - q_first + 1, nq_cap = (248u / g.n_st) & ~3u;
+    uint32_t nq = 0, best_lo = q_first;
+    for (uint32_t len = 4; nq == 0; len += 4) {
       uint64_t best = 0;
-      for (uint32_t lo = q_first; lo + nq <= q_last + 1; ++lo) {
+      uint32_t lo_best = q_first;
+      for (uint32_t lo = q_first; lo == q_first || lo + len <= q_last + 1; ++lo) {
         uint64_t mass = 0;
-        for (uint32_t q = lo; q < lo + nq; ++q) mass += qc[q];
-        if (mass > best) { best = mass; best_lo = lo; }
+        for (uint32_t q = lo; q < lo + len && q < 128; ++q) mass += qc[q];
+        if (mass > best) { best = mass; lo_best = lo; }
       }
+      if (len >= span || len + 4 > nq_cap || (double)best >= 0.995 * (double)q_mass) { nq = len; best_lo = lo_best; }
     }
-    g.q_lo = best_lo; g.n_q = nq; g.copies = copies;
+    if (nq > nq_cap) nq = nq_cap;  // more than 62 read files x strands: no window fits, everything takes the side list
+    g.q_lo = best_lo; g.n_q = nq;
   }
   const ScoreGeometry geo = out.geo;
   const uint32_t n_hot = geo.n_hot();
@@ -415,19 +415,26 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   struct DevWord { uint32_t dev, side; bool has_side; };
   auto encode = [&](uint32_t rec, uint32_t x1, uint32_t ref) {
     DevWord w{0, 0, false};
-    const uint32_t top = (rec & SR_TOP_BIT) ? DR_TOP_BIT : 0u;
+    const bool is_top = (rec & SR_TOP_BIT) != 0;
+    const uint32_t top = is_top ? DR_TOP_BIT : 0u;
     if (!(rec & SR_UNIQUE_BIT)) {
-      w.dev = DR_REDUNDANT | top | std::min<uint32_t>(x1, DR_X1_MASK) << DR_X1_SHIFT | n_hot;
+      w.dev = DR_REDUNDANT | top | std::min<uint32_t>(x1, DR_X1_MASK) << DR_X1_SHIFT | geo.special_counter(SC_TRASH);
       if (x1 >= DR_X1_MASK) { w.has_side = true; w.side = SIDE_BIG | x1; }
       return w;
     }
     const uint32_t qv = (rec >> SR_QUAL_SHIFT) & 127u, obs = rec & 7u;
-    if ((rec & SR_TRIM_BIT) || !(rec & SR_OK_BIT) || qv < geo.cutoff) { w.dev = DR_IDLE | top | n_hot; return w; }
+    if ((rec & SR_TRIM_BIT) || !(rec & SR_OK_BIT) || qv < geo.cutoff) {
+      w.dev = DR_IDLE | top | geo.special_counter(is_top ? SC_IDLE_TOP : SC_IDLE_BOT);
+      return w;
+    }
     const bool match = obs == ref;
     if (n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 4 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
-      w.dev = ((((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo)) * 4u + obs) | top | (match ? DR_MATCH_BIT : 0u) | DR_HOT_BIT;
+      const uint32_t sq = ((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo);
+      w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top;
+      if (match) w.dev |= DR_MATCH_BIT | ScoreGeometry::counter_of(sq);
+      else w.dev |= DR_SLOW_BIT | geo.special_counter(is_top ? SC_SLOW_TOP : SC_SLOW_BOT);
     } else {
-      w.dev = DR_COLD | top | n_hot;
+      w.dev = DR_COLD | top | geo.special_counter(is_top ? SC_COLD_TOP : SC_COLD_BOT);
       w.has_side = true; w.side = rec | (match ? SR_MATCH_BIT : 0u);
     }
     return w;
@@ -489,7 +496,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
   out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
-  std::fill(out.score_rec, out.score_rec + out.n_score_padded, n_hot);  // pad word: the zero cell, no other bit
+  std::fill(out.score_rec, out.score_rec + out.n_score_padded, geo.pad_word());  // pad word: the trash counter, no other bit
   out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 15) ? 8 : 4;
   out.hist_rec = alloc(out.n_hist * out.hist_bytes, &p2);
 

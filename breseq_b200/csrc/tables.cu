@@ -5,7 +5,7 @@
 //   L[b] = log10 pr[b],  M = max_b L[b],  r[b] = 10^(L[b] - M)          identify_mutations.cpp:3359-3384
 // and writes the class into every table that holds it: the full table (fit kernel, global), the
 // {L, M} table of all MAPQ values (tally kernel, global), and for the dominant MAPQ the fit
-// kernel's shared-memory image {r, M} and the tally kernel's three-plane, eight-copy image.
+// kernel's shared-memory image {r, M} and the tally kernel's image [obs][set, strand, quality] x {L, M}.
 // CUDA's log10/pow are within a couple of ulp of glibc's, i.e. 1e-16 relative on every term, far inside
 // the 1e-9 bar of the log-likelihood sums; slots whose decisions are close are re-evaluated on the
 // host with glibc in arrival order (finalize.cpp).
@@ -54,12 +54,10 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
   h.M = M;
   a.hotR[((size_t)st * a.Q + q) * 5u + obs] = h;
   if (obs < 4u && q >= p.t_qlo && q < p.t_qlo + p.t_nq) {
-    const size_t plane = ((size_t)p.t_nhot + 1) * p.t_copies;
-    const size_t cell0 = (((size_t)st * p.t_nq + (q - p.t_qlo)) * 4u + obs) * p.t_copies;
-    for (uint32_t cp = 0; cp < p.t_copies; ++cp) {
-      double* d0 = a.tallyT + (0 * plane + cell0 + cp) * 2, *d1 = a.tallyT + (1 * plane + cell0 + cp) * 2, *d2 = a.tallyT + (2 * plane + cell0 + cp) * 2;
-      d0[0] = L[0]; d0[1] = L[1]; d1[0] = L[2]; d1[1] = L[3]; d2[0] = L[4]; d2[1] = M;
-    }
+    double* d = reinterpret_cast<double*>(reinterpret_cast<char*>(a.tallyT) + (size_t)obs * p.t_stride + ((size_t)st * p.t_nq + (q - p.t_qlo)) * 48u);
+#pragma unroll
+    for (int b = 0; b < 5; ++b) d[b] = L[b];
+    d[5] = M;
   }
 }
 

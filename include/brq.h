@@ -81,7 +81,7 @@ typedef struct brq_stream_info {
   uint32_t n_targets, pinned;
   uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
   uint64_t n_side;                 /* side-list entries (scoring records outside the shared table, X1 >= 511) */
-  uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_copies;  /* geometry baked into score_rec */
+  uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_words;  /* geometry baked into score_rec */
   const uint32_t* score_rec;       /* host views, valid until the next staging call; word layout: csrc/brq_types.h */
   const uint32_t* side_rec;
   const uint32_t* side_off;

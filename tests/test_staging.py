@@ -65,8 +65,10 @@ def test_redundant_records_lead_each_slot(staged):
     real = np.zeros(len(rec), bool)
     real[np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))] = True
     g = s["geometry"]
-    pad = g["n_st"] * g["n_q"] * 4   # the zero cell of the likelihood table, no other bit
-    assert np.all(rec[~real] == pad) and np.all(rec[real] != pad), "pad words address the zero cell; records never equal them"
+    trash = g["n_st"] * g["n_q"] + 6   # pad words count into the trash counter after the class counters, no other bit
+    pad = (trash >> 2) * 128 + (trash & 3)
+    assert g["n_q"] % 4 == 0 and g["words"] == g["n_st"] * g["n_q"] // 4 + 2 and g["words"] <= 64
+    assert np.all(rec[~real] == pad) and np.all(rec[real] != pad), "pad words address the trash counter; records never equal them"
     assert len(rec) == s["n_score_padded"] and real.sum() == s["n_score"]
     uniq = ((rec >> 30) != 3).astype(np.int8)   # kind 3 = redundant
     uniq[~real] = 1   # padding follows the unique records

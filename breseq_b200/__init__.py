@@ -62,7 +62,7 @@ class _StreamInfo(C.Structure):
                 ("score_off", C.POINTER(C.c_uint64)),
                 ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
-                ("ins_count", C.POINTER(C.c_uint32))]
+                ("ins_count", C.POINTER(C.c_uint32)), ("round_slot", C.POINTER(C.c_uint32)), ("n_rounds", C.c_uint64)]
 
 
 class _ScoreParams(C.Structure):
@@ -332,6 +332,7 @@ class Context:
             "slot_ref": view(info.slot_ref, n_slots, np.uint8),
             "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
             "ins_count": view(info.ins_count, info.n_ins, np.uint32),
+            "round_slot": view(info.round_slot, info.n_rounds * 32, np.uint32),
         }
 
     def upload(self):

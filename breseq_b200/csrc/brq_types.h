@@ -173,6 +173,8 @@ struct PileupStream {
   uint32_t* side_rec = nullptr;        // side list: classic words of COLD records, SIDE_BIG | X1 of very redundant ones
   uint32_t* side_off = nullptr;        // [n_base + n_ins + 1] CSR into side_rec
   uint64_t n_side = 0;
+  uint32_t* round_slot = nullptr;      // [n_rounds * 32] slot of every lane of every tally round, ROUND_NO_SLOT = idle lane
+  uint64_t n_rounds = 0;
   ScoreGeometry geo;
   void* hist_rec = nullptr;            // n_hist records of hist_bytes (4 or 8) each
   uint32_t hist_bytes = 4;
@@ -191,6 +193,7 @@ struct PileupStream {
 };
 
 constexpr uint64_t HIST_OFF_REDUNDANT_BIT = 1ull << 63;
+constexpr uint32_t ROUND_NO_SLOT = 0xFFFFFFFFu, ROUND_BLOCK = 4096;
 
 // records [beg, end) of slot s in score_rec (padding excluded)
 #ifdef __CUDACC__

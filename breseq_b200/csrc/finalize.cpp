@@ -242,7 +242,7 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGe
   p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
   g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
   p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_nsq = sg.n_sq(); p.t_nw = sg.n_words();
-  p.t_stride = ((p.t_nsq * 48u + 127u) & ~127u) + 16u;
+  p.t_stride = p.t_nsq * 64u;
   g.n_tally_cells = (size_t)4 * p.t_stride / 16;
 }
 

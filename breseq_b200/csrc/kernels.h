@@ -55,8 +55,8 @@ struct ScoreParams {
   uint32_t fit_all;          // evaluate the EM fit on every column with scoring records (diagnostics / parity runs)
   // tally kernel: per-slot class histogram over sq = (set*2 + top) * t_nq + quality - t_qlo (t_nsq classes in
   // t_nsq / 4 words, then two words of special counters) and the shared-memory likelihood table of the dominant
-  // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M}, t_stride bytes between the four obs planes (16 mod 128: the planes
-  // start in different bank groups)
+  // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M, top strand ? 1 : 0, top strand ? 0 : 1} (64 bytes a class: the B operand
+  // of the contraction), t_stride bytes between the four obs planes
   uint32_t t_qlo, t_nq, t_nsq, t_nw, t_stride;
   uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
 };
@@ -72,7 +72,7 @@ struct HotTerms { double L[5]; double M; };    // M = max_b L[b]
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* side, const uint32_t* side_off,
-                        const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
+                        const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between);

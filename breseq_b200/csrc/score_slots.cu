@@ -133,25 +133,36 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ tally
+// D (8 slots x 8 columns) += A (8 slots x 4 classes) * B (4 classes x 8 columns), fp64 (DMMA.8x8x4).
+// Lane l = 4 g + t holds A[g][t], B[t][g] and D[g][2t], D[g][2t + 1].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint4 ldg_vec(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // Shared memory of one CTA (dynamic, base rounded up to the histogram block size):
 //   [n_warps x block]   per-warp class histograms: word w of lane l at w * 128 + l * 4 (bank l: conflict-free for any
 //                       mix of classes), four byte counters per word; block = 4 KB (<= 32 words) or 8 KB, and the
-//                       block is aligned to its size, so counter address = (record & 0x1FFF) | lane base
-//   [n_warps x 2 KB]    record rings: 4 stages x 32 lanes x 16 bytes
-//   [4 x t_stride]      likelihood table [obs][sq] x {L[0..4], M}
+//                       block is aligned to its size, so counter address = (record & 0x1FFF) | lane base.  The first
+//                       2 KB double as the scratch through which the contraction's result tiles reach their lanes.
+//   [4 x t_stride]      likelihood table [obs][sq] x 8 doubles (ScoreParams)
 __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
                                                                   const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
-                                                                  const uint8_t* __restrict__ slot_ref, uint64_t n_slots,
-                                                                  const double* __restrict__ tallyT, const HotTerms* __restrict__ coldT,
-                                                                  ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ worklist,
-                                                                  uint32_t* __restrict__ flagged, uint32_t* __restrict__ scalars,
-                                                                  uint32_t flagged_cap, uint32_t hist_block) {
+                                                                  const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ round_slot,
+                                                                  uint64_t n_rounds, const double* __restrict__ tallyT,
+                                                                  const HotTerms* __restrict__ coldT, ScoreParams p, ColumnOut* __restrict__ out,
+                                                                  uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
+                                                                  uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t sm0 = ((uint32_t)__cvta_generic_to_shared(sm_raw) + hist_block - 1u) & ~(hist_block - 1u);
-  const uint32_t hist = sm0 + warp * hist_block + lane * 4u;                                // this lane's word 0
-  const uint32_t ring = sm0 + n_warps_cta * hist_block + warp * (RING * 512u) + lane * 16u;  // this lane's cell of stage 0
-  const uint32_t tbl = sm0 + n_warps_cta * (hist_block + RING * 512u);
+  const uint32_t wbase = sm0 + warp * hist_block;   // this warp's histogram block
+  const uint32_t hist = wbase + lane * 4u;          // this lane's word 0
+  const uint32_t tbl = sm0 + n_warps_cta * hist_block;
   {
     const uint32_t n16 = p.t_stride / 4u;  // 16-byte cells of the table (4 planes of t_stride bytes)
     const uint4* src = reinterpret_cast<const uint4*>(tallyT);
@@ -163,59 +174,55 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   }
   __syncthreads();
   const double nan = __longlong_as_double(0x7ff8000000000000ll);
-  const uint32_t pad_word = (p.t_nw - 1u) * 128u + 2u;  // the trash counter (ScoreGeometry::pad_word)
   const uint32_t n_cw = p.t_nsq >> 2;                   // class words; the two special words follow
-  const uint32_t words_per_st = p.t_nq >> 2;
-  const uint64_t n_rounds = (n_slots + 31) >> 5;        // a warp takes 32 consecutive slots per round, one per lane
+  const uint32_t g8 = lane >> 2, t4 = lane & 3u;        // fragment coordinates of this lane in the contraction
+  const uint32_t a_sel = 0x4440u | t4;                  // byte t4 of a histogram word, zero-extended
+  const uint32_t a_base = wbase + g8 * 4u;              // word 0 of slot-lane g8 (m-tile mt adds 32 mt bytes)
+  const uint32_t b_off = t4 * 64u + g8 * 8u;            // B[t4][g8] inside a class word's four table rows
+  const uint32_t c_sts = wbase + g8 * 64u + t4 * 16u;   // scratch row of slot-lane g8 (m-tile mt adds 512 mt bytes)
+  const uint32_t c_lds = wbase + lane * 64u;            // this lane's scratch row
   const uint64_t n_warps = (uint64_t)gridDim.x * n_warps_cta;
   uint64_t round = (uint64_t)blockIdx.x * n_warps_cta + warp;
 
-  // slot geometry of a round: this lane's run of 128-bit vectors
-  struct Run { uint64_t beg; uint32_t n_vec, ref, side0, side1; };
-  auto load_run = [&](uint64_t r) {  // issued two rounds ahead: nothing here is waited for when the round starts
-    Run x{0, 0, 5, 0, 0};
-    const uint64_t s = (r << 5) + lane;
-    if (r < n_rounds && s < n_slots) {
-      const uint64_t o0 = off[s] & ~3ull, o1 = off[s + 1] & ~3ull;
-      x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 2);
-      x.ref = slot_ref[s]; x.side0 = side_off[s]; x.side1 = side_off[s + 1];
+  // this lane's slot of a round: its run of 128-bit vectors and what closes it.  Loaded a round ahead.
+  struct Run { uint64_t beg; uint32_t slot, n_vec, ref, side0, side1; };
+  auto load_run = [&](uint64_t r) {
+    Run x{0, ROUND_NO_SLOT, 0, 5, 0, 0};
+    if (r < n_rounds) {
+      x.slot = __ldg(round_slot + (r << 5) + lane);
+      if (x.slot != ROUND_NO_SLOT) {
+        const uint64_t o0 = off[x.slot] & ~3ull, o1 = off[x.slot + 1] & ~3ull;
+        x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 2);
+        x.ref = slot_ref[x.slot]; x.side0 = side_off[x.slot]; x.side1 = side_off[x.slot + 1];
+      }
     }
     return x;
   };
-  // the ring is primed with the run's first RING vectors (pad words where the run is shorter): always RING commits
-  auto prime = [&](const Run& x) {
-    const uint4* vp = reinterpret_cast<const uint4*>(rec + x.beg);
-#pragma unroll
-    for (int st = 0; st < RING; ++st) {
-      if ((uint32_t)st < x.n_vec) cp_async16(ring + (uint32_t)st * 512u, vp + st); else sts_fill16(ring + (uint32_t)st * 512u, pad_word);
-      cp_async_commit();
-    }
-  };
-  auto prefetch_region = [&](const Run& x) {  // the whole region of a round (32 consecutive runs) into L2, one request per warp
-    const uint64_t lo = __shfl_sync(0xFFFFFFFFu, x.beg, 0);
-    const uint64_t hi = __shfl_sync(0xFFFFFFFFu, x.beg + (uint64_t)x.n_vec * 4u, 31);
-    if (lane == 0 && hi > lo) prefetch_l2_bulk(rec + lo, (uint32_t)((hi - lo) * 4u));
-  };
 
-  Run cur = load_run(round), nxt = load_run(round + n_warps);
-  prime(cur);
+  Run cur = load_run(round);
+  // four vectors of the run are always on their way in registers: vector i + 4 is requested when vector i is used
+  const uint4* vp = reinterpret_cast<const uint4*>(rec + cur.beg);
+  uint4 v0, v1, v2, v3;
+  v0 = v1 = v2 = v3 = make_uint4(0, 0, 0, 0);
+  if (0 < cur.n_vec) v0 = ldg_vec(vp + 0);
+  if (1 < cur.n_vec) v1 = ldg_vec(vp + 1);
+  if (2 < cur.n_vec) v2 = ldg_vec(vp + 2);
+  if (3 < cur.n_vec) v3 = ldg_vec(vp + 3);
+
   for (; round < n_rounds; round += n_warps) {
-    const uint64_t my_slot = (round << 5) + lane;
-    const bool live = my_slot < n_slots;
-    prefetch_region(nxt);                            // next round's records: DRAM -> L2 while this round is tallied
-    const Run nxt2 = load_run(round + 2 * n_warps);  // its geometry is needed one round ahead
-    const uint32_t my_ref = cur.ref, side_cur = cur.side0, side_end = cur.side1;
+    const Run nxt = load_run(round + n_warps);  // first used when this round's records are in
+    const uint32_t my_slot = cur.slot, my_ref = cur.ref, n_vec = cur.n_vec;
+    const bool live = my_slot != ROUND_NO_SLOT;
 
     Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double red_top = 0.0, red_bot = 0.0;
     uint32_t raw_top = 0, raw_bot = 0, n = 0, c_ref = 0, u_top = 0, u_bot = 0;
-    bool in_head = true;  // still inside the run's leading redundant records
 
     // the scoring records of this lane's slot whose class is not in the shared table (another MAPQ, a '.'
     // observation, a quality outside the window) sit in the side list as classic words: their terms come from the
-    // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the walk below reads them.
-    uint32_t side_big = side_cur;
-    for (uint32_t e = side_cur; e < side_end; ++e) {
+    // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the head walk reads them.
+    uint32_t side_big = cur.side0;
+    for (uint32_t e = cur.side0; e < cur.side1; ++e) {
       const uint32_t w = __ldg(side + e);
       if (w & SIDE_BIG) continue;
       cold_add(kept, w, coldT, p);
@@ -223,96 +230,121 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       c_ref += (w >> 27) & 1u;
     }
 
-    const uint32_t tp0 = tbl + (my_ref < 4u ? my_ref : 0u) * p.t_stride;  // the plane of records matching this slot's base
-    const uint4* vp = reinterpret_cast<const uint4*>(rec + cur.beg);
-    uint32_t i = 0;  // vectors consumed by the warp in this round (lanes past their run see pad words)
-    const uint32_t n_it = __reduce_max_sync(0xFFFFFFFFu, cur.n_vec);
+    // redundant records lead the slot: an order-dependent double sum, taken in arrival order
+    // (identify_mutations.cpp:1605); the first record of any other kind (or a pad word) ends the walk
+    if (live && n_vec) {
+      const uint32_t cnt = n_vec * 4u;
+      uint32_t j = 0, r = v0.x;
+      while ((r >> DR_KIND_SHIFT) == 3u) {
+        uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
+        if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
+        const double inv = 1.0 / (double)red;
+        if (r & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
+        if (++j == cnt) break;
+        r = j == 1 ? v0.y : j == 2 ? v0.z : j == 3 ? v0.w : __ldg(rec + cur.beg + j);
+      }
+    }
+
+    // one 128-bit vector of the run: four records
+    auto tally4 = [&](const uint4& v) {
+      // every record increments one byte counter of this lane's histogram.  Two records are in flight at a
+      // time; when both address the same counter the second takes the first one's new value.
+      const uint32_t a0 = (v.x & DR_COUNTER_MASK) | hist, a1 = (v.y & DR_COUNTER_MASK) | hist,
+                     a2 = (v.z & DR_COUNTER_MASK) | hist, a3 = (v.w & DR_COUNTER_MASK) | hist;
+      {
+        const uint32_t c0 = lds_u8(a0) + 1u;
+        uint32_t c1 = lds_u8(a1) + 1u;
+        if (a1 == a0) c1 = c0 + 1u;
+        sts_u8(a0, c0); sts_u8(a1, c1);
+      }
+      {
+        const uint32_t c2 = lds_u8(a2) + 1u;
+        uint32_t c3 = lds_u8(a3) + 1u;
+        if (a3 == a2) c3 = c2 + 1u;
+        sts_u8(a2, c2); sts_u8(a3, c3);
+      }
+      if ((v.x | v.y | v.z | v.w) & DR_SLOW_BIT) {
+        // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
+        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(r[j] & DR_SLOW_BIT)) continue;
+          const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 3u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 64u;
+          const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
+          kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
+        }
+      }
+    };
+
+    const uint32_t n_max = __reduce_max_sync(0xFFFFFFFFu, n_vec), n_min = __reduce_min_sync(0xFFFFFFFFu, n_vec);
+    // the likelihood table of the round's reference base (rounds hold one base; "other" bases have no class counts)
+    const uint32_t ref_round = __reduce_min_sync(0xFFFFFFFFu, my_ref);
+    const uint32_t b_base = tbl + (ref_round < 4u ? ref_round : 0u) * p.t_stride + b_off;
+    uint32_t i = 0;  // vectors of the run consumed so far (a multiple of 4)
     bool more;
     do {
-      const uint32_t chunk_end = min(n_it, i + 63u);  // byte counters: at most 252 records between two contractions
-      cp_async_wait<RING - 1>();
-      uint4 v = lds_u32x4(ring + (i & (uint32_t)(RING - 1)) * 512u);
-      while (i < chunk_end) {
-        {  // the cell is free again: request the vector RING steps ahead, or pad words past the run
-          const uint32_t cell = ring + (i & (uint32_t)(RING - 1)) * 512u, ahead = i + (uint32_t)RING;
-          if (ahead < cur.n_vec) cp_async16(cell, vp + ahead); else sts_fill16(cell, pad_word);
-          cp_async_commit();
-        }
-        ++i;
-        cp_async_wait<RING - 1>();
-        const uint4 v_next = lds_u32x4(ring + (i & (uint32_t)(RING - 1)) * 512u);
-
-        if (in_head) {
-          // redundant records lead the slot: an order-dependent double sum, taken in arrival order
-          // (identify_mutations.cpp:1605); a pad word ends the walk like any non-redundant record does
-          const uint32_t r[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (in_head && (r[j] >> DR_KIND_SHIFT) == 3u) {
-              uint32_t red = (r[j] >> DR_X1_SHIFT) & DR_X1_MASK;
-              if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
-              const double inv = 1.0 / (double)red;
-              if (r[j] & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
-            } else in_head = false;
-          }
-        }
-        // every record increments one byte counter of this lane's histogram.  Two records are in flight at a
-        // time; when both address the same counter the second takes the first one's new value.
-        const uint32_t a0 = (v.x & DR_COUNTER_MASK) | hist, a1 = (v.y & DR_COUNTER_MASK) | hist,
-                       a2 = (v.z & DR_COUNTER_MASK) | hist, a3 = (v.w & DR_COUNTER_MASK) | hist;
-        {
-          const uint32_t c0 = lds_u8(a0) + 1u;
-          uint32_t c1 = lds_u8(a1) + 1u;
-          if (a1 == a0) c1 = c0 + 1u;
-          sts_u8(a0, c0); sts_u8(a1, c1);
-        }
-        {
-          const uint32_t c2 = lds_u8(a2) + 1u;
-          uint32_t c3 = lds_u8(a3) + 1u;
-          if (a3 == a2) c3 = c2 + 1u;
-          sts_u8(a2, c2); sts_u8(a3, c3);
-        }
-        if ((v.x | v.y | v.z | v.w) & DR_SLOW_BIT) {
-          // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
-          const uint32_t r[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (!(r[j] & DR_SLOW_BIT)) continue;
-            const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 3u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 48u;
-            const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
-            kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
-          }
-        }
-        v = v_next;
+      // byte counters: at most 240 records between two contractions
+      const uint32_t chunk_end = min(n_max, i + 60u), chunk_all = min(n_min, chunk_end);
+      for (; i + 4u <= chunk_all; i += 4u) {  // every lane has these four vectors
+        tally4(v0); if (i + 4u < n_vec) v0 = ldg_vec(vp + i + 4u);
+        tally4(v1); if (i + 5u < n_vec) v1 = ldg_vec(vp + i + 5u);
+        tally4(v2); if (i + 6u < n_vec) v2 = ldg_vec(vp + i + 6u);
+        tally4(v3); if (i + 7u < n_vec) v3 = ldg_vec(vp + i + 7u);
       }
-      more = i < n_it;
-      if (!more) {  // this round's records are all in: next round's first vectors travel during the contraction
-        prime(nxt);
+      for (; i < chunk_end; i += 4u) {         // the ragged end: lanes drop out as their runs end
+        if (i < n_vec) tally4(v0);
+        if (i + 4u < n_vec) v0 = ldg_vec(vp + i + 4u);
+        if (i + 1u < n_vec) tally4(v1);
+        if (i + 5u < n_vec) v1 = ldg_vec(vp + i + 5u);
+        if (i + 2u < n_vec) tally4(v2);
+        if (i + 6u < n_vec) v2 = ldg_vec(vp + i + 6u);
+        if (i + 3u < n_vec) tally4(v3);
+        if (i + 7u < n_vec) v3 = ldg_vec(vp + i + 7u);
+      }
+      more = i < n_max;
+      if (!more) {  // this round's records are all in: the next round's first vectors travel during the contraction
+        vp = reinterpret_cast<const uint4*>(rec + nxt.beg);
+        if (0 < nxt.n_vec) v0 = ldg_vec(vp + 0);
+        if (1 < nxt.n_vec) v1 = ldg_vec(vp + 1);
+        if (2 < nxt.n_vec) v2 = ldg_vec(vp + 2);
+        if (3 < nxt.n_vec) v3 = ldg_vec(vp + 3);
       }
 
-      // ---- contraction: sums += counts x table, for the classes matching the slot's reference base
-      uint32_t hp = hist, tp = tp0;
-      for (uint32_t st = 0; st < p.t_nsq; st += p.t_nq) {
-        uint32_t tot = 0;
-        for (uint32_t wq = 0; wq < words_per_st; ++wq, hp += 128u, tp += 192u) {
-          const uint32_t cw = lds_u32(hp);
-          if (!__any_sync(0xFFFFFFFFu, cw != 0u)) continue;
-          sts_u32(hp, 0u);
-          tot = __dp4a(cw, 0x01010101u, tot);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const double c = (double)((cw >> (8 * k)) & 255u);
-            const f64x2 x = lds_f64x2(tp + (uint32_t)k * 48u), y = lds_f64x2(tp + (uint32_t)k * 48u + 16u), z = lds_f64x2(tp + (uint32_t)k * 48u + 32u);
-            kept.l0 = fma(c, x.x, kept.l0); kept.l1 = fma(c, x.y, kept.l1); kept.l2 = fma(c, y.x, kept.l2);
-            kept.l3 = fma(c, y.y, kept.l3); kept.l4 = fma(c, z.x, kept.l4); kept.m = fma(c, z.y, kept.m);
-          }
+      // ---- contraction: sums[slot][column] += counts[slot][class] x table[class][column] on the fp64 tensor pipe.
+      // Four 8-slot tiles; one k-step per class word (4 classes): A = the word's four byte counters of eight slot
+      // lanes, B = the four table rows (columns L[0..4], M, top, bottom).
+      __syncwarp();
+      double d[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+      {
+        uint32_t ap = a_base, bp = b_base;
+        for (uint32_t kk = 0; kk < n_cw; ++kk, ap += 128u, bp += 256u) {
+          const uint32_t w0 = lds_u32(ap), w1 = lds_u32(ap + 32u), w2 = lds_u32(ap + 64u), w3 = lds_u32(ap + 96u);
+          if (!__any_sync(0xFFFFFFFFu, (w0 | w1 | w2 | w3) != 0u)) continue;
+          double bv;
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bv) : "r"(bp) : "memory");
+          dmma_8x8x4(d[0][0], d[0][1], (double)__byte_perm(w0, 0u, a_sel), bv);
+          dmma_8x8x4(d[1][0], d[1][1], (double)__byte_perm(w1, 0u, a_sel), bv);
+          dmma_8x8x4(d[2][0], d[2][1], (double)__byte_perm(w2, 0u, a_sel), bv);
+          dmma_8x8x4(d[3][0], d[3][1], (double)__byte_perm(w3, 0u, a_sel), bv);
         }
-        n += tot; c_ref += tot;
-        if ((st / p.t_nq) & 1u) u_top += tot; else u_bot += tot;  // st = set * 2 + top
       }
-      {  // special counters: idle / cold / slow records by strand (redundant and pad words count into the trash byte)
-        const uint32_t s0 = lds_u32(hist + n_cw * 128u), s1 = lds_u32(hist + (n_cw + 1u) * 128u);
-        sts_u32(hist + n_cw * 128u, 0u); sts_u32(hist + (n_cw + 1u) * 128u, 0u);
+      // special counters (idle / cold / slow records by strand; redundant and pad words count into the trash byte)
+      const uint32_t s0 = lds_u32(hist + n_cw * 128u), s1 = lds_u32(hist + (n_cw + 1u) * 128u);
+      __syncwarp();  // every lane has read the counters: the block's head becomes the scratch of the result tiles
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(c_sts + (uint32_t)mt * 512u), "d"(d[mt][0]), "d"(d[mt][1]) : "memory");
+      __syncwarp();
+      {
+        const f64x2 x = lds_f64x2(c_lds), y = lds_f64x2(c_lds + 16u), z = lds_f64x2(c_lds + 32u), c = lds_f64x2(c_lds + 48u);
+        kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
+        const uint32_t m_top = (uint32_t)c.x, m_bot = (uint32_t)c.y;  // matching HOT records by strand: exact small integers
+        n += m_top + m_bot; c_ref += m_top + m_bot; u_top += m_top; u_bot += m_bot;
+      }
+      __syncwarp();
+      for (uint32_t w = 0; w < p.t_nw; ++w) sts_u32(hist + w * 128u, 0u);
+      if (p.t_nw < 16u) for (uint32_t w = p.t_nw; w < 16u; ++w) sts_u32(hist + w * 128u, 0u);  // the scratch spans 16 words
+      {
         const uint32_t idle_t = s0 & 255u, idle_b = (s0 >> 8) & 255u, cold_t = (s0 >> 16) & 255u, cold_b = s0 >> 24,
                        slow_t = s1 & 255u, slow_b = (s1 >> 8) & 255u;
         u_top += idle_t + cold_t + slow_t; u_bot += idle_b + cold_b + slow_b;
@@ -320,7 +352,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       }
     } while (more);
 
-    cur = nxt; nxt = nxt2;
+    cur = nxt;
     if (!live) continue;
 
     const uint32_t ref = my_ref;
@@ -331,8 +363,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     const double slack = 1e-6;
     if (n > 0) {  // pure_genotype_call, identify_mutations.cpp:3398-3433
       best = 0;
+      double lb = ll[0];
 #pragma unroll
-      for (int b = 1; b < 5; ++b) if (ll[b] > ll[best]) best = b;
+      for (int b = 1; b < 5; ++b) if (ll[b] > lb) { best = b; lb = ll[b]; }
       double offv = -1.7976931348623157e308;
 #pragma unroll
       for (int b = 0; b < 5; ++b) if ((uint32_t)b != best) offv = fmax(offv, ll[b]);
@@ -340,16 +373,15 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 #pragma unroll
       for (int b = 0; b < 5; ++b) {
         if ((uint32_t)b == best) continue;
-        const double d = ll[b] - offv;
+        const double dd = ll[b] - offv;
         // the runner-up itself contributes exactly 1; anything below 2^-54 cannot change that sum
-        tot += (d == 0.0) ? 1.0 : (d < -17.0 ? 0.0 : pow(10.0, d));
+        tot += (dd == 0.0) ? 1.0 : (dd < -17.0 ? 0.0 : exp10(dd));
       }
-      consensus = (ll[best] - (log10(tot) + offv)) - p.log10_ref_length;
+      consensus = (lb - (log10(tot) + offv)) - p.log10_ref_length;
       // an RA row needs best != ref with a positive consensus score, or a presence score at the cutoff
       need_fit = p.fit_all != 0u || ref >= 5u || (best != ref && consensus > -slack);
       if (!need_fit) {
         const double ll_ref = ref == 0 ? ll[0] : ref == 1 ? ll[1] : ref == 2 ? ll[2] : ref == 3 ? ll[3] : ll[4];
-        // the sums are rounded differently from a record-by-record evaluation: a relative 1e-12 of margin on the bound
         const double bound = (kept.m - ll_ref) - (double)n * log10(((double)c_ref + 0.5) / ((double)n + 2.0)) - p.log10_ref_length;
         need_fit = !(bound < p.polymorphism_cutoff - slack);
       }
@@ -371,10 +403,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     o.n = n; o.bits = bits;
     out[my_slot] = o;
 
-    if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = (uint32_t)my_slot;
-    else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = (uint32_t)my_slot; }
+    if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = my_slot;
+    else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = my_slot; }
   }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------ fit
@@ -593,7 +624,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
 }
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* side, const uint32_t* side_off,
-                        const uint8_t* slot_ref, uint64_t n_slots, uint64_t n_records,
+                        const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between) {
@@ -602,15 +633,14 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const size_t smem_fit = (size_t)p.n_hot * 48;
   // histogram block per warp: 4 KB holds 32 words per lane, 8 KB the maximum of 64; as many warps as 227 KB allow
   const uint32_t hist_block = p.t_nw <= 32 ? 4096u : 8192u;
-  const size_t per_warp = hist_block + RING * 512, fixed = (size_t)4 * p.t_stride + hist_block;
+  const size_t per_warp = hist_block, fixed = (size_t)4 * p.t_stride + hist_block;
   int warps = TALLY_MAX_TPB / 32;
   while (warps > 1 && fixed + warps * per_warp > 227 * 1024) --warps;
   const size_t smem_tally = fixed + warps * per_warp;
-  const uint64_t n_rounds = (n_slots + 31) / 32;
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, off, side, side_off, slot_ref, n_slots, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);

@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -486,6 +486,30 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     if (sacc >= (1ull << 32)) throw std::runtime_error("more than 2^32 side-list entries in one staged stream");
     out.side_off[n_slots] = (uint32_t)sacc; out.n_side = sacc;
     out.side_rec = (uint32_t*)alloc(sacc * 4 + 16, &p3);
+    // Rounds of the tally kernel: 32 slots that share their reference base (its contraction multiplies the 32 class
+    // histograms with ONE base's likelihood table) and have about the same depth (its 32 lanes walk their runs in
+    // lock step).  Inside every block of ROUND_BLOCK consecutive slots the slots are grouped by base (A, C, G, T,
+    // other) and ordered by run length; a group is padded to whole rounds with ROUND_NO_SLOT.
+    {
+      if (n_slots >= ROUND_NO_SLOT) throw std::runtime_error("more than 2^32 - 2 slots in one staged stream");
+      std::vector<uint32_t> order;
+      order.reserve(n_slots + n_slots / 16 + 160);
+      std::vector<uint32_t> group[5];
+      auto vecs = [&](uint32_t s) { return (uint32_t)(((out.score_off[s + 1] & ~3ull) - (out.score_off[s] & ~3ull)) >> 2); };
+      for (uint64_t b0 = 0; b0 < n_slots; b0 += ROUND_BLOCK) {
+        const uint64_t b1 = std::min<uint64_t>(n_slots, b0 + ROUND_BLOCK);
+        for (auto& g : group) g.clear();
+        for (uint64_t s = b0; s < b1; ++s) group[out.slot_ref[s] < 4 ? out.slot_ref[s] : 4].push_back((uint32_t)s);
+        for (auto& g : group) {
+          std::stable_sort(g.begin(), g.end(), [&](uint32_t a, uint32_t b) { return vecs(a) < vecs(b); });
+          order.insert(order.end(), g.begin(), g.end());
+          while (order.size() & 31) order.push_back(ROUND_NO_SLOT);
+        }
+      }
+      out.n_rounds = order.size() / 32;
+      out.round_slot = (uint32_t*)alloc(order.size() * 4 + 16, &p3);
+      std::copy(order.begin(), order.end(), out.round_slot);
+    }
     acc = 0;
     for (uint64_t c = 0; c < out.n_base; ++c) {
       out.hist_off[c] = acc | ((cfg.want_hist && col_red[c]) ? HIST_OFF_REDUNDANT_BIT : 0);

@@ -91,6 +91,8 @@ typedef struct brq_stream_info {
   const uint8_t* slot_ref;
   const uint64_t* ins_parent;
   const uint32_t* ins_count;
+  const uint32_t* round_slot;      /* [n_rounds * 32] tally rounds: 32 slots of one reference base and similar depth; 0xFFFFFFFF = idle lane */
+  uint64_t n_rounds;
 } brq_stream_info;
 
 int brq_stream(brq_ctx* ctx, brq_stream_info* info);

@@ -211,8 +211,8 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
 def slot_ranges(stream):
     """(first index, record count) of every slot's run in ``score_rec`` (padding excluded)."""
     off = stream["score_off"]
-    beg = (off[:-1] & ~np.uint64(3)).astype(np.int64)
-    end = ((off[1:] & ~np.uint64(3)) - (off[1:] & np.uint64(3))).astype(np.int64)
+    beg = (off[:-1] & ~np.uint64(7)).astype(np.int64)
+    end = ((off[1:] & ~np.uint64(7)) - (off[1:] & np.uint64(7))).astype(np.int64)
     return beg, end - beg
 
 

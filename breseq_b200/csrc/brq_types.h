@@ -100,10 +100,10 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //                             cold entry of the side list
 //                    3 REDUNDANT
 // Within a slot the REDUNDANT records come first and the others follow, each part in arrival (BAM) order.
-// Every slot's run starts on a 16-byte boundary and is padded to a multiple of four records with pad
-// words (the trash counter, no other bit: never a real record), so the kernels read whole 128-bit vectors
-// that never straddle two slots.  score_off[s] is the run's first index (a multiple of 4); the low two bits of score_off[s + 1]
-// hold the number of pad words that end slot s's run.
+// Every slot's run starts on a 32-byte boundary and is padded to a multiple of eight records with pad
+// words (the trash counter, no other bit: never a real record), so the kernels read whole 256-bit vectors
+// that never straddle two slots.  score_off[s] is the run's first index (a multiple of 8); the low three bits of
+// score_off[s + 1] hold the number of pad words that end slot s's run.
 //
 // Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
 // records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
@@ -201,8 +201,8 @@ __host__ __device__
 #endif
 inline void score_slot_range(const uint64_t* score_off, uint64_t s, uint64_t& beg, uint64_t& end) {
   const uint64_t a = score_off[s], b = score_off[s + 1];
-  beg = a & ~3ull;
-  end = (b & ~3ull) - (b & 3ull);
+  beg = a & ~7ull;
+  end = (b & ~7ull) - (b & 7ull);
 }
 
 // Classic words of slot s in stream order (redundant first): f(classic word).  Redundant records come

@@ -138,11 +138,15 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-__device__ __forceinline__ uint4 ldg_vec(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+// one 256-bit vector of a run (eight records); a miss fills the whole 128-byte line in L2: the run's next vectors hit it
+struct Vec8 { uint4 a, b; };
+__device__ __forceinline__ Vec8 ldg_vec8(const Vec8* p) {
+  Vec8 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.a.x), "=r"(v.a.y), "=r"(v.a.z), "=r"(v.a.w), "=r"(v.b.x), "=r"(v.b.y), "=r"(v.b.z), "=r"(v.b.w) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // Shared memory of one CTA (dynamic, base rounded up to the histogram block size):
 //   [n_warps x block]   per-warp class histograms: word w of lane l at w * 128 + l * 4 (bank l: conflict-free for any
@@ -184,33 +188,42 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   const uint64_t n_warps = (uint64_t)gridDim.x * n_warps_cta;
   uint64_t round = (uint64_t)blockIdx.x * n_warps_cta + warp;
 
-  // this lane's slot of a round: its run of 128-bit vectors and what closes it.  Loaded a round ahead.
+  // this lane's slot of a round: its run of 256-bit vectors and what closes it.  Slot numbers are read two rounds
+  // ahead and the slot's geometry one round ahead, so no round starts by waiting for a chain of dependent loads.
   struct Run { uint64_t beg; uint32_t slot, n_vec, ref, side0, side1; };
-  auto load_run = [&](uint64_t r) {
-    Run x{0, ROUND_NO_SLOT, 0, 5, 0, 0};
-    if (r < n_rounds) {
-      x.slot = __ldg(round_slot + (r << 5) + lane);
-      if (x.slot != ROUND_NO_SLOT) {
-        const uint64_t o0 = off[x.slot] & ~3ull, o1 = off[x.slot + 1] & ~3ull;
-        x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 2);
-        x.ref = slot_ref[x.slot]; x.side0 = side_off[x.slot]; x.side1 = side_off[x.slot + 1];
-      }
+  auto load_slot = [&](uint64_t r) { return r < n_rounds ? __ldg(round_slot + (r << 5) + lane) : ROUND_NO_SLOT; };
+  auto load_run = [&](uint32_t slot) {
+    Run x{0, slot, 0, 5, 0, 0};
+    if (slot != ROUND_NO_SLOT) {
+      const uint64_t o0 = off[slot] & ~7ull, o1 = off[slot + 1] & ~7ull;
+      x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 3);
+      x.ref = slot_ref[slot]; x.side0 = side_off[slot]; x.side1 = side_off[slot + 1];
     }
     return x;
   };
+  // Two vectors of the run are always on their way in registers (vector i + 2 is requested when vector i is used);
+  // the lines behind them were asked into L2 half a round earlier, so the requests are L2 hits.
+  Vec8 V0, V1;
+  V0.a = V0.b = V1.a = V1.b = make_uint4(0, 0, 0, 0);
+  const Vec8* vp = nullptr;
+  auto start_run = [&](const Run& x) {
+    vp = reinterpret_cast<const Vec8*>(rec + x.beg);
+    if (0 < x.n_vec) V0 = ldg_vec8(vp + 0);
+    if (1 < x.n_vec) V1 = ldg_vec8(vp + 1);
+    if (4 < x.n_vec) prefetch_l2(vp + 4);
+    if (8 < x.n_vec) prefetch_l2(vp + 8);
+    if (12 < x.n_vec) prefetch_l2(vp + 12);
+    if (5 < x.n_vec) prefetch_l2(vp + min(x.n_vec, 16u) - 1u);
+    if (x.side1 > x.side0) prefetch_l2(side + x.side0);
+  };
 
-  Run cur = load_run(round);
-  // four vectors of the run are always on their way in registers: vector i + 4 is requested when vector i is used
-  const uint4* vp = reinterpret_cast<const uint4*>(rec + cur.beg);
-  uint4 v0, v1, v2, v3;
-  v0 = v1 = v2 = v3 = make_uint4(0, 0, 0, 0);
-  if (0 < cur.n_vec) v0 = ldg_vec(vp + 0);
-  if (1 < cur.n_vec) v1 = ldg_vec(vp + 1);
-  if (2 < cur.n_vec) v2 = ldg_vec(vp + 2);
-  if (3 < cur.n_vec) v3 = ldg_vec(vp + 3);
+  Run cur = load_run(load_slot(round));
+  uint32_t slot_nxt = load_slot(round + n_warps);
+  start_run(cur);
 
   for (; round < n_rounds; round += n_warps) {
-    const Run nxt = load_run(round + n_warps);  // first used when this round's records are in
+    const Run nxt = load_run(slot_nxt);  // first used when this round's records are in
+    slot_nxt = load_slot(round + 2 * n_warps);
     const uint32_t my_slot = cur.slot, my_ref = cur.ref, n_vec = cur.n_vec;
     const bool live = my_slot != ROUND_NO_SLOT;
 
@@ -220,32 +233,40 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 
     // the scoring records of this lane's slot whose class is not in the shared table (another MAPQ, a '.'
     // observation, a quality outside the window) sit in the side list as classic words: their terms come from the
-    // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the head walk reads them.
+    // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the head walk reads
+    // them.  Two entries per step, the next pair's words requested before this pair's table terms.
     uint32_t side_big = cur.side0;
-    for (uint32_t e = cur.side0; e < cur.side1; ++e) {
-      const uint32_t w = __ldg(side + e);
-      if (w & SIDE_BIG) continue;
-      cold_add(kept, w, coldT, p);
-      ++n;
-      c_ref += (w >> 27) & 1u;
+    {
+      uint32_t e = cur.side0;
+      uint32_t wa = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, wb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
+      while (e < cur.side1) {
+        e += 2u;
+        const uint32_t na = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, nb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
+        Sums ta = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, tb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (!(wa & SIDE_BIG)) { cold_add(ta, wa, coldT, p); ++n; c_ref += (wa >> 27) & 1u; }
+        if (!(wb & SIDE_BIG)) { cold_add(tb, wb, coldT, p); ++n; c_ref += (wb >> 27) & 1u; }
+        kept.l0 += ta.l0; kept.l1 += ta.l1; kept.l2 += ta.l2; kept.l3 += ta.l3; kept.l4 += ta.l4; kept.m += ta.m;
+        kept.l0 += tb.l0; kept.l1 += tb.l1; kept.l2 += tb.l2; kept.l3 += tb.l3; kept.l4 += tb.l4; kept.m += tb.m;
+        wa = na; wb = nb;
+      }
     }
 
     // redundant records lead the slot: an order-dependent double sum, taken in arrival order
     // (identify_mutations.cpp:1605); the first record of any other kind (or a pad word) ends the walk
     if (live && n_vec) {
-      const uint32_t cnt = n_vec * 4u;
-      uint32_t j = 0, r = v0.x;
+      const uint32_t cnt = n_vec * 8u;
+      uint32_t j = 0, r = V0.a.x;
       while ((r >> DR_KIND_SHIFT) == 3u) {
         uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
         if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
         const double inv = 1.0 / (double)red;
         if (r & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
         if (++j == cnt) break;
-        r = j == 1 ? v0.y : j == 2 ? v0.z : j == 3 ? v0.w : __ldg(rec + cur.beg + j);
+        r = j == 1 ? V0.a.y : j == 2 ? V0.a.z : j == 3 ? V0.a.w : __ldg(rec + cur.beg + j);
       }
     }
 
-    // one 128-bit vector of the run: four records
+    // half a vector: four records
     auto tally4 = [&](const uint4& v) {
       // every record increments one byte counter of this lane's histogram.  Two records are in flight at a
       // time; when both address the same counter the second takes the first one's new value.
@@ -280,35 +301,24 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     // the likelihood table of the round's reference base (rounds hold one base; "other" bases have no class counts)
     const uint32_t ref_round = __reduce_min_sync(0xFFFFFFFFu, my_ref);
     const uint32_t b_base = tbl + (ref_round < 4u ? ref_round : 0u) * p.t_stride + b_off;
-    uint32_t i = 0;  // vectors of the run consumed so far (a multiple of 4)
+    uint32_t i = 0;  // vectors of the run consumed so far (even)
     bool more;
     do {
       // byte counters: at most 240 records between two contractions
-      const uint32_t chunk_end = min(n_max, i + 60u), chunk_all = min(n_min, chunk_end);
-      for (; i + 4u <= chunk_all; i += 4u) {  // every lane has these four vectors
-        tally4(v0); if (i + 4u < n_vec) v0 = ldg_vec(vp + i + 4u);
-        tally4(v1); if (i + 5u < n_vec) v1 = ldg_vec(vp + i + 5u);
-        tally4(v2); if (i + 6u < n_vec) v2 = ldg_vec(vp + i + 6u);
-        tally4(v3); if (i + 7u < n_vec) v3 = ldg_vec(vp + i + 7u);
+      const uint32_t chunk_end = min(n_max, i + 30u), chunk_all = min(n_min, chunk_end);
+      for (; i + 2u <= chunk_all; i += 2u) {  // every lane has these two vectors
+        if ((i & 2u) && i + 18u < n_vec) prefetch_l2(vp + i + 18u);  // deep runs: keep L2 half a kilobyte ahead
+        tally4(V0.a); tally4(V0.b); if (i + 2u < n_vec) V0 = ldg_vec8(vp + i + 2u);
+        tally4(V1.a); tally4(V1.b); if (i + 3u < n_vec) V1 = ldg_vec8(vp + i + 3u);
       }
-      for (; i < chunk_end; i += 4u) {         // the ragged end: lanes drop out as their runs end
-        if (i < n_vec) tally4(v0);
-        if (i + 4u < n_vec) v0 = ldg_vec(vp + i + 4u);
-        if (i + 1u < n_vec) tally4(v1);
-        if (i + 5u < n_vec) v1 = ldg_vec(vp + i + 5u);
-        if (i + 2u < n_vec) tally4(v2);
-        if (i + 6u < n_vec) v2 = ldg_vec(vp + i + 6u);
-        if (i + 3u < n_vec) tally4(v3);
-        if (i + 7u < n_vec) v3 = ldg_vec(vp + i + 7u);
+      for (; i < chunk_end; i += 2u) {         // the ragged end: lanes drop out as their runs end
+        if (i < n_vec) { tally4(V0.a); tally4(V0.b); }
+        if (i + 2u < n_vec) V0 = ldg_vec8(vp + i + 2u);
+        if (i + 1u < n_vec) { tally4(V1.a); tally4(V1.b); }
+        if (i + 3u < n_vec) V1 = ldg_vec8(vp + i + 3u);
       }
       more = i < n_max;
-      if (!more) {  // this round's records are all in: the next round's first vectors travel during the contraction
-        vp = reinterpret_cast<const uint4*>(rec + nxt.beg);
-        if (0 < nxt.n_vec) v0 = ldg_vec(vp + 0);
-        if (1 < nxt.n_vec) v1 = ldg_vec(vp + 1);
-        if (2 < nxt.n_vec) v2 = ldg_vec(vp + 2);
-        if (3 < nxt.n_vec) v3 = ldg_vec(vp + 3);
-      }
+      if (!more) start_run(nxt);  // this round's records are all in: the next round's first vectors travel during the contraction
 
       // ---- contraction: sums[slot][column] += counts[slot][class] x table[class][column] on the fp64 tensor pipe.
       // Four 8-slot tiles; one k-step per class word (4 classes): A = the word's four byte counters of eight slot

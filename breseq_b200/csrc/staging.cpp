@@ -471,11 +471,11 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   // ---- offsets
   {
     uint64_t acc = 0;
-    uint64_t n_true = 0, pad = 0;  // runs padded to whole 128-bit vectors; the pad count rides in the next entry's low bits
+    uint64_t n_true = 0, pad = 0;  // runs padded to whole 256-bit vectors; the pad count rides in the next entry's low bits
     for (uint64_t s = 0; s < n_slots; ++s) {
       out.score_off[s] = acc | pad;
       const uint64_t cnt = cfg.want_score ? score_cnt[s] : 0;
-      pad = (4 - (cnt & 3)) & 3;
+      pad = (8 - (cnt & 7)) & 7;
       acc += cnt + pad; n_true += cnt;
     }
     out.score_off[n_slots] = acc | pad; out.n_score = n_true; out.n_score_padded = acc;
@@ -495,7 +495,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       std::vector<uint32_t> order;
       order.reserve(n_slots + n_slots / 16 + 160);
       std::vector<uint32_t> group[5];
-      auto vecs = [&](uint32_t s) { return (uint32_t)(((out.score_off[s + 1] & ~3ull) - (out.score_off[s] & ~3ull)) >> 2); };
+      auto vecs = [&](uint32_t s) { return (uint32_t)(((out.score_off[s + 1] & ~7ull) - (out.score_off[s] & ~7ull)) >> 3); };
       for (uint64_t b0 = 0; b0 < n_slots; b0 += ROUND_BLOCK) {
         const uint64_t b1 = std::min<uint64_t>(n_slots, b0 + ROUND_BLOCK);
         for (auto& g : group) g.clear();
@@ -626,7 +626,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         if (!cfg.want_score) return;
         score_words(i, ri, q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
           const DevWord w = encode(rec, x1, out.slot_ref[s]);
-          out.score_rec[(out.score_off[s] & ~3ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
+          out.score_rec[(out.score_off[s] & ~7ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
           if (w.has_side) out.side_rec[out.side_off[s] + (unique ? side_cur[s]++ : side_red_cur[s]++)] = w.side;
           const uint32_t kind = w.dev >> DR_KIND_SHIFT;
           if (kind == 0 || kind == 2) {  // a scoring record: exact statistics for the likelihood tables

@@ -76,7 +76,7 @@ int brq_stage_synthetic(brq_ctx* ctx, const brq_synth_spec* spec, const brq_stag
 
 typedef struct brq_stream_info {
   uint64_t n_base, n_ins, n_score_records, n_hist_records, n_reads;
-  uint64_t n_score_padded;         /* words in score_rec: every slot's run is padded to whole 128-bit vectors */
+  uint64_t n_score_padded;         /* words in score_rec: every slot's run is padded to whole 256-bit vectors */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
   uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
@@ -85,7 +85,7 @@ typedef struct brq_stream_info {
   const uint32_t* score_rec;       /* host views, valid until the next staging call; word layout: csrc/brq_types.h */
   const uint32_t* side_rec;
   const uint32_t* side_off;
-  const uint64_t* score_off;       /* slot s: first index score_off[s] & ~3, pad words (score_off[s+1] & 3) */
+  const uint64_t* score_off;       /* slot s: first index score_off[s] & ~7, pad words (score_off[s+1] & 7) */
   const void* hist_rec;
   const uint64_t* hist_off;
   const uint8_t* slot_ref;

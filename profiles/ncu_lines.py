@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-source-line share of executed warp instructions and stall samples of the first kernel in an ncu report.
-Usage: python profiles/ncu_lines.py gpurun_out/prof.ncu-rep [top_n]"""
+Usage: python profiles/ncu_lines.py gpurun_out/prof.ncu-rep [top_n] [inst|samples]"""
 import csv, sys, subprocess
 from collections import defaultdict
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
@@ -22,8 +22,9 @@ for r in rows:
         inst[key] += float(r[ix['Instructions Executed']] or 0); samp[key] += float(r[ix['# Samples']] or 0)
     except ValueError:
         continue
-    text[key] = r[1]
+    text.setdefault(key, r[1])
 ti, ts = sum(inst.values()), sum(samp.values())
 print('total warp instructions %.0f, samples %.0f' % (ti, ts))
-for k in sorted(inst, key=lambda k: -inst[k])[:top]:
+order = 'samples' if len(sys.argv) > 3 and sys.argv[3] == 'samples' else 'inst'
+for k in sorted(inst, key=lambda k: -(samp[k] if order == 'samples' else inst[k]))[:top]:
     print('%-22s %5d  inst %5.1f%%  samples %5.1f%%  %s' % (k[0][:22], k[1], 100 * inst[k] / ti, 100 * samp[k] / ts, text[k][:100]))

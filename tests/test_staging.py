@@ -61,7 +61,7 @@ def test_redundant_records_lead_each_slot(staged):
     d, ctx, s = staged
     rec = s["score_rec"]
     beg, cnt = bq.slot_ranges(s)
-    assert np.all(beg % 4 == 0), "every run starts on a 128-bit boundary"
+    assert np.all(beg % 8 == 0), "every run starts on a 256-bit boundary"
     real = np.zeros(len(rec), bool)
     real[np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))] = True
     g = s["geometry"]

@@ -62,7 +62,8 @@ class _StreamInfo(C.Structure):
                 ("score_off", C.POINTER(C.c_uint64)),
                 ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
-                ("ins_count", C.POINTER(C.c_uint32)), ("round_slot", C.POINTER(C.c_uint32)), ("n_rounds", C.c_uint64)]
+                ("ins_count", C.POINTER(C.c_uint32)), ("round_slot", C.POINTER(C.c_uint32)), ("n_rounds", C.c_uint64),
+                ("score_cnt", C.POINTER(C.c_uint32)), ("round_off", C.POINTER(C.c_uint64))]
 
 
 class _ScoreParams(C.Structure):
@@ -209,11 +210,16 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
 
 
 def slot_ranges(stream):
-    """(first index, record count) of every slot's run in ``score_rec`` (padding excluded)."""
-    off = stream["score_off"]
-    beg = (off[:-1] & ~np.uint64(7)).astype(np.int64)
-    end = ((off[1:] & ~np.uint64(7)) - (off[1:] & np.uint64(7))).astype(np.int64)
-    return beg, end - beg
+    """(first word, record count) of every slot in ``score_rec`` (round-major, lane-interleaved: see record_positions)."""
+    return stream["score_off"][:-1].astype(np.int64), stream["score_cnt"].astype(np.int64)
+
+
+def record_positions(stream):
+    """Word index in ``score_rec`` of every record, slot by slot in stream order: record j of a slot whose first word
+    is b sits at b + (j >> 3) * 256 + ((j >> 2) & 1) * 128 + (j & 3) (csrc/brq_types.h: score_index)."""
+    beg, cnt = slot_ranges(stream)
+    j = np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+    return np.repeat(beg, cnt) + (j >> 3) * 256 + ((j >> 2) & 1) * 128 + (j & 3)
 
 
 def decode_score_records(stream):
@@ -225,8 +231,7 @@ def decode_score_records(stream):
     g = stream["geometry"]
     beg, cnt = slot_ranges(stream)
     n_slots = len(beg)
-    pos = np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
-    d = stream["score_rec"][pos].astype(np.int64)
+    d = stream["score_rec"][record_positions(stream)].astype(np.int64)
     slot = np.repeat(np.arange(n_slots), cnt)
     kind = d >> 30
     n = len(d)
@@ -333,6 +338,8 @@ class Context:
             "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
             "ins_count": view(info.ins_count, info.n_ins, np.uint32),
             "round_slot": view(info.round_slot, info.n_rounds * 32, np.uint32),
+            "score_cnt": view(info.score_cnt, n_slots, np.uint32),
+            "round_off": view(info.round_off, info.n_rounds + 1, np.uint64),
         }
 
     def upload(self):

@@ -69,7 +69,8 @@ struct brq_ctx {
   bool staged = false, uploaded = false;
 
   DevBuf<uint32_t> d_score_rec, d_side_rec, d_side_off, d_round_slot, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
-  DevBuf<uint64_t> d_score_off, d_hist_off;
+  DevBuf<uint64_t> d_score_off, d_hist_off, d_round_off;
+  DevBuf<uint32_t> d_score_cnt;
   DevBuf<uint8_t> d_hist_rec;
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
@@ -188,11 +189,13 @@ void upload(brq_ctx* c) {
   if (!c->staged) throw std::runtime_error("nothing staged");
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
-  c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_slot_ref.ensure(n_slots);
+  c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_slot_ref.ensure(n_slots);
   c->d_hist_rec.ensure(st.n_hist * st.hist_bytes + 16);
   c->d_side_rec.ensure(st.n_side + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_side_rec.p, st.side_rec, st.n_side * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
@@ -345,7 +348,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
-  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_side_rec.p, c->d_side_off.p, c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
+  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
                      c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
@@ -435,7 +438,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -485,10 +488,10 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->n_reads = c->reads.size();
     info->n_score_padded = st.n_score_padded;
     info->n_side = st.n_side; info->side_rec = st.side_rec; info->side_off = st.side_off;
-    info->round_slot = st.round_slot; info->n_rounds = st.n_rounds;
+    info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
     info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words();
-    info->bytes_host = st.n_rounds * 128 + st.n_side * 4 + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
+    info->bytes_host = st.n_rounds * 136 + st.n_slots() * 4 + st.n_side * 4 + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();

@@ -100,10 +100,14 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //                             cold entry of the side list
 //                    3 REDUNDANT
 // Within a slot the REDUNDANT records come first and the others follow, each part in arrival (BAM) order.
-// Every slot's run starts on a 32-byte boundary and is padded to a multiple of eight records with pad
-// words (the trash counter, no other bit: never a real record), so the kernels read whole 256-bit vectors
-// that never straddle two slots.  score_off[s] is the run's first index (a multiple of 8); the low three bits of
-// score_off[s + 1] hold the number of pad words that end slot s's run.
+// The stream is ROUND-MAJOR AND LANE-INTERLEAVED.  The tally kernel works in rounds of 32 slots (round_slot: same
+// reference base, similar depth), one slot per lane.  Round r owns words [round_off[r], round_off[r + 1]): one 1 KB
+// "round vector" (ROUND_VECTOR_WORDS) per eight records of its deepest slot.  Round vector i holds records 8i .. 8i+7
+// of every lane: lane l's records 8i .. 8i+3 at word i*256 + 4l, its records 8i+4 .. 8i+7 at word i*256 + 128 + 4l, so
+// a warp reads a round vector with two fully coalesced 128-bit accesses per lane.  Lanes whose slot is shallower, and
+// idle lanes, are filled with pad words (the trash counter, no other bit: never a real record).
+// score_off[s] = first word of slot s (round_off[r] + 4 l), score_cnt[s] = its records; record j of slot s is word
+// score_index(score_off[s], j).
 //
 // Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
 // records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
@@ -165,7 +169,9 @@ struct PileupStream {
   std::vector<uint32_t> ins_count;     // [n_ins] insert_count (>= 1)
   // per slot
   uint8_t* slot_ref = nullptr;         // [n_base + n_ins] reference base index ('.' for sub-columns)
-  uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] padded CSR into score_rec (see above; score_slot_range())
+  uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] first word of every slot in score_rec (see above; score_index())
+  uint32_t* score_cnt = nullptr;       // [n_base + n_ins] records of every slot
+  uint64_t* round_off = nullptr;       // [n_rounds + 1] first word of every round in score_rec
   uint64_t* hist_off = nullptr;        // [n_base + 1] CSR into hist_rec; bit 63 of entry c = column c has a redundant read
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records
@@ -193,27 +199,23 @@ struct PileupStream {
 };
 
 constexpr uint64_t HIST_OFF_REDUNDANT_BIT = 1ull << 63;
-constexpr uint32_t ROUND_NO_SLOT = 0xFFFFFFFFu, ROUND_BLOCK = 4096;
+constexpr uint32_t ROUND_NO_SLOT = 0xFFFFFFFFu, ROUND_BLOCK = 4096, ROUND_VECTOR_WORDS = 256;
 
-// records [beg, end) of slot s in score_rec (padding excluded)
+// word of record j of the slot whose first word is `base` (round-major, lane-interleaved stream)
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline void score_slot_range(const uint64_t* score_off, uint64_t s, uint64_t& beg, uint64_t& end) {
-  const uint64_t a = score_off[s], b = score_off[s + 1];
-  beg = a & ~7ull;
-  end = (b & ~7ull) - (b & 7ull);
+inline uint64_t score_index(uint64_t base, uint64_t j) {
+  return base + (j >> 3) * ROUND_VECTOR_WORDS + ((j >> 2) & 1u) * (ROUND_VECTOR_WORDS / 2) + (j & 3u);
 }
 
 // Classic words of slot s in stream order (redundant first): f(classic word).  Redundant records come
 // back with their full X1 in a second argument (the classic field saturates at 8191).
 template <class F>
 inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
-  uint64_t beg, end;
-  score_slot_range(st.score_off, s, beg, end);
   uint32_t side = st.side_off[s];
-  for (uint64_t i = beg; i < end; ++i) {
-    const uint32_t d = st.score_rec[i], kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
+  for (uint64_t j = 0; j < st.score_cnt[s]; ++j) {
+    const uint32_t d = st.score_rec[score_index(st.score_off[s], j)], kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
     if (kind == 0) f(classic_of_hot(d, st.geo), 1u);
     else if (kind == 1) f(top | SR_UNIQUE_BIT | SR_TRIM_BIT, 1u);   // does not score; why is not kept
     else if (kind == 2) f(st.side_rec[side++], 1u);

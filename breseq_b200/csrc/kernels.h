@@ -71,7 +71,8 @@ struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 struct HotTerms { double L[5]; double M; };    // M = max_b L[b]
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
-void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* side, const uint32_t* side_off,
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,
+                        const uint32_t* side, const uint32_t* side_off,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,

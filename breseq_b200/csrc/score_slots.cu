@@ -138,14 +138,8 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-// one 256-bit vector of a run (eight records); a miss fills the whole 128-byte line in L2: the run's next vectors hit it
+// eight records of one lane: its share of a round vector
 struct Vec8 { uint4 a, b; };
-__device__ __forceinline__ Vec8 ldg_vec8(const Vec8* p) {
-  Vec8 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v.a.x), "=r"(v.a.y), "=r"(v.a.z), "=r"(v.a.w), "=r"(v.b.x), "=r"(v.b.y), "=r"(v.b.z), "=r"(v.b.w) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
 // Shared memory of one CTA (dynamic, base rounded up to the histogram block size):
@@ -153,8 +147,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 //                       mix of classes), four byte counters per word; block = 4 KB (<= 32 words) or 8 KB, and the
 //                       block is aligned to its size, so counter address = (record & 0x1FFF) | lane base.  The first
 //                       2 KB double as the scratch through which the contraction's result tiles reach their lanes.
+//   [n_warps x 4 KB]    record rings: 4 stages of one round vector (two planes of 32 lanes x 16 bytes)
 //   [4 x t_stride]      likelihood table [obs][sq] x 8 doubles (ScoreParams)
-__global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+__global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ round_off,
                                                                   const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                                   const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ round_slot,
                                                                   uint64_t n_rounds, const double* __restrict__ tallyT,
@@ -166,7 +161,8 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   const uint32_t sm0 = ((uint32_t)__cvta_generic_to_shared(sm_raw) + hist_block - 1u) & ~(hist_block - 1u);
   const uint32_t wbase = sm0 + warp * hist_block;   // this warp's histogram block
   const uint32_t hist = wbase + lane * 4u;          // this lane's word 0
-  const uint32_t tbl = sm0 + n_warps_cta * hist_block;
+  const uint32_t ring = sm0 + n_warps_cta * hist_block + warp * (RING * 1024u) + lane * 16u;  // this lane's cell of stage 0, first plane
+  const uint32_t tbl = sm0 + n_warps_cta * (hist_block + RING * 1024u);
   {
     const uint32_t n16 = p.t_stride / 4u;  // 16-byte cells of the table (4 planes of t_stride bytes)
     const uint4* src = reinterpret_cast<const uint4*>(tallyT);
@@ -188,41 +184,55 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   const uint64_t n_warps = (uint64_t)gridDim.x * n_warps_cta;
   uint64_t round = (uint64_t)blockIdx.x * n_warps_cta + warp;
 
-  // this lane's slot of a round: its run of 256-bit vectors and what closes it.  Slot numbers are read two rounds
-  // ahead and the slot's geometry one round ahead, so no round starts by waiting for a chain of dependent loads.
+  // A round: its records (round_off: warp-uniform) and this lane's slot with what closes it.  Slot numbers are read
+  // two rounds ahead and the rest one round ahead, so no round starts by waiting for a chain of dependent loads.
   struct Run { uint64_t beg; uint32_t slot, n_vec, ref, side0, side1; };
   auto load_slot = [&](uint64_t r) { return r < n_rounds ? __ldg(round_slot + (r << 5) + lane) : ROUND_NO_SLOT; };
-  auto load_run = [&](uint32_t slot) {
+  auto load_run = [&](uint64_t r, uint32_t slot) {
     Run x{0, slot, 0, 5, 0, 0};
-    if (slot != ROUND_NO_SLOT) {
-      const uint64_t o0 = off[slot] & ~7ull, o1 = off[slot + 1] & ~7ull;
-      x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) >> 3);
-      x.ref = slot_ref[slot]; x.side0 = side_off[slot]; x.side1 = side_off[slot + 1];
+    if (r < n_rounds) {
+      const uint64_t o0 = __ldg(round_off + r), o1 = __ldg(round_off + r + 1);
+      x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) / ROUND_VECTOR_WORDS);
     }
+    if (slot != ROUND_NO_SLOT) { x.ref = slot_ref[slot]; x.side0 = side_off[slot]; x.side1 = side_off[slot + 1]; }
     return x;
   };
-  // Two vectors of the run are always on their way in registers (vector i + 2 is requested when vector i is used);
-  // the lines behind them were asked into L2 half a round earlier, so the requests are L2 hits.
-  Vec8 V0, V1;
-  V0.a = V0.b = V1.a = V1.b = make_uint4(0, 0, 0, 0);
-  const Vec8* vp = nullptr;
+  // The warp streams the round's 1 KB vectors through a four-stage ring in shared memory with cp.async (LDGSTS, two
+  // fully coalesced 16-byte copies per lane and vector): four vectors are always on their way without holding
+  // registers, and wait_group counts them in order.  A lane only ever reads its own cells.
+  const uint4* vp = nullptr;  // this lane's 16 bytes of the round's first plane
+  auto fetch = [&](uint32_t stage, uint32_t i, bool on) {  // round vector i into a stage; always one commit
+    if (on) {
+      cp_async16(ring + stage * 1024u, vp + (size_t)i * (ROUND_VECTOR_WORDS / 4));
+      cp_async16(ring + stage * 1024u + 512u, vp + (size_t)i * (ROUND_VECTOR_WORDS / 4) + ROUND_VECTOR_WORDS / 8);
+    }
+    cp_async_commit();
+  };
   auto start_run = [&](const Run& x) {
-    vp = reinterpret_cast<const Vec8*>(rec + x.beg);
-    if (0 < x.n_vec) V0 = ldg_vec8(vp + 0);
-    if (1 < x.n_vec) V1 = ldg_vec8(vp + 1);
-    if (4 < x.n_vec) prefetch_l2(vp + 4);
-    if (8 < x.n_vec) prefetch_l2(vp + 8);
-    if (12 < x.n_vec) prefetch_l2(vp + 12);
-    if (5 < x.n_vec) prefetch_l2(vp + min(x.n_vec, 16u) - 1u);
+    vp = reinterpret_cast<const uint4*>(rec + x.beg) + lane;
+#pragma unroll
+    for (int st = 0; st < RING; ++st) fetch((uint32_t)st, (uint32_t)st, (uint32_t)st < x.n_vec);
+    // the rest of the round into L2 (one request per warp), and this lane's side-list entries
+    if (lane == 0 && x.n_vec > (uint32_t)RING)
+      prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, (x.n_vec - (uint32_t)RING) * (ROUND_VECTOR_WORDS * 4u));
     if (x.side1 > x.side0) prefetch_l2(side + x.side0);
   };
+  // round vector i: wait for it, read this lane's eight records, and hand the stage to vector i + RING
+  auto next_vec = [&](uint32_t i, uint32_t n_vec) {
+    Vec8 v;
+    const uint32_t stage = i & (uint32_t)(RING - 1), cell = ring + stage * 1024u;
+    cp_async_wait<RING - 1>();
+    v.a = lds_u32x4(cell); v.b = lds_u32x4(cell + 512u);
+    fetch(stage, i + (uint32_t)RING, i + (uint32_t)RING < n_vec);
+    return v;
+  };
 
-  Run cur = load_run(load_slot(round));
+  Run cur = load_run(round, load_slot(round));
   uint32_t slot_nxt = load_slot(round + n_warps);
   start_run(cur);
 
   for (; round < n_rounds; round += n_warps) {
-    const Run nxt = load_run(slot_nxt);  // first used when this round's records are in
+    const Run nxt = load_run(round + n_warps, slot_nxt);  // first used when this round's records are in
     slot_nxt = load_slot(round + 2 * n_warps);
     const uint32_t my_slot = cur.slot, my_ref = cur.ref, n_vec = cur.n_vec;
     const bool live = my_slot != ROUND_NO_SLOT;
@@ -255,14 +265,15 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     // (identify_mutations.cpp:1605); the first record of any other kind (or a pad word) ends the walk
     if (live && n_vec) {
       const uint32_t cnt = n_vec * 8u;
-      uint32_t j = 0, r = V0.a.x;
+      cp_async_wait<RING - 1>();  // the round's first vector is in stage 0
+      uint32_t j = 0, r = lds_u32(ring);
       while ((r >> DR_KIND_SHIFT) == 3u) {
         uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
         if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
         const double inv = 1.0 / (double)red;
         if (r & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
         if (++j == cnt) break;
-        r = j == 1 ? V0.a.y : j == 2 ? V0.a.z : j == 3 ? V0.a.w : __ldg(rec + cur.beg + j);
+        r = j < 4u ? lds_u32(ring + j * 4u) : j < 8u ? lds_u32(ring + 512u + (j - 4u) * 4u) : __ldg(rec + score_index(cur.beg + lane * 4u, j));
       }
     }
 
@@ -297,25 +308,18 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       }
     };
 
-    const uint32_t n_max = __reduce_max_sync(0xFFFFFFFFu, n_vec), n_min = __reduce_min_sync(0xFFFFFFFFu, n_vec);
     // the likelihood table of the round's reference base (rounds hold one base; "other" bases have no class counts)
     const uint32_t ref_round = __reduce_min_sync(0xFFFFFFFFu, my_ref);
     const uint32_t b_base = tbl + (ref_round < 4u ? ref_round : 0u) * p.t_stride + b_off;
-    uint32_t i = 0;  // vectors of the run consumed so far (even)
+    const uint32_t n_max = n_vec;  // the round's vectors: the same for every lane (shallower slots end in pad words)
+    uint32_t i = 0;  // round vectors consumed so far
     bool more;
     do {
       // byte counters: at most 240 records between two contractions
-      const uint32_t chunk_end = min(n_max, i + 30u), chunk_all = min(n_min, chunk_end);
-      for (; i + 2u <= chunk_all; i += 2u) {  // every lane has these two vectors
-        if ((i & 2u) && i + 18u < n_vec) prefetch_l2(vp + i + 18u);  // deep runs: keep L2 half a kilobyte ahead
-        tally4(V0.a); tally4(V0.b); if (i + 2u < n_vec) V0 = ldg_vec8(vp + i + 2u);
-        tally4(V1.a); tally4(V1.b); if (i + 3u < n_vec) V1 = ldg_vec8(vp + i + 3u);
-      }
-      for (; i < chunk_end; i += 2u) {         // the ragged end: lanes drop out as their runs end
-        if (i < n_vec) { tally4(V0.a); tally4(V0.b); }
-        if (i + 2u < n_vec) V0 = ldg_vec8(vp + i + 2u);
-        if (i + 1u < n_vec) { tally4(V1.a); tally4(V1.b); }
-        if (i + 3u < n_vec) V1 = ldg_vec8(vp + i + 3u);
+      const uint32_t chunk_end = min(n_max, i + 30u);
+      for (; i < chunk_end; ++i) {
+        const Vec8 v = next_vec(i, n_vec);
+        tally4(v.a); tally4(v.b);
       }
       more = i < n_max;
       if (!more) start_run(nxt);  // this round's records are all in: the next round's first vectors travel during the contraction
@@ -416,13 +420,14 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = my_slot;
     else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = my_slot; }
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------ fit
 namespace {
 
 struct GroupCtx {
-  const uint32_t* rec; uint64_t beg, end;   // the slot's device words [beg, beg + n_main) followed, in index space, by its side-list entries
+  const uint32_t* rec; uint64_t base, beg, end;   // index space [beg, end): the slot's n_main records (word score_index(base, k)), then its side-list entries
   const uint32_t* side; uint32_t side_beg; uint64_t n_main;
   uint32_t hot_base; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
   const uint32_t* cache;  // table codes of the slot's first FIT_CACHE records
@@ -453,7 +458,7 @@ __device__ __forceinline__ uint32_t code_of(const GroupCtx& g, uint32_t r) {
 __device__ __forceinline__ uint32_t classic_at(const GroupCtx& g, uint64_t i) {
   const uint64_t k = i - g.beg;
   if (k < g.n_main) {
-    const uint32_t d = __ldg(g.rec + i);
+    const uint32_t d = __ldg(g.rec + score_index(g.base, k));
     if ((d >> DR_KIND_SHIFT) != 0u) return 0u;
     const ScoreParams& p = *g.p;
     const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = p.t_qlo + sq % p.t_nq, st = sq / p.t_nq;
@@ -481,7 +486,7 @@ __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, do
 
 }  // namespace
 
-__global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off,
+__global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                                                           const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                           const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
                                                           const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
@@ -512,8 +517,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     w = __shfl_sync(g.mask, w, lane - g.sub);
     if (w >= n_work) break;
     const uint32_t slot = worklist[w];
-    score_slot_range(off, slot, g.beg, g.end);
-    g.n_main = g.end - g.beg;
+    g.base = off[slot]; g.beg = 0; g.n_main = cnt[slot]; g.end = g.n_main;
     g.side = side; g.side_beg = side_off[slot];
     g.end += side_off[slot + 1] - g.side_beg;
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
@@ -633,7 +637,8 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
   }
 }
 
-void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* side, const uint32_t* side_off,
+void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,
+                        const uint32_t* side, const uint32_t* side_off,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
@@ -643,17 +648,17 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const size_t smem_fit = (size_t)p.n_hot * 48;
   // histogram block per warp: 4 KB holds 32 words per lane, 8 KB the maximum of 64; as many warps as 227 KB allow
   const uint32_t hist_block = p.t_nw <= 32 ? 4096u : 8192u;
-  const size_t per_warp = hist_block, fixed = (size_t)4 * p.t_stride + hist_block;
+  const size_t per_warp = hist_block + RING * 1024, fixed = (size_t)4 * p.t_stride + hist_block;
   int warps = TALLY_MAX_TPB / 32;
   while (warps > 1 && fixed + warps * per_warp > 227 * 1024) --warps;
   const size_t smem_tally = fixed + warps * per_warp;
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
   note_launches(2);
 }
 

@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -470,15 +470,6 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
 
   // ---- offsets
   {
-    uint64_t acc = 0;
-    uint64_t n_true = 0, pad = 0;  // runs padded to whole 256-bit vectors; the pad count rides in the next entry's low bits
-    for (uint64_t s = 0; s < n_slots; ++s) {
-      out.score_off[s] = acc | pad;
-      const uint64_t cnt = cfg.want_score ? score_cnt[s] : 0;
-      pad = (8 - (cnt & 7)) & 7;
-      acc += cnt + pad; n_true += cnt;
-    }
-    out.score_off[n_slots] = acc | pad; out.n_score = n_true; out.n_score_padded = acc;
     bool p3 = false;
     out.side_off = (uint32_t*)alloc((n_slots + 1) * 4, &p3);
     uint64_t sacc = 0;
@@ -489,13 +480,17 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     // Rounds of the tally kernel: 32 slots that share their reference base (its contraction multiplies the 32 class
     // histograms with ONE base's likelihood table) and have about the same depth (its 32 lanes walk their runs in
     // lock step).  Inside every block of ROUND_BLOCK consecutive slots the slots are grouped by base (A, C, G, T,
-    // other) and ordered by run length; a group is padded to whole rounds with ROUND_NO_SLOT.
+    // other) and ordered by depth; a group is padded to whole rounds with ROUND_NO_SLOT.
+    out.score_cnt = (uint32_t*)alloc((n_slots + 1) * 4, &p3);
+    uint64_t n_true = 0;
+    for (uint64_t s = 0; s < n_slots; ++s) { out.score_cnt[s] = cfg.want_score ? score_cnt[s] : 0; n_true += out.score_cnt[s]; }
+    out.n_score = n_true;
     {
       if (n_slots >= ROUND_NO_SLOT) throw std::runtime_error("more than 2^32 - 2 slots in one staged stream");
       std::vector<uint32_t> order;
       order.reserve(n_slots + n_slots / 16 + 160);
       std::vector<uint32_t> group[5];
-      auto vecs = [&](uint32_t s) { return (uint32_t)(((out.score_off[s + 1] & ~7ull) - (out.score_off[s] & ~7ull)) >> 3); };
+      auto vecs = [&](uint32_t s) { return (out.score_cnt[s] + 7u) >> 3; };
       for (uint64_t b0 = 0; b0 < n_slots; b0 += ROUND_BLOCK) {
         const uint64_t b1 = std::min<uint64_t>(n_slots, b0 + ROUND_BLOCK);
         for (auto& g : group) g.clear();
@@ -509,8 +504,26 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       out.n_rounds = order.size() / 32;
       out.round_slot = (uint32_t*)alloc(order.size() * 4 + 16, &p3);
       std::copy(order.begin(), order.end(), out.round_slot);
+      // The record stream is round-major and lane-interleaved (brq_types.h): round r holds as many 1 KB round vectors
+      // as its deepest slot has 256-bit vectors; shallower lanes and idle lanes are filled with pad words.
+      out.round_off = (uint64_t*)alloc((out.n_rounds + 1) * 8, &p3);
+      uint64_t acc = 0;
+      for (uint64_t r = 0; r < out.n_rounds; ++r) {
+        out.round_off[r] = acc;
+        uint32_t deepest = 0;
+        for (uint32_t l = 0; l < 32; ++l) {
+          const uint32_t sl = out.round_slot[r * 32 + l];
+          if (sl == ROUND_NO_SLOT) continue;
+          out.score_off[sl] = acc + l * 4u;
+          deepest = std::max(deepest, vecs(sl));
+        }
+        acc += (uint64_t)deepest * ROUND_VECTOR_WORDS;
+      }
+      out.round_off[out.n_rounds] = acc;
+      out.score_off[n_slots] = acc;
+      out.n_score_padded = acc;
     }
-    acc = 0;
+    uint64_t acc = 0;
     for (uint64_t c = 0; c < out.n_base; ++c) {
       out.hist_off[c] = acc | ((cfg.want_hist && col_red[c]) ? HIST_OFF_REDUNDANT_BIT : 0);
       if (cfg.want_hist) acc += hist_cnt[c];
@@ -626,7 +639,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         if (!cfg.want_score) return;
         score_words(i, ri, q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
           const DevWord w = encode(rec, x1, out.slot_ref[s]);
-          out.score_rec[(out.score_off[s] & ~7ull) + (unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
+          out.score_rec[score_index(out.score_off[s], unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
           if (w.has_side) out.side_rec[out.side_off[s] + (unique ? side_cur[s]++ : side_red_cur[s]++)] = w.side;
           const uint32_t kind = w.dev >> DR_KIND_SHIFT;
           if (kind == 0 || kind == 2) {  // a scoring record: exact statistics for the likelihood tables

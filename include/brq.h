@@ -76,7 +76,7 @@ int brq_stage_synthetic(brq_ctx* ctx, const brq_synth_spec* spec, const brq_stag
 
 typedef struct brq_stream_info {
   uint64_t n_base, n_ins, n_score_records, n_hist_records, n_reads;
-  uint64_t n_score_padded;         /* words in score_rec: every slot's run is padded to whole 256-bit vectors */
+  uint64_t n_score_padded;         /* words in score_rec: round-major, lane-interleaved, padded (csrc/brq_types.h) */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
   uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
@@ -85,7 +85,7 @@ typedef struct brq_stream_info {
   const uint32_t* score_rec;       /* host views, valid until the next staging call; word layout: csrc/brq_types.h */
   const uint32_t* side_rec;
   const uint32_t* side_off;
-  const uint64_t* score_off;       /* slot s: first index score_off[s] & ~7, pad words (score_off[s+1] & 7) */
+  const uint64_t* score_off;       /* slot s: first word; record j at score_off[s] + (j>>3)*256 + ((j>>2)&1)*128 + (j&3) */
   const void* hist_rec;
   const uint64_t* hist_off;
   const uint8_t* slot_ref;
@@ -93,6 +93,8 @@ typedef struct brq_stream_info {
   const uint32_t* ins_count;
   const uint32_t* round_slot;      /* [n_rounds * 32] tally rounds: 32 slots of one reference base and similar depth; 0xFFFFFFFF = idle lane */
   uint64_t n_rounds;
+  const uint32_t* score_cnt;       /* [slots] records of every slot */
+  const uint64_t* round_off;       /* [n_rounds + 1] first word of every round in score_rec */
 } brq_stream_info;
 
 int brq_stream(brq_ctx* ctx, brq_stream_info* info);

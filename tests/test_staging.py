@@ -57,24 +57,54 @@ def test_score_stream_tallies_match_oracle(staged):
 
 
 def test_redundant_records_lead_each_slot(staged):
-    """Stream layout the scoring kernel relies on: within a slot, redundant records first, then unique ones."""
+    """Stream layout the scoring kernel relies on: round-major, lane-interleaved; within a slot, redundant records first."""
     d, ctx, s = staged
     rec = s["score_rec"]
     beg, cnt = bq.slot_ranges(s)
-    assert np.all(beg % 8 == 0), "every run starts on a 256-bit boundary"
+    n_slots = len(cnt)
+    # rounds: every slot sits in exactly one lane of one round; a round holds one reference base
+    order = s["round_slot"].astype(np.int64).reshape(-1, 32)
+    used = order[order != 0xFFFFFFFF]
+    assert np.array_equal(np.sort(used), np.arange(n_slots))
+    ref = np.minimum(s["slot_ref"], 4).astype(np.int64)
+    for row in order:
+        live = row[row != 0xFFFFFFFF]
+        assert len(set(ref[live])) <= 1
+    # geometry of the stream: slot of lane l of round r starts at round_off[r] + 4 l; the round is as long as its deepest slot
+    roff = s["round_off"].astype(np.int64)
+    r_idx, l_idx = np.nonzero(order != 0xFFFFFFFF)
+    assert np.array_equal(beg[order[r_idx, l_idx]], roff[r_idx] + 4 * l_idx)
+    vecs = (cnt + 7) // 8
+    deepest = np.zeros(len(order), np.int64)
+    np.maximum.at(deepest, r_idx, vecs[order[r_idx, l_idx]])
+    assert np.array_equal(np.diff(roff), deepest * 256) and roff[-1] == s["n_score_padded"] == len(rec)
+    pos = bq.record_positions(s)
+    assert len(np.unique(pos)) == len(pos) == s["n_score"], "no two records share a word"
     real = np.zeros(len(rec), bool)
-    real[np.repeat(beg, cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))] = True
+    real[pos] = True
     g = s["geometry"]
     trash = g["n_st"] * g["n_q"] + 6   # pad words count into the trash counter after the class counters, no other bit
     pad = (trash >> 2) * 128 + (trash & 3)
     assert g["n_q"] % 4 == 0 and g["words"] == g["n_st"] * g["n_q"] // 4 + 2 and g["words"] <= 64
     assert np.all(rec[~real] == pad) and np.all(rec[real] != pad), "pad words address the trash counter; records never equal them"
-    assert len(rec) == s["n_score_padded"] and real.sum() == s["n_score"]
-    uniq = ((rec >> 30) != 3).astype(np.int8)   # kind 3 = redundant
-    uniq[~real] = 1   # padding follows the unique records
-    step_down = np.nonzero(np.diff(uniq) < 0)[0] + 1   # a unique record followed by a redundant one ...
-    assert np.all(np.isin(step_down, beg)), "... is only allowed across a slot boundary"
-    assert (uniq == 0).sum() > 0
+    # within a slot: redundant records (kind 3) first
+    kind = rec[pos] >> 30
+    slot = np.repeat(np.arange(n_slots), cnt)
+    red = (kind == 3).astype(np.int64)
+    first = np.cumsum(cnt) - cnt
+    n_red = np.add.reduceat(red, first[cnt > 0]) if len(red) else np.zeros(0, np.int64)
+    j = np.arange(len(pos)) - np.repeat(first, cnt)
+    lead = np.zeros(n_slots, np.int64)
+    lead[cnt > 0] = n_red
+    assert np.array_equal(red == 1, j < lead[slot]), "redundant records lead their slot"
+    assert red.sum() > 0
+    # counters: a matching HOT record counts in its class, everything else in the special counters after the classes
+    hot_match = (kind == 0) & (((rec[pos] >> 28) & 1) == 1)
+    sq = (rec[pos] >> 16) & 0xFF
+    counter = rec[pos] & 0x1FFF
+    assert np.array_equal(counter[hot_match], (sq[hot_match] >> 2) * 128 + (sq[hot_match] & 3))
+    special = (counter >> 7) * 4 + (counter & 3) - g["n_st"] * g["n_q"]
+    assert np.all((special[~hot_match] >= 0) & (special[~hot_match] <= 6))
 
 
 def test_shards_partition_the_stream(datasets):

@@ -99,6 +99,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
 __device__ __forceinline__ void sts_u32(uint32_t shared_addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" :: "r"(shared_addr), "r"(v) : "memory");
 }
+// counter field of a device word: word * 128 + byte inside the lane's histogram (lane base `hist`, block-aligned)
+__device__ __forceinline__ void red_count(uint32_t hist, uint32_t w) {
+  const uint32_t addr = (w & (DR_COUNTER_MASK & ~3u)) | hist, one = 1u << ((w << 3) & 31u);
+  asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
+}
 __device__ __forceinline__ void sts_fill16(uint32_t shared_addr, uint32_t word) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(word) : "memory");
 }
@@ -121,6 +126,18 @@ __device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p,
 }
 
 struct Sums { double l0, l1, l2, l3, l4, m; };
+
+// 10^d for d in [-17, 0], relative error below 1e-14: 2^(n + f), |f| <= 1/2, 2^f by its Taylor polynomial of degree 13.
+// (The sum it feeds is 1 + terms <= 1 whose log10 is added to numbers of magnitude 1 to 10^4: far inside the 1e-9 bar.)
+__device__ __forceinline__ double exp10_neg(double d) {
+  const double x = d * 3.3219280948873623, n = rint(x), f = (x - n) * 0.6931471805599453;  // f in natural-log units
+  double q = 1.6059043836821613e-10;                                                       // 1/13!
+  q = fma(q, f, 2.08767569878681e-09); q = fma(q, f, 2.505210838544172e-08); q = fma(q, f, 2.755731922398589e-07);
+  q = fma(q, f, 2.755731922398589e-06); q = fma(q, f, 2.48015873015873e-05); q = fma(q, f, 1.984126984126984e-04);
+  q = fma(q, f, 1.388888888888889e-03); q = fma(q, f, 8.333333333333333e-03); q = fma(q, f, 4.1666666666666664e-02);
+  q = fma(q, f, 1.6666666666666666e-01); q = fma(q, f, 0.5); q = fma(q, f, 1.0); q = fma(q, f, 1.0);
+  return __hiloint2double(__double2hiint(q) + (int)n * 1048576, __double2loint(q));          // * 2^n, n in [-57, 0]: no underflow
+}
 
 // a scoring record whose class is not in the shared table (classic word from the side list): {L[0..4], M} from the global table
 __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
@@ -279,22 +296,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 
     // half a vector: four records
     auto tally4 = [&](const uint4& v) {
-      // every record increments one byte counter of this lane's histogram.  Two records are in flight at a
-      // time; when both address the same counter the second takes the first one's new value.
-      const uint32_t a0 = (v.x & DR_COUNTER_MASK) | hist, a1 = (v.y & DR_COUNTER_MASK) | hist,
-                     a2 = (v.z & DR_COUNTER_MASK) | hist, a3 = (v.w & DR_COUNTER_MASK) | hist;
-      {
-        const uint32_t c0 = lds_u8(a0) + 1u;
-        uint32_t c1 = lds_u8(a1) + 1u;
-        if (a1 == a0) c1 = c0 + 1u;
-        sts_u8(a0, c0); sts_u8(a1, c1);
-      }
-      {
-        const uint32_t c2 = lds_u8(a2) + 1u;
-        uint32_t c3 = lds_u8(a3) + 1u;
-        if (a3 == a2) c3 = c2 + 1u;
-        sts_u8(a2, c2); sts_u8(a3, c3);
-      }
+      // every record increments one byte counter of this lane's histogram: a shared-memory reduction (no return value,
+      // nothing to wait for) of 1 << 8 * byte on the counter's word
+      red_count(hist, v.x); red_count(hist, v.y); red_count(hist, v.z); red_count(hist, v.w);
       if ((v.x | v.y | v.z | v.w) & DR_SLOW_BIT) {
         // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
         const uint32_t r[4] = {v.x, v.y, v.z, v.w};
@@ -333,7 +337,6 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
         uint32_t ap = a_base, bp = b_base;
         for (uint32_t kk = 0; kk < n_cw; ++kk, ap += 128u, bp += 256u) {
           const uint32_t w0 = lds_u32(ap), w1 = lds_u32(ap + 32u), w2 = lds_u32(ap + 64u), w3 = lds_u32(ap + 96u);
-          if (!__any_sync(0xFFFFFFFFu, (w0 | w1 | w2 | w3) != 0u)) continue;
           double bv;
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bv) : "r"(bp) : "memory");
           dmma_8x8x4(d[0][0], d[0][1], (double)__byte_perm(w0, 0u, a_sel), bv);
@@ -389,14 +392,16 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
         if ((uint32_t)b == best) continue;
         const double dd = ll[b] - offv;
         // the runner-up itself contributes exactly 1; anything below 2^-54 cannot change that sum
-        tot += (dd == 0.0) ? 1.0 : (dd < -17.0 ? 0.0 : exp10(dd));
+        tot += (dd == 0.0) ? 1.0 : (dd < -17.0 ? 0.0 : exp10_neg(dd));
       }
       consensus = (lb - (log10(tot) + offv)) - p.log10_ref_length;
       // an RA row needs best != ref with a positive consensus score, or a presence score at the cutoff
       need_fit = p.fit_all != 0u || ref >= 5u || (best != ref && consensus > -slack);
       if (!need_fit) {
         const double ll_ref = ref == 0 ? ll[0] : ref == 1 ? ll[1] : ref == 2 ? ll[2] : ref == 3 ? ll[3] : ll[4];
-        const double bound = (kept.m - ll_ref) - (double)n * log10(((double)c_ref + 0.5) / ((double)n + 2.0)) - p.log10_ref_length;
+        // -n log10 g0[ref] in single precision (MUFU.LG2, relative error 2^-21), rounded up: the bound only has to be an upper bound
+        const float nlog = (float)n * (__log2f(((float)n + 2.0f) / ((float)c_ref + 0.5f)) * 0.30103001f) * 1.00001f + 1e-4f;
+        const double bound = (kept.m - ll_ref) + (double)nlog - p.log10_ref_length;
         need_fit = !(bound < p.polymorphism_cutoff - slack);
       }
     }

@@ -85,7 +85,9 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 // cell in the shared-memory likelihood table (geometry chosen per stream: ScoreGeometry).  The kernel
 // counts first and multiplies the counts into the table once per slot, so the common record costs one
 // AND/OR for its address and a byte increment.
-//   [12:0]  counter  byte offset of the record's counter inside its lane's histogram: word * 128 + byte.
+//   [12:0]  counter  the record's byte counter inside its lane's histogram: word * 128 + byte * 8, i.e. the word's byte
+//                    offset in [12:7] and the counter's bit position inside the word in [4:0] (the kernel adds
+//                    1 << (record & 31) to the word at (record & 0x1F80) | lane base).
 //                    HOT record matching the slot's reference base: class sq = (read_set*2 + top) * n_q + qual - q_lo,
 //                    word sq / 4, byte sq % 4.  Every other record counts in the special words that follow the
 //                    class words (ScoreGeometry::special_counter).
@@ -111,7 +113,7 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //
 // Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
 // records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
-constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
+constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
                    DR_OBS_SHIFT = 24, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
                    DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
                    SIDE_BIG = 1u << 31;
@@ -127,7 +129,7 @@ struct ScoreGeometry {
   uint32_t n_sq() const { return n_st * n_q; }            // classes of the per-slot histogram (<= 248)
   uint32_t n_words() const { return n_sq() / 4 + 2; }     // 32-bit histogram words per lane: class words + 2 special words
   uint32_t n_hot() const { return n_sq() * 4; }           // cells of the shared likelihood table
-  static uint32_t counter_of(uint32_t index) { return (index >> 2) * 128u + (index & 3u); }
+  static uint32_t counter_of(uint32_t index) { return (index >> 2) * 128u + (index & 3u) * 8u; }
   uint32_t special_counter(uint32_t which) const { return counter_of(n_sq() + which); }
   uint32_t pad_word() const { return special_counter(SC_TRASH); }
 };

@@ -99,9 +99,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
 __device__ __forceinline__ void sts_u32(uint32_t shared_addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" :: "r"(shared_addr), "r"(v) : "memory");
 }
-// counter field of a device word: word * 128 + byte inside the lane's histogram (lane base `hist`, block-aligned)
+// counter field of a device word: word * 128 + byte * 8 inside the lane's histogram (lane base `hist`, block-aligned)
 __device__ __forceinline__ void red_count(uint32_t hist, uint32_t w) {
-  const uint32_t addr = (w & (DR_COUNTER_MASK & ~3u)) | hist, one = 1u << ((w << 3) & 31u);
+  const uint32_t addr = (w & DR_COUNTER_WORD_MASK) | hist, one = 1u << (w & 31u);
   asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
 }
 __device__ __forceinline__ void sts_fill16(uint32_t shared_addr, uint32_t word) {
@@ -154,6 +154,10 @@ __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __
 // Lane l = 4 g + t holds A[g][t], B[t][g] and D[g][2t], D[g][2t + 1].
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// byte (selector 0x4440 | index) of a word as a double
+__device__ __forceinline__ double byte_to_double(uint32_t w, uint32_t sel) {
+  return (double)__byte_perm(w, 0u, sel);
 }
 // eight records of one lane: its share of a round vector
 struct Vec8 { uint4 a, b; };
@@ -235,9 +239,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     if (x.side1 > x.side0) prefetch_l2(side + x.side0);
   };
   // round vector i: wait for it, read this lane's eight records, and hand the stage to vector i + RING
-  auto next_vec = [&](uint32_t i, uint32_t n_vec) {
+  auto next_vec = [&](uint32_t stage, uint32_t i, uint32_t n_vec) {
     Vec8 v;
-    const uint32_t stage = i & (uint32_t)(RING - 1), cell = ring + stage * 1024u;
+    const uint32_t cell = ring + stage * 1024u;
     cp_async_wait<RING - 1>();
     v.a = lds_u32x4(cell); v.b = lds_u32x4(cell + 512u);
     fetch(stage, i + (uint32_t)RING, i + (uint32_t)RING < n_vec);
@@ -294,16 +298,17 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       }
     }
 
-    // half a vector: four records
-    auto tally4 = [&](const uint4& v) {
+    // this lane's share of a round vector: eight records
+    auto tally8 = [&](const Vec8& v) {
       // every record increments one byte counter of this lane's histogram: a shared-memory reduction (no return value,
       // nothing to wait for) of 1 << 8 * byte on the counter's word
-      red_count(hist, v.x); red_count(hist, v.y); red_count(hist, v.z); red_count(hist, v.w);
-      if ((v.x | v.y | v.z | v.w) & DR_SLOW_BIT) {
+      red_count(hist, v.a.x); red_count(hist, v.a.y); red_count(hist, v.a.z); red_count(hist, v.a.w);
+      red_count(hist, v.b.x); red_count(hist, v.b.y); red_count(hist, v.b.z); red_count(hist, v.b.w);
+      if (((v.a.x | v.a.y | v.a.z | v.a.w) | (v.b.x | v.b.y | v.b.z | v.b.w)) & DR_SLOW_BIT) {
         // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
-        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t r[8] = {v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           if (!(r[j] & DR_SLOW_BIT)) continue;
           const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 3u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 64u;
           const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
@@ -319,12 +324,13 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     uint32_t i = 0;  // round vectors consumed so far
     bool more;
     do {
-      // byte counters: at most 240 records between two contractions
-      const uint32_t chunk_end = min(n_max, i + 30u);
-      for (; i < chunk_end; ++i) {
-        const Vec8 v = next_vec(i, n_vec);
-        tally4(v.a); tally4(v.b);
+      // byte counters: at most 224 records between two contractions
+      const uint32_t chunk_end = min(n_max, i + 28u);
+      for (; i + 4u <= chunk_end; i += 4u) {  // i is a multiple of four here: the ring's stage numbers are constants
+#pragma unroll
+        for (uint32_t s4 = 0; s4 < 4u; ++s4) tally8(next_vec(s4, i + s4, n_vec));
       }
+      for (; i < chunk_end; ++i) tally8(next_vec(i & (uint32_t)(RING - 1), i, n_vec));
       more = i < n_max;
       if (!more) start_run(nxt);  // this round's records are all in: the next round's first vectors travel during the contraction
 
@@ -339,10 +345,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
           const uint32_t w0 = lds_u32(ap), w1 = lds_u32(ap + 32u), w2 = lds_u32(ap + 64u), w3 = lds_u32(ap + 96u);
           double bv;
           asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bv) : "r"(bp) : "memory");
-          dmma_8x8x4(d[0][0], d[0][1], (double)__byte_perm(w0, 0u, a_sel), bv);
-          dmma_8x8x4(d[1][0], d[1][1], (double)__byte_perm(w1, 0u, a_sel), bv);
-          dmma_8x8x4(d[2][0], d[2][1], (double)__byte_perm(w2, 0u, a_sel), bv);
-          dmma_8x8x4(d[3][0], d[3][1], (double)__byte_perm(w3, 0u, a_sel), bv);
+          dmma_8x8x4(d[0][0], d[0][1], byte_to_double(w0, a_sel), bv);
+          dmma_8x8x4(d[1][0], d[1][1], byte_to_double(w1, a_sel), bv);
+          dmma_8x8x4(d[2][0], d[2][1], byte_to_double(w2, a_sel), bv);
+          dmma_8x8x4(d[3][0], d[3][1], byte_to_double(w3, a_sel), bv);
         }
       }
       // special counters (idle / cold / slow records by strand; redundant and pad words count into the trash byte)

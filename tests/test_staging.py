@@ -84,7 +84,7 @@ def test_redundant_records_lead_each_slot(staged):
     real[pos] = True
     g = s["geometry"]
     trash = g["n_st"] * g["n_q"] + 6   # pad words count into the trash counter after the class counters, no other bit
-    pad = (trash >> 2) * 128 + (trash & 3)
+    pad = (trash >> 2) * 128 + (trash & 3) * 8
     assert g["n_q"] % 4 == 0 and g["words"] == g["n_st"] * g["n_q"] // 4 + 2 and g["words"] <= 64
     assert np.all(rec[~real] == pad) and np.all(rec[real] != pad), "pad words address the trash counter; records never equal them"
     # within a slot: redundant records (kind 3) first
@@ -102,8 +102,8 @@ def test_redundant_records_lead_each_slot(staged):
     hot_match = (kind == 0) & (((rec[pos] >> 28) & 1) == 1)
     sq = (rec[pos] >> 16) & 0xFF
     counter = rec[pos] & 0x1FFF
-    assert np.array_equal(counter[hot_match], (sq[hot_match] >> 2) * 128 + (sq[hot_match] & 3))
-    special = (counter >> 7) * 4 + (counter & 3) - g["n_st"] * g["n_q"]
+    assert np.array_equal(counter[hot_match], (sq[hot_match] >> 2) * 128 + (sq[hot_match] & 3) * 8)
+    special = (counter >> 7) * 4 + ((counter & 31) >> 3) - g["n_st"] * g["n_q"]
     assert np.all((special[~hot_match] >= 0) & (special[~hot_match] <= 6))
 
 

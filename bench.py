@@ -294,7 +294,7 @@ def main():
         e2e_s = (time.perf_counter() - t0) / n_e2e
         e2e_phase_ms = {k: 1e3 * v / (n_e2e + 1) for k, v in phase.items()}
     h2d = int(s["bytes_host"])
-    d2h = n_slots * 96 + 25 * 2 * 42 * 16
+    d2h = n_slots * 8 + 25 * 2 * 42 * 16  # 8-byte walk records of every column, the histograms (flagged slots' full results: a few KB)
 
     # ---- max over ranks, whole-job aggregate
     stats = torch.tensor([step_ms, e2e_s, float(n_records), k_ms["score"], k_ms["hist"]], dtype=torch.float64, device="cuda")

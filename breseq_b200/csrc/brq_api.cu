@@ -9,7 +9,10 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -85,14 +88,19 @@ struct brq_ctx {
   TableGeometry geo;
   bool have_device_tables = false;
   float ms_tally = 0, ms_fit = 0;
-  DevBuf<ColumnOut> d_cols;
+  DevBuf<ColumnOut> d_cols, d_fcols;
+  DevBuf<WalkOut> d_walk;
+  WalkOut* h_walk = nullptr;        // pinned: what the host's interval walk reads of every column
+  size_t h_walk_n = 0;
+  std::vector<ColumnOut> h_fcols;   // full results of the flagged slots, in the order of h_flagged
+  bool have_walk = false;
 
   CovSpec spec;
   bool have_spec = false, have_table = false, have_counts = false, have_cols = false;
   uint64_t cov_stride = 0, n_groups = 0;
   std::vector<uint64_t> h_counts, h_cov;
   std::vector<double> h_log10, h_log10_text, h_prob;
-  std::vector<ClassTerms> h_lut;
+  ClassLut h_lut;
   ScoreParams sp;
   brq_score_params last_params;
   std::vector<ColumnOut> h_cols;
@@ -148,7 +156,7 @@ void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
 void drop_stream(brq_ctx* c) {
   if (c->staged) free_stream(c->st, c->stage_cfg);
   c->staged = c->uploaded = false;
-  c->have_counts = c->have_cols = false;
+  c->have_counts = c->have_cols = c->have_walk = false;
 }
 
 void do_stage(brq_ctx* c) {
@@ -295,9 +303,9 @@ void install_table(brq_ctx* c) {
 }
 
 void ensure_host_lut(brq_ctx* c) {
-  if (!c->h_lut.empty()) return;
+  if (c->h_lut.ready()) return;
   if (!c->have_table || !c->staged) throw std::runtime_error("no error table");
-  build_class_lut(c->spec, c->h_prob, c->sp, c->geo, c->h_lut);
+  c->h_lut.reset(c->spec, c->h_prob, c->sp, c->geo);
 }
 
 void derive_table(brq_ctx* c) {
@@ -343,13 +351,14 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
                              "' exceeded enforced maximum value of '" + std::to_string(c->sp.max_set - 1) + "'.");
   const uint64_t n_slots = c->st.n_slots();
   c->d_cols.ensure(n_slots);
+  c->d_walk.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
   c->d_flagged.ensure(c->flagged_cap);
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
   launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
-                     c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
+                     c->d_cols.p, c->d_walk.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
@@ -357,6 +366,36 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaEventElapsedTime(&c->ms_tally, c->ev[5], c->ev[7]));
   CUDA_OK(cudaEventElapsedTime(&c->ms_fit, c->ev[7], c->ev[6]));
   c->have_cols = true;
+  c->have_walk = false;
+  c->h_cols.clear();
+}
+
+// What the evidence writer needs of the device results: the 8-byte walk records of every column (pinned), the flagged
+// list, and the full 96-byte results of the flagged slots only.
+void download_walk(brq_ctx* c) {
+  if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
+  const uint64_t n_slots = c->st.n_slots();
+  if (c->h_walk_n < n_slots) {
+    if (c->h_walk) cudaFreeHost(c->h_walk);
+    c->h_walk = nullptr; c->h_walk_n = 0;
+    CUDA_OK(cudaHostAlloc((void**)&c->h_walk, (n_slots ? n_slots : 1) * sizeof(WalkOut), cudaHostAllocDefault));
+    c->h_walk_n = n_slots;
+  }
+  uint32_t scal[2];
+  CUDA_OK(cudaMemcpyAsync(scal, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->h_walk, c->d_walk.p, n_slots * sizeof(WalkOut), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (scal[1] > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
+  c->h_flagged.resize(scal[1]);
+  c->h_fcols.resize(scal[1]);
+  if (scal[1]) {
+    c->d_fcols.ensure(scal[1]);
+    launch_gather_columns(c->d_cols.p, c->d_flagged.p, scal[1], c->d_fcols.p, c->stream);
+    CUDA_OK(cudaMemcpyAsync(c->h_flagged.data(), c->d_flagged.p, (size_t)scal[1] * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_fcols.data(), c->d_fcols.p, (size_t)scal[1] * sizeof(ColumnOut), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+  }
+  c->have_walk = true;
 }
 
 void download_columns(brq_ctx* c) {
@@ -373,7 +412,12 @@ void download_columns(brq_ctx* c) {
 }
 
 EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, const double* seed, uint32_t n_targets, int skip_mc) {
-  if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
+  const bool timing = getenv("BRQ_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
+  if (!c->have_walk) download_walk(c);
+  const auto t1 = now();
   if (n_targets != c->hdr.target_names.size())
     throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
                              "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
@@ -388,7 +432,11 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
   ensure_host_lut(c);
-  return write_evidence(gd_file, c->hdr, c->st, c->h_cols, c->h_flagged, c->sp, c->h_lut, ep);
+  const auto t2 = now();
+  const EvidenceCounts k = write_evidence(gd_file, c->hdr, c->st, c->h_walk, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep);
+  if (timing) fprintf(stderr, "[brq] evidence: download %.2f ms, lut %.2f ms, write_evidence %.2f ms (%zu flagged, %llu RA)\n",
+                      ms(t0, t1), ms(t1, t2), ms(t2, now()), c->h_flagged.size(), (unsigned long long)k.ra);
+  return k;
 }
 
 void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,
@@ -440,7 +488,8 @@ void brq_destroy(brq_ctx* c) {
   if (c->device >= 0) {
     c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
-    c->d_log10.release(); c->d_lut.release(); c->d_cols.release();
+    c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
+    if (c->h_walk) cudaFreeHost(c->h_walk);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -1,6 +1,7 @@
 #include "finalize.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -247,34 +248,41 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGe
 }
 
 // Host copy of the per-class terms, with the libm calls the reference makes (identify_mutations.cpp:3359-3384).
-// Only the host re-evaluation of flagged slots reads it (write_evidence); the kernels' tables are built on the device.
-void build_class_lut(const CovSpec& c, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g,
-                     std::vector<ClassTerms>& lut) {
-  const uint32_t Q = p.max_qual;
-  lut.assign(g.n_lut, ClassTerms());
+// Only the host re-evaluation of flagged slots reads it (write_evidence), and only for the classes those slots hold:
+// an entry is computed the first time it is asked for.
+void ClassLut::reset(const CovSpec& c, const std::vector<double>& prob_, const ScoreParams& p_, const TableGeometry& g_) {
+  spec = &c; prob = &prob_; p = &p_; g = &g_;
+  terms.assign(g_.n_lut, ClassTerms());
+  done.assign(g_.n_lut, 0);
+}
+
+const ClassTerms* ClassLut::get(size_t li) {
+  ClassTerms& t = terms[li];
+  if (done[li]) return &t;
+  const uint32_t Q = p->max_qual;
+  const uint32_t obs = (uint32_t)(li % 5), q = (uint32_t)((li / 5) % Q);
+  const size_t ms = (li / (5 * (size_t)Q)) % g->mapqs.size();
+  const uint32_t st = (uint32_t)(li / (5 * (size_t)Q * g->mapqs.size()));
   auto comp = [](uint32_t b) { return b < 4 ? 3 - b : 4u; };
-  for (uint32_t st = 0; st < g.n_st; ++st) for (size_t ms = 0; ms < g.mapqs.size(); ++ms) {
-    const uint32_t set = st >> 1, top = st & 1;
-    const double incorrect = pow(10, -(double)g.mapqs[ms] / 10);
-    const double correct = 1 - incorrect;
-    const double uniform = 1.0 / 5.0;
-    for (uint32_t q = 0; q < Q; ++q) for (uint32_t obs = 0; obs < 5; ++obs) {
-      ClassTerms& t = lut[(((size_t)st * g.mapqs.size() + ms) * Q + q) * 5 + obs];
-      const uint32_t o = top ? obs : comp(obs);
-      double mx = -std::numeric_limits<double>::max();
-      for (uint32_t b = 0; b < 5; ++b) {
-        const uint32_t rf = top ? b : comp(b);
-        const uint32_t idx = set * g.off_set + rf * g.off_ref + o * g.off_obs + q * g.off_qual;
-        double pr = correct * prob[idx] + incorrect * uniform;
-        if (pr < 0.0) pr = 0.0;
-        t.L[b] = log10(pr);
-        mx = std::max(mx, t.L[b]);
-      }
-      for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
-      t.M = mx;
-      t.r2 = 0.0;
-    }
+  const uint32_t set = st >> 1, top = st & 1;
+  const double incorrect = pow(10, -(double)g->mapqs[ms] / 10);
+  const double correct = 1 - incorrect;
+  const double uniform = 1.0 / 5.0;
+  const uint32_t o = top ? obs : comp(obs);
+  double mx = -std::numeric_limits<double>::max();
+  for (uint32_t b = 0; b < 5; ++b) {
+    const uint32_t rf = top ? b : comp(b);
+    const uint32_t idx = set * g->off_set + rf * g->off_ref + o * g->off_obs + q * g->off_qual;
+    double pr = correct * (*prob)[idx] + incorrect * uniform;
+    if (pr < 0.0) pr = 0.0;
+    t.L[b] = log10(pr);
+    mx = std::max(mx, t.L[b]);
   }
+  for (uint32_t b = 0; b < 5; ++b) t.r[b] = pow(10, t.L[b] - mx);
+  t.M = mx;
+  t.r2 = 0.0;
+  done[li] = 1;
+  return &t;
 }
 
 // ============================================================================== statistics
@@ -513,17 +521,22 @@ struct GdRow {
 }  // namespace
 
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
-                              const std::vector<ColumnOut>& cols, const std::vector<uint32_t>& flagged_in,
-                              const ScoreParams& sp, const std::vector<ClassTerms>& lut, const EvidenceParams& ep) {
+                              const WalkOut* walk, const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
+                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
   EvidenceCounts counts;
   const double nan = std::numeric_limits<double>::quiet_NaN();
-  std::vector<uint32_t> flagged(flagged_in);
-  std::sort(flagged.begin(), flagged.end());
+  // flagged slots in ascending order (the kernels append them in no particular order), each with its full result
+  std::vector<uint32_t> order(flagged_in.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return flagged_in[a] < flagged_in[b]; });
+  std::vector<uint32_t> flagged(order.size());
+  for (size_t i = 0; i < order.size(); ++i) flagged[i] = flagged_in[order[i]];
 
   // ---- re-evaluate flagged slots in arrival order
   struct Reval { bool base_predicted; bool emit; GdRow row; };
-  std::map<uint64_t, Reval> reval;
-  for (uint32_t slot : flagged) {
+  std::vector<Reval> reval(flagged.size());  // aligned with `flagged`
+  for (size_t fi = 0; fi < flagged.size(); ++fi) {
+    const uint32_t slot = flagged[fi];
     SlotEval s;
     memset(s.count, 0, sizeof s.count);
     for_each_classic(st, slot, [&](uint32_t r, uint32_t) {
@@ -531,14 +544,14 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
       if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) return;
       const uint32_t obs = r & 7, top = (r & SR_TOP_BIT) ? 1 : 0, mapq = (r >> SR_MAPQ_SHIFT) & 255, set = (r >> SR_SET_SHIFT) & 31;
       const size_t li = ((((size_t)set * 2 + top) * sp.n_mapq_slots + sp.mapq_slot[mapq]) * sp.max_qual + q) * 5 + obs;
-      s.reads.push_back(&lut[li]);
+      s.reads.push_back(lut.get(li));
       s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
       ++s.count[obs][top];
     });
     const uint8_t ref = st.slot_ref[slot];
     evaluate_slot(s, ref, ep);
     ++counts.rechecked;
-    const ColumnOut& co = cols[slot];
+    const ColumnOut& co = flagged_cols[order[fi]];
     const bool dev_emit = (co.bits & CO_EMIT) != 0, dev_pred = (co.bits & CO_BASE_PREDICTED) != 0;
     if (dev_pred != s.base_predicted || (dev_emit && !s.emit)) ++counts.overturned;
     Reval rv;
@@ -616,9 +629,11 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
       for (int b = 0; b < 5; ++b) { tot_top += s.count[b][1]; tot_bot += s.count[b][0]; }
       row.kv["total_cov"] = std::to_string(tot_top) + "/" + std::to_string(tot_bot);
     }
-    reval[slot] = rv;
+    reval[fi] = std::move(rv);
   }
 
+  const bool timing = getenv("BRQ_TIMING") != nullptr;
+  const auto t_reval = std::chrono::steady_clock::now();
   // ---- walk the columns in visit order: MC and UN interval state machines, RA rows spliced in
   std::vector<GdRow> rows;
   uint64_t next_id = 0;
@@ -626,6 +641,12 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   const uint32_t UNDEF = 0xFFFFFFFFu;
   struct Cov { double unique, redundant; int total; };
   size_t ins_cursor = 0;  // ins slots are ordered by (parent, insert_count)
+  // base slots are visited in ascending order and so are the insert sub-column slots: two cursors over the flagged list
+  size_t base_cur = 0, ins_cur = std::lower_bound(flagged.begin(), flagged.end(), (uint32_t)std::min<uint64_t>(st.n_base, 0xFFFFFFFFull)) - flagged.begin();
+  auto find_reval = [&](size_t& cur, uint64_t slot) -> const Reval* {
+    while (cur < flagged.size() && flagged[cur] < slot) ++cur;
+    return (cur < flagged.size() && flagged[cur] == slot) ? &reval[cur] : nullptr;
+  };
   for (size_t sgi = 0; sgi < st.segments.size(); ++sgi) {
     const Segment& sg = st.segments[sgi];
     const std::string& name = hdr.target_names[(size_t)sg.tid];
@@ -674,21 +695,21 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     if (prop >= 0.0) {
       for (int32_t c = sg.lo; c < sg.hi; ++c) {
         const uint64_t slot = sg.slot0 + (uint64_t)(c - sg.lo);
-        const ColumnOut& co = cols[slot];
+        const WalkOut& wo = walk[slot];  // written by the tally kernel from the same sums the full result holds
         Cov cv;
-        cv.unique = (double)co.unique[0] + (double)co.unique[1];
-        cv.redundant = co.redundant[0] + co.redundant[1];
-        cv.total = (int)round(cv.unique) + (int)round(cv.redundant);
-        bool predicted = (co.bits & CO_BASE_PREDICTED) != 0;
-        auto rv = reval.find(slot);
-        if (rv != reval.end()) predicted = rv->second.base_predicted;
+        cv.unique = (double)wo.unique;
+        cv.redundant = (wo.packed & 2u) ? 1.0 : 0.0;  // only its sign is looked at
+        cv.total = (int)(wo.packed >> 2);
+        bool predicted = (wo.packed & 1u) != 0;
+        const Reval* rv = find_reval(base_cur, slot);
+        if (rv) predicted = rv->base_predicted;
         if (!ep.skip_missing_coverage_prediction) deletion_step((uint32_t)c + 1, cv);
         unknown_step((uint32_t)c + 1, predicted);
-        if (rv != reval.end() && rv->second.emit) { add(rv->second.row); ++counts.ra; }
+        if (rv && rv->emit) { add(rv->row); ++counts.ra; }
         while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
         for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) {
-          auto iv = reval.find(st.n_base + ins_cursor);
-          if (iv != reval.end() && iv->second.emit) { add(iv->second.row); ++counts.ra; }
+          const Reval* iv = find_reval(ins_cur, st.n_base + ins_cursor);
+          if (iv && iv->emit) { add(iv->row); ++counts.ra; }
         }
       }
     }
@@ -709,6 +730,7 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     }
   }
 
+  if (timing) fprintf(stderr, "[brq] write_evidence: column walk %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_reval).count());
   // ---- GenomeDiff text (genome_diff.cpp:685-760; sort keys genome_diff_entry.cpp:280-324, 566-700)
   std::stable_sort(rows.begin(), rows.end(), [](const GdRow& x, const GdRow& y) {
     if (x.type != y.type) return x.type < y.type;  // RA (3) < MC (4) < UN (7)

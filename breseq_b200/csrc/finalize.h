@@ -49,9 +49,17 @@ struct TableGeometry {
 };
 void score_geometry(const CovSpec& spec, const uint32_t mapq_seen[8], const ScoreGeometry& stream_geometry, ScoreParams& p,
                     TableGeometry& g);
-// Host copy of the per-class terms for every (read_set, strand, MAPQ present, quality, obs); libm arithmetic as the reference.
-void build_class_lut(const CovSpec& spec, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g,
-                     std::vector<ClassTerms>& lut);
+// Host copy of the per-class terms (read_set, strand, MAPQ present, quality, obs), libm arithmetic as the reference;
+// entries are computed on first use (index (((set*2 + top) * n_mapq + mapq slot) * Q + quality) * 5 + obs).
+struct ClassLut {
+  const CovSpec* spec = nullptr; const std::vector<double>* prob = nullptr; const ScoreParams* p = nullptr; const TableGeometry* g = nullptr;
+  std::vector<ClassTerms> terms;
+  std::vector<uint8_t> done;
+  bool ready() const { return !terms.empty(); }
+  void clear() { terms.clear(); done.clear(); }
+  void reset(const CovSpec& spec, const std::vector<double>& prob, const ScoreParams& p, const TableGeometry& g);
+  const ClassTerms* get(size_t index);
+};
 
 struct EvidenceParams {
   double mutation_cutoff, polymorphism_cutoff, precision_decimal;
@@ -65,7 +73,7 @@ struct EvidenceCounts { uint64_t ra = 0, mc = 0, un = 0, rechecked = 0, overturn
 
 // `shard_first_col1` etc. are not needed: the stream knows its segments.
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
-                              const std::vector<ColumnOut>& cols, const std::vector<uint32_t>& flagged,
-                              const ScoreParams& sp, const std::vector<ClassTerms>& lut, const EvidenceParams& ep);
+                              const WalkOut* walk, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
+                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
 
 }  // namespace brq

@@ -39,6 +39,11 @@ struct ColumnOut {
 };
 static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
 
+// What the host's sequential MC / UN interval walk (identify_mutations.cpp:2262-2344, 2972-3007) reads of a column: 8 bytes
+// instead of the 96-byte result.  packed = total << 2 | (redundant > 0) << 1 | base_predicted, with
+// total = round(unique) + round(redundant) as the reference computes it.
+struct WalkOut { uint32_t unique, packed; };
+
 constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15,
                    CO_FIT = 1u << 24;
 
@@ -75,8 +80,10 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint32_t* side, const uint32_t* side_off,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between);
+// out[i] = cols[slots[i]]: the full results of the flagged slots, for the host re-evaluation
+void launch_gather_columns(const ColumnOut* cols, const uint32_t* slots, uint32_t n, ColumnOut* out, cudaStream_t s);
 
 // Fills every device likelihood table from the text-canonical probabilities (identify_mutations.cpp:3359-3384).
 struct TableBuildArgs {

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
                                                                   const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ round_slot,
                                                                   uint64_t n_rounds, const double* __restrict__ tallyT,
                                                                   const HotTerms* __restrict__ coldT, ScoreParams p, ColumnOut* __restrict__ out,
-                                                                  uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
+                                                                  WalkOut* __restrict__ walk, uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
                                                                   uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -427,6 +427,11 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     o.unique[0] = u_bot; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
     out[my_slot] = o;
+    {
+      const double red = red_bot + red_top;  // the sums the host's interval walk would form from the full result
+      const uint32_t total = (u_bot + u_top) + (uint32_t)(int)::round(red);
+      walk[my_slot] = WalkOut{u_bot + u_top, total << 2 | (red > 0.0 ? 2u : 0u) | (base_predicted ? 1u : 0u)};
+    }
 
     if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = my_slot;
     else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = my_slot; }
@@ -652,7 +657,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint32_t* side, const uint32_t* side_off,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
@@ -666,11 +671,24 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, walk, worklist, flagged, scalars, flagged_cap, hist_block);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
   note_launches(2);
+}
+
+__global__ void gather_columns_kernel(const ColumnOut* __restrict__ cols, const uint32_t* __restrict__ slots, uint32_t n, ColumnOut* __restrict__ out) {
+  // six 16-byte pieces per result
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 6u) return;
+  reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(cols + slots[i / 6u])[i % 6u];
+}
+
+void launch_gather_columns(const ColumnOut* cols, const uint32_t* slots, uint32_t n, ColumnOut* out, cudaStream_t s) {
+  if (!n) return;
+  gather_columns_kernel<<<(n * 6u + 255u) / 256u, 256, 0, s>>>(cols, slots, n, out);
+  note_launches(1);
 }
 
 }  // namespace brq

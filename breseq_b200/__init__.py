@@ -120,6 +120,8 @@ def load_library():
         "brq_columns_device": [C.c_void_p, P(C.c_void_p), P(C.c_uint64)],
         "brq_write_evidence": [C.c_void_p, C.c_char_p, P(C.c_double), P(C.c_double), C.c_uint32, C.c_int,
                                P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
+        "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
+        "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
                                 C.c_int, C.c_int, C.c_char_p, P(_StageOptions)],
         "brq_run_identify_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_double),
@@ -143,7 +145,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
-           "brq_write_evidence", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
+           "brq_write_evidence", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
 
 
@@ -415,6 +417,16 @@ class Context:
                                                 C.byref(ra), C.byref(mc), C.byref(un)))
         return {"RA": ra.value, "MC": mc.value, "UN": un.value}
 
+    def write_per_position_file(self, path, deletion_propagation_cutoff):
+        """The reference's per-position debug file (identify_mutations.cpp:1693-1733)."""
+        n = len(deletion_propagation_cutoff)
+        prop = (C.c_double * n)(*deletion_propagation_cutoff)
+        self._check(self.lib.brq_write_per_position_file(self.h, _b(path), prop, n))
+
+    def write_coverage_tsv(self, pattern):
+        """``<seq>.coverage.tsv`` of --predict-copy-number; '@' in ``pattern`` becomes the target name."""
+        self._check(self.lib.brq_write_coverage_tsv(self.h, _b(pattern)))
+
     def kernel_ms(self):
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()
         self.lib.brq_kernel_ms(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
@@ -466,10 +478,14 @@ def identify_mutations(bam, fasta, gd_file, deletion_propagation_cutoff, deletio
                        polymorphism_cutoff, polymorphism_precision_decimal, polymorphism_precision_places,
                        print_per_position_file=False, *, error_rates_file_name, base_quality_cutoff=3,
                        skip_missing_coverage_prediction=False, call_mutations_seq_ids=None, read_file_sets=None,
-                       total_reference_length=0, device=0, ctx=None):
-    """``breseq::identify_mutations()`` (identify_mutations.cpp:48-88): writes ``ra_mc_evidence.gd``."""
-    if print_per_position_file:
-        raise BrqError("print_per_position_file (debug dump) is not part of the accelerated path")
+                       total_reference_length=0, device=0, ctx=None, per_position_file_name=None,
+                       coverage_tsv_pattern=None):
+    """``breseq::identify_mutations()`` (identify_mutations.cpp:48-88): writes ``ra_mc_evidence.gd`` and, like the
+    reference, the per-position debug file when ``print_per_position_file`` (Settings::
+    mutation_identification_per_position_file_name = ``per_position_file_name``) and ``<seq>.coverage.tsv`` when
+    ``coverage_tsv_pattern`` is given (Settings::predict_copy_number / complete_coverage_text_file_name)."""
+    if print_per_position_file and not per_position_file_name:
+        raise BrqError("print_per_position_file needs per_position_file_name")
     own = ctx is None
     ctx = ctx or Context(device)
     try:
@@ -482,6 +498,10 @@ def identify_mutations(bam, fasta, gd_file, deletion_propagation_cutoff, deletio
         ctx._check(ctx.lib.brq_run_identify_mutations(ctx.h, _b(bam), _b(fasta), _b(error_rates_file_name), _b(gd_file),
                                                       prop, seed, n, C.byref(p), int(skip_missing_coverage_prediction),
                                                       C.byref(o)))
+        if print_per_position_file:
+            ctx.write_per_position_file(per_position_file_name, list(deletion_propagation_cutoff))
+        if coverage_tsv_pattern:
+            ctx.write_coverage_tsv(coverage_tsv_pattern)
     finally:
         if own:
             ctx.close()

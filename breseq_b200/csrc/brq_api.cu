@@ -247,7 +247,7 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
     launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
   }
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-  if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, c->d_cov.p, c->d_scalars.p, c->stream);
+  if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("error_count");
@@ -641,6 +641,21 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
     install_table(c);
     score_device(c, p);
     evidence(c, gd_file, prop, seed, n_targets, skip_mc);
+  });
+}
+
+int brq_write_per_position_file(brq_ctx* c, const char* path, const double* prop, uint32_t n_targets) {
+  return guarded(c, [&] {
+    if (n_targets != c->hdr.target_names.size()) throw std::runtime_error("the cutoff table does not match the BAM targets");
+    if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
+    write_per_position_file(path, c->hdr, c->st, c->h_cols, c->last_params.base_quality_cutoff, std::vector<double>(prop, prop + n_targets));
+  });
+}
+
+int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
+  return guarded(c, [&] {
+    if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
+    write_coverage_tsv(pattern, c->hdr, c->ref, c->st, c->h_cols);
   });
 }
 

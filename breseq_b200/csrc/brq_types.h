@@ -93,8 +93,9 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //                    class words (ScoreGeometry::special_counter).
 //   [13]    top      1 = read on the top strand (all kinds)
 //   [14]    slow     HOT but not matching the reference base: the kernel reads its table cell directly
+//   [15]    trimmed  REDUNDANT: is_trimmed() (only the per-position debug file looks at it)
 //   [23:16] sq       HOT: class index (above)         REDUNDANT: [24:16] X1; 511 = the value is the slot's next
-//   [25:24] obs      HOT: observed base A,C,G,T                  SIDE_BIG entry of the side list
+//   [25:24] obs      HOT: observed base A,C,G,T                  SIDE_BIG entry of the side list; [27:25] observed base
 //   [28]    match    HOT and obs equals the slot's reference base
 //   [31:30] kind     0 HOT    scores; dominant MAPQ, A/C/G/T observation, quality inside the table window
 //                    1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
@@ -114,7 +115,7 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 // Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
 // records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
 constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
-                   DR_OBS_SHIFT = 24, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
+                   DR_OBS_SHIFT = 24, DR_RED_TRIM_BIT = 1u << 15, DR_RED_OBS_SHIFT = 25, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
                    DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
                    SIDE_BIG = 1u << 31;
 // special counters, in the two histogram words after the class words
@@ -224,7 +225,7 @@ inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
     else {
       uint32_t x1 = (d >> DR_X1_SHIFT) & DR_X1_MASK;
       if (x1 == DR_X1_MASK) x1 = st.side_rec[side++] & ~SIDE_BIG;
-      f(top | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1);
+      f(top | ((d >> DR_RED_OBS_SHIFT) & 7u) | ((d & DR_RED_TRIM_BIT) ? SR_TRIM_BIT : 0u) | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1);
     }
   }
 }

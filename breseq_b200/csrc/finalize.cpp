@@ -285,6 +285,63 @@ const ClassTerms* ClassLut::get(size_t li) {
   return &t;
 }
 
+// ============================================================================== optional per-position outputs
+// identify_mutations.cpp:1693-1733: one line per (column, insert_count) in visit order:
+//   position insert_count ref_base consensus_score  then per base "X (bottom/top)" of the scoring records and
+//   "rX (bottom/top)" of the untrimmed redundant records.  Numbers go through the default ostream formatting.
+void write_per_position_file(const std::string& path, const BamHeader& hdr, const PileupStream& st, const std::vector<ColumnOut>& cols,
+                             uint32_t base_quality_cutoff, const std::vector<double>& deletion_propagation_cutoff) {
+  std::ofstream out(path.c_str());
+  if (!out) throw std::runtime_error("cannot create " + path);
+  auto line = [&](uint64_t slot, uint32_t position, uint32_t insert_count) {
+    uint32_t uniq[5][2] = {{0}}, red[5][2] = {{0}};
+    for_each_classic(st, slot, [&](uint32_t r, uint32_t) {
+      const uint32_t obs = r & 7u, top = (r & SR_TOP_BIT) ? 1u : 0u;
+      if (obs > 4) return;
+      if (!(r & SR_UNIQUE_BIT)) { if (!(r & SR_TRIM_BIT)) ++red[obs][top]; return; }
+      if ((r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || ((r >> SR_QUAL_SHIFT) & 127u) < base_quality_cutoff) return;
+      ++uniq[obs][top];
+    });
+    out << position << ' ' << insert_count << ' ' << index_to_char(st.slot_ref[slot]) << ' ' << format_default(cols[slot].consensus_score);
+    for (int b = 0; b < 5; ++b) out << ' ' << index_to_char((uint8_t)b) << " (" << uniq[b][0] << '/' << uniq[b][1] << ')';
+    for (int b = 0; b < 5; ++b) out << " r" << index_to_char((uint8_t)b) << " (" << red[b][0] << '/' << red[b][1] << ')';
+    out << '\n';
+  };
+  size_t ins_cursor = 0;
+  for (const Segment& sg : st.segments) {
+    if (deletion_propagation_cutoff[(size_t)sg.tid] < 0.0) continue;  // the callback returns before this point (:1319-1336)
+    for (int32_t c = sg.lo; c < sg.hi; ++c) {
+      const uint64_t slot = sg.slot0 + (uint64_t)(c - sg.lo);
+      line(slot, (uint32_t)c + 1, 0);
+      while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
+      for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) line(st.n_base + ins_cursor, (uint32_t)c + 1, st.ins_count[ins_cursor]);
+    }
+  }
+}
+
+// identify_mutations.cpp:2028-2052, 2173-2204: <seq>.coverage.tsv (--predict-copy-number), one file per visited target:
+//   position ref_base unique_cov redundant_cov total_cov, the sums over both strands, total as their plain sum.
+void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols) {
+  for (const Segment& sg : st.segments) {
+    std::string fn = pattern;
+    const std::string& name = hdr.target_names[(size_t)sg.tid];
+    const size_t at = fn.find('@');
+    if (at != std::string::npos) fn.replace(at, 1, name);
+    std::ofstream out(fn.c_str(), sg.lo == 0 ? std::ios::out : std::ios::app);
+    if (!out) throw std::runtime_error("cannot create " + fn);
+    if (sg.lo == 0) out << "position\tref_base\tunique_cov\tredundant_cov\ttotal_cov\n";
+    size_t ri = 0;
+    while (ri < ref.names.size() && ref.names[ri] != name) ++ri;
+    for (int32_t c = sg.lo; c < sg.hi; ++c) {
+      const ColumnOut& co = cols[sg.slot0 + (uint64_t)(c - sg.lo)];
+      const double unique = (double)co.unique[0] + (double)co.unique[1], redundant = co.redundant[0] + co.redundant[1];
+      // the reference prints the FASTA character of the column (reference_base_char_1), not the folded index
+      const char rc = ri < ref.seqs.size() ? ref.seqs[ri][(size_t)c] : index_to_char(st.slot_ref[sg.slot0 + (uint64_t)(c - sg.lo)]);
+      out << (c + 1) << '\t' << rc << '\t' << format_default(unique) << '\t' << format_default(redundant) << '\t' << format_default(unique + redundant) << '\n';
+    }
+  }
+}
+
 // ============================================================================== statistics
 namespace {
 

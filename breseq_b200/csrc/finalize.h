@@ -76,4 +76,9 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
                               const WalkOut* walk, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
 
+// Optional outputs of pass 2 (identify_mutations.cpp:1693-1733 and :2028-2052, 2173-2204); both read the full per-slot results.
+void write_per_position_file(const std::string& path, const BamHeader& hdr, const PileupStream& st, const std::vector<ColumnOut>& cols,
+                             uint32_t base_quality_cutoff, const std::vector<double>& deletion_propagation_cutoff);
+void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols);
+
 }  // namespace brq

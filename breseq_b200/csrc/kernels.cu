@@ -132,24 +132,39 @@ void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& la
 // ------------------------------------------------------------------------------------------
 // unique-only coverage histogram: one increment per column without redundant reads
 // ------------------------------------------------------------------------------------------
+// Depths crowd into a few dozen bins, so the increments go to a CTA-private copy of the histogram in shared memory
+// (when groups x (max depth + 1) fits) and reach the global bins once per CTA and non-zero bin.
+constexpr uint32_t COV_SHARED_BINS = 8192;
 __global__ void __launch_bounds__(256) coverage_hist_kernel(const uint64_t* __restrict__ hist_off, const uint8_t* __restrict__ group,
-                                                             uint64_t n_cols, uint32_t stride, unsigned long long* __restrict__ cov,
-                                                             uint32_t* __restrict__ err_out) {
+                                                             uint64_t n_cols, uint32_t stride, uint32_t n_bins,
+                                                             unsigned long long* __restrict__ cov, uint32_t* __restrict__ err_out) {
+  __shared__ uint32_t priv[COV_SHARED_BINS];
+  const bool use_shared = n_bins <= COV_SHARED_BINS;
+  if (use_shared) {
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) priv[i] = 0;
+    __syncthreads();
+  }
   const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cols; c += step) {
     const uint64_t a = hist_off[c], b = hist_off[c + 1];
     if (a & HIST_OFF_REDUNDANT_BIT) continue;
     const uint64_t depth = (b & ~HIST_OFF_REDUNDANT_BIT) - a;
     if (depth >= stride) { atomicOr(err_out, BRQ_ERR_DEPTH_RANGE); continue; }
-    atomicAdd(&cov[(uint64_t)group[c] * stride + depth], 1ull);
+    const uint64_t bin = (uint64_t)group[c] * stride + depth;
+    if (use_shared) atomicAdd(&priv[bin], 1u); else atomicAdd(&cov[bin], 1ull);
+  }
+  if (use_shared) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_bins; i += blockDim.x) if (priv[i]) atomicAdd(&cov[i], (unsigned long long)priv[i]);
   }
 }
 
-void launch_coverage_hist(const uint64_t* hist_off, const uint8_t* group, uint64_t n_cols, uint32_t stride,
+void launch_coverage_hist(const uint64_t* hist_off, const uint8_t* group, uint64_t n_cols, uint32_t stride, uint32_t n_groups,
                           unsigned long long* cov_hist, uint32_t* err, cudaStream_t s) {
   if (!n_cols) return;
   int blocks = (int)std::min<uint64_t>((n_cols + 255) / 256, 148 * 8);
-  coverage_hist_kernel<<<blocks, 256, 0, s>>>(hist_off, group, n_cols, stride, cov_hist, err);
+  const uint64_t n_bins = (uint64_t)stride * n_groups;
+  coverage_hist_kernel<<<blocks, 256, 0, s>>>(hist_off, group, n_cols, stride, (uint32_t)std::min<uint64_t>(n_bins, 0xFFFFFFFFull), cov_hist, err);
   ++g_launches;
 }
 

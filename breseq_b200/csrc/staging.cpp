@@ -418,7 +418,8 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     const bool is_top = (rec & SR_TOP_BIT) != 0;
     const uint32_t top = is_top ? DR_TOP_BIT : 0u;
     if (!(rec & SR_UNIQUE_BIT)) {
-      w.dev = DR_REDUNDANT | top | std::min<uint32_t>(x1, DR_X1_MASK) << DR_X1_SHIFT | geo.special_counter(SC_TRASH);
+      w.dev = DR_REDUNDANT | top | std::min<uint32_t>(x1, DR_X1_MASK) << DR_X1_SHIFT | geo.special_counter(SC_TRASH) |
+              (rec & 7u) << DR_RED_OBS_SHIFT | ((rec & SR_TRIM_BIT) ? DR_RED_TRIM_BIT : 0u);
       if (x1 >= DR_X1_MASK) { w.has_side = true; w.side = SIDE_BIG | x1; }
       return w;
     }

@@ -150,6 +150,16 @@ int brq_write_evidence(brq_ctx* ctx, const char* gd_file, const double* deletion
                        const double* deletion_seed_cutoff, uint32_t n_targets, int skip_missing_coverage_prediction,
                        uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un);
 
+/* Optional outputs of pass 2; both copy the full per-slot results to the host.
+ * brq_write_per_position_file: the debug file identify_mutations() writes with print_per_position_file = true
+ *   (identify_mutations.cpp:1693-1733, Settings::mutation_identification_per_position_file_name); targets whose
+ *   deletion_propagation_cutoff is negative are skipped like the reference skips them.
+ * brq_write_coverage_tsv: <seq>.coverage.tsv of --predict-copy-number (identify_mutations.cpp:2028-2052, 2173-2204,
+ *   Settings::complete_coverage_text_file_name); '@' in `pattern` is replaced by the target name.  The per-read-group
+ *   columns the reference adds for runs with more than one read group are not written. */
+int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
+int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
+
 /* ---- one-call adapters with the reference entry points' argument meaning --------------------- */
 int brq_run_error_count(brq_ctx* ctx, const char* bam, const char* fasta, const char* output_dir,
                         const char* error_rates_file, const char* const* readfiles, uint32_t n_readfiles,

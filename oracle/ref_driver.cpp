@@ -91,6 +91,10 @@ int main(int argc, char** argv) {
   settings.error_rates_base_qual_error_prob_file_name = out + "/base_qual_error_prob.#.tab";
   settings.mutation_identification_per_position_file_name = get("per-position", out + "/per_position_file.tab");
   settings.dp_candidate_regions_file_name = out + "/dp_candidate_regions.csv";
+  if (opt.count("coverage-tsv")) {  // <seq>.coverage.tsv (identify_mutations.cpp:2028-2052)
+    settings.predict_copy_number = true;
+    settings.complete_coverage_text_file_name = get("coverage-tsv", out + "/@.coverage.tsv");
+  }
   // user-chosen subset of targets (Settings::call_mutations_seq_id_set())
   vector<string> seq_ids = split_list(get("seq-ids", ""), ',');
   if (!seq_ids.empty()) {

@@ -46,7 +46,7 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             d = helpers.generate_inputs(name, tmp)
             out = os.path.join(tmp, "ref")
-            helpers.run_reference(d, out)
+            helpers.run_reference(d, out, coverage_tsv=(name == "deep"))
             for f in helpers.pass_output_names(d):
                 shutil.copy(os.path.join(out, f), os.path.join(gdir, f))
             with open(os.path.join(gdir, "inputs.sha256"), "w") as fh:
@@ -55,6 +55,10 @@ def main():
                 for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
                     shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))
                 shutil.copy(os.path.join(out, "per_position_file.tab"), os.path.join(gdir, "per_position_file.tab"))
+            if name == "deep":  # one read group: the optional outputs of pass 2 for a whole (small) dataset
+                shutil.copy(os.path.join(out, "per_position_file.tab"), os.path.join(gdir, "per_position_file.tab"))
+                tsv = helpers.contig_names(d)[0] + ".coverage.tsv"
+                shutil.copy(os.path.join(out, tsv), os.path.join(gdir, tsv))
         print("golden/%s: %d files" % (name, len(os.listdir(gdir))))
 
 

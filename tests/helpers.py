@@ -117,12 +117,14 @@ def make_dataset(name, outdir):
     return d
 
 
-def run_reference(d, outdir, per_position=True):
+def run_reference(d, outdir, per_position=True, coverage_tsv=False):
     """Both passes of the reference's own sources (oracle/_ref/ref_cli) on a dataset; returns seconds."""
     os.makedirs(outdir, exist_ok=True)
     ec, im = cli_args(d, outdir)
     if per_position:
         im += ["--per-position", os.path.join(outdir, "per_position_file.tab")]
+    if coverage_tsv:
+        im += ["--coverage-tsv", os.path.join(outdir, "@.coverage.tsv")]
     sec = 0.0
     for args in (ec, im):
         p = subprocess.run([REF_CLI] + [str(a) for a in args], check=True, capture_output=True, text=True)

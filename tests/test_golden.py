@@ -91,15 +91,17 @@ def test_live_reference_matches_committed_golden(name, datasets, tmp_path):
     assert_same_files(d, out, os.path.join(helpers.GOLDEN, name), "live reference vs committed golden")
 
 
-def run_cuda(d, out):
+def run_cuda(d, out, optional_outputs=False):
     os.makedirs(out, exist_ok=True)
     rates = os.path.join(out, "error_rates.tab")
     bq.error_count(d["bam"], d["fasta"], out, helpers.readfile_names(d), True, True, False, 3, helpers.covariates(d),
                    read_file_sets=helpers.read_file_sets(d), error_rates_file_name=rates)
     n = len(d["contig_lens"])
     bq.identify_mutations(d["bam"], d["fasta"], os.path.join(out, "ra_mc_evidence.gd"), [d["del_prop"]] * n, [d["del_seed"]] * n,
-                          d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"], False,
-                          error_rates_file_name=rates, read_file_sets=helpers.read_file_sets(d))
+                          d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"], optional_outputs,
+                          error_rates_file_name=rates, read_file_sets=helpers.read_file_sets(d),
+                          per_position_file_name=os.path.join(out, "per_position_file.tab") if optional_outputs else None,
+                          coverage_tsv_pattern=os.path.join(out, "@.coverage.tsv") if optional_outputs else None)
 
 
 @pytest.mark.gpu
@@ -115,5 +117,18 @@ def test_cuda_path_reproduces_reference_files(name, datasets, tmp_path):
 def test_cuda_path_on_committed_bam(built, tmp_path):
     d = tiny_from_fixture(str(tmp_path))
     out = str(tmp_path / "cuda")
-    run_cuda(d, out)
+    run_cuda(d, out, optional_outputs=True)
     assert_same_files(d, out, os.path.join(helpers.GOLDEN, "tiny"), "CUDA path on committed BAM")
+    # the per-position debug file (identify_mutations.cpp:1693-1733), byte for byte; insert sub-columns included
+    assert filecmp.cmp(os.path.join(out, "per_position_file.tab"), golden("tiny", "per_position_file.tab"), shallow=False)
+
+
+@pytest.mark.gpu
+def test_cuda_optional_outputs_match_reference(datasets, tmp_path):
+    """print_per_position_file and <seq>.coverage.tsv (--predict-copy-number) on the deep amplicon: what the reference wrote."""
+    d = datasets["deep"]
+    out = str(tmp_path / "cuda")
+    run_cuda(d, out, optional_outputs=True)
+    assert filecmp.cmp(os.path.join(out, "per_position_file.tab"), golden("deep", "per_position_file.tab"), shallow=False)
+    tsv = helpers.contig_names(d)[0] + ".coverage.tsv"
+    assert filecmp.cmp(os.path.join(out, tsv), golden("deep", tsv), shallow=False)

@@ -55,7 +55,7 @@ class _StreamInfo(C.Structure):
     _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
                 ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
                 ("bytes_host", C.c_uint64),
-                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("side_stride", C.c_uint32),
                 ("n_side", C.c_uint64), ("base_quality_cutoff", C.c_uint32), ("hot_mapq", C.c_uint32),
                 ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_words", C.c_uint32),
                 ("score_rec", C.POINTER(C.c_uint32)), ("side_rec", C.POINTER(C.c_uint32)), ("side_off", C.POINTER(C.c_uint32)),
@@ -248,7 +248,7 @@ def decode_score_records(stream):
     out["mapq"][hot] = g["hot_mapq"]
     out["match"][hot] = ((d[hot] >> 28) & 1) == 1
     # side list: per slot, the entries of its very redundant records first, then those of its cold records, in order
-    side, soff = stream["side_rec"].astype(np.int64), stream["side_off"].astype(np.int64)
+    side, soff = stream["side_rec"].astype(np.int64)[::stream["side_stride"]], stream["side_off"].astype(np.int64)
     x1 = (d >> 16) & 0x1FF
     big = (kind == 3) & (x1 == 0x1FF)
     cold = kind == 2
@@ -329,7 +329,8 @@ class Context:
             "n_score_padded": info.n_score_padded,
             "score_rec": view(info.score_rec, info.n_score_padded, np.uint32),
             "score_off": view(info.score_off, n_slots + 1, np.uint64),
-            "n_side": info.n_side, "side_rec": view(info.side_rec, info.n_side, np.uint32),
+            "n_side": info.n_side, "side_stride": info.side_stride,
+            "side_rec": view(info.side_rec, info.n_side * info.side_stride, np.uint32),
             "side_off": view(info.side_off, n_slots + 1, np.uint32),
             "geometry": {"base_quality_cutoff": info.base_quality_cutoff, "hot_mapq": info.hot_mapq, "q_lo": info.table_q_lo,
                          "n_q": info.table_n_q, "n_st": info.table_n_st, "words": info.table_words},

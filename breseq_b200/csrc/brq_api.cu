@@ -199,12 +199,12 @@ void upload(brq_ctx* c) {
   const uint64_t n_slots = st.n_slots();
   c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_slot_ref.ensure(n_slots);
   c->d_hist_rec.ensure(st.n_hist * st.hist_bytes + 16);
-  c->d_side_rec.ensure(st.n_side + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
+  c->d_side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_side_rec.p, st.side_rec, st.n_side * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_side_rec.p, st.side_rec, st.n_side * st.geo.side_stride * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
@@ -295,7 +295,7 @@ void install_table(brq_ctx* c) {
   TableBuildArgs a;
   a.prob = c->d_prob.p; a.slot_mapq = c->d_slot_mapq.p;
   a.n_st = g.n_st; a.n_mapq_slots = (uint32_t)g.mapqs.size(); a.Q = c->sp.max_qual;
-  a.off_set = g.off_set; a.off_ref = g.off_ref; a.off_obs = g.off_obs; a.off_qual = g.off_qual;
+  a.off_set = g.off_set; a.off_ref = g.off_ref; a.off_obs = g.off_obs; a.off_qual = g.off_qual; a.off_rpos = g.off_rpos; a.off_rep = g.off_rep;
   a.hot_slot = c->sp.mapq_slot[c->sp.hot_mapq];
   a.lut = c->d_lut.p; a.coldT = c->d_coldT.p; a.hotR = c->d_hotR.p; a.tallyT = c->d_tallyT.p;
   launch_build_tables(a, c->sp, c->stream);
@@ -349,6 +349,9 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   if (c->st.n_score && c->st.max_read_set_seen >= c->sp.max_set)
     throw std::runtime_error("Covariate 'read_set' with value '" + std::to_string(c->st.max_read_set_seen) +
                              "' exceeded enforced maximum value of '" + std::to_string(c->sp.max_set - 1) + "'.");
+  if (c->st.n_score && c->sp.n_rpos > 1 && c->st.max_score_rpos >= c->sp.n_rpos)
+    throw std::runtime_error("Covariate 'read_pos' with value '" + std::to_string(c->st.max_score_rpos) +
+                             "' exceeded enforced maximum value of '" + std::to_string(c->sp.n_rpos - 1) + "'.");
   const uint64_t n_slots = c->st.n_slots();
   c->d_cols.ensure(n_slots);
   c->d_walk.ensure(n_slots);
@@ -358,7 +361,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
   launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
-                     c->d_cols.p, c->d_walk.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->stream, c->ev[7]);
+                     c->d_cols.p, c->d_walk.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
@@ -539,8 +542,8 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->n_side = st.n_side; info->side_rec = st.side_rec; info->side_off = st.side_off;
     info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
-    info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words();
-    info->bytes_host = st.n_rounds * 136 + st.n_slots() * 4 + st.n_side * 4 + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
+    info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
+    info->bytes_host = st.n_rounds * 136 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
@@ -633,10 +636,21 @@ int brq_run_error_count(brq_ctx* c, const char* bam, const char* fasta, const ch
 int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, const char* error_rates_file, const char* gd_file,
                                const double* prop, const double* seed, uint32_t n_targets, const brq_score_params* p, int skip_mc,
                                const brq_stage_options* opt) {
-  int rc = brq_stage_bam(c, bam, fasta, opt);
-  if (rc) return rc;
   return guarded(c, [&] {
-    read_error_rates(error_rates_file, c->spec, c->h_log10);
+    // the error table names its covariates: a table with read_pos / base_repeat needs them in the staged records
+    CovSpec spec;
+    std::vector<double> log10_prob;
+    read_error_rates(error_rates_file, spec, log10_prob);
+    drop_stream(c);
+    c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
+    read_bam(bam, c->hdr, c->reads, c->threads);
+    read_fasta(fasta, c->ref);
+    apply_stage_options(c, opt);
+    c->stage_cfg.use_read_pos = c->stage_cfg.use_read_pos || spec.used[COV_READ_POS];
+    c->stage_cfg.use_base_repeat = c->stage_cfg.use_base_repeat || spec.used[COV_BASE_REPEAT];
+    if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff ? p->base_quality_cutoff : c->stage_cfg.base_quality_cutoff;
+    do_stage(c);
+    c->spec = spec; c->h_log10 = log10_prob;
     c->have_spec = true;
     install_table(c);
     score_device(c, p);

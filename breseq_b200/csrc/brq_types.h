@@ -112,8 +112,11 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 // score_off[s] = first word of slot s (round_off[r] + 4 l), score_cnt[s] = its records; record j of slot s is word
 // score_index(score_off[s], j).
 //
-// Side list (side_rec, CSR side_off per slot): in stream order, the classic words of the slot's COLD
-// records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.
+// Side list (side_rec, CSR side_off per slot, counted in entries): in stream order, the classic words of the slot's
+// COLD records, and for redundant records with X1 >= 511 an entry SIDE_BIG | X1.  A stream staged for the read_pos /
+// base_repeat covariates (ScoreGeometry::side_stride = 2) has no shared table: every scoring record is COLD and every
+// entry is two words, the classic word and [15:0] read_pos, [23:16] base_repeat of the record's quality position
+// (error_count.cpp:1049-1105).
 constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
                    DR_OBS_SHIFT = 24, DR_RED_TRIM_BIT = 1u << 15, DR_RED_OBS_SHIFT = 25, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
                    DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
@@ -127,6 +130,7 @@ struct ScoreGeometry {
   uint32_t hot_mapq = 0;   // the MAPQ value whose classes the shared table holds
   uint32_t q_lo = 0, n_q = 0;   // quality window of the shared table (n_q is a multiple of 4)
   uint32_t n_st = 2;       // (read sets) x 2 strands
+  uint32_t side_stride = 1;  // words per side-list entry: 2 when the records carry read_pos / base_repeat
   uint32_t n_sq() const { return n_st * n_q; }            // classes of the per-slot histogram (<= 248)
   uint32_t n_words() const { return n_sq() / 4 + 2; }     // 32-bit histogram words per lane: class words + 2 special words
   uint32_t n_hot() const { return n_sq() * 4; }           // cells of the shared likelihood table
@@ -196,6 +200,7 @@ struct PileupStream {
   uint32_t n_groups = 1;               // coverage groups present
   uint32_t max_qual_seen = 0;
   uint32_t max_hist_qual = 0, max_hist_rpos = 0;  // largest quality / read position in a valid histogram observation
+  uint32_t max_score_rpos = 0;                    // largest read position of a scoring record (streams staged with read_pos)
   uint32_t max_read_set_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
   uint64_t n_slots() const { return n_base + n_ins; }
@@ -212,20 +217,22 @@ inline uint64_t score_index(uint64_t base, uint64_t j) {
   return base + (j >> 3) * ROUND_VECTOR_WORDS + ((j >> 2) & 1u) * (ROUND_VECTOR_WORDS / 2) + (j & 3u);
 }
 
-// Classic words of slot s in stream order (redundant first): f(classic word).  Redundant records come
-// back with their full X1 in a second argument (the classic field saturates at 8191).
+// Classic words of slot s in stream order (redundant first): f(classic word, X1, ext).  Redundant records come
+// back with their full X1 (the classic field saturates at 8191); ext = read_pos | base_repeat << 16 of a scoring
+// record of a stream staged with them, else 0.
 template <class F>
 inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
   uint32_t side = st.side_off[s];
   for (uint64_t j = 0; j < st.score_cnt[s]; ++j) {
     const uint32_t d = st.score_rec[score_index(st.score_off[s], j)], kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
-    if (kind == 0) f(classic_of_hot(d, st.geo), 1u);
-    else if (kind == 1) f(top | SR_UNIQUE_BIT | SR_TRIM_BIT, 1u);   // does not score; why is not kept
-    else if (kind == 2) f(st.side_rec[side++], 1u);
+    const uint32_t ss = st.geo.side_stride;
+    if (kind == 0) f(classic_of_hot(d, st.geo), 1u, 0u);
+    else if (kind == 1) f(top | SR_UNIQUE_BIT | SR_TRIM_BIT, 1u, 0u);   // does not score; why is not kept
+    else if (kind == 2) { f(st.side_rec[(size_t)side * ss], 1u, ss == 2 ? st.side_rec[(size_t)side * ss + 1] : 0u); ++side; }
     else {
       uint32_t x1 = (d >> DR_X1_SHIFT) & DR_X1_MASK;
-      if (x1 == DR_X1_MASK) x1 = st.side_rec[side++] & ~SIDE_BIG;
-      f(top | ((d >> DR_RED_OBS_SHIFT) & 7u) | ((d & DR_RED_TRIM_BIT) ? SR_TRIM_BIT : 0u) | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1);
+      if (x1 == DR_X1_MASK) x1 = st.side_rec[(size_t)(side++) * ss] & ~SIDE_BIG;
+      f(top | ((d >> DR_RED_OBS_SHIFT) & 7u) | ((d & DR_RED_TRIM_BIT) ? SR_TRIM_BIT : 0u) | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1, 0u);
     }
   }
 }

@@ -214,8 +214,9 @@ void write_coverage_distributions(const std::string& dir, const std::vector<uint
 // kernel's table.  Cheap, so it runs on every table installation; the values are filled in either on
 // the device (build_tables_kernel, tables.cu) or on the host (build_class_lut and friends below).
 void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGeometry& sg, ScoreParams& p, TableGeometry& g) {
-  if (c.used[COV_READ_POS] || c.used[COV_BASE_REPEAT])
-    throw std::runtime_error("scoring with read_pos / base_repeat covariates is not implemented yet");
+  const bool wide = c.used[COV_READ_POS] || c.used[COV_BASE_REPEAT];
+  if (wide && sg.side_stride != 2)
+    throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
   if (!c.used[COV_OBS_BASE] || !c.used[COV_REF_BASE] || !c.used[COV_QUALITY])
     throw std::runtime_error("scoring needs ref_base, obs_base and quality covariates");
   const uint32_t n_set = c.used[COV_READ_SET] ? c.maxv[COV_READ_SET] : 1, Q = c.maxv[COV_QUALITY];
@@ -228,20 +229,24 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGe
   p.max_set = c.used[COV_READ_SET] ? n_set : 32;
   g.off_set = c.used[COV_READ_SET] ? c.offset[COV_READ_SET] : 0; g.off_ref = c.offset[COV_REF_BASE];
   g.off_obs = c.offset[COV_OBS_BASE]; g.off_qual = c.offset[COV_QUALITY];
+  g.off_rpos = c.used[COV_READ_POS] ? c.offset[COV_READ_POS] : 0; g.off_rep = c.used[COV_BASE_REPEAT] ? c.offset[COV_BASE_REPEAT] : 0;
+  p.n_rpos = c.used[COV_READ_POS] ? c.maxv[COV_READ_POS] : 1; p.n_rep = c.used[COV_BASE_REPEAT] ? c.maxv[COV_BASE_REPEAT] : 1;
+  const size_t W = (size_t)p.n_rpos * p.n_rep;  // classes per (set, strand, MAPQ, quality, obs) with read_pos / base_repeat
   if (n_set * 2 < sg.n_st)
     throw std::runtime_error("Covariate 'read_set' with value '" + std::to_string(sg.n_st / 2 - 1) +
                              "' exceeded enforced maximum value of '" + std::to_string(n_set - 1) + "'.");
   g.n_st = sg.n_st;  // the stream's words index the shared table with the stream's own set count
-  g.n_lut = (size_t)g.n_st * g.mapqs.size() * Q * 5;
+  g.n_lut = (size_t)g.n_st * g.mapqs.size() * Q * W * 5;
+  if (g.n_lut >= (1ull << 31)) throw std::runtime_error("too many record classes (read sets x MAPQ values x quality x read_pos x base_repeat)");
   // the dominant MAPQ and the tally kernel's shared-memory window were fixed when the stream was staged
   if (p.mapq_slot[sg.hot_mapq] == 255) throw std::runtime_error("the stream's dominant MAPQ is missing from its MAPQ set");
   p.hot_mapq = sg.hot_mapq;
   const size_t n_hot = (size_t)g.n_st * Q * 5;
-  p.n_hot = (n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // fit kernel: three CTAs per SM must each hold a copy
+  p.n_hot = (!wide && n_hot * 48 <= 96 * 1024) ? (uint32_t)n_hot : 0;  // fit kernel: three CTAs per SM must each hold a copy
   g.n_hotR = n_hot;
   // MAPQ range of the global table of the tally kernel
   p.mq_min = g.mapqs.front(); p.n_mq = g.mapqs.back() - g.mapqs.front() + 1;
-  g.n_cold = (size_t)g.n_st * p.n_mq * Q * 5;
+  g.n_cold = (size_t)g.n_st * p.n_mq * Q * W * 5;
   p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_nsq = sg.n_sq(); p.t_nw = sg.n_words();
   p.t_stride = p.t_nsq * 64u;
   g.n_tally_cells = (size_t)4 * p.t_stride / 16;
@@ -260,9 +265,11 @@ const ClassTerms* ClassLut::get(size_t li) {
   ClassTerms& t = terms[li];
   if (done[li]) return &t;
   const uint32_t Q = p->max_qual;
-  const uint32_t obs = (uint32_t)(li % 5), q = (uint32_t)((li / 5) % Q);
-  const size_t ms = (li / (5 * (size_t)Q)) % g->mapqs.size();
-  const uint32_t st = (uint32_t)(li / (5 * (size_t)Q * g->mapqs.size()));
+  const size_t W = (size_t)p->n_rpos * p->n_rep;
+  const uint32_t obs = (uint32_t)(li % 5), rr = (uint32_t)((li / 5) % W), q = (uint32_t)((li / (5 * W)) % Q);
+  const size_t ms = (li / (5 * W * Q)) % g->mapqs.size();
+  const uint32_t st = (uint32_t)(li / (5 * W * Q * g->mapqs.size()));
+  const uint32_t rpos = rr / p->n_rep, rpt = rr % p->n_rep;
   auto comp = [](uint32_t b) { return b < 4 ? 3 - b : 4u; };
   const uint32_t set = st >> 1, top = st & 1;
   const double incorrect = pow(10, -(double)g->mapqs[ms] / 10);
@@ -272,7 +279,7 @@ const ClassTerms* ClassLut::get(size_t li) {
   double mx = -std::numeric_limits<double>::max();
   for (uint32_t b = 0; b < 5; ++b) {
     const uint32_t rf = top ? b : comp(b);
-    const uint32_t idx = set * g->off_set + rf * g->off_ref + o * g->off_obs + q * g->off_qual;
+    const uint32_t idx = set * g->off_set + rf * g->off_ref + o * g->off_obs + q * g->off_qual + rpos * g->off_rpos + rpt * g->off_rep;
     double pr = correct * (*prob)[idx] + incorrect * uniform;
     if (pr < 0.0) pr = 0.0;
     t.L[b] = log10(pr);
@@ -295,7 +302,7 @@ void write_per_position_file(const std::string& path, const BamHeader& hdr, cons
   if (!out) throw std::runtime_error("cannot create " + path);
   auto line = [&](uint64_t slot, uint32_t position, uint32_t insert_count) {
     uint32_t uniq[5][2] = {{0}}, red[5][2] = {{0}};
-    for_each_classic(st, slot, [&](uint32_t r, uint32_t) {
+    for_each_classic(st, slot, [&](uint32_t r, uint32_t, uint32_t) {
       const uint32_t obs = r & 7u, top = (r & SR_TOP_BIT) ? 1u : 0u;
       if (obs > 4) return;
       if (!(r & SR_UNIQUE_BIT)) { if (!(r & SR_TRIM_BIT)) ++red[obs][top]; return; }
@@ -596,11 +603,12 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     const uint32_t slot = flagged[fi];
     SlotEval s;
     memset(s.count, 0, sizeof s.count);
-    for_each_classic(st, slot, [&](uint32_t r, uint32_t) {
+    for_each_classic(st, slot, [&](uint32_t r, uint32_t, uint32_t ext) {
       const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
       if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) return;
       const uint32_t obs = r & 7, top = (r & SR_TOP_BIT) ? 1 : 0, mapq = (r >> SR_MAPQ_SHIFT) & 255, set = (r >> SR_SET_SHIFT) & 31;
-      const size_t li = ((((size_t)set * 2 + top) * sp.n_mapq_slots + sp.mapq_slot[mapq]) * sp.max_qual + q) * 5 + obs;
+      const size_t rr = class_rr(ext, sp);
+      const size_t li = ((((((size_t)set * 2 + top) * sp.n_mapq_slots + sp.mapq_slot[mapq]) * sp.max_qual + q) * sp.n_rpos * sp.n_rep) + rr) * 5 + obs;
       s.reads.push_back(lut.get(li));
       s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
       ++s.count[obs][top];

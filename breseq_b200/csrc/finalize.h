@@ -44,7 +44,7 @@ void write_coverage_distributions(const std::string& dir, const std::vector<uint
 struct TableGeometry {
   std::vector<uint32_t> mapqs;   // MAPQ value of each slot
   uint32_t n_st = 0;             // read sets x 2 strands
-  uint32_t off_set = 0, off_ref = 0, off_obs = 0, off_qual = 0;  // covariate table strides
+  uint32_t off_set = 0, off_ref = 0, off_obs = 0, off_qual = 0, off_rpos = 0, off_rep = 0;  // covariate table strides (0 = unused)
   size_t n_lut = 0, n_hotR = 0, n_cold = 0, n_tally_cells = 0;
 };
 void score_geometry(const CovSpec& spec, const uint32_t mapq_seen[8], const ScoreGeometry& stream_geometry, ScoreParams& p,

@@ -64,7 +64,19 @@ struct ScoreParams {
   // of the contraction), t_stride bytes between the four obs planes
   uint32_t t_qlo, t_nq, t_nsq, t_nw, t_stride;
   uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
+  uint32_t n_rpos, n_rep;    // read_pos / base_repeat values of the table (1 = the covariate is not used); with them every
+                             // class index gains a factor n_rpos * n_rep between quality and obs (class_rr)
 };
+
+// read_pos * n_rep + min(base_repeat, n_rep - 1) of a record's extension word (brq_types.h): base_repeat clamps
+// (error_count.cpp:489-496), read_pos is range-checked on the host against the stream's maximum
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t class_rr(uint32_t ext, const ScoreParams& p) {
+  const uint32_t rpos = p.n_rpos > 1 ? (ext & 0xFFFFu) : 0u, rep = (ext >> 16) & 255u;
+  return rpos * p.n_rep + (rep < p.n_rep ? rep : p.n_rep - 1u);
+}
 
 // Per-class likelihood terms, built on the host with the same libm calls the reference makes
 // (identify_mutations.cpp:3359-3384) so the per-record terms are bit-identical.
@@ -81,7 +93,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
-                        cudaStream_t s, cudaEvent_t between);
+                        uint32_t side_stride, cudaStream_t s, cudaEvent_t between);
 // out[i] = cols[slots[i]]: the full results of the flagged slots, for the host re-evaluation
 void launch_gather_columns(const ColumnOut* cols, const uint32_t* slots, uint32_t n, ColumnOut* out, cudaStream_t s);
 
@@ -89,7 +101,7 @@ void launch_gather_columns(const ColumnOut* cols, const uint32_t* slots, uint32_
 struct TableBuildArgs {
   const double* prob;          // [n_bins] pow(10, log10 value read back from error_rates.tab)
   const uint8_t* slot_mapq;    // [n_mapq_slots] MAPQ value of each slot
-  uint32_t n_st, n_mapq_slots, Q, off_set, off_ref, off_obs, off_qual, hot_slot;
+  uint32_t n_st, n_mapq_slots, Q, off_set, off_ref, off_obs, off_qual, off_rpos, off_rep, hot_slot;
   ClassTerms* lut; HotTerms* coldT; HotRatios* hotR; double* tallyT;
 };
 void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s);

@@ -120,9 +120,9 @@ __device__ __forceinline__ bool eligible(uint32_t r, uint32_t cutoff) {
 __device__ __forceinline__ uint32_t hot_index(uint32_t r, uint32_t Q) {
   return (((r >> 10) & 63) * Q + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
 }
-__device__ __forceinline__ uint32_t cold_index(uint32_t r, const ScoreParams& p, const uint8_t* mapq_slot) {
+__device__ __forceinline__ uint32_t cold_index(uint32_t r, uint32_t ext, const ScoreParams& p, const uint8_t* mapq_slot) {
   const uint32_t hi = (r >> 10) & 63, mapq = (r >> SR_MAPQ_SHIFT) & 255;
-  return ((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * 5 + (r & 7);
+  return (((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * (p.n_rpos * p.n_rep) + class_rr(ext, p)) * 5 + (r & 7);
 }
 
 struct Sums { double l0, l1, l2, l3, l4, m; };
@@ -140,9 +140,9 @@ __device__ __forceinline__ double exp10_neg(double d) {
 }
 
 // a scoring record whose class is not in the shared table (classic word from the side list): {L[0..4], M} from the global table
-__device__ __forceinline__ void cold_add(Sums& a, uint32_t r, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
+__device__ __forceinline__ void cold_add(Sums& a, uint32_t r, uint32_t ext, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
   const uint32_t st = (r >> 10) & 63u, mapq = (r >> SR_MAPQ_SHIFT) & 255u, qual = (r >> SR_QUAL_SHIFT) & 127u;
-  const char* e = reinterpret_cast<const char*>(coldT + (((st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * 5u + (r & 7u)));
+  const char* e = reinterpret_cast<const char*>(coldT + ((((size_t)(st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * (p.n_rpos * p.n_rep) + class_rr(ext, p)) * 5u + (r & 7u)));
   const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
   a.l0 += x.x; a.l1 += x.y; a.l2 += y.x; a.l3 += y.y; a.l4 += z.x; a.m += z.y;
 }
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
                                                                   uint64_t n_rounds, const double* __restrict__ tallyT,
                                                                   const HotTerms* __restrict__ coldT, ScoreParams p, ColumnOut* __restrict__ out,
                                                                   WalkOut* __restrict__ walk, uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
-                                                                  uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block) {
+                                                                  uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block, uint32_t side_stride) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t sm0 = ((uint32_t)__cvta_generic_to_shared(sm_raw) + hist_block - 1u) & ~(hist_block - 1u);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     // the rest of the round into L2 (one request per warp), and this lane's side-list entries
     if (lane == 0 && x.n_vec > (uint32_t)RING)
       prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, (x.n_vec - (uint32_t)RING) * (ROUND_VECTOR_WORDS * 4u));
-    if (x.side1 > x.side0) prefetch_l2(side + x.side0);
+    if (x.side1 > x.side0) prefetch_l2(side + (size_t)x.side0 * side_stride);
   };
   // round vector i: wait for it, read this lane's eight records, and hand the stage to vector i + RING
   auto next_vec = [&](uint32_t stage, uint32_t i, uint32_t n_vec) {
@@ -267,18 +267,26 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     // global table.  SIDE_BIG entries (X1 of very redundant records) lead the slot's side range; the head walk reads
     // them.  Two entries per step, the next pair's words requested before this pair's table terms.
     uint32_t side_big = cur.side0;
-    {
+    if (side_stride == 1u) {
       uint32_t e = cur.side0;
       uint32_t wa = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, wb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
       while (e < cur.side1) {
         e += 2u;
         const uint32_t na = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, nb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
         Sums ta = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, tb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (!(wa & SIDE_BIG)) { cold_add(ta, wa, coldT, p); ++n; c_ref += (wa >> 27) & 1u; }
-        if (!(wb & SIDE_BIG)) { cold_add(tb, wb, coldT, p); ++n; c_ref += (wb >> 27) & 1u; }
+        if (!(wa & SIDE_BIG)) { cold_add(ta, wa, 0u, coldT, p); ++n; c_ref += (wa >> 27) & 1u; }
+        if (!(wb & SIDE_BIG)) { cold_add(tb, wb, 0u, coldT, p); ++n; c_ref += (wb >> 27) & 1u; }
         kept.l0 += ta.l0; kept.l1 += ta.l1; kept.l2 += ta.l2; kept.l3 += ta.l3; kept.l4 += ta.l4; kept.m += ta.m;
         kept.l0 += tb.l0; kept.l1 += tb.l1; kept.l2 += tb.l2; kept.l3 += tb.l3; kept.l4 += tb.l4; kept.m += tb.m;
         wa = na; wb = nb;
+      }
+    } else {
+      // read_pos / base_repeat streams: every scoring record is here, two words an entry (classic word, extension)
+      for (uint32_t e = cur.side0; e < cur.side1; ++e) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(side) + e);
+        if (w.x & SIDE_BIG) continue;
+        cold_add(kept, w.x, w.y, coldT, p);
+        ++n; c_ref += (w.x >> 27) & 1u;
       }
     }
 
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       uint32_t j = 0, r = lds_u32(ring);
       while ((r >> DR_KIND_SHIFT) == 3u) {
         uint32_t red = (r >> DR_X1_SHIFT) & DR_X1_MASK;
-        if (red == DR_X1_MASK) red = __ldg(side + side_big++) & ~SIDE_BIG;
+        if (red == DR_X1_MASK) red = __ldg(side + (size_t)(side_big++) * side_stride) & ~SIDE_BIG;
         const double inv = 1.0 / (double)red;
         if (r & DR_TOP_BIT) { red_top += inv; ++raw_top; } else { red_bot += inv; ++raw_bot; }
         if (++j == cnt) break;
@@ -444,7 +452,7 @@ namespace {
 
 struct GroupCtx {
   const uint32_t* rec; uint64_t base, beg, end;   // index space [beg, end): the slot's n_main records (word score_index(base, k)), then its side-list entries
-  const uint32_t* side; uint32_t side_beg; uint64_t n_main;
+  const uint32_t* side; uint32_t side_beg, side_stride; uint64_t n_main;
   uint32_t hot_base; const ClassTerms* lut; const uint8_t* mapq_slot; const ScoreParams* p;
   const uint32_t* cache;  // table codes of the slot's first FIT_CACHE records
   uint32_t sub, mask;     // lane within the group, shuffle mask of the group
@@ -463,25 +471,28 @@ __device__ __forceinline__ uint32_t group_sum_u32(uint32_t v, uint32_t mask) {
 
 // Where a record's class terms live: a byte offset into the shared table, CODE_COLD | index into
 // the global table, or CODE_NONE for a record that does not score.
-__device__ __forceinline__ uint32_t code_of(const GroupCtx& g, uint32_t r) {
+__device__ __forceinline__ uint32_t code_of(const GroupCtx& g, uint2 rx) {
   const ScoreParams& p = *g.p;
+  const uint32_t r = rx.x;
   if (!eligible(r, p.base_quality_cutoff)) return CODE_NONE;
   if (p.n_hot && ((r >> SR_MAPQ_SHIFT) & 255) == p.hot_mapq) return hot_index(r, p.max_qual) * 48u;
-  return CODE_COLD | cold_index(r, p, g.mapq_slot);
+  return CODE_COLD | cold_index(r, rx.y, p, g.mapq_slot);
 }
 // Classic word at index i of the slot's records for the fit: a HOT device word is decoded, a side-list
 // entry is taken as it is, everything else (IDLE, the COLD placeholder, REDUNDANT, padding) does not score.
-__device__ __forceinline__ uint32_t classic_at(const GroupCtx& g, uint64_t i) {
+__device__ __forceinline__ uint2 classic_at(const GroupCtx& g, uint64_t i) {  // {classic word, extension word}
   const uint64_t k = i - g.beg;
   if (k < g.n_main) {
     const uint32_t d = __ldg(g.rec + score_index(g.base, k));
-    if ((d >> DR_KIND_SHIFT) != 0u) return 0u;
+    if ((d >> DR_KIND_SHIFT) != 0u) return make_uint2(0u, 0u);
     const ScoreParams& p = *g.p;
     const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = p.t_qlo + sq % p.t_nq, st = sq / p.t_nq;
-    return obs | qual << SR_QUAL_SHIFT | st << 10 | p.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT;
+    return make_uint2(obs | qual << SR_QUAL_SHIFT | st << 10 | p.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT, 0u);
   }
-  const uint32_t w = __ldg(g.side + g.side_beg + (uint32_t)(k - g.n_main));
-  return (w & SIDE_BIG) ? 0u : w;
+  const size_t e = (size_t)(g.side_beg + (uint32_t)(k - g.n_main)) * g.side_stride;
+  const uint32_t w = __ldg(g.side + e);
+  if (w & SIDE_BIG) return make_uint2(0u, 0u);
+  return make_uint2(w, g.side_stride == 2u ? __ldg(g.side + e + 1) : 0u);
 }
 __device__ __forceinline__ uint32_t code_at(const GroupCtx& g, uint64_t i) {
   const uint64_t k = i - g.beg;
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
                                                           const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
                                                           const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
                                                           ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ flagged,
-                                                          uint32_t* __restrict__ scalars, uint32_t flagged_cap) {
+                                                          uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t side_stride) {
   extern __shared__ __align__(16) double sm[];
   __shared__ uint8_t mapq_slot[256];
   __shared__ uint32_t cache[FIT_TPB / FIT_LANES][FIT_CACHE];
@@ -534,12 +545,13 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     if (w >= n_work) break;
     const uint32_t slot = worklist[w];
     g.base = off[slot]; g.beg = 0; g.n_main = cnt[slot]; g.end = g.n_main;
-    g.side = side; g.side_beg = side_off[slot];
+    g.side = side; g.side_beg = side_off[slot]; g.side_stride = side_stride;
     g.end += side_off[slot + 1] - g.side_beg;
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
     for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-      const uint32_t r = classic_at(g, i);
-      const uint32_t code = code_of(g, r);
+      const uint2 rx = classic_at(g, i);
+      const uint32_t r = rx.x;
+      const uint32_t code = code_of(g, rx);
       if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
       if (code == CODE_NONE) continue;
 #pragma unroll
@@ -658,7 +670,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
-                        cudaStream_t s, cudaEvent_t between) {
+                        uint32_t side_stride, cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
   const size_t smem_fit = (size_t)p.n_hot * 48;
@@ -671,10 +683,10 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, walk, worklist, flagged, scalars, flagged_cap, hist_block);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, walk, worklist, flagged, scalars, flagged_cap, hist_block, side_stride);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap, side_stride);
   note_launches(2);
 }
 

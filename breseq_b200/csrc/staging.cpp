@@ -356,12 +356,13 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     }
     if (nq > nq_cap) nq = nq_cap;  // more than 62 read files x strands: no window fits, everything takes the side list
     g.q_lo = best_lo; g.n_q = nq;
+    if (cfg.use_read_pos || cfg.use_base_repeat) { g.n_q = 0; g.side_stride = 2; }  // classes too many for a shared table: all cold
   }
   const ScoreGeometry geo = out.geo;
   const uint32_t n_hot = geo.n_hot();
 
   // Classic words of one pileup entry: the column itself (k = 0) and its insert sub-columns
-  // (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105).  sink(slot, classic word, X1).
+  // (identify_mutations.cpp:1561-1657, error_count.cpp:1049-1105).  sink(slot, classic word, X1, ext).
   auto score_words = [&](size_t i, const ReadInfo& ri, int32_t q, bool is_del, int indel, uint64_t slot, auto&& sink) {
     const uint8_t* seq = R.bases.data() + R.seq_off[i];
     const uint8_t* qual = R.quals.data() + R.seq_off[i];
@@ -385,6 +386,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         if (past_base && ((uint32_t)L - q1 == (uint32_t)R.xr[i])) trimmed = true;
       }
       if (trimmed) rec |= SR_TRIM_BIT;
+      uint32_t ext = 0;  // read_pos and base_repeat of the quality position, when staged
       if (unique) {
         rec |= SR_UNIQUE_BIT;
         int32_t qp = q;
@@ -402,13 +404,24 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
           uint32_t qv = qual[qp];
           if (qv > 127) throw std::runtime_error("base quality above 127 cannot be packed");
           rec |= SR_OK_BIT | (qv << SR_QUAL_SHIFT);
+          if (geo.side_stride == 2) {
+            if (qp > 65535) throw std::runtime_error("read position above 65535 cannot be packed");
+            ext = (uint32_t)qp;
+            if (cfg.use_base_repeat) {  // alignment.cpp:371-390
+              const uint8_t b = seq[qp];
+              int32_t x = qp; uint32_t rp = 0;
+              if (!rev) { while (x < ri.qe0) { ++x; if (seq[x] != b) break; ++rp; } }
+              else { while (x > 0) { --x; if (seq[x] != b) break; ++rp; } }
+              ext |= std::min<uint32_t>(rp, 255u) << 16;
+            }
+          }
         }
         rec |= mapq << SR_MAPQ_SHIFT;
         rec |= (uint32_t)ri.read_set << SR_SET_SHIFT;
       } else {
         rec |= std::min<uint32_t>(R.x1[i], SR_RED_MASK) << SR_RED_SHIFT;
       }
-      sink(k == 0 ? slot : out.n_base + sub_first[slot] + k - 1, rec, R.x1[i]);
+      sink(k == 0 ? slot : out.n_base + sub_first[slot] + k - 1, rec, R.x1[i], ext);
     }
   };
   // Device stream word (and side-list entry, if any) of a classic word in a slot with reference base `ref`.
@@ -459,7 +472,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
         if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
         if (cfg.want_score)
-          score_words(i, info[i], q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
+          score_words(i, info[i], q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1, uint32_t) {
             ++score_cnt[s];
             if (!unique) ++red_cnt[s];
             const DevWord w = encode(rec, x1, out.slot_ref[s]);
@@ -477,7 +490,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     for (uint64_t s = 0; s < n_slots; ++s) { out.side_off[s] = (uint32_t)sacc; if (cfg.want_score) sacc += side_cnt[s]; }
     if (sacc >= (1ull << 32)) throw std::runtime_error("more than 2^32 side-list entries in one staged stream");
     out.side_off[n_slots] = (uint32_t)sacc; out.n_side = sacc;
-    out.side_rec = (uint32_t*)alloc(sacc * 4 + 16, &p3);
+    out.side_rec = (uint32_t*)alloc(sacc * 4 * out.geo.side_stride + 16, &p3);
     // Rounds of the tally kernel: 32 slots that share their reference base (its contraction multiplies the 32 class
     // histograms with ONE base's likelihood table) and have about the same depth (its 32 lanes walk their runs in
     // lock step).  Inside every block of ROUND_BLOCK consecutive slots the slots are grouped by base (A, C, G, T,
@@ -553,7 +566,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   std::vector<uint64_t> qual_counts((size_t)items.size() * 128, 0);
   std::vector<uint32_t> mapq_masks((size_t)items.size() * 8, 0);
   std::vector<uint64_t> mapq_counts((size_t)items.size() * 256, 0);
-  std::vector<uint32_t> max_quals(items.size(), 0), max_hquals(items.size(), 0), max_rposs(items.size(), 0);
+  std::vector<uint32_t> max_quals(items.size(), 0), max_hquals(items.size(), 0), max_rposs(items.size(), 0), max_srposs(items.size(), 0);
   run_items([&](size_t ii) {
     const Item& it = items[ii];
     const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
@@ -567,7 +580,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     uint32_t* mq_mask = &mapq_masks[ii * 8];
     uint64_t* mq_count = &mapq_counts[ii * 256];
     uint64_t* q_count = &qual_counts[ii * 128];
-    uint32_t max_q = 0, max_hq = 0, max_rp = 0;
+    uint32_t max_q = 0, max_hq = 0, max_rp = 0, max_srp = 0;
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
       const ReadInfo& ri = info[i];
@@ -638,10 +651,14 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         }
         // ---------------- identify_mutations records
         if (!cfg.want_score) return;
-        score_words(i, ri, q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1) {
+        score_words(i, ri, q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1, uint32_t ext) {
           const DevWord w = encode(rec, x1, out.slot_ref[s]);
           out.score_rec[score_index(out.score_off[s], unique ? score_cur[s]++ : red_cur[s]++)] = w.dev;
-          if (w.has_side) out.side_rec[out.side_off[s] + (unique ? side_cur[s]++ : side_red_cur[s]++)] = w.side;
+          if (w.has_side) {
+            const size_t e = (size_t)(out.side_off[s] + (unique ? side_cur[s]++ : side_red_cur[s]++)) * geo.side_stride;
+            out.side_rec[e] = w.side;
+            if (geo.side_stride == 2) { out.side_rec[e + 1] = ext; if ((w.side & SIDE_BIG) == 0 && (ext & 0xFFFFu) > max_srp) max_srp = ext & 0xFFFFu; }
+          }
           const uint32_t kind = w.dev >> DR_KIND_SHIFT;
           if (kind == 0 || kind == 2) {  // a scoring record: exact statistics for the likelihood tables
             const uint32_t qv = (rec >> SR_QUAL_SHIFT) & 127u;
@@ -650,7 +667,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         });
       });
     }
-    max_quals[ii] = max_q; max_hquals[ii] = max_hq; max_rposs[ii] = max_rp;
+    max_quals[ii] = max_q; max_hquals[ii] = max_hq; max_rposs[ii] = max_rp; max_srposs[ii] = max_srp;
   });
   if (cfg.want_score) out.mapq_seen[geo.hot_mapq >> 5] |= 1u << (geo.hot_mapq & 31);  // the shared table is always built
   for (size_t ii = 0; ii < items.size(); ++ii) {
@@ -660,6 +677,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     out.max_qual_seen = std::max(out.max_qual_seen, max_quals[ii]);
     out.max_hist_qual = std::max(out.max_hist_qual, max_hquals[ii]);
     out.max_hist_rpos = std::max(out.max_hist_rpos, max_rposs[ii]);
+    out.max_score_rpos = std::max(out.max_score_rpos, max_srposs[ii]);
   }
 }
 

@@ -17,10 +17,13 @@ namespace brq {
 void note_launches(int n);
 
 __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, ScoreParams p) {
-  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * 5u;
+  const uint32_t W = p.n_rpos * p.n_rep;
+  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * W * 5u;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cls) return;
-  const uint32_t obs = i % 5u, q = (i / 5u) % a.Q, ms = (i / (5u * a.Q)) % a.n_mapq_slots, st = i / (5u * a.Q * a.n_mapq_slots);
+  const uint32_t obs = i % 5u, rr = (i / 5u) % W, q = (i / (5u * W)) % a.Q, ms = (i / (5u * W * a.Q)) % a.n_mapq_slots,
+                 st = i / (5u * W * a.Q * a.n_mapq_slots);
+  const uint32_t rpos = rr / p.n_rep, rpt = rr % p.n_rep;
   const uint32_t set = st >> 1, top = st & 1u;
   const uint32_t mapq = a.slot_mapq[ms];
   const double incorrect = pow(10.0, -(double)mapq / 10.0), correct = 1.0 - incorrect, uniform = 1.0 / 5.0;
@@ -29,7 +32,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
 #pragma unroll
   for (uint32_t b = 0; b < 5; ++b) {
     const uint32_t rf = top ? b : (b < 4u ? 3u - b : 4u);
-    double pr = correct * a.prob[set * a.off_set + rf * a.off_ref + o * a.off_obs + q * a.off_qual] + incorrect * uniform;
+    double pr = correct * a.prob[set * a.off_set + rf * a.off_ref + o * a.off_obs + q * a.off_qual + rpos * a.off_rpos + rpt * a.off_rep] + incorrect * uniform;
     if (pr < 0.0) pr = 0.0;
     L[b] = log10(pr);
     M = fmax(M, L[b]);
@@ -46,13 +49,15 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
 #pragma unroll
   for (int b = 0; b < 5; ++b) c.L[b] = L[b];
   c.M = M;
-  a.coldT[(((size_t)st * p.n_mq + (mapq - p.mq_min)) * a.Q + q) * 5u + obs] = c;
+  a.coldT[((((size_t)st * p.n_mq + (mapq - p.mq_min)) * a.Q + q) * W + rr) * 5u + obs] = c;
   if (ms != a.hot_slot) return;
-  HotRatios h;
+  if (p.n_hot) {
+    HotRatios h;
 #pragma unroll
-  for (int b = 0; b < 5; ++b) h.r[b] = r[b];
-  h.M = M;
-  a.hotR[((size_t)st * a.Q + q) * 5u + obs] = h;
+    for (int b = 0; b < 5; ++b) h.r[b] = r[b];
+    h.M = M;
+    a.hotR[((size_t)st * a.Q + q) * 5u + obs] = h;
+  }
   if (obs < 4u && q >= p.t_qlo && q < p.t_qlo + p.t_nq) {
     double* d = reinterpret_cast<double*>(reinterpret_cast<char*>(a.tallyT) + (size_t)obs * p.t_stride + ((size_t)st * p.t_nq + (q - p.t_qlo)) * 64u);
 #pragma unroll
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
 }
 
 void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s) {
-  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * 5u;
+  const uint32_t n_cls = a.n_st * a.n_mapq_slots * a.Q * p.n_rpos * p.n_rep * 5u;
   if (!n_cls) return;
   build_tables_kernel<<<(n_cls + 255) / 256, 256, 0, s>>>(a, p);
   note_launches(1);

@@ -79,7 +79,7 @@ typedef struct brq_stream_info {
   uint64_t n_score_padded;         /* words in score_rec: round-major, lane-interleaved, padded (csrc/brq_types.h) */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
-  uint32_t hist_record_bytes, reserved;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files */
+  uint32_t hist_record_bytes, side_stride;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files; words per side-list entry (2 with read_pos / base_repeat) */
   uint64_t n_side;                 /* side-list entries (scoring records outside the shared table, X1 >= 511) */
   uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_words;  /* geometry baked into score_rec */
   const uint32_t* score_rec;       /* host views, valid until the next staging call; word layout: csrc/brq_types.h */

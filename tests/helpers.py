@@ -43,6 +43,14 @@ DATASETS = {
                  read_sets=[dict(name="amp", paired=False, read_len=100, coverage=1400.0)],
                  n_polymorphic=10, n_fixed=3, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
                  precision=1e-6, places=8, del_prop=100.0, del_seed=0.0),
+    # stand-in for BASELINE configs[3]: se36 + pe50 read groups (3 read files), polymorphism mode, and the
+    # read_pos covariate in BOTH passes: every scoring record is a class of its own table row (no shared table)
+    "ltee": dict(seed=13, contig_lens=[3000], prefix="ltee",
+                 read_sets=[dict(name="s36", paired=False, read_len=36, coverage=35.0),
+                            dict(name="p50", paired=True, read_len=50, coverage=50.0, frag_mean=160, frag_sd=15)],
+                 n_polymorphic=12, n_fixed=4, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
+                 precision=1e-6, places=8, del_prop=8.0, del_seed=0.0,
+                 covariates="read_set=3,obs_base,ref_base,quality=42,read_pos=50,base_repeat=4", big_table=True),
 }
 
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_cli")  # the reference's own sources (oracle/ref_build.sh)
@@ -66,7 +74,15 @@ def readfile_names(d):
 
 
 def covariates(d, n_qual=42):
+    if d.get("covariates"):
+        return d["covariates"]
     return "read_set=%d,obs_base,ref_base,quality=%d" % (len(readfile_names(d)), n_qual)
+
+
+def stage_kwargs(d):
+    """Staging options a dataset's covariate string asks for (brq_stage_options.use_read_pos / use_base_repeat)."""
+    c = covariates(d)
+    return dict(read_file_sets=read_file_sets(d), use_read_pos="read_pos" in c, use_base_repeat="base_repeat" in c)
 
 
 def run_oracle(*args):
@@ -134,7 +150,8 @@ def run_reference(d, outdir, per_position=True, coverage_tsv=False):
 
 def pass_output_names(d):
     """Files the two entry points write for a dataset (the drop-in boundary's file contract)."""
-    names = ["error_rates.tab", "ra_mc_evidence.gd"]
+    # a table with read_pos / base_repeat has 10^5 .. 10^6 rows: its golden is a checksum (test_golden.py), not a copy
+    names = ["ra_mc_evidence.gd"] if d.get("big_table") else ["error_rates.tab", "ra_mc_evidence.gd"]
     names += ["base_qual_error_prob.%s.tab" % rf for rf in readfile_names(d)]
     names += ["%d.unique_only_coverage_distribution.tab" % g for g in range(len(d["contig_lens"]))]
     return names

@@ -31,6 +31,9 @@ def sha256(path):
 def assert_same_files(d, got_dir, want_dir, label):
     for f in helpers.pass_output_names(d):
         assert filecmp.cmp(os.path.join(got_dir, f), os.path.join(want_dir, f), shallow=False), "%s: %s differs" % (label, f)
+    if d.get("big_table"):
+        want = open(os.path.join(want_dir, "error_rates.tab.sha256")).read().split()[0]
+        assert sha256(os.path.join(got_dir, "error_rates.tab")) == want, "%s: error_rates.tab differs" % label
 
 
 @pytest.mark.parametrize("name", NAMES)

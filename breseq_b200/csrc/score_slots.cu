@@ -52,6 +52,7 @@ constexpr int RING = 4;           // 16-byte stages of each lane's record ring (
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts
 constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
+constexpr int FIT_REG = 8;        // records per lane whose ratios stay in registers over the whole fit (slots up to 256 entries)
 constexpr uint32_t CODE_NONE = 0xFFFFFFFFu, CODE_COLD = 0x80000000u;
 
 struct f64x2 { double x, y; };
@@ -458,6 +459,13 @@ struct GroupCtx {
   uint32_t sub, mask;     // lane within the group, shuffle mask of the group
 };
 
+// 1 / x for x in (0, 5]: the hardware's 2^-23 approximation and two Newton steps (a couple of ulp; the EM stops at 1e-6)
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  return fma(fma(-x, r, 1.0), r, r);
+}
 __device__ __forceinline__ double group_sum(double v, uint32_t mask) {
 #pragma unroll
   for (int o = FIT_LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
@@ -513,7 +521,7 @@ __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, do
 
 }  // namespace
 
-__global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+__global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                                                           const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                           const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
                                                           const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
@@ -547,25 +555,75 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
     g.base = off[slot]; g.beg = 0; g.n_main = cnt[slot]; g.end = g.n_main;
     g.side = side; g.side_beg = side_off[slot]; g.side_stride = side_stride;
     g.end += side_off[slot + 1] - g.side_beg;
+    // what closes the slot, requested before anything waits on the records
+    const uint32_t ref = slot_ref[slot];
+    const double consensus = out[slot].consensus_score;
+    uint32_t bits = out[slot].bits;
+    // A slot of ordinary depth (up to 256 entries) keeps each lane's records' ratios in registers: its records are
+    // requested together (one round trip to DRAM instead of one per step), and the EM iterations, each a dependent
+    // chain, run without a load.
+    const bool in_regs = g.end - g.beg <= (uint64_t)(FIT_LANES * FIT_REG);
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
-    for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-      const uint2 rx = classic_at(g, i);
-      const uint32_t r = rx.x;
-      const uint32_t code = code_of(g, rx);
-      if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
-      if (code == CODE_NONE) continue;
+    double R[FIT_REG][5], Mr[FIT_REG];
+    bool ok[FIT_REG];
+    uint32_t k_max = 0;  // records per lane that hold anything (warp-uniform)
+    if (in_regs) {
+      uint2 rx[FIT_REG];
 #pragma unroll
-      for (int b = 0; b < 5; ++b) obs_count[b] += ((r & 7) == (uint32_t)b);
-      ++n;
+      for (int k = 0; k < FIT_REG; ++k) {
+        const uint64_t i = g.beg + g.sub + (uint64_t)k * FIT_LANES;
+        rx[k] = i < g.end ? classic_at(g, i) : make_uint2(0u, 0u);
+      }
+      // the scoring records are packed to the front (in index order) through the code cache, so that the loops below
+      // run over ceil(n / 32) records per lane instead of over every entry
+      uint32_t n_before = 0;
+#pragma unroll
+      for (int k = 0; k < FIT_REG; ++k) {
+        const uint32_t code = code_of(g, rx[k]);
+        const bool valid = code != CODE_NONE;
+        const uint32_t m = __ballot_sync(g.mask, valid);
+        if (valid) {
+          my_cache[n_before + __popc(m & ((1u << g.sub) - 1u))] = code;
+#pragma unroll
+          for (int b = 0; b < 5; ++b) obs_count[b] += ((rx[k].x & 7) == (uint32_t)b);
+          ++n;
+        }
+        n_before += __popc(m);
+      }
+      __syncwarp(g.mask);
+      k_max = (n_before + FIT_LANES - 1) / FIT_LANES;
+#pragma unroll
+      for (int k = 0; k < FIT_REG; ++k) {
+        Mr[k] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) R[k][b] = 0.0;
+        ok[k] = g.sub + (uint32_t)k * FIT_LANES < n_before;
+        if (ok[k]) load_ratios(g, my_cache[g.sub + (uint32_t)k * FIT_LANES], R[k], Mr[k]);
+      }
+      __syncwarp(g.mask);
+    } else {
+#pragma unroll
+      for (int k = 0; k < FIT_REG; ++k) {
+        ok[k] = false; Mr[k] = 0.0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) R[k][b] = 0.0;
+      }
+      for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+        const uint2 rx = classic_at(g, i);
+        const uint32_t r = rx.x;
+        const uint32_t code = code_of(g, rx);
+        if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
+        if (code == CODE_NONE) continue;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) obs_count[b] += ((r & 7) == (uint32_t)b);
+        ++n;
+      }
+      __syncwarp(g.mask);
     }
-    __syncwarp(g.mask);
 #pragma unroll
     for (int b = 0; b < 5; ++b) obs_count[b] = group_sum_u32(obs_count[b], g.mask);
     n = group_sum_u32(n, g.mask);
     if (n == 0) continue;
-    const uint32_t ref = slot_ref[slot];
-    const double consensus = out[slot].consensus_score;
-    uint32_t bits = out[slot].bits;
     const uint32_t best = bits & 7;
     bool recheck = (bits & CO_RECHECK) != 0;
     const double tol = p.precision_decimal, inv_n = 1.0 / (double)n, thr = 0.5 / (double)n;
@@ -585,6 +643,24 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
       uint32_t it = 1;
       for (; it <= 50; ++it) {
         double w[5] = {0, 0, 0, 0, 0};
+        if (in_regs) {
+          // branch-free, the four records' chains side by side: sums, then reciprocals, then responsibilities.
+          // (A record whose sum is zero contributes f itself, like the reference; an absent one contributes nothing:
+          // its ratios are zero and the select below drops it.)
+#pragma unroll
+          for (int k = 0; k < FIT_REG; ++k) {
+            if ((uint32_t)k >= k_max) break;  // warp-uniform
+            double a[5], sum = 0.0;
+#pragma unroll
+            for (int b = 0; b < 5; ++b) { a[b] = f[b] * R[k][b]; sum += a[b]; }
+            const double inv = sum > 1e-280 ? fast_rcp(sum) : 1.0 / (sum > 0.0 ? sum : 1.0);  // the approximation flushes subnormals
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+              const double term = sum > 0.0 ? a[b] * inv : f[b];
+              w[b] += ok[k] ? term : 0.0;
+            }
+          }
+        } else
         for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
           const uint32_t code = code_at(g, i);
           if (code == CODE_NONE) continue;
@@ -618,6 +694,20 @@ __global__ void __launch_bounds__(FIT_TPB, 3) fit_kernel(const uint32_t* __restr
       // sum_i (log10 s_i + M_i).  The s_i (each in (0, 1]) are multiplied up and one log10 is taken
       // per ~200 decades, which is the same sum to within a few ulps of its terms.
       double log_sum = 0.0, prod = 1.0, m_sum = 0.0;
+      if (in_regs) {
+#pragma unroll
+        for (int k = 0; k < FIT_REG; ++k) {
+          if ((uint32_t)k >= k_max) break;  // warp-uniform
+          if (!ok[k]) continue;
+          double sum = 0.0;
+#pragma unroll
+          for (int b = 0; b < 5; ++b) sum += f_prev[b] * R[k][b];
+          if (sum > 0.0) {
+            prod *= sum; m_sum += Mr[k];
+            if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
+          }
+        }
+      } else
       for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
         const uint32_t code = code_at(g, i);
         if (code == CODE_NONE) continue;

@@ -120,6 +120,7 @@ def load_library():
         "brq_columns_device": [C.c_void_p, P(C.c_void_p), P(C.c_uint64)],
         "brq_write_evidence": [C.c_void_p, C.c_char_p, P(C.c_double), P(C.c_double), C.c_uint32, C.c_int,
                                P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
+        "brq_d2h_bytes": [C.c_void_p, P(C.c_uint64), C.c_int],
         "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
@@ -145,7 +146,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
-           "brq_write_evidence", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
+           "brq_write_evidence", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
 
 
@@ -417,6 +418,11 @@ class Context:
         self._check(self.lib.brq_write_evidence(self.h, _b(gd_file), prop, seed, n, int(skip_missing_coverage_prediction),
                                                 C.byref(ra), C.byref(mc), C.byref(un)))
         return {"RA": ra.value, "MC": mc.value, "UN": un.value}
+
+    def d2h_bytes(self, reset=False):
+        n = C.c_uint64()
+        self.lib.brq_d2h_bytes(self.h, C.byref(n), int(reset))
+        return n.value
 
     def write_per_position_file(self, path, deletion_propagation_cutoff):
         """The reference's per-position debug file (identify_mutations.cpp:1693-1733)."""

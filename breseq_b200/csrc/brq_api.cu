@@ -90,10 +90,16 @@ struct brq_ctx {
   float ms_tally = 0, ms_fit = 0;
   DevBuf<ColumnOut> d_cols, d_fcols;
   DevBuf<WalkOut> d_walk;
-  WalkOut* h_walk = nullptr;        // pinned: what the host's interval walk reads of every column
-  size_t h_walk_n = 0;
+  DevBuf<WalkEvent> d_events;
+  DevBuf<uint8_t> d_mark;
+  DevBuf<uint32_t> d_seg_first, d_seg_last;
+  DevBuf<double> d_seg_prop;
+  DevBuf<uint64_t> d_ins_parent;
+  std::vector<WalkEvent> h_events;  // the columns the host's interval walk has to look at
+  std::vector<double> walk_prop;    // the propagation cutoffs h_events was compacted for
   std::vector<ColumnOut> h_fcols;   // full results of the flagged slots, in the order of h_flagged
   bool have_walk = false;
+  uint64_t d2h_bytes = 0;           // device -> host bytes since the last brq_d2h_bytes(reset) (bench bookkeeping)
 
   CovSpec spec;
   bool have_spec = false, have_table = false, have_counts = false, have_cols = false;
@@ -263,6 +269,7 @@ void download_hist(brq_ctx* c) {
   c->h_cov.resize(c->cov_stride * c->n_groups);
   CUDA_OK(cudaMemcpyAsync(c->h_counts.data(), c->d_counts.p, c->h_counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->h_cov.data(), c->d_cov.p, c->h_cov.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += (c->h_counts.size() + c->h_cov.size()) * 8;
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
@@ -319,6 +326,7 @@ void derive_table(brq_ctx* c) {
   CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
   c->h_log10.resize(lay.n_bins);
   CUDA_OK(cudaMemcpyAsync(c->h_log10.data(), c->d_log10.p, (size_t)lay.n_bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  c->d2h_bytes += (uint64_t)lay.n_bins * 8;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaEventElapsedTime(&c->ms_derive, c->ev[3], c->ev[4]));
   install_table(c);
@@ -373,34 +381,6 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->h_cols.clear();
 }
 
-// What the evidence writer needs of the device results: the 8-byte walk records of every column (pinned), the flagged
-// list, and the full 96-byte results of the flagged slots only.
-void download_walk(brq_ctx* c) {
-  if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
-  const uint64_t n_slots = c->st.n_slots();
-  if (c->h_walk_n < n_slots) {
-    if (c->h_walk) cudaFreeHost(c->h_walk);
-    c->h_walk = nullptr; c->h_walk_n = 0;
-    CUDA_OK(cudaHostAlloc((void**)&c->h_walk, (n_slots ? n_slots : 1) * sizeof(WalkOut), cudaHostAllocDefault));
-    c->h_walk_n = n_slots;
-  }
-  uint32_t scal[2];
-  CUDA_OK(cudaMemcpyAsync(scal, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->h_walk, c->d_walk.p, n_slots * sizeof(WalkOut), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_OK(cudaStreamSynchronize(c->stream));
-  if (scal[1] > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
-  c->h_flagged.resize(scal[1]);
-  c->h_fcols.resize(scal[1]);
-  if (scal[1]) {
-    c->d_fcols.ensure(scal[1]);
-    launch_gather_columns(c->d_cols.p, c->d_flagged.p, scal[1], c->d_fcols.p, c->stream);
-    CUDA_OK(cudaMemcpyAsync(c->h_flagged.data(), c->d_flagged.p, (size_t)scal[1] * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaMemcpyAsync(c->h_fcols.data(), c->d_fcols.p, (size_t)scal[1] * sizeof(ColumnOut), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-  }
-  c->have_walk = true;
-}
-
 void download_columns(brq_ctx* c) {
   if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
   const uint64_t n_slots = c->st.n_slots();
@@ -414,12 +394,67 @@ void download_columns(brq_ctx* c) {
   if (scal[1]) CUDA_OK(cudaMemcpy(c->h_flagged.data(), c->d_flagged.p, (size_t)scal[1] * 4, cudaMemcpyDeviceToHost));
 }
 
+// What the evidence writer needs of the device results: the walk records of the event columns (compacted on the device:
+// a few thousand of 4.6 M at C1), the flagged list, and the full 96-byte results of the flagged slots only.
+void download_walk(brq_ctx* c, const double* prop, uint32_t n_targets) {
+  if (!c->have_cols) throw std::runtime_error("brq_score_columns has not run");
+  const PileupStream& st = c->st;
+  const uint64_t n_slots = st.n_slots();
+  uint32_t scal[2];
+  CUDA_OK(cudaMemcpyAsync(scal, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (scal[1] > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
+  const uint32_t n_flagged = scal[1];
+  // segments of the visit order with their cutoffs
+  std::vector<uint32_t> first, last;
+  std::vector<double> sp;
+  for (const Segment& sg : st.segments) {
+    if (sg.hi <= sg.lo) continue;
+    first.push_back((uint32_t)sg.slot0); last.push_back((uint32_t)(sg.slot0 + (uint64_t)(sg.hi - sg.lo) - 1));
+    sp.push_back(prop[(size_t)sg.tid]);
+  }
+  c->h_events.clear();
+  if (!first.empty() && st.n_base) {
+    const uint32_t n_seg = (uint32_t)first.size();
+    c->d_seg_first.ensure(n_seg); c->d_seg_last.ensure(n_seg); c->d_seg_prop.ensure(n_seg);
+    c->d_mark.ensure(st.n_base); c->d_events.ensure(st.n_base); c->d_ins_parent.ensure(st.n_ins ? st.n_ins : 1);
+    CUDA_OK(cudaMemcpyAsync(c->d_seg_first.p, first.data(), n_seg * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_seg_last.p, last.data(), n_seg * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_seg_prop.p, sp.data(), n_seg * 8, cudaMemcpyHostToDevice, c->stream));
+    if (st.n_ins) CUDA_OK(cudaMemcpyAsync(c->d_ins_parent.p, st.ins_parent.data(), st.n_ins * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 3, 0, 4, c->stream));  // scalars[3]: the fit kernel's hand-out counter, free again
+    launch_walk_events(c->d_walk.p, st.n_base, c->d_seg_first.p, c->d_seg_last.p, c->d_seg_prop.p, n_seg, c->d_flagged.p,
+                       c->d_scalars.p + 1, c->flagged_cap, c->d_ins_parent.p, c->d_mark.p, c->d_events.p, c->d_scalars.p + 3, c->stream);
+    uint32_t n_events = 0;
+    CUDA_OK(cudaMemcpyAsync(&n_events, c->d_scalars.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->h_events.resize(n_events);
+    if (n_events) CUDA_OK(cudaMemcpyAsync(c->h_events.data(), c->d_events.p, (size_t)n_events * sizeof(WalkEvent), cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->h_flagged.resize(n_flagged);
+  c->h_fcols.resize(n_flagged);
+  if (n_flagged) {
+    c->d_fcols.ensure(n_flagged);
+    launch_gather_columns(c->d_cols.p, c->d_flagged.p, n_flagged, c->d_fcols.p, c->stream);
+    CUDA_OK(cudaMemcpyAsync(c->h_flagged.data(), c->d_flagged.p, (size_t)n_flagged * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->h_fcols.data(), c->d_fcols.p, (size_t)n_flagged * sizeof(ColumnOut), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  (void)n_slots;
+  c->d2h_bytes += 12 + c->h_events.size() * sizeof(WalkEvent) + (uint64_t)n_flagged * (4 + sizeof(ColumnOut));
+  c->walk_prop.assign(prop, prop + n_targets);
+  c->have_walk = true;
+}
+
 EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, const double* seed, uint32_t n_targets, int skip_mc) {
   const bool timing = getenv("BRQ_TIMING") != nullptr;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   const auto t0 = now();
-  if (!c->have_walk) download_walk(c);
+  if (n_targets != c->hdr.target_names.size())
+    throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
+                             "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
+  if (!c->have_walk || c->walk_prop != std::vector<double>(prop, prop + n_targets)) download_walk(c, prop, n_targets);
   const auto t1 = now();
   if (n_targets != c->hdr.target_names.size())
     throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
@@ -436,7 +471,7 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
   ensure_host_lut(c);
   const auto t2 = now();
-  const EvidenceCounts k = write_evidence(gd_file, c->hdr, c->st, c->h_walk, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep);
+  const EvidenceCounts k = write_evidence(gd_file, c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep);
   if (timing) fprintf(stderr, "[brq] evidence: download %.2f ms, lut %.2f ms, write_evidence %.2f ms (%zu flagged, %llu RA)\n",
                       ms(t0, t1), ms(t1, t2), ms(t2, now()), c->h_flagged.size(), (unsigned long long)k.ra);
   return k;
@@ -492,7 +527,7 @@ void brq_destroy(brq_ctx* c) {
     c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
-    if (c->h_walk) cudaFreeHost(c->h_walk);
+    c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -671,6 +706,13 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
     write_coverage_tsv(pattern, c->hdr, c->ref, c->st, c->h_cols);
   });
+}
+
+int brq_d2h_bytes(brq_ctx* c, uint64_t* bytes, int reset) {
+  if (!c) return 1;
+  if (bytes) *bytes = c->d2h_bytes;
+  if (reset) c->d2h_bytes = 0;
+  return 0;
 }
 
 int brq_launch_count(void) { return launch_count(); }

@@ -1,6 +1,7 @@
 #include "finalize.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -10,8 +11,10 @@
 #include <functional>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 namespace brq {
 
@@ -137,12 +140,24 @@ void read_error_rates(const std::string& path, CovSpec& c, std::vector<double>& 
 }
 
 void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& text, std::vector<double>& prob) {
-  text.resize(log10_prob.size());
-  prob.resize(log10_prob.size());
-  for (size_t i = 0; i < log10_prob.size(); ++i) {
-    text[i] = strtod(format_default(log10_prob[i]).c_str(), nullptr);
-    prob[i] = pow(10, text[i]);
-  }
+  const size_t n = log10_prob.size();
+  text.resize(n);
+  prob.resize(n);
+  auto run = [&](size_t lo, size_t hi) {
+    char buf[64];
+    for (size_t i = lo; i < hi; ++i) {
+      snprintf(buf, sizeof buf, "%.6g", log10_prob[i]);  // format_default
+      text[i] = strtod(buf, nullptr);
+      prob[i] = pow(10, text[i]);
+    }
+  };
+  // every entry is independent: a few threads for the default table (2100 rows), more for tables with read_pos
+  const size_t n_threads = n < 1024 ? 1 : std::min<size_t>(n < 65536 ? 4 : 16, std::max(1u, std::thread::hardware_concurrency()));
+  if (n_threads == 1) { run(0, n); return; }
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < n_threads; ++t) th.emplace_back(run, n * t / n_threads, n * (t + 1) / n_threads);
+  run(0, n / n_threads);
+  for (auto& x : th) x.join();
 }
 
 // error_count.cpp:697-785, index arithmetic restated literally (accumulate obs-major, read out b1*5+b2).
@@ -585,7 +600,7 @@ struct GdRow {
 }  // namespace
 
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
-                              const WalkOut* walk, const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
+                              const std::vector<WalkEvent>& events_in, const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
   EvidenceCounts counts;
   const double nan = std::numeric_limits<double>::quiet_NaN();
@@ -596,12 +611,19 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   std::vector<uint32_t> flagged(order.size());
   for (size_t i = 0; i < order.size(); ++i) flagged[i] = flagged_in[order[i]];
 
+  // the columns the interval walk has to look at, in ascending order (the device appends them in no particular order)
+  std::vector<WalkEvent> events(events_in);
+  std::sort(events.begin(), events.end(), [](const WalkEvent& a, const WalkEvent& b) { return a.slot < b.slot; });
+
   // ---- re-evaluate flagged slots in arrival order
   struct Reval { bool base_predicted; bool emit; GdRow row; };
   std::vector<Reval> reval(flagged.size());  // aligned with `flagged`
+  // first the records of every flagged slot (the class table fills in on demand: not thread-safe), then the fits, the
+  // profile-likelihood bounds and the bias tests of the slots side by side on a few threads: they are independent
+  std::vector<SlotEval> evals(flagged.size());
   for (size_t fi = 0; fi < flagged.size(); ++fi) {
     const uint32_t slot = flagged[fi];
-    SlotEval s;
+    SlotEval& s = evals[fi];
     memset(s.count, 0, sizeof s.count);
     for_each_classic(st, slot, [&](uint32_t r, uint32_t, uint32_t ext) {
       const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
@@ -613,12 +635,16 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
       s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
       ++s.count[obs][top];
     });
+  }
+  std::vector<uint8_t> overturned(flagged.size(), 0);
+  auto evaluate_one = [&](size_t fi) {
+    const uint32_t slot = flagged[fi];
+    SlotEval& s = evals[fi];
     const uint8_t ref = st.slot_ref[slot];
     evaluate_slot(s, ref, ep);
-    ++counts.rechecked;
     const ColumnOut& co = flagged_cols[order[fi]];
     const bool dev_emit = (co.bits & CO_EMIT) != 0, dev_pred = (co.bits & CO_BASE_PREDICTED) != 0;
-    if (dev_pred != s.base_predicted || (dev_emit && !s.emit)) ++counts.overturned;
+    if (dev_pred != s.base_predicted || (dev_emit && !s.emit)) overturned[fi] = 1;
     Reval rv;
     rv.base_predicted = s.base_predicted;
     rv.emit = s.emit;
@@ -695,7 +721,24 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
       row.kv["total_cov"] = std::to_string(tot_top) + "/" + std::to_string(tot_bot);
     }
     reval[fi] = std::move(rv);
+  };
+  {
+    const size_t n_threads = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), (flagged.size() + 3) / 4);
+    std::atomic<size_t> next{0};
+    std::exception_ptr failure;
+    std::mutex failure_lock;
+    auto worker = [&] {
+      try { for (size_t fi; (fi = next.fetch_add(1)) < flagged.size();) evaluate_one(fi); }
+      catch (...) { std::lock_guard<std::mutex> g(failure_lock); if (!failure) failure = std::current_exception(); }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < n_threads; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& x : th) x.join();
+    if (failure) std::rethrow_exception(failure);
   }
+  counts.rechecked = flagged.size();
+  for (uint8_t o : overturned) counts.overturned += o;
 
   const bool timing = getenv("BRQ_TIMING") != nullptr;
   const auto t_reval = std::chrono::steady_clock::now();
@@ -707,6 +750,7 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   struct Cov { double unique, redundant; int total; };
   size_t ins_cursor = 0;  // ins slots are ordered by (parent, insert_count)
   // base slots are visited in ascending order and so are the insert sub-column slots: two cursors over the flagged list
+  size_t ev_cur = 0;
   size_t base_cur = 0, ins_cur = std::lower_bound(flagged.begin(), flagged.end(), (uint32_t)std::min<uint64_t>(st.n_base, 0xFFFFFFFFull)) - flagged.begin();
   auto find_reval = [&](size_t& cur, uint64_t slot) -> const Reval* {
     while (cur < flagged.size() && flagged[cur] < slot) ++cur;
@@ -757,10 +801,15 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
         unknown_start = UNDEF;
       }
     };
+    // Only the event columns are walked: between two of them every column has unique coverage above the propagation
+    // cutoff and a predicted base, no interval is open, and all such a column does to the state is overwrite `last`,
+    // which the column before the next event overwrites again (it is an event itself: the neighbour of a non-boring one).
+    while (ev_cur < events.size() && events[ev_cur].slot < sg.slot0) ++ev_cur;
     if (prop >= 0.0) {
-      for (int32_t c = sg.lo; c < sg.hi; ++c) {
-        const uint64_t slot = sg.slot0 + (uint64_t)(c - sg.lo);
-        const WalkOut& wo = walk[slot];  // written by the tally kernel from the same sums the full result holds
+      for (; ev_cur < events.size() && events[ev_cur].slot < sg.slot0 + (uint64_t)(sg.hi - sg.lo); ++ev_cur) {
+        const uint64_t slot = events[ev_cur].slot;
+        const int32_t c = sg.lo + (int32_t)(slot - sg.slot0);
+        const WalkOut& wo = events[ev_cur].w;  // written by the tally kernel from the same sums the full result holds
         Cov cv;
         cv.unique = (double)wo.unique;
         cv.redundant = (wo.packed & 2u) ? 1.0 : 0.0;  // only its sign is looked at

@@ -73,7 +73,7 @@ struct EvidenceCounts { uint64_t ra = 0, mc = 0, un = 0, rechecked = 0, overturn
 
 // `shard_first_col1` etc. are not needed: the stream knows its segments.
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
-                              const WalkOut* walk, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
+                              const std::vector<WalkEvent>& events, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
 
 // Optional outputs of pass 2 (identify_mutations.cpp:1693-1733 and :2028-2052, 2173-2204); both read the full per-slot results.

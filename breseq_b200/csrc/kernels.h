@@ -43,6 +43,10 @@ static_assert(sizeof(ColumnOut) == 96, "ColumnOut must stay 96 bytes");
 // instead of the 96-byte result.  packed = total << 2 | (redundant > 0) << 1 | base_predicted, with
 // total = round(unique) + round(redundant) as the reference computes it.
 struct WalkOut { uint32_t unique, packed; };
+// A column the interval walk has to look at: the state machines only change state at columns whose unique coverage is at
+// or below the propagation cutoff, that are not predicted, that are flagged for host re-evaluation, or that open / close a
+// target; the walk needs those columns and their two neighbours (the flank coverages of an MC row), nothing else.
+struct WalkEvent { uint32_t slot; WalkOut w; };
 
 constexpr uint32_t CO_BASE_PREDICTED = 1u << 12, CO_UNIQUE_ONLY = 1u << 13, CO_EMIT = 1u << 14, CO_RECHECK = 1u << 15,
                    CO_FIT = 1u << 24;
@@ -94,6 +98,13 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
                         ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between);
+// Compacts the walk records to the columns the host's interval walk needs (WalkEvent), in no particular order.
+// seg_first / seg_last / seg_prop: first slot, last slot and deletion propagation cutoff of every visited segment
+// (cutoff < 0: the target is skipped); mark: scratch of n_base bytes; counter: one zeroed word.
+void launch_walk_events(const WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
+                        const double* seg_prop, uint32_t n_seg, const uint32_t* flagged, const uint32_t* n_flagged,
+                        uint32_t flagged_cap, const uint64_t* ins_parent, uint8_t* mark, WalkEvent* events, uint32_t* counter,
+                        cudaStream_t s);
 // out[i] = cols[slots[i]]: the full results of the flagged slots, for the host re-evaluation
 void launch_gather_columns(const ColumnOut* cols, const uint32_t* slots, uint32_t n, ColumnOut* out, cudaStream_t s);
 

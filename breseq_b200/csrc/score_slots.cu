@@ -780,6 +780,49 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   note_launches(2);
 }
 
+// ------------------------------------------------------------------------------------------ walk events
+__global__ void walk_mark_kernel(const WalkOut* __restrict__ walk, uint64_t n_base, const uint32_t* __restrict__ seg_first,
+                                 const uint32_t* __restrict__ seg_last, const double* __restrict__ seg_prop, uint32_t n_seg,
+                                 uint8_t* __restrict__ mark) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_base) return;
+  uint32_t lo = 0, hi = n_seg;  // the segment that holds slot c
+  while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_first[mid] <= c) lo = mid; else hi = mid; }
+  const double prop = seg_prop[lo];
+  const WalkOut w = walk[c];
+  const bool edge = c == seg_first[lo] || c == seg_last[lo];
+  mark[c] = prop >= 0.0 && (edge || (double)w.unique <= prop || !(w.packed & 1u));
+}
+
+__global__ void walk_mark_flagged_kernel(const uint32_t* __restrict__ flagged, const uint32_t* __restrict__ n_flagged, uint32_t cap,
+                                         uint64_t n_base, const uint64_t* __restrict__ ins_parent, uint8_t* __restrict__ mark) {
+  const uint32_t n = min(*n_flagged, cap);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = flagged[i];
+    mark[slot < n_base ? (uint64_t)slot : ins_parent[slot - n_base]] = 1;  // an insert sub-column's RA row follows its parent column
+  }
+}
+
+__global__ void walk_compact_kernel(const WalkOut* __restrict__ walk, const uint8_t* __restrict__ mark, uint64_t n_base,
+                                    WalkEvent* __restrict__ events, uint32_t* __restrict__ counter) {
+  const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_base) return;
+  const bool keep = mark[c] || (c > 0 && mark[c - 1]) || (c + 1 < n_base && mark[c + 1]);
+  if (keep) events[atomicAdd(counter, 1u)] = WalkEvent{(uint32_t)c, walk[c]};
+}
+
+void launch_walk_events(const WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
+                        const double* seg_prop, uint32_t n_seg, const uint32_t* flagged, const uint32_t* n_flagged,
+                        uint32_t flagged_cap, const uint64_t* ins_parent, uint8_t* mark, WalkEvent* events, uint32_t* counter,
+                        cudaStream_t s) {
+  if (!n_base || !n_seg) return;
+  const uint32_t blocks = (uint32_t)((n_base + 255) / 256);
+  walk_mark_kernel<<<blocks, 256, 0, s>>>(walk, n_base, seg_first, seg_last, seg_prop, n_seg, mark);
+  walk_mark_flagged_kernel<<<64, 256, 0, s>>>(flagged, n_flagged, flagged_cap, n_base, ins_parent, mark);
+  walk_compact_kernel<<<blocks, 256, 0, s>>>(walk, mark, n_base, events, counter);
+  note_launches(3);
+}
+
 __global__ void gather_columns_kernel(const ColumnOut* __restrict__ cols, const uint32_t* __restrict__ slots, uint32_t n, ColumnOut* __restrict__ out) {
   // six 16-byte pieces per result
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

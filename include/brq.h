@@ -157,6 +157,8 @@ int brq_write_evidence(brq_ctx* ctx, const char* gd_file, const double* deletion
  * brq_write_coverage_tsv: <seq>.coverage.tsv of --predict-copy-number (identify_mutations.cpp:2028-2052, 2173-2204,
  *   Settings::complete_coverage_text_file_name); '@' in `pattern` is replaced by the target name.  The per-read-group
  *   columns the reference adds for runs with more than one read group are not written. */
+/* bytes the context has copied device -> host since the last reset (histograms, error table, walk events, flagged slots) */
+int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
 int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
 

@@ -1,28 +1,35 @@
-// Per-slot scoring for sm_100a: a streaming tally kernel and an EM fit kernel.
+// Per-slot scoring for sm_100a: a streaming tally kernel, an EM fit kernel, and two small kernels that compact what
+// the host's finalisation reads.
 //
-//   tally_kernel  One thread per slot, a warp per 32 consecutive slots, persistent CTAs.  The kernel COUNTS FIRST AND
-//                 MULTIPLIES ONCE: a scoring record that matches its slot's reference base (all but ~0.1 % of them)
-//                 only increments a byte counter of its (read set, strand, quality) class in the lane's private
-//                 histogram in shared memory; when the slot's records are in, the counts are contracted with the
-//                 likelihood table {L[0..4], M} of the dominant MAPQ: sums[b] += count * L[class][b], one fused
-//                 multiply-add per class and hypothesis (identify_mutations.cpp:1392-1658, 3359-3384, 3398-3433).
-//                 A record-by-record kernel reads 48 bytes of table per record and is bound by shared-memory
-//                 bandwidth at about a third of the HBM rate; counting costs one address operation and a byte
-//                 increment per record, and the contraction (about 1200 instructions per slot, independent of depth)
-//                 walks the table with warp-uniform class index, so the 32 lanes read at most four different cells
-//                 (one per reference base) per load: one wavefront.
-//   histogram     word w of lane l lives at w * 128 + l * 4 of the warp's block: any mix of classes is bank-conflict
-//                 free, and the block is aligned to its size, so a counter's address is (record & 0x1FFF) | lane base.
-//                 Counters are bytes: a slot deeper than 252 records is contracted every 63 vectors.
-//                 Records that are not class counts (idle, redundant, cold, HOT-but-mismatching, padding) increment
-//                 special counters, so the loop is branch-free except for the rare mismatching HOT record, which
-//                 reads its own table cell, and the leading redundant records.
-//   record ring   Every lane streams its slot's 128-bit vectors through a private four-stage ring in shared memory
-//                 with cp.async (LDGSTS): four vectors per lane are always on their way without holding registers.
-//                 The first vectors of a warp's NEXT round are requested before the contraction of the current one,
-//                 and that round's whole region (32 consecutive runs) is pulled into L2 a round ahead.
+//   tally_kernel  One thread per slot, a warp per ROUND of 32 slots (staging groups them: one reference base, nearly
+//                 equal depth), persistent CTAs of 24 warps.  The kernel COUNTS FIRST AND MULTIPLIES ONCE: a scoring
+//                 record that matches its slot's reference base (all but ~0.1 % of them) only increments a byte counter
+//                 of its (read set, strand, quality) class in the lane's private histogram in shared memory; when the
+//                 round's records are in, the counts are contracted with the likelihood table of the round's base:
+//                     sums[slot][column] += counts[slot][class] x table[class][column]
+//                 (identify_mutations.cpp:1392-1658, 3359-3384, 3398-3433).
+//   counting      red.shared.add.u32 of 1 << 8*byte on the counter's word (ATOMS.ADD without return: no dependent
+//                 chain).  Word w of lane l lives at w * 128 + l * 4 of the warp's block: any mix of classes is
+//                 bank-conflict free, and the block is aligned to its size, so the address is
+//                 (record & 0x1F80) | lane base and the shift is record & 31.  Records that are not class counts (idle,
+//                 redundant, cold, HOT-but-mismatching, padding) increment special counters, so the loop is branch-free
+//                 except for one test per vector for the rare mismatching HOT record, which reads its own table cell.
+//                 Counters are bytes: a round deeper than 224 records is contracted every 28 vectors.
+//   contraction   on the fp64 tensor pipe: mma.sync.m8n8k4.f64 (DMMA.8x8x4), A = the byte counters of eight slot
+//                 lanes for one class word (four classes), B = the four table rows {L[0..4], M, top, bottom}; four
+//                 8-slot tiles per class word share B.  The last two columns count the matching records by strand.
+//                 Why the tensor pipe: a record-by-record kernel reads 48 bytes of table per record and a per-lane
+//                 contraction reads 48 bytes per class, both from shared memory at 12 wavefronts per 32 lookups (a
+//                 128-bit shared load takes four passes even when the lanes broadcast): the data pipe, not HBM, was
+//                 the bound.  Only register reuse of the table escapes it, and that is what the MMA fragments are.
+//   record ring   The stream is round-major and lane-interleaved (brq_types.h): a warp streams the round's 1 KB
+//                 vectors through a four-stage ring in shared memory with cp.async (two coalesced 16-byte copies per
+//                 lane and vector); wait_group counts them in order.  The next round's first vectors are requested
+//                 before the contraction of the current one, the rest of it goes to L2 with one bulk prefetch per
+//                 warp; slot numbers are read two rounds ahead, the slots' geometry one round ahead.
 //   cold records  Scoring records outside the shared table (another MAPQ, a '.' observation, a quality outside the
-//                 window) sit in the side list as classic words and read the global table of all MAPQ values.
+//                 window; every scoring record of a stream staged with read_pos / base_repeat) sit in the side list
+//                 as classic words and read the global table of all MAPQ values.
 //   redundant records  lead each slot's run (staging.cpp): their order-dependent sum of 1/X1
 //                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head: bit-exact.
 //   presence bound  The reference fits the 5-allele EM on every column, but its result only surfaces
@@ -35,9 +42,13 @@
 //                            >= n log10 g0[ref] + ll[ref],     g0[ref] >= (0.5 + c_ref) / (n + 2)
 //                 so  score <= (sum M - ll[ref]) - n log10((0.5 + c_ref)/(n + 2)) - log10(ref length).
 //                 Columns under the cutoff by a margin are final here; the others go to a work list.
-//   fit_kernel    one warp per work-list slot: the 5-allele EM fit, the presence score of the
-//                 top non-reference allele (second EM with it held out), emission flags
-//                 (identify_mutations.cpp:1797-1821, 3240-3344).
+//   fit_kernel    one warp per work-list slot: the 5-allele EM fit, the presence score of the top non-reference
+//                 allele (second EM with it held out), emission flags (identify_mutations.cpp:1797-1821, 3240-3344).
+//                 A slot of up to 256 entries packs its scoring records' ratios into registers once; an EM step is
+//                 then ceil(n / 32) records per lane, a Newton reciprocal each, and a 5-value butterfly.
+//   walk events   walk_mark / walk_compact kernels: the columns the host's MC / UN interval state machines have to see
+//                 (coverage at or below the propagation cutoff, not predicted, flagged, target ends, and their
+//                 neighbours), a few thousand of 4.6 M at C1; gather_columns: the full results of the flagged slots.
 #include "kernels.h"
 #include "brq_types.h"
 
@@ -66,11 +77,6 @@ __device__ __forceinline__ f64x2 ldg_f64x2(const void* p) {
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint4 ldg_stream_u32x4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
 
 // 16 bytes global -> shared without passing through registers (LDGSTS); completion is tracked per thread
 __device__ __forceinline__ void cp_async16(uint32_t shared_addr, const void* p) {
@@ -84,14 +90,6 @@ __device__ __forceinline__ uint4 lds_u32x4(uint32_t shared_addr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(shared_addr));
   return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t shared_addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_u8(uint32_t shared_addr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" :: "r"(shared_addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr) : "memory");
@@ -104,9 +102,6 @@ __device__ __forceinline__ void sts_u32(uint32_t shared_addr, uint32_t v) {
 __device__ __forceinline__ void red_count(uint32_t hist, uint32_t w) {
   const uint32_t addr = (w & DR_COUNTER_WORD_MASK) | hist, one = 1u << (w & 31u);
   asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(addr), "r"(one) : "memory");
-}
-__device__ __forceinline__ void sts_fill16(uint32_t shared_addr, uint32_t word) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(shared_addr), "r"(word) : "memory");
 }
 
 // ask L2 for [p, p + bytes) ahead of use (16-byte aligned, a multiple of 16 bytes)

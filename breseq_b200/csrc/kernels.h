@@ -89,7 +89,7 @@ inline uint32_t class_rr(uint32_t ext, const ScoreParams& p) {
 struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 
 // Shared-memory forms of the class terms for the dominant MAPQ, indexed ((set*2+top)*Q+qual)*5+obs.
-struct HotTerms { double L[5]; double M; };    // M = max_b L[b]
+struct alignas(32) HotTerms { double L[5]; double M; double pad[2]; };    // M = max_b L[b]; 64 bytes: one 256-bit and one 128-bit load
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,

@@ -138,9 +138,12 @@ __device__ __forceinline__ double exp10_neg(double d) {
 // a scoring record whose class is not in the shared table (classic word from the side list): {L[0..4], M} from the global table
 __device__ __forceinline__ void cold_add(Sums& a, uint32_t r, uint32_t ext, const HotTerms* __restrict__ coldT, const ScoreParams& p) {
   const uint32_t st = (r >> 10) & 63u, mapq = (r >> SR_MAPQ_SHIFT) & 255u, qual = (r >> SR_QUAL_SHIFT) & 127u;
-  const char* e = reinterpret_cast<const char*>(coldT + ((((size_t)(st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * (p.n_rpos * p.n_rep) + class_rr(ext, p)) * 5u + (r & 7u)));
-  const f64x2 x = ldg_f64x2(e), y = ldg_f64x2(e + 16), z = ldg_f64x2(e + 32);
-  a.l0 += x.x; a.l1 += x.y; a.l2 += y.x; a.l3 += y.y; a.l4 += z.x; a.m += z.y;
+  const HotTerms* e = coldT + ((((size_t)(st * p.n_mq + (mapq - p.mq_min)) * p.max_qual + qual) * (p.n_rpos * p.n_rep) + class_rr(ext, p)) * 5u + (r & 7u));
+  // 48 of the entry's 64 bytes in two requests (a scattered request costs the load unit per lane, not per byte)
+  double l0, l1, l2, l3;
+  asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(l0), "=d"(l1), "=d"(l2), "=d"(l3) : "l"(e));
+  const f64x2 z = ldg_f64x2(reinterpret_cast<const char*>(e) + 32);
+  a.l0 += l0; a.l1 += l1; a.l2 += l2; a.l3 += l3; a.l4 += z.x; a.m += z.y;
 }
 
 }  // namespace
@@ -430,7 +433,13 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     o.redundant[0] = red_bot; o.redundant[1] = red_top;
     o.unique[0] = u_bot; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
-    out[my_slot] = o;
+    {  // the 96-byte result in three 256-bit stores
+      const double* od = reinterpret_cast<const double*>(&o);
+      double* dst = reinterpret_cast<double*>(out + my_slot);
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst + 4 * j), "d"(od[4 * j]), "d"(od[4 * j + 1]), "d"(od[4 * j + 2]), "d"(od[4 * j + 3]) : "memory");
+    }
     {
       const double red = red_bot + red_top;  // the sums the host's interval walk would form from the full result
       const uint32_t total = (u_bot + u_top) + (uint32_t)(int)::round(red);

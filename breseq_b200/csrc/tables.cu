@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
   HotTerms c;
 #pragma unroll
   for (int b = 0; b < 5; ++b) c.L[b] = L[b];
-  c.M = M;
+  c.M = M; c.pad[0] = 0.0; c.pad[1] = 0.0;
   a.coldT[((((size_t)st * p.n_mq + (mapq - p.mq_min)) * a.Q + q) * W + rr) * 5u + obs] = c;
   if (ms != a.hot_slot) return;
   if (p.n_hot) {

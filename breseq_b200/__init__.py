@@ -254,11 +254,13 @@ def decode_score_records(stream):
     big = (kind == 3) & (x1 == 0x1FF)
     cold = kind == 2
     uses = big | cold
-    rank = np.cumsum(uses) - 1                       # index among all side-using records, in stream order
-    first = np.zeros(n_slots + 1, np.int64)
-    np.add.at(first, slot[uses] + 1, 1)
-    assert np.array_equal(np.cumsum(first), soff), "side_off does not match the records that use the side list"
-    entry = side[rank[uses]] if uses.any() else np.zeros(0, np.int64)
+    used = np.bincount(slot[uses], minlength=n_slots)   # entries every slot uses; its range is padded to an even count
+    assert np.array_equal(np.diff(soff), (used + 1) & ~1), "side_off does not match the records that use the side list"
+    before = np.cumsum(used) - used                      # side-using records before each slot
+    rank_in_slot = (np.cumsum(uses) - 1)[uses] - before[slot[uses]]
+    entry = side[soff[slot[uses]] + rank_in_slot] if uses.any() else np.zeros(0, np.int64)
+    pad_at = soff[:-1] + used
+    assert np.all(side[pad_at[used % 2 == 1]] == 0xFFFFFFFF), "odd ranges end in a pad entry"
     e_big, e_cold = entry[big[uses]], entry[cold[uses]]
     assert np.all(e_big >> 31 == 1) and np.all(e_cold >> 31 == 0)
     out["x1"][kind == 3] = x1[kind == 3]

@@ -73,7 +73,7 @@ struct brq_ctx {
 
   DevBuf<uint32_t> d_score_rec, d_side_rec, d_side_off, d_round_slot, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
   DevBuf<uint64_t> d_score_off, d_hist_off, d_round_off;
-  DevBuf<uint32_t> d_score_cnt;
+  DevBuf<uint32_t> d_score_cnt, d_round_side;
   DevBuf<uint8_t> d_hist_rec;
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
@@ -203,13 +203,14 @@ void upload(brq_ctx* c) {
   if (!c->staged) throw std::runtime_error("nothing staged");
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
-  c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_slot_ref.ensure(n_slots);
+  c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_round_side.ensure(st.n_rounds * 64 + 4); c->d_slot_ref.ensure(n_slots);
   c->d_hist_rec.ensure(st.n_hist * st.hist_bytes + 16);
   c->d_side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->d_round_side.p, st.round_side, st.n_rounds * 256, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_side_rec.p, st.side_rec, st.n_side * st.geo.side_stride * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
@@ -362,14 +363,13 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
                              "' exceeded enforced maximum value of '" + std::to_string(c->sp.n_rpos - 1) + "'.");
   const uint64_t n_slots = c->st.n_slots();
   c->d_cols.ensure(n_slots);
-  c->d_walk.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
   c->d_flagged.ensure(c->flagged_cap);
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
-  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
-                     c->d_cols.p, c->d_walk.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
+  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, reinterpret_cast<const uint2*>(c->d_round_side.p), c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
+                     c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
@@ -423,7 +423,8 @@ void download_walk(brq_ctx* c, const double* prop, uint32_t n_targets) {
     CUDA_OK(cudaMemcpyAsync(c->d_seg_prop.p, sp.data(), n_seg * 8, cudaMemcpyHostToDevice, c->stream));
     if (st.n_ins) CUDA_OK(cudaMemcpyAsync(c->d_ins_parent.p, st.ins_parent.data(), st.n_ins * 8, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 3, 0, 4, c->stream));  // scalars[3]: the fit kernel's hand-out counter, free again
-    launch_walk_events(c->d_walk.p, st.n_base, c->d_seg_first.p, c->d_seg_last.p, c->d_seg_prop.p, n_seg, c->d_flagged.p,
+    c->d_walk.ensure(st.n_base);
+    launch_walk_events(c->d_cols.p, c->d_walk.p, st.n_base, c->d_seg_first.p, c->d_seg_last.p, c->d_seg_prop.p, n_seg, c->d_flagged.p,
                        c->d_scalars.p + 1, c->flagged_cap, c->d_ins_parent.p, c->d_mark.p, c->d_events.p, c->d_scalars.p + 3, c->stream);
     uint32_t n_events = 0;
     CUDA_OK(cudaMemcpyAsync(&n_events, c->d_scalars.p + 3, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -524,7 +525,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release();
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
     c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
@@ -578,7 +579,7 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
     info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
-    info->bytes_host = st.n_rounds * 136 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
+    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();

@@ -120,7 +120,7 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
                    DR_OBS_SHIFT = 24, DR_RED_TRIM_BIT = 1u << 15, DR_RED_OBS_SHIFT = 25, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
                    DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
-                   SIDE_BIG = 1u << 31;
+                   SIDE_BIG = 1u << 31, SIDE_PAD = 0xFFFFFFFFu;  // SIDE_PAD fills a slot's side range to an even count
 // special counters, in the two histogram words after the class words
 enum : uint32_t { SC_IDLE_TOP = 0, SC_IDLE_BOT = 1, SC_COLD_TOP = 2, SC_COLD_BOT = 3, SC_SLOW_TOP = 4, SC_SLOW_BOT = 5, SC_TRASH = 6 };
 
@@ -179,6 +179,7 @@ struct PileupStream {
   uint64_t* score_off = nullptr;       // [n_base + n_ins + 1] first word of every slot in score_rec (see above; score_index())
   uint32_t* score_cnt = nullptr;       // [n_base + n_ins] records of every slot
   uint64_t* round_off = nullptr;       // [n_rounds + 1] first word of every round in score_rec
+  uint32_t* round_side = nullptr;      // [n_rounds * 32 * 2] per lane: side-list begin | reference base << 29, side-list end (used entries)
   uint64_t* hist_off = nullptr;        // [n_base + 1] CSR into hist_rec; bit 63 of entry c = column c has a redundant read
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records

@@ -93,15 +93,15 @@ struct alignas(32) HotTerms { double L[5]; double M; double pad[2]; };    // M =
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,
-                        const uint32_t* side, const uint32_t* side_off,
+                        const uint32_t* side, const uint32_t* side_off, const uint2* round_side,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between);
 // Compacts the walk records to the columns the host's interval walk needs (WalkEvent), in no particular order.
-// seg_first / seg_last / seg_prop: first slot, last slot and deletion propagation cutoff of every visited segment
+// walk: scratch of n_base records, filled here from the full results.  seg_first / seg_last / seg_prop: first slot, last slot and deletion propagation cutoff of every visited segment
 // (cutoff < 0: the target is skipped); mark: scratch of n_base bytes; counter: one zeroed word.
-void launch_walk_events(const WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
+void launch_walk_events(const ColumnOut* cols, WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
                         const double* seg_prop, uint32_t n_seg, const uint32_t* flagged, const uint32_t* n_flagged,
                         uint32_t flagged_cap, const uint64_t* ins_parent, uint8_t* mark, WalkEvent* events, uint32_t* counter,
                         cudaStream_t s);

@@ -170,11 +170,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 //   [n_warps x 4 KB]    record rings: 4 stages of one round vector (two planes of 32 lanes x 16 bytes)
 //   [4 x t_stride]      likelihood table [obs][sq] x 8 doubles (ScoreParams)
 __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ round_off,
-                                                                  const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
-                                                                  const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ round_slot,
+                                                                  const uint32_t* __restrict__ side, const uint2* __restrict__ round_side,
+                                                                  const uint32_t* __restrict__ round_slot,
                                                                   uint64_t n_rounds, const double* __restrict__ tallyT,
                                                                   const HotTerms* __restrict__ coldT, ScoreParams p, ColumnOut* __restrict__ out,
-                                                                  WalkOut* __restrict__ walk, uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
+                                                                  uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
                                                                   uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block, uint32_t side_stride) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -214,7 +214,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       const uint64_t o0 = __ldg(round_off + r), o1 = __ldg(round_off + r + 1);
       x.beg = o0; x.n_vec = (uint32_t)((o1 - o0) / ROUND_VECTOR_WORDS);
     }
-    if (slot != ROUND_NO_SLOT) { x.ref = slot_ref[slot]; x.side0 = side_off[slot]; x.side1 = side_off[slot + 1]; }
+    if (r < n_rounds) {  // coalesced: side-list range and reference base of this lane's slot
+      const uint2 m = __ldg(round_side + (r << 5) + lane);
+      x.ref = m.x >> 29; x.side0 = m.x & 0x1FFFFFFFu; x.side1 = m.y;
+    }
     return x;
   };
   // The warp streams the round's 1 KB vectors through a four-stage ring in shared memory with cp.async (LDGSTS, two
@@ -267,11 +270,15 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     // them.  Two entries per step, the next pair's words requested before this pair's table terms.
     uint32_t side_big = cur.side0;
     if (side_stride == 1u) {
+      // ranges start on even entries and are padded to even counts (SIDE_PAD reads as "skip"): one request per pair
       uint32_t e = cur.side0;
-      uint32_t wa = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, wb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
+      const uint2* side2 = reinterpret_cast<const uint2*>(side);
+      uint2 w2 = e < cur.side1 ? __ldg(side2 + (e >> 1)) : make_uint2(SIDE_PAD, SIDE_PAD);
+      uint32_t wa = w2.x, wb = w2.y;
       while (e < cur.side1) {
         e += 2u;
-        const uint32_t na = e < cur.side1 ? __ldg(side + e) : SIDE_BIG, nb = e + 1u < cur.side1 ? __ldg(side + e + 1u) : SIDE_BIG;
+        w2 = e < cur.side1 ? __ldg(side2 + (e >> 1)) : make_uint2(SIDE_PAD, SIDE_PAD);
+        const uint32_t na = w2.x, nb = w2.y;
         Sums ta = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, tb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (!(wa & SIDE_BIG)) { cold_add(ta, wa, 0u, coldT, p); ++n; c_ref += (wa >> 27) & 1u; }
         if (!(wb & SIDE_BIG)) { cold_add(tb, wb, 0u, coldT, p); ++n; c_ref += (wb >> 27) & 1u; }
@@ -440,12 +447,6 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       for (int j = 0; j < 3; ++j)
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst + 4 * j), "d"(od[4 * j]), "d"(od[4 * j + 1]), "d"(od[4 * j + 2]), "d"(od[4 * j + 3]) : "memory");
     }
-    {
-      const double red = red_bot + red_top;  // the sums the host's interval walk would form from the full result
-      const uint32_t total = (u_bot + u_top) + (uint32_t)(int)::round(red);
-      walk[my_slot] = WalkOut{u_bot + u_top, total << 2 | (red > 0.0 ? 2u : 0u) | (base_predicted ? 1u : 0u)};
-    }
-
     if (need_fit) worklist[atomicAdd(&scalars[2], 1u)] = my_slot;
     else if (recheck) { const uint32_t kf = atomicAdd(&scalars[1], 1u); if (kf < flagged_cap) flagged[kf] = my_slot; }
   }
@@ -760,10 +761,10 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
 }
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,
-                        const uint32_t* side, const uint32_t* side_off,
+                        const uint32_t* side, const uint32_t* side_off, const uint2* round_side,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, WalkOut* walk, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
@@ -777,7 +778,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, side_off, slot_ref, round_slot, n_rounds, tallyT, coldT, p, out, walk, worklist, flagged, scalars, flagged_cap, hist_block, side_stride);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, round_side, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block, side_stride);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap, side_stride);
@@ -785,7 +786,16 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
 }
 
 // ------------------------------------------------------------------------------------------ walk events
-__global__ void walk_mark_kernel(const WalkOut* __restrict__ walk, uint64_t n_base, const uint32_t* __restrict__ seg_first,
+// the 8-byte walk record of a column, from the sums of its full result (the arithmetic of position_coverage::sum(),
+// identify_mutations.h:115-120)
+__device__ __forceinline__ WalkOut walk_of(const ColumnOut& co) {
+  const uint32_t unique = co.unique[0] + co.unique[1];
+  const double red = co.redundant[0] + co.redundant[1];
+  const uint32_t total = unique + (uint32_t)(int)::round(red);
+  return WalkOut{unique, total << 2 | (red > 0.0 ? 2u : 0u) | ((co.bits & CO_BASE_PREDICTED) ? 1u : 0u)};
+}
+
+__global__ void walk_mark_kernel(const ColumnOut* __restrict__ cols, WalkOut* __restrict__ walk, uint64_t n_base, const uint32_t* __restrict__ seg_first,
                                  const uint32_t* __restrict__ seg_last, const double* __restrict__ seg_prop, uint32_t n_seg,
                                  uint8_t* __restrict__ mark) {
   const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -793,7 +803,8 @@ __global__ void walk_mark_kernel(const WalkOut* __restrict__ walk, uint64_t n_ba
   uint32_t lo = 0, hi = n_seg;  // the segment that holds slot c
   while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_first[mid] <= c) lo = mid; else hi = mid; }
   const double prop = seg_prop[lo];
-  const WalkOut w = walk[c];
+  const WalkOut w = walk_of(cols[c]);
+  walk[c] = w;
   const bool edge = c == seg_first[lo] || c == seg_last[lo];
   mark[c] = prop >= 0.0 && (edge || (double)w.unique <= prop || !(w.packed & 1u));
 }
@@ -815,13 +826,13 @@ __global__ void walk_compact_kernel(const WalkOut* __restrict__ walk, const uint
   if (keep) events[atomicAdd(counter, 1u)] = WalkEvent{(uint32_t)c, walk[c]};
 }
 
-void launch_walk_events(const WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
+void launch_walk_events(const ColumnOut* cols, WalkOut* walk, uint64_t n_base, const uint32_t* seg_first, const uint32_t* seg_last,
                         const double* seg_prop, uint32_t n_seg, const uint32_t* flagged, const uint32_t* n_flagged,
                         uint32_t flagged_cap, const uint64_t* ins_parent, uint8_t* mark, WalkEvent* events, uint32_t* counter,
                         cudaStream_t s) {
   if (!n_base || !n_seg) return;
   const uint32_t blocks = (uint32_t)((n_base + 255) / 256);
-  walk_mark_kernel<<<blocks, 256, 0, s>>>(walk, n_base, seg_first, seg_last, seg_prop, n_seg, mark);
+  walk_mark_kernel<<<blocks, 256, 0, s>>>(cols, walk, n_base, seg_first, seg_last, seg_prop, n_seg, mark);
   walk_mark_flagged_kernel<<<64, 256, 0, s>>>(flagged, n_flagged, flagged_cap, n_base, ins_parent, mark);
   walk_compact_kernel<<<blocks, 256, 0, s>>>(walk, mark, n_base, events, counter);
   note_launches(3);

@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -487,10 +487,13 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     bool p3 = false;
     out.side_off = (uint32_t*)alloc((n_slots + 1) * 4, &p3);
     uint64_t sacc = 0;
-    for (uint64_t s = 0; s < n_slots; ++s) { out.side_off[s] = (uint32_t)sacc; if (cfg.want_score) sacc += side_cnt[s]; }
-    if (sacc >= (1ull << 32)) throw std::runtime_error("more than 2^32 side-list entries in one staged stream");
+    // every slot's range starts on an even entry and is padded to an even count with SIDE_PAD (the tally kernel reads
+    // two entries per request)
+    for (uint64_t s = 0; s < n_slots; ++s) { out.side_off[s] = (uint32_t)sacc; if (cfg.want_score) sacc += (side_cnt[s] + 1u) & ~1u; }
+    if (sacc >= (1ull << 29)) throw std::runtime_error("more than 2^29 side-list entries in one staged stream");
     out.side_off[n_slots] = (uint32_t)sacc; out.n_side = sacc;
     out.side_rec = (uint32_t*)alloc(sacc * 4 * out.geo.side_stride + 16, &p3);
+    std::fill(out.side_rec, out.side_rec + sacc * out.geo.side_stride, SIDE_PAD);
     // Rounds of the tally kernel: 32 slots that share their reference base (its contraction multiplies the 32 class
     // histograms with ONE base's likelihood table) and have about the same depth (its 32 lanes walk their runs in
     // lock step).  Inside every block of ROUND_BLOCK consecutive slots the slots are grouped by base (A, C, G, T,
@@ -534,6 +537,13 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         acc += (uint64_t)deepest * ROUND_VECTOR_WORDS;
       }
       out.round_off[out.n_rounds] = acc;
+      // what a lane needs of its slot besides the records, round-major so that the warp reads it coalesced
+      out.round_side = (uint32_t*)alloc(order.size() * 8 + 16, &p3);
+      for (size_t i = 0; i < order.size(); ++i) {
+        const uint32_t sl = order[i];
+        out.round_side[2 * i] = sl == ROUND_NO_SLOT ? (5u << 29) : (out.side_off[sl] | (uint32_t)out.slot_ref[sl] << 29);
+        out.round_side[2 * i + 1] = sl == ROUND_NO_SLOT ? 0u : out.side_off[sl] + (cfg.want_score ? side_cnt[sl] : 0u);
+      }
       out.score_off[n_slots] = acc;
       out.n_score_padded = acc;
     }

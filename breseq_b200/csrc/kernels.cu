@@ -66,13 +66,31 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
   return v;
 }
 
+// JOINT: the shared-memory atomic unit, not HBM, bounds a kernel that issues two atomics per record (5 cycles per warp
+// instruction and SM, scripts/micro/atoms_rate.cu).  All but ~0.2 % of the records are the same pair of observations: the
+// aligned base matches the reference (ref == obs, quality qa) and the next base of the read is aligned too (('.', '.'),
+// quality qb).  Those records take ONE atomic on a CTA-private joint histogram over (read set, base, qa, qb), whose two
+// marginals are added to the covariate histogram when the CTA is done; every other record takes the two-atomic path.
+__device__ __forceinline__ bool joint_index(uint32_t lo, uint32_t n_set, uint32_t Q, uint32_t& idx) {
+  // valid A, valid B, B = ('.', '.'), and ref A == obs A
+  constexpr uint32_t kMask = 1u << HR_VALIDA | 1u << HR_VALIDB | 7u << HR_REFB | 7u << HR_OBSB;
+  constexpr uint32_t kWant = 1u << HR_VALIDA | 1u << HR_VALIDB | 4u << HR_REFB | 4u << HR_OBSB;
+  if ((((lo & kMask) ^ kWant) | ((lo ^ (lo >> HR_OBSA)) & 7u)) != 0u) return false;
+  const uint32_t set = n_set > 1 ? (lo >> HR_SET) : 0u;
+  idx = ((set * 4u + (lo & 3u)) * Q + ((lo >> HR_QUALA) & 127u)) * Q + ((lo >> HR_QUALB) & 127u);
+  return true;
+}
+
 // `rec` holds n records of 4 bytes (WIDE = false: four per 128-bit load) or 8 bytes (WIDE: two per load)
-template <bool SMEM, bool WIDE>
-__global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ rec, uint64_t n, CovLayout lay,
-                                                    unsigned long long* __restrict__ counts) {
+template <bool SMEM, bool WIDE, bool JOINT = false>
+__global__ void __launch_bounds__(JOINT ? 1024 : 256) hist_kernel(const void* __restrict__ rec, uint64_t n, CovLayout lay,
+                                                    unsigned long long* __restrict__ counts, uint32_t joint_sets = 0) {
   extern __shared__ uint32_t sh[];
+  uint32_t* joint = sh + ((lay.n_bins + 3u) & ~3u);   // JOINT: [joint_sets][4][Q][Q] after the covariate histogram
+  const uint32_t n_joint = JOINT ? joint_sets * 4u * lay.max_qual * lay.max_qual : 0u;
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i < lay.n_bins; i += blockDim.x) sh[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_joint; i += blockDim.x) joint[i] = 0;
     __syncthreads();
   }
   const uint4* vec = reinterpret_cast<const uint4*>(rec);
@@ -82,7 +100,15 @@ __global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ rec,
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   auto one = [&](const uint4& v) {
     if (WIDE) { hist_record<SMEM, true>(v.x, v.y, lay, sh, counts); hist_record<SMEM, true>(v.z, v.w, lay, sh, counts); }
-    else {
+    else if (JOINT) {
+      const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t idx;
+        if (joint_index(r[j], joint_sets, lay.max_qual, idx)) atomicAdd(&joint[idx], 1u);
+        else hist_record<SMEM, false>(r[j], 0u, lay, sh, counts);
+      }
+    } else {
       hist_record<SMEM, false>(v.x, 0u, lay, sh, counts); hist_record<SMEM, false>(v.y, 0u, lay, sh, counts);
       hist_record<SMEM, false>(v.z, 0u, lay, sh, counts); hist_record<SMEM, false>(v.w, 0u, lay, sh, counts);
     }
@@ -103,6 +129,18 @@ __global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ rec,
   }
   if (SMEM) {
     __syncthreads();
+    if (JOINT) {  // the two marginals of the joint histogram
+      const uint32_t Q = lay.max_qual;
+      for (uint32_t i = threadIdx.x; i < n_joint; i += blockDim.x) {
+        const uint32_t c = joint[i];
+        if (!c) continue;
+        const uint32_t qb = i % Q, qa = (i / Q) % Q, base = (i / (Q * Q)) & 3u, set = i / (4u * Q * Q);
+        const uint32_t off = set * lay.off_set;
+        atomicAdd(&sh[off + base * lay.off_ref + base * lay.off_obs + qa * lay.off_qual], c);
+        atomicAdd(&sh[off + 4u * lay.off_ref + 4u * lay.off_obs + qb * lay.off_qual], c);
+      }
+      __syncthreads();
+    }
     for (uint32_t b = threadIdx.x; b < lay.n_bins; b += blockDim.x) {
       uint32_t v = sh[b];
       if (v) atomicAdd(&counts[b], (unsigned long long)v);
@@ -113,6 +151,18 @@ __global__ void __launch_bounds__(256) hist_kernel(const void* __restrict__ rec,
 void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
   const int kSMs = 148;
   const size_t smem = (size_t)lay.n_bins * 4;
+  // joint histogram of the dominant record kind: needs exactly the four default covariates and has to fit beside the table
+  const uint32_t joint_sets = lay.off_set ? lay.max_set : 1u;
+  const size_t smem_joint = (((size_t)lay.n_bins + 3) & ~(size_t)3) * 4 + (size_t)joint_sets * 4 * lay.max_qual * lay.max_qual * 4;
+  if (!wide && lay.off_qual && lay.off_ref && lay.off_obs && !lay.off_rpos && !lay.off_rep && lay.max_qual <= 64 &&
+      joint_sets <= 8 && smem_joint <= 110 * 1024) {
+    // CTAs of 1024 threads share one joint histogram: two of them keep the SM's 64 warps busy
+    const int per_sm = (int)std::min<size_t>(2, std::max<size_t>(1, (220 * 1024) / smem_joint));
+    cudaFuncSetAttribute(hist_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_joint);
+    hist_kernel<true, false, true><<<kSMs * per_sm, 1024, smem_joint, s>>>(rec, n_rec, lay, counts, joint_sets);
+    ++g_launches;
+    return;
+  }
   if (smem <= 200 * 1024) {
     int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
     if (wide) {

@@ -312,7 +312,8 @@ def main():
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         score_bytes = 4 * n_records + 104 * n_slots           # 4 B/record + 8 B offsets + 96 B result per slot
-        hist_bytes = 8 * n_hist + 8 * int(s["n_base"])
+        # pass 1 is charged the bytes its records really have (4 per record at the default covariates, not SURVEY.md 8d's 8)
+        hist_bytes = int(s["hist_rec"].itemsize) * n_hist + 8 * int(s["n_base"])
         # the dominant kernel is the tally kernel: it moves all of the scoring pass's algorithmic bytes (the fit kernel
         # re-reads a few hundred slots); its duration is measured with CUDA events on the launching stream
         achieved = score_bytes / (k_ms["tally"] * 1e-3) / 1e9 if k_ms["tally"] > 0 else 0.0

@@ -249,6 +249,8 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
     too_big(COV_QUALITY, "quality", st.max_hist_qual);
     too_big(COV_READ_SET, "read_set", st.max_read_set_seen);
     too_big(COV_READ_POS, "read_pos", st.max_hist_rpos);
+    if (c->spec.used[COV_BASE_REPEAT] && c->spec.maxv[COV_BASE_REPEAT] > 32)
+      throw std::runtime_error("base_repeat above 32 is not supported (the staged records keep five bits of it)");
     if (st.hist_bytes == 4 && (lay.off_rpos || lay.off_rep))
       throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
     launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);

@@ -155,13 +155,16 @@ inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
 //       next base also aligned      ('.', '.')         quality of the next base on the read strand
 //       deletion of exactly 1 base  (ref base, '.')    quality of the next base on the read strand
 //       insertion of exactly 1 base ('.', inserted)    quality of the inserted base
-//   [31:28] read_set (low four bits)
+//   [30:28] read_set (low three bits)
+//   [31]    fast: the dominant kind of record, which the kernel counts with ONE atomic on a joint histogram: observation A
+//           valid with ref == obs, and observation B either ('.', '.') or absent (then [26:20] reads 127)
 // That is the whole record (4 bytes) unless the run uses the read_pos / base_repeat covariates or has
-// more than 16 read files; then records are 8 bytes and the high word adds
-//   [15:0] read_pos of A (0-based query index)  [23:16] base_repeat of A  [29:24] base_repeat of B  [31:30] read_set bits 5:4
+// more than 8 read files; then records are 8 bytes and the high word adds
+//   [15:0] read_pos of A (0-based query index)  [23:16] base_repeat of A  [28:24] base_repeat of B (saturated at 31)
+//   [31:29] read_set bits 5:3
 // Base indices A,C,G,T,'.' = 0..4.
 constexpr int HR_REFA = 0, HR_OBSA = 3, HR_QUALA = 6, HR_VALIDA = 13, HR_REFB = 14, HR_OBSB = 17, HR_QUALB = 20, HR_VALIDB = 27,
-              HR_SET = 28, HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_SET_HI = 62;
+              HR_SET = 28, HR_FAST = 31, HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_SET_HI = 61;
 
 // Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
 struct Segment { int32_t tid, lo, hi; uint64_t slot0; };

@@ -46,8 +46,8 @@ __device__ __forceinline__ void hist_add(uint32_t* sh, unsigned long long* count
 // lo = the 4-byte record; hi = the high word of an 8-byte record (WIDE: read_pos / base_repeat covariates, > 16 read files)
 template <bool SMEM, bool WIDE>
 __device__ __forceinline__ void hist_record(uint32_t lo, uint32_t hi, const CovLayout& lay, uint32_t* sh, unsigned long long* counts) {
-  uint32_t base = (lo >> HR_SET) * lay.off_set;
-  if (WIDE) base += ((hi >> (HR_SET_HI - 32)) << 4) * lay.off_set + (hi & 0xFFFFu) * lay.off_rpos;
+  uint32_t base = ((lo >> HR_SET) & 7u) * lay.off_set;
+  if (WIDE) base += ((hi >> (HR_SET_HI - 32)) << 3) * lay.off_set + (hi & 0xFFFFu) * lay.off_rpos;
   if (lo & (1u << HR_VALIDA)) {
     uint32_t idx = base + (lo & 7u) * lay.off_ref + ((lo >> HR_OBSA) & 7u) * lay.off_obs + ((lo >> HR_QUALA) & 127u) * lay.off_qual;
     if (WIDE) idx += min((hi >> (HR_REPA - 32)) & 255u, lay.max_rep - 1) * lay.off_rep;
@@ -55,7 +55,7 @@ __device__ __forceinline__ void hist_record(uint32_t lo, uint32_t hi, const CovL
   }
   if (lo & (1u << HR_VALIDB)) {
     uint32_t idx = base + ((lo >> HR_REFB) & 7u) * lay.off_ref + ((lo >> HR_OBSB) & 7u) * lay.off_obs + ((lo >> HR_QUALB) & 127u) * lay.off_qual;
-    if (WIDE) idx += min((hi >> (HR_REPB - 32)) & 63u, lay.max_rep - 1) * lay.off_rep;
+    if (WIDE) idx += min((hi >> (HR_REPB - 32)) & 31u, lay.max_rep - 1) * lay.off_rep;
     hist_add<SMEM>(sh, counts, idx);
   }
 }
@@ -71,14 +71,11 @@ __device__ __forceinline__ uint4 ld_stream_u32x4(const uint4* p) {
 // aligned base matches the reference (ref == obs, quality qa) and the next base of the read is aligned too (('.', '.'),
 // quality qb).  Those records take ONE atomic on a CTA-private joint histogram over (read set, base, qa, qb), whose two
 // marginals are added to the covariate histogram when the CTA is done; every other record takes the two-atomic path.
-__device__ __forceinline__ bool joint_index(uint32_t lo, uint32_t n_set, uint32_t Q, uint32_t& idx) {
-  // valid A, valid B, B = ('.', '.'), and ref A == obs A
-  constexpr uint32_t kMask = 1u << HR_VALIDA | 1u << HR_VALIDB | 7u << HR_REFB | 7u << HR_OBSB;
-  constexpr uint32_t kWant = 1u << HR_VALIDA | 1u << HR_VALIDB | 4u << HR_REFB | 4u << HR_OBSB;
-  if ((((lo & kMask) ^ kWant) | ((lo ^ (lo >> HR_OBSA)) & 7u)) != 0u) return false;
-  const uint32_t set = n_set > 1 ? (lo >> HR_SET) : 0u;
-  idx = ((set * 4u + (lo & 3u)) * Q + ((lo >> HR_QUALA) & 127u)) * Q + ((lo >> HR_QUALB) & 127u);
-  return true;
+// index of a fast record (brq_types.h: HR_FAST) in the joint histogram [sets][4 bases][Q][Q + 1]; an absent B reads quality
+// 127 and lands in column Q
+__device__ __forceinline__ uint32_t joint_index(uint32_t lo, uint32_t n_set, uint32_t Q) {
+  const uint32_t set = n_set > 1 ? ((lo >> HR_SET) & 7u) : 0u, qb = min((lo >> HR_QUALB) & 127u, Q);
+  return ((set * 4u + (lo & 3u)) * Q + ((lo >> HR_QUALA) & 127u)) * (Q + 1u) + qb;
 }
 
 // `rec` holds n records of 4 bytes (WIDE = false: four per 128-bit load) or 8 bytes (WIDE: two per load)
@@ -86,8 +83,8 @@ template <bool SMEM, bool WIDE, bool JOINT = false>
 __global__ void __launch_bounds__(JOINT ? 1024 : 256) hist_kernel(const void* __restrict__ rec, uint64_t n, CovLayout lay,
                                                     unsigned long long* __restrict__ counts, uint32_t joint_sets = 0) {
   extern __shared__ uint32_t sh[];
-  uint32_t* joint = sh + ((lay.n_bins + 3u) & ~3u);   // JOINT: [joint_sets][4][Q][Q] after the covariate histogram
-  const uint32_t n_joint = JOINT ? joint_sets * 4u * lay.max_qual * lay.max_qual : 0u;
+  uint32_t* joint = sh + ((lay.n_bins + 3u) & ~3u);   // JOINT: [joint_sets][4][Q][Q + 1] after the covariate histogram
+  const uint32_t n_joint = JOINT ? joint_sets * 4u * lay.max_qual * (lay.max_qual + 1u) : 0u;
   if (SMEM) {
     for (uint32_t i = threadIdx.x; i < lay.n_bins; i += blockDim.x) sh[i] = 0;
     for (uint32_t i = threadIdx.x; i < n_joint; i += blockDim.x) joint[i] = 0;
@@ -104,8 +101,7 @@ __global__ void __launch_bounds__(JOINT ? 1024 : 256) hist_kernel(const void* __
       const uint32_t r[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t idx;
-        if (joint_index(r[j], joint_sets, lay.max_qual, idx)) atomicAdd(&joint[idx], 1u);
+        if ((int32_t)r[j] < 0) atomicAdd(&joint[joint_index(r[j], joint_sets, lay.max_qual)], 1u);
         else hist_record<SMEM, false>(r[j], 0u, lay, sh, counts);
       }
     } else {
@@ -134,10 +130,10 @@ __global__ void __launch_bounds__(JOINT ? 1024 : 256) hist_kernel(const void* __
       for (uint32_t i = threadIdx.x; i < n_joint; i += blockDim.x) {
         const uint32_t c = joint[i];
         if (!c) continue;
-        const uint32_t qb = i % Q, qa = (i / Q) % Q, base = (i / (Q * Q)) & 3u, set = i / (4u * Q * Q);
+        const uint32_t qb = i % (Q + 1u), qa = (i / (Q + 1u)) % Q, base = (i / ((Q + 1u) * Q)) & 3u, set = i / (4u * Q * (Q + 1u));
         const uint32_t off = set * lay.off_set;
         atomicAdd(&sh[off + base * lay.off_ref + base * lay.off_obs + qa * lay.off_qual], c);
-        atomicAdd(&sh[off + 4u * lay.off_ref + 4u * lay.off_obs + qb * lay.off_qual], c);
+        if (qb < Q) atomicAdd(&sh[off + 4u * lay.off_ref + 4u * lay.off_obs + qb * lay.off_qual], c);
       }
       __syncthreads();
     }
@@ -153,7 +149,7 @@ void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& la
   const size_t smem = (size_t)lay.n_bins * 4;
   // joint histogram of the dominant record kind: needs exactly the four default covariates and has to fit beside the table
   const uint32_t joint_sets = lay.off_set ? lay.max_set : 1u;
-  const size_t smem_joint = (((size_t)lay.n_bins + 3) & ~(size_t)3) * 4 + (size_t)joint_sets * 4 * lay.max_qual * lay.max_qual * 4;
+  const size_t smem_joint = (((size_t)lay.n_bins + 3) & ~(size_t)3) * 4 + (size_t)joint_sets * 4 * lay.max_qual * (lay.max_qual + 1) * 4;
   if (!wide && lay.off_qual && lay.off_ref && lay.off_obs && !lay.off_rpos && !lay.off_rep && lay.max_qual <= 64 &&
       joint_sets <= 8 && smem_joint <= 110 * 1024) {
     // CTAs of 1024 threads share one joint histogram: two of them keep the SM's 64 warps busy

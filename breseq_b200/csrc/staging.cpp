@@ -558,7 +558,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   }
   out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
   std::fill(out.score_rec, out.score_rec + out.n_score_padded, geo.pad_word());  // pad word: the trash counter, no other bit
-  out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 15) ? 8 : 4;
+  out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7) ? 8 : 4;
   out.hist_rec = alloc(out.n_hist * out.hist_bytes, &p2);
 
   // ---- pass B: fill.  Within every slot the redundant records come first and the unique ones
@@ -614,7 +614,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
             rec |= (uint64_t)strand(refA) << HR_REFA | (uint64_t)strand(obsA) << HR_OBSA | (uint64_t)qa << HR_QUALA | 1ull << HR_VALIDA;
             if (qa > max_hq) max_hq = qa;
           }
-          rec |= (uint64_t)(ri.read_set & 15u) << HR_SET | (uint64_t)(ri.read_set >> 4) << HR_SET_HI;
+          rec |= (uint64_t)(ri.read_set & 7u) << HR_SET | (uint64_t)(ri.read_set >> 3) << HR_SET_HI;
           if (q > 65535) throw std::runtime_error("read position above 65535 cannot be packed");
           rec |= (uint64_t)q << HR_RPOS;
           if ((uint32_t)q > max_rp) max_rp = (uint32_t)q;
@@ -652,7 +652,16 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
             if (valid) {
               rec |= (uint64_t)fB << HR_REFB | (uint64_t)oB << HR_OBSB | (uint64_t)qual[m] << HR_QUALB | 1ull << HR_VALIDB;
               if (qual[m] > max_hq) max_hq = qual[m];
-              if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 63) << HR_REPB;
+              if (cfg.use_base_repeat) rec |= std::min<uint64_t>(base_repeat(m), 31) << HR_REPB;
+            }
+          }
+          {  // the fast kind: A valid with ref == obs, B ('.', '.') or absent
+            const bool a_match = (rec >> HR_VALIDA & 1) && ((rec >> HR_REFA & 7) == (rec >> HR_OBSA & 7));
+            const bool b_valid = rec >> HR_VALIDB & 1;
+            const bool b_dots = b_valid && (rec >> HR_REFB & 7) == kBaseGap && (rec >> HR_OBSB & 7) == kBaseGap;
+            if (a_match && (b_dots || !b_valid)) {
+              rec |= 1ull << HR_FAST;
+              if (!b_valid) rec |= 127ull << HR_QUALB;
             }
           }
           const uint64_t at = (out.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT) + hist_cur[slot]++;

@@ -203,7 +203,10 @@ def emulate_hist(hist_rec, n_sets, n_qual):
     def f(sh, m):
         return ((r >> np.uint64(sh)) & np.uint64(m)).astype(np.int64)
     refA, obsA, qa, validA = f(0, 7), f(3, 7), f(6, 127), f(13, 1)
-    refB, obsB, qb, validB, rset = f(14, 7), f(17, 7), f(20, 127), f(27, 1), f(28, 15) + 16 * f(62, 3)
+    refB, obsB, qb, validB, rset = f(14, 7), f(17, 7), f(20, 127), f(27, 1), f(28, 7) + 8 * f(61, 7)
+    fast = f(31, 1)   # the dominant kind: A valid with ref == obs, B ('.', '.') or absent (its quality field then reads 127)
+    assert np.array_equal(fast == 1, (validA == 1) & (refA == obsA) & (((validB == 1) & (refB == 4) & (obsB == 4)) | (validB == 0)))
+    assert np.all(qb[(fast == 1) & (validB == 0)] == 127)
     N = n_sets
     counts = np.zeros(N * 25 * n_qual, np.int64)
     np.add.at(counts, (rset + refA * N + obsA * 5 * N + qa * 25 * N)[validA == 1], 1)

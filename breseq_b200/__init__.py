@@ -121,6 +121,9 @@ def load_library():
         "brq_write_evidence": [C.c_void_p, C.c_char_p, P(C.c_double), P(C.c_double), C.c_uint32, C.c_int,
                                P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_d2h_bytes": [C.c_void_p, P(C.c_uint64), C.c_int],
+        "brq_evidence_export": [C.c_void_p, P(C.c_double), C.c_uint32, P(C.c_void_p), P(C.c_uint64)],
+        "brq_write_evidence_merged": [C.c_void_p, P(C.c_void_p), P(C.c_uint64), C.c_uint32, C.c_char_p, P(C.c_double), P(C.c_double),
+                                      C.c_uint32, C.c_int, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
@@ -146,7 +149,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
-           "brq_write_evidence", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
+           "brq_write_evidence", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
 
 
@@ -419,6 +422,28 @@ class Context:
         ra, mc, un = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self.lib.brq_write_evidence(self.h, _b(gd_file), prop, seed, n, int(skip_missing_coverage_prediction),
                                                 C.byref(ra), C.byref(mc), C.byref(un)))
+        return {"RA": ra.value, "MC": mc.value, "UN": un.value}
+
+    def evidence_export(self, deletion_propagation_cutoff):
+        """This context's share of the evidence of a run sharded by reference range, as bytes (see write_evidence_merged)."""
+        n = len(deletion_propagation_cutoff)
+        prop = (C.c_double * n)(*deletion_propagation_cutoff)
+        p, size = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.brq_evidence_export(self.h, prop, n, C.byref(p), C.byref(size)))
+        return C.string_at(p.value, size.value)
+
+    def write_evidence_merged(self, gd_file, shards, deletion_propagation_cutoff, deletion_seed_cutoff,
+                              skip_missing_coverage_prediction=False):
+        """``ra_mc_evidence.gd`` of a sharded run from the shares of all its contexts (any order)."""
+        n = len(deletion_propagation_cutoff)
+        prop = (C.c_double * n)(*deletion_propagation_cutoff)
+        seed = (C.c_double * n)(*deletion_seed_cutoff)
+        bufs = [C.create_string_buffer(b, len(b)) for b in shards]
+        ptrs = (C.c_void_p * len(bufs))(*[C.cast(b, C.c_void_p) for b in bufs])
+        sizes = (C.c_uint64 * len(bufs))(*[len(b) for b in shards])
+        ra, mc, un = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.brq_write_evidence_merged(self.h, ptrs, sizes, len(bufs), _b(gd_file), prop, seed, n,
+                                                       int(skip_missing_coverage_prediction), C.byref(ra), C.byref(mc), C.byref(un)))
         return {"RA": ra.value, "MC": mc.value, "UN": un.value}
 
     def d2h_bytes(self, reset=False):

@@ -99,6 +99,7 @@ struct brq_ctx {
   std::vector<double> walk_prop;    // the propagation cutoffs h_events was compacted for
   std::vector<ColumnOut> h_fcols;   // full results of the flagged slots, in the order of h_flagged
   bool have_walk = false;
+  std::string shard_blob;           // brq_evidence_export
   uint64_t d2h_bytes = 0;           // device -> host bytes since the last brq_d2h_bytes(reset) (bench bookkeeping)
 
   CovSpec spec;
@@ -459,9 +460,6 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
                              "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
   if (!c->have_walk || c->walk_prop != std::vector<double>(prop, prop + n_targets)) download_walk(c, prop, n_targets);
   const auto t1 = now();
-  if (n_targets != c->hdr.target_names.size())
-    throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
-                             "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
   EvidenceParams ep;
   ep.mutation_cutoff = c->last_params.mutation_cutoff;
   ep.polymorphism_cutoff = c->last_params.polymorphism_cutoff;
@@ -478,6 +476,26 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   if (timing) fprintf(stderr, "[brq] evidence: download %.2f ms, lut %.2f ms, write_evidence %.2f ms (%zu flagged, %llu RA)\n",
                       ms(t0, t1), ms(t1, t2), ms(t2, now()), c->h_flagged.size(), (unsigned long long)k.ra);
   return k;
+}
+
+// This context's share of the evidence of a run sharded by reference range: event columns and RA rows, as bytes.
+void evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets) {
+  if (n_targets != c->hdr.target_names.size())
+    throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
+                             "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
+  if (!c->have_walk || c->walk_prop != std::vector<double>(prop, prop + n_targets)) download_walk(c, prop, n_targets);
+  EvidenceParams ep;
+  ep.mutation_cutoff = c->last_params.mutation_cutoff;
+  ep.polymorphism_cutoff = c->last_params.polymorphism_cutoff;
+  ep.precision_decimal = c->last_params.polymorphism_precision_decimal;
+  ep.precision_places = c->last_params.polymorphism_precision_places;
+  ep.base_quality_cutoff = c->last_params.base_quality_cutoff;
+  ep.log10_ref_length = c->sp.log10_ref_length;
+  ep.skip_missing_coverage_prediction = false;
+  ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
+  ep.deletion_seed_cutoff.assign(n_targets, 0.0);
+  ensure_host_lut(c);
+  c->shard_blob = serialize_shard(collect_evidence(c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep));
 }
 
 void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,
@@ -708,6 +726,34 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
   return guarded(c, [&] {
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
     write_coverage_tsv(pattern, c->hdr, c->ref, c->st, c->h_cols);
+  });
+}
+
+int brq_evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets, const void** data, uint64_t* bytes) {
+  return guarded(c, [&] {
+    evidence_export(c, prop, n_targets);
+    *data = c->shard_blob.data(); *bytes = c->shard_blob.size();
+  });
+}
+
+int brq_write_evidence_merged(brq_ctx* c, const void* const* shards, const uint64_t* sizes, uint32_t n_shards, const char* gd_file,
+                              const double* prop, const double* seed, uint32_t n_targets, int skip_mc,
+                              uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un) {
+  return guarded(c, [&] {
+    std::vector<EvidenceShard> parsed;
+    for (uint32_t i = 0; i < n_shards; ++i) parsed.push_back(parse_shard(shards[i], sizes[i]));
+    std::vector<const EvidenceShard*> ptrs;
+    for (const EvidenceShard& sh : parsed) ptrs.push_back(&sh);
+    EvidenceParams ep;
+    ep.mutation_cutoff = ep.polymorphism_cutoff = ep.precision_decimal = 0.0;
+    ep.precision_places = 0; ep.base_quality_cutoff = 0; ep.log10_ref_length = 0.0;
+    ep.skip_missing_coverage_prediction = skip_mc != 0;
+    ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
+    ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
+    const EvidenceCounts k = walk_evidence(ptrs, ep, gd_file);
+    if (n_ra) *n_ra = k.ra;
+    if (n_mc) *n_mc = k.mc;
+    if (n_un) *n_un = k.un;
   });
 }
 

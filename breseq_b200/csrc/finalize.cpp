@@ -588,22 +588,77 @@ void evaluate_slot(SlotEval& s, uint8_t ref, const EvidenceParams& ep) {
   s.emit = passed_consensus || passed_poly;
 }
 
-struct GdRow {
-  int type;  // 0 RA, 1 MC, 2 UN
-  uint64_t id;
-  std::string seq_id;
-  uint64_t a = 0, b = 0, c = 0, d = 0;  // RA: position, insert ; MC: start, end, start_range, end_range ; UN: start, end
-  std::string ref_base, new_base;
-  std::map<std::string, std::string> kv;
-};
-
 }  // namespace
 
-EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
-                              const std::vector<WalkEvent>& events_in, const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
-                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
+// ============================================================================== shard serialisation
+namespace {
+struct Writer {
+  std::string out;
+  void u32(uint32_t v) { out.append(reinterpret_cast<const char*>(&v), 4); }
+  void u64(uint64_t v) { out.append(reinterpret_cast<const char*>(&v), 8); }
+  void str(const std::string& s) { u32((uint32_t)s.size()); out.append(s); }
+};
+struct Reader {
+  const char* p; const char* end;
+  void need(size_t n) { if ((size_t)(end - p) < n) throw std::runtime_error("truncated evidence shard"); }
+  uint32_t u32() { need(4); uint32_t v; memcpy(&v, p, 4); p += 4; return v; }
+  uint64_t u64() { need(8); uint64_t v; memcpy(&v, p, 8); p += 8; return v; }
+  std::string str() { const uint32_t n = u32(); need(n); std::string s(p, n); p += n; return s; }
+};
+constexpr uint32_t SHARD_MAGIC = 0x31515242u;  // "BRQ1"
+}  // namespace
+
+std::string serialize_shard(const EvidenceShard& sh) {
+  Writer w;
+  w.u32(SHARD_MAGIC);
+  w.u32((uint32_t)sh.target_names.size());
+  for (size_t i = 0; i < sh.target_names.size(); ++i) { w.str(sh.target_names[i]); w.u32(sh.target_lens[i]); }
+  w.u32((uint32_t)sh.segments.size());
+  for (const auto& sg : sh.segments) { w.u32((uint32_t)sg.tid); w.u32((uint32_t)sg.lo); w.u32((uint32_t)sg.hi); }
+  w.u64(sh.rechecked); w.u64(sh.overturned);
+  w.u64(sh.events.size());
+  for (const EvidenceEvent& e : sh.events) {
+    w.u32(e.tid); w.u32(e.pos1); w.u32(e.unique); w.u32(e.packed); w.u32((uint32_t)e.rows.size());
+    for (const GdRow& r : e.rows) {
+      w.u32((uint32_t)r.type); w.str(r.seq_id); w.u64(r.a); w.u64(r.b); w.u64(r.c); w.u64(r.d); w.str(r.ref_base); w.str(r.new_base);
+      w.u32((uint32_t)r.kv.size());
+      for (const auto& kv : r.kv) { w.str(kv.first); w.str(kv.second); }
+    }
+  }
+  return w.out;
+}
+
+EvidenceShard parse_shard(const void* data, size_t bytes) {
+  Reader r{static_cast<const char*>(data), static_cast<const char*>(data) + bytes};
+  if (r.u32() != SHARD_MAGIC) throw std::runtime_error("not an evidence shard");
+  EvidenceShard sh;
+  const uint32_t nt = r.u32();
+  for (uint32_t i = 0; i < nt; ++i) { sh.target_names.push_back(r.str()); sh.target_lens.push_back(r.u32()); }
+  const uint32_t ns = r.u32();
+  for (uint32_t i = 0; i < ns; ++i) { EvidenceShard::Seg sg; sg.tid = (int32_t)r.u32(); sg.lo = (int32_t)r.u32(); sg.hi = (int32_t)r.u32(); sh.segments.push_back(sg); }
+  sh.rechecked = r.u64(); sh.overturned = r.u64();
+  const uint64_t ne = r.u64();
+  for (uint64_t i = 0; i < ne; ++i) {
+    EvidenceEvent e;
+    e.tid = r.u32(); e.pos1 = r.u32(); e.unique = r.u32(); e.packed = r.u32();
+    const uint32_t nr = r.u32();
+    for (uint32_t k = 0; k < nr; ++k) {
+      GdRow g;
+      g.type = (int)r.u32(); g.seq_id = r.str(); g.a = r.u64(); g.b = r.u64(); g.c = r.u64(); g.d = r.u64(); g.ref_base = r.str(); g.new_base = r.str();
+      const uint32_t nk = r.u32();
+      for (uint32_t j = 0; j < nk; ++j) { std::string key = r.str(); g.kv[key] = r.str(); }
+      e.rows.push_back(std::move(g));
+    }
+    sh.events.push_back(std::move(e));
+  }
+  return sh;
+}
+
+// ---- one shard's share of the evidence: the event columns with their target coordinates and the RA rows to emit at them
+EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, const std::vector<WalkEvent>& events_in,
+                               const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
+                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
   EvidenceCounts counts;
-  const double nan = std::numeric_limits<double>::quiet_NaN();
   // flagged slots in ascending order (the kernels append them in no particular order), each with its full result
   std::vector<uint32_t> order(flagged_in.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
@@ -740,14 +795,11 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
   counts.rechecked = flagged.size();
   for (uint8_t o : overturned) counts.overturned += o;
 
-  const bool timing = getenv("BRQ_TIMING") != nullptr;
-  const auto t_reval = std::chrono::steady_clock::now();
-  // ---- walk the columns in visit order: MC and UN interval state machines, RA rows spliced in
-  std::vector<GdRow> rows;
-  uint64_t next_id = 0;
-  auto add = [&](GdRow r) { r.id = ++next_id; rows.push_back(std::move(r)); };
-  const uint32_t UNDEF = 0xFFFFFFFFu;
-  struct Cov { double unique, redundant; int total; };
+
+  EvidenceShard sh;
+  sh.target_names = hdr.target_names; sh.target_lens = hdr.target_lens;
+  sh.rechecked = counts.rechecked; sh.overturned = counts.overturned;
+  for (const Segment& sg : st.segments) sh.segments.push_back({sg.tid, sg.lo, sg.hi});
   size_t ins_cursor = 0;  // ins slots are ordered by (parent, insert_count)
   // base slots are visited in ascending order and so are the insert sub-column slots: two cursors over the flagged list
   size_t ev_cur = 0;
@@ -756,11 +808,64 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     while (cur < flagged.size() && flagged[cur] < slot) ++cur;
     return (cur < flagged.size() && flagged[cur] == slot) ? &reval[cur] : nullptr;
   };
-  for (size_t sgi = 0; sgi < st.segments.size(); ++sgi) {
-    const Segment& sg = st.segments[sgi];
-    const std::string& name = hdr.target_names[(size_t)sg.tid];
-    const uint32_t tlen = hdr.target_lens[(size_t)sg.tid];
-    const double prop = ep.deletion_propagation_cutoff[(size_t)sg.tid], seed = ep.deletion_seed_cutoff[(size_t)sg.tid];
+  for (const Segment& sg : st.segments) {
+    while (ev_cur < events.size() && events[ev_cur].slot < sg.slot0) ++ev_cur;
+    for (; ev_cur < events.size() && events[ev_cur].slot < sg.slot0 + (uint64_t)(sg.hi - sg.lo); ++ev_cur) {
+      const uint64_t slot = events[ev_cur].slot;
+      EvidenceEvent e;
+      e.tid = (uint32_t)sg.tid; e.pos1 = (uint32_t)(sg.lo + (int32_t)(slot - sg.slot0)) + 1;
+      e.unique = events[ev_cur].w.unique; e.packed = events[ev_cur].w.packed;
+      const Reval* rv = find_reval(base_cur, slot);
+      if (rv) e.packed = (e.packed & ~1u) | (rv->base_predicted ? 1u : 0u);  // the host's verdict replaces the kernel's
+      if (rv && rv->emit) e.rows.push_back(rv->row);
+      while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
+      for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) {
+        const Reval* iv = find_reval(ins_cur, st.n_base + ins_cursor);
+        if (iv && iv->emit) e.rows.push_back(iv->row);
+      }
+      sh.events.push_back(std::move(e));
+    }
+  }
+  return sh;
+}
+
+// ---- the interval walk over the event columns of all shards of a run, and the GenomeDiff file
+EvidenceCounts walk_evidence(const std::vector<const EvidenceShard*>& shards, const EvidenceParams& ep, const std::string& gd_path) {
+  if (shards.empty()) throw std::runtime_error("no evidence shards");
+  EvidenceCounts counts;
+  const double nan = std::numeric_limits<double>::quiet_NaN();
+  const std::vector<std::string>& names = shards[0]->target_names;
+  const std::vector<uint32_t>& lens = shards[0]->target_lens;
+  for (const EvidenceShard* sp : shards) {
+    if (sp->target_names != names || sp->target_lens != lens) throw std::runtime_error("evidence shards of different references");
+    counts.rechecked += sp->rechecked; counts.overturned += sp->overturned;
+  }
+  if (ep.deletion_propagation_cutoff.size() != names.size() || ep.deletion_seed_cutoff.size() != names.size())
+    throw std::runtime_error("Number of targets in BAM file [" + std::to_string(names.size()) + "] does not match number in cutoff table [" +
+                             std::to_string(ep.deletion_propagation_cutoff.size()) + "].");
+  // per target: its pieces (shard, segment) in coordinate order; targets in visit order (alphabetical, pileup_base.cpp:364-385)
+  struct Piece { int32_t lo, hi; const EvidenceShard* sh; };
+  std::vector<std::vector<Piece>> pieces(names.size());
+  for (const EvidenceShard* sp : shards) for (const auto& sg : sp->segments) if (sg.hi > sg.lo) pieces[(size_t)sg.tid].push_back({sg.lo, sg.hi, sp});
+  std::vector<size_t> visit;
+  for (size_t t = 0; t < names.size(); ++t) if (!pieces[t].empty()) visit.push_back(t);
+  std::sort(visit.begin(), visit.end(), [&](size_t a, size_t b) { return names[a] < names[b]; });
+  // cursor into every shard's event list (a shard's events are in visit order too)
+  std::map<const EvidenceShard*, size_t> cursor;
+  for (const EvidenceShard* sp : shards) cursor[sp] = 0;
+
+  std::vector<GdRow> rows;
+  uint64_t next_id = 0;
+  auto add = [&](GdRow r) { r.id = ++next_id; rows.push_back(std::move(r)); };
+  const uint32_t UNDEF = 0xFFFFFFFFu;
+  struct Cov { double unique, redundant; int total; };
+  for (size_t tid : visit) {
+    std::vector<Piece>& pc = pieces[tid];
+    std::sort(pc.begin(), pc.end(), [](const Piece& a, const Piece& b) { return a.lo < b.lo; });
+    for (size_t i = 1; i < pc.size(); ++i) if (pc[i].lo != pc[i - 1].hi) throw std::runtime_error("evidence shards do not tile target " + names[tid]);
+    const std::string& name = names[tid];
+    const uint32_t tlen = lens[tid];
+    const double prop = ep.deletion_propagation_cutoff[tid], seed = ep.deletion_seed_cutoff[tid];
     uint32_t del_start = UNDEF, del_end = UNDEF, red_start = UNDEF, red_end = UNDEF, unknown_start = UNDEF;
     bool reaches_seed = false, red_zero = false;
     Cov last = {nan, nan, 0}, left_out = {nan, nan, 0}, left_in = {nan, nan, 0};
@@ -804,30 +909,22 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     // Only the event columns are walked: between two of them every column has unique coverage above the propagation
     // cutoff and a predicted base, no interval is open, and all such a column does to the state is overwrite `last`,
     // which the column before the next event overwrites again (it is an event itself: the neighbour of a non-boring one).
-    while (ev_cur < events.size() && events[ev_cur].slot < sg.slot0) ++ev_cur;
-    if (prop >= 0.0) {
-      for (; ev_cur < events.size() && events[ev_cur].slot < sg.slot0 + (uint64_t)(sg.hi - sg.lo); ++ev_cur) {
-        const uint64_t slot = events[ev_cur].slot;
-        const int32_t c = sg.lo + (int32_t)(slot - sg.slot0);
-        const WalkOut& wo = events[ev_cur].w;  // written by the tally kernel from the same sums the full result holds
+    for (const Piece& piece : pc) {
+      size_t& cur = cursor[piece.sh];
+      const std::vector<EvidenceEvent>& ev = piece.sh->events;
+      for (; cur < ev.size() && ev[cur].tid == tid && (int32_t)ev[cur].pos1 <= piece.hi; ++cur) {
+        if (prop < 0.0) continue;
+        const EvidenceEvent& e = ev[cur];
         Cov cv;
-        cv.unique = (double)wo.unique;
-        cv.redundant = (wo.packed & 2u) ? 1.0 : 0.0;  // only its sign is looked at
-        cv.total = (int)(wo.packed >> 2);
-        bool predicted = (wo.packed & 1u) != 0;
-        const Reval* rv = find_reval(base_cur, slot);
-        if (rv) predicted = rv->base_predicted;
-        if (!ep.skip_missing_coverage_prediction) deletion_step((uint32_t)c + 1, cv);
-        unknown_step((uint32_t)c + 1, predicted);
-        if (rv && rv->emit) { add(rv->row); ++counts.ra; }
-        while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
-        for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) {
-          const Reval* iv = find_reval(ins_cur, st.n_base + ins_cursor);
-          if (iv && iv->emit) { add(iv->row); ++counts.ra; }
-        }
+        cv.unique = (double)e.unique;
+        cv.redundant = (e.packed & 2u) ? 1.0 : 0.0;  // only its sign is looked at
+        cv.total = (int)(e.packed >> 2);
+        if (!ep.skip_missing_coverage_prediction) deletion_step(e.pos1, cv);
+        unknown_step(e.pos1, (e.packed & 1u) != 0);
+        for (const GdRow& r : e.rows) { add(r); ++counts.ra; }
       }
     }
-    if ((uint32_t)sg.hi == tlen) {  // at_target_end, identify_mutations.cpp:2117-2164
+    if ((uint32_t)pc.back().hi == tlen) {  // at_target_end, identify_mutations.cpp:2117-2164
       if (prop >= 0.0) {
         if (!ep.skip_missing_coverage_prediction) deletion_step(tlen + 1, Cov{nan, nan, 0});
         unknown_step(tlen + 1, true);
@@ -844,7 +941,6 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     }
   }
 
-  if (timing) fprintf(stderr, "[brq] write_evidence: column walk %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_reval).count());
   // ---- GenomeDiff text (genome_diff.cpp:685-760; sort keys genome_diff_entry.cpp:280-324, 566-700)
   std::stable_sort(rows.begin(), rows.end(), [](const GdRow& x, const GdRow& y) {
     if (x.type != y.type) return x.type < y.type;  // RA (3) < MC (4) < UN (7)
@@ -868,6 +964,13 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
     os << '\n';
   }
   return counts;
+}
+
+EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
+                              const std::vector<WalkEvent>& events, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
+                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
+  const EvidenceShard sh = collect_evidence(hdr, st, events, flagged, flagged_cols, sp, lut, ep);
+  return walk_evidence({&sh}, ep, gd_path);
 }
 
 }  // namespace brq

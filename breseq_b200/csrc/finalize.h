@@ -5,6 +5,7 @@
 #include "brq_types.h"
 #include "kernels.h"
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -71,7 +72,37 @@ struct EvidenceParams {
 };
 struct EvidenceCounts { uint64_t ra = 0, mc = 0, un = 0, rechecked = 0, overturned = 0; };
 
-// `shard_first_col1` etc. are not needed: the stream knows its segments.
+// One row of ra_mc_evidence.gd before ids are assigned.
+struct GdRow {
+  int type = 0;  // 0 RA, 1 MC, 2 UN
+  uint64_t id = 0;
+  std::string seq_id;
+  uint64_t a = 0, b = 0, c = 0, d = 0;  // RA: position, insert ; MC: start, end, start_range, end_range ; UN: start, end
+  std::string ref_base, new_base;
+  std::map<std::string, std::string> kv;
+};
+// A column the interval walk looks at, in target coordinates, with the host's verdict on base_predicted folded into
+// `packed` (WalkOut) and the RA rows to emit at it (its own, then its insert sub-columns').
+struct EvidenceEvent { uint32_t tid = 0, pos1 = 0, unique = 0, packed = 0; std::vector<GdRow> rows; };
+// What one context (one coordinate shard of a run) contributes to ra_mc_evidence.gd.  The MC / UN intervals cross shard
+// boundaries, so a sharded run walks the shards' events together (walk_evidence): the events are a few thousand per shard.
+struct EvidenceShard {
+  struct Seg { int32_t tid, lo, hi; };
+  std::vector<std::string> target_names;
+  std::vector<uint32_t> target_lens;
+  std::vector<Seg> segments;           // in visit order
+  std::vector<EvidenceEvent> events;   // in visit order, ascending position inside a target
+  uint64_t rechecked = 0, overturned = 0;
+};
+EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, const std::vector<WalkEvent>& events,
+                               const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
+                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
+EvidenceCounts walk_evidence(const std::vector<const EvidenceShard*>& shards, const EvidenceParams& ep, const std::string& gd_path);
+// flat byte form of a shard, for the trip between ranks
+std::string serialize_shard(const EvidenceShard& sh);
+EvidenceShard parse_shard(const void* data, size_t bytes);
+
+// collect_evidence + walk_evidence for an unsharded run
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
                               const std::vector<WalkEvent>& events, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);

@@ -157,6 +157,15 @@ int brq_write_evidence(brq_ctx* ctx, const char* gd_file, const double* deletion
  * brq_write_coverage_tsv: <seq>.coverage.tsv of --predict-copy-number (identify_mutations.cpp:2028-2052, 2173-2204,
  *   Settings::complete_coverage_text_file_name); '@' in `pattern` is replaced by the target name.  The per-read-group
  *   columns the reference adds for runs with more than one read group are not written. */
+/* A run sharded by reference range (brq_stage_options.shard_rank / shard_count, one context per GPU): the MC and UN
+ * intervals cross shard boundaries, so every context exports its share of the evidence (the event columns of its range
+ * and its RA rows: a few hundred KB, valid until the next call on the context), the shares are gathered on one rank
+ * (any transport) and brq_write_evidence_merged walks them together and writes ra_mc_evidence.gd.  `ctx` of the merged
+ * call only carries the error message: it needs no device and no staged stream. */
+int brq_evidence_export(brq_ctx* ctx, const double* deletion_propagation_cutoff, uint32_t n_targets, const void** data, uint64_t* bytes);
+int brq_write_evidence_merged(brq_ctx* ctx, const void* const* shards, const uint64_t* sizes, uint32_t n_shards, const char* gd_file,
+                              const double* deletion_propagation_cutoff, const double* deletion_seed_cutoff, uint32_t n_targets,
+                              int skip_missing_coverage_prediction, uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un);
 /* bytes the context has copied device -> host since the last reset (histograms, error table, walk events, flagged slots) */
 int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);

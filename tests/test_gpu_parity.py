@@ -185,3 +185,47 @@ def test_read_pos_and_base_repeat_covariates(datasets, tmp_path):
     with pytest.raises(bq.BrqError):
         ctx.error_count(cov)
     ctx.close()
+
+
+class _DevArray:
+    """A device buffer of the library as a CUDA array (int64) torch can wrap."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+
+
+@pytest.mark.parametrize("name,world", [("lambda", 2), ("multi", 3), ("tiny", 2), ("ltee", 2)])
+def test_sharded_run_merges_to_the_unsharded_evidence(name, world, datasets, tmp_path):
+    """A run sharded by reference range (one context per shard, as one per GPU): the histograms are summed (the path's one
+    collective), every shard scores its range, and the shards' evidence shares walked together give the unsharded
+    ra_mc_evidence.gd byte for byte: MC / UN intervals and row ids cross shard boundaries."""
+    import torch
+    d = datasets[name]
+    n = len(d["contig_lens"])
+    prop, seed = [d["del_prop"]] * n, [d["del_seed"]] * n
+    ctxs = [bq.Context(device=0) for _ in range(world)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.stage_bam(d["bam"], d["fasta"], shard=(r, world), **helpers.stage_kwargs(d))
+            c.error_count(helpers.covariates(d))
+            c.sync()
+        parts = [torch.as_tensor(_DevArray(*c.hist_device()[:2]), device="cuda:0") for c in ctxs]
+        total = torch.stack(parts).sum(dim=0)
+        for p in parts:
+            p.copy_(total)
+        torch.cuda.synchronize()
+        counts, _ = ctxs[-1].hist_download()
+        assert np.array_equal(counts.astype(np.int64), helpers.oracle_counts(d["oracle_counts"]))
+        params = bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"])
+        shares = []
+        for c in ctxs:
+            c.derive_error_table()
+            c.score_columns(params)
+            shares.append(c.evidence_export(prop))
+        gd = str(tmp_path / "merged.gd")
+        k = ctxs[0].write_evidence_merged(gd, shares[::-1], prop, seed)
+        assert open(gd).read() == open(d["oracle_gd"]).read()
+        assert k["RA"] + k["MC"] + k["UN"] == len(helpers.parse_gd(gd))
+    finally:
+        for c in ctxs:
+            c.close()

@@ -223,16 +223,20 @@ def main():
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
+    ext_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local)) if world > 1 else None
+
+    hist_view = {}
+
     def allreduce_hist():
         if world == 1:
             return
         c, n, v, m = ctx.hist_device()
-        ctx.sync()
-        # every rank sizes its coverage histogram by its own deepest column: reduce the counts only
-        # over the common prefix, which is all the table derivation needs
-        t = torch.as_tensor(DevArray(c, n), device="cuda:%d" % local)
-        dist.all_reduce(t)
-        torch.cuda.synchronize()
+        # every rank sizes its coverage histogram by its own deepest column: reduce the counts only, which is all the
+        # table derivation needs.  The collective is ordered on the context's own stream: no host synchronisation.
+        if hist_view.get("key") != (c, n):  # the buffer is allocated once: wrap it once
+            hist_view["key"], hist_view["t"] = (c, n), torch.as_tensor(DevArray(c, n), device="cuda:%d" % local)
+        with torch.cuda.stream(ext_stream):
+            dist.all_reduce(hist_view["t"])
 
     def step():
         ctx.error_count(COVARIATES)

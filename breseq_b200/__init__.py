@@ -121,6 +121,7 @@ def load_library():
         "brq_write_evidence": [C.c_void_p, C.c_char_p, P(C.c_double), P(C.c_double), C.c_uint32, C.c_int,
                                P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_d2h_bytes": [C.c_void_p, P(C.c_uint64), C.c_int],
+        "brq_cuda_stream": [C.c_void_p, P(C.c_void_p)],
         "brq_evidence_export": [C.c_void_p, P(C.c_double), C.c_uint32, P(C.c_void_p), P(C.c_uint64)],
         "brq_write_evidence_merged": [C.c_void_p, P(C.c_void_p), P(C.c_uint64), C.c_uint32, C.c_char_p, P(C.c_double), P(C.c_double),
                                       C.c_uint32, C.c_int, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
@@ -149,7 +150,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_stage_synthetic", "brq_stream", "brq_upload", "brq_sync", "brq_error_count", "brq_hist_device",
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
-           "brq_write_evidence", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
+           "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
 
 
@@ -445,6 +446,12 @@ class Context:
         self._check(self.lib.brq_write_evidence_merged(self.h, ptrs, sizes, len(bufs), _b(gd_file), prop, seed, n,
                                                        int(skip_missing_coverage_prediction), C.byref(ra), C.byref(mc), C.byref(un)))
         return {"RA": ra.value, "MC": mc.value, "UN": un.value}
+
+    def cuda_stream(self):
+        """cudaStream_t of the context as an integer (torch.cuda.ExternalStream takes it)."""
+        p = C.c_void_p()
+        self._check(self.lib.brq_cuda_stream(self.h, C.byref(p)))
+        return p.value or 0
 
     def d2h_bytes(self, reset=False):
         n = C.c_uint64()

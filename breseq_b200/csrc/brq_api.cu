@@ -757,6 +757,10 @@ int brq_write_evidence_merged(brq_ctx* c, const void* const* shards, const uint6
   });
 }
 
+int brq_cuda_stream(brq_ctx* c, void** stream) {
+  return guarded(c, [&] { c->need_device(); *stream = (void*)c->stream; });
+}
+
 int brq_d2h_bytes(brq_ctx* c, uint64_t* bytes, int reset) {
   if (!c) return 1;
   if (bytes) *bytes = c->d2h_bytes;

@@ -166,6 +166,9 @@ int brq_evidence_export(brq_ctx* ctx, const double* deletion_propagation_cutoff,
 int brq_write_evidence_merged(brq_ctx* ctx, const void* const* shards, const uint64_t* sizes, uint32_t n_shards, const char* gd_file,
                               const double* deletion_propagation_cutoff, const double* deletion_seed_cutoff, uint32_t n_targets,
                               int skip_missing_coverage_prediction, uint64_t* n_ra, uint64_t* n_mc, uint64_t* n_un);
+/* the CUDA stream (cudaStream_t) all of the context's device work is ordered on: a caller that enqueues its allreduce of
+ * the brq_hist_device() buffers on it (or makes its own stream wait on it) needs no host synchronisation */
+int brq_cuda_stream(brq_ctx* ctx, void** stream);
 /* bytes the context has copied device -> host since the last reset (histograms, error table, walk events, flagged slots) */
 int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);

@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; reported in config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs)")
+    ap.add_argument("--coverage", type=float, default=None, help="override the read depth (other BASELINE shapes; reported in config)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
@@ -207,6 +208,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = bq.Context(device=local)
+    if args.coverage:
+        READ_SETS[0]["coverage"] = float(args.coverage)
     genome = int(GENOME * args.scale)
     spec = bq.SynthSpec(seed=2 + rank, read_sets=READ_SETS, contig_lens=[genome], contig_prefix="REL606_range%d" % rank,
                         n_polymorphic=40, n_fixed=10, n_gaps=3)
@@ -333,6 +336,7 @@ def main():
         cfg["records_per_gpu"] = n_records
         cfg["slots_per_gpu"] = n_slots
         cfg["genome_scale"] = args.scale
+        cfg["coverage"] = READ_SETS[0]["coverage"]
         cfg["kernel_ms"] = k_ms
         cfg["staging_seconds"] = t_stage
         cfg["e2e_phase_ms"] = e2e_phase_ms

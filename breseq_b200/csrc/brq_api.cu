@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -99,6 +100,7 @@ struct brq_ctx {
   std::vector<double> walk_prop;    // the propagation cutoffs h_events was compacted for
   std::vector<ColumnOut> h_fcols;   // full results of the flagged slots, in the order of h_flagged
   bool have_walk = false;
+  std::unique_ptr<WorkerPool> pool; // parked host threads for short data-parallel jobs
   std::string shard_blob;           // brq_evidence_export
   uint64_t d2h_bytes = 0;           // device -> host bytes since the last brq_d2h_bytes(reset) (bench bookkeeping)
 
@@ -281,7 +283,8 @@ void download_hist(brq_ctx* c) {
 // likelihood table of pass 2, built on the device.  No synchronisation: the scoring kernels are
 // stream-ordered behind the table build.
 void install_table(brq_ctx* c) {
-  canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob);
+  if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+  canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob, c->pool.get());
   c->have_table = true;
   c->h_lut.clear();  // the host copy (re-evaluation of flagged slots) is rebuilt on demand
   c->have_device_tables = false;

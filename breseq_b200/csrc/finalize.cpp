@@ -4,6 +4,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -139,7 +140,53 @@ void read_error_rates(const std::string& path, CovSpec& c, std::vector<double>& 
   }
 }
 
-void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& text, std::vector<double>& prob) {
+struct WorkerPool::Impl {
+  std::mutex m;
+  std::condition_variable wake, done;
+  std::vector<std::thread> threads;
+  const std::function<void(size_t, size_t)>* job = nullptr;
+  uint64_t generation = 0;
+  size_t pending = 0;
+  bool stop = false;
+  std::exception_ptr failure;
+};
+
+WorkerPool::WorkerPool(size_t n_threads) : impl_(new Impl), n_(n_threads) {
+  for (size_t t = 0; t < n_; ++t)
+    impl_->threads.emplace_back([this, t] {
+      uint64_t seen = 0;
+      for (;;) {
+        const std::function<void(size_t, size_t)>* job;
+        {
+          std::unique_lock<std::mutex> lk(impl_->m);
+          impl_->wake.wait(lk, [&] { return impl_->stop || impl_->generation != seen; });
+          if (impl_->stop) return;
+          seen = impl_->generation; job = impl_->job;
+        }
+        try { (*job)(t + 1, n_ + 1); }
+        catch (...) { std::lock_guard<std::mutex> g(impl_->m); if (!impl_->failure) impl_->failure = std::current_exception(); }
+        { std::lock_guard<std::mutex> g(impl_->m); if (--impl_->pending == 0) impl_->done.notify_one(); }
+      }
+    });
+}
+
+WorkerPool::~WorkerPool() {
+  { std::lock_guard<std::mutex> g(impl_->m); impl_->stop = true; }
+  impl_->wake.notify_all();
+  for (auto& t : impl_->threads) t.join();
+  delete impl_;
+}
+
+void WorkerPool::run(const std::function<void(size_t, size_t)>& job) {
+  { std::lock_guard<std::mutex> g(impl_->m); impl_->job = &job; impl_->pending = n_; impl_->failure = nullptr; ++impl_->generation; }
+  impl_->wake.notify_all();
+  job(0, n_ + 1);
+  std::unique_lock<std::mutex> lk(impl_->m);
+  impl_->done.wait(lk, [&] { return impl_->pending == 0; });
+  if (impl_->failure) std::rethrow_exception(impl_->failure);
+}
+
+void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& text, std::vector<double>& prob, WorkerPool* pool) {
   const size_t n = log10_prob.size();
   text.resize(n);
   prob.resize(n);
@@ -151,13 +198,13 @@ void canonicalise_table(const std::vector<double>& log10_prob, std::vector<doubl
       prob[i] = pow(10, text[i]);
     }
   };
-  // every entry is independent: a few threads for the default table (2100 rows), more for tables with read_pos
-  const size_t n_threads = n < 1024 ? 1 : std::min<size_t>(n < 65536 ? 4 : 16, std::max(1u, std::thread::hardware_concurrency()));
-  if (n_threads == 1) { run(0, n); return; }
-  std::vector<std::thread> th;
-  for (size_t t = 1; t < n_threads; ++t) th.emplace_back(run, n * t / n_threads, n * (t + 1) / n_threads);
-  run(0, n / n_threads);
-  for (auto& x : th) x.join();
+  // every entry is independent
+  if (!pool || n < 512) { run(0, n); return; }
+  pool->run([&](size_t part, size_t parts) { run(n * part / parts, n * (part + 1) / parts); });
+}
+
+void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& text, std::vector<double>& prob) {
+  canonicalise_table(log10_prob, text, prob, nullptr);
 }
 
 // error_count.cpp:697-785, index arithmetic restated literally (accumulate obs-major, read out b1*5+b2).

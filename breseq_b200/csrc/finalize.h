@@ -5,6 +5,7 @@
 #include "brq_types.h"
 #include "kernels.h"
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -36,6 +37,22 @@ void write_error_rates(const std::string& path, const CovSpec& spec, const std::
 void read_error_rates(const std::string& path, CovSpec& spec, std::vector<double>& log10_prob);
 // log10 table -> the values pass 2 actually uses: text round trip, then pow(10, x)
 void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& log10_text, std::vector<double>& prob);
+
+// A few parked threads for the host's short data-parallel jobs (table canonicalisation, 0.4 ms of libc calls on one
+// thread): waking them costs microseconds, creating them would cost as much as the job.
+class WorkerPool {
+ public:
+  explicit WorkerPool(size_t n_threads);
+  ~WorkerPool();
+  size_t size() const { return n_ + 1; }   // the caller works too
+  // job(part, n_parts) for part in [0, n_parts), n_parts = size(); returns when all parts are done
+  void run(const std::function<void(size_t, size_t)>& job);
+ private:
+  struct Impl;
+  Impl* impl_;
+  size_t n_;
+};
+void canonicalise_table(const std::vector<double>& log10_prob, std::vector<double>& log10_text, std::vector<double>& prob, WorkerPool* pool);
 void write_base_qual_tables(const std::string& pattern, const CovSpec& spec, const std::vector<uint64_t>& counts,
                             const std::vector<std::string>& readfiles);
 void write_count_table(const std::string& path, const CovSpec& spec, const std::vector<uint64_t>& counts);

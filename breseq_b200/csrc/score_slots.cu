@@ -59,10 +59,11 @@ void note_launches(int n);
 namespace {
 
 constexpr int TALLY_MAX_TPB = 768;
+constexpr uint32_t PREFETCH_VECTORS = 16;  // round vectors (KB) of a round kept in L2 ahead of the record ring
 constexpr int RING = 4;           // 16-byte stages of each lane's record ring (a power of two)
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts
-constexpr int FIT_CACHE = 256;    // records per slot whose table code is cached in shared memory
+constexpr uint32_t FIT_HASH = 1024;  // slots of a warp's class -> count table (deep slots are fitted by class)
 constexpr int FIT_REG = 8;        // records per lane whose ratios stay in registers over the whole fit (slots up to 256 entries)
 constexpr uint32_t CODE_NONE = 0xFFFFFFFFu, CODE_COLD = 0x80000000u;
 
@@ -236,8 +237,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 #pragma unroll
     for (int st = 0; st < RING; ++st) fetch((uint32_t)st, (uint32_t)st, (uint32_t)st < x.n_vec);
     // the rest of the round into L2 (one request per warp), and this lane's side-list entries
+    // (at most PREFETCH_VECTORS of it: 3552 warps prefetching whole deep rounds would evict each other from the 126 MB L2;
+    // the record loop keeps that distance ahead of the ring)
     if (lane == 0 && x.n_vec > (uint32_t)RING)
-      prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, (x.n_vec - (uint32_t)RING) * (ROUND_VECTOR_WORDS * 4u));
+      prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, min(x.n_vec - (uint32_t)RING, PREFETCH_VECTORS) * (ROUND_VECTOR_WORDS * 4u));
     if (x.side1 > x.side0) prefetch_l2(side + (size_t)x.side0 * side_stride);
   };
   // round vector i: wait for it, read this lane's eight records, and hand the stage to vector i + RING
@@ -341,6 +344,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       // byte counters: at most 224 records between two contractions
       const uint32_t chunk_end = min(n_max, i + 28u);
       for (; i + 4u <= chunk_end; i += 4u) {  // i is a multiple of four here: the ring's stage numbers are constants
+        // deep rounds: every eighth vector asks L2 for the next eight beyond the prefetch distance
+        if ((i & 7u) == 0u && lane == 0 && i + (uint32_t)RING + PREFETCH_VECTORS < n_vec)
+          prefetch_l2_bulk(rec + cur.beg + (uint64_t)(i + (uint32_t)RING + PREFETCH_VECTORS) * ROUND_VECTOR_WORDS,
+                           min(n_vec - (i + (uint32_t)RING + PREFETCH_VECTORS), 8u) * (ROUND_VECTOR_WORDS * 4u));
 #pragma unroll
         for (uint32_t s4 = 0; s4 < 4u; ++s4) tally8(next_vec(s4, i + s4, n_vec));
       }
@@ -509,7 +516,8 @@ __device__ __forceinline__ uint2 classic_at(const GroupCtx& g, uint64_t i) {  //
 }
 __device__ __forceinline__ uint32_t code_at(const GroupCtx& g, uint64_t i) {
   const uint64_t k = i - g.beg;
-  return k < FIT_CACHE ? g.cache[k] : code_of(g, classic_at(g, i));
+  (void)k;
+  return code_of(g, classic_at(g, i));  // only the record-by-record path of a slot with too many classes gets here
 }
 // r[0..4] and M = max_b L[b]
 __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, double* rr, double& M) {
@@ -534,7 +542,9 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
                                                           uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t side_stride) {
   extern __shared__ __align__(16) double sm[];
   __shared__ uint8_t mapq_slot[256];
-  __shared__ uint32_t cache[FIT_TPB / FIT_LANES][FIT_CACHE];
+  // per warp, after the hot table: FIT_HASH class codes and FIT_HASH counts (the first 256 codes double as the
+  // code cache of a shallow slot)
+  uint32_t* warp_tab = reinterpret_cast<uint32_t*>(sm + (size_t)p.n_hot * 6) + (threadIdx.x / FIT_LANES) * (2u * FIT_HASH);
   const uint32_t n_work = scalars[2];
   if ((uint64_t)blockIdx.x * (FIT_TPB / FIT_LANES) >= n_work) return;  // the work list is short: most CTAs have nothing to do
   {
@@ -549,7 +559,8 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
   g.rec = rec; g.hot_base = (uint32_t)__cvta_generic_to_shared(sm); g.lut = lut; g.mapq_slot = mapq_slot; g.p = &p;
   g.sub = lane % FIT_LANES;
   g.mask = FIT_LANES == 32 ? 0xFFFFFFFFu : (((1u << (FIT_LANES & 31)) - 1u) << (lane - g.sub));
-  uint32_t* my_cache = cache[threadIdx.x / FIT_LANES];
+  uint32_t* my_cache = warp_tab;
+  uint32_t* my_count = warp_tab + FIT_HASH;
   g.cache = my_cache;
   for (;;) {
     uint32_t w = 0;
@@ -569,9 +580,10 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
     // chain, run without a load.
     const bool in_regs = g.end - g.beg <= (uint64_t)(FIT_LANES * FIT_REG);
     uint32_t obs_count[5] = {0, 0, 0, 0, 0}, n = 0;
-    double R[FIT_REG][5], Mr[FIT_REG];
+    double R[FIT_REG][5], Mr[FIT_REG], Cn[FIT_REG];  // ratios, max log-likelihood and weight (1, or the class count)
     bool ok[FIT_REG];
-    uint32_t k_max = 0;  // records per lane that hold anything (warp-uniform)
+    bool by_class = false;
+    uint32_t k_max = 0;  // records (or classes) per lane that hold anything (warp-uniform)
     if (in_regs) {
       uint2 rx[FIT_REG];
 #pragma unroll
@@ -599,7 +611,7 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       k_max = (n_before + FIT_LANES - 1) / FIT_LANES;
 #pragma unroll
       for (int k = 0; k < FIT_REG; ++k) {
-        Mr[k] = 0.0;
+        Mr[k] = 0.0; Cn[k] = 1.0;
 #pragma unroll
         for (int b = 0; b < 5; ++b) R[k][b] = 0.0;
         ok[k] = g.sub + (uint32_t)k * FIT_LANES < n_before;
@@ -607,23 +619,68 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       }
       __syncwarp(g.mask);
     } else {
-#pragma unroll
-      for (int k = 0; k < FIT_REG; ++k) {
-        ok[k] = false; Mr[k] = 0.0;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) R[k][b] = 0.0;
-      }
+      // A deep slot is fitted BY CLASS: its records fall into a few hundred (read set, strand, MAPQ, quality, obs)
+      // classes, and a record's responsibilities depend on its class alone, so an EM step over classes weighted by
+      // their counts is the same sum with a tenth of the terms.  The warp counts the classes in a hash table in
+      // shared memory, packs the table, and keeps up to FIT_REG classes per lane in registers.
+      for (uint32_t h = g.sub; h < FIT_HASH; h += FIT_LANES) { my_cache[h] = CODE_NONE; my_count[h] = 0u; }
+      __syncwarp(g.mask);
+      bool overflow = false;
       for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
-        const uint2 rx = classic_at(g, i);
-        const uint32_t r = rx.x;
-        const uint32_t code = code_of(g, rx);
-        if (i - g.beg < FIT_CACHE) my_cache[i - g.beg] = code;
+        const uint32_t code = code_of(g, classic_at(g, i));
         if (code == CODE_NONE) continue;
-#pragma unroll
-        for (int b = 0; b < 5; ++b) obs_count[b] += ((r & 7) == (uint32_t)b);
-        ++n;
+        uint32_t h = (code * 2654435761u) >> 22;
+        uint32_t probes = 0;
+        for (; probes < FIT_HASH; ++probes, h = (h + 1u) & (FIT_HASH - 1u)) {
+          const uint32_t old = atomicCAS(&my_cache[h], CODE_NONE, code);
+          if (old == CODE_NONE || old == code) { atomicAdd(&my_count[h], 1u); break; }
+        }
+        if (probes == FIT_HASH) overflow = true;
       }
       __syncwarp(g.mask);
+      // pack the occupied slots to the front (in place: a slot's new position is never above its old one)
+      uint32_t n_classes = 0;
+      for (uint32_t h0 = 0; h0 < FIT_HASH; h0 += FIT_LANES) {
+        const uint32_t code = my_cache[h0 + g.sub], cnt = my_count[h0 + g.sub];
+        const uint32_t m = __ballot_sync(g.mask, code != CODE_NONE);
+        __syncwarp(g.mask);
+        if (code != CODE_NONE) {
+          const uint32_t at = n_classes + __popc(m & ((1u << g.sub) - 1u));
+          my_cache[at] = code; my_count[at] = cnt;
+        }
+        n_classes += __popc(m);
+        __syncwarp(g.mask);
+      }
+      by_class = !__any_sync(g.mask, overflow) && n_classes <= (uint32_t)(FIT_LANES * FIT_REG);
+      k_max = by_class ? (n_classes + FIT_LANES - 1) / FIT_LANES : 0u;
+#pragma unroll
+      for (int k = 0; k < FIT_REG; ++k) {
+        Mr[k] = 0.0; Cn[k] = 1.0;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) R[k][b] = 0.0;
+        const uint32_t at = g.sub + (uint32_t)k * FIT_LANES;
+        ok[k] = by_class && at < n_classes;
+        if (ok[k]) {
+          const uint32_t code = my_cache[at], cnt = my_count[at];
+          load_ratios(g, code, R[k], Mr[k]);
+          Cn[k] = (double)cnt;
+          // the class index ends in the observed base (hot: index * 48, cold: CODE_COLD | index)
+          const uint32_t obs = ((code & CODE_COLD) ? (code & ~CODE_COLD) : code / 48u) % 5u;
+#pragma unroll
+          for (int b = 0; b < 5; ++b) obs_count[b] += obs == (uint32_t)b ? cnt : 0u;
+          n += cnt;
+        }
+      }
+      __syncwarp(g.mask);
+      if (!by_class) {  // more classes than the registers hold (read_pos covariates on a deep column): record by record
+        for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
+          const uint2 rx = classic_at(g, i);
+          if (code_of(g, rx) == CODE_NONE) continue;
+#pragma unroll
+          for (int b = 0; b < 5; ++b) obs_count[b] += ((rx.x & 7) == (uint32_t)b);
+          ++n;
+        }
+      }
     }
 #pragma unroll
     for (int b = 0; b < 5; ++b) obs_count[b] = group_sum_u32(obs_count[b], g.mask);
@@ -648,8 +705,8 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       uint32_t it = 1;
       for (; it <= 50; ++it) {
         double w[5] = {0, 0, 0, 0, 0};
-        if (in_regs) {
-          // branch-free, the four records' chains side by side: sums, then reciprocals, then responsibilities.
+        if (in_regs || by_class) {
+          // branch-free, the records' (classes') chains side by side: sums, then reciprocals, then responsibilities.
           // (A record whose sum is zero contributes f itself, like the reference; an absent one contributes nothing:
           // its ratios are zero and the select below drops it.)
 #pragma unroll
@@ -662,7 +719,7 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
 #pragma unroll
             for (int b = 0; b < 5; ++b) {
               const double term = sum > 0.0 ? a[b] * inv : f[b];
-              w[b] += ok[k] ? term : 0.0;
+              w[b] += ok[k] ? Cn[k] * term : 0.0;
             }
           }
         } else
@@ -699,7 +756,7 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       // sum_i (log10 s_i + M_i).  The s_i (each in (0, 1]) are multiplied up and one log10 is taken
       // per ~200 decades, which is the same sum to within a few ulps of its terms.
       double log_sum = 0.0, prod = 1.0, m_sum = 0.0;
-      if (in_regs) {
+      if (in_regs || by_class) {
 #pragma unroll
         for (int k = 0; k < FIT_REG; ++k) {
           if ((uint32_t)k >= k_max) break;  // warp-uniform
@@ -708,8 +765,11 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
 #pragma unroll
           for (int b = 0; b < 5; ++b) sum += f_prev[b] * R[k][b];
           if (sum > 0.0) {
-            prod *= sum; m_sum += Mr[k];
-            if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
+            if (by_class) { log_sum += Cn[k] * log10(sum); m_sum += Cn[k] * Mr[k]; }
+            else {
+              prod *= sum; m_sum += Mr[k];
+              if (prod < 1e-200) { log_sum += log10(prod); prod = 1.0; }
+            }
           }
         }
       } else
@@ -768,7 +828,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
-  const size_t smem_fit = (size_t)p.n_hot * 48;
+  const size_t smem_fit = (size_t)p.n_hot * 48 + (size_t)(FIT_TPB / FIT_LANES) * 2 * FIT_HASH * 4;
   // histogram block per warp: 4 KB holds 32 words per lane, 8 KB the maximum of 64; as many warps as 227 KB allow
   const uint32_t hist_block = p.t_nw <= 32 ? 4096u : 8192u;
   const size_t per_warp = hist_block + RING * 1024, fixed = (size_t)4 * p.t_stride + hist_block;

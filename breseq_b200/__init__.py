@@ -247,7 +247,7 @@ def decode_score_records(stream):
            "mapq": np.full(n, -1), "match": np.zeros(n, bool)}
     hot = kind == 0
     t = (d[hot] >> 16) & 0xFF
-    out["obs"][hot] = (d[hot] >> 24) & 3
+    out["obs"][hot] = (d[hot] >> 24) & 7
     out["qual"][hot] = g["q_lo"] + t % max(1, g["n_q"])
     out["read_set"][hot] = (t // max(1, g["n_q"])) >> 1
     out["mapq"][hot] = g["hot_mapq"]

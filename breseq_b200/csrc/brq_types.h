@@ -95,9 +95,11 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //   [14]    slow     HOT but not matching the reference base: the kernel reads its table cell directly
 //   [15]    trimmed  REDUNDANT: is_trimmed() (only the per-position debug file looks at it)
 //   [23:16] sq       HOT: class index (above)         REDUNDANT: [24:16] X1; 511 = the value is the slot's next
-//   [25:24] obs      HOT: observed base A,C,G,T                  SIDE_BIG entry of the side list; [27:25] observed base
+//   [26:24] obs      HOT: observed base A,C,G,T,'.'              SIDE_BIG entry of the side list; [27:25] observed base
 //   [28]    match    HOT and obs equals the slot's reference base
-//   [31:30] kind     0 HOT    scores; dominant MAPQ, A/C/G/T observation, quality inside the table window
+//   [31:30] kind     0 HOT    scores; dominant MAPQ, quality inside the table window (any observation, '.' included:
+//                             a read without an inserted base is a '.' observation of the insert sub-column, and
+//                             nearly every record of such a slot is one)
 //                    1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
 //                    2 COLD   scores, class outside the shared table; its classic word is the slot's next
 //                             cold entry of the side list
@@ -133,7 +135,7 @@ struct ScoreGeometry {
   uint32_t side_stride = 1;  // words per side-list entry: 2 when the records carry read_pos / base_repeat
   uint32_t n_sq() const { return n_st * n_q; }            // classes of the per-slot histogram (<= 248)
   uint32_t n_words() const { return n_sq() / 4 + 2; }     // 32-bit histogram words per lane: class words + 2 special words
-  uint32_t n_hot() const { return n_sq() * 4; }           // cells of the shared likelihood table
+  uint32_t n_hot() const { return n_sq() * 5; }           // cells of the shared likelihood table
   static uint32_t counter_of(uint32_t index) { return (index >> 2) * 128u + (index & 3u) * 8u; }
   uint32_t special_counter(uint32_t which) const { return counter_of(n_sq() + which); }
   uint32_t pad_word() const { return special_counter(SC_TRASH); }
@@ -141,7 +143,7 @@ struct ScoreGeometry {
 
 // classic word of a HOT device word
 inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
-  const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = g.q_lo + sq % g.n_q, st = sq / g.n_q;
+  const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 7u, qual = g.q_lo + sq % g.n_q, st = sq / g.n_q;
   return obs | qual << SR_QUAL_SHIFT | st << 10 | g.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT |
          ((d & DR_MATCH_BIT) ? SR_MATCH_BIT : 0u);
 }

@@ -311,7 +311,7 @@ void score_geometry(const CovSpec& c, const uint32_t mapq_seen[8], const ScoreGe
   g.n_cold = (size_t)g.n_st * p.n_mq * Q * W * 5;
   p.t_qlo = sg.q_lo; p.t_nq = sg.n_q; p.t_nsq = sg.n_sq(); p.t_nw = sg.n_words();
   p.t_stride = p.t_nsq * 64u;
-  g.n_tally_cells = (size_t)4 * p.t_stride / 16;
+  g.n_tally_cells = (size_t)5 * p.t_stride / 16;  // five observation planes
 }
 
 // Host copy of the per-class terms, with the libm calls the reference makes (identify_mutations.cpp:3359-3384).

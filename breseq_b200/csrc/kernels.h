@@ -65,7 +65,7 @@ struct ScoreParams {
   // tally kernel: per-slot class histogram over sq = (set*2 + top) * t_nq + quality - t_qlo (t_nsq classes in
   // t_nsq / 4 words, then two words of special counters) and the shared-memory likelihood table of the dominant
   // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M, top strand ? 1 : 0, top strand ? 0 : 1} (64 bytes a class: the B operand
-  // of the contraction), t_stride bytes between the four obs planes
+  // of the contraction), t_stride bytes between the five obs planes (A, C, G, T, .)
   uint32_t t_qlo, t_nq, t_nsq, t_nw, t_stride;
   uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
   uint32_t n_rpos, n_rep;    // read_pos / base_repeat values of the table (1 = the covariate is not used); with them every

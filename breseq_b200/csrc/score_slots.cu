@@ -169,7 +169,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 //                       block is aligned to its size, so counter address = (record & 0x1FFF) | lane base.  The first
 //                       2 KB double as the scratch through which the contraction's result tiles reach their lanes.
 //   [n_warps x 4 KB]    record rings: 4 stages of one round vector (two planes of 32 lanes x 16 bytes)
-//   [4 x t_stride]      likelihood table [obs][sq] x 8 doubles (ScoreParams)
+//   [5 x t_stride]      likelihood table [obs][sq] x 8 doubles (ScoreParams), obs = A, C, G, T, '.'
 __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ round_off,
                                                                   const uint32_t* __restrict__ side, const uint2* __restrict__ round_side,
                                                                   const uint32_t* __restrict__ round_slot,
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   const uint32_t ring = sm0 + n_warps_cta * hist_block + warp * (RING * 1024u) + lane * 16u;  // this lane's cell of stage 0, first plane
   const uint32_t tbl = sm0 + n_warps_cta * (hist_block + RING * 1024u);
   {
-    const uint32_t n16 = p.t_stride / 4u;  // 16-byte cells of the table (4 planes of t_stride bytes)
+    const uint32_t n16 = 5u * (p.t_stride / 16u);  // 16-byte cells of the table (5 observation planes of t_stride bytes)
     const uint4* src = reinterpret_cast<const uint4*>(tallyT);
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) {
       const uint4 v = src[i];
@@ -327,16 +327,16 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (!(r[j] & DR_SLOW_BIT)) continue;
-          const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 3u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 64u;
+          const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 7u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 64u;
           const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
           kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
         }
       }
     };
 
-    // the likelihood table of the round's reference base (rounds hold one base; "other" bases have no class counts)
+    // the likelihood table of the round's reference base (rounds hold one base; insert sub-columns have '.', N columns no class counts)
     const uint32_t ref_round = __reduce_min_sync(0xFFFFFFFFu, my_ref);
-    const uint32_t b_base = tbl + (ref_round < 4u ? ref_round : 0u) * p.t_stride + b_off;
+    const uint32_t b_base = tbl + (ref_round < 5u ? ref_round : 0u) * p.t_stride + b_off;
     const uint32_t n_max = n_vec;  // the round's vectors: the same for every lane (shallower slots end in pad words)
     uint32_t i = 0;  // round vectors consumed so far
     bool more;
@@ -506,7 +506,7 @@ __device__ __forceinline__ uint2 classic_at(const GroupCtx& g, uint64_t i) {  //
     const uint32_t d = __ldg(g.rec + score_index(g.base, k));
     if ((d >> DR_KIND_SHIFT) != 0u) return make_uint2(0u, 0u);
     const ScoreParams& p = *g.p;
-    const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 3u, qual = p.t_qlo + sq % p.t_nq, st = sq / p.t_nq;
+    const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 7u, qual = p.t_qlo + sq % p.t_nq, st = sq / p.t_nq;
     return make_uint2(obs | qual << SR_QUAL_SHIFT | st << 10 | p.hot_mapq << SR_MAPQ_SHIFT | SR_UNIQUE_BIT | SR_OK_BIT, 0u);
   }
   const size_t e = (size_t)(g.side_beg + (uint32_t)(k - g.n_main)) * g.side_stride;
@@ -831,7 +831,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const size_t smem_fit = (size_t)p.n_hot * 48 + (size_t)(FIT_TPB / FIT_LANES) * 2 * FIT_HASH * 4;
   // histogram block per warp: 4 KB holds 32 words per lane, 8 KB the maximum of 64; as many warps as 227 KB allow
   const uint32_t hist_block = p.t_nw <= 32 ? 4096u : 8192u;
-  const size_t per_warp = hist_block + RING * 1024, fixed = (size_t)4 * p.t_stride + hist_block;
+  const size_t per_warp = hist_block + RING * 1024, fixed = (size_t)5 * p.t_stride + hist_block;
   int warps = TALLY_MAX_TPB / 32;
   while (warps > 1 && fixed + warps * per_warp > 227 * 1024) --warps;
   const size_t smem_tally = fixed + warps * per_warp;

@@ -442,7 +442,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       return w;
     }
     const bool match = obs == ref;
-    if (n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 4 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
+    if (n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 5 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
       const uint32_t sq = ((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo);
       w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top;
       if (match) w.dev |= DR_MATCH_BIT | ScoreGeometry::counter_of(sq);

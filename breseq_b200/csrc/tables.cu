@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
     h.M = M;
     a.hotR[((size_t)st * a.Q + q) * 5u + obs] = h;
   }
-  if (obs < 4u && q >= p.t_qlo && q < p.t_qlo + p.t_nq) {
+  if (q >= p.t_qlo && q < p.t_qlo + p.t_nq) {
     double* d = reinterpret_cast<double*>(reinterpret_cast<char*>(a.tallyT) + (size_t)obs * p.t_stride + ((size_t)st * p.t_nq + (q - p.t_qlo)) * 64u);
 #pragma unroll
     for (int b = 0; b < 5; ++b) d[b] = L[b];

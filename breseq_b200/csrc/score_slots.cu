@@ -49,6 +49,7 @@
 //   walk events   walk_mark / walk_compact kernels: the columns the host's MC / UN interval state machines have to see
 //                 (coverage at or below the propagation cutoff, not predicted, flagged, target ends, and their
 //                 neighbours), a few thousand of 4.6 M at C1; gather_columns: the full results of the flagged slots.
+#include <cstdlib>
 #include "kernels.h"
 #include "brq_types.h"
 
@@ -59,7 +60,7 @@ void note_launches(int n);
 namespace {
 
 constexpr int TALLY_MAX_TPB = 768;
-constexpr uint32_t PREFETCH_VECTORS = 16;  // round vectors (KB) of a round kept in L2 ahead of the record ring
+constexpr uint32_t PREFETCH_VECTORS = 4;   // round vectors (KB) of a round kept in L2 ahead of the record ring (BRQ_TALLY_PREFETCH overrides; -1 = none)
 constexpr int RING = 4;           // 16-byte stages of each lane's record ring (a power of two)
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
                                                                   uint64_t n_rounds, const double* __restrict__ tallyT,
                                                                   const HotTerms* __restrict__ coldT, ScoreParams p, ColumnOut* __restrict__ out,
                                                                   uint32_t* __restrict__ worklist, uint32_t* __restrict__ flagged,
-                                                                  uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block, uint32_t side_stride) {
+                                                                  uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t hist_block, uint32_t side_stride, uint32_t pf_vec) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const uint32_t n_warps_cta = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t sm0 = ((uint32_t)__cvta_generic_to_shared(sm_raw) + hist_block - 1u) & ~(hist_block - 1u);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   // fully coalesced 16-byte copies per lane and vector): four vectors are always on their way without holding
   // registers, and wait_group counts them in order.  A lane only ever reads its own cells.
   const uint4* vp = nullptr;  // this lane's 16 bytes of the round's first plane
+  const bool pf_on = pf_vec - 1u < 0xFFFFu;
   auto fetch = [&](uint32_t stage, uint32_t i, bool on) {  // round vector i into a stage; always one commit
     if (on) {
       cp_async16(ring + stage * 1024u, vp + (size_t)i * (ROUND_VECTOR_WORDS / 4));
@@ -237,10 +239,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 #pragma unroll
     for (int st = 0; st < RING; ++st) fetch((uint32_t)st, (uint32_t)st, (uint32_t)st < x.n_vec);
     // the rest of the round into L2 (one request per warp), and this lane's side-list entries
-    // (at most PREFETCH_VECTORS of it: 3552 warps prefetching whole deep rounds would evict each other from the 126 MB L2;
+    // (at most pf_vec vectors of it: 3552 warps prefetching whole deep rounds would evict each other from the 126 MB L2;
     // the record loop keeps that distance ahead of the ring)
-    if (lane == 0 && x.n_vec > (uint32_t)RING)
-      prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, min(x.n_vec - (uint32_t)RING, PREFETCH_VECTORS) * (ROUND_VECTOR_WORDS * 4u));
+    if (lane == 0 && x.n_vec > (uint32_t)RING && pf_on)
+      prefetch_l2_bulk(rec + x.beg + (uint64_t)RING * ROUND_VECTOR_WORDS, min(x.n_vec - (uint32_t)RING, pf_vec) * (ROUND_VECTOR_WORDS * 4u));
     if (x.side1 > x.side0) prefetch_l2(side + (size_t)x.side0 * side_stride);
   };
   // round vector i: wait for it, read this lane's eight records, and hand the stage to vector i + RING
@@ -345,9 +347,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       const uint32_t chunk_end = min(n_max, i + 28u);
       for (; i + 4u <= chunk_end; i += 4u) {  // i is a multiple of four here: the ring's stage numbers are constants
         // deep rounds: every eighth vector asks L2 for the next eight beyond the prefetch distance
-        if ((i & 7u) == 0u && lane == 0 && i + (uint32_t)RING + PREFETCH_VECTORS < n_vec)
-          prefetch_l2_bulk(rec + cur.beg + (uint64_t)(i + (uint32_t)RING + PREFETCH_VECTORS) * ROUND_VECTOR_WORDS,
-                           min(n_vec - (i + (uint32_t)RING + PREFETCH_VECTORS), 8u) * (ROUND_VECTOR_WORDS * 4u));
+        if ((i & 7u) == 0u && lane == 0 && pf_on && i + (uint32_t)RING + pf_vec < n_vec)
+          prefetch_l2_bulk(rec + cur.beg + (uint64_t)(i + (uint32_t)RING + pf_vec) * ROUND_VECTOR_WORDS,
+                           min(n_vec - (i + (uint32_t)RING + pf_vec), 8u) * (ROUND_VECTOR_WORDS * 4u));
 #pragma unroll
         for (uint32_t s4 = 0; s4 < 4u; ++s4) tally8(next_vec(s4, i + s4, n_vec));
       }
@@ -837,8 +839,9 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   const size_t smem_tally = fixed + warps * per_warp;
   const int blocks = (int)std::min<uint64_t>((n_rounds + warps - 1) / warps, (uint64_t)kSMs);
   (void)n_records;
+  static const uint32_t pf_vec = [] { const char* e = getenv("BRQ_TALLY_PREFETCH"); return e ? (uint32_t)atoi(e) : PREFETCH_VECTORS; }();  // -1: no L2 prefetch
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
-  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, round_side, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block, side_stride);
+  tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, round_side, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block, side_stride, pf_vec);
   if (between) cudaEventRecord(between, s);
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
   fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap, side_stride);

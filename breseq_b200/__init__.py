@@ -63,7 +63,8 @@ class _StreamInfo(C.Structure):
                 ("hist_rec", C.c_void_p), ("hist_off", C.POINTER(C.c_uint64)),
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
                 ("ins_count", C.POINTER(C.c_uint32)), ("round_slot", C.POINTER(C.c_uint32)), ("n_rounds", C.c_uint64),
-                ("score_cnt", C.POINTER(C.c_uint32)), ("round_off", C.POINTER(C.c_uint64))]
+                ("score_cnt", C.POINTER(C.c_uint32)), ("round_off", C.POINTER(C.c_uint64)),
+                ("hist16", C.POINTER(C.c_uint16)), ("hist_exc", C.POINTER(C.c_uint32)), ("n_hist16", C.c_uint64), ("n_hist_exc", C.c_uint64)]
 
 
 class _ScoreParams(C.Structure):
@@ -344,6 +345,9 @@ class Context:
             "hist_rec": view(C.cast(info.hist_rec, C.POINTER(C.c_uint64 if info.hist_record_bytes == 8 else C.c_uint32)),
                              info.n_hist_records, np.uint64 if info.hist_record_bytes == 8 else np.uint32),
             "hist_off": view(info.hist_off, info.n_base + 1, np.uint64),
+            # compact form the device reads (None when the stream has 8-byte histogram records): csrc/brq_types.h
+            "hist16": view(info.hist16, info.n_hist16, np.uint16) if info.hist16 else None,
+            "hist_exc": view(info.hist_exc, info.n_hist_exc, np.uint32) if info.hist16 else None,
             "slot_ref": view(info.slot_ref, n_slots, np.uint8),
             "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
             "ins_count": view(info.ins_count, info.n_ins, np.uint32),

@@ -76,6 +76,7 @@ struct brq_ctx {
   DevBuf<uint64_t> d_score_off, d_hist_off, d_round_off;
   DevBuf<uint32_t> d_score_cnt, d_round_side;
   DevBuf<uint8_t> d_hist_rec;
+  size_t hist_exc_at = 0;   // byte offset of the exception records inside d_hist_rec (compact form)
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
   DevBuf<double> d_log10;
@@ -207,7 +208,9 @@ void upload(brq_ctx* c) {
   const PileupStream& st = c->st;
   const uint64_t n_slots = st.n_slots();
   c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_round_side.ensure(st.n_rounds * 64 + 4); c->d_slot_ref.ensure(n_slots);
-  c->d_hist_rec.ensure(st.n_hist * st.hist_bytes + 16);
+  // the histogram records: the compact form when staging built it (16-bit fast records, then the 4-byte exceptions)
+  c->hist_exc_at = (st.n_hist16 * 2 + 31) & ~(size_t)15;
+  c->d_hist_rec.ensure(st.hist16 ? c->hist_exc_at + st.n_hist_exc * 4 + 16 : st.n_hist * st.hist_bytes + 16);
   c->d_side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
   CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -218,7 +221,12 @@ void upload(brq_ctx* c) {
   CUDA_OK(cudaMemcpyAsync(c->d_side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * st.hist_bytes, cudaMemcpyHostToDevice, c->stream));
+  if (st.hist16) {
+    CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist16, st.n_hist16 * 2, cudaMemcpyHostToDevice, c->stream));
+    if (st.n_hist_exc) CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p + c->hist_exc_at, st.hist_exc, st.n_hist_exc * 4, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * st.hist_bytes, cudaMemcpyHostToDevice, c->stream));
+  }
   CUDA_OK(cudaMemcpyAsync(c->d_hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
   c->uploaded = true;
@@ -256,7 +264,8 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
       throw std::runtime_error("base_repeat above 32 is not supported (the staged records keep five bits of it)");
     if (st.hist_bytes == 4 && (lay.off_rpos || lay.off_rep))
       throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
-    launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
+    if (st.hist16) launch_hist16(c->d_hist_rec.p, st.n_hist16, reinterpret_cast<const uint32_t*>(c->d_hist_rec.p + c->hist_exc_at), st.n_hist_exc, lay, c->d_counts.p, c->stream);
+    else launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
   }
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
@@ -602,10 +611,11 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
     info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
-    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + st.n_hist * st.hist_bytes + (st.n_base + 1) * 8 + st.n_base;
+    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
+    info->hist16 = st.hist16; info->n_hist16 = st.n_hist16; info->hist_exc = st.hist_exc; info->n_hist_exc = st.n_hist_exc;
   });
 }
 

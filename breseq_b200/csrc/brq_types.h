@@ -165,8 +165,34 @@ inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
 //   [15:0] read_pos of A (0-based query index)  [23:16] base_repeat of A  [28:24] base_repeat of B (saturated at 31)
 //   [31:29] read_set bits 5:3
 // Base indices A,C,G,T,'.' = 0..4.
+// COMPACT FORM (hist16 + hist_exc).  All but ~0.3 % of the 4-byte records are `fast`, and a fast record is four small
+// numbers: staging re-packs it into 16 bits
+//   [1:0] base (ref == obs)   [7:2] quality of A   [13:8] quality of B, 63 = no observation B   [15:14] read_set
+// and moves every other record (not fast, a quality above 62, a read_set above 3) unchanged into the exception stream
+// hist_exc.  The device reads only these two streams: half the bytes over PCIe and out of HBM.  Order is not kept
+// (a histogram does not need it); hist_rec / hist_off stay on the host as the positional form (tests, shard merges).
 constexpr int HR_REFA = 0, HR_OBSA = 3, HR_QUALA = 6, HR_VALIDA = 13, HR_REFB = 14, HR_OBSB = 17, HR_QUALB = 20, HR_VALIDB = 27,
               HR_SET = 28, HR_FAST = 31, HR_RPOS = 32, HR_REPA = 48, HR_REPB = 56, HR_SET_HI = 61;
+
+#ifdef __CUDACC__
+#define BRQ_HD __host__ __device__
+#else
+#define BRQ_HD
+#endif
+// 16-bit form of a fast record -> the 4-byte record it stands for
+BRQ_HD inline uint32_t hist16_expand(uint32_t r) {
+  const uint32_t base = r & 3u, qa = (r >> 2) & 63u, qb = (r >> 8) & 63u, set = r >> 14;
+  return base | base << HR_OBSA | qa << HR_QUALA | 1u << HR_VALIDA | set << HR_SET | 1u << HR_FAST |
+         (qb == 63u ? 127u << HR_QUALB : (4u << HR_REFB | 4u << HR_OBSB | qb << HR_QUALB | 1u << HR_VALIDB));
+}
+// 4-byte record -> its 16-bit form, or 0x10000 when it has none (expansion must give the record back bit for bit)
+inline uint32_t hist16_pack(uint32_t lo) {
+  if (!(lo >> HR_FAST)) return 0x10000u;
+  const uint32_t qa = (lo >> HR_QUALA) & 127u, qb = (lo >> HR_QUALB) & 127u, set = (lo >> HR_SET) & 7u;
+  if (qa > 62u || (qb > 62u && qb != 127u) || set > 3u) return 0x10000u;
+  const uint32_t r = (lo & 3u) | qa << 2 | (qb == 127u ? 63u : qb) << 8 | set << 14;
+  return hist16_expand(r) == lo ? r : 0x10000u;
+}
 
 // Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
 struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
@@ -197,6 +223,9 @@ struct PileupStream {
   ScoreGeometry geo;
   void* hist_rec = nullptr;            // n_hist records of hist_bytes (4 or 8) each
   uint32_t hist_bytes = 4;
+  uint16_t* hist16 = nullptr;          // compact form of the fast records (above); null when hist_bytes == 8
+  uint32_t* hist_exc = nullptr;        // the records without a 16-bit form, unchanged
+  uint64_t n_hist16 = 0, n_hist_exc = 0;
   uint64_t n_score = 0, n_hist = 0;    // records (padding not counted)
   uint64_t n_score_padded = 0;         // words in score_rec
   uint32_t mapq_seen[8] = {0};         // 256-bit mask of MAPQ values present among scoring records

@@ -144,6 +144,89 @@ __global__ void __launch_bounds__(JOINT ? 1024 : 256) hist_kernel(const void* __
   }
 }
 
+// The compact form (brq_types.h): `rec16` holds n16 fast records of 16 bits (eight per 128-bit load), `exc` the n_exc
+// records without a 16-bit form (4 bytes, generic path).  JOINT as above: one atomic per fast record on the CTA's joint
+// histogram; otherwise a fast record is expanded to its 4-byte form and takes the generic two-atomic path.
+__device__ __forceinline__ uint32_t joint_index16(uint32_t r, uint32_t n_set, uint32_t Q) {  // [sets][4 bases][Q][Q + 1]; r: 16 bits
+  const uint32_t set = n_set > 1 ? r >> 14 : 0u;
+  return ((set * 4u + (r & 3u)) * Q + ((r >> 2) & 63u)) * (Q + 1u) + min((r >> 8) & 63u, Q);
+}
+template <bool SMEM, bool JOINT>
+__global__ void __launch_bounds__(JOINT ? 1024 : 256) hist16_kernel(const uint4* __restrict__ rec16, uint64_t n16, const uint32_t* __restrict__ exc, uint64_t n_exc,
+                                                                      CovLayout lay, unsigned long long* __restrict__ counts, uint32_t joint_sets) {
+  extern __shared__ uint32_t sh[];
+  uint32_t* joint = sh + ((lay.n_bins + 3u) & ~3u);
+  const uint32_t n_joint = JOINT ? joint_sets * 4u * lay.max_qual * (lay.max_qual + 1u) : 0u;
+  if (SMEM) {
+    for (uint32_t i = threadIdx.x; i < lay.n_bins; i += blockDim.x) sh[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_joint; i += blockDim.x) joint[i] = 0;
+    __syncthreads();
+  }
+  const uint32_t Q = lay.max_qual;
+  auto fast = [&](uint32_t r) {  // r: one 16-bit record
+    if (JOINT) atomicAdd(&joint[joint_index16(r, joint_sets, Q)], 1u);
+    else hist_record<SMEM, false>(hist16_expand(r), 0u, lay, sh, counts);
+  };
+  auto one = [&](const uint4& v) {
+    fast(v.x & 0xFFFFu); fast(v.x >> 16); fast(v.y & 0xFFFFu); fast(v.y >> 16);
+    fast(v.z & 0xFFFFu); fast(v.z >> 16); fast(v.w & 0xFFFFu); fast(v.w >> 16);
+  };
+  const uint64_t n_vec = n16 / 8, stride = (uint64_t)gridDim.x * blockDim.x, tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t i = tid;
+  for (; i + 3 * stride < n_vec; i += 4 * stride) {  // four 128-bit loads in flight per thread
+    const uint4 a = ld_stream_u32x4(rec16 + i), b = ld_stream_u32x4(rec16 + i + stride);
+    const uint4 c = ld_stream_u32x4(rec16 + i + 2 * stride), d = ld_stream_u32x4(rec16 + i + 3 * stride);
+    one(a); one(b); one(c); one(d);
+  }
+  for (; i < n_vec; i += stride) one(ld_stream_u32x4(rec16 + i));
+  if (tid == 0) {  // the last partial vector
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(rec16);
+    for (uint64_t k = n_vec * 8; k < n16; ++k) fast(h[k]);
+  }
+  for (uint64_t k = tid; k < n_exc; k += stride) hist_record<SMEM, false>(ld_stream_u32(exc + k), 0u, lay, sh, counts);
+  if (SMEM) {
+    __syncthreads();
+    if (JOINT) {  // the two marginals of the joint histogram
+      for (uint32_t j = threadIdx.x; j < n_joint; j += blockDim.x) {
+        const uint32_t c = joint[j];
+        if (!c) continue;
+        const uint32_t qb = j % (Q + 1u), qa = (j / (Q + 1u)) % Q, base = (j / ((Q + 1u) * Q)) & 3u, set = j / (4u * Q * (Q + 1u));
+        const uint32_t off = set * lay.off_set;
+        atomicAdd(&sh[off + base * lay.off_ref + base * lay.off_obs + qa * lay.off_qual], c);
+        if (qb < Q) atomicAdd(&sh[off + 4u * lay.off_ref + 4u * lay.off_obs + qb * lay.off_qual], c);
+      }
+      __syncthreads();
+    }
+    for (uint32_t b = threadIdx.x; b < lay.n_bins; b += blockDim.x) {
+      const uint32_t v = sh[b];
+      if (v) atomicAdd(&counts[b], (unsigned long long)v);
+    }
+  }
+}
+
+void launch_hist16(const void* rec16, uint64_t n16, const uint32_t* exc, uint64_t n_exc, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
+  const int kSMs = 148;
+  const size_t smem = (size_t)lay.n_bins * 4;
+  const uint4* r = static_cast<const uint4*>(rec16);
+  // the joint histogram needs exactly the four default covariates, every quality a fast record can hold inside the
+  // table (<= 62 < max_qual is checked by the caller against the stream's maxima), and room beside the table
+  const uint32_t joint_sets = lay.off_set ? lay.max_set : 1u;
+  const size_t smem_joint = (((size_t)lay.n_bins + 3) & ~(size_t)3) * 4 + (size_t)joint_sets * 4 * lay.max_qual * (lay.max_qual + 1) * 4;
+  if (lay.off_qual && lay.off_ref && lay.off_obs && !lay.off_rpos && !lay.off_rep && lay.max_qual <= 64 &&
+      joint_sets <= 8 && smem_joint <= 110 * 1024) {
+    const int per_sm = (int)std::min<size_t>(2, std::max<size_t>(1, (220 * 1024) / smem_joint));
+    cudaFuncSetAttribute(hist16_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_joint);
+    hist16_kernel<true, true><<<kSMs * per_sm, 1024, smem_joint, s>>>(r, n16, exc, n_exc, lay, counts, joint_sets);
+  } else if (smem <= 200 * 1024) {
+    const int per_sm = smem <= 24 * 1024 ? 8 : (smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1));
+    cudaFuncSetAttribute(hist16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    hist16_kernel<true, false><<<kSMs * per_sm, 256, smem, s>>>(r, n16, exc, n_exc, lay, counts, 0u);
+  } else {
+    hist16_kernel<false, false><<<kSMs * 8, 256, 0, s>>>(r, n16, exc, n_exc, lay, counts, 0u);
+  }
+  ++g_launches;
+}
+
 void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& lay, unsigned long long* counts, cudaStream_t s) {
   const int kSMs = 148;
   const size_t smem = (size_t)lay.n_bins * 4;

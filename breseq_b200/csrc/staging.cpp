@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side, (void*)s.hist16, (void*)s.hist_exc})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -697,6 +697,39 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     out.max_hist_qual = std::max(out.max_hist_qual, max_hquals[ii]);
     out.max_hist_rpos = std::max(out.max_hist_rpos, max_rposs[ii]);
     out.max_score_rpos = std::max(out.max_score_rpos, max_srposs[ii]);
+  }
+
+  // ---- compact histogram streams (brq_types.h): fast records in 16 bits, the others unchanged
+  if (cfg.want_hist && cfg.compact_hist && out.hist_bytes == 4) {
+    const uint32_t* h = static_cast<const uint32_t*>(out.hist_rec);
+    const size_t n = out.n_hist, n_parts = (size_t)std::max(1, n_threads) * 4;
+    std::vector<uint64_t> c16(n_parts + 1, 0), cex(n_parts + 1, 0);
+    auto parts = [&](auto&& body) {
+      std::atomic<size_t> next(0);
+      auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n_parts) break; body(k, n * k / n_parts, n * (k + 1) / n_parts); } };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+      work();
+      for (auto& t : pool) t.join();
+    };
+    parts([&](size_t k, size_t lo, size_t hi) {
+      uint64_t a = 0;
+      for (size_t i = lo; i < hi; ++i) a += hist16_pack(h[i]) < 0x10000u;
+      c16[k + 1] = a; cex[k + 1] = (hi - lo) - a;
+    });
+    for (size_t k = 0; k < n_parts; ++k) { c16[k + 1] += c16[k]; cex[k + 1] += cex[k]; }
+    out.n_hist16 = c16[n_parts]; out.n_hist_exc = cex[n_parts];
+    bool p4 = false;
+    out.hist16 = (uint16_t*)alloc(out.n_hist16 * 2 + 32, &p4);
+    out.hist_exc = (uint32_t*)alloc(out.n_hist_exc * 4 + 32, &p4);
+    parts([&](size_t k, size_t lo, size_t hi) {
+      uint16_t* d16 = out.hist16 + c16[k];
+      uint32_t* dex = out.hist_exc + cex[k];
+      for (size_t i = lo; i < hi; ++i) {
+        const uint32_t r = hist16_pack(h[i]);
+        if (r < 0x10000u) *d16++ = (uint16_t)r; else *dex++ = h[i];
+      }
+    });
   }
 }
 

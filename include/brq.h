@@ -95,6 +95,10 @@ typedef struct brq_stream_info {
   uint64_t n_rounds;
   const uint32_t* score_cnt;       /* [slots] records of every slot */
   const uint64_t* round_off;       /* [n_rounds + 1] first word of every round in score_rec */
+  /* compact form of hist_rec, what brq_upload copies when present: the `fast` records in 16 bits each, the others unchanged (csrc/brq_types.h) */
+  const uint16_t* hist16;
+  const uint32_t* hist_exc;
+  uint64_t n_hist16, n_hist_exc;
 } brq_stream_info;
 
 int brq_stream(brq_ctx* ctx, brq_stream_info* info);

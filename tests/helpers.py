@@ -214,6 +214,15 @@ def emulate_hist(hist_rec, n_sets, n_qual):
     return counts
 
 
+def expand_hist16(h16):
+    """4-byte records of the 16-bit fast records (csrc/brq_types.h: hist16_expand)."""
+    r = h16.astype(np.uint32)
+    base, qa, qb, rset = r & 3, (r >> 2) & 63, (r >> 8) & 63, r >> 14
+    lo = base | base << 3 | qa << 6 | np.uint32(1 << 13) | rset << 28 | np.uint32(1 << 31)
+    b = np.where(qb == 63, np.uint32(127 << 20), np.uint32(4 << 14 | 4 << 17 | 1 << 27) | qb << 20)
+    return (lo | b).astype(np.uint32)
+
+
 def emulate_coverage_hist(hist_off):
     red = (hist_off[:-1] >> np.uint64(63)).astype(bool)
     off = (hist_off & np.uint64((1 << 63) - 1)).astype(np.int64)

@@ -26,6 +26,20 @@ def test_histogram_stream_matches_oracle_counts(staged):
     assert np.array_equal(mine, ora)
 
 
+def test_compact_histogram_stream_is_the_same_records(staged):
+    """hist16 + hist_exc (what the device reads) hold exactly the records of hist_rec, as a multiset."""
+    d, ctx, s = staged
+    if s["hist_rec"].dtype == np.uint64:
+        assert s["hist16"] is None  # 8-byte records (read_pos / base_repeat) have no compact form
+        return
+    assert s["hist16"] is not None and len(s["hist16"]) + len(s["hist_exc"]) == len(s["hist_rec"])
+    both = np.concatenate([helpers.expand_hist16(s["hist16"]), s["hist_exc"]])
+    assert np.array_equal(np.sort(both), np.sort(s["hist_rec"]))
+    if len(s["hist_rec"]):  # the exceptions are the few records that are not `fast` (or do not fit 6-bit qualities / 2-bit sets)
+        assert len(s["hist_exc"]) <= 0.05 * len(s["hist_rec"]) + 64
+    assert np.all((s["hist_exc"] >> 31 == 0) | (((s["hist_exc"] >> 6) & 127) > 62) | ((((s["hist_exc"] >> 20) & 127) > 62) & (((s["hist_exc"] >> 20) & 127) != 127)) | (((s["hist_exc"] >> 28) & 7) > 3))
+
+
 def test_unique_only_coverage_matches_oracle(staged):
     d, ctx, s = staged
     names = helpers.contig_names(d)

@@ -262,10 +262,15 @@ def main():
     ctx.event_record(0)
     t0 = time.perf_counter()
     k_ms = {"hist": 0.0, "coverage": 0.0, "derive": 0.0, "score": 0.0, "tally": 0.0, "fit": 0.0}
+    step_walls = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         step()
+        step_walls.append((time.perf_counter() - ts) * 1e3)
         for k, v in ctx.kernel_ms().items():
             k_ms[k] += v
+    if os.environ.get("BRQ_BENCH_STEP_TIMES"):  # debugging aid: every step ends in a synchronisation, so its wall time is its duration
+        print("step wall ms: " + " ".join("%.3f" % w for w in step_walls), file=sys.stderr)
     ctx.event_record(1)
     barrier()
     wall = time.perf_counter() - t0

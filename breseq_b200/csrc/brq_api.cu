@@ -110,6 +110,11 @@ struct brq_ctx {
   uint64_t cov_stride = 0, n_groups = 0;
   std::vector<uint64_t> h_counts, h_cov;
   std::vector<double> h_log10, h_log10_text, h_prob;
+  double* h_log10_pinned = nullptr;  // landing buffer of the device-derived log10 table
+  size_t n_log10_pinned = 0;
+  bool host_table_pending = false;   // the host copies above are stale until host_table_ready()
+  bool derive_timed = true;
+  DevBuf<uint32_t> d_table_err;
   ClassLut h_lut;
   ScoreParams sp;
   brq_score_params last_params;
@@ -121,9 +126,14 @@ struct brq_ctx {
     if (device < 0) throw std::runtime_error("this context has no CUDA device (brq_config.device < 0): compute calls are unavailable");
   }
   void check_device_errors(const char* what) {
-    uint32_t scal[2];
+    uint32_t scal[2], table_err = 0;
     CUDA_OK(cudaMemcpyAsync(scal, d_scalars.p, 8, cudaMemcpyDeviceToHost, stream));
+    if (d_table_err.p) CUDA_OK(cudaMemcpyAsync(&table_err, d_table_err.p, 4, cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
+    if (table_err) {
+      CUDA_OK(cudaMemsetAsync(d_table_err.p, 0, 4, stream));
+      throw std::runtime_error(std::string(what) + ": an error-table value is outside the range of the device's six-digit text round trip (csrc/canonical.h)");
+    }
     if (scal[0]) {
       std::string m = std::string(what) + ": ";
       if (scal[0] & BRQ_ERR_QUALITY_RANGE) m += "covariate 'quality' exceeded its maximum; ";
@@ -276,6 +286,7 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   CUDA_OK(cudaEventElapsedTime(&c->ms_cov, c->ev[1], c->ev[2]));
   c->have_counts = true;
   c->have_table = false;
+  c->host_table_pending = false;
 }
 
 void download_hist(brq_ctx* c) {
@@ -288,13 +299,23 @@ void download_hist(brq_ctx* c) {
   CUDA_OK(cudaStreamSynchronize(c->stream));
 }
 
-// h_log10 -> text-canonical probabilities (host: the reference's ostream / strtod round trip) -> every
-// likelihood table of pass 2, built on the device.  No synchronisation: the scoring kernels are
-// stream-ordered behind the table build.
-void install_table(brq_ctx* c) {
+// The error table reaches pass 2 through the reference's text round trip (six significant digits, error_count.cpp:629-690).
+// Two ways in: derive_table() has the log10 table on the device and canonicalises it there (canonical.h: no host work
+// inside a step; the host copies for the files and the re-evaluation of flagged slots are made when first asked for,
+// host_table_ready()); a table loaded from a file or imported is canonicalised on the host and uploaded.
+bool host_table_ready(brq_ctx* c) {
+  if (!c->host_table_pending) return false;
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->h_log10.assign(c->h_log10_pinned, c->h_log10_pinned + c->n_log10_pinned);
   if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
   canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob, c->pool.get());
-  c->have_table = true;
+  c->host_table_pending = false;
+  return true;
+}
+
+// every likelihood table of pass 2, built on the device from d_prob.  No synchronisation: the scoring kernels are
+// stream-ordered behind the table build.
+void build_device_tables(brq_ctx* c) {
   c->h_lut.clear();  // the host copy (re-evaluation of flagged slots) is rebuilt on demand
   c->have_device_tables = false;
   if (!c->staged) return;
@@ -304,7 +325,6 @@ void install_table(brq_ctx* c) {
   c->d_lut.ensure(g.n_lut);
   c->d_coldT.ensure(g.n_cold);
   c->d_hotR.ensure(g.n_hotR);
-  c->d_prob.ensure(c->h_prob.size());
   c->d_slot_mapq.ensure(g.mapqs.size());
   if (c->d_tallyT.n != g.n_tally_cells * 2 || !c->d_tallyT.p) {  // absent classes and the zero cells stay zero
     c->d_tallyT.ensure(g.n_tally_cells * 2);
@@ -313,7 +333,6 @@ void install_table(brq_ctx* c) {
   CUDA_OK(cudaMemsetAsync(c->d_coldT.p, 0, g.n_cold * sizeof(HotTerms), c->stream));
   uint8_t* slot_mapq = c->h_slot_mapq;
   for (size_t i = 0; i < g.mapqs.size(); ++i) slot_mapq[i] = (uint8_t)g.mapqs[i];
-  CUDA_OK(cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), c->h_prob.size() * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_mapq.p, slot_mapq, g.mapqs.size(), cudaMemcpyHostToDevice, c->stream));
   TableBuildArgs a;
   a.prob = c->d_prob.p; a.slot_mapq = c->d_slot_mapq.p;
@@ -325,9 +344,24 @@ void install_table(brq_ctx* c) {
   c->have_device_tables = true;
 }
 
+// h_log10 (loaded or imported) -> text-canonical probabilities on the host -> the device tables
+void install_table(brq_ctx* c) {
+  if (!host_table_ready(c)) {  // (a pending device-derived table becomes the host's first: re-install after a new staging call)
+    if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+    canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob, c->pool.get());
+  }
+  c->have_table = true;
+  if (c->device >= 0 && c->staged) {
+    c->d_prob.ensure(c->h_prob.size());
+    CUDA_OK(cudaMemcpyAsync(c->d_prob.p, c->h_prob.data(), c->h_prob.size() * 8, cudaMemcpyHostToDevice, c->stream));
+  }
+  build_device_tables(c);
+}
+
 void ensure_host_lut(brq_ctx* c) {
   if (c->h_lut.ready()) return;
   if (!c->have_table || !c->staged) throw std::runtime_error("no error table");
+  host_table_ready(c);
   c->h_lut.reset(c->spec, c->h_prob, c->sp, c->geo);
 }
 
@@ -340,12 +374,22 @@ void derive_table(brq_ctx* c) {
   CUDA_OK(cudaEventRecord(c->ev[3], c->stream));
   launch_derive_table(c->d_counts.p, lay, c->d_log10.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[4], c->stream));
-  c->h_log10.resize(lay.n_bins);
-  CUDA_OK(cudaMemcpyAsync(c->h_log10.data(), c->d_log10.p, (size_t)lay.n_bins * 8, cudaMemcpyDeviceToHost, c->stream));
+  // text round trip on the device, then the likelihood tables: nothing here waits for the host
+  c->d_prob.ensure(lay.n_bins);
+  c->d_table_err.ensure(1);
+  CUDA_OK(cudaMemsetAsync(c->d_table_err.p, 0, 4, c->stream));
+  launch_canonical_table(c->d_log10.p, lay.n_bins, c->d_prob.p, c->d_table_err.p, c->stream);
+  if (c->n_log10_pinned < lay.n_bins) {
+    if (c->h_log10_pinned) cudaFreeHost(c->h_log10_pinned);
+    CUDA_OK(cudaHostAlloc((void**)&c->h_log10_pinned, (size_t)lay.n_bins * 8, cudaHostAllocDefault));
+  }
+  c->n_log10_pinned = lay.n_bins;
+  CUDA_OK(cudaMemcpyAsync(c->h_log10_pinned, c->d_log10.p, (size_t)lay.n_bins * 8, cudaMemcpyDeviceToHost, c->stream));
   c->d2h_bytes += (uint64_t)lay.n_bins * 8;
-  CUDA_OK(cudaStreamSynchronize(c->stream));
-  CUDA_OK(cudaEventElapsedTime(&c->ms_derive, c->ev[3], c->ev[4]));
-  install_table(c);
+  c->host_table_pending = true;   // h_log10 / h_prob: made by host_table_ready() when the files or flagged slots need them
+  c->derive_timed = false;        // ev[3], ev[4] are read by kernel_ms()
+  c->have_table = true;
+  build_device_tables(c);
 }
 
 void score_device(brq_ctx* c, const brq_score_params* p) {
@@ -518,6 +562,7 @@ void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rat
   if (do_errors) {
     if (!c->have_table) throw std::runtime_error("brq_derive_error_table has not run");
     if (counts_dump && *counts_dump) write_count_table(counts_dump, c->spec, c->h_counts);
+    host_table_ready(c);
     write_error_rates(error_rates_file && *error_rates_file ? error_rates_file : dir + "/error_rates.tab", c->spec, c->h_log10);
     std::vector<std::string> rf;
     for (uint32_t i = 0; i < n_readfiles; ++i) rf.push_back(readfiles[i]);
@@ -557,7 +602,8 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release();
+    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release(); c->d_table_err.release();
+    if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
     c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
@@ -645,6 +691,7 @@ int brq_derive_error_table(brq_ctx* c) { return guarded(c, [&] { derive_table(c)
 int brq_error_table(brq_ctx* c, const double** log10_prob, uint64_t* n_bins) {
   return guarded(c, [&] {
     if (!c->have_table) throw std::runtime_error("no error table");
+    host_table_ready(c);
     *log10_prob = c->h_log10.data(); *n_bins = c->h_log10.size();
   });
 }
@@ -656,6 +703,7 @@ int brq_write_error_count_files(brq_ctx* c, const char* output_dir, const char* 
 
 int brq_load_error_table(brq_ctx* c, const char* error_rates_file) {
   return guarded(c, [&] {
+    c->host_table_pending = false;
     read_error_rates(error_rates_file, c->spec, c->h_log10);
     c->have_spec = true;
     install_table(c);
@@ -719,6 +767,7 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
     c->stage_cfg.use_base_repeat = c->stage_cfg.use_base_repeat || spec.used[COV_BASE_REPEAT];
     if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff ? p->base_quality_cutoff : c->stage_cfg.base_quality_cutoff;
     do_stage(c);
+    c->host_table_pending = false;
     c->spec = spec; c->h_log10 = log10_prob;
     c->have_spec = true;
     install_table(c);
@@ -811,6 +860,9 @@ int brq_kernel_ms(brq_ctx* c, float* hist_ms, float* coverage_ms, float* derive_
   if (!c) return 1;
   if (hist_ms) *hist_ms = c->ms_hist;
   if (coverage_ms) *coverage_ms = c->ms_cov;
+  if (!c->derive_timed && c->device >= 0) {  // derive_table() does not wait for its own kernels
+    if (cudaEventSynchronize(c->ev[4]) == cudaSuccess && cudaEventElapsedTime(&c->ms_derive, c->ev[3], c->ev[4]) == cudaSuccess) c->derive_timed = true;
+  }
   if (derive_ms) *derive_ms = c->ms_derive;
   if (score_ms) *score_ms = c->ms_score;
   return 0;

@@ -8,6 +8,7 @@
 // All of it is HBM-bound integer/byte work plus fp64 scalar math: no tensor cores.
 #include "kernels.h"
 #include "brq_types.h"
+#include "canonical.h"
 
 #include <atomic>
 #include <cmath>
@@ -310,6 +311,23 @@ __global__ void derive_table_kernel(const unsigned long long* __restrict__ count
   for (uint32_t k = 0; k < 5; ++k) sum += counts[base + k * lay.off_obs];
   // two log10 calls and a subtraction, the shape the reference uses
   out[i] = log10((double)counts[i] + 1.0) - log10((double)sum + 5.0);
+}
+
+// The reference writes the table as text with six significant digits and scoring reads it back (error_count.cpp:629-690,
+// 1032-1040): prob = 10^(the text's value).  canonical.h computes that value exactly, without the text, so a step has
+// no host round trip between the histogram and the likelihood tables.  err is set when a value is outside its range.
+__global__ void canonical_table_kernel(const double* __restrict__ log10_prob, uint32_t n, double* __restrict__ prob, uint32_t* __restrict__ err) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool ok = true;
+  const double t = text_canonical_6g(log10_prob[i], &ok);
+  if (!ok) atomicOr(err, 1u);
+  prob[i] = pow(10.0, t);
+}
+
+void launch_canonical_table(const double* log10_prob, uint32_t n_bins, double* prob, uint32_t* err, cudaStream_t s) {
+  canonical_table_kernel<<<(n_bins + 255) / 256, 256, 0, s>>>(log10_prob, n_bins, prob, err);
+  ++g_launches;
 }
 
 void launch_derive_table(const unsigned long long* counts, const CovLayout& lay, double* log10_prob, cudaStream_t s) {

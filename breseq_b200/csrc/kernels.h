@@ -118,6 +118,8 @@ struct TableBuildArgs {
 void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s);
 
 void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& lay, unsigned long long* counts, cudaStream_t s);
+// log10 table -> probabilities through the six-significant-digit text round trip, on the device (canonical.h)
+void launch_canonical_table(const double* log10_prob, uint32_t n_bins, double* prob, uint32_t* err, cudaStream_t s);
 // the compact form: n16 fast records of 16 bits and n_exc 4-byte records without a 16-bit form (brq_types.h)
 void launch_hist16(const void* rec16, uint64_t n16, const uint32_t* exc, uint64_t n_exc, const CovLayout& lay, unsigned long long* counts, cudaStream_t s);
 void launch_coverage_hist(const uint64_t* hist_off, const uint8_t* group, uint64_t n_cols, uint32_t stride, uint32_t n_groups,

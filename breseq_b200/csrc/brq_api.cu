@@ -114,6 +114,7 @@ struct brq_ctx {
   size_t n_log10_pinned = 0;
   bool host_table_pending = false;   // the host copies above are stale until host_table_ready()
   bool derive_timed = true;
+  bool hist_check_pending = false;   // error_count's kernels have not been checked / timed yet (finish_error_count)
   DevBuf<uint32_t> d_table_err;
   ClassLut h_lut;
   ScoreParams sp;
@@ -177,6 +178,7 @@ void drop_stream(brq_ctx* c) {
   if (c->staged) free_stream(c->st, c->stage_cfg);
   c->staged = c->uploaded = false;
   c->have_counts = c->have_cols = c->have_walk = false;
+  c->hist_check_pending = false;
 }
 
 void do_stage(brq_ctx* c) {
@@ -281,16 +283,25 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
   CUDA_OK(cudaGetLastError());
-  c->check_device_errors("error_count");
-  CUDA_OK(cudaEventElapsedTime(&c->ms_hist, c->ev[0], c->ev[1]));
-  CUDA_OK(cudaEventElapsedTime(&c->ms_cov, c->ev[1], c->ev[2]));
+  // no synchronisation here: the kernels' error word and their event times are read by finish_error_count() when the
+  // counts are downloaded or the timings asked for, and by the check that ends score_columns
+  c->hist_check_pending = true;
   c->have_counts = true;
   c->have_table = false;
   c->host_table_pending = false;
 }
 
+void finish_error_count(brq_ctx* c) {
+  if (!c->hist_check_pending) return;
+  c->hist_check_pending = false;
+  c->check_device_errors("error_count");
+  CUDA_OK(cudaEventElapsedTime(&c->ms_hist, c->ev[0], c->ev[1]));
+  CUDA_OK(cudaEventElapsedTime(&c->ms_cov, c->ev[1], c->ev[2]));
+}
+
 void download_hist(brq_ctx* c) {
   if (!c->have_counts) throw std::runtime_error("brq_error_count has not run");
+  finish_error_count(c);
   c->h_counts.resize(c->spec.n_bins);
   c->h_cov.resize(c->cov_stride * c->n_groups);
   CUDA_OK(cudaMemcpyAsync(c->h_counts.data(), c->d_counts.p, c->h_counts.size() * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -424,7 +435,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->d_cols.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
   c->d_flagged.ensure(c->flagged_cap);
-  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 1, 0, 12, c->stream));  // the error word [0] may still hold pass 1's verdict
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
   launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, reinterpret_cast<const uint2*>(c->d_round_side.p), c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
@@ -432,6 +443,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
+  if (c->hist_check_pending) finish_error_count(c);  // (its error word was just checked; this reads the event times)
   CUDA_OK(cudaEventElapsedTime(&c->ms_score, c->ev[5], c->ev[6]));
   CUDA_OK(cudaEventElapsedTime(&c->ms_tally, c->ev[5], c->ev[7]));
   CUDA_OK(cudaEventElapsedTime(&c->ms_fit, c->ev[7], c->ev[6]));
@@ -858,6 +870,7 @@ int brq_score_phase_ms(brq_ctx* c, float* tally_ms, float* fit_ms) {
 
 int brq_kernel_ms(brq_ctx* c, float* hist_ms, float* coverage_ms, float* derive_ms, float* score_ms) {
   if (!c) return 1;
+  if (c->hist_check_pending) { const int rc = guarded(c, [&] { finish_error_count(c); }); if (rc) return rc; }
   if (hist_ms) *hist_ms = c->ms_hist;
   if (coverage_ms) *coverage_ms = c->ms_cov;
   if (!c->derive_timed && c->device >= 0) {  // derive_table() does not wait for its own kernels

@@ -27,9 +27,11 @@
 //                 lane and vector); wait_group counts them in order.  The next round's first vectors are requested
 //                 before the contraction of the current one, the rest of it goes to L2 with one bulk prefetch per
 //                 warp; slot numbers are read two rounds ahead, the slots' geometry one round ahead.
-//   cold records  Scoring records outside the shared table (another MAPQ, a '.' observation, a quality outside the
-//                 window; every scoring record of a stream staged with read_pos / base_repeat) sit in the side list
-//                 as classic words and read the global table of all MAPQ values.
+//   cold records  Scoring records outside the shared table (another MAPQ, a quality outside the window; every scoring
+//                 record of a stream staged with read_pos / base_repeat) sit in the side list as classic words and read
+//                 the global table of all MAPQ values.  '.' observations are ordinary classes (a fifth observation
+//                 plane of the shared table): a read without an inserted base is a '.' observation of the insert
+//                 sub-column, so nearly every record of such a slot is one, and whole rounds of them close the stream.
 //   redundant records  lead each slot's run (staging.cpp): their order-dependent sum of 1/X1
 //                 (identify_mutations.cpp:1605) is a short sequential walk of the slot's head: bit-exact.
 //   presence bound  The reference fits the 5-allele EM on every column, but its result only surfaces

@@ -187,6 +187,32 @@ def test_read_pos_and_base_repeat_covariates(datasets, tmp_path):
     ctx.close()
 
 
+def test_compact_histogram_stream_with_other_covariates(datasets, tmp_path):
+    """The 16-bit histogram records (csrc/brq_types.h) under covariate strings other than the default: counts bit-exact."""
+    d = datasets["multi"]
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    s = ctx.stream()
+    assert s["hist16"] is not None and len(s["hist16"]) > 0.9 * len(s["hist_rec"])
+    # a quality axis of 64: the joint histogram no longer fits beside the table, every record takes the generic path
+    cov = "read_set=3,obs_base,ref_base,quality=64"
+    out = str(tmp_path)
+    ec, _ = helpers.cli_args(d, out)
+    ec[ec.index("--covariates") + 1] = cov
+    dump = os.path.join(out, "counts.tab")
+    helpers.run_oracle(*ec, "--counts-dump", dump)
+    ctx.error_count(cov)
+    counts, _ = ctx.hist_download()
+    assert np.array_equal(counts.astype(np.int64), helpers.oracle_counts(dump))
+    # no read_set covariate: one set plane in the joint histogram whatever the records' read sets are; the counts are
+    # the default table summed over the read sets (index = read_set + 3 * (ref + 5 * obs + 25 * quality))
+    ctx.error_count("obs_base,ref_base,quality=42")
+    counts, _ = ctx.hist_download()
+    full = helpers.oracle_counts(d["oracle_counts"])
+    assert np.array_equal(counts.astype(np.int64), full.reshape(-1, 3).sum(axis=1))
+    ctx.close()
+
+
 class _DevArray:
     """A device buffer of the library as a CUDA array (int64) torch can wrap."""
 

@@ -64,7 +64,9 @@ class _StreamInfo(C.Structure):
                 ("slot_ref", C.POINTER(C.c_uint8)), ("ins_parent", C.POINTER(C.c_uint64)),
                 ("ins_count", C.POINTER(C.c_uint32)), ("round_slot", C.POINTER(C.c_uint32)), ("n_rounds", C.c_uint64),
                 ("score_cnt", C.POINTER(C.c_uint32)), ("round_off", C.POINTER(C.c_uint64)),
-                ("hist16", C.POINTER(C.c_uint16)), ("hist_exc", C.POINTER(C.c_uint32)), ("n_hist16", C.c_uint64), ("n_hist_exc", C.c_uint64)]
+                ("hist16", C.POINTER(C.c_uint16)), ("hist_exc", C.POINTER(C.c_uint32)), ("n_hist16", C.c_uint64), ("n_hist_exc", C.c_uint64),
+                ("score16", C.POINTER(C.c_uint16)), ("score_exc", C.POINTER(C.c_uint32)), ("score_exc_off", C.POINTER(C.c_uint32)),
+                ("n_score_exc", C.c_uint64)]
 
 
 class _ScoreParams(C.Structure):
@@ -348,6 +350,10 @@ class Context:
             # compact form the device reads (None when the stream has 8-byte histogram records): csrc/brq_types.h
             "hist16": view(info.hist16, info.n_hist16, np.uint16) if info.hist16 else None,
             "hist_exc": view(info.hist_exc, info.n_hist_exc, np.uint32) if info.hist16 else None,
+            # transfer form of score_rec (None when not built): low halves, exception words, CSR per (round, lane)
+            "score16": view(info.score16, info.n_score_padded, np.uint16) if info.score16 else None,
+            "score_exc": view(info.score_exc, info.n_score_exc, np.uint32) if info.score16 else None,
+            "score_exc_off": view(info.score_exc_off, info.n_rounds * 32 + 1, np.uint32) if info.score16 else None,
             "slot_ref": view(info.slot_ref, n_slots, np.uint8),
             "ins_parent": view(info.ins_parent, info.n_ins, np.uint64),
             "ins_count": view(info.ins_count, info.n_ins, np.uint32),

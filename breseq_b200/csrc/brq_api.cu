@@ -75,7 +75,8 @@ struct brq_ctx {
   DevBuf<uint32_t> d_score_rec, d_side_rec, d_side_off, d_round_slot, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
   DevBuf<uint64_t> d_score_off, d_hist_off, d_round_off;
   DevBuf<uint32_t> d_score_cnt, d_round_side;
-  DevBuf<uint8_t> d_hist_rec;
+  DevBuf<uint8_t> d_hist_rec, d_score16;   // d_score16: transfer form of the scoring stream (low halves)
+  DevBuf<uint32_t> d_score_exc, d_score_exc_off;
   size_t hist_exc_at = 0;   // byte offset of the exception records inside d_hist_rec (compact form)
   DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
@@ -224,7 +225,14 @@ void upload(brq_ctx* c) {
   c->hist_exc_at = (st.n_hist16 * 2 + 31) & ~(size_t)15;
   c->d_hist_rec.ensure(st.hist16 ? c->hist_exc_at + st.n_hist_exc * 4 + 16 : st.n_hist * st.hist_bytes + 16);
   c->d_side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
-  CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
+  if (st.score16) {  // the transfer form: low halves + exception words, expanded to score_rec on the device (end of this function)
+    c->d_score16.ensure(st.n_score_padded * 2 + 64); c->d_score_exc.ensure(st.n_score_exc + 8); c->d_score_exc_off.ensure(st.n_rounds * 32 + 1);
+    CUDA_OK(cudaMemcpyAsync(c->d_score16.p, st.score16, st.n_score_padded * 2, cudaMemcpyHostToDevice, c->stream));
+    if (st.n_score_exc) CUDA_OK(cudaMemcpyAsync(c->d_score_exc.p, st.score_exc, st.n_score_exc * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->d_score_exc_off.p, st.score_exc_off, (st.n_rounds * 32 + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
+  }
   CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -241,6 +249,9 @@ void upload(brq_ctx* c) {
   }
   CUDA_OK(cudaMemcpyAsync(c->d_hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(c->d_slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
+  if (st.score16)
+    launch_expand_score(reinterpret_cast<const uint16_t*>(c->d_score16.p), c->d_round_off.p, c->d_round_slot.p, c->d_slot_ref.p, c->d_score_exc.p,
+                        c->d_score_exc_off.p, st.n_rounds, st.geo, c->d_score_rec.p, c->stream);
   c->uploaded = true;
 }
 
@@ -614,7 +625,7 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release(); c->d_table_err.release();
+    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
     c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
@@ -669,11 +680,12 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
     info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
-    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + st.n_score_padded * 4 + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
+    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + (st.score16 ? st.n_score_padded * 2 + st.n_score_exc * 4 + (st.n_rounds * 32 + 1) * 4 : st.n_score_padded * 4) + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
     info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
     info->hist16 = st.hist16; info->n_hist16 = st.n_hist16; info->hist_exc = st.hist_exc; info->n_hist_exc = st.n_hist_exc;
+    info->score16 = st.score16; info->score_exc = st.score_exc; info->score_exc_off = st.score_exc_off; info->n_score_exc = st.n_score_exc;
   });
 }
 

@@ -141,6 +141,31 @@ struct ScoreGeometry {
   uint32_t pad_word() const { return special_counter(SC_TRASH); }
 };
 
+// TRANSFER FORM of score_rec (score16 + score_exc): what crosses PCIe.  The low half of a device word decides the word
+// for every kind of record but two: a HOT record matching its slot's reference base is its counter (class = the
+// counter's word and byte, observation = the slot's base), IDLE / COLD / pad words are their special counter.  Staging
+// sends the low halves (u16, same round-major geometry as score_rec) with bit 15 set on the records whose word does not
+// come back that way (REDUNDANT and HOT-but-mismatching ones, 2 %), and those words in full, per lane of every round
+// in record order (score_exc, CSR score_exc_off[round * 32 + lane]); expand_score_kernel rebuilds score_rec in HBM,
+// bit for bit (staging checks every word), so the kernels and the host never see the transfer form.
+struct ScoreRecon { uint32_t c_idle_top, c_idle_bot, c_cold_top, c_cold_bot, c_trash; };
+inline ScoreRecon score_recon_of(const ScoreGeometry& g) {
+  return {g.special_counter(SC_IDLE_TOP), g.special_counter(SC_IDLE_BOT), g.special_counter(SC_COLD_TOP), g.special_counter(SC_COLD_BOT),
+          g.special_counter(SC_TRASH)};
+}
+constexpr uint32_t S16_EXCEPTION = 0x8000u;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t score_word_from16(uint32_t lo, uint32_t ref, const ScoreRecon& g) {  // lo: 15 bits, ref: the slot's base index
+  const uint32_t c = lo & DR_COUNTER_MASK, top = lo & DR_TOP_BIT;
+  if (c == g.c_trash) return lo;
+  if (c == (top ? g.c_idle_top : g.c_idle_bot)) return DR_IDLE | lo;
+  if (c == (top ? g.c_cold_top : g.c_cold_bot)) return DR_COLD | lo;
+  const uint32_t sq = ((c >> 7) << 2) | ((c >> 3) & 3u);
+  return sq << DR_SQ_SHIFT | ref << DR_OBS_SHIFT | DR_MATCH_BIT | lo;
+}
+
 // classic word of a HOT device word
 inline uint32_t classic_of_hot(uint32_t d, const ScoreGeometry& g) {
   const uint32_t sq = (d >> DR_SQ_SHIFT) & DR_SQ_MASK, obs = (d >> DR_OBS_SHIFT) & 7u, qual = g.q_lo + sq % g.n_q, st = sq / g.n_q;
@@ -215,6 +240,10 @@ struct PileupStream {
   uint8_t* slot_group = nullptr;       // [n_base] coverage group of the column's target
   // records
   uint32_t* score_rec = nullptr;       // device stream words
+  uint16_t* score16 = nullptr;         // transfer form of score_rec (above): low halves, [n_score_padded]
+  uint32_t* score_exc = nullptr;       // the words the low halves do not determine, per (round, lane) in record order
+  uint32_t* score_exc_off = nullptr;   // [n_rounds * 32 + 1] CSR into score_exc
+  uint64_t n_score_exc = 0;
   uint32_t* side_rec = nullptr;        // side list: classic words of COLD records, SIDE_BIG | X1 of very redundant ones
   uint32_t* side_off = nullptr;        // [n_base + n_ins + 1] CSR into side_rec
   uint64_t n_side = 0;

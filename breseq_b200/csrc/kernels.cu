@@ -313,6 +313,53 @@ __global__ void derive_table_kernel(const unsigned long long* __restrict__ count
   out[i] = log10((double)counts[i] + 1.0) - log10((double)sum + 5.0);
 }
 
+// ------------------------------------------------------------------------------------------
+// transfer form of the scoring stream -> score_rec (brq_types.h): one warp per round, one lane per slot, the words
+// written in the stream's own round-major order (two coalesced 128-bit stores per lane and round vector).  A flagged
+// low half takes the lane's next exception word; every other word is decided by its low half and the slot's base.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expand_score_kernel(const uint16_t* __restrict__ s16, const uint64_t* __restrict__ round_off,
+                                                            const uint32_t* __restrict__ round_slot, const uint8_t* __restrict__ slot_ref,
+                                                            const uint32_t* __restrict__ exc, const uint32_t* __restrict__ exc_off,
+                                                            uint64_t n_rounds, ScoreRecon rc, uint32_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t n_warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rounds; r += n_warps) {
+    const uint64_t beg = round_off[r], n_vec = (round_off[r + 1] - beg) / ROUND_VECTOR_WORDS;
+    const uint32_t sl = round_slot[(r << 5) + lane], ref = sl == ROUND_NO_SLOT ? 5u : (uint32_t)slot_ref[sl];
+    uint32_t cur = exc_off[(r << 5) + lane];
+    const uint16_t* src = s16 + beg + lane * 4u;
+    uint32_t* dst = out + beg + lane * 4u;
+    auto word = [&](uint32_t v) { return (v & S16_EXCEPTION) ? __ldg(exc + cur++) : score_word_from16(v, ref, rc); };
+    auto four = [&](uint2 v) { uint4 o; o.x = word(v.x & 0xFFFFu); o.y = word(v.x >> 16); o.z = word(v.y & 0xFFFFu); o.w = word(v.y >> 16); return o; };
+    auto ld8 = [&](const uint16_t* p) { uint2 v; asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p)); return v; };
+    uint64_t i = 0;
+    for (; i + 4 <= n_vec; i += 4) {  // eight 64-bit loads in flight per lane
+      uint2 a[4], b[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a[k] = ld8(src + (i + k) * ROUND_VECTOR_WORDS); b[k] = ld8(src + (i + k) * ROUND_VECTOR_WORDS + ROUND_VECTOR_WORDS / 2); }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        *reinterpret_cast<uint4*>(dst + (i + k) * ROUND_VECTOR_WORDS) = four(a[k]);
+        *reinterpret_cast<uint4*>(dst + (i + k) * ROUND_VECTOR_WORDS + ROUND_VECTOR_WORDS / 2) = four(b[k]);
+      }
+    }
+    for (; i < n_vec; ++i) {
+      const uint2 a = ld8(src + i * ROUND_VECTOR_WORDS), b = ld8(src + i * ROUND_VECTOR_WORDS + ROUND_VECTOR_WORDS / 2);
+      *reinterpret_cast<uint4*>(dst + i * ROUND_VECTOR_WORDS) = four(a);
+      *reinterpret_cast<uint4*>(dst + i * ROUND_VECTOR_WORDS + ROUND_VECTOR_WORDS / 2) = four(b);
+    }
+  }
+}
+
+void launch_expand_score(const uint16_t* s16, const uint64_t* round_off, const uint32_t* round_slot, const uint8_t* slot_ref, const uint32_t* exc,
+                         const uint32_t* exc_off, uint64_t n_rounds, const ScoreGeometry& geo, uint32_t* score_rec, cudaStream_t s) {
+  if (!n_rounds) return;
+  const int blocks = (int)std::min<uint64_t>((n_rounds + 7) / 8, 148 * 8);
+  expand_score_kernel<<<blocks, 256, 0, s>>>(s16, round_off, round_slot, slot_ref, exc, exc_off, n_rounds, score_recon_of(geo), score_rec);
+  ++g_launches;
+}
+
 // The reference writes the table as text with six significant digits and scoring reads it back (error_count.cpp:629-690,
 // 1032-1040): prob = 10^(the text's value).  canonical.h computes that value exactly, without the text, so a step has
 // no host round trip between the histogram and the likelihood tables.  err is set when a value is outside its range.

@@ -118,6 +118,10 @@ struct TableBuildArgs {
 void launch_build_tables(const TableBuildArgs& a, const ScoreParams& p, cudaStream_t s);
 
 void launch_hist(const void* rec, uint64_t n_rec, bool wide, const CovLayout& lay, unsigned long long* counts, cudaStream_t s);
+// transfer form of the scoring stream (low halves + exception words) -> score_rec in HBM (brq_types.h)
+struct ScoreGeometry;
+void launch_expand_score(const uint16_t* s16, const uint64_t* round_off, const uint32_t* round_slot, const uint8_t* slot_ref, const uint32_t* exc,
+                         const uint32_t* exc_off, uint64_t n_rounds, const ScoreGeometry& geo, uint32_t* score_rec, cudaStream_t s);
 // log10 table -> probabilities through the six-significant-digit text round trip, on the device (canonical.h)
 void launch_canonical_table(const double* log10_prob, uint32_t n_bins, double* prob, uint32_t* err, cudaStream_t s);
 // the compact form: n16 fast records of 16 bits and n_exc 4-byte records without a 16-bit form (brq_types.h)

@@ -109,7 +109,7 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
-  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side, (void*)s.hist16, (void*)s.hist_exc})
+  for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side, (void*)s.hist16, (void*)s.hist_exc, (void*)s.score16, (void*)s.score_exc, (void*)s.score_exc_off})
     if (p) rel(p, s.pinned);
   s = PileupStream();
 }
@@ -697,6 +697,59 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     out.max_hist_qual = std::max(out.max_hist_qual, max_hquals[ii]);
     out.max_hist_rpos = std::max(out.max_hist_rpos, max_rposs[ii]);
     out.max_score_rpos = std::max(out.max_score_rpos, max_srposs[ii]);
+  }
+
+  // ---- transfer form of the scoring stream (brq_types.h): low halves + the words they do not determine
+  if (cfg.want_score && cfg.compact_score && out.n_rounds && out.n_rounds * 32 < (1ull << 32) - 1) {
+    const ScoreRecon rc = score_recon_of(geo);
+    const uint64_t n_lanes = out.n_rounds * 32;
+    bool p5 = false;
+    out.score16 = (uint16_t*)alloc(out.n_score_padded * 2 + 32, &p5);
+    out.score_exc_off = (uint32_t*)alloc((n_lanes + 1) * 4, &p5);
+    const size_t n_parts = (size_t)std::max(1, n_threads) * 8;
+    auto parts = [&](auto&& body) {
+      std::atomic<size_t> next(0);
+      auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n_parts) break; body(out.n_rounds * k / n_parts, out.n_rounds * (k + 1) / n_parts); } };
+      std::vector<std::thread> pool;
+      for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+      work();
+      for (auto& t : pool) t.join();
+    };
+    // pass 1: low halves, exception flags, exceptions per lane (words visited in memory order)
+    parts([&](uint64_t r0, uint64_t r1) {
+      for (uint64_t r = r0; r < r1; ++r) {
+        const uint64_t beg = out.round_off[r], end = out.round_off[r + 1];
+        uint32_t ref[32], n_exc[32];
+        for (uint32_t l = 0; l < 32; ++l) {
+          const uint32_t sl = out.round_slot[r * 32 + l];
+          ref[l] = sl == ROUND_NO_SLOT ? 5u : out.slot_ref[sl]; n_exc[l] = 0;
+        }
+        for (uint64_t p = beg; p < end; ++p) {  // word p belongs to lane (p - beg) / 4 % 32
+          const uint32_t l = (uint32_t)((p - beg) >> 2) & 31u, w = out.score_rec[p], lo = w & 0x7FFFu;
+          const bool same = !(w & S16_EXCEPTION) && score_word_from16(lo, ref[l], rc) == w;
+          out.score16[p] = (uint16_t)(same ? lo : (lo | S16_EXCEPTION));
+          n_exc[l] += !same;
+        }
+        for (uint32_t l = 0; l < 32; ++l) out.score_exc_off[r * 32 + l + 1] = n_exc[l];
+      }
+    });
+    out.score_exc_off[0] = 0;
+    uint64_t acc = 0;
+    for (uint64_t i = 1; i <= n_lanes; ++i) { acc += out.score_exc_off[i]; out.score_exc_off[i] = (uint32_t)acc; }
+    if (acc >= (1ull << 32)) throw std::runtime_error("more than 2^32 exception words in the scoring stream's transfer form");
+    out.n_score_exc = acc;
+    out.score_exc = (uint32_t*)alloc(acc * 4 + 32, &p5);
+    // pass 2: the exception words, per lane in record order (memory order visits a lane's records in order)
+    parts([&](uint64_t r0, uint64_t r1) {
+      for (uint64_t r = r0; r < r1; ++r) {
+        if (out.score_exc_off[r * 32 + 32] == out.score_exc_off[r * 32]) continue;
+        const uint64_t beg = out.round_off[r], end = out.round_off[r + 1];
+        uint32_t* dst[32];
+        for (uint32_t l = 0; l < 32; ++l) dst[l] = out.score_exc + out.score_exc_off[r * 32 + l];
+        for (uint64_t p = beg; p < end; ++p)
+          if (out.score16[p] & S16_EXCEPTION) *dst[(uint32_t)((p - beg) >> 2) & 31u]++ = out.score_rec[p];
+      }
+    });
   }
 
   // ---- compact histogram streams (brq_types.h): fast records in 16 bits, the others unchanged

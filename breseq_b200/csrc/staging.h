@@ -23,6 +23,7 @@ struct StageConfig {
   uint32_t base_quality_cutoff = 3;    // Settings::base_quality_cutoff: decides which records score (settings.cpp:1335)
   int threads = 8;
   bool want_hist = true, want_score = true;
+  bool compact_score = true;           // also build the transfer form of score_rec (brq_types.h: score16 + score_exc)
   bool compact_hist = true;            // also build the 16-bit histogram stream the device reads (brq_types.h)
   uint32_t shard_rank = 0, shard_count = 1;         // contiguous reference-coordinate shard staged by this call
   // buffer allocator (pinned when a device is present); both must be set together

@@ -99,6 +99,12 @@ typedef struct brq_stream_info {
   const uint16_t* hist16;
   const uint32_t* hist_exc;
   uint64_t n_hist16, n_hist_exc;
+  /* transfer form of score_rec, what brq_upload copies when present: the low half of every word, bit 15 set where the word
+   * does not follow from it, and those words in full per (round, lane) in record order (csrc/brq_types.h) */
+  const uint16_t* score16;         /* [n_score_padded] */
+  const uint32_t* score_exc;       /* [n_score_exc] */
+  const uint32_t* score_exc_off;   /* [n_rounds * 32 + 1] */
+  uint64_t n_score_exc;
 } brq_stream_info;
 
 int brq_stream(brq_ctx* ctx, brq_stream_info* info);

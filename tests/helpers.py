@@ -223,6 +223,39 @@ def expand_hist16(h16):
     return (lo | b).astype(np.uint32)
 
 
+def expand_score16(s):
+    """score_rec rebuilt from its transfer form (csrc/brq_types.h: score_word_from16, expand_score_kernel), in numpy."""
+    g = s["geometry"]
+    n_sq = g["n_st"] * g["n_q"]
+
+    def counter(which):
+        i = n_sq + which
+        return (i >> 2) * 128 + (i & 3) * 8
+    lo16 = s["score16"].astype(np.uint32)
+    p = np.arange(len(lo16), dtype=np.int64)
+    roff = s["round_off"].astype(np.int64)
+    r = np.searchsorted(roff, p, side="right") - 1
+    lane = ((p - roff[r]) >> 2) & 31
+    key = r * 32 + lane
+    sl = s["round_slot"][key]
+    ref = np.where(sl == 0xFFFFFFFF, 5, s["slot_ref"][np.minimum(sl, len(s["slot_ref"]) - 1)]).astype(np.uint32)
+    lo = lo16 & 0x7FFF
+    c, top = lo & 0x1FFF, (lo >> 13) & 1
+    sq = ((c >> 7) << 2) | ((c >> 3) & 3)
+    out = (sq << 16) | (ref << 24) | np.uint32(1 << 28) | lo                                   # HOT, matching the slot's base
+    out = np.where(c == np.where(top == 1, counter(2), counter(3)), np.uint32(2 << 30) | lo, out)  # COLD
+    out = np.where(c == np.where(top == 1, counter(0), counter(1)), np.uint32(1 << 30) | lo, out)  # IDLE
+    out = np.where(c == counter(6), lo, out)                                                       # pad
+    flagged = np.flatnonzero(lo16 & 0x8000)
+    if len(flagged):
+        order = np.argsort(key[flagged], kind="stable")          # memory order within a lane is record order
+        k = key[flagged][order]
+        first = np.flatnonzero(np.r_[True, k[1:] != k[:-1]])
+        rank = np.arange(len(k)) - np.repeat(first, np.diff(np.r_[first, len(k)]))
+        out[flagged[order]] = s["score_exc"][s["score_exc_off"].astype(np.int64)[k] + rank]
+    return out.astype(np.uint32)
+
+
 def emulate_coverage_hist(hist_off):
     red = (hist_off[:-1] >> np.uint64(63)).astype(bool)
     off = (hist_off & np.uint64((1 << 63) - 1)).astype(np.int64)

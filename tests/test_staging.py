@@ -40,6 +40,17 @@ def test_compact_histogram_stream_is_the_same_records(staged):
     assert np.all((s["hist_exc"] >> 31 == 0) | (((s["hist_exc"] >> 6) & 127) > 62) | ((((s["hist_exc"] >> 20) & 127) > 62) & (((s["hist_exc"] >> 20) & 127) != 127)) | (((s["hist_exc"] >> 28) & 7) > 3))
 
 
+def test_score_transfer_form_expands_to_the_stream(staged):
+    """score16 + score_exc (what crosses PCIe) rebuild score_rec bit for bit; the exceptions are the few redundant and
+    mismatching records."""
+    d, ctx, s = staged
+    assert s["score16"] is not None and len(s["score16"]) == len(s["score_rec"])
+    assert np.array_equal(helpers.expand_score16(s), s["score_rec"])
+    assert int(s["score_exc_off"][-1]) == len(s["score_exc"])
+    if d["name"] != "ltee" and len(s["score_rec"]):
+        assert len(s["score_exc"]) <= 0.15 * int(s["n_score"]) + 64
+
+
 def test_unique_only_coverage_matches_oracle(staged):
     d, ctx, s = staged
     names = helpers.contig_names(d)

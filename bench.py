@@ -133,7 +133,7 @@ def run_cpu_once(bam, fasta, out, cli=None, count_records=True):
 def config_block(n_gpus):
     return {"workload": "E. coli REL606 4.6 Mb clone mode, synthetic 100x pe150 reads (BASELINE configs[1]); one 4 629 812 bp "
                         "coordinate range per GPU", "covariates": COVARIATES, "records_per_gpu": None,
-            "l2_policy": "inputs (about 4 GB per GPU) are far larger than the 126 MB L2; no explicit flush",
+            "l2_policy": "inputs (about 3 GB per GPU in HBM) are far larger than the 126 MB L2; no explicit flush",
             "parallelism": "reference-range sharding x%d, one sum-allreduce of the integer histograms" % n_gpus}
 
 

@@ -267,6 +267,7 @@ struct PileupStream {
   uint32_t max_score_rpos = 0;                    // largest read position of a scoring record (streams staged with read_pos)
   uint32_t max_read_set_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
+  bool score_rec_plain = false, hist_rec_plain = false;  // ... except these two: plain memory when only their transfer / compact form is uploaded
   uint64_t n_slots() const { return n_base + n_ins; }
 };
 

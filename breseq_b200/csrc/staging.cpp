@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -110,12 +111,21 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
   for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side, (void*)s.hist16, (void*)s.hist_exc, (void*)s.score16, (void*)s.score_exc, (void*)s.score_exc_off})
-    if (p) rel(p, s.pinned);
+    if (p) rel(p, s.pinned && !(p == (void*)s.score_rec && s.score_rec_plain) && !(p == (void*)s.hist_rec && s.hist_rec_plain));
   s = PileupStream();
 }
 
 void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const StageConfig& cfg, PileupStream& out) {
   auto alloc = cfg.alloc ? cfg.alloc : default_alloc;
+  // BRQ_STAGE_TIMES=1: wall time of every phase on stderr (staging is upstream of the measured path)
+  static const bool phase_times = getenv("BRQ_STAGE_TIMES") != nullptr;
+  auto phase_t0 = std::chrono::steady_clock::now();
+  auto phase_done = [&](const char* what) {
+    if (!phase_times) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "stage: %-22s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - phase_t0).count());
+    phase_t0 = t;
+  };
   const size_t n_reads = R.size();
   const size_t n_targets = hdr.target_names.size();
   out = PileupStream();
@@ -167,6 +177,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     }
   }
 
+  phase_done("setup");
   // ---- per-read derived values
   std::vector<uint32_t> part_base, part_count;
   make_read_file_partition(hdr.read_groups, cfg.read_file_sets, part_base, part_count);
@@ -247,6 +258,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     if (!error.empty()) throw std::runtime_error(error);
   };
 
+  phase_done("per-read values");
   // ---- pass A1: which insert sub-columns exist.  Level k+1 exists iff a UNIQUE read has an
   // insertion longer than k after the column and a non-N base at level k
   // (identify_mutations.cpp:1577 precedes :1598).
@@ -296,6 +308,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   }
   const uint64_t n_slots = out.n_slots();
 
+  phase_done("pass A1");
   // ---- per-slot reference bases and coverage groups; offset arrays
   bool pinned = false, p2 = false;
   out.slot_ref = (uint8_t*)alloc(n_slots, &pinned);
@@ -454,6 +467,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     return w;
   };
 
+  phase_done("geometry");
   // ---- pass A2: record counts per slot
   std::vector<uint32_t> score_cnt(cfg.want_score ? n_slots : 0, 0), hist_cnt(cfg.want_hist ? out.n_base : 0, 0);
   std::vector<uint32_t> red_cnt(cfg.want_score ? n_slots : 0, 0);  // redundant records per slot: they lead the slot's run
@@ -482,6 +496,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     }
   });
 
+  phase_done("pass A2 (counts)");
   // ---- offsets
   {
     bool p3 = false;
@@ -556,10 +571,15 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     if (cfg.want_hist) for (uint64_t c = 0; c < out.n_base; ++c) if (hist_cnt[c] > out.max_hist_depth) out.max_hist_depth = hist_cnt[c];
     for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
-  out.score_rec = (uint32_t*)alloc(out.n_score_padded * 4, &p2);
+  phase_done("offsets and rounds");
+  // the positional forms stay in plain memory when only their transfer / compact forms cross PCIe (pinning gigabytes is slow)
+  const bool build_score16 = cfg.want_score && cfg.compact_score && out.n_rounds && out.n_rounds * 32 < (1ull << 32) - 1;
+  const bool build_hist16 = cfg.want_hist && cfg.compact_hist && !(cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7);
+  out.score_rec_plain = build_score16; out.hist_rec_plain = build_hist16;
+  out.score_rec = (uint32_t*)(build_score16 ? default_alloc(out.n_score_padded * 4, &p2) : alloc(out.n_score_padded * 4, &p2));
   std::fill(out.score_rec, out.score_rec + out.n_score_padded, geo.pad_word());  // pad word: the trash counter, no other bit
   out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7) ? 8 : 4;
-  out.hist_rec = alloc(out.n_hist * out.hist_bytes, &p2);
+  out.hist_rec = build_hist16 ? default_alloc(out.n_hist * out.hist_bytes, &p2) : alloc(out.n_hist * out.hist_bytes, &p2);
 
   // ---- pass B: fill.  Within every slot the redundant records come first and the unique ones
   // follow, each part in arrival (BAM) order: redundant records never score, so the scoring records
@@ -699,8 +719,9 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     out.max_score_rpos = std::max(out.max_score_rpos, max_srposs[ii]);
   }
 
+  phase_done("pass B (fill)");
   // ---- transfer form of the scoring stream (brq_types.h): low halves + the words they do not determine
-  if (cfg.want_score && cfg.compact_score && out.n_rounds && out.n_rounds * 32 < (1ull << 32) - 1) {
+  if (build_score16) {
     const ScoreRecon rc = score_recon_of(geo);
     const uint64_t n_lanes = out.n_rounds * 32;
     bool p5 = false;
@@ -752,8 +773,9 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     });
   }
 
+  phase_done("score transfer form");
   // ---- compact histogram streams (brq_types.h): fast records in 16 bits, the others unchanged
-  if (cfg.want_hist && cfg.compact_hist && out.hist_bytes == 4) {
+  if (build_hist16) {
     const uint32_t* h = static_cast<const uint32_t*>(out.hist_rec);
     const size_t n = out.n_hist, n_parts = (size_t)std::max(1, n_threads) * 4;
     std::vector<uint64_t> c16(n_parts + 1, 0), cex(n_parts + 1, 0);
@@ -784,6 +806,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       }
     });
   }
+  phase_done("compact histogram");
 }
 
 }  // namespace brq

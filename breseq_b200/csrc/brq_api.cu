@@ -690,7 +690,13 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
 }
 
 int brq_upload(brq_ctx* c) { return guarded(c, [&] { upload(c); }); }
-int brq_sync(brq_ctx* c) { return guarded(c, [&] { c->need_device(); CUDA_OK(cudaStreamSynchronize(c->stream)); }); }
+int brq_sync(brq_ctx* c) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (c->hist_check_pending) finish_error_count(c);  // synchronises, and reports what pass 1's kernels flagged
+    else CUDA_OK(cudaStreamSynchronize(c->stream));
+  });
+}
 
 int brq_error_count(brq_ctx* c, const char* covariates, int do_coverage, int do_errors) {
   return guarded(c, [&] { error_count_device(c, covariates ? covariates : "", do_coverage != 0, do_errors != 0); });

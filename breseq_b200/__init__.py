@@ -36,7 +36,9 @@ class _StageOptions(C.Structure):
                 ("read_file_sets", C.POINTER(_ReadFileSet)), ("n_read_file_sets", C.c_uint32),
                 ("coverage_group_of_tid", C.POINTER(C.c_uint32)), ("n_targets", C.c_uint32),
                 ("use_base_repeat", C.c_uint32), ("use_read_pos", C.c_uint32), ("shard_rank", C.c_uint32),
-                ("shard_count", C.c_uint32), ("base_quality_cutoff", C.c_uint32)]
+                ("shard_count", C.c_uint32), ("base_quality_cutoff", C.c_uint32),
+                ("preprocess_stage", C.c_uint32), ("unmatched_end_minimum_read_length", C.c_uint32),
+                ("require_match_fraction", C.c_double)]
 
 
 class _SynthReadSet(C.Structure):
@@ -113,6 +115,7 @@ def load_library():
         "brq_sync": [C.c_void_p],
         "brq_error_count": [C.c_void_p, C.c_char_p, C.c_int, C.c_int],
         "brq_hist_device": [C.c_void_p, P(C.c_void_p), P(C.c_uint64), P(C.c_void_p), P(C.c_uint64)],
+        "brq_preprocess_read_starts": [C.c_void_p, P(P(C.c_uint64)), P(C.c_uint32)],
         "brq_hist_download": [C.c_void_p, P(P(C.c_uint64)), P(C.c_uint64), P(P(C.c_uint64)), P(C.c_uint64), P(C.c_uint64)],
         "brq_derive_error_table": [C.c_void_p],
         "brq_error_table": [C.c_void_p, P(P(C.c_double)), P(C.c_uint64)],
@@ -154,7 +157,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
-           "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms"]
+           "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts"]
 
 
 def _b(s):
@@ -194,7 +197,8 @@ class SynthSpec:
 
 
 def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, use_read_pos=False,
-                   shard=(0, 1), base_quality_cutoff=3):
+                   shard=(0, 1), base_quality_cutoff=3, preprocess_stage=False, unmatched_end_minimum_read_length=50,
+                   require_match_fraction=0.9):
     keep = []
     o = _StageOptions()
     if seq_ids:
@@ -216,6 +220,9 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
     o.use_read_pos = int(use_read_pos)
     o.shard_rank, o.shard_count = shard
     o.base_quality_cutoff = base_quality_cutoff
+    o.preprocess_stage = int(preprocess_stage)
+    o.unmatched_end_minimum_read_length = unmatched_end_minimum_read_length
+    o.require_match_fraction = require_match_fraction
     return o, keep
 
 
@@ -372,6 +379,13 @@ class Context:
     def error_count(self, covariates, do_coverage=True, do_errors=True):
         self._check(self.lib.brq_error_count(self.h, _b(covariates), int(do_coverage), int(do_errors)))
 
+    def preprocess_read_starts(self):
+        """Per BAM tid, the position-strand combinations (without, with) a read start inside the junction read-end bound
+        (stream staged with ``preprocess_stage=True``; error_count.cpp:157-166, 191-194)."""
+        p, n = C.POINTER(C.c_uint64)(), C.c_uint32()
+        self._check(self.lib.brq_preprocess_read_starts(self.h, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value * 2,)).copy().reshape(n.value, 2)
+
     def hist_device(self):
         c, n, v, m = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
         self._check(self.lib.brq_hist_device(self.h, C.byref(c), C.byref(n), C.byref(v), C.byref(m)))
@@ -502,24 +516,32 @@ class Context:
 # ----------------------------------------------------------------------------------------------
 def error_count(bam, fasta, output_dir, readfiles, do_coverage=True, do_errors=True, preprocess_stage=False,
                 min_qual_score=0, covariates="", *, call_mutations_seq_ids=None, read_file_sets=None,
-                coverage_group_of_tid=None, error_rates_file_name=None, device=0, ctx=None):
+                coverage_group_of_tid=None, error_rates_file_name=None, device=0, ctx=None,
+                unmatched_end_minimum_read_length=50, require_match_fraction=0.9):
     """``breseq::error_count()`` (error_count.cpp:50-68): writes ``error_rates.tab``,
     ``base_qual_error_prob.<readfile>.tab`` and ``<group>.unique_only_coverage_distribution.tab``.
 
     ``min_qual_score`` is accepted and unused, as in the reference (error_count.h:295).
-    ``preprocess_stage`` (read-start bookkeeping for candidate junctions) is outside this path.
+    With ``preprocess_stage`` (the stage 03 call, breseq_cmdline.cpp:1969) the return value is what the reference leaves in
+    ``Summary::preprocess_error_count``: ``no_pos_hash_per_position_pr`` per BAM tid (error_count.cpp:217-229; the two
+    ``Settings`` fields its read-end bound reads are keywords); otherwise None.
     """
-    if preprocess_stage:
-        raise BrqError("preprocess_stage=True (stage 03 coverage pre-pass) is not part of the accelerated path")
     own = ctx is None
     ctx = ctx or Context(device)
     try:
         o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets,
                                  coverage_groups=coverage_group_of_tid, use_base_repeat="base_repeat" in covariates,
-                                 use_read_pos="read_pos" in covariates)
+                                 use_read_pos="read_pos" in covariates, preprocess_stage=preprocess_stage,
+                                 unmatched_end_minimum_read_length=unmatched_end_minimum_read_length,
+                                 require_match_fraction=require_match_fraction)
         arr = _str_array(list(readfiles))
         ctx._check(ctx.lib.brq_run_error_count(ctx.h, _b(bam), _b(fasta), _b(output_dir), _b(error_rates_file_name), arr,
                                                len(readfiles), int(do_coverage), int(do_errors), _b(covariates), C.byref(o)))
+        if preprocess_stage:
+            c = ctx.preprocess_read_starts().astype(np.float64)
+            total = c.sum(axis=1)
+            return [float(c[t, 0] / total[t]) if total[t] else 1.0 for t in range(len(c))]
+        return None
     finally:
         if own:
             ctx.close()

@@ -171,6 +171,9 @@ void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
   s.use_base_repeat = o->use_base_repeat != 0;
   s.use_read_pos = o->use_read_pos != 0;
   s.base_quality_cutoff = o->base_quality_cutoff ? o->base_quality_cutoff : 3;
+  s.preprocess_stage = o->preprocess_stage != 0;
+  s.unmatched_end_minimum_read_length = o->unmatched_end_minimum_read_length ? o->unmatched_end_minimum_read_length : 50;
+  s.unmatched_end_length_factor = 1.0 - (o->require_match_fraction != 0.0 ? o->require_match_fraction : 0.9);
   s.shard_rank = o->shard_rank;
   s.shard_count = o->shard_count ? o->shard_count : 1;
 }
@@ -700,6 +703,14 @@ int brq_sync(brq_ctx* c) {
 
 int brq_error_count(brq_ctx* c, const char* covariates, int do_coverage, int do_errors) {
   return guarded(c, [&] { error_count_device(c, covariates ? covariates : "", do_coverage != 0, do_errors != 0); });
+}
+
+int brq_preprocess_read_starts(brq_ctx* c, const uint64_t** counts, uint32_t* n_targets) {
+  return guarded(c, [&] {
+    if (!c->staged) throw std::runtime_error("nothing staged");
+    if (c->st.read_start_counts.empty()) throw std::runtime_error("the stream was staged without brq_stage_options.preprocess_stage");
+    *counts = c->st.read_start_counts.data(); *n_targets = (uint32_t)(c->st.read_start_counts.size() / 2);
+  });
 }
 
 int brq_hist_device(brq_ctx* c, void** counts, uint64_t* n_bins, void** coverage, uint64_t* n_coverage) {

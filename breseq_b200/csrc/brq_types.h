@@ -262,6 +262,7 @@ struct PileupStream {
   uint64_t qual_count[128] = {0};      // scoring records per quality value
   uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
   uint32_t n_groups = 1;               // coverage groups present
+  std::vector<uint64_t> read_start_counts;  // preprocess stage: [BAM tid][0 = without, 1 = with a read start] position-strand combinations of this shard
   uint32_t max_qual_seen = 0;
   uint32_t max_hist_qual = 0, max_hist_rpos = 0;  // largest quality / read position in a valid histogram observation
   uint32_t max_score_rpos = 0;                    // largest read position of a scoring record (streams staged with read_pos)

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -46,6 +47,7 @@ struct ReadInfo {
   int32_t end;         // exclusive reference end
   int32_t qs0, qe0;    // first/last non-soft-clipped query index (alignment.cpp:248-288)
   int32_t qb_end0;     // query_bounds_0 end (alignment.cpp:104-218, min_qual == 0)
+  int32_t qb_start0;   // query_bounds_0 start: soft clips among the leading S / H / N operations
   uint8_t read_set;
   bool rev;
 };
@@ -208,6 +210,13 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       if (op == 4) be1 -= (int32_t)(cig[k] >> 4);
     }
     ri.qb_end0 = be1 - 1;
+    int32_t bs1 = 1;
+    for (uint32_t k = 0; k < nc; ++k) {
+      uint32_t op = cig[k] & 0xf;
+      if (op != 4 && op != 5 && op != 3) break;
+      if (op == 4) bs1 += (int32_t)(cig[k] >> 4);
+    }
+    ri.qb_start0 = bs1 - 1;
     uint32_t g = R.rg[i];
     ri.read_set = 0;
     if (!part_base.empty() && g < part_base.size())
@@ -473,6 +482,11 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   std::vector<uint32_t> red_cnt(cfg.want_score ? n_slots : 0, 0);  // redundant records per slot: they lead the slot's run
   std::vector<uint32_t> side_cnt(cfg.want_score ? n_slots : 0, 0), side_red_cnt(cfg.want_score ? n_slots : 0, 0);
   std::vector<uint8_t> col_red(cfg.want_hist ? out.n_base : 0, 0);
+  std::vector<uint8_t> col_qstart(cfg.want_hist && cfg.preprocess_stage ? out.n_base : 0, 0);  // bit 0 / 1: a top / bottom strand read starts here
+  auto junction_read_end_min = [&](uint32_t L) -> uint32_t {  // Settings::required_junction_read_end_min_coordinate, settings.h:345-354
+    const int32_t max_len = (int32_t)floor((double)((int32_t)L - (int32_t)cfg.unmatched_end_minimum_read_length) * cfg.unmatched_end_length_factor);
+    return max_len <= 0 ? L : L - (uint32_t)max_len;
+  };
   run_items([&](size_t ii) {
     const Item& it = items[ii];
     const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
@@ -485,6 +499,10 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
         const uint64_t slot = s0 + (uint64_t)c;
         if ((uint32_t)q >= L && !is_del) throw std::runtime_error("CIGAR longer than the read sequence");
         if (cfg.want_hist && !is_del) { if (unique) ++hist_cnt[slot]; else col_red[slot] = 1; }
+        if (!col_qstart.empty() && !is_del && unique && q == 0) {  // error_count.cpp:157-166; query_stranded_end_1: alignment.cpp:228-239
+          const uint32_t stranded_end_1 = info[i].rev ? L - (uint32_t)(info[i].qb_start0 + 1) + 1 : (uint32_t)info[i].qb_end0 + 1;
+          if (stranded_end_1 >= junction_read_end_min(L)) col_qstart[slot] |= info[i].rev ? 2 : 1;
+        }
         if (cfg.want_score)
           score_words(i, info[i], q, is_del, indel, slot, [&](uint64_t s, uint32_t rec, uint32_t x1, uint32_t) {
             ++score_cnt[s];
@@ -497,6 +515,17 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   });
 
   phase_done("pass A2 (counts)");
+  if (!col_qstart.empty()) {  // error_count.cpp:191-194: columns without a redundant read, both strands
+    out.read_start_counts.assign(n_targets * 2, 0);
+    for (const Segment& sg : out.segments)
+      for (int32_t c = sg.lo; c < sg.hi; ++c) {
+        const uint64_t slot = sg.slot0 + (uint64_t)(c - sg.lo);
+        if (col_red[slot]) continue;
+        ++out.read_start_counts[(size_t)sg.tid * 2 + (col_qstart[slot] & 1)];
+        ++out.read_start_counts[(size_t)sg.tid * 2 + ((col_qstart[slot] >> 1) & 1)];
+      }
+  }
+
   // ---- offsets
   {
     bool p3 = false;

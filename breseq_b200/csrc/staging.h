@@ -23,6 +23,11 @@ struct StageConfig {
   uint32_t base_quality_cutoff = 3;    // Settings::base_quality_cutoff: decides which records score (settings.cpp:1335)
   int threads = 8;
   bool want_hist = true, want_score = true;
+  // the stage 03 (preprocess) call of error_count (breseq_cmdline.cpp:1969): also count, per target, the position-strand
+  // combinations with / without a read start inside the junction read-end bound (error_count.cpp:157-166, 191-194, 217-229)
+  bool preprocess_stage = false;
+  uint32_t unmatched_end_minimum_read_length = 50;   // settings.cpp:1309
+  double unmatched_end_length_factor = 0.1;          // 1 - require_match_fraction (settings.cpp:1308)
   bool compact_score = true;           // also build the transfer form of score_rec (brq_types.h: score16 + score_exc)
   bool compact_hist = true;            // also build the 16-bit histogram stream the device reads (brq_types.h)
   uint32_t shard_rank = 0, shard_count = 1;         // contiguous reference-coordinate shard staged by this call

@@ -48,6 +48,11 @@ typedef struct brq_stage_options {
   uint32_t use_read_pos;                   /* the covariate string names read_pos (either one: 8-byte histogram records) */
   uint32_t shard_rank, shard_count;        /* contiguous reference-coordinate shard of this process; 0,1 = all */
   uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff (decides which records score); 0 = the default, 3 */
+  /* error_count(..., preprocess_stage = true), the stage 03 call (breseq_cmdline.cpp:1969, error_count.cpp:157-166, 191-194,
+   * 217-229): also count the position-strand combinations with / without a read start inside the junction read-end bound */
+  uint32_t preprocess_stage;
+  uint32_t unmatched_end_minimum_read_length;  /* Settings::unmatched_end_minimum_read_length; 0 = the default, 50 */
+  double require_match_fraction;               /* Settings::require_match_fraction; 0 = the default, 0.9 */
 } brq_stage_options;
 
 int brq_stage_bam(brq_ctx* ctx, const char* bam, const char* fasta, const brq_stage_options* opt);
@@ -114,6 +119,10 @@ int brq_sync(brq_ctx* ctx);
 /* ---- pass 1: error_count (error_count.cpp:125-199, 854-1026) --------------------------------- */
 int brq_error_count(brq_ctx* ctx, const char* covariates, int do_coverage, int do_errors);
 /* device views for the one collective of the path (sum-allreduce of both integer histograms) */
+/* preprocess stage (brq_stage_options.preprocess_stage): per BAM tid, the position-strand combinations of the staged range
+ * without [2 tid] and with [2 tid + 1] a read start; Summary::preprocess_error_count[seq_id].no_pos_hash_per_position_pr is
+ * without / (without + with), 1.0 when both are zero (error_count.cpp:217-229).  Shards add up. */
+int brq_preprocess_read_starts(brq_ctx* ctx, const uint64_t** counts, uint32_t* n_targets);
 int brq_hist_device(brq_ctx* ctx, void** counts_u64, uint64_t* n_bins, void** coverage_u64, uint64_t* n_coverage);
 int brq_hist_download(brq_ctx* ctx, const uint64_t** counts, uint64_t* n_bins, const uint64_t** coverage,
                       uint64_t* coverage_stride, uint64_t* n_groups);

@@ -542,6 +542,10 @@ struct ErrorCountPileup : PileupDriver {
   vector<vector<uint32_t> > unique_only_coverage;
   uint32_t on_group = 0;
 
+  bool preprocess_stage = false;
+  uint64_t read_found_starting_at_pos[2] = {0, 0};
+  std::map<string, double> no_pos_hash_per_position_pr;
+
   ErrorCountPileup(const Settings& s, const string& bam, const string& fasta, bool errors, const string& covariates)
       : PileupDriver(bam, fasta), settings(s), do_errors(errors) {
     table.read_covariates(covariates);
@@ -550,31 +554,54 @@ struct ErrorCountPileup : PileupDriver {
     table.rg_map = &read_groups;
     table.partition = ReadFilePartition::make(read_groups, s.read_file_sets);
   }
-  void at_target_start(uint32_t tid) { on_group = settings.seq_id_to_coverage_group.find(target_name(tid))->second; }
+  void at_target_start(uint32_t tid) {  // error_count.cpp:201-214
+    on_group = settings.seq_id_to_coverage_group.find(target_name(tid))->second;
+    if (preprocess_stage) { read_found_starting_at_pos[0] = 0; read_found_starting_at_pos[1] = 0; }
+  }
+  void at_target_end(uint32_t tid) {  // error_count.cpp:217-229
+    if (!preprocess_stage) return;
+    const double total = (double)(read_found_starting_at_pos[0] + read_found_starting_at_pos[1]);
+    no_pos_hash_per_position_pr[target_name(tid)] = total != 0 ? (double)read_found_starting_at_pos[0] / total : 1.0;
+  }
+  uint32_t required_junction_read_end_min_coordinate(uint32_t read_length) const {  // settings.h:345-354
+    const int32_t max_len = (int32_t)floor((double)((int32_t)read_length - (int32_t)settings.unmatched_end_minimum_read_length) *
+                                           settings.unmatched_end_length_factor);
+    return max_len <= 0 ? read_length : read_length - (uint32_t)max_len;
+  }
   void pileup_callback(uint32_t tid, uint32_t pos1, int n, const bam_pileup1_t* pile) {  // error_count.cpp:125-199
     vector<uint32_t>& cov = unique_only_coverage[on_group];
     size_t unique_coverage = 0;
     bool has_redundant_reads = false;
+    int has_query_start[2] = {0, 0};
     for (int k = 0; k < n; ++k) {
       Aln i(&pile[k]);
       if (i.is_del()) continue;
       if (i.redundancy() > 1) { has_redundant_reads = true; continue; }
       ++unique_coverage;
+      if (preprocess_stage && i.qpos1() == 1) {  // :157-166; query_stranded_end_1: alignment.cpp:228-239
+        uint32_t qs0, qe0;
+        i.query_bounds_0(qs0, qe0);
+        const uint32_t stranded_end_1 = i.reversed() ? i.read_length() - (qs0 + 1) + 1 : qe0 + 1;
+        if (stranded_end_1 >= required_junction_read_end_min_coordinate(i.read_length())) has_query_start[i.reversed() ? 1 : 0] = 1;
+      }
       if (!do_errors) continue;
       table.count_alignment_position(i, pos1 - 1, refs[tid]);
     }
     if (!has_redundant_reads) {
       if (unique_coverage >= cov.size()) cov.resize(unique_coverage + 1, 0);
       ++cov[unique_coverage];
+      if (preprocess_stage) { read_found_starting_at_pos[has_query_start[0]]++; read_found_starting_at_pos[has_query_start[1]]++; }
     }
   }
 };
 
 void error_count(const Settings& settings, const string& bam, const string& fasta, const string& output_dir,
                  const vector<string>& readfiles, bool do_coverage, bool do_errors, const string& covariates,
-                 const string& counts_dump_file) {
+                 const string& counts_dump_file, bool preprocess_stage, std::map<string, double>* no_pos_hash_per_position_pr) {
   ErrorCountPileup ecp(settings, bam, fasta, do_errors, covariates);
+  ecp.preprocess_stage = preprocess_stage;
   ecp.do_pileup(settings.call_mutations_seq_ids);
+  if (no_pos_hash_per_position_pr) *no_pos_hash_per_position_pr = ecp.no_pos_hash_per_position_pr;
   if (do_coverage) {  // print_coverage :239-253
     for (size_t i = 0; i < ecp.unique_only_coverage.size(); ++i) {
       string fn = settings.unique_only_coverage_distribution_file_name;

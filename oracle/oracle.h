@@ -37,13 +37,18 @@ struct Settings {
   std::string unique_only_coverage_distribution_file_name;  // contains '@' replaced by the group index
   std::string base_qual_error_prob_file_name;               // contains '#' replaced by the read file name
   uint64_t total_reference_sequence_length = 0;
+  // stage 03 (preprocess) call of error_count: junction read-end bound of settings.h:345-354 (settings.cpp:1308-1309)
+  uint32_t unmatched_end_minimum_read_length = 50;
+  double unmatched_end_length_factor = 0.1;                 // 1 - require_match_fraction
 };
 
 // error_count.h:41-52
 void error_count(const Settings& settings, const std::string& bam, const std::string& fasta,
                  const std::string& output_dir, const std::vector<std::string>& readfiles,
                  bool do_coverage, bool do_errors, const std::string& covariates,
-                 const std::string& counts_dump_file /* "" = none: raw count table, idx-ordered text */);
+                 const std::string& counts_dump_file /* "" = none: raw count table, idx-ordered text */,
+                 bool preprocess_stage = false,
+                 std::map<std::string, double>* no_pos_hash_per_position_pr = nullptr /* Summary::preprocess_error_count, per seq id */);
 
 struct ColumnDump {  // one per (column, insert_count); written raw to --columns-out
   uint32_t tid, pos1, insert_count, n;

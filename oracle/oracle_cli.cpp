@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE -- command-line driver for the CPU oracle (see oracle.h).
 //   oracle_cli error_count        --bam B --fasta F --out DIR --covariates S [--readfiles a,b] [--read-sets n:2,m:1]
-//                                 [--seq-ids a,b] [--counts-dump FILE] [--error-rates FILE] [--no-coverage] [--no-errors]
+//                                 [--seq-ids a,b] [--counts-dump FILE] [--error-rates FILE] [--no-coverage] [--no-errors] [--preprocess]
 //   oracle_cli identify_mutations --bam B --fasta F --error-rates FILE --gd OUT.gd [--del-prop a,b] [--del-seed a,b]
 //                                 [--mutation-cutoff 10] [--polymorphism-cutoff 2] [--precision 1e-6] [--places 8]
 //                                 [--base-quality-cutoff 3] [--skip-mc] [--columns-out FILE] [--read-sets ...] [--seq-ids ...]
@@ -35,7 +35,7 @@ int main(int argc, char** argv) {
     string k = argv[i];
     if (k.rfind("--", 0) != 0) { cerr << "bad argument " << k << endl; return 2; }
     k = k.substr(2);
-    if (k == "no-coverage" || k == "no-errors" || k == "skip-mc") opt[k] = "1";
+    if (k == "no-coverage" || k == "no-errors" || k == "skip-mc" || k == "preprocess") opt[k] = "1";
     else if (i + 1 < argc) opt[k] = argv[++i];
   }
   auto get = [&](const string& k, const string& d) { return opt.count(k) ? opt[k] : d; };
@@ -71,8 +71,16 @@ int main(int argc, char** argv) {
   auto t0 = chrono::steady_clock::now();
   unsigned long long records = 0;
   if (cmd == "error_count") {
+    // --preprocess: the stage 03 call (breseq_cmdline.cpp:1969); Summary::preprocess_error_count goes to <out>/preprocess_error_count.tab
+    map<string, double> pr;
     oracle::error_count(st, get("bam", ""), get("fasta", ""), out, split(get("readfiles", ""), ','), !opt.count("no-coverage"),
-                        !opt.count("no-errors"), get("covariates", ""), get("counts-dump", ""));
+                        !opt.count("no-errors"), get("covariates", ""), get("counts-dump", ""), opt.count("preprocess") > 0, &pr);
+    if (opt.count("preprocess")) {
+      FILE* f = fopen((out + "/preprocess_error_count.tab").c_str(), "w");
+      if (!f) { cerr << "cannot write preprocess_error_count.tab" << endl; return 1; }
+      for (const auto& kv : pr) fprintf(f, "%s\t%.17g\n", kv.first.c_str(), kv.second);
+      fclose(f);
+    }
   } else if (cmd == "identify_mutations") {
     vector<double> prop, seed;
     for (const string& s : split(get("del-prop", ""), ',')) prop.push_back(atof(s.c_str()));

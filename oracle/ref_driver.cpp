@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
     string k = argv[i];
     if (k.rfind("--", 0) != 0) { cerr << "bad argument " << k << endl; return 2; }
     k = k.substr(2);
-    if (k == "no-coverage" || k == "no-errors" || k == "skip-mc" || k == "polymorphism-prediction") opt[k] = "1";
+    if (k == "no-coverage" || k == "no-errors" || k == "skip-mc" || k == "polymorphism-prediction" || k == "preprocess") opt[k] = "1";
     else if (i + 1 < argc) opt[k] = argv[++i];
   }
   auto get = [&](const string& k, const string& d) { return opt.count(k) ? opt[k] : d; };
@@ -105,8 +105,14 @@ int main(int argc, char** argv) {
   auto t0 = chrono::steady_clock::now();
   if (cmd == "error_count") {
     error_count(settings, summary, get("bam", ""), get("fasta", ""), out, split_list(get("readfiles", ""), ','),
-                !opt.count("no-coverage"), !opt.count("no-errors"), false, (uint8_t)settings.base_quality_cutoff,
+                !opt.count("no-coverage"), !opt.count("no-errors"), opt.count("preprocess") > 0, (uint8_t)settings.base_quality_cutoff,
                 get("covariates", ""));
+    if (opt.count("preprocess")) {  // the stage 03 call (breseq_cmdline.cpp:1969): what it leaves in the Summary
+      FILE* f = fopen((out + "/preprocess_error_count.tab").c_str(), "w");
+      if (!f) { cerr << "cannot write preprocess_error_count.tab" << endl; return 1; }
+      for (const auto& kv : summary.preprocess_error_count) fprintf(f, "%s\t%.17g\n", kv.first.c_str(), kv.second.no_pos_hash_per_position_pr);
+      fclose(f);
+    }
   } else if (cmd == "identify_mutations") {
     vector<double> prop, seed;
     for (const string& s : split_list(get("del-prop", ""), ',')) prop.push_back(atof(s.c_str()));

@@ -14,6 +14,7 @@ htslib shim.  What they wrote is committed here:
 
     <name>/error_rates.tab, base_qual_error_prob.*.tab, *.unique_only_coverage_distribution.tab,
     <name>/ra_mc_evidence.gd, <name>/inputs.sha256 (so generator drift is detected, not silently absorbed)
+    <name>/preprocess_error_count.tab  (error_count(..., preprocess_stage = true): Summary::preprocess_error_count per seq id)
     tiny/reference.bam, tiny/reference.fasta(.fai), tiny/per_position_file.tab   (inputs kept for the smallest case)
 
 The fixtures pin (a) oracle/oracle.cpp, (b) the CUDA path, against the reference's real arithmetic
@@ -54,6 +55,8 @@ def main():
             if d.get("big_table"):  # too many rows to commit: the checksum of what the reference wrote
                 with open(os.path.join(gdir, "error_rates.tab.sha256"), "w") as fh:
                     fh.write("%s  error_rates.tab\n" % sha256(os.path.join(out, "error_rates.tab")))
+            with open(os.path.join(gdir, helpers.PREPROCESS_TAB), "w") as fh:  # the stage 03 call (preprocess_stage = true)
+                fh.write(helpers.run_preprocess(helpers.REF_CLI, d, os.path.join(tmp, "ref_preprocess")))
             if name == "tiny":
                 for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
                     shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))

@@ -148,6 +148,31 @@ def run_reference(d, outdir, per_position=True, coverage_tsv=False):
     return sec
 
 
+PREPROCESS_TAB = "preprocess_error_count.tab"  # seq id <tab> no_pos_hash_per_position_pr (%.17g), what the stage 03 call leaves in the Summary
+
+
+def run_preprocess(cli, d, outdir):
+    """error_count(..., preprocess_stage = true) (breseq_cmdline.cpp:1969: coverage only) through oracle_cli or ref_cli;
+    returns the text of <outdir>/preprocess_error_count.tab."""
+    os.makedirs(outdir, exist_ok=True)
+    ec, _ = cli_args(d, outdir)
+    subprocess.run([cli] + [str(a) for a in ec] + ["--preprocess", "--no-errors"], check=True, capture_output=True, text=True)
+    return open(os.path.join(outdir, PREPROCESS_TAB)).read()
+
+
+def product_preprocess_tab(d, shards=1):
+    """The same table from the product's staging layer (host only: no device is needed for it); shards add up."""
+    names = contig_names(d)
+    total = np.zeros((len(names), 2), np.float64)
+    for rank in range(shards):
+        ctx = bq.Context(device=-1)
+        ctx.stage_bam(d["bam"], d["fasta"], preprocess_stage=True, shard=(rank, shards), **stage_kwargs(d))
+        total += ctx.preprocess_read_starts()
+        ctx.close()
+    rows = sorted((names[t], total[t, 0] / total[t].sum() if total[t].sum() else 1.0) for t in range(len(names)))
+    return "".join("%s\t%.17g\n" % r for r in rows)
+
+
 def pass_output_names(d):
     """Files the two entry points write for a dataset (the drop-in boundary's file contract)."""
     # a table with read_pos / base_repeat has 10^5 .. 10^6 rows: its golden is a checksum (test_golden.py), not a copy

@@ -51,6 +51,18 @@ def test_oracle_reproduces_reference_files(name, datasets):
     assert_same_files(d, d["oracle_dir"], os.path.join(helpers.GOLDEN, name), "oracle vs reference golden")
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_preprocess_stage_matches_reference(name, datasets, tmp_path):
+    """error_count(..., preprocess_stage = true), the stage 03 call (breseq_cmdline.cpp:1969): the oracle's and the product's
+    no_pos_hash_per_position_pr (error_count.cpp:157-166, 191-194, 217-229) against what the reference build left in its
+    Summary, to 17 significant digits; a run sharded by reference range adds up to the same numbers."""
+    d = datasets[name]
+    want = open(golden(name, helpers.PREPROCESS_TAB)).read()
+    assert helpers.run_preprocess(helpers.ORACLE_CLI, d, str(tmp_path / "oracle")) == want
+    assert helpers.product_preprocess_tab(d) == want
+    assert helpers.product_preprocess_tab(d, shards=3) == want
+
+
 def tiny_from_fixture(tmp):
     """The committed BAM itself (not a regenerated one)."""
     d = dict(helpers.DATASETS["tiny"])

@@ -1,8 +1,11 @@
 // sm_100a kernels of the read-alignment evidence pileup.
 //
-//  hist_kernel           error_count covariate histogram  (error_count.cpp:125-199, 854-997)
-//  coverage_hist_kernel  unique-only coverage histogram   (error_count.cpp:180-191)
-//  derive_table_kernel   counts -> log10 probabilities    (error_count.cpp:1005-1026)
+//  hist16_kernel, hist_kernel   error_count covariate histogram  (error_count.cpp:125-199, 854-997): 16-bit fast records +
+//                               exceptions (the form the device reads at the default covariates), or 4- / 8-byte records
+//  coverage_hist_kernel         unique-only coverage histogram   (error_count.cpp:180-191)
+//  derive_table_kernel          counts -> log10 probabilities    (error_count.cpp:1005-1026)
+//  canonical_table_kernel       log10 table -> probabilities through the six-digit text round trip (error_count.cpp:629-690)
+//  expand_score_kernel          PCIe transfer form of the scoring stream -> score_rec (brq_types.h)
 //  (per-slot scoring -- coverage tally, 5-way log-likelihood sums, consensus call, EM fit -- is in score_slots.cu)
 //
 // All of it is HBM-bound integer/byte work plus fp64 scalar math: no tensor cores.

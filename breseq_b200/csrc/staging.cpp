@@ -266,6 +266,16 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     for (auto& t : pool) t.join();
     if (!error.empty()) throw std::runtime_error(error);
   };
+  // [0, n) cut into parts handed out to the threads: body(first, last)
+  auto parallel_ranges = [&](uint64_t n, auto&& body) {
+    const size_t n_parts = (size_t)n_threads * 8;
+    std::atomic<size_t> next(0);
+    auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n_parts) break; body(n * k / n_parts, n * (k + 1) / n_parts); } };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  };
 
   phase_done("per-read values");
   // ---- pass A1: which insert sub-columns exist.  Level k+1 exists iff a UNIQUE read has an
@@ -345,12 +355,19 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   // scoring records closely and cost no column walk; the exact per-record histograms are gathered in pass B.
   if (cfg.want_score) {
     std::vector<uint64_t> mq(256, 0), qc(128, 0);
-    for (size_t i = 0; i < R.size(); ++i) {
-      if (!in_pileup(i) || R.x1[i] != 1) continue;
-      mq[R.mapq[i]] += info[i].L;
-      const uint8_t* qual = R.quals.data() + R.seq_off[i];
-      for (uint32_t k = 0; k < info[i].L; ++k) ++qc[qual[k] & 127];
-    }
+    std::mutex merge_mu;
+    parallel_ranges(R.size(), [&](uint64_t lo, uint64_t hi) {  // (sums: the order of the parts does not matter)
+      uint64_t mq_l[256] = {0}, qc_l[128] = {0};
+      for (size_t i = lo; i < hi; ++i) {
+        if (!in_pileup(i) || R.x1[i] != 1) continue;
+        mq_l[R.mapq[i]] += info[i].L;
+        const uint8_t* qual = R.quals.data() + R.seq_off[i];
+        for (uint32_t k = 0; k < info[i].L; ++k) ++qc_l[qual[k] & 127];
+      }
+      std::lock_guard<std::mutex> g(merge_mu);
+      for (int m = 0; m < 256; ++m) mq[m] += mq_l[m];
+      for (int q = 0; q < 128; ++q) qc[q] += qc_l[q];
+    });
     ScoreGeometry& g = out.geo;
     g.cutoff = cfg.base_quality_cutoff;
     g.n_st = (out.max_read_set_seen + 1) * 2;
@@ -606,7 +623,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   const bool build_hist16 = cfg.want_hist && cfg.compact_hist && !(cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7);
   out.score_rec_plain = build_score16; out.hist_rec_plain = build_hist16;
   out.score_rec = (uint32_t*)(build_score16 ? default_alloc(out.n_score_padded * 4, &p2) : alloc(out.n_score_padded * 4, &p2));
-  std::fill(out.score_rec, out.score_rec + out.n_score_padded, geo.pad_word());  // pad word: the trash counter, no other bit
+  parallel_ranges(out.n_score_padded, [&](uint64_t lo, uint64_t hi) { std::fill(out.score_rec + lo, out.score_rec + hi, geo.pad_word()); });  // pad word: the trash counter, no other bit (threads: the first touch of 2 GB)
   out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7) ? 8 : 4;
   out.hist_rec = build_hist16 ? default_alloc(out.n_hist * out.hist_bytes, &p2) : alloc(out.n_hist * out.hist_bytes, &p2);
 
@@ -636,9 +653,10 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       if (b > 5 || b == 4) throw std::runtime_error(std::string("Unrecognized base char in reference: ") + rs[(size_t)p]);
       return b;
     };
-    uint32_t* mq_mask = &mapq_masks[ii * 8];
-    uint64_t* mq_count = &mapq_counts[ii * 256];
-    uint64_t* q_count = &qual_counts[ii * 128];
+    // per-item statistics are gathered on the stack and stored once: neighbouring items run on different threads, and
+    // their slices of the shared vectors share cache lines (the 32-byte MAPQ masks did for every scoring record)
+    uint32_t mq_mask[8] = {0};
+    uint64_t mq_count[256] = {0}, q_count[128] = {0};
     uint32_t max_q = 0, max_hq = 0, max_rp = 0, max_srp = 0;
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
@@ -736,6 +754,9 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       });
     }
     max_quals[ii] = max_q; max_hquals[ii] = max_hq; max_rposs[ii] = max_rp; max_srposs[ii] = max_srp;
+    std::copy(mq_mask, mq_mask + 8, &mapq_masks[ii * 8]);
+    std::copy(mq_count, mq_count + 256, &mapq_counts[ii * 256]);
+    std::copy(q_count, q_count + 128, &qual_counts[ii * 128]);
   });
   if (cfg.want_score) out.mapq_seen[geo.hot_mapq >> 5] |= 1u << (geo.hot_mapq & 31);  // the shared table is always built
   for (size_t ii = 0; ii < items.size(); ++ii) {
@@ -756,15 +777,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     bool p5 = false;
     out.score16 = (uint16_t*)alloc(out.n_score_padded * 2 + 32, &p5);
     out.score_exc_off = (uint32_t*)alloc((n_lanes + 1) * 4, &p5);
-    const size_t n_parts = (size_t)std::max(1, n_threads) * 8;
-    auto parts = [&](auto&& body) {
-      std::atomic<size_t> next(0);
-      auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n_parts) break; body(out.n_rounds * k / n_parts, out.n_rounds * (k + 1) / n_parts); } };
-      std::vector<std::thread> pool;
-      for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
-      work();
-      for (auto& t : pool) t.join();
-    };
+    auto parts = [&](auto&& body) { parallel_ranges(out.n_rounds, body); };
     // pass 1: low halves, exception flags, exceptions per lane (words visited in memory order)
     parts([&](uint64_t r0, uint64_t r1) {
       for (uint64_t r = r0; r < r1; ++r) {

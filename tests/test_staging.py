@@ -1,5 +1,7 @@
 """Host staging against the oracle, without a GPU: the staged streams must carry exactly what the
 reference counts.  The numpy re-statements in helpers.py play the kernels' part."""
+import os
+
 import numpy as np
 import pytest
 
@@ -165,3 +167,35 @@ def test_empty_and_subset_targets(datasets):
     with pytest.raises(bq.BrqError):
         c.stage_bam(d["bam"], d["fasta"], seq_ids=["no_such_contig"])
     c.close()
+
+
+def test_compact_histogram_stream_routes_wide_read_sets_to_exceptions(tmp_path):
+    """Five read files: read sets 4 and above do not fit the two bits of a 16-bit record, so those records travel as
+    exceptions; together the two streams are still exactly the positional records, and count like the oracle."""
+    d = dict(seed=17, contig_lens=[1500], prefix="five",
+             read_sets=[dict(name="a", paired=True, read_len=60, coverage=12.0, frag_mean=180, frag_sd=15),
+                        dict(name="b", paired=True, read_len=60, coverage=12.0, frag_mean=180, frag_sd=15),
+                        dict(name="c", paired=False, read_len=36, coverage=10.0)],
+             n_polymorphic=4, n_fixed=2, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision=1e-6, places=8,
+             del_prop=5.0, del_seed=0.0)
+    d["bam"], d["fasta"] = str(tmp_path / "reference.bam"), str(tmp_path / "reference.fasta")
+    ctx = bq.Context(device=-1)
+    ctx.synth_write(helpers.synth_spec(d), d["bam"], d["fasta"])
+    ctx.stage_bam(d["bam"], d["fasta"], read_file_sets=helpers.read_file_sets(d))
+    s = ctx.stream()
+    h, h16, exc = s["hist_rec"], s["hist16"], s["hist_exc"]
+    assert h.dtype == np.uint32 and h16 is not None
+    assert np.array_equal(np.sort(np.concatenate([helpers.expand_hist16(h16), exc])), np.sort(h))
+    sets = (h >> 28) & 7
+    assert sets.max() == 4 and np.all(helpers.expand_hist16(h16) >> 28 & 7 <= 3)
+    fast_wide = ((h >> 31) == 1) & (sets > 3)
+    assert fast_wide.sum() > 0 and np.count_nonzero(((exc >> 31) == 1) & (((exc >> 28) & 7) > 3)) == fast_wide.sum()
+    # the covariate histogram of both streams together is the oracle's
+    out = str(tmp_path / "oracle")
+    os.makedirs(out)
+    ec, _ = helpers.cli_args(d, out)
+    dump = os.path.join(out, "counts.tab")
+    helpers.run_oracle(*ec, "--counts-dump", dump)
+    mine = helpers.emulate_hist(np.concatenate([helpers.expand_hist16(h16), exc]), 5, 42)
+    assert np.array_equal(mine, helpers.oracle_counts(dump))
+    ctx.close()

@@ -2,6 +2,9 @@
 
 #include <zlib.h>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -112,7 +115,16 @@ void parse_rg_lines(const std::string& text, ReadGroups& rg) {
 }  // namespace
 
 void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int threads) {
+  static const bool phase_times = getenv("BRQ_STAGE_TIMES") != nullptr;  // wall time of every phase on stderr
+  auto phase_t0 = std::chrono::steady_clock::now();
+  auto phase_done = [&](const char* what) {
+    if (!phase_times) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "read_bam: %-19s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - phase_t0).count());
+    phase_t0 = t;
+  };
   std::vector<uint8_t> in = slurp(path);
+  phase_done("read file");
   size_t total = 0;
   std::vector<BgzfBlock> blocks = index_blocks(in, total);
   std::vector<uint8_t> u(total);
@@ -137,6 +149,7 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
   }
   in.clear();
   in.shrink_to_fit();
+  phase_done("inflate");
 
   if (u.size() < 12 || memcmp(u.data(), "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
   size_t p = 4;
@@ -154,23 +167,49 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
   parse_rg_lines(hdr.text, hdr.read_groups);
   const ReadGroups& rg = hdr.read_groups;
 
+  // Records: one serial walk finds every record and sizes the arrays (prefix sums of the CIGAR and sequence lengths),
+  // then the threads decode disjoint record ranges into them.
+  std::vector<size_t> rec_at;  // offset of every record's fixed part
+  const size_t n0 = reads.size();
+  uint64_t n_cig_total = reads.cigars.size(), n_seq_total = reads.bases.size();
+  std::vector<uint64_t> cig_off, seq_off;
   while (p + 4 <= u.size()) {
-    int32_t block = rd<int32_t>(&u[p]);
+    const int32_t block = rd<int32_t>(&u[p]);
+    if (block < 32 || p + 4 + (size_t)block > u.size()) throw std::runtime_error("truncated BAM record");
     const uint8_t* x = &u[p + 4];
-    if (p + 4 + (size_t)block > u.size()) throw std::runtime_error("truncated BAM record");
-    int32_t tid = rd<int32_t>(x), pos = rd<int32_t>(x + 4);
-    uint8_t l_name = x[8], mapq = x[9];
-    uint16_t n_cigar = rd<uint16_t>(x + 12), flag = rd<uint16_t>(x + 14);
-    int32_t l_seq = rd<int32_t>(x + 16);
+    const uint8_t l_name = x[8];
+    const uint16_t n_cigar = rd<uint16_t>(x + 12);
+    const int32_t l_seq = rd<int32_t>(x + 16);
+    if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cigar + (((size_t)l_seq + 1) >> 1) + (size_t)l_seq > (size_t)block)
+      throw std::runtime_error("truncated BAM record");
+    rec_at.push_back(p + 4);
+    cig_off.push_back(n_cig_total); seq_off.push_back(n_seq_total);
+    n_cig_total += n_cigar; n_seq_total += (uint64_t)l_seq;
+    p += 4 + (size_t)block;
+  }
+  phase_done("find records");
+  const size_t n_new = rec_at.size(), n_all = n0 + n_new;
+  reads.tid.resize(n_all); reads.pos.resize(n_all); reads.flag.resize(n_all); reads.mapq.resize(n_all);
+  reads.n_cigar.resize(n_all); reads.cigar_off.resize(n_all); reads.l_seq.resize(n_all); reads.seq_off.resize(n_all);
+  reads.x1.resize(n_all); reads.xl.resize(n_all); reads.xr.resize(n_all); reads.as.resize(n_all); reads.rg.resize(n_all);
+  reads.cigars.resize(n_cig_total); reads.bases.resize(n_seq_total); reads.quals.resize(n_seq_total);
+  auto decode = [&](size_t r) {
+    const uint8_t* x = &u[rec_at[r]];
+    const int32_t block = rd<int32_t>(x - 4);
+    const size_t i = n0 + r;
+    const uint8_t l_name = x[8];
+    const uint16_t n_cigar = rd<uint16_t>(x + 12);
+    const int32_t l_seq = rd<int32_t>(x + 16);
     const uint8_t* q = x + 32 + l_name;
-    reads.tid.push_back(tid); reads.pos.push_back(pos); reads.flag.push_back(flag); reads.mapq.push_back(mapq);
-    reads.n_cigar.push_back(n_cigar); reads.cigar_off.push_back(reads.cigars.size());
-    for (int k = 0; k < n_cigar; ++k) reads.cigars.push_back(rd<uint32_t>(q + 4 * k));
+    reads.tid[i] = rd<int32_t>(x); reads.pos[i] = rd<int32_t>(x + 4); reads.flag[i] = rd<uint16_t>(x + 14); reads.mapq[i] = x[9];
+    reads.n_cigar[i] = n_cigar; reads.cigar_off[i] = cig_off[r];
+    for (int k = 0; k < n_cigar; ++k) reads.cigars[cig_off[r] + (size_t)k] = rd<uint32_t>(q + 4 * k);
     q += 4 * (size_t)n_cigar;
-    reads.l_seq.push_back((uint32_t)l_seq); reads.seq_off.push_back(reads.bases.size());
-    for (int i = 0; i < l_seq; ++i) reads.bases.push_back((q[i >> 1] >> ((~i & 1) << 2)) & 0xf);
+    reads.l_seq[i] = (uint32_t)l_seq; reads.seq_off[i] = seq_off[r];
+    uint8_t* bases = reads.bases.data() + seq_off[r];
+    for (int b = 0; b < l_seq; ++b) bases[b] = (q[b >> 1] >> ((~b & 1) << 2)) & 0xf;
     q += ((size_t)l_seq + 1) >> 1;
-    reads.quals.insert(reads.quals.end(), q, q + l_seq);
+    memcpy(reads.quals.data() + seq_off[r], q, (size_t)l_seq);
     q += l_seq;
     uint32_t x1 = 1; int32_t xl = -1, xr = -1, as = 0; uint8_t rgi = 0;
     bool seen_x1 = false, seen_xl = false, seen_xr = false, seen_rg = false;  // bam_aux_get returns the FIRST match
@@ -204,9 +243,28 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
         throw std::runtime_error("unknown aux type in BAM record");
       }
     }
-    reads.x1.push_back(x1); reads.xl.push_back(xl); reads.xr.push_back(xr); reads.as.push_back(as); reads.rg.push_back(rgi);
-    p += 4 + (size_t)block;
+    reads.x1[i] = x1; reads.xl[i] = xl; reads.xr[i] = xr; reads.as[i] = as; reads.rg[i] = rgi;
+  };
+  {
+    std::atomic<size_t> next(0);
+    std::mutex err_mu;
+    std::string err;
+    auto work = [&]() {
+      try {
+        for (;;) {
+          const size_t r0 = next.fetch_add(4096);
+          if (r0 >= n_new) break;
+          for (size_t r = r0; r < std::min(r0 + 4096, n_new); ++r) decode(r);
+        }
+      } catch (const std::exception& e) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = e.what(); next = n_new; }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (!err.empty()) throw std::runtime_error(err);
   }
+  phase_done("decode records");
 }
 
 // ---------------------------------------------------------------------------------- writers

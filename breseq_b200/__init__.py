@@ -38,7 +38,8 @@ class _StageOptions(C.Structure):
                 ("use_base_repeat", C.c_uint32), ("use_read_pos", C.c_uint32), ("shard_rank", C.c_uint32),
                 ("shard_count", C.c_uint32), ("base_quality_cutoff", C.c_uint32),
                 ("preprocess_stage", C.c_uint32), ("unmatched_end_minimum_read_length", C.c_uint32),
-                ("require_match_fraction", C.c_double)]
+                ("require_match_fraction", C.c_double), ("shard_lo", C.c_uint64), ("shard_hi", C.c_uint64),
+                ("staging", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class _SynthReadSet(C.Structure):
@@ -57,7 +58,8 @@ class _StreamInfo(C.Structure):
     _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
                 ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
                 ("bytes_host", C.c_uint64),
-                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("hist_record_bytes", C.c_uint32), ("side_stride", C.c_uint32),
+                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("device_built", C.c_uint32), ("reserved0", C.c_uint32),
+                ("hist_record_bytes", C.c_uint32), ("side_stride", C.c_uint32),
                 ("n_side", C.c_uint64), ("base_quality_cutoff", C.c_uint32), ("hot_mapq", C.c_uint32),
                 ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_words", C.c_uint32),
                 ("score_rec", C.POINTER(C.c_uint32)), ("side_rec", C.POINTER(C.c_uint32)), ("side_off", C.POINTER(C.c_uint32)),
@@ -198,7 +200,7 @@ class SynthSpec:
 
 def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, use_read_pos=False,
                    shard=(0, 1), base_quality_cutoff=3, preprocess_stage=False, unmatched_end_minimum_read_length=50,
-                   require_match_fraction=0.9):
+                   require_match_fraction=0.9, shard_bounds=None, staging="auto"):
     keep = []
     o = _StageOptions()
     if seq_ids:
@@ -223,6 +225,9 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
     o.preprocess_stage = int(preprocess_stage)
     o.unmatched_end_minimum_read_length = unmatched_end_minimum_read_length
     o.require_match_fraction = require_match_fraction
+    if shard_bounds is not None:
+        o.shard_lo, o.shard_hi = shard_bounds
+    o.staging = {"auto": 0, "host": 1, "device": 2}[staging]
     return o, keep
 
 
@@ -343,6 +348,7 @@ class Context:
         return {
             "n_base": info.n_base, "n_ins": info.n_ins, "n_score": info.n_score_records, "n_hist": info.n_hist_records,
             "n_reads": info.n_reads, "bytes_host": info.bytes_host, "pinned": bool(info.pinned), "n_targets": info.n_targets,
+            "device_built": bool(info.device_built), "n_hist16": info.n_hist16, "n_hist_exc": info.n_hist_exc, "n_rounds": info.n_rounds,
             "n_score_padded": info.n_score_padded,
             "score_rec": view(info.score_rec, info.n_score_padded, np.uint32),
             "score_off": view(info.score_off, n_slots + 1, np.uint64),

@@ -2,6 +2,7 @@
 #include "../../include/brq.h"
 
 #include "bam_io.h"
+#include "expand.h"
 #include "finalize.h"
 #include "kernels.h"
 #include "staging.h"
@@ -22,12 +23,6 @@
 
 using namespace brq;
 
-#define CUDA_OK(call)                                                                                  \
-  do {                                                                                                 \
-    cudaError_t e_ = (call);                                                                           \
-    if (e_ != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
-  } while (0)
-
 namespace {
 
 void* pinned_alloc(size_t bytes, bool* pinned) {
@@ -40,19 +35,6 @@ void* pinned_alloc(size_t bytes, bool* pinned) {
   return p;
 }
 void pinned_release(void* p, bool pinned) { if (pinned) cudaFreeHost(p); else free(p); }
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  void ensure(size_t want) {
-    if (want <= n && p) return;
-    release();
-    CUDA_OK(cudaMalloc((void**)&p, (want ? want : 1) * sizeof(T)));
-    n = want;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-};
 
 }  // namespace
 
@@ -72,13 +54,13 @@ struct brq_ctx {
   PileupStream st;
   bool staged = false, uploaded = false;
 
-  DevBuf<uint32_t> d_score_rec, d_side_rec, d_side_off, d_round_slot, d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
-  DevBuf<uint64_t> d_score_off, d_hist_off, d_round_off;
-  DevBuf<uint32_t> d_score_cnt, d_round_side;
-  DevBuf<uint8_t> d_hist_rec, d_score16;   // d_score16: transfer form of the scoring stream (low halves)
+  StreamDev ds;                   // the staged stream in HBM (uploaded from the host's staging, or built there by the expander)
+  ReadsDev d_reads;               // device staging: the aligned reads in HBM
+  ExpandScratch xs;
+  FlaggedRecordsHost flagged_records;  // device-built streams: the records of the flagged slots, for the host re-evaluation
+  DevBuf<uint32_t> d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
+  DevBuf<uint8_t> d_score16;   // transfer form of the scoring stream (low halves)
   DevBuf<uint32_t> d_score_exc, d_score_exc_off;
-  size_t hist_exc_at = 0;   // byte offset of the exception records inside d_hist_rec (compact form)
-  DevBuf<uint8_t> d_slot_ref, d_slot_group;
   DevBuf<unsigned long long> d_counts, d_cov;
   DevBuf<double> d_log10;
   DevBuf<ClassTerms> d_lut;
@@ -104,6 +86,16 @@ struct brq_ctx {
   bool have_walk = false;
   std::unique_ptr<WorkerPool> pool; // parked host threads for short data-parallel jobs
   std::string shard_blob;           // brq_evidence_export
+  // host copies of a device-built stream's arrays, made on demand (brq_stream, the per-position file, the coverage TSV)
+  struct Mirror {
+    bool valid = false;
+    std::vector<uint32_t> score_rec, side_rec, side_off, round_slot, score_cnt;
+    std::vector<uint64_t> score_off, hist_off, round_off;
+    std::vector<uint8_t> slot_ref, hist_pos;
+    std::vector<uint16_t> hist16;
+    std::vector<uint32_t> hist_exc;
+  } mirror;
+  bool host_hist_valid = false;     // h_counts / h_cov hold the counts of the current stream's last brq_error_count
   uint64_t d2h_bytes = 0;           // device -> host bytes since the last brq_d2h_bytes(reset) (bench bookkeeping)
 
   CovSpec spec;
@@ -154,6 +146,11 @@ namespace {
 template <class F>
 int guarded(brq_ctx* ctx, F&& f) {
   if (!ctx) return 1;
+  // every call runs on the context's device whatever the calling thread's current device is, and leaves that as it was
+  int prev_device = -1;
+  const bool guard = ctx->device >= 0 && cudaGetDevice(&prev_device) == cudaSuccess && prev_device != ctx->device;
+  if (guard) cudaSetDevice(ctx->device);
+  struct Restore { bool on; int dev; ~Restore() { if (on) cudaSetDevice(dev); } } restore{guard, prev_device};
   try { f(); ctx->error.clear(); return 0; }
   catch (const std::exception& e) { ctx->error = e.what(); return 1; }
   catch (...) { ctx->error = "unknown error"; return 1; }
@@ -170,25 +167,93 @@ void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
   if (o->coverage_group_of_tid) s.coverage_group_of_tid.assign(o->coverage_group_of_tid, o->coverage_group_of_tid + o->n_targets);
   s.use_base_repeat = o->use_base_repeat != 0;
   s.use_read_pos = o->use_read_pos != 0;
-  s.base_quality_cutoff = o->base_quality_cutoff ? o->base_quality_cutoff : 3;
+  // Settings::base_quality_cutoff: 0 is a value the reference accepts (every quality scores); BRQ_DEFAULT_BASE_QUALITY_CUTOFF = unset
+  s.base_quality_cutoff = o->base_quality_cutoff == BRQ_DEFAULT_BASE_QUALITY_CUTOFF ? 3 : o->base_quality_cutoff;
   s.preprocess_stage = o->preprocess_stage != 0;
   s.unmatched_end_minimum_read_length = o->unmatched_end_minimum_read_length ? o->unmatched_end_minimum_read_length : 50;
   s.unmatched_end_length_factor = 1.0 - (o->require_match_fraction != 0.0 ? o->require_match_fraction : 0.9);
   s.shard_rank = o->shard_rank;
   s.shard_count = o->shard_count ? o->shard_count : 1;
+  s.shard_lo = o->shard_lo; s.shard_hi = o->shard_hi; s.shard_explicit = o->shard_hi > o->shard_lo;
+  s.staging_mode = (int)o->staging;
 }
 
 void drop_stream(brq_ctx* c) {
-  if (c->staged) free_stream(c->st, c->stage_cfg);
+  free_stream(c->st, c->stage_cfg);   // (a stream whose staging failed half-way still owns its buffers)
   c->staged = c->uploaded = false;
   c->have_counts = c->have_cols = c->have_walk = false;
   c->hist_check_pending = false;
+  c->host_hist_valid = false;
+  c->mirror = brq_ctx::Mirror();
+}
+
+// BAM records (c->reads) -> the streams.  On the device (the default when the context has one): the reads cross PCIe and
+// expand.cu's kernels build the streams in HBM; BRQ_HOST_STAGING=1 or brq_stage_options.staging = 1 keeps the host's
+// staging.cpp (the checker of the device path: tests compare the two streams array by array).
+bool device_staging(const brq_ctx* c) {
+  static const bool env_host = getenv("BRQ_HOST_STAGING") != nullptr;
+  if (c->device < 0) return false;
+  if (c->stage_cfg.staging_mode == 1) return false;
+  if (c->stage_cfg.staging_mode == 2) return true;
+  return !env_host;
 }
 
 void do_stage(brq_ctx* c) {
-  stage(c->hdr, c->ref, c->reads, c->stage_cfg, c->st);
+  if (c->stage_cfg.staging_mode == 2 && c->device < 0) throw std::runtime_error("device staging needs a context with a CUDA device");
+  if (device_staging(c)) {
+    static const bool times = getenv("BRQ_STAGE_TIMES") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    c->d_reads.upload(c->reads, c->stream);
+    if (times) { CUDA_OK(cudaStreamSynchronize(c->stream)); fprintf(stderr, "stage (device): upload %.1f ms (%.1f MB)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), c->d_reads.bytes / 1e6); }
+    const auto t1 = std::chrono::steady_clock::now();
+    expand_on_device(c->hdr, c->ref, c->reads, c->d_reads, c->stage_cfg, c->xs, c->ds, c->st, c->stream);
+    if (times) fprintf(stderr, "stage (device): expand %.1f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+    c->staged = true;
+    c->uploaded = true;   // the stream was born in HBM
+    return;
+  }
+  try {
+    stage(c->hdr, c->ref, c->reads, c->stage_cfg, c->st);
+  } catch (...) {
+    free_stream(c->st, c->stage_cfg);
+    throw;
+  }
   c->staged = true;
   c->uploaded = false;
+}
+
+// host copies of a device-built stream (tests, optional outputs): a PileupStream whose pointers lead into c->mirror
+PileupStream host_view(brq_ctx* c) {
+  PileupStream v = c->st;
+  if (!c->st.device_built) return v;
+  brq_ctx::Mirror& m = c->mirror;
+  const PileupStream& st = c->st;
+  const uint64_t n_slots = st.n_slots();
+  if (!m.valid) {
+    auto down = [&](auto& vec, const auto* dev, size_t n) {
+      vec.resize(n + 1);
+      if (n) CUDA_OK(cudaMemcpyAsync(vec.data(), dev, n * sizeof(*dev), cudaMemcpyDeviceToHost, c->stream));
+    };
+    down(m.score_rec, c->ds.score_rec.p, st.n_score_padded); down(m.side_rec, c->ds.side_rec.p, st.n_side * st.geo.side_stride);
+    down(m.side_off, c->ds.side_off.p, n_slots + 1); down(m.round_slot, c->ds.round_slot.p, st.n_rounds * 32);
+    down(m.score_cnt, c->ds.score_cnt.p, n_slots); down(m.score_off, c->ds.score_off.p, n_slots + 1);
+    down(m.hist_off, c->ds.hist_off.p, st.n_base + 1); down(m.round_off, c->ds.round_off.p, st.n_rounds + 1);
+    down(m.slot_ref, c->ds.slot_ref.p, n_slots);
+    if (st.hist_compact) {
+      down(m.hist_pos, c->xs.hist_pos.p, st.n_hist * st.hist_bytes);
+      down(m.hist16, reinterpret_cast<const uint16_t*>(c->ds.hist_rec.p), st.n_hist16);
+      down(m.hist_exc, reinterpret_cast<const uint32_t*>(c->ds.hist_rec.p + c->ds.hist_exc_at), st.n_hist_exc);
+    } else {
+      down(m.hist_pos, c->ds.hist_rec.p, st.n_hist * st.hist_bytes);
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    m.valid = true;
+  }
+  v.score_rec = m.score_rec.data(); v.side_rec = m.side_rec.data(); v.side_off = m.side_off.data(); v.round_slot = m.round_slot.data();
+  v.score_cnt = m.score_cnt.data(); v.score_off = m.score_off.data(); v.hist_off = m.hist_off.data(); v.round_off = m.round_off.data();
+  v.slot_ref = m.slot_ref.data(); v.hist_rec = m.hist_pos.data();
+  if (st.hist_compact) { v.hist16 = m.hist16.data(); v.hist_exc = m.hist_exc.data(); }
+  return v;
 }
 
 SynthConfig synth_config(const brq_synth_spec* sp, int threads) {
@@ -222,39 +287,40 @@ void upload(brq_ctx* c) {
   c->need_device();
   if (!c->staged) throw std::runtime_error("nothing staged");
   const PileupStream& st = c->st;
+  if (st.device_built) { c->uploaded = true; return; }   // built in HBM by the expander
   const uint64_t n_slots = st.n_slots();
-  c->d_score_rec.ensure(st.n_score_padded + 64); c->d_round_slot.ensure(st.n_rounds * 32 + 4); c->d_score_off.ensure(n_slots + 1); c->d_score_cnt.ensure(n_slots + 1); c->d_round_off.ensure(st.n_rounds + 1); c->d_round_side.ensure(st.n_rounds * 64 + 4); c->d_slot_ref.ensure(n_slots);
+  c->ds.score_rec.ensure(st.n_score_padded + 64); c->ds.round_slot.ensure(st.n_rounds * 32 + 4); c->ds.score_off.ensure(n_slots + 1); c->ds.score_cnt.ensure(n_slots + 1); c->ds.round_off.ensure(st.n_rounds + 1); c->ds.round_side.ensure(st.n_rounds * 64 + 4); c->ds.slot_ref.ensure(n_slots);
   // the histogram records: the compact form when staging built it (16-bit fast records, then the 4-byte exceptions)
-  c->hist_exc_at = (st.n_hist16 * 2 + 31) & ~(size_t)15;
-  c->d_hist_rec.ensure(st.hist16 ? c->hist_exc_at + st.n_hist_exc * 4 + 16 : st.n_hist * st.hist_bytes + 16);
-  c->d_side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->d_side_off.ensure(n_slots + 1); c->d_hist_off.ensure(st.n_base + 1); c->d_slot_group.ensure(st.n_base);
+  c->ds.hist_exc_at = (st.n_hist16 * 2 + 31) & ~(size_t)15;
+  c->ds.hist_rec.ensure(st.hist16 ? c->ds.hist_exc_at + st.n_hist_exc * 4 + 16 : st.n_hist * st.hist_bytes + 16);
+  c->ds.side_rec.ensure(st.n_side * st.geo.side_stride + 4); c->ds.side_off.ensure(n_slots + 1); c->ds.hist_off.ensure(st.n_base + 1); c->ds.slot_group.ensure(st.n_base);
   if (st.score16) {  // the transfer form: low halves + exception words, expanded to score_rec on the device (end of this function)
     c->d_score16.ensure(st.n_score_padded * 2 + 64); c->d_score_exc.ensure(st.n_score_exc + 8); c->d_score_exc_off.ensure(st.n_rounds * 32 + 1);
     CUDA_OK(cudaMemcpyAsync(c->d_score16.p, st.score16, st.n_score_padded * 2, cudaMemcpyHostToDevice, c->stream));
     if (st.n_score_exc) CUDA_OK(cudaMemcpyAsync(c->d_score_exc.p, st.score_exc, st.n_score_exc * 4, cudaMemcpyHostToDevice, c->stream));
     CUDA_OK(cudaMemcpyAsync(c->d_score_exc_off.p, st.score_exc_off, (st.n_rounds * 32 + 1) * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
-    CUDA_OK(cudaMemcpyAsync(c->d_score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->ds.score_rec.p, st.score_rec, st.n_score_padded * 4, cudaMemcpyHostToDevice, c->stream));
   }
-  CUDA_OK(cudaMemcpyAsync(c->d_score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_round_side.p, st.round_side, st.n_rounds * 256, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_side_rec.p, st.side_rec, st.n_side * st.geo.side_stride * 4, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.score_off.p, st.score_off, (n_slots + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.score_cnt.p, st.score_cnt, n_slots * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.round_off.p, st.round_off, (st.n_rounds + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.round_side.p, st.round_side, st.n_rounds * 256, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.side_rec.p, st.side_rec, st.n_side * st.geo.side_stride * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.side_off.p, st.side_off, (n_slots + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.round_slot.p, st.round_slot, st.n_rounds * 128, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.slot_ref.p, st.slot_ref, n_slots, cudaMemcpyHostToDevice, c->stream));
   if (st.hist16) {
-    CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist16, st.n_hist16 * 2, cudaMemcpyHostToDevice, c->stream));
-    if (st.n_hist_exc) CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p + c->hist_exc_at, st.hist_exc, st.n_hist_exc * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->ds.hist_rec.p, st.hist16, st.n_hist16 * 2, cudaMemcpyHostToDevice, c->stream));
+    if (st.n_hist_exc) CUDA_OK(cudaMemcpyAsync(c->ds.hist_rec.p + c->ds.hist_exc_at, st.hist_exc, st.n_hist_exc * 4, cudaMemcpyHostToDevice, c->stream));
   } else {
-    CUDA_OK(cudaMemcpyAsync(c->d_hist_rec.p, st.hist_rec, st.n_hist * st.hist_bytes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->ds.hist_rec.p, st.hist_rec, st.n_hist * st.hist_bytes, cudaMemcpyHostToDevice, c->stream));
   }
-  CUDA_OK(cudaMemcpyAsync(c->d_hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-  CUDA_OK(cudaMemcpyAsync(c->d_slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.hist_off.p, st.hist_off, (st.n_base + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(c->ds.slot_group.p, st.slot_group, st.n_base, cudaMemcpyHostToDevice, c->stream));
   if (st.score16)
-    launch_expand_score(reinterpret_cast<const uint16_t*>(c->d_score16.p), c->d_round_off.p, c->d_round_slot.p, c->d_slot_ref.p, c->d_score_exc.p,
-                        c->d_score_exc_off.p, st.n_rounds, st.geo, c->d_score_rec.p, c->stream);
+    launch_expand_score(reinterpret_cast<const uint16_t*>(c->d_score16.p), c->ds.round_off.p, c->ds.round_slot.p, c->ds.slot_ref.p, c->d_score_exc.p,
+                        c->d_score_exc_off.p, st.n_rounds, st.geo, c->ds.score_rec.p, c->stream);
   c->uploaded = true;
 }
 
@@ -290,16 +356,17 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
       throw std::runtime_error("base_repeat above 32 is not supported (the staged records keep five bits of it)");
     if (st.hist_bytes == 4 && (lay.off_rpos || lay.off_rep))
       throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
-    if (st.hist16) launch_hist16(c->d_hist_rec.p, st.n_hist16, reinterpret_cast<const uint32_t*>(c->d_hist_rec.p + c->hist_exc_at), st.n_hist_exc, lay, c->d_counts.p, c->stream);
-    else launch_hist(c->d_hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
+    if (st.hist_compact) launch_hist16(c->ds.hist_rec.p, st.n_hist16, reinterpret_cast<const uint32_t*>(c->ds.hist_rec.p + c->ds.hist_exc_at), st.n_hist_exc, lay, c->d_counts.p, c->stream);
+    else launch_hist(c->ds.hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
   }
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
-  if (do_coverage) launch_coverage_hist(c->d_hist_off.p, c->d_slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
+  if (do_coverage) launch_coverage_hist(c->ds.hist_off.p, c->ds.slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
   CUDA_OK(cudaGetLastError());
   // no synchronisation here: the kernels' error word and their event times are read by finish_error_count() when the
   // counts are downloaded or the timings asked for, and by the check that ends score_columns
   c->hist_check_pending = true;
+  c->host_hist_valid = false;
   c->have_counts = true;
   c->have_table = false;
   c->host_table_pending = false;
@@ -322,6 +389,7 @@ void download_hist(brq_ctx* c) {
   CUDA_OK(cudaMemcpyAsync(c->h_cov.data(), c->d_cov.p, c->h_cov.size() * 8, cudaMemcpyDeviceToHost, c->stream));
   c->d2h_bytes += (c->h_counts.size() + c->h_cov.size()) * 8;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  c->host_hist_valid = true;
 }
 
 // The error table reaches pass 2 through the reference's text round trip (six significant digits, error_count.cpp:629-690).
@@ -452,7 +520,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 1, 0, 12, c->stream));  // the error word [0] may still hold pass 1's verdict
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
-  launch_score_slots(c->d_score_rec.p, c->d_score_off.p, c->d_score_cnt.p, c->d_round_off.p, c->d_side_rec.p, c->d_side_off.p, reinterpret_cast<const uint2*>(c->d_round_side.p), c->d_slot_ref.p, c->d_round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
+  launch_score_slots(c->ds.score_rec.p, c->ds.score_off.p, c->ds.score_cnt.p, c->ds.round_off.p, c->ds.side_rec.p, c->ds.side_off.p, reinterpret_cast<const uint2*>(c->ds.round_side.p), c->ds.slot_ref.p, c->ds.round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
                      c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
@@ -527,9 +595,18 @@ void download_walk(brq_ctx* c, const double* prop, uint32_t n_targets) {
   }
   CUDA_OK(cudaStreamSynchronize(c->stream));
   (void)n_slots;
+  if (st.device_built) gather_flagged_records(c->ds, st, c->d_flagged.p, n_flagged, c->flagged_records, c->stream, &c->d2h_bytes);
   c->d2h_bytes += 12 + c->h_events.size() * sizeof(WalkEvent) + (uint64_t)n_flagged * (4 + sizeof(ColumnOut));
   c->walk_prop.assign(prop, prop + n_targets);
   c->have_walk = true;
+}
+
+// where collect_evidence finds the flagged slots' records: in the host stream, or (device staging) in what download_walk gathered
+const FlaggedRecords* flagged_view(brq_ctx* c, FlaggedRecords& fr) {
+  if (!c->st.device_built) return nullptr;
+  const FlaggedRecordsHost& h = c->flagged_records;
+  fr.word_off = h.word_off.data(); fr.side_off = h.side_off.data(); fr.words = h.words.data(); fr.side = h.side.data(); fr.ref = h.ref.data();
+  return &fr;
 }
 
 EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, const double* seed, uint32_t n_targets, int skip_mc) {
@@ -554,7 +631,8 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
   ensure_host_lut(c);
   const auto t2 = now();
-  const EvidenceCounts k = write_evidence(gd_file, c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep);
+  FlaggedRecords fr;
+  const EvidenceCounts k = write_evidence(gd_file, c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep, flagged_view(c, fr));
   if (timing) fprintf(stderr, "[brq] evidence: download %.2f ms, lut %.2f ms, write_evidence %.2f ms (%zu flagged, %llu RA)\n",
                       ms(t0, t1), ms(t1, t2), ms(t2, now()), c->h_flagged.size(), (unsigned long long)k.ra);
   return k;
@@ -577,12 +655,13 @@ void evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets) {
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(n_targets, 0.0);
   ensure_host_lut(c);
-  c->shard_blob = serialize_shard(collect_evidence(c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep));
+  FlaggedRecords fr;
+  c->shard_blob = serialize_shard(collect_evidence(c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep, flagged_view(c, fr)));
 }
 
 void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,
                        uint32_t n_readfiles, int do_coverage, int do_errors, const char* counts_dump) {
-  if (c->h_counts.size() != c->spec.n_bins) download_hist(c);
+  if (!c->host_hist_valid) download_hist(c);
   std::string dir = output_dir ? output_dir : ".";
   if (do_coverage) write_coverage_distributions(dir, c->h_cov, c->cov_stride, c->n_groups);
   if (do_errors) {
@@ -628,9 +707,9 @@ void brq_destroy(brq_ctx* c) {
   if (!c) return;
   drop_stream(c);
   if (c->device >= 0) {
-    c->d_score_rec.release(); c->d_round_slot.release(); c->d_side_rec.release(); c->d_side_off.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_score_off.release(); c->d_score_cnt.release(); c->d_round_off.release(); c->d_round_side.release(); c->d_hist_rec.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
+    c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
-    c->d_hist_off.release(); c->d_slot_ref.release(); c->d_slot_group.release(); c->d_counts.release(); c->d_cov.release();
+    c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
     c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -674,7 +753,8 @@ int brq_stage_synthetic(brq_ctx* c, const brq_synth_spec* spec, const brq_stage_
 int brq_stream(brq_ctx* c, brq_stream_info* info) {
   return guarded(c, [&] {
     if (!c->staged) throw std::runtime_error("nothing staged");
-    const PileupStream& st = c->st;
+    const PileupStream view = host_view(c);   // (a device-built stream is copied to the host here, once)
+    const PileupStream& st = view;
     memset(info, 0, sizeof *info);
     info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
     info->n_reads = c->reads.size();
@@ -683,10 +763,11 @@ int brq_stream(brq_ctx* c, brq_stream_info* info) {
     info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
     info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
     info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
-    info->bytes_host = st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + (st.score16 ? st.n_score_padded * 2 + st.n_score_exc * 4 + (st.n_rounds * 32 + 1) * 4 : st.n_score_padded * 4) + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
+    info->device_built = st.device_built ? 1u : 0u;
+    info->bytes_host = st.device_built ? st.bytes_uploaded : st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + (st.score16 ? st.n_score_padded * 2 + st.n_score_exc * 4 + (st.n_rounds * 32 + 1) * 4 : st.n_score_padded * 4) + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
     info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
     info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
-    info->slot_ref = st.slot_ref; info->ins_parent = st.ins_parent.data(); info->ins_count = st.ins_count.data();
+    info->slot_ref = st.slot_ref; info->ins_parent = c->st.ins_parent.data(); info->ins_count = c->st.ins_count.data();
     info->hist16 = st.hist16; info->n_hist16 = st.n_hist16; info->hist_exc = st.hist_exc; info->n_hist_exc = st.n_hist_exc;
     info->score16 = st.score16; info->score_exc = st.score_exc; info->score_exc_off = st.score_exc_off; info->n_score_exc = st.n_score_exc;
   });
@@ -806,7 +887,7 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
     apply_stage_options(c, opt);
     c->stage_cfg.use_read_pos = c->stage_cfg.use_read_pos || spec.used[COV_READ_POS];
     c->stage_cfg.use_base_repeat = c->stage_cfg.use_base_repeat || spec.used[COV_BASE_REPEAT];
-    if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff ? p->base_quality_cutoff : c->stage_cfg.base_quality_cutoff;
+    if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff;   // the score parameters carry Settings::base_quality_cutoff
     do_stage(c);
     c->host_table_pending = false;
     c->spec = spec; c->h_log10 = log10_prob;
@@ -821,14 +902,16 @@ int brq_write_per_position_file(brq_ctx* c, const char* path, const double* prop
   return guarded(c, [&] {
     if (n_targets != c->hdr.target_names.size()) throw std::runtime_error("the cutoff table does not match the BAM targets");
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
-    write_per_position_file(path, c->hdr, c->st, c->h_cols, c->last_params.base_quality_cutoff, std::vector<double>(prop, prop + n_targets));
+    const PileupStream view = host_view(c);
+    write_per_position_file(path, c->hdr, view, c->h_cols, c->last_params.base_quality_cutoff, std::vector<double>(prop, prop + n_targets));
   });
 }
 
 int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
   return guarded(c, [&] {
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
-    write_coverage_tsv(pattern, c->hdr, c->ref, c->st, c->h_cols);
+    const PileupStream view = host_view(c);
+    write_coverage_tsv(pattern, c->hdr, c->ref, view, c->h_cols);
   });
 }
 

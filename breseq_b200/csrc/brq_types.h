@@ -268,6 +268,9 @@ struct PileupStream {
   uint32_t max_score_rpos = 0;                    // largest read position of a scoring record (streams staged with read_pos)
   uint32_t max_read_set_seen = 0;
   bool pinned = false;                 // buffers came from cudaHostAlloc
+  bool device_built = false;           // built in HBM by the expander (expand.cu): the record arrays above are null on the host
+  bool hist_compact = false;           // the device reads the compact histogram streams (hist16 + hist_exc)
+  uint64_t bytes_uploaded = 0;         // device_built: bytes of reads and reference that crossed PCIe for it
   bool score_rec_plain = false, hist_rec_plain = false;  // ... except these two: plain memory when only their transfer / compact form is uploaded
   uint64_t n_slots() const { return n_base + n_ins; }
 };
@@ -283,24 +286,31 @@ inline uint64_t score_index(uint64_t base, uint64_t j) {
   return base + (j >> 3) * ROUND_VECTOR_WORDS + ((j >> 2) & 1u) * (ROUND_VECTOR_WORDS / 2) + (j & 3u);
 }
 
-// Classic words of slot s in stream order (redundant first): f(classic word, X1, ext).  Redundant records come
-// back with their full X1 (the classic field saturates at 8191); ext = read_pos | base_repeat << 16 of a scoring
-// record of a stream staged with them, else 0.
-template <class F>
-inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
-  uint32_t side = st.side_off[s];
-  for (uint64_t j = 0; j < st.score_cnt[s]; ++j) {
-    const uint32_t d = st.score_rec[score_index(st.score_off[s], j)], kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
-    const uint32_t ss = st.geo.side_stride;
-    if (kind == 0) f(classic_of_hot(d, st.geo), 1u, 0u);
+// Classic words of one slot in stream order (redundant first): f(classic word, X1, ext).  word(j) = the slot's j-th device
+// word, side = the slot's side-list entries (ss words each).  Redundant records come back with their full X1 (the classic
+// field saturates at 8191); ext = read_pos | base_repeat << 16 of a scoring record of a stream staged with them, else 0.
+template <class W, class F>
+inline void for_each_classic_words(const ScoreGeometry& geo, uint64_t cnt, W&& word, const uint32_t* side_entries, F&& f) {
+  const uint32_t ss = geo.side_stride;
+  uint32_t side = 0;
+  for (uint64_t j = 0; j < cnt; ++j) {
+    const uint32_t d = word(j), kind = d >> DR_KIND_SHIFT, top = (d & DR_TOP_BIT) ? SR_TOP_BIT : 0u;
+    if (kind == 0) f(classic_of_hot(d, geo), 1u, 0u);
     else if (kind == 1) f(top | SR_UNIQUE_BIT | SR_TRIM_BIT, 1u, 0u);   // does not score; why is not kept
-    else if (kind == 2) { f(st.side_rec[(size_t)side * ss], 1u, ss == 2 ? st.side_rec[(size_t)side * ss + 1] : 0u); ++side; }
+    else if (kind == 2) { f(side_entries[(size_t)side * ss], 1u, ss == 2 ? side_entries[(size_t)side * ss + 1] : 0u); ++side; }
     else {
       uint32_t x1 = (d >> DR_X1_SHIFT) & DR_X1_MASK;
-      if (x1 == DR_X1_MASK) x1 = st.side_rec[(size_t)(side++) * ss] & ~SIDE_BIG;
+      if (x1 == DR_X1_MASK) x1 = side_entries[(size_t)(side++) * ss] & ~SIDE_BIG;
       f(top | ((d >> DR_RED_OBS_SHIFT) & 7u) | ((d & DR_RED_TRIM_BIT) ? SR_TRIM_BIT : 0u) | (x1 < SR_RED_MASK ? x1 : SR_RED_MASK) << SR_RED_SHIFT, x1, 0u);
     }
   }
+}
+// ... of slot s of a stream whose arrays are on the host
+template <class F>
+inline void for_each_classic(const PileupStream& st, uint64_t s, F&& f) {
+  const uint64_t base = st.score_off[s];
+  for_each_classic_words(st.geo, st.score_cnt[s], [&](uint64_t j) { return st.score_rec[score_index(base, j)]; },
+                         st.side_rec + (size_t)st.side_off[s] * st.geo.side_stride, f);
 }
 
 }  // namespace brq

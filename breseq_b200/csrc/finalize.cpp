@@ -704,7 +704,7 @@ EvidenceShard parse_shard(const void* data, size_t bytes) {
 // ---- one shard's share of the evidence: the event columns with their target coordinates and the RA rows to emit at them
 EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, const std::vector<WalkEvent>& events_in,
                                const std::vector<uint32_t>& flagged_in, const std::vector<ColumnOut>& flagged_cols,
-                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
+                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep, const FlaggedRecords* fr) {
   EvidenceCounts counts;
   // flagged slots in ascending order (the kernels append them in no particular order), each with its full result
   std::vector<uint32_t> order(flagged_in.size());
@@ -727,7 +727,7 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
     const uint32_t slot = flagged[fi];
     SlotEval& s = evals[fi];
     memset(s.count, 0, sizeof s.count);
-    for_each_classic(st, slot, [&](uint32_t r, uint32_t, uint32_t ext) {
+    auto take = [&](uint32_t r, uint32_t, uint32_t ext) {
       const uint32_t q = (r >> SR_QUAL_SHIFT) & 127;
       if (!(r & SR_UNIQUE_BIT) || (r & SR_TRIM_BIT) || !(r & SR_OK_BIT) || q < ep.base_quality_cutoff) return;
       const uint32_t obs = r & 7, top = (r & SR_TOP_BIT) ? 1 : 0, mapq = (r >> SR_MAPQ_SHIFT) & 255, set = (r >> SR_SET_SHIFT) & 31;
@@ -736,13 +736,21 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
       s.reads.push_back(lut.get(li));
       s.obs.push_back((uint8_t)obs); s.qual.push_back((uint8_t)q);
       ++s.count[obs][top];
-    });
+    };
+    if (fr) {  // the stream is in HBM only: the slot's records were gathered there (entry order[fi] of the unsorted list)
+      const size_t e = order[fi];
+      const uint32_t* w = fr->words + fr->word_off[e];
+      for_each_classic_words(st.geo, fr->word_off[e + 1] - fr->word_off[e], [&](uint64_t j) { return w[j]; },
+                             fr->side + (size_t)fr->side_off[e] * st.geo.side_stride, take);
+    } else {
+      for_each_classic(st, slot, take);
+    }
   }
   std::vector<uint8_t> overturned(flagged.size(), 0);
   auto evaluate_one = [&](size_t fi) {
     const uint32_t slot = flagged[fi];
     SlotEval& s = evals[fi];
-    const uint8_t ref = st.slot_ref[slot];
+    const uint8_t ref = fr ? fr->ref[order[fi]] : st.slot_ref[slot];
     evaluate_slot(s, ref, ep);
     const ColumnOut& co = flagged_cols[order[fi]];
     const bool dev_emit = (co.bits & CO_EMIT) != 0, dev_pred = (co.bits & CO_BASE_PREDICTED) != 0;
@@ -770,10 +778,10 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
       row.kv["frequency"] = format_double(reported(s.variant), ep.precision_places, true);
       std::string spectrum;
       for (uint8_t b = 0; b < 5; ++b) {
-        const double fr = reported(b);
-        if (fr <= 0.0) continue;
+        const double freq = reported(b);
+        if (freq <= 0.0) continue;
         if (!spectrum.empty()) spectrum += ",";
-        spectrum += std::string(1, index_to_char(b)) + ":" + format_double(fr, ep.precision_places, true);
+        spectrum += std::string(1, index_to_char(b)) + ":" + format_double(freq, ep.precision_places, true);
       }
       row.kv["allele_frequencies"] = spectrum;
       // profile-likelihood bounds, identify_mutations.cpp:3175-3217
@@ -1015,8 +1023,8 @@ EvidenceCounts walk_evidence(const std::vector<const EvidenceShard*>& shards, co
 
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
                               const std::vector<WalkEvent>& events, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
-                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep) {
-  const EvidenceShard sh = collect_evidence(hdr, st, events, flagged, flagged_cols, sp, lut, ep);
+                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep, const FlaggedRecords* fr) {
+  const EvidenceShard sh = collect_evidence(hdr, st, events, flagged, flagged_cols, sp, lut, ep, fr);
   return walk_evidence({&sh}, ep, gd_path);
 }
 

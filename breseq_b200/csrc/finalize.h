@@ -111,9 +111,17 @@ struct EvidenceShard {
   std::vector<EvidenceEvent> events;   // in visit order, ascending position inside a target
   uint64_t rechecked = 0, overturned = 0;
 };
+// The records of the flagged slots when the stream lives in HBM only (device staging): per entry i of `flagged` (in the
+// order given), its device words in record order, its side-list entries and its reference base.
+struct FlaggedRecords {
+  const uint64_t* word_off; const uint64_t* side_off;   // [n + 1] each; side_off in entries
+  const uint32_t* words; const uint32_t* side;
+  const uint8_t* ref;
+};
+// fr = nullptr: the records are read from st's host arrays
 EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, const std::vector<WalkEvent>& events,
                                const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
-                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
+                               const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep, const FlaggedRecords* fr = nullptr);
 EvidenceCounts walk_evidence(const std::vector<const EvidenceShard*>& shards, const EvidenceParams& ep, const std::string& gd_path);
 // flat byte form of a shard, for the trip between ranks
 std::string serialize_shard(const EvidenceShard& sh);
@@ -122,7 +130,7 @@ EvidenceShard parse_shard(const void* data, size_t bytes);
 // collect_evidence + walk_evidence for an unsharded run
 EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, const PileupStream& st,
                               const std::vector<WalkEvent>& events, const std::vector<uint32_t>& flagged, const std::vector<ColumnOut>& flagged_cols,
-                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep);
+                              const ScoreParams& sp, ClassLut& lut, const EvidenceParams& ep, const FlaggedRecords* fr = nullptr);
 
 // Optional outputs of pass 2 (identify_mutations.cpp:1693-1733 and :2028-2052, 2173-2204); both read the full per-slot results.
 void write_per_position_file(const std::string& path, const BamHeader& hdr, const PileupStream& st, const std::vector<ColumnOut>& cols,

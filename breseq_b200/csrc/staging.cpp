@@ -110,6 +110,78 @@ inline int32_t tlen_of(const std::string& s) { return (int32_t)s.size(); }
 
 }  // namespace
 
+
+// Targets in visit order (std::set<string> iteration == sorted strings; pileup_base.cpp:364-385), clipped to this
+// process's contiguous coordinate shard: fills out.segments / out.n_base and the reference sequence of every segment.
+void plan_segments(const BamHeader& hdr, const RefSet& ref, const StageConfig& cfg, PileupStream& out, std::vector<const std::string*>& refseq) {
+  const size_t n_targets = hdr.target_names.size();
+  std::vector<std::string> ids = cfg.call_seq_ids.empty() ? hdr.target_names : cfg.call_seq_ids;
+  std::sort(ids.begin(), ids.end());
+  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+  refseq.clear();
+  std::vector<Segment> full;
+  uint64_t total_cols = 0;
+  for (const std::string& id : ids) {
+    size_t tid = std::find(hdr.target_names.begin(), hdr.target_names.end(), id) - hdr.target_names.begin();
+    if (tid == n_targets) throw std::runtime_error("Could not find seq_id: " + id);
+    size_t r = std::find(ref.names.begin(), ref.names.end(), id) - ref.names.begin();
+    if (r == ref.names.size() || ref.seqs[r].size() != hdr.target_lens[tid])
+      throw std::runtime_error("reference sequence missing or of the wrong length: " + id);
+    full.push_back({(int32_t)tid, 0, (int32_t)hdr.target_lens[tid], total_cols});
+    total_cols += hdr.target_lens[tid];
+    refseq.push_back(&ref.seqs[r]);
+  }
+  // this process's shard: [g_lo, g_hi) of the concatenated visit-order columns.  Explicit bounds (StageConfig::shard_lo /
+  // shard_hi, set by a caller that balances the shards by record count) win over the even split by columns.
+  const uint64_t n_sh = std::max<uint32_t>(1, cfg.shard_count), rk = std::min<uint64_t>(cfg.shard_rank, n_sh - 1);
+  uint64_t g_lo = total_cols * rk / n_sh, g_hi = total_cols * (rk + 1) / n_sh;
+  if (cfg.shard_hi > cfg.shard_lo || cfg.shard_explicit) { g_lo = std::min<uint64_t>(cfg.shard_lo, total_cols); g_hi = std::min<uint64_t>(cfg.shard_hi, total_cols); }
+  std::vector<const std::string*> kept;
+  for (size_t v = 0; v < full.size(); ++v) {
+    const uint64_t a = full[v].slot0, b = a + (uint64_t)full[v].hi;
+    const uint64_t lo = std::max(a, g_lo), hi = std::min(b, g_hi);
+    if (lo >= hi) continue;
+    out.segments.push_back({full[v].tid, (int32_t)(lo - a), (int32_t)(hi - a), out.n_base});
+    out.n_base += hi - lo;
+    kept.push_back(refseq[v]);
+  }
+  refseq.swap(kept);
+}
+
+// Table geometry of the device stream words (ScoreGeometry) from per-read statistics: mq[m] = bases of unique reads with
+// MAPQ m, qc[q] = bases of unique reads with quality q.
+ScoreGeometry choose_geometry(const uint64_t* mq, const uint64_t* qc, const StageConfig& cfg, uint32_t max_read_set_seen) {
+  ScoreGeometry g;
+  g.cutoff = cfg.base_quality_cutoff;
+  g.n_st = (max_read_set_seen + 1) * 2;
+  g.hot_mapq = 0;
+  for (uint32_t m = 1; m < 256; ++m) if (mq[m] > mq[g.hot_mapq]) g.hot_mapq = m;
+  // The per-slot class histogram of the tally kernel holds (read set, strand, quality) classes, at most 62
+  // four-byte words per lane, and its contraction with the likelihood table walks every word: the table covers
+  // the narrowest window of quality values (a multiple of four) that holds 99.5 % of the records; the few
+  // records outside it take the side list.
+  uint32_t q_first = 128, q_last = 0;
+  uint64_t q_mass = 0;
+  for (uint32_t q = g.cutoff; q < 128; ++q) if (qc[q]) { q_first = std::min(q_first, q); q_last = q; q_mass += qc[q]; }
+  if (q_first > q_last) { q_first = g.cutoff; q_last = g.cutoff; }
+  const uint32_t span = q_last - q_first + 1, nq_cap = (248u / g.n_st) & ~3u;
+  uint32_t nq = 0, best_lo = q_first;
+  for (uint32_t len = 4; nq == 0; len += 4) {
+    uint64_t best = 0;
+    uint32_t lo_best = q_first;
+    for (uint32_t lo = q_first; lo == q_first || lo + len <= q_last + 1; ++lo) {
+      uint64_t mass = 0;
+      for (uint32_t q = lo; q < lo + len && q < 128; ++q) mass += qc[q];
+      if (mass > best) { best = mass; lo_best = lo; }
+    }
+    if (len >= span || len + 4 > nq_cap || (double)best >= 0.995 * (double)q_mass) { nq = len; best_lo = lo_best; }
+  }
+  if (nq > nq_cap) nq = nq_cap;  // more than 62 read files x strands: no window fits, everything takes the side list
+  g.q_lo = best_lo; g.n_q = nq;
+  if (cfg.use_read_pos || cfg.use_base_repeat) { g.n_q = 0; g.side_stride = 2; }  // classes too many for a shared table: all cold
+  return g;
+}
+
 void free_stream(PileupStream& s, const StageConfig& cfg) {
   auto rel = cfg.release ? cfg.release : default_release;
   for (void* p : {(void*)s.slot_ref, (void*)s.score_off, (void*)s.hist_off, (void*)s.slot_group, (void*)s.score_rec, (void*)s.hist_rec, (void*)s.side_rec, (void*)s.side_off, (void*)s.round_slot, (void*)s.score_cnt, (void*)s.round_off, (void*)s.round_side, (void*)s.hist16, (void*)s.hist_exc, (void*)s.score16, (void*)s.score_exc, (void*)s.score_exc_off})
@@ -132,37 +204,8 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   const size_t n_targets = hdr.target_names.size();
   out = PileupStream();
 
-  // ---- targets in visit order (std::set<string> iteration == sorted strings; pileup_base.cpp:364-385)
-  std::vector<std::string> ids = cfg.call_seq_ids.empty() ? hdr.target_names : cfg.call_seq_ids;
-  std::sort(ids.begin(), ids.end());
-  ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
   std::vector<const std::string*> refseq;
-  std::vector<Segment> full;
-  uint64_t total_cols = 0;
-  for (const std::string& id : ids) {
-    size_t tid = std::find(hdr.target_names.begin(), hdr.target_names.end(), id) - hdr.target_names.begin();
-    if (tid == n_targets) throw std::runtime_error("Could not find seq_id: " + id);
-    size_t r = std::find(ref.names.begin(), ref.names.end(), id) - ref.names.begin();
-    if (r == ref.names.size() || ref.seqs[r].size() != hdr.target_lens[tid])
-      throw std::runtime_error("reference sequence missing or of the wrong length: " + id);
-    full.push_back({(int32_t)tid, 0, (int32_t)hdr.target_lens[tid], total_cols});
-    total_cols += hdr.target_lens[tid];
-    refseq.push_back(&ref.seqs[r]);
-  }
-  {  // clip to this process's contiguous coordinate shard
-    const uint64_t n_sh = std::max<uint32_t>(1, cfg.shard_count), rk = std::min<uint64_t>(cfg.shard_rank, n_sh - 1);
-    const uint64_t g_lo = total_cols * rk / n_sh, g_hi = total_cols * (rk + 1) / n_sh;
-    std::vector<const std::string*> kept;
-    for (size_t v = 0; v < full.size(); ++v) {
-      const uint64_t a = full[v].slot0, b = a + (uint64_t)full[v].hi;
-      const uint64_t lo = std::max(a, g_lo), hi = std::min(b, g_hi);
-      if (lo >= hi) continue;
-      out.segments.push_back({full[v].tid, (int32_t)(lo - a), (int32_t)(hi - a), out.n_base});
-      out.n_base += hi - lo;
-      kept.push_back(refseq[v]);
-    }
-    refseq.swap(kept);
-  }
+  plan_segments(hdr, ref, cfg, out, refseq);
   const size_t n_visit = out.segments.size();
 
   // ---- read ranges per target; the BAM must be coordinate sorted (htslib's pileup aborts otherwise)
@@ -368,34 +411,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       for (int m = 0; m < 256; ++m) mq[m] += mq_l[m];
       for (int q = 0; q < 128; ++q) qc[q] += qc_l[q];
     });
-    ScoreGeometry& g = out.geo;
-    g.cutoff = cfg.base_quality_cutoff;
-    g.n_st = (out.max_read_set_seen + 1) * 2;
-    g.hot_mapq = 0;
-    for (uint32_t m = 1; m < 256; ++m) if (mq[m] > mq[g.hot_mapq]) g.hot_mapq = m;
-    // The per-slot class histogram of the tally kernel holds (read set, strand, quality) classes, at most 62
-    // four-byte words per lane, and its contraction with the likelihood table walks every word: the table covers
-    // the narrowest window of quality values (a multiple of four) that holds 99.5 % of the records; the few
-    // records outside it take the side list.
-    uint32_t q_first = 128, q_last = 0;
-    uint64_t q_mass = 0;
-    for (uint32_t q = g.cutoff; q < 128; ++q) if (qc[q]) { q_first = std::min(q_first, q); q_last = q; q_mass += qc[q]; }
-    if (q_first > q_last) { q_first = g.cutoff; q_last = g.cutoff; }
-    const uint32_t span = q_last - q_first + 1, nq_cap = (248u / g.n_st) & ~3u;
-    uint32_t nq = 0, best_lo = q_first;
-    for (uint32_t len = 4; nq == 0; len += 4) {
-      uint64_t best = 0;
-      uint32_t lo_best = q_first;
-      for (uint32_t lo = q_first; lo == q_first || lo + len <= q_last + 1; ++lo) {
-        uint64_t mass = 0;
-        for (uint32_t q = lo; q < lo + len && q < 128; ++q) mass += qc[q];
-        if (mass > best) { best = mass; lo_best = lo; }
-      }
-      if (len >= span || len + 4 > nq_cap || (double)best >= 0.995 * (double)q_mass) { nq = len; best_lo = lo_best; }
-    }
-    if (nq > nq_cap) nq = nq_cap;  // more than 62 read files x strands: no window fits, everything takes the side list
-    g.q_lo = best_lo; g.n_q = nq;
-    if (cfg.use_read_pos || cfg.use_base_repeat) { g.n_q = 0; g.side_stride = 2; }  // classes too many for a shared table: all cold
+    out.geo = choose_geometry(mq.data(), qc.data(), cfg, out.max_read_set_seen);
   }
   const ScoreGeometry geo = out.geo;
   const uint32_t n_hot = geo.n_hot();
@@ -621,7 +637,7 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
   // the positional forms stay in plain memory when only their transfer / compact forms cross PCIe (pinning gigabytes is slow)
   const bool build_score16 = cfg.want_score && cfg.compact_score && out.n_rounds && out.n_rounds * 32 < (1ull << 32) - 1;
   const bool build_hist16 = cfg.want_hist && cfg.compact_hist && !(cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7);
-  out.score_rec_plain = build_score16; out.hist_rec_plain = build_hist16;
+  out.score_rec_plain = build_score16; out.hist_rec_plain = build_hist16; out.hist_compact = build_hist16;
   out.score_rec = (uint32_t*)(build_score16 ? default_alloc(out.n_score_padded * 4, &p2) : alloc(out.n_score_padded * 4, &p2));
   parallel_ranges(out.n_score_padded, [&](uint64_t lo, uint64_t hi) { std::fill(out.score_rec + lo, out.score_rec + hi, geo.pad_word()); });  // pad word: the trash counter, no other bit (threads: the first touch of 2 GB)
   out.hist_bytes = (cfg.use_base_repeat || cfg.use_read_pos || out.max_read_set_seen > 7) ? 8 : 4;

@@ -31,6 +31,11 @@ struct StageConfig {
   bool compact_score = true;           // also build the transfer form of score_rec (brq_types.h: score16 + score_exc)
   bool compact_hist = true;            // also build the 16-bit histogram stream the device reads (brq_types.h)
   uint32_t shard_rank = 0, shard_count = 1;         // contiguous reference-coordinate shard staged by this call
+  // ... or its explicit bounds [shard_lo, shard_hi) in the concatenated visit-order columns (a caller that balances the
+  // shards by record count, SURVEY.md 8e, computes them with shard_bounds_by_records)
+  uint64_t shard_lo = 0, shard_hi = 0;
+  bool shard_explicit = false;
+  int staging_mode = 0;                             // 0 = on the device when the context has one, 1 = host, 2 = device
   // buffer allocator (pinned when a device is present); both must be set together
   void* (*alloc)(size_t bytes, bool* pinned) = nullptr;
   void (*release)(void* p, bool pinned) = nullptr;
@@ -40,6 +45,10 @@ struct StageConfig {
 // packable range, a deletion with no following read base, ...).
 void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& reads, const StageConfig& cfg, PileupStream& out);
 void free_stream(PileupStream& s, const StageConfig& cfg);
+
+// The host-side plan both staging paths share: the visited targets clipped to the shard, and the table geometry.
+void plan_segments(const BamHeader& hdr, const RefSet& ref, const StageConfig& cfg, PileupStream& out, std::vector<const std::string*>& refseq);
+ScoreGeometry choose_geometry(const uint64_t* mq, const uint64_t* qc, const StageConfig& cfg, uint32_t max_read_set_seen);
 
 // Flat read-file index of each read group (alignment.cpp:565-605).
 void make_read_file_partition(const ReadGroups& rg, const std::vector<ReadFileSetInfo>& sets,

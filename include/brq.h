@@ -47,13 +47,22 @@ typedef struct brq_stage_options {
   uint32_t use_base_repeat;                /* the covariate string names base_repeat */
   uint32_t use_read_pos;                   /* the covariate string names read_pos (either one: 8-byte histogram records) */
   uint32_t shard_rank, shard_count;        /* contiguous reference-coordinate shard of this process; 0,1 = all */
-  uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff (decides which records score); 0 = the default, 3 */
+  uint32_t base_quality_cutoff;            /* Settings::base_quality_cutoff (decides which records score; 0 is a value:
+                                              every quality scores); BRQ_DEFAULT_BASE_QUALITY_CUTOFF = the default, 3 */
   /* error_count(..., preprocess_stage = true), the stage 03 call (breseq_cmdline.cpp:1969, error_count.cpp:157-166, 191-194,
    * 217-229): also count the position-strand combinations with / without a read start inside the junction read-end bound */
   uint32_t preprocess_stage;
   uint32_t unmatched_end_minimum_read_length;  /* Settings::unmatched_end_minimum_read_length; 0 = the default, 50 */
   double require_match_fraction;               /* Settings::require_match_fraction; 0 = the default, 0.9 */
+  /* explicit bounds of this process's shard in the concatenated visit-order columns (shard_hi > shard_lo): set by a caller
+   * that balances its shards by record count (brq_shard_bounds); wins over shard_rank / shard_count */
+  uint64_t shard_lo, shard_hi;
+  /* where the streams are built: 0 = on the device when the context has one (csrc/expand.cu: the reads cross PCIe, kernels
+   * expand the CIGARs and classify the records in HBM), 1 = on the host (csrc/staging.cpp), 2 = on the device or fail */
+  uint32_t staging;
+  uint32_t reserved;
 } brq_stage_options;
+#define BRQ_DEFAULT_BASE_QUALITY_CUTOFF 0xFFFFFFFFu
 
 int brq_stage_bam(brq_ctx* ctx, const char* bam, const char* fasta, const brq_stage_options* opt);
 
@@ -84,6 +93,7 @@ typedef struct brq_stream_info {
   uint64_t n_score_padded;         /* words in score_rec: round-major, lane-interleaved, padded (csrc/brq_types.h) */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
+  uint32_t device_built, reserved0;  /* the stream was built in HBM (brq_stage_options.staging); the views below are copies made by this call */
   uint32_t hist_record_bytes, side_stride;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files; words per side-list entry (2 with read_pos / base_repeat) */
   uint64_t n_side;                 /* side-list entries (scoring records outside the shared table, X1 >= 511) */
   uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_words;  /* geometry baked into score_rec */

@@ -2,21 +2,28 @@
 """bench.py -- aligned bases/sec of error_count + identify_mutations on B200.
 
   python bench.py --gpus 1 --steps 10 --warmup 3          (one JSON line on stdout)
-  torchrun ... bench.py --gpus N ...                        (one rank per GPU; weak scaling)
-  python bench.py --impl reference ...                      (the CPU implementation, same metric)
+  torchrun ... bench.py --gpus N ...                        (one rank per GPU; strong scaling)
+  python bench.py --impl reference ...                      (the reference's own CPU code, same metric)
+  python bench.py --config c1                               (BASELINE configs[1] instead of configs[2])
 
-Workload (BASELINE.json configs[1]): E. coli REL606-sized reference
-(4 629 812 bp, one contig), synthetic 100x pe150 reads, one paired read set (read_set=2, Q=42).
-At N GPUs every rank holds one such coordinate range (its own contig of an N x 4.6 Mb genome):
-weak scaling, no data-path collective except the sum-allreduce of the integer histograms.
+Workload (BASELINE.json configs[2], SURVEY.md 8d C2, the configuration the north star quotes its target on): ONE E. coli
+REL606-sized reference (4 629 812 bp, one contig), synthetic 1000x pe150 reads of one paired read set (read_set=2, Q=42),
+population / polymorphism mode cutoffs (settings.cpp:858-913: mutation 10, polymorphism 2, precision 1e-6, 8 places).
+At N GPUs the genome is cut into N contiguous reference-coordinate ranges with the same number of aligned bases (prefix
+sum of the read starts), one per rank: STRONG scaling.  The only data-path collective is the sum-allreduce
+of the integer covariate and coverage histograms; the MC / UN intervals and the evidence ids cross the range boundaries,
+so every rank exports its share of the evidence and rank 0 walks the shares together and writes ONE ra_mc_evidence.gd.
 
-A "step" is one pass of both kernels' path over the resident stream:
-  covariate histogram + coverage histogram -> [allreduce] -> table derivation + text
-  canonicalisation + class table -> per-slot scoring.
-`value` times that with the stream already in HBM; `e2e` adds the host->device copy of the
-pinned stream, the device->host copy of the per-slot results and the host finalisation that
-writes error_rates.tab and ra_mc_evidence.gd, i.e. what the reference-facing call does after
-BAM staging.
+A "step" is one pass of both kernels' path over the resident streams:
+  covariate histogram + coverage histogram -> allreduce -> table derivation + text canonicalisation + likelihood tables
+  -> per-slot scoring (tally + fit).
+`value` times that with the streams already in HBM.  `e2e` is the same job through the C ABI from HOST buffers (the decoded
+reads of the rank's range in page-locked host memory): H2D of the reads, CIGAR expansion and record classification on the
+device (csrc/expand.cu), both passes, the allreduce, D2H of histograms / walk events / flagged slots, the host
+finalisation, the gather of the evidence shares and the files (error_rates.tab, base_qual_error_prob.*.tab, coverage
+distribution, ra_mc_evidence.gd) written by rank 0.  `e2e_from_bam` goes one step further back, to where the reference's
+arm starts: a BAM on disk (BASELINE configs[1]'s, 4.6 Mb at 100x: the largest whose file this run writes in seconds)
+through brq_run_error_count + brq_run_identify_mutations to the same files on disk, on rank 0's GPU.
 """
 import argparse
 import json
@@ -31,11 +38,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GENOME = 4629812
-READ_SETS = [dict(name="REL606_pe150", paired=True, read_len=150, coverage=100.0, frag_mean=400, frag_sd=40)]
 COVARIATES = "read_set=2,obs_base,ref_base,quality=42"
-MUTATION_CUTOFF, POLYMORPHISM_CUTOFF, PRECISION, PLACES = 10.0, 10.0, 1e-6, 3  # clone / consensus mode (settings.cpp:914-960)
-CPU_SAMPLE_DIV = 64  # the reference arm runs the same model on a 1/64-length reference, once per host core and step
-CPU_BASELINE_DIV = 16  # the cpu_baseline leg of the main arm: one thread, about 10 s of CPU work
+CONFIGS = {
+    # name: label, depth, (mutation, polymorphism, precision, places), deletion propagation cutoff, CPU sample divisors
+    "c2": dict(label="E. coli REL606 4.6 Mb population/polymorphism mode, synthetic 1000x pe150 (BASELINE configs[2])",
+               coverage=1000.0, cutoffs=(10.0, 2.0, 1e-6, 8), del_prop=300.0, cpu_div=256, cpu_baseline_div=128),
+    "c1": dict(label="E. coli REL606 4.6 Mb clone mode, synthetic 100x pe150 (BASELINE configs[1])",
+               coverage=100.0, cutoffs=(10.0, 10.0, 1e-6, 3), del_prop=30.0, cpu_div=64, cpu_baseline_div=16),
+}
+# kept for tests / scripts that import the workload definition (configs[1])
+READ_SETS = [dict(name="REL606_pe150", paired=True, read_len=150, coverage=100.0, frag_mean=400, frag_sd=40)]
+MUTATION_CUTOFF, POLYMORPHISM_CUTOFF, PRECISION, PLACES = CONFIGS["c1"]["cutoffs"]
+
+
+def read_sets(cfg):
+    return [dict(name="REL606_pe150", paired=True, read_len=150, coverage=float(cfg["coverage"]), frag_mean=400, frag_sd=40)]
 
 
 def measured_peak_gbs():
@@ -85,18 +102,6 @@ def oracle_cli():
     return path
 
 
-def cpu_sample(tmp, seed=2, div=CPU_SAMPLE_DIV):
-    """The C1 model on a 1/div-length reference, written as BAM + FASTA for the CPU arms."""
-    import breseq_b200 as bq
-    ctx = bq.Context(device=-1)
-    spec = bq.SynthSpec(seed=seed, read_sets=READ_SETS, contig_lens=[GENOME // div], contig_prefix="REL606s",
-                        n_polymorphic=4, n_fixed=2, n_gaps=1)
-    bam, fasta = os.path.join(tmp, "s.bam"), os.path.join(tmp, "s.fasta")
-    ctx.synth_write(spec, bam, fasta)
-    ctx.close()
-    return bam, fasta
-
-
 def ref_cli():
     """The reference's own sources compiled against the htslib shim (oracle/ref_build.sh), if prebuilt."""
     path = os.path.join(ROOT, "oracle", "_ref", "ref_cli")
@@ -107,7 +112,18 @@ def cpu_kind():
     return "reference" if ref_cli() else "port"
 
 
-def run_cpu_once(bam, fasta, out, cli=None, count_records=True):
+def write_sample_bam(tmp, cfg, div, seed=2):
+    """The config's read model on a 1/div-length reference, written as BAM + FASTA by a CHILD process (the CPU arms must not
+    load the product's library into the process that times them)."""
+    bam, fasta = os.path.join(tmp, "s.bam"), os.path.join(tmp, "s.fasta")
+    code = ("import sys; sys.path.insert(0, %r); import breseq_b200 as bq; ctx = bq.Context(device=-1); "
+            "spec = bq.SynthSpec(seed=%d, read_sets=%r, contig_lens=[%d], contig_prefix='REL606s', n_polymorphic=4, n_fixed=2, n_gaps=1); "
+            "ctx.synth_write(spec, %r, %r); ctx.close()" % (ROOT, seed, read_sets(cfg), GENOME // div, bam, fasta))
+    subprocess.run([sys.executable, "-c", code], check=True)
+    return bam, fasta
+
+
+def run_cpu_once(bam, fasta, out, cfg, cli=None, count_records=True):
     """Both passes of the CPU implementation on one BAM; returns (records, seconds).
 
     `cli` = oracle/_ref/ref_cli (the reference's own code, kind "reference") when it was built, else
@@ -115,12 +131,13 @@ def run_cpu_once(bam, fasta, out, cli=None, count_records=True):
     the two entry points with steady_clock, the bracket the reference's own ExecutionTime uses."""
     cli = cli or ref_cli() or oracle_cli()
     os.makedirs(out, exist_ok=True)
-    sets = READ_SETS[0]["name"] + ":2"
+    sets = "REL606_pe150:2"
+    mc, pc, prec, places = cfg["cutoffs"]
     ec = ["error_count", "--bam", bam, "--fasta", fasta, "--out", out, "--covariates", COVARIATES, "--readfiles", "r1,r2",
           "--read-sets", sets]
     im = ["identify_mutations", "--bam", bam, "--fasta", fasta, "--out", out, "--error-rates", os.path.join(out, "error_rates.tab"),
-          "--gd", os.path.join(out, "o.gd"), "--read-sets", sets, "--del-prop", "30", "--del-seed", "0", "--mutation-cutoff",
-          str(MUTATION_CUTOFF), "--polymorphism-cutoff", str(POLYMORPHISM_CUTOFF), "--places", str(PLACES)]
+          "--gd", os.path.join(out, "o.gd"), "--read-sets", sets, "--del-prop", str(cfg["del_prop"]), "--del-seed", "0", "--mutation-cutoff",
+          str(mc), "--polymorphism-cutoff", str(pc), "--precision", str(prec), "--places", str(places)]
     a = json.loads(subprocess.run([cli] + ec, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
     b = json.loads(subprocess.run([cli] + im, check=True, capture_output=True, text=True).stdout.strip().splitlines()[-1])
     records = b["records"]
@@ -130,36 +147,41 @@ def run_cpu_once(bam, fasta, out, cli=None, count_records=True):
     return records, a["seconds"] + b["seconds"]
 
 
-def config_block(n_gpus):
-    return {"workload": "E. coli REL606 4.6 Mb clone mode, synthetic 100x pe150 reads (BASELINE configs[1]); one 4 629 812 bp "
-                        "coordinate range per GPU", "covariates": COVARIATES, "records_per_gpu": None,
-            "l2_policy": "inputs (about 3 GB per GPU in HBM) are far larger than the 126 MB L2; no explicit flush",
-            "parallelism": "reference-range sharding x%d, one sum-allreduce of the integer histograms" % n_gpus}
+def config_block(name, cfg, n_gpus):
+    return {"workload": cfg["label"] + "; one 4 629 812 bp genome cut into %d reference-coordinate range%s of equal aligned bases"
+                        % (n_gpus, "" if n_gpus == 1 else "s"),
+            "config": name, "covariates": COVARIATES, "coverage": cfg["coverage"],
+            "cutoffs": dict(zip(("mutation", "polymorphism", "precision", "places"), cfg["cutoffs"])),
+            "l2_policy": "inputs (tens of GB of streams per run in HBM) are far larger than the 126 MB L2; no explicit flush",
+            "parallelism": "reference-range sharding x%d (strong scaling), one sum-allreduce of the integer histograms, "
+                           "evidence shares gathered to rank 0" % n_gpus}
 
 
-def reference_arm(args):
+def reference_arm(args, name, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = min(os.cpu_count() or 1, 32)
+    div = cfg["cpu_div"]
     with tempfile.TemporaryDirectory() as tmp:
-        bam, fasta = cpu_sample(tmp)
+        bam, fasta = write_sample_bam(tmp, cfg, div)
         times, records = [], 0
-        n_sample, _ = run_cpu_once(bam, fasta, os.path.join(tmp, "count"), cli=oracle_cli())  # untimed: records in the sample
+        n_sample, _ = run_cpu_once(bam, fasta, os.path.join(tmp, "count"), cfg, cli=oracle_cli())  # untimed: records in the sample
 
         def one_step(tag):
             # `cores` independent processes, one coordinate range each (the reference itself is
             # single-threaded on this path; sharding by reference range is how it would be spread)
             t0 = time.perf_counter()
-            procs, results = [], [None] * cores
+            results = [None] * cores
 
             def worker(i):
-                results[i] = (n_sample, run_cpu_once(bam, fasta, os.path.join(tmp, "%s_%d" % (tag, i)), count_records=False)[1])
+                results[i] = (n_sample, run_cpu_once(bam, fasta, os.path.join(tmp, "%s_%d" % (tag, i)), cfg, count_records=False)[1])
             th = [threading.Thread(target=worker, args=(i,)) for i in range(cores)]
             [t.start() for t in th]
             [t.join() for t in th]
             return sum(r[0] for r in results), time.perf_counter() - t0
-        for w in range(args.warmup if args.warmup < 2 else 1):
+        n_warm = min(args.warmup, 1)   # a warm-up step costs as much as a timed one here: one is enough to fault the binary in
+        for w in range(n_warm):
             one_step("w%d" % w)
         for k in range(args.steps):
             n, dt = one_step("s%d" % k)
@@ -167,15 +189,52 @@ def reference_arm(args):
         dt = sum(times) / len(times)
         value = records / dt
     kind = cpu_kind()
+    sample = ("%s read model on a 1/%d-length reference (%d bp; a per-record rate: the CPU path is linear in records), %d concurrent "
+              "single-threaded processes, one reference range each" % (name, div, GENOME // div, cores))
     line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": value, "unit": "aligned bases/s",
-            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_block(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "aligned bases/s", "cores": cores, "kind": kind,
-                             "sample": "C1 read model on a 1/%d-length reference (%d bp), %d concurrent single-threaded "
-                                       "processes, one reference range each" % (CPU_SAMPLE_DIV, GENOME // CPU_SAMPLE_DIV, cores)},
+            "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": n_warm, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_block(name, cfg, args.gpus),
+            "cpu_baseline": {"value": value, "unit": "aligned bases/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "aligned bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def e2e_from_bam(bq, local, tmp):
+    """BAM on disk -> error_rates.tab + ra_mc_evidence.gd on disk through the one-call adapters, BASELINE configs[1] on one GPU."""
+    cfg = CONFIGS["c1"]
+    ctx = bq.Context(device=-1)
+    spec = bq.SynthSpec(seed=2, read_sets=read_sets(cfg), contig_lens=[GENOME], contig_prefix="REL606", n_polymorphic=40, n_fixed=10, n_gaps=3)
+    bam, fasta = os.path.join(tmp, "c1.bam"), os.path.join(tmp, "c1.fasta")
+    t0 = time.perf_counter()
+    ctx.synth_write(spec, bam, fasta)
+    t_write = time.perf_counter() - t0
+    ctx.close()
+    mc, pc, prec, places = cfg["cutoffs"]
+    runs = []
+    n_records = 0
+    for k in range(3):
+        out = os.path.join(tmp, "from_bam_%d" % k)
+        os.makedirs(out)
+        ctx = bq.Context(device=local)
+        t0 = time.perf_counter()
+        bq.error_count(bam, fasta, out, ["r1", "r2"], covariates=COVARIATES, read_file_sets=spec.read_file_sets(),
+                       error_rates_file_name=os.path.join(out, "error_rates.tab"), ctx=ctx)
+        t1 = time.perf_counter()
+        bq.identify_mutations(bam, fasta, os.path.join(out, "ra_mc_evidence.gd"), [cfg["del_prop"]], [0.0], mc, pc, prec, places,
+                              error_rates_file_name=os.path.join(out, "error_rates.tab"), read_file_sets=spec.read_file_sets(), ctx=ctx)
+        t2 = time.perf_counter()
+        n_records = int(ctx.stream_summary()["n_score"])
+        ctx.close()
+        runs.append({"error_count_s": t1 - t0, "identify_mutations_s": t2 - t1, "total_s": t2 - t0})
+    best = min(runs, key=lambda r: r["total_s"])
+    return {"value": n_records / best["total_s"], "unit": "aligned bases/s", "records": n_records, "seconds": best["total_s"],
+            "error_count_seconds": best["error_count_s"], "identify_mutations_seconds": best["identify_mutations_s"],
+            "runs_total_seconds": [r["total_s"] for r in runs], "bam_bytes": os.path.getsize(bam), "bam_write_seconds": t_write,
+            "workload": CONFIGS["c1"]["label"] + ": BAM + FASTA on disk -> error_rates.tab, base_qual_error_prob.*.tab, coverage distribution and "
+                        "ra_mc_evidence.gd on disk through brq_run_error_count + brq_run_identify_mutations (BGZF inflate and BAM decode on "
+                        "the host, everything after it on one GPU; a fresh context per run, the best of three)",
+            "n_gpus_used": 1}
 
 
 def main():
@@ -184,12 +243,20 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; reported in config)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiler runs)")
-    ap.add_argument("--coverage", type=float, default=None, help="override the read depth (other BASELINE shapes; reported in config)")
+    ap.add_argument("--no-bam", action="store_true", help="skip the e2e_from_bam leg (profiler runs)")
+    ap.add_argument("--coverage", type=float, default=None, help="override the read depth (debugging only; reported in config)")
+    ap.add_argument("--staging", default="auto", choices=["auto", "host", "device"])
     args = ap.parse_args()
+    name = args.config
+    cfg = dict(CONFIGS[name])
+    if args.coverage:
+        cfg["coverage"] = float(args.coverage)
+        cfg["del_prop"] = 0.3 * float(args.coverage)
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, name, cfg)
         return
 
     import numpy as np
@@ -203,44 +270,53 @@ def main():
     stdout_fd = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
-    ctx = bq.Context(device=local)
-    if args.coverage:
-        READ_SETS[0]["coverage"] = float(args.coverage)
+    mc, pc, prec, places = cfg["cutoffs"]
     genome = int(GENOME * args.scale)
-    spec = bq.SynthSpec(seed=2 + rank, read_sets=READ_SETS, contig_lens=[genome], contig_prefix="REL606_range%d" % rank,
-                        n_polymorphic=40, n_fixed=10, n_gaps=3)
+    rs = read_sets(cfg)
+    ctx = bq.Context(device=local)
+    full = bq.SynthSpec(seed=2, read_sets=rs, contig_lens=[genome], contig_prefix="REL606", n_polymorphic=40, n_fixed=10, n_gaps=3)
+    bounds = ctx.synth_shard_bounds(full, world)   # equal aligned bases per range; every rank computes the same cuts
+    lo, hi = bounds[rank], bounds[rank + 1]
+    spec = bq.SynthSpec(seed=2, read_sets=rs, contig_lens=[genome], contig_prefix="REL606", n_polymorphic=40, n_fixed=10, n_gaps=3,
+                        window=(lo, hi) if world > 1 else (0, 0))
     t0 = time.perf_counter()
-    ctx.stage_synthetic(spec, read_file_sets=spec.read_file_sets())
+    ctx.stage_synthetic(spec, read_file_sets=spec.read_file_sets(), shard_bounds=(lo, hi) if world > 1 else None, staging=args.staging)
+    ctx.sync()
     t_stage = time.perf_counter() - t0
-    s = ctx.stream()
+    s = ctx.stream_summary()
     n_records, n_slots, n_hist = int(s["n_score"]), int(s["n_base"] + s["n_ins"]), int(s["n_hist"])
     ctx.upload()
     ctx.sync()
-    params = bq.Context.score_params(MUTATION_CUTOFF, POLYMORPHISM_CUTOFF, PRECISION, PLACES)
+    params = bq.Context.score_params(mc, pc, prec, places)
 
     class DevArray:
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
 
-    ext_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local)) if world > 1 else None
-
+    ext_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev) if world > 1 else None
+    if world > 1:  # the ranks sum their coverage histograms too: one depth axis for all
+        depth = torch.tensor([ctx.max_coverage_depth()], dtype=torch.int64, device=dev)
+        dist.all_reduce(depth, op=dist.ReduceOp.MAX)
+        ctx.set_min_coverage_depth(int(depth.item()))
     hist_view = {}
 
     def allreduce_hist():
         if world == 1:
             return
         c, n, v, m = ctx.hist_device()
-        # every rank sizes its coverage histogram by its own deepest column: reduce the counts only, which is all the
-        # table derivation needs.  The collective is ordered on the context's own stream: no host synchronisation.
-        if hist_view.get("key") != (c, n):  # the buffer is allocated once: wrap it once
-            hist_view["key"], hist_view["t"] = (c, n), torch.as_tensor(DevArray(c, n), device="cuda:%d" % local)
+        # the collective is ordered on the context's own stream: no host synchronisation
+        if hist_view.get("key") != (c, n, v, m):  # the buffers are allocated once: wrap them once
+            hist_view["key"] = (c, n, v, m)
+            hist_view["t"] = [torch.as_tensor(DevArray(c, n), device=dev), torch.as_tensor(DevArray(v, m), device=dev)]
         with torch.cuda.stream(ext_stream):
-            dist.all_reduce(hist_view["t"])
+            for t in hist_view["t"]:
+                dist.all_reduce(t)
 
     def step():
         ctx.error_count(COVARIATES)
@@ -282,22 +358,49 @@ def main():
     for k in k_ms:
         k_ms[k] /= args.steps
 
-    # ---- end to end through the C ABI with host buffers: H2D + kernels + D2H + host finalisation
+    # ---- end to end through the C ABI from HOST buffers: H2D of the reads + device staging + kernels + D2H + finalisation + files
+    t0 = time.perf_counter()
+    ctx.pin_reads()   # the e2e contract's "pinned host memory": page-locking the decoded reads is input preparation, like staging was
+    t_pin = time.perf_counter() - t0
+    device_built = bool(s["device_built"])
     with tempfile.TemporaryDirectory() as tmp:
         phase = {}
 
-        def timed(name, fn, *a):
+        def timed(name_, fn, *a):
             t = time.perf_counter()
-            fn(*a)
-            phase[name] = phase.get(name, 0.0) + time.perf_counter() - t
+            r = fn(*a)
+            phase[name_] = phase.get(name_, 0.0) + time.perf_counter() - t
+            return r
+
+        def gather_evidence():
+            blob = ctx.evidence_export([cfg["del_prop"]])
+            if world == 1:
+                return [blob]
+            n = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(sizes, n)
+            cap = max(int(x.item()) for x in sizes)
+            buf = torch.zeros(cap, dtype=torch.uint8, device=dev)
+            buf[:len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+            parts = [torch.zeros(cap, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+            dist.gather(buf, parts, dst=0)
+            if rank != 0:
+                return None
+            return [bytes(p[:int(sz.item())].cpu().numpy().tobytes()) for p, sz in zip(parts, sizes)]
 
         def e2e_step():
-            timed("h2d", lambda: (ctx.upload(), ctx.sync()))
-            # (neither call waits for its kernels any more: the phase ends in a synchronisation so that it reads as kernel time)
+            if device_built:
+                timed("h2d_reads_and_expand", lambda: (ctx.restage(), ctx.sync()))
+            else:
+                timed("h2d_stream", lambda: (ctx.upload(), ctx.sync()))
+            # (neither call waits for its kernels: the phase ends in a synchronisation so that it reads as kernel time)
             timed("pass1_kernels", lambda: (ctx.error_count(COVARIATES), allreduce_hist(), ctx.derive_error_table(), ctx.sync()))
-            timed("pass1_files", ctx.write_error_count_files, tmp, os.path.join(tmp, "error_rates.tab"), ["r1", "r2"])
+            if rank == 0:
+                timed("pass1_files", ctx.write_error_count_files, tmp, os.path.join(tmp, "error_rates.tab"), ["r1", "r2"])
             timed("pass2_kernels", ctx.score_columns, params)
-            timed("d2h_finalise_gd", ctx.write_evidence, os.path.join(tmp, "ra_mc_evidence.gd"), [30.0], [0.0])
+            shares = timed("d2h_finalise_gather", gather_evidence)
+            if rank == 0:
+                timed("merged_gd", ctx.write_evidence_merged, os.path.join(tmp, "ra_mc_evidence.gd"), shares, [cfg["del_prop"]], [0.0])
         e2e_step()
         barrier()
         phase.clear()  # the first pass through the C ABI warms caches and allocations: not part of the averages
@@ -308,68 +411,90 @@ def main():
             e2e_step()
         barrier()
         e2e_s = (time.perf_counter() - t0) / n_e2e
-        d2h = ctx.d2h_bytes() // n_e2e  # counted by the library: histograms, error table, walk events, flagged slots
+        d2h = ctx.d2h_bytes() // n_e2e  # counted by the library: histograms, error table, walk events, flagged slots and their records
         e2e_phase_ms = {k: 1e3 * v / n_e2e for k, v in phase.items()}
-    h2d = int(s["bytes_host"])
+        gd_rows = sum(1 for l in open(os.path.join(tmp, "ra_mc_evidence.gd")) if not l.startswith("#")) if rank == 0 else 0
+    h2d = int(ctx.stream_summary()["bytes_host"])
 
     # ---- max over ranks, whole-job aggregate
-    stats = torch.tensor([step_ms, e2e_s, float(n_records), k_ms["score"], k_ms["hist"]], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([step_ms, e2e_s, float(n_records), k_ms["score"], k_ms["hist"], k_ms["tally"], float(h2d), float(d2h), t_stage],
+                         dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        allr = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allr, stats)
+        per_rank = {"records": [int(x[2].item()) for x in allr], "tally_ms": [round(x[5].item(), 4) for x in allr],
+                    "score_ms": [round(x[3].item(), 4) for x in allr], "hist_ms": [round(x[4].item(), 4) for x in allr],
+                    "bounds": bounds}
         step_ms, e2e_s, total_records = mx[0].item(), mx[1].item(), sm[2].item()
+        h2d, d2h = int(sm[6].item()), int(sm[7].item())
     else:
         total_records = float(n_records)
 
     if rank == 0:
         peak, peak_kind = measured_peak_gbs()
         score_bytes = 4 * n_records + 104 * n_slots           # 4 B/record + 8 B offsets + 96 B result per slot
-        # pass 1 is charged the bytes its records really have (4 per record at the default covariates, not SURVEY.md 8d's 8)
-        if s.get("hist16") is not None:  # the compact form: 2 bytes per fast record, 4 per exception
-            hist_bytes = 2 * len(s["hist16"]) + 4 * len(s["hist_exc"]) + 8 * int(s["n_base"])
+        # pass 1 is charged the bytes its records really have (2 per fast record, 4 per exception; SURVEY.md 8d budgets 8)
+        if s["hist_compact"]:
+            hist_bytes = 2 * int(s["n_hist16"]) + 4 * int(s["n_hist_exc"]) + 8 * int(s["n_base"])
         else:
-            hist_bytes = int(s["hist_rec"].itemsize) * n_hist + 8 * int(s["n_base"])
+            hist_bytes = int(s["hist_record_bytes"]) * n_hist + 8 * int(s["n_base"])
         # the dominant kernel is the tally kernel: it moves all of the scoring pass's algorithmic bytes (the fit kernel
-        # re-reads a few hundred slots); its duration is measured with CUDA events on the launching stream
+        # re-reads the work-list slots); its duration is measured with CUDA events on the launching stream (rank 0's here)
         achieved = score_bytes / (k_ms["tally"] * 1e-3) / 1e9 if k_ms["tally"] > 0 else 0.0
         pass_gbs = score_bytes / (k_ms["score"] * 1e-3) / 1e9 if k_ms["score"] > 0 else 0.0
         traffic = None
-        try:  # DRAM bytes of one launch from the committed ncu capture of the same workload
+        try:  # DRAM bytes of one launch from the committed ncu capture of the same workload and rank count
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 t = json.load(f)
-            traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+            if t.get("config") == name and int(t.get("n_gpus", 1)) == world and args.scale == 1.0 and args.coverage is None:
+                traffic = int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
         except Exception:
             pass
-        cfg = config_block(world)
-        cfg["records_per_gpu"] = n_records
-        cfg["slots_per_gpu"] = n_slots
-        cfg["genome_scale"] = args.scale
-        cfg["coverage"] = READ_SETS[0]["coverage"]
-        if args.coverage is not None or args.scale != 1.0:  # another shape than configs[1]: say so in the label
-            cfg["workload"] = ("E. coli REL606-like %.2f x 4.6 Mb, synthetic %gx pe150 reads (not BASELINE configs[1]: --scale / --coverage "
-                               "override; 1000x at full scale is configs[2]'s shape); one coordinate range per GPU" % (args.scale, READ_SETS[0]["coverage"]))
-            cfg["l2_policy"] = "inputs are far larger than the 126 MB L2; no explicit flush"
-            traffic = None  # the committed ncu capture is of configs[1]
-        cfg["kernel_ms"] = k_ms
-        cfg["staging_seconds"] = t_stage
-        cfg["e2e_phase_ms"] = e2e_phase_ms
-        cfg["hist_kernel_gbs"] = hist_bytes / (k_ms["hist"] * 1e-3) / 1e9 if k_ms["hist"] > 0 else 0.0
+        cb = config_block(name, cfg, world)
+        cb["records"] = int(total_records)
+        cb["records_rank0"] = n_records
+        cb["slots_rank0"] = n_slots
+        cb["genome_scale"] = args.scale
+        if args.coverage is not None or args.scale != 1.0:  # another shape than the named config: say so in the label
+            cb["workload"] = ("NOT a BASELINE config (--scale %.3f / --coverage %g override of %s): " % (args.scale, cfg["coverage"], name)) + cb["workload"]
+        cb["kernel_ms_rank0"] = k_ms
+        cb["staging"] = "device (csrc/expand.cu)" if device_built else "host (csrc/staging.cpp)"
+        cb["staging_seconds"] = t_stage
+        cb["staging_note"] = "read synthesis + H2D + device staging of the rank's range, once, before the timed regions (max over ranks)"
+        cb["pin_reads_seconds"] = t_pin
+        cb["e2e_phase_ms_rank0"] = e2e_phase_ms
+        cb["e2e_evidence_rows"] = gd_rows
+        cb["hist_kernel_gbs"] = hist_bytes / (k_ms["hist"] * 1e-3) / 1e9 if k_ms["hist"] > 0 else 0.0
+        if per_rank:
+            cb["per_rank"] = per_rank
         cpu = None
         if not args.no_cpu:
             with tempfile.TemporaryDirectory() as tmp:
-                bam, fasta = cpu_sample(tmp, div=CPU_BASELINE_DIV)
-                n_cpu, t_cpu = run_cpu_once(bam, fasta, os.path.join(tmp, "o"))
+                div = cfg["cpu_baseline_div"]
+                bam, fasta = write_sample_bam(tmp, cfg, div)
+                n_cpu, t_cpu = run_cpu_once(bam, fasta, os.path.join(tmp, "o"), cfg)
             cpu = {"value": n_cpu / t_cpu, "unit": "aligned bases/s", "cores": 1, "kind": cpu_kind(),
-                   "sample": "C1 read model on a 1/%d-length reference (%d bp): %d records in %.1f s, one thread"
-                             % (CPU_BASELINE_DIV, GENOME // CPU_BASELINE_DIV, n_cpu, t_cpu)}
+                   "sample": "%s read model on a 1/%d-length reference (%d bp): %d records in %.1f s, one thread; a per-record rate "
+                             "(the CPU path is linear in records), the full workload is %d x the sample"
+                             % (name, div, GENOME // div, n_cpu, t_cpu, int(total_records) // max(1, n_cpu))}
+        from_bam = None
+        if not args.no_bam:
+            with tempfile.TemporaryDirectory() as tmp:
+                ctx.close()   # (its streams make room for the second workload)
+                ctx = None
+                from_bam = e2e_from_bam(bq, local, tmp)
         line = {"metric": "aligned bases/sec, error_count+identify_mutations", "value": total_records / (step_ms * 1e-3),
                 "unit": "aligned bases/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": launches,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cb, "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": total_records / e2e_s, "unit": "aligned bases/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h},
+                        "d2h_bytes_per_step": d2h, "seconds_per_step": e2e_s},
+                "e2e_from_bam": from_bam,
                 "roofline": {"bound": "hbm", "kernel": "tally_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                              "algorithmic_bytes": score_bytes, "scoring_pass_frac": pass_gbs / peak},
@@ -378,8 +503,10 @@ def main():
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -51,14 +51,14 @@ class _SynthSpec(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("contig_lens", C.POINTER(C.c_uint32)), ("n_contigs", C.c_uint32),
                 ("contig_prefix", C.c_char_p), ("fasta", C.c_char_p), ("sets", C.POINTER(_SynthReadSet)),
                 ("n_sets", C.c_uint32), ("n_polymorphic", C.c_uint32), ("n_fixed", C.c_uint32), ("n_gaps", C.c_uint32),
-                ("min_freq_ppm", C.c_uint32), ("max_freq_ppm", C.c_uint32)]
+                ("min_freq_ppm", C.c_uint32), ("max_freq_ppm", C.c_uint32), ("window_lo", C.c_uint64), ("window_hi", C.c_uint64)]
 
 
 class _StreamInfo(C.Structure):
     _fields_ = [("n_base", C.c_uint64), ("n_ins", C.c_uint64), ("n_score_records", C.c_uint64),
                 ("n_hist_records", C.c_uint64), ("n_reads", C.c_uint64), ("n_score_padded", C.c_uint64),
                 ("bytes_host", C.c_uint64),
-                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("device_built", C.c_uint32), ("reserved0", C.c_uint32),
+                ("n_targets", C.c_uint32), ("pinned", C.c_uint32), ("device_built", C.c_uint32), ("hist_compact", C.c_uint32),
                 ("hist_record_bytes", C.c_uint32), ("side_stride", C.c_uint32),
                 ("n_side", C.c_uint64), ("base_quality_cutoff", C.c_uint32), ("hot_mapq", C.c_uint32),
                 ("table_q_lo", C.c_uint32), ("table_n_q", C.c_uint32), ("table_n_st", C.c_uint32), ("table_words", C.c_uint32),
@@ -113,6 +113,13 @@ def load_library():
         "brq_synth_write": [C.c_void_p, P(_SynthSpec), C.c_char_p, C.c_char_p],
         "brq_stage_synthetic": [C.c_void_p, P(_SynthSpec), P(_StageOptions)],
         "brq_stream": [C.c_void_p, P(_StreamInfo)],
+        "brq_stream_summary": [C.c_void_p, P(_StreamInfo)],
+        "brq_pin_reads": [C.c_void_p],
+        "brq_max_coverage_depth": [C.c_void_p, P(C.c_uint64)],
+        "brq_set_min_coverage_depth": [C.c_void_p, C.c_uint64],
+        "brq_restage": [C.c_void_p],
+        "brq_synth_shard_bounds": [C.c_void_p, P(_SynthSpec), C.c_uint32, P(C.c_uint64)],
+        "brq_bam_shard_bounds": [C.c_void_p, C.c_char_p, C.c_uint32, P(C.c_uint64)],
         "brq_upload": [C.c_void_p],
         "brq_sync": [C.c_void_p],
         "brq_error_count": [C.c_void_p, C.c_char_p, C.c_int, C.c_int],
@@ -159,7 +166,8 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_hist_download", "brq_derive_error_table", "brq_error_table", "brq_write_error_count_files",
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
-           "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts"]
+           "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
+           "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds"]
 
 
 def _b(s):
@@ -177,7 +185,7 @@ class SynthSpec:
     """Synthetic aligned reads (SURVEY.md section 8d value distributions)."""
 
     def __init__(self, seed, read_sets, contig_lens=None, fasta=None, contig_prefix="contig",
-                 n_polymorphic=60, n_fixed=10, n_gaps=2, min_freq_ppm=50000, max_freq_ppm=500000):
+                 n_polymorphic=60, n_fixed=10, n_gaps=2, min_freq_ppm=50000, max_freq_ppm=500000, window=(0, 0)):
         self.keep = []
         sets = (_SynthReadSet * len(read_sets))()
         for i, rs in enumerate(read_sets):
@@ -190,7 +198,7 @@ class SynthSpec:
             lens = (C.c_uint32 * len(contig_lens))(*contig_lens)
         self.keep += [sets, lens]
         self.c = _SynthSpec(seed, lens, 0 if contig_lens is None else len(contig_lens), _b(contig_prefix), _b(fasta),
-                            sets, len(read_sets), n_polymorphic, n_fixed, n_gaps, min_freq_ppm, max_freq_ppm)
+                            sets, len(read_sets), n_polymorphic, n_fixed, n_gaps, min_freq_ppm, max_freq_ppm, window[0], window[1])
         self.read_sets = read_sets
 
     def read_file_sets(self):
@@ -335,6 +343,43 @@ class Context:
 
     def synth_write(self, spec, bam_out, fasta_out):
         self._check(self.lib.brq_synth_write(self.h, C.byref(spec.c), _b(bam_out), _b(fasta_out)))
+
+    def stream_summary(self):
+        """Counts and geometry of the staged stream (no array views: nothing is copied from HBM)."""
+        info = _StreamInfo()
+        self._check(self.lib.brq_stream_summary(self.h, C.byref(info)))
+        return {"n_base": info.n_base, "n_ins": info.n_ins, "n_score": info.n_score_records, "n_hist": info.n_hist_records,
+                "n_reads": info.n_reads, "bytes_host": info.bytes_host, "n_score_padded": info.n_score_padded, "n_side": info.n_side,
+                "n_rounds": info.n_rounds, "device_built": bool(info.device_built), "hist_compact": bool(info.hist_compact),
+                "n_hist16": info.n_hist16, "n_hist_exc": info.n_hist_exc, "hist_record_bytes": info.hist_record_bytes,
+                "side_stride": info.side_stride}
+
+    def max_coverage_depth(self):
+        d = C.c_uint64()
+        self._check(self.lib.brq_max_coverage_depth(self.h, C.byref(d)))
+        return d.value
+
+    def set_min_coverage_depth(self, depth):
+        """Floor of the coverage histogram's depth axis (the maximum over the ranks of a sharded run, so the ranks can sum)."""
+        self.lib.brq_set_min_coverage_depth(self.h, int(depth))
+
+    def pin_reads(self):
+        """Page-lock the host copy of the reads (device staging then copies them at PCIe speed)."""
+        self._check(self.lib.brq_pin_reads(self.h))
+
+    def restage(self):
+        """Stage again from the host copy of the reads: H2D + expansion on the device (or host staging)."""
+        self._check(self.lib.brq_restage(self.h))
+
+    def synth_shard_bounds(self, spec, n_shards):
+        b = (C.c_uint64 * (n_shards + 1))()
+        self._check(self.lib.brq_synth_shard_bounds(self.h, C.byref(spec.c), n_shards, b))
+        return list(b)
+
+    def bam_shard_bounds(self, bam, n_shards):
+        b = (C.c_uint64 * (n_shards + 1))()
+        self._check(self.lib.brq_bam_shard_bounds(self.h, _b(bam), n_shards, b))
+        return list(b)
 
     def stream(self):
         info = _StreamInfo()

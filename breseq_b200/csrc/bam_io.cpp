@@ -271,57 +271,6 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
 
 namespace {
 
-struct BgzfWriter {
-  FILE* f;
-  int level;
-  std::vector<uint8_t> buf;
-  explicit BgzfWriter(const std::string& path, int lvl) : f(fopen(path.c_str(), "wb")), level(lvl) {
-    if (!f) throw std::runtime_error("cannot create " + path);
-    buf.reserve(0xff00);
-  }
-  void flush_block() {
-    uint8_t out[0x10000];
-    z_stream zs;
-    memset(&zs, 0, sizeof zs);
-    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
-    zs.next_in = buf.data();
-    zs.avail_in = (uInt)buf.size();
-    zs.next_out = out + 18;
-    zs.avail_out = sizeof(out) - 18 - 8;
-    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) throw std::runtime_error("deflate overflow");
-    size_t clen = zs.total_out;
-    deflateEnd(&zs);
-    static const uint8_t head[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
-    memcpy(out, head, 12);
-    out[12] = 'B'; out[13] = 'C'; out[14] = 2; out[15] = 0;
-    uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1);
-    memcpy(out + 16, &bsize, 2);
-    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf.data(), (uInt)buf.size());
-    uint32_t isize = (uint32_t)buf.size();
-    memcpy(out + 18 + clen, &crc, 4);
-    memcpy(out + 18 + clen + 4, &isize, 4);
-    fwrite(out, 1, 18 + clen + 8, f);
-    buf.clear();
-  }
-  void write(const void* p, size_t n) {
-    const uint8_t* s = (const uint8_t*)p;
-    while (n) {
-      size_t room = 0xff00 - buf.size();
-      size_t k = n < room ? n : room;
-      buf.insert(buf.end(), s, s + k);
-      s += k; n -= k;
-      if (buf.size() == 0xff00) flush_block();
-    }
-  }
-  template <typename T> void put(T v) { write(&v, sizeof(T)); }
-  void close() {
-    if (!buf.empty()) flush_block();
-    flush_block();  // empty member = BGZF EOF marker
-    fclose(f);
-    f = nullptr;
-  }
-};
-
 uint16_t reg2bin(int64_t beg, int64_t end) {
   --end;
   if (beg >> 14 == end >> 14) return (uint16_t)(((1 << 15) - 1) / 7 + (beg >> 14));
@@ -334,61 +283,122 @@ uint16_t reg2bin(int64_t beg, int64_t end) {
 
 }  // namespace
 
-void write_bam(const std::string& path, const BamHeader& hdr, const ReadBatch& r, int level) {
-  BgzfWriter w(path, level);
-  w.write("BAM\1", 4);
-  w.put<int32_t>((int32_t)hdr.text.size());
-  w.write(hdr.text.data(), hdr.text.size());
-  w.put<int32_t>((int32_t)hdr.target_names.size());
-  for (size_t i = 0; i < hdr.target_names.size(); ++i) {
-    w.put<int32_t>((int32_t)hdr.target_names[i].size() + 1);
-    w.write(hdr.target_names[i].c_str(), hdr.target_names[i].size() + 1);
-    w.put<int32_t>((int32_t)hdr.target_lens[i]);
+// One BAM record of `r` appended to `rec` (block_size prefix included).
+static void append_record(std::vector<uint8_t>& rec, const BamHeader& hdr, const ReadBatch& r, size_t i) {
+  const size_t start = rec.size();
+  std::string name = i < r.names.size() ? r.names[i] : ("r" + std::to_string(i));
+  auto put = [&](const void* p, size_t n) { rec.insert(rec.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+  auto put32 = [&](int32_t v) { put(&v, 4); };
+  auto put16 = [&](uint16_t v) { put(&v, 2); };
+  put32(0);  // block_size, patched below
+  const uint32_t* cig = &r.cigars[r.cigar_off[i]];
+  int64_t rlen = 0;
+  for (uint32_t k = 0; k < r.n_cigar[i]; ++k) {
+    uint32_t op = cig[k] & 0xf;
+    if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cig[k] >> 4;
   }
-  std::vector<uint8_t> rec;
-  for (size_t i = 0; i < r.size(); ++i) {
-    std::string name = i < r.names.size() ? r.names[i] : ("r" + std::to_string(i));
-    rec.clear();
-    auto put = [&](const void* p, size_t n) { rec.insert(rec.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
+  put32(r.tid[i]); put32(r.pos[i]);
+  rec.push_back((uint8_t)(name.size() + 1)); rec.push_back(r.mapq[i]);
+  put16(reg2bin(r.pos[i], r.pos[i] + (rlen ? rlen : 1)));
+  put16((uint16_t)r.n_cigar[i]); put16(r.flag[i]);
+  put32((int32_t)r.l_seq[i]); put32(-1); put32(-1); put32(0);
+  put(name.c_str(), name.size() + 1);
+  put(cig, 4 * (size_t)r.n_cigar[i]);
+  const uint8_t* b = &r.bases[r.seq_off[i]];
+  for (uint32_t j = 0; j < r.l_seq[i]; j += 2) {
+    uint8_t hi = b[j], lo = (j + 1 < r.l_seq[i]) ? b[j + 1] : 0;
+    rec.push_back((uint8_t)((hi << 4) | lo));
+  }
+  put(&r.quals[r.seq_off[i]], r.l_seq[i]);
+  auto tag_int = [&](const char* t, int64_t v) {
+    rec.push_back((uint8_t)t[0]); rec.push_back((uint8_t)t[1]);
+    if (v >= 0 && v < 256) { rec.push_back('C'); rec.push_back((uint8_t)v); }
+    else { rec.push_back('i'); int32_t x = (int32_t)v; put(&x, 4); }
+  };
+  tag_int("AS", r.as[i]);
+  if (r.x1[i] != 1 || (i % 3) != 0) tag_int("X1", r.x1[i]);  // leave the tag off some unique reads: absent == 1
+  if (!hdr.read_groups.ids.empty()) {
+    const std::string& id = hdr.read_groups.ids[r.rg[i]];
+    rec.push_back('R'); rec.push_back('G'); rec.push_back('Z');
+    put(id.c_str(), id.size() + 1);
+  }
+  if (r.xl[i] >= 0) tag_int("XL", r.xl[i]);
+  if (r.xr[i] >= 0) tag_int("XR", r.xr[i]);
+  const int32_t block = (int32_t)(rec.size() - start - 4);
+  memcpy(&rec[start], &block, 4);
+}
+
+// The file is the same bytes whatever the thread count: records are serialised over contiguous read ranges, the
+// uncompressed image is cut into members of 0xff00 bytes, and the members are deflated side by side.
+void write_bam(const std::string& path, const BamHeader& hdr, const ReadBatch& r, int level, int threads) {
+  if (threads < 1) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  std::vector<uint8_t> head;
+  {
+    auto put = [&](const void* p, size_t n) { head.insert(head.end(), (const uint8_t*)p, (const uint8_t*)p + n); };
     auto put32 = [&](int32_t v) { put(&v, 4); };
-    auto put16 = [&](uint16_t v) { put(&v, 2); };
-    const uint32_t* cig = &r.cigars[r.cigar_off[i]];
-    int64_t rlen = 0;
-    for (uint32_t k = 0; k < r.n_cigar[i]; ++k) {
-      uint32_t op = cig[k] & 0xf;
-      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cig[k] >> 4;
+    put("BAM\1", 4);
+    put32((int32_t)hdr.text.size());
+    put(hdr.text.data(), hdr.text.size());
+    put32((int32_t)hdr.target_names.size());
+    for (size_t i = 0; i < hdr.target_names.size(); ++i) {
+      put32((int32_t)hdr.target_names[i].size() + 1);
+      put(hdr.target_names[i].c_str(), hdr.target_names[i].size() + 1);
+      put32((int32_t)hdr.target_lens[i]);
     }
-    put32(r.tid[i]); put32(r.pos[i]);
-    rec.push_back((uint8_t)(name.size() + 1)); rec.push_back(r.mapq[i]);
-    put16(reg2bin(r.pos[i], r.pos[i] + (rlen ? rlen : 1)));
-    put16((uint16_t)r.n_cigar[i]); put16(r.flag[i]);
-    put32((int32_t)r.l_seq[i]); put32(-1); put32(-1); put32(0);
-    put(name.c_str(), name.size() + 1);
-    put(cig, 4 * (size_t)r.n_cigar[i]);
-    const uint8_t* b = &r.bases[r.seq_off[i]];
-    for (uint32_t j = 0; j < r.l_seq[i]; j += 2) {
-      uint8_t hi = b[j], lo = (j + 1 < r.l_seq[i]) ? b[j + 1] : 0;
-      rec.push_back((uint8_t)((hi << 4) | lo));
-    }
-    put(&r.quals[r.seq_off[i]], r.l_seq[i]);
-    auto tag_int = [&](const char* t, int64_t v) {
-      rec.push_back((uint8_t)t[0]); rec.push_back((uint8_t)t[1]);
-      if (v >= 0 && v < 256) { rec.push_back('C'); rec.push_back((uint8_t)v); }
-      else { rec.push_back('i'); int32_t x = (int32_t)v; put(&x, 4); }
-    };
-    tag_int("AS", r.as[i]);
-    if (r.x1[i] != 1 || (i % 3) != 0) tag_int("X1", r.x1[i]);  // leave the tag off some unique reads: absent == 1
-    if (!hdr.read_groups.ids.empty()) {
-      const std::string& id = hdr.read_groups.ids[r.rg[i]];
-      rec.push_back('R'); rec.push_back('G'); rec.push_back('Z');
-      put(id.c_str(), id.size() + 1);
-    }
-    if (r.xl[i] >= 0) tag_int("XL", r.xl[i]);
-    if (r.xr[i] >= 0) tag_int("XR", r.xr[i]);
-    w.put<int32_t>((int32_t)rec.size());
-    w.write(rec.data(), rec.size());
   }
-  w.close();
+  const size_t n = r.size(), n_parts = (size_t)threads * 4;
+  std::vector<std::vector<uint8_t>> parts(n_parts);
+  auto run = [&](size_t n_jobs, auto&& body) {
+    std::atomic<size_t> next(0);
+    auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n_jobs) break; body(k); } };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  };
+  run(n_parts, [&](size_t k) {
+    std::vector<uint8_t>& out = parts[k];
+    const size_t lo = n * k / n_parts, hi = n * (k + 1) / n_parts;
+    for (size_t i = lo; i < hi; ++i) append_record(out, hdr, r, i);
+  });
+  std::vector<size_t> part_at(n_parts + 1, head.size());
+  for (size_t k = 0; k < n_parts; ++k) part_at[k + 1] = part_at[k] + parts[k].size();
+  const size_t total = part_at[n_parts];
+  std::vector<uint8_t> u(total);
+  memcpy(u.data(), head.data(), head.size());
+  run(n_parts, [&](size_t k) { if (!parts[k].empty()) memcpy(&u[part_at[k]], parts[k].data(), parts[k].size()); std::vector<uint8_t>().swap(parts[k]); });
+  const size_t member = 0xff00, n_members = (total + member - 1) / member;
+  std::vector<std::vector<uint8_t>> packed(n_members + 1);
+  auto deflate_member = [&](const uint8_t* src, size_t len, std::vector<uint8_t>& out) {
+    out.resize(0x10000);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+    zs.next_in = const_cast<Bytef*>(src);
+    zs.avail_in = (uInt)len;
+    zs.next_out = out.data() + 18;
+    zs.avail_out = (uInt)(out.size() - 18 - 8);
+    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw std::runtime_error("deflate overflow"); }
+    const size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    static const uint8_t h12[12] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0};
+    memcpy(out.data(), h12, 12);
+    out[12] = 'B'; out[13] = 'C'; out[14] = 2; out[15] = 0;
+    const uint16_t bsize = (uint16_t)(clen + 18 + 8 - 1);
+    memcpy(out.data() + 16, &bsize, 2);
+    const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), src, (uInt)len), isize = (uint32_t)len;
+    memcpy(out.data() + 18 + clen, &crc, 4);
+    memcpy(out.data() + 18 + clen + 4, &isize, 4);
+    out.resize(18 + clen + 8);
+  };
+  run(n_members + 1, [&](size_t k) {
+    if (k == n_members) deflate_member(u.data(), 0, packed[k]);  // empty member = BGZF EOF marker
+    else deflate_member(&u[k * member], std::min(member, total - k * member), packed[k]);
+  });
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) throw std::runtime_error("cannot create " + path);
+  for (const auto& m : packed) if (fwrite(m.data(), 1, m.size(), f) != m.size()) { fclose(f); throw std::runtime_error("short write on " + path); }
+  fclose(f);
 }
 
 void read_fasta(const std::string& path, RefSet& ref) {

@@ -17,7 +17,7 @@ struct BamHeader {
 void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int threads);
 
 // Serialise `reads` (already coordinate sorted) as BGZF-compressed BAM.
-void write_bam(const std::string& path, const BamHeader& hdr, const ReadBatch& reads, int level = 1);
+void write_bam(const std::string& path, const BamHeader& hdr, const ReadBatch& reads, int level = 1, int threads = 0);
 
 void read_fasta(const std::string& path, RefSet& ref);
 void write_fasta(const std::string& path, const RefSet& ref, bool with_fai = true);

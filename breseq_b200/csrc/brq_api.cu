@@ -21,6 +21,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/stat.h>
+
 using namespace brq;
 
 namespace {
@@ -95,6 +97,9 @@ struct brq_ctx {
     std::vector<uint16_t> hist16;
     std::vector<uint32_t> hist_exc;
   } mirror;
+  std::string reads_source;         // the BAM + FASTA the reads / reference came from, with size and mtime (load_inputs)
+  uint64_t min_cov_depth = 0;       // brq_set_min_coverage_depth
+  std::vector<void*> pinned_reads;  // page-locked arrays of `reads` (brq_pin_reads)
   bool host_hist_valid = false;     // h_counts / h_cov hold the counts of the current stream's last brq_error_count
   uint64_t d2h_bytes = 0;           // device -> host bytes since the last brq_d2h_bytes(reset) (bench bookkeeping)
 
@@ -268,11 +273,53 @@ SynthConfig synth_config(const brq_synth_spec* sp, int threads) {
   }
   cfg.n_polymorphic = sp->n_polymorphic; cfg.n_fixed = sp->n_fixed; cfg.n_gaps = sp->n_gaps;
   if (sp->max_freq_ppm) { cfg.min_freq_ppm = sp->min_freq_ppm; cfg.max_freq_ppm = sp->max_freq_ppm; }
+  cfg.window_lo = sp->window_lo; cfg.window_hi = sp->window_hi;
   return cfg;
 }
 
-void synth_into(brq_ctx* c, const brq_synth_spec* sp) {
+void unpin_reads(brq_ctx* c) {
+  for (void* p : c->pinned_reads) cudaHostUnregister(p);
+  c->pinned_reads.clear();
+}
+void clear_inputs(brq_ctx* c) {
+  unpin_reads(c);
+  c->reads_source.clear();
   c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
+}
+
+// BAM + FASTA -> c->reads / c->hdr / c->ref, unless they are what the context already holds (the reference calls error_count()
+// and identify_mutations() on the same reference.bam one after the other: the second call finds the reads decoded)
+std::string source_key(const char* bam, const char* fasta) {
+  std::string key;
+  for (const char* path : {bam, fasta}) {
+    struct stat sb;
+    if (stat(path, &sb) != 0) return std::string();
+    key += std::string(path) + "|" + std::to_string((long long)sb.st_size) + "|" + std::to_string((long long)sb.st_mtim.tv_sec) + "." + std::to_string((long long)sb.st_mtim.tv_nsec) + "|";
+  }
+  return key;
+}
+bool load_inputs(brq_ctx* c, const char* bam, const char* fasta) {  // true when the inputs were (re)read
+  const std::string key = source_key(bam, fasta);
+  if (!key.empty() && key == c->reads_source && !c->hdr.target_names.empty()) return false;
+  drop_stream(c);
+  clear_inputs(c);
+  read_bam(bam, c->hdr, c->reads, c->threads);
+  read_fasta(fasta, c->ref);
+  c->reads_source = key;
+  return true;
+}
+bool same_stage_config(const StageConfig& a, const StageConfig& b) {
+  auto sets = [](const StageConfig& x) { std::string t; for (const auto& s : x.read_file_sets) t += s.base_name + ":" + std::to_string(s.n_files) + ","; return t; };
+  return a.call_seq_ids == b.call_seq_ids && a.coverage_group_of_tid == b.coverage_group_of_tid && sets(a) == sets(b) &&
+         a.use_base_repeat == b.use_base_repeat && a.use_read_pos == b.use_read_pos && a.base_quality_cutoff == b.base_quality_cutoff &&
+         a.want_hist == b.want_hist && a.want_score == b.want_score && a.preprocess_stage == b.preprocess_stage &&
+         a.unmatched_end_minimum_read_length == b.unmatched_end_minimum_read_length && a.unmatched_end_length_factor == b.unmatched_end_length_factor &&
+         a.shard_rank == b.shard_rank && a.shard_count == b.shard_count && a.shard_lo == b.shard_lo && a.shard_hi == b.shard_hi &&
+         a.shard_explicit == b.shard_explicit && a.staging_mode == b.staging_mode;
+}
+
+void synth_into(brq_ctx* c, const brq_synth_spec* sp) {
+  clear_inputs(c);
   if (sp->contig_lens) {
     std::vector<uint32_t> lens(sp->contig_lens, sp->contig_lens + sp->n_contigs);
     synth_reference(sp->seed, lens, sp->contig_prefix ? sp->contig_prefix : "contig", c->ref);
@@ -333,7 +380,7 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   const PileupStream& st = c->st;
   // coverage histogram geometry: groups x (max depth + 1)
   const uint32_t n_groups = st.n_groups;
-  c->cov_stride = st.max_hist_depth + 1;
+  c->cov_stride = std::max<uint64_t>(st.max_hist_depth, c->min_cov_depth) + 1;
   c->n_groups = n_groups;
   c->d_counts.ensure(lay.n_bins);
   c->d_cov.ensure(c->cov_stride * n_groups);
@@ -705,7 +752,9 @@ brq_ctx* brq_create(const brq_config* cfg) {
 
 void brq_destroy(brq_ctx* c) {
   if (!c) return;
+  if (c->device >= 0) cudaSetDevice(c->device);
   drop_stream(c);
+  unpin_reads(c);
   if (c->device >= 0) {
     c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
@@ -723,10 +772,8 @@ const char* brq_last_error(const brq_ctx* c) { return c ? c->error.c_str() : "nu
 
 int brq_stage_bam(brq_ctx* c, const char* bam, const char* fasta, const brq_stage_options* opt) {
   return guarded(c, [&] {
+    load_inputs(c, bam, fasta);
     drop_stream(c);
-    c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
-    read_bam(bam, c->hdr, c->reads, c->threads);
-    read_fasta(fasta, c->ref);
     apply_stage_options(c, opt);
     do_stage(c);
   });
@@ -750,26 +797,116 @@ int brq_stage_synthetic(brq_ctx* c, const brq_synth_spec* spec, const brq_stage_
   });
 }
 
+static void fill_stream_info(brq_ctx* c, const PileupStream& st, brq_stream_info* info, bool views) {
+  memset(info, 0, sizeof *info);
+  info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
+  info->n_reads = c->reads.size();
+  info->n_score_padded = st.n_score_padded;
+  info->n_side = st.n_side; info->n_rounds = st.n_rounds;
+  info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
+  info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
+  info->device_built = st.device_built ? 1u : 0u;
+  info->bytes_host = st.device_built ? st.bytes_uploaded : st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + (st.score16 ? st.n_score_padded * 2 + st.n_score_exc * 4 + (st.n_rounds * 32 + 1) * 4 : st.n_score_padded * 4) + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
+  info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
+  info->hist_record_bytes = st.hist_bytes;
+  info->n_hist16 = st.n_hist16; info->n_hist_exc = st.n_hist_exc; info->n_score_exc = st.n_score_exc;
+  info->hist_compact = st.hist_compact ? 1u : 0u;
+  if (!views) return;
+  info->side_rec = st.side_rec; info->side_off = st.side_off;
+  info->round_slot = st.round_slot; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
+  info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_off = st.hist_off;
+  info->slot_ref = st.slot_ref; info->ins_parent = c->st.ins_parent.data(); info->ins_count = c->st.ins_count.data();
+  info->hist16 = st.hist16; info->hist_exc = st.hist_exc;
+  info->score16 = st.score16; info->score_exc = st.score_exc; info->score_exc_off = st.score_exc_off;
+}
+
 int brq_stream(brq_ctx* c, brq_stream_info* info) {
   return guarded(c, [&] {
     if (!c->staged) throw std::runtime_error("nothing staged");
     const PileupStream view = host_view(c);   // (a device-built stream is copied to the host here, once)
-    const PileupStream& st = view;
-    memset(info, 0, sizeof *info);
-    info->n_base = st.n_base; info->n_ins = st.n_ins; info->n_score_records = st.n_score; info->n_hist_records = st.n_hist;
-    info->n_reads = c->reads.size();
-    info->n_score_padded = st.n_score_padded;
-    info->n_side = st.n_side; info->side_rec = st.side_rec; info->side_off = st.side_off;
-    info->round_slot = st.round_slot; info->n_rounds = st.n_rounds; info->score_cnt = st.score_cnt; info->round_off = st.round_off;
-    info->base_quality_cutoff = st.geo.cutoff; info->hot_mapq = st.geo.hot_mapq; info->table_q_lo = st.geo.q_lo; info->table_n_q = st.geo.n_q;
-    info->table_n_st = st.geo.n_st; info->table_words = st.geo.n_words(); info->side_stride = st.geo.side_stride;
-    info->device_built = st.device_built ? 1u : 0u;
-    info->bytes_host = st.device_built ? st.bytes_uploaded : st.n_rounds * 392 + st.n_slots() * 4 + st.n_side * 4 * st.geo.side_stride + (st.n_slots() + 1) * 4 + (st.score16 ? st.n_score_padded * 2 + st.n_score_exc * 4 + (st.n_rounds * 32 + 1) * 4 : st.n_score_padded * 4) + (st.n_slots() + 1) * 8 + st.n_slots() + (st.hist16 ? st.n_hist16 * 2 + st.n_hist_exc * 4 : st.n_hist * st.hist_bytes) + (st.n_base + 1) * 8 + st.n_base;
-    info->n_targets = (uint32_t)c->hdr.target_names.size(); info->pinned = st.pinned;
-    info->score_rec = st.score_rec; info->score_off = st.score_off; info->hist_rec = st.hist_rec; info->hist_record_bytes = st.hist_bytes; info->hist_off = st.hist_off;
-    info->slot_ref = st.slot_ref; info->ins_parent = c->st.ins_parent.data(); info->ins_count = c->st.ins_count.data();
-    info->hist16 = st.hist16; info->n_hist16 = st.n_hist16; info->hist_exc = st.hist_exc; info->n_hist_exc = st.n_hist_exc;
-    info->score16 = st.score16; info->score_exc = st.score_exc; info->score_exc_off = st.score_exc_off; info->n_score_exc = st.n_score_exc;
+    fill_stream_info(c, view, info, true);
+  });
+}
+
+int brq_stream_summary(brq_ctx* c, brq_stream_info* info) {
+  return guarded(c, [&] {
+    if (!c->staged) throw std::runtime_error("nothing staged");
+    fill_stream_info(c, c->st, info, false);
+  });
+}
+
+int brq_pin_reads(brq_ctx* c) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (!c->pinned_reads.empty()) return;
+    auto pin = [&](auto& vec) {
+      if (vec.empty()) return;
+      if (cudaHostRegister(vec.data(), vec.size() * sizeof(vec[0]), cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return; }  // (stays pageable)
+      c->pinned_reads.push_back(vec.data());
+    };
+    ReadBatch& R = c->reads;
+    pin(R.tid); pin(R.pos); pin(R.flag); pin(R.mapq); pin(R.rg); pin(R.x1); pin(R.xl); pin(R.xr); pin(R.l_seq); pin(R.seq_off);
+    pin(R.n_cigar); pin(R.cigar_off); pin(R.bases); pin(R.quals); pin(R.cigars);
+  });
+}
+
+int brq_restage(brq_ctx* c) {
+  return guarded(c, [&] {
+    if (c->hdr.target_names.empty()) throw std::runtime_error("no reads to stage: call brq_stage_bam or brq_stage_synthetic first");
+    drop_stream(c);
+    do_stage(c);
+  });
+}
+
+int brq_set_min_coverage_depth(brq_ctx* c, uint64_t depth) {
+  if (!c) return 1;
+  c->min_cov_depth = depth;
+  return 0;
+}
+
+int brq_max_coverage_depth(brq_ctx* c, uint64_t* depth) {
+  return guarded(c, [&] { if (!c->staged) throw std::runtime_error("nothing staged"); *depth = c->st.max_hist_depth; });
+}
+
+int brq_synth_shard_bounds(brq_ctx* c, const brq_synth_spec* sp, uint32_t n_shards, uint64_t* bounds) {
+  return guarded(c, [&] {
+    RefSet ref;
+    if (sp->contig_lens) {
+      std::vector<uint32_t> lens(sp->contig_lens, sp->contig_lens + sp->n_contigs);
+      synth_reference(sp->seed, lens, sp->contig_prefix ? sp->contig_prefix : "contig", ref);
+    } else {
+      read_fasta(sp->fasta, ref);
+    }
+    const std::vector<uint64_t> b = synth_shard_bounds(synth_config(sp, c->threads), ref, n_shards);
+    std::copy(b.begin(), b.end(), bounds);
+  });
+}
+
+int brq_bam_shard_bounds(brq_ctx* c, const char* bam, uint32_t n_shards, uint64_t* bounds) {
+  return guarded(c, [&] {
+    BamHeader hdr; ReadBatch R;
+    read_bam(bam, hdr, R, c->threads);
+    // visit order = alphabetical target names (pileup_base.cpp:364-385); weights = aligned query bases by start column
+    std::vector<size_t> order(hdr.target_names.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return hdr.target_names[a] < hdr.target_names[b]; });
+    std::vector<uint64_t> slot0(order.size(), 0);
+    uint64_t total = 0;
+    for (size_t t : order) { slot0[t] = total; total += hdr.target_lens[t]; }
+    const uint64_t bin = 256, n_bins = (total + bin - 1) / bin;
+    std::vector<uint64_t> w(n_bins + 1, 0);
+    uint64_t all = 0;
+    for (size_t i = 0; i < R.size(); ++i) {
+      if (R.tid[i] < 0 || (R.flag[i] & 4) || (size_t)R.tid[i] >= slot0.size()) continue;
+      w[(slot0[(size_t)R.tid[i]] + (uint64_t)std::max(0, R.pos[i])) / bin] += R.l_seq[i]; all += R.l_seq[i];
+    }
+    bounds[0] = 0; bounds[n_shards] = total;
+    uint64_t acc = 0, b = 0;
+    for (uint32_t k = 1; k < n_shards; ++k) {
+      const uint64_t want = all / n_shards * k;
+      while (b < n_bins && acc + w[b] <= want) acc += w[b++];
+      bounds[k] = std::max(bounds[k - 1], std::min(total, b * bin));
+    }
   });
 }
 
@@ -880,15 +1017,14 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
     CovSpec spec;
     std::vector<double> log10_prob;
     read_error_rates(error_rates_file, spec, log10_prob);
-    drop_stream(c);
-    c->hdr = BamHeader(); c->ref = RefSet(); c->reads = ReadBatch();
-    read_bam(bam, c->hdr, c->reads, c->threads);
-    read_fasta(fasta, c->ref);
+    const bool fresh = load_inputs(c, bam, fasta);
+    const StageConfig before = c->stage_cfg;
     apply_stage_options(c, opt);
     c->stage_cfg.use_read_pos = c->stage_cfg.use_read_pos || spec.used[COV_READ_POS];
     c->stage_cfg.use_base_repeat = c->stage_cfg.use_base_repeat || spec.used[COV_BASE_REPEAT];
     if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff;   // the score parameters carry Settings::base_quality_cutoff
-    do_stage(c);
+    // the stream error_count() staged from the same BAM with the same options is still there: no second staging
+    if (fresh || !c->staged || !same_stage_config(before, c->stage_cfg)) { drop_stream(c); do_stage(c); }
     c->host_table_pending = false;
     c->spec = spec; c->h_log10 = log10_prob;
     c->have_spec = true;

@@ -58,7 +58,7 @@ struct alignas(16) ReadMeta {
   uint8_t mapq, read_set, flags, pad;
 };
 static_assert(sizeof(ReadMeta) == 64, "ReadMeta is read as four 128-bit words");
-constexpr uint8_t RM_LIVE = 1, RM_REV = 2, RM_HAS_INS = 4;
+constexpr uint8_t RM_LIVE = 1, RM_REV = 2, RM_HAS_INS = 4, RM_SIMPLE = 8;  // SIMPLE: one M / = / X run between clips: no CIGAR walk per column
 // flags the pileup engine never shows a callback.  htslib 1.x sam.c, bam_plp_push(): "Skip only unmapped reads here, any
 // additional filtering must be done in iter->func" -- the BAM_DEF_MASK that bam_plp_init() stores in flag_mask is no longer
 // applied at push (samtools mpileup filters SECONDARY / QCFAIL / DUP in its own read function; breseq's read functions,
@@ -186,11 +186,13 @@ BRQ_HD inline ReadMeta prep_read(const RawReads& R, uint64_t i, const uint32_t* 
   m.x1 = R.x1[i]; m.xl = R.xl[i]; m.xr = R.xr[i]; m.mapq = R.mapq[i]; m.pad = 0;
   int32_t rlen = 0, qlen = 0;
   bool has_ins = false;
+  uint32_t n_match_ops = 0, n_other_ops = 0;   // other: anything but M / = / X and the clips S, H
   for (uint32_t k = 0; k < nc; ++k) {
     const uint32_t op = cig[k] & 0xf; const int32_t l = (int32_t)(cig[k] >> 4);
     if (xop_ref(op)) rlen += l;
     if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qlen += l;
     if (op == 1) has_ins = true;
+    if (xop_match(op)) ++n_match_ops; else if (op != 4 && op != 5) ++n_other_ops;
   }
   m.end = m.pos + (rlen ? rlen : 1);
   int32_t qs1 = 1;
@@ -221,7 +223,8 @@ BRQ_HD inline ReadMeta prep_read(const RawReads& R, uint64_t i, const uint32_t* 
   const int32_t tid = R.tid[i];
   if (tid >= 0 && rlen > 1) BRQ_AMAXI32(&max_span[tid], rlen);
   const bool live = tid >= 0 && !(R.flag[i] & PILEUP_FLAG_MASK) && nc > 0;
-  m.flags = (uint8_t)((live ? RM_LIVE : 0) | ((R.flag[i] & 16) ? RM_REV : 0) | (has_ins ? RM_HAS_INS : 0));
+  m.flags = (uint8_t)((live ? RM_LIVE : 0) | ((R.flag[i] & 16) ? RM_REV : 0) | (has_ins ? RM_HAS_INS : 0) |
+                      (n_match_ops == 1 && n_other_ops == 0 ? RM_SIMPLE : 0));
   // the BAM must be coordinate sorted (htslib's pileup aborts otherwise); reads without a target sort last
   if (i > 0) {
     const int32_t pt = R.tid[i - 1];
@@ -548,11 +551,16 @@ BRQ_HD inline void tile_lane(const ExpandArgs& a, uint32_t tile, uint32_t l) {
       if (a.want_hist) st.hist_at = a.hist_off[st.slot] & ~HIST_OFF_REDUNDANT_BIT;
     }
   }
+  // the next read's 64 bytes are requested while this one is visited (the loop is a chain of dependent loads otherwise)
+  ReadMeta nxt = first < last ? a.meta[first] : ReadMeta();
   for (uint32_t i = first; i < last; ++i) {
-    const ReadMeta m = a.meta[i];
+    const ReadMeta m = nxt;
+    if (i + 1 < last) nxt = a.meta[i + 1];
     if (!(m.flags & RM_LIVE) || m.end <= c0) continue;   // (uniform across the tile)
     if (!live_lane || c < m.pos || c >= m.end) continue;
-    const ColumnHit h = column_hit(a.cigars + m.cigar_off, m.n_cigar, m.pos, c);
+    ColumnHit h;
+    if (m.flags & RM_SIMPLE) { h.has = true; h.is_del = false; h.indel = 0; h.q = m.qs0 + (c - m.pos); }   // one aligned run after the leading clip
+    else h = column_hit(a.cigars + m.cigar_off, m.n_cigar, m.pos, c);
     if (!h.has) continue;
     visit_entry<FILL>(a, sg, m, h, st);
   }

@@ -132,6 +132,53 @@ bool make_read(const Model& m, int32_t tid, int32_t start, bool reversed, uint32
   return true;
 }
 
+
+// planted variants and sample gaps: a pure function of the configuration and the reference
+void plant(const SynthConfig& cfg, const RefSet& ref, const std::vector<uint64_t>& cum, std::vector<SynthVariant>& variants, std::vector<Gap>& gaps) {
+  const uint64_t total = ref.total_length();
+  auto locate = [&](uint64_t g, int32_t& tid, int32_t& pos) {
+    size_t t = std::upper_bound(cum.begin(), cum.end(), g) - cum.begin() - 1;
+    tid = (int32_t)t; pos = (int32_t)(g - cum[t]);
+  };
+  variants.clear();
+  gaps.clear();
+    Rng rng(mix3(cfg.seed, 0xA11E1E, 0));
+    uint32_t n_var = cfg.n_polymorphic + cfg.n_fixed;
+    std::vector<uint64_t> gpos;
+    for (uint32_t i = 0; i < n_var; ++i) {
+      for (int tries = 0; tries < 1000; ++tries) {
+        uint64_t g = rng.next() % total;
+        bool ok = true;
+        for (uint64_t o : gpos) if ((g > o ? g - o : o - g) < 12) { ok = false; break; }
+        int32_t tid, pos; locate(g, tid, pos);
+        if (pos < 5 || pos + 8 >= (int32_t)ref.seqs[(size_t)tid].size()) ok = false;
+        if (ok) { gpos.push_back(g); break; }
+      }
+    }
+    for (size_t i = 0; i < gpos.size(); ++i) {
+      SynthVariant v;
+      locate(gpos[i], v.tid, v.pos0);
+      uint32_t k = rng.below(10);
+      v.kind = k < 6 ? 0 : (k < 8 ? 1 : 2);
+      v.len = v.kind == 0 ? 1 : (uint8_t)(1 + (rng.below(4) == 0 ? 1 + rng.below(2) : 0));
+      uint8_t refb = char_to_index(ref.seqs[(size_t)v.tid][(size_t)v.pos0]);
+      for (int a = 0; a < 3; ++a) v.alt[a] = (uint8_t)rng.below(4);
+      if (v.kind == 0) v.alt[0] = (uint8_t)(((refb < 4 ? refb : 0) + 1 + rng.below(3)) & 3);
+      v.freq_ppm = i < cfg.n_polymorphic ? cfg.min_freq_ppm + rng.below(cfg.max_freq_ppm - cfg.min_freq_ppm + 1) : 1000000u;
+      variants.push_back(v);
+    }
+    for (uint32_t i = 0; i < cfg.n_gaps; ++i) {
+      Gap g;
+      uint32_t len = cfg.gap_min + rng.below(cfg.gap_max - cfg.gap_min + 1);
+      int32_t pos; locate(rng.next() % total, g.tid, pos);
+      int32_t tl = (int32_t)ref.seqs[(size_t)g.tid].size();
+      if ((int32_t)len + 200 >= tl) continue;
+      g.beg = std::min(std::max(pos, 100), tl - (int32_t)len - 100);
+      g.end = g.beg + (int32_t)len;
+      gaps.push_back(g);
+    }
+}
+
 }  // namespace
 
 void synth_reference(uint64_t seed, const std::vector<uint32_t>& lens, const std::string& prefix, RefSet& ref) {
@@ -166,45 +213,7 @@ void synth_reads(const SynthConfig& cfg, const RefSet& ref, BamHeader& hdr, Read
     tid = (int32_t)t; pos = (int32_t)(g - cum[t]);
   };
 
-  // planted variants and sample gaps
-  variants.clear();
-  {
-    Rng rng(mix3(cfg.seed, 0xA11E1E, 0));
-    uint32_t n_var = cfg.n_polymorphic + cfg.n_fixed;
-    std::vector<uint64_t> gpos;
-    for (uint32_t i = 0; i < n_var; ++i) {
-      for (int tries = 0; tries < 1000; ++tries) {
-        uint64_t g = rng.next() % total;
-        bool ok = true;
-        for (uint64_t o : gpos) if ((g > o ? g - o : o - g) < 12) { ok = false; break; }
-        int32_t tid, pos; locate(g, tid, pos);
-        if (pos < 5 || pos + 8 >= (int32_t)ref.seqs[(size_t)tid].size()) ok = false;
-        if (ok) { gpos.push_back(g); break; }
-      }
-    }
-    for (size_t i = 0; i < gpos.size(); ++i) {
-      SynthVariant v;
-      locate(gpos[i], v.tid, v.pos0);
-      uint32_t k = rng.below(10);
-      v.kind = k < 6 ? 0 : (k < 8 ? 1 : 2);
-      v.len = v.kind == 0 ? 1 : (uint8_t)(1 + (rng.below(4) == 0 ? 1 + rng.below(2) : 0));
-      uint8_t refb = char_to_index(ref.seqs[(size_t)v.tid][(size_t)v.pos0]);
-      for (int a = 0; a < 3; ++a) v.alt[a] = (uint8_t)rng.below(4);
-      if (v.kind == 0) v.alt[0] = (uint8_t)(((refb < 4 ? refb : 0) + 1 + rng.below(3)) & 3);
-      v.freq_ppm = i < cfg.n_polymorphic ? cfg.min_freq_ppm + rng.below(cfg.max_freq_ppm - cfg.min_freq_ppm + 1) : 1000000u;
-      variants.push_back(v);
-    }
-    for (uint32_t i = 0; i < cfg.n_gaps; ++i) {
-      Gap g;
-      uint32_t len = cfg.gap_min + rng.below(cfg.gap_max - cfg.gap_min + 1);
-      int32_t pos; locate(rng.next() % total, g.tid, pos);
-      int32_t tl = (int32_t)ref.seqs[(size_t)g.tid].size();
-      if ((int32_t)len + 200 >= tl) continue;
-      g.beg = std::min(std::max(pos, 100), tl - (int32_t)len - 100);
-      g.end = g.beg + (int32_t)len;
-      m.gaps.push_back(g);
-    }
-  }
+  plant(cfg, ref, cum, variants, m.gaps);
   m.var_by_tid.assign(n_t, {});
   {
     std::vector<uint32_t> order(variants.size());
@@ -231,6 +240,10 @@ void synth_reads(const SynthConfig& cfg, const RefSet& ref, BamHeader& hdr, Read
 
   // fragments, generated in parallel over contiguous fragment ranges
   int threads = std::max(1, cfg.threads);
+  const bool windowed = cfg.window_hi > cfg.window_lo;
+  uint64_t reach = 0;  // how far before the window a fragment that still overlaps it can start
+  for (const SynthReadSet& s : cfg.sets) reach = std::max<uint64_t>(reach, (uint64_t)(s.paired ? s.frag_mean + 10 * s.frag_sd : 0) + 2 * s.read_len + 64);
+  const uint64_t win_lo = cfg.window_lo > reach ? cfg.window_lo - reach : 0, win_hi = cfg.window_hi;
   std::vector<std::vector<TmpRead>> parts((size_t)threads * cfg.sets.size());
   for (size_t si = 0; si < cfg.sets.size(); ++si) {
     const SynthReadSet& s = cfg.sets[si];
@@ -243,7 +256,9 @@ void synth_reads(const SynthConfig& cfg, const RefSet& ref, BamHeader& hdr, Read
       for (uint64_t f = lo; f < hi; ++f) {
         uint64_t gid = ((uint64_t)si << 40) | f;
         Rng rng(mix3(cfg.seed, 0xF4A6 + si, f));
-        int32_t tid, pos; locate(rng.next() % total, tid, pos);
+        const uint64_t g = rng.next() % total;
+        if (windowed && (g < win_lo || g >= win_hi)) continue;
+        int32_t tid, pos; locate(g, tid, pos);
         int32_t tl = (int32_t)ref.seqs[(size_t)tid].size();
         bool flip = rng.below(2);
         if (!s.paired) {
@@ -293,6 +308,75 @@ void synth_reads(const SynthConfig& cfg, const RefSet& ref, BamHeader& hdr, Read
     reads.quals.insert(reads.quals.end(), r->quals.begin(), r->quals.end());
     reads.cigars.insert(reads.cigars.end(), r->cigar.begin(), r->cigar.end());
   }
+}
+
+std::vector<uint64_t> synth_shard_bounds(const SynthConfig& cfg, const RefSet& ref, uint32_t n_shards) {
+  const uint64_t total = ref.total_length();
+  std::vector<uint64_t> bounds(n_shards + 1, 0);
+  bounds[n_shards] = total;
+  if (n_shards <= 1 || !total) return bounds;
+  const size_t n_t = ref.seqs.size();
+  std::vector<uint64_t> cum(n_t + 1, 0);
+  for (size_t t = 0; t < n_t; ++t) cum[t + 1] = cum[t] + ref.seqs[t].size();
+  std::vector<SynthVariant> variants;
+  std::vector<Gap> gaps;
+  plant(cfg, ref, cum, variants, gaps);
+  // Aligned bases by the bin their read starts in, from the first draws of every fragment's generator (position, strand,
+  // fragment length: what synth_reads draws before it makes a read), with its rejections at contig ends and sample gaps.
+  const uint64_t bin = 64, n_bins = (total + bin - 1) / bin;
+  std::vector<uint64_t> w(n_bins + 1, 0);
+  const int threads = std::max(1, cfg.threads);
+  for (size_t si = 0; si < cfg.sets.size(); ++si) {
+    const SynthReadSet& s = cfg.sets[si];
+    const uint64_t n_frag = (uint64_t)(s.coverage * (double)total / ((double)s.read_len * (s.paired ? 2 : 1)) + 0.5);
+    std::vector<std::vector<uint64_t>> part((size_t)threads, std::vector<uint64_t>(n_bins + 1, 0));
+    auto work = [&](int t) {
+      std::vector<uint64_t>& mine = part[(size_t)t];
+      auto add_read = [&](int32_t tid, int32_t pos) {
+        for (const Gap& g : gaps) if (g.tid == tid && pos < g.end && pos + (int32_t)s.read_len > g.beg) return;
+        mine[(cum[(size_t)tid] + (uint64_t)pos) / bin] += s.read_len;
+      };
+      for (uint64_t f = n_frag * (uint64_t)t / (uint64_t)threads; f < n_frag * (uint64_t)(t + 1) / (uint64_t)threads; ++f) {
+        Rng rng(mix3(cfg.seed, 0xF4A6 + si, f));
+        const uint64_t g = rng.next() % total;
+        const size_t ti = std::upper_bound(cum.begin(), cum.end(), g) - cum.begin() - 1;
+        const int32_t tid = (int32_t)ti, pos = (int32_t)(g - cum[ti]), tl = (int32_t)ref.seqs[ti].size();
+        rng.below(2);
+        if (!s.paired) {
+          if (pos + (int32_t)s.read_len + 8 > tl) continue;
+          add_read(tid, pos);
+        } else {
+          int32_t F = (int32_t)floor(s.frag_mean + s.frag_sd * rng.normal() + 0.5);
+          if (F < (int32_t)s.read_len) F = (int32_t)s.read_len;
+          if (pos + F + 8 > tl) continue;
+          add_read(tid, pos);
+          add_read(tid, pos + F - (int32_t)s.read_len);
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (auto& v : part) for (uint64_t b = 0; b < n_bins; ++b) w[b] += v[b];
+  }
+  // a read of L bases starting in bin b lays its bases over the next L columns: spread the weights before cutting
+  uint32_t max_len = 1;
+  for (const SynthReadSet& s : cfg.sets) max_len = std::max(max_len, s.read_len);
+  const uint64_t spread = std::max<uint64_t>(1, max_len / bin);
+  std::vector<double> d(n_bins + spread + 1, 0.0);
+  for (uint64_t b = 0; b < n_bins; ++b) for (uint64_t k = 0; k < spread; ++k) d[b + k] += (double)w[b] / (double)spread;
+  double all = 0.0;
+  for (uint64_t b = 0; b < n_bins; ++b) all += d[b];
+  double acc = 0.0;
+  uint64_t b = 0;
+  for (uint32_t k = 1; k < n_shards; ++k) {
+    const double want = all * (double)k / (double)n_shards;
+    while (b < n_bins && acc + d[b] <= want) acc += d[b++];
+    bounds[k] = std::min(total, b * bin);
+  }
+  for (uint32_t k = 1; k <= n_shards; ++k) if (bounds[k] < bounds[k - 1]) bounds[k] = bounds[k - 1];
+  return bounds;
 }
 
 }  // namespace brq

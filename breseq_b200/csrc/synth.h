@@ -43,6 +43,9 @@ struct SynthConfig {
   uint32_t redundant_ppm = 20000;
   uint32_t trim_ppm = 50000;
   int threads = 8;
+  // only the fragments that can overlap columns [window_lo, window_hi) of the concatenated contigs (window_hi > window_lo):
+  // a rank of a run sharded by reference range generates its own share; every read is the same as in the full run
+  uint64_t window_lo = 0, window_hi = 0;
 };
 
 // Uniform random ACGT reference (GC ~ 50 %); contig i is named "<prefix><i+1>" (zero padded so
@@ -52,5 +55,10 @@ void synth_reference(uint64_t seed, const std::vector<uint32_t>& contig_lens, co
 // Generate the reads of `cfg` against `ref`; fills reads (coordinate sorted), hdr and variants.
 void synth_reads(const SynthConfig& cfg, const RefSet& ref, BamHeader& hdr, ReadBatch& reads,
                  std::vector<SynthVariant>& variants);
+
+// Cut points of `n_shards` contiguous coordinate shards with about the same number of aligned bases (balance
+// by record count, not by columns): bounds[0] = 0 .. bounds[n_shards] = total length, in concatenated-contig columns.
+// A pure function of the configuration (fragment start positions only): every rank computes the same cuts.
+std::vector<uint64_t> synth_shard_bounds(const SynthConfig& cfg, const RefSet& ref, uint32_t n_shards);
 
 }  // namespace brq

@@ -83,17 +83,25 @@ typedef struct brq_synth_spec {
   uint32_t n_sets;
   uint32_t n_polymorphic, n_fixed, n_gaps;
   uint32_t min_freq_ppm, max_freq_ppm;
+  /* only the reads that can overlap columns [window_lo, window_hi) of the concatenated contigs (window_hi > window_lo): a
+   * rank of a run sharded by reference range generates its own share; each read is the same as in the full run */
+  uint64_t window_lo, window_hi;
 } brq_synth_spec;
 
 int brq_synth_write(brq_ctx* ctx, const brq_synth_spec* spec, const char* bam_out, const char* fasta_out);
 int brq_stage_synthetic(brq_ctx* ctx, const brq_synth_spec* spec, const brq_stage_options* opt);
+/* cut points (n_shards + 1 values, concatenated visit-order columns) of shards with about the same number of aligned bases
+ * (balance by record count); a pure function of the spec, so every rank computes the same cuts */
+int brq_synth_shard_bounds(brq_ctx* ctx, const brq_synth_spec* spec, uint32_t n_shards, uint64_t* bounds);
+/* the same for a BAM, from its records' start positions (one pass over the file's records) */
+int brq_bam_shard_bounds(brq_ctx* ctx, const char* bam, uint32_t n_shards, uint64_t* bounds);
 
 typedef struct brq_stream_info {
   uint64_t n_base, n_ins, n_score_records, n_hist_records, n_reads;
   uint64_t n_score_padded;         /* words in score_rec: round-major, lane-interleaved, padded (csrc/brq_types.h) */
   uint64_t bytes_host;             /* bytes of the staged stream (what brq_upload copies) */
   uint32_t n_targets, pinned;
-  uint32_t device_built, reserved0;  /* the stream was built in HBM (brq_stage_options.staging); the views below are copies made by this call */
+  uint32_t device_built, hist_compact;  /* the stream was built in HBM (brq_stage_options.staging: the views below are copies made by this call); the device reads the compact histogram streams */
   uint32_t hist_record_bytes, side_stride;  /* 4, or 8 with read_pos / base_repeat / more than 16 read files; words per side-list entry (2 with read_pos / base_repeat) */
   uint64_t n_side;                 /* side-list entries (scoring records outside the shared table, X1 >= 511) */
   uint32_t base_quality_cutoff, hot_mapq, table_q_lo, table_n_q, table_n_st, table_words;  /* geometry baked into score_rec */
@@ -123,6 +131,12 @@ typedef struct brq_stream_info {
 } brq_stream_info;
 
 int brq_stream(brq_ctx* ctx, brq_stream_info* info);
+/* the counts and geometry of brq_stream_info without the array views (nothing is copied from HBM) */
+int brq_stream_summary(brq_ctx* ctx, brq_stream_info* info);
+/* device staging with the reads kept on the host (brq_stage_synthetic / brq_stage_bam leave them there): page-lock them once
+ * (later brq_restage calls then copy at PCIe speed) and stage again from the host copy (H2D + expansion; what `e2e` times) */
+int brq_pin_reads(brq_ctx* ctx);
+int brq_restage(brq_ctx* ctx);
 int brq_upload(brq_ctx* ctx);      /* host stream -> HBM (asynchronous on the ctx stream) */
 int brq_sync(brq_ctx* ctx);
 
@@ -133,6 +147,10 @@ int brq_error_count(brq_ctx* ctx, const char* covariates, int do_coverage, int d
  * without [2 tid] and with [2 tid + 1] a read start; Summary::preprocess_error_count[seq_id].no_pos_hash_per_position_pr is
  * without / (without + with), 1.0 when both are zero (error_count.cpp:217-229).  Shards add up. */
 int brq_preprocess_read_starts(brq_ctx* ctx, const uint64_t** counts, uint32_t* n_targets);
+/* A run sharded by reference range sizes the coverage histogram of every rank alike, so that the ranks can sum them: the
+ * deepest unique column of this context's range, and a floor for the histogram's depth axis (the maximum over the ranks). */
+int brq_max_coverage_depth(brq_ctx* ctx, uint64_t* depth);
+int brq_set_min_coverage_depth(brq_ctx* ctx, uint64_t depth);
 int brq_hist_device(brq_ctx* ctx, void** counts_u64, uint64_t* n_bins, void** coverage_u64, uint64_t* n_coverage);
 int brq_hist_download(brq_ctx* ctx, const uint64_t** counts, uint64_t* n_bins, const uint64_t** coverage,
                       uint64_t* coverage_stride, uint64_t* n_groups);

@@ -65,3 +65,35 @@ def test_two_rank_shards_allreduce_to_the_whole_genome_table(name, datasets, tmp
     cat_n = np.concatenate([x["n"][:int(x["n_base"])] for x in r])
     assert np.array_equal(cat_unique, tf["unique"][:nb]) and np.array_equal(cat_n, tf["n"][:nb])
     full.close()
+
+
+def test_record_balanced_shards_from_windowed_reads():
+    """bench.py's N > 1 input path: cut points with equal aligned bases (balance by record count), each rank
+    generating only the reads that can overlap its range.  Every shard staged from its windowed reads must be the shard
+    staged from the whole read set, array by array, and the shards must balance better than an even split by columns."""
+    d = dict(helpers.DATASETS["multi"])
+    d["n_gaps"] = 3
+    world = 3
+    ctx = bq.Context(device=-1)
+    spec = helpers.synth_spec(d)
+    bounds = ctx.synth_shard_bounds(spec, world)
+    assert bounds[0] == 0 and bounds[-1] == sum(d["contig_lens"]) and bounds == sorted(bounds)
+    records = []
+    for rank in range(world):
+        lo, hi = bounds[rank], bounds[rank + 1]
+        ctx.stage_synthetic(spec, read_file_sets=helpers.read_file_sets(d), shard_bounds=(lo, hi))
+        a = ctx.stream()
+        a = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in a.items()}
+        win = bq.SynthSpec(seed=d["seed"], read_sets=d["read_sets"], contig_lens=d["contig_lens"], contig_prefix=d["prefix"],
+                           n_polymorphic=d["n_polymorphic"], n_fixed=d["n_fixed"], n_gaps=d["n_gaps"], window=(lo, hi))
+        w = bq.Context(device=-1)
+        w.stage_synthetic(win, read_file_sets=helpers.read_file_sets(d), shard_bounds=(lo, hi))
+        b = w.stream()
+        assert b["n_reads"] < a["n_reads"]
+        for k in ("score_rec", "score_off", "score_cnt", "side_rec", "side_off", "hist_rec", "hist_off", "round_slot", "slot_ref",
+                  "ins_parent", "ins_count"):
+            assert np.array_equal(a[k], b[k]), k
+        records.append(int(a["n_score"]))
+        w.close()
+    ctx.close()
+    assert max(records) < 1.1 * (sum(records) / world), records

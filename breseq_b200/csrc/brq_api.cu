@@ -60,7 +60,7 @@ struct brq_ctx {
   ReadsDev d_reads;               // device staging: the aligned reads in HBM
   ExpandScratch xs;
   FlaggedRecordsHost flagged_records;  // device-built streams: the records of the flagged slots, for the host re-evaluation
-  DevBuf<uint32_t> d_flagged, d_worklist, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] spare
+  DevBuf<uint32_t> d_flagged, d_worklist, d_survivors, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] fit hand-out, [4] n_survivors, [5] screen hand-out
   DevBuf<uint8_t> d_score16;   // transfer form of the scoring stream (low halves)
   DevBuf<uint32_t> d_score_exc, d_score_exc_off;
   DevBuf<unsigned long long> d_counts, d_cov;
@@ -386,7 +386,7 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   c->d_cov.ensure(c->cov_stride * n_groups);
   CUDA_OK(cudaMemsetAsync(c->d_counts.p, 0, (size_t)lay.n_bins * 8, c->stream));
   CUDA_OK(cudaMemsetAsync(c->d_cov.p, 0, c->cov_stride * n_groups * 8, c->stream));
-  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 16, c->stream));
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 32, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
   if (do_errors) {
     // the reference ASSERTs when a counted covariate value exceeds the table (error_count.cpp:485-488); the stream's
@@ -564,11 +564,12 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   c->d_cols.ensure(n_slots);
   c->flagged_cap = (uint32_t)std::min<uint64_t>(n_slots, 1u << 26);
   c->d_flagged.ensure(c->flagged_cap);
-  CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 1, 0, 12, c->stream));  // the error word [0] may still hold pass 1's verdict
+  CUDA_OK(cudaMemsetAsync(c->d_scalars.p + 1, 0, 28, c->stream));  // the error word [0] may still hold pass 1's verdict
   CUDA_OK(cudaEventRecord(c->ev[5], c->stream));
   c->d_worklist.ensure(n_slots);
+  c->d_survivors.ensure(n_slots);
   launch_score_slots(c->ds.score_rec.p, c->ds.score_off.p, c->ds.score_cnt.p, c->ds.round_off.p, c->ds.side_rec.p, c->ds.side_off.p, reinterpret_cast<const uint2*>(c->ds.round_side.p), c->ds.slot_ref.p, c->ds.round_slot.p, c->st.n_rounds, n_slots, c->st.n_score, c->d_lut.p, c->d_tallyT.p, c->d_coldT.p, c->d_hotR.p, c->sp,
-                     c->d_cols.p, c->d_worklist.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
+                     c->d_cols.p, c->d_worklist.p, c->d_survivors.p, c->d_flagged.p, c->d_scalars.p, c->flagged_cap, c->st.geo.side_stride, c->stream, c->ev[7]);
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
@@ -740,8 +741,8 @@ brq_ctx* brq_create(const brq_config* cfg) {
       CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
       for (auto& e : c->ev) CUDA_OK(cudaEventCreate(&e));
       for (auto& e : c->user_ev) CUDA_OK(cudaEventCreate(&e));
-      c->d_scalars.ensure(4);
-      CUDA_OK(cudaMemset(c->d_scalars.p, 0, 16));
+      c->d_scalars.ensure(8);
+      CUDA_OK(cudaMemset(c->d_scalars.p, 0, 32));
     } catch (const std::exception& e) {
       c->error = std::string("no usable CUDA device: ") + e.what();
       c->device = -2;  // poisoned: every compute call reports the error
@@ -756,7 +757,7 @@ void brq_destroy(brq_ctx* c) {
   drop_stream(c);
   unpin_reads(c);
   if (c->device >= 0) {
-    c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
+    c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_survivors.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
     c->d_counts.release(); c->d_cov.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();

@@ -96,7 +96,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint32_t* side, const uint32_t* side_off, const uint2* round_side,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* survivors, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between);
 // Compacts the walk records to the columns the host's interval walk needs (WalkEvent), in no particular order.
 // walk: scratch of n_base records, filled here from the full results.  seg_first / seg_last / seg_prop: first slot, last slot and deletion propagation cutoff of every visited segment

@@ -538,9 +538,135 @@ __device__ __forceinline__ void load_ratios(const GroupCtx& g, uint32_t code, do
 
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------ screen
+// Most work-list slots of a deep run are noise: a handful of stray mismatches whose presence score is far below the cutoff
+// (1000x, polymorphism mode: one slot in six passes the tally's bound, one in eight thousand emits).  Two EM fits of a dozen
+// iterations each settle nothing the two likelihood bounds below do not settle in ONE pass over the slot's classes:
+//   L_full (the reference's iterate) <= max_f L(f) <= L(f~) + n log10 max_b D_b(f~),   D_b = (1/n) sum_i r_ib / s_i(f~)
+//        (Jensen: L(f) - L(f~) = sum_i log(s_i / s~_i) <= n log((1/n) sum_i s_i / s~_i) = n log sum_b f_b D_b), any f~ inside
+//        the simplex; f~ = the EM's own start, (0.5 + c_b) / (n + 2.5);
+//   L_null(v) (the reference's iterate) >= LL_null(g0(v)),   g0(v) = the null EM's start (0.5 + c_b) / (n + 2 - c_v), b != v
+//        (an EM step never lowers the likelihood, identify_mutations.cpp:3240-3318);
+// so  score(v) <= sum_i [log10 s~_i - log10 s_null,i(v)] + n log10 max_b D_b - log10(reference length)  for every v != ref
+// (the per-record maxima M_i cancel).  A slot whose bound is under the cutoff by a margin for all four candidates cannot emit
+// an RA row through the polymorphism test; it keeps the tally's result (no fit: variant_score NaN, like every slot the
+// tally's own bound settled).  The others go on to fit_kernel.  One warp per slot: the HOT records are counted into a dense
+// [5][n_sq] array (their device words name the cell; MATCH.ANY elects one writer per cell), the few cold records are terms
+// of their own; single-precision logarithms (the margin of 0.25 covers their rounding many times over).
+constexpr int SCREEN_TPB = 256;
+constexpr float SCREEN_MARGIN = 0.25f;
+__global__ void __launch_bounds__(SCREEN_TPB) screen_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ cnt,
+                                                             const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
+                                                             const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
+                                                             const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
+                                                             ScoreParams p, const ColumnOut* __restrict__ out, uint32_t* __restrict__ survivors,
+                                                             uint32_t* __restrict__ scalars) {
+  extern __shared__ __align__(16) unsigned char screen_sm[];
+  __shared__ uint8_t mapq_slot[256];
+  float* ratio = reinterpret_cast<float*>(screen_sm);                       // [n_hot][5], index ((st * Q + qual) * 5 + obs) like the fit's table
+  const uint32_t n_cells = 5u * p.t_nsq;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(ratio + (size_t)p.n_hot * 5) + (threadIdx.x >> 5) * n_cells;
+  const uint32_t n_work = scalars[2];
+  if ((uint64_t)blockIdx.x * (SCREEN_TPB / 32) >= n_work) return;
+  for (uint32_t i = threadIdx.x; i < p.n_hot * 5u; i += blockDim.x) ratio[i] = (float)hotR[i / 5u].r[i % 5u];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) mapq_slot[i] = p.mapq_slot[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31u;
+  const float log10_2 = 0.30102999566f;
+  for (;;) {
+    uint32_t w = 0;
+    if (lane == 0) w = atomicAdd(&scalars[5], 1u);
+    w = __shfl_sync(0xFFFFFFFFu, w, 0);
+    if (w >= n_work) break;
+    const uint32_t slot = worklist[w];
+    const uint32_t ref = slot_ref[slot], bits = out[slot].bits, best = bits & 7u;
+    const double consensus = out[slot].consensus_score;
+    // a consensus call against the reference emits whatever the presence score says; a slot without a reference base has
+    // no reference allele to hold: both need the fit
+    // (and a consensus score within rounding of its cutoff is re-checked on the host: the fit kernel flags it)
+    bool keep = ref >= 5u || (best != ref && consensus > -1e-6) || (bits & CO_RECHECK);
+    if (!keep) {
+      const uint64_t base = off[slot];
+      const uint32_t n_main = cnt[slot], s0 = side_off[slot], s1 = side_off[slot + 1];
+      for (uint32_t h = lane; h < n_cells; h += 32) hist[h] = 0u;
+      __syncwarp();
+      for (uint32_t j0 = 0; j0 < n_main; j0 += 128u) {  // four requests in flight per lane
+        uint32_t d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t j = j0 + (uint32_t)u * 32u + lane; d[u] = j < n_main ? __ldg(rec + score_index(base, j)) : DR_IDLE; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool hot = (d[u] >> DR_KIND_SHIFT) == 0u;
+          const uint32_t idx = hot ? ((d[u] >> DR_OBS_SHIFT) & 7u) * p.t_nsq + ((d[u] >> DR_SQ_SHIFT) & DR_SQ_MASK) : 0xFFFFFFFFu;
+          const uint32_t m = __match_any_sync(0xFFFFFFFFu, idx);
+          if (hot && lane == (uint32_t)(__ffs(m) - 1)) hist[idx] += (uint32_t)__popc(m);
+          __syncwarp();
+        }
+      }
+      // observations per base: the dense cells, then the cold records (side list: classic words)
+      uint32_t c[5] = {0, 0, 0, 0, 0};
+      for (uint32_t h = lane; h < n_cells; h += 32) { const uint32_t v = hist[h], o = h / p.t_nsq; c[0] += o == 0 ? v : 0; c[1] += o == 1 ? v : 0; c[2] += o == 2 ? v : 0; c[3] += o == 3 ? v : 0; c[4] += o == 4 ? v : 0; }
+      for (uint32_t e = s0 + lane; e < s1; e += 32) { const uint32_t sw = __ldg(side + e); if (!(sw & SIDE_BIG)) { const uint32_t o = sw & 7u; c[0] += o == 0; c[1] += o == 1; c[2] += o == 2; c[3] += o == 3; c[4] += o == 4; } }
+#pragma unroll
+      for (int b = 0; b < 5; ++b) c[b] = __reduce_add_sync(0xFFFFFFFFu, c[b]);
+      const uint32_t n = c[0] + c[1] + c[2] + c[3] + c[4];
+      if (n == 0) continue;   // (warp-uniform) nothing scores here: nothing to emit, the tally's result stands
+      float wgt[5], inv_null[5];
+#pragma unroll
+      for (int b = 0; b < 5; ++b) { wgt[b] = 0.5f + (float)c[b]; inv_null[b] = 1.0f / ((float)n + 2.0f - (float)c[b]); }
+      const float inv_tot = 1.0f / ((float)n + 2.5f);
+      float D[5] = {0, 0, 0, 0, 0}, T[5] = {0, 0, 0, 0, 0};
+      auto term = [&](const float* r, float count) {
+        const float A = wgt[0] * r[0] + wgt[1] * r[1] + wgt[2] * r[2] + wgt[3] * r[3] + wgt[4] * r[4];
+        const float s_full = A * inv_tot, k = count / s_full;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+          D[b] += k * r[b];
+          const float s_null = (A - wgt[b] * r[b]) * inv_null[b];   // zero or negative rounding: the logarithm says +inf / NaN and the slot goes on
+          T[b] += count * __log2f(s_full / s_null);
+        }
+      };
+      for (uint32_t h = lane; h < n_cells; h += 32) {
+        const uint32_t v = hist[h];
+        if (!v) continue;
+        const uint32_t obs = h / p.t_nsq, sq = h % p.t_nsq;
+        term(ratio + (((sq / p.t_nq) * p.max_qual + p.t_qlo + sq % p.t_nq) * 5u + obs) * 5u, (float)v);
+      }
+      for (uint32_t e = s0 + lane; e < s1; e += 32) {
+        const uint32_t sw = __ldg(side + e);
+        if (sw & SIDE_BIG) continue;
+        const double* rd = lut[cold_index(sw, 0u, p, mapq_slot)].r;
+        const float r[5] = {(float)rd[0], (float)rd[1], (float)rd[2], (float)rd[3], (float)rd[4]};
+        term(r, 1.0f);
+      }
+      float maxD = 0.0f;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { D[b] += __shfl_xor_sync(0xFFFFFFFFu, D[b], o); T[b] += __shfl_xor_sync(0xFFFFFFFFu, T[b], o); }
+        maxD = fmaxf(maxD, D[b]);
+      }
+      const float slack = (float)n * __log2f(fmaxf(maxD / (float)n, 1.0f)) * log10_2;
+      float bound = -3.0e38f;
+      bool bad = false;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        if ((uint32_t)b == ref) continue;
+        const float sc = T[b] * log10_2 + slack - (float)p.log10_ref_length;
+        bad = bad || !(sc == sc) || sc > 3.0e38f;
+        bound = fmaxf(bound, sc);
+      }
+      keep = bad || !(bound < (float)p.polymorphism_cutoff - SCREEN_MARGIN);
+    }
+    if (keep && lane == 0) survivors[atomicAdd(&scalars[4], 1u)] = slot;
+  }
+}
+
 __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restrict__ rec, const uint64_t* __restrict__ off, const uint32_t* __restrict__ cnt,
                                                           const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                           const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
+                                                          const uint32_t* __restrict__ n_work_ptr,
                                                           const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
                                                           ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ flagged,
                                                           uint32_t* __restrict__ scalars, uint32_t flagged_cap, uint32_t side_stride) {
@@ -549,7 +675,7 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
   // per warp, after the hot table: FIT_HASH class codes and FIT_HASH counts (the first 256 codes double as the
   // code cache of a shallow slot)
   uint32_t* warp_tab = reinterpret_cast<uint32_t*>(sm + (size_t)p.n_hot * 6) + (threadIdx.x / FIT_LANES) * (2u * FIT_HASH);
-  const uint32_t n_work = scalars[2];
+  const uint32_t n_work = *n_work_ptr;
   if ((uint64_t)blockIdx.x * (FIT_TPB / FIT_LANES) >= n_work) return;  // the work list is short: most CTAs have nothing to do
   {
     const double* src = reinterpret_cast<const double*>(hotR);
@@ -627,9 +753,65 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       // classes, and a record's responsibilities depend on its class alone, so an EM step over classes weighted by
       // their counts is the same sum with a tenth of the terms.  The warp counts the classes in a hash table in
       // shared memory, packs the table, and keeps up to FIT_REG classes per lane in registers.
+      // Counting without a hash when the stream has a shared table: a HOT record's device word names its cell
+      // (observation, class) directly, so the warp counts into a dense [5][n_sq] array, lanes that hold the same cell
+      // agreeing on one writer (MATCH.ANY: no atomics, no probe chains; thirty-two lanes adding to the same few cells with
+      // shared-memory atomics serialise, which is what made this phase twenty times the EM it feeds).  The few records
+      // outside the shared table (side list: another MAPQ, a quality outside the window) are classes of one record each.
+      const uint32_t n_cells = 5u * p.t_nsq;
+      bool overflow = false;
+      uint32_t n_classes = 0;
+      bool counted = false;
+      if (p.n_hot != 0u && n_cells <= FIT_HASH && side_stride == 1u) {
+        for (uint32_t h = g.sub; h < n_cells; h += FIT_LANES) my_count[h] = 0u;
+        __syncwarp(g.mask);
+        for (uint64_t j0 = 0; j0 < g.n_main; j0 += 4u * FIT_LANES) {  // four requests in flight per lane
+          uint32_t d[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint64_t j = j0 + (uint64_t)u * FIT_LANES + g.sub;
+            d[u] = j < g.n_main ? __ldg(g.rec + score_index(g.base, j)) : DR_IDLE;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool hot = (d[u] >> DR_KIND_SHIFT) == 0u;
+            const uint32_t idx = hot ? ((d[u] >> DR_OBS_SHIFT) & 7u) * p.t_nsq + ((d[u] >> DR_SQ_SHIFT) & DR_SQ_MASK) : 0xFFFFFFFFu;
+            const uint32_t m = __match_any_sync(g.mask, idx);
+            if (hot && g.sub == (uint32_t)(__ffs(m) - 1)) my_count[idx] += (uint32_t)__popc(m);
+            __syncwarp(g.mask);
+          }
+        }
+        // the occupied cells, packed to the front as (table code, count)
+        for (uint32_t h0 = 0; h0 < n_cells; h0 += FIT_LANES) {
+          const uint32_t h = h0 + g.sub, cnt = h < n_cells ? my_count[h] : 0u;
+          const uint32_t m = __ballot_sync(g.mask, cnt != 0u);
+          __syncwarp(g.mask);
+          if (cnt) {
+            const uint32_t at = n_classes + __popc(m & ((1u << g.sub) - 1u));
+            const uint32_t obs = h / p.t_nsq, sq = h % p.t_nsq;
+            my_cache[at] = (((sq / p.t_nq) * p.max_qual + p.t_qlo + sq % p.t_nq) * 5u + obs) * 48u;
+            my_count[at] = cnt;
+          }
+          n_classes += __popc(m);
+          __syncwarp(g.mask);
+        }
+        // side-list entries (classic words of the cold records; SIDE_BIG / pad entries do not score)
+        const uint32_t side_end = g.side_beg + (uint32_t)(g.end - g.n_main);
+        for (uint32_t e0 = g.side_beg; e0 < side_end; e0 += FIT_LANES) {
+          const uint32_t e = e0 + g.sub, w = e < side_end ? __ldg(g.side + e) : SIDE_PAD;
+          const bool valid = !(w & SIDE_BIG);
+          const uint32_t m = __ballot_sync(g.mask, valid);
+          const uint32_t at = n_classes + __popc(m & ((1u << g.sub) - 1u));
+          if (valid && at < FIT_HASH) { my_cache[at] = CODE_COLD | cold_index(w, 0u, p, mapq_slot); my_count[at] = 1u; }
+          n_classes += __popc(m);
+        }
+        __syncwarp(g.mask);
+        counted = n_classes <= (uint32_t)(FIT_LANES * FIT_REG);
+      }
+      if (!counted) {
+      n_classes = 0;
       for (uint32_t h = g.sub; h < FIT_HASH; h += FIT_LANES) { my_cache[h] = CODE_NONE; my_count[h] = 0u; }
       __syncwarp(g.mask);
-      bool overflow = false;
       for (uint64_t i = g.beg + g.sub; i < g.end; i += FIT_LANES) {
         const uint32_t code = code_of(g, classic_at(g, i));
         if (code == CODE_NONE) continue;
@@ -643,7 +825,6 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
       }
       __syncwarp(g.mask);
       // pack the occupied slots to the front (in place: a slot's new position is never above its old one)
-      uint32_t n_classes = 0;
       for (uint32_t h0 = 0; h0 < FIT_HASH; h0 += FIT_LANES) {
         const uint32_t code = my_cache[h0 + g.sub], cnt = my_count[h0 + g.sub];
         const uint32_t m = __ballot_sync(g.mask, code != CODE_NONE);
@@ -654,6 +835,7 @@ __global__ void __launch_bounds__(FIT_TPB, 1) fit_kernel(const uint32_t* __restr
         }
         n_classes += __popc(m);
         __syncwarp(g.mask);
+      }
       }
       by_class = !__any_sync(g.mask, overflow) && n_classes <= (uint32_t)(FIT_LANES * FIT_REG);
       k_max = by_class ? (n_classes + FIT_LANES - 1) / FIT_LANES : 0u;
@@ -828,7 +1010,7 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
                         const uint32_t* side, const uint32_t* side_off, const uint2* round_side,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,
                         const ClassTerms* lut, const double* tallyT, const HotTerms* coldT, const HotRatios* hotR, const ScoreParams& p,
-                        ColumnOut* out, uint32_t* worklist, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
+                        ColumnOut* out, uint32_t* worklist, uint32_t* survivors, uint32_t* flagged, uint32_t* scalars, uint32_t flagged_cap,
                         uint32_t side_stride, cudaStream_t s, cudaEvent_t between) {
   if (!n_slots) return;
   const int kSMs = 148;
@@ -845,8 +1027,19 @@ void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t
   cudaFuncSetAttribute(tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tally);
   tally_kernel<<<blocks, warps * 32, smem_tally, s>>>(rec, round_off, side, round_side, round_slot, n_rounds, tallyT, coldT, p, out, worklist, flagged, scalars, flagged_cap, hist_block, side_stride, pf_vec);
   if (between) cudaEventRecord(between, s);
+  // the screen (one pass of likelihood bounds per work-list slot) in front of the fit, where the stream has a shared table
+  static const bool no_screen = getenv("BRQ_NO_SCREEN") != nullptr;
+  const size_t smem_screen = (size_t)p.n_hot * 5 * 4 + (size_t)(SCREEN_TPB / 32) * 5 * p.t_nsq * 4 + 16;
+  const bool screen = !no_screen && !p.fit_all && p.n_hot != 0 && side_stride == 1 && smem_screen <= 200 * 1024;
+  if (screen) {
+    cudaFuncSetAttribute(screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_screen);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem_screen));
+    screen_kernel<<<kSMs * per_sm, SCREEN_TPB, smem_screen, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, survivors, scalars);
+    note_launches(1);
+  }
   cudaFuncSetAttribute(fit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fit);
-  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, worklist, lut, hotR, p, out, flagged, scalars, flagged_cap, side_stride);
+  fit_kernel<<<kSMs * 3, FIT_TPB, smem_fit, s>>>(rec, off, cnt, side, side_off, slot_ref, screen ? survivors : worklist, screen ? scalars + 4 : scalars + 2,
+                                                 lut, hotR, p, out, flagged, scalars, flagged_cap, side_stride);
   note_launches(2);
 }
 

@@ -39,7 +39,7 @@ class _StageOptions(C.Structure):
                 ("shard_count", C.c_uint32), ("base_quality_cutoff", C.c_uint32),
                 ("preprocess_stage", C.c_uint32), ("unmatched_end_minimum_read_length", C.c_uint32),
                 ("require_match_fraction", C.c_double), ("shard_lo", C.c_uint64), ("shard_hi", C.c_uint64),
-                ("staging", C.c_uint32), ("reserved", C.c_uint32)]
+                ("staging", C.c_uint32), ("reserved", C.c_uint32), ("user_evidence_gd", C.c_char_p)]
 
 
 class _SynthReadSet(C.Structure):
@@ -88,6 +88,7 @@ assert COLUMN_DTYPE.itemsize == 96
 
 CO_BASE_PREDICTED, CO_UNIQUE_ONLY, CO_EMIT, CO_RECHECK, CO_FIT = 1 << 12, 1 << 13, 1 << 14, 1 << 15, 1 << 24
 SCORE_FIT_ALL_COLUMNS = 1
+SCORE_POLYMORPHISM_PREDICTION = 2
 
 _lib = None
 
@@ -208,7 +209,7 @@ class SynthSpec:
 
 def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_base_repeat=False, use_read_pos=False,
                    shard=(0, 1), base_quality_cutoff=3, preprocess_stage=False, unmatched_end_minimum_read_length=50,
-                   require_match_fraction=0.9, shard_bounds=None, staging="auto"):
+                   require_match_fraction=0.9, shard_bounds=None, staging="auto", user_evidence_gd=None):
     keep = []
     o = _StageOptions()
     if seq_ids:
@@ -236,6 +237,10 @@ def _stage_options(seq_ids=None, read_file_sets=None, coverage_groups=None, use_
     if shard_bounds is not None:
         o.shard_lo, o.shard_hi = shard_bounds
     o.staging = {"auto": 0, "host": 1, "device": 2}[staging]
+    if user_evidence_gd:
+        path = _b(user_evidence_gd)
+        keep.append(path)
+        o.user_evidence_gd = path
     return o, keep
 
 
@@ -470,9 +475,10 @@ class Context:
     # ---- pass 2
     @staticmethod
     def score_params(mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision_decimal=1e-6, precision_places=8,
-                     base_quality_cutoff=3, total_reference_length=0, fit_all_columns=False):
+                     base_quality_cutoff=3, total_reference_length=0, fit_all_columns=False, polymorphism_prediction=False):
         return _ScoreParams(mutation_cutoff, polymorphism_cutoff, precision_decimal, precision_places, base_quality_cutoff,
-                            total_reference_length, SCORE_FIT_ALL_COLUMNS if fit_all_columns else 0, 0)
+                            total_reference_length, (SCORE_FIT_ALL_COLUMNS if fit_all_columns else 0) |
+                            (SCORE_POLYMORPHISM_PREDICTION if polymorphism_prediction else 0), 0)
 
     def score_columns(self, params=None):
         p = params or self.score_params()
@@ -603,7 +609,7 @@ def identify_mutations(bam, fasta, gd_file, deletion_propagation_cutoff, deletio
                        print_per_position_file=False, *, error_rates_file_name, base_quality_cutoff=3,
                        skip_missing_coverage_prediction=False, call_mutations_seq_ids=None, read_file_sets=None,
                        total_reference_length=0, device=0, ctx=None, per_position_file_name=None,
-                       coverage_tsv_pattern=None):
+                       coverage_tsv_pattern=None, user_evidence_genome_diff_file_name=None, polymorphism_prediction=False):
     """``breseq::identify_mutations()`` (identify_mutations.cpp:48-88): writes ``ra_mc_evidence.gd`` and, like the
     reference, the per-position debug file when ``print_per_position_file`` (Settings::
     mutation_identification_per_position_file_name = ``per_position_file_name``) and ``<seq>.coverage.tsv`` when
@@ -613,12 +619,14 @@ def identify_mutations(bam, fasta, gd_file, deletion_propagation_cutoff, deletio
     own = ctx is None
     ctx = ctx or Context(device)
     try:
-        o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets)
+        o, keep = _stage_options(seq_ids=call_mutations_seq_ids, read_file_sets=read_file_sets, base_quality_cutoff=base_quality_cutoff,
+                                 user_evidence_gd=user_evidence_genome_diff_file_name)
         n = len(deletion_propagation_cutoff)
         prop = (C.c_double * n)(*deletion_propagation_cutoff)
         seed = (C.c_double * n)(*deletion_seed_cutoff)
         p = Context.score_params(mutation_cutoff, polymorphism_cutoff, polymorphism_precision_decimal,
-                                 polymorphism_precision_places, base_quality_cutoff, total_reference_length)
+                                 polymorphism_precision_places, base_quality_cutoff, total_reference_length,
+                                 polymorphism_prediction=polymorphism_prediction)
         ctx._check(ctx.lib.brq_run_identify_mutations(ctx.h, _b(bam), _b(fasta), _b(error_rates_file_name), _b(gd_file),
                                                       prop, seed, n, C.byref(p), int(skip_missing_coverage_prediction),
                                                       C.byref(o)))

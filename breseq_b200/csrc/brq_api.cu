@@ -181,6 +181,7 @@ void apply_stage_options(brq_ctx* c, const brq_stage_options* o) {
   s.shard_count = o->shard_count ? o->shard_count : 1;
   s.shard_lo = o->shard_lo; s.shard_hi = o->shard_hi; s.shard_explicit = o->shard_hi > o->shard_lo;
   s.staging_mode = (int)o->staging;
+  if (o->user_evidence_gd && *o->user_evidence_gd) s.user_evidence = read_user_evidence_gd(o->user_evidence_gd);
 }
 
 void drop_stream(brq_ctx* c) {
@@ -208,6 +209,13 @@ void do_stage(brq_ctx* c) {
   if (device_staging(c)) {
     static const bool times = getenv("BRQ_STAGE_TIMES") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
+    if (!c->d_reads.ring.parallel_for) {
+      if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+      WorkerPool* pool = c->pool.get();
+      c->d_reads.ring.parallel_for = [pool](size_t n_parts, const std::function<void(size_t)>& body) {
+        pool->run([&](size_t part, size_t n_workers) { for (size_t p = part; p < n_parts; p += n_workers) body(p); });
+      };
+    }
     c->d_reads.upload(c->reads, c->stream);
     if (times) { CUDA_OK(cudaStreamSynchronize(c->stream)); fprintf(stderr, "stage (device): upload %.1f ms (%.1f MB)\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), c->d_reads.bytes / 1e6); }
     const auto t1 = std::chrono::steady_clock::now();
@@ -315,7 +323,10 @@ bool same_stage_config(const StageConfig& a, const StageConfig& b) {
          a.want_hist == b.want_hist && a.want_score == b.want_score && a.preprocess_stage == b.preprocess_stage &&
          a.unmatched_end_minimum_read_length == b.unmatched_end_minimum_read_length && a.unmatched_end_length_factor == b.unmatched_end_length_factor &&
          a.shard_rank == b.shard_rank && a.shard_count == b.shard_count && a.shard_lo == b.shard_lo && a.shard_hi == b.shard_hi &&
-         a.shard_explicit == b.shard_explicit && a.staging_mode == b.staging_mode;
+         a.shard_explicit == b.shard_explicit && a.staging_mode == b.staging_mode && a.user_skip_cutoff == b.user_skip_cutoff &&
+         a.user_evidence.size() == b.user_evidence.size() &&
+         std::equal(a.user_evidence.begin(), a.user_evidence.end(), b.user_evidence.begin(), [](const UserRa& x, const UserRa& y) {
+           return x.seq_id == y.seq_id && x.position == y.position && x.insert_position == y.insert_position && x.ref_base == y.ref_base && x.new_base == y.new_base; });
 }
 
 void synth_into(brq_ctx* c, const brq_synth_spec* sp) {
@@ -605,7 +616,33 @@ void download_walk(brq_ctx* c, const double* prop, uint32_t n_targets) {
   CUDA_OK(cudaMemcpyAsync(scal, c->d_scalars.p, 8, cudaMemcpyDeviceToHost, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
   if (scal[1] > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
-  const uint32_t n_flagged = scal[1];
+  uint32_t n_flagged = scal[1];
+  if (!st.user_columns.empty()) {
+    // user evidence: the slots the list meets are re-evaluated on the host whatever the kernels decided (their rows need the
+    // full fit, identify_mutations.cpp:1914-2019): they join the flagged list here
+    std::vector<uint32_t> have(n_flagged), extra;
+    if (n_flagged) CUDA_OK(cudaMemcpy(have.data(), c->d_flagged.p, (size_t)n_flagged * 4, cudaMemcpyDeviceToHost));
+    std::sort(have.begin(), have.end());
+    for (const UserColumn& uc : st.user_columns) {
+      if (uc.slot == ~0ull) continue;
+      for (const auto& lv : uc.consumed) {
+        uint64_t slot = uc.slot;
+        if (lv.first > 0) {
+          slot = ~0ull;
+          const size_t j0 = std::lower_bound(st.ins_parent.begin(), st.ins_parent.end(), uc.slot) - st.ins_parent.begin();
+          for (size_t j = j0; j < st.ins_parent.size() && st.ins_parent[j] == uc.slot; ++j) if (st.ins_count[j] == lv.first) slot = st.n_base + j;
+          if (slot == ~0ull) continue;
+        }
+        if (!std::binary_search(have.begin(), have.end(), (uint32_t)slot) && std::find(extra.begin(), extra.end(), (uint32_t)slot) == extra.end()) extra.push_back((uint32_t)slot);
+      }
+    }
+    if (!extra.empty()) {
+      if (n_flagged + extra.size() > c->flagged_cap) throw std::runtime_error("flagged-slot list overflow");
+      CUDA_OK(cudaMemcpy(c->d_flagged.p + n_flagged, extra.data(), extra.size() * 4, cudaMemcpyHostToDevice));
+      n_flagged += (uint32_t)extra.size();
+      CUDA_OK(cudaMemcpy(c->d_scalars.p + 1, &n_flagged, 4, cudaMemcpyHostToDevice));
+    }
+  }
   // segments of the visit order with their cutoffs
   std::vector<uint32_t> first, last;
   std::vector<double> sp;
@@ -675,6 +712,7 @@ EvidenceCounts evidence(brq_ctx* c, const char* gd_file, const double* prop, con
   ep.base_quality_cutoff = c->last_params.base_quality_cutoff;
   ep.log10_ref_length = c->sp.log10_ref_length;
   ep.skip_missing_coverage_prediction = skip_mc != 0;
+  ep.polymorphism_prediction = (c->last_params.flags & BRQ_SCORE_POLYMORPHISM_PREDICTION) != 0;
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(seed, seed + n_targets);
   ensure_host_lut(c);
@@ -700,6 +738,7 @@ void evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets) {
   ep.base_quality_cutoff = c->last_params.base_quality_cutoff;
   ep.log10_ref_length = c->sp.log10_ref_length;
   ep.skip_missing_coverage_prediction = false;
+  ep.polymorphism_prediction = (c->last_params.flags & BRQ_SCORE_POLYMORPHISM_PREDICTION) != 0;
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(n_targets, 0.0);
   ensure_host_lut(c);
@@ -840,10 +879,18 @@ int brq_pin_reads(brq_ctx* c) {
   return guarded(c, [&] {
     c->need_device();
     if (!c->pinned_reads.empty()) return;
+    static const bool verbose = getenv("BRQ_STAGE_TIMES") != nullptr;
     auto pin = [&](auto& vec) {
       if (vec.empty()) return;
-      if (cudaHostRegister(vec.data(), vec.size() * sizeof(vec[0]), cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return; }  // (stays pageable)
-      c->pinned_reads.push_back(vec.data());
+      // in pieces: a registration the system refuses (locked-memory limits) leaves only its own piece pageable
+      const size_t bytes = vec.size() * sizeof(vec[0]), piece = (size_t)1 << 30;
+      char* base = reinterpret_cast<char*>(vec.data());
+      for (size_t at = 0; at < bytes; at += piece) {
+        const size_t len = std::min(piece, bytes - at);
+        const cudaError_t e = cudaHostRegister(base + at, len, cudaHostRegisterDefault);
+        if (e != cudaSuccess) { cudaGetLastError(); if (verbose) fprintf(stderr, "pin_reads: %zu bytes stay pageable (%s)\n", len, cudaGetErrorString(e)); continue; }
+        c->pinned_reads.push_back(base + at);
+      }
     };
     ReadBatch& R = c->reads;
     pin(R.tid); pin(R.pos); pin(R.flag); pin(R.mapq); pin(R.rg); pin(R.x1); pin(R.xl); pin(R.xr); pin(R.l_seq); pin(R.seq_off);
@@ -1024,6 +1071,7 @@ int brq_run_identify_mutations(brq_ctx* c, const char* bam, const char* fasta, c
     c->stage_cfg.use_read_pos = c->stage_cfg.use_read_pos || spec.used[COV_READ_POS];
     c->stage_cfg.use_base_repeat = c->stage_cfg.use_base_repeat || spec.used[COV_BASE_REPEAT];
     if (p) c->stage_cfg.base_quality_cutoff = p->base_quality_cutoff;   // the score parameters carry Settings::base_quality_cutoff
+    if (!c->stage_cfg.user_evidence.empty()) c->stage_cfg.user_skip_cutoff.assign(prop, prop + n_targets);  // skipped targets never look at the user list
     // the stream error_count() staged from the same BAM with the same options is still there: no second staging
     if (fresh || !c->staged || !same_stage_config(before, c->stage_cfg)) { drop_stream(c); do_stage(c); }
     c->host_table_pending = false;

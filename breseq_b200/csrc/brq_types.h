@@ -219,6 +219,18 @@ inline uint32_t hist16_pack(uint32_t lo) {
   return hist16_expand(r) == lo ? r : 0x10000u;
 }
 
+// User evidence (Settings::user_evidence_genome_diff_file_name, identify_mutations.cpp:879, 1013-1020): RA rows the user wants
+// reported whatever the data says, stripped to their specification and sorted like cGenomeDiff::sort().
+struct UserRa { std::string seq_id; uint32_t position = 0, insert_position = 0; std::string ref_base, new_base; };
+// A column where the pileup meets the list: the insert sub-columns the list forces there (identify_mutations.cpp:1346-1355)
+// and the entries it consumes, by insert level (:1914-2019).
+struct UserColumn {
+  int32_t tid = 0; uint32_t pos1 = 0;          // target and 1-based position
+  uint64_t slot = 0;                            // base slot, ~0 when the column is outside this shard
+  uint32_t force_max = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> consumed;  // (insert level, index into the list), in list order
+};
+
 // Columns [lo, hi) (0-based) of BAM target `tid` occupy base slots slot0 .. slot0 + (hi - lo).
 struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
 
@@ -226,6 +238,7 @@ struct Segment { int32_t tid, lo, hi; uint64_t slot0; };
 struct PileupStream {
   // geometry
   std::vector<Segment> segments;       // visited targets in visit (alphabetical seq id) order, clipped to this shard
+  std::vector<Segment> visit_targets;  // every visited target, whole (slot0 = its first column in the concatenated visit order)
   uint64_t n_base = 0;                 // base columns (sum of segment lengths)
   uint64_t n_ins = 0;                  // insert sub-column slots, appended after the base slots
   std::vector<uint64_t> ins_parent;    // [n_ins] base slot of each sub-column
@@ -262,6 +275,8 @@ struct PileupStream {
   uint64_t qual_count[128] = {0};      // scoring records per quality value
   uint64_t max_hist_depth = 0;         // deepest unique, non-deleted column (sizes the coverage histogram)
   uint32_t n_groups = 1;               // coverage groups present
+  std::vector<UserRa> user_list;            // the user evidence the stream was staged with
+  std::vector<UserColumn> user_columns;     // ... and where the pileup meets it, in visit order
   std::vector<uint64_t> read_start_counts;  // preprocess stage: [BAM tid][0 = without, 1 = with a read start] position-strand combinations of this shard
   uint32_t max_qual_seen = 0;
   uint32_t max_hist_qual = 0, max_hist_rpos = 0;  // largest quality / read position in a valid histogram observation

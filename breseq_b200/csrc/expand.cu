@@ -33,13 +33,52 @@ int expand_launch_count() { return g_expand_launches; }
 static inline void launched(int n = 1) { g_expand_launches += n; note_launches(n); }
 
 // ------------------------------------------------------------------------------------------ buffers
+void UploadRing::copy(void* dst_device, const void* src_host, size_t bytes, cudaStream_t s) {
+  if (!bytes) return;
+  cudaPointerAttributes attr;
+  const bool locked = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (locked || bytes < ((size_t)1 << 20)) {  // page-locked already (brq_pin_reads), or too small to matter
+    CUDA_OK(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, s));
+    return;
+  }
+  for (size_t at = 0; at < bytes; at += SLOT_BYTES) {
+    const size_t len = std::min(SLOT_BYTES, bytes - at);
+    const int k = next;
+    next = (next + 1) % SLOTS;
+    if (!slot[k]) {
+      CUDA_OK(cudaHostAlloc(&slot[k], SLOT_BYTES, cudaHostAllocDefault));
+      CUDA_OK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    } else {
+      CUDA_OK(cudaEventSynchronize(done[k]));   // the copy that last used this slot has left it
+    }
+    const char* src = static_cast<const char*>(src_host) + at;
+    char* stage = static_cast<char*>(slot[k]);
+    if (parallel_for) {
+      const size_t parts = 8, step = (len + parts - 1) / parts;
+      parallel_for(parts, [&](size_t p) { const size_t a = p * step; if (a < len) memcpy(stage + a, src + a, std::min(step, len - a)); });
+    } else {
+      memcpy(stage, src, len);
+    }
+    CUDA_OK(cudaMemcpyAsync(static_cast<char*>(dst_device) + at, stage, len, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaEventRecord(done[k], s));
+  }
+}
+void UploadRing::release() {
+  for (int k = 0; k < SLOTS; ++k) {
+    if (slot[k]) cudaFreeHost(slot[k]);
+    if (done[k]) cudaEventDestroy(done[k]);
+    slot[k] = nullptr; done[k] = nullptr;
+  }
+}
+
 void ReadsDev::upload(const ReadBatch& R, cudaStream_t s) {
   n = R.size();
   bytes = 0;
   auto up = [&](auto& buf, const auto& vec) {
     using T = typename std::remove_reference<decltype(*buf.p)>::type;
     buf.ensure(vec.size() + 16);
-    if (!vec.empty()) CUDA_OK(cudaMemcpyAsync(buf.p, vec.data(), vec.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    ring.copy(buf.p, vec.data(), vec.size() * sizeof(T), s);
     bytes += vec.size() * sizeof(T);
   };
   up(tid, R.tid); up(pos, R.pos); up(flag, R.flag); up(mapq, R.mapq); up(rg, R.rg); up(x1, R.x1); up(xl, R.xl); up(xr, R.xr);
@@ -56,6 +95,7 @@ RawReads ReadsDev::view() const {
 void ReadsDev::release() {
   tid.release(); pos.release(); xl.release(); xr.release(); flag.release(); mapq.release(); rg.release(); bases.release(); quals.release();
   x1.release(); l_seq.release(); n_cigar.release(); cigars.release(); seq_off.release(); cigar_off.release();
+  ring.release();
   n = bytes = 0;
 }
 void StreamDev::release() {
@@ -489,6 +529,32 @@ void expand_on_device(const BamHeader& hdr, const RefSet& ref, const ReadBatch& 
   if (n_reads && n_visit) { ins_support_kernel<<<blocks_for(n_reads), 256, 0, s>>>(a); launched(); }
   sub_k_kernel<<<blocks_for(n_base), 256, 0, s>>>(X.ins_mask.p, n_base, X.sub_k.p);
   launched();
+  if (!cfg.user_evidence.empty()) {
+    // user evidence: the columns where the pileup meets the list and the insert levels it forces there (staging.cpp does the
+    // same with its host masks): a handful of columns, each read back and patched on its own
+    CUDA_OK(cudaStreamSynchronize(s));
+    st.user_list = cfg.user_evidence;
+    auto slot_of = [&](size_t v, uint32_t pos1) -> uint64_t {
+      for (const Segment& sg : st.segments)
+        if (sg.tid == st.visit_targets[v].tid && (int32_t)pos1 - 1 >= sg.lo && (int32_t)pos1 - 1 < sg.hi) return sg.slot0 + (uint64_t)((int32_t)pos1 - 1 - sg.lo);
+      return ~0ull;
+    };
+    auto mask_at = [&](uint64_t slot) { uint64_t m = 0; CUDA_OK(cudaMemcpy(&m, X.ins_mask.p + slot, 8, cudaMemcpyDeviceToHost)); return m; };
+    st.user_columns = plan_user_evidence(cfg.user_evidence, hdr, st.visit_targets, cfg.user_skip_cutoff, [&](size_t v, uint32_t pos1, uint32_t force_max) {
+      const uint64_t slot = slot_of(v, pos1);
+      return slot == ~0ull ? force_max : insert_levels(mask_at(slot), force_max);
+    });
+    for (UserColumn& c : st.user_columns) {
+      size_t v = 0;
+      while (v < st.visit_targets.size() && st.visit_targets[v].tid != c.tid) ++v;
+      c.slot = slot_of(v, c.pos1);
+      if (c.slot == ~0ull || !c.force_max) continue;
+      uint8_t have = 0;
+      CUDA_OK(cudaMemcpy(&have, X.sub_k.p + c.slot, 1, cudaMemcpyDeviceToHost));
+      const uint8_t K = (uint8_t)std::max<uint32_t>(have, insert_levels(mask_at(c.slot), c.force_max));
+      CUDA_OK(cudaMemcpy(X.sub_k.p + c.slot, &K, 1, cudaMemcpyHostToDevice));
+    }
+  }
   exclusive_scan<FU8, uint32_t, true>(FU8{X.sub_k.p}, n_base, X.sub_first.p, X.scan_tmp, d_tot + 0, s);
 
   phase_done("per-read kernels, sub-columns");

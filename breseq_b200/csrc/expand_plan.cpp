@@ -36,7 +36,6 @@ void make_expand_plan(const BamHeader& hdr, const RefSet& ref, const std::vector
     const uint32_t g = cfg.coverage_group_of_tid.empty() ? (uint32_t)sg.tid : cfg.coverage_group_of_tid[(size_t)sg.tid];
     if (g > 255) throw std::runtime_error("more than 256 coverage groups are not supported");
     e.group = g;
-    if (g + 1 > st.n_groups) st.n_groups = g + 1;
     const std::string& rs = *refseq[v];
     const size_t take = std::min<size_t>((size_t)(sg.hi - sg.lo) + 1, rs.size() - (size_t)sg.lo);
     memcpy(&plan.refbytes[ref_off], rs.data() + sg.lo, take);

@@ -718,7 +718,7 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
   std::sort(events.begin(), events.end(), [](const WalkEvent& a, const WalkEvent& b) { return a.slot < b.slot; });
 
   // ---- re-evaluate flagged slots in arrival order
-  struct Reval { bool base_predicted; bool emit; GdRow row; };
+  struct Reval { bool base_predicted; bool emit; GdRow row; std::vector<GdRow> user_rows; };
   std::vector<Reval> reval(flagged.size());  // aligned with `flagged`
   // first the records of every flagged slot (the class table fills in on demand: not thread-safe), then the fits, the
   // profile-likelihood bounds and the bias tests of the slots side by side on a few threads: they are independent
@@ -744,6 +744,21 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
                              fr->side + (size_t)fr->side_off[e] * st.geo.side_stride, take);
     } else {
       for_each_classic(st, slot, take);
+    }
+  }
+  // user evidence: which list entries meet which slot (the column itself for insert level 0, else its sub-column slot)
+  std::map<uint64_t, std::vector<uint32_t>> user_at;
+  for (const UserColumn& uc : st.user_columns) {
+    if (uc.slot == ~0ull) continue;
+    for (const auto& lv : uc.consumed) {
+      uint64_t slot = uc.slot;
+      if (lv.first > 0) {
+        const size_t j0 = std::lower_bound(st.ins_parent.begin(), st.ins_parent.end(), uc.slot) - st.ins_parent.begin();
+        slot = ~0ull;
+        for (size_t j = j0; j < st.ins_parent.size() && st.ins_parent[j] == uc.slot; ++j) if (st.ins_count[j] == lv.first) slot = st.n_base + j;
+        if (slot == ~0ull) continue;
+      }
+      user_at[slot].push_back(lv.second);
     }
   }
   std::vector<uint8_t> overturned(flagged.size(), 0);
@@ -830,6 +845,70 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
       for (int b = 0; b < 5; ++b) { tot_top += s.count[b][1]; tot_bot += s.count[b][0]; }
       row.kv["total_cov"] = std::to_string(tot_top) + "/" + std::to_string(tot_bot);
     }
+    const auto ua = user_at.find(slot);
+    if (ua != user_at.end()) {  // identify_mutations.cpp:1914-2019
+      const uint32_t n = s.n();
+      auto reported = [&](uint8_t b) { return (n == 0 || b >= 5) ? 0.0 : (s.f[b] < 0.5 / (double)n ? 0.0 : s.f[b]); };
+      const uint64_t parent = slot < st.n_base ? slot : st.ins_parent[slot - st.n_base];
+      const uint32_t level = slot < st.n_base ? 0u : st.ins_count[slot - st.n_base];
+      (void)parent;
+      for (uint32_t ei : ua->second) {
+        const UserRa& e = st.user_list[ei];
+        // the row the data already produced (same specification: cDiffEntry::compare): it only gains the mark
+        if (s.emit && rv.row.seq_id == e.seq_id && rv.row.a == e.position && rv.row.b == e.insert_position && rv.row.ref_base == e.ref_base &&
+            rv.row.new_base == e.new_base) { rv.row.kv["user_defined"] = "1"; continue; }
+        GdRow u;
+        u.type = 0; u.seq_id = e.seq_id; u.a = e.position; u.b = level; u.ref_base = e.ref_base; u.new_base = e.new_base;
+        u.kv["user_defined"] = "1";
+        const uint8_t uref = e.ref_base.size() == 1 ? char_to_index(e.ref_base[0]) : 255, uvar = e.new_base.size() == 1 ? char_to_index(e.new_base[0]) : 255;
+        if (uref > 5 || uvar > 5) throw std::runtime_error("Unrecognized base char in user evidence: " + e.ref_base + " " + e.new_base);
+        double score = std::numeric_limits<double>::quiet_NaN(), f_var = 0.0;
+        if (uvar < 5) {
+          if (n) { const Fit null_fit = fit_ordered(s, 0x1F & ~(1u << uvar), ep.precision_decimal); score = (s.log10_likelihood - null_fit.ll) - ep.log10_ref_length; }
+          f_var = reported(uvar);
+        }
+        const double f_ref = reported(uref);
+        const bool var_major = f_var > f_ref;
+        const uint8_t mj = var_major ? uvar : uref, mn = var_major ? uref : uvar;
+        u.kv["major_base"] = var_major ? e.new_base : e.ref_base;
+        u.kv["minor_base"] = var_major ? e.ref_base : e.new_base;
+        u.kv["major_frequency"] = format_double(var_major ? f_var : f_ref, ep.precision_places, true);
+        u.kv["frequency"] = format_double(f_var, ep.precision_places, true);
+        std::string spectrum;
+        for (uint8_t b = 0; b < 5; ++b) {
+          const double freq = reported(b);
+          if (freq <= 0.0) continue;
+          if (!spectrum.empty()) spectrum += ",";
+          spectrum += std::string(1, index_to_char(b)) + ":" + format_double(freq, ep.precision_places, true);
+        }
+        u.kv["allele_frequencies"] = spectrum;
+        double lower = 0.0, upper = 1.0;
+        if (n > 0 && uvar < 5) {
+          const double drop = 0.587566, tol = ep.precision_decimal, f_hat = s.f[uvar];
+          const double target = profile_ll(s, uvar, f_hat, tol) - drop;
+          if (!(profile_ll(s, uvar, 0.0, tol) >= target)) {
+            double lo = 0.0, hi = f_hat;
+            for (int i = 0; i < 40 && (hi - lo) > tol; ++i) { const double mid = 0.5 * (lo + hi); if (profile_ll(s, uvar, mid, tol) >= target) hi = mid; else lo = mid; }
+            lower = hi;
+          }
+          if (!(profile_ll(s, uvar, 1.0, tol) >= target)) {
+            double lo = f_hat, hi = 1.0;
+            for (int i = 0; i < 40 && (hi - lo) > tol; ++i) { const double mid = 0.5 * (lo + hi); if (profile_ll(s, uvar, mid, tol) >= target) lo = mid; else hi = mid; }
+            upper = lo;
+          }
+        }
+        u.kv["frequency_lower"] = format_double(lower, ep.precision_places, true);
+        u.kv["frequency_upper"] = format_double(upper, ep.precision_places, true);
+        u.kv["prediction"] = ep.polymorphism_prediction ? "polymorphism" : (f_var > 0.5 ? "consensus" : "polymorphism");
+        u.kv["score"] = format_double(score, 1, false);
+        auto cov = [&](uint8_t b) { return std::to_string(s.count[b][1]) + "/" + std::to_string(s.count[b][0]); };
+        u.kv["ref_cov"] = cov(uref); u.kv["new_cov"] = cov(uvar); u.kv["major_cov"] = cov(mj); u.kv["minor_cov"] = cov(mn);
+        uint32_t tot_top = 0, tot_bot = 0;
+        for (int b = 0; b < 5; ++b) { tot_top += s.count[b][1]; tot_bot += s.count[b][0]; }
+        u.kv["total_cov"] = std::to_string(tot_top) + "/" + std::to_string(tot_bot);
+        rv.user_rows.push_back(std::move(u));
+      }
+    }
     reval[fi] = std::move(rv);
   };
   {
@@ -873,10 +952,12 @@ EvidenceShard collect_evidence(const BamHeader& hdr, const PileupStream& st, con
       const Reval* rv = find_reval(base_cur, slot);
       if (rv) e.packed = (e.packed & ~1u) | (rv->base_predicted ? 1u : 0u);  // the host's verdict replaces the kernel's
       if (rv && rv->emit) e.rows.push_back(rv->row);
+      if (rv) for (const GdRow& u : rv->user_rows) e.rows.push_back(u);
       while (ins_cursor < st.n_ins && st.ins_parent[ins_cursor] < slot) ++ins_cursor;
       for (; ins_cursor < st.n_ins && st.ins_parent[ins_cursor] == slot; ++ins_cursor) {
         const Reval* iv = find_reval(ins_cur, st.n_base + ins_cursor);
         if (iv && iv->emit) e.rows.push_back(iv->row);
+        if (iv) for (const GdRow& u : iv->user_rows) e.rows.push_back(u);
       }
       sh.events.push_back(std::move(e));
     }

@@ -85,6 +85,7 @@ struct EvidenceParams {
   uint32_t base_quality_cutoff;
   double log10_ref_length;
   bool skip_missing_coverage_prediction;
+  bool polymorphism_prediction = false;   // Settings::polymorphism_prediction: only words the `prediction` field of user-evidence rows
   std::vector<double> deletion_propagation_cutoff, deletion_seed_cutoff;  // by BAM tid
 };
 struct EvidenceCounts { uint64_t ra = 0, mc = 0, un = 0, rechecked = 0, overturned = 0; };

@@ -5,7 +5,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -130,12 +132,17 @@ void plan_segments(const BamHeader& hdr, const RefSet& ref, const StageConfig& c
     full.push_back({(int32_t)tid, 0, (int32_t)hdr.target_lens[tid], total_cols});
     total_cols += hdr.target_lens[tid];
     refseq.push_back(&ref.seqs[r]);
+    // coverage groups of the whole run, not of this shard: the ranks of a sharded run sum their coverage histograms
+    const uint32_t g = cfg.coverage_group_of_tid.empty() ? (uint32_t)tid : cfg.coverage_group_of_tid[tid];
+    if (g > 255) throw std::runtime_error("more than 256 coverage groups are not supported");
+    if (g + 1 > out.n_groups) out.n_groups = g + 1;
   }
   // this process's shard: [g_lo, g_hi) of the concatenated visit-order columns.  Explicit bounds (StageConfig::shard_lo /
   // shard_hi, set by a caller that balances the shards by record count) win over the even split by columns.
   const uint64_t n_sh = std::max<uint32_t>(1, cfg.shard_count), rk = std::min<uint64_t>(cfg.shard_rank, n_sh - 1);
   uint64_t g_lo = total_cols * rk / n_sh, g_hi = total_cols * (rk + 1) / n_sh;
   if (cfg.shard_hi > cfg.shard_lo || cfg.shard_explicit) { g_lo = std::min<uint64_t>(cfg.shard_lo, total_cols); g_hi = std::min<uint64_t>(cfg.shard_hi, total_cols); }
+  out.visit_targets = full;
   std::vector<const std::string*> kept;
   for (size_t v = 0; v < full.size(); ++v) {
     const uint64_t a = full[v].slot0, b = a + (uint64_t)full[v].hi;
@@ -146,6 +153,66 @@ void plan_segments(const BamHeader& hdr, const RefSet& ref, const StageConfig& c
     kept.push_back(refseq[v]);
   }
   refseq.swap(kept);
+}
+
+std::vector<UserRa> read_user_evidence_gd(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) throw std::runtime_error("cannot open " + path);
+  std::vector<UserRa> list;
+  char* line = nullptr;
+  size_t cap = 0;
+  ssize_t n;
+  while ((n = getline(&line, &cap, f)) >= 0) {
+    while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+    std::vector<std::string> fld;
+    for (char* p = line;;) { char* t = strchr(p, '\t'); fld.emplace_back(p, t ? (size_t)(t - p) : strlen(p)); if (!t) break; p = t + 1; }
+    if (fld.size() < 8 || fld[0] != "RA") continue;   // type, id, parents, then the specification: seq_id position insert_position ref_base new_base
+    UserRa e;
+    e.seq_id = fld[3]; e.position = (uint32_t)strtoul(fld[4].c_str(), nullptr, 10); e.insert_position = (uint32_t)strtoul(fld[5].c_str(), nullptr, 10);
+    e.ref_base = fld[6]; e.new_base = fld[7];
+    list.push_back(e);
+  }
+  free(line);
+  fclose(f);
+  // cDiffEntry::compare for two RA rows: seq_id (as a string), position, then the specification fields in order
+  std::stable_sort(list.begin(), list.end(), [](const UserRa& a, const UserRa& b) {
+    if (a.seq_id != b.seq_id) return a.seq_id < b.seq_id;
+    if (a.position != b.position) return a.position < b.position;
+    if (a.insert_position != b.insert_position) return a.insert_position < b.insert_position;
+    if (a.ref_base != b.ref_base) return a.ref_base < b.ref_base;
+    return a.new_base < b.new_base;
+  });
+  return list;
+}
+
+std::vector<UserColumn> plan_user_evidence(const std::vector<UserRa>& list, const BamHeader& hdr, const std::vector<Segment>& visit_full,
+                                           const std::vector<double>& skip_cutoff,
+                                           const std::function<uint32_t(size_t, uint32_t, uint32_t)>& levels) {
+  std::vector<UserColumn> out;
+  size_t front = 0;
+  for (size_t v = 0; v < visit_full.size() && front < list.size(); ++v) {
+    const int32_t tid = visit_full[v].tid;
+    if (!skip_cutoff.empty() && skip_cutoff[(size_t)tid] < 0.0) continue;   // the callback returns before it looks at the list (identify_mutations.cpp:1319-1336)
+    const std::string& name = hdr.target_names[(size_t)tid];
+    const uint32_t len = hdr.target_lens[(size_t)tid];
+    uint32_t done = 0;   // columns of this target already passed
+    while (front < list.size()) {
+      const uint32_t p = list[front].position;
+      if (p <= done || p > len) break;   // no later column of this target has the front entry's position
+      UserColumn c;
+      c.tid = tid; c.pos1 = p; c.slot = ~0ull;
+      for (size_t u = front; u < list.size() && list[u].position == p; ++u) c.force_max = list[u].insert_position;
+      const uint32_t top = levels(v, p, c.force_max);
+      for (uint32_t k = 0; k <= top; ++k)
+        while (front < list.size() && list[front].seq_id == name && list[front].position == p && list[front].insert_position == k) {
+          c.consumed.emplace_back(k, (uint32_t)front);
+          ++front;
+        }
+      out.push_back(c);
+      done = p;
+    }
+  }
+  return out;
 }
 
 // Table geometry of the device stream words (ScoreGeometry) from per-read statistics: mq[m] = bases of unique reads with
@@ -354,17 +421,44 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     std::sort(all.begin(), all.end(), [](const InsSupport& a, const InsSupport& b) { return a.slot < b.slot; });
     sub_first.assign(out.n_base, 0xFFFFFFFFu);
     sub_k.assign(out.n_base, 0);
+    std::map<uint64_t, uint64_t> mask_of;   // base slot -> which insert levels the reads support
     for (size_t a = 0; a < all.size();) {
       size_t b = a; uint64_t mask = 0;
       while (b < all.size() && all[b].slot == all[a].slot) mask |= all[b++].mask;
-      uint32_t K = 0;
-      while (K < 63 && (mask >> K & 1)) ++K;
-      if (K) {
-        sub_first[all[a].slot] = (uint32_t)out.ins_parent.size();
-        sub_k[all[a].slot] = (uint8_t)K;
-        for (uint32_t k = 1; k <= K; ++k) { out.ins_parent.push_back(all[a].slot); out.ins_count.push_back(k); }
-      }
+      if (mask) mask_of[all[a].slot] = mask;
       a = b;
+    }
+    // user evidence: the columns where the pileup meets the list, the levels it forces there (identify_mutations.cpp:1346-1355)
+    std::map<uint64_t, uint32_t> forced;
+    if (!cfg.user_evidence.empty()) {
+      out.user_list = cfg.user_evidence;
+      auto slot_of = [&](size_t v, uint32_t pos1) -> uint64_t {  // base slot of a column of visited target v, ~0 outside this shard
+        for (const Segment& sg : out.segments)
+          if (sg.tid == out.visit_targets[v].tid && (int32_t)pos1 - 1 >= sg.lo && (int32_t)pos1 - 1 < sg.hi) return sg.slot0 + (uint64_t)((int32_t)pos1 - 1 - sg.lo);
+        return ~0ull;
+      };
+      out.user_columns = plan_user_evidence(cfg.user_evidence, hdr, out.visit_targets, cfg.user_skip_cutoff, [&](size_t v, uint32_t pos1, uint32_t force_max) {
+        const uint64_t slot = slot_of(v, pos1);
+        if (slot == ~0ull) return force_max;   // another shard's column: its read support is not known here
+        const auto m = mask_of.find(slot);
+        return insert_levels(m == mask_of.end() ? 0 : m->second, force_max);
+      });
+      for (UserColumn& c : out.user_columns) {
+        size_t v = 0;
+        while (v < out.visit_targets.size() && out.visit_targets[v].tid != c.tid) ++v;
+        c.slot = slot_of(v, c.pos1);
+        if (c.slot != ~0ull && c.force_max) forced[c.slot] = std::max(forced[c.slot], c.force_max);
+      }
+    }
+    for (const auto& f : forced) if (!mask_of.count(f.first)) mask_of[f.first] = 0;
+    for (const auto& m : mask_of) {
+      const auto f = forced.find(m.first);
+      const uint32_t K = insert_levels(m.second, f == forced.end() ? 0 : f->second);
+      if (K) {
+        sub_first[m.first] = (uint32_t)out.ins_parent.size();
+        sub_k[m.first] = (uint8_t)K;
+        for (uint32_t k = 1; k <= K; ++k) { out.ins_parent.push_back(m.first); out.ins_count.push_back(k); }
+      }
     }
     out.n_ins = out.ins_parent.size();
   }
@@ -631,7 +725,6 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     }
     out.hist_off[out.n_base] = acc; out.n_hist = acc;
     if (cfg.want_hist) for (uint64_t c = 0; c < out.n_base; ++c) if (hist_cnt[c] > out.max_hist_depth) out.max_hist_depth = hist_cnt[c];
-    for (uint64_t c = 0; c < out.n_base; ++c) if (out.slot_group[c] + 1u > out.n_groups) out.n_groups = out.slot_group[c] + 1u;
   }
   phase_done("offsets and rounds");
   // the positional forms stay in plain memory when only their transfer / compact forms cross PCIe (pinning gigabytes is slow)

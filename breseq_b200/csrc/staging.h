@@ -10,6 +10,8 @@
 #include "bam_io.h"
 #include "brq_types.h"
 
+#include <functional>
+
 namespace brq {
 
 struct ReadFileSetInfo { std::string base_name; uint32_t n_files; };
@@ -35,6 +37,8 @@ struct StageConfig {
   // shards by record count, SURVEY.md 8e, computes them with shard_bounds_by_records)
   uint64_t shard_lo = 0, shard_hi = 0;
   bool shard_explicit = false;
+  std::vector<UserRa> user_evidence;               // Settings::user_evidence_genome_diff_file_name, read and sorted (read_user_evidence_gd)
+  std::vector<double> user_skip_cutoff;             // optional, by BAM tid: targets with a negative deletion propagation cutoff are not visited
   int staging_mode = 0;                             // 0 = on the device when the context has one, 1 = host, 2 = device
   // buffer allocator (pinned when a device is present); both must be set together
   void* (*alloc)(size_t bytes, bool* pinned) = nullptr;
@@ -49,6 +53,24 @@ void free_stream(PileupStream& s, const StageConfig& cfg);
 // The host-side plan both staging paths share: the visited targets clipped to the shard, and the table geometry.
 void plan_segments(const BamHeader& hdr, const RefSet& ref, const StageConfig& cfg, PileupStream& out, std::vector<const std::string*>& refseq);
 ScoreGeometry choose_geometry(const uint64_t* mq, const uint64_t* qc, const StageConfig& cfg, uint32_t max_read_set_seen);
+
+// RA rows of a GenomeDiff file, stripped to their specification and sorted like cGenomeDiff::sort() (genome_diff_entry.cpp:566-690).
+std::vector<UserRa> read_user_evidence_gd(const std::string& path);
+// Walks the visited targets in visit order the way the pileup meets the user list (identify_mutations.cpp:1346-1355, 1914-2019):
+// at a column whose position is that of the list's front entry, the insert levels up to the LAST front-run entry's are
+// forced (the run is matched by position alone, as there), and the front entries naming this target, position and a
+// processed level are consumed in order.  levels(visit index, pos1, force_max) = the highest insert level the column ends up
+// with (read support and force together).  Entries the walk never reaches stay at the front and block the rest, as there.
+std::vector<UserColumn> plan_user_evidence(const std::vector<UserRa>& list, const BamHeader& hdr, const std::vector<Segment>& visit_full,
+                                           const std::vector<double>& skip_cutoff,
+                                           const std::function<uint32_t(size_t, uint32_t, uint32_t)>& levels);
+// highest insert level of a column: level k + 1 exists iff bit k of `mask` is set (a unique read has a longer insertion and a
+// base there) or the user list forces it (k < force_max)
+inline uint32_t insert_levels(uint64_t mask, uint32_t force_max) {
+  uint32_t L = 0;
+  while (L < 63 && ((mask >> L & 1) || L < force_max)) ++L;
+  return L;
+}
 
 // Flat read-file index of each read group (alignment.cpp:565-605).
 void make_read_file_partition(const ReadGroups& rg, const std::vector<ReadFileSetInfo>& sets,

@@ -61,6 +61,10 @@ typedef struct brq_stage_options {
    * expand the CIGARs and classify the records in HBM), 1 = on the host (csrc/staging.cpp), 2 = on the device or fail */
   uint32_t staging;
   uint32_t reserved;
+  /* Settings::user_evidence_genome_diff_file_name (identify_mutations.cpp:879, 1013-1020): a GenomeDiff file whose RA rows are
+   * reported whatever the data says; NULL = none.  Forces the insert sub-columns the rows name (:1346-1355); the rows come out
+   * of brq_write_evidence with user_defined=1 (:1914-2019) */
+  const char* user_evidence_gd;
 } brq_stage_options;
 #define BRQ_DEFAULT_BASE_QUALITY_CUTOFF 0xFFFFFFFFu
 
@@ -178,6 +182,8 @@ typedef struct brq_score_params {
  * result.  By default the kernel first bounds each column's presence score from above and runs the fit only where an RA
  * row is possible; this flag forces the fit on every column with scoring records (diagnostics, parity runs). */
 #define BRQ_SCORE_FIT_ALL_COLUMNS 1u
+/* Settings::polymorphism_prediction: words the `prediction` field of user-evidence rows (identify_mutations.cpp:1992-1996) */
+#define BRQ_SCORE_POLYMORPHISM_PREDICTION 2u
 
 typedef struct brq_column {  /* one per slot: base columns of the visited targets, then insert sub-columns */
   double ll[5];

@@ -10,6 +10,13 @@
 //   * the pileup engine: bam_plp_push / bam_plp_next / resolve_cigar2 semantics
 //     (qpos on deletions = first read base AFTER the deletion; indel look-ahead merging of
 //      consecutive D / I runs with P skipped; only BAM_FUNMAP and tid<0 dropped at push).
+//     THE FLAG MASK (decided, not guessed twice): bam_plp_init() still stores BAM_DEF_MASK (UNMAP | SECONDARY | QCFAIL | DUP)
+//     in iter->flag_mask, but since htslib 1.0 bam_plp_push() tests only BAM_FUNMAP -- its own comment reads "Skip only
+//     unmapped reads here, any additional filtering must be done in iter->func" -- which is why samtools mpileup filters
+//     the other three flags in its read callback (mplp_func, --excl-flags).  breseq's read callbacks (pileup_base.cpp:225-236,
+//     290-301) filter nothing, so SECONDARY / QCFAIL / DUP records reach both pileup callbacks and are counted.  The
+//     product (csrc/staging.cpp in_pileup, csrc/expand_core.h PILEUP_FLAG_MASK) does the same; tests/test_pileup_semantics.py
+//     feeds flagged reads to the oracle and the staging layer and checks the hand-derived counts.
 // The whole BAM is inflated into memory at hts_open(): this is a checker, not a product.
 #include "htslib/sam.h"
 #include "htslib/faidx.h"

@@ -19,6 +19,7 @@
 #include <iomanip>
 #include <iostream>
 #include <limits>
+#include <deque>
 #include <list>
 #include <sstream>
 
@@ -830,6 +831,35 @@ struct IdentifyMutationsPileup : PileupDriver {
     table.log10_prob_to_prob();
     table.rg_map = &read_groups;
     table.partition = ReadFilePartition::make(read_groups, s.read_file_sets);
+    if (!s.user_evidence_genome_diff_file_name.empty()) load_user_ra_evidence_from_gd(s.user_evidence_genome_diff_file_name);  // :878-881
+  }
+  // :1013-1020: the RA rows of the user's GenomeDiff, stripped to their specification, in cGenomeDiff::sort() order
+  // (cDiffEntry::compare, genome_diff_entry.cpp:566-690: seq_id as a string, position, then the specification fields)
+  std::deque<GdEntry> user_evidence_ra_list;
+  void load_user_ra_evidence_from_gd(const string& path) {
+    FILE* f = fopen(path.c_str(), "r");
+    ORACLE_ASSERT(f != nullptr, "cannot open the user evidence GenomeDiff");
+    char* line = nullptr; size_t cap = 0; ssize_t n;
+    vector<GdEntry> rows;
+    while ((n = getline(&line, &cap, f)) >= 0) {
+      while (n > 0 && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = 0;
+      vector<string> fld;
+      for (char* p = line;;) { char* t = strchr(p, '\t'); fld.emplace_back(p, t ? (size_t)(t - p) : strlen(p)); if (!t) break; p = t + 1; }
+      if (fld.size() < 8 || fld[0] != "RA") continue;
+      GdEntry e; e.type = "RA"; e.spec = {fld[3], fld[4], fld[5], fld[6], fld[7]};
+      rows.push_back(e);
+    }
+    free(line); fclose(f);
+    std::stable_sort(rows.begin(), rows.end(), [](const GdEntry& a, const GdEntry& b) {
+      if (a.spec[0] != b.spec[0]) return a.spec[0] < b.spec[0];
+      const unsigned long pa = strtoul(a.spec[1].c_str(), nullptr, 10), pb = strtoul(b.spec[1].c_str(), nullptr, 10);
+      if (pa != pb) return pa < pb;
+      const unsigned long ia = strtoul(a.spec[2].c_str(), nullptr, 10), ib = strtoul(b.spec[2].c_str(), nullptr, 10);
+      if (ia != ib) return ia < ib;
+      if (a.spec[3] != b.spec[3]) return a.spec[3] < b.spec[3];
+      return a.spec[4] < b.spec[4];
+    });
+    user_evidence_ra_list.assign(rows.begin(), rows.end());
   }
   void add(GdEntry e) { e.id = ++id_counter; gd.push_back(e); }
 
@@ -1027,7 +1057,11 @@ struct IdentifyMutationsPileup : PileupDriver {
     if (this_prop_cutoff < 0.0) return;
     int32_t insert_count = -1;
     bool next_insert_count_exists = true;
-    while (next_insert_count_exists) {
+    // :1346-1355: levels the user list forces here; the front run is matched by POSITION alone, the last entry's level wins
+    int32_t force_insert_count_max = 0;
+    for (auto u = user_evidence_ra_list.begin(); u != user_evidence_ra_list.end() && strtoul(u->spec[1].c_str(), nullptr, 10) == position; ++u)
+      force_insert_count_max = (int32_t)strtol(u->spec[2].c_str(), nullptr, 10);
+    while (next_insert_count_exists || insert_count < force_insert_count_max) {
       ++insert_count;
       next_insert_count_exists = false;
       char ref_base_char = '.';
@@ -1150,6 +1184,49 @@ struct IdentifyMutationsPileup : PileupDriver {
         mut.kv["minor_cov"] = covs(minor_char);
         mut.kv["total_cov"] = std::to_string(total_cov[2]) + "/" + std::to_string(total_cov[0]);
         add(mut);
+      }
+      // :1914-2019: user evidence at this position and insert level that the data did not already report
+      while (!user_evidence_ra_list.empty() && user_evidence_ra_list.front().spec[0] == target_name(tid) &&
+             strtoul(user_evidence_ra_list.front().spec[1].c_str(), nullptr, 10) == position &&
+             strtol(user_evidence_ra_list.front().spec[2].c_str(), nullptr, 10) == insert_count) {
+        const GdEntry& user = user_evidence_ra_list.front();
+        if (emitted && gd.back().type == "RA" && gd.back().spec == user.spec) {
+          gd.back().kv["user_defined"] = "1";
+        } else {
+          GdEntry mut;
+          mut.type = "RA";
+          mut.spec = user.spec;
+          mut.kv["user_defined"] = "1";
+          const char user_ref = user.spec[3][0], user_new = user.spec[4][0];
+          const uint8_t user_ref_index = basechar2index(user_ref), user_variant_index = basechar2index(user_new);
+          double user_score = numeric_limits<double>::quiet_NaN(), user_variant_frequency = 0.0;
+          if (user_variant_index < 5) {
+            user_score = variant_presence_score(pdata, amodel, user_variant_index);
+            user_variant_frequency = amodel.reported_frequency(user_variant_index);
+          }
+          const double user_ref_frequency = amodel.reported_frequency(user_ref_index);
+          const bool variant_is_major = user_variant_frequency > user_ref_frequency;
+          const char mj = variant_is_major ? user_new : user_ref, mn = variant_is_major ? user_ref : user_new;
+          mut.kv["major_base"] = string(1, mj);
+          mut.kv["minor_base"] = string(1, mn);
+          mut.kv["major_frequency"] = to_string_double(variant_is_major ? user_variant_frequency : user_ref_frequency, precision_places, true);
+          mut.kv["frequency"] = to_string_double(user_variant_frequency, precision_places, true);
+          mut.kv["allele_frequencies"] = amodel.spectrum_string(precision_places);
+          double lower, upper;
+          frequency_bounds(pdata, amodel, user_variant_index, lower, upper);
+          mut.kv["frequency_lower"] = to_string_double(lower, precision_places, true);
+          mut.kv["frequency_upper"] = to_string_double(upper, precision_places, true);
+          mut.kv["prediction"] = settings.polymorphism_prediction ? "polymorphism" : (user_variant_frequency > 0.5 ? "consensus" : "polymorphism");
+          mut.kv["score"] = to_string_double(user_score, 1);
+          auto covs = [&](char c) { uint8_t b = basechar2index(c); return std::to_string((int32_t)pos_info[b][2]) + "/" + std::to_string((int32_t)pos_info[b][0]); };
+          mut.kv["ref_cov"] = covs(user_ref);
+          mut.kv["new_cov"] = covs(user_new);
+          mut.kv["major_cov"] = covs(mj);
+          mut.kv["minor_cov"] = covs(mn);
+          mut.kv["total_cov"] = std::to_string(total_cov[2]) + "/" + std::to_string(total_cov[0]);
+          add(mut);
+        }
+        user_evidence_ra_list.pop_front();
       }
       if (dump) {
         ColumnDump d;

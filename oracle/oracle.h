@@ -33,6 +33,8 @@ struct Settings {
   std::vector<ReadFileSet> read_file_sets;                  // empty for the standalone ERROR_COUNT path
   uint32_t base_quality_cutoff = 3;                         // settings.cpp:1335
   bool skip_missing_coverage_prediction = false;            // settings.cpp:843
+  bool polymorphism_prediction = false;                     // settings.cpp:857 (words the `prediction` field of user-evidence rows)
+  std::string user_evidence_genome_diff_file_name;          // RA rows reported whatever the data says (identify_mutations.cpp:879)
   std::string error_rates_file_name;                        // 07_error_calibration/error_rates.tab
   std::string unique_only_coverage_distribution_file_name;  // contains '@' replaced by the group index
   std::string base_qual_error_prob_file_name;               // contains '#' replaced by the read file name

@@ -63,6 +63,8 @@ int main(int argc, char** argv) {
   }
   st.base_quality_cutoff = (uint32_t)atoi(get("base-quality-cutoff", "3").c_str());
   st.skip_missing_coverage_prediction = opt.count("skip-mc") > 0;
+  st.polymorphism_prediction = opt.count("polymorphism-prediction") > 0;
+  st.user_evidence_genome_diff_file_name = get("user-evidence", "");
   string out = get("out", ".");
   st.error_rates_file_name = get("error-rates", out + "/error_rates.tab");
   st.unique_only_coverage_distribution_file_name = "@.unique_only_coverage_distribution.tab";

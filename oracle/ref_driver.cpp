@@ -85,6 +85,7 @@ int main(int argc, char** argv) {
 
   settings.base_quality_cutoff = (uint32_t)atoi(get("base-quality-cutoff", "3").c_str());
   settings.skip_missing_coverage_prediction = opt.count("skip-mc") > 0;
+  settings.user_evidence_genome_diff_file_name = get("user-evidence", "");  // Settings::user_evidence_genome_diff_file_name (--user-evidence-gd)
   settings.polymorphism_prediction = opt.count("polymorphism-prediction") > 0;
   settings.error_rates_file_name = get("error-rates", out + "/error_rates.tab");
   settings.unique_only_coverage_distribution_file_name = out + "/@.unique_only_coverage_distribution.tab";

@@ -57,6 +57,13 @@ def main():
                     fh.write("%s  error_rates.tab\n" % sha256(os.path.join(out, "error_rates.tab")))
             with open(os.path.join(gdir, helpers.PREPROCESS_TAB), "w") as fh:  # the stage 03 call (preprocess_stage = true)
                 fh.write(helpers.run_preprocess(helpers.REF_CLI, d, os.path.join(tmp, "ref_preprocess")))
+            if name == "lambda":  # user evidence (Settings::user_evidence_genome_diff_file_name): the committed input list, what the reference reports for it
+                import subprocess
+                user = os.path.join(HERE, "..", "user_evidence_lambda.gd")
+                shutil.copy(user, os.path.join(gdir, "user_evidence.gd"))
+                _, im = helpers.cli_args(d, out, gd=os.path.join(out, "user.gd"))
+                subprocess.run([helpers.REF_CLI] + [str(a) for a in im] + ["--user-evidence", user], check=True, capture_output=True)
+                shutil.copy(os.path.join(out, "user.gd"), os.path.join(gdir, "ra_mc_evidence.user_evidence.gd"))
             if name == "tiny":
                 for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
                     shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))

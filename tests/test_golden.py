@@ -147,3 +147,96 @@ def test_cuda_optional_outputs_match_reference(datasets, tmp_path):
     assert filecmp.cmp(os.path.join(out, "per_position_file.tab"), golden("deep", "per_position_file.tab"), shallow=False)
     tsv = helpers.contig_names(d)[0] + ".coverage.tsv"
     assert filecmp.cmp(os.path.join(out, tsv), golden("deep", tsv), shallow=False)
+
+
+# ---- user evidence (Settings::user_evidence_genome_diff_file_name; identify_mutations.cpp:879, 1013-1020, 1346-1355, 1914-2019)
+USER_GD = os.path.join(helpers.GOLDEN, "lambda", "user_evidence.gd")
+USER_GOLDEN = os.path.join(helpers.GOLDEN, "lambda", "ra_mc_evidence.user_evidence.gd")
+
+
+def test_oracle_reports_user_evidence_like_the_reference(datasets, tmp_path):
+    """Eight user rows on the lambda dataset: one the data already reports (it only gains user_defined=1), absent alleles,
+    forced insert sub-columns (insert_position 2 and 3 where no read has an insertion that long), a reference base of N."""
+    d = datasets["lambda"]
+    out = str(tmp_path)
+    _, im = helpers.cli_args(d, out, rates=d["oracle_rates"], gd=os.path.join(out, "o.gd"))
+    helpers.run_oracle(*im, "--user-evidence", USER_GD)
+    assert open(os.path.join(out, "o.gd")).read() == open(USER_GOLDEN).read()
+
+
+def test_user_evidence_forces_insert_sub_columns_in_host_staging(datasets):
+    d = datasets["lambda"]
+    plain, forced = bq.Context(device=-1), bq.Context(device=-1)
+    plain.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
+    forced.stage_bam(d["bam"], d["fasta"], user_evidence_gd=USER_GD, **helpers.stage_kwargs(d))
+    a, b = plain.stream(), forced.stream()
+    have = {(int(p), int(k)) for p, k in zip(a["ins_parent"], a["ins_count"])}
+    want = {(int(p), int(k)) for p, k in zip(b["ins_parent"], b["ins_count"])}
+    assert have < want
+    assert {(4999, 1), (4999, 2), (15183, 2), (15183, 3), (29999, 1)} <= want - have | have   # 0-based parent slot, level
+    # a forced sub-column holds a '.' observation of every read that spans the column
+    for p, k in want - have:
+        s = int(b["n_base"]) + [i for i, (q, j) in enumerate(zip(b["ins_parent"], b["ins_count"])) if (int(q), int(j)) == (p, k)][0]
+        assert b["score_cnt"][s] == b["score_cnt"][p] or b["score_cnt"][s] > 0
+    plain.close()
+    forced.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("staging", ["device", "host"])
+def test_cuda_path_reports_user_evidence_like_the_reference(staging, datasets, tmp_path):
+    d = datasets["lambda"]
+    out = str(tmp_path)
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], user_evidence_gd=USER_GD, staging=staging, **helpers.stage_kwargs(d))
+    ctx.load_error_table(os.path.join(helpers.GOLDEN, "lambda", "error_rates.tab"))
+    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"]))
+    ctx.write_evidence(os.path.join(out, "ra_mc_evidence.gd"), [d["del_prop"]], [d["del_seed"]])
+    assert open(os.path.join(out, "ra_mc_evidence.gd")).read() == open(USER_GOLDEN).read()
+    ctx.close()
+    # the one-call adapter, through the reference's own option name
+    bq.identify_mutations(d["bam"], d["fasta"], os.path.join(out, "adapter.gd"), [d["del_prop"]], [d["del_seed"]], d["mutation_cutoff"],
+                          d["polymorphism_cutoff"], d["precision"], d["places"], error_rates_file_name=os.path.join(helpers.GOLDEN, "lambda", "error_rates.tab"),
+                          read_file_sets=helpers.read_file_sets(d), user_evidence_genome_diff_file_name=USER_GD)
+    assert open(os.path.join(out, "adapter.gd")).read() == open(USER_GOLDEN).read()
+
+
+@pytest.mark.gpu
+def test_user_evidence_across_targets_and_shards(datasets, tmp_path):
+    """Several targets: entries consumed target by target in visit order, an entry for a position no column has (it blocks
+    the rest of the list, as in the reference), and the same run cut into three shards."""
+    d = datasets["multi"]
+    names = helpers.contig_names(d)
+    user = str(tmp_path / "user.gd")
+    with open(user, "w") as f:
+        f.write("#=GENOME_DIFF\t1.0\n")
+        rows = [(names[0], 100, 0, "A", "C"), (names[0], 100, 1, ".", "G"), (names[0], 3000, 0, "T", "G"), (names[1], 50, 0, "C", "T"),
+                (names[1], 3499, 2, ".", "A"), (names[2], 999999, 0, "A", "C"), (names[2], 10, 0, "A", "C")]
+        for i, r in enumerate(rows):
+            f.write("RA\t%d\t.\t%s\t%d\t%d\t%s\t%s\n" % ((i + 1,) + r))
+    n = len(names)
+    out = str(tmp_path)
+    _, im = helpers.cli_args(d, out, rates=d["oracle_rates"], gd=os.path.join(out, "o.gd"))
+    helpers.run_oracle(*im, "--user-evidence", user)
+    want = open(os.path.join(out, "o.gd")).read()
+    assert want.count("user_defined=1") == 5   # the entry past its target's end blocks the one behind it
+    params = bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"])
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], user_evidence_gd=user, **helpers.stage_kwargs(d))
+    ctx.load_error_table(d["oracle_rates"])
+    ctx.score_columns(params)
+    ctx.write_evidence(os.path.join(out, "one.gd"), [d["del_prop"]] * n, [d["del_seed"]] * n)
+    assert open(os.path.join(out, "one.gd")).read() == want
+    ctx.close()
+    shares = []
+    for rank in range(3):
+        c = bq.Context(device=0)
+        c.stage_bam(d["bam"], d["fasta"], user_evidence_gd=user, shard=(rank, 3), **helpers.stage_kwargs(d))
+        c.load_error_table(d["oracle_rates"])
+        c.score_columns(params)
+        shares.append(c.evidence_export([d["del_prop"]] * n))
+        c.close()
+    m = bq.Context(device=-1)
+    m.write_evidence_merged(os.path.join(out, "merged.gd"), shares, [d["del_prop"]] * n, [d["del_seed"]] * n)
+    m.close()
+    assert open(os.path.join(out, "merged.gd")).read() == want

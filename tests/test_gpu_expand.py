@@ -77,3 +77,25 @@ def test_device_staging_needs_a_device():
     with pytest.raises(bq.BrqError, match="device staging needs"):
         ctx.stage_synthetic(spec, staging="device")
     ctx.close()
+
+
+def test_hand_derived_cigar_cases_on_the_device(tmp_path):
+    """The known-answer reads of tests/test_pileup_semantics.py (soft / hard clips, deletions, insertions with padding,
+    reference skips, flagged reads) through the device expander: the same streams as host staging."""
+    import minibam
+    import test_pileup_semantics as kat
+    for name, (read, _, _) in sorted(kat.CASES.items()):
+        bam, fasta = str(tmp_path / (name + ".bam")), str(tmp_path / (name + ".fasta"))
+        minibam.write(bam, fasta, [("chr", kat.REF)], [read])
+        d = dict(bam=bam, fasta=fasta, read_sets=[])
+        out = []
+        for staging in ("host", "device"):
+            ctx = bq.Context(device=0)
+            ctx.stage_bam(bam, fasta, staging=staging)
+            s = ctx.stream()
+            o = {k: (None if s[k] is None else np.array(s[k], copy=True)) for k in ARRAYS}
+            o.update({k: s[k] for k in SCALARS})
+            o["device_built"] = s["device_built"]
+            out.append(o)
+            ctx.close()
+        compare(out[0], out[1])

@@ -61,7 +61,27 @@ CASES = {
     # an N in the read: no substitution observation there, and no '..' pointing at it
     "n_in_read": (dict(tid=0, pos=0, cigar="4M", seq="ANGT", qual=[30, 2, 32, 33]),
                   [("A", "A", 30), ("G", "G", 32), ("T", "T", 33), (".", ".", 32), (".", ".", 33)], {1: 4}),
+    # a padding operation inside an insertion run is skipped: 2M1I1P1I2M reports indel = +2 at the base before it, which is
+    # not a one-base insertion, so that base has NO second observation (error_count.cpp:963: indel == +1 only)
+    "pad_inside_insertion": (dict(tid=0, pos=0, cigar="2M1I1P1I2M", seq="ACTTGT", qual=[30, 31, 32, 33, 34, 35]),
+                             [("A", "A", 30), ("C", "C", 31), ("G", "G", 34), ("T", "T", 35), (".", ".", 31), (".", ".", 35)], {1: 4}),
+    # a reference skip (N) is a deleted column for the pileup (is_del): pass 1 skips it; the base before it sees indel == 0
+    # (only a D after a non-D operation is reported), so it reports '..' with the quality of the next read base
+    "reference_skip": (dict(tid=0, pos=0, cigar="2M2N2M", seq="ACAC", qual=[30, 31, 32, 33]),
+                       [("A", "A", 30), ("C", "C", 31), ("A", "A", 32), ("C", "C", 33), (".", ".", 31), (".", ".", 32), (".", ".", 33)], {1: 4}),
+    # hard clips consume nothing: the same bins as forward_match
+    "hard_clips": (dict(tid=0, pos=0, cigar="3H4M2H", seq="ACGT", qual=[30, 31, 32, 33]),
+                   [("A", "A", 30), ("C", "C", 31), ("G", "G", 32), ("T", "T", 33), (".", ".", 31), (".", ".", 32), (".", ".", 33)],
+                   {1: 4}),
 }
+# reads the pileup engine keeps although samtools' defaults would drop them: bam_plp_push only tests BAM_FUNMAP
+# (oracle/hts_shim/hts_shim.cpp header; csrc/expand_core.h PILEUP_FLAG_MASK)
+for _flag, _name in ((256, "secondary"), (512, "qc_fail"), (1024, "duplicate")):
+    CASES["flagged_" + _name] = (dict(tid=0, pos=0, cigar="4M", seq="ACGT", qual=[30, 31, 32, 33], flag=_flag),
+                                 [("A", "A", 30), ("C", "C", 31), ("G", "G", 32), ("T", "T", 33), (".", ".", 31), (".", ".", 32), (".", ".", 33)],
+                                 {1: 4})
+# ... and the one it drops
+CASES["flagged_unmapped"] = (dict(tid=0, pos=0, cigar="4M", seq="ACGT", qual=[30, 31, 32, 33], flag=4), [], {})
 
 
 def run_case(tmp_path, name, reads):

@@ -63,7 +63,10 @@ struct brq_ctx {
   DevBuf<uint32_t> d_flagged, d_worklist, d_survivors, d_scalars;  // d_scalars: [0] err, [1] n_flagged, [2] n_work, [3] fit hand-out, [4] n_survivors, [5] screen hand-out
   DevBuf<uint8_t> d_score16;   // transfer form of the scoring stream (low halves)
   DevBuf<uint32_t> d_score_exc, d_score_exc_off;
-  DevBuf<unsigned long long> d_counts, d_cov;
+  // both integer histograms in ONE allocation (the covariate counts, then the coverage histogram): a sharded run sums them
+  // with one collective
+  DevBuf<unsigned long long> d_hist;
+  struct HistView { unsigned long long* p = nullptr; } d_counts, d_cov;
   DevBuf<double> d_log10;
   DevBuf<ClassTerms> d_lut;
   DevBuf<HotTerms> d_coldT;
@@ -393,10 +396,10 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   const uint32_t n_groups = st.n_groups;
   c->cov_stride = std::max<uint64_t>(st.max_hist_depth, c->min_cov_depth) + 1;
   c->n_groups = n_groups;
-  c->d_counts.ensure(lay.n_bins);
-  c->d_cov.ensure(c->cov_stride * n_groups);
-  CUDA_OK(cudaMemsetAsync(c->d_counts.p, 0, (size_t)lay.n_bins * 8, c->stream));
-  CUDA_OK(cudaMemsetAsync(c->d_cov.p, 0, c->cov_stride * n_groups * 8, c->stream));
+  c->d_hist.ensure((size_t)lay.n_bins + c->cov_stride * n_groups);
+  c->d_counts.p = c->d_hist.p;
+  c->d_cov.p = c->d_hist.p + lay.n_bins;
+  CUDA_OK(cudaMemsetAsync(c->d_hist.p, 0, ((size_t)lay.n_bins + c->cov_stride * n_groups) * 8, c->stream));
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 32, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
   if (do_errors) {
@@ -798,7 +801,7 @@ void brq_destroy(brq_ctx* c) {
   if (c->device >= 0) {
     c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_survivors.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
-    c->d_counts.release(); c->d_cov.release();
+    c->d_hist.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
     c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);

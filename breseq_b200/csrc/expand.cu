@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256) read_starts_kernel(ExpandArgs a, unsigned
 
 // ------------------------------------------------------------------------------------------ the tile passes
 template <bool FILL>
-__global__ void __launch_bounds__(256) tile_kernel(ExpandArgs a) {
+__global__ void __launch_bounds__(256, 4) tile_kernel(ExpandArgs a) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (tile >= a.n_tiles) return;
   tile_lane<FILL>(a, tile, threadIdx.x & 31u);

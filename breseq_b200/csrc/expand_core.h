@@ -113,7 +113,8 @@ struct ExpandArgs {
 
 BRQ_HD inline bool xop_ref(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
 BRQ_HD inline bool xop_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
-BRQ_HD inline uint8_t xnibble_to_index(uint8_t bam4) { return bam4 == 1 ? 0 : bam4 == 2 ? 1 : bam4 == 4 ? 2 : bam4 == 8 ? 3 : 5; }
+// BAM 4-bit code -> base index (1, 2, 4, 8 = A, C, G, T; anything else is N): sixteen 4-bit entries in one constant
+BRQ_HD inline uint8_t xnibble_to_index(uint8_t bam4) { return (uint8_t)((0x5555555355525105ull >> ((bam4 & 15u) * 4u)) & 15u); }
 // FASTA character -> base index; 255 = not a base the reference accepts (NUL, the byte past a target's end, reads as kBaseNul)
 BRQ_HD inline uint8_t xchar_to_index(uint8_t c) {
   return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : c == 'N' ? 5 : c == 0 ? (uint8_t)kBaseNul : 255;
@@ -274,6 +275,7 @@ BRQ_HD inline void ins_support(const ExpandArgs& a, uint64_t i) {
 // ---- the lane of a tile: one column and what it accumulates
 struct LaneState {
   uint32_t slot, K, sub0, ref;     // base slot, its sub-columns (count, first sub-column slot), reference base index
+  uint32_t ref_next;               // base index of the NEXT reference column (kBaseNul past the target's end; 255 = not a base)
   int32_t col;                      // column inside the target
   // count pass
   uint32_t n_score, n_red, n_side, n_side_red, n_hist, red_flag, qstart;
@@ -360,11 +362,10 @@ BRQ_HD inline void visit_entry(const ExpandArgs& a, const ExpandSeg& sg, const R
       if ((uint32_t)q > st.max_rp) st.max_rp = (uint32_t)q;
       if (a.use_base_repeat) { const uint32_t rp = base_repeat_of(seq, q, revb, m.qe0); rec |= (uint64_t)(rp < 255u ? rp : 255u) << HR_REPA; }
       uint32_t cls = 0; int32_t mq = -1; uint32_t refb = kBaseNul;
-      auto ref_index = [&](int32_t p) -> uint32_t {  // forward-strand reference base; the byte past the target's end is the NUL terminator
-        if (p >= sg.tlen) return kBaseNul;
-        const uint8_t b = xchar_to_index(a.ref[sg.ref_off + (uint32_t)(p - sg.lo)]);
-        if (b > 5 || b == 4) { BRQ_AOR32(err, EXP_ERR_REFCHAR); return kBaseN; }
-        return b;
+      auto ref_index = [&](int32_t p) -> uint32_t {  // forward-strand reference base of this column or the next (per-lane constants)
+        if (p == c) return st.ref;
+        if (st.ref_next == 255u) { BRQ_AOR32(err, EXP_ERR_REFCHAR); return kBaseN; }
+        return st.ref_next;
       };
       bool dead = false;
       if (indel == 0) {
@@ -534,7 +535,7 @@ BRQ_HD inline void tile_lane(const ExpandArgs& a, uint32_t tile, uint32_t l) {
   LaneState st;
   st.col = c;
   st.slot = sg.slot0 + (uint32_t)(c - sg.lo);
-  st.K = 0; st.sub0 = 0; st.ref = 5;
+  st.K = 0; st.sub0 = 0; st.ref = 5; st.ref_next = kBaseNul;
   st.n_score = st.n_red = st.n_side = st.n_side_red = st.n_hist = st.red_flag = st.qstart = 0;
   st.max_q = st.max_hq = st.max_rp = st.max_srp = 0;
   st.score_off = st.hist_at = 0; st.cur_u = st.cur_r = st.side_u = st.side_r = 0;
@@ -542,6 +543,10 @@ BRQ_HD inline void tile_lane(const ExpandArgs& a, uint32_t tile, uint32_t l) {
     st.K = a.want_score ? a.sub_k[st.slot] : 0u;
     st.sub0 = a.n_base + a.sub_first[st.slot];
     st.ref = a.slot_ref[st.slot];
+    {  // the next column's base: the byte past the target's end is the FASTA buffer's NUL terminator
+      const uint8_t b = c + 1 >= sg.tlen ? (uint8_t)kBaseNul : xchar_to_index(a.ref[sg.ref_off + (uint32_t)(c + 1 - sg.lo)]);
+      st.ref_next = (b > 5 && b != kBaseNul) || b == 4 ? 255u : b;
+    }
     if (FILL) {
       if (a.want_score) {
         st.score_off = a.score_off[st.slot];

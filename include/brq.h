@@ -155,6 +155,8 @@ int brq_preprocess_read_starts(brq_ctx* ctx, const uint64_t** counts, uint32_t* 
  * deepest unique column of this context's range, and a floor for the histogram's depth axis (the maximum over the ranks). */
 int brq_max_coverage_depth(brq_ctx* ctx, uint64_t* depth);
 int brq_set_min_coverage_depth(brq_ctx* ctx, uint64_t depth);
+/* (the coverage histogram follows the counts in one allocation: coverage == counts + n_bins, so one collective over
+ * n_bins + n_coverage words sums both) */
 int brq_hist_device(brq_ctx* ctx, void** counts_u64, uint64_t* n_bins, void** coverage_u64, uint64_t* n_coverage);
 int brq_hist_download(brq_ctx* ctx, const uint64_t** counts, uint64_t* n_bins, const uint64_t** coverage,
                       uint64_t* coverage_stride, uint64_t* n_groups);

@@ -211,7 +211,7 @@ def test_user_evidence_across_targets_and_shards(datasets, tmp_path):
     with open(user, "w") as f:
         f.write("#=GENOME_DIFF\t1.0\n")
         rows = [(names[0], 100, 0, "A", "C"), (names[0], 100, 1, ".", "G"), (names[0], 3000, 0, "T", "G"), (names[1], 50, 0, "C", "T"),
-                (names[1], 3499, 2, ".", "A"), (names[2], 999999, 0, "A", "C"), (names[2], 10, 0, "A", "C")]
+                (names[1], 3499, 2, ".", "A"), (names[1], 999999, 0, "A", "C"), (names[2], 10, 0, "A", "C")]
         for i, r in enumerate(rows):
             f.write("RA\t%d\t.\t%s\t%d\t%d\t%s\t%s\n" % ((i + 1,) + r))
     n = len(names)
@@ -219,7 +219,7 @@ def test_user_evidence_across_targets_and_shards(datasets, tmp_path):
     _, im = helpers.cli_args(d, out, rates=d["oracle_rates"], gd=os.path.join(out, "o.gd"))
     helpers.run_oracle(*im, "--user-evidence", user)
     want = open(os.path.join(out, "o.gd")).read()
-    assert want.count("user_defined=1") == 5   # the entry past its target's end blocks the one behind it
+    assert want.count("user_defined=1") == 5   # the entry past its target's end is never consumed and blocks the one behind it
     params = bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"])
     ctx = bq.Context(device=0)
     ctx.stage_bam(d["bam"], d["fasta"], user_evidence_gd=user, **helpers.stage_kwargs(d))

@@ -1,5 +1,9 @@
 #include "bam_io.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #include <atomic>
 #include <chrono>
@@ -14,23 +18,36 @@ namespace brq {
 
 namespace {
 
-std::vector<uint8_t> slurp(const std::string& path) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) throw std::runtime_error("cannot open " + path);
-  fseek(f, 0, SEEK_END);
-  long n = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> buf((size_t)n);
-  if (n && fread(buf.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); throw std::runtime_error("short read on " + path); }
-  fclose(f);
-  return buf;
-}
+// the file as it lies in the page cache: no copy, the inflate threads read it in place
+struct MappedFile {
+  const uint8_t* p = nullptr;
+  size_t n = 0;
+  explicit MappedFile(const std::string& path) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw std::runtime_error("cannot open " + path);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); throw std::runtime_error("cannot stat " + path); }
+    n = (size_t)sb.st_size;
+    if (n) {
+      void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m == MAP_FAILED) { close(fd); throw std::runtime_error("cannot map " + path); }
+      madvise(m, n, MADV_SEQUENTIAL);
+      p = static_cast<const uint8_t*>(m);
+    }
+    close(fd);
+  }
+  ~MappedFile() { if (p) munmap(const_cast<uint8_t*>(p), n); }
+  MappedFile(const MappedFile&) = delete;
+  MappedFile& operator=(const MappedFile&) = delete;
+  size_t size() const { return n; }
+  const uint8_t& operator[](size_t i) const { return p[i]; }
+};
 
 struct BgzfBlock { size_t cdata, clen, uoff; uint32_t isize; };
 
 // Pass 1 over the compressed image: block boundaries and output offsets, so the members can be
 // inflated independently.
-std::vector<BgzfBlock> index_blocks(const std::vector<uint8_t>& in, size_t& total) {
+std::vector<BgzfBlock> index_blocks(const MappedFile& in, size_t& total) {
   std::vector<BgzfBlock> blocks;
   size_t p = 0;
   total = 0;
@@ -60,7 +77,7 @@ std::vector<BgzfBlock> index_blocks(const std::vector<uint8_t>& in, size_t& tota
   return blocks;
 }
 
-void inflate_block(const std::vector<uint8_t>& in, const BgzfBlock& b, uint8_t* out) {
+void inflate_block(const MappedFile& in, const BgzfBlock& b, uint8_t* out) {
   if (!b.isize) return;
   z_stream zs;
   memset(&zs, 0, sizeof zs);
@@ -123,77 +140,47 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
     fprintf(stderr, "read_bam: %-19s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t - phase_t0).count());
     phase_t0 = t;
   };
-  std::vector<uint8_t> in = slurp(path);
-  phase_done("read file");
+  MappedFile in(path);
+  phase_done("map file");
   size_t total = 0;
   std::vector<BgzfBlock> blocks = index_blocks(in, total);
-  std::vector<uint8_t> u(total);
+  phase_done("index members");
+  RawVec<uint8_t> u;   // (uninitialised: the inflate threads touch every page first)
+  u.resize(total);
   if (threads < 1) threads = 1;
-  {
-    std::atomic<size_t> next(0);
-    std::atomic<bool> failed(false);
-    auto work = [&]() {
-      try {
-        for (;;) {
-          size_t i = next.fetch_add(16);
-          if (i >= blocks.size()) break;
-          for (size_t j = i; j < std::min(i + 16, blocks.size()); ++j) inflate_block(in, blocks[j], u.data());
-        }
-      } catch (...) { failed = true; }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
-    if (failed) throw std::runtime_error("corrupt BGZF payload in " + path);
-  }
-  in.clear();
-  in.shrink_to_fit();
-  phase_done("inflate");
 
-  if (u.size() < 12 || memcmp(u.data(), "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
-  size_t p = 4;
-  int32_t l_text = rd<int32_t>(&u[p]); p += 4;
-  hdr.text.assign((const char*)&u[p], (size_t)l_text);
-  hdr.text = hdr.text.c_str();  // cut at the first NUL, as a C string consumer would see it
-  p += (size_t)l_text;
-  int32_t n_ref = rd<int32_t>(&u[p]); p += 4;
-  for (int i = 0; i < n_ref; ++i) {
-    int32_t l_name = rd<int32_t>(&u[p]); p += 4;
-    hdr.target_names.emplace_back((const char*)&u[p]);
-    p += (size_t)l_name;
-    hdr.target_lens.push_back((uint32_t)rd<int32_t>(&u[p])); p += 4;
-  }
-  parse_rg_lines(hdr.text, hdr.read_groups);
-  const ReadGroups& rg = hdr.read_groups;
+  // ONE PIPELINE: the worker threads inflate the members (in file order, sixteen at a time); this thread follows the
+  // inflated prefix, parses the header, finds every record (a serial chain: each record's length leads to the next) and
+  // hands finished runs of records back to the workers, which decode them when no member is left to inflate.  The
+  // record walk and the decode hide behind the inflate instead of following it.
+  constexpr size_t CHUNK = 16, RUN = 8192;
+  const size_t n_chunks = (blocks.size() + CHUNK - 1) / CHUNK;
+  std::vector<std::atomic<uint8_t>> chunk_done(n_chunks + 1);
+  for (auto& f : chunk_done) f.store(0, std::memory_order_relaxed);
+  std::vector<size_t> chunk_end(n_chunks + 1, 0);   // uncompressed offset where every chunk ends
+  for (size_t k = 0; k < n_chunks; ++k) { const BgzfBlock& last = blocks[std::min(blocks.size(), (k + 1) * CHUNK) - 1]; chunk_end[k] = last.uoff + last.isize; }
+  std::atomic<size_t> next_chunk(0), runs_published(0), next_run(0);
+  std::atomic<bool> failed(false), walk_finished(false);
+  std::mutex err_mu;
+  std::string err;
+  auto fail = [&](const std::string& what) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = what; failed = true; };
 
-  // Records: one serial walk finds every record and sizes the arrays (prefix sums of the CIGAR and sequence lengths),
-  // then the threads decode disjoint record ranges into them.
-  std::vector<size_t> rec_at;  // offset of every record's fixed part
+  // destination arrays at their upper bounds (untouched pages cost nothing; trimmed when the walk is done): a record is at
+  // least 36 bytes, a base at least one and a half, a CIGAR operation four
   const size_t n0 = reads.size();
-  uint64_t n_cig_total = reads.cigars.size(), n_seq_total = reads.bases.size();
-  std::vector<uint64_t> cig_off, seq_off;
-  while (p + 4 <= u.size()) {
-    const int32_t block = rd<int32_t>(&u[p]);
-    if (block < 32 || p + 4 + (size_t)block > u.size()) throw std::runtime_error("truncated BAM record");
-    const uint8_t* x = &u[p + 4];
-    const uint8_t l_name = x[8];
-    const uint16_t n_cigar = rd<uint16_t>(x + 12);
-    const int32_t l_seq = rd<int32_t>(x + 16);
-    if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cigar + (((size_t)l_seq + 1) >> 1) + (size_t)l_seq > (size_t)block)
-      throw std::runtime_error("truncated BAM record");
-    rec_at.push_back(p + 4);
-    cig_off.push_back(n_cig_total); seq_off.push_back(n_seq_total);
-    n_cig_total += n_cigar; n_seq_total += (uint64_t)l_seq;
-    p += 4 + (size_t)block;
-  }
-  phase_done("find records");
-  const size_t n_new = rec_at.size(), n_all = n0 + n_new;
-  reads.tid.resize(n_all); reads.pos.resize(n_all); reads.flag.resize(n_all); reads.mapq.resize(n_all);
-  reads.n_cigar.resize(n_all); reads.cigar_off.resize(n_all); reads.l_seq.resize(n_all); reads.seq_off.resize(n_all);
-  reads.x1.resize(n_all); reads.xl.resize(n_all); reads.xr.resize(n_all); reads.as.resize(n_all); reads.rg.resize(n_all);
-  reads.cigars.resize(n_cig_total); reads.bases.resize(n_seq_total); reads.quals.resize(n_seq_total);
+  const uint64_t n_cig0 = reads.cigars.size(), n_seq0 = reads.bases.size();
+  const size_t max_reads = total / 36 + 1, max_seq = total * 2 / 3 + 16, max_cig = total / 4 + 1;
+  auto grow = [&](auto& v, size_t n) { v.resize(n); };
+  grow(reads.tid, n0 + max_reads); grow(reads.pos, n0 + max_reads); grow(reads.flag, n0 + max_reads); grow(reads.mapq, n0 + max_reads);
+  grow(reads.n_cigar, n0 + max_reads); grow(reads.cigar_off, n0 + max_reads); grow(reads.l_seq, n0 + max_reads); grow(reads.seq_off, n0 + max_reads);
+  grow(reads.x1, n0 + max_reads); grow(reads.xl, n0 + max_reads); grow(reads.xr, n0 + max_reads); grow(reads.as, n0 + max_reads); grow(reads.rg, n0 + max_reads);
+  grow(reads.cigars, n_cig0 + max_cig); grow(reads.bases, n_seq0 + max_seq); grow(reads.quals, n_seq0 + max_seq);
+  RawVec<size_t> rec_at;     // offset of every record's fixed part
+  rec_at.resize(max_reads);
+  const ReadGroups* rgp = &hdr.read_groups;   // (filled by the walker before the first run is published)
+
   auto decode = [&](size_t r) {
+    const ReadGroups& rg = *rgp;
     const uint8_t* x = &u[rec_at[r]];
     const int32_t block = rd<int32_t>(x - 4);
     const size_t i = n0 + r;
@@ -202,14 +189,13 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
     const int32_t l_seq = rd<int32_t>(x + 16);
     const uint8_t* q = x + 32 + l_name;
     reads.tid[i] = rd<int32_t>(x); reads.pos[i] = rd<int32_t>(x + 4); reads.flag[i] = rd<uint16_t>(x + 14); reads.mapq[i] = x[9];
-    reads.n_cigar[i] = n_cigar; reads.cigar_off[i] = cig_off[r];
-    for (int k = 0; k < n_cigar; ++k) reads.cigars[cig_off[r] + (size_t)k] = rd<uint32_t>(q + 4 * k);
+    const uint64_t cig_at = reads.cigar_off[i], seq_at = reads.seq_off[i];   // (written by the walker)
+    for (int k = 0; k < n_cigar; ++k) reads.cigars[cig_at + (size_t)k] = rd<uint32_t>(q + 4 * k);
     q += 4 * (size_t)n_cigar;
-    reads.l_seq[i] = (uint32_t)l_seq; reads.seq_off[i] = seq_off[r];
-    uint8_t* bases = reads.bases.data() + seq_off[r];
+    uint8_t* bases = reads.bases.data() + seq_at;
     for (int b = 0; b < l_seq; ++b) bases[b] = (q[b >> 1] >> ((~b & 1) << 2)) & 0xf;
     q += ((size_t)l_seq + 1) >> 1;
-    memcpy(reads.quals.data() + seq_off[r], q, (size_t)l_seq);
+    memcpy(reads.quals.data() + seq_at, q, (size_t)l_seq);
     q += l_seq;
     uint32_t x1 = 1; int32_t xl = -1, xr = -1, as = 0; uint8_t rgi = 0;
     bool seen_x1 = false, seen_xl = false, seen_xr = false, seen_rg = false;  // bam_aux_get returns the FIRST match
@@ -219,6 +205,7 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
       const uint8_t* v = q + 3;
       size_t sz = aux_value_size(type);
       if (sz) {
+        if (v + sz > end) throw std::runtime_error("truncated aux field in BAM record");
         if (t0 == 'X' && t1 == '1' && !seen_x1) { x1 = (uint32_t)aux_int(type, v); seen_x1 = true; }
         else if (t0 == 'X' && t1 == 'L' && !seen_xl) { xl = (int32_t)aux_int(type, v); seen_xl = true; }
         else if (t0 == 'X' && t1 == 'R' && !seen_xr) { xr = (int32_t)aux_int(type, v); seen_xr = true; }
@@ -236,35 +223,123 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
         }
         q = z + 1;
       } else if (type == 'B') {
+        if (v + 5 > end) throw std::runtime_error("truncated aux array in BAM record");
         uint8_t st = v[0];
         uint32_t n = rd<uint32_t>(v + 1);
-        q = v + 5 + (size_t)n * aux_value_size(st);
+        const size_t es = aux_value_size(st);
+        if (!es || (size_t)(end - (v + 5)) / es < n) throw std::runtime_error("truncated aux array in BAM record");
+        q = v + 5 + (size_t)n * es;
       } else {
         throw std::runtime_error("unknown aux type in BAM record");
       }
     }
     reads.x1[i] = x1; reads.xl[i] = xl; reads.xr[i] = xr; reads.as[i] = as; reads.rg[i] = rgi;
   };
-  {
-    std::atomic<size_t> next(0);
-    std::mutex err_mu;
-    std::string err;
-    auto work = [&]() {
-      try {
-        for (;;) {
-          const size_t r0 = next.fetch_add(4096);
-          if (r0 >= n_new) break;
-          for (size_t r = r0; r < std::min(r0 + 4096, n_new); ++r) decode(r);
+
+  std::atomic<size_t> n_found(0);   // records the walker has found so far (the last run may be short)
+  auto work = [&]() {
+    try {
+      for (;;) {
+        if (failed) return;
+        const size_t k = next_chunk.load() < n_chunks ? next_chunk.fetch_add(1) : n_chunks;
+        if (k < n_chunks) {
+          for (size_t j = k * CHUNK; j < std::min(blocks.size(), (k + 1) * CHUNK); ++j) inflate_block(in, blocks[j], u.data());
+          chunk_done[k].store(1, std::memory_order_release);
+          continue;
         }
-      } catch (const std::exception& e) { std::lock_guard<std::mutex> g(err_mu); if (err.empty()) err = e.what(); next = n_new; }
-    };
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
-    if (!err.empty()) throw std::runtime_error(err);
-  }
-  phase_done("decode records");
+        const size_t have = runs_published.load(std::memory_order_acquire);
+        size_t r = next_run.load();
+        if (r < have) {
+          if (!next_run.compare_exchange_strong(r, r + 1)) continue;
+          const size_t lo = r * RUN, hi = std::min(n_found.load(std::memory_order_acquire), lo + RUN);
+          for (size_t i = lo; i < hi; ++i) decode(i);
+          continue;
+        }
+        if (walk_finished.load(std::memory_order_acquire) && next_run.load() >= runs_published.load(std::memory_order_acquire)) return;
+        std::this_thread::yield();
+      }
+    } catch (const std::exception& e) { fail(e.what()); }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+
+  // ---- the walker (this thread).  need(p): every byte below p is inflated (it inflates, too, while it has to wait)
+  size_t ready = 0, ready_chunk = 0;
+  auto need = [&](size_t p) {
+    if (p > total) p = total;
+    while (ready < p) {
+      if (failed) throw std::runtime_error("corrupt BGZF payload in " + path);
+      if (ready_chunk < n_chunks && chunk_done[ready_chunk].load(std::memory_order_acquire)) { ready = chunk_end[ready_chunk++]; continue; }
+      const size_t k = next_chunk.load() < n_chunks ? next_chunk.fetch_add(1) : n_chunks;
+      if (k < n_chunks) {
+        try { for (size_t j = k * CHUNK; j < std::min(blocks.size(), (k + 1) * CHUNK); ++j) inflate_block(in, blocks[j], u.data()); }
+        catch (const std::exception& e) { fail(e.what()); throw; }
+        chunk_done[k].store(1, std::memory_order_release);
+      } else {
+        std::this_thread::yield();
+      }
+    }
+  };
+  size_t n_new = 0;
+  uint64_t n_cig_total = n_cig0, n_seq_total = n_seq0;
+  try {
+    need(12);
+    if (total < 12 || memcmp(u.data(), "BAM\1", 4) != 0) throw std::runtime_error(path + " is not a BAM file");
+    size_t p = 4;
+    const int32_t l_text = rd<int32_t>(&u[p]); p += 4;
+    if (l_text < 0 || p + (size_t)l_text + 4 > total) throw std::runtime_error("truncated BAM header");
+    need(p + (size_t)l_text + 4);
+    hdr.text.assign((const char*)&u[p], (size_t)l_text);
+    hdr.text = hdr.text.c_str();  // cut at the first NUL, as a C string consumer would see it
+    p += (size_t)l_text;
+    const int32_t n_ref = rd<int32_t>(&u[p]); p += 4;
+    if (n_ref < 0) throw std::runtime_error("truncated BAM header");
+    for (int i = 0; i < n_ref; ++i) {
+      need(p + 4);
+      if (p + 4 > total) throw std::runtime_error("truncated BAM header");
+      const int32_t l_name = rd<int32_t>(&u[p]); p += 4;
+      if (l_name < 1 || p + (size_t)l_name + 4 > total) throw std::runtime_error("truncated BAM header");
+      need(p + (size_t)l_name + 4);
+      hdr.target_names.emplace_back((const char*)&u[p], strnlen((const char*)&u[p], (size_t)l_name));
+      p += (size_t)l_name;
+      hdr.target_lens.push_back((uint32_t)rd<int32_t>(&u[p])); p += 4;
+    }
+    parse_rg_lines(hdr.text, hdr.read_groups);
+    // records: one serial walk finds every record and gives it its place in the arrays (prefix sums of the CIGAR and
+    // sequence lengths); a run of RUN records is published to the decoders once its last byte is inflated
+    while (p + 4 <= total) {
+      need(p + 36);
+      const int32_t block = rd<int32_t>(&u[p]);
+      if (block < 32 || p + 4 + (size_t)block > total) throw std::runtime_error("truncated BAM record");
+      const uint8_t* x = &u[p + 4];
+      const uint8_t l_name = x[8];
+      const uint16_t n_cigar = rd<uint16_t>(x + 12);
+      const int32_t l_seq = rd<int32_t>(x + 16);
+      if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cigar + (((size_t)l_seq + 1) >> 1) + (size_t)l_seq > (size_t)block)
+        throw std::runtime_error("truncated BAM record");
+      if (n_new >= max_reads) throw std::runtime_error("truncated BAM record");
+      rec_at[n_new] = p + 4;
+      reads.n_cigar[n0 + n_new] = n_cigar; reads.cigar_off[n0 + n_new] = n_cig_total;
+      reads.l_seq[n0 + n_new] = (uint32_t)l_seq; reads.seq_off[n0 + n_new] = n_seq_total;
+      n_cig_total += n_cigar; n_seq_total += (uint64_t)l_seq;
+      p += 4 + (size_t)block;
+      ++n_new;
+      if (n_new % RUN == 0) { need(p); n_found.store(n_new, std::memory_order_release); runs_published.store(n_new / RUN, std::memory_order_release); }
+    }
+    need(total);
+    n_found.store(n_new, std::memory_order_release);
+    runs_published.store((n_new + RUN - 1) / RUN, std::memory_order_release);
+  } catch (const std::exception& e) { fail(e.what()); }
+  walk_finished.store(true, std::memory_order_release);
+  work();   // the walker decodes, too, now
+  for (auto& t : pool) t.join();
+  if (failed) throw std::runtime_error(err.empty() ? "corrupt BGZF payload in " + path : err);
+  const size_t n_all = n0 + n_new;
+  reads.tid.resize(n_all); reads.pos.resize(n_all); reads.flag.resize(n_all); reads.mapq.resize(n_all);
+  reads.n_cigar.resize(n_all); reads.cigar_off.resize(n_all); reads.l_seq.resize(n_all); reads.seq_off.resize(n_all);
+  reads.x1.resize(n_all); reads.xl.resize(n_all); reads.xr.resize(n_all); reads.as.resize(n_all); reads.rg.resize(n_all);
+  reads.cigars.resize(n_cig_total); reads.bases.resize(n_seq_total); reads.quals.resize(n_seq_total);
+  phase_done("inflate, find and decode records");
 }
 
 // ---------------------------------------------------------------------------------- writers

@@ -9,7 +9,9 @@
 // "record" = one (read, slot) incidence.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace brq {
@@ -39,22 +41,34 @@ struct ReadGroups {
   std::vector<std::string> libraries;
 };
 
+// std::vector whose resize() leaves new elements uninitialised: the read arrays are gigabytes that the decode threads fill
+// at once, and value-initialising them first is a single-threaded pass over all of that memory.
+template <class T>
+struct NoInit : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInit<U>; };
+  NoInit() = default;
+  template <class U> NoInit(const NoInit<U>&) {}
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+  template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+};
+template <class T> using RawVec = std::vector<T, NoInit<T>>;
+
 // Reads of one BAM, structure-of-arrays, in file (coordinate) order.
 struct ReadBatch {
-  std::vector<int32_t> tid, pos;       // 0-based leftmost reference position
-  std::vector<uint16_t> flag;
-  std::vector<uint8_t> mapq;
-  std::vector<uint8_t> rg;             // resolved read-group index (0 when unresolvable)
-  std::vector<uint32_t> x1;            // X1:i redundancy; 1 when the tag is absent
-  std::vector<int32_t> xl, xr;         // XL/XR:i trims; -1 when the tag is absent
-  std::vector<int32_t> as;             // AS:i (carried for the writer only)
-  std::vector<uint32_t> l_seq;
-  std::vector<uint64_t> seq_off;       // into bases/quals
-  std::vector<uint32_t> n_cigar;
-  std::vector<uint64_t> cigar_off;     // into cigars
-  std::vector<uint8_t> bases;          // one BAM 4-bit code per byte (1,2,4,8,15)
-  std::vector<uint8_t> quals;          // raw phred
-  std::vector<uint32_t> cigars;        // BAM encoding: len<<4 | op
+  RawVec<int32_t> tid, pos;       // 0-based leftmost reference position
+  RawVec<uint16_t> flag;
+  RawVec<uint8_t> mapq;
+  RawVec<uint8_t> rg;             // resolved read-group index (0 when unresolvable)
+  RawVec<uint32_t> x1;            // X1:i redundancy; 1 when the tag is absent
+  RawVec<int32_t> xl, xr;         // XL/XR:i trims; -1 when the tag is absent
+  RawVec<int32_t> as;             // AS:i (carried for the writer only)
+  RawVec<uint32_t> l_seq;
+  RawVec<uint64_t> seq_off;       // into bases/quals
+  RawVec<uint32_t> n_cigar;
+  RawVec<uint64_t> cigar_off;     // into cigars
+  RawVec<uint8_t> bases;          // one BAM 4-bit code per byte (1,2,4,8,15)
+  RawVec<uint8_t> quals;          // raw phred
+  RawVec<uint32_t> cigars;        // BAM encoding: len<<4 | op
   std::vector<std::string> names;      // optional (writer); may be empty
   size_t size() const { return tid.size(); }
 };

@@ -22,6 +22,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <type_traits>
 #include <vector>
 
@@ -33,8 +35,29 @@ int expand_launch_count() { return g_expand_launches; }
 static inline void launched(int n = 1) { g_expand_launches += n; note_launches(n); }
 
 // ------------------------------------------------------------------------------------------ buffers
+// the staging buffers belong to the process, not to a context: a fresh context on the same device finds them allocated
+// (page-locking 64 MB costs tens of milliseconds, a whole C1 upload costs little more)
+namespace {
+struct RingSlots { void* slot[UploadRing::SLOTS] = {nullptr}; cudaEvent_t done[UploadRing::SLOTS] = {nullptr}; int next = 0; std::mutex mu; };
+RingSlots& ring_of_current_device() {
+  static std::mutex mu;
+  static std::map<int, RingSlots*> rings;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  RingSlots*& r = rings[dev];
+  if (!r) r = new RingSlots;
+  return *r;
+}
+}  // namespace
+
 void UploadRing::copy(void* dst_device, const void* src_host, size_t bytes, cudaStream_t s) {
   if (!bytes) return;
+  RingSlots& R = ring_of_current_device();
+  std::lock_guard<std::mutex> ring_guard(R.mu);
+  void** slot = R.slot;
+  cudaEvent_t* done = R.done;
+  int& next = R.next;
   cudaPointerAttributes attr;
   const bool locked = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
@@ -64,13 +87,7 @@ void UploadRing::copy(void* dst_device, const void* src_host, size_t bytes, cuda
     CUDA_OK(cudaEventRecord(done[k], s));
   }
 }
-void UploadRing::release() {
-  for (int k = 0; k < SLOTS; ++k) {
-    if (slot[k]) cudaFreeHost(slot[k]);
-    if (done[k]) cudaEventDestroy(done[k]);
-    slot[k] = nullptr; done[k] = nullptr;
-  }
-}
+void UploadRing::release() {}   // (the buffers are the process's: see ring_of_current_device)
 
 void ReadsDev::upload(const ReadBatch& R, cudaStream_t s) {
   n = R.size();
@@ -204,8 +221,9 @@ __global__ void __launch_bounds__(256) read_starts_kernel(ExpandArgs a, unsigned
 }
 
 // ------------------------------------------------------------------------------------------ the tile passes
+// (the count pass fits 64 registers: four CTAs per SM; the fill pass spills there and runs faster with three)
 template <bool FILL>
-__global__ void __launch_bounds__(256, 4) tile_kernel(ExpandArgs a) {
+__global__ void __launch_bounds__(256, FILL ? 3 : 4) tile_kernel(ExpandArgs a) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (tile >= a.n_tiles) return;
   tile_lane<FILL>(a, tile, threadIdx.x & 31u);
@@ -474,7 +492,7 @@ void expand_on_device(const BamHeader& hdr, const RefSet& ref, const ReadBatch& 
   st = PileupStream();
   st.device_built = true;
   ExpandPlan plan;
-  make_expand_plan(hdr, ref, host.tid, cfg, st, plan);
+  make_expand_plan(hdr, ref, host.tid.data(), host.tid.size(), cfg, st, plan);
   const std::vector<ExpandSeg>& segs = plan.segs;
   const std::vector<uint8_t>& refbytes = plan.refbytes;
   const std::vector<int32_t>& seg_of_tid = plan.seg_of_tid;

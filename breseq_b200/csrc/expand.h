@@ -10,24 +10,21 @@
 
 namespace brq {
 
-// The aligned reads of a BAM in HBM, structure-of-arrays in file order: what crosses PCIe on the device staging path
-// (about 2.3 bytes per aligned base: base code, quality, and 60 bytes per read).
 // Pageable host memory -> HBM at PCIe speed: a ring of page-locked staging buffers that a few host threads fill (memcpy)
 // while the copy engine drains the ones before (one cudaMemcpyAsync per piece; a plain cudaMemcpyAsync from pageable memory
 // goes through the driver's single staging thread at a sixth of the link's speed, and page-locking gigabytes of existing
 // memory costs more than the copy it speeds up).
 struct UploadRing {
   static constexpr int SLOTS = 4;
-  static constexpr size_t SLOT_BYTES = (size_t)32 << 20;
-  void* slot[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t done[SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  int next = 0;
+  static constexpr size_t SLOT_BYTES = (size_t)16 << 20;
   // parallel_for(n_parts, body(part)): the context's parked worker threads
   std::function<void(size_t, const std::function<void(size_t)>&)> parallel_for;
   void copy(void* dst_device, const void* src_host, size_t bytes, cudaStream_t s);
   void release();
 };
 
+// The aligned reads of a BAM in HBM, structure-of-arrays in file order: what crosses PCIe on the device staging path
+// (about 2.3 bytes per aligned base: base code, quality, and 60 bytes per read).
 struct ReadsDev {
   DevBuf<int32_t> tid, pos, xl, xr;
   DevBuf<uint16_t> flag;

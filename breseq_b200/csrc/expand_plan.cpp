@@ -5,17 +5,17 @@
 
 namespace brq {
 
-void make_expand_plan(const BamHeader& hdr, const RefSet& ref, const std::vector<int32_t>& tid, const StageConfig& cfg, PileupStream& st,
+void make_expand_plan(const BamHeader& hdr, const RefSet& ref, const int32_t* tid, size_t n_reads, const StageConfig& cfg, PileupStream& st,
                       ExpandPlan& plan) {
   const size_t n_targets = hdr.target_names.size();
   std::vector<const std::string*> refseq;
   plan_segments(hdr, ref, cfg, st, refseq);
   const size_t n_visit = st.segments.size();
   if (st.n_base >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 - 2 slots in one staged stream");
-  if (tid.size() >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 reads in one staging call");
+  if (n_reads >= 0xFFFFFFF0ull) throw std::runtime_error("more than 2^32 reads in one staging call");
   // read ranges per target (the BAM is coordinate sorted: the device checks it)
   std::vector<uint32_t> t_first(n_targets, 0), t_last(n_targets, 0);
-  for (size_t i = 0; i < tid.size(); ++i) {
+  for (size_t i = 0; i < n_reads; ++i) {
     const int32_t t = tid[i];
     if (t < 0 || (size_t)t >= n_targets) continue;
     if (t_last[(size_t)t] == 0) t_first[(size_t)t] = (uint32_t)i;

@@ -15,7 +15,7 @@ struct ExpandPlan {
 };
 
 // Fills st.segments / n_base / n_groups (plan_segments) and the plan.  `tid`: BAM tid of every read, in file order.
-void make_expand_plan(const BamHeader& hdr, const RefSet& ref, const std::vector<int32_t>& tid, const StageConfig& cfg, PileupStream& st,
+void make_expand_plan(const BamHeader& hdr, const RefSet& ref, const int32_t* tid, size_t n_reads, const StageConfig& cfg, PileupStream& st,
                       ExpandPlan& plan);
 
 }  // namespace brq

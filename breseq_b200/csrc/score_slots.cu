@@ -62,7 +62,7 @@ void note_launches(int n);
 namespace {
 
 constexpr int TALLY_MAX_TPB = 768;
-constexpr uint32_t PREFETCH_VECTORS = 4;   // round vectors (KB) of a round kept in L2 ahead of the record ring (BRQ_TALLY_PREFETCH overrides; -1 = none)
+constexpr uint32_t PREFETCH_VECTORS = 2;   // round vectors (KB) of a round kept in L2 ahead of the record ring (BRQ_TALLY_PREFETCH overrides; -1 = none)
 constexpr int RING = 4;           // 16-byte stages of each lane's record ring (a power of two)
 constexpr int FIT_TPB = 256;
 constexpr int FIT_LANES = 32;     // lanes cooperating on one slot: the work list is short, so a slot's latency is what counts

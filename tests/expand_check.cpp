@@ -64,7 +64,7 @@ bool run_case(const Case& c) {
   // ------------------------------------------------------------------ the device sequence, serially
   PileupStream D;
   ExpandPlan plan;
-  make_expand_plan(hdr, ref, R.tid, cfg, D, plan);
+  make_expand_plan(hdr, ref, R.tid.data(), R.tid.size(), cfg, D, plan);
   const uint32_t n_base = (uint32_t)D.n_base;
   const size_t n_targets = hdr.target_names.size();
   RawReads raw;

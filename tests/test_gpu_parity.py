@@ -255,3 +255,38 @@ def test_sharded_run_merges_to_the_unsharded_evidence(name, world, datasets, tmp
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_one_context_two_bams_through_the_adapter(datasets, tmp_path):
+    """A context reused for a second BAM through brq_run_error_count (same covariates) must write the second BAM's files:
+    the host copies of the histograms belong to the stream they were downloaded from."""
+    a, b = datasets["tiny"], datasets["multi"]
+    ctx = bq.Context(device=0)
+    for d, sub in ((a, "a"), (b, "b")):
+        out = str(tmp_path / sub)
+        os.makedirs(out)
+        cov = "read_set=3,obs_base,ref_base,quality=42"
+        bq.error_count(d["bam"], d["fasta"], out, helpers.readfile_names(d), covariates=cov, read_file_sets=helpers.read_file_sets(d),
+                       error_rates_file_name=os.path.join(out, "error_rates.tab"), ctx=ctx)
+        assert helpers.covariates(d) == cov
+        assert filecmp.cmp(os.path.join(out, "error_rates.tab"), d["oracle_rates"], shallow=False)
+        for rf in helpers.readfile_names(d):
+            name = "base_qual_error_prob.%s.tab" % rf
+            assert filecmp.cmp(os.path.join(out, name), os.path.join(d["oracle_dir"], name), shallow=False), name
+        for g in range(len(d["contig_lens"])):
+            name = "%d.unique_only_coverage_distribution.tab" % g
+            assert filecmp.cmp(os.path.join(out, name), os.path.join(d["oracle_dir"], name), shallow=False), name
+    ctx.close()
+
+
+def test_base_quality_cutoff_zero_is_a_value(datasets, tmp_path):
+    """Settings::base_quality_cutoff = 0 (every quality scores) runs and matches the oracle run with the same cutoff."""
+    d = datasets["tiny"]
+    out = str(tmp_path)
+    _, im = helpers.cli_args(d, out, rates=d["oracle_rates"], gd=os.path.join(out, "o.gd"))
+    helpers.run_oracle(*im, "--base-quality-cutoff", "0")
+    n = len(d["contig_lens"])
+    bq.identify_mutations(d["bam"], d["fasta"], os.path.join(out, "p.gd"), [d["del_prop"]] * n, [d["del_seed"]] * n, d["mutation_cutoff"],
+                          d["polymorphism_cutoff"], d["precision"], d["places"], error_rates_file_name=d["oracle_rates"],
+                          read_file_sets=helpers.read_file_sets(d), base_quality_cutoff=0)
+    assert open(os.path.join(out, "p.gd")).read() == open(os.path.join(out, "o.gd")).read()

@@ -318,11 +318,17 @@ def main():
         with torch.cuda.stream(ext_stream):
             dist.all_reduce(hist_view["t"])
 
+    call_s = {"error_count": 0.0, "allreduce": 0.0, "derive": 0.0, "score": 0.0}
+
     def step():
-        ctx.error_count(COVARIATES)
-        allreduce_hist()
-        ctx.derive_error_table()
-        ctx.score_columns(params)
+        # (host time inside each call; only the last one waits for the device)
+        t0 = time.perf_counter(); ctx.error_count(COVARIATES)
+        t1 = time.perf_counter(); allreduce_hist()
+        t2 = time.perf_counter(); ctx.derive_error_table()
+        t3 = time.perf_counter(); ctx.score_columns(params)
+        t4 = time.perf_counter()
+        for k, v in zip(call_s, (t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+            call_s[k] += v
 
     def barrier():
         if world > 1:
@@ -333,6 +339,8 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     launches0 = ctx.launch_count()
+    for k in call_s:
+        call_s[k] = 0.0
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -466,6 +474,7 @@ def main():
         if args.coverage is not None or args.scale != 1.0:  # another shape than the named config: say so in the label
             cb["workload"] = ("NOT a BASELINE config (--scale %.3f / --coverage %g override of %s): " % (args.scale, cfg["coverage"], name)) + cb["workload"]
         cb["kernel_ms_rank0"] = k_ms
+        cb["host_call_ms_rank0"] = {k: 1e3 * v / args.steps for k, v in call_s.items()}
         cb["staging"] = "device (csrc/expand.cu)" if device_built else "host (csrc/staging.cpp)"
         cb["staging_seconds"] = t_stage
         cb["staging_note"] = "read synthesis + H2D + device staging of the rank's range, once, before the timed regions (max over ranks)"

@@ -213,7 +213,7 @@ void do_stage(brq_ctx* c) {
     static const bool times = getenv("BRQ_STAGE_TIMES") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
     if (!c->d_reads.ring.parallel_for) {
-      if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+      if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 16) - 1)));
       WorkerPool* pool = c->pool.get();
       c->d_reads.ring.parallel_for = [pool](size_t n_parts, const std::function<void(size_t)>& body) {
         pool->run([&](size_t part, size_t n_workers) { for (size_t p = part; p < n_parts; p += n_workers) body(p); });
@@ -461,7 +461,7 @@ bool host_table_ready(brq_ctx* c) {
   if (!c->host_table_pending) return false;
   CUDA_OK(cudaStreamSynchronize(c->stream));
   c->h_log10.assign(c->h_log10_pinned, c->h_log10_pinned + c->n_log10_pinned);
-  if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+  if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 16) - 1)));
   canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob, c->pool.get());
   c->host_table_pending = false;
   return true;
@@ -501,7 +501,7 @@ void build_device_tables(brq_ctx* c) {
 // h_log10 (loaded or imported) -> text-canonical probabilities on the host -> the device tables
 void install_table(brq_ctx* c) {
   if (!host_table_ready(c)) {  // (a pending device-derived table becomes the host's first: re-install after a new staging call)
-    if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 8) - 1)));
+    if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 16) - 1)));
     canonicalise_table(c->h_log10, c->h_log10_text, c->h_prob, c->pool.get());
   }
   c->have_table = true;

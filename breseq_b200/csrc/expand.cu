@@ -78,7 +78,7 @@ void UploadRing::copy(void* dst_device, const void* src_host, size_t bytes, cuda
     const char* src = static_cast<const char*>(src_host) + at;
     char* stage = static_cast<char*>(slot[k]);
     if (parallel_for) {
-      const size_t parts = 8, step = (len + parts - 1) / parts;
+      const size_t parts = 16, step = (len + parts - 1) / parts;
       parallel_for(parts, [&](size_t p) { const size_t a = p * step; if (a < len) memcpy(stage + a, src + a, std::min(step, len - a)); });
     } else {
       memcpy(stage, src, len);

@@ -336,13 +336,15 @@ def main():
         torch.cuda.synchronize()
         ctx.sync()
 
+    # the clock sampler starts before the warm-up: its first nvidia-smi query initialises the tool and holds a driver lock for
+    # tens of milliseconds, which a kernel launch of the first timed step would otherwise wait for
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     launches0 = ctx.launch_count()
     for k in call_s:
         call_s[k] = 0.0
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     ctx.event_record(0)
     t0 = time.perf_counter()
@@ -475,6 +477,7 @@ def main():
             cb["workload"] = ("NOT a BASELINE config (--scale %.3f / --coverage %g override of %s): " % (args.scale, cfg["coverage"], name)) + cb["workload"]
         cb["kernel_ms_rank0"] = k_ms
         cb["host_call_ms_rank0"] = {k: 1e3 * v / args.steps for k, v in call_s.items()}
+        cb["step_wall_ms_rank0"] = [round(w, 3) for w in step_walls]
         cb["staging"] = "device (csrc/expand.cu)" if device_built else "host (csrc/staging.cpp)"
         cb["staging_seconds"] = t_stage
         cb["staging_note"] = "read synthesis + H2D + device staging of the rank's range, once, before the timed regions (max over ranks)"

@@ -89,6 +89,7 @@ assert COLUMN_DTYPE.itemsize == 96
 CO_BASE_PREDICTED, CO_UNIQUE_ONLY, CO_EMIT, CO_RECHECK, CO_FIT = 1 << 12, 1 << 13, 1 << 14, 1 << 15, 1 << 24
 SCORE_FIT_ALL_COLUMNS = 1
 SCORE_POLYMORPHISM_PREDICTION = 2
+SCORE_KEEP_BOUNDS = 4
 
 _lib = None
 
@@ -475,10 +476,10 @@ class Context:
     # ---- pass 2
     @staticmethod
     def score_params(mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision_decimal=1e-6, precision_places=8,
-                     base_quality_cutoff=3, total_reference_length=0, fit_all_columns=False, polymorphism_prediction=False):
+                     base_quality_cutoff=3, total_reference_length=0, fit_all_columns=False, polymorphism_prediction=False, keep_bounds=False):
         return _ScoreParams(mutation_cutoff, polymorphism_cutoff, precision_decimal, precision_places, base_quality_cutoff,
                             total_reference_length, (SCORE_FIT_ALL_COLUMNS if fit_all_columns else 0) |
-                            (SCORE_POLYMORPHISM_PREDICTION if polymorphism_prediction else 0), 0)
+                            (SCORE_POLYMORPHISM_PREDICTION if polymorphism_prediction else 0) | (SCORE_KEEP_BOUNDS if keep_bounds else 0), 0)
 
     def score_columns(self, params=None):
         p = params or self.score_params()

@@ -387,6 +387,9 @@ void upload(brq_ctx* c) {
 
 void error_count_device(brq_ctx* c, const std::string& covariates, bool do_coverage, bool do_errors) {
   c->need_device();
+  static const bool call_times = getenv("BRQ_TIMING") != nullptr;
+  const auto ct0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) { if (call_times) fprintf(stderr, "[brq] error_count: %s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ct0).count()); };
   if (!c->uploaded) upload(c);
   c->spec = parse_covariates(covariates.empty() && !do_errors ? std::string("obs_base,ref_base,quality=1") : covariates);
   c->have_spec = true;
@@ -402,6 +405,7 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   CUDA_OK(cudaMemsetAsync(c->d_hist.p, 0, ((size_t)lay.n_bins + c->cov_stride * n_groups) * 8, c->stream));
   CUDA_OK(cudaMemsetAsync(c->d_scalars.p, 0, 32, c->stream));
   CUDA_OK(cudaEventRecord(c->ev[0], c->stream));
+  lap("memsets queued");
   if (do_errors) {
     // the reference ASSERTs when a counted covariate value exceeds the table (error_count.cpp:485-488); the stream's
     // maxima are known from staging, so the check costs the kernel nothing
@@ -420,10 +424,12 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
     if (st.hist_compact) launch_hist16(c->ds.hist_rec.p, st.n_hist16, reinterpret_cast<const uint32_t*>(c->ds.hist_rec.p + c->ds.hist_exc_at), st.n_hist_exc, lay, c->d_counts.p, c->stream);
     else launch_hist(c->ds.hist_rec.p, st.n_hist, st.hist_bytes == 8, lay, c->d_counts.p, c->stream);
   }
+  lap("histogram kernel queued");
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   if (do_coverage) launch_coverage_hist(c->ds.hist_off.p, c->ds.slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
   CUDA_OK(cudaGetLastError());
+  lap("coverage kernel queued");
   // no synchronisation here: the kernels' error word and their event times are read by finish_error_count() when the
   // counts are downloaded or the timings asked for, and by the check that ends score_columns
   c->hist_check_pending = true;
@@ -563,6 +569,7 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
     throw std::runtime_error("the stream was staged for base_quality_cutoff " + std::to_string(c->st.geo.cutoff) + ", not " +
                              std::to_string(p->base_quality_cutoff) + " (brq_stage_options.base_quality_cutoff)");
   c->sp.fit_all = (p->flags & BRQ_SCORE_FIT_ALL_COLUMNS) ? 1u : 0u;
+  c->sp.keep_bounds = (p->flags & BRQ_SCORE_KEEP_BOUNDS) ? 1u : 0u;
   // the reference ASSERTs when a covariate value exceeds the table (error_count.cpp:485-488); the
   // stream's maxima are known from staging, so the check costs the kernels nothing
   if (c->st.n_score && c->st.max_qual_seen >= c->sp.max_qual)

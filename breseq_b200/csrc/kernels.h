@@ -62,6 +62,7 @@ struct ScoreParams {
   uint32_t hot_mapq;         // the dominant MAPQ value, whose class terms are staged in shared memory
   uint32_t n_hot;            // entries of the hot tables (max_set * 2 * max_qual * 5), 0 = disabled
   uint32_t fit_all;          // evaluate the EM fit on every column with scoring records (diagnostics / parity runs)
+  uint32_t keep_bounds;      // diagnostics: a slot the bounds settled keeps its upper bound in variant_score (else NaN)
   // tally kernel: per-slot class histogram over sq = (set*2 + top) * t_nq + quality - t_qlo (t_nsq classes in
   // t_nsq / 4 words, then two words of special counters) and the shared-memory likelihood table of the dominant
   // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M, top strand ? 1 : 0, top strand ? 0 : 1} (64 bytes a class: the B operand

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
 
     const uint32_t ref = my_ref;
     const double ll[5] = {kept.l0, kept.l1, kept.l2, kept.l3, kept.l4};
-    double consensus = nan;
+    double consensus = nan, kept_bound = nan;
     uint32_t best = 5;
     bool need_fit = false;
     const double slack = 1e-6;
@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
         const float nlog = (float)n * (__log2f(((float)n + 2.0f) / ((float)c_ref + 0.5f)) * 0.30103001f) * 1.00001f + 1e-4f;
         const double bound = (kept.m - ll_ref) + (double)nlog - p.log10_ref_length;
         need_fit = !(bound < p.polymorphism_cutoff - slack);
+        if (p.keep_bounds) kept_bound = bound;
       }
     }
     const bool base_predicted = consensus >= p.mutation_cutoff;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     ColumnOut o;
 #pragma unroll
     for (int b = 0; b < 5; ++b) o.ll[b] = ll[b];
-    o.consensus_score = consensus; o.variant_score = nan;
+    o.consensus_score = consensus; o.variant_score = need_fit ? nan : kept_bound;
     o.redundant[0] = red_bot; o.redundant[1] = red_top;
     o.unique[0] = u_bot; o.unique[1] = u_top; o.raw_redundant[0] = raw_bot; o.raw_redundant[1] = raw_top;
     o.n = n; o.bits = bits;
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(SCREEN_TPB) screen_kernel(const uint32_t* __re
                                                              const uint32_t* __restrict__ side, const uint32_t* __restrict__ side_off,
                                                              const uint8_t* __restrict__ slot_ref, const uint32_t* __restrict__ worklist,
                                                              const ClassTerms* __restrict__ lut, const HotRatios* __restrict__ hotR,
-                                                             ScoreParams p, const ColumnOut* __restrict__ out, uint32_t* __restrict__ survivors,
+                                                             ScoreParams p, ColumnOut* __restrict__ out, uint32_t* __restrict__ survivors,
                                                              uint32_t* __restrict__ scalars) {
   extern __shared__ __align__(16) unsigned char screen_sm[];
   __shared__ uint8_t mapq_slot[256];
@@ -658,6 +659,7 @@ __global__ void __launch_bounds__(SCREEN_TPB) screen_kernel(const uint32_t* __re
         bound = fmaxf(bound, sc);
       }
       keep = bad || !(bound < (float)p.polymorphism_cutoff - SCREEN_MARGIN);
+      if (!keep && p.keep_bounds && lane == 0) out[slot].variant_score = (double)bound;
     }
     if (keep && lane == 0) survivors[atomicAdd(&scalars[4], 1u)] = slot;
   }

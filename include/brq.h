@@ -186,6 +186,10 @@ typedef struct brq_score_params {
 #define BRQ_SCORE_FIT_ALL_COLUMNS 1u
 /* Settings::polymorphism_prediction: words the `prediction` field of user-evidence rows (identify_mutations.cpp:1992-1996) */
 #define BRQ_SCORE_POLYMORPHISM_PREDICTION 2u
+/* diagnostics: a slot whose presence score the kernels only BOUNDED (the bound is under the cutoff: no fit) reports that upper
+ * bound in brq_column.variant_score instead of NaN; bit 24 of `bits` still says that no fit ran (parity tests check
+ * bound >= the reference's score on every column) */
+#define BRQ_SCORE_KEEP_BOUNDS 4u
 
 typedef struct brq_column {  /* one per slot: base columns of the visited targets, then insert sub-columns */
   double ll[5];

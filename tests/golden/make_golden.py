@@ -41,6 +41,8 @@ def main():
     if not os.path.exists(helpers.REF_CLI):
         sys.exit("oracle/_ref/ref_cli is missing: run oracle/ref_build.sh where /root/reference exists")
     for name in helpers.DATASETS:
+        if helpers.DATASETS[name].get("no_golden"):
+            continue
         gdir = os.path.join(HERE, name)
         shutil.rmtree(gdir, ignore_errors=True)
         os.makedirs(gdir)

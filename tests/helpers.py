@@ -51,6 +51,12 @@ DATASETS = {
                  n_polymorphic=12, n_fixed=4, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
                  precision=1e-6, places=8, del_prop=8.0, del_seed=0.0,
                  covariates="read_set=3,obs_base,ref_base,quality=42,read_pos=50,base_repeat=4", big_table=True),
+    # the north-star shape in small: polymorphism mode at 1000x, where the work list is a sixth of the columns and the screen
+    # kernel (one pass of likelihood bounds) settles nearly all of it
+    "pop1000": dict(seed=23, contig_lens=[12000], prefix="pop",
+                    read_sets=[dict(name="pp", paired=True, read_len=150, coverage=1000.0, frag_mean=400, frag_sd=40)],
+                    n_polymorphic=12, n_fixed=3, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0,
+                    precision=1e-6, places=8, del_prop=300.0, del_seed=0.0, no_golden=True),
 }
 
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "ref_cli")  # the reference's own sources (oracle/ref_build.sh)

@@ -17,7 +17,7 @@ import pytest
 import breseq_b200 as bq
 import helpers
 
-NAMES = list(helpers.DATASETS)
+NAMES = [n for n in helpers.DATASETS if not helpers.DATASETS[n].get("no_golden")]
 
 
 def golden(name, f):

@@ -290,3 +290,66 @@ def test_base_quality_cutoff_zero_is_a_value(datasets, tmp_path):
                           d["polymorphism_cutoff"], d["precision"], d["places"], error_rates_file_name=d["oracle_rates"],
                           read_file_sets=helpers.read_file_sets(d), base_quality_cutoff=0)
     assert open(os.path.join(out, "p.gd")).read() == open(os.path.join(out, "o.gd")).read()
+
+
+# ---- how far the device's arithmetic is from the reference's, and what the decisions' slack has to cover
+FIT_SLACK = 1e-6       # score_slots.cu: a fitted slot emits when variant_score >= cutoff - slack; emitting slots are re-evaluated on the host
+SCREEN_MARGIN = 0.25   # score_slots.cu SCREEN_MARGIN
+
+
+@pytest.mark.parametrize("name", ["deep", "lambda", "pop1000"])
+def test_fit_parity_margins(name, datasets):
+    """Every column fitted on the device (BRQ_SCORE_FIT_ALL_COLUMNS) against the oracle's fit: ABSOLUTE differences of the
+    presence score and the frequencies, the columns whose EM stopped at another iteration listed one by one.  The slack of
+    the emit decision must be ten times what is measured here; a column is never lost to rounding."""
+    d = datasets[name]
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
+    ctx.load_error_table(d["oracle_rates"])
+    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"], fit_all_columns=True))
+    cols, _ = ctx.columns_download()
+    o = helpers.oracle_columns(d["oracle_columns"])
+    g = cols[helpers.oracle_slots(o, ctx.stream(), helpers.visit_slot0(helpers.contig_names(d), d["contig_lens"]))]
+    ctx.close()
+    fit = ((g["bits"] & bq.CO_FIT) != 0) & ~np.isnan(o["variant_score"]) & ~np.isnan(g["variant_score"])
+    dv = np.abs(g["variant_score"][fit] - o["variant_score"][fit])
+    it_g, it_o = ((g["bits"] >> 16) & 0xFF)[fit], o["iterations"][fit]
+    same = it_g == it_o
+    idx = np.flatnonzero(fit)
+    print("\n%s: %d fitted columns with a variant; |d variant_score| max %.3g (same iteration count: %.3g); %d columns stop at another iteration"
+          % (name, fit.sum(), dv.max(), dv[same].max(), (~same).sum()))
+    for k in np.flatnonzero(~same)[:50]:
+        i = idx[k]
+        print("  tid %d pos %d ins %d: iterations device %d oracle %d, variant_score device %.12g oracle %.12g (cutoff %g)"
+              % (o["tid"][i], o["pos1"][i], o["insert_count"][i], it_g[k], it_o[k], g["variant_score"][i], o["variant_score"][i], d["polymorphism_cutoff"]))
+    assert dv[same].max() <= 1e-8, "device fit differs from the reference's beyond 1e-8 absolute"
+    assert dv.max() <= FIT_SLACK / 10, "the emit slack (1e-6) must be ten times the largest difference"
+    # a column that stops at another iteration is either far from the cutoff or flagged for the host's verdict
+    near = np.abs(o["variant_score"][fit] - d["polymorphism_cutoff"]) < 10 * FIT_SLACK
+    flagged = ((g["bits"] & (bq.CO_EMIT | bq.CO_RECHECK)) != 0)[fit]
+    assert np.all(flagged[near & ~same])
+
+
+@pytest.mark.parametrize("name", ["deep", "lambda", "pop1000", "multi"])
+def test_presence_bounds_hold_on_every_column(name, datasets):
+    """BRQ_SCORE_KEEP_BOUNDS: a slot the kernels did not fit reports the upper bound that settled it (the tally's, or the
+    screen kernel's); it must be at or above the reference's presence score on EVERY such column, and under the cutoff by
+    the decision's margin."""
+    d = datasets[name]
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
+    ctx.load_error_table(d["oracle_rates"])
+    ctx.score_columns(bq.Context.score_params(d["mutation_cutoff"], d["polymorphism_cutoff"], d["precision"], d["places"], keep_bounds=True))
+    cols, _ = ctx.columns_download()
+    o = helpers.oracle_columns(d["oracle_columns"])
+    g = cols[helpers.oracle_slots(o, ctx.stream(), helpers.visit_slot0(helpers.contig_names(d), d["contig_lens"]))]
+    ctx.close()
+    settled = ((g["bits"] & bq.CO_FIT) == 0) & (o["n"] > 0)
+    assert settled.sum() > 0.5 * (o["n"] > 0).sum()
+    bound = g["variant_score"][settled]
+    assert np.all(np.isfinite(bound)) and bound.max() < d["polymorphism_cutoff"] - FIT_SLACK / 2
+    v = ~np.isnan(o["variant_score"][settled])
+    gap = bound[v] - o["variant_score"][settled][v]
+    print("\n%s: %d settled columns, bound - reference score: min %.3g, median %.3g" % (name, settled.sum(), gap.min(), np.median(gap)))
+    assert gap.min() >= 0.0, "a bound is below the reference's presence score"
+    assert not np.any(o["emitted"][settled])

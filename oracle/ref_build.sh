@@ -47,3 +47,25 @@ $CXX $FLAGS -I"$REF" -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
 $CXX -std=c++17 -O2 -w -I"$HERE/hts_shim" -c "$HERE/hts_shim/hts_shim.cpp" -o "$OUT/obj/hts_shim.o"
 $CXX -o "$OUT/ref_cli" "$OUT/obj/ref_driver.o" $OBJS "$OUT/obj/hts_shim.o" -lz -lpthread
 echo "ref_build: built $OUT/ref_cli"
+
+# ---- the drop-in, compiled for real: the same reference objects with the two entry points' bodies renamed at compile time
+# (-Derror_count=error_count_cpu -Didentify_mutations=identify_mutations_cpu: the reference's sources are compiled where they
+# lie, nothing is copied) and adapters/breseq_adapter.cpp providing breseq::error_count() / breseq::identify_mutations() over
+# libbrq.so.  ref_cli_brq takes ref_cli's command line; tests/test_gpu_adapter.py diffs what the two write.
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/breseq_b200/libbrq.so" ]; then
+  RENAME="-Derror_count=error_count_cpu -Didentify_mutations=identify_mutations_cpu"
+  for s in error_count identify_mutations; do
+    if [ ! -f "$OUT/obj/${s}_renamed.o" ] || [ "$REF/$s.cpp" -nt "$OUT/obj/${s}_renamed.o" ]; then
+      $CXX $FLAGS $RENAME -c "$REF/$s.cpp" -o "$OUT/obj/${s}_renamed.o"
+    fi
+  done
+  $CXX $FLAGS -I"$REF" -I"$REPO/include" -c "$REPO/adapters/breseq_adapter.cpp" -o "$OUT/obj/breseq_adapter.o"
+  OBJS_BRQ=""
+  for s in $SRCS; do
+    case $s in error_count|identify_mutations) OBJS_BRQ="$OBJS_BRQ $OUT/obj/${s}_renamed.o" ;; *) OBJS_BRQ="$OBJS_BRQ $OUT/obj/$s.o" ;; esac
+  done
+  $CXX -o "$OUT/ref_cli_brq" "$OUT/obj/ref_driver.o" "$OUT/obj/breseq_adapter.o" $OBJS_BRQ "$OUT/obj/hts_shim.o" \
+       -L"$REPO/breseq_b200" -lbrq -Wl,-rpath,'$ORIGIN/../../breseq_b200' -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,/usr/local/cuda/lib64 -lz -lpthread
+  echo "ref_build: built $OUT/ref_cli_brq"
+fi

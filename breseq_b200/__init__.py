@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrq.so")
+LIB_PATH = os.environ.get("BRQ_LIB_PATH") or os.path.join(_HERE, "libbrq.so")
 
 
 class BrqError(RuntimeError):

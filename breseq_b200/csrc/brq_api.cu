@@ -594,6 +594,11 @@ void score_device(brq_ctx* c, const brq_score_params* p) {
   CUDA_OK(cudaEventRecord(c->ev[6], c->stream));
   CUDA_OK(cudaGetLastError());
   c->check_device_errors("score_columns");
+  if (getenv("BRQ_TIMING")) {
+    uint32_t sc[8];
+    CUDA_OK(cudaMemcpy(sc, c->d_scalars.p, sizeof sc, cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[brq] score: %u slots on the tally's work list, %u after the screen, %u flagged\n", sc[2], sc[4], sc[1]);
+  }
   if (c->hist_check_pending) finish_error_count(c);  // (its error word was just checked; this reads the event times)
   CUDA_OK(cudaEventElapsedTime(&c->ms_score, c->ev[5], c->ev[6]));
   CUDA_OK(cudaEventElapsedTime(&c->ms_tally, c->ev[5], c->ev[7]));

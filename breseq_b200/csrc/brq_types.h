@@ -106,17 +106,19 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 //                    word sq / 4, byte sq % 4.  Every other record counts in the special words that follow the
 //                    class words (ScoreGeometry::special_counter).
 //   [13]    top      1 = read on the top strand (all kinds)
-//   [14]    slow     HOT but not matching the reference base: the kernel reads its table cell directly
+//   [14]    (unused)
 //   [15]    trimmed  REDUNDANT: is_trimmed() (only the per-position debug file looks at it)
 //   [23:16] sq       HOT: class index (above)         REDUNDANT: [24:16] X1; 511 = the value is the slot's next
 //   [26:24] obs      HOT: observed base A,C,G,T,'.'              SIDE_BIG entry of the side list; [27:25] observed base
-//   [28]    match    HOT and obs equals the slot's reference base
-//   [31:30] kind     0 HOT    scores; dominant MAPQ, quality inside the table window (any observation, '.' included:
-//                             a read without an inserted base is a '.' observation of the insert sub-column, and
-//                             nearly every record of such a slot is one)
+//   [28]    match    HOT (every HOT record matches the slot's reference base)
+//   [31:30] kind     0 HOT    scores; dominant MAPQ, quality inside the table window, observation = the slot's reference
+//                             base ('.' included: a read without an inserted base is a '.' observation of the insert
+//                             sub-column, and nearly every record of such a slot is one)
 //                    1 IDLE   unique but does not score (trimmed, unresolvable, quality below the cutoff)
-//                    2 COLD   scores, class outside the shared table; its classic word is the slot's next
-//                             cold entry of the side list
+//                    2 COLD   scores, but not as a count of a shared-table class: another MAPQ, a quality outside the
+//                             window, or an observation that does not match the reference base (a sequencing error
+//                             or a variant, one record in a thousand: the presence bound of the tally kernel needs
+//                             them one by one).  Its classic word is the slot's next cold entry of the side list
 //                    3 REDUNDANT
 // Within a slot the REDUNDANT records come first and the others follow, each part in arrival (BAM) order.
 // The stream is ROUND-MAJOR AND LANE-INTERLEAVED.  The tally kernel works in rounds of 32 slots (round_slot: same
@@ -133,7 +135,7 @@ constexpr uint32_t SR_OBS_SHIFT = 0, SR_QUAL_SHIFT = 3, SR_TOP_BIT = 1u << 10, S
 // base_repeat covariates (ScoreGeometry::side_stride = 2) has no shared table: every scoring record is COLD and every
 // entry is two words, the classic word and [15:0] read_pos, [23:16] base_repeat of the record's quality position
 // (error_count.cpp:1049-1105).
-constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SLOW_BIT = 1u << 14, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
+constexpr uint32_t DR_COUNTER_MASK = 0x1FFFu, DR_COUNTER_WORD_MASK = 0x1F80u, DR_TOP_BIT = 1u << 13, DR_SQ_SHIFT = 16, DR_SQ_MASK = 0xFFu,
                    DR_OBS_SHIFT = 24, DR_RED_TRIM_BIT = 1u << 15, DR_RED_OBS_SHIFT = 25, DR_X1_SHIFT = 16, DR_X1_MASK = 0x1FFu, DR_MATCH_BIT = 1u << 28,
                    DR_KIND_SHIFT = 30, DR_IDLE = 1u << 30, DR_COLD = 2u << 30, DR_REDUNDANT = 3u << 30,
                    SIDE_BIG = 1u << 31, SIDE_PAD = 0xFFFFFFFFu;  // SIDE_PAD fills a slot's side range to an even count
@@ -159,7 +161,7 @@ struct ScoreGeometry {
 // for every kind of record but two: a HOT record matching its slot's reference base is its counter (class = the
 // counter's word and byte, observation = the slot's base), IDLE / COLD / pad words are their special counter.  Staging
 // sends the low halves (u16, same round-major geometry as score_rec) with bit 15 set on the records whose word does not
-// come back that way (REDUNDANT and HOT-but-mismatching ones, 2 %), and those words in full, per lane of every round
+// come back that way (REDUNDANT ones), and those words in full, per lane of every round
 // in record order (score_exc, CSR score_exc_off[round * 32 + lane]); expand_score_kernel rebuilds score_rec in HBM,
 // bit for bit (staging checks every word), so the kernels and the host never see the transfer form.
 struct ScoreRecon { uint32_t c_idle_top, c_idle_bot, c_cold_top, c_cold_bot, c_trash; };

@@ -306,11 +306,11 @@ BRQ_HD inline DevWordX encode_word(const ScoreGeometry& geo, uint32_t rec, uint3
     return w;
   }
   const bool match = obs == ref;
-  if (n_sq && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 5 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
+  // HOT: a record of the shared table's classes that MATCHES the reference base.  One that does not (a sequencing error or a
+  // variant: one in a thousand) is COLD like a record of another MAPQ: its terms come from its side-list entry
+  if (match && n_sq && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 5 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
     const uint32_t sq = ((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo);
-    w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top;
-    if (match) w.dev |= DR_MATCH_BIT | ((sq >> 2) * 128u + (sq & 3u) * 8u);
-    else w.dev |= DR_SLOW_BIT | special(is_top ? SC_SLOW_TOP : SC_SLOW_BOT);
+    w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top | DR_MATCH_BIT | ((sq >> 2) * 128u + (sq & 3u) * 8u);
   } else {
     w.dev = DR_COLD | top | special(is_top ? SC_COLD_TOP : SC_COLD_BOT);
     w.has_side = true; w.side = rec | (match ? SR_MATCH_BIT : 0u);

@@ -65,7 +65,7 @@ struct ScoreParams {
   uint32_t keep_bounds;      // diagnostics: a slot the bounds settled keeps its upper bound in variant_score (else NaN)
   // tally kernel: per-slot class histogram over sq = (set*2 + top) * t_nq + quality - t_qlo (t_nsq classes in
   // t_nsq / 4 words, then two words of special counters) and the shared-memory likelihood table of the dominant
-  // MAPQ, [obs A,C,G,T][sq] x {L[0..4], M, top strand ? 1 : 0, top strand ? 0 : 1} (64 bytes a class: the B operand
+  // MAPQ, [obs A,C,G,T,'.'][sq] x {L[0..4], ratio column, top strand ? 1 : 0, top strand ? 0 : 1} (64 bytes a class: the B operand
   // of the contraction), t_stride bytes between the five obs planes (A, C, G, T, .)
   uint32_t t_qlo, t_nq, t_nsq, t_nw, t_stride;
   uint32_t mq_min, n_mq;     // MAPQ range of the global table the other scoring records read
@@ -90,7 +90,7 @@ inline uint32_t class_rr(uint32_t ext, const ScoreParams& p) {
 struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 
 // Shared-memory forms of the class terms for the dominant MAPQ, indexed ((set*2+top)*Q+qual)*5+obs.
-struct alignas(32) HotTerms { double L[5]; double M; double pad[2]; };    // M = max_b L[b]; 64 bytes: one 256-bit and one 128-bit load
+struct alignas(32) HotTerms { double L[5]; double M; double pad[2]; };    // M: the class's ratio column, max over b != obs of 10^(L[b] - L[obs]) (the presence bound); 64 bytes: one 256-bit and one 128-bit load
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,

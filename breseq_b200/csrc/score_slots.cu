@@ -125,7 +125,8 @@ __device__ __forceinline__ uint32_t cold_index(uint32_t r, uint32_t ext, const S
   return (((hi * p.n_mapq_slots + mapq_slot[mapq]) * p.max_qual + ((r >> SR_QUAL_SHIFT) & 127)) * (p.n_rpos * p.n_rep) + class_rr(ext, p)) * 5 + (r & 7);
 }
 
-struct Sums { double l0, l1, l2, l3, l4, m; };
+struct Sums { double l0, l1, l2, l3, l4, m; };  // (m: the sum of the records' ratio column, see the presence bound)
+__device__ __forceinline__ float up_float(double x) { return __double2float_ru(x); }
 
 // 10^d for d in [-17, 0], relative error below 1e-14: 2^(n + f), |f| <= 1/2, 2^f by its Taylor polynomial of degree 13.
 // (The sum it feeds is 1 + terms <= 1 whose log10 is added to numbers of magnitude 1 to 10^4: far inside the 1e-9 bar.)
@@ -270,6 +271,20 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
     Sums kept = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double red_top = 0.0, red_bot = 0.0;
     uint32_t raw_top = 0, raw_bot = 0, n = 0, c_ref = 0, u_top = 0, u_bot = 0;
+    // What the presence bound (closing arithmetic) needs of the slot's records besides their count: the sum of the ratio
+    // column over all of them, and of the records that do not match the reference base (all of them are side-list entries),
+    // by observed base g (g' = g - (g > ref)), their number (four byte counters, 255 = many) and the sum of L[g] - L[ref].
+    float rho = 0.f, mis_rho = 0.f, mis_gain0 = 0.f, mis_gain1 = 0.f, mis_gain2 = 0.f, mis_gain3 = 0.f;
+    uint32_t mis_cnt = 0;
+    auto mismatch = [&](const Sums& t, uint32_t obs) {
+      const double l_obs = obs == 0u ? t.l0 : obs == 1u ? t.l1 : obs == 2u ? t.l2 : obs == 3u ? t.l3 : t.l4;
+      const double l_ref = my_ref == 0u ? t.l0 : my_ref == 1u ? t.l1 : my_ref == 2u ? t.l2 : my_ref == 3u ? t.l3 : t.l4;
+      const float gain = up_float(l_obs - l_ref);
+      const uint32_t g = min(obs - (obs > my_ref ? 1u : 0u), 3u);
+      mis_gain0 += g == 0u ? gain : 0.f; mis_gain1 += g == 1u ? gain : 0.f; mis_gain2 += g == 2u ? gain : 0.f; mis_gain3 += g == 3u ? gain : 0.f;
+      if (((mis_cnt >> (8u * g)) & 255u) != 255u) mis_cnt += 1u << (8u * g);
+      mis_rho += up_float(t.m);
+    };
 
     // the scoring records of this lane's slot whose class is not in the shared table (another MAPQ, a '.'
     // observation, a quality outside the window) sit in the side list as classic words: their terms come from the
@@ -287,10 +302,10 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
         w2 = e < cur.side1 ? __ldg(side2 + (e >> 1)) : make_uint2(SIDE_PAD, SIDE_PAD);
         const uint32_t na = w2.x, nb = w2.y;
         Sums ta = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, tb = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        if (!(wa & SIDE_BIG)) { cold_add(ta, wa, 0u, coldT, p); ++n; c_ref += (wa >> 27) & 1u; }
-        if (!(wb & SIDE_BIG)) { cold_add(tb, wb, 0u, coldT, p); ++n; c_ref += (wb >> 27) & 1u; }
-        kept.l0 += ta.l0; kept.l1 += ta.l1; kept.l2 += ta.l2; kept.l3 += ta.l3; kept.l4 += ta.l4; kept.m += ta.m;
-        kept.l0 += tb.l0; kept.l1 += tb.l1; kept.l2 += tb.l2; kept.l3 += tb.l3; kept.l4 += tb.l4; kept.m += tb.m;
+        if (!(wa & SIDE_BIG)) { cold_add(ta, wa, 0u, coldT, p); ++n; c_ref += (wa >> 27) & 1u; if (!(wa & SR_MATCH_BIT)) mismatch(ta, wa & 7u); }
+        if (!(wb & SIDE_BIG)) { cold_add(tb, wb, 0u, coldT, p); ++n; c_ref += (wb >> 27) & 1u; if (!(wb & SR_MATCH_BIT)) mismatch(tb, wb & 7u); }
+        kept.l0 += ta.l0; kept.l1 += ta.l1; kept.l2 += ta.l2; kept.l3 += ta.l3; kept.l4 += ta.l4; rho += up_float(ta.m);
+        kept.l0 += tb.l0; kept.l1 += tb.l1; kept.l2 += tb.l2; kept.l3 += tb.l3; kept.l4 += tb.l4; rho += up_float(tb.m);
         wa = na; wb = nb;
       }
     } else {
@@ -298,8 +313,11 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       for (uint32_t e = cur.side0; e < cur.side1; ++e) {
         const uint2 w = __ldg(reinterpret_cast<const uint2*>(side) + e);
         if (w.x & SIDE_BIG) continue;
-        cold_add(kept, w.x, w.y, coldT, p);
+        Sums t = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        cold_add(t, w.x, w.y, coldT, p);
         ++n; c_ref += (w.x >> 27) & 1u;
+        if (!(w.x & SR_MATCH_BIT)) mismatch(t, w.x & 7u);
+        kept.l0 += t.l0; kept.l1 += t.l1; kept.l2 += t.l2; kept.l3 += t.l3; kept.l4 += t.l4; rho += up_float(t.m);
       }
     }
 
@@ -325,17 +343,6 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       // nothing to wait for) of 1 << 8 * byte on the counter's word
       red_count(hist, v.a.x); red_count(hist, v.a.y); red_count(hist, v.a.z); red_count(hist, v.a.w);
       red_count(hist, v.b.x); red_count(hist, v.b.y); red_count(hist, v.b.z); red_count(hist, v.b.w);
-      if (((v.a.x | v.a.y | v.a.z | v.a.w) | (v.b.x | v.b.y | v.b.z | v.b.w)) & DR_SLOW_BIT) {
-        // a HOT record that does not match the reference base (sequencing error or a variant): its own table cell
-        const uint32_t r[8] = {v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (!(r[j] & DR_SLOW_BIT)) continue;
-          const uint32_t e = tbl + ((r[j] >> DR_OBS_SHIFT) & 7u) * p.t_stride + ((r[j] >> DR_SQ_SHIFT) & DR_SQ_MASK) * 64u;
-          const f64x2 x = lds_f64x2(e), y = lds_f64x2(e + 16u), z = lds_f64x2(e + 32u);
-          kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
-        }
-      }
     };
 
     // the likelihood table of the round's reference base (rounds hold one base; insert sub-columns have '.', N columns no class counts)
@@ -376,8 +383,8 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
           dmma_8x8x4(d[3][0], d[3][1], byte_to_double(w3, a_sel), bv);
         }
       }
-      // special counters (idle / cold / slow records by strand; redundant and pad words count into the trash byte)
-      const uint32_t s0 = lds_u32(hist + n_cw * 128u), s1 = lds_u32(hist + (n_cw + 1u) * 128u);
+      // special counters (idle / cold records by strand; redundant and pad words count into the trash byte)
+      const uint32_t s0 = lds_u32(hist + n_cw * 128u);
       __syncwarp();  // every lane has read the counters: the block's head becomes the scratch of the result tiles
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       __syncwarp();
       {
         const f64x2 x = lds_f64x2(c_lds), y = lds_f64x2(c_lds + 16u), z = lds_f64x2(c_lds + 32u), c = lds_f64x2(c_lds + 48u);
-        kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; kept.m += z.y;
+        kept.l0 += x.x; kept.l1 += x.y; kept.l2 += y.x; kept.l3 += y.y; kept.l4 += z.x; rho += up_float(z.y);
         const uint32_t m_top = (uint32_t)c.x, m_bot = (uint32_t)c.y;  // matching HOT records by strand: exact small integers
         n += m_top + m_bot; c_ref += m_top + m_bot; u_top += m_top; u_bot += m_bot;
       }
@@ -393,10 +400,8 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       for (uint32_t w = 0; w < p.t_nw; ++w) sts_u32(hist + w * 128u, 0u);
       if (p.t_nw < 16u) for (uint32_t w = p.t_nw; w < 16u; ++w) sts_u32(hist + w * 128u, 0u);  // the scratch spans 16 words
       {
-        const uint32_t idle_t = s0 & 255u, idle_b = (s0 >> 8) & 255u, cold_t = (s0 >> 16) & 255u, cold_b = s0 >> 24,
-                       slow_t = s1 & 255u, slow_b = (s1 >> 8) & 255u;
-        u_top += idle_t + cold_t + slow_t; u_bot += idle_b + cold_b + slow_b;
-        n += slow_t + slow_b;
+        const uint32_t idle_t = s0 & 255u, idle_b = (s0 >> 8) & 255u, cold_t = (s0 >> 16) & 255u, cold_b = s0 >> 24;
+        u_top += idle_t + cold_t; u_bot += idle_b + cold_b;
       }
     } while (more);
 
@@ -429,11 +434,40 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
       // an RA row needs best != ref with a positive consensus score, or a presence score at the cutoff
       need_fit = p.fit_all != 0u || ref >= 5u || (best != ref && consensus > -slack);
       if (!need_fit) {
-        const double ll_ref = ref == 0 ? ll[0] : ref == 1 ? ll[1] : ref == 2 ? ll[2] : ref == 3 ? ll[3] : ll[4];
-        // -n log10 g0[ref] in single precision (MUFU.LG2, relative error 2^-21), rounded up: the bound only has to be an upper bound
-        const float nlog = (float)n * (__log2f(((float)n + 2.0f) / ((float)c_ref + 0.5f)) * 0.30103001f) * 1.00001f + 1e-4f;
-        const double bound = (kept.m - ll_ref) + (double)nlog - p.log10_ref_length;
-        need_fit = !(bound < p.polymorphism_cutoff - slack);
+        // An upper bound of the presence score of EVERY candidate v != ref (variant_presence_score,
+        // identify_mutations.cpp:3329-3344: LL of the five-allele fit minus LL of the fit without v, minus log10 of the
+        // reference length), from sums the record loop has anyway.  Write a record's likelihoods relative to its own
+        // observation, r'_b = 10^(L[b] - L[obs]), rho = max over b != obs of r'_b (the tables' ratio column), and group the
+        // records by observed base g (n_g of them; the matching ones are group ref):
+        //  * five-allele fit: s_i(f) <= f_g + rho_i; the mean inside the logarithm (Jensen); any f on the simplex:
+        //      LL_5 <= sum_g n_g log10(n_g (1 + P) / n),  P = sum_g mean rho_g <= (sum over the matching records) / n_ref + sum over the others
+        //    (the maximum of sum_g n_g log10(f_g + rho_g) under sum f = 1, signs of f free);
+        //  * fit without v: an EM step never lowers the likelihood, so its LL is at least the one of its start
+        //    g0_b = (0.5 + n_b) / (2 + n - n_v) >= (0.5 + n_b) / (n + 2) (:3251-3266), and a mixture is at least one of its
+        //    terms: records of group w != v by allele w (r'_w = 1), records of group v by the reference base (r'_ref =
+        //    10^-(L[v] - L[ref])).
+        // The per-record normalisers cancel between the two.  Single precision, rounded up by more than its error; a NaN or an
+        // infinity (a class whose observation has probability zero) sends the slot on.
+        const uint32_t c0 = mis_cnt & 255u, c1 = (mis_cnt >> 8) & 255u, c2 = (mis_cnt >> 16) & 255u, c3 = mis_cnt >> 24;
+        const bool many = c0 == 255u || c1 == 255u || c2 == 255u || c3 == 255u || n > (1u << 20);
+        const float LG = 0.30103001f;
+        const float fn2 = (float)n + 2.0f, f_ref = (float)c_ref;
+        const float scale = (1.0f + rho / fmaxf(f_ref, 1.0f) + mis_rho) / (float)n;   // (rho: over all records, not less than over the matching ones)
+        const float lg_ref = __log2f((f_ref + 0.5f) / fn2);
+        float upper = c_ref ? f_ref * __log2f(f_ref * scale) : 0.f;
+        float lower = f_ref * lg_ref;
+        float best_v = 0.f;
+        auto group = [&](uint32_t c, float gain) {
+          if (!c) return;
+          const float fc = (float)c, lg_g = __log2f((fc + 0.5f) / fn2);
+          upper += fc * __log2f(fc * scale);
+          lower += fc * lg_g;
+          best_v = fmaxf(best_v, fc * (lg_g - lg_ref) * LG + gain);
+        };
+        group(c0, mis_gain0); group(c1, mis_gain1); group(c2, mis_gain2); group(c3, mis_gain3);
+        const float bound_f = (upper - lower) * LG + best_v + (2e-3f + (float)n * 2e-6f);
+        const double bound = (double)bound_f - p.log10_ref_length;
+        need_fit = many || !(bound < p.polymorphism_cutoff - slack);
         if (p.keep_bounds) kept_bound = bound;
       }
     }

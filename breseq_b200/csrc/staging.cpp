@@ -591,11 +591,10 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
       return w;
     }
     const bool match = obs == ref;
-    if (n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 5 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
+    // HOT: a record of the shared table's classes that MATCHES the reference base; one that does not is COLD (side list)
+    if (match && n_hot && ((rec >> SR_MAPQ_SHIFT) & 255u) == geo.hot_mapq && obs < 5 && qv >= geo.q_lo && qv - geo.q_lo < geo.n_q) {
       const uint32_t sq = ((rec >> 10) & 63u) * geo.n_q + (qv - geo.q_lo);
-      w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top;
-      if (match) w.dev |= DR_MATCH_BIT | ScoreGeometry::counter_of(sq);
-      else w.dev |= DR_SLOW_BIT | geo.special_counter(is_top ? SC_SLOW_TOP : SC_SLOW_BOT);
+      w.dev = sq << DR_SQ_SHIFT | obs << DR_OBS_SHIFT | top | DR_MATCH_BIT | ScoreGeometry::counter_of(sq);
     } else {
       w.dev = DR_COLD | top | geo.special_counter(is_top ? SC_COLD_TOP : SC_COLD_BOT);
       w.has_side = true; w.side = rec | (match ? SR_MATCH_BIT : 0u);

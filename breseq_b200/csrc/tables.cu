@@ -45,10 +45,15 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
   for (int b = 0; b < 5; ++b) { t.L[b] = L[b]; t.r[b] = r[b]; }
   t.r2 = 0.0; t.M = M;
   a.lut[i] = t;
+  // the class's best likelihood ratio against its own observation, max over b != obs of 10^(L[b] - L[obs]): what the tally
+  // kernel's presence bound needs of a record besides its terms (score_slots.cu)
+  double rho = 0.0;
+#pragma unroll
+  for (uint32_t b = 0; b < 5; ++b) if (b != obs) rho = fmax(rho, pow(10.0, L[b] - L[obs]));
   HotTerms c;
 #pragma unroll
   for (int b = 0; b < 5; ++b) c.L[b] = L[b];
-  c.M = M; c.pad[0] = 0.0; c.pad[1] = 0.0;
+  c.M = rho; c.pad[0] = 0.0; c.pad[1] = 0.0;
   a.coldT[((((size_t)st * p.n_mq + (mapq - p.mq_min)) * a.Q + q) * W + rr) * 5u + obs] = c;
   if (ms != a.hot_slot) return;
   if (p.n_hot) {
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(256) build_tables_kernel(TableBuildArgs a, Sco
     double* d = reinterpret_cast<double*>(reinterpret_cast<char*>(a.tallyT) + (size_t)obs * p.t_stride + ((size_t)st * p.t_nq + (q - p.t_qlo)) * 64u);
 #pragma unroll
     for (int b = 0; b < 5; ++b) d[b] = L[b];
-    d[5] = M; d[6] = top ? 1.0 : 0.0; d[7] = top ? 0.0 : 1.0;  // the last two columns count the class by strand
+    d[5] = rho; d[6] = top ? 1.0 : 0.0; d[7] = top ? 0.0 : 1.0;  // the last two columns count the class by strand
   }
 }
 

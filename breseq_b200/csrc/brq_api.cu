@@ -744,7 +744,12 @@ void evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets) {
   if (n_targets != c->hdr.target_names.size())
     throw std::runtime_error("Number of targets in BAM file [" + std::to_string(c->hdr.target_names.size()) +
                              "] does not match number in cutoff table [" + std::to_string(n_targets) + "].");
+  const bool timing = getenv("BRQ_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t0 = now();
   if (!c->have_walk || c->walk_prop != std::vector<double>(prop, prop + n_targets)) download_walk(c, prop, n_targets);
+  const auto t1 = now();
   EvidenceParams ep;
   ep.mutation_cutoff = c->last_params.mutation_cutoff;
   ep.polymorphism_cutoff = c->last_params.polymorphism_cutoff;
@@ -757,8 +762,11 @@ void evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets) {
   ep.deletion_propagation_cutoff.assign(prop, prop + n_targets);
   ep.deletion_seed_cutoff.assign(n_targets, 0.0);
   ensure_host_lut(c);
+  const auto t2 = now();
   FlaggedRecords fr;
   c->shard_blob = serialize_shard(collect_evidence(c->hdr, c->st, c->h_events, c->h_flagged, c->h_fcols, c->sp, c->h_lut, ep, flagged_view(c, fr)));
+  if (timing) fprintf(stderr, "[brq] evidence_export: download %.2f ms, lut %.2f ms, collect %.2f ms (%zu flagged, %zu events, %zu record words, %zu side entries)\n",
+                      ms(t0, t1), ms(t1, t2), ms(t2, now()), c->h_flagged.size(), c->h_events.size(), c->flagged_records.words.size(), c->flagged_records.side.size());
 }
 
 void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rates_file, const char* const* readfiles,

@@ -207,7 +207,9 @@ __global__ void __launch_bounds__(TALLY_MAX_TPB, 1) tally_kernel(const uint32_t*
   const uint32_t c_sts = wbase + g8 * 64u + t4 * 16u;   // scratch row of slot-lane g8 (m-tile mt adds 512 mt bytes)
   const uint32_t c_lds = wbase + lane * 64u;            // this lane's scratch row
   const uint64_t n_warps = (uint64_t)gridDim.x * n_warps_cta;
-  uint64_t round = (uint64_t)blockIdx.x * n_warps_cta + warp;
+  // rounds go to the warps CTA by CTA (warp w of CTA b takes rounds w * gridDim.x + b, + n_warps, ...): when the rounds do not
+  // divide by the warps, the warps with one round more are spread over all SMs instead of filling the first few
+  uint64_t round = (uint64_t)warp * gridDim.x + blockIdx.x;
 
   // A round: its records (round_off: warp-uniform) and this lane's slot with what closes it.  Slot numbers are read
   // two rounds ahead and the rest one round ahead, so no round starts by waiting for a chain of dependent loads.

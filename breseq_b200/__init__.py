@@ -94,6 +94,12 @@ SCORE_KEEP_BOUNDS = 4
 _lib = None
 
 
+class CoverageFit(C.Structure):  # brq_coverage_fit
+    _fields_ = [("average", C.c_double), ("variance", C.c_double), ("relative_variance", C.c_double),
+                ("nbinom_size_parameter", C.c_double), ("nbinom_mean_parameter", C.c_double),
+                ("deletion_coverage_propagation_cutoff", C.c_double), ("censor_start", C.c_uint32), ("censor_end", C.c_uint32)]
+
+
 def load_library():
     """dlopen ``libbrq.so``; fails loudly when the extension has not been built."""
     global _lib
@@ -144,6 +150,8 @@ def load_library():
                                       C.c_uint32, C.c_int, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
+        "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
+        "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
                                 C.c_int, C.c_int, C.c_char_p, P(_StageOptions)],
         "brq_run_identify_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_double),
@@ -169,7 +177,8 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_load_error_table", "brq_score_columns", "brq_columns_download", "brq_columns_device",
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
-           "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds"]
+           "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
+           "brq_fit_coverage_distribution", "brq_fit_coverage_file"]
 
 
 def _b(s):
@@ -549,6 +558,26 @@ class Context:
     def write_coverage_tsv(self, pattern):
         """``<seq>.coverage.tsv`` of --predict-copy-number; '@' in ``pattern`` becomes the target name."""
         self._check(self.lib.brq_write_coverage_tsv(self.h, _b(pattern)))
+
+    @staticmethod
+    def _fit_dict(f):
+        return {"average": f.average, "variance": f.variance, "relative_variance": f.relative_variance,
+                "nbinom_size_parameter": f.nbinom_size_parameter, "nbinom_mean_parameter": f.nbinom_mean_parameter,
+                "deletion_coverage_propagation_cutoff": f.deletion_coverage_propagation_cutoff,
+                "censor_start": f.censor_start, "censor_end": f.censor_end}
+
+    def fit_coverage_distribution(self, coverage_group, deletion_propagation_pr_cutoff):
+        """Censored negative-binomial fit of a coverage group's unique-only coverage histogram (the last error_count's) and
+        the deletion-propagation cutoff (CoverageDistribution::fit, coverage_distribution.cpp:115-400)."""
+        f = CoverageFit()
+        self._check(self.lib.brq_fit_coverage_distribution(self.h, coverage_group, C.c_double(deletion_propagation_pr_cutoff), C.byref(f)))
+        return self._fit_dict(f)
+
+    def fit_coverage_file(self, path, deletion_propagation_pr_cutoff):
+        """The same fit from a ``<group>.unique_only_coverage_distribution.tab`` (host only)."""
+        f = CoverageFit()
+        self._check(self.lib.brq_fit_coverage_file(self.h, _b(path), C.c_double(deletion_propagation_pr_cutoff), C.byref(f)))
+        return self._fit_dict(f)
 
     def kernel_ms(self):
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()

@@ -3,6 +3,7 @@
 
 #include "bam_io.h"
 #include "expand.h"
+#include "coverage_fit.h"
 #include "finalize.h"
 #include "kernels.h"
 #include "staging.h"
@@ -1148,6 +1149,49 @@ int brq_write_evidence_merged(brq_ctx* c, const void* const* shards, const uint6
     if (n_ra) *n_ra = k.ra;
     if (n_mc) *n_mc = k.mc;
     if (n_un) *n_un = k.un;
+  });
+}
+
+namespace {
+void fill_fit(const CoverageFit& f, brq_coverage_fit* out) {
+  out->average = f.average; out->variance = f.variance; out->relative_variance = f.relative_variance;
+  out->nbinom_size_parameter = f.nb_size; out->nbinom_mean_parameter = f.nb_mu;
+  out->deletion_coverage_propagation_cutoff = f.deletion_coverage_propagation_cutoff;
+  out->censor_start = f.censor_start; out->censor_end = f.censor_end;
+}
+// the context's parked threads take the fit's independent restarts
+std::function<void(size_t, const std::function<void(size_t)>&)> fit_threads(brq_ctx* c) {
+  if (!c->pool) c->pool.reset(new WorkerPool((size_t)std::max(1, std::min(c->threads, 16) - 1)));
+  WorkerPool* pool = c->pool.get();
+  return [pool](size_t n_jobs, const std::function<void(size_t)>& job) {
+    pool->run([&](size_t part, size_t n_workers) { for (size_t j = part; j < n_jobs; j += n_workers) job(j); });
+  };
+}
+}  // namespace
+
+int brq_fit_coverage_distribution(brq_ctx* c, uint32_t group, double pr_cutoff, brq_coverage_fit* out) {
+  return guarded(c, [&] {
+    if (!c->have_counts && !c->host_hist_valid) throw std::runtime_error("brq_error_count has not run");
+    if (!c->host_hist_valid) download_hist(c);
+    if (group >= c->n_groups) throw std::runtime_error("no such coverage group");
+    // the histogram as its file would be read back (error_count.cpp:239-253, coverage_distribution.cpp:34-65): depths 1 .. the deepest seen
+    const uint64_t* h = c->h_cov.data() + (size_t)group * c->cov_stride;
+    uint32_t N = 0;
+    for (uint64_t j = 0; j < c->cov_stride; ++j) if (h[j]) N = (uint32_t)j;
+    std::vector<double> n((size_t)N + 1, 0.0);
+    for (uint32_t j = 1; j <= N; ++j) n[j] = (double)h[j];
+    const auto threads = fit_threads(c);
+    fill_fit(fit_coverage_distribution(n, N, pr_cutoff, &threads), out);
+  });
+}
+
+int brq_fit_coverage_file(brq_ctx* c, const char* path, double pr_cutoff, brq_coverage_fit* out) {
+  return guarded(c, [&] {
+    std::vector<double> n;
+    uint32_t N = 0;
+    read_coverage_distribution(path, n, N);
+    const auto threads = fit_threads(c);
+    fill_fit(fit_coverage_distribution(n, N, pr_cutoff, &threads), out);
   });
 }
 

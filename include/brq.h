@@ -233,6 +233,22 @@ int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
 int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
 
+/* ---- between the passes: the coverage fit ---------------------------------------------------------
+ * CoverageDistribution::fit (coverage_distribution.cpp:115-400, 422-436) without its plot: the censored negative-binomial fit
+ * of a coverage group's unique-only coverage histogram and the deletion-propagation cutoff analyze_unique_coverage_distribution
+ * stores in Summary::unique_coverage (:510-606) and stage 08 hands to identify_mutations() as deletion_propagation_cutoff.
+ * deletion_propagation_pr_cutoff is the caller's (the reference uses 0.05 / sqrt(length of the group's sequences), :548).
+ * brq_fit_coverage_distribution takes the histogram of the context's last brq_error_count (no file round trip);
+ * brq_fit_coverage_file reads a <group>.unique_only_coverage_distribution.tab (host only: needs no device). */
+typedef struct brq_coverage_fit {
+  double average, variance, relative_variance;          /* Summary::unique_coverage[seq_id].average ... */
+  double nbinom_size_parameter, nbinom_mean_parameter;  /* 0 / 0 = the fit failed */
+  double deletion_coverage_propagation_cutoff;          /* -1 = the reference sequence itself is missing */
+  uint32_t censor_start, censor_end;                    /* the fitting window around the histogram's peak */
+} brq_coverage_fit;
+int brq_fit_coverage_distribution(brq_ctx* ctx, uint32_t coverage_group, double deletion_propagation_pr_cutoff, brq_coverage_fit* out);
+int brq_fit_coverage_file(brq_ctx* ctx, const char* distribution_file, double deletion_propagation_pr_cutoff, brq_coverage_fit* out);
+
 /* ---- one-call adapters with the reference entry points' argument meaning --------------------- */
 int brq_run_error_count(brq_ctx* ctx, const char* bam, const char* fasta, const char* output_dir,
                         const char* error_rates_file, const char* const* readfiles, uint32_t n_readfiles,

@@ -13,6 +13,7 @@
 // writers, and (b) serve as the `kind: "reference"` CPU baseline.  The htslib layer under it is
 // still the shim (htslib itself is not in this image): parity at the BAM-decode/pileup boundary
 // remains a restatement.
+#include "coverage_distribution.h"
 #include "error_count.h"
 #include "identify_mutations.h"
 #include "reference_sequence.h"
@@ -51,6 +52,20 @@ int main(int argc, char** argv) {
   }
   auto get = [&](const string& k, const string& d) { return opt.count(k) ? opt[k] : d; };
   const string out = get("out", ".");
+
+  if (cmd == "fit_coverage") {
+    // CoverageDistribution::fit (coverage_distribution.cpp:422-498) on a <group>.unique_only_coverage_distribution.tab with the
+    // probability cutoff analyze_unique_coverage_distribution derives (:548: 0.05 / sqrt(sequence length)).  fit() also draws
+    // its plot through `gnuplot`: the caller puts a do-nothing stand-in on PATH (tests/golden/make_golden.py).
+    const double pr = atof(get("pr-cutoff", "0.01").c_str());
+    CoverageDistributionFitResult r = CoverageDistribution::fit(get("distribution", ""), out + "/coverage_plot.svg", pr);
+    char line[512];
+    snprintf(line, sizeof line, "average\t%.17g\nvariance\t%.17g\nrelative_variance\t%.17g\nnb_fit_size\t%.17g\nnb_fit_mu\t%.17g\n"
+             "deletion_coverage_propagation_cutoff\t%.17g\n", r.average, r.variance, r.relative_variance, r.nb_fit_size, r.nb_fit_mu,
+             r.deletion_coverage_propagation_cutoff);
+    cout << line;
+    return 0;
+  }
 
   Settings::set_global_paths();  // as breseq_cmdline.cpp:2885 does first thing in main()
   Summary summary;

@@ -60,6 +60,21 @@ def test_error_rate_files_byte_identical(run):
         assert filecmp.cmp(os.path.join(run["out"], name), os.path.join(d["oracle_dir"], name), shallow=False), name
 
 
+def test_coverage_fit_from_the_device_histogram(run):
+    """the fit between the passes takes the histogram pass 1 left in HBM: same doubles as from the file the reference reads back"""
+    if run["mode"] != "bounded":
+        pytest.skip("once per dataset")
+    d, ctx = run["d"], run["ctx"]
+    host = bq.Context(device=-1)
+    for g in range(len(d["contig_lens"])):
+        path = os.path.join(run["out"], "%d.unique_only_coverage_distribution.tab" % g)
+        if not os.path.exists(path):
+            continue
+        for pr in (0.05 / np.sqrt(float(sum(d["contig_lens"]))), 0.01):
+            a, b = ctx.fit_coverage_distribution(g, pr), host.fit_coverage_file(path, pr)
+            assert {k: float(v).hex() for k, v in a.items()} == {k: float(v).hex() for k, v in b.items()}, (g, pr, a, b)
+
+
 def test_coverage_bit_exact(run):
     g, o = run["g"], run["o"]
     assert np.array_equal(g["unique"], o["unique"].astype(np.uint32))

@@ -153,7 +153,8 @@ def config_block(name, cfg, n_gpus):
             "config": name, "covariates": COVARIATES, "coverage": cfg["coverage"],
             "cutoffs": dict(zip(("mutation", "polymorphism", "precision", "places"), cfg["cutoffs"])),
             "l2_policy": "inputs (tens of GB of streams per run in HBM) are far larger than the 126 MB L2; no explicit flush",
-            "parallelism": "reference-range sharding x%d (strong scaling), one sum-allreduce of the integer histograms, "
+            "parallelism": "reference-range sharding x%d (strong scaling), one sum of the integer histograms over the ranks (fused into "
+                           "pass 1: in-kernel NVLink reductions, csrc/exchange.cu; BRQ_BENCH_NCCL=1: an NCCL allreduce), "
                            "evidence shares gathered to rank 0" % n_gpus}
 
 
@@ -305,9 +306,17 @@ def main():
         dist.all_reduce(depth, op=dist.ReduceOp.MAX)
         ctx.set_min_coverage_depth(int(depth.item()))
     hist_view = {}
+    # the collective of pass 1: fused into brq_error_count (csrc/exchange.cu: the ranks add their histograms into each other's
+    # memory over NVLink, no library call, no host in the loop), or BRQ_BENCH_NCCL=1: an NCCL allreduce between the calls
+    fused = world > 1 and not os.environ.get("BRQ_BENCH_NCCL")
+    if fused:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.hist_exchange_export())
+        ctx.hist_exchange_attach(handles, rank)
+        dist.barrier()
 
     def allreduce_hist():
-        if world == 1:
+        if world == 1 or fused:
             return
         c, n, v, m = ctx.hist_device()
         # the collective is ordered on the context's own stream: no host synchronisation
@@ -484,6 +493,7 @@ def main():
             cb["workload"] = ("NOT a BASELINE config (--scale %.3f / --coverage %g override of %s): " % (args.scale, cfg["coverage"], name)) + cb["workload"]
         cb["kernel_ms_rank0"] = k_ms
         cb["host_call_ms_rank0"] = {k: 1e3 * v / args.steps for k, v in call_s.items()}
+        cb["histogram_collective"] = "none (one rank)" if world == 1 else ("fused into pass 1 (csrc/exchange.cu; its wait for the peers is inside kernel_ms.coverage)" if fused else "NCCL allreduce")
         cb["step_wall_ms_rank0"] = [round(w, 3) for w in step_walls]
         cb["staging"] = "device (csrc/expand.cu)" if device_built else "host (csrc/staging.cpp)"
         cb["staging_seconds"] = t_stage

@@ -152,6 +152,8 @@ def load_library():
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
+        "brq_hist_exchange_export": [C.c_void_p, C.c_void_p, P(C.c_uint64)],
+        "brq_hist_exchange_attach": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
                                 C.c_int, C.c_int, C.c_char_p, P(_StageOptions)],
         "brq_run_identify_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_double),
@@ -178,7 +180,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
-           "brq_fit_coverage_distribution", "brq_fit_coverage_file"]
+           "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach"]
 
 
 def _b(s):
@@ -578,6 +580,19 @@ class Context:
         f = CoverageFit()
         self._check(self.lib.brq_fit_coverage_file(self.h, _b(path), C.c_double(deletion_propagation_pr_cutoff), C.byref(f)))
         return self._fit_dict(f)
+
+    def hist_exchange_export(self):
+        """64-byte handle of this context's inbox for the fused collective of pass 1 (exchange it with the peer ranks)."""
+        h = C.create_string_buffer(64)
+        cap = C.c_uint64()
+        self._check(self.lib.brq_hist_exchange_export(self.h, h, C.byref(cap)))
+        return h.raw
+
+    def hist_exchange_attach(self, handles, rank):
+        """``handles``: every rank's 64-byte handle in rank order.  From now on error_count() sums the ranks' histograms itself."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * len(handles)
+        self._check(self.lib.brq_hist_exchange_attach(self.h, blob, len(handles), rank))
 
     def kernel_ms(self):
         a, b, c, d = C.c_float(), C.c_float(), C.c_float(), C.c_float()

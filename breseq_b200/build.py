@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbrq.so")
 
-CU_SOURCES = ["kernels.cu", "score_slots.cu", "tables.cu", "expand.cu", "brq_api.cu"]
+CU_SOURCES = ["kernels.cu", "score_slots.cu", "tables.cu", "expand.cu", "exchange.cu", "brq_api.cu"]
 CPP_SOURCES = ["bam_io.cpp", "staging.cpp", "synth.cpp", "finalize.cpp", "expand_plan.cpp", "coverage_fit.cpp"]
 
 NVCC_FLAGS = [

@@ -67,6 +67,14 @@ struct brq_ctx {
   // both integer histograms in ONE allocation (the covariate counts, then the coverage histogram): a sharded run sums them
   // with one collective
   DevBuf<unsigned long long> d_hist;
+  // the fused collective of pass 1 (exchange.cu): this rank's inbox (two copies + counters, one allocation its peers map through
+  // CUDA IPC), the peers' inboxes as mapped here, the step counter that picks the copy, and the kernel's completion counter
+  void* exchange_inbox = nullptr;
+  uint64_t exchange_capacity = 0;
+  HistPeers peers{};
+  std::vector<void*> peer_mappings;
+  uint64_t exchange_step = 0;
+  DevBuf<uint32_t> d_exchange_done;
   struct HistView { unsigned long long* p = nullptr; } d_counts, d_cov;
   DevBuf<double> d_log10;
   DevBuf<ClassTerms> d_lut;
@@ -144,6 +152,7 @@ struct brq_ctx {
       if (scal[0] & BRQ_ERR_READPOS_RANGE) m += "covariate 'read_pos' exceeded its maximum; ";
       if (scal[0] & BRQ_ERR_CLASS_OVERFLOW) m += "too many distinct record classes in one column; ";
       if (scal[0] & BRQ_ERR_DEPTH_RANGE) m += "column depth beyond the coverage histogram; ";
+      if (scal[0] & BRQ_ERR_PEER_TIMEOUT) m += "a peer rank's histograms did not arrive (brq_hist_exchange_attach: every rank has to call brq_error_count); ";
       CUDA_OK(cudaMemsetAsync(d_scalars.p, 0, 4, stream));
       throw std::runtime_error(m);
     }
@@ -428,6 +437,12 @@ void error_count_device(brq_ctx* c, const std::string& covariates, bool do_cover
   lap("histogram kernel queued");
   CUDA_OK(cudaEventRecord(c->ev[1], c->stream));
   if (do_coverage) launch_coverage_hist(c->ds.hist_off.p, c->ds.slot_group.p, st.n_base, (uint32_t)c->cov_stride, n_groups, c->d_cov.p, c->d_scalars.p, c->stream);
+  if (c->peers.world > 1) {
+    // the ranks' histograms meet here, inside pass 1's own stream work (exchange.cu): no collective call by the caller
+    const uint64_t words = (uint64_t)lay.n_bins + c->cov_stride * n_groups;
+    if (words > c->exchange_capacity) throw std::runtime_error("the histograms are larger than the exchange inbox (brq_hist_exchange_export)");
+    launch_hist_exchange(c->d_hist.p, words, c->peers, (uint32_t)(c->exchange_step++ & 1u), c->d_exchange_done.p, c->d_scalars.p, 5.0, c->stream);
+  }
   CUDA_OK(cudaEventRecord(c->ev[2], c->stream));
   CUDA_OK(cudaGetLastError());
   lap("coverage kernel queued");
@@ -823,6 +838,10 @@ void brq_destroy(brq_ctx* c) {
     c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_survivors.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
     c->d_hist.release();
+    for (void* m : c->peer_mappings) cudaIpcCloseMemHandle(m);
+    c->peer_mappings.clear();
+    if (c->exchange_inbox) { cudaFree(c->exchange_inbox); c->exchange_inbox = nullptr; }
+    c->d_exchange_done.release();
     c->d_log10.release(); c->d_lut.release(); c->d_cols.release(); c->d_fcols.release(); c->d_walk.release();
     c->d_events.release(); c->d_mark.release(); c->d_seg_first.release(); c->d_seg_last.release(); c->d_seg_prop.release(); c->d_ins_parent.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -1192,6 +1211,51 @@ int brq_fit_coverage_file(brq_ctx* c, const char* path, double pr_cutoff, brq_co
     read_coverage_distribution(path, n, N);
     const auto threads = fit_threads(c);
     fill_fit(fit_coverage_distribution(n, N, pr_cutoff, &threads), out);
+  });
+}
+
+// ---- the fused collective of pass 1 (exchange.cu)
+int brq_hist_exchange_export(brq_ctx* c, void* handle64, uint64_t* capacity_words) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  return guarded(c, [&] {
+    c->need_device();
+    if (!c->exchange_inbox) {
+      c->exchange_capacity = (uint64_t)1 << 20;   // words per copy: covariate bins + coverage groups x depths of any run so far
+      const size_t bytes = 2 * c->exchange_capacity * 8 + 64;
+      CUDA_OK(cudaMalloc(&c->exchange_inbox, bytes));
+      CUDA_OK(cudaMemset(c->exchange_inbox, 0, bytes));
+      c->d_exchange_done.ensure(1);
+      CUDA_OK(cudaMemset(c->d_exchange_done.p, 0, 4));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_OK(cudaIpcGetMemHandle(&h, c->exchange_inbox));
+    memcpy(handle64, &h, 64);
+    if (capacity_words) *capacity_words = c->exchange_capacity;
+  });
+}
+
+int brq_hist_exchange_attach(brq_ctx* c, const void* handles, uint32_t world, uint32_t rank) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (!c->exchange_inbox) throw std::runtime_error("brq_hist_exchange_export has not run");
+    if (world < 1 || world > 16 || rank >= world) throw std::runtime_error("brq_hist_exchange_attach: 1 to 16 ranks");
+    for (void* m : c->peer_mappings) cudaIpcCloseMemHandle(m);
+    c->peer_mappings.clear();
+    HistPeers P{};
+    P.world = world; P.rank = rank; P.capacity = c->exchange_capacity;
+    for (uint32_t r = 0; r < world; ++r) {
+      void* base = c->exchange_inbox;
+      if (r != rank) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)r * 64, 64);
+        CUDA_OK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_mappings.push_back(base);
+      }
+      P.inbox[r] = static_cast<unsigned long long*>(base);
+      P.arrived[r] = reinterpret_cast<uint32_t*>(static_cast<char*>(base) + 2 * c->exchange_capacity * 8);
+    }
+    c->peers = P;
+    c->exchange_step = 0;
   });
 }
 

@@ -20,6 +20,7 @@ enum : uint32_t {
   BRQ_ERR_READPOS_RANGE = 4,
   BRQ_ERR_CLASS_OVERFLOW = 8,   // more distinct record classes in one column than the class table holds
   BRQ_ERR_DEPTH_RANGE = 16,     // unique depth beyond the coverage histogram
+  BRQ_ERR_PEER_TIMEOUT = 32,    // a peer's share of the histograms did not arrive (exchange.cu)
 };
 
 // Per-slot result of the scoring kernel: 96 bytes.
@@ -93,6 +94,16 @@ struct ClassTerms { double L[5]; double r2; double r[5]; double M; };
 struct alignas(32) HotTerms { double L[5]; double M; double pad[2]; };    // M: the class's ratio column, max over b != obs of 10^(L[b] - L[obs]) (the presence bound); 64 bytes: one 256-bit and one 128-bit load
 struct HotRatios { double r[5]; double M; };   // M = max_b L[b]
 
+// The fused collective of pass 1 (exchange.cu): every rank's inbox (two histogram-shaped copies of `capacity` words) and its two
+// arrival counters, as mapped into this process.
+struct HistPeers {
+  unsigned long long* inbox[16];
+  uint32_t* arrived[16];
+  uint32_t world, rank;
+  uint64_t capacity;
+};
+void launch_hist_exchange(unsigned long long* local, uint64_t n, const HistPeers& peers, uint32_t copy, uint32_t* done, uint32_t* err,
+                          double timeout_seconds, cudaStream_t s);
 void launch_score_slots(const uint32_t* rec, const uint64_t* off, const uint32_t* cnt, const uint64_t* round_off,
                         const uint32_t* side, const uint32_t* side_off, const uint2* round_side,
                         const uint8_t* slot_ref, const uint32_t* round_slot, uint64_t n_rounds, uint64_t n_slots, uint64_t n_records,

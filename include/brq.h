@@ -233,6 +233,18 @@ int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
 int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
 
+/* ---- the collective of a sharded run, fused into pass 1 (csrc/exchange.cu) ------------------------------------------------
+ * Instead of summing the brq_hist_device() buffers with a collective library between brq_error_count and
+ * brq_derive_error_table, the ranks (one process per GPU of one NVLink / NVSwitch box, up to 16) can let pass 1 do it: every
+ * context exports a handle of its inbox (64 bytes, a CUDA IPC memory handle), the handles are exchanged once by any means
+ * (MPI, torch.distributed, a file) and attached in rank order; from then on every brq_error_count ends in a kernel that adds
+ * the rank's histograms into its peers' inboxes over NVLink and its own inbox into its histograms, so that the histograms of
+ * every rank hold the run's totals when the call's stream work is done.  All ranks have to call brq_error_count the same
+ * number of times with the same histogram shape (covariates, coverage groups, brq_set_min_coverage_depth); a rank whose peers
+ * do not show up within five seconds reports it with the next synchronising call.  world = 1 detaches. */
+int brq_hist_exchange_export(brq_ctx* ctx, void* handle64, uint64_t* capacity_words);
+int brq_hist_exchange_attach(brq_ctx* ctx, const void* handles, uint32_t world, uint32_t rank);
+
 /* ---- between the passes: the coverage fit ---------------------------------------------------------
  * CoverageDistribution::fit (coverage_distribution.cpp:115-400, 422-436) without its plot: the censored negative-binomial fit
  * of a coverage group's unique-only coverage histogram and the deletion-propagation cutoff analyze_unique_coverage_distribution

@@ -1,6 +1,7 @@
 """The N > 1 path on GPUs: a run sharded by reference range over NCCL ranks (one process per GPU, launched the way the driver
 launches bench.py) must write the evidence file of the unsharded run, byte for byte: record-balanced range cuts, device
-staging of every rank's own reads, the sum-allreduce of both integer histograms, every rank's evidence share gathered to
+staging of every rank's own reads, the sum of both integer histograms over the ranks (an NCCL allreduce, or fused into pass 1:
+csrc/exchange.cu), every rank's evidence share gathered to
 rank 0 and walked together.  Needs two GPUs (skipped on a one-GPU box; `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py`)."""
 import filecmp
 import os
@@ -32,14 +33,26 @@ ctx.stage_bam(d["bam"], d["fasta"], shard_bounds=(bounds[rank], bounds[rank + 1]
 depth = torch.tensor([ctx.max_coverage_depth()], dtype=torch.int64, device=dev)
 dist.all_reduce(depth, op=dist.ReduceOp.MAX)
 ctx.set_min_coverage_depth(int(depth.item()))
-ctx.error_count(helpers.covariates(d))
+if not %(fused)r:
+    ctx.error_count(helpers.covariates(d))
 class DevArray:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-c, n, v, m = ctx.hist_device()
-with torch.cuda.stream(torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)):
-    assert v == c + 8 * n
-    dist.all_reduce(torch.as_tensor(DevArray(c, n + m), device=dev))   # both histograms: one allocation, one collective
+if %(fused)r:
+    # the collective fused into pass 1 (csrc/exchange.cu): handles exchanged once, then error_count() sums over the ranks itself;
+    # called twice so that both inbox copies and their clearing are exercised
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.hist_exchange_export())
+    ctx.hist_exchange_attach(handles, rank)
+    dist.barrier()
+    ctx.error_count(helpers.covariates(d))
+    ctx.error_count(helpers.covariates(d))
+    ctx.error_count(helpers.covariates(d))
+else:
+    c, n, v, m = ctx.hist_device()
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.cuda_stream(), device=dev)):
+        assert v == c + 8 * n
+        dist.all_reduce(torch.as_tensor(DevArray(c, n + m), device=dev))   # both histograms: one allocation, one collective
 ctx.derive_error_table()
 nt = len(d["contig_lens"])
 if rank == 0:
@@ -62,8 +75,9 @@ dist.destroy_process_group()
 '''
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "fused"])
 @pytest.mark.parametrize("name", ["multi", "lambda"])
-def test_two_nccl_ranks_write_the_unsharded_evidence(name, datasets, tmp_path):
+def test_two_nccl_ranks_write_the_unsharded_evidence(name, fused, datasets, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -72,7 +86,7 @@ def test_two_nccl_ranks_write_the_unsharded_evidence(name, datasets, tmp_path):
     for f in ("reference.bam", "reference.fasta"):
         os.symlink(os.path.join(d["dir"], f), os.path.join(out, f))
     script = os.path.join(out, "worker.py")
-    open(script, "w").write(WORKER % dict(root=ROOT, name=name, out=out))
+    open(script, "w").write(WORKER % dict(root=ROOT, name=name, out=out, fused=fused))
     port = 29600 + (os.getpid() % 2000)
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), script], capture_output=True, text=True, timeout=150)

@@ -4,6 +4,7 @@
 #include "bam_io.h"
 #include "expand.h"
 #include "coverage_fit.h"
+#include "coverage_table.h"
 #include "finalize.h"
 #include "kernels.h"
 #include "staging.h"
@@ -67,6 +68,7 @@ struct brq_ctx {
   // both integer histograms in ONE allocation (the covariate counts, then the coverage histogram): a sharded run sums them
   // with one collective
   DevBuf<unsigned long long> d_hist;
+  DevBuf<CoverageColumn> d_coverage_columns;   // brq_write_coverage_table
   // the fused collective of pass 1 (exchange.cu): this rank's inbox (two copies + counters, one allocation its peers map through
   // CUDA IPC), the peers' inboxes as mapped here, the step counter that picks the copy, and the kernel's completion counter
   void* exchange_inbox = nullptr;
@@ -837,7 +839,7 @@ void brq_destroy(brq_ctx* c) {
   if (c->device >= 0) {
     c->ds.release(); c->d_reads.release(); c->xs.release(); c->d_flagged.release(); c->d_worklist.release(); c->d_survivors.release(); c->d_tallyT.release(); c->d_coldT.release(); c->d_prob.release(); c->d_slot_mapq.release(); c->d_hotR.release(); c->d_scalars.release(); c->d_table_err.release(); c->d_score16.release(); c->d_score_exc.release(); c->d_score_exc_off.release();
     if (c->h_log10_pinned) { cudaFreeHost(c->h_log10_pinned); c->h_log10_pinned = nullptr; }
-    c->d_hist.release();
+    c->d_hist.release(); c->d_coverage_columns.release();
     for (void* m : c->peer_mappings) cudaIpcCloseMemHandle(m);
     c->peer_mappings.clear();
     if (c->exchange_inbox) { cudaFree(c->exchange_inbox); c->exchange_inbox = nullptr; }
@@ -1140,6 +1142,20 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
     const PileupStream view = host_view(c);
     write_coverage_tsv(pattern, c->hdr, c->ref, view, c->h_cols);
+  });
+}
+
+int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv) {
+  return guarded(c, [&] {
+    c->need_device();
+    if (!c->staged || !c->st.device_built) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
+    coverage_columns_on_device(c->xs, c->st.n_base, c->d_coverage_columns, c->stream);
+    std::vector<CoverageColumn> cols(c->st.n_base);
+    if (!cols.empty()) CUDA_OK(cudaMemcpyAsync(cols.data(), c->d_coverage_columns.p, cols.size() * sizeof(CoverageColumn), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaGetLastError());
+    c->d2h_bytes += cols.size() * sizeof(CoverageColumn);
+    write_coverage_table(path, c->hdr, c->ref, c->st, cols, region ? region : "", resolution, total_only != 0, csv != 0);
   });
 }
 

@@ -1,0 +1,16 @@
+// BAM2COV's per-position coverage table (coverage_output.cpp:190-283): the host writer over the columns the device walk counted
+// (expand_core.h: coverage_lane).
+#pragma once
+#include "bam_io.h"
+#include "brq_types.h"
+#include "expand_core.h"
+
+#include <string>
+#include <vector>
+
+namespace brq {
+
+void write_coverage_table(const std::string& path, const BamHeader& hdr, const RefSet& ref, const PileupStream& st,
+                          const std::vector<CoverageColumn>& cols, const std::string& region, uint32_t resolution, bool total_only, bool csv);
+
+}  // namespace brq

@@ -124,6 +124,7 @@ void ExpandScratch::release() {
   part.release(); stats.release(); sub_first.release(); red_cnt.release(); side_cnt.release(); side_red_cnt.release(); hist_cnt.release();
   sub_cur.release(); block_entries.release(); block_base.release(); round_vecs.release(); scan_tmp32.release(); ins_mask.release();
   geo_stats.release(); scan_tmp.release(); ins_parent.release(); totals.release(); read_starts.release(); ins_count.release(); hist_pos.release();
+  have_walk_args = false;
 }
 
 namespace {
@@ -222,6 +223,12 @@ __global__ void __launch_bounds__(256) read_starts_kernel(ExpandArgs a, unsigned
 
 // ------------------------------------------------------------------------------------------ the tile passes
 // (the count pass fits 64 registers: four CTAs per SM; the fill pass spills there and runs faster with three)
+__global__ void __launch_bounds__(256, 4) coverage_tile_kernel(ExpandArgs a, CoverageColumn* __restrict__ out) {
+  const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (tile >= a.n_tiles) return;
+  coverage_lane(a, tile, threadIdx.x & 31u, out);
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(256, FILL ? 3 : 4) tile_kernel(ExpandArgs a) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -479,6 +486,7 @@ inline uint32_t blocks_for(uint64_t n, uint32_t tpb = 256) { return (uint32_t)st
 void expand_on_device(const BamHeader& hdr, const RefSet& ref, const ReadBatch& host, const ReadsDev& reads, const StageConfig& cfg,
                       ExpandScratch& X, StreamDev& out, PileupStream& st, cudaStream_t s) {
   const size_t n_targets = hdr.target_names.size();
+  X.have_walk_args = false;
   // BRQ_STAGE_TIMES=1: wall time of every phase on stderr (each ends in a synchronisation then)
   static const bool phase_times = getenv("BRQ_STAGE_TIMES") != nullptr;
   auto phase_t0 = std::chrono::steady_clock::now();
@@ -617,6 +625,7 @@ void expand_on_device(const BamHeader& hdr, const RefSet& ref, const ReadBatch& 
   CUDA_OK(cudaMemsetAsync(X.col_qstart.p, 0, (size_t)n_base + 1, s));
   a.score_cnt = out.score_cnt.p; a.red_cnt = X.red_cnt.p; a.side_cnt = X.side_cnt.p; a.side_red_cnt = X.side_red_cnt.p;
   a.hist_cnt = X.hist_cnt.p; a.col_red = X.col_red.p; a.col_qstart = X.col_qstart.p;
+  X.walk_args = a; X.have_walk_args = true;   // (what a later walk over the same reads needs: coverage_columns_on_device)
   if (tiles) { tile_kernel<false><<<blocks_for((uint64_t)tiles * 32), 256, 0, s>>>(a); launched(); }
   if (cfg.preprocess_stage && cfg.want_hist) {
     X.read_starts.ensure(n_targets * 2 + 2);
@@ -748,6 +757,13 @@ void gather_flagged_records(const StreamDev& ds, const PileupStream& st, const u
   CUDA_OK(cudaStreamSynchronize(s));
   if (d2h_bytes) *d2h_bytes += (uint64_t)n * sizeof(SlotInfo) + out.words.size() * 4 + out.side.size() * 4;
   d_info.release(); d_off.release(); d_words.release(); d_side.release();
+}
+
+void coverage_columns_on_device(const ExpandScratch& X, uint64_t n_base, DevBuf<CoverageColumn>& out, cudaStream_t s) {
+  if (!X.have_walk_args) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
+  out.ensure(n_base + 1);
+  const ExpandArgs& a = X.walk_args;
+  if (a.n_tiles) { coverage_tile_kernel<<<blocks_for((uint64_t)a.n_tiles * 32), 256, 0, s>>>(a, out.p); launched(); }
 }
 
 }  // namespace brq

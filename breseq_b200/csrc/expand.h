@@ -57,6 +57,8 @@ struct ExpandScratch {
   DevBuf<uint64_t> ins_mask, geo_stats, scan_tmp, ins_parent, totals, read_starts;
   DevBuf<uint32_t> ins_count;
   DevBuf<uint8_t> hist_pos;   // positional histogram records before compaction
+  ExpandArgs walk_args;       // the last staging's reads, segments and tiles (valid until the next staging)
+  bool have_walk_args = false;
   void release();
 };
 
@@ -77,6 +79,10 @@ struct FlaggedRecordsHost {
 };
 void gather_flagged_records(const StreamDev& ds, const PileupStream& st, const uint32_t* d_slots, uint32_t n, FlaggedRecordsHost& out,
                             cudaStream_t stream, uint64_t* d2h_bytes);
+
+// BAM2COV (coverage_output.cpp:307-470): per base slot of the staged range, the coverage table's counts, from a walk over the
+// reads of the last staging
+void coverage_columns_on_device(const ExpandScratch& scratch, uint64_t n_base, DevBuf<CoverageColumn>& out, cudaStream_t stream);
 
 int expand_launch_count();
 

@@ -581,4 +581,45 @@ BRQ_HD inline void tile_lane(const ExpandArgs& a, uint32_t tile, uint32_t l) {
   }
 }
 
+// ---- BAM2COV: the per-position coverage table of coverage_output::pileup_callback (coverage_output.cpp:307-470), from the same
+// tile walk.  Per column, by strand (index 1 = reversed): unique reads covering it with an aligned base (a deletion or a
+// reference skip over the column does not count), the reads among them whose first base it is, redundant reads (X1 > 1) as a
+// count and as the sum of 1 / X1 in BAM order.
+// `covered`: the pileup engine reports the column at all (any read spans it, deletions included): what the table's tail rule needs.
+struct CoverageColumn { uint32_t unique[2], raw_redundant[2], begin[2], covered, pad; double redundant[2]; };
+static_assert(sizeof(CoverageColumn) == 48, "CoverageColumn layout");
+
+BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l, CoverageColumn* out) {
+  const ExpandSeg& sg = seg_of_tile(a, tile);
+  const int32_t c0 = sg.lo + (int32_t)((tile - sg.tile0) * 32u), c1 = c0 + 32 < sg.hi ? c0 + 32 : sg.hi;
+  const int32_t c = c0 + (int32_t)l;
+  uint32_t first, last;
+  tile_candidates(a, sg, c0, c1, first, last);
+  const bool live_lane = c < c1;
+  CoverageColumn col = {{0, 0}, {0, 0}, {0, 0}, 0, 0, {0.0, 0.0}};
+  ReadMeta nxt = first < last ? a.meta[first] : ReadMeta();
+  for (uint32_t i = first; i < last; ++i) {
+    const ReadMeta m = nxt;
+    if (i + 1 < last) nxt = a.meta[i + 1];
+    if (!(m.flags & RM_LIVE) || m.end <= c0) continue;
+    if (!live_lane || c < m.pos || c >= m.end) continue;
+    ColumnHit h;
+    if (m.flags & RM_SIMPLE) { h.has = true; h.is_del = false; h.indel = 0; h.q = m.qs0 + (c - m.pos); }
+    else h = column_hit(a.cigars + m.cigar_off, m.n_cigar, m.pos, c);
+    if (!h.has) continue;
+    col.covered = 1;
+    if (h.is_del) continue;   // :370-373
+    const uint32_t rev = (m.flags & RM_REV) ? 1u : 0u;
+    if (m.x1 == 1) {
+      ++col.unique[rev];
+      // the read's first base in its own orientation (:385-393): query position 1, or the last one of a reversed read
+      if (rev ? h.q == (int32_t)m.l_seq - 1 : h.q == 0) ++col.begin[rev];
+    } else {
+      ++col.raw_redundant[rev];
+      col.redundant[rev] += 1.0 / (double)m.x1;
+    }
+  }
+  if (live_lane) out[sg.slot0 + (uint32_t)(c - sg.lo)] = col;
+}
+
 }  // namespace brq

@@ -232,6 +232,14 @@ int brq_cuda_stream(brq_ctx* ctx, void** stream);
 int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
 int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
+/* BAM2COV's table (`breseq BAM2COV -t`, coverage_output::table + pileup_callback, coverage_output.cpp:190-283, 307-470) for
+ * region "seq_id:start-end" of the staged BAM: per position the unique coverage by strand (reads with an aligned base there:
+ * a deletion over the position does not count), the redundant coverage by strand as the sum of 1 / X1 and as a count, and the
+ * unique reads that begin there; or with total_only the three sums.  resolution = 0 writes every position, otherwise about
+ * that many (the reference's thinning rule); csv = comma instead of tab.  The region's averages follow as '#' lines.  A walk
+ * over the reads of the last staging on the device (a few ms): needs device staging.  Not written: the per-read-group
+ * columns, the read-begin and GC side files, the reference average line (-a). */
+int brq_write_coverage_table(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv);
 
 /* ---- the collective of a sharded run, fused into pass 1 (csrc/exchange.cu) ------------------------------------------------
  * Instead of summing the brq_hist_device() buffers with a collective library between brq_error_count and

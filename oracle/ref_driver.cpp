@@ -14,6 +14,7 @@
 // still the shim (htslib itself is not in this image): parity at the BAM-decode/pileup boundary
 // remains a restatement.
 #include "coverage_distribution.h"
+#include "coverage_output.h"
 #include "error_count.h"
 #include "identify_mutations.h"
 #include "reference_sequence.h"
@@ -64,6 +65,16 @@ int main(int argc, char** argv) {
              "deletion_coverage_propagation_cutoff\t%.17g\n", r.average, r.variance, r.relative_variance, r.nb_fit_size, r.nb_fit_mu,
              r.deletion_coverage_propagation_cutoff);
     cout << line;
+    return 0;
+  }
+
+  if (cmd == "coverage_table") {
+    // `breseq BAM2COV -t`: coverage_output::table (coverage_output.cpp:190-283) --bam --fasta --region seq:start-end
+    // --resolution N (0 = every position) [--total-only 1] [--format tsv|csv] --table FILE
+    coverage_output co(get("bam", ""), get("fasta", ""));
+    co.total_only(get("total-only", "0") == "1");
+    co.output_format(get("format", "tsv"));
+    co.table(get("region", ""), get("table", out + "/coverage.tab"), (uint32_t)atoi(get("resolution", "0").c_str()));
     return 0;
   }
 

@@ -1,0 +1,42 @@
+"""BAM2COV's table from the CUDA path (brq_write_coverage_table: coverage_tile_kernel over the reads staged in HBM) against the
+tables the reference build's coverage_output::table wrote (tests/golden/<name>/coverage_table.<k>.tab): byte for byte."""
+import filecmp
+import os
+
+import pytest
+
+import breseq_b200 as bq
+import helpers
+from test_coverage_table import requests
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.DATASETS if not helpers.DATASETS[n].get("no_golden")])
+def test_coverage_tables_byte_identical(name, datasets, tmp_path):
+    d = datasets[name]
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], staging="device", **helpers.stage_kwargs(d))
+    for table, region, resolution, total_only, fmt in requests(name):
+        out = str(tmp_path / table)
+        ctx.write_coverage_table(region, out, int(resolution), total_only == "1", fmt == "csv")
+        assert filecmp.cmp(out, os.path.join(helpers.GOLDEN, name, table), shallow=False), (name, table, region)
+    # the walk does not disturb the passes: they still run on the same staged stream
+    ctx.error_count(helpers.covariates(d))
+    ctx.close()
+
+
+def test_coverage_table_needs_device_staging_and_a_region_inside_it(datasets, tmp_path):
+    d = datasets["multi"]
+    names = helpers.contig_names(d)
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(d["bam"], d["fasta"], staging="host", **helpers.stage_kwargs(d))
+    with pytest.raises(bq.BrqError):
+        ctx.write_coverage_table(names[0] + ":1-100", str(tmp_path / "a.tab"))
+    ctx.stage_bam(d["bam"], d["fasta"], staging="device", seq_ids=[names[0]], **helpers.stage_kwargs(d))
+    ctx.write_coverage_table(names[0] + ":1-100", str(tmp_path / "b.tab"))
+    with pytest.raises(bq.BrqError):
+        ctx.write_coverage_table(names[1] + ":1-100", str(tmp_path / "c.tab"))   # not a visited target
+    with pytest.raises(bq.BrqError):
+        ctx.write_coverage_table("nosuch:1-100", str(tmp_path / "d.tab"))
+    ctx.close()

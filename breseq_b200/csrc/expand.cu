@@ -53,15 +53,30 @@ RingSlots& ring_of_current_device() {
 
 void UploadRing::copy(void* dst_device, const void* src_host, size_t bytes, cudaStream_t s) {
   if (!bytes) return;
+  // brq_pin_reads registers an array in pieces, and the system may refuse some: every quarter-gigabyte span is looked at
+  // on its own (copied directly when both of its ends are page-locked, through the ring otherwise)
+  const size_t SPAN = (size_t)256 << 20;
+  if (bytes > SPAN) {
+    for (size_t at = 0; at < bytes; at += SPAN)
+      copy(static_cast<char*>(dst_device) + at, static_cast<const char*>(src_host) + at, std::min(SPAN, bytes - at), s);
+    return;
+  }
   RingSlots& R = ring_of_current_device();
   std::lock_guard<std::mutex> ring_guard(R.mu);
   void** slot = R.slot;
   cudaEvent_t* done = R.done;
   int& next = R.next;
-  cudaPointerAttributes attr;
-  const bool locked = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  if (locked || bytes < ((size_t)1 << 20)) {  // page-locked already (brq_pin_reads), or too small to matter
+  auto page_locked = [](const void* p) {
+    cudaPointerAttributes attr;
+    const bool yes = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    return yes;
+  };
+  if (bytes < ((size_t)1 << 20)) {  // too small to matter
+    CUDA_OK(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, s));
+    return;
+  }
+  if (page_locked(src_host) && page_locked(static_cast<const char*>(src_host) + bytes - 1)) {
     CUDA_OK(cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, s));
     return;
   }

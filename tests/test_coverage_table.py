@@ -49,3 +49,62 @@ def test_bad_regions_are_refused(checker, datasets, tmp_path):
     for region in ("nosuchseq:1-10", first, first + ":0-10", first + ":10-5", first + ":1-99999999", first + ":1-2-3"):
         p = subprocess.run([checker, d["bam"], d["fasta"], region, "0", "0", "0", str(tmp_path / "x.tab")], capture_output=True, text=True)
         assert p.returncode == 1 and "coverage_check:" in p.stderr, region
+
+
+# ---- known answers worked out by hand from coverage_output.cpp:307-470 -----------------------------------------------------
+# One BAM with the awkward cases side by side on a 19-base reference.  Columns (1-based) and what each read adds:
+#   r1  forward  2M1D2M at 1   unique, aligned at 1 2 4 5 (3 is deleted: no coverage there); begins at 1 (top)
+#   r2  reverse  2S3M1S at 5   unique, aligned at 5 6 7; a reversed read begins at its LAST base: query index 5 of 6 is soft
+#                              clipped, so no aligned position is its first base: no begin count
+#   r3  reverse  4M at 3       unique, aligned at 3..6; begins at 6 (bottom)
+#   r4  forward  4M at 2, X1=3 redundant: 1/3 at 2..5, raw count 1
+#   r5  forward  2M2N2M at 8   unique, aligned at 8 9 12 13 (10 11 are a reference skip); begins at 8
+#   r6  forward  3H4M at 10    unique, aligned at 10..13; hard clips are not part of the read: begins at 10
+#   r7  reverse  4M at 10, X1=2 redundant on the bottom strand: 0.5 at 10..13
+#   r8  unmapped flag          never seen
+KAT_REF = "ACGTACGTACGTTTGACCA"
+KAT_READS = [dict(tid=0, pos=0, cigar="2M1D2M", seq="ACTA", qual=[30] * 4),
+             dict(tid=0, pos=1, cigar="4M", seq="CGTA", qual=[30] * 4, tags={"X1": 3}),
+             dict(tid=0, pos=2, cigar="4M", seq="GTAC", qual=[30] * 4, flag=16),
+             dict(tid=0, pos=4, cigar="2S3M1S", seq="TTACGA", qual=[30] * 6, flag=16),
+             dict(tid=0, pos=7, cigar="2M2N2M", seq="TATT", qual=[30] * 4),
+             dict(tid=0, pos=9, cigar="3H4M", seq="CGTT", qual=[30] * 4),
+             dict(tid=0, pos=9, cigar="4M", seq="CGTT", qual=[30] * 4, flag=16, tags={"X1": 2}),
+             dict(tid=0, pos=12, cigar="4M", seq="TTGA", qual=[30] * 4, flag=4)]
+#            pos: unique_top unique_bot red_top red_bot raw_top raw_bot begin_top begin_bot
+KAT_ROWS = {1: (1, 0, "0", "0", 0, 0, 1, 0), 2: (1, 0, "0.333333", "0", 1, 0, 0, 0), 3: (0, 1, "0.333333", "0", 1, 0, 0, 0),
+            4: (1, 1, "0.333333", "0", 1, 0, 0, 0), 5: (1, 2, "0.333333", "0", 1, 0, 0, 0), 6: (0, 2, "0", "0", 0, 0, 0, 1),
+            7: (0, 1, "0", "0", 0, 0, 0, 0), 8: (1, 0, "0", "0", 0, 0, 1, 0), 9: (1, 0, "0", "0", 0, 0, 0, 0),
+            10: (1, 0, "0", "0.5", 0, 1, 1, 0), 11: (1, 0, "0", "0.5", 0, 1, 0, 0), 12: (2, 0, "0", "0.5", 0, 1, 0, 0),
+            13: (2, 0, "0", "0.5", 0, 1, 0, 0), 14: (0, 0, "0", "0", 0, 0, 0, 0)}
+
+
+def kat_inputs(tmp_path):
+    import minibam
+    bam, fasta = str(tmp_path / "kat.bam"), str(tmp_path / "kat.fasta")
+    minibam.write(bam, fasta, [("chr", KAT_REF)], KAT_READS)
+    return bam, fasta
+
+
+def kat_expected_text():
+    lines = ["position\tref_base\tunique_top_cov\tunique_bot_cov\tredundant_top_cov\tredundant_bot_cov\traw_redundant_top_cov\t"
+             "raw_redundant_bot_cov\tunique_top_begin\tunique_bot_begin"]
+    for pos in range(1, 15):
+        lines.append("\t".join([str(pos), KAT_REF[pos - 1]] + [str(x) for x in KAT_ROWS[pos]]))
+    return "\n".join(lines) + "\n"
+
+
+def test_hand_derived_coverage_rows(checker, tmp_path):
+    """deletion, reference skip, soft and hard clips, both strands, redundant and unmapped reads: the walk, and the reference
+    build itself where it is at hand, against rows worked out by hand"""
+    bam, fasta = kat_inputs(tmp_path)
+    mine = str(tmp_path / "mine.tab")
+    p = subprocess.run([checker, bam, fasta, "chr:1-14", "0", "0", "0", mine], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    body = "".join(l for l in open(mine) if not l.startswith("#"))
+    assert body == kat_expected_text()
+    if os.path.exists(helpers.REF_CLI):
+        ref = str(tmp_path / "ref.tab")
+        subprocess.run([helpers.REF_CLI, "coverage_table", "--bam", bam, "--fasta", fasta, "--region", "chr:1-14", "--table", ref],
+                       check=True, cwd=str(tmp_path))
+        assert open(ref).read() == open(mine).read()

@@ -40,3 +40,19 @@ def test_coverage_table_needs_device_staging_and_a_region_inside_it(datasets, tm
     with pytest.raises(bq.BrqError):
         ctx.write_coverage_table("nosuch:1-100", str(tmp_path / "d.tab"))
     ctx.close()
+
+
+def test_hand_derived_coverage_rows_on_the_device(tmp_path):
+    """the known-answer BAM of test_coverage_table.py (deletion, reference skip, clips, both strands, redundant and unmapped
+    reads) through the CUDA path"""
+    from test_coverage_table import kat_expected_text, kat_inputs
+    bam, fasta = kat_inputs(tmp_path)
+    ctx = bq.Context(device=0)
+    ctx.stage_bam(bam, fasta, staging="device")
+    out = str(tmp_path / "gpu.tab")
+    ctx.write_coverage_table("chr:1-14", out)
+    assert "".join(l for l in open(out) if not l.startswith("#")) == kat_expected_text()
+    ctx.write_coverage_table("chr:1-19", out, total_only=True)   # the tail past the last read: zero rows to the region's end
+    rows = [l.split("\t") for l in open(out) if not l.startswith("#")][1:]
+    assert [r[0] for r in rows] == [str(i) for i in range(1, 20)] and rows[-1][2:] == ["0", "0", "0\n"]
+    ctx.close()

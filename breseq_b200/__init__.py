@@ -150,7 +150,7 @@ def load_library():
                                       C.c_uint32, C.c_int, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
-        "brq_write_coverage_table": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int],
+        "brq_write_coverage_table": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
         "brq_hist_exchange_export": [C.c_void_p, C.c_void_p, P(C.c_uint64)],
@@ -562,9 +562,9 @@ class Context:
         """``<seq>.coverage.tsv`` of --predict-copy-number; '@' in ``pattern`` becomes the target name."""
         self._check(self.lib.brq_write_coverage_tsv(self.h, _b(pattern)))
 
-    def write_coverage_table(self, region, path, resolution=0, total_only=False, csv=False):
+    def write_coverage_table(self, region, path, resolution=0, total_only=False, csv=False, per_read_group=False):
         """BAM2COV's table for ``seq_id:start-end`` of the staged BAM (coverage_output.cpp:190-283, 307-470)."""
-        self._check(self.lib.brq_write_coverage_table(self.h, _b(region), _b(path), resolution, int(total_only), int(csv)))
+        self._check(self.lib.brq_write_coverage_table(self.h, _b(region), _b(path), resolution, int(total_only), int(csv), int(per_read_group)))
 
     @staticmethod
     def _fit_dict(f):

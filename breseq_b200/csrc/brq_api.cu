@@ -1145,17 +1145,25 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
   });
 }
 
-int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv) {
+int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv, int per_read_group) {
   return guarded(c, [&] {
     c->need_device();
     if (!c->staged || !c->st.device_built) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
-    coverage_columns_on_device(c->xs, c->st.n_base, c->d_coverage_columns, c->stream);
-    std::vector<CoverageColumn> cols(c->st.n_base);
-    if (!cols.empty()) CUDA_OK(cudaMemcpyAsync(cols.data(), c->d_coverage_columns.p, cols.size() * sizeof(CoverageColumn), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_OK(cudaStreamSynchronize(c->stream));
-    CUDA_OK(cudaGetLastError());
-    c->d2h_bytes += cols.size() * sizeof(CoverageColumn);
-    write_coverage_table(path, c->hdr, c->ref, c->st, cols, region ? region : "", resolution, total_only != 0, csv != 0);
+    const size_t n_base = c->st.n_base;
+    auto walk = [&](uint32_t group, std::vector<CoverageColumn>& cols) {
+      coverage_columns_on_device(c->xs, n_base, c->d_coverage_columns, group, c->stream);
+      cols.resize(n_base);
+      if (n_base) CUDA_OK(cudaMemcpyAsync(cols.data(), c->d_coverage_columns.p, n_base * sizeof(CoverageColumn), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      CUDA_OK(cudaGetLastError());
+      c->d2h_bytes += n_base * sizeof(CoverageColumn);
+    };
+    std::vector<CoverageColumn> cols;
+    walk(COVERAGE_ALL_GROUPS, cols);
+    // one more walk per read group: at least one set, like bam2cov --per-read-group (coverage_output.h:142-143)
+    std::vector<std::vector<CoverageColumn>> by_group(per_read_group ? std::max<size_t>(c->hdr.read_groups.ids.size(), 1) : 0);
+    for (size_t g = 0; g < by_group.size(); ++g) walk((uint32_t)g, by_group[g]);
+    write_coverage_table(path, c->hdr, c->ref, c->st, cols, by_group, region ? region : "", resolution, total_only != 0, csv != 0);
   });
 }
 

@@ -23,7 +23,8 @@ std::string number(double v) {   // an ostream's default formatting of a double
 // `resolution` rows when it is not 0 (pileup_base.cpp:121-134: kept where (position + start) is a multiple of
 // floor(size / resolution)), then the region's averages as commented lines.
 void write_coverage_table(const std::string& path, const BamHeader& hdr, const RefSet& ref, const PileupStream& st,
-                          const std::vector<CoverageColumn>& cols, const std::string& region, uint32_t resolution, bool total_only, bool csv) {
+                          const std::vector<CoverageColumn>& cols, const std::vector<std::vector<CoverageColumn>>& by_group,
+                          const std::string& region, uint32_t resolution, bool total_only, bool csv) {
   const size_t colon = region.find(':');
   if (colon == std::string::npos || region.find(':', colon + 1) != std::string::npos)
     throw std::runtime_error("Expected exactly one colon in region string:" + region);
@@ -60,9 +61,12 @@ void write_coverage_table(const std::string& path, const BamHeader& hdr, const R
   if (!out) throw std::runtime_error("cannot create " + path);
   const char* d = csv ? "," : "\t";
   out << "position" << d << "ref_base";
-  if (total_only) out << d << "unique_cov" << d << "redundant_cov" << d << "total_cov";
-  else out << d << "unique_top_cov" << d << "unique_bot_cov" << d << "redundant_top_cov" << d << "redundant_bot_cov" << d << "raw_redundant_top_cov" << d
-           << "raw_redundant_bot_cov" << d << "unique_top_begin" << d << "unique_bot_begin";
+  const std::vector<std::string> names = total_only ? std::vector<std::string>{"unique_cov", "redundant_cov", "total_cov"}
+                                                    : std::vector<std::string>{"unique_top_cov", "unique_bot_cov", "redundant_top_cov", "redundant_bot_cov",
+                                                                               "raw_redundant_top_cov", "raw_redundant_bot_cov", "unique_top_begin", "unique_bot_begin"};
+  for (const std::string& nm : names) out << d << nm;
+  for (size_t g = 0; g < by_group.size(); ++g)   // the per-read-group repeats follow the aggregate columns (:236-244)
+    for (const std::string& nm : names) out << d << "RG-" << g << "_" << nm;
   out << '\n';
   // Which positions get a row (pileup_base.cpp:141-200, 308-358 with coverage_output.cpp:318-330).  Up to the last column the
   // pileup engine reports (L: the last position of the region any read spans), the handled positions: inside the region and,
@@ -85,28 +89,41 @@ void write_coverage_table(const std::string& path, const BamHeader& hdr, const R
   }
   const CoverageColumn none = {{0, 0}, {0, 0}, {0, 0}, 0, 0, {0.0, 0.0}};
   uint32_t n_positions = 0;
-  double sum_unique = 0, sum_repeat = 0, sum_all = 0;
-  for (uint32_t pos : rows) {
-    const CoverageColumn* at = pos > L ? nullptr : column(pos);   // (past L nothing is covered; before the region's start nothing is counted)
-    const CoverageColumn& c = at ? *at : none;
-    const char rc = ri < ref.seqs.size() ? ref.seqs[ri][(size_t)pos - 1] : 'N';
-    ++n_positions;
-    sum_unique += c.unique[0] + c.unique[1];
-    sum_repeat += c.redundant[0] + c.redundant[1];
-    sum_all += c.unique[0] + c.unique[1] + c.redundant[0] + c.redundant[1];
-    out << pos << d << rc << d;
+  struct Sum { double unique = 0, repeat = 0, all = 0; };
+  Sum total;
+  std::vector<Sum> group_total(by_group.size());
+  auto cells = [&](const CoverageColumn& c, Sum& sum) {
+    sum.unique += c.unique[0] + c.unique[1];
+    sum.repeat += c.redundant[0] + c.redundant[1];
+    sum.all += c.unique[0] + c.unique[1] + c.redundant[0] + c.redundant[1];
     if (total_only)
-      out << (c.unique[0] + c.unique[1]) << d << number(c.redundant[0] + c.redundant[1]) << d
+      out << d << (c.unique[0] + c.unique[1]) << d << number(c.redundant[0] + c.redundant[1]) << d
           << number(c.unique[0] + c.unique[1] + c.redundant[0] + c.redundant[1]);
     else
-      out << c.unique[0] << d << c.unique[1] << d << number(c.redundant[0]) << d << number(c.redundant[1]) << d
+      out << d << c.unique[0] << d << c.unique[1] << d << number(c.redundant[0]) << d << number(c.redundant[1]) << d
           << c.raw_redundant[0] << d << c.raw_redundant[1] << d << c.begin[0] << d << c.begin[1];
+  };
+  for (uint32_t pos : rows) {
+    const bool counted = pos <= L && column(pos) != nullptr;   // (past L nothing is covered; before the region's start nothing is counted)
+    const uint64_t at = counted ? seg->slot0 + (uint64_t)((int64_t)pos - 1 - seg->lo) : 0;
+    const char rc = ri < ref.seqs.size() ? ref.seqs[ri][(size_t)pos - 1] : 'N';
+    ++n_positions;
+    out << pos << d << rc;
+    cells(counted ? cols[at] : none, total);
+    for (size_t g = 0; g < by_group.size(); ++g) cells(counted ? by_group[g][at] : none, group_total[g]);
     out << '\n';
   }
+  const double sum_unique = total.unique, sum_repeat = total.repeat, sum_all = total.all;
   out << "#" << d << "region_unique_average_cov" << d << number(sum_unique / n_positions) << '\n';
   out << "#" << d << "region_repeat_average_cov" << d << number(sum_repeat / n_positions) << '\n';
   out << "#" << d << "region_average_cov" << d << number(sum_all / n_positions) << '\n';
   out << "#" << d << "number_of_positions" << d << n_positions << '\n';
+  for (size_t g = 0; g < by_group.size(); ++g) {   // the groups' averages over the same positions (:270-279)
+    const std::string pre = "RG-" + std::to_string(g) + "_";
+    out << "#" << d << pre << "region_unique_average_cov" << d << number(group_total[g].unique / n_positions) << '\n';
+    out << "#" << d << pre << "region_repeat_average_cov" << d << number(group_total[g].repeat / n_positions) << '\n';
+    out << "#" << d << pre << "region_average_cov" << d << number(group_total[g].all / n_positions) << '\n';
+  }
 }
 
 }  // namespace brq

@@ -10,7 +10,9 @@
 
 namespace brq {
 
+// by_group: empty, or one array per read group (the table then repeats its columns per group, prefixed "RG-<n>_")
 void write_coverage_table(const std::string& path, const BamHeader& hdr, const RefSet& ref, const PileupStream& st,
-                          const std::vector<CoverageColumn>& cols, const std::string& region, uint32_t resolution, bool total_only, bool csv);
+                          const std::vector<CoverageColumn>& cols, const std::vector<std::vector<CoverageColumn>>& by_group,
+                          const std::string& region, uint32_t resolution, bool total_only, bool csv);
 
 }  // namespace brq

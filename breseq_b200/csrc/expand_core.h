@@ -55,7 +55,7 @@ struct alignas(16) ReadMeta {
   int32_t xl, xr;            // XL / XR:i trims, -1 when absent
   int32_t qs0, qe0;          // first / last non-soft-clipped query index (alignment.cpp:248-288)
   int32_t qb_end0, qb_start0;  // query_bounds_0 (alignment.cpp:104-218, min_qual == 0)
-  uint8_t mapq, read_set, flags, pad;
+  uint8_t mapq, read_set, flags, rg;   // rg: the read group's index among the header's @RG lines (0 when there is none)
 };
 static_assert(sizeof(ReadMeta) == 64, "ReadMeta is read as four 128-bit words");
 constexpr uint8_t RM_LIVE = 1, RM_REV = 2, RM_HAS_INS = 4, RM_SIMPLE = 8;  // SIMPLE: one M / = / X run between clips: no CIGAR walk per column
@@ -184,7 +184,7 @@ BRQ_HD inline ReadMeta prep_read(const RawReads& R, uint64_t i, const uint32_t* 
   const uint32_t* cig = R.cigars + R.cigar_off[i];
   const uint32_t nc = R.n_cigar[i];
   m.pos = R.pos[i]; m.l_seq = R.l_seq[i]; m.n_cigar = nc; m.seq_off = R.seq_off[i]; m.cigar_off = R.cigar_off[i];
-  m.x1 = R.x1[i]; m.xl = R.xl[i]; m.xr = R.xr[i]; m.mapq = R.mapq[i]; m.pad = 0;
+  m.x1 = R.x1[i]; m.xl = R.xl[i]; m.xr = R.xr[i]; m.mapq = R.mapq[i]; m.rg = R.rg[i];
   int32_t rlen = 0, qlen = 0;
   bool has_ins = false;
   uint32_t n_match_ops = 0, n_other_ops = 0;   // other: anything but M / = / X and the clips S, H
@@ -589,7 +589,9 @@ BRQ_HD inline void tile_lane(const ExpandArgs& a, uint32_t tile, uint32_t l) {
 struct CoverageColumn { uint32_t unique[2], raw_redundant[2], begin[2], covered, pad; double redundant[2]; };
 static_assert(sizeof(CoverageColumn) == 48, "CoverageColumn layout");
 
-BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l, CoverageColumn* out) {
+// group: only the reads of that read group count (the table's per-read-group column sets), COVERAGE_ALL_GROUPS: every read
+constexpr uint32_t COVERAGE_ALL_GROUPS = 0xFFFFFFFFu;
+BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l, CoverageColumn* out, uint32_t group = COVERAGE_ALL_GROUPS) {
   const ExpandSeg& sg = seg_of_tile(a, tile);
   const int32_t c0 = sg.lo + (int32_t)((tile - sg.tile0) * 32u), c1 = c0 + 32 < sg.hi ? c0 + 32 : sg.hi;
   const int32_t c = c0 + (int32_t)l;
@@ -608,7 +610,7 @@ BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l,
     else h = column_hit(a.cigars + m.cigar_off, m.n_cigar, m.pos, c);
     if (!h.has) continue;
     col.covered = 1;
-    if (h.is_del) continue;   // :370-373
+    if (h.is_del || (group != COVERAGE_ALL_GROUPS && m.rg != group)) continue;   // :370-373, :380
     const uint32_t rev = (m.flags & RM_REV) ? 1u : 0u;
     if (m.x1 == 1) {
       ++col.unique[rev];

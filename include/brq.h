@@ -237,9 +237,11 @@ int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
  * a deletion over the position does not count), the redundant coverage by strand as the sum of 1 / X1 and as a count, and the
  * unique reads that begin there; or with total_only the three sums.  resolution = 0 writes every position, otherwise about
  * that many (the reference's thinning rule); csv = comma instead of tab.  The region's averages follow as '#' lines.  A walk
- * over the reads of the last staging on the device (a few ms): needs device staging.  Not written: the per-read-group
- * columns, the read-begin and GC side files, the reference average line (-a). */
-int brq_write_coverage_table(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv);
+ * over the reads of the last staging on the device (a few ms): needs device staging.  per_read_group repeats the columns and
+ * the averages once per @RG of the header (prefix "RG-<n>_", at least RG-0; one more walk per group).  Not written: the
+ * read-begin and GC side files, the reference average line (-a). */
+int brq_write_coverage_table(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv,
+                             int per_read_group);
 
 /* ---- the collective of a sharded run, fused into pass 1 (csrc/exchange.cu) ------------------------------------------------
  * Instead of summing the brq_hist_device() buffers with a collective library between brq_error_count and

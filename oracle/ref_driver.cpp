@@ -70,10 +70,11 @@ int main(int argc, char** argv) {
 
   if (cmd == "coverage_table") {
     // `breseq BAM2COV -t`: coverage_output::table (coverage_output.cpp:190-283) --bam --fasta --region seq:start-end
-    // --resolution N (0 = every position) [--total-only 1] [--format tsv|csv] --table FILE
+    // --resolution N (0 = every position) [--total-only 1] [--per-read-group 1] [--format tsv|csv] --table FILE
     coverage_output co(get("bam", ""), get("fasta", ""));
     co.total_only(get("total-only", "0") == "1");
     co.output_format(get("format", "tsv"));
+    co.per_read_group(get("per-read-group", "0") == "1");
     co.table(get("region", ""), get("table", out + "/coverage.tab"), (uint32_t)atoi(get("resolution", "0").c_str()));
     return 0;
   }

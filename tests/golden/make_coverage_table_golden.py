@@ -6,7 +6,8 @@ coverage_output.cpp:190-283, compiled unmodified from /root/reference).
 
 For every test dataset (tests/helpers.py: inputs written by the product's seeded generator; inputs.sha256 pins them) a few
 (region, resolution, total_only, format) requests: the whole first sequence thinned to about 600 rows, a window with commas in
-its coordinates at full resolution, the tail of the last sequence as totals in CSV, and a single position.  The tables land in
+its coordinates at full resolution, the tail of the last sequence as totals in CSV, a single position, and two tables with
+the per-read-group column sets.  The tables land in
 tests/golden/<name>/coverage_table.<k>.tab and the requests in tests/golden/<name>/coverage_tables.tsv."""
 import os
 import subprocess
@@ -29,7 +30,9 @@ def requests_for(d):
             ("%s:%s-%s" % (first, "{:,}".format(lo), "{:,}".format(hi)), 0, 0, "tsv"),
             ("%s:%d-%d" % (last, max(1, n1 - 199), n1), 0, 1, "csv"),
             ("%s:%d" % (first, min(50, n0)), 0, 0, "tsv"),
-            ("%s:1-%d" % (last, n1), 37, 1, "tsv")]
+            ("%s:1-%d" % (last, n1), 37, 1, "tsv"),
+            ("%s:%d-%d" % (first, min(201, n0), min(n0, 500)), 0, 0, "tsv", 1),      # per read group, all columns
+            ("%s:1-%d" % (last, n1), 90, 1, "csv", 1)]                              # per read group, totals, thinned
 
 
 def main():
@@ -42,14 +45,17 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             d = helpers.generate_inputs(name, tmp)
             rows = []
-            for k, (region, resolution, total_only, fmt) in enumerate(requests_for(d)):
+            for k, req in enumerate(requests_for(d)):
+                region, resolution, total_only, fmt = req[:4]
+                per_rg = req[4] if len(req) > 4 else 0
                 out = os.path.join(gdir, "coverage_table.%d.tab" % k)
                 subprocess.run([helpers.REF_CLI, "coverage_table", "--bam", d["bam"], "--fasta", d["fasta"], "--region", region,
-                                "--resolution", str(resolution), "--total-only", str(total_only), "--format", fmt, "--table", out],
+                                "--resolution", str(resolution), "--total-only", str(total_only), "--format", fmt, "--per-read-group", str(per_rg),
+                                "--table", out],
                                check=True, cwd=tmp)
-                rows.append("\t".join([os.path.basename(out), region, str(resolution), str(total_only), fmt]))
+                rows.append("\t".join([os.path.basename(out), region, str(resolution), str(total_only), fmt, str(per_rg)]))
             with open(os.path.join(gdir, "coverage_tables.tsv"), "w") as fh:
-                fh.write("table\tregion\tresolution\ttotal_only\tformat\n" + "\n".join(rows) + "\n")
+                fh.write("table\tregion\tresolution\ttotal_only\tformat\tper_read_group\n" + "\n".join(rows) + "\n")
         print(name, len(rows))
 
 

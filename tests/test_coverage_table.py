@@ -34,10 +34,10 @@ def checker(tmp_path_factory):
 def test_coverage_walk_reproduces_the_reference_tables(name, checker, datasets, tmp_path):
     d = datasets[name]
     reqs = requests(name)
-    assert len(reqs) == 5
-    for table, region, resolution, total_only, fmt in reqs:
+    assert len(reqs) == 7
+    for table, region, resolution, total_only, fmt, per_rg in reqs:
         out = str(tmp_path / table)
-        p = subprocess.run([checker, d["bam"], d["fasta"], region, resolution, total_only, "1" if fmt == "csv" else "0", out],
+        p = subprocess.run([checker, d["bam"], d["fasta"], region, resolution, total_only, "1" if fmt == "csv" else "0", out, per_rg],
                            capture_output=True, text=True)
         assert p.returncode == 0, p.stderr
         assert filecmp.cmp(out, os.path.join(helpers.GOLDEN, name, table), shallow=False), (name, table, region)

@@ -17,9 +17,9 @@ def test_coverage_tables_byte_identical(name, datasets, tmp_path):
     d = datasets[name]
     ctx = bq.Context(device=0)
     ctx.stage_bam(d["bam"], d["fasta"], staging="device", **helpers.stage_kwargs(d))
-    for table, region, resolution, total_only, fmt in requests(name):
+    for table, region, resolution, total_only, fmt, per_rg in requests(name):
         out = str(tmp_path / table)
-        ctx.write_coverage_table(region, out, int(resolution), total_only == "1", fmt == "csv")
+        ctx.write_coverage_table(region, out, int(resolution), total_only == "1", fmt == "csv", per_rg == "1")
         assert filecmp.cmp(out, os.path.join(helpers.GOLDEN, name, table), shallow=False), (name, table, region)
     # the walk does not disturb the passes: they still run on the same staged stream
     ctx.error_count(helpers.covariates(d))

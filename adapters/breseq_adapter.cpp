@@ -130,8 +130,7 @@ void identify_mutations(const Settings& settings, const Summary& summary, const 
                         double polymorphism_precision_decimal, uint32_t polymorphism_precision_places, bool print_per_position_file)
 {
   // options that hang other detectors on the same pileup stay on the reference's own body
-  if (settings.predict_soft_clipping || settings.predict_missing_pairs || settings.predict_pair_distance ||
-      (settings.predict_copy_number && settings.read_file_sets.size() > 1)) {   // per-read-group coverage columns
+  if (settings.predict_soft_clipping || settings.predict_missing_pairs || settings.predict_pair_distance) {
     identify_mutations_cpu(settings, summary, bam, fasta, gd_file, ref_seq_info, deletion_propagation_cutoff, deletion_seed_cutoffs,
                            mutation_cutoff, polymorphism_cutoff, polymorphism_precision_decimal, polymorphism_precision_places,
                            print_per_position_file);

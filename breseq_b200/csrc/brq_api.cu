@@ -1141,7 +1141,21 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
   return guarded(c, [&] {
     if (c->h_cols.size() != c->st.n_slots()) download_columns(c);
     const PileupStream view = host_view(c);
-    write_coverage_tsv(pattern, c->hdr, c->ref, view, c->h_cols);
+    // a BAM with two or more read groups gets the three columns once more per group (identify_mutations.cpp:858-862,
+    // 1588-1610, 2046-2050): pass 2's coverage tallies split by read group, from one walk per group over the reads in HBM
+    std::vector<std::vector<CoverageColumn>> by_group;
+    if (c->hdr.read_groups.ids.size() > 1) {
+      if (!c->st.device_built) throw std::runtime_error("the per-read-group columns of the coverage TSV need reads staged on the device");
+      by_group.resize(c->hdr.read_groups.ids.size());
+      for (size_t g = 0; g < by_group.size(); ++g) {
+        coverage_columns_on_device(c->xs, c->st.n_base, c->d_coverage_columns, (uint32_t)g, true, c->stream);
+        by_group[g].resize(c->st.n_base);
+        if (c->st.n_base) CUDA_OK(cudaMemcpyAsync(by_group[g].data(), c->d_coverage_columns.p, c->st.n_base * sizeof(CoverageColumn), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += c->st.n_base * sizeof(CoverageColumn);
+      }
+    }
+    write_coverage_tsv(pattern, c->hdr, c->ref, view, c->h_cols, by_group);
   });
 }
 
@@ -1151,7 +1165,7 @@ int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, u
     if (!c->staged || !c->st.device_built) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
     const size_t n_base = c->st.n_base;
     auto walk = [&](uint32_t group, std::vector<CoverageColumn>& cols) {
-      coverage_columns_on_device(c->xs, n_base, c->d_coverage_columns, group, c->stream);
+      coverage_columns_on_device(c->xs, n_base, c->d_coverage_columns, group, false, c->stream);
       cols.resize(n_base);
       if (n_base) CUDA_OK(cudaMemcpyAsync(cols.data(), c->d_coverage_columns.p, n_base * sizeof(CoverageColumn), cudaMemcpyDeviceToHost, c->stream));
       CUDA_OK(cudaStreamSynchronize(c->stream));

@@ -238,10 +238,10 @@ __global__ void __launch_bounds__(256) read_starts_kernel(ExpandArgs a, unsigned
 
 // ------------------------------------------------------------------------------------------ the tile passes
 // (the count pass fits 64 registers: four CTAs per SM; the fill pass spills there and runs faster with three)
-__global__ void __launch_bounds__(256, 4) coverage_tile_kernel(ExpandArgs a, CoverageColumn* __restrict__ out, uint32_t group) {
+__global__ void __launch_bounds__(256, 4) coverage_tile_kernel(ExpandArgs a, CoverageColumn* __restrict__ out, uint32_t group, bool include_deleted) {
   const uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (tile >= a.n_tiles) return;
-  coverage_lane(a, tile, threadIdx.x & 31u, out, group);
+  coverage_lane(a, tile, threadIdx.x & 31u, out, group, include_deleted);
 }
 
 template <bool FILL>
@@ -774,11 +774,11 @@ void gather_flagged_records(const StreamDev& ds, const PileupStream& st, const u
   d_info.release(); d_off.release(); d_words.release(); d_side.release();
 }
 
-void coverage_columns_on_device(const ExpandScratch& X, uint64_t n_base, DevBuf<CoverageColumn>& out, uint32_t group, cudaStream_t s) {
+void coverage_columns_on_device(const ExpandScratch& X, uint64_t n_base, DevBuf<CoverageColumn>& out, uint32_t group, bool include_deleted, cudaStream_t s) {
   if (!X.have_walk_args) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
   out.ensure(n_base + 1);
   const ExpandArgs& a = X.walk_args;
-  if (a.n_tiles) { coverage_tile_kernel<<<blocks_for((uint64_t)a.n_tiles * 32), 256, 0, s>>>(a, out.p, group); launched(); }
+  if (a.n_tiles) { coverage_tile_kernel<<<blocks_for((uint64_t)a.n_tiles * 32), 256, 0, s>>>(a, out.p, group, include_deleted); launched(); }
 }
 
 }  // namespace brq

@@ -82,8 +82,10 @@ void gather_flagged_records(const StreamDev& ds, const PileupStream& st, const u
 
 // BAM2COV (coverage_output.cpp:307-470): per base slot of the staged range, the coverage table's counts, from a walk over the
 // reads of the last staging
-// (group: COVERAGE_ALL_GROUPS, or the index of the one read group whose reads count)
-void coverage_columns_on_device(const ExpandScratch& scratch, uint64_t n_base, DevBuf<CoverageColumn>& out, uint32_t group, cudaStream_t stream);
+// (group: COVERAGE_ALL_GROUPS, or the index of the one read group whose reads count; include_deleted: pass 2's notion of
+// coverage, where a deletion over the column counts)
+void coverage_columns_on_device(const ExpandScratch& scratch, uint64_t n_base, DevBuf<CoverageColumn>& out, uint32_t group, bool include_deleted,
+                                cudaStream_t stream);
 
 int expand_launch_count();
 

@@ -591,7 +591,9 @@ static_assert(sizeof(CoverageColumn) == 48, "CoverageColumn layout");
 
 // group: only the reads of that read group count (the table's per-read-group column sets), COVERAGE_ALL_GROUPS: every read
 constexpr uint32_t COVERAGE_ALL_GROUPS = 0xFFFFFFFFu;
-BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l, CoverageColumn* out, uint32_t group = COVERAGE_ALL_GROUPS) {
+// include_deleted: a deletion or reference skip over the column counts as coverage, as in pass 2's tallies (<seq>.coverage.tsv)
+BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l, CoverageColumn* out, uint32_t group = COVERAGE_ALL_GROUPS,
+                                 bool include_deleted = false) {
   const ExpandSeg& sg = seg_of_tile(a, tile);
   const int32_t c0 = sg.lo + (int32_t)((tile - sg.tile0) * 32u), c1 = c0 + 32 < sg.hi ? c0 + 32 : sg.hi;
   const int32_t c = c0 + (int32_t)l;
@@ -610,12 +612,12 @@ BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l,
     else h = column_hit(a.cigars + m.cigar_off, m.n_cigar, m.pos, c);
     if (!h.has) continue;
     col.covered = 1;
-    if (h.is_del || (group != COVERAGE_ALL_GROUPS && m.rg != group)) continue;   // :370-373, :380
+    if ((h.is_del && !include_deleted) || (group != COVERAGE_ALL_GROUPS && m.rg != group)) continue;   // :370-373, :380
     const uint32_t rev = (m.flags & RM_REV) ? 1u : 0u;
     if (m.x1 == 1) {
       ++col.unique[rev];
       // the read's first base in its own orientation (:385-393): query position 1, or the last one of a reversed read
-      if (rev ? h.q == (int32_t)m.l_seq - 1 : h.q == 0) ++col.begin[rev];
+      if (!h.is_del && (rev ? h.q == (int32_t)m.l_seq - 1 : h.q == 0)) ++col.begin[rev];
     } else {
       ++col.raw_redundant[rev];
       col.redundant[rev] += 1.0 / (double)m.x1;

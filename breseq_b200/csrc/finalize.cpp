@@ -391,7 +391,8 @@ void write_per_position_file(const std::string& path, const BamHeader& hdr, cons
 
 // identify_mutations.cpp:2028-2052, 2173-2204: <seq>.coverage.tsv (--predict-copy-number), one file per visited target:
 //   position ref_base unique_cov redundant_cov total_cov, the sums over both strands, total as their plain sum.
-void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols) {
+void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols,
+                        const std::vector<std::vector<CoverageColumn>>& by_group) {
   for (const Segment& sg : st.segments) {
     std::string fn = pattern;
     const std::string& name = hdr.target_names[(size_t)sg.tid];
@@ -399,7 +400,11 @@ void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const 
     if (at != std::string::npos) fn.replace(at, 1, name);
     std::ofstream out(fn.c_str(), sg.lo == 0 ? std::ios::out : std::ios::app);
     if (!out) throw std::runtime_error("cannot create " + fn);
-    if (sg.lo == 0) out << "position\tref_base\tunique_cov\tredundant_cov\ttotal_cov\n";
+    if (sg.lo == 0) {
+      out << "position\tref_base\tunique_cov\tredundant_cov\ttotal_cov";
+      for (size_t g = 0; g < by_group.size(); ++g) out << "\tRG-" << g << "_unique_cov\tRG-" << g << "_redundant_cov\tRG-" << g << "_total_cov";
+      out << '\n';
+    }
     size_t ri = 0;
     while (ri < ref.names.size() && ref.names[ri] != name) ++ri;
     for (int32_t c = sg.lo; c < sg.hi; ++c) {
@@ -407,7 +412,13 @@ void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const 
       const double unique = (double)co.unique[0] + (double)co.unique[1], redundant = co.redundant[0] + co.redundant[1];
       // the reference prints the FASTA character of the column (reference_base_char_1), not the folded index
       const char rc = ri < ref.seqs.size() ? ref.seqs[ri][(size_t)c] : index_to_char(st.slot_ref[sg.slot0 + (uint64_t)(c - sg.lo)]);
-      out << (c + 1) << '\t' << rc << '\t' << format_default(unique) << '\t' << format_default(redundant) << '\t' << format_default(unique + redundant) << '\n';
+      out << (c + 1) << '\t' << rc << '\t' << format_default(unique) << '\t' << format_default(redundant) << '\t' << format_default(unique + redundant);
+      for (const std::vector<CoverageColumn>& grp : by_group) {   // position_coverage::sum(): bottom strand + top strand
+        const CoverageColumn& k = grp[sg.slot0 + (uint64_t)(c - sg.lo)];
+        const double gu = (double)k.unique[1] + (double)k.unique[0], gr = k.redundant[1] + k.redundant[0];
+        out << '\t' << format_default(gu) << '\t' << format_default(gr) << '\t' << format_default(gu + gr);
+      }
+      out << '\n';
     }
   }
 }

@@ -3,6 +3,7 @@
 #pragma once
 #include "bam_io.h"
 #include "brq_types.h"
+#include "expand_core.h"
 #include "kernels.h"
 
 #include <functional>
@@ -136,6 +137,8 @@ EvidenceCounts write_evidence(const std::string& gd_path, const BamHeader& hdr, 
 // Optional outputs of pass 2 (identify_mutations.cpp:1693-1733 and :2028-2052, 2173-2204); both read the full per-slot results.
 void write_per_position_file(const std::string& path, const BamHeader& hdr, const PileupStream& st, const std::vector<ColumnOut>& cols,
                              uint32_t base_quality_cutoff, const std::vector<double>& deletion_propagation_cutoff);
-void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols);
+// by_group: empty, or per read group the coverage walk's columns with pass 2's notion of coverage (expand_core.h: coverage_lane)
+void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols,
+                        const std::vector<std::vector<CoverageColumn>>& by_group);
 
 }  // namespace brq

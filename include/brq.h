@@ -214,8 +214,9 @@ int brq_write_evidence(brq_ctx* ctx, const char* gd_file, const double* deletion
  *   (identify_mutations.cpp:1693-1733, Settings::mutation_identification_per_position_file_name); targets whose
  *   deletion_propagation_cutoff is negative are skipped like the reference skips them.
  * brq_write_coverage_tsv: <seq>.coverage.tsv of --predict-copy-number (identify_mutations.cpp:2028-2052, 2173-2204,
- *   Settings::complete_coverage_text_file_name); '@' in `pattern` is replaced by the target name.  The per-read-group
- *   columns the reference adds for runs with more than one read group are not written. */
+ *   Settings::complete_coverage_text_file_name); '@' in `pattern` is replaced by the target name.  A BAM with two or
+ *   more read groups gets the three columns once more per group ("RG-<n>_", :858-862): one walk per group over the reads the
+ *   last staging left in HBM (needs device staging then). */
 /* A run sharded by reference range (brq_stage_options.shard_rank / shard_count, one context per GPU): the MC and UN
  * intervals cross shard boundaries, so every context exports its share of the evidence (the event columns of its range
  * and its RA rows: a few hundred KB, valid until the next call on the context), the shares are gathered on one rank

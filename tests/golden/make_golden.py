@@ -16,6 +16,7 @@ htslib shim.  What they wrote is committed here:
     <name>/ra_mc_evidence.gd, <name>/inputs.sha256 (so generator drift is detected, not silently absorbed)
     <name>/preprocess_error_count.tab  (error_count(..., preprocess_stage = true): Summary::preprocess_error_count per seq id)
     tiny/reference.bam, tiny/reference.fasta(.fai), tiny/per_position_file.tab   (inputs kept for the smallest case)
+    tiny/<seq>.coverage.tsv   (two read groups: the --predict-copy-number table with its per-read-group columns)
 
 The fixtures pin (a) oracle/oracle.cpp, (b) the CUDA path, against the reference's real arithmetic
 and file writers.  The BAM decode / pileup layer under the reference is still oracle/hts_shim.
@@ -44,12 +45,11 @@ def main():
         if helpers.DATASETS[name].get("no_golden"):
             continue
         gdir = os.path.join(HERE, name)
-        shutil.rmtree(gdir, ignore_errors=True)
-        os.makedirs(gdir)
+        os.makedirs(gdir, exist_ok=True)   # (coverage_table.* are make_coverage_table_golden.py's: left alone)
         with tempfile.TemporaryDirectory() as tmp:
             d = helpers.generate_inputs(name, tmp)
             out = os.path.join(tmp, "ref")
-            helpers.run_reference(d, out, coverage_tsv=(name == "deep"))
+            helpers.run_reference(d, out, coverage_tsv=(name in ("deep", "tiny")))
             for f in helpers.pass_output_names(d):
                 shutil.copy(os.path.join(out, f), os.path.join(gdir, f))
             with open(os.path.join(gdir, "inputs.sha256"), "w") as fh:
@@ -70,6 +70,8 @@ def main():
                 for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
                     shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))
                 shutil.copy(os.path.join(out, "per_position_file.tab"), os.path.join(gdir, "per_position_file.tab"))
+                for c in helpers.contig_names(d):  # two read groups: <seq>.coverage.tsv with its per-read-group columns
+                    shutil.copy(os.path.join(out, c + ".coverage.tsv"), os.path.join(gdir, c + ".coverage.tsv"))
             if name == "deep":  # one read group: the optional outputs of pass 2 for a whole (small) dataset
                 shutil.copy(os.path.join(out, "per_position_file.tab"), os.path.join(gdir, "per_position_file.tab"))
                 tsv = helpers.contig_names(d)[0] + ".coverage.tsv"

@@ -136,6 +136,10 @@ def test_cuda_path_on_committed_bam(built, tmp_path):
     assert_same_files(d, out, os.path.join(helpers.GOLDEN, "tiny"), "CUDA path on committed BAM")
     # the per-position debug file (identify_mutations.cpp:1693-1733), byte for byte; insert sub-columns included
     assert filecmp.cmp(os.path.join(out, "per_position_file.tab"), golden("tiny", "per_position_file.tab"), shallow=False)
+    # <seq>.coverage.tsv of a BAM with two read groups: the three aggregate columns and the same three per read group
+    # (identify_mutations.cpp:858-862, 2046-2050)
+    for c in helpers.contig_names(d):
+        assert filecmp.cmp(os.path.join(out, c + ".coverage.tsv"), golden("tiny", c + ".coverage.tsv"), shallow=False), c
 
 
 @pytest.mark.gpu

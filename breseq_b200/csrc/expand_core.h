@@ -613,6 +613,8 @@ BRQ_HD inline void coverage_lane(const ExpandArgs& a, uint32_t tile, uint32_t l,
     if (!h.has) continue;
     col.covered = 1;
     if ((h.is_del && !include_deleted) || (group != COVERAGE_ALL_GROUPS && m.rg != group)) continue;   // :370-373, :380
+    // pass 2 does not count a read whose base here is N, not even as coverage (identify_mutations.cpp:1575-1576); bam2cov does
+    if (include_deleted && !h.is_del && (uint32_t)h.q < m.l_seq && xnibble_to_index(a.bases[m.seq_off + (uint32_t)h.q]) > 3) continue;
     const uint32_t rev = (m.flags & RM_REV) ? 1u : 0u;
     if (m.x1 == 1) {
       ++col.unique[rev];

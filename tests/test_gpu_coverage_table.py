@@ -56,3 +56,27 @@ def test_hand_derived_coverage_rows_on_the_device(tmp_path):
     rows = [l.split("\t") for l in open(out) if not l.startswith("#")][1:]
     assert [r[0] for r in rows] == [str(i) for i in range(1, 20)] and rows[-1][2:] == ["0", "0", "0\n"]
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["multi", "ltee"])
+def test_read_group_columns_of_the_coverage_tsv_add_up(name, datasets, tmp_path):
+    """<seq>.coverage.tsv of a BAM with several read groups: the per-read-group columns come from the coverage walk, the
+    aggregate ones from the tally kernel; two independent counts of the same pileup, so every row has to add up (the golden
+    of `tiny` pins the bytes; this covers the larger datasets)."""
+    from test_golden import run_cuda
+    d = datasets[name]
+    out = str(tmp_path / "cuda")
+    run_cuda(d, out, optional_outputs=True)
+    rows = 0
+    for c in helpers.contig_names(d):
+        lines = open(os.path.join(out, c + ".coverage.tsv")).read().splitlines()
+        head = lines[0].split("\t")
+        n_rg = (len(head) - 5) // 3
+        assert n_rg >= 2 and head[5] == "RG-0_unique_cov"
+        for l in lines[1:]:
+            f = l.split("\t")
+            unique, redundant = float(f[2]), float(f[3])
+            assert unique == sum(float(f[5 + 3 * g]) for g in range(n_rg)), l
+            assert abs(redundant - sum(float(f[6 + 3 * g]) for g in range(n_rg))) < 1e-4 * max(1.0, redundant), l
+            rows += 1
+    assert rows == sum(d["contig_lens"])

@@ -131,7 +131,7 @@ void parse_rg_lines(const std::string& text, ReadGroups& rg) {
 
 }  // namespace
 
-void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int threads) {
+void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int threads, const ReadSpans* span_of) {
   static const bool phase_times = getenv("BRQ_STAGE_TIMES") != nullptr;  // wall time of every phase on stderr
   auto phase_t0 = std::chrono::steady_clock::now();
   auto phase_done = [&](const char* what) {
@@ -305,6 +305,18 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
       hdr.target_lens.push_back((uint32_t)rd<int32_t>(&u[p])); p += 4;
     }
     parse_rg_lines(hdr.text, hdr.read_groups);
+    // a shard's spans (see bam_io.h): which records to keep, and where a sorted file can be left
+    std::vector<std::pair<int32_t, int32_t>> spans;
+    int32_t last_tid = -1, last_end = 0;
+    bool sorted_file = false;
+    if (span_of) {
+      spans = (*span_of)(hdr);
+      spans.resize(hdr.target_names.size(), std::make_pair(0, 0));
+      for (size_t t = 0; t < spans.size(); ++t) if (spans[t].first < spans[t].second) { last_tid = (int32_t)t; last_end = spans[t].second; }
+      const size_t hd = hdr.text.find("@HD");
+      sorted_file = hd != std::string::npos && hdr.text.find("SO:coordinate", hd) < hdr.text.find('\n', hd);
+    }
+    bool stopped = false;
     // records: one serial walk finds every record and gives it its place in the arrays (prefix sums of the CIGAR and
     // sequence lengths); a run of RUN records is published to the decoders once its last byte is inflated
     while (p + 4 <= total) {
@@ -317,6 +329,21 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
       const int32_t l_seq = rd<int32_t>(x + 16);
       if (l_seq < 0 || 32 + (size_t)l_name + 4 * (size_t)n_cigar + (((size_t)l_seq + 1) >> 1) + (size_t)l_seq > (size_t)block)
         throw std::runtime_error("truncated BAM record");
+      if (span_of) {
+        const int32_t tid = rd<int32_t>(x), pos = rd<int32_t>(x + 4);
+        // (targets come in header order in a sorted file, unplaced reads last)
+        if (sorted_file && (tid < 0 || tid > last_tid || (tid == last_tid && pos >= last_end))) { stopped = true; break; }
+        bool keep = tid >= 0 && (size_t)tid < spans.size() && spans[(size_t)tid].first < spans[(size_t)tid].second && pos < spans[(size_t)tid].second;
+        if (keep) {
+          need(p + 4 + 32 + (size_t)l_name + 4 * (size_t)n_cigar);
+          int64_t end = pos;
+          const uint8_t* cg = x + 32 + l_name;
+          for (int k = 0; k < n_cigar; ++k) { const uint32_t c = rd<uint32_t>(cg + 4 * k), op = c & 15u; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += c >> 4; }
+          if (end == pos) end = pos + 1;
+          keep = end > spans[(size_t)tid].first;
+        }
+        if (!keep) { p += 4 + (size_t)block; continue; }
+      }
       if (n_new >= max_reads) throw std::runtime_error("truncated BAM record");
       rec_at[n_new] = p + 4;
       reads.n_cigar[n0 + n_new] = n_cigar; reads.cigar_off[n0 + n_new] = n_cig_total;
@@ -326,7 +353,8 @@ void read_bam(const std::string& path, BamHeader& hdr, ReadBatch& reads, int thr
       ++n_new;
       if (n_new % RUN == 0) { need(p); n_found.store(n_new, std::memory_order_release); runs_published.store(n_new / RUN, std::memory_order_release); }
     }
-    need(total);
+    if (stopped) { next_chunk.store(n_chunks); need(std::min(p, total)); }   // the members behind the shard are not inflated
+    else need(total);
     n_found.store(n_new, std::memory_order_release);
     runs_published.store((n_new + RUN - 1) / RUN, std::memory_order_release);
   } catch (const std::exception& e) { fail(e.what()); }

@@ -321,13 +321,33 @@ std::string source_key(const char* bam, const char* fasta) {
   }
   return key;
 }
-bool load_inputs(brq_ctx* c, const char* bam, const char* fasta) {  // true when the inputs were (re)read
-  const std::string key = source_key(bam, fasta);
+// shard: a configuration whose shard settings say which reference range this context stages (a rank of a sharded run): only
+// the reads that overlap it are decoded, and a coordinate-sorted BAM is not read past it (bam_io.h: ReadSpans)
+bool load_inputs(brq_ctx* c, const char* bam, const char* fasta, const StageConfig* shard = nullptr) {  // true when the inputs were (re)read
+  std::string key = source_key(bam, fasta);
+  const bool ranged = shard && (shard->shard_count > 1 || shard->shard_explicit || shard->shard_hi > shard->shard_lo);
+  if (ranged && !key.empty()) {
+    key += "shard " + std::to_string(shard->shard_rank) + "/" + std::to_string(shard->shard_count) + " " + std::to_string(shard->shard_lo) + "-" +
+           std::to_string(shard->shard_hi) + (shard->shard_explicit ? "e" : "") + " of";
+    for (const std::string& id : shard->call_seq_ids) key += " " + id;
+  }
   if (!key.empty() && key == c->reads_source && !c->hdr.target_names.empty()) return false;
   drop_stream(c);
   clear_inputs(c);
-  read_bam(bam, c->hdr, c->reads, c->threads);
   read_fasta(fasta, c->ref);
+  if (ranged) {
+    const ReadSpans spans = [&](const BamHeader& hdr) {
+      PileupStream plan;
+      std::vector<const std::string*> refseq;
+      plan_segments(hdr, c->ref, *shard, plan, refseq);
+      std::vector<std::pair<int32_t, int32_t>> by_tid(hdr.target_names.size(), std::make_pair(0, 0));
+      for (const Segment& sg : plan.segments) by_tid[(size_t)sg.tid] = std::make_pair(sg.lo, sg.hi);
+      return by_tid;
+    };
+    read_bam(bam, c->hdr, c->reads, c->threads, &spans);
+  } else {
+    read_bam(bam, c->hdr, c->reads, c->threads);
+  }
   c->reads_source = key;
   return true;
 }
@@ -857,7 +877,10 @@ const char* brq_last_error(const brq_ctx* c) { return c ? c->error.c_str() : "nu
 
 int brq_stage_bam(brq_ctx* c, const char* bam, const char* fasta, const brq_stage_options* opt) {
   return guarded(c, [&] {
-    load_inputs(c, bam, fasta);
+    // (the options first: a sharded run's rank reads only its own range of the BAM)
+    StageConfig wanted = c->stage_cfg;
+    { const StageConfig kept = c->stage_cfg; apply_stage_options(c, opt); wanted = c->stage_cfg; c->stage_cfg = kept; }
+    load_inputs(c, bam, fasta, &wanted);
     drop_stream(c);
     apply_stage_options(c, opt);
     do_stage(c);

@@ -25,7 +25,7 @@ def checker(tmp_path_factory):
     exe = str(tmp_path_factory.mktemp("covcheck") / "coverage_check")
     csrc = os.path.join(ROOT, "breseq_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "coverage_check.cpp")] + [os.path.join(csrc, f) for f in
-                                                                   ("staging.cpp", "bam_io.cpp", "expand_plan.cpp", "coverage_table.cpp")]
+                                                                   ("staging.cpp", "bam_io.cpp", "inflate.cpp", "expand_plan.cpp", "coverage_table.cpp")]
     subprocess.run(["g++", "-O2", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-o", exe] + srcs + ["-lz", "-lpthread"], check=True)
     return exe
 

@@ -13,7 +13,7 @@ def test_expander_logic_equals_host_staging(tmp_path):
     exe = str(tmp_path / "expand_check")
     csrc = os.path.join(ROOT, "breseq_b200", "csrc")
     srcs = [os.path.join(ROOT, "tests", "expand_check.cpp")] + [os.path.join(csrc, f) for f in
-                                                                 ("staging.cpp", "synth.cpp", "bam_io.cpp", "expand_plan.cpp")]
+                                                                 ("staging.cpp", "synth.cpp", "bam_io.cpp", "inflate.cpp", "expand_plan.cpp")]
     subprocess.run(["g++", "-O2", "-std=c++17", "-w", "-o", exe] + srcs + ["-lz", "-lpthread"], check=True)
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr

@@ -309,7 +309,7 @@ def main():
     hist_view = {}
     # the collective of pass 1: fused into brq_error_count (csrc/exchange.cu: the ranks add their histograms into each other's
     # memory over NVLink, no library call, no host in the loop), or BRQ_BENCH_NCCL=1: an NCCL allreduce between the calls
-    fused = world > 1 and not os.environ.get("BRQ_BENCH_NCCL")
+    fused = 1 < world <= 16 and not os.environ.get("BRQ_BENCH_NCCL")
     if fused:
         handles = [None] * world
         dist.all_gather_object(handles, ctx.hist_exchange_export())

@@ -618,7 +618,6 @@ void stage(const BamHeader& hdr, const RefSet& ref, const ReadBatch& R, const St
     const uint64_t s0 = out.segments[it.v].slot0 - (uint64_t)out.segments[it.v].lo;  // slot = s0 + column
     for (size_t i = it.first_read; i < it.last_read; ++i) {
       if (!in_pileup(i) || info[i].end <= it.lo) continue;
-      const uint8_t* seq = R.bases.data() + R.seq_off[i];
       const bool unique = R.x1[i] == 1;
       const uint32_t L = info[i].L;
       walk_read(R.cigars.data() + R.cigar_off[i], R.n_cigar[i], R.pos[i], it.lo, it.hi, [&](int32_t c, int32_t q, bool is_del, int indel) {

@@ -185,9 +185,8 @@ void synth_reference(uint64_t seed, const std::vector<uint32_t>& lens, const std
   int width = 1;
   for (size_t n = lens.size(); n >= 10; n /= 10) ++width;
   for (size_t i = 0; i < lens.size(); ++i) {
-    char name[64];
-    if (lens.size() == 1) snprintf(name, sizeof name, "%s", prefix.c_str());
-    else snprintf(name, sizeof name, "%s%0*zu", prefix.c_str(), width, i + 1);
+    std::string name = prefix;
+    if (lens.size() != 1) { const std::string digits = std::to_string(i + 1); name += std::string(digits.size() < (size_t)width ? (size_t)width - digits.size() : 0, '0') + digits; }
     ref.names.push_back(name);
     std::string s(lens[i], 'A');
     Rng rng(mix3(seed, 0x5EF, i));

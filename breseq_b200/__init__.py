@@ -150,6 +150,7 @@ def load_library():
                                       C.c_uint32, C.c_int, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)],
         "brq_write_per_position_file": [C.c_void_p, C.c_char_p, P(C.c_double), C.c_uint32],
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
+        "brq_write_per_position_counts": [C.c_void_p, C.c_char_p, C.c_char_p],
         "brq_write_coverage_table": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
@@ -181,7 +182,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
-           "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table"]
+           "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts"]
 
 
 def _b(s):
@@ -561,6 +562,10 @@ class Context:
     def write_coverage_tsv(self, pattern):
         """``<seq>.coverage.tsv`` of --predict-copy-number; '@' in ``pattern`` becomes the target name."""
         self._check(self.lib.brq_write_coverage_tsv(self.h, _b(pattern)))
+
+    def write_per_position_counts(self, covariates, path):
+        """``error_counts.tab`` of a covariate string with ref_pos: every position's non-empty bins (error_count.cpp:193-198)."""
+        self._check(self.lib.brq_write_per_position_counts(self.h, _b(covariates), _b(path)))
 
     def write_coverage_table(self, region, path, resolution=0, total_only=False, csv=False, per_read_group=False):
         """BAM2COV's table for ``seq_id:start-end`` of the staged BAM (coverage_output.cpp:190-283, 307-470)."""

@@ -812,6 +812,13 @@ void write_pass1_files(brq_ctx* c, const char* output_dir, const char* error_rat
   if (!c->host_hist_valid) download_hist(c);
   std::string dir = output_dir ? output_dir : ".";
   if (do_coverage) write_coverage_distributions(dir, c->h_cov, c->cov_stride, c->n_groups);
+  if (do_errors && c->spec.per_position) {
+    // covariates with ref_pos: the reference prints every position's counts during the pileup and writes no error rates
+    // (error_count.cpp:105-111, 193-198, 255-275)
+    const PileupStream view = host_view(c);
+    write_count_table_per_position(dir + "/error_counts.tab", c->spec, view);
+    return;
+  }
   if (do_errors) {
     if (!c->have_table) throw std::runtime_error("brq_derive_error_table has not run");
     if (counts_dump && *counts_dump) write_count_table(counts_dump, c->spec, c->h_counts);
@@ -1120,7 +1127,7 @@ int brq_run_error_count(brq_ctx* c, const char* bam, const char* fasta, const ch
   if (rc) return rc;
   return guarded(c, [&] {
     error_count_device(c, covariates ? covariates : "", do_coverage != 0, do_errors != 0);
-    if (do_errors) derive_table(c);
+    if (do_errors && !c->spec.per_position) derive_table(c);
     write_pass1_files(c, output_dir, error_rates_file, readfiles, n_readfiles, do_coverage, do_errors, nullptr);
   });
 }
@@ -1179,6 +1186,15 @@ int brq_write_coverage_tsv(brq_ctx* c, const char* pattern) {
       }
     }
     write_coverage_tsv(pattern, c->hdr, c->ref, view, c->h_cols, by_group);
+  });
+}
+
+int brq_write_per_position_counts(brq_ctx* c, const char* covariates, const char* path) {
+  return guarded(c, [&] {
+    if (!c->staged) throw std::runtime_error("nothing staged");
+    const CovSpec spec = parse_covariates(covariates ? covariates : "");
+    const PileupStream view = host_view(c);
+    write_count_table_per_position(path, spec, view);
   });
 }
 

@@ -50,7 +50,6 @@ CovSpec parse_covariates(const std::string& s) {
     c.offset[i] = cur; cur *= c.maxv[i];
   }
   c.n_bins = cur;
-  if (c.per_position) throw std::runtime_error("covariate ref_pos (per-position count dump) is not supported");
   return c;
 }
 
@@ -124,6 +123,66 @@ void write_count_table(const std::string& path, const CovSpec& c, const std::vec
   for (int i = 0; i < COV_COUNT; ++i) if (c.used[i]) out << kCovNames[i] << '\t';
   out << "count\n";
   write_table_rows(out, c, counts.size(), [&](size_t i) { return std::to_string(counts[i]); });
+}
+
+// The count table of a covariate string that names ref_pos (error_count.cpp:105-111, 193-198, 803-846): the table is too big to
+// keep per position, so the reference prints every position's non-empty bins as the pileup passes it and clears the table.
+// Here: the positional histogram records of every column (hist_rec / hist_off of a stream on the host), both observations of
+// each (kernels.cu: hist_record), counted into the column's bins and printed in bin order.
+void write_count_table_per_position(const std::string& path, const CovSpec& c, const PileupStream& st) {
+  std::ofstream out(path.c_str());
+  if (!out) throw std::runtime_error("cannot create " + path);
+  out << c.text() << '\n';
+  out << "ref_pos\t";
+  for (int i = 0; i < COV_COUNT; ++i) if (c.used[i]) out << kCovNames[i] << '\t';
+  out << "count\n";
+  if (!st.hist_rec || !st.hist_off) throw std::runtime_error("the per-position count table needs the histogram records on the host");
+  const CovLayout lay = to_layout(c);
+  const bool wide = st.hist_bytes == 8;
+  if (!wide && (lay.off_rpos || lay.off_rep)) throw std::runtime_error("the stream was staged without read_pos / base_repeat (brq_stage_options.use_read_pos, use_base_repeat)");
+  std::vector<uint32_t> bins(c.n_bins, 0), touched;
+  const uint8_t* rec = static_cast<const uint8_t*>(st.hist_rec);
+  auto check = [&](int cov, uint32_t v) {
+    if (c.used[cov] && !c.clamp[cov] && v >= c.maxv[cov])
+      throw std::runtime_error(std::string("Covariate '") + kCovNames[cov] + "' with value '" + std::to_string(v) + "' exceeded enforced maximum value of '" +
+                               std::to_string(c.maxv[cov] - 1) + "'.");
+  };
+  for (const Segment& sg : st.segments) {
+    for (int32_t col = sg.lo; col < sg.hi; ++col) {
+      const uint64_t slot = sg.slot0 + (uint64_t)(col - sg.lo);
+      const uint64_t r0 = st.hist_off[slot] & ~HIST_OFF_REDUNDANT_BIT, r1 = st.hist_off[slot + 1] & ~HIST_OFF_REDUNDANT_BIT;
+      touched.clear();
+      for (uint64_t r = r0; r < r1; ++r) {
+        uint32_t lo, hi = 0;
+        memcpy(&lo, rec + r * st.hist_bytes, 4);
+        if (wide) memcpy(&hi, rec + r * st.hist_bytes + 4, 4);
+        const uint32_t set = ((lo >> HR_SET) & 7u) | (wide ? (hi >> (HR_SET_HI - 32)) << 3 : 0u), rpos = wide ? (hi & 0xFFFFu) : 0u;
+        check(COV_READ_SET, set);
+        uint32_t base = set * lay.off_set;
+        if (lay.off_rpos) { check(COV_READ_POS, rpos); base += rpos * lay.off_rpos; }
+        auto observe = [&](uint32_t ref, uint32_t obs, uint32_t qual, uint32_t rep) {
+          check(COV_QUALITY, qual);
+          uint32_t idx = base + ref * lay.off_ref + obs * lay.off_obs + qual * lay.off_qual;
+          if (lay.off_rep) idx += std::min(rep, lay.max_rep - 1) * lay.off_rep;
+          if (bins[idx]++ == 0) touched.push_back(idx);
+        };
+        if (lo & (1u << HR_VALIDA)) observe(lo & 7u, (lo >> HR_OBSA) & 7u, (lo >> HR_QUALA) & 127u, wide ? (hi >> (HR_REPA - 32)) & 255u : 0u);
+        if (lo & (1u << HR_VALIDB)) observe((lo >> HR_REFB) & 7u, (lo >> HR_OBSB) & 7u, (lo >> HR_QUALB) & 127u, wide ? (hi >> (HR_REPB - 32)) & 31u : 0u);
+      }
+      std::sort(touched.begin(), touched.end());
+      for (uint32_t idx : touched) {
+        out << (col + 1) << '\t';
+        for (int i = 0; i < COV_COUNT; ++i) {
+          if (!c.used[i]) continue;
+          const uint32_t j = (idx / c.offset[i]) % c.maxv[i];
+          if (i == COV_REF_BASE || i == COV_OBS_BASE) out << index_to_char((uint8_t)j) << '\t';
+          else out << j << '\t';
+        }
+        out << bins[idx] << '\n';
+        bins[idx] = 0;
+      }
+    }
+  }
 }
 
 void read_error_rates(const std::string& path, CovSpec& c, std::vector<double>& t) {

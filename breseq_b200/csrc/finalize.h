@@ -57,6 +57,9 @@ void canonicalise_table(const std::vector<double>& log10_prob, std::vector<doubl
 void write_base_qual_tables(const std::string& pattern, const CovSpec& spec, const std::vector<uint64_t>& counts,
                             const std::vector<std::string>& readfiles);
 void write_count_table(const std::string& path, const CovSpec& spec, const std::vector<uint64_t>& counts);
+// a covariate string that names ref_pos: every position's non-empty bins (error_count.cpp:193-198, 803-846), counted on the host
+// from the positional histogram records of a stream whose arrays are on the host
+void write_count_table_per_position(const std::string& path, const CovSpec& spec, const PileupStream& st);
 void write_coverage_distributions(const std::string& dir, const std::vector<uint64_t>& cov, uint64_t stride, uint64_t n_groups);
 
 // Sizes and index maps of the likelihood tables (see score_geometry in finalize.cpp, build_tables_kernel in tables.cu).

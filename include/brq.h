@@ -233,6 +233,11 @@ int brq_cuda_stream(brq_ctx* ctx, void** stream);
 int brq_d2h_bytes(brq_ctx* ctx, uint64_t* bytes, int reset);
 int brq_write_per_position_file(brq_ctx* ctx, const char* path, const double* deletion_propagation_cutoff, uint32_t n_targets);
 int brq_write_coverage_tsv(brq_ctx* ctx, const char* pattern);
+/* The per-position count table of a covariate string that names ref_pos (error_count.cpp:105-111, 193-198, 803-846:
+ * `error_counts.tab`, every position's non-empty covariate bins in bin order; a debugging output, gigabytes for a genome).
+ * brq_run_error_count / brq_write_error_count_files write it instead of the error rates when the covariates say so; this call
+ * writes it from any staged stream (the histogram records are counted on the host: no device needed after staging). */
+int brq_write_per_position_counts(brq_ctx* ctx, const char* covariates, const char* path);
 /* BAM2COV's table (`breseq BAM2COV -t`, coverage_output::table + pileup_callback, coverage_output.cpp:190-283, 307-470) for
  * region "seq_id:start-end" of the staged BAM: per position the unique coverage by strand (reads with an aligned base there:
  * a deletion over the position does not count), the redundant coverage by strand as the sum of 1 / X1 and as a count, and the

@@ -17,6 +17,7 @@ htslib shim.  What they wrote is committed here:
     <name>/preprocess_error_count.tab  (error_count(..., preprocess_stage = true): Summary::preprocess_error_count per seq id)
     tiny/reference.bam, tiny/reference.fasta(.fai), tiny/per_position_file.tab   (inputs kept for the smallest case)
     tiny/<seq>.coverage.tsv   (two read groups: the --predict-copy-number table with its per-read-group columns)
+    tiny/, ltee/error_counts.per_position.sha256   (covariates with ref_pos: checksum of the reference's per-position error_counts.tab)
 
 The fixtures pin (a) oracle/oracle.cpp, (b) the CUDA path, against the reference's real arithmetic
 and file writers.  The BAM decode / pileup layer under the reference is still oracle/hts_shim.
@@ -66,6 +67,15 @@ def main():
                 _, im = helpers.cli_args(d, out, gd=os.path.join(out, "user.gd"))
                 subprocess.run([helpers.REF_CLI] + [str(a) for a in im] + ["--user-evidence", user], check=True, capture_output=True)
                 shutil.copy(os.path.join(out, "user.gd"), os.path.join(gdir, "ra_mc_evidence.user_evidence.gd"))
+            if name in ("tiny", "ltee"):  # the per-position count table of a covariate string with ref_pos (too long to commit: its checksum)
+                import subprocess
+                pp = os.path.join(tmp, "ref_per_position")
+                os.makedirs(pp)
+                ec, _ = helpers.cli_args(d, pp)
+                ec[ec.index("--covariates") + 1] = "ref_pos," + helpers.covariates(d)
+                subprocess.run([helpers.REF_CLI] + [str(a) for a in ec], check=True, capture_output=True)
+                with open(os.path.join(gdir, "error_counts.per_position.sha256"), "w") as fh:
+                    fh.write("%s  error_counts.tab\n" % sha256(os.path.join(pp, "error_counts.tab")))
             if name == "tiny":
                 for f in ("reference.bam", "reference.fasta", "reference.fasta.fai"):
                     shutil.copy(os.path.join(tmp, f), os.path.join(gdir, f))

@@ -244,3 +244,39 @@ def test_user_evidence_across_targets_and_shards(datasets, tmp_path):
     m.write_evidence_merged(os.path.join(out, "merged.gd"), shares, [d["del_prop"]] * n, [d["del_seed"]] * n)
     m.close()
     assert open(os.path.join(out, "merged.gd")).read() == want
+
+
+# ---- covariates with ref_pos: the per-position count table (error_count.cpp:105-111, 193-198, 803-846)
+def _sha(path):
+    import hashlib
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["tiny", "ltee"])
+def test_per_position_count_table_matches_reference(name, datasets, tmp_path):
+    """`ref_pos` in the covariate string: every position's non-empty bins, counted on the host from the staged histogram records
+    (ltee: read_pos and base_repeat covariates, eight-byte records); the reference's file is too long to commit, its checksum is"""
+    d = datasets[name]
+    want = open(golden(name, "error_counts.per_position.sha256")).read().split()[0]
+    ctx = bq.Context(device=-1)
+    ctx.stage_bam(d["bam"], d["fasta"], **helpers.stage_kwargs(d))
+    out = str(tmp_path / "error_counts.tab")
+    ctx.write_per_position_counts("ref_pos," + helpers.covariates(d), out)
+    assert _sha(out) == want
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_error_count_with_ref_pos_writes_the_per_position_table(datasets, tmp_path):
+    """through the entry point: brq_run_error_count with ref_pos writes error_counts.tab (from the device-built stream) and the
+    coverage distributions, and no error rates, as the reference does"""
+    d = datasets["tiny"]
+    out = str(tmp_path / "cuda")
+    os.makedirs(out)
+    bq.error_count(d["bam"], d["fasta"], out, helpers.readfile_names(d), True, True, False, 3, "ref_pos," + helpers.covariates(d),
+                   read_file_sets=helpers.read_file_sets(d), error_rates_file_name=os.path.join(out, "error_rates.tab"))
+    assert _sha(os.path.join(out, "error_counts.tab")) == open(golden("tiny", "error_counts.per_position.sha256")).read().split()[0]
+    assert not os.path.exists(os.path.join(out, "error_rates.tab"))
+    for g in range(len(d["contig_lens"])):
+        nm = "%d.unique_only_coverage_distribution.tab" % g
+        assert filecmp.cmp(os.path.join(out, nm), golden("tiny", nm), shallow=False)

@@ -44,7 +44,7 @@ def build(verbose=False, force=False):
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
     if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lz", "-lpthread", "-cudart", "shared"]
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lz", "-lpthread", "-cudart", "shared"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -100,6 +100,20 @@ class CoverageFit(C.Structure):  # brq_coverage_fit
                 ("deletion_coverage_propagation_cutoff", C.c_double), ("censor_start", C.c_uint32), ("censor_end", C.c_uint32)]
 
 
+class RaFilterOptions(C.Structure):  # brq_ra_filter_options: the members of breseq::Settings test_RA_evidence reads
+    _fields_ = [("polymorphism_prediction", C.c_int32), ("mutation_log10_e_value_cutoff", C.c_double),
+                ("consensus_frequency_cutoff", C.c_double),
+                ("consensus_minimum_variant_coverage", C.c_uint32), ("consensus_minimum_total_coverage", C.c_uint32),
+                ("consensus_minimum_variant_coverage_each_strand", C.c_uint32), ("consensus_minimum_total_coverage_each_strand", C.c_uint32),
+                ("consensus_reject_indel_homopolymer_length", C.c_uint32), ("consensus_reject_surrounding_homopolymer_length", C.c_uint32),
+                ("polymorphism_log10_e_value_cutoff", C.c_double), ("polymorphism_frequency_cutoff", C.c_double),
+                ("polymorphism_minimum_variant_coverage", C.c_uint32), ("polymorphism_minimum_total_coverage", C.c_uint32),
+                ("polymorphism_minimum_variant_coverage_each_strand", C.c_uint32), ("polymorphism_minimum_total_coverage_each_strand", C.c_uint32),
+                ("polymorphism_reject_indel_homopolymer_length", C.c_uint32), ("polymorphism_reject_surrounding_homopolymer_length", C.c_uint32),
+                ("polymorphism_fisher_strand_p_value_cutoff", C.c_double), ("polymorphism_ks_quality_p_value_cutoff", C.c_double),
+                ("polymorphism_no_indels", C.c_int32)]
+
+
 def load_library():
     """dlopen ``libbrq.so``; fails loudly when the extension has not been built."""
     global _lib
@@ -154,6 +168,7 @@ def load_library():
         "brq_write_coverage_table": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
+        "brq_test_ra_evidence": [C.c_void_p, C.c_char_p, C.c_char_p, P(RaFilterOptions), C.c_char_p, P(C.c_uint32)],
         "brq_hist_exchange_export": [C.c_void_p, C.c_void_p, P(C.c_uint64)],
         "brq_hist_exchange_attach": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
@@ -170,6 +185,8 @@ def load_library():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.brq_ra_filter_defaults.argtypes = [C.c_int, P(RaFilterOptions)]
+    lib.brq_ra_filter_defaults.restype = None
     _lib = lib
     return lib
 
@@ -182,7 +199,8 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_write_evidence", "brq_cuda_stream", "brq_evidence_export", "brq_write_evidence_merged", "brq_d2h_bytes", "brq_write_per_position_file", "brq_write_coverage_tsv", "brq_run_error_count", "brq_run_identify_mutations", "brq_launch_count", "brq_kernel_ms",
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
-           "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts"]
+           "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts",
+           "brq_ra_filter_defaults", "brq_test_ra_evidence"]
 
 
 def _b(s):
@@ -590,6 +608,27 @@ class Context:
         f = CoverageFit()
         self._check(self.lib.brq_fit_coverage_file(self.h, _b(path), C.c_double(deletion_propagation_pr_cutoff), C.byref(f)))
         return self._fit_dict(f)
+
+    def ra_filter_defaults(self, polymorphism_prediction=False):
+        """The thresholds breseq's Settings hold for the mode without further options, as a dict."""
+        o = RaFilterOptions()
+        self.lib.brq_ra_filter_defaults(int(bool(polymorphism_prediction)), C.byref(o))
+        return {name: getattr(o, name) for name, _ in RaFilterOptions._fields_}
+
+    def test_RA_evidence(self, gd_in, fasta, gd_out, polymorphism_prediction=False, **settings):
+        """The Output stage's filter over the RA rows of ``gd_in`` (identify_mutations.cpp:687-749): ``gd_out`` holds the rows
+        that stay, annotated with prediction= / *_reject=.  ``settings``: members of breseq::Settings by name, over the mode's
+        defaults.  Returns the counts {rows, consensus, polymorphism, rejected_kept, deleted}.  Host only."""
+        o = RaFilterOptions()
+        self.lib.brq_ra_filter_defaults(int(bool(polymorphism_prediction)), C.byref(o))
+        names = {name for name, _ in RaFilterOptions._fields_}
+        for k, v in settings.items():
+            if k not in names:
+                raise BrqError("test_RA_evidence: breseq::Settings has no member %r that the filter reads" % k)
+            setattr(o, k, v)
+        n = (C.c_uint32 * 5)()
+        self._check(self.lib.brq_test_ra_evidence(self.h, _b(gd_in), _b(fasta), C.byref(o), _b(gd_out), n))
+        return dict(zip(("rows", "consensus", "polymorphism", "rejected_kept", "deleted"), list(n)))
 
     def hist_exchange_export(self):
         """64-byte handle of this context's inbox for the fused collective of pass 1 (exchange it with the peer ranks)."""

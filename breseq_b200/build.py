@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbrq.so")
 
 CU_SOURCES = ["kernels.cu", "score_slots.cu", "tables.cu", "expand.cu", "exchange.cu", "brq_api.cu"]
-CPP_SOURCES = ["bam_io.cpp", "staging.cpp", "synth.cpp", "finalize.cpp", "expand_plan.cpp", "coverage_fit.cpp", "coverage_table.cpp", "inflate.cpp"]
+CPP_SOURCES = ["bam_io.cpp", "staging.cpp", "synth.cpp", "finalize.cpp", "expand_plan.cpp", "coverage_fit.cpp", "coverage_table.cpp", "inflate.cpp", "ra_filter.cpp"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -4,6 +4,7 @@
 #include "bam_io.h"
 #include "expand.h"
 #include "coverage_fit.h"
+#include "ra_filter.h"
 #include "coverage_table.h"
 #include "finalize.h"
 #include "kernels.h"
@@ -1288,6 +1289,65 @@ int brq_fit_coverage_file(brq_ctx* c, const char* path, double pr_cutoff, brq_co
     read_coverage_distribution(path, n, N);
     const auto threads = fit_threads(c);
     fill_fit(fit_coverage_distribution(n, N, pr_cutoff, &threads), out);
+  });
+}
+
+// ---- the Output stage's RA filter (ra_filter.cpp)
+void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* out) {
+  const RaFilterOptions o = ra_filter_defaults(polymorphism_prediction != 0);
+  out->polymorphism_prediction = o.polymorphism_prediction;
+  out->mutation_log10_e_value_cutoff = o.mutation_log10_e_value_cutoff;
+  out->consensus_frequency_cutoff = o.consensus_frequency_cutoff;
+  out->consensus_minimum_variant_coverage = o.consensus_minimum_variant_coverage;
+  out->consensus_minimum_total_coverage = o.consensus_minimum_total_coverage;
+  out->consensus_minimum_variant_coverage_each_strand = o.consensus_minimum_variant_coverage_each_strand;
+  out->consensus_minimum_total_coverage_each_strand = o.consensus_minimum_total_coverage_each_strand;
+  out->consensus_reject_indel_homopolymer_length = o.consensus_reject_indel_homopolymer_length;
+  out->consensus_reject_surrounding_homopolymer_length = o.consensus_reject_surrounding_homopolymer_length;
+  out->polymorphism_log10_e_value_cutoff = o.polymorphism_log10_e_value_cutoff;
+  out->polymorphism_frequency_cutoff = o.polymorphism_frequency_cutoff;
+  out->polymorphism_minimum_variant_coverage = o.polymorphism_minimum_variant_coverage;
+  out->polymorphism_minimum_total_coverage = o.polymorphism_minimum_total_coverage;
+  out->polymorphism_minimum_variant_coverage_each_strand = o.polymorphism_minimum_variant_coverage_each_strand;
+  out->polymorphism_minimum_total_coverage_each_strand = o.polymorphism_minimum_total_coverage_each_strand;
+  out->polymorphism_reject_indel_homopolymer_length = o.polymorphism_reject_indel_homopolymer_length;
+  out->polymorphism_reject_surrounding_homopolymer_length = o.polymorphism_reject_surrounding_homopolymer_length;
+  out->polymorphism_fisher_strand_p_value_cutoff = o.polymorphism_fisher_strand_p_value_cutoff;
+  out->polymorphism_ks_quality_p_value_cutoff = o.polymorphism_ks_quality_p_value_cutoff;
+  out->polymorphism_no_indels = o.polymorphism_no_indels;
+}
+
+int brq_test_ra_evidence(brq_ctx* c, const char* gd_in, const char* fasta, const brq_ra_filter_options* in, const char* gd_out,
+                         uint32_t* counts5) {
+  return guarded(c, [&] {
+    RaFilterOptions o;
+    o.polymorphism_prediction = in->polymorphism_prediction != 0;
+    o.mutation_log10_e_value_cutoff = in->mutation_log10_e_value_cutoff;
+    o.consensus_frequency_cutoff = in->consensus_frequency_cutoff;
+    o.consensus_minimum_variant_coverage = in->consensus_minimum_variant_coverage;
+    o.consensus_minimum_total_coverage = in->consensus_minimum_total_coverage;
+    o.consensus_minimum_variant_coverage_each_strand = in->consensus_minimum_variant_coverage_each_strand;
+    o.consensus_minimum_total_coverage_each_strand = in->consensus_minimum_total_coverage_each_strand;
+    o.consensus_reject_indel_homopolymer_length = in->consensus_reject_indel_homopolymer_length;
+    o.consensus_reject_surrounding_homopolymer_length = in->consensus_reject_surrounding_homopolymer_length;
+    o.polymorphism_log10_e_value_cutoff = in->polymorphism_log10_e_value_cutoff;
+    o.polymorphism_frequency_cutoff = in->polymorphism_frequency_cutoff;
+    o.polymorphism_minimum_variant_coverage = in->polymorphism_minimum_variant_coverage;
+    o.polymorphism_minimum_total_coverage = in->polymorphism_minimum_total_coverage;
+    o.polymorphism_minimum_variant_coverage_each_strand = in->polymorphism_minimum_variant_coverage_each_strand;
+    o.polymorphism_minimum_total_coverage_each_strand = in->polymorphism_minimum_total_coverage_each_strand;
+    o.polymorphism_reject_indel_homopolymer_length = in->polymorphism_reject_indel_homopolymer_length;
+    o.polymorphism_reject_surrounding_homopolymer_length = in->polymorphism_reject_surrounding_homopolymer_length;
+    o.polymorphism_fisher_strand_p_value_cutoff = in->polymorphism_fisher_strand_p_value_cutoff;
+    o.polymorphism_ks_quality_p_value_cutoff = in->polymorphism_ks_quality_p_value_cutoff;
+    o.polymorphism_no_indels = in->polymorphism_no_indels != 0;
+    RefSet ref;
+    read_fasta(fasta, ref);
+    normalise_reference(ref);
+    const RaFilterCounts n = test_ra_evidence(gd_in, ref, o, gd_out);
+    if (counts5) {
+      counts5[0] = n.rows; counts5[1] = n.consensus; counts5[2] = n.polymorphism; counts5[3] = n.rejected_kept; counts5[4] = n.deleted;
+    }
   });
 }
 

@@ -1,0 +1,309 @@
+// See ra_filter.h.  A row is held the way the reference holds it -- every column and key=value field in one ordered string map
+// (cDiffEntry is a map<string,string>, genome_diff_entry.h:150) -- because the filter's reads of absent keys (operator[]) and
+// the writer's rule "fixed columns first, then whatever is left in key order, empty values skipped" (cDiffEntry::marshal,
+// genome_diff_entry.cpp:1323-1369) are part of what the output looks like.
+#include "ra_filter.h"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <vector>
+
+namespace brq {
+namespace {
+
+typedef std::map<std::string, std::string> Row;
+const char* const RA_COLUMNS[] = {"seq_id", "position", "insert_position", "ref_base", "new_base"};   // line_specification[RA]
+
+std::vector<std::string> split(const std::string& s, char sep) {   // common.h:648-679: an empty string has no parts
+  std::vector<std::string> out;
+  if (s.empty()) return out;
+  size_t start = 0;
+  for (;;) {
+    size_t end = s.find(sep, start);
+    out.push_back(s.substr(start, end == std::string::npos ? std::string::npos : end - start));
+    if (end == std::string::npos) break;
+    start = end + 1;
+  }
+  return out;
+}
+
+template <typename T>
+T number(const std::string& s) {   // from_string<T>, common.h:892-899
+  if (s.empty()) throw std::runtime_error("evidence row: a number is expected where a field is empty or absent");
+  T t = T();
+  std::istringstream iss(s);
+  iss >> t;
+  return t;
+}
+
+double number_or_na(const std::string& s) {   // double_from_string, common.h:939-950
+  std::string u;
+  for (char c : s) u.push_back((char)toupper((unsigned char)c));
+  if (u == "NA" || u == "#NA" || u == "NAN") return std::numeric_limits<double>::quiet_NaN();
+  if (u == "INF") return std::numeric_limits<double>::infinity();
+  if (u == "-INF") return -std::numeric_limits<double>::infinity();
+  return number<double>(s);
+}
+
+bool has(const Row& r, const char* k) { return r.count(k) > 0; }
+
+void add_reject_reason(Row& r, const char* reason) {   // genome_diff_entry.cpp:1399-1416
+  if (!has(r, "reject")) { r["reject"] = reason; return; }
+  std::vector<std::string> now = split(r["reject"], ',');
+  for (const std::string& s : now) if (s == reason) return;
+  now.push_back(reason);
+  std::string joined;
+  for (size_t i = 0; i < now.size(); ++i) joined += (i ? "," : "") + now[i];
+  r["reject"] = joined;
+}
+
+double strand_sum(Row& r, const char* k, double* top = nullptr, double* bot = nullptr) {
+  std::vector<std::string> tb = split(r[k], '/');
+  if (tb.size() < 2) throw std::runtime_error(std::string("evidence row: ") + k + " is not top/bottom");
+  const double t = number<double>(tb[0]), b = number<double>(tb[1]);
+  if (top) *top = t;
+  if (bot) *bot = b;
+  return t + b;
+}
+
+// ---- the reference sequence the way FastaSequence::get_sequence_1 answers (fasta.h:58-95): (0,0) is empty, anything else is
+// pulled into the sequence
+struct Reference {
+  const RefSet& ref;
+  const std::string& seq(const std::string& id) const {
+    for (size_t i = 0; i < ref.names.size(); ++i) if (ref.names[i] == id) return ref.seqs[i];
+    throw std::runtime_error("evidence row names a sequence the FASTA does not hold: " + id);
+  }
+  static std::string base(const std::string& s, int64_t p) {
+    if (p == 0 || s.empty()) return std::string();
+    if (p < 1) p = 1;
+    if (p > (int64_t)s.size()) p = (int64_t)s.size();
+    return std::string(1, s[(size_t)p - 1]);
+  }
+};
+
+// identify_mutations.cpp:129-172
+void polymorphism_bias(Row& r, const RaFilterOptions& o) {
+  if (o.polymorphism_ks_quality_p_value_cutoff != 0 && has(r, "ks_quality_p_value") &&
+      number<double>(r["ks_quality_p_value"]) < o.polymorphism_ks_quality_p_value_cutoff)
+    add_reject_reason(r, "KS_BASE_QUALITY");
+  if (o.polymorphism_fisher_strand_p_value_cutoff != 0 && has(r, "fisher_strand_p_value") &&
+      number<double>(r["fisher_strand_p_value"]) < o.polymorphism_fisher_strand_p_value_cutoff)
+    add_reject_reason(r, "FISHER_STRAND");
+}
+
+// identify_mutations.cpp:231-322: only an allele that differs from the reference base has to show on both strands
+void polymorphism_coverage(Row& r, const RaFilterOptions& o) {
+  if (o.polymorphism_minimum_variant_coverage_each_strand > 0) {
+    const double need = o.polymorphism_minimum_variant_coverage_each_strand;
+    bool passed = true;
+    const std::string ref_base = has(r, "ref_base") ? r["ref_base"] : "";
+    bool major_is_variant = has(r, "major_base") && r["major_base"] != ref_base;
+    bool minor_is_variant = has(r, "minor_base") && r["minor_base"] != ref_base;
+    if (!major_is_variant && !minor_is_variant) major_is_variant = minor_is_variant = true;
+    double top, bot;
+    if (major_is_variant && has(r, "major_cov")) { strand_sum(r, "major_cov", &top, &bot); passed = passed && top >= need && bot >= need; }
+    if (minor_is_variant && has(r, "minor_cov")) { strand_sum(r, "minor_cov", &top, &bot); passed = passed && top >= need && bot >= need; }
+    if (!passed) add_reject_reason(r, "VARIANT_STRAND_COVERAGE");
+  }
+  if (o.polymorphism_minimum_total_coverage_each_strand > 0) {
+    double top, bot;
+    strand_sum(r, "total_cov", &top, &bot);
+    if (!(top >= o.polymorphism_minimum_total_coverage_each_strand && bot >= o.polymorphism_minimum_total_coverage_each_strand))
+      add_reject_reason(r, "TOTAL_STRAND_COVERAGE");
+  }
+  if (o.polymorphism_minimum_variant_coverage > 0) {
+    const bool major = strand_sum(r, "major_cov") >= o.polymorphism_minimum_variant_coverage;
+    const bool minor = strand_sum(r, "minor_cov") >= o.polymorphism_minimum_variant_coverage;
+    if (!(major && minor)) add_reject_reason(r, "VARIANT_COVERAGE");
+  }
+  if (o.polymorphism_minimum_total_coverage > 0 && strand_sum(r, "total_cov") < o.polymorphism_minimum_total_coverage)
+    add_reject_reason(r, "TOTAL_COVERAGE");
+}
+
+// identify_mutations.cpp:324-367
+void consensus_coverage(Row& r, const RaFilterOptions& o) {
+  double top, bot;
+  if (o.consensus_minimum_variant_coverage_each_strand > 0) {
+    strand_sum(r, "major_cov", &top, &bot);
+    if (top < o.consensus_minimum_variant_coverage_each_strand || bot < o.consensus_minimum_variant_coverage_each_strand)
+      add_reject_reason(r, "VARIANT_STRAND_COVERAGE");
+  }
+  if (o.consensus_minimum_total_coverage_each_strand > 0) {
+    strand_sum(r, "total_cov", &top, &bot);
+    if (top < o.consensus_minimum_total_coverage_each_strand || bot < o.consensus_minimum_total_coverage_each_strand)
+      add_reject_reason(r, "TOTAL_STRAND_COVERAGE");
+  }
+  if (o.consensus_minimum_variant_coverage > 0 && strand_sum(r, "major_cov") < o.consensus_minimum_variant_coverage)
+    add_reject_reason(r, "VARIANT_COVERAGE");
+  if (o.consensus_minimum_total_coverage > 0 && strand_sum(r, "total_cov") < o.consensus_minimum_total_coverage)
+    add_reject_reason(r, "TOTAL_COVERAGE");
+}
+
+// identify_mutations.cpp:369-485: an indel that lengthens or shortens a run of its own base; a substitution that joins two runs
+void indel_homopolymer(Row& r, const Reference& R, uint32_t indel_length, uint32_t surrounding_length, bool no_indel_polymorphisms) {
+  const bool is_indel = r["ref_base"] == "." || r["new_base"] == ".";
+  if (indel_length && is_indel) {
+    const std::string& s = R.seq(r["seq_id"]);
+    int32_t mut_pos = (int32_t)number<uint32_t>(r["position"]);
+    const bool is_insertion = number<int32_t>(r["insert_position"]) > 0;
+    const std::string mut_base = r["ref_base"] == "." ? r["new_base"] : r["ref_base"];
+    int32_t run = 0;
+    bool no_match = false;
+    if (is_insertion && R.base(s, mut_pos) != mut_base) {   // not the base before: the base after, then
+      ++mut_pos;
+      if (mut_pos > (int32_t)s.size() || R.base(s, mut_pos) != mut_base) no_match = true;
+    }
+    if (!no_match) {
+      int32_t first = mut_pos - 1;
+      while (R.base(s, first) == mut_base && first > 0) --first;
+      ++first;
+      int32_t last = mut_pos + 1;
+      while (R.base(s, last) == mut_base && last <= (int32_t)s.size()) ++last;
+      --last;
+      run = last - first + 1;
+    }
+    if (run >= (int32_t)indel_length) add_reject_reason(r, "INDEL_HOMOPOLYMER");
+  }
+  if (surrounding_length && r["ref_base"] != "." && r["new_base"] != ".") {
+    const std::string& s = R.seq(r["seq_id"]);
+    const int32_t mut_pos = number<int32_t>(r["position"]);
+    const std::string mut_base = r["new_base"];
+    int32_t first = mut_pos - 1;
+    while (first >= 1 && R.base(s, first) == mut_base) --first;
+    ++first;
+    int32_t last = mut_pos + 1;
+    while (last <= (int32_t)s.size() && R.base(s, last) == mut_base) ++last;
+    --last;
+    if (first < mut_pos && last > mut_pos && last - first + 1 >= (int32_t)surrounding_length) add_reject_reason(r, "SURROUNDING_HOMOPOLYMER");
+  }
+  if (no_indel_polymorphisms && is_indel) add_reject_reason(r, "POLYMORPHIC_INDEL");
+}
+
+double ra_score(const Row& r) {   // identify_mutations.cpp:180-192: evidence from before the two scores were merged
+  if (has(r, "score")) return number_or_na(r.at("score"));
+  double legacy = std::numeric_limits<double>::quiet_NaN();
+  if (has(r, "consensus_score")) legacy = number_or_na(r.at("consensus_score"));
+  if (has(r, "polymorphism_score")) {
+    const double p = number_or_na(r.at("polymorphism_score"));
+    if (std::isnan(legacy) || p > legacy) legacy = p;
+  }
+  return legacy;
+}
+
+// One row through the two questions (identify_mutations.cpp:522-685).  The modes differ in the bound the consensus question
+// reads -- the lower one ("confidently the majority") in consensus mode, the upper one ("cannot rule out fixed") in polymorphism
+// mode -- and in what happens to a row that answers neither.  Returns whether the row is deleted.
+bool test_row(Row& r, const Reference& R, const RaFilterOptions& o, RaFilterCounts& n) {
+  const double score = ra_score(r);
+  double lower, upper;
+  if (has(r, "frequency_lower") && has(r, "frequency_upper")) {
+    lower = number<double>(r["frequency_lower"]);
+    upper = number<double>(r["frequency_upper"]);
+  } else {
+    // identify_mutations.cpp:215-228 rebuilds Clopper-Pearson bounds from total_cov for evidence written before the bounds were
+    // recorded; every file of this library's pass 2 (and of the reference's) records them
+    throw std::runtime_error("evidence row " + r["_id"] + " carries no frequency_lower / frequency_upper (evidence of an older breseq?)");
+  }
+
+  if (score < o.mutation_log10_e_value_cutoff) add_reject_reason(r, "SCORE_CUTOFF");
+  if (o.consensus_frequency_cutoff > 0.0 && (o.polymorphism_prediction ? upper : lower) < o.consensus_frequency_cutoff)
+    add_reject_reason(r, "FREQUENCY_CUTOFF");
+  consensus_coverage(r, o);
+  indel_homopolymer(r, R, o.consensus_reject_indel_homopolymer_length, o.consensus_reject_surrounding_homopolymer_length, false);
+  if (!has(r, "reject")) {
+    r["prediction"] = "consensus";
+    ++n.consensus;
+    return r["ref_base"] == r["major_base"];   // nothing but the reference base
+  }
+  r["consensus_reject"] = r["reject"];
+  r.erase("reject");
+
+  if (score < o.polymorphism_log10_e_value_cutoff) add_reject_reason(r, "SCORE_CUTOFF");
+  if (o.polymorphism_frequency_cutoff > 0.0 && lower < o.polymorphism_frequency_cutoff) add_reject_reason(r, "FREQUENCY_CUTOFF");
+  polymorphism_bias(r, o);
+  polymorphism_coverage(r, o);
+  indel_homopolymer(r, R, o.polymorphism_reject_indel_homopolymer_length, o.polymorphism_reject_surrounding_homopolymer_length,
+                    o.polymorphism_no_indels);
+  if (!has(r, "reject")) {
+    r["prediction"] = "polymorphism";
+    ++n.polymorphism;
+    return false;
+  }
+  if (!o.polymorphism_prediction) {   // consensus mode drops the row
+    r["polymorphism_reject"] = r["reject"];
+    r.erase("reject");
+    return true;
+  }
+  r["prediction"] = "polymorphism";   // polymorphism mode keeps it, marked rejected
+  ++n.rejected_kept;
+  return false;
+}
+
+}  // namespace
+
+RaFilterOptions ra_filter_defaults(bool polymorphism_prediction) {
+  RaFilterOptions o;   // the consensus-mode values are the member initialisers
+  o.polymorphism_prediction = polymorphism_prediction;
+  if (polymorphism_prediction) {
+    o.consensus_frequency_cutoff = 0.95;
+    o.polymorphism_log10_e_value_cutoff = 2;
+    o.polymorphism_frequency_cutoff = 0.05;
+  }
+  return o;
+}
+
+void normalise_reference(RefSet& ref) {
+  for (std::string& s : ref.seqs)
+    for (char& c : s) {
+      c = (char)toupper((unsigned char)c);
+      if (!strchr("ATCGN", c) || c == 0) c = 'N';
+    }
+}
+
+RaFilterCounts test_ra_evidence(const std::string& gd_in, const RefSet& ref, const RaFilterOptions& opt, const std::string& gd_out) {
+  std::ifstream in(gd_in);
+  if (!in) throw std::runtime_error("cannot open " + gd_in);
+  const Reference R{ref};
+  RaFilterCounts n;
+  std::string out, line;
+  while (std::getline(in, line)) {
+    if (line.compare(0, 3, "RA\t") != 0) { out += line; out += '\n'; continue; }
+    std::vector<std::string> col = split(line, '\t');
+    if (col.size() < 8) throw std::runtime_error("evidence row with fewer than eight columns: " + line);
+    Row r;
+    for (int i = 0; i < 5; ++i) r[RA_COLUMNS[i]] = col[3 + i];
+    for (size_t i = 8; i < col.size(); ++i) {
+      const size_t eq = col[i].find('=');
+      if (eq == std::string::npos || eq == 0 || eq + 1 == col[i].size()) continue;   // cKeyValuePair::valid, common.h:1284
+      r[col[i].substr(0, eq)] = col[i].substr(eq + 1);
+    }
+    if (!has(r, "score") && !has(r, "consensus_score") && !has(r, "polymorphism_score"))
+      throw std::runtime_error("Expected field 'score' in evidence item\n" + line);
+    if (!has(r, "frequency")) throw std::runtime_error("Expected field 'frequency' in evidence item\n" + line);
+    r["_id"] = col[1];   // for messages; keys with a leading underscore are never written
+    ++n.rows;
+    bool gone = test_row(r, R, opt, n);
+    if (has(r, "user_defined")) gone = false;   // user evidence is classified, never dropped
+    if (gone) { ++n.deleted; continue; }
+    out += col[0] + '\t' + col[1] + '\t' + col[2];
+    for (int i = 0; i < 5; ++i) { out += '\t'; out += r[RA_COLUMNS[i]]; r.erase(RA_COLUMNS[i]); }
+    for (const auto& kv : r) {
+      if (kv.first[0] == '_' || kv.second.empty()) continue;
+      out += '\t' + kv.first + '=' + kv.second;
+    }
+    out += '\n';
+  }
+  std::ofstream f(gd_out, std::ios::binary);
+  if (!f) throw std::runtime_error("cannot create " + gd_out);
+  f << out;
+  if (!f.flush()) throw std::runtime_error("cannot write " + gd_out);
+  return n;
+}
+
+}  // namespace brq

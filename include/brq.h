@@ -277,6 +277,38 @@ typedef struct brq_coverage_fit {
 int brq_fit_coverage_distribution(brq_ctx* ctx, uint32_t coverage_group, double deletion_propagation_pr_cutoff, brq_coverage_fit* out);
 int brq_fit_coverage_file(brq_ctx* ctx, const char* distribution_file, double deletion_propagation_pr_cutoff, brq_coverage_fit* out);
 
+/* ---- after pass 2: the Output stage's filter over the RA rows ---------------------------------------
+ * test_RA_evidence (identify_mutations.cpp:687-749; called at breseq_cmdline.cpp:2614 between reading ra_mc_evidence.gd and
+ * merging it into evidence.gd): every RA row is asked whether its variant is the consensus (score >= mutation cutoff, the 95 %
+ * bound of its frequency >= consensus_frequency_cutoff -- the lower bound in consensus mode, the upper one in polymorphism
+ * mode -- coverage minima, homopolymer rules) and, failing that, whether it is present at all (polymorphism cutoffs, strand and
+ * quality bias p-values, both-strand coverage of the variant allele).  The row gains prediction=consensus|polymorphism and
+ * consensus_reject= / polymorphism_reject= / reject= with the reasons; a row that answers neither is dropped in consensus mode
+ * and kept with reject= in polymorphism mode; a consensus row whose major base is the reference base is dropped; user_defined
+ * rows are never dropped.  gd_in -> gd_out, every other line as it was (the reference holds the rows in memory: its own
+ * writer would add a #=TITLE line).  The members are breseq::Settings' (settings.h:473-500); brq_ra_filter_defaults fills them
+ * with what settings.cpp:862-896 / :918-948 leaves there for the mode.  Host only.  counts5 (may be NULL): RA rows read,
+ * predicted consensus, predicted polymorphism, kept rejected, deleted. */
+typedef struct brq_ra_filter_options {
+  int32_t polymorphism_prediction;
+  double mutation_log10_e_value_cutoff;
+  double consensus_frequency_cutoff;
+  uint32_t consensus_minimum_variant_coverage, consensus_minimum_total_coverage;
+  uint32_t consensus_minimum_variant_coverage_each_strand, consensus_minimum_total_coverage_each_strand;
+  uint32_t consensus_reject_indel_homopolymer_length, consensus_reject_surrounding_homopolymer_length;
+  double polymorphism_log10_e_value_cutoff;
+  double polymorphism_frequency_cutoff;
+  uint32_t polymorphism_minimum_variant_coverage, polymorphism_minimum_total_coverage;
+  uint32_t polymorphism_minimum_variant_coverage_each_strand, polymorphism_minimum_total_coverage_each_strand;
+  uint32_t polymorphism_reject_indel_homopolymer_length, polymorphism_reject_surrounding_homopolymer_length;
+  double polymorphism_fisher_strand_p_value_cutoff;
+  double polymorphism_ks_quality_p_value_cutoff;
+  int32_t polymorphism_no_indels;
+} brq_ra_filter_options;
+void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* out);
+int brq_test_ra_evidence(brq_ctx* ctx, const char* gd_in, const char* fasta, const brq_ra_filter_options* options,
+                         const char* gd_out, uint32_t* counts5);
+
 /* ---- one-call adapters with the reference entry points' argument meaning --------------------- */
 int brq_run_error_count(brq_ctx* ctx, const char* bam, const char* fasta, const char* output_dir,
                         const char* error_rates_file, const char* const* readfiles, uint32_t n_readfiles,

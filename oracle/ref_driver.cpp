@@ -151,6 +151,41 @@ int main(int argc, char** argv) {
                        prop, seed, atof(get("mutation-cutoff", "10").c_str()), atof(get("polymorphism-cutoff", "2").c_str()),
                        atof(get("precision", "1e-6").c_str()), (uint32_t)atoi(get("places", "8").c_str()),
                        opt.count("per-position") > 0);
+  } else if (cmd == "test_ra") {
+    // the Output stage's filter over the RA rows (breseq_cmdline.cpp:2609-2614 -> test_RA_evidence, identify_mutations.cpp:687-749):
+    // --gd-in FILE --gd-out FILE, thresholds as --<Settings member> VALUE (the members settings.cpp:862-948 sets per mode)
+    struct { const char* name; double* d; uint32_t* u; bool* b; } knobs[] = {
+      {"mutation_log10_e_value_cutoff", &settings.mutation_log10_e_value_cutoff, 0, 0},
+      {"consensus_frequency_cutoff", &settings.consensus_frequency_cutoff, 0, 0},
+      {"consensus_minimum_variant_coverage", 0, &settings.consensus_minimum_variant_coverage, 0},
+      {"consensus_minimum_total_coverage", 0, &settings.consensus_minimum_total_coverage, 0},
+      {"consensus_minimum_variant_coverage_each_strand", 0, &settings.consensus_minimum_variant_coverage_each_strand, 0},
+      {"consensus_minimum_total_coverage_each_strand", 0, &settings.consensus_minimum_total_coverage_each_strand, 0},
+      {"consensus_reject_indel_homopolymer_length", 0, &settings.consensus_reject_indel_homopolymer_length, 0},
+      {"consensus_reject_surrounding_homopolymer_length", 0, &settings.consensus_reject_surrounding_homopolymer_length, 0},
+      {"polymorphism_log10_e_value_cutoff", &settings.polymorphism_log10_e_value_cutoff, 0, 0},
+      {"polymorphism_frequency_cutoff", &settings.polymorphism_frequency_cutoff, 0, 0},
+      {"polymorphism_minimum_variant_coverage", 0, &settings.polymorphism_minimum_variant_coverage, 0},
+      {"polymorphism_minimum_total_coverage", 0, &settings.polymorphism_minimum_total_coverage, 0},
+      {"polymorphism_minimum_variant_coverage_each_strand", 0, &settings.polymorphism_minimum_variant_coverage_each_strand, 0},
+      {"polymorphism_minimum_total_coverage_each_strand", 0, &settings.polymorphism_minimum_total_coverage_each_strand, 0},
+      {"polymorphism_reject_indel_homopolymer_length", 0, &settings.polymorphism_reject_indel_homopolymer_length, 0},
+      {"polymorphism_reject_surrounding_homopolymer_length", 0, &settings.polymorphism_reject_surrounding_homopolymer_length, 0},
+      {"polymorphism_fisher_strand_p_value_cutoff", &settings.polymorphism_fisher_strand_p_value_cutoff, 0, 0},
+      {"polymorphism_ks_quality_p_value_cutoff", &settings.polymorphism_ks_quality_p_value_cutoff, 0, 0},
+      {"polymorphism_no_indels", 0, 0, &settings.polymorphism_no_indels},
+    };
+    for (auto& k : knobs) {
+      if (!opt.count(k.name)) continue;
+      const string v = opt[k.name];
+      if (k.d) *k.d = atof(v.c_str());
+      if (k.u) *k.u = (uint32_t)strtoul(v.c_str(), 0, 10);
+      if (k.b) *k.b = atoi(v.c_str()) != 0;
+    }
+    cGenomeDiff gd;
+    gd.read(get("gd-in", ""));
+    test_RA_evidence(gd, ref_seq_info, settings);
+    gd.write(get("gd-out", out + "/filtered.gd"));
   } else {
     cerr << "unknown command " << cmd << endl;
     return 2;

@@ -1,0 +1,98 @@
+"""The Output stage's filter over pass 2's RA rows (brq_test_ra_evidence, csrc/ra_filter.cpp) against what the reference's own
+test_RA_evidence (identify_mutations.cpp:687-749) wrote for the same files and settings (tests/golden/make_ra_filter_golden.py).
+Host only: no device involved."""
+import hashlib
+import json
+import os
+import re
+
+import pytest
+
+import breseq_b200 as bq
+import helpers
+
+GOLD = os.path.join(helpers.GOLDEN, "ra_filter")
+SETS = json.load(open(os.path.join(GOLD, "option_sets.json")))
+EXPECTED = [line.rstrip("\n").split("\t") for line in list(open(os.path.join(GOLD, "expected.tsv")))[1:]]
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = bq.Context(device=-1)
+    yield c
+    c.close()
+
+
+def filtered(ctx, gd_in, fasta, option_set, tmp_path):
+    out = str(tmp_path / "filtered.gd")
+    counts = ctx.test_RA_evidence(gd_in, fasta, out, option_set["polymorphism_prediction"], **option_set["settings"])
+    return open(out).read(), counts
+
+
+@pytest.mark.parametrize("k", range(len(SETS)))
+def test_corner_cases_like_the_reference(ctx, k, tmp_path):
+    text, counts = filtered(ctx, os.path.join(GOLD, "edge.gd"), os.path.join(GOLD, "edge.fasta"), SETS[k], tmp_path)
+    assert text == open(os.path.join(GOLD, "edge.%d.gd" % k)).read()
+    kept = [line for line in text.splitlines() if line.startswith("RA\t")]
+    assert counts["rows"] == 17 and counts["rows"] - counts["deleted"] == len(kept)
+    assert counts["consensus"] + counts["polymorphism"] + counts["rejected_kept"] >= len(kept)   # a consensus call of the reference base is counted, then dropped
+    # what is not an RA row passes through untouched
+    assert [line for line in text.splitlines() if not line.startswith("RA\t")] == \
+        [line for line in open(os.path.join(GOLD, "edge.gd")).read().splitlines() if not line.startswith("RA\t")]
+
+
+def test_every_reject_reason_is_exercised():
+    """The golden files are only worth what they reach: every reason the filter can give shows up in them."""
+    seen = set()
+    for k in range(len(SETS)):
+        for m in re.finditer(r"reject=([A-Z_,]+)", open(os.path.join(GOLD, "edge.%d.gd" % k)).read()):
+            seen.update(m.group(1).split(","))
+    assert seen >= {"SCORE_CUTOFF", "FREQUENCY_CUTOFF", "VARIANT_STRAND_COVERAGE", "TOTAL_STRAND_COVERAGE", "VARIANT_COVERAGE", "TOTAL_COVERAGE",
+                    "INDEL_HOMOPOLYMER", "SURROUNDING_HOMOPOLYMER", "POLYMORPHIC_INDEL", "KS_BASE_QUALITY", "FISHER_STRAND", "EXISTING"}
+
+
+def test_dataset_evidence_like_the_reference(ctx, datasets, tmp_path):
+    """The reference's own pass-2 files of the test datasets through every option set: the hash of what the reference kept."""
+    for name, gd, k, kept, digest in EXPECTED:
+        text, counts = filtered(ctx, os.path.join(helpers.GOLDEN, name, gd), datasets[name]["fasta"], SETS[int(k)], tmp_path)
+        assert hashlib.sha256(text.encode()).hexdigest() == digest, (name, gd, k)
+        assert counts["rows"] - counts["deleted"] == int(kept)
+
+
+def test_modes_differ_where_the_reference_says(ctx, tmp_path):
+    """Consensus mode drops a row that answers neither question, polymorphism mode keeps it with reject=; user_defined rows always stay."""
+    gd, fa = os.path.join(GOLD, "edge.gd"), os.path.join(GOLD, "edge.fasta")
+    cons, _ = filtered(ctx, gd, fa, SETS[0], tmp_path)
+    poly, _ = filtered(ctx, gd, fa, SETS[1], tmp_path)
+    ids = lambda text: {line.split("\t")[1] for line in text.splitlines() if line.startswith("RA\t")}
+    assert "13" not in ids(cons) and "13" in ids(poly)
+    row13 = [line for line in poly.splitlines() if line.startswith("RA\t13\t")][0]
+    assert "\treject=" in row13 and "\tprediction=polymorphism" in row13 and "polymorphism_reject" not in row13
+    assert "9" in ids(cons) and "12" not in ids(cons) and "12" not in ids(poly)
+
+
+def test_defaults_are_the_modes_of_settings_cpp(ctx):
+    c, p = ctx.ra_filter_defaults(False), ctx.ra_filter_defaults(True)
+    assert (c["consensus_frequency_cutoff"], c["polymorphism_frequency_cutoff"], c["polymorphism_log10_e_value_cutoff"]) == (0.5, 0.1, 10.0)   # settings.cpp:918-948
+    assert (p["consensus_frequency_cutoff"], p["polymorphism_frequency_cutoff"], p["polymorphism_log10_e_value_cutoff"]) == (0.95, 0.05, 2.0)  # settings.cpp:862-896
+    for o in (c, p):
+        assert o["polymorphism_minimum_variant_coverage_each_strand"] == 2 and o["polymorphism_fisher_strand_p_value_cutoff"] == 0.05
+        assert o["polymorphism_ks_quality_p_value_cutoff"] == 0 and o["mutation_log10_e_value_cutoff"] == 10
+
+
+def test_errors_are_loud(ctx, tmp_path):
+    fa = os.path.join(GOLD, "edge.fasta")
+    with pytest.raises(bq.BrqError, match="cannot open"):
+        ctx.test_RA_evidence(str(tmp_path / "absent.gd"), fa, str(tmp_path / "o.gd"))
+    bad = tmp_path / "bad.gd"
+    bad.write_text("#=GENOME_DIFF\t1.0\nRA\t1\t.\tedge\t5\t0\tT\tA\tfrequency=1\tmajor_base=A\tmajor_cov=5/5\ttotal_cov=5/5\n")
+    with pytest.raises(bq.BrqError, match="score"):
+        ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"))
+    bad.write_text("#=GENOME_DIFF\t1.0\nRA\t1\t.\tedge\t5\t0\tT\tA\tfrequency=1\tscore=20\tmajor_base=A\tmajor_cov=5/5\ttotal_cov=5/5\n")
+    with pytest.raises(bq.BrqError, match="frequency_lower"):
+        ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"))
+    bad.write_text("#=GENOME_DIFF\t1.0\nRA\t1\t.\telsewhere\t5\t0\tT\t.\tfrequency=1\tfrequency_lower=0.9\tfrequency_upper=1\tscore=20\tmajor_base=.\tmajor_cov=5/5\ttotal_cov=5/5\n")
+    with pytest.raises(bq.BrqError, match="elsewhere"):
+        ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"), consensus_reject_indel_homopolymer_length=3)
+    with pytest.raises(bq.BrqError, match="no member"):
+        ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"), not_a_setting=1)

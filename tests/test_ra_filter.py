@@ -96,3 +96,63 @@ def test_errors_are_loud(ctx, tmp_path):
         ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"), consensus_reject_indel_homopolymer_length=3)
     with pytest.raises(bq.BrqError, match="no member"):
         ctx.test_RA_evidence(str(bad), fa, str(tmp_path / "o.gd"), not_a_setting=1)
+
+
+@pytest.mark.skipif(not os.path.exists(helpers.REF_CLI), reason="oracle/_ref/ref_cli (the reference build) is not here")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_rows_against_the_reference_build(ctx, seed, tmp_path):
+    """Rows and thresholds drawn at random (runs of equal bases in the sequence, thin strands, p-values and scores on either side
+    of the cutoffs, user_defined and pre-rejected rows), live through ref_cli test_ra and through the library."""
+    import random
+    import subprocess
+    rng = random.Random(seed)
+    seq = "".join(rng.choice("ACGT") * rng.choice([1, 1, 1, 2, 3, 5, 7]) for _ in range(120))
+    fasta = tmp_path / "random.fasta"
+    fasta.write_text(">r\n%s\n" % seq)
+    rows, rid = [], 0
+    for pos in sorted(rng.sample(range(1, len(seq) + 1), 90)):
+        for ins in ([0] if rng.random() < 0.7 else [1, 2]):
+            rid += 1
+            ref = "." if ins else seq[pos - 1]
+            new = rng.choice("ACGT") if ins else rng.choice("ACGT.".replace(ref, ""))
+            major, minor = (new, ref) if rng.random() < 0.5 else (ref, new)
+            f = rng.random()
+            lo, hi = max(0.0, f - rng.random() * 0.3), min(1.0, f + rng.random() * 0.3)
+            cov = lambda: "%d/%d" % (rng.choice([0, 1, 2, 3, 8, 20, 40]), rng.choice([0, 1, 2, 5, 9, 25, 40]))
+            kv = {"frequency": "%.8e" % f, "frequency_lower": "%.8e" % lo, "frequency_upper": "%.8e" % hi, "major_base": major,
+                  "minor_base": minor, "major_cov": cov(), "minor_cov": cov(), "total_cov": cov(),
+                  "fisher_strand_p_value": "%.5e" % rng.choice([1.0, 0.5, 0.04, 1e-5]), "ks_quality_p_value": "%.5e" % rng.choice([1.0, 0.3, 0.02]),
+                  "score": rng.choice(["NA", "%.1f" % (rng.random() * 60), "1.5", "12.0"])}
+            if rng.random() < 0.1:
+                kv["user_defined"] = "1"
+            if rng.random() < 0.1:
+                kv["reject"] = rng.choice(["EXISTING", "SCORE_CUTOFF", "A,B"])
+            if rng.random() < 0.1:
+                del kv["score"]
+                kv[rng.choice(["consensus_score", "polymorphism_score"])] = "%.1f" % (rng.random() * 40)
+            rows.append("\t".join(["RA", str(rid), ".", "r", str(pos), str(ins), ref, new] + ["%s=%s" % (k, kv[k]) for k in sorted(kv)]))
+    gd = tmp_path / "random.gd"
+    gd.write_text("#=GENOME_DIFF\t1.0\n" + "\n".join(rows) + "\n")
+    for trial in range(4):
+        poly = rng.random() < 0.5
+        settings = {"mutation_log10_e_value_cutoff": rng.choice([10.0, 30.0]), "polymorphism_log10_e_value_cutoff": rng.choice([2.0, 10.0]),
+                    "consensus_frequency_cutoff": rng.choice([0.0, 0.5, 0.95]), "polymorphism_frequency_cutoff": rng.choice([0.0, 0.05, 0.2]),
+                    "polymorphism_fisher_strand_p_value_cutoff": rng.choice([0.0, 0.05]), "polymorphism_ks_quality_p_value_cutoff": rng.choice([0.0, 0.05]),
+                    "polymorphism_no_indels": rng.choice([0, 1])}
+        for name in ("consensus_minimum_variant_coverage", "consensus_minimum_total_coverage", "consensus_minimum_variant_coverage_each_strand",
+                     "consensus_minimum_total_coverage_each_strand", "polymorphism_minimum_variant_coverage", "polymorphism_minimum_total_coverage",
+                     "polymorphism_minimum_variant_coverage_each_strand", "polymorphism_minimum_total_coverage_each_strand"):
+            settings[name] = rng.choice([0, 0, 2, 10])
+        for name in ("consensus_reject_indel_homopolymer_length", "polymorphism_reject_indel_homopolymer_length",
+                     "consensus_reject_surrounding_homopolymer_length", "polymorphism_reject_surrounding_homopolymer_length"):
+            settings[name] = rng.choice([0, 2, 4, 6])
+        own, counts = filtered(ctx, str(gd), str(fasta), {"polymorphism_prediction": poly, "settings": settings}, tmp_path)
+        out = tmp_path / "ref.gd"
+        args = [helpers.REF_CLI, "test_ra", "--fasta", str(fasta), "--gd-in", str(gd), "--gd-out", str(out), "--out", str(tmp_path)]
+        args += ["--polymorphism-prediction"] if poly else []
+        for k, v in settings.items():
+            args += ["--" + k, repr(v)]
+        subprocess.run(args, check=True, capture_output=True, cwd=str(tmp_path))
+        ref = "".join(line for line in open(out) if not line.startswith("#=TITLE"))
+        assert own == ref, (seed, trial, settings)
+        assert counts["rows"] == len(rows)

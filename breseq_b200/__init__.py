@@ -169,6 +169,7 @@ def load_library():
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
         "brq_test_ra_evidence": [C.c_void_p, C.c_char_p, C.c_char_p, P(RaFilterOptions), C.c_char_p, P(C.c_uint32)],
+        "brq_predict_ra_mutations": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, P(C.c_uint32)],
         "brq_hist_exchange_export": [C.c_void_p, C.c_void_p, P(C.c_uint64)],
         "brq_hist_exchange_attach": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32],
         "brq_run_error_count": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, P(C.c_char_p), C.c_uint32,
@@ -200,7 +201,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
            "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts",
-           "brq_ra_filter_defaults", "brq_test_ra_evidence"]
+           "brq_ra_filter_defaults", "brq_test_ra_evidence", "brq_predict_ra_mutations"]
 
 
 def _b(s):
@@ -629,6 +630,15 @@ class Context:
         n = (C.c_uint32 * 5)()
         self._check(self.lib.brq_test_ra_evidence(self.h, _b(gd_in), _b(fasta), C.byref(o), _b(gd_out), n))
         return dict(zip(("rows", "consensus", "polymorphism", "rejected_kept", "deleted"), list(n)))
+
+    def predict_ra_mutations(self, gd_in, fasta, gd_out, polymorphism_prediction=False, targeted_sequencing=False,
+                             call_mutations_overlapping_missing_coverage=False):
+        """SNP / DEL / INS / SUB rows from the RA rows test_RA_evidence() accepted (mutation_predictor.cpp:1955-2211): ``gd_out`` =
+        the mutation rows in front of the evidence rows.  Returns the counts {SNP, DEL, INS, SUB, ra_marked_deleted}.  Host only."""
+        n = (C.c_uint32 * 5)()
+        self._check(self.lib.brq_predict_ra_mutations(self.h, _b(gd_in), _b(fasta), int(bool(polymorphism_prediction)), int(bool(targeted_sequencing)),
+                                                      int(bool(call_mutations_overlapping_missing_coverage)), _b(gd_out), n))
+        return dict(zip(("SNP", "DEL", "INS", "SUB", "ra_marked_deleted"), list(n)))
 
     def hist_exchange_export(self):
         """64-byte handle of this context's inbox for the fused collective of pass 1 (exchange it with the peer ranks)."""

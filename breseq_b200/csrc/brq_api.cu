@@ -1351,6 +1351,18 @@ int brq_test_ra_evidence(brq_ctx* c, const char* gd_in, const char* fasta, const
   });
 }
 
+int brq_predict_ra_mutations(brq_ctx* c, const char* gd_in, const char* fasta, int polymorphism_prediction, int targeted_sequencing,
+                             int call_mutations_overlapping_missing_coverage, const char* gd_out, uint32_t* counts5) {
+  return guarded(c, [&] {
+    RefSet ref;
+    read_fasta(fasta, ref);
+    normalise_reference(ref);
+    const RaMutationCounts n = predict_ra_mutations(gd_in, ref, polymorphism_prediction != 0, targeted_sequencing != 0,
+                                                    call_mutations_overlapping_missing_coverage != 0, gd_out);
+    if (counts5) { counts5[0] = n.snp; counts5[1] = n.del; counts5[2] = n.ins; counts5[3] = n.sub; counts5[4] = n.ra_marked_deleted; }
+  });
+}
+
 // ---- the fused collective of pass 1 (exchange.cu)
 int brq_hist_exchange_export(brq_ctx* c, void* handle64, uint64_t* capacity_words) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");

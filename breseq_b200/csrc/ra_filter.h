@@ -42,4 +42,15 @@ RaFilterCounts test_ra_evidence(const std::string& gd_in, const RefSet& ref, con
 
 void normalise_reference(RefSet& ref);
 
+// The RA step of mutation prediction (MutationPredictor::predictRAtoSNPorDELorINSorSUB, mutation_predictor.cpp:1955-2211) on
+// an evidence file test_ra_evidence() has been through: RA rows inside an MC row are marked deleted=1 (unless the run is
+// targeted sequencing or calls mutations over missing coverage), the accepted rows -- consensus calls, in polymorphism mode also
+// polymorphisms -- are walked in position order, neighbours joined, and every group becomes a SNP, DEL, INS or SUB row that
+// names its RA rows as evidence.  gd_out: the '#' lines, the new mutation rows in the GenomeDiff order, then the evidence rows.
+struct RaMutationCounts {
+  uint32_t snp = 0, del = 0, ins = 0, sub = 0, ra_marked_deleted = 0;
+};
+RaMutationCounts predict_ra_mutations(const std::string& gd_in, const RefSet& ref, bool polymorphism_prediction, bool targeted_sequencing,
+                                      bool call_mutations_overlapping_missing_coverage, const std::string& gd_out);
+
 }  // namespace brq

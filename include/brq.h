@@ -309,6 +309,19 @@ void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* 
 int brq_test_ra_evidence(brq_ctx* ctx, const char* gd_in, const char* fasta, const brq_ra_filter_options* options,
                          const char* gd_out, uint32_t* counts5);
 
+/* The RA step of mutation prediction on the filtered file: MutationPredictor::predictRAtoSNPorDELorINSorSUB
+ * (mutation_predictor.cpp:1955-2211, called from MutationPredictor::predict, :2946).  RA rows that lie inside an MC row are
+ * marked deleted=1 (not in targeted_sequencing runs; not with call_mutations_overlapping_missing_coverage; never user_defined
+ * rows); the accepted rows (prediction=consensus; in polymorphism mode every row without reject=) are taken in position
+ * order, neighbouring ones joined (never polymorphisms), and each group becomes a SNP, DEL, INS or SUB row with its RA rows as
+ * evidence, ids drawn like cGenomeDiff::new_unique_id, frequency= in polymorphism mode; consensus mode does not call inserted
+ * columns that do not start at insert position 1.  gd_out = the '#' lines, the mutation rows in GenomeDiff order, the evidence
+ * rows.  The three switches are Settings::polymorphism_prediction, ::targeted_sequencing,
+ * ::call_mutations_overlapping_missing_coverage.  An input that already holds mutation rows is refused.  Host only.
+ * counts5 (may be NULL): SNP, DEL, INS, SUB rows made, RA rows marked deleted. */
+int brq_predict_ra_mutations(brq_ctx* ctx, const char* gd_in, const char* fasta, int polymorphism_prediction, int targeted_sequencing,
+                             int call_mutations_overlapping_missing_coverage, const char* gd_out, uint32_t* counts5);
+
 /* ---- one-call adapters with the reference entry points' argument meaning --------------------- */
 int brq_run_error_count(brq_ctx* ctx, const char* bam, const char* fasta, const char* output_dir,
                         const char* error_rates_file, const char* const* readfiles, uint32_t n_readfiles,

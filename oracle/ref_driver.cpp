@@ -17,6 +17,7 @@
 #include "coverage_output.h"
 #include "error_count.h"
 #include "identify_mutations.h"
+#include "mutation_predictor.h"
 #include "reference_sequence.h"
 #include "settings.h"
 #include "summary.h"
@@ -186,6 +187,19 @@ int main(int argc, char** argv) {
     gd.read(get("gd-in", ""));
     test_RA_evidence(gd, ref_seq_info, settings);
     gd.write(get("gd-out", out + "/filtered.gd"));
+  } else if (cmd == "predict_ra") {
+    // the RA step of mutation prediction (MutationPredictor::predict, mutation_predictor.cpp:2946 ->
+    // predictRAtoSNPorDELorINSorSUB, :1955-2211) on an evidence file test_ra has been through: --gd-in FILE --gd-out FILE
+    // [--polymorphism-prediction] [--targeted-sequencing 1] [--call-mutations-overlapping-missing-coverage 1]
+    settings.targeted_sequencing = get("targeted-sequencing", "0") == "1";
+    settings.call_mutations_overlapping_missing_coverage = get("call-mutations-overlapping-missing-coverage", "0") == "1";
+    cGenomeDiff gd;
+    gd.read(get("gd-in", ""));
+    MutationPredictor mp(ref_seq_info);
+    diff_entry_list_t ra = gd.get_list(make_vector<gd_entry_type>(RA));
+    diff_entry_list_t mc = gd.get_list(make_vector<gd_entry_type>(MC));
+    mp.predictRAtoSNPorDELorINSorSUB(settings, summary, gd, ra, mc);
+    gd.write(get("gd-out", out + "/predicted.gd"));
   } else {
     cerr << "unknown command " << cmd << endl;
     return 2;

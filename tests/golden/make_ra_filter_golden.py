@@ -9,8 +9,11 @@ and tests/golden/ra_filter/edge.gd + edge.fasta, a hand-written file of the corn
 the sequence, substitutions joining runs, a row that already carries reject=, user_defined rows, legacy score fields, score=NA,
 a consensus call of the reference base, a row failing both questions).  Each goes through the option sets of
 tests/golden/ra_filter/option_sets.json (members of breseq::Settings by name over the mode's defaults).  The reference's writer
-adds a #=TITLE line from the file name, which is dropped.  Results: tests/golden/ra_filter/edge.<set>.gd in full and, for the
-datasets, tests/golden/ra_filter/expected.tsv (dataset, file, set, rows kept, sha256 of the output)."""
+adds a #=TITLE line from the file name, which is dropped.  Every filtered file then goes through ref_cli predict_ra
+(MutationPredictor::predictRAtoSNPorDELorINSorSUB, mutation_predictor.cpp:1955-2211) three times: as is, as a targeted-sequencing
+run, and with mutations called over missing coverage.  Results: tests/golden/ra_filter/edge.<set>.gd and
+edge.<set>.predicted.gd in full and, for the datasets, tests/golden/ra_filter/expected.tsv (dataset, file, set, rows kept, sha256
+of the filtered file and of the three predicted files)."""
 import hashlib
 import json
 import os
@@ -49,6 +52,21 @@ def reference_filter(ctx, gd_in, fasta, option_set, tmp):
     return "".join(line for line in open(out) if not line.startswith("#=TITLE"))
 
 
+SWITCHES = [(0, 0), (1, 0), (0, 1)]   # (targeted_sequencing, call_mutations_overlapping_missing_coverage)
+
+
+def reference_predict(filtered_text, fasta, polymorphism_prediction, targeted, over_mc, tmp):
+    """predict_ra on a filtered file: the mutation rows in front of the evidence rows, minus the #=TITLE line."""
+    gd_in, out = os.path.join(tmp, "to_predict.gd"), os.path.join(tmp, "predicted.gd")
+    open(gd_in, "w").write(filtered_text)
+    args = [helpers.REF_CLI, "predict_ra", "--fasta", fasta, "--gd-in", gd_in, "--gd-out", out, "--out", tmp,
+            "--targeted-sequencing", str(targeted), "--call-mutations-overlapping-missing-coverage", str(over_mc)]
+    if polymorphism_prediction:
+        args.append("--polymorphism-prediction")
+    subprocess.run(args, check=True, capture_output=True, cwd=tmp)
+    return "".join(line for line in open(out) if not line.startswith("#=TITLE"))
+
+
 def main():
     if not os.path.exists(helpers.REF_CLI):
         sys.exit("oracle/_ref/ref_cli is missing: run oracle/ref_build.sh where /root/reference exists")
@@ -58,6 +76,8 @@ def main():
         for k, s in enumerate(sets):
             text = reference_filter(ctx, os.path.join(OUT, "edge.gd"), os.path.join(OUT, "edge.fasta"), s, tmp)
             open(os.path.join(OUT, "edge.%d.gd" % k), "w").write(text)
+            predicted = reference_predict(text, os.path.join(OUT, "edge.fasta"), s["polymorphism_prediction"], 0, 0, tmp)
+            open(os.path.join(OUT, "edge.%d.predicted.gd" % k), "w").write(predicted)
         rows = []
         fasta = {}
         for name, gd in DATASET_FILES:
@@ -66,9 +86,13 @@ def main():
             for k, s in enumerate(sets):
                 text = reference_filter(ctx, os.path.join(HERE, name, gd), fasta[name], s, tmp)
                 kept = sum(1 for line in text.splitlines() if line.startswith("RA\t"))
-                rows.append("%s\t%s\t%d\t%d\t%s" % (name, gd, k, kept, hashlib.sha256(text.encode()).hexdigest()))
+                digests = [hashlib.sha256(text.encode()).hexdigest()]
+                for targeted, over_mc in SWITCHES:
+                    predicted = reference_predict(text, fasta[name], s["polymorphism_prediction"], targeted, over_mc, tmp)
+                    digests.append(hashlib.sha256(predicted.encode()).hexdigest())
+                rows.append("%s\t%s\t%d\t%d\t%s" % (name, gd, k, kept, "\t".join(digests)))
     with open(os.path.join(OUT, "expected.tsv"), "w") as fh:
-        fh.write("dataset\tfile\toption_set\tra_rows_kept\tsha256\n" + "\n".join(rows) + "\n")
+        fh.write("dataset\tfile\toption_set\tra_rows_kept\tsha256\tsha256_predicted\tsha256_predicted_targeted\tsha256_predicted_over_mc\n" + "\n".join(rows) + "\n")
     print(len(sets), "option sets,", len(rows), "dataset outputs")
 
 

@@ -13,6 +13,7 @@ import helpers
 
 GOLD = os.path.join(helpers.GOLDEN, "ra_filter")
 SETS = json.load(open(os.path.join(GOLD, "option_sets.json")))
+SWITCHES = [(0, 0), (1, 0), (0, 1)]   # (targeted_sequencing, call_mutations_overlapping_missing_coverage), as in the generator
 EXPECTED = [line.rstrip("\n").split("\t") for line in list(open(os.path.join(GOLD, "expected.tsv")))[1:]]
 
 
@@ -53,10 +54,57 @@ def test_every_reject_reason_is_exercised():
 
 def test_dataset_evidence_like_the_reference(ctx, datasets, tmp_path):
     """The reference's own pass-2 files of the test datasets through every option set: the hash of what the reference kept."""
-    for name, gd, k, kept, digest in EXPECTED:
+    for name, gd, k, kept, digest, *predicted in EXPECTED:
         text, counts = filtered(ctx, os.path.join(helpers.GOLDEN, name, gd), datasets[name]["fasta"], SETS[int(k)], tmp_path)
         assert hashlib.sha256(text.encode()).hexdigest() == digest, (name, gd, k)
         assert counts["rows"] - counts["deleted"] == int(kept)
+        # ... and on into the RA step of mutation prediction, under its three switches
+        for (targeted, over_mc), want in zip(SWITCHES, predicted):
+            out = str(tmp_path / "predicted.gd")
+            n = ctx.predict_ra_mutations(str(tmp_path / "filtered.gd"), datasets[name]["fasta"], out, SETS[int(k)]["polymorphism_prediction"], targeted, over_mc)
+            got = open(out).read()
+            assert hashlib.sha256(got.encode()).hexdigest() == want, (name, gd, k, targeted, over_mc)
+            assert n["SNP"] + n["DEL"] + n["INS"] + n["SUB"] == sum(1 for line in got.splitlines() if line[:4] in ("SNP\t", "DEL\t", "INS\t", "SUB\t"))
+
+
+@pytest.mark.parametrize("k", range(len(SETS)))
+def test_corner_cases_become_the_reference_s_mutations(ctx, k, tmp_path):
+    out = str(tmp_path / "predicted.gd")
+    n = ctx.predict_ra_mutations(os.path.join(GOLD, "edge.%d.gd" % k), os.path.join(GOLD, "edge.fasta"), out, SETS[k]["polymorphism_prediction"])
+    assert open(out).read() == open(os.path.join(GOLD, "edge.%d.predicted.gd" % k)).read()
+    row_1_stayed = "\nRA\t1\t" in open(os.path.join(GOLD, "edge.%d.gd" % k)).read()
+    assert n["ra_marked_deleted"] == int(row_1_stayed)    # row 1 sits in the MC row at 1-2
+
+
+def test_neighbouring_calls_join(ctx, tmp_path):
+    """Hand-made: two neighbouring consensus SNPs become one SUB, a run of deleted bases one DEL, inserted columns 1 and 2 one INS;
+    in polymorphism mode a polymorphic neighbour stays on its own; an insertion that starts at column 2 is not called in
+    consensus mode (mutation_predictor.cpp:2140-2146)."""
+    fasta = tmp_path / "j.fasta"
+    fasta.write_text(">j\nACGTACGTACGTACGTACGT\n")
+    common = "frequency=1.0e+00\tmajor_cov=9/9\tminor_cov=0/0\ttotal_cov=9/9\tscore=50.0\tprediction=consensus"
+    def ra(i, pos, ins, ref, new, extra=common):
+        return "RA\t%d\t.\tj\t%d\t%d\t%s\t%s\tmajor_base=%s\tminor_base=%s\t%s" % (i, pos, ins, ref, new, new, ref, extra)
+    poly = common.replace("frequency=1.0e+00", "frequency=4.0e-01").replace("prediction=consensus", "prediction=polymorphism")
+    rows = [ra(1, 2, 0, "C", "T"), ra(2, 3, 0, "G", "A"),                      # -> SUB 2 (size 2, TA)
+            ra(3, 6, 0, "C", "."), ra(4, 7, 0, "G", "."), ra(5, 8, 0, "T", "."),   # -> DEL 6 size 3
+            ra(6, 10, 1, ".", "G"), ra(7, 10, 2, ".", "G"),                    # -> INS 10 GG
+            ra(8, 13, 2, ".", "A"),                                            # starts at column 2: dropped in consensus mode
+            ra(9, 15, 0, "G", "C"), ra(10, 16, 0, "T", "C", poly)]             # consensus + polymorphic neighbour
+    gd = tmp_path / "j.gd"
+    gd.write_text("#=GENOME_DIFF\t1.0\n" + "\n".join(rows) + "\n")
+    out = tmp_path / "o.gd"
+    n = ctx.predict_ra_mutations(str(gd), str(fasta), str(out))
+    muts = [line.split("\t") for line in out.read_text().splitlines() if line[:2] not in ("RA", "#=")]
+    assert [m[:1] + m[2:] for m in muts] == [["SUB", "1,2", "j", "2", "2", "TA"], ["DEL", "3,4,5", "j", "6", "3"], ["INS", "6,7", "j", "10", "GG"],
+                                            ["SNP", "9", "j", "15", "C"]]
+    assert [m[1] for m in muts] == ["11", "12", "13", "14"] and n == {"SNP": 1, "DEL": 1, "INS": 1, "SUB": 1, "ra_marked_deleted": 0}
+    n = ctx.predict_ra_mutations(str(gd), str(fasta), str(out), polymorphism_prediction=True)
+    muts = [line.split("\t") for line in out.read_text().splitlines() if line[:2] not in ("RA", "#=")]
+    assert [m[:1] + m[2:] for m in muts] == [
+        ["SUB", "1,2", "j", "2", "2", "TA", "frequency=1"], ["DEL", "3,4,5", "j", "6", "3", "frequency=1"],
+        ["INS", "6,7", "j", "10", "GG", "frequency=1", "insert_position=1"], ["INS", "8", "j", "13", "A", "frequency=1", "insert_position=2"],
+        ["SNP", "9", "j", "15", "C", "frequency=1"], ["SNP", "10", "j", "16", "C", "frequency=4.0e-01"]]
 
 
 def test_modes_differ_where_the_reference_says(ctx, tmp_path):
@@ -99,7 +147,7 @@ def test_errors_are_loud(ctx, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.exists(helpers.REF_CLI), reason="oracle/_ref/ref_cli (the reference build) is not here")
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
 def test_random_rows_against_the_reference_build(ctx, seed, tmp_path):
     """Rows and thresholds drawn at random (runs of equal bases in the sequence, thin strands, p-values and scores on either side
     of the cutoffs, user_defined and pre-rejected rows), live through ref_cli test_ra and through the library."""
@@ -131,6 +179,12 @@ def test_random_rows_against_the_reference_build(ctx, seed, tmp_path):
                 del kv["score"]
                 kv[rng.choice(["consensus_score", "polymorphism_score"])] = "%.1f" % (rng.random() * 40)
             rows.append("\t".join(["RA", str(rid), ".", "r", str(pos), str(ins), ref, new] + ["%s=%s" % (k, kv[k]) for k in sorted(kv)]))
+    for k in range(4):   # missing coverage over some of the rows
+        start = rng.randrange(1, len(seq) - 20)
+        rid += 1
+        rows.append("MC\t%d\t.\tr\t%d\t%d\t0\t0\tleft_inside_cov=0\tleft_outside_cov=9\tright_inside_cov=0\tright_outside_cov=9" % (rid, start, start + rng.randrange(0, 12)))
+    rows.sort(key=lambda line: (line[:2] != "RA", int(line.split("\t")[4]), int(line.split("\t")[5])))   # RA rows, then MC rows, by position: the GenomeDiff order
+    n_ra = sum(1 for line in rows if line.startswith("RA\t"))
     gd = tmp_path / "random.gd"
     gd.write_text("#=GENOME_DIFF\t1.0\n" + "\n".join(rows) + "\n")
     for trial in range(4):
@@ -155,4 +209,14 @@ def test_random_rows_against_the_reference_build(ctx, seed, tmp_path):
         subprocess.run(args, check=True, capture_output=True, cwd=str(tmp_path))
         ref = "".join(line for line in open(out) if not line.startswith("#=TITLE"))
         assert own == ref, (seed, trial, settings)
-        assert counts["rows"] == len(rows)
+        assert counts["rows"] == n_ra
+        # on into the RA step of mutation prediction
+        targeted, over_mc = rng.choice([(0, 0), (0, 0), (1, 0), (0, 1)])
+        predicted = str(tmp_path / "predicted.gd")
+        ctx.predict_ra_mutations(str(tmp_path / "filtered.gd"), str(fasta), predicted, poly, targeted, over_mc)
+        args = [helpers.REF_CLI, "predict_ra", "--fasta", str(fasta), "--gd-in", str(tmp_path / "filtered.gd"), "--gd-out", str(out), "--out", str(tmp_path),
+                "--targeted-sequencing", str(targeted), "--call-mutations-overlapping-missing-coverage", str(over_mc)]
+        args += ["--polymorphism-prediction"] if poly else []
+        subprocess.run(args, check=True, capture_output=True, cwd=str(tmp_path))
+        ref = "".join(line for line in open(out) if not line.startswith("#=TITLE"))
+        assert open(predicted).read() == ref, (seed, trial, "predict", targeted, over_mc)

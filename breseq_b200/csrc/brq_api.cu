@@ -1317,6 +1317,11 @@ void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* 
   out->polymorphism_no_indels = o.polymorphism_no_indels;
 }
 
+void brq_binomial_frequency_bounds(double k, double n, double alpha, double* lower, double* upper) {
+  *lower = binomial_frequency_lower_bound(k, n, alpha);
+  *upper = binomial_frequency_upper_bound(k, n, alpha);
+}
+
 int brq_test_ra_evidence(brq_ctx* c, const char* gd_in, const char* fasta, const brq_ra_filter_options* in, const char* gd_out,
                          uint32_t* counts5) {
   return guarded(c, [&] {

@@ -180,6 +180,169 @@ double incbet(double aa, double bb, double xx) {
   if (flipped) t = t <= MACHEP ? 1.0 - MACHEP : 1.0 - t;
   return t;
 }
+
+// ---- the inverse of incbet in x (Cephes incbi.c; the reference's copy: stats.cpp:1076-1318) and the inverse normal it starts
+// from (ndtri.c; :1747-1796).  incbi alternates two searches until one of them is satisfied: bracketing with an adaptive split
+// ("halve") and Newton steps from inside the bracket ("newton", entered once); the bracket may be mirrored (x -> 1 - x, a <-> b)
+// when it closes in on 1.  Written as a three-state loop; every arithmetic step in the order the published code takes it.
+double ndtri(double p) {
+  static const double P0[5] = {-5.99633501014107895267E1, 9.80010754185999661536E1, -5.66762857469070293439E1, 1.39312609387279679503E1,
+                               -1.23916583867381258016E0};
+  static const double Q0[8] = {1.95448858338141759834E0, 4.67627912898881538453E0, 8.63602421390890590575E1, -2.25462687854119370527E2,
+                               2.00260212380060660359E2, -8.20372256168333339912E1, 1.59056225126211695515E1, -1.18331621121330003142E0};
+  static const double P1[9] = {4.05544892305962419923E0, 3.15251094599893866154E1, 5.71628192246421288162E1, 4.40805073893200834700E1,
+                               1.46849561928858024014E1, 2.18663306850790267539E0, -1.40256079171354495875E-1, -3.50424626827848203418E-2,
+                               -8.57456785154685413611E-4};
+  static const double Q1[8] = {1.57799883256466749731E1, 4.53907635128879210584E1, 4.13172038254672030440E1, 1.50425385692907503408E1,
+                               2.50464946208309415979E0, -1.42182922854787788574E-1, -3.80806407691578277194E-2, -9.33259480895457427372E-4};
+  static const double P2[9] = {3.23774891776946035970E0, 6.91522889068984211695E0, 3.93881025292474443415E0, 1.33303460815807542389E0,
+                               2.01485389549179081538E-1, 1.23716634817820021358E-2, 3.01581553508235416007E-4, 2.65806974686737550832E-6,
+                               6.23974539184983293730E-9};
+  static const double Q2[8] = {6.02427039364742014255E0, 3.67983563856160859403E0, 1.37702099489081330271E0, 2.16236993594496635890E-1,
+                               1.34204006088543189037E-2, 3.28014464682127739104E-4, 2.89247864745380683936E-6, 6.79019408009981274425E-9};
+  const double MAXNUM = 1.79769313486231570815E308, EXP_M2 = 0.13533528323661269189, SQRT_2PI = 2.50662827463100050242E0;
+  if (p <= 0.0) return -MAXNUM;
+  if (p >= 1.0) return MAXNUM;
+  bool lower_tail = true;
+  double y = p;
+  if (y > 1.0 - EXP_M2) { y = 1.0 - y; lower_tail = false; }
+  if (y > EXP_M2) {   // the middle: a rational function of (p - 1/2)^2
+    y = y - 0.5;
+    const double y2 = y * y;
+    double x = y + y * (y2 * horner(y2, P0, 4) / horner_monic(y2, Q0, 8));
+    return x * SQRT_2PI;
+  }
+  double x = sqrt(-2.0 * log(y));
+  const double x0 = x - log(x) / x, z = 1.0 / x;
+  const double x1 = x < 8.0 ? z * horner(z, P1, 8) / horner_monic(z, Q1, 8) : z * horner(z, P2, 8) / horner_monic(z, Q2, 8);
+  x = x0 - x1;
+  return lower_tail ? -x : x;
+}
+
+double incbi(double aa, double bb, double yy0) {
+  if (yy0 <= 0) return 0.0;
+  if (yy0 >= 1.0) return 1.0;
+  double x0 = 0.0, yl = 0.0, x1 = 1.0, yh = 1.0;   // the bracket and incbet at its ends
+  double a, b, y0, x = 0, y = 0, tolerance;
+  bool mirrored = false, newton_used = false;
+  enum { HALVE, NEWTON, DONE } state;
+  auto mirror = [&](bool on) {
+    mirrored = on;
+    if (on) { a = bb; b = aa; y0 = 1.0 - yy0; } else { a = aa; b = bb; y0 = yy0; }
+  };
+  if (aa <= 1.0 || bb <= 1.0) {
+    tolerance = 1.0e-6;
+    mirror(false);
+    x = a / (a + b);
+    y = incbet(a, b, x);
+    state = HALVE;
+  } else {
+    tolerance = 1.0e-4;
+    double yp = -ndtri(yy0);   // a normal approximation of the answer
+    if (yy0 > 0.5) { mirror(true); yp = -yp; } else { mirror(false); }
+    const double lgm = (yp * yp - 3.0) / 6.0;
+    x = 2.0 / (1.0 / (2.0 * a - 1.0) + 1.0 / (2.0 * b - 1.0));
+    double d = yp * sqrt(x + lgm) / x - (1.0 / (2.0 * b - 1.0) - 1.0 / (2.0 * a - 1.0)) * (lgm + 5.0 / 6.0 - 2.0 / (3.0 * x));
+    d = 2.0 * d;
+    if (d < MINLOG) {
+      x = 0.0;
+      state = DONE;
+    } else {
+      x = a / (a + b * exp(d));
+      y = incbet(a, b, x);
+      yp = (y - y0) / y0;
+      state = fabs(yp) < 0.2 ? NEWTON : HALVE;
+    }
+  }
+  while (state != DONE) {
+    if (state == HALVE) {
+      int dir = 0;          // how many steps in a row went the same way
+      double di = 0.5;      // where the bracket is split
+      int i = 0;
+      for (; i < 100; ++i) {
+        if (i != 0) {
+          x = x0 + di * (x1 - x0);
+          if (x == 1.0) x = 1.0 - MACHEP;
+          if (x == 0.0) {
+            di = 0.5;
+            x = x0 + di * (x1 - x0);
+            if (x == 0.0) { state = DONE; break; }
+          }
+          y = incbet(a, b, x);
+          double yp = (x1 - x0) / (x1 + x0);
+          if (fabs(yp) < tolerance) { state = NEWTON; break; }
+          yp = (y - y0) / y0;
+          if (fabs(yp) < tolerance) { state = NEWTON; break; }
+        }
+        if (y < y0) {
+          x0 = x;
+          yl = y;
+          if (dir < 0) { dir = 0; di = 0.5; }
+          else if (dir > 3) di = 1.0 - (1.0 - di) * (1.0 - di);
+          else if (dir > 1) di = 0.5 * di + 0.5;
+          else di = (y0 - y) / (yh - yl);
+          dir += 1;
+          if (x0 > 0.75) {   // closing in on 1: continue on the mirrored problem, from a fresh bracket
+            mirror(!mirrored);
+            x = 1.0 - x;
+            y = incbet(a, b, x);
+            x0 = 0.0; yl = 0.0; x1 = 1.0; yh = 1.0;
+            dir = 0; di = 0.5; i = -1;
+            continue;
+          }
+        } else {
+          x1 = x;
+          if (mirrored && x1 < MACHEP) { x = 0.0; state = DONE; break; }
+          yh = y;
+          if (dir > 0) { dir = 0; di = 0.5; }
+          else if (dir < -3) di = di * di;
+          else if (dir < -1) di = 0.5 * di;
+          else di = (y - y0) / (yh - yl);
+          dir -= 1;
+        }
+      }
+      if (i == 100) {   // the bracket did not close
+        if (x0 >= 1.0) { x = 1.0 - MACHEP; state = DONE; }
+        else if (x <= 0.0) { x = 0.0; state = DONE; }
+        else state = NEWTON;
+      }
+    } else {   // NEWTON
+      if (newton_used) { state = DONE; break; }
+      newton_used = true;
+      const double lgm = lgam(a + b) - lgam(a) - lgam(b);
+      state = HALVE;   // unless a step below is small enough
+      for (int i = 0; i < 8; ++i) {
+        if (i != 0) y = incbet(a, b, x);
+        if (y < yl) { x = x0; y = yl; }
+        else if (y > yh) { x = x1; y = yh; }
+        else if (y < y0) { x0 = x; yl = y; }
+        else { x1 = x; yh = y; }
+        if (x == 1.0 || x == 0.0) break;
+        double d = (a - 1.0) * log(x) + (b - 1.0) * log(1.0 - x) + lgm;   // log of the density at x
+        if (d < MINLOG) { state = DONE; break; }
+        if (d > MAXLOG) break;
+        d = exp(d);
+        d = (y - y0) / d;
+        double xt = x - d;
+        if (xt <= x0) {
+          y = (x - x0) / (x1 - x0);
+          xt = x0 + 0.5 * y * (x - x0);
+          if (xt <= 0.0) break;
+        }
+        if (xt >= x1) {
+          y = (x1 - x) / (x1 - x0);
+          xt = x1 - 0.5 * y * (x1 - x);
+          if (xt >= 1.0) break;
+        }
+        x = xt;
+        if (fabs(d / x) < 128.0 * MACHEP) { state = DONE; break; }
+      }
+      if (state == HALVE) tolerance = 256.0 * MACHEP;
+    }
+  }
+  if (mirrored) x = x <= MACHEP ? 1.0 - MACHEP : 1.0 - x;
+  return x;
+}
 }  // namespace cephes
 
 // Nelder-Mead over two parameters with the reference's coefficients, start simplex, ordering and stopping rule
@@ -234,6 +397,25 @@ bool simplex_minimize(F&& objective, const double start[2], double best[2]) {
 }
 
 }  // namespace
+
+// stats.cpp:2394-2414
+double binomial_frequency_lower_bound(double k, double n, double alpha) {
+  if (!(alpha > 0.0) || !(alpha < 1.0) || !(n > 0.0)) return 0.0;
+  if (k < 0.0) k = 0.0;
+  if (k > n) k = n;
+  if (k <= 0.0) return 0.0;
+  if (k >= n) return pow(alpha, 1.0 / k);
+  return cephes::incbi(k, n - k + 1.0, alpha);
+}
+
+double binomial_frequency_upper_bound(double k, double n, double alpha) {
+  if (!(alpha > 0.0) || !(alpha < 1.0) || !(n > 0.0)) return 1.0;
+  if (k < 0.0) k = 0.0;
+  if (k > n) k = n;
+  if (k >= n) return 1.0;
+  if (k <= 0.0) return 1.0 - pow(alpha, 1.0 / n);
+  return cephes::incbi(k + 1.0, n - k, 1.0 - alpha);
+}
 
 double nbinom_cdf(double k, double size, double mu) {
   return cephes::incbet(size, k + 1.0, size / (size + mu));

@@ -28,4 +28,8 @@ void read_coverage_distribution(const std::string& path, std::vector<double>& n,
 double nbinom_cdf(double k, double size, double mu);
 uint32_t nbinom_quantile(double target_pr, double size, double mu);
 
+// Exact (Clopper-Pearson) one-sided confidence bounds on k / n (stats.cpp:2394-2414, through the inverse incomplete beta)
+double binomial_frequency_lower_bound(double k, double n, double alpha = 0.05);
+double binomial_frequency_upper_bound(double k, double n, double alpha = 0.05);
+
 }  // namespace brq

@@ -4,6 +4,8 @@
 // genome_diff_entry.cpp:1323-1369) are part of what the output looks like.
 #include "ra_filter.h"
 
+#include "coverage_fit.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -207,9 +209,18 @@ bool test_row(Row& r, const Reference& R, const RaFilterOptions& o, RaFilterCoun
     lower = number<double>(r["frequency_lower"]);
     upper = number<double>(r["frequency_upper"]);
   } else {
-    // identify_mutations.cpp:215-228 rebuilds Clopper-Pearson bounds from total_cov for evidence written before the bounds were
-    // recorded; every file of this library's pass 2 (and of the reference's) records them
-    throw std::runtime_error("evidence row " + r["_id"] + " carries no frequency_lower / frequency_upper (evidence of an older breseq?)");
+    // evidence written before the bounds were recorded: Clopper-Pearson bounds with the raw read count as n
+    // (identify_mutations.cpp:215-228); without usable depth, the point estimate
+    lower = upper = number<double>(r["frequency"]);
+    std::vector<std::string> tb = has(r, "total_cov") ? split(r["total_cov"], '/') : std::vector<std::string>();
+    if (tb.size() >= 2) {
+      const double depth = number<double>(tb[0]) + number<double>(tb[1]);
+      if (depth > 0.0) {
+        const double k = number<double>(r["frequency"]) * depth;
+        lower = binomial_frequency_lower_bound(k, depth);
+        upper = binomial_frequency_upper_bound(k, depth);
+      }
+    }
   }
 
   if (score < o.mutation_log10_e_value_cutoff) add_reject_reason(r, "SCORE_CUTOFF");

@@ -306,6 +306,10 @@ typedef struct brq_ra_filter_options {
   int32_t polymorphism_no_indels;
 } brq_ra_filter_options;
 void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* out);
+/* The exact (Clopper-Pearson) one-sided bounds on k / n the filter falls back to for rows without frequency_lower /
+ * frequency_upper, i.e. evidence of an older breseq: binomial_frequency_lower_bound / _upper_bound (stats.h:134-135,
+ * stats.cpp:2394-2414; the inverse incomplete beta behind them restated from Cephes like the reference's copy). */
+void brq_binomial_frequency_bounds(double k, double n, double alpha, double* lower, double* upper);
 int brq_test_ra_evidence(brq_ctx* ctx, const char* gd_in, const char* fasta, const brq_ra_filter_options* options,
                          const char* gd_out, uint32_t* counts5);
 

@@ -20,6 +20,7 @@
 #include "mutation_predictor.h"
 #include "reference_sequence.h"
 #include "settings.h"
+#include "stats.h"
 #include "summary.h"
 
 #include <chrono>
@@ -66,6 +67,14 @@ int main(int argc, char** argv) {
              "deletion_coverage_propagation_cutoff\t%.17g\n", r.average, r.variance, r.relative_variance, r.nb_fit_size, r.nb_fit_mu,
              r.deletion_coverage_propagation_cutoff);
     cout << line;
+    return 0;
+  }
+
+  if (cmd == "binomial_bounds") {
+    // binomial_frequency_lower_bound / _upper_bound (stats.cpp:2394-2414) for "k n" pairs read from stdin, at --alpha
+    const double alpha = atof(get("alpha", "0.05").c_str());
+    double k, n;
+    while (cin >> k >> n) printf("%.17g\t%.17g\n", binomial_frequency_lower_bound(k, n, alpha), binomial_frequency_upper_bound(k, n, alpha));
     return 0;
   }
 

@@ -7,7 +7,9 @@ test_RA_evidence (identify_mutations.cpp:687-749), cGenomeDiff::write, compiled 
 Inputs: every committed ra_mc_evidence.gd of tests/golden/<dataset>/ (the reference's own pass-2 output on the test datasets)
 and tests/golden/ra_filter/edge.gd + edge.fasta, a hand-written file of the corner cases (indels at either end of a run and of
 the sequence, substitutions joining runs, a row that already carries reject=, user_defined rows, legacy score fields, score=NA,
-a consensus call of the reference base, a row failing both questions).  Each goes through the option sets of
+a consensus call of the reference base, a row failing both questions), and legacy.gd, the same rows without frequency_lower /
+frequency_upper (evidence of an older breseq: the filter rebuilds Clopper-Pearson bounds from total_cov; binomial_bounds.tsv pins
+those bounds themselves).  Each goes through the option sets of
 tests/golden/ra_filter/option_sets.json (members of breseq::Settings by name over the mode's defaults).  The reference's writer
 adds a #=TITLE line from the file name, which is dropped.  Every filtered file then goes through ref_cli predict_ra
 (MutationPredictor::predictRAtoSNPorDELorINSorSUB, mutation_predictor.cpp:1955-2211) three times: as is, as a targeted-sequencing
@@ -67,6 +69,24 @@ def reference_predict(filtered_text, fasta, polymorphism_prediction, targeted, o
     return "".join(line for line in open(out) if not line.startswith("#=TITLE"))
 
 
+def write_binomial_bounds():
+    """binomial_frequency_lower_bound / _upper_bound (stats.cpp:2394-2414) of the reference build for a fixed list of (k, n, alpha)."""
+    import random
+    rng = random.Random(7)
+    pairs = [(f * n, n) for n in (1, 2, 3, 5, 10, 29, 100, 292, 1000, 1e5) for f in (0, 0.001, 0.02, 0.24, 0.48, 0.5, 0.9, 0.982, 0.999, 1.0)]
+    for _ in range(300):
+        n = rng.choice([rng.randint(1, 50), rng.randint(1, 3000), rng.random() * 200])
+        pairs.append((rng.random() * n if rng.random() < 0.7 else float(rng.randint(0, int(n))), n))
+    pairs += [(0.5, 0.5), (0.2, 1.0), (1e-9, 10), (10 - 1e-9, 10), (-1, 5), (7, 5), (3, 0), (0.3, 0.9)]
+    with open(os.path.join(OUT, "binomial_bounds.tsv"), "w") as fh:
+        fh.write("k\tn\talpha\tlower\tupper\n")
+        for alpha in (0.05, 0.5, 0.001):
+            p = subprocess.run([helpers.REF_CLI, "binomial_bounds", "--alpha", repr(alpha)], input="".join("%r %r\n" % kn for kn in pairs),
+                               capture_output=True, text=True, check=True)
+            for (k, n), line in zip(pairs, p.stdout.strip().splitlines()):
+                fh.write("%r\t%r\t%r\t%s\n" % (k, n, alpha, line))
+
+
 def main():
     if not os.path.exists(helpers.REF_CLI):
         sys.exit("oracle/_ref/ref_cli is missing: run oracle/ref_build.sh where /root/reference exists")
@@ -78,6 +98,10 @@ def main():
             open(os.path.join(OUT, "edge.%d.gd" % k), "w").write(text)
             predicted = reference_predict(text, os.path.join(OUT, "edge.fasta"), s["polymorphism_prediction"], 0, 0, tmp)
             open(os.path.join(OUT, "edge.%d.predicted.gd" % k), "w").write(predicted)
+            # the same rows as an older breseq wrote them, without frequency_lower / frequency_upper: Clopper-Pearson bounds
+            text = reference_filter(ctx, os.path.join(OUT, "legacy.gd"), os.path.join(OUT, "edge.fasta"), s, tmp)
+            open(os.path.join(OUT, "legacy.%d.gd" % k), "w").write(text)
+        write_binomial_bounds()
         rows = []
         fasta = {}
         for name, gd in DATASET_FILES:

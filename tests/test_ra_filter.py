@@ -238,3 +238,22 @@ def test_random_rows_against_the_reference_build(ctx, seed, tmp_path):
         subprocess.run(args, check=True, capture_output=True, cwd=str(tmp_path))
         ref = "".join(line for line in open(out) if not line.startswith("#=TITLE"))
         assert open(predicted).read() == ref, (seed, trial, "predict", targeted, over_mc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted({row[0] for row in EXPECTED}))
+def test_from_the_bam_to_mutation_rows(name, datasets, tmp_path):
+    """The whole chain on the CUDA path -- error_count, identify_mutations, the RA filter, the RA step of mutation prediction --
+    ends in the files the reference's chain ends in (both modes of the filter, the default switches of the prediction)."""
+    from test_golden import run_cuda
+    d = datasets[name]
+    out = str(tmp_path / "cuda")
+    run_cuda(d, out)
+    c = bq.Context(device=-1)
+    for _, gd, k, kept, digest, predicted, *_ in [row for row in EXPECTED if row[0] == name and row[1] == "ra_mc_evidence.gd" and row[2] in ("0", "1")]:
+        poly = SETS[int(k)]["polymorphism_prediction"]
+        counts = c.test_RA_evidence(os.path.join(out, gd), d["fasta"], str(tmp_path / "filtered.gd"), poly)
+        assert hashlib.sha256(open(tmp_path / "filtered.gd", "rb").read()).hexdigest() == digest and counts["rows"] - counts["deleted"] == int(kept)
+        c.predict_ra_mutations(str(tmp_path / "filtered.gd"), d["fasta"], str(tmp_path / "predicted.gd"), poly)
+        assert hashlib.sha256(open(tmp_path / "predicted.gd", "rb").read()).hexdigest() == predicted
+    c.close()

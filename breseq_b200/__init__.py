@@ -188,6 +188,8 @@ def load_library():
         fn.restype = C.c_int
     lib.brq_binomial_frequency_bounds.argtypes = [C.c_double, C.c_double, C.c_double, P(C.c_double), P(C.c_double)]
     lib.brq_binomial_frequency_bounds.restype = None
+    lib.brq_fisher_strand_p_value.argtypes = [C.c_uint32] * 4
+    lib.brq_fisher_strand_p_value.restype = C.c_double
     lib.brq_ra_filter_defaults.argtypes = [C.c_int, P(RaFilterOptions)]
     lib.brq_ra_filter_defaults.restype = None
     _lib = lib
@@ -203,7 +205,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
            "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts",
-           "brq_ra_filter_defaults", "brq_test_ra_evidence", "brq_predict_ra_mutations", "brq_binomial_frequency_bounds"]
+           "brq_ra_filter_defaults", "brq_test_ra_evidence", "brq_predict_ra_mutations", "brq_binomial_frequency_bounds", "brq_fisher_strand_p_value"]
 
 
 def _b(s):
@@ -222,6 +224,11 @@ def binomial_frequency_bounds(k, n, alpha=0.05):
     lo, hi = C.c_double(), C.c_double()
     load_library().brq_binomial_frequency_bounds(k, n, alpha, C.byref(lo), C.byref(hi))
     return lo.value, hi.value
+
+
+def fisher_strand_p_value(minor_top, minor_bottom, major_top, major_bottom):
+    """fisher_strand_p_value of an RA row from the strand counts of its two alleles (stats.cpp:2144-2171)."""
+    return load_library().brq_fisher_strand_p_value(minor_top, minor_bottom, major_top, major_bottom)
 
 
 class SynthSpec:

@@ -1322,6 +1322,10 @@ void brq_binomial_frequency_bounds(double k, double n, double alpha, double* low
   *upper = binomial_frequency_upper_bound(k, n, alpha);
 }
 
+double brq_fisher_strand_p_value(uint32_t minor_top, uint32_t minor_bottom, uint32_t major_top, uint32_t major_bottom) {
+  return fisher_strand_p_value(minor_top, minor_bottom, major_top, major_bottom);
+}
+
 int brq_test_ra_evidence(brq_ctx* c, const char* gd_in, const char* fasta, const brq_ra_filter_options* in, const char* gd_out,
                          uint32_t* counts5) {
   return guarded(c, [&] {

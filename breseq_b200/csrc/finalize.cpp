@@ -546,6 +546,14 @@ double ks_less(const std::vector<uint32_t>& x_by_q, const std::vector<uint32_t>&
   return exp(-2.0 * statistic * statistic * n_eff);
 }
 
+}  // namespace
+
+double fisher_strand_p_value(uint32_t minor_top, uint32_t minor_bottom, uint32_t major_top, uint32_t major_bottom) {
+  return fisher_2x2(minor_top, minor_bottom, major_top, major_bottom);
+}
+
+namespace {
+
 // ============================================================================== per-slot re-evaluation
 // Everything below walks the slot's records in arrival order and accumulates exactly as the
 // reference's per-read loops do, so the numbers printed into RA rows carry the reference's

@@ -144,4 +144,7 @@ void write_per_position_file(const std::string& path, const BamHeader& hdr, cons
 void write_coverage_tsv(const std::string& pattern, const BamHeader& hdr, const RefSet& ref, const PileupStream& st, const std::vector<ColumnOut>& cols,
                         const std::vector<std::vector<CoverageColumn>>& by_group);
 
+// Two-sided Fisher exact test on a 2x2 table of strand counts (stats.cpp:2144-2171)
+double fisher_strand_p_value(uint32_t minor_top, uint32_t minor_bottom, uint32_t major_top, uint32_t major_bottom);
+
 }  // namespace brq

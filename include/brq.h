@@ -310,6 +310,10 @@ void brq_ra_filter_defaults(int polymorphism_prediction, brq_ra_filter_options* 
  * frequency_upper, i.e. evidence of an older breseq: binomial_frequency_lower_bound / _upper_bound (stats.h:134-135,
  * stats.cpp:2394-2414; the inverse incomplete beta behind them restated from Cephes like the reference's copy). */
 void brq_binomial_frequency_bounds(double k, double n, double alpha, double* lower, double* upper);
+/* fisher_strand_p_value of an RA row: the two-sided Fisher exact test (stats.cpp:2144-2171) on the strand counts of the minor
+ * and the major allele, as pass 2's finalisation evaluates it (identify_mutations.cpp:3009-3033).  Exposed for known-answer
+ * tests against the rows of the reference's own test suite. */
+double brq_fisher_strand_p_value(uint32_t minor_top, uint32_t minor_bottom, uint32_t major_top, uint32_t major_bottom);
 int brq_test_ra_evidence(brq_ctx* ctx, const char* gd_in, const char* fasta, const brq_ra_filter_options* options,
                          const char* gd_out, uint32_t* counts5);
 

@@ -138,6 +138,11 @@ def main():
     with open(os.path.join(OUT, "fisher_kat.tsv"), "w") as fh:
         fh.write("major_cov\tminor_cov\tfisher_strand_p_value\n" + "".join("%s\t%s\t%s\n" % (k[0], k[1], v) for k, v in sorted(kat.items())))
     print(len(kat), "Fisher known answers")
+    # the two per-read-group BAM2COV tables of the suite, as they are (tests/test_coverage_table.py rebuilds reads out of them)
+    import shutil
+    os.makedirs(os.path.join(OUT, "bam2cov"), exist_ok=True)
+    for name in ("no_read_groups", "multiple_read_groups"):
+        shutil.copy(os.path.join(REF_TESTS, "bam2cov_per_read_group", "expected.%s.tab" % name), os.path.join(OUT, "bam2cov", "per_read_group.%s.tab" % name))
     with open(os.path.join(OUT, "tests.json"), "w") as fh:
         fh.write(json.dumps(index, indent=1) + "\n")
 

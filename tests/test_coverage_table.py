@@ -108,3 +108,125 @@ def test_hand_derived_coverage_rows(checker, tmp_path):
         subprocess.run([helpers.REF_CLI, "coverage_table", "--bam", bam, "--fasta", fasta, "--region", "chr:1-14", "--table", ref],
                        check=True, cwd=str(tmp_path))
         assert open(ref).read() == open(mine).read()
+
+
+# ---- the reference's own BAM2COV fixture, with its missing input rebuilt from the table itself ------------------------------------
+def reads_from_table(rows, seq, first, last):
+    """A set of reads whose coverage IS the table.  Per strand the read-begin column gives one end of every read (a forward read
+    begins at its leftmost base, a reversed one at its rightmost: coverage_output.cpp:395-447); the other ends are placed so that
+    as few reads as possible are open (the tightest monotone envelope of the coverage column), and where the coverage dips below
+    the number of open reads, that many of them carry a deleted base there -- which BAM2COV does not count.  Open reads are closed
+    oldest first; deletions go to the newest ones.  Reads reach 20 bases past either end of the window."""
+    positions = list(range(first, last + 1))
+    lo, hi = first - 20, last + 20
+    out = []
+    for strand, cov_col, begin_col in ((0, 0, 6), (1, 1, 7)):
+        cov = [rows[p][cov_col] for p in positions]
+        begin = [rows[p][begin_col] for p in positions]
+        n = len(positions)
+        if strand == 0:   # opens known (begin), closes chosen: open[i] = R[i] + B[i], R non-increasing and as small as the coverage allows
+            B = [0] * n
+            for i in range(1, n):
+                B[i] = B[i - 1] + begin[i]
+            R = [0] * n
+            for i in range(n - 1, -1, -1):
+                R[i] = max(cov[i] - B[i], R[i + 1] if i + 1 < n else 0)
+            opened = [R[0]] + begin[1:]
+            closed_after = [R[i] - R[i + 1] for i in range(n - 1)] + [0]          # reads whose last base is positions[i]
+            first_lefts = [lo] * (R[0] - begin[0]) + [first] * begin[0]
+        else:             # closes known (begin = right ends), opens chosen: open[i] = S[i] - C[i], S non-decreasing and minimal
+            closed_after = begin[:]
+            C = [0] * n
+            for i in range(1, n):
+                C[i] = C[i - 1] + closed_after[i - 1]
+            S = [0] * n
+            for i in range(n):
+                S[i] = max(cov[i] + C[i], S[i - 1] if i else 0)
+            opened = [S[0]] + [S[i] - S[i - 1] for i in range(1, n)]
+            first_lefts = [lo] * S[0]
+        open_reads = []   # [left, deleted positions], oldest first
+        for i, p in enumerate(positions):
+            open_reads += [[left, []] for left in first_lefts] if i == 0 else [[p, []] for _ in range(opened[i])]
+            deleted = len(open_reads) - cov[i]
+            carriers = [r for r in open_reads[closed_after[i]:] if r[0] < p]      # not ending here, not starting here
+            assert 0 <= deleted <= len(carriers) and closed_after[i] <= len(open_reads), (p, strand)
+            for r in carriers[len(carriers) - deleted:]:
+                r[1].append(p)
+            for left, dels in open_reads[:closed_after[i]]:
+                out.append((left, p, strand, dels))
+            open_reads = open_reads[closed_after[i]:]
+        out += [(left, hi, strand, dels) for left, dels in open_reads]
+    out.sort(key=lambda r: (r[0], r[1], r[2]))
+    reads = []
+    for left, right, strand, dels in out:
+        cigar, bases, run_start, p = "", "", left, left
+        while p <= right:
+            if p in dels:
+                q = p
+                while q + 1 in dels:
+                    q += 1
+                cigar += "%dM%dD" % (p - run_start, q - p + 1)
+                bases += seq[run_start - 1:p - 1]
+                run_start = p = q + 1
+            else:
+                p += 1
+        cigar += "%dM" % (right + 1 - run_start)
+        bases += seq[run_start - 1:right]
+        reads.append(dict(tid=0, pos=left - 1, cigar=cigar, seq=bases, qual=[30] * len(bases), flag=16 * strand))
+    return reads
+
+
+def fasta_records(path):
+    out = []
+    for block in open(path).read().split(">")[1:]:
+        name, seq = block.split("\n", 1)
+        out.append((name.split()[0], seq.replace("\n", "")))
+    return out
+
+
+REBUILT_TABLES = [("per_read_group.no_read_groups.tab", "bull_1.fasta"), ("per_read_group.multiple_read_groups.tab", "lambda_split.fasta")]
+
+
+def rebuilt_inputs(table, fasta_fixture, tmp_path):
+    """(bam, fasta, region, path of the table the reference suite expects) with the BAM rebuilt from that table."""
+    import minibam
+    want = os.path.join(helpers.GOLDEN, "reference_tests", "bam2cov", table)
+    lines = [line.rstrip("\n").split("\t") for line in open(want)]
+    n_groups = sum(1 for c in lines[0] if c.endswith("_unique_top_cov") and c.startswith("RG-"))
+    rows = [dict() for _ in range(n_groups)]
+    for c in lines[1:]:
+        if c[0].isdigit():
+            assert [int(x) for x in c[2:10]] == [sum(int(c[10 + 8 * g + k]) for g in range(n_groups)) for k in range(8)]   # groups add up
+            for g in range(n_groups):
+                v = [int(x) for x in c[10 + 8 * g:18 + 8 * g]]
+                assert v[2:6] == [0, 0, 0, 0]                        # no redundant reads in these windows
+                rows[g][int(c[0])] = v
+    first, last = min(rows[0]), max(rows[0])
+    contigs = fasta_records(os.path.join(helpers.GOLDEN, "reference_tests", fasta_fixture))
+    name, seq = contigs[0]
+    groups = ["rg%d" % g for g in range(n_groups)] if n_groups > 1 else []
+    reads = []
+    for g in range(n_groups):
+        for r in reads_from_table(rows[g], seq, first, last):
+            if groups:
+                r["tags"] = {"RG": groups[g]}
+            reads.append(r)
+    reads.sort(key=lambda r: r["pos"])
+    assert any("D" in r["cigar"] for r in reads) or table != "per_read_group.no_read_groups.tab"   # the dip at 665 needs deletions
+    bam, fasta = str(tmp_path / "rebuilt.bam"), str(tmp_path / "rebuilt.fasta")
+    minibam.write(bam, fasta, contigs, reads, read_groups=groups)
+    return bam, fasta, "%s:%d-%d" % (name, first, last), want
+
+
+@pytest.mark.parametrize("table, fasta_fixture", REBUILT_TABLES)
+def test_reference_suite_table_from_reads_rebuilt_out_of_it(table, fasta_fixture, checker, tmp_path):
+    """/root/reference/tests/bam2cov_per_read_group/expected.*.tab (`breseq BAM2COV --format TSV --per-read-group`: rachael:657-767 of
+    bull_1.bam, which has no @RG line, and NC_001416-0:8000-8110 of lambda_mult_ref_read's BAM with four read groups, two of them
+    empty; neither BAM is in the checkout): reads rebuilt from the coverage and begin columns of each read group, put through the
+    walk and the table writer, give the file back byte for byte -- header, the RG-<n> column sets, every row (the dips where
+    reads have a base deleted included), the averages."""
+    bam, fasta, region, want = rebuilt_inputs(table, fasta_fixture, tmp_path)
+    out = str(tmp_path / "table.tab")
+    p = subprocess.run([checker, bam, fasta, region, "600", "0", "0", out, "1"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out).read() == open(want).read()

@@ -80,3 +80,19 @@ def test_read_group_columns_of_the_coverage_tsv_add_up(name, datasets, tmp_path)
             assert abs(redundant - sum(float(f[6 + 3 * g]) for g in range(n_rg))) < 1e-4 * max(1.0, redundant), l
             rows += 1
     assert rows == sum(d["contig_lens"])
+
+
+def test_reference_suite_tables_on_the_device(tmp_path):
+    """the two BAM2COV tables of the reference's own test suite, their BAMs rebuilt from the tables (test_coverage_table.py),
+    through the CUDA path: byte for byte"""
+    from test_coverage_table import REBUILT_TABLES, rebuilt_inputs
+    for table, fasta_fixture in REBUILT_TABLES:
+        sub = tmp_path / table
+        sub.mkdir()
+        bam, fasta, region, want = rebuilt_inputs(table, fasta_fixture, sub)
+        ctx = bq.Context(device=0)
+        ctx.stage_bam(bam, fasta, staging="device")
+        out = str(sub / "gpu.tab")
+        ctx.write_coverage_table(region, out, 600, False, False, True)
+        assert open(out).read() == open(want).read(), table
+        ctx.close()

@@ -166,6 +166,7 @@ def load_library():
         "brq_write_coverage_tsv": [C.c_void_p, C.c_char_p],
         "brq_write_per_position_counts": [C.c_void_p, C.c_char_p, C.c_char_p],
         "brq_write_coverage_table": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int],
+        "brq_write_coverage_table_with_average": [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_double],
         "brq_fit_coverage_distribution": [C.c_void_p, C.c_uint32, C.c_double, P(CoverageFit)],
         "brq_fit_coverage_file": [C.c_void_p, C.c_char_p, C.c_double, P(CoverageFit)],
         "brq_test_ra_evidence": [C.c_void_p, C.c_char_p, C.c_char_p, P(RaFilterOptions), C.c_char_p, P(C.c_uint32)],
@@ -205,7 +206,7 @@ EXPORTS = ["brq_create", "brq_destroy", "brq_last_error", "brq_version", "brq_st
            "brq_event_record", "brq_event_elapsed_ms", "brq_score_phase_ms", "brq_preprocess_read_starts",
            "brq_stream_summary", "brq_max_coverage_depth", "brq_set_min_coverage_depth", "brq_pin_reads", "brq_restage", "brq_synth_shard_bounds", "brq_bam_shard_bounds",
            "brq_fit_coverage_distribution", "brq_fit_coverage_file", "brq_hist_exchange_export", "brq_hist_exchange_attach", "brq_write_coverage_table", "brq_write_per_position_counts",
-           "brq_ra_filter_defaults", "brq_test_ra_evidence", "brq_predict_ra_mutations", "brq_binomial_frequency_bounds", "brq_fisher_strand_p_value"]
+           "brq_ra_filter_defaults", "brq_test_ra_evidence", "brq_predict_ra_mutations", "brq_binomial_frequency_bounds", "brq_fisher_strand_p_value", "brq_write_coverage_table_with_average"]
 
 
 def _b(s):
@@ -602,9 +603,14 @@ class Context:
         """``error_counts.tab`` of a covariate string with ref_pos: every position's non-empty bins (error_count.cpp:193-198)."""
         self._check(self.lib.brq_write_per_position_counts(self.h, _b(covariates), _b(path)))
 
-    def write_coverage_table(self, region, path, resolution=0, total_only=False, csv=False, per_read_group=False):
-        """BAM2COV's table for ``seq_id:start-end`` of the staged BAM (coverage_output.cpp:190-283, 307-470)."""
-        self._check(self.lib.brq_write_coverage_table(self.h, _b(region), _b(path), resolution, int(total_only), int(csv), int(per_read_group)))
+    def write_coverage_table(self, region, path, resolution=0, total_only=False, csv=False, per_read_group=False, reference_average=None):
+        """BAM2COV's table for ``seq_id:start-end`` of the staged BAM (coverage_output.cpp:190-283, 307-470); ``reference_average``
+        (BAM2COV -a): the sequence's fit average, printed as one more '#' line."""
+        if reference_average is None:
+            self._check(self.lib.brq_write_coverage_table(self.h, _b(region), _b(path), resolution, int(total_only), int(csv), int(per_read_group)))
+        else:
+            self._check(self.lib.brq_write_coverage_table_with_average(self.h, _b(region), _b(path), resolution, int(total_only), int(csv),
+                                                                       int(per_read_group), float(reference_average)))
 
     @staticmethod
     def _fit_dict(f):

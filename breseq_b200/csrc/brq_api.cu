@@ -1199,7 +1199,8 @@ int brq_write_per_position_counts(brq_ctx* c, const char* covariates, const char
   });
 }
 
-int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv, int per_read_group) {
+static int coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv, int per_read_group,
+                          const double* reference_average) {
   return guarded(c, [&] {
     c->need_device();
     if (!c->staged || !c->st.device_built) throw std::runtime_error("the coverage table needs reads staged on the device (brq_stage_options.staging = 0 or 2)");
@@ -1217,8 +1218,17 @@ int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, u
     // one more walk per read group: at least one set, like bam2cov --per-read-group (coverage_output.h:142-143)
     std::vector<std::vector<CoverageColumn>> by_group(per_read_group ? std::max<size_t>(c->hdr.read_groups.ids.size(), 1) : 0);
     for (size_t g = 0; g < by_group.size(); ++g) walk((uint32_t)g, by_group[g]);
-    write_coverage_table(path, c->hdr, c->ref, c->st, cols, by_group, region ? region : "", resolution, total_only != 0, csv != 0);
+    write_coverage_table(path, c->hdr, c->ref, c->st, cols, by_group, region ? region : "", resolution, total_only != 0, csv != 0, reference_average);
   });
+}
+
+int brq_write_coverage_table(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv, int per_read_group) {
+  return coverage_table(c, region, path, resolution, total_only, csv, per_read_group, nullptr);
+}
+
+int brq_write_coverage_table_with_average(brq_ctx* c, const char* region, const char* path, uint32_t resolution, int total_only, int csv,
+                                          int per_read_group, double reference_unique_average_cov) {
+  return coverage_table(c, region, path, resolution, total_only, csv, per_read_group, &reference_unique_average_cov);
 }
 
 int brq_evidence_export(brq_ctx* c, const double* prop, uint32_t n_targets, const void** data, uint64_t* bytes) {

@@ -24,7 +24,7 @@ std::string number(double v) {   // an ostream's default formatting of a double
 // floor(size / resolution)), then the region's averages as commented lines.
 void write_coverage_table(const std::string& path, const BamHeader& hdr, const RefSet& ref, const PileupStream& st,
                           const std::vector<CoverageColumn>& cols, const std::vector<std::vector<CoverageColumn>>& by_group,
-                          const std::string& region, uint32_t resolution, bool total_only, bool csv) {
+                          const std::string& region, uint32_t resolution, bool total_only, bool csv, const double* reference_average) {
   const size_t colon = region.find(':');
   if (colon == std::string::npos || region.find(':', colon + 1) != std::string::npos)
     throw std::runtime_error("Expected exactly one colon in region string:" + region);
@@ -114,6 +114,7 @@ void write_coverage_table(const std::string& path, const BamHeader& hdr, const R
     out << '\n';
   }
   const double sum_unique = total.unique, sum_repeat = total.repeat, sum_all = total.all;
+  if (reference_average) out << "#" << d << "reference_unique_average_cov" << d << number(*reference_average) << '\n';
   out << "#" << d << "region_unique_average_cov" << d << number(sum_unique / n_positions) << '\n';
   out << "#" << d << "region_repeat_average_cov" << d << number(sum_repeat / n_positions) << '\n';
   out << "#" << d << "region_average_cov" << d << number(sum_all / n_positions) << '\n';

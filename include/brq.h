@@ -245,9 +245,14 @@ int brq_write_per_position_counts(brq_ctx* ctx, const char* covariates, const ch
  * that many (the reference's thinning rule); csv = comma instead of tab.  The region's averages follow as '#' lines.  A walk
  * over the reads of the last staging on the device (a few ms): needs device staging.  per_read_group repeats the columns and
  * the averages once per @RG of the header (prefix "RG-<n>_", at least RG-0; one more walk per group).  Not written: the
- * read-begin and GC side files, the reference average line (-a). */
+ * read-begin and GC side files. */
 int brq_write_coverage_table(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv,
                              int per_read_group);
+/* BAM2COV -a (--show-average): the same table with "# reference_unique_average_cov <value>" in front of the region's averages,
+ * the value being Summary::references.reference[seq_id].coverage_average of breseq's summary.json (coverage_output.cpp:197-212,
+ * 259-262) -- the caller reads it there, or takes brq_fit_coverage_distribution's nbinom mean. */
+int brq_write_coverage_table_with_average(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv,
+                                          int per_read_group, double reference_unique_average_cov);
 
 /* ---- the collective of a sharded run, fused into pass 1 (csrc/exchange.cu) ------------------------------------------------
  * Instead of summing the brq_hist_device() buffers with a collective library between brq_error_count and

@@ -20,7 +20,7 @@
 using namespace brq;
 
 int main(int argc, char** argv) {
-  if (argc != 8 && argc != 9) { fprintf(stderr, "usage: coverage_check BAM FASTA REGION RESOLUTION TOTAL_ONLY CSV OUT [PER_READ_GROUP]\n"); return 2; }
+  if (argc < 8 || argc > 10) { fprintf(stderr, "usage: coverage_check BAM FASTA REGION RESOLUTION TOTAL_ONLY CSV OUT [PER_READ_GROUP [REFERENCE_AVERAGE]]\n"); return 2; }
   try {
     BamHeader hdr; ReadBatch R; RefSet ref;
     read_fasta(argv[2], ref);
@@ -47,14 +47,16 @@ int main(int argc, char** argv) {
     std::vector<CoverageColumn> cols(D.n_base + 1);
     for (uint32_t t = 0; t < plan.tiles; ++t) for (uint32_t l = 0; l < 32; ++l) coverage_lane(a, t, l, cols.data());
     std::vector<std::vector<CoverageColumn>> by_group;
-    if (argc == 9 && atoi(argv[8])) {
+    if (argc >= 9 && atoi(argv[8])) {
       by_group.resize(hdr.read_groups.ids.size() > 1 ? hdr.read_groups.ids.size() : 1);
       for (size_t g = 0; g < by_group.size(); ++g) {
         by_group[g].resize(D.n_base + 1);
         for (uint32_t t = 0; t < plan.tiles; ++t) for (uint32_t l = 0; l < 32; ++l) coverage_lane(a, t, l, by_group[g].data(), (uint32_t)g);
       }
     }
-    write_coverage_table(argv[7], hdr, ref, D, cols, by_group, argv[3], (uint32_t)atoi(argv[4]), atoi(argv[5]) != 0, atoi(argv[6]) != 0);
+    const double reference_average = argc >= 10 ? atof(argv[9]) : 0;   // BAM2COV -a
+    write_coverage_table(argv[7], hdr, ref, D, cols, by_group, argv[3], (uint32_t)atoi(argv[4]), atoi(argv[5]) != 0, atoi(argv[6]) != 0,
+                         argc >= 10 ? &reference_average : nullptr);
   } catch (const std::exception& e) {
     fprintf(stderr, "coverage_check: %s\n", e.what());
     return 1;

@@ -143,6 +143,9 @@ def main():
     os.makedirs(os.path.join(OUT, "bam2cov"), exist_ok=True)
     for name in ("no_read_groups", "multiple_read_groups"):
         shutil.copy(os.path.join(REF_TESTS, "bam2cov_per_read_group", "expected.%s.tab" % name), os.path.join(OUT, "bam2cov", "per_read_group.%s.tab" % name))
+    # ... and its two `BAM2COV -a` tables at the default resolution (summary.json there: coverage_average 330.7552)
+    shutil.copy(os.path.join(REF_TESTS, "bam2cov", "expected.tab"), os.path.join(OUT, "bam2cov", "show_average.tab"))
+    shutil.copy(os.path.join(REF_TESTS, "bam2cov_csv", "expected.csv"), os.path.join(OUT, "bam2cov", "show_average.csv"))
     with open(os.path.join(OUT, "tests.json"), "w") as fh:
         fh.write(json.dumps(index, indent=1) + "\n")
 

@@ -230,3 +230,63 @@ def test_reference_suite_table_from_reads_rebuilt_out_of_it(table, fasta_fixture
     p = subprocess.run([checker, bam, fasta, region, "600", "0", "0", out, "1"], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert open(out).read() == open(want).read()
+
+
+def fill_between_printed_rows(rows):
+    """A thinned table prints every k-th position.  The rows in between are free: each gets the read begins (forward strand) or the
+    read ends (reversed strand) that let the coverage move from one printed row to the next without deletions."""
+    printed = sorted(rows)
+    full = {printed[0]: rows[printed[0]]}
+    for a, b in zip(printed, printed[1:]):
+        for q in range(a + 1, b):
+            full[q] = list(full[q - 1])
+            full[q][6] = full[q][7] = 0
+        if b - a > 1:
+            q = b - 1
+            rise = rows[b][0] - rows[b][6] - rows[a][0]            # forward: what begins at b is printed; the rest began before b
+            if rise > 0:
+                full[q][0] += rise
+                full[q][6] = rise
+            # reversed: reads that end at a leave behind a; what else is missing at b ended (= "began") on a row in between
+            fall = (rows[a][1] - rows[a][7]) - rows[b][1]
+            for k in range(a + 1, b):
+                full[k][1] = rows[a][1] - rows[a][7]
+            if fall > 0:
+                full[q][7] = fall
+        full[b] = rows[b]
+    return full
+
+
+THINNED_TABLES = [("show_average.tab", False), ("show_average.csv", True)]
+REFERENCE_AVERAGE = 330.7552   # references.reference[rachael].coverage_average in the suite's summary.json
+
+
+def thinned_inputs(table, csv, tmp_path):
+    import minibam
+    want = os.path.join(helpers.GOLDEN, "reference_tests", "bam2cov", table)
+    rows = {}
+    for line in open(want):
+        c = line.rstrip("\n").split("," if csv else "\t")
+        if c[0].isdigit():
+            assert c[4:8] == ["0", "0", "0", "0"]
+            rows[int(c[0])] = [int(c[2]), int(c[3]), 0, 0, 0, 0, int(c[8]), int(c[9])]
+    first, last = min(rows), max(rows)
+    assert (first, last, len(rows)) == (657, 2167, 756)
+    full = fill_between_printed_rows(rows)
+    name, seq = fasta_records(os.path.join(helpers.GOLDEN, "reference_tests", "bull_1.fasta"))[0]
+    bam, fasta = str(tmp_path / "rebuilt.bam"), str(tmp_path / "rebuilt.fasta")
+    minibam.write(bam, fasta, [(name, seq)], reads_from_table(full, seq, first, last))
+    return bam, fasta, "%s:%d-%d" % (name, first, last), want
+
+
+@pytest.mark.parametrize("table, csv", THINNED_TABLES)
+def test_reference_suite_thinned_tables_with_the_reference_average(table, csv, checker, tmp_path):
+    """/root/reference/tests/bam2cov/expected.tab and bam2cov_csv/expected.csv (`BAM2COV -a -r rachael:657-2167` at the default
+    resolution of 600: every second position of 1511, as a table and as CSV; -a adds the fit average of summary.json, 330.7552).
+    Reads rebuilt from the printed rows (the rows in between are free), through the walk and the writer: byte for byte, i.e. the
+    thinning rule, the averages over the printed rows only, number_of_positions, the -a line, the CSV form."""
+    bam, fasta, region, want = thinned_inputs(table, csv, tmp_path)
+    out = str(tmp_path / "table.out")
+    p = subprocess.run([checker, bam, fasta, region, "600", "0", "1" if csv else "0", out, "0", repr(REFERENCE_AVERAGE)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out).read() == open(want).read()

@@ -85,7 +85,7 @@ def test_read_group_columns_of_the_coverage_tsv_add_up(name, datasets, tmp_path)
 def test_reference_suite_tables_on_the_device(tmp_path):
     """the two BAM2COV tables of the reference's own test suite, their BAMs rebuilt from the tables (test_coverage_table.py),
     through the CUDA path: byte for byte"""
-    from test_coverage_table import REBUILT_TABLES, rebuilt_inputs
+    from test_coverage_table import REBUILT_TABLES, REFERENCE_AVERAGE, THINNED_TABLES, rebuilt_inputs, thinned_inputs
     for table, fasta_fixture in REBUILT_TABLES:
         sub = tmp_path / table
         sub.mkdir()
@@ -94,5 +94,15 @@ def test_reference_suite_tables_on_the_device(tmp_path):
         ctx.stage_bam(bam, fasta, staging="device")
         out = str(sub / "gpu.tab")
         ctx.write_coverage_table(region, out, 600, False, False, True)
+        assert open(out).read() == open(want).read(), table
+        ctx.close()
+    for table, csv in THINNED_TABLES:   # BAM2COV -a at the default resolution, as a table and as CSV
+        sub = tmp_path / table
+        sub.mkdir()
+        bam, fasta, region, want = thinned_inputs(table, csv, sub)
+        ctx = bq.Context(device=0)
+        ctx.stage_bam(bam, fasta, staging="device")
+        out = str(sub / "gpu.out")
+        ctx.write_coverage_table(region, out, 600, False, csv, False, reference_average=REFERENCE_AVERAGE)
         assert open(out).read() == open(want).read(), table
         ctx.close()

@@ -245,7 +245,7 @@ int brq_write_per_position_counts(brq_ctx* ctx, const char* covariates, const ch
  * that many (the reference's thinning rule); csv = comma instead of tab.  The region's averages follow as '#' lines.  A walk
  * over the reads of the last staging on the device (a few ms): needs device staging.  per_read_group repeats the columns and
  * the averages once per @RG of the header (prefix "RG-<n>_", at least RG-0; one more walk per group).  Not written: the
- * read-begin and GC side files. */
+ * read-begin and GC side files (their options are commented out in breseq's own command line, breseq_cmdline.cpp:332, 487-489). */
 int brq_write_coverage_table(brq_ctx* ctx, const char* region, const char* path, uint32_t resolution, int total_only, int csv,
                              int per_read_group);
 /* BAM2COV -a (--show-average): the same table with "# reference_unique_average_cov <value>" in front of the region's averages,

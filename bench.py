@@ -311,9 +311,30 @@ def main():
     # memory over NVLink, no library call, no host in the loop), or BRQ_BENCH_NCCL=1: an NCCL allreduce between the calls
     fused = 1 < world <= 16 and not os.environ.get("BRQ_BENCH_NCCL")
     if fused:
+        # every rank has to end up on the same side: if one of them cannot export or map a peer's inbox (no peer access between
+        # two of the GPUs, IPC not permitted in the container), all fall back to the NCCL allreduce and the line says so
+        why, own = None, None
+        try:
+            own = ctx.hist_exchange_export()
+        except bq.BrqError as e:
+            why = str(e)
         handles = [None] * world
-        dist.all_gather_object(handles, ctx.hist_exchange_export())
-        ctx.hist_exchange_attach(handles, rank)
+        dist.all_gather_object(handles, own)
+        if why is None and all(h is not None for h in handles):
+            try:
+                ctx.hist_exchange_attach(handles, rank)
+            except bq.BrqError as e:
+                why = str(e)
+        elif why is None:
+            why = "a peer could not export its inbox"
+        reasons = [None] * world
+        dist.all_gather_object(reasons, why)
+        if any(r is not None for r in reasons):
+            if why is None:
+                ctx.hist_exchange_attach([own], 0)   # detach: one rank, no exchange
+            fused = False
+            if rank == 0:
+                print("bench: fused histogram exchange unavailable (%s): NCCL allreduce instead" % next(r for r in reasons if r is not None), file=sys.stderr)
         dist.barrier()
 
     def allreduce_hist():

@@ -158,6 +158,37 @@ def config_block(name, cfg, n_gpus):
                            "evidence shares gathered to rank 0" % n_gpus}
 
 
+def setup_fused_exchange(ctx, dist, rank, world):
+    """Attach the ranks' contexts to each other for the fused histogram exchange (csrc/exchange.cu).  Every rank has to end up on
+    the same side: if one of them cannot export or map a peer's inbox (no peer access between two of the GPUs, IPC not permitted
+    in the container), all of them detach, the caller sums with an NCCL allreduce instead and the bench line says so.
+    Returns whether the exchange is on."""
+    why, own = None, None
+    try:
+        own = ctx.hist_exchange_export()
+    except Exception as e:   # breseq_b200.BrqError
+        why = str(e)
+    handles = [None] * world
+    dist.all_gather_object(handles, own)
+    if why is None and all(h is not None for h in handles):
+        try:
+            ctx.hist_exchange_attach(handles, rank)
+        except Exception as e:
+            why = str(e)
+    elif why is None:
+        why = "a peer could not export its inbox"
+    reasons = [None] * world
+    dist.all_gather_object(reasons, why)
+    failed = [r for r in reasons if r is not None]
+    if failed:
+        if why is None:
+            ctx.hist_exchange_attach([own], 0)   # detach: one rank, no exchange
+        if rank == 0:
+            print("bench: fused histogram exchange unavailable (%s): NCCL allreduce instead" % failed[0], file=sys.stderr)
+    dist.barrier()
+    return not failed
+
+
 def reference_arm(args, name, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -311,31 +342,7 @@ def main():
     # memory over NVLink, no library call, no host in the loop), or BRQ_BENCH_NCCL=1: an NCCL allreduce between the calls
     fused = 1 < world <= 16 and not os.environ.get("BRQ_BENCH_NCCL")
     if fused:
-        # every rank has to end up on the same side: if one of them cannot export or map a peer's inbox (no peer access between
-        # two of the GPUs, IPC not permitted in the container), all fall back to the NCCL allreduce and the line says so
-        why, own = None, None
-        try:
-            own = ctx.hist_exchange_export()
-        except bq.BrqError as e:
-            why = str(e)
-        handles = [None] * world
-        dist.all_gather_object(handles, own)
-        if why is None and all(h is not None for h in handles):
-            try:
-                ctx.hist_exchange_attach(handles, rank)
-            except bq.BrqError as e:
-                why = str(e)
-        elif why is None:
-            why = "a peer could not export its inbox"
-        reasons = [None] * world
-        dist.all_gather_object(reasons, why)
-        if any(r is not None for r in reasons):
-            if why is None:
-                ctx.hist_exchange_attach([own], 0)   # detach: one rank, no exchange
-            fused = False
-            if rank == 0:
-                print("bench: fused histogram exchange unavailable (%s): NCCL allreduce instead" % next(r for r in reasons if r is not None), file=sys.stderr)
-        dist.barrier()
+        fused = setup_fused_exchange(ctx, dist, rank, world)
 
     def allreduce_hist():
         if world == 1 or fused:

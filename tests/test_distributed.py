@@ -97,3 +97,52 @@ def test_record_balanced_shards_from_windowed_reads():
         w.close()
     ctx.close()
     assert max(records) < 1.1 * (sum(records) / world), records
+
+
+class _FakeExchangeContext:
+    """Stands in for a device context in bench.setup_fused_exchange: records what it was asked, fails where told to."""
+
+    def __init__(self, rank, fail_export=False, fail_attach=False):
+        self.rank, self.fail_export, self.fail_attach, self.calls = rank, fail_export, fail_attach, []
+
+    def hist_exchange_export(self):
+        if self.fail_export:
+            raise bq.BrqError("cudaIpcGetMemHandle: not permitted")
+        return bytes([self.rank]) * 64
+
+    def hist_exchange_attach(self, handles, rank):
+        self.calls.append((len(handles), rank))
+        if self.fail_attach and len(handles) > 1:
+            raise bq.BrqError("cudaIpcOpenMemHandle: peer access is not supported")
+        assert all(len(h) == 64 for h in handles)
+
+
+def _exchange_worker(rank, world, port, out_dir, failing_rank, how):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, helpers.ROOT)
+        import bench
+        ctx = _FakeExchangeContext(rank, fail_export=(how == "export" and rank == failing_rank), fail_attach=(how == "attach" and rank == failing_rank))
+        on = bench.setup_fused_exchange(ctx, dist, rank, world)
+        with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as f:
+            f.write("%d %r\n" % (on, ctx.calls))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("how", ["none", "export", "attach"])
+def test_ranks_agree_on_the_fused_exchange_or_all_fall_back(how, tmp_path):
+    """bench.py --gpus N: the ranks attach to each other's inboxes for the fused histogram exchange, or -- if any one of them cannot
+    -- every rank detaches and reports that the NCCL allreduce is to be used.  No rank is left waiting for the others."""
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_exchange_worker, args=(WORLD, port, str(tmp_path), 1, how), nprocs=WORLD, join=True)
+    got = [open(str(tmp_path / ("rank%d.txt" % k))).read().split(" ", 1) for k in range(WORLD)]
+    assert [g[0] for g in got] == (["1", "1"] if how == "none" else ["0", "0"])
+    calls = [eval(g[1]) for g in got]
+    if how == "none":
+        assert calls == [[(2, 0)], [(2, 1)]]
+    elif how == "export":
+        assert calls == [[], []]                         # nobody attached
+    else:
+        assert calls == [[(2, 0), (1, 0)], [(2, 1)]]     # rank 0 had attached and detaches again

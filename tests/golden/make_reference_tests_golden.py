@@ -146,6 +146,21 @@ def main():
     # ... and its two `BAM2COV -a` tables at the default resolution (summary.json there: coverage_average 330.7552)
     shutil.copy(os.path.join(REF_TESTS, "bam2cov", "expected.tab"), os.path.join(OUT, "bam2cov", "show_average.tab"))
     shutil.copy(os.path.join(REF_TESTS, "bam2cov_csv", "expected.csv"), os.path.join(OUT, "bam2cov", "show_average.csv"))
+    # the suite's user-evidence file, and what the reference build (oracle/_ref/ref_cli) reports for it on reads simulated over the
+    # real lambda sequence (tests/test_reference_suite.py holds the read model): the golden of the oracle's and the library's parsers
+    shutil.copy(os.path.join(REF_TESTS, "lambda_polymorphism_user_evidence", "user_evidence.gd"), os.path.join(OUT, "lambda_user_evidence.input.gd"))
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import tempfile
+    import helpers
+    import test_reference_suite as suite
+    if os.path.exists(helpers.REF_CLI):
+        with tempfile.TemporaryDirectory() as tmp:
+            d = suite.user_evidence_inputs(os.path.join(tmp, "in"))
+            os.makedirs(os.path.join(tmp, "ref"))
+            open(suite.USER_WANT, "w").write(suite.run_both_passes(helpers.REF_CLI, d, os.path.join(tmp, "ref"), suite.USER_GD))
+    else:
+        print("oracle/_ref/ref_cli is missing: lambda_user_evidence.ra_mc_evidence.gd left as it is")
     with open(os.path.join(OUT, "tests.json"), "w") as fh:
         fh.write(json.dumps(index, indent=1) + "\n")
 

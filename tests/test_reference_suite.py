@@ -95,3 +95,59 @@ def test_fisher_strand_p_values_of_the_reference_suite(built):
         a, b = map(int, major.split("/"))
         c, d = map(int, minor.split("/"))
         assert "%.5e" % bq.fisher_strand_p_value(c, d, a, b) == want, (major, minor)
+
+
+# ---- the suite's user-evidence file (tests/lambda_polymorphism_user_evidence/user_evidence.gd: RA rows that duplicate real evidence,
+# rows for alleles no read shows, inserted columns up to insert_position 10, a JC row and comment lines in between) on reads
+# simulated over the real lambda sequence, C0's read model (se35, ~107x, polymorphism mode)
+USER_GD = os.path.join(DIR, "lambda_user_evidence.input.gd")
+USER_WANT = os.path.join(DIR, "lambda_user_evidence.ra_mc_evidence.gd")
+USER_DATASET = dict(seed=1, contig_lens=[48502], prefix="unused", read_sets=[dict(name="lambda", paired=False, read_len=35, coverage=107.0)],
+                    n_polymorphic=60, n_fixed=10, n_gaps=1, mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision=1e-6, places=8,
+                    del_prop=12.0, del_seed=0.0)
+
+
+def user_evidence_inputs(outdir):
+    d = dict(USER_DATASET)
+    os.makedirs(outdir, exist_ok=True)
+    d["bam"], d["fasta"] = os.path.join(outdir, "reference.bam"), os.path.join(outdir, "reference.fasta")
+    spec = bq.SynthSpec(seed=d["seed"], read_sets=d["read_sets"], fasta=os.path.join(DIR, "lambda.fasta"), n_polymorphic=d["n_polymorphic"],
+                        n_fixed=d["n_fixed"], n_gaps=d["n_gaps"])
+    ctx = bq.Context(device=-1)
+    ctx.synth_write(spec, d["bam"], d["fasta"])
+    ctx.close()
+    return d
+
+
+def run_both_passes(cli, d, outdir, user_gd):
+    import subprocess
+    ec, im = helpers.cli_args(d, outdir)
+    for args in (ec, im + ["--user-evidence", user_gd]):
+        subprocess.run([cli] + [str(a) for a in args], check=True, capture_output=True, text=True)
+    return open(os.path.join(outdir, "ra_mc_evidence.gd")).read()
+
+
+def test_suite_user_evidence_file_through_the_oracle(built, tmp_path):
+    """The oracle reads the suite's file like the reference build did (golden: lambda_user_evidence.ra_mc_evidence.gd): the JC row
+    and the comment lines are passed over, every RA row comes out -- marked on a row the data reports anyway, as a row of its own
+    for an allele no read shows, with forced sub-columns up to insert_position 10."""
+    d = user_evidence_inputs(str(tmp_path / "in"))
+    os.makedirs(str(tmp_path / "oracle"))
+    got = run_both_passes(helpers.ORACLE_CLI, d, str(tmp_path / "oracle"), USER_GD)
+    assert got == open(USER_WANT).read()
+    rows = [line.split("\t") for line in got.splitlines() if line.startswith("RA\t") and "user_defined=1" in line]
+    asked = [line.split("\t")[3:8] for line in open(USER_GD) if line.startswith("RA\t")]
+    assert sorted(r[3:8] for r in rows) == sorted([a[0], a[1], a[2], a[3], a[4].strip()] for a in asked)
+    if os.path.exists(helpers.REF_CLI):   # where the reference build is at hand: the golden is still what it writes
+        os.makedirs(str(tmp_path / "ref"))
+        assert run_both_passes(helpers.REF_CLI, d, str(tmp_path / "ref"), USER_GD) == got
+
+
+def test_suite_user_evidence_file_forces_its_sub_columns_in_host_staging(built, tmp_path):
+    d = user_evidence_inputs(str(tmp_path / "in"))
+    forced = bq.Context(device=-1)
+    forced.stage_bam(d["bam"], d["fasta"], user_evidence_gd=USER_GD, read_file_sets=[("lambda", 1)])
+    s = forced.stream()
+    have = {(int(p), int(k)) for p, k in zip(s["ins_parent"], s["ins_count"])}
+    assert {(100, k) for k in range(1, 11)} <= have and (133, 1) in have     # rows at 101 / insert 10 and 134 / insert 1 (0-based parents)
+    forced.close()

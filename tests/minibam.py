@@ -40,9 +40,9 @@ def write(bam_path, fasta_path, contigs, reads, read_groups=()):
             f.write(">%s\n%s\n" % (name, seq))
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, len(s)) for n, s in contigs)
     text += "".join("@RG\tID:%s\tLB:%s\n" % (g, g) for g in read_groups)
-    raw = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs))
+    parts = [b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(contigs))]   # joined once: many reads
     for name, seq in contigs:
-        raw += struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", len(seq))
+        parts.append(struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", len(seq)))
     for i, r in enumerate(reads):
         name = r.get("name", "read%d" % i).encode() + b"\0"
         cig = _cigar(r["cigar"])
@@ -55,7 +55,8 @@ def write(bam_path, fasta_path, contigs, reads, read_groups=()):
         body += name + b"".join(struct.pack("<I", c) for c in cig) + bytes(packed) + bytes(r["qual"])
         for k, v in r.get("tags", {}).items():
             body += _tag(k, v)
-        raw += struct.pack("<i", len(body)) + body
+        parts.append(struct.pack("<i", len(body)) + body)
+    raw = b"".join(parts)
     with open(bam_path, "wb") as f:
         for p in range(0, len(raw), 0xFF00):
             f.write(_bgzf_block(raw[p:p + 0xFF00]))

@@ -29,6 +29,7 @@ struct Case {
   bool read_pos, base_repeat, preprocess;
   uint32_t shard_rank, shard_count;
   bool want_hist = true, want_score = true;
+  std::string bam, fasta;   // reads from a BAM on disk instead of the generator (expand_check --bam BAM FASTA READ_SET)
 };
 
 SynthReadSet rs(const char* name, bool paired, uint32_t len, double cov, double fm = 400, double fs = 40) {
@@ -44,12 +45,17 @@ bool same(const char* what, const T* a, const T* b, size_t n, const std::string&
 
 bool run_case(const Case& c) {
   RefSet ref; BamHeader hdr; ReadBatch R; std::vector<SynthVariant> variants;
-  synth_reference(c.seed, c.contigs, "ctg", ref);
-  SynthConfig sc; sc.seed = c.seed; sc.sets = c.sets; sc.n_polymorphic = c.n_poly; sc.n_fixed = c.n_fixed; sc.n_gaps = c.n_gaps; sc.threads = 4;
-  synth_reads(sc, ref, hdr, R, variants);
-  // a few flagged reads the pileup keeps (secondary, QC fail, duplicate) and one it drops (unmapped with a position)
-  for (size_t i = 0; i < R.size(); i += 97) R.flag[i] |= (i % 3 == 0 ? 256 : i % 3 == 1 ? 512 : 1024);
-  if (R.size() > 50) R.flag[50] |= 4;
+  if (!c.bam.empty()) {
+    read_fasta(c.fasta, ref);
+    read_bam(c.bam, hdr, R, 4);
+  } else {
+    synth_reference(c.seed, c.contigs, "ctg", ref);
+    SynthConfig sc; sc.seed = c.seed; sc.sets = c.sets; sc.n_polymorphic = c.n_poly; sc.n_fixed = c.n_fixed; sc.n_gaps = c.n_gaps; sc.threads = 4;
+    synth_reads(sc, ref, hdr, R, variants);
+    // a few flagged reads the pileup keeps (secondary, QC fail, duplicate) and one it drops (unmapped with a position)
+    for (size_t i = 0; i < R.size(); i += 97) R.flag[i] |= (i % 3 == 0 ? 256 : i % 3 == 1 ? 512 : 1024);
+    if (R.size() > 50) R.flag[50] |= 4;
+  }
 
   StageConfig cfg;
   cfg.threads = 4;
@@ -238,6 +244,14 @@ int main(int argc, char** argv) {
   {
     Case hist_only = cases[1]; hist_only.name = "multi, histogram only"; hist_only.want_score = false; cases.push_back(hist_only);
     Case score_only = cases[1]; score_only.name = "multi, scoring only"; score_only.want_hist = false; cases.push_back(score_only);
+  }
+  if (argc == 5 && std::string(argv[1]) == "--bam") {   // one single-end read set, reads from a BAM on disk
+    Case external = cases[0];
+    external.name = "external BAM";
+    external.sets = {rs(argv[4], false, 0, 0.0)};
+    external.bam = argv[2];
+    external.fasta = argv[3];
+    return run_case(external) ? 0 : 1;
   }
   bool ok = true;
   for (const Case& c : cases) {

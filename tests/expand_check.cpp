@@ -29,7 +29,7 @@ struct Case {
   bool read_pos, base_repeat, preprocess;
   uint32_t shard_rank, shard_count;
   bool want_hist = true, want_score = true;
-  std::string bam, fasta;   // reads from a BAM on disk instead of the generator (expand_check --bam BAM FASTA READ_SET)
+  std::string bam, fasta;   // reads from a BAM on disk instead of the generator (expand_check --bam BAM FASTA READ_SET [paired])
 };
 
 SynthReadSet rs(const char* name, bool paired, uint32_t len, double cov, double fm = 400, double fs = 40) {
@@ -245,10 +245,10 @@ int main(int argc, char** argv) {
     Case hist_only = cases[1]; hist_only.name = "multi, histogram only"; hist_only.want_score = false; cases.push_back(hist_only);
     Case score_only = cases[1]; score_only.name = "multi, scoring only"; score_only.want_hist = false; cases.push_back(score_only);
   }
-  if (argc == 5 && std::string(argv[1]) == "--bam") {   // one single-end read set, reads from a BAM on disk
+  if ((argc == 5 || argc == 6) && std::string(argv[1]) == "--bam") {   // one read set (single-end, or "paired"), reads from a BAM on disk
     Case external = cases[0];
     external.name = "external BAM";
-    external.sets = {rs(argv[4], false, 0, 0.0)};
+    external.sets = {rs(argv[4], argc == 6, 0, 0.0)};
     external.bam = argv[2];
     external.fasta = argv[3];
     return run_case(external) ? 0 : 1;

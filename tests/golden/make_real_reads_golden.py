@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""Golden outputs of the REFERENCE BUILD (oracle/_ref/ref_cli) for the real reads of the reference's test suite (lambda, tmv plasmid), placed
+without gaps (tests/test_real_reads.py builds the BAMs): tests/golden/real_<name>/ra_mc_evidence.gd, outputs.sha256 (all four
+files of the two passes) and inputs.sha256 (the BAM).
+
+    python tests/golden/make_real_reads_golden.py        # after g.build(); needs /root/reference"""
+import os
+import shutil
+import sys
+import tempfile
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+import test_real_reads as t  # noqa: E402
+
+
+def main():
+    if not os.path.exists(helpers.REF_CLI):
+        sys.exit("oracle/_ref/ref_cli is missing: run oracle/ref_build.sh where /root/reference exists")
+    for name in sorted(t.REAL):
+        gold = t.gold_dir(name)
+        os.makedirs(gold, exist_ok=True)
+        with tempfile.TemporaryDirectory() as tmp:
+            d = t.build_inputs(name, os.path.join(tmp, "in"))
+            out = os.path.join(tmp, "ref")
+            t.run_passes(helpers.REF_CLI, d, out)
+            shutil.copy(os.path.join(out, "ra_mc_evidence.gd"), os.path.join(gold, "ra_mc_evidence.gd"))
+            with open(os.path.join(gold, "outputs.sha256"), "w") as fh:
+                for f in helpers.pass_output_names(d):
+                    fh.write("%s  %s\n" % (t.sha256(os.path.join(out, f)), f))
+            with open(os.path.join(gold, "inputs.sha256"), "w") as fh:
+                fh.write("%s  reference.bam (%d reads)\n" % (t.sha256(d["bam"]), d["n_reads"]))
+        print("real_" + name + ":", d["n_reads"], "reads")
+
+
+if __name__ == "__main__":
+    main()

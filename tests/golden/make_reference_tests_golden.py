@@ -125,6 +125,10 @@ def main():
         open(os.path.join(OUT, test + ".gd"), "w").write("\n".join(keep) + "\n")
         index[test] = {"polymorphism_prediction": poly, "settings": settings, "fasta": fasta, "rename": rename}
         print(test, sum(1 for r in keep if r.startswith("RA\t")), "RA rows")
+    # one more reference sequence, for the real reads of tests/test_real_reads.py
+    with open(os.path.join(OUT, "tmv_plasmid.fasta"), "w") as fh:
+        for name, seq in genbank_sequences(["tmv_plasmid/tmv-plasmid.gbk"]):
+            fh.write(">%s\n" % name + "".join(seq[i:i + 70] + "\n" for i in range(0, len(seq), 70)))
     # known answers for the strand-bias test of pass 2's finalisation: every distinct (major_cov, minor_cov) -> fisher_strand_p_value
     # among the RA rows of ALL the suite's expected.gd files (the long_ltee_* runs included)
     import glob

@@ -1,10 +1,11 @@
-"""REAL reads with their real base qualities through the path: the five lambda read files of the reference's own test suite
-(/root/reference/tests/data/lambda/lambda_mixed_population.*.fastq.gz, 200 000 Illumina reads of 35 bases with N runs and
-quality-2 tails), placed on the lambda sequence without gaps by tests/tools/ungapped_align.cpp (bowtie2, which breseq aligns with,
-is not in this image), ~145 000 reads, ~105x.
+"""REAL reads with their real base qualities through the path: read files of the reference's own test suite -- the five lambda
+files (/root/reference/tests/data/lambda/lambda_mixed_population.*.fastq.gz, 200 000 Illumina reads of 35 bases with N runs and
+quality-2 tails; ~145 000 placed, ~105x) and the paired 150-base reads of its tmv_plasmid tests (9193 pairs, binned qualities; two
+read files, ~200x on 10.4 kb) -- placed on their reference without gaps by tests/tools/ungapped_align.cpp (bowtie2, which breseq
+aligns with, is not in this image).
 
 * the oracle writes, byte for byte, what the reference build wrote for this BAM (tests/golden/real_lambda/: the evidence file and
-  the hashes of the other three, made by tests/golden/make_real_lambda_golden.py) -- and still does where the build is at hand;
+  the hashes of the other three, made by tests/golden/make_real_reads_golden.py) -- and still does where the build is at hand;
 * host staging carries exactly the records the oracle counts;
 * against the suite's own expected.gd for these reads (tests/lambda_polymorphism, aligned with bowtie2 and passed through the
   stages in front of the pileup, so not the same alignments): every consensus substitution it lists is among the rows found here,
@@ -20,35 +21,52 @@ import pytest
 import breseq_b200 as bq
 import helpers
 
-READS_DIR = "/root/reference/tests/data/lambda"
-READ_FILES = [os.path.join(READS_DIR, "lambda_mixed_population.%s.fastq.gz" % x) for x in "AB345"]
-GOLD = os.path.join(helpers.GOLDEN, "real_lambda")
-LAMBDA_FASTA = os.path.join(helpers.GOLDEN, "reference_tests", "lambda.fasta")
-DATASET = dict(seed=0, contig_lens=[48502], prefix="unused", read_sets=[dict(name="lambda", paired=False, read_len=35, coverage=105.0)],
-               mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision=1e-6, places=8, del_prop=12.0, del_seed=0.0)
+DATA = "/root/reference/tests/data"
+FIXTURES = os.path.join(helpers.GOLDEN, "reference_tests")
+# name -> reference FASTA (fixture), read files (one per read file of the run: two = a paired set, second file flagged 128), the
+# read set's name, run settings (lambda: polymorphism mode like the suite's lambda_polymorphism; tmv: consensus mode like its tmv tests)
+REAL = {
+    "lambda": dict(fasta=os.path.join(FIXTURES, "lambda.fasta"),
+                   files=[[os.path.join(DATA, "lambda", "lambda_mixed_population.%s.fastq.gz" % x) for x in "AB345"]], set_name="lambda",
+                   settings=dict(mutation_cutoff=10.0, polymorphism_cutoff=2.0, precision=1e-6, places=8, del_prop=12.0, del_seed=0.0), min_reads=140000),
+    # 9193 pairs of 150-base reads (binned qualities) on a 10.4 kb plasmid that carries two overlapping deletions
+    "tmv": dict(fasta=os.path.join(FIXTURES, "tmv_plasmid.fasta"),
+                files=[[os.path.join(DATA, "tmv_plasmid", "D3-9_1P.fastq.gz")], [os.path.join(DATA, "tmv_plasmid", "D3-9_2P.fastq.gz")]], set_name="D3-9",
+                settings=dict(mutation_cutoff=10.0, polymorphism_cutoff=10.0, precision=1e-6, places=3, del_prop=20.0, del_seed=0.0), min_reads=13000),
+}
 
-pytestmark = pytest.mark.skipif(not all(os.path.exists(f) for f in READ_FILES), reason="the reference suite's lambda read files are not here")
+pytestmark = pytest.mark.skipif(not all(os.path.exists(f) for r in REAL.values() for group in r["files"] for f in group),
+                                reason="the reference suite's read files are not here")
 
 
-def build_inputs(outdir):
+def gold_dir(name):
+    return os.path.join(helpers.GOLDEN, "real_" + name)
+
+
+def build_inputs(name, outdir):
     """BAM + FASTA of the placed reads; returns the dataset dict the helpers take."""
     import minibam
+    r = REAL[name]
     os.makedirs(outdir, exist_ok=True)
     tool = os.path.join(outdir, "ungapped_align")
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", tool, os.path.join(helpers.ROOT, "tests", "tools", "ungapped_align.cpp"), "-lz"], check=True)
-    tsv = os.path.join(outdir, "placed.tsv")
-    subprocess.run([tool, LAMBDA_FASTA, tsv] + READ_FILES, check=True, capture_output=True)
-    name, seq = open(LAMBDA_FASTA).read().split("\n", 1)
+    contig, seq = open(r["fasta"]).read().split("\n", 1)
     seq = seq.replace("\n", "")
+    paired = len(r["files"]) == 2
     reads = []
-    for line in open(tsv):
-        n, flag, pos, bases, quals = line.rstrip("\n").split("\t")
-        reads.append(dict(name=n, tid=0, pos=int(pos), cigar="%dM" % len(bases), seq=bases, qual=[ord(c) - 33 for c in quals], flag=int(flag),
-                          tags={"RG": "lambda", "X1": 1}))
-    reads.sort(key=lambda r: r["pos"])   # stable: file order within a position
-    d = dict(DATASET)
+    for k, group in enumerate(r["files"]):
+        tsv = os.path.join(outdir, "placed%d.tsv" % k)
+        subprocess.run([tool, r["fasta"], tsv] + group, check=True, capture_output=True)
+        for line in open(tsv):
+            n, flag, pos, bases, quals = line.rstrip("\n").split("\t")
+            flag = int(flag) | ((1 | (64 if k == 0 else 128)) if paired else 0)
+            reads.append(dict(name=n.split()[0], tid=0, pos=int(pos), cigar="%dM" % len(bases), seq=bases, qual=[ord(c) - 33 for c in quals], flag=flag,
+                              tags={"RG": r["set_name"], "X1": 1}))
+    reads.sort(key=lambda x: x["pos"])   # stable: file order within a position
+    d = dict(seed=0, contig_lens=[len(seq)], prefix="unused", read_sets=[dict(name=r["set_name"], paired=paired, read_len=len(reads[0]["seq"]), coverage=100.0)])
+    d.update(r["settings"])
     d["bam"], d["fasta"] = os.path.join(outdir, "reference.bam"), os.path.join(outdir, "reference.fasta")
-    minibam.write(d["bam"], d["fasta"], [(name[1:], seq)], reads, read_groups=["lambda"])
+    minibam.write(d["bam"], d["fasta"], [(contig[1:], seq)], reads, read_groups=[r["set_name"]])
     d["n_reads"] = len(reads)
     return d
 
@@ -60,10 +78,11 @@ def run_passes(cli, d, outdir, extra_ec=(), extra_im=()):
         subprocess.run([cli] + [str(a) for a in args], check=True, capture_output=True, text=True)
 
 
-@pytest.fixture(scope="module")
-def real(built, tmp_path_factory):
-    root = str(tmp_path_factory.mktemp("real_lambda"))
-    d = build_inputs(os.path.join(root, "in"))
+@pytest.fixture(scope="module", params=sorted(REAL))
+def real(request, built, tmp_path_factory):
+    root = str(tmp_path_factory.mktemp("real_" + request.param))
+    d = build_inputs(request.param, os.path.join(root, "in"))
+    d["real_name"] = request.param
     odir = os.path.join(root, "oracle")
     d["oracle_dir"], d["oracle_counts"], d["oracle_columns"] = odir, os.path.join(odir, "error_counts.tab"), os.path.join(odir, "columns.bin")
     d["oracle_rates"], d["oracle_gd"] = os.path.join(odir, "error_rates.tab"), os.path.join(odir, "ra_mc_evidence.gd")
@@ -76,10 +95,11 @@ def sha256(path):
 
 
 def test_oracle_writes_what_the_reference_build_wrote(real, tmp_path):
-    assert sha256(real["bam"]) == open(os.path.join(GOLD, "inputs.sha256")).read().split()[0], "the placed reads are not the ones the golden was made from"
-    assert real["n_reads"] > 140000
-    assert open(real["oracle_gd"]).read() == open(os.path.join(GOLD, "ra_mc_evidence.gd")).read()
-    want = dict(line.split()[::-1] for line in open(os.path.join(GOLD, "outputs.sha256")))
+    gold = gold_dir(real["real_name"])
+    assert sha256(real["bam"]) == open(os.path.join(gold, "inputs.sha256")).read().split()[0], "the placed reads are not the ones the golden was made from"
+    assert real["n_reads"] > REAL[real["real_name"]]["min_reads"]
+    assert open(real["oracle_gd"]).read() == open(os.path.join(gold, "ra_mc_evidence.gd")).read()
+    want = dict(line.split()[::-1] for line in open(os.path.join(gold, "outputs.sha256")))
     for f in helpers.pass_output_names(real):
         assert sha256(os.path.join(real["oracle_dir"], f)) == want[f], f
     if os.path.exists(helpers.REF_CLI):
@@ -101,6 +121,8 @@ def test_host_staging_carries_the_oracle_s_records(real):
 
 
 def test_rows_agree_with_the_suite_s_expected_gd(real):
+    if real["real_name"] != "lambda":
+        pytest.skip("the lambda reads only")
     def rows(path):
         out = {}
         for line in open(path):
@@ -126,5 +148,7 @@ def test_device_expander_logic_on_the_real_reads(real, tmp_path):
     srcs = [os.path.join(helpers.ROOT, "tests", "expand_check.cpp")] + [os.path.join(csrc, f) for f in
                                                                          ("staging.cpp", "synth.cpp", "bam_io.cpp", "inflate.cpp", "expand_plan.cpp")]
     subprocess.run(["g++", "-O2", "-std=c++17", "-w", "-o", exe] + srcs + ["-lz", "-lpthread"], check=True)
-    p = subprocess.run([exe, "--bam", real["bam"], real["fasta"], "lambda"], capture_output=True, text=True)
+    set_name = REAL[real["real_name"]]["set_name"]
+    p = subprocess.run([exe, "--bam", real["bam"], real["fasta"], set_name] + (["paired"] if len(REAL[real["real_name"]]["files"]) == 2 else []),
+                       capture_output=True, text=True)
     assert p.returncode == 0 and "equal" in p.stdout and "DIFFERENT" not in p.stdout, p.stdout + p.stderr

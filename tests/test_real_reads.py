@@ -140,15 +140,20 @@ def test_rows_agree_with_the_suite_s_expected_gd(real):
     assert diff[len(diff) // 2] < 0.02 and diff[-1] < 0.25
 
 
-def test_device_expander_logic_on_the_real_reads(real, tmp_path):
-    """csrc/expand_core.h (what the kernels of csrc/expand.cu run per read and per (read, column)), executed serially on the CPU by
-    tests/expand_check.cpp over the real reads: every stream equals host staging's bit for bit."""
-    exe = str(tmp_path / "expand_check")
+@pytest.fixture(scope="module")
+def expand_check(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("expand_check") / "expand_check")
     csrc = os.path.join(helpers.ROOT, "breseq_b200", "csrc")
     srcs = [os.path.join(helpers.ROOT, "tests", "expand_check.cpp")] + [os.path.join(csrc, f) for f in
                                                                          ("staging.cpp", "synth.cpp", "bam_io.cpp", "inflate.cpp", "expand_plan.cpp")]
     subprocess.run(["g++", "-O2", "-std=c++17", "-w", "-o", exe] + srcs + ["-lz", "-lpthread"], check=True)
+    return exe
+
+
+def test_device_expander_logic_on_the_real_reads(real, expand_check):
+    """csrc/expand_core.h (what the kernels of csrc/expand.cu run per read and per (read, column)), executed serially on the CPU by
+    tests/expand_check.cpp over the real reads: every stream equals host staging's bit for bit."""
     set_name = REAL[real["real_name"]]["set_name"]
-    p = subprocess.run([exe, "--bam", real["bam"], real["fasta"], set_name] + (["paired"] if len(REAL[real["real_name"]]["files"]) == 2 else []),
+    p = subprocess.run([expand_check, "--bam", real["bam"], real["fasta"], set_name] + (["paired"] if len(REAL[real["real_name"]]["files"]) == 2 else []),
                        capture_output=True, text=True)
     assert p.returncode == 0 and "equal" in p.stdout and "DIFFERENT" not in p.stdout, p.stdout + p.stderr

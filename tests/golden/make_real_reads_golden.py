@@ -28,6 +28,8 @@ def main():
             out = os.path.join(tmp, "ref")
             t.run_passes(helpers.REF_CLI, d, out)
             shutil.copy(os.path.join(out, "ra_mc_evidence.gd"), os.path.join(gold, "ra_mc_evidence.gd"))
+            # the coverage histogram of real reads: one more input of the coverage-fit goldens (make_coverage_fit_golden.py globs it)
+            shutil.copy(os.path.join(out, "0.unique_only_coverage_distribution.tab"), os.path.join(gold, "0.unique_only_coverage_distribution.tab"))
             with open(os.path.join(gold, "outputs.sha256"), "w") as fh:
                 for f in helpers.pass_output_names(d):
                     fh.write("%s  %s\n" % (t.sha256(os.path.join(out, f)), f))

@@ -6,6 +6,7 @@ files of the two passes) and inputs.sha256 (the BAM).
     python tests/golden/make_real_reads_golden.py        # after g.build(); needs /root/reference"""
 import os
 import shutil
+import subprocess
 import sys
 import tempfile
 
@@ -33,6 +34,13 @@ def main():
             with open(os.path.join(gold, "outputs.sha256"), "w") as fh:
                 for f in helpers.pass_output_names(d):
                     fh.write("%s  %s\n" % (t.sha256(os.path.join(out, f)), f))
+            with open(os.path.join(gold, "coverage_tables.sha256"), "w") as fh:   # BAM2COV's tables of the same BAM (coverage_output::table)
+                for cname, span, resolution, total_only, per_rg in t.COVERAGE_REQUESTS:
+                    table = os.path.join(tmp, cname + ".tab")
+                    subprocess.run([helpers.REF_CLI, "coverage_table", "--bam", d["bam"], "--fasta", d["fasta"], "--region", t.coverage_request_args(d, span),
+                                    "--resolution", str(resolution), "--total-only", str(total_only), "--format", "tsv", "--per-read-group", str(per_rg),
+                                    "--table", table], check=True, cwd=tmp, capture_output=True)
+                    fh.write("%s  %s\n" % (t.sha256(table), cname))
             with open(os.path.join(gold, "inputs.sha256"), "w") as fh:
                 fh.write("%s  reference.bam (%d reads)\n" % (t.sha256(d["bam"]), d["n_reads"]))
         print("real_" + name + ":", d["n_reads"], "reads")

@@ -157,3 +157,41 @@ def test_device_expander_logic_on_the_real_reads(real, expand_check):
     p = subprocess.run([expand_check, "--bam", real["bam"], real["fasta"], set_name] + (["paired"] if len(REAL[real["real_name"]]["files"]) == 2 else []),
                        capture_output=True, text=True)
     assert p.returncode == 0 and "equal" in p.stdout and "DIFFERENT" not in p.stdout, p.stdout + p.stderr
+
+
+COVERAGE_REQUESTS = [("whole", None, 600, 0, 0), ("window", (2001, 2600), 0, 0, 1)]   # name, span (None = all), resolution, total_only, per_read_group
+
+
+def coverage_request_args(d, span):
+    contig = open(d["fasta"]).readline()[1:].split()[0]
+    lo, hi = span or (1, d["contig_lens"][0])
+    return "%s:%d-%d" % (contig, lo, min(hi, d["contig_lens"][0]))
+
+
+@pytest.fixture(scope="module")
+def coverage_check(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("covcheck") / "coverage_check")
+    csrc = os.path.join(helpers.ROOT, "breseq_b200", "csrc")
+    srcs = [os.path.join(helpers.ROOT, "tests", "coverage_check.cpp")] + [os.path.join(csrc, f) for f in
+                                                                           ("staging.cpp", "bam_io.cpp", "inflate.cpp", "expand_plan.cpp", "coverage_table.cpp")]
+    subprocess.run(["g++", "-O2", "-std=c++17", "-w", "-I/usr/local/cuda/include", "-o", exe] + srcs + ["-lz", "-lpthread"], check=True)
+    return exe
+
+
+def test_bam2cov_tables_of_the_real_reads(real, coverage_check, tmp_path):
+    """BAM2COV's table over the real reads -- the whole sequence thinned to 600 rows, a window at full resolution with the
+    per-read-group columns -- from the walk the device kernel wraps and the product's writer: the files the reference build's
+    coverage_output::table wrote (hashes in tests/golden/real_<name>/coverage_tables.sha256)."""
+    want = dict(line.split()[::-1] for line in open(os.path.join(gold_dir(real["real_name"]), "coverage_tables.sha256")))
+    for name, span, resolution, total_only, per_rg in COVERAGE_REQUESTS:
+        region = coverage_request_args(real, span)
+        out = str(tmp_path / (name + ".tab"))
+        p = subprocess.run([coverage_check, real["bam"], real["fasta"], region, str(resolution), str(total_only), "0", out, str(per_rg)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert sha256(out) == want[name], (real["real_name"], name)
+        if os.path.exists(helpers.REF_CLI):
+            ref_out = str(tmp_path / (name + ".ref.tab"))
+            subprocess.run([helpers.REF_CLI, "coverage_table", "--bam", real["bam"], "--fasta", real["fasta"], "--region", region, "--resolution", str(resolution),
+                            "--total-only", str(total_only), "--format", "tsv", "--per-read-group", str(per_rg), "--table", ref_out], check=True, cwd=str(tmp_path),
+                           capture_output=True)
+            assert sha256(ref_out) == want[name], "live reference build: " + name

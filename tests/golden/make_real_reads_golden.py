@@ -41,6 +41,11 @@ def main():
                                     "--resolution", str(resolution), "--total-only", str(total_only), "--format", "tsv", "--per-read-group", str(per_rg),
                                     "--table", table], check=True, cwd=tmp, capture_output=True)
                     fh.write("%s  %s\n" % (t.sha256(table), cname))
+            d["real_name"] = name
+            import hashlib
+            filtered, predicted = t.ra_chain_reference(d, d["polymorphism_cutoff"] < d["mutation_cutoff"], os.path.join(tmp, "chain"))
+            with open(os.path.join(gold, "ra_chain.sha256"), "w") as fh:   # the Output stage's RA filter and the RA step of mutation prediction
+                fh.write("%s  filtered\n%s  predicted\n" % (hashlib.sha256(filtered.encode()).hexdigest(), hashlib.sha256(predicted.encode()).hexdigest()))
             with open(os.path.join(gold, "inputs.sha256"), "w") as fh:
                 fh.write("%s  reference.bam (%d reads)\n" % (t.sha256(d["bam"]), d["n_reads"]))
         print("real_" + name + ":", d["n_reads"], "reads")

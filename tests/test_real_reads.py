@@ -195,3 +195,40 @@ def test_bam2cov_tables_of_the_real_reads(real, coverage_check, tmp_path):
                             "--total-only", str(total_only), "--format", "tsv", "--per-read-group", str(per_rg), "--table", ref_out], check=True, cwd=str(tmp_path),
                            capture_output=True)
             assert sha256(ref_out) == want[name], "live reference build: " + name
+
+
+def ra_chain_reference(d, polymorphism_prediction, workdir):
+    """(filtered, predicted) texts of the reference build for the dataset's evidence file, mode defaults, minus the #=TITLE lines."""
+    os.makedirs(workdir, exist_ok=True)
+    gd = os.path.join(gold_dir(d["real_name"]), "ra_mc_evidence.gd")
+    mode = ["--polymorphism-prediction"] if polymorphism_prediction else []
+    ctx = bq.Context(device=-1)
+    knobs = []
+    for k, v in ctx.ra_filter_defaults(polymorphism_prediction).items():
+        if k != "polymorphism_prediction":
+            knobs += ["--" + k, repr(v)]
+    ctx.close()
+    filtered, predicted = os.path.join(workdir, "filtered.gd"), os.path.join(workdir, "predicted.gd")
+    subprocess.run([helpers.REF_CLI, "test_ra", "--fasta", d["fasta"], "--gd-in", gd, "--gd-out", filtered, "--out", workdir] + mode + knobs,
+                   check=True, capture_output=True, cwd=workdir)
+    subprocess.run([helpers.REF_CLI, "predict_ra", "--fasta", d["fasta"], "--gd-in", filtered, "--gd-out", predicted, "--out", workdir] + mode,
+                   check=True, capture_output=True, cwd=workdir)
+    strip = lambda path: "".join(line for line in open(path) if not line.startswith("#=TITLE"))
+    return strip(filtered), strip(predicted)
+
+
+def test_filter_and_prediction_on_the_real_evidence(real, tmp_path):
+    """The evidence of the real reads on through the Output stage's RA filter and the RA step of mutation prediction (the mode of
+    the run, default thresholds): the reference build's files (hashes in tests/golden/real_<name>/ra_chain.sha256)."""
+    poly = real["polymorphism_cutoff"] < real["mutation_cutoff"]
+    want = dict(line.split()[::-1] for line in open(os.path.join(gold_dir(real["real_name"]), "ra_chain.sha256")))
+    ctx = bq.Context(device=-1)
+    filtered, predicted = str(tmp_path / "filtered.gd"), str(tmp_path / "predicted.gd")
+    ctx.test_RA_evidence(real["oracle_gd"], real["fasta"], filtered, poly)
+    n = ctx.predict_ra_mutations(filtered, real["fasta"], predicted, poly)
+    ctx.close()
+    assert sha256(filtered) == want["filtered"] and sha256(predicted) == want["predicted"]
+    assert n["SNP"] >= 1
+    if os.path.exists(helpers.REF_CLI):
+        ref_filtered, ref_predicted = ra_chain_reference(real, poly, str(tmp_path / "ref"))
+        assert open(filtered).read() == ref_filtered and open(predicted).read() == ref_predicted
